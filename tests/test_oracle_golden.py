@@ -1,0 +1,140 @@
+"""CPU: the oracle restatement reproduces the reference outputs stored in tests/golden/ (parity pinning)."""
+import glob
+import json
+import os
+
+import pytest
+import torch
+
+from oracle import encodings as oenc
+from oracle import iwe as oiwe
+from oracle import spiking as osp
+from tests.conftest import GOLDEN, load_golden
+
+torch.set_num_threads(1)
+
+CELLS = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "cell_*.npz")))
+FIRENETS = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "firenet_*.npz")))
+LOSSES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "loss_*.npz")))
+
+
+def test_manifest_lists_every_fixture():
+    man = json.load(open(os.path.join(GOLDEN, "MANIFEST.json")))
+    on_disk = {os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, "*.npz"))}
+    assert on_disk == set(man["files"]) and len(on_disk) >= 20
+
+
+def cell_params(g):
+    return {k[2:]: v for k, v in g.items() if k.startswith("p_")}
+
+
+@pytest.mark.parametrize("name", CELLS)
+def test_cell_step_matches_reference(name):
+    g = load_golden(name)
+    _, neuron, _, reset, _ = name.split("_")
+    x = g["x"].requires_grad_(True)
+    st = g["state"].requires_grad_(True)
+    p = {k: v.requires_grad_(True) for k, v in cell_params(g).items()}
+    out, ns = osp.cell_step(neuron, x, st, p, hard_reset=(reset == "hard"), width=float(g["width"]))
+    assert torch.equal(out, g["out"]) and torch.equal(ns, g["new_state"])
+    ((out * g["g_out"]).sum() + (ns * g["g_state"]).sum()).backward()
+    torch.testing.assert_close(x.grad, g["grad_x"], rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(st.grad, g["grad_state"], rtol=1e-5, atol=1e-7)
+    for k, v in p.items():
+        if "grad_" + k in g:
+            torch.testing.assert_close(v.grad, g["grad_" + k], rtol=1e-4, atol=1e-6)
+
+
+def firenet_params(g, neuron):
+    params = {}
+    for layer in osp.FIRENET_LAYERS:
+        p = {"ff": g[f"sd_{layer}.ff.weight"]}
+        if f"sd_{layer}.rec.weight" in g:
+            p["rec"] = g[f"sd_{layer}.rec.weight"]
+        for k in ("leak", "thresh", "leak_v", "leak_pt", "leak_t", "add_pt", "t0", "t1"):
+            if f"sd_{layer}.{k}" in g:
+                p[k] = g[f"sd_{layer}.{k}"]
+        params[layer] = p
+    params["pred"] = {"weight": g["sd_pred.conv2d.weight"], "bias": g["sd_pred.conv2d.bias"]}
+    return params
+
+
+@pytest.mark.parametrize("name", FIRENETS)
+def test_firenet_rollout_matches_reference(name):
+    g = load_golden(name)
+    neuron = name.split("_")[1]
+    params = firenet_params(g, neuron)
+    leaves = []
+    for lp in params.values():
+        for k in lp:
+            lp[k] = lp[k].clone().requires_grad_(True)
+            leaves.append(lp[k])
+    T = sum(1 for k in g if k.startswith("x_"))
+    states, loss = [None] * 7, 0
+    for t in range(T):
+        flow, states, _ = osp.firenet_step(neuron, params, states, g[f"x_{t}"])
+        assert torch.equal(flow, g[f"flow_{t}"])
+        loss = loss + (flow * g[f"gw_{t}"]).sum()
+    for i in range(7):
+        if f"state_{i}" in g:
+            assert torch.equal(states[i], g[f"state_{i}"])
+    loss.backward()
+    for layer, lp in params.items():
+        for k, v in lp.items():
+            key = f"grad_{layer}.{k}" + (".weight" if k in ("ff", "rec") else "") if layer != "pred" else f"grad_pred.conv2d.{k}"
+            if key in g:
+                torch.testing.assert_close(v.grad, g[key], rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", LOSSES)
+def test_event_warping_loss_matches_reference(name):
+    g = load_golden(name)
+    scaling, smask, overwrite, weight, T, N = g["cfg"].tolist()
+    T = int(T)
+    flow = g["flow"].requires_grad_(True)  # [B,T,2,H,W]
+    H, W = flow.shape[-2:]
+    if overwrite:
+        fm = [flow[:, -1:]]
+        em = g["event_mask"].sum(1, keepdim=True).clamp(max=1)
+    else:
+        fm, em = [flow], g["event_mask"]
+    loss = oiwe.event_warping_loss(g["events"], g["pol_mask"], g["pass_of_event"].long(), fm, em, (H, W), weight=weight,
+                                   loss_scaling=bool(scaling), smoothing_mask=bool(smask), overwrite_intermediate=bool(overwrite), passes=T)
+    torch.testing.assert_close(loss.detach(), g["loss"], rtol=1e-6, atol=0)
+    loss.backward()
+    for t in range(T):
+        if f"grad_{t}" in g:
+            torch.testing.assert_close(flow.grad[:, t], g[f"grad_{t}"], rtol=1e-5, atol=1e-8)
+
+
+def test_iwe_image_and_interpolation_match_reference():
+    g = load_golden("iwe_image")
+    H, W = g["flow"].shape[-2:]
+    pm = g["pol_mask"]
+    for rnd, key in ((True, "iwe_round"), (False, "iwe_bilinear")):
+        out = oiwe.pol_iwe(g["flow"], g["events"], (H, W), pm[:, :, 0:1], pm[:, :, 1:2], flow_scaling=max(H, W), round_idx=rnd)
+        assert torch.equal(out, g[key])
+    ev_flow = oiwe.gather_event_flow(g["flow"], g["events"], (H, W))
+    for tref in (0, 1):
+        idx, w = oiwe.warp_and_split(g["events"], ev_flow, tref, (H, W), max(H, W))
+        assert torch.equal(idx, g[f"idx_tref{tref}"]) and torch.equal(w, g[f"w_tref{tref}"])
+
+
+def test_encodings_match_reference():
+    g = load_golden("encodings")
+    B = g["ts"].shape[0]
+    H, W = g["cnt_0"].shape[-2:]
+    for b in range(B):
+        a = (g["xs"][b], g["ys"][b], g["ps"][b])
+        assert torch.equal(oenc.events_to_channels(*a, (H, W)), g[f"cnt_{b}"])
+        assert torch.equal(oenc.event_mask(*a, (H, W))[0], g[f"mask_{b}"])
+        for bins in (2, 5):
+            assert torch.equal(oenc.events_to_voxel(g["xs"][b], g["ys"][b], g["ts"][b], g["ps"][b], bins, (H, W)), g[f"voxel{bins}_{b}"])
+
+
+def test_surrogate_curves_closed_form():
+    # models/spiking_util.py:112-141 (__main__ curves)
+    x = torch.linspace(-5, 5, 1001)
+    assert torch.allclose(osp.surrogate_grad(x, 10.0, "arctanspike"), 1 / (1 + 10 * x * x))
+    assert torch.allclose(osp.surrogate_grad(x, 10.0, "superspike"), 1 / (1 + 10 * x.abs()) ** 2)
+    assert torch.allclose(osp.surrogate_grad(x, 1.0, "trianglespike"), torch.relu(1 - x.abs()))
