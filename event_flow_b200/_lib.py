@@ -1,0 +1,151 @@
+"""
+ctypes binding of libeventflow.so (include/eventflow.h).  There is NO fallback: if the library is missing or a call
+fails, an exception is raised -- the product path never computes on the CPU or through stock PyTorch ops.
+"""
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libeventflow.so")
+
+EF_LIF, EF_PLIF, EF_ALIF, EF_XLIF = 0, 1, 2, 3
+NEURON_CODES = {"lif": EF_LIF, "plif": EF_PLIF, "alif": EF_ALIF, "xlif": EF_XLIF}
+SURROGATE_CODES = {"arctanspike": 0, "superspike": 1, "trianglespike": 2, "mgspike": 3}
+
+_f32p = C.c_void_p  # all device pointers travel as void*
+_i32 = C.c_int32
+
+
+class LifConvParams(C.Structure):
+    _fields_ = [
+        ("B", _i32), ("Cin", _i32), ("C", _i32), ("H", _i32), ("W", _i32),
+        ("ksize", _i32), ("stride", _i32), ("neuron", _i32), ("hard_reset", _i32), ("surrogate", _i32),
+        ("act_width", C.c_float),
+        ("x", _f32p), ("x_c8", _f32p), ("v_in", _f32p), ("z_in", _f32p), ("z_in_c8", _f32p), ("aux_in", _f32p),
+        ("w_ff", _f32p), ("w_rec", _f32p), ("leak", _f32p), ("thresh", _f32p), ("leak_aux", _f32p), ("add_pt", _f32p),
+        ("t0", _f32p), ("t1", _f32p), ("residual", _f32p), ("w_split", _f32p),
+        ("v_out", _f32p), ("z_out", _f32p), ("z_out_c8", _f32p), ("aux_out", _f32p), ("out", _f32p), ("out_c8", _f32p),
+    ]  # fmt: skip
+
+
+class LifConvBwdParams(C.Structure):
+    _fields_ = [
+        ("f", LifConvParams),
+        ("g_out", _f32p), ("g_v_out", _f32p), ("g_z_out", _f32p), ("g_aux_out", _f32p),
+        ("scratch_gI", _f32p), ("scratch_gP", _f32p),
+        ("g_x", _f32p), ("g_v_in", _f32p), ("g_z_in", _f32p), ("g_aux_in", _f32p),
+        ("g_w_ff", _f32p), ("g_w_rec", _f32p), ("g_leak", _f32p), ("g_thresh", _f32p), ("g_leak_aux", _f32p),
+        ("g_add_pt", _f32p), ("g_t0", _f32p), ("g_t1", _f32p),
+    ]  # fmt: skip
+
+
+class PredParams(C.Structure):
+    _fields_ = [
+        ("B", _i32), ("Cin", _i32), ("Cout", _i32), ("H", _i32), ("W", _i32),
+        ("x", _f32p), ("x_c8", _f32p), ("w", _f32p), ("b", _f32p), ("y", _f32p),
+        ("g_y", _f32p), ("g_x", _f32p), ("g_w", _f32p), ("g_b", _f32p),
+    ]  # fmt: skip
+
+
+class IweLossParams(C.Structure):
+    _fields_ = [
+        ("S", _i32), ("B", _i32), ("T", _i32), ("T_maps", _i32), ("H", _i32), ("W", _i32),
+        ("n_total", _i32), ("n_per_pass", _i32),
+        ("flow_scaling", C.c_float), ("weight", C.c_float),
+        ("loss_scaling", _i32), ("smoothing_mask", _i32), ("overwrite_intermediate", _i32),
+        ("events", _f32p), ("pol_mask", _f32p), ("flow_maps", _f32p), ("event_mask", _f32p), ("pass_offsets", _f32p),
+        ("workspace", _f32p), ("loss", _f32p), ("g_loss", _f32p), ("g_flow_maps", _f32p),
+    ]  # fmt: skip
+
+
+class IweImageParams(C.Structure):
+    _fields_ = [
+        ("B", _i32), ("N", _i32), ("H", _i32), ("W", _i32), ("round_idx", _i32),
+        ("tref", C.c_float), ("flow_scaling", C.c_float),
+        ("events", _f32p), ("pol_mask", _f32p), ("flow", _f32p), ("event_flow", _f32p), ("iwe", _f32p),
+    ]  # fmt: skip
+
+
+class EncodeParams(C.Structure):
+    _fields_ = [
+        ("B", _i32), ("N", _i32), ("H", _i32), ("W", _i32), ("num_bins", _i32), ("round_ts", _i32),
+        ("events", _f32p), ("cnt", _f32p), ("voxel", _f32p), ("mask", _f32p), ("pol_mask", _f32p),
+    ]  # fmt: skip
+
+
+EXPORTS = {
+    # name: (restype, argtypes)
+    "ef_version": (C.c_int, []),
+    "ef_last_error": (C.c_char_p, []),
+    "ef_device_ok": (C.c_int, []),
+    "ef_lif_conv_fwd": (C.c_int, [C.POINTER(LifConvParams), C.c_void_p]),
+    "ef_lif_conv_bwd": (C.c_int, [C.POINTER(LifConvBwdParams), C.c_void_p]),
+    "ef_split_weights_elems": (C.c_int64, [_i32, _i32, _i32]),
+    "ef_split_weights": (C.c_int, [C.c_void_p, C.c_void_p, _i32, _i32, C.c_void_p, C.c_void_p]),
+    "ef_pack_c8": (C.c_int, [C.c_void_p, C.c_void_p, _i32, _i32, _i32, _i32, C.c_void_p]),
+    "ef_unpack_c8": (C.c_int, [C.c_void_p, C.c_void_p, _i32, _i32, _i32, _i32, C.c_void_p]),
+    "ef_pred_fwd": (C.c_int, [C.POINTER(PredParams), C.c_void_p]),
+    "ef_pred_bwd": (C.c_int, [C.POINTER(PredParams), C.c_void_p]),
+    "ef_iwe_loss_workspace_elems": (C.c_int64, [_i32, _i32, _i32, _i32]),
+    "ef_iwe_loss_fwd": (C.c_int, [C.POINTER(IweLossParams), C.c_void_p]),
+    "ef_iwe_loss_bwd": (C.c_int, [C.POINTER(IweLossParams), C.c_void_p]),
+    "ef_iwe_image": (C.c_int, [C.POINTER(IweImageParams), C.c_void_p]),
+    "ef_encode_events": (C.c_int, [C.POINTER(EncodeParams), C.c_void_p]),
+    "ef_grad_sqnorm": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "ef_clip_adam": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_float, C.c_float,
+                               C.c_float, C.c_float, C.c_float, _i32, C.c_void_p]),
+}  # fmt: skip
+
+_lib = None
+LAUNCHES = 0  # number of library compute calls issued by this process (bench.py reports kernel launches from it)
+
+
+class EventFlowError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libeventflow.so once.  Raises if it has not been built (python -c 'import __graft_entry__ as g; g.build()')."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise EventFlowError(
+                f"{LIB_PATH} is missing: build it with `make` (or __graft_entry__.build()). There is no CPU / PyTorch fallback."
+            )
+        h = C.CDLL(LIB_PATH)
+        for name, (res, args) in EXPORTS.items():
+            fn = getattr(h, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = h
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().ef_last_error().decode(errors="replace")
+        raise EventFlowError(f"{what} failed (rc={rc}): {msg}")
+
+
+def ptr(t):
+    """Device pointer of a tensor (or None).  Tensors must be contiguous CUDA tensors."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise EventFlowError("event_flow_b200 kernels need CUDA tensors; got a %s tensor (no CPU fallback)" % t.device)
+    if not t.is_contiguous():
+        raise EventFlowError("event_flow_b200 kernels need contiguous tensors")
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name, params):
+    """Invoke a struct-taking entry point on the current torch stream."""
+    global LAUNCHES
+    LAUNCHES += 1
+    check(getattr(lib(), name)(C.byref(params), stream()), name)

@@ -1,0 +1,35 @@
+// Library-level entry points: version, error string, device check.
+#include "common.cuh"
+
+namespace ef {
+
+char* last_error_buf() {
+  static thread_local char buf[512] = "";
+  return buf;
+}
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(last_error_buf(), 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int check_launch(const char* what) {
+  const cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) return EF_OK;
+  return fail((int)e, "%s: %s", what, cudaGetErrorString(e));
+}
+
+}  // namespace ef
+
+extern "C" int ef_version(void) { return EF_VERSION; }
+extern "C" const char* ef_last_error(void) { return ef::last_error_buf(); }
+
+extern "C" int ef_device_ok(void) {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return ef::fail(-1, "ef_device_ok: no CUDA device");
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return ef::fail(-1, "ef_device_ok: attribute query failed");
+  return major == 10 ? 1 : 0;
+}

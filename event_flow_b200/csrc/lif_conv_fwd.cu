@@ -1,0 +1,229 @@
+// Fused conv3x3 + spiking neuron update, fp32 CUDA-core kernel (general shapes: any Cin, C, stride 1|2, all neuron kinds).
+// This is the kernel for the head layer (Cin = 2..5, fractional voxel inputs) and for every shape the tcgen05 kernel in
+// lif_conv_fwd_tc.cu does not cover.  Reference: models/spiking_submodules.py:96-126 and siblings (see eventflow.h).
+#include "common.cuh"
+
+namespace ef {
+
+constexpr int TW = 16, TH = 16;      // output tile
+constexpr int NTHREADS = 128;        // 16 x 8 threads, two output rows per thread (ty and ty + 8)
+constexpr int COB = 32;              // output channels per block
+constexpr int WPITCH = 36;           // padded row of the weight tile (floats), keeps float4 alignment
+
+template <int STRIDE>
+struct Geo {
+  static constexpr int CK = STRIDE == 1 ? 8 : 4;              // input channels per smem stage
+  static constexpr int HH = (TH - 1) * STRIDE + 3;            // halo rows
+  static constexpr int HW = (TW - 1) * STRIDE + 3;            // halo cols
+};
+
+__device__ __forceinline__ float ld_act(const float* f32, const uint16_t* c8, int b, int c, int y, int x, int C, int H, int W) {
+  if (f32) return f32[(((size_t)b * C + c) * H + y) * W + x];
+  const uint16_t u = c8[((((size_t)b * (C >> 3) + (c >> 3)) * H + y) * W + x) * 8 + (c & 7)];
+  return __uint_as_float(((uint32_t)u) << 16);
+}
+
+// Accumulate one convolution (input `src`, weights `w`) into acc[2][COB].
+template <int STRIDE, bool TRACE>
+__device__ __forceinline__ void conv_accumulate(float (&acc)[2][COB], const float* __restrict__ src_f32,
+                                                const uint16_t* __restrict__ src_c8, const float* __restrict__ w, int b, int Cin,
+                                                int H, int W, int co0, int C, int oy0, int ox0, float* s_x, float* s_w,
+                                                float* s_abs) {
+  using G = Geo<STRIDE>;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int iy0 = oy0 * STRIDE - 1, ix0 = ox0 * STRIDE - 1;
+  for (int ci0 = 0; ci0 < Cin; ci0 += G::CK) {
+    __syncthreads();
+    // input halo tile, zero-filled outside the image / beyond Cin
+    for (int i = tid; i < G::CK * G::HH * G::HW; i += NTHREADS) {
+      const int ci = i / (G::HH * G::HW), r = i % (G::HH * G::HW), hy = r / G::HW, hx = r % G::HW;
+      const int y = iy0 + hy, x = ix0 + hx, c = ci0 + ci;
+      float v = 0.f;
+      if (c < Cin && y >= 0 && y < H && x >= 0 && x < W) v = ld_act(src_f32, src_c8, b, c, y, x, Cin, H, W);
+      s_x[i] = v;
+    }
+    // weight tile [ci*9+tap][co]
+    for (int i = tid; i < COB * G::CK * 9; i += NTHREADS) {
+      const int co = i / (G::CK * 9), r = i % (G::CK * 9), ci = r / 9;
+      float v = 0.f;
+      if (co0 + co < C && ci0 + ci < Cin) v = w[((size_t)(co0 + co) * Cin + ci0) * 9 + r];
+      s_w[r * WPITCH + co] = v;
+    }
+    __syncthreads();
+    if (TRACE) {  // sum_c |x| per halo position (PLIF / XLIF pre-synaptic trace input)
+      for (int i = tid; i < G::HH * G::HW; i += NTHREADS) {
+        float a = 0.f;
+#pragma unroll
+        for (int ci = 0; ci < G::CK; ++ci) a += fabsf(s_x[ci * G::HH * G::HW + i]);
+        s_abs[i] += a;
+      }
+    }
+#pragma unroll 1
+    for (int ci = 0; ci < G::CK; ++ci) {
+      const float* sx = s_x + ci * G::HH * G::HW;
+      float xa[9], xb[9];
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          xa[dy * 3 + dx] = sx[(ty * STRIDE + dy) * G::HW + tx * STRIDE + dx];
+          xb[dy * 3 + dx] = sx[((ty + 8) * STRIDE + dy) * G::HW + tx * STRIDE + dx];
+        }
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const float4* wr = reinterpret_cast<const float4*>(s_w + (ci * 9 + tap) * WPITCH);
+#pragma unroll
+        for (int q = 0; q < COB / 4; ++q) {
+          const float4 w4 = wr[q];
+          acc[0][4 * q + 0] = fmaf(xa[tap], w4.x, acc[0][4 * q + 0]);
+          acc[0][4 * q + 1] = fmaf(xa[tap], w4.y, acc[0][4 * q + 1]);
+          acc[0][4 * q + 2] = fmaf(xa[tap], w4.z, acc[0][4 * q + 2]);
+          acc[0][4 * q + 3] = fmaf(xa[tap], w4.w, acc[0][4 * q + 3]);
+          acc[1][4 * q + 0] = fmaf(xb[tap], w4.x, acc[1][4 * q + 0]);
+          acc[1][4 * q + 1] = fmaf(xb[tap], w4.y, acc[1][4 * q + 1]);
+          acc[1][4 * q + 2] = fmaf(xb[tap], w4.z, acc[1][4 * q + 2]);
+          acc[1][4 * q + 3] = fmaf(xb[tap], w4.w, acc[1][4 * q + 3]);
+        }
+      }
+    }
+  }
+}
+
+template <int NEURON, bool HARD, int STRIDE>
+__global__ void __launch_bounds__(NTHREADS) lif_conv_fwd_kernel(const ef_lif_conv_params p, int Ho, int Wo) {
+  using G = Geo<STRIDE>;
+  constexpr bool TRACE = (NEURON == EF_PLIF || NEURON == EF_XLIF);
+  constexpr int SX = (G::CK * G::HH * G::HW > 8 * 18 * 18) ? G::CK * G::HH * G::HW : 8 * 18 * 18;
+  __shared__ __align__(16) float s_x[SX];
+  __shared__ __align__(16) float s_w[8 * 9 * WPITCH];
+  __shared__ float s_abs[TRACE ? G::HH * G::HW : 1];
+  __shared__ ChanConst s_k[COB];
+
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int cblocks = (p.C + COB - 1) / COB;
+  const int b = blockIdx.z / cblocks, co0 = (blockIdx.z % cblocks) * COB;
+  const int ox0 = blockIdx.x * TW, oy0 = blockIdx.y * TH;
+
+  if (tid < COB && co0 + tid < p.C) s_k[tid] = load_chan_const(p, co0 + tid);
+  if (TRACE)
+    for (int i = tid; i < G::HH * G::HW; i += NTHREADS) s_abs[i] = 0.f;
+
+  float acc[2][COB];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < COB; ++j) acc[i][j] = 0.f;
+
+  conv_accumulate<STRIDE, TRACE>(acc, p.x, p.x_c8, p.w_ff, b, p.Cin, p.H, p.W, co0, p.C, oy0, ox0, s_x, s_w, s_abs);
+  if (p.w_rec && (p.z_in || p.z_in_c8))  // recurrent current: stride-1 conv of the previous spikes at output resolution
+    conv_accumulate<1, false>(acc, p.z_in, p.z_in_c8, p.w_rec, b, p.C, Ho, Wo, co0, p.C, oy0, ox0, s_x, s_w, s_abs);
+  __syncthreads();
+
+  const size_t plane = (size_t)Ho * Wo;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int oy = oy0 + ty + half * 8, ox = ox0 + tx;
+    if (oy >= Ho || ox >= Wo) continue;
+    float P = 0.f;
+    if (TRACE) {
+      float s = 0.f;
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) s += s_abs[((ty + half * 8) * STRIDE + dy) * G::HW + tx * STRIDE + dx] / (float)p.Cin;
+      P = s / 9.0f;
+    }
+    const size_t pix = (size_t)oy * Wo + ox;
+    uint32_t zpk[COB / 2], opk[COB / 2];
+#pragma unroll
+    for (int co = 0; co < COB; ++co) {
+      const int c = co0 + co;
+      float zo = 0.f, oo = 0.f;
+      if (c < p.C) {
+        const size_t o = ((size_t)b * p.C + c) * plane + pix;
+        const float v = p.v_in ? p.v_in[o] : 0.f;
+        float z = 0.f;
+        if (p.z_in) z = p.z_in[o];
+        else if (p.z_in_c8) z = ld_act(nullptr, p.z_in_c8, b, c, oy, ox, p.C, Ho, Wo);
+        const float aux = p.aux_in ? p.aux_in[o] : 0.f;
+        float vo, ao, thr;
+        neuron_update<NEURON, HARD>(acc[half][co], v, z, aux, P, s_k[co], vo, zo, ao, thr);
+        p.v_out[o] = vo;
+        if (p.z_out) p.z_out[o] = zo;
+        if (p.aux_out) p.aux_out[o] = ao;
+        oo = p.residual ? __fadd_rn(zo, p.residual[o]) : zo;
+        if (p.out) p.out[o] = oo;
+      }
+      if (co & 1) {
+        zpk[co >> 1] = (zpk[co >> 1] & 0xffffu) | (pack_bf16x2(0.f, zo) & 0xffff0000u);
+        opk[co >> 1] = (opk[co >> 1] & 0xffffu) | (pack_bf16x2(0.f, oo) & 0xffff0000u);
+      } else {
+        zpk[co >> 1] = pack_bf16x2(zo, 0.f) & 0xffffu;
+        opk[co >> 1] = pack_bf16x2(oo, 0.f) & 0xffffu;
+      }
+    }
+    // channel-blocked bf16 outputs: 16 B per (pixel, 8-channel group)
+#pragma unroll
+    for (int g = 0; g < COB / 8; ++g) {
+      const int cg = (co0 >> 3) + g;
+      if (cg * 8 >= p.C) break;
+      const size_t o8 = ((((size_t)b * (p.C >> 3) + cg) * Ho + oy) * Wo + ox) * 8;
+      if (p.z_out_c8) *reinterpret_cast<uint4*>(p.z_out_c8 + o8) = make_uint4(zpk[4 * g], zpk[4 * g + 1], zpk[4 * g + 2], zpk[4 * g + 3]);
+      if (p.out_c8) *reinterpret_cast<uint4*>(p.out_c8 + o8) = make_uint4(opk[4 * g], opk[4 * g + 1], opk[4 * g + 2], opk[4 * g + 3]);
+    }
+  }
+}
+
+template <int NEURON, bool HARD>
+static int launch_generic(const ef_lif_conv_params& p, int Ho, int Wo, cudaStream_t st) {
+  dim3 grid(cdiv(Wo, TW), cdiv(Ho, TH), p.B * cdiv(p.C, COB));
+  if (p.stride == 1)
+    lif_conv_fwd_kernel<NEURON, HARD, 1><<<grid, NTHREADS, 0, st>>>(p, Ho, Wo);
+  else
+    lif_conv_fwd_kernel<NEURON, HARD, 2><<<grid, NTHREADS, 0, st>>>(p, Ho, Wo);
+  return check_launch("lif_conv_fwd_kernel");
+}
+
+int lif_conv_fwd_generic(const ef_lif_conv_params& p, cudaStream_t st) {
+  const int Ho = (p.H - 1) / p.stride + 1, Wo = (p.W - 1) / p.stride + 1;
+  switch (p.neuron * 2 + (p.hard_reset ? 1 : 0)) {
+    case EF_LIF * 2 + 0: return launch_generic<EF_LIF, false>(p, Ho, Wo, st);
+    case EF_LIF * 2 + 1: return launch_generic<EF_LIF, true>(p, Ho, Wo, st);
+    case EF_PLIF * 2 + 0: return launch_generic<EF_PLIF, false>(p, Ho, Wo, st);
+    case EF_PLIF * 2 + 1: return launch_generic<EF_PLIF, true>(p, Ho, Wo, st);
+    case EF_ALIF * 2 + 0: return launch_generic<EF_ALIF, false>(p, Ho, Wo, st);
+    case EF_ALIF * 2 + 1: return launch_generic<EF_ALIF, true>(p, Ho, Wo, st);
+    case EF_XLIF * 2 + 0: return launch_generic<EF_XLIF, false>(p, Ho, Wo, st);
+    case EF_XLIF * 2 + 1: return launch_generic<EF_XLIF, true>(p, Ho, Wo, st);
+  }
+  return fail(EF_EINVAL, "ef_lif_conv_fwd: bad neuron kind %d", p.neuron);
+}
+
+int validate_lif_conv(const ef_lif_conv_params& p, const char* who) {
+  EF_REQUIRE(p.B > 0 && p.Cin > 0 && p.C > 0 && p.H > 0 && p.W > 0, EF_EINVAL, "%s: non-positive dimension", who);
+  EF_REQUIRE(p.ksize == 3, EF_EUNSUPPORTED, "%s: kernel_size %d not supported (3 only)", who, p.ksize);
+  EF_REQUIRE(p.stride == 1 || p.stride == 2, EF_EUNSUPPORTED, "%s: stride %d not supported", who, p.stride);
+  EF_REQUIRE(p.neuron >= EF_LIF && p.neuron <= EF_XLIF, EF_EINVAL, "%s: bad neuron kind %d", who, p.neuron);
+  EF_REQUIRE(p.x || p.x_c8, EF_ENULL, "%s: x is NULL", who);
+  EF_REQUIRE(!p.x_c8 || p.Cin % 8 == 0, EF_EINVAL, "%s: c8 input needs Cin %% 8 == 0", who);
+  EF_REQUIRE(!(p.z_in_c8 || p.z_out_c8 || p.out_c8) || p.C % 8 == 0, EF_EINVAL, "%s: c8 spikes need C %% 8 == 0", who);
+  EF_REQUIRE(p.w_ff && p.leak && p.v_out, EF_ENULL, "%s: w_ff / leak / v_out is NULL", who);
+  if (p.neuron == EF_LIF || p.neuron == EF_PLIF) EF_REQUIRE(p.thresh, EF_ENULL, "%s: thresh is NULL", who);
+  if (p.neuron != EF_LIF) EF_REQUIRE(p.leak_aux, EF_ENULL, "%s: leak_pt / leak_t is NULL", who);
+  if (p.neuron == EF_PLIF) EF_REQUIRE(p.add_pt, EF_ENULL, "%s: add_pt is NULL", who);
+  if (p.neuron == EF_ALIF || p.neuron == EF_XLIF) EF_REQUIRE(p.t0 && p.t1, EF_ENULL, "%s: t0 / t1 is NULL", who);
+  if (p.neuron != EF_LIF) EF_REQUIRE(p.aux_out, EF_ENULL, "%s: aux_out is NULL", who);
+  return EF_OK;
+}
+
+int lif_conv_fwd_tc(const ef_lif_conv_params& p, cudaStream_t st);  // lif_conv_fwd_tc.cu
+bool lif_conv_tc_eligible(const ef_lif_conv_params& p);
+
+}  // namespace ef
+
+extern "C" int ef_lif_conv_fwd(const ef_lif_conv_params* p, void* stream) {
+  EF_REQUIRE(p, EF_ENULL, "ef_lif_conv_fwd: params is NULL");
+  if (int rc = ef::validate_lif_conv(*p, "ef_lif_conv_fwd")) return rc;
+  if (ef::lif_conv_tc_eligible(*p)) return ef::lif_conv_fwd_tc(*p, ef::as_stream(stream));
+  return ef::lif_conv_fwd_generic(*p, ef::as_stream(stream));
+}

@@ -1,0 +1,134 @@
+// Prediction head: flow = tanh(conv1x1(x) + b), forward and backward.
+// Reference: models/submodules.py:52-61 (ConvLayer.forward) as instantiated at models/model.py:197-199.
+#include "common.cuh"
+
+namespace ef {
+
+constexpr int PRED_MAX_CIN = 64, PRED_MAX_COUT = 4;
+
+__device__ __forceinline__ float ld_x(const ef_pred_params& p, int b, int c, size_t pix, size_t hw) {
+  if (p.x) return p.x[((size_t)b * p.Cin + c) * hw + pix];
+  const uint16_t u = p.x_c8[(((size_t)b * (p.Cin >> 3) + (c >> 3)) * hw + pix) * 8 + (c & 7)];
+  return __uint_as_float(((uint32_t)u) << 16);
+}
+
+__global__ void __launch_bounds__(256) pred_fwd_kernel(const ef_pred_params p) {
+  __shared__ float s_w[PRED_MAX_COUT * PRED_MAX_CIN], s_b[PRED_MAX_COUT];
+  for (int i = threadIdx.x; i < p.Cout * p.Cin; i += 256) s_w[i] = p.w[i];
+  if (threadIdx.x < p.Cout) s_b[threadIdx.x] = p.b[threadIdx.x];
+  __syncthreads();
+  const size_t hw = (size_t)p.H * p.W;
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= (size_t)p.B * hw) return;
+  const int b = i / hw;
+  const size_t pix = i % hw;
+  float acc[PRED_MAX_COUT];
+#pragma unroll
+  for (int o = 0; o < PRED_MAX_COUT; ++o) acc[o] = 0.f;
+  for (int c = 0; c < p.Cin; ++c) {
+    const float xv = ld_x(p, b, c, pix, hw);
+#pragma unroll
+    for (int o = 0; o < PRED_MAX_COUT; ++o)
+      if (o < p.Cout) acc[o] = fmaf(xv, s_w[o * p.Cin + c], acc[o]);
+  }
+#pragma unroll
+  for (int o = 0; o < PRED_MAX_COUT; ++o)
+    if (o < p.Cout) p.y[((size_t)b * p.Cout + o) * hw + pix] = tanhf(acc[o] + s_b[o]);
+}
+
+// g_pre = g_y (1 - y^2); g_x = W^T g_pre; g_w += sum g_pre x; g_b += sum g_pre
+constexpr int PB_PIX = 4;
+__global__ void __launch_bounds__(256) pred_bwd_kernel(const ef_pred_params p) {
+  __shared__ float s_w[PRED_MAX_COUT * PRED_MAX_CIN];
+  __shared__ float s_acc[PRED_MAX_COUT * PRED_MAX_CIN + PRED_MAX_COUT];
+  for (int i = threadIdx.x; i < p.Cout * p.Cin; i += 256) s_w[i] = p.w[i];
+  for (int i = threadIdx.x; i < PRED_MAX_COUT * PRED_MAX_CIN + PRED_MAX_COUT; i += 256) s_acc[i] = 0.f;
+  __syncthreads();
+  const size_t hw = (size_t)p.H * p.W, n = (size_t)p.B * hw;
+  const int lane = threadIdx.x & 31;
+  for (int c0 = 0; c0 < p.Cin; c0 += 8) {  // 8 input channels at a time keeps the register footprint small
+    float gw[PRED_MAX_COUT][8], gb[PRED_MAX_COUT];
+#pragma unroll
+    for (int o = 0; o < PRED_MAX_COUT; ++o) {
+      gb[o] = 0.f;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) gw[o][c] = 0.f;
+    }
+    for (int k = 0; k < PB_PIX; ++k) {
+      const size_t i = ((size_t)blockIdx.x * PB_PIX + k) * 256 + threadIdx.x;
+      if (i >= n) break;
+      const int b = i / hw;
+      const size_t pix = i % hw;
+      float gp[PRED_MAX_COUT];
+#pragma unroll
+      for (int o = 0; o < PRED_MAX_COUT; ++o) {
+        gp[o] = 0.f;
+        if (o < p.Cout) {
+          const size_t oo = ((size_t)b * p.Cout + o) * hw + pix;
+          const float y = p.y[oo];
+          gp[o] = p.g_y[oo] * (1.0f - y * y);
+          gb[o] += gp[o];
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        if (c0 + c >= p.Cin) break;
+        const float xv = ld_x(p, b, c0 + c, pix, hw);
+        float gx = 0.f;
+#pragma unroll
+        for (int o = 0; o < PRED_MAX_COUT; ++o)
+          if (o < p.Cout) {
+            gw[o][c] = fmaf(gp[o], xv, gw[o][c]);
+            gx = fmaf(gp[o], s_w[o * p.Cin + c0 + c], gx);
+          }
+        if (p.g_x) p.g_x[((size_t)b * p.Cin + c0 + c) * hw + pix] = gx;
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < PRED_MAX_COUT; ++o) {
+      if (o >= p.Cout) break;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float r = warp_sum(gw[o][c]);
+        if (lane == 0 && c0 + c < p.Cin) atomicAdd(&s_acc[o * p.Cin + c0 + c], r);
+      }
+      if (c0 == 0) {
+        const float r = warp_sum(gb[o]);
+        if (lane == 0) atomicAdd(&s_acc[PRED_MAX_COUT * PRED_MAX_CIN + o], r);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < p.Cout * p.Cin; i += 256)
+    if (p.g_w) atomicAdd(p.g_w + i, s_acc[i]);
+  if (threadIdx.x < p.Cout && p.g_b) atomicAdd(p.g_b + threadIdx.x, s_acc[PRED_MAX_COUT * PRED_MAX_CIN + threadIdx.x]);
+}
+
+static int validate_pred(const ef_pred_params& p, const char* who) {
+  EF_REQUIRE(p.B > 0 && p.Cin > 0 && p.Cout > 0 && p.H > 0 && p.W > 0, EF_EINVAL, "%s: bad dimensions", who);
+  EF_REQUIRE(p.Cin <= PRED_MAX_CIN && p.Cout <= PRED_MAX_COUT, EF_EUNSUPPORTED, "%s: Cin <= %d, Cout <= %d", who, PRED_MAX_CIN, PRED_MAX_COUT);
+  EF_REQUIRE((p.x || p.x_c8) && p.w && p.b && p.y, EF_ENULL, "%s: NULL tensor", who);
+  EF_REQUIRE(!p.x_c8 || p.Cin % 8 == 0, EF_EINVAL, "%s: c8 input needs Cin %% 8 == 0", who);
+  return EF_OK;
+}
+
+}  // namespace ef
+
+extern "C" int ef_pred_fwd(const ef_pred_params* p, void* stream) {
+  using namespace ef;
+  EF_REQUIRE(p, EF_ENULL, "ef_pred_fwd: params is NULL");
+  if (int rc = validate_pred(*p, "ef_pred_fwd")) return rc;
+  const size_t n = (size_t)p->B * p->H * p->W;
+  pred_fwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(*p);
+  return check_launch("pred_fwd_kernel");
+}
+
+extern "C" int ef_pred_bwd(const ef_pred_params* p, void* stream) {
+  using namespace ef;
+  EF_REQUIRE(p, EF_ENULL, "ef_pred_bwd: params is NULL");
+  if (int rc = validate_pred(*p, "ef_pred_bwd")) return rc;
+  EF_REQUIRE(p->g_y, EF_ENULL, "ef_pred_bwd: g_y is NULL");
+  const size_t n = (size_t)p->B * p->H * p->W;
+  pred_bwd_kernel<<<(unsigned)((n + 256 * PB_PIX - 1) / (256 * PB_PIX)), 256, 0, as_stream(stream)>>>(*p);
+  return check_launch("pred_bwd_kernel");
+}

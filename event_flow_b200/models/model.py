@@ -1,0 +1,168 @@
+"""
+Model zoo with the class names, constructor contract, state API and output dict of models/model.py.
+Round 1: the spiking FireNet family (FireNet base :148-286; LIFFireNet :636, PLIFFireNet :648, ALIFFireNet :660,
+XLIFFireNet :672, LIFFireFlowNet :684).  Each forward pass is 7 fused conv+neuron kernels and one prediction-head kernel.
+"""
+import torch
+
+from .base import BaseModel
+from .model_util import copy_states
+from .spiking_submodules import (
+    ConvALIF,
+    ConvALIFRecurrent,
+    ConvLIF,
+    ConvLIFRecurrent,
+    ConvPLIF,
+    ConvPLIFRecurrent,
+    ConvXLIF,
+    ConvXLIFRecurrent,
+)
+from .submodules import ConvLayer
+
+
+class FireNet(BaseModel):
+    """
+    7-cell chain head-G1-R1a-R1b-G2-R2a-R2b + 1x1 tanh prediction (models/model.py:148-286).
+    The base class itself (ANN cells: ConvLayer_ / ConvGRU) is not on the CUDA path yet; use the spiking subclasses.
+    """
+
+    head_neuron = None
+    ff_neuron = None
+    rec_neuron = None
+    residual = False
+    num_recurrent_units = 7
+    w_scale_pred = None
+
+    def __init__(self, unet_kwargs):
+        super().__init__()
+        if self.head_neuron is None:
+            raise NotImplementedError("ANN FireNet (ConvLayer_/ConvGRU cells) is not implemented in this version; use LIFFireNet etc.")
+        self.num_bins = unet_kwargs["num_bins"]
+        base_num_channels = unet_kwargs["base_num_channels"]
+        kernel_size = unet_kwargs["kernel_size"]
+        self.encoding = unet_kwargs["encoding"]
+        self.norm_input = False if "norm_input" not in unet_kwargs.keys() else unet_kwargs["norm_input"]
+        self.mask = unet_kwargs["mask_output"]
+        ff_act, rec_act = unet_kwargs["activations"]
+        # the reference shares one class-level list of dicts between all models (model.py:159,171-173); per-instance here
+        kwargs = dict(unet_kwargs["spiking_neuron"]) if type(unet_kwargs.get("spiking_neuron")) is dict else {}
+
+        self.head = self.head_neuron(self.num_bins, base_num_channels, kernel_size, activation=ff_act, **kwargs)
+        self.G1 = self.rec_neuron(base_num_channels, base_num_channels, kernel_size, activation=rec_act, **kwargs)
+        self.R1a = self.ff_neuron(base_num_channels, base_num_channels, kernel_size, activation=ff_act, **kwargs)
+        self.R1b = self.ff_neuron(base_num_channels, base_num_channels, kernel_size, activation=ff_act, **kwargs)
+        self.G2 = self.rec_neuron(base_num_channels, base_num_channels, kernel_size, activation=rec_act, **kwargs)
+        self.R2a = self.ff_neuron(base_num_channels, base_num_channels, kernel_size, activation=ff_act, **kwargs)
+        self.R2b = self.ff_neuron(base_num_channels, base_num_channels, kernel_size, activation=ff_act, **kwargs)
+        self.pred = ConvLayer(base_num_channels, out_channels=2, kernel_size=1, activation="tanh", w_scale=self.w_scale_pred)
+        self.reset_states()
+
+    @property
+    def states(self):
+        return copy_states(self._states)
+
+    @states.setter
+    def states(self, states):
+        self._states = states
+
+    def detach_states(self):
+        detached_states = []
+        for state in self.states:
+            if type(state) is tuple:
+                detached_states.append(tuple(hidden.detach() for hidden in state))
+            else:
+                detached_states.append(state.detach())
+        self.states = detached_states
+
+    def reset_states(self):
+        self._states = [None] * self.num_recurrent_units
+
+    def init_cropping(self, width, height):
+        pass
+
+    def forward(self, event_voxel, event_cnt, log=False):
+        """
+        :param event_voxel: N x num_bins x H x W
+        :param event_cnt: N x 2 x H x W per-polarity event counts
+        :return {"flow": [N x 2 x H x W], "activity": dict | None}
+        """
+        if self.encoding == "voxel":
+            x = event_voxel
+        elif self.encoding == "cnt" and self.num_bins == 2:
+            x = event_cnt
+        else:
+            print("Model error: Incorrect input encoding.")
+            raise AttributeError
+
+        if self.norm_input:  # model.py:247-252 (in place on the caller's tensor, like the reference)
+            mean, stddev = x[x != 0].mean(), x[x != 0].std()
+            x[x != 0] = (x[x != 0] - mean) / stddev
+
+        x1, self._states[0] = self.head(x, self._states[0])
+        x2, self._states[1] = self.G1(x1, self._states[1])
+        x3, self._states[2] = self.R1a(x2, self._states[2])
+        x4, self._states[3] = self.R1b(x3, self._states[3], residual=x2 if self.residual else 0)
+        x5, self._states[4] = self.G2(x4, self._states[4])
+        x6, self._states[5] = self.R2a(x5, self._states[5])
+        x7, self._states[6] = self.R2b(x6, self._states[6], residual=x5 if self.residual else 0)
+        flow = self.pred(x7)
+
+        if log:
+            activity = {}
+            name = ["0:input", "1:head", "2:G1", "3:R1a", "4:R1b", "5:G2", "6:R2a", "7:R2b", "8:pred"]
+            for n, l in zip(name, [x, x1, x2, x3, x4, x5, x6, x7, flow]):
+                activity[n] = l.detach().ne(0).float().mean().item()
+        else:
+            activity = None
+
+        return {"flow": [flow], "activity": activity}
+
+
+class LIFFireNet(FireNet):
+    """models/model.py:636-645."""
+
+    head_neuron = ConvLIF
+    ff_neuron = ConvLIF
+    rec_neuron = ConvLIFRecurrent
+    residual = False
+    w_scale_pred = 0.01
+
+
+class PLIFFireNet(FireNet):
+    """models/model.py:648-657."""
+
+    head_neuron = ConvPLIF
+    ff_neuron = ConvPLIF
+    rec_neuron = ConvPLIFRecurrent
+    residual = False
+    w_scale_pred = 0.01
+
+
+class ALIFFireNet(FireNet):
+    """models/model.py:660-669."""
+
+    head_neuron = ConvALIF
+    ff_neuron = ConvALIF
+    rec_neuron = ConvALIFRecurrent
+    residual = False
+    w_scale_pred = 0.01
+
+
+class XLIFFireNet(FireNet):
+    """models/model.py:672-681."""
+
+    head_neuron = ConvXLIF
+    ff_neuron = ConvXLIF
+    rec_neuron = ConvXLIFRecurrent
+    residual = False
+    w_scale_pred = 0.01
+
+
+class LIFFireFlowNet(FireNet):
+    """models/model.py:684-693."""
+
+    head_neuron = ConvLIF
+    ff_neuron = ConvLIF
+    rec_neuron = ConvLIF
+    residual = False
+    w_scale_pred = 0.01

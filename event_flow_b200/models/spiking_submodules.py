@@ -1,0 +1,177 @@
+"""
+Spiking conv cells with the constructor signatures, parameter names (state_dict keys), initialisers and forward contract
+of models/spiking_submodules.py (ConvLIF :24, ConvPLIF :129, ConvALIF :230, ConvXLIF :337, ConvLIFRecurrent :438,
+ConvPLIFRecurrent :554, ConvALIFRecurrent :660, ConvXLIFRecurrent :771).  forward() is ONE fused CUDA kernel
+(ef_lif_conv_fwd) instead of conv2d + ~15 pointwise ops; backward is ef_lif_conv_bwd.
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+from . import spiking_util as spiking
+
+
+class _SpikingConvCell(nn.Module):
+    neuron = None  # "lif" | "plif" | "alif" | "xlif"
+    recurrent = False
+
+    def _build(self, input_size, hidden_size, kernel_size, stride, activation, act_width, leak_group, thresh_group, learn_leak,
+               learn_thresh, hard_reset, detach, norm):
+        if norm is not None:
+            raise NotImplementedError("norm=%r: no shipped config uses cell normalisation; not implemented on the CUDA path" % (norm,))
+        if not detach:
+            raise NotImplementedError("detach=False (differentiable reset) is not implemented on the CUDA path")
+        padding = kernel_size // 2
+        self.input_size, self.hidden_size, self.stride = input_size, hidden_size, stride
+        # parameter creation order follows the reference so that the same torch seed gives the same initial values
+        self.ff = nn.Conv2d(input_size, hidden_size, kernel_size, stride=stride, padding=padding, bias=False)
+        if self.recurrent:
+            self.rec = nn.Conv2d(hidden_size, hidden_size, kernel_size, padding=padding, bias=False)
+        for group, learn in ((leak_group, learn_leak), (thresh_group, learn_thresh)):
+            for name, (mu, sd) in group:
+                value = torch.randn(hidden_size, 1, 1) * sd + mu
+                if learn:
+                    setattr(self, name, nn.Parameter(value))
+                else:
+                    self.register_buffer(name, value)
+        nn.init.uniform_(self.ff.weight, -math.sqrt(1 / input_size), math.sqrt(1 / input_size))
+        if self.recurrent:
+            nn.init.uniform_(self.rec.weight, -math.sqrt(1 / hidden_size), math.sqrt(1 / hidden_size))
+        assert isinstance(activation, str), "Spiking neurons need a valid activation, see models/spiking_util.py for choices"
+        self.spike_fn = getattr(spiking, activation)
+        self.activation = activation
+        self.register_buffer("act_width", torch.tensor(act_width))
+        self.hard_reset = hard_reset
+        self.detach = detach
+        self.norm = None
+
+    def forward(self, input_, prev_state, residual=0):
+        chan = {n: getattr(self, n) for n in ops.param_names(self.neuron)}
+        return ops.cell_step(
+            self.neuron,
+            input_,
+            prev_state,
+            self.ff.weight,
+            self.rec.weight if self.recurrent else None,
+            chan,
+            hard_reset=self.hard_reset,
+            surrogate=self.activation,
+            width=float(self.act_width),
+            stride=self.stride,
+            residual=residual,
+        )
+
+
+class ConvLIF(_SpikingConvCell):
+    """models/spiking_submodules.py:24-126."""
+
+    neuron = "lif"
+
+    def __init__(self, input_size, hidden_size, kernel_size, stride=1, activation="arctanspike", act_width=10.0, leak=(-4.0, 0.1),
+                 thresh=(0.8, 0.0), learn_leak=True, learn_thresh=True, hard_reset=True, detach=True, norm=None):
+        super().__init__()
+        self._build(input_size, hidden_size, kernel_size, stride, activation, act_width, [("leak", leak)], [("thresh", thresh)],
+                    learn_leak, learn_thresh, hard_reset, detach, norm)
+
+
+class ConvPLIF(_SpikingConvCell):
+    """models/spiking_submodules.py:129-227."""
+
+    neuron = "plif"
+
+    def __init__(self, input_size, hidden_size, kernel_size, stride=1, activation="arctanspike", act_width=10.0, leak_v=(-4.0, 0.1),
+                 leak_pt=(-4.0, 0.1), add_pt=(-2.0, 0.1), thresh=(0.8, 0.0), learn_leak=True, learn_thresh=True, hard_reset=True,
+                 detach=True, norm=None):
+        super().__init__()
+        self._build(input_size, hidden_size, kernel_size, stride, activation, act_width,
+                    [("leak_v", leak_v), ("leak_pt", leak_pt), ("add_pt", add_pt)], [("thresh", thresh)], learn_leak, learn_thresh,
+                    hard_reset, detach, norm)
+
+
+class ConvALIF(_SpikingConvCell):
+    """models/spiking_submodules.py:230-334."""
+
+    neuron = "alif"
+
+    def __init__(self, input_size, hidden_size, kernel_size, stride=1, activation="arctanspike", act_width=10.0, leak_v=(-4.0, 0.1),
+                 leak_t=(-4.0, 0.1), t0=(0.01, 0.0), t1=(1.8, 0.0), learn_leak=True, learn_thresh=False, hard_reset=False,
+                 detach=True, norm=None):
+        super().__init__()
+        self._build(input_size, hidden_size, kernel_size, stride, activation, act_width, [("leak_v", leak_v), ("leak_t", leak_t)],
+                    [("t0", t0), ("t1", t1)], learn_leak, learn_thresh, hard_reset, detach, norm)
+
+
+class ConvXLIF(_SpikingConvCell):
+    """models/spiking_submodules.py:337-435."""
+
+    neuron = "xlif"
+
+    def __init__(self, input_size, hidden_size, kernel_size, stride=1, activation="arctanspike", act_width=10.0, leak_v=(-4.0, 0.1),
+                 leak_pt=(-4.0, 0.1), t0=(0.01, 0.0), t1=(1.8, 0.0), learn_leak=True, learn_thresh=False, hard_reset=False,
+                 detach=True, norm=None):
+        super().__init__()
+        self._build(input_size, hidden_size, kernel_size, stride, activation, act_width, [("leak_v", leak_v), ("leak_pt", leak_pt)],
+                    [("t0", t0), ("t1", t1)], learn_leak, learn_thresh, hard_reset, detach, norm)
+
+
+class ConvLIFRecurrent(_SpikingConvCell):
+    """models/spiking_submodules.py:438-551."""
+
+    neuron, recurrent = "lif", True
+
+    def __init__(self, input_size, hidden_size, kernel_size, activation="arctanspike", act_width=10.0, leak=(-4.0, 0.1),
+                 thresh=(0.8, 0.0), learn_leak=True, learn_thresh=True, hard_reset=True, detach=True, norm=None):
+        super().__init__()
+        self._build(input_size, hidden_size, kernel_size, 1, activation, act_width, [("leak", leak)], [("thresh", thresh)],
+                    learn_leak, learn_thresh, hard_reset, detach, norm)
+
+    def forward(self, input_, prev_state):
+        return super().forward(input_, prev_state)
+
+
+class ConvPLIFRecurrent(_SpikingConvCell):
+    """models/spiking_submodules.py:554-657."""
+
+    neuron, recurrent = "plif", True
+
+    def __init__(self, input_size, hidden_size, kernel_size, activation="arctanspike", act_width=10.0, leak_v=(-4.0, 0.1),
+                 leak_pt=(-4.0, 0.1), add_pt=(-2.0, 0.1), thresh=(0.8, 0.0), learn_leak=True, learn_thresh=True, hard_reset=True,
+                 detach=True, norm=None):
+        super().__init__()
+        self._build(input_size, hidden_size, kernel_size, 1, activation, act_width,
+                    [("leak_v", leak_v), ("leak_pt", leak_pt), ("add_pt", add_pt)], [("thresh", thresh)], learn_leak, learn_thresh,
+                    hard_reset, detach, norm)
+
+
+class ConvALIFRecurrent(_SpikingConvCell):
+    """models/spiking_submodules.py:660-768."""
+
+    neuron, recurrent = "alif", True
+
+    def __init__(self, input_size, hidden_size, kernel_size, activation="arctanspike", act_width=10.0, leak_v=(-4.0, 0.1),
+                 leak_t=(-4.0, 0.1), t0=(0.01, 0.0), t1=(1.8, 0.0), learn_leak=True, learn_thresh=False, hard_reset=False,
+                 detach=True, norm=None):
+        super().__init__()
+        self._build(input_size, hidden_size, kernel_size, 1, activation, act_width, [("leak_v", leak_v), ("leak_t", leak_t)],
+                    [("t0", t0), ("t1", t1)], learn_leak, learn_thresh, hard_reset, detach, norm)
+
+    def forward(self, input_, prev_state):
+        return super().forward(input_, prev_state)
+
+
+class ConvXLIFRecurrent(_SpikingConvCell):
+    """models/spiking_submodules.py:771-875."""
+
+    neuron, recurrent = "xlif", True
+
+    def __init__(self, input_size, hidden_size, kernel_size, activation="arctanspike", act_width=10.0, leak_v=(-4.0, 0.1),
+                 leak_pt=(-4.0, 0.1), t0=(0.01, 0.0), t1=(1.8, 0.0), learn_leak=True, learn_thresh=False, hard_reset=False,
+                 detach=True, norm=None):
+        super().__init__()
+        self._build(input_size, hidden_size, kernel_size, 1, activation, act_width, [("leak_v", leak_v), ("leak_pt", leak_pt)],
+                    [("t0", t0), ("t1", t1)], learn_leak, learn_thresh, hard_reset, detach, norm)
+
+    def forward(self, input_, prev_state):
+        return super().forward(input_, prev_state)

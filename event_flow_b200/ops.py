@@ -1,0 +1,294 @@
+"""
+Host-side operators over libeventflow.so: tensor allocation, argument marshalling and torch.autograd glue.
+Every function here launches CUDA kernels through the C ABI (event_flow_b200/_lib.py); none has a CPU path.
+"""
+
+import torch
+
+from . import _lib as L
+
+_N_STATE = {"lif": 2, "plif": 3, "alif": 3, "xlif": 3}
+# per-channel parameter names of each neuron kind, in the order of the C struct fields
+#                 leak      thresh    leak_aux   add_pt    t0    t1
+_PARAM_FIELDS = {
+    "lif": ("leak", "thresh", None, None, None, None),
+    "plif": ("leak_v", "thresh", "leak_pt", "add_pt", None, None),
+    "alif": ("leak_v", None, "leak_t", None, "t0", "t1"),
+    "xlif": ("leak_v", None, "leak_pt", None, "t0", "t1"),
+}
+_STRUCT_FIELDS = ("leak", "thresh", "leak_aux", "add_pt", "t0", "t1")
+
+
+def param_names(neuron):
+    """Names of the per-channel parameters of a neuron kind (reference attribute names)."""
+    return tuple(n for n in _PARAM_FIELDS[neuron] if n is not None)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise L.EventFlowError("event_flow_b200 has no CPU path: tensors must live on a CUDA device (got %s)" % t.device)
+
+
+def _c(t):
+    return None if t is None else t.contiguous()
+
+
+def _fill_cell_params(p, neuron, x, state_in, w_ff, w_rec, chan, residual, state_out, out, hard_reset, surrogate, width, stride):
+    B, Cin, H, W = x.shape
+    Cout = w_ff.shape[0]
+    p.B, p.Cin, p.C, p.H, p.W = B, Cin, Cout, H, W
+    p.ksize, p.stride = w_ff.shape[-1], stride
+    p.neuron, p.hard_reset = L.NEURON_CODES[neuron], int(bool(hard_reset))
+    p.surrogate, p.act_width = L.SURROGATE_CODES[surrogate], float(width)
+    p.x = L.ptr(x)
+    if state_in is not None:
+        p.v_in, p.z_in = L.ptr(state_in[0]), L.ptr(state_in[1])
+        if state_in.shape[0] > 2:
+            p.aux_in = L.ptr(state_in[2])
+    p.w_ff, p.w_rec = L.ptr(w_ff), L.ptr(w_rec)
+    for field, name in zip(_STRUCT_FIELDS, _PARAM_FIELDS[neuron]):
+        if name is not None:
+            setattr(p, field, L.ptr(chan[name]))
+    p.residual = L.ptr(residual)
+    p.v_out, p.z_out = L.ptr(state_out[0]), L.ptr(state_out[1])
+    if state_out.shape[0] > 2:
+        p.aux_out = L.ptr(state_out[2])
+    p.out = L.ptr(out)
+
+
+class _CellStep(torch.autograd.Function):
+    """One fused conv + neuron step on fp32 NCHW tensors (the reference cells' own tensor contract)."""
+
+    @staticmethod
+    def forward(ctx, meta, x, state_in, w_ff, w_rec, residual, *chan_vals):
+        neuron, hard_reset, surrogate, width, stride = meta
+        names = param_names(neuron)
+        chan = {n: _c(v.reshape(-1)) for n, v in zip(names, chan_vals)}
+        x, state_in, w_ff, w_rec, residual = _c(x), _c(state_in), _c(w_ff), _c(w_rec), _c(residual)
+        _need_cuda(x, state_in, w_ff, w_rec, residual, *chan.values())
+        B, _, H, W = x.shape
+        Cout = w_ff.shape[0]
+        Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+        state_out = torch.empty((_N_STATE[neuron], B, Cout, Ho, Wo), device=x.device, dtype=torch.float32)
+        out = torch.empty((B, Cout, Ho, Wo), device=x.device, dtype=torch.float32)  # z (+ residual); a tensor of its own
+        p = L.LifConvParams()
+        _fill_cell_params(p, neuron, x, state_in, w_ff, w_rec, chan, residual, state_out, out, hard_reset, surrogate, width, stride)
+        L.call("ef_lif_conv_fwd", p)
+        ctx.meta = meta
+        ctx.chan_names = names
+        ctx.save_for_backward(x, state_in, w_ff, w_rec, residual, state_out, *[chan[n] for n in names])
+        ctx.chan_shapes = [v.shape for v in chan_vals]
+        ctx.has_residual = residual is not None
+        return out, state_out
+
+    @staticmethod
+    def backward(ctx, g_out, g_state):
+        neuron, hard_reset, surrogate, width, stride = ctx.meta
+        x, state_in, w_ff, w_rec, residual, state_out, *chan_vals = ctx.saved_tensors
+        names = ctx.chan_names
+        chan = dict(zip(names, chan_vals))
+        q = L.LifConvBwdParams()
+        _fill_cell_params(q.f, neuron, x, state_in, w_ff, w_rec, chan, None, state_out, None, hard_reset, surrogate, width, stride)
+        B, Cin, H, W = x.shape
+        S, _, Cout, Ho, Wo = state_out.shape
+        dev = x.device
+        g_out = _c(g_out)
+        g_state = _c(g_state)
+        q.g_out = L.ptr(g_out)
+        if g_state is not None:
+            q.g_v_out, q.g_z_out = L.ptr(g_state[0]), L.ptr(g_state[1])
+            if S > 2:
+                q.g_aux_out = L.ptr(g_state[2])
+        scratch = torch.empty((B, Cout, Ho, Wo), device=dev, dtype=torch.float32)
+        q.scratch_gI = L.ptr(scratch)
+        need = ctx.needs_input_grad  # (meta, x, state_in, w_ff, w_rec, residual, *chan)
+        g_x = torch.empty_like(x) if need[1] else None
+        q.g_x = L.ptr(g_x)
+        scratch_p = None
+        if g_x is not None and neuron in ("plif", "xlif"):
+            scratch_p = torch.empty((B, Ho, Wo), device=dev, dtype=torch.float32)
+            q.scratch_gP = L.ptr(scratch_p)
+        g_state_in = None
+        if state_in is not None and need[2]:
+            g_state_in = torch.empty_like(state_in)
+            q.g_v_in, q.g_z_in = L.ptr(g_state_in[0]), L.ptr(g_state_in[1])
+            if S > 2:
+                q.g_aux_in = L.ptr(g_state_in[2])
+        g_w_ff = torch.zeros_like(w_ff) if need[3] else None
+        q.g_w_ff = L.ptr(g_w_ff)
+        g_w_rec = torch.zeros_like(w_rec) if (w_rec is not None and need[4]) else None
+        q.g_w_rec = L.ptr(g_w_rec)
+        g_chan = []
+        for i, (field, name) in enumerate([(f, n) for f, n in zip(_STRUCT_FIELDS, _PARAM_FIELDS[neuron]) if n is not None]):
+            if need[6 + i]:
+                g = torch.zeros(Cout, device=dev, dtype=torch.float32)
+                setattr(q, "g_" + field, L.ptr(g))
+                g_chan.append(g.view(ctx.chan_shapes[i]))
+            else:
+                g_chan.append(None)
+        L.call("ef_lif_conv_bwd", q)
+        g_res = g_out if (ctx.has_residual and need[5]) else None
+        return (None, g_x, g_state_in, g_w_ff, g_w_rec, g_res, *g_chan)
+
+
+def cell_step(neuron, x, state, w_ff, w_rec, chan, *, hard_reset, surrogate="arctanspike", width=10.0, stride=1, residual=None):
+    """
+    Fused forward of a spiking conv cell.  Mirrors `cell.forward(input_, prev_state, residual)` of
+    models/spiking_submodules.py: returns (out, new_state) with new_state = stack([v, z(, trace)]).
+    :param chan: dict of per-channel parameters named as in the reference module (leak, thresh, leak_v, ...)
+    """
+    if neuron not in _N_STATE:
+        raise ValueError(neuron)
+    if torch.is_tensor(residual) is False:
+        residual = None if (residual is None or residual == 0) else torch.as_tensor(residual)
+    meta = (neuron, bool(hard_reset), surrogate, float(width), int(stride))
+    vals = [chan[n] for n in param_names(neuron)]
+    return _CellStep.apply(meta, x, state, w_ff, w_rec, residual, *vals)
+
+
+class _Pred(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b):
+        x, w, b = _c(x), _c(w), _c(b)
+        _need_cuda(x, w, b)
+        B, Cin, H, W = x.shape
+        Cout = w.shape[0]
+        y = torch.empty((B, Cout, H, W), device=x.device, dtype=torch.float32)
+        p = L.PredParams()
+        p.B, p.Cin, p.Cout, p.H, p.W = B, Cin, Cout, H, W
+        p.x, p.w, p.b, p.y = L.ptr(x), L.ptr(w), L.ptr(b), L.ptr(y)
+        L.call("ef_pred_fwd", p)
+        ctx.save_for_backward(x, w, b, y)
+        return y
+
+    @staticmethod
+    def backward(ctx, g_y):
+        x, w, b, y = ctx.saved_tensors
+        g_y = _c(g_y)
+        B, Cin, H, W = x.shape
+        Cout = w.shape[0]
+        p = L.PredParams()
+        p.B, p.Cin, p.Cout, p.H, p.W = B, Cin, Cout, H, W
+        p.x, p.w, p.b, p.y, p.g_y = L.ptr(x), L.ptr(w), L.ptr(b), L.ptr(y), L.ptr(g_y)
+        g_x = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        g_w = torch.zeros_like(w)
+        g_b = torch.zeros_like(b)
+        p.g_x, p.g_w, p.g_b = L.ptr(g_x), L.ptr(g_w), L.ptr(g_b)
+        L.call("ef_pred_bwd", p)
+        return g_x, g_w, g_b
+
+
+def pred_head(x, weight, bias):
+    """tanh(conv1x1(x) + b): ConvLayer(kernel_size=1, activation="tanh") of models/model.py:197-199."""
+    return _Pred.apply(x, weight.reshape(weight.shape[0], -1), bias)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# event-warping loss
+# ---------------------------------------------------------------------------------------------------------------------
+class _EventWarpingLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, flow_maps, events, pol_mask, event_mask, pass_offsets, meta):
+        # flow_maps [S,B,Tm,2,H,W]; events [B,N,4]; pol_mask [B,N,2]; event_mask [B,Tm,H,W]; pass_offsets int32 [T+1] | None
+        T, n_per_pass, flow_scaling, weight, loss_scaling, smoothing_mask, overwrite = meta
+        flow_maps, events, pol_mask, event_mask = _c(flow_maps), _c(events), _c(pol_mask), _c(event_mask)
+        _need_cuda(flow_maps, events, pol_mask, event_mask)
+        S, B, Tm, _, H, W = flow_maps.shape
+        p = L.IweLossParams()
+        p.S, p.B, p.T, p.T_maps, p.H, p.W = S, B, T, Tm, H, W
+        p.n_total, p.n_per_pass = events.shape[1], n_per_pass
+        p.flow_scaling, p.weight = float(flow_scaling), float(weight)
+        p.loss_scaling, p.smoothing_mask, p.overwrite_intermediate = int(loss_scaling), int(smoothing_mask), int(overwrite)
+        ws = torch.empty(L.lib().ef_iwe_loss_workspace_elems(S, B, H, W), device=flow_maps.device, dtype=torch.float32)
+        loss = torch.empty((), device=flow_maps.device, dtype=torch.float32)
+        p.events, p.pol_mask, p.flow_maps, p.event_mask = L.ptr(events), L.ptr(pol_mask), L.ptr(flow_maps), L.ptr(event_mask)
+        p.workspace, p.loss = L.ptr(ws), L.ptr(loss)
+        p.pass_offsets = L.ptr(pass_offsets)
+        L.call("ef_iwe_loss_fwd", p)
+        ctx.p = p
+        ctx.save_for_backward(flow_maps, events, pol_mask, event_mask, ws, pass_offsets)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g_loss):
+        flow_maps, events, pol_mask, event_mask, ws, _ = ctx.saved_tensors
+        p = ctx.p
+        g_loss = g_loss.contiguous().to(torch.float32)
+        g_maps = torch.empty_like(flow_maps)
+        p.g_loss, p.g_flow_maps = L.ptr(g_loss), L.ptr(g_maps)
+        L.call("ef_iwe_loss_bwd", p)
+        p.g_loss = p.g_flow_maps = None
+        return g_maps, None, None, None, None, None
+
+
+def event_warping_loss(flow_maps, events, pol_mask, event_mask, *, passes, n_per_pass, flow_scaling, weight, loss_scaling=True,
+                       smoothing_mask=True, overwrite_intermediate=False, pass_offsets=None):
+    """EventWarping.forward (loss/flow.py:176-301) on a window in map form; differentiable wrt flow_maps."""
+    meta = (int(passes), int(n_per_pass), float(flow_scaling), float(weight), bool(loss_scaling), bool(smoothing_mask),
+            bool(overwrite_intermediate))
+    return _EventWarpingLoss.apply(flow_maps, events, pol_mask, event_mask, pass_offsets, meta)
+
+
+def iwe_image(events, pol_mask, res, *, flow=None, event_flow=None, tref=1.0, flow_scaling=128.0, round_idx=True):
+    """Per-polarity image of warped events [B,2,H,W] (utils/iwe.py:95-153)."""
+    events, pol_mask, flow, event_flow = _c(events), _c(pol_mask), _c(flow), _c(event_flow)
+    _need_cuda(events, pol_mask, flow, event_flow)
+    B, N = events.shape[:2]
+    H, W = res
+    out = torch.empty((B, 2, H, W), device=events.device, dtype=torch.float32)
+    p = L.IweImageParams()
+    p.B, p.N, p.H, p.W, p.round_idx = B, N, H, W, int(round_idx)
+    p.tref, p.flow_scaling = float(tref), float(flow_scaling)
+    p.events, p.pol_mask, p.flow, p.event_flow, p.iwe = L.ptr(events), L.ptr(pol_mask), L.ptr(flow), L.ptr(event_flow), L.ptr(out)
+    L.call("ef_iwe_image", p)
+    return out
+
+
+def encode_events(events, res, num_bins, *, round_ts=False, want=("cnt", "voxel", "mask", "pol_mask")):
+    """Event encodings of one batch (dataloader/encodings.py:30-85, base.py:148-222).  events [B,N,4] (ts,y,x,p)."""
+    events = _c(events)
+    _need_cuda(events)
+    B, N = events.shape[:2]
+    H, W = res
+    dev = events.device
+    out = {}
+    p = L.EncodeParams()
+    p.B, p.N, p.H, p.W, p.num_bins, p.round_ts = B, N, H, W, int(num_bins), int(round_ts)
+    p.events = L.ptr(events)
+    if "cnt" in want:
+        out["event_cnt"] = torch.empty((B, 2, H, W), device=dev, dtype=torch.float32)
+        p.cnt = L.ptr(out["event_cnt"])
+    if "voxel" in want:
+        out["event_voxel"] = torch.empty((B, num_bins, H, W), device=dev, dtype=torch.float32)
+        p.voxel = L.ptr(out["event_voxel"])
+    if "mask" in want:
+        out["event_mask"] = torch.empty((B, 1, H, W), device=dev, dtype=torch.float32)
+        p.mask = L.ptr(out["event_mask"])
+    if "pol_mask" in want:
+        out["event_list_pol_mask"] = torch.empty((B, N, 2), device=dev, dtype=torch.float32)
+        p.pol_mask = L.ptr(out["event_list_pol_mask"])
+    L.call("ef_encode_events", p)
+    return out
+
+
+def pack_c8(x):
+    """fp32 NCHW -> bf16 channel-blocked [B,C/8,H,W,8] (internal spike format)."""
+    x = _c(x)
+    _need_cuda(x)
+    B, Cc, H, W = x.shape
+    out = torch.empty((B, Cc // 8, H, W, 8), device=x.device, dtype=torch.bfloat16)
+    L.LAUNCHES += 1
+    L.check(L.lib().ef_pack_c8(L.ptr(x), L.ptr(out), B, Cc, H, W, L.stream()), "ef_pack_c8")
+    return out
+
+
+def unpack_c8(x):
+    """bf16 channel-blocked -> fp32 NCHW."""
+    x = _c(x)
+    _need_cuda(x)
+    B, G, H, W, _ = x.shape
+    out = torch.empty((B, G * 8, H, W), device=x.device, dtype=torch.float32)
+    L.LAUNCHES += 1
+    L.check(L.lib().ef_unpack_c8(L.ptr(x), L.ptr(out), B, G * 8, H, W, L.stream()), "ef_unpack_c8")
+    return out

@@ -1,0 +1,241 @@
+/*
+ * eventflow.h -- C ABI of libeventflow.so: B200 (sm_100a) kernels for the two hot paths of tudelft/event_flow.
+ *
+ * The reference is pure Python/PyTorch and has no FFI; what each entry point REPLACES is therefore a span of the
+ * reference's Python (file:line into the reference tree), listed with every declaration.  INTEGRATION.md shows the
+ * ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions (all entry points):
+ *   - plain C types only; every tensor pointer is a DEVICE pointer into caller-owned memory (torch storage);
+ *     the library never allocates, frees or keeps a pointer after the call returns;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); work is enqueued asynchronously;
+ *   - returns 0 on success, <0 for an argument / shape error, >0 = the cudaError_t of a failed launch;
+ *     ef_last_error() returns a thread-local message for the last non-zero return of the calling thread;
+ *   - fp32 tensors are dense NCHW.  "c8" tensors are the internal spike format: bf16, channel-blocked
+ *     [B, C/8, H, W, 8] (16 bytes = 8 channels of one pixel), exact for the values a spiking layer emits
+ *     ({0,1}, or {0,1,2} with a residual);
+ *   - a NULL optional pointer means "absent" (zero state, no residual, output not wanted).
+ */
+#ifndef EVENTFLOW_H_
+#define EVENTFLOW_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EF_VERSION 100 /* 0.1.0 */
+
+/* neuron models: models/spiking_submodules.py ConvLIF :24, ConvPLIF :129, ConvALIF :230, ConvXLIF :337 (+Recurrent) */
+enum { EF_LIF = 0, EF_PLIF = 1, EF_ALIF = 2, EF_XLIF = 3 };
+/* surrogate gradients: models/spiking_util.py ArctanSpike :82, SuperSpike :28, TriangleSpike :68, MultiGaussSpike :46 */
+enum { EF_ARCTAN = 0, EF_SUPERSPIKE = 1, EF_TRIANGLE = 2, EF_MULTIGAUSS = 3 };
+/* error codes */
+enum { EF_OK = 0, EF_EINVAL = -1, EF_EUNSUPPORTED = -2, EF_ENULL = -3 };
+
+int ef_version(void);
+const char* ef_last_error(void);
+/* 1 if the visible device is compute capability 10.x (tcgen05/TMA kernels usable), 0 if another GPU, <0 on error. */
+int ef_device_ok(void);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Fused conv3x3 + spiking-neuron update, one timestep of one cell.
+ * Replaces the whole forward() of ConvLIF / ConvLIFRecurrent / ConvPLIF(Recurrent) / ConvALIF(Recurrent) /
+ * ConvXLIF(Recurrent): models/spiking_submodules.py:96-126, 191-227, 299-334, 399-435, 516-551, 618-657, 730-768,
+ * 836-875, including the spike function models/spiking_util.py:19-21,96-109.
+ *
+ *   I      = conv(x, w_ff, stride, pad k/2) [+ conv(z_in, w_rec, 1, pad k/2)]
+ *   v_out  = LIF/PLIF/ALIF/XLIF update of (v_in, z_in, aux_in) with hard or soft reset
+ *   z_out  = (v_out - thresh_t > 0);   out = z_out + residual
+ *
+ * Inputs may be given as fp32 NCHW or as c8 bf16; when BOTH x_c8 (and z_in_c8) are given, C == 32, Cin == 32,
+ * ksize == 3, stride == 1, the tcgen05 tensor-core kernel runs (3-way bf16 split of the weights, fp32-exact products);
+ * otherwise the fp32 CUDA-core kernel runs.  Per-channel parameter arrays are the RAW parameters of the reference
+ * module ([C] floats; sigmoid / clamp are applied inside, spiking_submodules.py:108-112).
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct ef_lif_conv_params {
+  int32_t B, Cin, C, H, W;      /* x is [B,Cin,H,W]; outputs are [B,C,Ho,Wo], Ho = (H-1)/stride+1                    */
+  int32_t ksize, stride;        /* ksize 3 (pad 1); stride 1 or 2                                                     */
+  int32_t neuron, hard_reset;   /* EF_LIF.. ; 1 = hard reset, 0 = soft reset                                          */
+  int32_t surrogate;            /* EF_ARCTAN.. (backward only)                                                        */
+  float act_width;              /* surrogate width (buffer act_width)                                                 */
+  /* inputs */
+  const float* x;               /* [B,Cin,H,W] fp32, or NULL when x_c8 is given                                       */
+  const uint16_t* x_c8;         /* [B,Cin/8,H,W,8] bf16, or NULL                                                      */
+  const float* v_in;            /* [B,C,Ho,Wo] or NULL (zeros)                                                        */
+  const float* z_in;            /* [B,C,Ho,Wo] fp32 previous spikes or NULL                                           */
+  const uint16_t* z_in_c8;      /* same in c8, or NULL                                                                */
+  const float* aux_in;          /* third state (PLIF/XLIF trace pt, ALIF trace t) or NULL                             */
+  const float* w_ff;            /* [C,Cin,k,k]                                                                        */
+  const float* w_rec;           /* [C,C,k,k] or NULL (non-recurrent cell)                                             */
+  const float* leak;            /* [C] leak (LIF) / leak_v                                                            */
+  const float* thresh;          /* [C] thresh (LIF, PLIF) or NULL                                                     */
+  const float* leak_aux;        /* [C] leak_pt (PLIF, XLIF) / leak_t (ALIF) or NULL                                   */
+  const float* add_pt;          /* [C] add_pt (PLIF) or NULL                                                          */
+  const float* t0;              /* [C] t0 (ALIF, XLIF) or NULL                                                        */
+  const float* t1;              /* [C] t1 (ALIF, XLIF) or NULL                                                        */
+  const float* residual;        /* [B,C,Ho,Wo] fp32 or NULL                                                           */
+  /* tensor-core path only: weights pre-split by ef_split_weights (bf16 hi/mid/lo, UMMA layout) or NULL (CUDA cores)  */
+  const uint16_t* w_split;
+  /* outputs (each optional except v_out) */
+  float* v_out;                 /* [B,C,Ho,Wo]                                                                        */
+  float* z_out;                 /* [B,C,Ho,Wo] fp32 spikes (state plane 1) or NULL                                    */
+  uint16_t* z_out_c8;           /* spikes in c8 or NULL                                                               */
+  float* aux_out;               /* third state or NULL                                                                */
+  float* out;                   /* z_out + residual, fp32, or NULL                                                    */
+  uint16_t* out_c8;             /* z_out + residual in c8 or NULL (only differs from z_out_c8 with a residual)        */
+} ef_lif_conv_params;
+
+int ef_lif_conv_fwd(const ef_lif_conv_params* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Backward of one cell-step (what autograd derives from the spans above; recurrences in SURVEY.md 8a).
+ * Given g_out (dL/d out), g_v_out, g_z_out, g_aux_out (dL/d new state from step t+1, NULL = 0) and the tensors the
+ * forward read/wrote, produces g_x, g_v_in, g_z_in, g_aux_in and ACCUMULATES (+=) weight / per-channel gradients.
+ * scratch_gI: caller-provided [B,C,Ho,Wo] fp32 workspace (receives g_I = (1-leak) g_v).
+ * scratch_gP: caller-provided [B,Ho,Wo] fp32 workspace, only needed for PLIF / XLIF cells when g_x is wanted (holds the
+ * channel-summed gradient of the pre-synaptic trace input); may be NULL otherwise.
+ * Limits of this version: fp32 NCHW tensors only, stride 1 only.
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct ef_lif_conv_bwd_params {
+  ef_lif_conv_params f;         /* the forward call (inputs + v_out/aux_out as written by it); fp32 tensors required  */
+  const float* g_out;           /* [B,C,Ho,Wo] or NULL                                                                */
+  const float* g_v_out;         /* or NULL                                                                            */
+  const float* g_z_out;         /* or NULL                                                                            */
+  const float* g_aux_out;       /* or NULL                                                                            */
+  float* scratch_gI;            /* [B,C,Ho,Wo] workspace                                                              */
+  float* scratch_gP;            /* [B,Ho,Wo] workspace (PLIF / XLIF with g_x) or NULL                                 */
+  float* g_x;                   /* [B,Cin,H,W] or NULL (head layer)                                                   */
+  float* g_v_in;                /* [B,C,Ho,Wo] or NULL                                                                */
+  float* g_z_in;                /* [B,C,Ho,Wo] or NULL                                                                */
+  float* g_aux_in;              /* or NULL                                                                            */
+  float* g_w_ff;                /* [C,Cin,k,k] += , or NULL                                                           */
+  float* g_w_rec;               /* [C,C,k,k] +=, or NULL                                                              */
+  float* g_leak;                /* [C] += raw-parameter gradients (through sigmoid / clamp), each may be NULL         */
+  float* g_thresh;
+  float* g_leak_aux;
+  float* g_add_pt;
+  float* g_t0;
+  float* g_t1;
+} ef_lif_conv_bwd_params;
+
+int ef_lif_conv_bwd(const ef_lif_conv_bwd_params* p, void* stream);
+
+/* Split fp32 conv weights [C,Cin,3,3] (+ optional recurrent [C,C,3,3]) into three bf16 terms hi+mid+lo == w exactly,
+ * laid out as the tcgen05 B operand.  out: uint16 [ef_split_weights_elems(Cin, C, has_rec)].  (no reference analogue) */
+int64_t ef_split_weights_elems(int32_t Cin, int32_t C, int32_t has_rec);
+int ef_split_weights(const float* w_ff, const float* w_rec, int32_t Cin, int32_t C, uint16_t* out, void* stream);
+
+/* fp32 NCHW <-> c8 bf16 layout conversion at the API boundary (model.states getter/setter, first input). */
+int ef_pack_c8(const float* src, uint16_t* dst, int32_t B, int32_t C, int32_t H, int32_t W, void* stream);
+int ef_unpack_c8(const uint16_t* src, float* dst, int32_t B, int32_t C, int32_t H, int32_t W, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Prediction head: flow = tanh(conv1x1(x, w) + b).  Replaces ConvLayer.forward, models/submodules.py:52-61 as built
+ * at models/model.py:197-199 (32 -> 2 channels).  x may be fp32 NCHW or c8.
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct ef_pred_params {
+  int32_t B, Cin, Cout, H, W;
+  const float* x;               /* [B,Cin,H,W] or NULL                                                                */
+  const uint16_t* x_c8;         /* or NULL                                                                            */
+  const float* w;               /* [Cout,Cin]                                                                         */
+  const float* b;               /* [Cout]                                                                             */
+  float* y;                     /* [B,Cout,H,W] = tanh(...)                                                           */
+  /* backward only */
+  const float* g_y;             /* [B,Cout,H,W]                                                                       */
+  float* g_x;                   /* [B,Cin,H,W]                                                                        */
+  float* g_w;                   /* [Cout,Cin] +=                                                                      */
+  float* g_b;                   /* [Cout] +=                                                                          */
+} ef_pred_params;
+
+int ef_pred_fwd(const ef_pred_params* p, void* stream);
+int ef_pred_bwd(const ef_pred_params* p, void* stream); /* needs y (forward output), x, g_y */
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Contrast-maximisation event-warping loss over one training window.
+ * Replaces EventWarping.forward (loss/flow.py:176-301) with utils/iwe.py:4-92 (purge_unfeasible, get_interpolation,
+ * interpolate) and the per-event flow gather of event_flow_association (loss/flow.py:65-79), and -- ef_iwe_loss_bwd --
+ * the autograd graph of all of it (analytic gradient).
+ *
+ * Window in "map form": events [B,Ntot,4] (ts,y,x,p; ts already offset by pass index, loss/flow.py:90),
+ * pol_mask [B,Ntot,2], flow maps [S,B,T,2,H,W] (scale, sample, pass, (x,y), H, W), event_mask [B,T,H,W].
+ * Events of pass t occupy columns [t*n_per_pass, (t+1)*n_per_pass) (or [pass_offsets[t], pass_offsets[t+1]) when passes
+ * have different lengths).  With overwrite_intermediate, T_maps == 1 and every
+ * event reads map 0 (loss/flow.py:118-146).
+ *
+ * workspace: float[ef_iwe_loss_workspace_elems(S,B,H,W)], zeroed by the call itself; holds the 8 IWE images per
+ * (scale, sample), the per-(scale,sample,direction) sums and pixel counts, kept for the backward.
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct ef_iwe_loss_params {
+  int32_t S, B, T, T_maps, H, W; /* T = number of passes (max_ts); T_maps = T, or 1 with overwrite_intermediate       */
+  int32_t n_total, n_per_pass;   /* Ntot events per sample; events per pass                                           */
+  float flow_scaling;            /* loss/flow.py:40 (default max(H,W))                                                */
+  float weight;                  /* flow_regul_weight                                                                 */
+  int32_t loss_scaling;          /* divide by #pixels with events (loss/flow.py:221-225)                              */
+  int32_t smoothing_mask;        /* mask smoothness terms with the event masks (:184-190, :280-286)                   */
+  int32_t overwrite_intermediate;
+  const float* events;           /* [B,Ntot,4]                                                                        */
+  const float* pol_mask;         /* [B,Ntot,2]                                                                        */
+  const float* flow_maps;        /* [S,B,T_maps,2,H,W]                                                                */
+  const float* event_mask;       /* [B,T_maps,H,W] (only read when smoothing_mask)                                    */
+  const int32_t* pass_offsets;   /* device int32[T+1], first event column of each pass (ragged passes), or NULL =      */
+                                 /* uniform passes of n_per_pass events                                               */
+  float* workspace;
+  float* loss;                   /* [1]                                                                               */
+  /* backward only */
+  const float* g_loss;           /* [1] upstream gradient (device)                                                    */
+  float* g_flow_maps;            /* [S,B,T_maps,2,H,W], overwritten                                                   */
+} ef_iwe_loss_params;
+
+int64_t ef_iwe_loss_workspace_elems(int32_t S, int32_t B, int32_t H, int32_t W);
+int ef_iwe_loss_fwd(const ef_iwe_loss_params* p, void* stream);
+int ef_iwe_loss_bwd(const ef_iwe_loss_params* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Per-polarity image of warped events.  Replaces compute_pol_iwe / deblur_events (utils/iwe.py:95-153) and the
+ * IWE half of BaseValidationLoss.compute_window_iwe (loss/flow.py:452-465).
+ * iwe: [B,2,H,W], overwritten.  round_idx: nearest pixel, half-to-even (torch.round) instead of bilinear.
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct ef_iwe_image_params {
+  int32_t B, N, H, W;
+  int32_t round_idx;
+  float tref, flow_scaling;
+  const float* events;           /* [B,N,4]                                                                           */
+  const float* pol_mask;         /* [B,N,2]                                                                           */
+  const float* flow;             /* [B,2,H,W] flow map, gathered per event; or NULL if event_flow given               */
+  const float* event_flow;       /* [B,N,2] (fy,fx) per event or NULL                                                 */
+  float* iwe;                    /* [B,2,H,W]                                                                         */
+} ef_iwe_image_params;
+
+int ef_iwe_image(const ef_iwe_image_params* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Event encodings for one batch.  Replaces dataloader/encodings.py:30-85 (events_to_image/voxel/channels) and
+ * dataloader/base.py:148-222 (cnt, mask, voxel, polarity mask).  events: [B,N,4] (ts,y,x,p).  Outputs overwritten;
+ * any may be NULL.  Counts are integer-valued fp32 and bit-exact.
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct ef_encode_params {
+  int32_t B, N, H, W, num_bins, round_ts;
+  const float* events;
+  float* cnt;                    /* [B,2,H,W]                                                                         */
+  float* voxel;                  /* [B,num_bins,H,W]                                                                  */
+  float* mask;                   /* [B,1,H,W]                                                                         */
+  float* pol_mask;               /* [B,N,2]                                                                           */
+} ef_encode_params;
+
+int ef_encode_events(const ef_encode_params* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Fused gradient-norm clip + Adam on one flat fp32 parameter buffer.  Replaces clip_grad_norm_ + Adam.step
+ * (train_flow.py:157-163).  Two launches: ef_grad_sqnorm accumulates sum(g^2) into sqnorm[1] (caller zeroes), then
+ * ef_clip_adam applies g *= min(1, max_norm/(sqrt(sqnorm)+1e-6)) and the Adam update (bias-corrected, eps outside sqrt).
+ * ------------------------------------------------------------------------------------------------------------------ */
+int ef_grad_sqnorm(const float* g, int64_t n, float* sqnorm, void* stream);
+int ef_clip_adam(float* param, const float* g, float* m, float* v, int64_t n, const float* sqnorm, float max_norm, float lr,
+                 float beta1, float beta2, float eps, int32_t step, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EVENTFLOW_H_ */

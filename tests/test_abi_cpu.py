@@ -1,0 +1,123 @@
+"""CPU: the C-ABI library loads, exports every symbol include/eventflow.h declares, and the ctypes structs match the C layout."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "eventflow.h")
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ef_[a-z0-9_]+)\s*\(", src)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from event_flow_b200 import _lib
+
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__ as g
+
+        g.build()
+    return _lib
+
+
+def test_library_exports_every_declared_symbol(lib):
+    h = ctypes.CDLL(lib.LIB_PATH)
+    names = declared_symbols()
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(h, n), f"{n} declared in eventflow.h but not exported"
+    assert set(names) == set(lib.EXPORTS), "ctypes binding and header disagree"
+
+
+def test_version_and_error_string(lib):
+    assert lib.lib().ef_version() == 100
+    assert isinstance(lib.lib().ef_last_error(), bytes)
+
+
+def test_argument_errors_are_reported_without_a_gpu(lib):
+    h = lib.lib()
+    assert h.ef_lif_conv_fwd(None, None) == -3 and b"NULL" in h.ef_last_error()
+    p = lib.LifConvParams()
+    assert h.ef_lif_conv_fwd(ctypes.byref(p), None) == -1  # non-positive dims
+    p.B = p.Cin = p.C = p.H = p.W = 8
+    p.ksize, p.stride = 5, 1
+    assert h.ef_lif_conv_fwd(ctypes.byref(p), None) == -2 and b"kernel_size" in h.ef_last_error()
+    q = lib.IweLossParams()
+    assert h.ef_iwe_loss_fwd(ctypes.byref(q), None) == -1
+    assert h.ef_iwe_image(None, None) == -3
+    assert h.ef_encode_events(None, None) == -3
+    assert h.ef_pack_c8(None, None, 1, 8, 4, 4, None) == -3
+
+
+def test_ctypes_structs_match_c_layout(lib, tmp_path):
+    structs = {
+        "ef_lif_conv_params": lib.LifConvParams,
+        "ef_lif_conv_bwd_params": lib.LifConvBwdParams,
+        "ef_pred_params": lib.PredParams,
+        "ef_iwe_loss_params": lib.IweLossParams,
+        "ef_iwe_image_params": lib.IweImageParams,
+        "ef_encode_params": lib.EncodeParams,
+    }
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void){"]
+    for cname, cls in structs.items():
+        lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines.append("return 0;}")
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-o", str(exe), str(src)])  # the header is plain C
+    out = dict(l.split() for l in subprocess.check_output([str(exe)]).decode().splitlines())
+    for cname, cls in structs.items():
+        assert int(out[cname]) == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(out[f"{cname}.{fname}"]) == getattr(cls, fname).offset, f"{cname}.{fname}"
+
+
+def test_product_path_refuses_cpu_tensors(lib):
+    import torch
+
+    from event_flow_b200 import ops
+
+    with pytest.raises(lib.EventFlowError):
+        ops.pack_c8(torch.zeros(1, 8, 4, 4))
+    from event_flow_b200.models.model import LIFFireNet
+
+    cfg = dict(name="x", encoding="cnt", round_encoding=False, norm_input=False, num_bins=2, base_num_channels=32, kernel_size=3,
+               activations=["arctanspike", "arctanspike"], mask_output=True, spiking_neuron={})
+    m = LIFFireNet(cfg)
+    with pytest.raises(lib.EventFlowError):
+        m(torch.zeros(1, 2, 16, 16), torch.zeros(1, 2, 16, 16))
+
+
+def test_dropin_names_and_state_dict_keys(lib):
+    import event_flow_b200
+
+    event_flow_b200.install_dropin()
+    from models.model import LIFFireNet  # noqa: resolves to this package
+
+    assert LIFFireNet.__module__ == "event_flow_b200.models.model"
+    cfg = dict(name="x", encoding="cnt", round_encoding=False, norm_input=False, num_bins=2, base_num_channels=32, kernel_size=3,
+               activations=["arctanspike", "arctanspike"], mask_output=True,
+               spiking_neuron=dict(leak=[-4.0, 0.1], thresh=[0.8, 0.1], learn_leak=True, learn_thresh=True, hard_reset=True))
+    m = LIFFireNet(cfg)
+    keys = set(m.state_dict().keys())
+    # {head,R1a,R1b,R2a,R2b}.{leak,thresh,ff.weight,act_width}, {G1,G2}.{..,rec.weight}, pred.conv2d.{weight,bias}
+    want = {f"{l}.{k}" for l in ("head", "G1", "R1a", "R1b", "G2", "R2a", "R2b") for k in ("leak", "thresh", "ff.weight", "act_width")}
+    want |= {"G1.rec.weight", "G2.rec.weight", "pred.conv2d.weight", "pred.conv2d.bias"}
+    assert keys == want
+    assert m.G1.rec.weight.shape == (32, 32, 3, 3) and m.head.leak.shape == (32, 1, 1) and m.head.act_width.shape == ()
+    assert "Trainable parameters: 74818" in str(m)
+    for s in ("models", "loss", "utils", "dataloader"):
+        sys.modules.pop(s, None)
+    for s in [k for k in sys.modules if k.split(".")[0] in ("models", "loss", "utils", "dataloader")]:
+        sys.modules.pop(s, None)

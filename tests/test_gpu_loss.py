@@ -1,0 +1,178 @@
+"""
+GPU parity of hot path B (T5, T6): event-warping loss value and analytic gradient against the reference's golden numbers
+(random flows, zero flow = all ties, half-integer flows + out-of-bounds), IWE images, encodings, and a known-answer test.
+Tolerances: loss rel 1e-5, d loss / d flow rel 1e-3 (north-star), counts / rounded IWEs bit-exact.
+"""
+import glob
+import os
+
+import pytest
+import torch
+
+from oracle import encodings as oenc
+from oracle import iwe as oiwe
+from tests.conftest import GOLDEN, load_golden
+from tests.util import assert_rel
+
+pytestmark = pytest.mark.gpu
+LOSSES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "loss_*.npz")))
+DEV = "cuda"
+
+
+def cuda_loss_from_golden(g):
+    from event_flow_b200.loss.flow import EventWarping
+
+    scaling, smask, overwrite, weight, T, N = g["cfg"].tolist()
+    T, N = int(T), int(N)
+    flow = g["flow"].to(DEV)
+    H, W = flow.shape[-2:]
+    cfg = {"loader": {"resolution": [H, W]}, "loss": {"flow_regul_weight": weight, "overwrite_intermediate": bool(overwrite)},
+           "model": {"mask_output": bool(smask)}}
+    L = EventWarping(cfg, DEV, loss_scaling=bool(scaling))
+    flows = [flow[:, t].clone().requires_grad_(True) for t in range(T)]
+    ev = g["events"].clone()
+    for t in range(T):
+        e = ev[:, t * N:(t + 1) * N].clone()
+        e[:, :, 0] -= t  # the fixture stores offset timestamps; the API offsets them itself (loss/flow.py:90)
+        L.event_flow_association([flows[t]], e.to(DEV), g["pol_mask"][:, t * N:(t + 1) * N].to(DEV), g["event_mask"][:, t:t + 1].to(DEV))
+    assert L.num_events == T * N
+    if overwrite:
+        L.overwrite_intermediate_flow([flows[-1]])
+    loss = L()
+    loss.backward()
+    return loss, flows
+
+
+@pytest.mark.parametrize("name", LOSSES)
+def test_event_warping_loss_and_gradient_match_reference(name):
+    g = load_golden(name)
+    loss, flows = cuda_loss_from_golden(g)
+    assert_rel(loss, g["loss"], 1e-5, "loss")
+    for t, f in enumerate(flows):
+        if f"grad_{t}" in g:
+            assert_rel(f.grad, g[f"grad_{t}"], 1e-3, f"grad[{t}]")
+        else:
+            assert f.grad is None or f.grad.abs().max() == 0
+
+
+def test_iwe_image_matches_reference():
+    from event_flow_b200.utils.iwe import compute_pol_iwe
+
+    g = load_golden("iwe_image")
+    H, W = g["flow"].shape[-2:]
+    pm = g["pol_mask"].to(DEV)
+    for rnd, key in ((True, "iwe_round"), (False, "iwe_bilinear")):
+        out = compute_pol_iwe(g["flow"].to(DEV), g["events"].to(DEV), (H, W), pm[:, :, 0:1], pm[:, :, 1:2], flow_scaling=max(H, W), round_idx=rnd)
+        if rnd:
+            assert torch.equal(out.cpu(), g[key])
+        else:
+            torch.testing.assert_close(out.cpu(), g[key], rtol=1e-5, atol=1e-6)
+
+
+def test_encodings_match_reference_counts_bit_exact():
+    from event_flow_b200.dataloader import encodings as E
+
+    g = load_golden("encodings")
+    B = g["ts"].shape[0]
+    H, W = g["cnt_0"].shape[-2:]
+    ev = torch.stack([g["ts"], g["ys"], g["xs"], g["ps"]], dim=2).to(DEV)
+    for bins in (2, 5):
+        d = E.encode_batch(ev, (H, W), bins)
+        for b in range(B):
+            assert torch.equal(d["event_cnt"][b].cpu(), g[f"cnt_{b}"])
+            assert torch.equal(d["event_mask"][b, 0].cpu(), g[f"mask_{b}"])
+            torch.testing.assert_close(d["event_voxel"][b].cpu(), g[f"voxel{bins}_{b}"], rtol=1e-5, atol=1e-6)
+            assert torch.equal(d["event_list_pol_mask"][b].cpu(), oenc.polarity_mask(g["ps"][b]))
+    one = E.events_to_channels(g["xs"][0].to(DEV), g["ys"][0].to(DEV), g["ps"][0].to(DEV), (H, W))
+    assert torch.equal(one.cpu(), g["cnt_0"])
+
+
+def test_full_size_window_against_oracle_and_properties():
+    """cfg-2 size (B=8, 128x128, T=10, N=1000): loss vs oracle; invariances the domain offers (size-independent checks)."""
+    from event_flow_b200 import ops
+
+    B, H, W, T, N = 8, 128, 128, 10, 1000
+    g = torch.Generator().manual_seed(0)
+    evs, pms, masks = [], [], []
+    for t in range(T):
+        d = oenc.encode_window(*oenc.synthetic_events(B, N, H, W, 50 + t), H, W, 2)
+        e = d["event_list"].clone()
+        e[:, :, 0] += t
+        evs.append(e), pms.append(d["event_list_pol_mask"]), masks.append(d["event_mask"])
+    events, pol, mask = torch.cat(evs, 1), torch.cat(pms, 1), torch.cat(masks, 1)
+    flow = (torch.rand((1, B, T, 2, H, W), generator=g) - 0.5) * 0.1
+    kw = dict(passes=T, n_per_pass=N, flow_scaling=128, weight=0.001)
+    fd = flow.to(DEV).requires_grad_(True)
+    loss = ops.event_warping_loss(fd, events.to(DEV), pol.to(DEV), mask.to(DEV), **kw)
+    loss.backward()
+    fo = flow[0].clone().requires_grad_(True)
+    loss_o = oiwe.event_warping_loss(events, pol, torch.arange(T).repeat_interleave(N), [fo], mask, (H, W), weight=0.001, passes=T)
+    loss_o.backward()
+    assert_rel(loss, loss_o, 1e-5, "loss")
+    assert_rel(fd.grad[0], fo.grad, 1e-3, "grad")
+    # property: the loss is invariant to the order of events inside a pass (scatter-add commutes)
+    perm = torch.cat([t * N + torch.randperm(N, generator=g) for t in range(T)])
+    loss_p = ops.event_warping_loss(flow.to(DEV), events[:, perm].to(DEV), pol[:, perm].to(DEV), mask.to(DEV), **kw)
+    assert_rel(loss_p, loss, 1e-5, "permutation invariance")
+    # property: the loss is a sum over samples -> batch halves add up (smoothness weight 0 isolates the event terms)
+    kw0 = dict(kw, weight=0.0)
+    full = ops.event_warping_loss(flow.to(DEV), events.to(DEV), pol.to(DEV), mask.to(DEV), **kw0)
+    h1 = ops.event_warping_loss(flow[:, :4].contiguous().to(DEV), events[:4].to(DEV), pol[:4].to(DEV), mask[:4].to(DEV), **kw0)
+    h2 = ops.event_warping_loss(flow[:, 4:].contiguous().to(DEV), events[4:].to(DEV), pol[4:].to(DEV), mask[4:].to(DEV), **kw0)
+    assert_rel(h1 + h2, full, 1e-5, "additivity over the batch")
+
+
+def test_known_answer_constant_flow_minimises_loss():
+    """tools/demo_iwe.py:69-91 idea: events generated by a known constant flow -> the loss over a (u,v) grid is minimal there."""
+    from event_flow_b200 import ops
+
+    H = W = 64
+    N, T = 4000, 1
+    g = torch.Generator().manual_seed(1)
+    u_true, v_true = 6.0, -4.0  # px per window
+    x0 = torch.rand(N, generator=g) * (W - 20) + 10
+    y0 = torch.rand(N, generator=g) * (H - 20) + 10
+    pts = torch.randint(0, 40, (N,), generator=g)  # 40 point sources -> sharp IWE when compensated
+    x0, y0 = x0[pts], y0[pts]
+    ts = torch.sort(torch.rand(N, generator=g))[0]
+    xs, ys = torch.round(x0 + u_true * ts), torch.round(y0 + v_true * ts)
+    ps = torch.ones(N)
+    events = torch.stack([ts, ys, xs, ps], 1).unsqueeze(0).to(DEV)
+    pol = oenc.polarity_mask(ps).unsqueeze(0).to(DEV)
+    mask = torch.ones(1, 1, H, W, device=DEV)
+    best, best_uv = None, None
+    for u in range(-8, 9, 2):
+        for v in range(-8, 9, 2):
+            flow = torch.zeros(1, 1, 1, 2, H, W, device=DEV)
+            flow[..., 0, :, :], flow[..., 1, :, :] = u, v
+            l = ops.event_warping_loss(flow, events, pol, mask, passes=T, n_per_pass=N, flow_scaling=1.0, weight=0.0).item()
+            if best is None or l < best:
+                best, best_uv = l, (u, v)
+    assert best_uv == (6, -4), best_uv
+
+
+def test_empty_and_ragged_windows():
+    from event_flow_b200 import ops
+    from event_flow_b200.loss.flow import EventWarping
+
+    H, W = 16, 20
+    # ragged passes (different event counts per pass) against the oracle
+    Ns = [40, 75, 10]
+    g = torch.Generator().manual_seed(4)
+    cfg = {"loader": {"resolution": [H, W]}, "loss": {"flow_regul_weight": 0.01, "overwrite_intermediate": False}, "model": {"mask_output": True}}
+    L = EventWarping(cfg, DEV)
+    evs, pms, masks, flows = [], [], [], []
+    for t, n in enumerate(Ns):
+        d = oenc.encode_window(*oenc.synthetic_events(2, n, H, W, 70 + t), H, W, 2)
+        f = (torch.rand((2, 2, H, W), generator=g) - 0.5) * 0.2
+        L.event_flow_association([f.to(DEV)], d["event_list"].clone().to(DEV), d["event_list_pol_mask"].to(DEV), d["event_mask"].to(DEV))
+        e = d["event_list"].clone()
+        e[:, :, 0] += t
+        evs.append(e), pms.append(d["event_list_pol_mask"]), masks.append(d["event_mask"]), flows.append(f)
+    pass_of = torch.cat([torch.full((n,), t) for t, n in enumerate(Ns)])
+    loss_o = oiwe.event_warping_loss(torch.cat(evs, 1), torch.cat(pms, 1), pass_of, [torch.stack(flows, 1)], torch.cat(masks, 1), (H, W),
+                                     weight=0.01, passes=3)
+    assert_rel(L(), loss_o, 1e-5, "ragged passes")
+    # empty event list: IWE image is all zeros, no launch failure
+    out = ops.iwe_image(torch.zeros(1, 0, 4, device=DEV), torch.zeros(1, 0, 2, device=DEV), (H, W), flow=torch.zeros(1, 2, H, W, device=DEV))
+    assert out.abs().sum().item() == 0

@@ -1,0 +1,33 @@
+"""Shared helpers for the GPU parity tests."""
+import torch
+
+
+def spike_band_compare(v_mine, z_mine, v_ref, z_ref, thresh, band=1e-5, v_atol=2e-5):
+    """
+    SURVEY T1: membrane potentials agree to summation-order noise; spikes agree exactly outside a band |v - thresh| < band.
+    Returns (max|dv|, flips outside band, flips inside band).
+    """
+    dv = (v_mine - v_ref).abs().max().item()
+    near = (v_ref - thresh).abs() < band
+    diff = z_mine != z_ref
+    out_flips = (diff & ~near).sum().item()
+    in_flips = (diff & near).sum().item()
+    assert dv <= v_atol, f"max|dv| = {dv:.3e} > {v_atol}"
+    assert out_flips == 0, f"{out_flips} spike flips outside the |v-thresh|<{band} band"
+    return dv, out_flips, in_flips
+
+
+def rel_err(a, b):
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+
+
+def assert_rel(a, b, tol, what=""):
+    r = rel_err(a.detach().cpu().double(), b.detach().cpu().double())
+    assert r <= tol, f"{what}: max-abs rel err {r:.3e} > {tol}"
+    return r
+
+
+def firenet_cfg(bins, encoding, neuron="lif"):
+    sn = dict(leak=[-4.0, 0.1], thresh=[0.8, 0.1], learn_leak=True, learn_thresh=True, hard_reset=True) if neuron == "lif" else {}
+    return dict(name="x", encoding=encoding, round_encoding=False, norm_input=False, num_bins=bins, base_num_channels=32,
+                kernel_size=3, activations=["arctanspike", "arctanspike"], mask_output=True, spiking_neuron=sn)
