@@ -1,0 +1,329 @@
+"""
+bench.py -- headline benchmark of the event_flow hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1], "cfg2"): LIFFireNet, 5-bin voxel input, 128x128, batch 8 per GPU, one training window =
+10 timesteps of 1000 events per sample: 10 forward passes + the EventWarping loss.  One "step" = that window.
+metric = events/s over the whole job (all ranks), inputs resident in HBM (`value`) and end-to-end from pinned host event
+lists (`e2e`: H2D of the raw events each timestep, device-side encoding, model, loss, D2H of the loss).
+Also reported: the full train step (forward + loss + BPTT + gradient all-reduce + clip + Adam) under "train".
+The reference arm (--impl reference) times the CPU restatement of the reference's path (oracle/, "port") on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H = W = 128
+B_PER_GPU = 8
+T = 10
+N_EV = 1000
+BINS = 5
+LIF = dict(leak=[-4.0, 0.1], thresh=[0.8, 0.1], learn_leak=True, learn_thresh=True, hard_reset=True)
+MODEL_CFG = dict(name="LIFFireNet", encoding="voxel", round_encoding=False, norm_input=False, num_bins=BINS, base_num_channels=32,
+                 kernel_size=3, activations=["arctanspike", "arctanspike"], mask_output=True, spiking_neuron=LIF)
+LOSS_CFG = {"loader": {"resolution": [H, W]}, "loss": {"flow_regul_weight": 0.001, "overwrite_intermediate": False, "clip_grad": 100.0},
+            "model": {"mask_output": True}}
+WORKLOAD = "cfg2: LIFFireNet fwd x10 + EventWarping loss, 128x128, 5 voxel bins, 1000 ev/window, batch 8 per GPU"
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+def make_events(rank, step):
+    """Raw event lists of one window: T tensors [B,N,4] (ts,y,x,p); seed 1234 + 1000*rank + t."""
+    from oracle.encodings import synthetic_events
+
+    out = []
+    for t in range(T):
+        ts, ys, xs, ps = synthetic_events(B_PER_GPU, N_EV, H, W, 1234 + 1000 * rank + 100 * step + t)
+        out.append(torch.stack([ts, ys, xs, ps], dim=2))
+    return out
+
+
+def scale_weights(model):
+    """Reference init (seed 0) with conv weights x2.5 so that spikes reach the prediction layer on 1000 ev / 128^2."""
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if n.endswith("ff.weight") or n.endswith("rec.weight"):
+                p.mul_(2.5)
+        model.pred.conv2d.weight.mul_(20.0)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.25)
+            self.proc.terminate()
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+
+    from event_flow_b200 import _lib
+    from event_flow_b200.dataloader.encodings import encode_batch
+    from event_flow_b200.loss.flow import EventWarping
+    from event_flow_b200.models.model import LIFFireNet
+    from event_flow_b200.parallel import DataParallelTrainer
+
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert _lib.lib().ef_device_ok() == 1, "this benchmark needs a compute-capability 10.x GPU (B200)"
+
+    torch.manual_seed(0)
+    model = LIFFireNet(MODEL_CFG)
+    scale_weights(model)
+    model = model.to(dev).train()
+    lossf = EventWarping(LOSS_CFG, dev)
+    trainer = DataParallelTrainer(model, lr=2e-4, clip_grad=100.0)
+
+    n_windows = 4  # distinct input windows cycled through (device-resident for `value`, pinned host for `e2e`)
+    host = [[e.pin_memory() for e in make_events(rank, s)] for s in range(n_windows)]
+    resident = []
+    for win in host:
+        enc = []
+        for e in win:
+            ed = e.to(dev)
+            d = encode_batch(ed, (H, W), BINS)
+            enc.append((d["event_voxel"], d["event_cnt"], ed, d["event_list_pol_mask"], d["event_mask"]))
+        resident.append(enc)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def fwd_loss_resident(k):
+        model.reset_states()
+        lossf.reset()
+        with torch.no_grad():
+            for vox, cnt, ev, pm, mask in resident[k % n_windows]:
+                out = model(vox, cnt)
+                lossf.event_flow_association(out["flow"], ev.clone(), pm, mask)
+            return lossf()
+
+    def fwd_loss_e2e(k):
+        model.reset_states()
+        lossf.reset()
+        with torch.no_grad():
+            for e in host[k % n_windows]:
+                ed = e.to(dev, non_blocking=True)
+                d = encode_batch(ed, (H, W), BINS)
+                out = model(d["event_voxel"], d["event_cnt"])
+                lossf.event_flow_association(out["flow"], ed, d["event_list_pol_mask"], d["event_mask"])
+            return lossf().item()  # D2H read of the result
+
+    def train_step(k):
+        model.reset_states()
+        lossf.reset()
+        for vox, cnt, ev, pm, mask in resident[k % n_windows]:
+            out = model(vox, cnt)
+            lossf.event_flow_association(out["flow"], ev.clone(), pm, mask)
+        loss = lossf()
+        loss.backward()
+        trainer.step()
+        model.detach_states()
+        return loss
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for k in range(warmup):
+            fn(k)
+        barrier()
+        evs = []
+        n0 = _lib.lib().ef_launch_count()
+        for k in range(steps):
+            flush.fill_(k & 0xFF)  # L2 flush between timed iterations (outside the timed events)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn(warmup + k)
+            e1.record()
+            evs.append((e0, e1))
+        barrier()
+        launches = _lib.lib().ef_launch_count() - n0
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item() / steps, launches // steps
+
+    events_per_step = B_PER_GPU * T * N_EV * world
+    with ClockSampler(local) as clocks:
+        ms_value, launches = timed(fwd_loss_resident, args.steps, args.warmup)
+        ms_e2e, _ = timed(fwd_loss_e2e, args.steps, args.warmup)
+        ms_train, launches_train = timed(train_step, max(2, args.steps // 2), max(3, args.warmup // 2))
+
+    # roofline of the dominant kernel: fused conv+LIF step of the 32->32 hidden layers, per-launch CUDA-event durations
+    _lib.PROFILE = []
+    fwd_loss_resident(0)
+    torch.cuda.synchronize()
+    prof, _lib.PROFILE = _lib.PROFILE, None
+    hidden = [a.elapsed_time(b) for name, tag, a, b in prof if name == "ef_lif_conv_fwd" and tag and tag[0] == 32]
+    allk = sum(a.elapsed_time(b) for _, _, a, b in prof)
+    pk, pk_kind = peaks()
+    bytes_per_launch = 4 * H * W * (32 + 2 * 2 * 32) * B_PER_GPU  # 4*HW*(Cin + 2*S_r*C) per sample, fp32 reference semantics
+    avg_ms = sum(hidden) / max(1, len(hidden))
+    achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9 if hidden else None
+    roofline = {"bound": "hbm", "kernel": "fused conv3x3+LIF step, 32->32 ch (ef_lif_conv_fwd)", "achieved": achieved, "peak": pk["hbm_gbs"],
+                "unit": "GB/s", "frac": (achieved / pk["hbm_gbs"]) if achieved else None, "traffic": None, "peak_source": pk_kind + " (burst copy)",
+                "bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_ms, "launches_per_step": len(hidden),
+                "share_of_step": (sum(hidden) / allk) if allk else None}
+
+    if rank == 0:
+        cpu = cpu_baseline(sample_steps=1)
+        line = {
+            "metric": "events/s (LIFFireNet fwd + EventWarping loss)", "value": events_per_step / (ms_value * 1e-3), "unit": "events/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_value, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "global_batch": B_PER_GPU * world, "timesteps": T, "events_per_window": N_EV, "resolution": [H, W],
+                       "parallelism": f"dp{world}", "l2": "256 MB write between timed iterations (L2 flush)", "weights": "reference init seed 0, conv x2.5"},
+            "e2e": {"value": events_per_step / (ms_e2e * 1e-3), "unit": "events/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": T * B_PER_GPU * N_EV * 4 * 4, "d2h_bytes_per_step": 4,
+                    "path": "pinned host event lists -> H2D -> ef_encode_events -> LIFFireNet x10 -> EventWarping -> loss.item()"},
+            "gpu_launches": int(launches),
+            "train": {"ms_per_step": ms_train, "events_per_s": events_per_step / (ms_train * 1e-3), "gpu_launches": int(launches_train),
+                      "what": "fwd x10 + loss + BPTT + grad all-reduce(SUM) + clip(100) + Adam, batch 8 per GPU"},
+            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks.summary(),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU baseline / reference arm: the oracle restatement of the reference's path on the host cores
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_step(params, windows):
+    from oracle import iwe as oiwe
+    from oracle import spiking as osp
+
+    states = [None] * 7
+    flows, evs, pms, masks = [], [], [], []
+    with torch.no_grad():
+        for t, d in enumerate(windows):
+            flow, states, _ = osp.firenet_step("lif", params, states, d["event_voxel"])
+            flows.append(flow)
+            e = d["event_list"].clone()
+            e[:, :, 0] += t
+            evs.append(e), pms.append(d["event_list_pol_mask"]), masks.append(d["event_mask"])
+        return oiwe.event_warping_loss(torch.cat(evs, 1), torch.cat(pms, 1), torch.arange(T).repeat_interleave(N_EV), [torch.stack(flows, 1)],
+                                       torch.cat(masks, 1), (H, W), weight=0.001, passes=T)
+
+
+def cpu_setup():
+    from oracle import encodings as oenc
+    from oracle import spiking as osp
+
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    params = osp.init_firenet_params("lif", BINS, 32, seed=0, weight_gain=2.5)
+    params["pred"]["weight"] = params["pred"]["weight"] * 20.0
+    windows = []
+    for e in make_events(0, 0):
+        windows.append(oenc.encode_window(e[:, :, 0], e[:, :, 1], e[:, :, 2], e[:, :, 3], H, W, BINS))
+    return cores, params, windows
+
+
+def cpu_baseline(sample_steps=1):
+    cores, params, windows = cpu_setup()
+    cpu_step(params, windows)  # warm-up
+    t0 = time.perf_counter()
+    for _ in range(sample_steps):
+        cpu_step(params, windows)
+    dt = (time.perf_counter() - t0) / sample_steps
+    return {"value": B_PER_GPU * T * N_EV / dt, "unit": "events/s", "cores": cores, "kind": "port", "ms_per_step": dt * 1e3,
+            "sample": f"{sample_steps} full window(s) of the same workload (batch 8, 10 timesteps) after 1 warm-up, torch-CPU fp32 oracle, {cores} threads"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    cores, params, windows = cpu_setup()
+    for _ in range(max(1, min(args.warmup, 2))):
+        cpu_step(params, windows)
+    steps = max(1, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_step(params, windows)
+    dt = (time.perf_counter() - t0) / steps
+    v = B_PER_GPU * T * N_EV / dt
+    sample = f"{steps} full windows (batch 8, 10 timesteps; one rank's share) after warm-up, torch-CPU fp32 oracle port of the reference, {cores} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": "events/s (LIFFireNet fwd + EventWarping loss)", "value": v, "unit": "events/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "global_batch": B_PER_GPU, "parallelism": "cpu"},
+        "cpu_baseline": {"value": v, "unit": "events/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    a = ap.parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -81,6 +81,7 @@ EXPORTS = {
     "ef_version": (C.c_int, []),
     "ef_last_error": (C.c_char_p, []),
     "ef_device_ok": (C.c_int, []),
+    "ef_launch_count": (C.c_uint64, []),
     "ef_lif_conv_fwd": (C.c_int, [C.POINTER(LifConvParams), C.c_void_p]),
     "ef_lif_conv_bwd": (C.c_int, [C.POINTER(LifConvBwdParams), C.c_void_p]),
     "ef_split_weights_elems": (C.c_int64, [_i32, _i32, _i32]),
@@ -144,8 +145,18 @@ def stream():
     return torch.cuda.current_stream().cuda_stream
 
 
-def call(name, params):
+PROFILE = None  # set to a list to record (name, tag, start_event, end_event) around every struct-taking call (bench.py roofline)
+
+
+def call(name, params, tag=None):
     """Invoke a struct-taking entry point on the current torch stream."""
     global LAUNCHES
     LAUNCHES += 1
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(getattr(lib(), name)(C.byref(params), stream()), name)
+        e1.record()
+        PROFILE.append((name, tag, e0, e1))
+        return
     check(getattr(lib(), name)(C.byref(params), stream()), name)

@@ -16,7 +16,10 @@ int fail(int code, const char* fmt, ...) {
   return code;
 }
 
+static unsigned long long g_launches = 0;  // kernels launched by this library in this process (bench.py: gpu_launches)
+
 int check_launch(const char* what) {
+  __atomic_add_fetch(&g_launches, 1ull, __ATOMIC_RELAXED);
   const cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) return EF_OK;
   return fail((int)e, "%s: %s", what, cudaGetErrorString(e));
@@ -25,6 +28,7 @@ int check_launch(const char* what) {
 }  // namespace ef
 
 extern "C" int ef_version(void) { return EF_VERSION; }
+extern "C" uint64_t ef_launch_count(void) { return __atomic_load_n(&ef::g_launches, __ATOMIC_RELAXED); }
 extern "C" const char* ef_last_error(void) { return ef::last_error_buf(); }
 
 extern "C" int ef_device_ok(void) {

@@ -441,7 +441,7 @@ extern "C" int ef_iwe_image(const ef_iwe_image_params* pp, void* stream) {
   EF_REQUIRE(pp, EF_ENULL, "ef_iwe_image: params is NULL");
   const ef_iwe_image_params& p = *pp;
   EF_REQUIRE(p.B > 0 && p.N >= 0 && p.H > 0 && p.W > 0, EF_EINVAL, "ef_iwe_image: bad dimensions");
-  EF_REQUIRE(p.events && p.pol_mask && p.iwe && (p.flow || p.event_flow), EF_ENULL, "ef_iwe_image: NULL tensor");
+  EF_REQUIRE(p.iwe && (p.N == 0 || (p.events && p.pol_mask && (p.flow || p.event_flow))), EF_ENULL, "ef_iwe_image: NULL tensor");
   cudaStream_t st = as_stream(stream);
   cudaMemsetAsync(p.iwe, 0, (size_t)p.B * 2 * p.H * p.W * sizeof(float), st);
   if (p.N == 0) return EF_OK;

@@ -74,7 +74,7 @@ class _CellStep(torch.autograd.Function):
         out = torch.empty((B, Cout, Ho, Wo), device=x.device, dtype=torch.float32)  # z (+ residual); a tensor of its own
         p = L.LifConvParams()
         _fill_cell_params(p, neuron, x, state_in, w_ff, w_rec, chan, residual, state_out, out, hard_reset, surrogate, width, stride)
-        L.call("ef_lif_conv_fwd", p)
+        L.call("ef_lif_conv_fwd", p, tag=(x.shape[1], Cout, w_rec is not None))
         ctx.meta = meta
         ctx.chan_names = names
         ctx.save_for_backward(x, state_in, w_ff, w_rec, residual, state_out, *[chan[n] for n in names])

@@ -38,6 +38,8 @@ int ef_version(void);
 const char* ef_last_error(void);
 /* 1 if the visible device is compute capability 10.x (tcgen05/TMA kernels usable), 0 if another GPU, <0 on error. */
 int ef_device_ok(void);
+/* number of CUDA kernels this library has launched in the calling process (monotonic; memsets not counted). */
+uint64_t ef_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Fused conv3x3 + spiking-neuron update, one timestep of one cell.

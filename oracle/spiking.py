@@ -184,6 +184,30 @@ def firenet_step(neuron, params, states, x, **cell_kwargs):
     return flow, new_states, acts
 
 
+def firenet_layerwise_check(neuron, params, captured, **cell_kwargs):
+    """
+    Per-LAYER teacher-forced check of one FireNet step computed elsewhere (the CUDA path).
+    :param captured: {layer: (x_in, state_in | None, out, state_out)} CPU tensors captured from the path under test
+    :return list of (layer, max|dv|, spike flips outside a 1e-5 band around threshold, spike flips inside, neurons)
+    Every layer's oracle output is computed from the inputs the tested path actually fed to that layer, so a single
+    borderline spike cannot cascade into the next layer's comparison (threshold chaos).
+    """
+    report = []
+    for name in FIRENET_LAYERS:
+        x_in, st_in, out, st_out = captured[name]
+        out_o, st_o = cell_step(neuron, x_in, st_in, params[name], **cell_kwargs)
+        p = params[name]
+        if neuron in ("lif", "plif"):
+            thr = p["thresh"].clamp_min(0.01)
+        else:
+            thr = p["t0"].clamp_min(0.01) + p["t1"].clamp_min(0) * st_o[2]
+        dv = (st_out[0] - st_o[0]).abs().max().item()
+        near = (st_o[0] - thr).abs() < 1e-5
+        diff = st_out[1] != st_o[1]
+        report.append((name, dv, int((diff & ~near).sum()), int((diff & near).sum()), st_o[1].numel()))
+    return report
+
+
 def init_firenet_params(neuron, num_bins, channels=32, ksize=3, seed=0, weight_gain=1.0, thresh=(0.8, 0.1)):
     """
     Random parameters with the reference's initialisers (spiking_submodules.py:60-75,487-490; model.py:197-199 with

@@ -56,9 +56,10 @@ def test_firenet_rollout_and_bptt_match_reference_golden(name):
 
 
 @pytest.mark.parametrize("neuron", osp.NEURONS)
-def test_firenet_teacher_forced_steps_match_oracle(neuron):
-    """Each step: the oracle starts from the CUDA path's previous states, so rounding chaos cannot accumulate."""
+def test_firenet_teacher_forced_layers_match_oracle(neuron):
+    """Free-running CUDA rollout; every layer of every step is re-computed by the oracle from the inputs the CUDA path fed it."""
     import event_flow_b200.models.model as M
+    from tests.util import capture_layers, oracle_params_of
 
     cls = {"lif": M.LIFFireNet, "plif": M.PLIFFireNet, "alif": M.ALIFFireNet, "xlif": M.XLIFFireNet}[neuron]
     B, H, W, T, bins = 2, 48, 64, 5, 5
@@ -69,35 +70,25 @@ def test_firenet_teacher_forced_steps_match_oracle(neuron):
             if n.endswith("ff.weight") or n.endswith("rec.weight"):
                 p.mul_(2.5)
         m.pred.conv2d.weight.mul_(20.0)
-    params = {}
-    for l in osp.FIRENET_LAYERS:
-        cell = getattr(m, l)
-        params[l] = {"ff": cell.ff.weight.detach().clone()}
-        if hasattr(cell, "rec"):
-            params[l]["rec"] = cell.rec.weight.detach().clone()
-        for k in ("leak", "thresh", "leak_v", "leak_pt", "leak_t", "add_pt", "t0", "t1"):
-            if hasattr(cell, k):
-                params[l][k] = getattr(cell, k).detach().clone()
-    params["pred"] = {"weight": m.pred.conv2d.weight.detach().clone(), "bias": m.pred.conv2d.bias.detach().clone()}
+    params = oracle_params_of(m)
     m = m.to(DEV)
-    states = [None] * 7
-    flips = total = 0
+    captured, handles = capture_layers(m)
+    flips_in = total = 0
     for t in range(T):
         d = oenc.encode_window(*oenc.synthetic_events(B, 600, H, W, 300 + t), H, W, bins)
         out = m(d["event_voxel"].to(DEV), d["event_cnt"].to(DEV), log=True)
-        flow_o, states_o, acts_o = osp.firenet_step(neuron, params, states, d["event_voxel"])
-        mine = [s.detach().cpu() for s in m.states]
-        for i, (a, b) in enumerate(zip(mine, states_o)):
-            assert (a[0] - b[0]).abs().max() < 5e-5, (t, i)
-            flips += (a[1] != b[1]).sum().item()
-            total += a[1].numel()
-            if a.shape[0] == 3:
-                assert (a[2] - b[2]).abs().max() < 1e-5
-        if all(torch.equal(a[1], b[1]) for a, b in zip(mine, states_o)):
-            torch.testing.assert_close(out["flow"][0].detach().cpu(), flow_o, rtol=1e-4, atol=1e-6)
-        assert out["activity"]["4:R1b"] > 0.01  # spikes propagate: the test is not vacuous
-        states = mine
-    assert flips <= 1e-5 * total + 2, f"{flips} spike flips of {total}"
+        for name, dv, out_flips, in_flips, n in osp.firenet_layerwise_check(neuron, params, captured):
+            assert dv < 2e-5, (t, name, dv)
+            assert out_flips == 0, (t, name, out_flips)
+            flips_in += in_flips
+            total += n
+        x7 = captured["R2b"][2]
+        torch.testing.assert_close(out["flow"][0].detach().cpu(), osp.pred_head(x7, params["pred"]["weight"], params["pred"]["bias"]),
+                                   rtol=1e-5, atol=1e-7)
+        assert out["activity"]["4:R1b"] > 0.01 and out["activity"]["7:R2b"] > 0.01  # spikes propagate: not vacuous
+    for h in handles:
+        h.remove()
+    assert flips_in <= 1e-5 * total + 2, f"{flips_in} in-band spike flips of {total}"
 
 
 def test_state_api_reset_detach_set():

@@ -1,0 +1,62 @@
+"""GPU: fused clip + Adam against torch's own clip_grad_norm_ + Adam; 1-GPU DP trainer step; bench-sized forward sanity."""
+import pytest
+import torch
+
+from oracle import encodings as oenc
+from tests.util import firenet_cfg
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.mark.parametrize("clip", [100.0, 0.5])
+def test_clip_adam_matches_torch(clip):
+    from event_flow_b200.parallel import DataParallelTrainer
+
+    torch.manual_seed(0)
+    lin = torch.nn.Sequential(torch.nn.Conv2d(3, 8, 3), torch.nn.Conv2d(8, 4, 1)).to(DEV)
+    ref = torch.nn.Sequential(torch.nn.Conv2d(3, 8, 3), torch.nn.Conv2d(8, 4, 1)).to(DEV)
+    ref.load_state_dict(lin.state_dict())
+    tr = DataParallelTrainer(lin, lr=2e-4, clip_grad=clip)
+    opt = torch.optim.Adam(ref.parameters(), lr=2e-4)
+    for it in range(5):
+        x = torch.randn(4, 3, 12, 12, device=DEV)
+        (lin(x) ** 2).sum().backward()
+        (ref(x) ** 2).sum().backward()
+        total = torch.nn.utils.clip_grad_norm_(ref.parameters(), clip)
+        tr.step()
+        torch.testing.assert_close(tr.grad_norm(), total, rtol=1e-5, atol=0)
+        opt.step()
+        opt.zero_grad()
+        for a, b in zip(lin.parameters(), ref.parameters()):
+            torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-7)
+            assert a.grad.abs().max() == 0
+
+
+def test_trainer_step_on_firenet_changes_parameters_and_keeps_grad_views():
+    from event_flow_b200.loss.flow import EventWarping
+    from event_flow_b200.models.model import LIFFireNet
+    from event_flow_b200.parallel import DataParallelTrainer
+
+    Hh = Ww = 64
+    torch.manual_seed(0)
+    m = LIFFireNet(firenet_cfg(5, "voxel"))
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if n.endswith("ff.weight") or n.endswith("rec.weight"):
+                p.mul_(2.5)
+        m.pred.conv2d.weight.mul_(50.0)
+    m = m.to(DEV)
+    tr = DataParallelTrainer(m)
+    cfg = {"loader": {"resolution": [Hh, Ww]}, "loss": {"flow_regul_weight": 0.001, "overwrite_intermediate": False}, "model": {"mask_output": True}}
+    L = EventWarping(cfg, DEV)
+    before = tr.flat_param.clone()
+    for t in range(3):
+        d = oenc.encode_window(*oenc.synthetic_events(2, 500, Hh, Ww, 40 + t), Hh, Ww, 5)
+        out = m(d["event_voxel"].to(DEV), d["event_cnt"].to(DEV))
+        L.event_flow_association(out["flow"], d["event_list"].to(DEV), d["event_list_pol_mask"].to(DEV), d["event_mask"].to(DEV))
+    L().backward()
+    assert tr.flat_grad.abs().max() > 0
+    tr.step()
+    assert (tr.flat_param - before).abs().max() > 0 and tr.flat_grad.abs().max() == 0
+    assert torch.isfinite(tr.flat_param).all()

@@ -31,3 +31,37 @@ def firenet_cfg(bins, encoding, neuron="lif"):
     sn = dict(leak=[-4.0, 0.1], thresh=[0.8, 0.1], learn_leak=True, learn_thresh=True, hard_reset=True) if neuron == "lif" else {}
     return dict(name="x", encoding=encoding, round_encoding=False, norm_input=False, num_bins=bins, base_num_channels=32,
                 kernel_size=3, activations=["arctanspike", "arctanspike"], mask_output=True, spiking_neuron=sn)
+
+
+def capture_layers(model):
+    """Forward hooks recording (x_in, state_in, out, state_out) of the 7 FireNet cells as CPU tensors."""
+    from oracle.spiking import FIRENET_LAYERS
+
+    captured, handles = {}, []
+
+    def mk(name):
+        def hook(mod, inputs, output):
+            st = inputs[1] if len(inputs) > 1 else None
+            captured[name] = (inputs[0].detach().cpu(), None if st is None else st.detach().cpu(), output[0].detach().cpu(),
+                              output[1].detach().cpu())
+        return hook
+
+    for l in FIRENET_LAYERS:
+        handles.append(getattr(model, l).register_forward_hook(mk(l)))
+    return captured, handles
+
+
+def oracle_params_of(model):
+    from oracle.spiking import FIRENET_LAYERS
+
+    params = {}
+    for l in FIRENET_LAYERS:
+        cell = getattr(model, l)
+        params[l] = {"ff": cell.ff.weight.detach().cpu().clone()}
+        if hasattr(cell, "rec"):
+            params[l]["rec"] = cell.rec.weight.detach().cpu().clone()
+        for k in ("leak", "thresh", "leak_v", "leak_pt", "leak_t", "add_pt", "t0", "t1"):
+            if hasattr(cell, k):
+                params[l][k] = getattr(cell, k).detach().cpu().clone()
+    params["pred"] = {"weight": model.pred.conv2d.weight.detach().cpu().clone(), "bias": model.pred.conv2d.bias.detach().cpu().clone()}
+    return params
