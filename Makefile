@@ -14,7 +14,7 @@ build/%.o: event_flow_b200/csrc/%.cu event_flow_b200/csrc/common.cuh include/eve
 
 $(LIB): $(OBJ)
 	@mkdir -p event_flow_b200/lib
-	$(NVCC) -shared $(ARCH) -o $@ $(OBJ) -lcuda
+	$(NVCC) -shared $(ARCH) -o $@ $(OBJ)
 
 clean:
 	rm -rf build event_flow_b200/lib

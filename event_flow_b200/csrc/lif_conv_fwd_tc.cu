@@ -1,12 +1,492 @@
-// tcgen05 tensor-core path of the fused conv + LIF step (placeholder until the kernel lands: never eligible).
+// Fused conv3x3 + LIF step on the 5th-generation tensor cores (tcgen05 / TMEM / TMA), sm_100a only.
+//
+// Implicit GEMM per 16x8-pixel tile:  D[128 px, 32 ch] = sum over 9 taps, 32 (or 64 with the recurrent conv) input channels
+//   A = bf16 spikes, read tap-shifted straight out of ONE halo tile in shared memory (no im2col copy): the halo tile is
+//       stored channel-group-major [4 groups][18 x 10 px][8 ch] (exactly the c8 global layout, brought in by one TMA box
+//       with hardware zero-fill = the conv padding), which is the canonical K-major no-swizzle UMMA layout with
+//       core-matrix stride (SBO) = one halo row and K-chunk stride (LBO) = one channel group;
+//   B = weights, split into three bf16 terms hi+mid+lo == w (exact), resident in shared memory for the whole kernel;
+//   D = fp32 accumulator in tensor memory, double buffered.
+// Spikes are {0,1,2}: exactly representable in bf16, so every product is exact and only the fp32 summation order differs
+// from the CPU path (no TF32/BF16 rounding may enter a spiking conv).
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2-5 = epilogue
+// (tcgen05.ld -> neuron update -> staged TMA stores).  Persistent over tiles; mbarrier pipelines between the roles.
+// Reference semantics: models/spiking_submodules.py:96-126 (ConvLIF), :516-551 (ConvLIFRecurrent).
+#include <cuda.h>
+
+#include <mutex>
+#include <unordered_map>
+
 #include "common.cuh"
 
 namespace ef {
-bool lif_conv_tc_eligible(const ef_lif_conv_params&) { return false; }
-int lif_conv_fwd_tc(const ef_lif_conv_params&, cudaStream_t) { return fail(EF_EUNSUPPORTED, "tensor-core path not built"); }
+
+constexpr int TC_TH = 16, TC_TW = 8;                  // output tile (rows x cols) = 128 GEMM rows
+constexpr int TC_HH = TC_TH + 2, TC_HW = TC_TW + 2;   // halo tile
+constexpr int A_GROUP_BYTES = TC_HH * TC_HW * 16;     // one 8-channel group of the halo tile (2880 B)
+constexpr int A_TILE_BYTES = 4 * A_GROUP_BYTES;       // 11520 B
+constexpr int Z_TILE_BYTES = 4 * 128 * 16;            // centre spikes, c8: 8192 B
+constexpr int V_TILE_BYTES = 32 * 128 * 4;            // fp32 [32 ch][16][8]: 16384 B
+constexpr int W_BLOCK_BYTES = 32 * 16 * 2;            // one (split, tap, k-step) weight block [32 n][16 k] bf16
+constexpr int W_CONV_BYTES = 3 * 9 * 2 * W_BLOCK_BYTES;  // 55296 B per convolution
+constexpr int TC_THREADS = 192;
+constexpr int TMEM_COLS = 64;                         // 2 accumulator buffers x 32 fp32 columns
+
+struct TcSmemLayout {
+  int w_off, stage_off, stage_bytes, x_off, z_off, v_off, out_off, outz_off, bar_off, total, nstage;
+};
+
+__host__ __device__ inline TcSmemLayout tc_smem_layout(bool rec) {
+  TcSmemLayout l;
+  l.nstage = rec ? 2 : 3;
+  l.w_off = 0;
+  const int wbytes = rec ? 2 * W_CONV_BYTES : W_CONV_BYTES;
+  l.x_off = 0;
+  l.z_off = A_TILE_BYTES;                                   // rec: halo tile of z; ff: centre tile of z
+  l.v_off = l.z_off + (rec ? A_TILE_BYTES : Z_TILE_BYTES);
+  l.stage_bytes = l.v_off + V_TILE_BYTES;
+  l.stage_off = wbytes;
+  l.out_off = l.stage_off + l.nstage * l.stage_bytes;       // v_out staging
+  l.outz_off = l.out_off + V_TILE_BYTES;                    // z_out staging
+  l.bar_off = l.outz_off + Z_TILE_BYTES;
+  l.total = l.bar_off + 256;
+  return l;
+}
+
+struct TcParams {
+  int B, H, W, tiles_x, tiles_y, n_tiles;
+  int has_rec, has_v, has_z, hard_reset;
+  const uint16_t* w_split;
+  const float* leak;
+  const float* thresh;
+};
+
+// ---- PTX wrappers -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded spin: a protocol bug traps (kernel error the host sees) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) __trap();  // ~2 s at 1.9 GHz
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
+               "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+               "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(map), "r"(src), "r"(c0), "r"(c1),
+               "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map), "r"(src), "r"(c0), "r"(c1),
+               "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// K-major, no-swizzle shared-memory matrix descriptor: 8 rows x 16 B core matrices; SBO between 8-row groups, LBO between
+// the two 16-byte K chunks of one K=16 MMA.  (cute/arch/mma_sm100_desc.hpp: version 1 at bit 46, layout type 0 at bit 61.)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+// kind::f16 instruction descriptor: D = F32, A = B = BF16, both K-major, N = 32, M = 128.
+constexpr uint32_t UMMA_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(UMMA_IDESC), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+        "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---- the kernel ----------------------------------------------------------------------------------------------------
+template <bool HARD>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_zh,
+                       const __grid_constant__ CUtensorMap map_zc, const __grid_constant__ CUtensorMap map_vin,
+                       const __grid_constant__ CUtensorMap map_vout, const __grid_constant__ CUtensorMap map_zout) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const bool rec = p.has_rec != 0;
+  const TcSmemLayout L = tc_smem_layout(rec);
+  const int NST = L.nstage;
+  const uint32_t s_base = smem_u32(smem);
+  // barriers: [0] weights, [1..NST] full, [1+NST..2NST] empty, then acc_full[2], acc_empty[2]; then the TMEM address word
+  const uint32_t bar_w = s_base + L.bar_off;
+  auto bar_full = [&](int s) { return bar_w + 8u * (1 + s); };
+  auto bar_empty = [&](int s) { return bar_w + 8u * (1 + NST + s); };
+  auto bar_accf = [&](int a) { return bar_w + 8u * (1 + 2 * NST + a); };
+  auto bar_acce = [&](int a) { return bar_w + 8u * (3 + 2 * NST + a); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.bar_off + 8 * (5 + 2 * NST));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(bar_w, 1);
+    for (int s = 0; s < NST; ++s) {
+      mbar_init(bar_full(s), 1);
+      mbar_init(bar_empty(s), 1 + 4);  // MMA commit + one arrive per epilogue warp
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_accf(a), 1);
+      mbar_init(bar_acce(a), 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {  // TMEM allocation (whole warp), address lands in shared memory
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int n_my = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const uint32_t stage_tx = A_TILE_BYTES + (p.has_z ? (rec ? A_TILE_BYTES : Z_TILE_BYTES) : 0) + (p.has_v ? V_TILE_BYTES : 0);
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      const uint32_t wbytes = rec ? 2 * W_CONV_BYTES : W_CONV_BYTES;
+      mbar_expect_tx(bar_w, wbytes);
+      for (uint32_t off = 0; off < wbytes; off += 13824)  // 55296 = 4 x 13824
+        bulk_load_1d(s_base + L.w_off + off, reinterpret_cast<const uint8_t*>(p.w_split) + off, 13824, bar_w);
+      for (int it = 0; it < n_my; ++it) {
+        const int tile = blockIdx.x + it * gridDim.x;
+        const int b = tile / (p.tiles_x * p.tiles_y), r = tile % (p.tiles_x * p.tiles_y);
+        const int y0 = (r / p.tiles_x) * TC_TH, x0 = (r % p.tiles_x) * TC_TW;
+        const int s = it % NST;
+        const uint32_t ph = (it / NST) & 1;
+        mbar_wait(bar_empty(s), ph ^ 1);
+        const uint32_t st = s_base + L.stage_off + s * L.stage_bytes;
+        mbar_expect_tx(bar_full(s), stage_tx);
+        tma_load_5d(st + L.x_off, &map_x, bar_full(s), 0, x0 - 1, y0 - 1, 0, b);
+        if (p.has_z) {
+          if (rec) tma_load_5d(st + L.z_off, &map_zh, bar_full(s), 0, x0 - 1, y0 - 1, 0, b);
+          else tma_load_5d(st + L.z_off, &map_zc, bar_full(s), 0, x0, y0, 0, b);
+        }
+        if (p.has_v) tma_load_4d(st + L.v_off, &map_vin, bar_full(s), x0, y0, 0, b);
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      mbar_wait(bar_w, 0);
+      for (int it = 0; it < n_my; ++it) {
+        const int s = it % NST, a = it & 1;
+        const uint32_t ph = (it / NST) & 1, aph = (it >> 1) & 1;
+        mbar_wait(bar_acce(a), aph ^ 1);
+        mbar_wait(bar_full(s), ph);
+        tc_fence_after();
+        const uint32_t st = s_base + L.stage_off + s * L.stage_bytes;
+        const uint32_t d_tmem = tmem_base + a * 32;
+        uint32_t acc = 0;
+        const int nconv = (rec && p.has_z) ? 2 : 1;
+        for (int cv = 0; cv < nconv; ++cv) {
+          const uint32_t a_tile = st + (cv == 0 ? L.x_off : L.z_off);
+          const uint32_t w_conv = s_base + L.w_off + cv * W_CONV_BYTES;
+#pragma unroll 1
+          for (int tap = 0; tap < 9; ++tap) {
+            const int dy = tap / 3, dx = tap % 3;
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+              const uint64_t adesc = umma_desc(a_tile + (dy * TC_HW + dx) * 16 + ks * 2 * A_GROUP_BYTES, A_GROUP_BYTES, TC_HW * 16);
+#pragma unroll
+              for (int sp = 0; sp < 3; ++sp) {
+                const uint64_t bdesc = umma_desc(w_conv + ((sp * 9 + tap) * 2 + ks) * W_BLOCK_BYTES, 512, 128);
+                umma_bf16(d_tmem, adesc, bdesc, acc);
+                acc = 1;
+              }
+            }
+          }
+        }
+        umma_commit(bar_empty(s));  // the stage's operand tiles may be overwritten once these MMAs have read them
+        umma_commit(bar_accf(a));   // accumulator complete
+      }
+    }
+  } else {
+    // =============================== epilogue (4 warps = 128 rows) ===============================
+    const int q = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int m = q * 32 + lane;            // GEMM row = pixel within the tile
+    const int ph_ = m >> 3, pw_ = m & 7;    // (row, col) inside the 16 x 8 tile
+    const bool store_thread = (threadIdx.x == 64);
+    float lam[32], thr[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+      lam[c] = sigmoidf_acc(__ldg(p.leak + c));
+      thr[c] = fmaxf(__ldg(p.thresh + c), 0.01f);
+    }
+    float* vout_s = reinterpret_cast<float*>(smem + L.out_off);
+    uint4* zout_s = reinterpret_cast<uint4*>(smem + L.outz_off);
+    for (int it = 0; it < n_my; ++it) {
+      const int tile = blockIdx.x + it * gridDim.x;
+      const int b = tile / (p.tiles_x * p.tiles_y), r = tile % (p.tiles_x * p.tiles_y);
+      const int y0 = (r / p.tiles_x) * TC_TH, x0 = (r % p.tiles_x) * TC_TW;
+      const int s = it % NST, a = it & 1;
+      const uint32_t ph = (it / NST) & 1, aph = (it >> 1) & 1;
+      const uint8_t* st = smem + L.stage_off + s * L.stage_bytes;
+
+      mbar_wait(bar_full(s), ph);  // v_in / z_in of this tile have landed (acquire)
+      // previous spikes of this pixel, 4 x 8 channels
+      uint4 zq[4];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        if (!p.has_z) zq[g] = make_uint4(0, 0, 0, 0);
+        else if (rec) zq[g] = *reinterpret_cast<const uint4*>(st + L.z_off + g * A_GROUP_BYTES + ((ph_ + 1) * TC_HW + pw_ + 1) * 16);
+        else zq[g] = *reinterpret_cast<const uint4*>(st + L.z_off + (g * 128 + m) * 16);
+      }
+      const float* vin_s = reinterpret_cast<const float*>(st + L.v_off);
+
+      mbar_wait(bar_accf(a), aph);
+      tc_fence_after();
+      uint32_t accr[32];
+      tmem_ld32(tmem_base + a * 32 + ((uint32_t)(q * 32) << 16), accr);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_acce(a));  // accumulator buffer may be overwritten by the MMA of tile it+2
+
+      if (it > 0) {  // staging buffers are free once the previous tile's TMA stores have read them
+        if (store_thread) bulk_wait_read0();
+        named_bar_sync(1, 128);
+      }
+      uint32_t zpk[16];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        const float I = __uint_as_float(accr[c]);
+        const float v = p.has_v ? vin_s[c * 128 + m] : 0.f;
+        const uint32_t zw = (&zq[c >> 3].x)[(c & 7) >> 1];
+        const float z = (c & 1) ? bf16_hi(zw) : bf16_lo(zw);
+        const float oml = __fsub_rn(1.0f, lam[c]);
+        float vo;
+        if (HARD) vo = __fadd_rn(__fmul_rn(__fmul_rn(v, lam[c]), __fsub_rn(1.0f, z)), __fmul_rn(oml, I));
+        else vo = __fsub_rn(__fadd_rn(__fmul_rn(v, lam[c]), __fmul_rn(oml, I)), __fmul_rn(z, thr[c]));
+        const float zo = (__fsub_rn(vo, thr[c]) > 0.f) ? 1.0f : 0.f;
+        vout_s[c * 128 + m] = vo;
+        const uint32_t zb = zo > 0.f ? 0x3F80u : 0u;  // bf16(1.0) = 0x3F80
+        if (c & 1) zpk[c >> 1] |= zb << 16;
+        else zpk[c >> 1] = zb;
+      }
+#pragma unroll
+      for (int g = 0; g < 4; ++g) zout_s[g * 128 + m] = make_uint4(zpk[4 * g], zpk[4 * g + 1], zpk[4 * g + 2], zpk[4 * g + 3]);
+
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_empty(s));  // done reading this stage's v_in / z_in
+      fence_proxy_async();                        // make the staged results visible to the TMA engine
+      named_bar_sync(1, 128);
+      if (store_thread) {
+        tma_store_4d(&map_vout, smem_u32(vout_s), x0, y0, 0, b);
+        tma_store_5d(&map_zout, smem_u32(zout_s), 0, x0, y0, 0, b);
+        bulk_commit();
+      }
+    }
+    if (store_thread) bulk_wait0();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---- weight split kernel --------------------------------------------------------------------------------------------
+// out block index ((conv*3 + split)*9 + tap)*2 + ks ; inside a block element (n, k) at (k/8)*256 + (n/8)*64 + (n%8)*8 + k%8 (uint16 units)
+__global__ void split_weights_kernel(const float* __restrict__ w_ff, const float* __restrict__ w_rec, uint16_t* __restrict__ out, int nconv) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // over nconv * 32 (n) * 32 (ci) * 9 (tap)
+  if (i >= nconv * 32 * 32 * 9) return;
+  const int tap = i % 9, ci = (i / 9) % 32, n = (i / (9 * 32)) % 32, cv = i / (9 * 32 * 32);
+  const float w = (cv == 0 ? w_ff : w_rec)[(n * 32 + ci) * 9 + tap];
+  const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+  const float r1 = w - __bfloat162float(hi);
+  const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+  const float r2 = r1 - __bfloat162float(mid);
+  const __nv_bfloat16 lo = __float2bfloat16_rn(r2);
+  const __nv_bfloat16 parts[3] = {hi, mid, lo};
+  const int ks = ci >> 4, k = ci & 15;
+  for (int sp = 0; sp < 3; ++sp) {
+    const size_t blk = ((size_t)(cv * 3 + sp) * 9 + tap) * 2 + ks;
+    out[blk * 512 + (k >> 3) * 256 + (n >> 3) * 64 + (n & 7) * 8 + (k & 7)] = *reinterpret_cast<const uint16_t*>(&parts[sp]);
+  }
+}
+
+// ---- host side: tensor maps -----------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  });
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr;
+  int B, H, W, kind;
+  bool operator==(const MapKey& o) const { return ptr == o.ptr && B == o.B && H == o.H && W == o.W && kind == o.kind; }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    return std::hash<const void*>()(k.ptr) ^ (size_t)(k.B * 1000003u) ^ ((size_t)k.H << 20) ^ ((size_t)k.W << 8) ^ (size_t)k.kind;
+  }
+};
+
+// kind 0: c8 halo box (18x10), 1: c8 centre box (16x8), 2: fp32 NCHW box [32][16][8]
+static int get_map(const void* ptr, int B, int H, int W, int kind, CUtensorMap* out) {
+  static thread_local std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  const MapKey key{ptr, B, H, W, kind};
+  auto it = cache.find(key);
+  if (it != cache.end()) {
+    *out = it->second;
+    return EF_OK;
+  }
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return fail(EF_EUNSUPPORTED, "cuTensorMapEncodeTiled is not available from this driver");
+  CUresult r;
+  if (kind < 2) {
+    const cuuint64_t dims[5] = {8, (cuuint64_t)W, (cuuint64_t)H, 4, (cuuint64_t)B};
+    const cuuint64_t strides[4] = {16, (cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)4 * H * W * 16};
+    const cuuint32_t box[5] = {8, (cuuint32_t)(kind == 0 ? TC_HW : TC_TW), (cuuint32_t)(kind == 0 ? TC_HH : TC_TH), 4, 1};
+    const cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else {
+    const cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, 32, (cuuint64_t)B};
+    const cuuint64_t strides[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)32 * H * W * 4};
+    const cuuint32_t box[4] = {TC_TW, TC_TH, 32, 1};
+    const cuuint32_t es[4] = {1, 1, 1, 1};
+    r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
+  if (r != CUDA_SUCCESS) return fail(EF_EINVAL, "cuTensorMapEncodeTiled failed (CUresult %d) for kind %d, B=%d H=%d W=%d ptr=%p", (int)r, kind, B, H, W, ptr);
+  if (cache.size() > 4096) cache.clear();
+  cache.emplace(key, *out);
+  return EF_OK;
+}
+
+bool lif_conv_tc_eligible(const ef_lif_conv_params& p) {
+  return p.w_split && p.x_c8 && p.z_out_c8 && p.Cin == 32 && p.C == 32 && p.ksize == 3 && p.stride == 1 && p.neuron == EF_LIF &&
+         !p.residual && !p.out && !p.z_out && !p.out_c8 && (p.W % 4 == 0) && (!p.v_in == !p.z_in_c8) && !p.z_in && !p.x &&
+         ((uintptr_t)p.x_c8 % 16 == 0) && ((uintptr_t)p.v_out % 16 == 0);
+}
+
+int lif_conv_fwd_tc(const ef_lif_conv_params& p, cudaStream_t st) {
+  static int n_sms = 0;
+  if (n_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const bool rec = p.w_rec != nullptr;
+  TcParams q;
+  q.B = p.B, q.H = p.H, q.W = p.W;
+  q.tiles_x = cdiv(p.W, TC_TW), q.tiles_y = cdiv(p.H, TC_TH), q.n_tiles = p.B * q.tiles_x * q.tiles_y;
+  q.has_rec = rec, q.has_v = p.v_in != nullptr, q.has_z = p.z_in_c8 != nullptr, q.hard_reset = p.hard_reset;
+  q.w_split = p.w_split, q.leak = p.leak, q.thresh = p.thresh;
+  CUtensorMap mx, mzh, mzc, mvi, mvo, mzo;
+  int rc;
+  if ((rc = get_map(p.x_c8, p.B, p.H, p.W, 0, &mx))) return rc;
+  if ((rc = get_map(p.v_out, p.B, p.H, p.W, 2, &mvo))) return rc;
+  if ((rc = get_map(p.z_out_c8, p.B, p.H, p.W, 1, &mzo))) return rc;
+  mzh = mx, mzc = mzo, mvi = mvo;  // placeholders when there is no previous state
+  if (q.has_z) {
+    if ((rc = get_map(p.z_in_c8, p.B, p.H, p.W, rec ? 0 : 1, rec ? &mzh : &mzc))) return rc;
+  }
+  if (q.has_v && (rc = get_map(p.v_in, p.B, p.H, p.W, 2, &mvi))) return rc;
+  const TcSmemLayout L = tc_smem_layout(rec);
+  const int grid = q.n_tiles < n_sms ? q.n_tiles : n_sms;
+  auto kern = p.hard_reset ? lif_conv_fwd_tc_kernel<true> : lif_conv_fwd_tc_kernel<false>;
+  static bool attr_set[2] = {false, false};
+  if (!attr_set[p.hard_reset ? 1 : 0]) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+      return check_launch("cudaFuncSetAttribute(lif_conv_fwd_tc_kernel)");
+    attr_set[p.hard_reset ? 1 : 0] = true;
+  }
+  kern<<<grid, TC_THREADS, L.total, st>>>(q, mx, mzh, mzc, mvi, mvo, mzo);
+  return check_launch("lif_conv_fwd_tc_kernel");
+}
+
 }  // namespace ef
 
-extern "C" int64_t ef_split_weights_elems(int32_t, int32_t, int32_t) { return 0; }
-extern "C" int ef_split_weights(const float*, const float*, int32_t, int32_t, uint16_t*, void*) {
-  return ef::fail(EF_EUNSUPPORTED, "tensor-core path not built");
+extern "C" int64_t ef_split_weights_elems(int32_t Cin, int32_t C, int32_t has_rec) {
+  if (Cin != 32 || C != 32) return 0;
+  return (int64_t)(has_rec ? 2 : 1) * ef::W_CONV_BYTES / 2;
+}
+
+extern "C" int ef_split_weights(const float* w_ff, const float* w_rec, int32_t Cin, int32_t C, uint16_t* out, void* stream) {
+  using namespace ef;
+  EF_REQUIRE(w_ff && out, EF_ENULL, "ef_split_weights: NULL tensor");
+  EF_REQUIRE(Cin == 32 && C == 32, EF_EUNSUPPORTED, "ef_split_weights: the tensor-core path covers 32 -> 32 channels (got %d -> %d)", Cin, C);
+  const int nconv = w_rec ? 2 : 1;
+  split_weights_kernel<<<cdiv(nconv * 32 * 32 * 9, 256), 256, 0, as_stream(stream)>>>(w_ff, w_rec, out, nconv);
+  return check_launch("split_weights_kernel");
 }

@@ -292,3 +292,48 @@ def unpack_c8(x):
     L.LAUNCHES += 1
     L.check(L.lib().ef_unpack_c8(L.ptr(x), L.ptr(out), B, G * 8, H, W, L.stream()), "ef_unpack_c8")
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# internal-format (c8 spikes) LIF step: the building block of the fast model path
+# ---------------------------------------------------------------------------------------------------------------------
+def split_weights(w_ff, w_rec=None):
+    """fp32 conv weights -> three exact bf16 terms in the tcgen05 B-operand layout (uint16 tensor)."""
+    w_ff, w_rec = _c(w_ff.detach()), (None if w_rec is None else _c(w_rec.detach()))
+    _need_cuda(w_ff, w_rec)
+    C, Cin = w_ff.shape[:2]
+    n = L.lib().ef_split_weights_elems(Cin, C, int(w_rec is not None))
+    if n == 0:
+        return None
+    out = torch.empty(n, device=w_ff.device, dtype=torch.int16)
+    L.LAUNCHES += 1
+    L.check(L.lib().ef_split_weights(L.ptr(w_ff), L.ptr(w_rec), Cin, C, L.ptr(out), L.stream()), "ef_split_weights")
+    return out
+
+
+def lif_step_c8(x_c8, v_in, z_in_c8, w_ff, w_rec, leak, thresh, *, hard_reset=True, w_split=None, x_f32=None):
+    """
+    One fused conv + LIF step on the internal formats: spikes bf16 [B,C/8,H,W,8], membrane fp32 NCHW.
+    With `w_split` (ops.split_weights) and 32->32 channels the tcgen05 kernel runs, otherwise the CUDA-core kernel.
+    `x_f32` (fp32 NCHW) may replace x_c8 for the first layer.  Returns (v_out, z_out_c8).  No autograd.
+    """
+    if x_c8 is not None:
+        B, G, H, W, _ = x_c8.shape
+        Cin = G * 8
+    else:
+        B, Cin, H, W = x_f32.shape
+    C = w_ff.shape[0]
+    dev = w_ff.device
+    v_out = torch.empty((B, C, H, W), device=dev, dtype=torch.float32)
+    z_out = torch.empty((B, C // 8, H, W, 8), device=dev, dtype=torch.bfloat16)
+    p = L.LifConvParams()
+    p.B, p.Cin, p.C, p.H, p.W = B, Cin, C, H, W
+    p.ksize, p.stride, p.neuron, p.hard_reset = 3, 1, L.EF_LIF, int(hard_reset)
+    p.surrogate, p.act_width = 0, 10.0
+    p.x, p.x_c8 = L.ptr(x_f32), L.ptr(x_c8)
+    p.v_in, p.z_in_c8 = L.ptr(v_in), L.ptr(z_in_c8)
+    p.w_ff, p.w_rec, p.w_split = L.ptr(w_ff), L.ptr(w_rec), L.ptr(w_split)
+    p.leak, p.thresh = L.ptr(leak), L.ptr(thresh)
+    p.v_out, p.z_out_c8 = L.ptr(v_out), L.ptr(z_out)
+    L.call("ef_lif_conv_fwd", p, tag=(Cin, C, w_rec is not None))
+    return v_out, z_out
