@@ -2,11 +2,16 @@
 import torch
 
 
-def spike_band_compare(v_mine, z_mine, v_ref, z_ref, thresh, band=1e-5, v_atol=2e-5):
+def spike_band_compare(v_mine, z_mine, v_ref, z_ref, thresh, band=1e-5, v_atol=None):
     """
     SURVEY T1: membrane potentials agree to summation-order noise; spikes agree exactly outside a band |v - thresh| < band.
+    Summation-order noise of an fp32 accumulation scales with the magnitude of the sum: measured against an fp64 oracle
+    (tools/tc_accuracy_probe.py, profiles/r01_tc_accuracy.txt) it is 0.3e-6*max|v| for the CPU path, 0.7e-6*max|v| for the
+    CUDA-core kernel and 1.6e-6*max|v| for the tensor-core kernel (truncating fp32 accumulate), hence 3e-6*max|v|, floor 2e-5.
     Returns (max|dv|, flips outside band, flips inside band).
     """
+    if v_atol is None:
+        v_atol = max(2e-5, 3e-6 * v_ref.abs().max().item())
     dv = (v_mine - v_ref).abs().max().item()
     near = (v_ref - thresh).abs() < band
     diff = z_mine != z_ref
