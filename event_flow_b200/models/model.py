@@ -5,6 +5,7 @@ XLIFFireNet :672, LIFFireFlowNet :684).  Each forward pass is 7 fused conv+neuro
 """
 import torch
 
+from .. import fast
 from .base import BaseModel
 from .model_util import copy_states
 from .spiking_submodules import (
@@ -59,13 +60,19 @@ class FireNet(BaseModel):
 
     @property
     def states(self):
+        if self._fast is not None:  # internal (c8 spike) state -> the reference's stacked fp32 format; fresh tensors = clones
+            return fast.states_of(self)
         return copy_states(self._states)
 
     @states.setter
     def states(self, states):
         self._states = states
+        self._fast = None  # converted to the internal format again by the next forward pass
 
     def detach_states(self):
+        if self._fast is not None:  # cut the BPTT chain without copying any state
+            self._fast.detach()
+            return
         detached_states = []
         for state in self.states:
             if type(state) is tuple:
@@ -76,6 +83,7 @@ class FireNet(BaseModel):
 
     def reset_states(self):
         self._states = [None] * self.num_recurrent_units
+        self._fast = None
 
     def init_cropping(self, width, height):
         pass
@@ -97,6 +105,9 @@ class FireNet(BaseModel):
         if self.norm_input:  # model.py:247-252 (in place on the caller's tensor, like the reference)
             mean, stddev = x[x != 0].mean(), x[x != 0].std()
             x[x != 0] = (x[x != 0] - mean) / stddev
+
+        if fast.eligible(self, x):  # LIF, 32 channels: tcgen05 kernels on the internal spike format, one autograd node per step
+            return fast.forward(self, x, log)
 
         x1, self._states[0] = self.head(x, self._states[0])
         x2, self._states[1] = self.G1(x1, self._states[1])

@@ -35,6 +35,7 @@ class DataParallelTrainer:
         self.n, self.lr, self.clip, self.betas, self.eps = n, lr, clip_grad, betas, eps
         self.group = process_group
         self.step_count = 0
+        self.model = model
 
     @property
     def world_size(self):
@@ -67,6 +68,9 @@ class DataParallelTrainer:
         )
         L.LAUNCHES += 2
         self.flat_grad.zero_()
+        from . import fast
+
+        fast.invalidate_weights(self.model)  # the kernel wrote the parameters behind torch's version counters
 
     def _view_of(self, p):
         if not hasattr(self, "_offsets"):

@@ -98,10 +98,10 @@ int ef_lif_conv_fwd(const ef_lif_conv_params* p, void* stream);
  * scratch_gI: caller-provided [B,C,Ho,Wo] fp32 workspace (receives g_I = (1-leak) g_v).
  * scratch_gP: caller-provided [B,Ho,Wo] fp32 workspace, only needed for PLIF / XLIF cells when g_x is wanted (holds the
  * channel-summed gradient of the pre-synaptic trace input); may be NULL otherwise.
- * Limits of this version: fp32 NCHW tensors only, stride 1 only.
+ * Inputs x / z_in may be given in either layout (fp32 NCHW or c8), gradients are fp32 NCHW.  Limits of this version: stride 1.
  * ------------------------------------------------------------------------------------------------------------------ */
 typedef struct ef_lif_conv_bwd_params {
-  ef_lif_conv_params f;         /* the forward call (inputs + v_out/aux_out as written by it); fp32 tensors required  */
+  ef_lif_conv_params f;         /* the forward call: its inputs and the v_out / aux_out it wrote (other outputs ignored) */
   const float* g_out;           /* [B,C,Ho,Wo] or NULL                                                                */
   const float* g_v_out;         /* or NULL                                                                            */
   const float* g_z_out;         /* or NULL                                                                            */

@@ -91,27 +91,82 @@ def test_firenet_teacher_forced_layers_match_oracle(neuron):
     assert flips_in <= 1e-5 * total + 2, f"{flips_in} in-band spike flips of {total}"
 
 
-def test_state_api_reset_detach_set():
+@pytest.mark.parametrize("neuron", ["lif", "alif"])
+def test_state_api_reset_detach_set(neuron):
     import event_flow_b200.models.model as M
 
-    m = M.LIFFireNet(firenet_cfg(2, "cnt")).to(DEV)
+    cls = {"lif": M.LIFFireNet, "alif": M.ALIFFireNet}[neuron]
+    n_state = 2 if neuron == "lif" else 3
+    m = cls(firenet_cfg(2, "cnt", neuron)).to(DEV)
     assert m.states == [None] * 7
     x = torch.randint(0, 3, (1, 2, 32, 32)).float().to(DEV)
     m(x, x)
     s = m.states
-    assert len(s) == 7 and s[0].shape == (2, 1, 32, 32, 32) and s[0].dtype == torch.float32
+    assert len(s) == 7 and s[0].shape == (n_state, 1, 32, 32, 32) and s[0].dtype == torch.float32
+    assert set(s[3][1].unique().tolist()) <= {0.0, 1.0}
+    before = m.states[0].clone()
     s[0].zero_()  # clones: mutating them must not touch the model (model_util.py:96-102)
-    assert m.states[0].abs().sum() > 0
-    assert m._states[0].requires_grad
+    assert torch.equal(m.states[0], before)
     m.detach_states()
-    assert not m._states[0].requires_grad
+    assert all(not t.requires_grad for t in m.states)
     m.states = [torch.zeros_like(t) for t in s]
     out = m(x, x)
     m.reset_states()
     out2 = m(x, x)
     torch.testing.assert_close(out["flow"][0], out2["flow"][0])  # zero state == reset state
+    # state round trip: setting the states read back continues the rollout identically
+    a = m(x, x)["flow"][0].clone()
+    saved = m.states
+    b = m(x, x)["flow"][0].clone()
+    m.states = saved
+    c = m(x, x)["flow"][0].clone()
+    assert torch.equal(b, c) and a.shape == b.shape
     with pytest.raises(AttributeError):
-        M.LIFFireNet(firenet_cfg(5, "cnt")).to(DEV)(x, x)  # cnt encoding needs num_bins == 2 (model.py:240-244)
+        cls(firenet_cfg(5, "cnt", neuron)).to(DEV)(x, x)  # cnt encoding needs num_bins == 2 (model.py:240-244)
+
+
+def test_truncated_bptt_matches_oracle_over_two_windows():
+    """detach_states() cuts the gradient at the window boundary exactly like the reference (train_flow.py:170, model.py:211-221)."""
+    import event_flow_b200.models.model as M
+    from tests.util import oracle_params_of
+
+    B, Hh, Ww, T, bins = 1, 16, 16, 3, 5
+    torch.manual_seed(3)
+    m = M.LIFFireNet(firenet_cfg(bins, "voxel"))
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if n.endswith("ff.weight") or n.endswith("rec.weight"):
+                p.mul_(2.5)
+        m.pred.conv2d.weight.mul_(20.0)
+    params = oracle_params_of(m)
+    for lp in params.values():
+        for k in lp:
+            lp[k].requires_grad_(True)
+    m = m.to(DEV)
+    g = torch.Generator().manual_seed(0)
+    xs = [oenc.encode_window(*oenc.synthetic_events(B, 300, Hh, Ww, 500 + t), Hh, Ww, bins)["event_voxel"] for t in range(2 * T)]
+    gw = [torch.rand((B, 2, Hh, Ww), generator=g) - 0.5 for _ in range(2 * T)]
+    states = [None] * 7
+    for win in range(2):
+        loss = loss_o = 0
+        for t in range(win * T, (win + 1) * T):
+            loss = loss + (m(xs[t].to(DEV), None)["flow"][0] * gw[t].to(DEV)).sum()
+            f, states, _ = osp.firenet_step("lif", params, states, xs[t])
+            loss_o = loss_o + (f * gw[t]).sum()
+        m.zero_grad()
+        loss.backward()
+        for lp in params.values():
+            for v in lp.values():
+                v.grad = None
+        loss_o.backward()
+        same_spikes = all(torch.equal(a[1].cpu(), b[1].detach()) for a, b in zip(m.states, states))
+        if same_spikes:
+            for l in osp.FIRENET_LAYERS:
+                assert_rel(getattr(m, l).ff.weight.grad, params[l]["ff"].grad, 2e-3, f"window {win} {l}.ff")
+                assert_rel(getattr(m, l).leak.grad, params[l]["leak"].grad, 2e-3, f"window {win} {l}.leak")
+            assert_rel(m.G1.rec.weight.grad, params["G1"]["rec"].grad, 2e-3, f"window {win} G1.rec")
+        m.detach_states()
+        states = [s.detach() for s in states]
 
 
 def test_dropin_training_loop_like_train_flow():

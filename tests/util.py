@@ -53,6 +53,7 @@ def capture_layers(model):
 
     for l in FIRENET_LAYERS:
         handles.append(getattr(model, l).register_forward_hook(mk(l)))
+    model._capture = captured  # the fused fast path does not call the cells' forward(); it fills the same dict itself
     return captured, handles
 
 
