@@ -174,6 +174,95 @@ __global__ void __launch_bounds__(NTHREADS) lif_conv_fwd_kernel(const ef_lif_con
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Head layer of the fast path: few input channels (event counts / voxel bins, Cin <= 8, fractional values allowed),
+// 32 output channels, LIF.  One thread = one pixel x 32 channels; 32 x 8 pixel tile so that every fp32 NCHW access of a
+// warp is one 128-byte line.  Writes the membrane fp32 NCHW and the spikes in c8 for the tensor-core layers.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int HD_TW = 32, HD_TH = 8, HD_THREADS = 256, HD_MAXC = 8;
+
+template <bool HARD>
+__global__ void __launch_bounds__(HD_THREADS) lif_head_fwd_kernel(const ef_lif_conv_params p) {
+  __shared__ float s_x[HD_MAXC * (HD_TH + 2) * (HD_TW + 2)];
+  __shared__ __align__(16) float s_w[HD_MAXC * 9 * 32];
+  __shared__ ChanConst s_k[32];
+  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+  const int b = blockIdx.z, x0 = blockIdx.x * HD_TW, y0 = blockIdx.y * HD_TH;
+  const int Cin = p.Cin, H = p.H, W = p.W;
+  if (tid < 32) s_k[tid] = load_chan_const(p, tid);
+  for (int i = tid; i < Cin * 9 * 32; i += HD_THREADS) {  // s_w[(ci*9 + tap)*32 + co] = w[co][ci][tap]
+    const int co = i & 31, r = i >> 5;
+    s_w[i] = p.w_ff[(size_t)co * Cin * 9 + r];
+  }
+  constexpr int HW_ = HD_TW + 2, HH_ = HD_TH + 2;
+  for (int i = tid; i < Cin * HH_ * HW_; i += HD_THREADS) {
+    const int ci = i / (HH_ * HW_), r = i % (HH_ * HW_), y = y0 - 1 + r / HW_, x = x0 - 1 + r % HW_;
+    s_x[i] = (y >= 0 && y < H && x >= 0 && x < W) ? p.x[(((size_t)b * Cin + ci) * H + y) * W + x] : 0.f;
+  }
+  __syncthreads();
+  float acc[32];
+#pragma unroll
+  for (int c = 0; c < 32; ++c) acc[c] = 0.f;
+  for (int ci = 0; ci < Cin; ++ci) {
+    float xv[9];
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) xv[dy * 3 + dx] = s_x[(ci * HH_ + ty + dy) * HW_ + tx + dx];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const float4* wr = reinterpret_cast<const float4*>(s_w + (ci * 9 + tap) * 32);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 w4 = wr[q];
+        acc[4 * q + 0] = fmaf(xv[tap], w4.x, acc[4 * q + 0]);
+        acc[4 * q + 1] = fmaf(xv[tap], w4.y, acc[4 * q + 1]);
+        acc[4 * q + 2] = fmaf(xv[tap], w4.z, acc[4 * q + 2]);
+        acc[4 * q + 3] = fmaf(xv[tap], w4.w, acc[4 * q + 3]);
+      }
+    }
+  }
+  const int y = y0 + ty, x = x0 + tx;
+  if (y >= H || x >= W) return;
+  const size_t plane = (size_t)H * W, pix = (size_t)y * W + x;
+  uint4 zq[4];
+#pragma unroll
+  for (int g = 0; g < 4; ++g)
+    zq[g] = p.z_in_c8 ? *reinterpret_cast<const uint4*>(p.z_in_c8 + (((size_t)b * 4 + g) * plane + pix) * 8) : make_uint4(0, 0, 0, 0);
+  uint32_t zpk[16];
+#pragma unroll
+  for (int c = 0; c < 32; ++c) {
+    const size_t o = ((size_t)b * 32 + c) * plane + pix;
+    const float v = p.v_in ? __ldg(p.v_in + o) : 0.f;
+    const uint32_t zw = (&zq[c >> 3].x)[(c & 7) >> 1];
+    const float z = (c & 1) ? bf16_hi(zw) : bf16_lo(zw);
+    float vo, zo, ao, thr;
+    neuron_update<EF_LIF, HARD>(acc[c], v, z, 0.f, 0.f, s_k[c], vo, zo, ao, thr);
+    p.v_out[o] = vo;
+    const uint32_t zb = zo > 0.f ? 0x3F80u : 0u;
+    if (c & 1) zpk[c >> 1] |= zb << 16;
+    else zpk[c >> 1] = zb;
+  }
+#pragma unroll
+  for (int g = 0; g < 4; ++g)
+    *reinterpret_cast<uint4*>(p.z_out_c8 + (((size_t)b * 4 + g) * plane + pix) * 8) = make_uint4(zpk[4 * g], zpk[4 * g + 1], zpk[4 * g + 2], zpk[4 * g + 3]);
+}
+
+static bool head_eligible(const ef_lif_conv_params& p) {
+  return p.neuron == EF_LIF && p.C == 32 && p.Cin <= HD_MAXC && p.stride == 1 && p.x && !p.x_c8 && !p.w_rec && !p.z_in && !p.residual && !p.out &&
+         !p.z_out && !p.out_c8 && p.z_out_c8 && (!p.v_in == !p.z_in_c8);
+}
+
+static int launch_head(const ef_lif_conv_params& p, cudaStream_t st) {
+  dim3 grid(cdiv(p.W, HD_TW), cdiv(p.H, HD_TH), p.B);
+  if (p.hard_reset)
+    lif_head_fwd_kernel<true><<<grid, HD_THREADS, 0, st>>>(p);
+  else
+    lif_head_fwd_kernel<false><<<grid, HD_THREADS, 0, st>>>(p);
+  return check_launch("lif_head_fwd_kernel");
+}
+
 template <int NEURON, bool HARD>
 static int launch_generic(const ef_lif_conv_params& p, int Ho, int Wo, cudaStream_t st) {
   dim3 grid(cdiv(Wo, TW), cdiv(Ho, TH), p.B * cdiv(p.C, COB));
@@ -225,5 +314,6 @@ extern "C" int ef_lif_conv_fwd(const ef_lif_conv_params* p, void* stream) {
   EF_REQUIRE(p, EF_ENULL, "ef_lif_conv_fwd: params is NULL");
   if (int rc = ef::validate_lif_conv(*p, "ef_lif_conv_fwd")) return rc;
   if (ef::lif_conv_tc_eligible(*p)) return ef::lif_conv_fwd_tc(*p, ef::as_stream(stream));
+  if (ef::head_eligible(*p)) return ef::launch_head(*p, ef::as_stream(stream));
   return ef::lif_conv_fwd_generic(*p, ef::as_stream(stream));
 }

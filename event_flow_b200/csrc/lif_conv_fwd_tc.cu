@@ -5,12 +5,16 @@
 //       stored channel-group-major [4 groups][18 x 10 px][8 ch] (exactly the c8 global layout, brought in by one TMA box
 //       with hardware zero-fill = the conv padding), which is the canonical K-major no-swizzle UMMA layout with
 //       core-matrix stride (SBO) = one halo row and K-chunk stride (LBO) = one channel group;
-//   B = weights, split into three bf16 terms hi+mid+lo == w (exact), resident in shared memory for the whole kernel;
-//   D = fp32 accumulator in tensor memory, double buffered.
+//   B = weights, split into three bf16 terms hi+mid+lo == w (exact), resident in shared memory for the whole kernel and
+//       stacked along N: one MMA per (tap, k-step) with N = 96 = {hi, mid, lo} x 32 channels, so the A tile is read from
+//       shared memory once instead of three times (N = 32 MMAs are shared-memory-bandwidth bound: 5 KB per 16-cycle MMA);
+//   D = fp32 accumulator in tensor memory, 96 columns (three partial sums, added in the epilogue), double buffered.
 // Spikes are {0,1,2}: exactly representable in bf16, so every product is exact and only the fp32 summation order differs
 // from the CPU path (no TF32/BF16 rounding may enter a spiking conv).
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2-5 = epilogue
-// (tcgen05.ld -> neuron update -> staged TMA stores).  Persistent over tiles; mbarrier pipelines between the roles.
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2-9 = epilogue: each warp owns a
+// TMEM lane quadrant (32 pixels) and one half of the channels; membrane potentials go straight global <-> registers
+// (32-byte row segments are a poor fit for TMA), spikes leave through a staged TMA store.  Persistent over tiles; mbarrier
+// pipelines between the roles.
 // Reference semantics: models/spiking_submodules.py:96-126 (ConvLIF), :516-551 (ConvLIFRecurrent).
 #include <cuda.h>
 
@@ -26,28 +30,27 @@ constexpr int TC_HH = TC_TH + 2, TC_HW = TC_TW + 2;   // halo tile
 constexpr int A_GROUP_BYTES = TC_HH * TC_HW * 16;     // one 8-channel group of the halo tile (2880 B)
 constexpr int A_TILE_BYTES = 4 * A_GROUP_BYTES;       // 11520 B
 constexpr int Z_TILE_BYTES = 4 * 128 * 16;            // centre spikes, c8: 8192 B
-constexpr int V_TILE_BYTES = 32 * 128 * 4;            // fp32 [32 ch][16][8]: 16384 B
-constexpr int W_BLOCK_BYTES = 32 * 16 * 2;            // one (split, tap, k-step) weight block [32 n][16 k] bf16
-constexpr int W_CONV_BYTES = 3 * 9 * 2 * W_BLOCK_BYTES;  // 55296 B per convolution
-constexpr int TC_THREADS = 192;
-constexpr int TMEM_COLS = 64;                         // 2 accumulator buffers x 32 fp32 columns
+constexpr int W_BLOCK_BYTES = 96 * 16 * 2;            // one (tap, k-step) weight block [96 n = 3 splits x 32 ch][16 k] bf16
+constexpr int W_CONV_BYTES = 9 * 2 * W_BLOCK_BYTES;   // 55296 B per convolution
+constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_THREADS = 32 * (2 + TC_EPI_WARPS);
+constexpr int ACC_COLS = 96;                          // fp32 accumulator columns per tile
+constexpr int TMEM_COLS = 256;                        // 2 accumulator buffers x 96 columns, rounded up to a power of two
 
 struct TcSmemLayout {
-  int w_off, stage_off, stage_bytes, x_off, z_off, v_off, out_off, outz_off, bar_off, total, nstage;
+  int w_off, stage_off, stage_bytes, x_off, z_off, outz_off, bar_off, total, nstage;
 };
 
 __host__ __device__ inline TcSmemLayout tc_smem_layout(bool rec) {
   TcSmemLayout l;
-  l.nstage = rec ? 2 : 3;
+  l.nstage = 4;
   l.w_off = 0;
   const int wbytes = rec ? 2 * W_CONV_BYTES : W_CONV_BYTES;
   l.x_off = 0;
   l.z_off = A_TILE_BYTES;                                   // rec: halo tile of z; ff: centre tile of z
-  l.v_off = l.z_off + (rec ? A_TILE_BYTES : Z_TILE_BYTES);
-  l.stage_bytes = l.v_off + V_TILE_BYTES;
+  l.stage_bytes = l.z_off + (rec ? A_TILE_BYTES : Z_TILE_BYTES);
   l.stage_off = wbytes;
-  l.out_off = l.stage_off + l.nstage * l.stage_bytes;       // v_out staging
-  l.outz_off = l.out_off + V_TILE_BYTES;                    // z_out staging
+  l.outz_off = l.stage_off + l.nstage * l.stage_bytes;      // z_out staging
   l.bar_off = l.outz_off + Z_TILE_BYTES;
   l.total = l.bar_off + 256;
   return l;
@@ -59,6 +62,8 @@ struct TcParams {
   const uint16_t* w_split;
   const float* leak;
   const float* thresh;
+  const float* v_in;
+  float* v_out;
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------------
@@ -133,8 +138,8 @@ __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
   return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
 }
-// kind::f16 instruction descriptor: D = F32, A = B = BF16, both K-major, N = 32, M = 128.
-constexpr uint32_t UMMA_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+// kind::f16 instruction descriptor: D = F32, A = B = BF16, both K-major, N = 96, M = 128.
+constexpr uint32_t UMMA_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((96u >> 3) << 17) | ((128u >> 4) << 24);
 
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
   asm volatile(
@@ -149,26 +154,22 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {  // 32 lanes x 16 columns, no wait
   asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
-        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
-        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
-        "=r"(r[31])
+        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---- the kernel ----------------------------------------------------------------------------------------------------
 template <bool HARD>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_zh,
-                       const __grid_constant__ CUtensorMap map_zc, const __grid_constant__ CUtensorMap map_vin,
-                       const __grid_constant__ CUtensorMap map_vout, const __grid_constant__ CUtensorMap map_zout) {
+                       const __grid_constant__ CUtensorMap map_zc, const __grid_constant__ CUtensorMap map_zout) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const bool rec = p.has_rec != 0;
   const TcSmemLayout L = tc_smem_layout(rec);
@@ -187,11 +188,11 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
     mbar_init(bar_w, 1);
     for (int s = 0; s < NST; ++s) {
       mbar_init(bar_full(s), 1);
-      mbar_init(bar_empty(s), 1 + 4);  // MMA commit + one arrive per epilogue warp
+      mbar_init(bar_empty(s), 1 + TC_EPI_WARPS);  // MMA commit + one arrive per epilogue warp
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_accf(a), 1);
-      mbar_init(bar_acce(a), 4);
+      mbar_init(bar_acce(a), TC_EPI_WARPS);
     }
     fence_barrier_init();
   }
@@ -205,7 +206,7 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
   const uint32_t tmem_base = *tmem_slot;
 
   const int n_my = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  const uint32_t stage_tx = A_TILE_BYTES + (p.has_z ? (rec ? A_TILE_BYTES : Z_TILE_BYTES) : 0) + (p.has_v ? V_TILE_BYTES : 0);
+  const uint32_t stage_tx = A_TILE_BYTES + (p.has_z ? (rec ? A_TILE_BYTES : Z_TILE_BYTES) : 0);
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
@@ -228,7 +229,6 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
           if (rec) tma_load_5d(st + L.z_off, &map_zh, bar_full(s), 0, x0 - 1, y0 - 1, 0, b);
           else tma_load_5d(st + L.z_off, &map_zc, bar_full(s), 0, x0, y0, 0, b);
         }
-        if (p.has_v) tma_load_4d(st + L.v_off, &map_vin, bar_full(s), x0, y0, 0, b);
       }
     }
   } else if (warp == 1) {
@@ -242,7 +242,7 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
         mbar_wait(bar_full(s), ph);
         tc_fence_after();
         const uint32_t st = s_base + L.stage_off + s * L.stage_bytes;
-        const uint32_t d_tmem = tmem_base + a * 32;
+        const uint32_t d_tmem = tmem_base + a * ACC_COLS;
         uint32_t acc = 0;
         const int nconv = (rec && p.has_z) ? 2 : 1;
         for (int cv = 0; cv < nconv; ++cv) {
@@ -254,12 +254,9 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) {
               const uint64_t adesc = umma_desc(a_tile + (dy * TC_HW + dx) * 16 + ks * 2 * A_GROUP_BYTES, A_GROUP_BYTES, TC_HW * 16);
-#pragma unroll
-              for (int sp = 0; sp < 3; ++sp) {
-                const uint64_t bdesc = umma_desc(w_conv + ((sp * 9 + tap) * 2 + ks) * W_BLOCK_BYTES, 512, 128);
-                umma_bf16(d_tmem, adesc, bdesc, acc);
-                acc = 1;
-              }
+              const uint64_t bdesc = umma_desc(w_conv + (tap * 2 + ks) * W_BLOCK_BYTES, 96 * 16, 128);
+              umma_bf16(d_tmem, adesc, bdesc, acc);
+              acc = 1;
             }
           }
         }
@@ -268,19 +265,21 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
       }
     }
   } else {
-    // =============================== epilogue (4 warps = 128 rows) ===============================
-    const int q = warp & 3;                 // TMEM lane quadrant this warp may access
+    // =============================== epilogue (8 warps: 4 lane quadrants x 2 channel halves) ===============================
+    const int q = warp & 3;                 // TMEM lane quadrant this warp may access (warp id % 4)
+    const int hsel = (warp - 2) >> 2;       // channel half: channels [16*hsel, 16*hsel + 16)
     const int m = q * 32 + lane;            // GEMM row = pixel within the tile
     const int ph_ = m >> 3, pw_ = m & 7;    // (row, col) inside the 16 x 8 tile
     const bool store_thread = (threadIdx.x == 64);
-    float lam[32], thr[32];
+    const int c0 = 16 * hsel;
+    float lam[16], thr[16];
 #pragma unroll
-    for (int c = 0; c < 32; ++c) {
-      lam[c] = sigmoidf_acc(__ldg(p.leak + c));
-      thr[c] = fmaxf(__ldg(p.thresh + c), 0.01f);
+    for (int j = 0; j < 16; ++j) {
+      lam[j] = sigmoidf_acc(__ldg(p.leak + c0 + j));
+      thr[j] = fmaxf(__ldg(p.thresh + c0 + j), 0.01f);
     }
-    float* vout_s = reinterpret_cast<float*>(smem + L.out_off);
     uint4* zout_s = reinterpret_cast<uint4*>(smem + L.outz_off);
+    const size_t plane = (size_t)p.H * p.W;
     for (int it = 0; it < n_my; ++it) {
       const int tile = blockIdx.x + it * gridDim.x;
       const int b = tile / (p.tiles_x * p.tiles_y), r = tile % (p.tiles_x * p.tiles_y);
@@ -288,56 +287,64 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
       const int s = it % NST, a = it & 1;
       const uint32_t ph = (it / NST) & 1, aph = (it >> 1) & 1;
       const uint8_t* st = smem + L.stage_off + s * L.stage_bytes;
+      const int gy = y0 + ph_, gx = x0 + pw_;
+      const bool inb = gy < p.H && gx < p.W;
+      const size_t vo = ((size_t)b * 32 + c0) * plane + (size_t)gy * p.W + gx;
 
-      mbar_wait(bar_full(s), ph);  // v_in / z_in of this tile have landed (acquire)
-      // previous spikes of this pixel, 4 x 8 channels
-      uint4 zq[4];
+      // previous membrane potential: 16 independent global loads in flight while the MMAs of this tile run
+      float vin[16];
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
+      for (int j = 0; j < 16; ++j) vin[j] = (p.has_v && inb) ? __ldg(p.v_in + vo + j * plane) : 0.f;
+
+      mbar_wait(bar_full(s), ph);  // z_in of this tile has landed (acquire)
+      uint4 zq[2];
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        const int gg = 2 * hsel + g;
         if (!p.has_z) zq[g] = make_uint4(0, 0, 0, 0);
-        else if (rec) zq[g] = *reinterpret_cast<const uint4*>(st + L.z_off + g * A_GROUP_BYTES + ((ph_ + 1) * TC_HW + pw_ + 1) * 16);
-        else zq[g] = *reinterpret_cast<const uint4*>(st + L.z_off + (g * 128 + m) * 16);
+        else if (rec) zq[g] = *reinterpret_cast<const uint4*>(st + L.z_off + gg * A_GROUP_BYTES + ((ph_ + 1) * TC_HW + pw_ + 1) * 16);
+        else zq[g] = *reinterpret_cast<const uint4*>(st + L.z_off + (gg * 128 + m) * 16);
       }
-      const float* vin_s = reinterpret_cast<const float*>(st + L.v_off);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_empty(s));  // done reading this stage
 
       mbar_wait(bar_accf(a), aph);
       tc_fence_after();
-      uint32_t accr[32];
-      tmem_ld32(tmem_base + a * 32 + ((uint32_t)(q * 32) << 16), accr);
+      uint32_t a_hi[16], a_mid[16], a_lo[16];
+      const uint32_t tacc = tmem_base + a * ACC_COLS + c0 + ((uint32_t)(q * 32) << 16);
+      tmem_ld16(tacc, a_hi);
+      tmem_ld16(tacc + 32, a_mid);
+      tmem_ld16(tacc + 64, a_lo);
+      tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_acce(a));  // accumulator buffer may be overwritten by the MMA of tile it+2
 
-      if (it > 0) {  // staging buffers are free once the previous tile's TMA stores have read them
+      uint32_t zpk[8];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float I = __fadd_rn(__fadd_rn(__uint_as_float(a_lo[j]), __uint_as_float(a_mid[j])), __uint_as_float(a_hi[j]));
+        const float v = vin[j];
+        const uint32_t zw = (&zq[j >> 3].x)[(j & 7) >> 1];
+        const float z = (j & 1) ? bf16_hi(zw) : bf16_lo(zw);
+        const float oml = __fsub_rn(1.0f, lam[j]);
+        float vn;
+        if (HARD) vn = __fadd_rn(__fmul_rn(__fmul_rn(v, lam[j]), __fsub_rn(1.0f, z)), __fmul_rn(oml, I));
+        else vn = __fsub_rn(__fadd_rn(__fmul_rn(v, lam[j]), __fmul_rn(oml, I)), __fmul_rn(z, thr[j]));
+        if (inb) p.v_out[vo + j * plane] = vn;
+        const uint32_t zb = (__fsub_rn(vn, thr[j]) > 0.f) ? 0x3F80u : 0u;  // bf16(1.0) = 0x3F80
+        if (j & 1) zpk[j >> 1] |= zb << 16;
+        else zpk[j >> 1] = zb;
+      }
+      if (it > 0) {  // the staging buffer is free once the previous tile's TMA store has read it
         if (store_thread) bulk_wait_read0();
-        named_bar_sync(1, 128);
-      }
-      uint32_t zpk[16];
-#pragma unroll
-      for (int c = 0; c < 32; ++c) {
-        const float I = __uint_as_float(accr[c]);
-        const float v = p.has_v ? vin_s[c * 128 + m] : 0.f;
-        const uint32_t zw = (&zq[c >> 3].x)[(c & 7) >> 1];
-        const float z = (c & 1) ? bf16_hi(zw) : bf16_lo(zw);
-        const float oml = __fsub_rn(1.0f, lam[c]);
-        float vo;
-        if (HARD) vo = __fadd_rn(__fmul_rn(__fmul_rn(v, lam[c]), __fsub_rn(1.0f, z)), __fmul_rn(oml, I));
-        else vo = __fsub_rn(__fadd_rn(__fmul_rn(v, lam[c]), __fmul_rn(oml, I)), __fmul_rn(z, thr[c]));
-        const float zo = (__fsub_rn(vo, thr[c]) > 0.f) ? 1.0f : 0.f;
-        vout_s[c * 128 + m] = vo;
-        const uint32_t zb = zo > 0.f ? 0x3F80u : 0u;  // bf16(1.0) = 0x3F80
-        if (c & 1) zpk[c >> 1] |= zb << 16;
-        else zpk[c >> 1] = zb;
+        named_bar_sync(1, 32 * TC_EPI_WARPS);
       }
 #pragma unroll
-      for (int g = 0; g < 4; ++g) zout_s[g * 128 + m] = make_uint4(zpk[4 * g], zpk[4 * g + 1], zpk[4 * g + 2], zpk[4 * g + 3]);
-
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_empty(s));  // done reading this stage's v_in / z_in
-      fence_proxy_async();                        // make the staged results visible to the TMA engine
-      named_bar_sync(1, 128);
+      for (int g = 0; g < 2; ++g) zout_s[(2 * hsel + g) * 128 + m] = make_uint4(zpk[4 * g], zpk[4 * g + 1], zpk[4 * g + 2], zpk[4 * g + 3]);
+      fence_proxy_async();  // make the staged spikes visible to the TMA engine
+      named_bar_sync(1, 32 * TC_EPI_WARPS);
       if (store_thread) {
-        tma_store_4d(&map_vout, smem_u32(vout_s), x0, y0, 0, b);
         tma_store_5d(&map_zout, smem_u32(zout_s), 0, x0, y0, 0, b);
         bulk_commit();
       }
@@ -354,7 +361,8 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
 }
 
 // ---- weight split kernel --------------------------------------------------------------------------------------------
-// out block index ((conv*3 + split)*9 + tap)*2 + ks ; inside a block element (n, k) at (k/8)*256 + (n/8)*64 + (n%8)*8 + k%8 (uint16 units)
+// out block index (conv*9 + tap)*2 + ks ; inside a block, row n' = split*32 + n, element (n', k) at (k/8)*768 + (n'/8)*64 + (n'%8)*8 + k%8
+// (uint16 units): K-major no-swizzle core matrices, SBO = 128 B between 8-row groups, LBO = 1536 B between the two K chunks
 __global__ void split_weights_kernel(const float* __restrict__ w_ff, const float* __restrict__ w_rec, uint16_t* __restrict__ out, int nconv) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;  // over nconv * 32 (n) * 32 (ci) * 9 (tap)
   if (i >= nconv * 32 * 32 * 9) return;
@@ -367,9 +375,10 @@ __global__ void split_weights_kernel(const float* __restrict__ w_ff, const float
   const __nv_bfloat16 lo = __float2bfloat16_rn(r2);
   const __nv_bfloat16 parts[3] = {hi, mid, lo};
   const int ks = ci >> 4, k = ci & 15;
+  const size_t blk = ((size_t)cv * 9 + tap) * 2 + ks;
   for (int sp = 0; sp < 3; ++sp) {
-    const size_t blk = ((size_t)(cv * 3 + sp) * 9 + tap) * 2 + ks;
-    out[blk * 512 + (k >> 3) * 256 + (n >> 3) * 64 + (n & 7) * 8 + (k & 7)] = *reinterpret_cast<const uint16_t*>(&parts[sp]);
+    const int nn = sp * 32 + n;
+    out[blk * 1536 + (k >> 3) * 768 + (nn >> 3) * 64 + (nn & 7) * 8 + (k & 7)] = *reinterpret_cast<const uint16_t*>(&parts[sp]);
   }
 }
 
@@ -400,7 +409,7 @@ struct MapKeyHash {
   }
 };
 
-// kind 0: c8 halo box (18x10), 1: c8 centre box (16x8), 2: fp32 NCHW box [32][16][8]
+// kind 0: c8 halo box (18x10), 1: c8 centre box (16x8)
 static int get_map(const void* ptr, int B, int H, int W, int kind, CUtensorMap* out) {
   static thread_local std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
   const MapKey key{ptr, B, H, W, kind};
@@ -412,19 +421,12 @@ static int get_map(const void* ptr, int B, int H, int W, int kind, CUtensorMap* 
   EncodeTiledFn enc = encode_fn();
   if (!enc) return fail(EF_EUNSUPPORTED, "cuTensorMapEncodeTiled is not available from this driver");
   CUresult r;
-  if (kind < 2) {
+  {
     const cuuint64_t dims[5] = {8, (cuuint64_t)W, (cuuint64_t)H, 4, (cuuint64_t)B};
     const cuuint64_t strides[4] = {16, (cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)4 * H * W * 16};
     const cuuint32_t box[5] = {8, (cuuint32_t)(kind == 0 ? TC_HW : TC_TW), (cuuint32_t)(kind == 0 ? TC_HH : TC_TH), 4, 1};
     const cuuint32_t es[5] = {1, 1, 1, 1, 1};
     r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  } else {
-    const cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, 32, (cuuint64_t)B};
-    const cuuint64_t strides[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)32 * H * W * 4};
-    const cuuint32_t box[4] = {TC_TW, TC_TH, 32, 1};
-    const cuuint32_t es[4] = {1, 1, 1, 1};
-    r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   }
   if (r != CUDA_SUCCESS) return fail(EF_EINVAL, "cuTensorMapEncodeTiled failed (CUresult %d) for kind %d, B=%d H=%d W=%d ptr=%p", (int)r, kind, B, H, W, ptr);
@@ -435,8 +437,8 @@ static int get_map(const void* ptr, int B, int H, int W, int kind, CUtensorMap* 
 
 bool lif_conv_tc_eligible(const ef_lif_conv_params& p) {
   return p.w_split && p.x_c8 && p.z_out_c8 && p.Cin == 32 && p.C == 32 && p.ksize == 3 && p.stride == 1 && p.neuron == EF_LIF &&
-         !p.residual && !p.out && !p.z_out && !p.out_c8 && (p.W % 4 == 0) && (!p.v_in == !p.z_in_c8) && !p.z_in && !p.x &&
-         ((uintptr_t)p.x_c8 % 16 == 0) && ((uintptr_t)p.v_out % 16 == 0);
+         !p.residual && !p.out && !p.z_out && !p.out_c8 && (!p.v_in == !p.z_in_c8) && !p.z_in && !p.x && ((uintptr_t)p.x_c8 % 16 == 0) &&
+         ((uintptr_t)p.z_out_c8 % 16 == 0) && p.v_in != p.v_out;
 }
 
 int lif_conv_fwd_tc(const ef_lif_conv_params& p, cudaStream_t st) {
@@ -451,17 +453,15 @@ int lif_conv_fwd_tc(const ef_lif_conv_params& p, cudaStream_t st) {
   q.B = p.B, q.H = p.H, q.W = p.W;
   q.tiles_x = cdiv(p.W, TC_TW), q.tiles_y = cdiv(p.H, TC_TH), q.n_tiles = p.B * q.tiles_x * q.tiles_y;
   q.has_rec = rec, q.has_v = p.v_in != nullptr, q.has_z = p.z_in_c8 != nullptr, q.hard_reset = p.hard_reset;
-  q.w_split = p.w_split, q.leak = p.leak, q.thresh = p.thresh;
-  CUtensorMap mx, mzh, mzc, mvi, mvo, mzo;
+  q.w_split = p.w_split, q.leak = p.leak, q.thresh = p.thresh, q.v_in = p.v_in, q.v_out = p.v_out;
+  CUtensorMap mx, mzh, mzc, mzo;
   int rc;
   if ((rc = get_map(p.x_c8, p.B, p.H, p.W, 0, &mx))) return rc;
-  if ((rc = get_map(p.v_out, p.B, p.H, p.W, 2, &mvo))) return rc;
   if ((rc = get_map(p.z_out_c8, p.B, p.H, p.W, 1, &mzo))) return rc;
-  mzh = mx, mzc = mzo, mvi = mvo;  // placeholders when there is no previous state
+  mzh = mx, mzc = mzo;  // placeholders when there is no previous state
   if (q.has_z) {
     if ((rc = get_map(p.z_in_c8, p.B, p.H, p.W, rec ? 0 : 1, rec ? &mzh : &mzc))) return rc;
   }
-  if (q.has_v && (rc = get_map(p.v_in, p.B, p.H, p.W, 2, &mvi))) return rc;
   const TcSmemLayout L = tc_smem_layout(rec);
   const int grid = q.n_tiles < n_sms ? q.n_tiles : n_sms;
   auto kern = p.hard_reset ? lif_conv_fwd_tc_kernel<true> : lif_conv_fwd_tc_kernel<false>;
@@ -471,7 +471,7 @@ int lif_conv_fwd_tc(const ef_lif_conv_params& p, cudaStream_t st) {
       return check_launch("cudaFuncSetAttribute(lif_conv_fwd_tc_kernel)");
     attr_set[p.hard_reset ? 1 : 0] = true;
   }
-  kern<<<grid, TC_THREADS, L.total, st>>>(q, mx, mzh, mzc, mvi, mvo, mzo);
+  kern<<<grid, TC_THREADS, L.total, st>>>(q, mx, mzh, mzc, mzo);
   return check_launch("lif_conv_fwd_tc_kernel");
 }
 

@@ -25,7 +25,7 @@ def make_case(B, H, W, rec, seed, with_state=True, density=0.3):
 
 @pytest.mark.parametrize("rec", [False, True])
 @pytest.mark.parametrize("hard", [True, False])
-@pytest.mark.parametrize("shape", [(1, 16, 8), (2, 37, 52), (8, 128, 128), (3, 16, 20)])
+@pytest.mark.parametrize("shape", [(1, 16, 8), (2, 37, 52), (8, 128, 128), (3, 16, 20), (1, 5, 3), (2, 33, 47)])
 @pytest.mark.parametrize("with_state", [True, False])
 def test_tc_kernel_matches_cuda_core_kernel_and_oracle(rec, hard, shape, with_state):
     from event_flow_b200 import ops
@@ -59,12 +59,35 @@ def test_weight_split_is_exact():
     w[0, 0, 0, 0], w[0, 0, 0, 1], w[0, 0, 0, 2] = 1.0, 3.0e-5, -0.333333343267
     wr = torch.randn((32, 32, 3, 3), generator=g)
     sp = ops.split_weights(w.to(DEV), wr.to(DEV)).cpu()
-    assert sp.numel() == 2 * 3 * 9 * 2 * 512
-    blocks = sp.view(2, 3, 9, 2, 2, 4, 8, 8)  # conv, split, tap, ks, k/8, n/8, n%8, k%8
-    f = (blocks.to(torch.int32) & 0xFFFF) << 16
-    vals = f.view(torch.float32) if f.dtype == torch.float32 else f.to(torch.int32).view(torch.float32)
-    # -> [conv, split, tap, n, ci]
-    vals = vals.permute(0, 1, 2, 5, 6, 3, 4, 7).reshape(2, 3, 9, 32, 32)
+    assert sp.numel() == 2 * 9 * 2 * 96 * 16
+    blocks = sp.view(2, 9, 2, 2, 12, 8, 8)  # conv, tap, ks, k/8, n'/8, n'%8, k%8 with n' = split*32 + n
+    vals = ((blocks.to(torch.int32) & 0xFFFF) << 16).view(torch.float32)
+    vals = vals.permute(0, 1, 4, 5, 2, 3, 6).reshape(2, 9, 3, 32, 32)  # -> [conv, tap, split, n, ci]
+    vals = vals.permute(0, 2, 1, 3, 4)  # -> [conv, split, tap, n, ci]
     for cv, ref in enumerate((w, wr)):
         total = (vals[cv, 2] + vals[cv, 1]) + vals[cv, 0]  # lo + mid + hi, exact in fp32
         assert torch.equal(total.permute(1, 2, 0).reshape(32, 32, 3, 3), ref)
+
+
+@pytest.mark.parametrize("cin,hard,with_state", [(5, True, True), (2, True, False), (5, False, True), (8, True, True)])
+def test_head_kernel_matches_generic_and_oracle(cin, hard, with_state):
+    """Dedicated head kernel (few fractional input channels -> 32 LIF channels, c8 spikes out)."""
+    from event_flow_b200 import ops
+
+    B, H, W = 3, 37, 70
+    g = torch.Generator().manual_seed(cin)
+    params = osp.init_firenet_params("lif", cin, 32, seed=2, weight_gain=3.0)["head"]
+    x = torch.randn((B, cin, H, W), generator=g) * (torch.rand((B, cin, H, W), generator=g) < 0.4)
+    st = None
+    if with_state:
+        st = torch.rand((2, B, 32, H, W), generator=g) * 1.2 - 0.1
+        st[1] = (st[1] < 0.3).float()
+    pd = {k: v.to(DEV).contiguous() for k, v in params.items()}
+    v_in = z_in = None
+    if st is not None:
+        v_in, z_in = st[0].to(DEV).contiguous(), ops.pack_c8(st[1].to(DEV))
+    v_h, z_h = ops.lif_step_c8(None, v_in, z_in, pd["ff"], None, pd["leak"].reshape(-1), pd["thresh"].reshape(-1), hard_reset=hard,
+                               x_f32=x.to(DEV).contiguous())
+    out_o, ns_o = osp.cell_step("lif", x, st, params, hard_reset=hard)
+    spike_band_compare(v_h.cpu(), ops.unpack_c8(z_h).cpu(), ns_o[0], ns_o[1], params["thresh"].clamp_min(0.01))
+    assert ops.unpack_c8(z_h).mean() > 0.02
