@@ -15,12 +15,68 @@ from . import ops
 LAYERS = ("head", "G1", "R1a", "R1b", "G2", "R2a", "R2b")
 
 
+N_L = len(LAYERS)
+
+
 class _Carry:
-    """dL/d(v, z) of every layer's state, handed from the backward of step t+1 to the backward of step t."""
+    """
+    BPTT side channel of one window: dL/d(v, z) of every layer's state, handed from the backward of step t+1 to the
+    backward of step t, and the flat parameter-gradient buffer the kernels accumulate into over the whole window.
+    """
 
     def __init__(self):
-        self.g_v = [None] * len(LAYERS)
-        self.g_z = [None] * len(LAYERS)
+        self.g_v = [None] * N_L
+        self.g_z = [None] * N_L
+        self.flat = None      # fp32 [n_params]: += by every step's backward kernels, handed to autograd by the window's first step
+        self.sweep = 0        # number of backward steps executed in the current sweep (0 = next call starts a new sweep)
+
+
+class _Slot:
+    """Activations of one model step: membrane fp32 [B,32,H,W] and spikes bf16 [B,4,H,W,8] of the 7 layers, one allocation."""
+
+    def __init__(self, B, H, W, dev):
+        nv, nz = B * 32 * H * W * 4, B * 32 * H * W * 2
+        self.slab = torch.empty(N_L * (nv + nz), device=dev, dtype=torch.uint8)
+        self.v, self.z = [], []
+        o = 0
+        for _ in range(N_L):
+            self.v.append(self.slab[o:o + nv].view(torch.float32).view(B, 32, H, W))
+            o += nv
+        for _ in range(N_L):
+            self.z.append(self.slab[o:o + nz].view(torch.bfloat16).view(B, 4, H, W, 8))
+            o += nz
+        self.flow = torch.empty((B, 2, H, W), device=dev, dtype=torch.float32)
+        self.x_in = None   # static copy of the model input (graph replay reads a fixed address)
+        self.graphs = {}   # (pointer signature) -> torch.cuda.CUDAGraph of this step's 8 kernels
+
+
+class _Arena:
+    """
+    Activation storage owned by the model and reused window after window (no allocator traffic in steady state, static
+    addresses for CUDA-graph replay).  Two banks alternate per BPTT window: window w writes bank w%2, its initial state
+    lives in bank (w-1)%2.  CONTRACT: the saved activations of a window are recycled two detach_states()/reset_states()
+    calls later, i.e. loss.backward() of a window must run before the window after next starts (train_flow.py:154-171 does).
+    """
+
+    def __init__(self, B, H, W, dev):
+        self.key = (B, H, W, dev)
+        self.banks = ([], [])
+        self.parity = 0
+        self.bwd = None
+
+    def slot(self, parity, idx):
+        bank = self.banks[parity]
+        while len(bank) <= idx:
+            bank.append(_Slot(*self.key))
+        return bank[idx]
+
+    def bwd_buffers(self):
+        if self.bwd is None:
+            B, H, W, dev = self.key
+            mk = lambda: torch.empty((B, 32, H, W), device=dev, dtype=torch.float32)  # noqa: E731
+            self.bwd = {"g_h": [mk(), mk()], "scratch": mk(), "g_v": [[mk() for _ in range(N_L)] for _ in range(2)],
+                        "g_z": [[mk() for _ in range(N_L)] for _ in range(2)]}
+        return self.bwd
 
 
 class FastState:
@@ -31,10 +87,14 @@ class FastState:
         self.z = [None] * n        # bf16 [B,C/8,H,W,8]
         self.token = None          # scalar autograd token ordering the steps of one BPTT window
         self.carry = _Carry()
+        self.step = 0              # index of the next step inside the current window
 
-    def detach(self):
+    def detach(self, arena=None):
         self.token = None
         self.carry = _Carry()
+        self.step = 0
+        if arena is not None:
+            arena.parity ^= 1
 
 
 def eligible(model, x):
@@ -51,7 +111,10 @@ def eligible(model, x):
 
 
 def _split_cache(model):
-    """bf16 hi/mid/lo weight images of the hidden layers, rebuilt when a weight tensor changed."""
+    """
+    bf16 hi/mid/lo weight images of the hidden layers.  The buffers are allocated once (stable addresses for CUDA-graph
+    replay) and re-filled in place when a weight tensor changed.
+    """
     cache = model.__dict__.setdefault("_w_split_cache", {})
     out = {}
     for name in LAYERS[1:]:
@@ -60,7 +123,8 @@ def _split_cache(model):
         key = (cell.ff.weight._version, cell.ff.weight.data_ptr(), None if rec is None else rec._version, model.__dict__.get("_w_epoch", 0))
         hit = cache.get(name)
         if hit is None or hit[0] != key:
-            hit = (key, ops.split_weights(cell.ff.weight, rec))
+            buf = None if hit is None or hit[1].device != cell.ff.weight.device else hit[1]
+            hit = (key, ops.split_weights(cell.ff.weight, rec, out=buf))
             cache[name] = hit
         out[name] = hit[1]
     return out
@@ -97,6 +161,26 @@ def _fill_fwd(p, B, Cin, H, W, cell, x_f32, x_c8, v_in, z_in, v_out, leak, thres
     p.v_out = L.ptr(v_out)
 
 
+def _launch_step(model, x, v_in, z_in, slot, splits, B, Cin0, H, W):
+    """The 8 kernels of one model step: head, 6 tensor-core cells, prediction head.  All tensors are caller-provided."""
+    h = None
+    for i, name in enumerate(LAYERS):
+        cell = getattr(model, name)
+        leak, thresh = cell.leak.detach().reshape(-1), cell.thresh.detach().reshape(-1)
+        p = L.LifConvParams()
+        _fill_fwd(p, B, Cin0 if i == 0 else 32, H, W, cell, x if i == 0 else None, h, v_in[i], z_in[i], slot.v[i], leak, thresh)
+        p.z_out_c8 = L.ptr(slot.z[i])
+        if i > 0:
+            p.w_split = L.ptr(splits[name])
+        L.call("ef_lif_conv_fwd", p, tag=(p.Cin, 32, cell.recurrent))
+        h = slot.z[i]
+    w, b = model.pred.conv2d.weight.detach(), model.pred.conv2d.bias.detach()
+    pp = L.PredParams()
+    pp.B, pp.Cin, pp.Cout, pp.H, pp.W = B, 32, 2, H, W
+    pp.x_c8, pp.w, pp.b, pp.y = L.ptr(h), L.ptr(w), L.ptr(b), L.ptr(slot.flow)
+    L.call("ef_pred_fwd", pp)
+
+
 class _FireNetStep(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model, x, token, *params):
@@ -104,44 +188,55 @@ class _FireNetStep(torch.autograd.Function):
         x = x.contiguous()
         B, Cin0, H, W = x.shape
         dev = x.device
-        splits = _split_cache(model)
-        saved = []
-        zs = []
-        h = None
-        for i, name in enumerate(LAYERS):
+        for name in LAYERS:
             cell = getattr(model, name)
             if not hasattr(cell, "_act_width_f"):
                 cell._act_width_f = float(cell.act_width)
-            leak, thresh = cell.leak.detach().reshape(-1), cell.thresh.detach().reshape(-1)
-            v_in, z_in = fs.v[i], fs.z[i]
-            v_out = torch.empty((B, 32, H, W), device=dev, dtype=torch.float32)
-            z_out = torch.empty((B, 4, H, W, 8), device=dev, dtype=torch.bfloat16)
-            p = L.LifConvParams()
-            _fill_fwd(p, B, Cin0 if i == 0 else 32, H, W, cell, x if i == 0 else None, h, v_in, z_in, v_out, leak, thresh)
-            p.z_out_c8 = L.ptr(z_out)
-            if i > 0:
-                p.w_split = L.ptr(splits[name])
-            L.call("ef_lif_conv_fwd", p, tag=(p.Cin, 32, cell.recurrent))
-            saved.append((x if i == 0 else None, h, v_in, z_in, v_out))
-            cap = model.__dict__.get("_capture")
+        splits = _split_cache(model)
+        arena = model.__dict__.get("_arena")
+        if arena is None or arena.key != (B, H, W, dev):
+            arena = model.__dict__["_arena"] = _Arena(B, H, W, dev)
+        slot = arena.slot(arena.parity, fs.step)
+        fs.step += 1
+        v_in, z_in = list(fs.v), list(fs.z)
+        cap = model.__dict__.get("_capture")
+        use_graph = (model.__dict__.get("_use_graphs", True) and cap is None and L.PROFILE is None
+                     and not torch.cuda.is_current_stream_capturing())
+        if use_graph:
+            # CUDA-graph replay of the step: the input is copied to a fixed address, everything else already is static
+            if slot.x_in is None or slot.x_in.shape != x.shape:
+                slot.x_in, slot.graphs = torch.empty_like(x), {}
+            slot.x_in.copy_(x)
+            key = (tuple(p.data_ptr() for p in params), tuple(0 if v is None else v.data_ptr() for v in v_in),
+                   tuple(splits[n].data_ptr() for n in LAYERS[1:]))
+            g = slot.graphs.get(key)
+            if g is None:
+                _launch_step(model, slot.x_in, v_in, z_in, slot, splits, B, Cin0, H, W)  # eager: results + lazy init
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    _launch_step(model, slot.x_in, v_in, z_in, slot, splits, B, Cin0, H, W)
+                slot.graphs[key] = g
+            else:
+                g.replay()
+                L.LAUNCHES += 1
+            x_used = slot.x_in
+        else:
+            _launch_step(model, x, v_in, z_in, slot, splits, B, Cin0, H, W)
+            x_used = x
+        saved = []
+        for i, name in enumerate(LAYERS):
+            saved.append((x_used if i == 0 else None, slot.z[i - 1] if i > 0 else None, v_in[i], z_in[i], slot.v[i]))
             if cap is not None:  # test hook: what this layer consumed and produced, in the reference's tensor format
-                xin = x if i == 0 else ops.unpack_c8(h)
-                sin = None if v_in is None else torch.stack([v_in, ops.unpack_c8(z_in)]).cpu()
-                zo = ops.unpack_c8(z_out)
-                cap[name] = (xin.detach().cpu(), sin, zo.cpu(), torch.stack([v_out, zo]).cpu())
-            fs.v[i], fs.z[i] = v_out, z_out
-            zs.append(z_out)
-            h = z_out
-        w, b = model.pred.conv2d.weight.detach(), model.pred.conv2d.bias.detach()
-        flow = torch.empty((B, 2, H, W), device=dev, dtype=torch.float32)
-        pp = L.PredParams()
-        pp.B, pp.Cin, pp.Cout, pp.H, pp.W = B, 32, 2, H, W
-        pp.x_c8, pp.w, pp.b, pp.y = L.ptr(h), L.ptr(w), L.ptr(b), L.ptr(flow)
-        L.call("ef_pred_fwd", pp)
-        ctx.model, ctx.saved, ctx.flow, ctx.first, ctx.z_last = model, saved, flow, token is None, h
-        ctx.carry = fs.carry
+                xin = x if i == 0 else ops.unpack_c8(slot.z[i - 1])
+                sin = None if v_in[i] is None else torch.stack([v_in[i], ops.unpack_c8(z_in[i])]).cpu()
+                zo = ops.unpack_c8(slot.z[i])
+                cap[name] = (xin.detach().cpu(), sin, zo.cpu(), torch.stack([slot.v[i], zo]).cpu())
+            fs.v[i], fs.z[i] = slot.v[i], slot.z[i]
+        flow = slot.flow.clone()  # the caller may keep the flow for as long as it likes; the slot is recycled
+        ctx.model, ctx.saved, ctx.flow, ctx.first, ctx.z_last = model, saved, slot.flow, token is None, slot.z[N_L - 1]
+        ctx.carry, ctx.arena = fs.carry, arena
         ctx.shapes = (B, Cin0, H, W)
-        model._last_spikes = zs
+        model._last_spikes = list(slot.z)
         new_token = torch.zeros((), device=dev, dtype=torch.float32)
         return flow, new_token
 
@@ -151,14 +246,23 @@ class _FireNetStep(torch.autograd.Function):
         B, Cin0, H, W = ctx.shapes
         params = _params_of(model)
         dev = ctx.flow.device
-        flat = torch.zeros(sum(p.numel() for p in params), device=dev, dtype=torch.float32)
+        buf = ctx.arena.bwd_buffers()
+        if carry.sweep == 0:  # first backward call of this sweep = last step of the window
+            n = sum(p.numel() for p in params)
+            if carry.flat is None:
+                carry.flat = torch.zeros(n, device=dev, dtype=torch.float32)
+            else:
+                carry.flat.zero_()
+            carry.g_v, carry.g_z = [None] * N_L, [None] * N_L
+        par = carry.sweep & 1  # ping-pong of the state-gradient buffers between consecutive steps
+        carry.sweep += 1
         grads, o = [], 0
         for p in params:
-            grads.append(flat[o:o + p.numel()].view(p.shape))
+            grads.append(carry.flat[o:o + p.numel()].view(p.shape))
             o += p.numel()
         gi = len(grads) - 2
         # prediction head
-        g_h = torch.empty((B, 32, H, W), device=dev, dtype=torch.float32)
+        g_h = buf["g_h"][0]
         pp = L.PredParams()
         pp.B, pp.Cin, pp.Cout, pp.H, pp.W = B, 32, 2, H, W
         z7 = ctx.z_last
@@ -177,16 +281,15 @@ class _FireNetStep(torch.autograd.Function):
             q = L.LifConvBwdParams()
             _fill_fwd(q.f, B, Cin0 if i == 0 else 32, H, W, cell, x_f32, x_c8, v_in, z_in, v_out, leak, thresh)
             q.g_out, q.g_v_out, q.g_z_out = L.ptr(g_h), L.ptr(carry.g_v[i]), L.ptr(carry.g_z[i])
-            scratch = torch.empty((B, 32, H, W), device=dev, dtype=torch.float32)
-            q.scratch_gI = L.ptr(scratch)
-            g_x = torch.empty((B, 32, H, W), device=dev, dtype=torch.float32) if i > 0 else None
+            q.scratch_gI = L.ptr(buf["scratch"])
+            g_x = (buf["g_h"][1] if g_h is buf["g_h"][0] else buf["g_h"][0]) if i > 0 else None
             q.g_x = L.ptr(g_x)
             g_v_in = g_z_in = None
             if not ctx.first and v_in is not None:
-                g_v_in = torch.empty((B, 32, H, W), device=dev, dtype=torch.float32)
+                g_v_in = buf["g_v"][par][i]
                 q.g_v_in = L.ptr(g_v_in)
                 if cell.recurrent:
-                    g_z_in = torch.empty((B, 32, H, W), device=dev, dtype=torch.float32)
+                    g_z_in = buf["g_z"][par][i]
                     q.g_z_in = L.ptr(g_z_in)
             k = gi
             q.g_w_ff = L.ptr(grads[k])
@@ -198,11 +301,11 @@ class _FireNetStep(torch.autograd.Function):
             L.call("ef_lif_conv_bwd", q)
             carry.g_v[i], carry.g_z[i] = g_v_in, g_z_in
             g_h = g_x
-        out = []
-        for p, g in zip(params, grads):
-            out.append(g if p.requires_grad else None)
-        g_tok = None if ctx.first else torch.zeros((), device=dev, dtype=torch.float32)
-        return (None, None, g_tok, *out)
+        if not ctx.first:  # parameter gradients keep accumulating in carry.flat; the window's first step hands them over
+            return (None, None, torch.zeros((), device=dev, dtype=torch.float32), *([None] * len(params)))
+        carry.sweep = 0
+        out = [g.clone() if p.requires_grad else None for p, g in zip(params, grads)]
+        return (None, None, None, *out)
 
 
 def forward(model, x, log=False):
@@ -223,7 +326,7 @@ def forward(model, x, log=False):
     else:
         with torch.no_grad():
             flow, _ = _FireNetStep.forward(_NoCtx(), model, x, None, *params)
-        fs.detach()
+        fs.detach(model.__dict__.get("_arena"))
     activity = None
     if log:
         names = ["0:input", "1:head", "2:G1", "3:R1a", "4:R1b", "5:G2", "6:R2a", "7:R2b", "8:pred"]
@@ -234,6 +337,11 @@ def forward(model, x, log=False):
 
 class _NoCtx:
     """Stand-in for the autograd context when the step runs without gradient tracking."""
+
+
+def detach(model):
+    """End of a BPTT window (model.detach_states()): cut the chain, switch the activation bank."""
+    model._fast.detach(model.__dict__.get("_arena"))
 
 
 def states_of(model):

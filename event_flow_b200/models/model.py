@@ -71,7 +71,7 @@ class FireNet(BaseModel):
 
     def detach_states(self):
         if self._fast is not None:  # cut the BPTT chain without copying any state
-            self._fast.detach()
+            fast.detach(self)
             return
         detached_states = []
         for state in self.states:
@@ -83,6 +83,8 @@ class FireNet(BaseModel):
 
     def reset_states(self):
         self._states = [None] * self.num_recurrent_units
+        if getattr(self, "_fast", None) is not None:
+            fast.detach(self)  # a new sequence is also a window boundary for the activation arena
         self._fast = None
 
     def init_cropping(self, width, height):

@@ -297,15 +297,16 @@ def unpack_c8(x):
 # ---------------------------------------------------------------------------------------------------------------------
 # internal-format (c8 spikes) LIF step: the building block of the fast model path
 # ---------------------------------------------------------------------------------------------------------------------
-def split_weights(w_ff, w_rec=None):
-    """fp32 conv weights -> three exact bf16 terms in the tcgen05 B-operand layout (uint16 tensor)."""
+def split_weights(w_ff, w_rec=None, out=None):
+    """fp32 conv weights -> three exact bf16 terms in the tcgen05 B-operand layout (uint16 tensor); `out` is refilled in place."""
     w_ff, w_rec = _c(w_ff.detach()), (None if w_rec is None else _c(w_rec.detach()))
     _need_cuda(w_ff, w_rec)
     C, Cin = w_ff.shape[:2]
     n = L.lib().ef_split_weights_elems(Cin, C, int(w_rec is not None))
     if n == 0:
         return None
-    out = torch.empty(n, device=w_ff.device, dtype=torch.int16)
+    if out is None or out.numel() != n:
+        out = torch.empty(n, device=w_ff.device, dtype=torch.int16)
     L.LAUNCHES += 1
     L.check(L.lib().ef_split_weights(L.ptr(w_ff), L.ptr(w_rec), Cin, C, L.ptr(out), L.stream()), "ef_split_weights")
     return out
