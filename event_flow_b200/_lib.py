@@ -101,7 +101,8 @@ EXPORTS = {
 }  # fmt: skip
 
 _lib = None
-LAUNCHES = 0  # number of library compute calls issued by this process (bench.py reports kernel launches from it)
+LAUNCHES = 0  # number of library compute calls issued by this process
+GRAPH_KERNELS = 0  # kernels executed through CUDA-graph replays (not seen by ef_launch_count)
 
 
 class EventFlowError(RuntimeError):

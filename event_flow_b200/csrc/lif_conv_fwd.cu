@@ -180,15 +180,14 @@ __global__ void __launch_bounds__(NTHREADS) lif_conv_fwd_kernel(const ef_lif_con
 // 32 output channels, LIF.  One thread = one pixel x 32 channels; 32 x 8 pixel tile so that every fp32 NCHW access of a
 // warp is one 128-byte line.  Writes the membrane fp32 NCHW and the spikes in c8 for the tensor-core layers.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int HD_TW = 32, HD_TH = 8, HD_THREADS = 256, HD_MAXC = 8;
+constexpr int HD_TW = 32, HD_TH = 2, HD_THREADS = 64, HD_MAXC = 8;
 
 template <bool HARD>
-__global__ void __launch_bounds__(HD_THREADS) lif_head_fwd_kernel(const ef_lif_conv_params p) {
+__global__ void __launch_bounds__(HD_THREADS) lif_head_fwd_kernel(const ef_lif_conv_params p, int tiles_x, int tiles_y, int n_tiles) {
   __shared__ float s_x[HD_MAXC * (HD_TH + 2) * (HD_TW + 2)];
   __shared__ __align__(16) float s_w[HD_MAXC * 9 * 32];
   __shared__ ChanConst s_k[32];
   const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
-  const int b = blockIdx.z, x0 = blockIdx.x * HD_TW, y0 = blockIdx.y * HD_TH;
   const int Cin = p.Cin, H = p.H, W = p.W;
   if (tid < 32) s_k[tid] = load_chan_const(p, tid);
   for (int i = tid; i < Cin * 9 * 32; i += HD_THREADS) {  // s_w[(ci*9 + tap)*32 + co] = w[co][ci][tap]
@@ -196,57 +195,67 @@ __global__ void __launch_bounds__(HD_THREADS) lif_head_fwd_kernel(const ef_lif_c
     s_w[i] = p.w_ff[(size_t)co * Cin * 9 + r];
   }
   constexpr int HW_ = HD_TW + 2, HH_ = HD_TH + 2;
-  for (int i = tid; i < Cin * HH_ * HW_; i += HD_THREADS) {
-    const int ci = i / (HH_ * HW_), r = i % (HH_ * HW_), y = y0 - 1 + r / HW_, x = x0 - 1 + r % HW_;
-    s_x[i] = (y >= 0 && y < H && x >= 0 && x < W) ? p.x[(((size_t)b * Cin + ci) * H + y) * W + x] : 0.f;
-  }
-  __syncthreads();
-  float acc[32];
+  const size_t plane = (size_t)H * W;
+  // persistent over tiles: the grid is sized to the machine (no tail wave), weights are staged once per CTA
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int b = tile / (tiles_x * tiles_y), r = tile % (tiles_x * tiles_y);
+    const int x0 = (r % tiles_x) * HD_TW, y0 = (r / tiles_x) * HD_TH;
+    __syncthreads();
+    for (int i = tid; i < Cin * HH_ * HW_; i += HD_THREADS) {
+      const int ci = i / (HH_ * HW_), q = i % (HH_ * HW_), y = y0 - 1 + q / HW_, x = x0 - 1 + q % HW_;
+      s_x[i] = (y >= 0 && y < H && x >= 0 && x < W) ? __ldg(p.x + (((size_t)b * Cin + ci) * H + y) * W + x) : 0.f;
+    }
+    const int y = y0 + ty, x = x0 + tx;
+    const bool inb = y < H && x < W;
+    const size_t pix = (size_t)y * W + x;
+    // previous state: issued before the convolution so that the DRAM latency overlaps the FMAs
+    float vin[32];
+    uint4 zq[4];
 #pragma unroll
-  for (int c = 0; c < 32; ++c) acc[c] = 0.f;
-  for (int ci = 0; ci < Cin; ++ci) {
-    float xv[9];
+    for (int c = 0; c < 32; ++c) vin[c] = (inb && p.v_in) ? __ldg(p.v_in + ((size_t)b * 32 + c) * plane + pix) : 0.f;
 #pragma unroll
-    for (int dy = 0; dy < 3; ++dy)
+    for (int g = 0; g < 4; ++g)
+      zq[g] = (inb && p.z_in_c8) ? __ldg(reinterpret_cast<const uint4*>(p.z_in_c8 + (((size_t)b * 4 + g) * plane + pix) * 8)) : make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    float acc[32];
 #pragma unroll
-      for (int dx = 0; dx < 3; ++dx) xv[dy * 3 + dx] = s_x[(ci * HH_ + ty + dy) * HW_ + tx + dx];
+    for (int c = 0; c < 32; ++c) acc[c] = 0.f;
+    for (int ci = 0; ci < Cin; ++ci) {
+      float xv[9];
 #pragma unroll
-    for (int tap = 0; tap < 9; ++tap) {
-      const float4* wr = reinterpret_cast<const float4*>(s_w + (ci * 9 + tap) * 32);
+      for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float4 w4 = wr[q];
-        acc[4 * q + 0] = fmaf(xv[tap], w4.x, acc[4 * q + 0]);
-        acc[4 * q + 1] = fmaf(xv[tap], w4.y, acc[4 * q + 1]);
-        acc[4 * q + 2] = fmaf(xv[tap], w4.z, acc[4 * q + 2]);
-        acc[4 * q + 3] = fmaf(xv[tap], w4.w, acc[4 * q + 3]);
+        for (int dx = 0; dx < 3; ++dx) xv[dy * 3 + dx] = s_x[(ci * HH_ + ty + dy) * HW_ + tx + dx];
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const float4* wr = reinterpret_cast<const float4*>(s_w + (ci * 9 + tap) * 32);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 w4 = wr[q];
+          acc[4 * q + 0] = fmaf(xv[tap], w4.x, acc[4 * q + 0]);
+          acc[4 * q + 1] = fmaf(xv[tap], w4.y, acc[4 * q + 1]);
+          acc[4 * q + 2] = fmaf(xv[tap], w4.z, acc[4 * q + 2]);
+          acc[4 * q + 3] = fmaf(xv[tap], w4.w, acc[4 * q + 3]);
+        }
       }
     }
+    if (!inb) continue;
+    uint32_t zpk[16];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+      const uint32_t zw = (&zq[c >> 3].x)[(c & 7) >> 1];
+      const float z = (c & 1) ? bf16_hi(zw) : bf16_lo(zw);
+      float vo, zo, ao, thr;
+      neuron_update<EF_LIF, HARD>(acc[c], vin[c], z, 0.f, 0.f, s_k[c], vo, zo, ao, thr);
+      p.v_out[((size_t)b * 32 + c) * plane + pix] = vo;
+      const uint32_t zb = zo > 0.f ? 0x3F80u : 0u;
+      if (c & 1) zpk[c >> 1] |= zb << 16;
+      else zpk[c >> 1] = zb;
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      *reinterpret_cast<uint4*>(p.z_out_c8 + (((size_t)b * 4 + g) * plane + pix) * 8) = make_uint4(zpk[4 * g], zpk[4 * g + 1], zpk[4 * g + 2], zpk[4 * g + 3]);
   }
-  const int y = y0 + ty, x = x0 + tx;
-  if (y >= H || x >= W) return;
-  const size_t plane = (size_t)H * W, pix = (size_t)y * W + x;
-  uint4 zq[4];
-#pragma unroll
-  for (int g = 0; g < 4; ++g)
-    zq[g] = p.z_in_c8 ? *reinterpret_cast<const uint4*>(p.z_in_c8 + (((size_t)b * 4 + g) * plane + pix) * 8) : make_uint4(0, 0, 0, 0);
-  uint32_t zpk[16];
-#pragma unroll
-  for (int c = 0; c < 32; ++c) {
-    const size_t o = ((size_t)b * 32 + c) * plane + pix;
-    const float v = p.v_in ? __ldg(p.v_in + o) : 0.f;
-    const uint32_t zw = (&zq[c >> 3].x)[(c & 7) >> 1];
-    const float z = (c & 1) ? bf16_hi(zw) : bf16_lo(zw);
-    float vo, zo, ao, thr;
-    neuron_update<EF_LIF, HARD>(acc[c], v, z, 0.f, 0.f, s_k[c], vo, zo, ao, thr);
-    p.v_out[o] = vo;
-    const uint32_t zb = zo > 0.f ? 0x3F80u : 0u;
-    if (c & 1) zpk[c >> 1] |= zb << 16;
-    else zpk[c >> 1] = zb;
-  }
-#pragma unroll
-  for (int g = 0; g < 4; ++g)
-    *reinterpret_cast<uint4*>(p.z_out_c8 + (((size_t)b * 4 + g) * plane + pix) * 8) = make_uint4(zpk[4 * g], zpk[4 * g + 1], zpk[4 * g + 2], zpk[4 * g + 3]);
 }
 
 static bool head_eligible(const ef_lif_conv_params& p) {
@@ -255,11 +264,26 @@ static bool head_eligible(const ef_lif_conv_params& p) {
 }
 
 static int launch_head(const ef_lif_conv_params& p, cudaStream_t st) {
-  dim3 grid(cdiv(p.W, HD_TW), cdiv(p.H, HD_TH), p.B);
+  static int n_sms = 0;
+  if (n_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  static int per_sm[2] = {0, 0};
+  const int hi = p.hard_reset ? 1 : 0;
+  if (per_sm[hi] == 0) {
+    if (hi) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[hi], lif_head_fwd_kernel<true>, HD_THREADS, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[hi], lif_head_fwd_kernel<false>, HD_THREADS, 0);
+    if (per_sm[hi] < 1) per_sm[hi] = 1;
+  }
+  const int tiles_x = cdiv(p.W, HD_TW), tiles_y = cdiv(p.H, HD_TH), n_tiles = tiles_x * tiles_y * p.B;
+  const int slots = n_sms * per_sm[hi];  // persistent grid = exactly one resident wave
+  const int grid = n_tiles < slots ? n_tiles : slots;
   if (p.hard_reset)
-    lif_head_fwd_kernel<true><<<grid, HD_THREADS, 0, st>>>(p);
+    lif_head_fwd_kernel<true><<<grid, HD_THREADS, 0, st>>>(p, tiles_x, tiles_y, n_tiles);
   else
-    lif_head_fwd_kernel<false><<<grid, HD_THREADS, 0, st>>>(p);
+    lif_head_fwd_kernel<false><<<grid, HD_THREADS, 0, st>>>(p, tiles_x, tiles_y, n_tiles);
   return check_launch("lif_head_fwd_kernel");
 }
 

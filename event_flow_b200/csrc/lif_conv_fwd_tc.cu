@@ -95,8 +95,8 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000ll) __trap();  // ~2 s at 1.9 GHz
+  for (uint32_t n = 1; !mbar_try_wait(bar, parity); ++n) {
+    if ((n & 1023u) == 0 && clock64() - t0 > 4000000000ll) __trap();  // ~2 s at 1.9 GHz
   }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -280,21 +280,36 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
     }
     uint4* zout_s = reinterpret_cast<uint4*>(smem + L.outz_off);
     const size_t plane = (size_t)p.H * p.W;
+    // membrane potential of the NEXT tile is prefetched into registers while the current tile is processed, so that the
+    // DRAM latency of these loads (the only operand not staged by TMA) is off the per-tile critical path
+    auto tile_origin = [&](int it_, int& b_, int& y0_, int& x0_) {
+      const int tile_ = blockIdx.x + it_ * gridDim.x;
+      b_ = tile_ / (p.tiles_x * p.tiles_y);
+      const int r_ = tile_ % (p.tiles_x * p.tiles_y);
+      y0_ = (r_ / p.tiles_x) * TC_TH, x0_ = (r_ % p.tiles_x) * TC_TW;
+    };
+    auto load_v = [&](int it_, float (&dst)[16]) {
+      int b_, y0_, x0_;
+      tile_origin(it_, b_, y0_, x0_);
+      const int gy_ = y0_ + ph_, gx_ = x0_ + pw_;
+      const bool ok = p.has_v && it_ < n_my && gy_ < p.H && gx_ < p.W;
+      const size_t o_ = ((size_t)b_ * 32 + c0) * plane + (size_t)gy_ * p.W + gx_;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) dst[j] = ok ? __ldg(p.v_in + o_ + j * plane) : 0.f;
+    };
+    float vin[16];
+    load_v(0, vin);
     for (int it = 0; it < n_my; ++it) {
-      const int tile = blockIdx.x + it * gridDim.x;
-      const int b = tile / (p.tiles_x * p.tiles_y), r = tile % (p.tiles_x * p.tiles_y);
-      const int y0 = (r / p.tiles_x) * TC_TH, x0 = (r % p.tiles_x) * TC_TW;
+      int b, y0, x0;
+      tile_origin(it, b, y0, x0);
       const int s = it % NST, a = it & 1;
       const uint32_t ph = (it / NST) & 1, aph = (it >> 1) & 1;
       const uint8_t* st = smem + L.stage_off + s * L.stage_bytes;
       const int gy = y0 + ph_, gx = x0 + pw_;
       const bool inb = gy < p.H && gx < p.W;
       const size_t vo = ((size_t)b * 32 + c0) * plane + (size_t)gy * p.W + gx;
-
-      // previous membrane potential: 16 independent global loads in flight while the MMAs of this tile run
-      float vin[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) vin[j] = (p.has_v && inb) ? __ldg(p.v_in + vo + j * plane) : 0.f;
+      float vnext[16];
+      load_v(it + 1, vnext);
 
       mbar_wait(bar_full(s), ph);  // z_in of this tile has landed (acquire)
       uint4 zq[2];
@@ -342,6 +357,8 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
       }
 #pragma unroll
       for (int g = 0; g < 2; ++g) zout_s[(2 * hsel + g) * 128 + m] = make_uint4(zpk[4 * g], zpk[4 * g + 1], zpk[4 * g + 2], zpk[4 * g + 3]);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) vin[j] = vnext[j];
       fence_proxy_async();  // make the staged spikes visible to the TMA engine
       named_bar_sync(1, 32 * TC_EPI_WARPS);
       if (store_thread) {

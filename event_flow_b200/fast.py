@@ -218,7 +218,7 @@ class _FireNetStep(torch.autograd.Function):
                 slot.graphs[key] = g
             else:
                 g.replay()
-                L.LAUNCHES += 1
+                L.GRAPH_KERNELS += N_L + 1
             x_used = slot.x_in
         else:
             _launch_step(model, x, v_in, z_in, slot, splits, B, Cin0, H, W)
