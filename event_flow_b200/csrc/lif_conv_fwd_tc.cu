@@ -64,7 +64,15 @@ struct TcParams {
   const float* thresh;
   const float* v_in;
   float* v_out;
+  long long* trace;  // debug: per-CTA timeline (clock64), NULL in production
 };
+
+constexpr int TRACE_SLOTS = 8, TRACE_MAX_TILES = 32;  // [cta][tile][slot]
+#define EF_TRACE(it_, slot_)                                                                              \
+  do {                                                                                                    \
+    if (p.trace && (it_) < TRACE_MAX_TILES)                                                               \
+      p.trace[((size_t)blockIdx.x * TRACE_MAX_TILES + (it_)) * TRACE_SLOTS + (slot_)] = clock64() - t_cta; \
+  } while (0)
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -184,6 +192,7 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.bar_off + 8 * (5 + 2 * NST));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long t_cta = clock64();
   if (threadIdx.x == 0) {
     mbar_init(bar_w, 1);
     for (int s = 0; s < NST; ++s) {
@@ -229,6 +238,7 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
           if (rec) tma_load_5d(st + L.z_off, &map_zh, bar_full(s), 0, x0 - 1, y0 - 1, 0, b);
           else tma_load_5d(st + L.z_off, &map_zc, bar_full(s), 0, x0, y0, 0, b);
         }
+        EF_TRACE(it, 0);
       }
     }
   } else if (warp == 1) {
@@ -241,6 +251,7 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
         mbar_wait(bar_acce(a), aph ^ 1);
         mbar_wait(bar_full(s), ph);
         tc_fence_after();
+        EF_TRACE(it, 1);
         const uint32_t st = s_base + L.stage_off + s * L.stage_bytes;
         const uint32_t d_tmem = tmem_base + a * ACC_COLS;
         uint32_t acc = 0;
@@ -262,6 +273,7 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
         }
         umma_commit(bar_empty(s));  // the stage's operand tiles may be overwritten once these MMAs have read them
         umma_commit(bar_accf(a));   // accumulator complete
+        EF_TRACE(it, 2);
       }
     }
   } else {
@@ -325,6 +337,7 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
 
       mbar_wait(bar_accf(a), aph);
       tc_fence_after();
+      if (store_thread) EF_TRACE(it, 3);
       uint32_t a_hi[16], a_mid[16], a_lo[16];
       const uint32_t tacc = tmem_base + a * ACC_COLS + c0 + ((uint32_t)(q * 32) << 16);
       tmem_ld16(tacc, a_hi);
@@ -334,6 +347,7 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_acce(a));  // accumulator buffer may be overwritten by the MMA of tile it+2
+      if (store_thread) EF_TRACE(it, 4);
 
       uint32_t zpk[8];
 #pragma unroll
@@ -351,6 +365,7 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
         if (j & 1) zpk[j >> 1] |= zb << 16;
         else zpk[j >> 1] = zb;
       }
+      if (store_thread) EF_TRACE(it, 5);
       if (it > 0) {  // the staging buffer is free once the previous tile's TMA store has read it
         if (store_thread) bulk_wait_read0();
         named_bar_sync(1, 32 * TC_EPI_WARPS);
@@ -364,9 +379,13 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
       if (store_thread) {
         tma_store_5d(&map_zout, smem_u32(zout_s), 0, x0, y0, 0, b);
         bulk_commit();
+        EF_TRACE(it, 6);
       }
     }
-    if (store_thread) bulk_wait0();
+    if (store_thread) {
+      bulk_wait0();
+      EF_TRACE(n_my > 0 ? n_my - 1 : 0, 7);
+    }
   }
 
   tc_fence_before();
@@ -452,6 +471,8 @@ static int get_map(const void* ptr, int B, int H, int W, int kind, CUtensorMap* 
   return EF_OK;
 }
 
+static long long* g_tc_trace = nullptr;  // set through ef_debug_tc_trace (tools/tc_timeline.py)
+
 bool lif_conv_tc_eligible(const ef_lif_conv_params& p) {
   return p.w_split && p.x_c8 && p.z_out_c8 && p.Cin == 32 && p.C == 32 && p.ksize == 3 && p.stride == 1 && p.neuron == EF_LIF &&
          !p.residual && !p.out && !p.z_out && !p.out_c8 && (!p.v_in == !p.z_in_c8) && !p.z_in && !p.x && ((uintptr_t)p.x_c8 % 16 == 0) &&
@@ -471,6 +492,7 @@ int lif_conv_fwd_tc(const ef_lif_conv_params& p, cudaStream_t st) {
   q.tiles_x = cdiv(p.W, TC_TW), q.tiles_y = cdiv(p.H, TC_TH), q.n_tiles = p.B * q.tiles_x * q.tiles_y;
   q.has_rec = rec, q.has_v = p.v_in != nullptr, q.has_z = p.z_in_c8 != nullptr, q.hard_reset = p.hard_reset;
   q.w_split = p.w_split, q.leak = p.leak, q.thresh = p.thresh, q.v_in = p.v_in, q.v_out = p.v_out;
+  q.trace = g_tc_trace;
   CUtensorMap mx, mzh, mzc, mzo;
   int rc;
   if ((rc = get_map(p.x_c8, p.B, p.H, p.W, 0, &mx))) return rc;
@@ -493,6 +515,11 @@ int lif_conv_fwd_tc(const ef_lif_conv_params& p, cudaStream_t st) {
 }
 
 }  // namespace ef
+
+extern "C" int ef_debug_tc_trace(long long* buf) {  // buf: device int64 [n_ctas][32 tiles][8 slots] or NULL to switch tracing off
+  ef::g_tc_trace = buf;
+  return EF_OK;
+}
 
 extern "C" int64_t ef_split_weights_elems(int32_t Cin, int32_t C, int32_t has_rec) {
   if (Cin != 32 || C != 32) return 0;

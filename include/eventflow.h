@@ -129,6 +129,10 @@ int ef_lif_conv_bwd(const ef_lif_conv_bwd_params* p, void* stream);
 int64_t ef_split_weights_elems(int32_t Cin, int32_t C, int32_t has_rec);
 int ef_split_weights(const float* w_ff, const float* w_rec, int32_t Cin, int32_t C, uint16_t* out, void* stream);
 
+/* Debug aid: subsequent tensor-core launches write a per-CTA clock64 timeline into buf (device int64 [n_ctas][32][8]);
+ * NULL switches it off (default).  Not part of the reference's interface. */
+int ef_debug_tc_trace(long long* buf);
+
 /* fp32 NCHW <-> c8 bf16 layout conversion at the API boundary (model.states getter/setter, first input). */
 int ef_pack_c8(const float* src, uint16_t* dst, int32_t B, int32_t C, int32_t H, int32_t W, void* stream);
 int ef_unpack_c8(const uint16_t* src, float* dst, int32_t B, int32_t C, int32_t H, int32_t W, void* stream);
