@@ -24,10 +24,10 @@ class LifConvParams(C.Structure):
         ("B", _i32), ("Cin", _i32), ("C", _i32), ("H", _i32), ("W", _i32),
         ("ksize", _i32), ("stride", _i32), ("neuron", _i32), ("hard_reset", _i32), ("surrogate", _i32),
         ("act_width", C.c_float),
-        ("x", _f32p), ("x_c8", _f32p), ("v_in", _f32p), ("z_in", _f32p), ("z_in_c8", _f32p), ("aux_in", _f32p),
+        ("x", _f32p), ("x_cl", _f32p), ("v_in", _f32p), ("z_in", _f32p), ("z_in_cl", _f32p), ("aux_in", _f32p),
         ("w_ff", _f32p), ("w_rec", _f32p), ("leak", _f32p), ("thresh", _f32p), ("leak_aux", _f32p), ("add_pt", _f32p),
         ("t0", _f32p), ("t1", _f32p), ("residual", _f32p), ("w_split", _f32p),
-        ("v_out", _f32p), ("z_out", _f32p), ("z_out_c8", _f32p), ("aux_out", _f32p), ("out", _f32p), ("out_c8", _f32p),
+        ("v_out", _f32p), ("z_out", _f32p), ("z_out_cl", _f32p), ("aux_out", _f32p), ("out", _f32p), ("out_cl", _f32p),
     ]  # fmt: skip
 
 
@@ -45,7 +45,7 @@ class LifConvBwdParams(C.Structure):
 class PredParams(C.Structure):
     _fields_ = [
         ("B", _i32), ("Cin", _i32), ("Cout", _i32), ("H", _i32), ("W", _i32),
-        ("x", _f32p), ("x_c8", _f32p), ("w", _f32p), ("b", _f32p), ("y", _f32p),
+        ("x", _f32p), ("x_cl", _f32p), ("w", _f32p), ("b", _f32p), ("y", _f32p),
         ("g_y", _f32p), ("g_x", _f32p), ("g_w", _f32p), ("g_b", _f32p),
     ]  # fmt: skip
 
@@ -87,8 +87,8 @@ EXPORTS = {
     "ef_split_weights_elems": (C.c_int64, [_i32, _i32, _i32]),
     "ef_split_weights": (C.c_int, [C.c_void_p, C.c_void_p, _i32, _i32, C.c_void_p, C.c_void_p]),
     "ef_debug_tc_trace": (C.c_int, [C.c_void_p]),
-    "ef_pack_c8": (C.c_int, [C.c_void_p, C.c_void_p, _i32, _i32, _i32, _i32, C.c_void_p]),
-    "ef_unpack_c8": (C.c_int, [C.c_void_p, C.c_void_p, _i32, _i32, _i32, _i32, C.c_void_p]),
+    "ef_pack_cl": (C.c_int, [C.c_void_p, C.c_void_p, _i32, _i32, _i32, _i32, C.c_void_p]),
+    "ef_unpack_cl": (C.c_int, [C.c_void_p, C.c_void_p, _i32, _i32, _i32, _i32, C.c_void_p]),
     "ef_pred_fwd": (C.c_int, [C.POINTER(PredParams), C.c_void_p]),
     "ef_pred_bwd": (C.c_int, [C.POINTER(PredParams), C.c_void_p]),
     "ef_iwe_loss_workspace_elems": (C.c_int64, [_i32, _i32, _i32, _i32]),

@@ -12,10 +12,10 @@ namespace ef {
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int PW_THREADS = 256, PW_PER_THREAD = 4;
 
-// activation read in either layout: fp32 NCHW or c8 (bf16 channel-blocked [B, C/8, H, W, 8])
-__device__ __forceinline__ float ld_act2(const float* f32, const uint16_t* c8, int b, int c, size_t pix, int C, size_t hw) {
+// activation read in either layout: fp32 NCHW or cl (bf16 channels-last [B, H, W, C])
+__device__ __forceinline__ float ld_act2(const float* f32, const uint16_t* cl, int b, int c, size_t pix, int C, size_t hw) {
   if (f32) return f32[((size_t)b * C + c) * hw + pix];
-  const uint16_t u = c8[(((size_t)b * (C >> 3) + (c >> 3)) * hw + pix) * 8 + (c & 7)];
+  const uint16_t u = cl[((size_t)b * hw + pix) * C + c];
   return __uint_as_float(((uint32_t)u) << 16);
 }
 
@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(PW_THREADS) lif_bwd_pointwise_kernel(const ef_
     const size_t o = base + pix;
     const float v_p = p.v_in ? p.v_in[o] : 0.f;
     float z_p = 0.f;
-    if (p.z_in || p.z_in_c8) z_p = ld_act2(p.z_in, p.z_in_c8, b, c, pix, p.C, plane);
+    if (p.z_in || p.z_in_cl) z_p = ld_act2(p.z_in, p.z_in_cl, b, c, pix, p.C, plane);
     const float a_p = (NEURON != EF_LIF && p.aux_in) ? p.aux_in[o] : 0.f;
     const float v_n = p.v_out[o];
     const float a_n = (NEURON != EF_LIF) ? p.aux_out[o] : 0.f;
@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(DG_THREADS) conv_dgrad_kernel(const float* __r
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int WG_THREADS = 128, WG_GP = 257;
 
-__global__ void __launch_bounds__(WG_THREADS) conv_wgrad_kernel(const float* __restrict__ in, const uint16_t* __restrict__ in_c8,
+__global__ void __launch_bounds__(WG_THREADS) conv_wgrad_kernel(const float* __restrict__ in, const uint16_t* __restrict__ in_cl,
                                                                 const float* __restrict__ g_I,
                                                                 float* __restrict__ g_w, int B, int Cin, int C, int H, int W,
                                                                 int Ho, int Wo) {
@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(WG_THREADS) conv_wgrad_kernel(const float* __r
     for (int i = tid; i < 8 * HH * HW; i += WG_THREADS) {
       const int ci = i / (HH * HW), r = i % (HH * HW), y = iy0 + r / HW, x = ix0 + r % HW;
       float v = 0.f;
-      if (ci0 + ci < Cin && y >= 0 && y < H && x >= 0 && x < W) v = ld_act2(in, in_c8, b, ci0 + ci, (size_t)y * W + x, Cin, (size_t)H * W);
+      if (ci0 + ci < Cin && y >= 0 && y < H && x >= 0 && x < W) v = ld_act2(in, in_cl, b, ci0 + ci, (size_t)y * W + x, Cin, (size_t)H * W);
       s_x[i] = v;
     }
     __syncthreads();
@@ -324,7 +324,7 @@ extern "C" int ef_lif_conv_bwd(const ef_lif_conv_bwd_params* q, void* stream) {
   const ef_lif_conv_params& p = q->f;
   EF_REQUIRE(p.B > 0 && p.Cin > 0 && p.C > 0 && p.H > 0 && p.W > 0, EF_EINVAL, "ef_lif_conv_bwd: non-positive dimension");
   EF_REQUIRE(p.ksize == 3 && p.stride == 1, EF_EUNSUPPORTED, "ef_lif_conv_bwd: kernel_size 3, stride 1 only in this version");
-  EF_REQUIRE((p.x || p.x_c8) && p.w_ff && p.leak && p.v_out && q->scratch_gI, EF_ENULL, "ef_lif_conv_bwd: x / w_ff / leak / v_out / scratch is NULL");
+  EF_REQUIRE((p.x || p.x_cl) && p.w_ff && p.leak && p.v_out && q->scratch_gI, EF_ENULL, "ef_lif_conv_bwd: x / w_ff / leak / v_out / scratch is NULL");
   EF_REQUIRE(p.x || !(p.neuron == EF_PLIF || p.neuron == EF_XLIF) || !q->g_x, EF_EUNSUPPORTED, "ef_lif_conv_bwd: PLIF / XLIF data gradient needs the fp32 input");
   EF_REQUIRE(p.neuron == EF_LIF || p.aux_out, EF_ENULL, "ef_lif_conv_bwd: aux_out is NULL");
   cudaStream_t st = as_stream(stream);
@@ -356,19 +356,19 @@ extern "C" int ef_lif_conv_bwd(const ef_lif_conv_bwd_params* q, void* stream) {
     conv_dgrad_kernel<<<grid, DG_THREADS, 0, st>>>(q->scratch_gI, p.w_ff, q->g_x, 0, p.B, p.Cin, p.C, p.H, p.W, gP_sum, p.x);
     if ((rc = check_launch("conv_dgrad_kernel(ff)"))) return rc;
   }
-  if (p.w_rec && q->g_z_in && (p.z_in || p.z_in_c8)) {
+  if (p.w_rec && q->g_z_in && (p.z_in || p.z_in_cl)) {
     dim3 grid(cdiv(Wo, 16), cdiv(Ho, 16), p.B * cdiv(p.C, DG_CIB));
     conv_dgrad_kernel<<<grid, DG_THREADS, 0, st>>>(q->scratch_gI, p.w_rec, q->g_z_in, 1, p.B, p.C, p.C, Ho, Wo, nullptr, nullptr);
     if ((rc = check_launch("conv_dgrad_kernel(rec)"))) return rc;
   }
   if (q->g_w_ff) {
     dim3 grid(cdiv(Wo, 16), cdiv(Ho, 16), p.B * cdiv(p.C, 32));
-    conv_wgrad_kernel<<<grid, WG_THREADS, 0, st>>>(p.x, p.x_c8, q->scratch_gI, q->g_w_ff, p.B, p.Cin, p.C, p.H, p.W, Ho, Wo);
+    conv_wgrad_kernel<<<grid, WG_THREADS, 0, st>>>(p.x, p.x_cl, q->scratch_gI, q->g_w_ff, p.B, p.Cin, p.C, p.H, p.W, Ho, Wo);
     if ((rc = check_launch("conv_wgrad_kernel(ff)"))) return rc;
   }
-  if (p.w_rec && q->g_w_rec && (p.z_in || p.z_in_c8)) {
+  if (p.w_rec && q->g_w_rec && (p.z_in || p.z_in_cl)) {
     dim3 grid(cdiv(Wo, 16), cdiv(Ho, 16), p.B * cdiv(p.C, 32));
-    conv_wgrad_kernel<<<grid, WG_THREADS, 0, st>>>(p.z_in, p.z_in_c8, q->scratch_gI, q->g_w_rec, p.B, p.C, p.C, Ho, Wo, Ho, Wo);
+    conv_wgrad_kernel<<<grid, WG_THREADS, 0, st>>>(p.z_in, p.z_in_cl, q->scratch_gI, q->g_w_rec, p.B, p.C, p.C, Ho, Wo, Ho, Wo);
     if ((rc = check_launch("conv_wgrad_kernel(rec)"))) return rc;
   }
   return EF_OK;

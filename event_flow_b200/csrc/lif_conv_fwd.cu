@@ -17,16 +17,16 @@ struct Geo {
   static constexpr int HW = (TW - 1) * STRIDE + 3;            // halo cols
 };
 
-__device__ __forceinline__ float ld_act(const float* f32, const uint16_t* c8, int b, int c, int y, int x, int C, int H, int W) {
+__device__ __forceinline__ float ld_act(const float* f32, const uint16_t* cl, int b, int c, int y, int x, int C, int H, int W) {
   if (f32) return f32[(((size_t)b * C + c) * H + y) * W + x];
-  const uint16_t u = c8[((((size_t)b * (C >> 3) + (c >> 3)) * H + y) * W + x) * 8 + (c & 7)];
+  const uint16_t u = cl[(((size_t)b * H + y) * W + x) * C + c];
   return __uint_as_float(((uint32_t)u) << 16);
 }
 
 // Accumulate one convolution (input `src`, weights `w`) into acc[2][COB].
 template <int STRIDE, bool TRACE>
 __device__ __forceinline__ void conv_accumulate(float (&acc)[2][COB], const float* __restrict__ src_f32,
-                                                const uint16_t* __restrict__ src_c8, const float* __restrict__ w, int b, int Cin,
+                                                const uint16_t* __restrict__ src_cl, const float* __restrict__ w, int b, int Cin,
                                                 int H, int W, int co0, int C, int oy0, int ox0, float* s_x, float* s_w,
                                                 float* s_abs) {
   using G = Geo<STRIDE>;
@@ -39,7 +39,7 @@ __device__ __forceinline__ void conv_accumulate(float (&acc)[2][COB], const floa
       const int ci = i / (G::HH * G::HW), r = i % (G::HH * G::HW), hy = r / G::HW, hx = r % G::HW;
       const int y = iy0 + hy, x = ix0 + hx, c = ci0 + ci;
       float v = 0.f;
-      if (c < Cin && y >= 0 && y < H && x >= 0 && x < W) v = ld_act(src_f32, src_c8, b, c, y, x, Cin, H, W);
+      if (c < Cin && y >= 0 && y < H && x >= 0 && x < W) v = ld_act(src_f32, src_cl, b, c, y, x, Cin, H, W);
       s_x[i] = v;
     }
     // weight tile [ci*9+tap][co]
@@ -114,9 +114,9 @@ __global__ void __launch_bounds__(NTHREADS) lif_conv_fwd_kernel(const ef_lif_con
 #pragma unroll
     for (int j = 0; j < COB; ++j) acc[i][j] = 0.f;
 
-  conv_accumulate<STRIDE, TRACE>(acc, p.x, p.x_c8, p.w_ff, b, p.Cin, p.H, p.W, co0, p.C, oy0, ox0, s_x, s_w, s_abs);
-  if (p.w_rec && (p.z_in || p.z_in_c8))  // recurrent current: stride-1 conv of the previous spikes at output resolution
-    conv_accumulate<1, false>(acc, p.z_in, p.z_in_c8, p.w_rec, b, p.C, Ho, Wo, co0, p.C, oy0, ox0, s_x, s_w, s_abs);
+  conv_accumulate<STRIDE, TRACE>(acc, p.x, p.x_cl, p.w_ff, b, p.Cin, p.H, p.W, co0, p.C, oy0, ox0, s_x, s_w, s_abs);
+  if (p.w_rec && (p.z_in || p.z_in_cl))  // recurrent current: stride-1 conv of the previous spikes at output resolution
+    conv_accumulate<1, false>(acc, p.z_in, p.z_in_cl, p.w_rec, b, p.C, Ho, Wo, co0, p.C, oy0, ox0, s_x, s_w, s_abs);
   __syncthreads();
 
   const size_t plane = (size_t)Ho * Wo;
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(NTHREADS) lif_conv_fwd_kernel(const ef_lif_con
         const float v = p.v_in ? p.v_in[o] : 0.f;
         float z = 0.f;
         if (p.z_in) z = p.z_in[o];
-        else if (p.z_in_c8) z = ld_act(nullptr, p.z_in_c8, b, c, oy, ox, p.C, Ho, Wo);
+        else if (p.z_in_cl) z = ld_act(nullptr, p.z_in_cl, b, c, oy, ox, p.C, Ho, Wo);
         const float aux = p.aux_in ? p.aux_in[o] : 0.f;
         float vo, ao, thr;
         neuron_update<NEURON, HARD>(acc[half][co], v, z, aux, P, s_k[co], vo, zo, ao, thr);
@@ -162,14 +162,14 @@ __global__ void __launch_bounds__(NTHREADS) lif_conv_fwd_kernel(const ef_lif_con
         opk[co >> 1] = pack_bf16x2(oo, 0.f) & 0xffffu;
       }
     }
-    // channel-blocked bf16 outputs: 16 B per (pixel, 8-channel group)
+    // channels-last bf16 outputs: 16 B per (pixel, 8-channel group)
 #pragma unroll
     for (int g = 0; g < COB / 8; ++g) {
       const int cg = (co0 >> 3) + g;
       if (cg * 8 >= p.C) break;
-      const size_t o8 = ((((size_t)b * (p.C >> 3) + cg) * Ho + oy) * Wo + ox) * 8;
-      if (p.z_out_c8) *reinterpret_cast<uint4*>(p.z_out_c8 + o8) = make_uint4(zpk[4 * g], zpk[4 * g + 1], zpk[4 * g + 2], zpk[4 * g + 3]);
-      if (p.out_c8) *reinterpret_cast<uint4*>(p.out_c8 + o8) = make_uint4(opk[4 * g], opk[4 * g + 1], opk[4 * g + 2], opk[4 * g + 3]);
+      const size_t o8 = (((size_t)b * Ho + oy) * Wo + ox) * p.C + cg * 8;
+      if (p.z_out_cl) *reinterpret_cast<uint4*>(p.z_out_cl + o8) = make_uint4(zpk[4 * g], zpk[4 * g + 1], zpk[4 * g + 2], zpk[4 * g + 3]);
+      if (p.out_cl) *reinterpret_cast<uint4*>(p.out_cl + o8) = make_uint4(opk[4 * g], opk[4 * g + 1], opk[4 * g + 2], opk[4 * g + 3]);
     }
   }
 }
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(NTHREADS) lif_conv_fwd_kernel(const ef_lif_con
 // ---------------------------------------------------------------------------------------------------------------
 // Head layer of the fast path: few input channels (event counts / voxel bins, Cin <= 8, fractional values allowed),
 // 32 output channels, LIF.  One thread = one pixel x 32 channels; 32 x 8 pixel tile so that every fp32 NCHW access of a
-// warp is one 128-byte line.  Writes the membrane fp32 NCHW and the spikes in c8 for the tensor-core layers.
+// warp is one 128-byte line.  Writes the membrane fp32 NCHW and the spikes in cl for the tensor-core layers.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int HD_TW = 32, HD_TH = 2, HD_THREADS = 64, HD_MAXC = 8;
 
@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(HD_THREADS) lif_head_fwd_kernel(const ef_lif_c
     for (int c = 0; c < 32; ++c) vin[c] = (inb && p.v_in) ? __ldg(p.v_in + ((size_t)b * 32 + c) * plane + pix) : 0.f;
 #pragma unroll
     for (int g = 0; g < 4; ++g)
-      zq[g] = (inb && p.z_in_c8) ? __ldg(reinterpret_cast<const uint4*>(p.z_in_c8 + (((size_t)b * 4 + g) * plane + pix) * 8)) : make_uint4(0, 0, 0, 0);
+      zq[g] = (inb && p.z_in_cl) ? __ldg(reinterpret_cast<const uint4*>(p.z_in_cl + ((size_t)b * plane + pix) * 32 + g * 8)) : make_uint4(0, 0, 0, 0);
     __syncthreads();
     float acc[32];
 #pragma unroll
@@ -254,13 +254,13 @@ __global__ void __launch_bounds__(HD_THREADS) lif_head_fwd_kernel(const ef_lif_c
     }
 #pragma unroll
     for (int g = 0; g < 4; ++g)
-      *reinterpret_cast<uint4*>(p.z_out_c8 + (((size_t)b * 4 + g) * plane + pix) * 8) = make_uint4(zpk[4 * g], zpk[4 * g + 1], zpk[4 * g + 2], zpk[4 * g + 3]);
+      *reinterpret_cast<uint4*>(p.z_out_cl + ((size_t)b * plane + pix) * 32 + g * 8) = make_uint4(zpk[4 * g], zpk[4 * g + 1], zpk[4 * g + 2], zpk[4 * g + 3]);
   }
 }
 
 static bool head_eligible(const ef_lif_conv_params& p) {
-  return p.neuron == EF_LIF && p.C == 32 && p.Cin <= HD_MAXC && p.stride == 1 && p.x && !p.x_c8 && !p.w_rec && !p.z_in && !p.residual && !p.out &&
-         !p.z_out && !p.out_c8 && p.z_out_c8 && (!p.v_in == !p.z_in_c8);
+  return p.neuron == EF_LIF && p.C == 32 && p.Cin <= HD_MAXC && p.stride == 1 && p.x && !p.x_cl && !p.w_rec && !p.z_in && !p.residual && !p.out &&
+         !p.z_out && !p.out_cl && p.z_out_cl && (!p.v_in == !p.z_in_cl);
 }
 
 static int launch_head(const ef_lif_conv_params& p, cudaStream_t st) {
@@ -317,9 +317,9 @@ int validate_lif_conv(const ef_lif_conv_params& p, const char* who) {
   EF_REQUIRE(p.ksize == 3, EF_EUNSUPPORTED, "%s: kernel_size %d not supported (3 only)", who, p.ksize);
   EF_REQUIRE(p.stride == 1 || p.stride == 2, EF_EUNSUPPORTED, "%s: stride %d not supported", who, p.stride);
   EF_REQUIRE(p.neuron >= EF_LIF && p.neuron <= EF_XLIF, EF_EINVAL, "%s: bad neuron kind %d", who, p.neuron);
-  EF_REQUIRE(p.x || p.x_c8, EF_ENULL, "%s: x is NULL", who);
-  EF_REQUIRE(!p.x_c8 || p.Cin % 8 == 0, EF_EINVAL, "%s: c8 input needs Cin %% 8 == 0", who);
-  EF_REQUIRE(!(p.z_in_c8 || p.z_out_c8 || p.out_c8) || p.C % 8 == 0, EF_EINVAL, "%s: c8 spikes need C %% 8 == 0", who);
+  EF_REQUIRE(p.x || p.x_cl, EF_ENULL, "%s: x is NULL", who);
+  EF_REQUIRE(!p.x_cl || p.Cin % 8 == 0, EF_EINVAL, "%s: cl input needs Cin %% 8 == 0", who);
+  EF_REQUIRE(!(p.z_in_cl || p.z_out_cl || p.out_cl) || p.C % 8 == 0, EF_EINVAL, "%s: cl spikes need C %% 8 == 0", who);
   EF_REQUIRE(p.w_ff && p.leak && p.v_out, EF_ENULL, "%s: w_ff / leak / v_out is NULL", who);
   if (p.neuron == EF_LIF || p.neuron == EF_PLIF) EF_REQUIRE(p.thresh, EF_ENULL, "%s: thresh is NULL", who);
   if (p.neuron != EF_LIF) EF_REQUIRE(p.leak_aux, EF_ENULL, "%s: leak_pt / leak_t is NULL", who);

@@ -1,14 +1,16 @@
 // Fused conv3x3 + LIF step on the 5th-generation tensor cores (tcgen05 / TMEM / TMA), sm_100a only.
 //
-// Implicit GEMM per 16x8-pixel tile:  D[128 px, 32 ch] = sum over 9 taps, 32 (or 64 with the recurrent conv) input channels
-//   A = bf16 spikes, read tap-shifted straight out of ONE halo tile in shared memory (no im2col copy): the halo tile is
-//       stored channel-group-major [4 groups][18 x 10 px][8 ch] (exactly the c8 global layout, brought in by one TMA box
-//       with hardware zero-fill = the conv padding), which is the canonical K-major no-swizzle UMMA layout with
-//       core-matrix stride (SBO) = one halo row and K-chunk stride (LBO) = one channel group;
+// Implicit GEMM per 16x8-pixel tile:  D[128 px, 96] = sum over 9 taps, 32 (or 64 with the recurrent conv) input channels
+//   A = bf16 spikes, channels-last.  Three TMA boxes per tile (x offsets -1, 0, +1; 18 rows x 8 px x 32 ch each, hardware
+//       zero-fill = the conv padding) land in shared memory in the canonical 64-byte-swizzled K-major UMMA layout: one
+//       pixel = one 64-byte row, one tile row (8 px) = one 512-byte swizzle atom.  A tap (dy, dx) is then just a
+//       descriptor start address: copy dx, plus dy atoms -- no im2col copy, every start stays atom-aligned;
 //   B = weights, split into three bf16 terms hi+mid+lo == w (exact), resident in shared memory for the whole kernel and
 //       stacked along N: one MMA per (tap, k-step) with N = 96 = {hi, mid, lo} x 32 channels, so the A tile is read from
-//       shared memory once instead of three times (N = 32 MMAs are shared-memory-bandwidth bound: 5 KB per 16-cycle MMA);
+//       shared memory once instead of three times; same swizzled K-major layout (written by ef_split_weights);
 //   D = fp32 accumulator in tensor memory, 96 columns (three partial sums, added in the epilogue), double buffered.
+// (A first version read tap-shifted windows of ONE un-swizzled halo tile; measured ~200 cycles per MMA, 3.6x the
+//  swizzled rate -- profiles/r01_tc_timeline.txt.)
 // Spikes are {0,1,2}: exactly representable in bf16, so every product is exact and only the fp32 summation order differs
 // from the CPU path (no TF32/BF16 rounding may enter a spiking conv).
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2-9 = epilogue: each warp owns a
@@ -26,12 +28,14 @@
 namespace ef {
 
 constexpr int TC_TH = 16, TC_TW = 8;                  // output tile (rows x cols) = 128 GEMM rows
-constexpr int TC_HH = TC_TH + 2, TC_HW = TC_TW + 2;   // halo tile
-constexpr int A_GROUP_BYTES = TC_HH * TC_HW * 16;     // one 8-channel group of the halo tile (2880 B)
-constexpr int A_TILE_BYTES = 4 * A_GROUP_BYTES;       // 11520 B
-constexpr int Z_TILE_BYTES = 4 * 128 * 16;            // centre spikes, c8: 8192 B
-constexpr int W_BLOCK_BYTES = 96 * 16 * 2;            // one (tap, k-step) weight block [96 n = 3 splits x 32 ch][16 k] bf16
-constexpr int W_CONV_BYTES = 9 * 2 * W_BLOCK_BYTES;   // 55296 B per convolution
+constexpr int TC_HH = TC_TH + 2;                      // rows of an operand copy (halo above and below)
+constexpr int PIX_BYTES = 64;                         // 32 channels bf16 = one K-major row
+constexpr int ATOM_BYTES = 8 * PIX_BYTES;             // one tile row = one 64B-swizzle atom (8 rows x 64 B)
+constexpr int COPY_BYTES = TC_HH * ATOM_BYTES;        // one x-shifted operand copy: 9216 B
+constexpr int A_TILE_BYTES = 3 * COPY_BYTES;          // dx = -1, 0, +1: 27648 B
+constexpr int Z_TILE_BYTES = 128 * PIX_BYTES;         // centre spikes (not swizzled): 8192 B
+constexpr int W_BLOCK_BYTES = 96 * PIX_BYTES;         // one tap: [96 n = 3 splits x 32 ch][32 k] bf16, 64B-swizzled: 6144 B
+constexpr int W_CONV_BYTES = 9 * W_BLOCK_BYTES;       // 55296 B per convolution
 constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_THREADS = 32 * (2 + TC_EPI_WARPS);
 constexpr int ACC_COLS = 96;                          // fp32 accumulator columns per tile
@@ -43,7 +47,7 @@ struct TcSmemLayout {
 
 __host__ __device__ inline TcSmemLayout tc_smem_layout(bool rec) {
   TcSmemLayout l;
-  l.nstage = 4;
+  l.nstage = rec ? 2 : 4;
   l.w_off = 0;
   const int wbytes = rec ? 2 * W_CONV_BYTES : W_CONV_BYTES;
   l.x_off = 0;
@@ -52,7 +56,7 @@ __host__ __device__ inline TcSmemLayout tc_smem_layout(bool rec) {
   l.stage_off = wbytes;
   l.outz_off = l.stage_off + l.nstage * l.stage_bytes;      // z_out staging
   l.bar_off = l.outz_off + Z_TILE_BYTES;
-  l.total = l.bar_off + 256;
+  l.total = l.bar_off + 256 + 1024;  // + slack to align the carve-up to 1024 B at run time
   return l;
 }
 
@@ -141,10 +145,11 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
-// K-major, no-swizzle shared-memory matrix descriptor: 8 rows x 16 B core matrices; SBO between 8-row groups, LBO between
-// the two 16-byte K chunks of one K=16 MMA.  (cute/arch/mma_sm100_desc.hpp: version 1 at bit 46, layout type 0 at bit 61.)
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+// K-major, 64-byte-swizzled shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp): rows of 64 B, 8-row atoms of
+// 512 B (SBO between atoms), 16-byte chunks XOR-swizzled by address bits [7:8]; version 1 at bit 46, layout type 4
+// (SWIZZLE_64B) at bits 61-63; LBO is not used by swizzled K-major layouts (canonical value 1).
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(ATOM_BYTES >> 4) << 32) | (1ull << 46) | (4ull << 61);
 }
 // kind::f16 instruction descriptor: D = F32, A = B = BF16, both K-major, N = 96, M = 128.
 constexpr uint32_t UMMA_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((96u >> 3) << 17) | ((128u >> 4) << 24);
@@ -178,7 +183,8 @@ template <bool HARD>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_zh,
                        const __grid_constant__ CUtensorMap map_zc, const __grid_constant__ CUtensorMap map_zout) {
-  extern __shared__ __align__(1024) uint8_t smem[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // swizzle atoms need an aligned carve-up
   const bool rec = p.has_rec != 0;
   const TcSmemLayout L = tc_smem_layout(rec);
   const int NST = L.nstage;
@@ -233,10 +239,15 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
         mbar_wait(bar_empty(s), ph ^ 1);
         const uint32_t st = s_base + L.stage_off + s * L.stage_bytes;
         mbar_expect_tx(bar_full(s), stage_tx);
-        tma_load_5d(st + L.x_off, &map_x, bar_full(s), 0, x0 - 1, y0 - 1, 0, b);
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) tma_load_4d(st + L.x_off + dx * COPY_BYTES, &map_x, bar_full(s), 0, x0 + dx - 1, y0 - 1, b);
         if (p.has_z) {
-          if (rec) tma_load_5d(st + L.z_off, &map_zh, bar_full(s), 0, x0 - 1, y0 - 1, 0, b);
-          else tma_load_5d(st + L.z_off, &map_zc, bar_full(s), 0, x0, y0, 0, b);
+          if (rec) {
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) tma_load_4d(st + L.z_off + dx * COPY_BYTES, &map_zh, bar_full(s), 0, x0 + dx - 1, y0 - 1, b);
+          } else {
+            tma_load_4d(st + L.z_off, &map_zc, bar_full(s), 0, x0, y0, b);
+          }
         }
         EF_TRACE(it, 0);
       }
@@ -264,8 +275,8 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
             const int dy = tap / 3, dx = tap % 3;
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) {
-              const uint64_t adesc = umma_desc(a_tile + (dy * TC_HW + dx) * 16 + ks * 2 * A_GROUP_BYTES, A_GROUP_BYTES, TC_HW * 16);
-              const uint64_t bdesc = umma_desc(w_conv + (tap * 2 + ks) * W_BLOCK_BYTES, 96 * 16, 128);
+              const uint64_t adesc = umma_desc_sw64(a_tile + dx * COPY_BYTES + dy * ATOM_BYTES + ks * 32);
+              const uint64_t bdesc = umma_desc_sw64(w_conv + tap * W_BLOCK_BYTES + ks * 32);
               umma_bf16(d_tmem, adesc, bdesc, acc);
               acc = 1;
             }
@@ -329,8 +340,9 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
       for (int g = 0; g < 2; ++g) {
         const int gg = 2 * hsel + g;
         if (!p.has_z) zq[g] = make_uint4(0, 0, 0, 0);
-        else if (rec) zq[g] = *reinterpret_cast<const uint4*>(st + L.z_off + gg * A_GROUP_BYTES + ((ph_ + 1) * TC_HW + pw_ + 1) * 16);
-        else zq[g] = *reinterpret_cast<const uint4*>(st + L.z_off + (gg * 128 + m) * 16);
+        else if (rec)  // centre of the dx = 0 copy (swizzled: 16-byte chunk index XOR ((pixel-in-row >> 1) & 3))
+          zq[g] = *reinterpret_cast<const uint4*>(st + L.z_off + COPY_BYTES + (ph_ + 1) * ATOM_BYTES + pw_ * PIX_BYTES + ((gg ^ ((pw_ >> 1) & 3)) << 4));
+        else zq[g] = *reinterpret_cast<const uint4*>(st + L.z_off + m * PIX_BYTES + gg * 16);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_empty(s));  // done reading this stage
@@ -371,13 +383,13 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
         named_bar_sync(1, 32 * TC_EPI_WARPS);
       }
 #pragma unroll
-      for (int g = 0; g < 2; ++g) zout_s[(2 * hsel + g) * 128 + m] = make_uint4(zpk[4 * g], zpk[4 * g + 1], zpk[4 * g + 2], zpk[4 * g + 3]);
+      for (int g = 0; g < 2; ++g) zout_s[m * 4 + 2 * hsel + g] = make_uint4(zpk[4 * g], zpk[4 * g + 1], zpk[4 * g + 2], zpk[4 * g + 3]);
 #pragma unroll
       for (int j = 0; j < 16; ++j) vin[j] = vnext[j];
       fence_proxy_async();  // make the staged spikes visible to the TMA engine
       named_bar_sync(1, 32 * TC_EPI_WARPS);
       if (store_thread) {
-        tma_store_5d(&map_zout, smem_u32(zout_s), 0, x0, y0, 0, b);
+        tma_store_4d(&map_zout, smem_u32(zout_s), 0, x0, y0, b);
         bulk_commit();
         EF_TRACE(it, 6);
       }
@@ -397,8 +409,8 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
 }
 
 // ---- weight split kernel --------------------------------------------------------------------------------------------
-// out block index (conv*9 + tap)*2 + ks ; inside a block, row n' = split*32 + n, element (n', k) at (k/8)*768 + (n'/8)*64 + (n'%8)*8 + k%8
-// (uint16 units): K-major no-swizzle core matrices, SBO = 128 B between 8-row groups, LBO = 1536 B between the two K chunks
+// out block index conv*9 + tap; inside a block row n' = split*32 + n holds K = 32 input channels (64 B); 8-row atoms of
+// 512 B; the 16-byte chunk k/8 of row r = n'%8 is stored at chunk (k/8) ^ ((r >> 1) & 3)  (64-byte swizzle)
 __global__ void split_weights_kernel(const float* __restrict__ w_ff, const float* __restrict__ w_rec, uint16_t* __restrict__ out, int nconv) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;  // over nconv * 32 (n) * 32 (ci) * 9 (tap)
   if (i >= nconv * 32 * 32 * 9) return;
@@ -410,11 +422,11 @@ __global__ void split_weights_kernel(const float* __restrict__ w_ff, const float
   const float r2 = r1 - __bfloat162float(mid);
   const __nv_bfloat16 lo = __float2bfloat16_rn(r2);
   const __nv_bfloat16 parts[3] = {hi, mid, lo};
-  const int ks = ci >> 4, k = ci & 15;
-  const size_t blk = ((size_t)cv * 9 + tap) * 2 + ks;
+  const size_t blk = (size_t)cv * 9 + tap;
   for (int sp = 0; sp < 3; ++sp) {
-    const int nn = sp * 32 + n;
-    out[blk * 1536 + (k >> 3) * 768 + (nn >> 3) * 64 + (nn & 7) * 8 + (k & 7)] = *reinterpret_cast<const uint16_t*>(&parts[sp]);
+    const int nn = sp * 32 + n, r = nn & 7;
+    const int chunk = (ci >> 3) ^ ((r >> 1) & 3);
+    out[blk * (W_BLOCK_BYTES / 2) + (nn >> 3) * 256 + r * 32 + chunk * 8 + (ci & 7)] = *reinterpret_cast<const uint16_t*>(&parts[sp]);
   }
 }
 
@@ -445,7 +457,7 @@ struct MapKeyHash {
   }
 };
 
-// kind 0: c8 halo box (18x10), 1: c8 centre box (16x8)
+// kind 0: operand copy box (32 ch x 8 px x 18 rows, 64B swizzle); kind 1: centre box (32 ch x 8 px x 16 rows, no swizzle)
 static int get_map(const void* ptr, int B, int H, int W, int kind, CUtensorMap* out) {
   static thread_local std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
   const MapKey key{ptr, B, H, W, kind};
@@ -458,12 +470,13 @@ static int get_map(const void* ptr, int B, int H, int W, int kind, CUtensorMap* 
   if (!enc) return fail(EF_EUNSUPPORTED, "cuTensorMapEncodeTiled is not available from this driver");
   CUresult r;
   {
-    const cuuint64_t dims[5] = {8, (cuuint64_t)W, (cuuint64_t)H, 4, (cuuint64_t)B};
-    const cuuint64_t strides[4] = {16, (cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)4 * H * W * 16};
-    const cuuint32_t box[5] = {8, (cuuint32_t)(kind == 0 ? TC_HW : TC_TW), (cuuint32_t)(kind == 0 ? TC_HH : TC_TH), 4, 1};
-    const cuuint32_t es[5] = {1, 1, 1, 1, 1};
-    r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    const cuuint64_t dims[4] = {32, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    const cuuint64_t strides[3] = {PIX_BYTES, (cuuint64_t)W * PIX_BYTES, (cuuint64_t)H * W * PIX_BYTES};
+    const cuuint32_t box[4] = {32, TC_TW, (cuuint32_t)(kind == 0 ? TC_HH : TC_TH), 1};
+    const cuuint32_t es[4] = {1, 1, 1, 1};
+    r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            kind == 0 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   }
   if (r != CUDA_SUCCESS) return fail(EF_EINVAL, "cuTensorMapEncodeTiled failed (CUresult %d) for kind %d, B=%d H=%d W=%d ptr=%p", (int)r, kind, B, H, W, ptr);
   if (cache.size() > 4096) cache.clear();
@@ -474,9 +487,9 @@ static int get_map(const void* ptr, int B, int H, int W, int kind, CUtensorMap* 
 static long long* g_tc_trace = nullptr;  // set through ef_debug_tc_trace (tools/tc_timeline.py)
 
 bool lif_conv_tc_eligible(const ef_lif_conv_params& p) {
-  return p.w_split && p.x_c8 && p.z_out_c8 && p.Cin == 32 && p.C == 32 && p.ksize == 3 && p.stride == 1 && p.neuron == EF_LIF &&
-         !p.residual && !p.out && !p.z_out && !p.out_c8 && (!p.v_in == !p.z_in_c8) && !p.z_in && !p.x && ((uintptr_t)p.x_c8 % 16 == 0) &&
-         ((uintptr_t)p.z_out_c8 % 16 == 0) && p.v_in != p.v_out;
+  return p.w_split && p.x_cl && p.z_out_cl && p.Cin == 32 && p.C == 32 && p.ksize == 3 && p.stride == 1 && p.neuron == EF_LIF &&
+         !p.residual && !p.out && !p.z_out && !p.out_cl && (!p.v_in == !p.z_in_cl) && !p.z_in && !p.x && ((uintptr_t)p.x_cl % 16 == 0) &&
+         ((uintptr_t)p.z_out_cl % 16 == 0) && p.v_in != p.v_out;
 }
 
 int lif_conv_fwd_tc(const ef_lif_conv_params& p, cudaStream_t st) {
@@ -490,16 +503,16 @@ int lif_conv_fwd_tc(const ef_lif_conv_params& p, cudaStream_t st) {
   TcParams q;
   q.B = p.B, q.H = p.H, q.W = p.W;
   q.tiles_x = cdiv(p.W, TC_TW), q.tiles_y = cdiv(p.H, TC_TH), q.n_tiles = p.B * q.tiles_x * q.tiles_y;
-  q.has_rec = rec, q.has_v = p.v_in != nullptr, q.has_z = p.z_in_c8 != nullptr, q.hard_reset = p.hard_reset;
+  q.has_rec = rec, q.has_v = p.v_in != nullptr, q.has_z = p.z_in_cl != nullptr, q.hard_reset = p.hard_reset;
   q.w_split = p.w_split, q.leak = p.leak, q.thresh = p.thresh, q.v_in = p.v_in, q.v_out = p.v_out;
   q.trace = g_tc_trace;
   CUtensorMap mx, mzh, mzc, mzo;
   int rc;
-  if ((rc = get_map(p.x_c8, p.B, p.H, p.W, 0, &mx))) return rc;
-  if ((rc = get_map(p.z_out_c8, p.B, p.H, p.W, 1, &mzo))) return rc;
+  if ((rc = get_map(p.x_cl, p.B, p.H, p.W, 0, &mx))) return rc;
+  if ((rc = get_map(p.z_out_cl, p.B, p.H, p.W, 1, &mzo))) return rc;
   mzh = mx, mzc = mzo;  // placeholders when there is no previous state
   if (q.has_z) {
-    if ((rc = get_map(p.z_in_c8, p.B, p.H, p.W, rec ? 0 : 1, rec ? &mzh : &mzc))) return rc;
+    if ((rc = get_map(p.z_in_cl, p.B, p.H, p.W, rec ? 0 : 1, rec ? &mzh : &mzc))) return rc;
   }
   const TcSmemLayout L = tc_smem_layout(rec);
   const int grid = q.n_tiles < n_sms ? q.n_tiles : n_sms;

@@ -8,7 +8,7 @@ constexpr int PRED_MAX_CIN = 64, PRED_MAX_COUT = 4;
 
 __device__ __forceinline__ float ld_x(const ef_pred_params& p, int b, int c, size_t pix, size_t hw) {
   if (p.x) return p.x[((size_t)b * p.Cin + c) * hw + pix];
-  const uint16_t u = p.x_c8[(((size_t)b * (p.Cin >> 3) + (c >> 3)) * hw + pix) * 8 + (c & 7)];
+  const uint16_t u = p.x_cl[((size_t)b * hw + pix) * p.Cin + c];
   return __uint_as_float(((uint32_t)u) << 16);
 }
 
@@ -107,8 +107,8 @@ __global__ void __launch_bounds__(256) pred_bwd_kernel(const ef_pred_params p) {
 static int validate_pred(const ef_pred_params& p, const char* who) {
   EF_REQUIRE(p.B > 0 && p.Cin > 0 && p.Cout > 0 && p.H > 0 && p.W > 0, EF_EINVAL, "%s: bad dimensions", who);
   EF_REQUIRE(p.Cin <= PRED_MAX_CIN && p.Cout <= PRED_MAX_COUT, EF_EUNSUPPORTED, "%s: Cin <= %d, Cout <= %d", who, PRED_MAX_CIN, PRED_MAX_COUT);
-  EF_REQUIRE((p.x || p.x_c8) && p.w && p.b && p.y, EF_ENULL, "%s: NULL tensor", who);
-  EF_REQUIRE(!p.x_c8 || p.Cin % 8 == 0, EF_EINVAL, "%s: c8 input needs Cin %% 8 == 0", who);
+  EF_REQUIRE((p.x || p.x_cl) && p.w && p.b && p.y, EF_ENULL, "%s: NULL tensor", who);
+  EF_REQUIRE(!p.x_cl || p.Cin % 8 == 0, EF_EINVAL, "%s: cl input needs Cin %% 8 == 0", who);
   return EF_OK;
 }
 

@@ -1,7 +1,7 @@
 """
 Fast path of the spiking FireNet chain (models/model.py:254-265) on the internal formats.
 
-Between the cells, spikes never exist as fp32 NCHW tensors: every cell writes bf16 channel-blocked spikes ("c8") that the
+Between the cells, spikes never exist as fp32 NCHW tensors: every cell writes bf16 channels-last spikes ("cl") that the
 next cell's tcgen05 kernel consumes through TMA; membrane potentials stay fp32 NCHW (the reference's state format).  One
 torch.autograd node per MODEL step (instead of ~100 per step in the reference) carries the BPTT: the per-layer state
 gradients travel from step t+1 to step t in a side structure (`_Carry`), the autograd graph only orders the steps through
@@ -32,7 +32,7 @@ class _Carry:
 
 
 class _Slot:
-    """Activations of one model step: membrane fp32 [B,32,H,W] and spikes bf16 [B,4,H,W,8] of the 7 layers, one allocation."""
+    """Activations of one model step: membrane fp32 [B,32,H,W] and spikes bf16 [B,H,W,32] of the 7 layers, one allocation."""
 
     def __init__(self, B, H, W, dev):
         nv, nz = B * 32 * H * W * 4, B * 32 * H * W * 2
@@ -43,7 +43,7 @@ class _Slot:
             self.v.append(self.slab[o:o + nv].view(torch.float32).view(B, 32, H, W))
             o += nv
         for _ in range(N_L):
-            self.z.append(self.slab[o:o + nz].view(torch.bfloat16).view(B, 4, H, W, 8))
+            self.z.append(self.slab[o:o + nz].view(torch.bfloat16).view(B, H, W, 32))
             o += nz
         self.flow = torch.empty((B, 2, H, W), device=dev, dtype=torch.float32)
         self.x_in = None   # static copy of the model input (graph replay reads a fixed address)
@@ -84,7 +84,7 @@ class FastState:
 
     def __init__(self, n):
         self.v = [None] * n        # fp32 [B,C,H,W]
-        self.z = [None] * n        # bf16 [B,C/8,H,W,8]
+        self.z = [None] * n        # bf16 channels-last [B,H,W,C]
         self.token = None          # scalar autograd token ordering the steps of one BPTT window
         self.carry = _Carry()
         self.step = 0              # index of the next step inside the current window
@@ -149,12 +149,12 @@ def _params_of(model):
     return ps
 
 
-def _fill_fwd(p, B, Cin, H, W, cell, x_f32, x_c8, v_in, z_in, v_out, leak, thresh):
+def _fill_fwd(p, B, Cin, H, W, cell, x_f32, x_cl, v_in, z_in, v_out, leak, thresh):
     p.B, p.Cin, p.C, p.H, p.W = B, Cin, 32, H, W
     p.ksize, p.stride, p.neuron, p.hard_reset = 3, 1, L.EF_LIF, int(cell.hard_reset)
     p.surrogate, p.act_width = L.SURROGATE_CODES[cell.activation], float(cell._act_width_f)
-    p.x, p.x_c8 = L.ptr(x_f32), L.ptr(x_c8)
-    p.v_in, p.z_in_c8 = L.ptr(v_in), L.ptr(z_in)
+    p.x, p.x_cl = L.ptr(x_f32), L.ptr(x_cl)
+    p.v_in, p.z_in_cl = L.ptr(v_in), L.ptr(z_in)
     p.w_ff = L.ptr(cell.ff.weight)
     p.w_rec = L.ptr(cell.rec.weight) if cell.recurrent else None
     p.leak, p.thresh = L.ptr(leak), L.ptr(thresh)
@@ -169,7 +169,7 @@ def _launch_step(model, x, v_in, z_in, slot, splits, B, Cin0, H, W):
         leak, thresh = cell.leak.detach().reshape(-1), cell.thresh.detach().reshape(-1)
         p = L.LifConvParams()
         _fill_fwd(p, B, Cin0 if i == 0 else 32, H, W, cell, x if i == 0 else None, h, v_in[i], z_in[i], slot.v[i], leak, thresh)
-        p.z_out_c8 = L.ptr(slot.z[i])
+        p.z_out_cl = L.ptr(slot.z[i])
         if i > 0:
             p.w_split = L.ptr(splits[name])
         L.call("ef_lif_conv_fwd", p, tag=(p.Cin, 32, cell.recurrent))
@@ -177,7 +177,7 @@ def _launch_step(model, x, v_in, z_in, slot, splits, B, Cin0, H, W):
     w, b = model.pred.conv2d.weight.detach(), model.pred.conv2d.bias.detach()
     pp = L.PredParams()
     pp.B, pp.Cin, pp.Cout, pp.H, pp.W = B, 32, 2, H, W
-    pp.x_c8, pp.w, pp.b, pp.y = L.ptr(h), L.ptr(w), L.ptr(b), L.ptr(slot.flow)
+    pp.x_cl, pp.w, pp.b, pp.y = L.ptr(h), L.ptr(w), L.ptr(b), L.ptr(slot.flow)
     L.call("ef_pred_fwd", pp)
 
 
@@ -227,9 +227,9 @@ class _FireNetStep(torch.autograd.Function):
         for i, name in enumerate(LAYERS):
             saved.append((x_used if i == 0 else None, slot.z[i - 1] if i > 0 else None, v_in[i], z_in[i], slot.v[i]))
             if cap is not None:  # test hook: what this layer consumed and produced, in the reference's tensor format
-                xin = x if i == 0 else ops.unpack_c8(slot.z[i - 1])
-                sin = None if v_in[i] is None else torch.stack([v_in[i], ops.unpack_c8(z_in[i])]).cpu()
-                zo = ops.unpack_c8(slot.z[i])
+                xin = x if i == 0 else ops.unpack_cl(slot.z[i - 1])
+                sin = None if v_in[i] is None else torch.stack([v_in[i], ops.unpack_cl(z_in[i])]).cpu()
+                zo = ops.unpack_cl(slot.z[i])
                 cap[name] = (xin.detach().cpu(), sin, zo.cpu(), torch.stack([slot.v[i], zo]).cpu())
             fs.v[i], fs.z[i] = slot.v[i], slot.z[i]
         flow = slot.flow.clone()  # the caller may keep the flow for as long as it likes; the slot is recycled
@@ -269,17 +269,17 @@ class _FireNetStep(torch.autograd.Function):
         w, b = model.pred.conv2d.weight.detach(), model.pred.conv2d.bias.detach()
         if g_flow is None:
             g_flow = torch.zeros_like(ctx.flow)
-        pp.x_c8, pp.w, pp.b, pp.y, pp.g_y = L.ptr(z7), L.ptr(w), L.ptr(b), L.ptr(ctx.flow), L.ptr(g_flow.contiguous())
+        pp.x_cl, pp.w, pp.b, pp.y, pp.g_y = L.ptr(z7), L.ptr(w), L.ptr(b), L.ptr(ctx.flow), L.ptr(g_flow.contiguous())
         pp.g_x, pp.g_w, pp.g_b = L.ptr(g_h), L.ptr(grads[gi]), L.ptr(grads[gi + 1])
         L.call("ef_pred_bwd", pp)
         # cells, last to first
         for i in reversed(range(len(LAYERS))):
             cell = getattr(model, LAYERS[i])
-            x_f32, x_c8, v_in, z_in, v_out = ctx.saved[i]
+            x_f32, x_cl, v_in, z_in, v_out = ctx.saved[i]
             gi -= 4 if cell.recurrent else 3
             leak, thresh = cell.leak.detach().reshape(-1), cell.thresh.detach().reshape(-1)
             q = L.LifConvBwdParams()
-            _fill_fwd(q.f, B, Cin0 if i == 0 else 32, H, W, cell, x_f32, x_c8, v_in, z_in, v_out, leak, thresh)
+            _fill_fwd(q.f, B, Cin0 if i == 0 else 32, H, W, cell, x_f32, x_cl, v_in, z_in, v_out, leak, thresh)
             q.g_out, q.g_v_out, q.g_z_out = L.ptr(g_h), L.ptr(carry.g_v[i]), L.ptr(carry.g_z[i])
             q.scratch_gI = L.ptr(buf["scratch"])
             g_x = (buf["g_h"][1] if g_h is buf["g_h"][0] else buf["g_h"][0]) if i > 0 else None
@@ -316,7 +316,7 @@ def forward(model, x, log=False):
         for i, s in enumerate(model._states):  # states set through the reference-format API are converted once
             if s is not None:
                 fs.v[i] = s[0].detach().contiguous()
-                fs.z[i] = ops.pack_c8(s[1].detach())
+                fs.z[i] = ops.pack_cl(s[1].detach())
         model._fast = fs
     params = _params_of(model)
     need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
@@ -349,5 +349,5 @@ def states_of(model):
     fs = model._fast
     out = []
     for v, z in zip(fs.v, fs.z):
-        out.append(None if v is None else torch.stack([v, ops.unpack_c8(z)]))
+        out.append(None if v is None else torch.stack([v, ops.unpack_cl(z)]))
     return out

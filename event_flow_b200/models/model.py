@@ -60,7 +60,7 @@ class FireNet(BaseModel):
 
     @property
     def states(self):
-        if self._fast is not None:  # internal (c8 spike) state -> the reference's stacked fp32 format; fresh tensors = clones
+        if self._fast is not None:  # internal (cl spike) state -> the reference's stacked fp32 format; fresh tensors = clones
             return fast.states_of(self)
         return copy_states(self._states)
 

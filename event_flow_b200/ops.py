@@ -272,30 +272,30 @@ def encode_events(events, res, num_bins, *, round_ts=False, want=("cnt", "voxel"
     return out
 
 
-def pack_c8(x):
-    """fp32 NCHW -> bf16 channel-blocked [B,C/8,H,W,8] (internal spike format)."""
+def pack_cl(x):
+    """fp32 NCHW -> bf16 channels-last [B,H,W,C] (internal spike format)."""
     x = _c(x)
     _need_cuda(x)
     B, Cc, H, W = x.shape
-    out = torch.empty((B, Cc // 8, H, W, 8), device=x.device, dtype=torch.bfloat16)
+    out = torch.empty((B, H, W, Cc), device=x.device, dtype=torch.bfloat16)
     L.LAUNCHES += 1
-    L.check(L.lib().ef_pack_c8(L.ptr(x), L.ptr(out), B, Cc, H, W, L.stream()), "ef_pack_c8")
+    L.check(L.lib().ef_pack_cl(L.ptr(x), L.ptr(out), B, Cc, H, W, L.stream()), "ef_pack_cl")
     return out
 
 
-def unpack_c8(x):
-    """bf16 channel-blocked -> fp32 NCHW."""
+def unpack_cl(x):
+    """bf16 channels-last [B,H,W,C] -> fp32 NCHW."""
     x = _c(x)
     _need_cuda(x)
-    B, G, H, W, _ = x.shape
-    out = torch.empty((B, G * 8, H, W), device=x.device, dtype=torch.float32)
+    B, H, W, Cc = x.shape
+    out = torch.empty((B, Cc, H, W), device=x.device, dtype=torch.float32)
     L.LAUNCHES += 1
-    L.check(L.lib().ef_unpack_c8(L.ptr(x), L.ptr(out), B, G * 8, H, W, L.stream()), "ef_unpack_c8")
+    L.check(L.lib().ef_unpack_cl(L.ptr(x), L.ptr(out), B, Cc, H, W, L.stream()), "ef_unpack_cl")
     return out
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-# internal-format (c8 spikes) LIF step: the building block of the fast model path
+# internal-format (cl spikes) LIF step: the building block of the fast model path
 # ---------------------------------------------------------------------------------------------------------------------
 def split_weights(w_ff, w_rec=None, out=None):
     """fp32 conv weights -> three exact bf16 terms in the tcgen05 B-operand layout (uint16 tensor); `out` is refilled in place."""
@@ -312,29 +312,28 @@ def split_weights(w_ff, w_rec=None, out=None):
     return out
 
 
-def lif_step_c8(x_c8, v_in, z_in_c8, w_ff, w_rec, leak, thresh, *, hard_reset=True, w_split=None, x_f32=None):
+def lif_step_cl(x_cl, v_in, z_in_cl, w_ff, w_rec, leak, thresh, *, hard_reset=True, w_split=None, x_f32=None):
     """
-    One fused conv + LIF step on the internal formats: spikes bf16 [B,C/8,H,W,8], membrane fp32 NCHW.
+    One fused conv + LIF step on the internal formats: spikes bf16 channels-last [B,H,W,C], membrane fp32 NCHW.
     With `w_split` (ops.split_weights) and 32->32 channels the tcgen05 kernel runs, otherwise the CUDA-core kernel.
-    `x_f32` (fp32 NCHW) may replace x_c8 for the first layer.  Returns (v_out, z_out_c8).  No autograd.
+    `x_f32` (fp32 NCHW) may replace x_cl for the first layer.  Returns (v_out, z_out_cl).  No autograd.
     """
-    if x_c8 is not None:
-        B, G, H, W, _ = x_c8.shape
-        Cin = G * 8
+    if x_cl is not None:
+        B, H, W, Cin = x_cl.shape
     else:
         B, Cin, H, W = x_f32.shape
     C = w_ff.shape[0]
     dev = w_ff.device
     v_out = torch.empty((B, C, H, W), device=dev, dtype=torch.float32)
-    z_out = torch.empty((B, C // 8, H, W, 8), device=dev, dtype=torch.bfloat16)
+    z_out = torch.empty((B, H, W, C), device=dev, dtype=torch.bfloat16)
     p = L.LifConvParams()
     p.B, p.Cin, p.C, p.H, p.W = B, Cin, C, H, W
     p.ksize, p.stride, p.neuron, p.hard_reset = 3, 1, L.EF_LIF, int(hard_reset)
     p.surrogate, p.act_width = 0, 10.0
-    p.x, p.x_c8 = L.ptr(x_f32), L.ptr(x_c8)
-    p.v_in, p.z_in_c8 = L.ptr(v_in), L.ptr(z_in_c8)
+    p.x, p.x_cl = L.ptr(x_f32), L.ptr(x_cl)
+    p.v_in, p.z_in_cl = L.ptr(v_in), L.ptr(z_in_cl)
     p.w_ff, p.w_rec, p.w_split = L.ptr(w_ff), L.ptr(w_rec), L.ptr(w_split)
     p.leak, p.thresh = L.ptr(leak), L.ptr(thresh)
-    p.v_out, p.z_out_c8 = L.ptr(v_out), L.ptr(z_out)
+    p.v_out, p.z_out_cl = L.ptr(v_out), L.ptr(z_out)
     L.call("ef_lif_conv_fwd", p, tag=(Cin, C, w_rec is not None))
     return v_out, z_out

@@ -11,9 +11,9 @@
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); work is enqueued asynchronously;
  *   - returns 0 on success, <0 for an argument / shape error, >0 = the cudaError_t of a failed launch;
  *     ef_last_error() returns a thread-local message for the last non-zero return of the calling thread;
- *   - fp32 tensors are dense NCHW.  "c8" tensors are the internal spike format: bf16, channel-blocked
- *     [B, C/8, H, W, 8] (16 bytes = 8 channels of one pixel), exact for the values a spiking layer emits
- *     ({0,1}, or {0,1,2} with a residual);
+ *   - fp32 tensors are dense NCHW.  "cl" tensors are the internal spike format: bf16, channels-last [B, H, W, C]
+ *     (all channels of a pixel contiguous: the layout TMA boxes and tcgen05 K-major operands want), exact for the
+ *     values a spiking layer emits ({0,1}, or {0,1,2} with a residual); C must be a multiple of 8;
  *   - a NULL optional pointer means "absent" (zero state, no residual, output not wanted).
  */
 #ifndef EVENTFLOW_H_
@@ -51,7 +51,7 @@ uint64_t ef_launch_count(void);
  *   v_out  = LIF/PLIF/ALIF/XLIF update of (v_in, z_in, aux_in) with hard or soft reset
  *   z_out  = (v_out - thresh_t > 0);   out = z_out + residual
  *
- * Inputs may be given as fp32 NCHW or as c8 bf16; when BOTH x_c8 (and z_in_c8) are given, C == 32, Cin == 32,
+ * Inputs may be given as fp32 NCHW or as cl bf16; when BOTH x_cl (and z_in_cl) are given, C == 32, Cin == 32,
  * ksize == 3, stride == 1, the tcgen05 tensor-core kernel runs (3-way bf16 split of the weights, fp32-exact products);
  * otherwise the fp32 CUDA-core kernel runs.  Per-channel parameter arrays are the RAW parameters of the reference
  * module ([C] floats; sigmoid / clamp are applied inside, spiking_submodules.py:108-112).
@@ -63,11 +63,11 @@ typedef struct ef_lif_conv_params {
   int32_t surrogate;            /* EF_ARCTAN.. (backward only)                                                        */
   float act_width;              /* surrogate width (buffer act_width)                                                 */
   /* inputs */
-  const float* x;               /* [B,Cin,H,W] fp32, or NULL when x_c8 is given                                       */
-  const uint16_t* x_c8;         /* [B,Cin/8,H,W,8] bf16, or NULL                                                      */
+  const float* x;               /* [B,Cin,H,W] fp32, or NULL when x_cl is given                                       */
+  const uint16_t* x_cl;         /* [B,H,W,Cin] bf16, or NULL                                                          */
   const float* v_in;            /* [B,C,Ho,Wo] or NULL (zeros)                                                        */
   const float* z_in;            /* [B,C,Ho,Wo] fp32 previous spikes or NULL                                           */
-  const uint16_t* z_in_c8;      /* same in c8, or NULL                                                                */
+  const uint16_t* z_in_cl;      /* same in cl, or NULL                                                                */
   const float* aux_in;          /* third state (PLIF/XLIF trace pt, ALIF trace t) or NULL                             */
   const float* w_ff;            /* [C,Cin,k,k]                                                                        */
   const float* w_rec;           /* [C,C,k,k] or NULL (non-recurrent cell)                                             */
@@ -83,10 +83,10 @@ typedef struct ef_lif_conv_params {
   /* outputs (each optional except v_out) */
   float* v_out;                 /* [B,C,Ho,Wo]                                                                        */
   float* z_out;                 /* [B,C,Ho,Wo] fp32 spikes (state plane 1) or NULL                                    */
-  uint16_t* z_out_c8;           /* spikes in c8 or NULL                                                               */
+  uint16_t* z_out_cl;           /* spikes in cl or NULL                                                               */
   float* aux_out;               /* third state or NULL                                                                */
   float* out;                   /* z_out + residual, fp32, or NULL                                                    */
-  uint16_t* out_c8;             /* z_out + residual in c8 or NULL (only differs from z_out_c8 with a residual)        */
+  uint16_t* out_cl;             /* z_out + residual in cl or NULL (only differs from z_out_cl with a residual)        */
 } ef_lif_conv_params;
 
 int ef_lif_conv_fwd(const ef_lif_conv_params* p, void* stream);
@@ -98,7 +98,7 @@ int ef_lif_conv_fwd(const ef_lif_conv_params* p, void* stream);
  * scratch_gI: caller-provided [B,C,Ho,Wo] fp32 workspace (receives g_I = (1-leak) g_v).
  * scratch_gP: caller-provided [B,Ho,Wo] fp32 workspace, only needed for PLIF / XLIF cells when g_x is wanted (holds the
  * channel-summed gradient of the pre-synaptic trace input); may be NULL otherwise.
- * Inputs x / z_in may be given in either layout (fp32 NCHW or c8), gradients are fp32 NCHW.  Limits of this version: stride 1.
+ * Inputs x / z_in may be given in either layout (fp32 NCHW or cl), gradients are fp32 NCHW.  Limits of this version: stride 1.
  * ------------------------------------------------------------------------------------------------------------------ */
 typedef struct ef_lif_conv_bwd_params {
   ef_lif_conv_params f;         /* the forward call: its inputs and the v_out / aux_out it wrote (other outputs ignored) */
@@ -133,18 +133,18 @@ int ef_split_weights(const float* w_ff, const float* w_rec, int32_t Cin, int32_t
  * NULL switches it off (default).  Not part of the reference's interface. */
 int ef_debug_tc_trace(long long* buf);
 
-/* fp32 NCHW <-> c8 bf16 layout conversion at the API boundary (model.states getter/setter, first input). */
-int ef_pack_c8(const float* src, uint16_t* dst, int32_t B, int32_t C, int32_t H, int32_t W, void* stream);
-int ef_unpack_c8(const uint16_t* src, float* dst, int32_t B, int32_t C, int32_t H, int32_t W, void* stream);
+/* fp32 NCHW <-> cl bf16 layout conversion at the API boundary (model.states getter/setter, first input). */
+int ef_pack_cl(const float* src, uint16_t* dst, int32_t B, int32_t C, int32_t H, int32_t W, void* stream);
+int ef_unpack_cl(const uint16_t* src, float* dst, int32_t B, int32_t C, int32_t H, int32_t W, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Prediction head: flow = tanh(conv1x1(x, w) + b).  Replaces ConvLayer.forward, models/submodules.py:52-61 as built
- * at models/model.py:197-199 (32 -> 2 channels).  x may be fp32 NCHW or c8.
+ * at models/model.py:197-199 (32 -> 2 channels).  x may be fp32 NCHW or cl.
  * ------------------------------------------------------------------------------------------------------------------ */
 typedef struct ef_pred_params {
   int32_t B, Cin, Cout, H, W;
   const float* x;               /* [B,Cin,H,W] or NULL                                                                */
-  const uint16_t* x_c8;         /* or NULL                                                                            */
+  const uint16_t* x_cl;         /* or NULL                                                                            */
   const float* w;               /* [Cout,Cin]                                                                         */
   const float* b;               /* [Cout]                                                                             */
   float* y;                     /* [B,Cout,H,W] = tanh(...)                                                           */

@@ -54,7 +54,7 @@ def test_argument_errors_are_reported_without_a_gpu(lib):
     assert h.ef_iwe_loss_fwd(ctypes.byref(q), None) == -1
     assert h.ef_iwe_image(None, None) == -3
     assert h.ef_encode_events(None, None) == -3
-    assert h.ef_pack_c8(None, None, 1, 8, 4, 4, None) == -3
+    assert h.ef_pack_cl(None, None, 1, 8, 4, 4, None) == -3
 
 
 def test_ctypes_structs_match_c_layout(lib, tmp_path):
@@ -89,7 +89,7 @@ def test_product_path_refuses_cpu_tensors(lib):
     from event_flow_b200 import ops
 
     with pytest.raises(lib.EventFlowError):
-        ops.pack_c8(torch.zeros(1, 8, 4, 4))
+        ops.pack_cl(torch.zeros(1, 8, 4, 4))
     from event_flow_b200.models.model import LIFFireNet
 
     cfg = dict(name="x", encoding="cnt", round_encoding=False, norm_input=False, num_bins=2, base_num_channels=32, kernel_size=3,

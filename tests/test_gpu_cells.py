@@ -139,12 +139,12 @@ def test_head_layer_fractional_inputs_stride2_and_residual():
         assert torch.equal(out.cpu() - res, ns[1].cpu())
 
 
-def test_c8_layout_roundtrip_and_c8_inputs():
+def test_cl_layout_roundtrip_and_cl_inputs():
     from event_flow_b200 import ops
 
     g = torch.Generator().manual_seed(2)
     x = torch.randint(0, 3, (2, 32, 19, 23), generator=g).float().to(DEV)
-    packed = ops.pack_c8(x)
-    assert packed.shape == (2, 4, 19, 23, 8) and packed.dtype == torch.bfloat16
-    assert torch.equal(packed.float().permute(0, 1, 4, 2, 3).reshape(2, 32, 19, 23), x)
-    assert torch.equal(ops.unpack_c8(packed), x)
+    packed = ops.pack_cl(x)
+    assert packed.shape == (2, 19, 23, 32) and packed.dtype == torch.bfloat16
+    assert torch.equal(packed.float().permute(0, 3, 1, 2), x)
+    assert torch.equal(ops.unpack_cl(packed), x)

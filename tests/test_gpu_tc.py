@@ -1,5 +1,5 @@
 """
-GPU parity of the tcgen05 (tensor-core) fused conv + LIF kernel: against the fp32 CUDA-core kernel on identical c8 inputs,
+GPU parity of the tcgen05 (tensor-core) fused conv + LIF kernel: against the fp32 CUDA-core kernel on identical cl inputs,
 and against the CPU oracle.  Same tolerances as T1: |dv| <= 2e-5, spikes exact outside |v - thresh| < 1e-5.
 """
 import pytest
@@ -33,18 +33,18 @@ def test_tc_kernel_matches_cuda_core_kernel_and_oracle(rec, hard, shape, with_st
     B, H, W = shape
     params, x, st = make_case(B, H, W, rec, seed=B * 7 + H, with_state=with_state)
     pd = {k: v.to(DEV).contiguous() for k, v in params.items()}
-    x_c8 = ops.pack_c8(x.to(DEV))
+    x_cl = ops.pack_cl(x.to(DEV))
     v_in = z_in = None
     if st is not None:
-        v_in, z_in = st[0].to(DEV).contiguous(), ops.pack_c8(st[1].to(DEV))
+        v_in, z_in = st[0].to(DEV).contiguous(), ops.pack_cl(st[1].to(DEV))
     w_split = ops.split_weights(pd["ff"], pd.get("rec"))
     assert w_split is not None
     leak, thresh = pd["leak"].reshape(-1), pd["thresh"].reshape(-1)
-    v_tc, z_tc = ops.lif_step_c8(x_c8, v_in, z_in, pd["ff"], pd.get("rec"), leak, thresh, hard_reset=hard, w_split=w_split)
-    v_cc, z_cc = ops.lif_step_c8(x_c8, v_in, z_in, pd["ff"], pd.get("rec"), leak, thresh, hard_reset=hard, w_split=None)
+    v_tc, z_tc = ops.lif_step_cl(x_cl, v_in, z_in, pd["ff"], pd.get("rec"), leak, thresh, hard_reset=hard, w_split=w_split)
+    v_cc, z_cc = ops.lif_step_cl(x_cl, v_in, z_in, pd["ff"], pd.get("rec"), leak, thresh, hard_reset=hard, w_split=None)
     torch.cuda.synchronize()
     thr = params["thresh"].clamp_min(0.01)
-    z_tc_f, z_cc_f = ops.unpack_c8(z_tc).cpu(), ops.unpack_c8(z_cc).cpu()
+    z_tc_f, z_cc_f = ops.unpack_cl(z_tc).cpu(), ops.unpack_cl(z_cc).cpu()
     spike_band_compare(v_tc.cpu(), z_tc_f, v_cc.cpu(), z_cc_f, thr)
     out_o, ns_o = osp.cell_step("lif", x, st, params, hard_reset=hard)
     dv, _, in_flips = spike_band_compare(v_tc.cpu(), z_tc_f, ns_o[0], ns_o[1], thr)
@@ -59,11 +59,13 @@ def test_weight_split_is_exact():
     w[0, 0, 0, 0], w[0, 0, 0, 1], w[0, 0, 0, 2] = 1.0, 3.0e-5, -0.333333343267
     wr = torch.randn((32, 32, 3, 3), generator=g)
     sp = ops.split_weights(w.to(DEV), wr.to(DEV)).cpu()
-    assert sp.numel() == 2 * 9 * 2 * 96 * 16
-    blocks = sp.view(2, 9, 2, 2, 12, 8, 8)  # conv, tap, ks, k/8, n'/8, n'%8, k%8 with n' = split*32 + n
-    vals = ((blocks.to(torch.int32) & 0xFFFF) << 16).view(torch.float32)
-    vals = vals.permute(0, 1, 4, 5, 2, 3, 6).reshape(2, 9, 3, 32, 32)  # -> [conv, tap, split, n, ci]
-    vals = vals.permute(0, 2, 1, 3, 4)  # -> [conv, split, tap, n, ci]
+    assert sp.numel() == 2 * 9 * 96 * 32
+    raw = ((sp.view(2, 9, 12, 8, 4, 8).to(torch.int32) & 0xFFFF) << 16).view(torch.float32)  # conv, tap, atom, row, phys chunk, k%8
+    vals = torch.empty(2, 9, 12, 8, 4, 8)
+    for r in range(8):  # undo the 64-byte swizzle: logical chunk = physical chunk ^ ((row >> 1) & 3)
+        for c in range(4):
+            vals[:, :, :, r, c] = raw[:, :, :, r, c ^ ((r >> 1) & 3)]
+    vals = vals.reshape(2, 9, 3, 32, 32).permute(0, 2, 1, 3, 4)  # -> [conv, split, tap, n, ci]
     for cv, ref in enumerate((w, wr)):
         total = (vals[cv, 2] + vals[cv, 1]) + vals[cv, 0]  # lo + mid + hi, exact in fp32
         assert torch.equal(total.permute(1, 2, 0).reshape(32, 32, 3, 3), ref)
@@ -71,7 +73,7 @@ def test_weight_split_is_exact():
 
 @pytest.mark.parametrize("cin,hard,with_state", [(5, True, True), (2, True, False), (5, False, True), (8, True, True)])
 def test_head_kernel_matches_generic_and_oracle(cin, hard, with_state):
-    """Dedicated head kernel (few fractional input channels -> 32 LIF channels, c8 spikes out)."""
+    """Dedicated head kernel (few fractional input channels -> 32 LIF channels, cl spikes out)."""
     from event_flow_b200 import ops
 
     B, H, W = 3, 37, 70
@@ -85,9 +87,9 @@ def test_head_kernel_matches_generic_and_oracle(cin, hard, with_state):
     pd = {k: v.to(DEV).contiguous() for k, v in params.items()}
     v_in = z_in = None
     if st is not None:
-        v_in, z_in = st[0].to(DEV).contiguous(), ops.pack_c8(st[1].to(DEV))
-    v_h, z_h = ops.lif_step_c8(None, v_in, z_in, pd["ff"], None, pd["leak"].reshape(-1), pd["thresh"].reshape(-1), hard_reset=hard,
+        v_in, z_in = st[0].to(DEV).contiguous(), ops.pack_cl(st[1].to(DEV))
+    v_h, z_h = ops.lif_step_cl(None, v_in, z_in, pd["ff"], None, pd["leak"].reshape(-1), pd["thresh"].reshape(-1), hard_reset=hard,
                                x_f32=x.to(DEV).contiguous())
     out_o, ns_o = osp.cell_step("lif", x, st, params, hard_reset=hard)
-    spike_band_compare(v_h.cpu(), ops.unpack_c8(z_h).cpu(), ns_o[0], ns_o[1], params["thresh"].clamp_min(0.01))
-    assert ops.unpack_c8(z_h).mean() > 0.02
+    spike_band_compare(v_h.cpu(), ops.unpack_cl(z_h).cpu(), ns_o[0], ns_o[1], params["thresh"].clamp_min(0.01))
+    assert ops.unpack_cl(z_h).mean() > 0.02

@@ -19,27 +19,27 @@ for rec in (False, True):
         st = torch.rand((2, B, 32, H, W), generator=g) * 1.2 - 0.1
         st[1] = (st[1] < 0.3).float()
         pd = {k: v.to(DEV).contiguous() for k, v in params.items()}
-        x_c8, v_in, z_in = ops.pack_c8(x.to(DEV)), st[0].to(DEV).contiguous(), ops.pack_c8(st[1].to(DEV))
+        x_cl, v_in, z_in = ops.pack_cl(x.to(DEV)), st[0].to(DEV).contiguous(), ops.pack_cl(st[1].to(DEV))
         ws = ops.split_weights(pd["ff"], pd.get("rec"))
         leak, thresh = pd["leak"].reshape(-1), pd["thresh"].reshape(-1)
-        args = (x_c8, v_in, z_in, pd["ff"], pd.get("rec"), leak, thresh)
-        v_tc, z_tc = ops.lif_step_c8(*args, hard_reset=True, w_split=ws)
-        v_cc, z_cc = ops.lif_step_c8(*args, hard_reset=True, w_split=None)
+        args = (x_cl, v_in, z_in, pd["ff"], pd.get("rec"), leak, thresh)
+        v_tc, z_tc = ops.lif_step_cl(*args, hard_reset=True, w_split=ws)
+        v_cc, z_cc = ops.lif_step_cl(*args, hard_reset=True, w_split=None)
         _, ns32 = osp.cell_step("lif", x, st, params, hard_reset=True)
         p64 = {k: v.double() for k, v in params.items()}
         _, ns64 = osp.cell_step("lif", x.double(), st.double(), p64, hard_reset=True)
         e = lambda a: (a.double().cpu() - ns64[0]).abs().max().item()
         thr = params["thresh"].clamp_min(0.01).double()
         near = (ns64[0] - thr).abs() < 1e-5
-        fl = lambda z: ((ops.unpack_c8(z).cpu().double() != ns64[1]) & ~near).sum().item()
+        fl = lambda z: ((ops.unpack_cl(z).cpu().double() != ns64[1]) & ~near).sum().item()
         times = {}
         for name, wsx in (("tc", ws), ("cc", None)):
             for _ in range(3):
-                ops.lif_step_c8(*args, hard_reset=True, w_split=wsx)
+                ops.lif_step_cl(*args, hard_reset=True, w_split=wsx)
             t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             t0.record()
             for _ in range(20):
-                ops.lif_step_c8(*args, hard_reset=True, w_split=wsx)
+                ops.lif_step_cl(*args, hard_reset=True, w_split=wsx)
             t1.record()
             torch.cuda.synchronize()
             times[name] = t0.elapsed_time(t1) / 20 * 1e3

@@ -17,12 +17,12 @@ for rec in (False, True):
     ws = ops.split_weights(pd["ff"], pd.get("rec"))
     for B in (1, 2, 4, 8, 16, 32):
         g = torch.Generator().manual_seed(1)
-        x_c8 = ops.pack_c8((torch.rand((B, 32, H, W), generator=g) < 0.3).float().to(DEV))
-        z_c8 = ops.pack_c8((torch.rand((B, 32, H, W), generator=g) < 0.3).float().to(DEV))
+        x_cl = ops.pack_cl((torch.rand((B, 32, H, W), generator=g) < 0.3).float().to(DEV))
+        z_cl = ops.pack_cl((torch.rand((B, 32, H, W), generator=g) < 0.3).float().to(DEV))
         v = (torch.rand((B, 32, H, W), generator=g) * 1.2 - 0.1).to(DEV)
-        args = (x_c8, v, z_c8, pd["ff"], pd.get("rec"), pd["leak"].reshape(-1), pd["thresh"].reshape(-1))
+        args = (x_cl, v, z_cl, pd["ff"], pd.get("rec"), pd["leak"].reshape(-1), pd["thresh"].reshape(-1))
         for _ in range(3):
-            ops.lif_step_c8(*args, hard_reset=True, w_split=ws)
+            ops.lif_step_cl(*args, hard_reset=True, w_split=ws)
         # warm L2 (back-to-back) and cold (flush between launches)
         res = []
         for cold in (False, True):
@@ -32,7 +32,7 @@ for rec in (False, True):
                     flush.fill_(1)
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-                ops.lif_step_c8(*args, hard_reset=True, w_split=ws)
+                ops.lif_step_cl(*args, hard_reset=True, w_split=ws)
                 e1.record()
                 torch.cuda.synchronize()
                 ts.append(e0.elapsed_time(e1) * 1e3)

@@ -13,25 +13,25 @@ DEV = "cuda"
 B, H, W = int(sys.argv[1]) if len(sys.argv) > 1 else 8, 128, 128
 rec = len(sys.argv) > 2 and sys.argv[2] == "rec"
 g = torch.Generator().manual_seed(1)
-x_c8 = ops.pack_c8((torch.rand((B, 32, H, W), generator=g) < 0.3).float().to(DEV))
-z_c8 = ops.pack_c8((torch.rand((B, 32, H, W), generator=g) < 0.3).float().to(DEV))
+x_cl = ops.pack_cl((torch.rand((B, 32, H, W), generator=g) < 0.3).float().to(DEV))
+z_cl = ops.pack_cl((torch.rand((B, 32, H, W), generator=g) < 0.3).float().to(DEV))
 v = (torch.rand((B, 32, H, W), generator=g) * 1.2 - 0.1).to(DEV)
 params = osp.init_firenet_params("lif", 32, 32, seed=1, weight_gain=2.0)["G1" if rec else "R1a"]
 pd = {k: t.to(DEV).contiguous() for k, t in params.items()}
 ws = ops.split_weights(pd["ff"], pd.get("rec"))
-args = (x_c8, v, z_c8, pd["ff"], pd.get("rec"), pd["leak"].reshape(-1), pd["thresh"].reshape(-1))
+args = (x_cl, v, z_cl, pd["ff"], pd.get("rec"), pd["leak"].reshape(-1), pd["thresh"].reshape(-1))
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
 for _ in range(3):
-    ops.lif_step_c8(*args, hard_reset=True, w_split=ws)
+    ops.lif_step_cl(*args, hard_reset=True, w_split=ws)
 trace = torch.zeros((148, 32, 8), dtype=torch.int64, device=DEV)
 for cold in (True, False):
     trace.zero_()
     if cold:
         flush.fill_(1)
     else:
-        ops.lif_step_c8(*args, hard_reset=True, w_split=ws)
+        ops.lif_step_cl(*args, hard_reset=True, w_split=ws)
     L.lib().ef_debug_tc_trace(trace.data_ptr())
-    ops.lif_step_c8(*args, hard_reset=True, w_split=ws)
+    ops.lif_step_cl(*args, hard_reset=True, w_split=ws)
     torch.cuda.synchronize()
     L.lib().ef_debug_tc_trace(None)
     t = trace.cpu().double()
