@@ -27,12 +27,11 @@
 
 namespace ef {
 
-constexpr int TC_TH = 16, TC_TW = 8;                  // output tile (rows x cols) = 128 GEMM rows
-constexpr int TC_HH = TC_TH + 2;                      // rows of an operand copy (halo above and below)
+// Output tile = 128 pixels = TH rows x TW cols, TW a multiple of 8 (one 8-pixel run = one swizzle atom).  Two shapes:
+//   4 x 32  feed-forward cells: every fp32 membrane access of a warp is one full 128-byte line;
+//   16 x 8  recurrent cells (two operand tensors + two weight sets in shared memory: the smaller copies leave room for 2 stages).
 constexpr int PIX_BYTES = 64;                         // 32 channels bf16 = one K-major row
-constexpr int ATOM_BYTES = 8 * PIX_BYTES;             // one tile row = one 64B-swizzle atom (8 rows x 64 B)
-constexpr int COPY_BYTES = TC_HH * ATOM_BYTES;        // one x-shifted operand copy: 9216 B
-constexpr int A_TILE_BYTES = 3 * COPY_BYTES;          // dx = -1, 0, +1: 27648 B
+constexpr int ATOM_BYTES = 8 * PIX_BYTES;             // 8 pixels = one 64B-swizzle atom (8 rows x 64 B)
 constexpr int Z_TILE_BYTES = 128 * PIX_BYTES;         // centre spikes (not swizzled): 8192 B
 constexpr int W_BLOCK_BYTES = 96 * PIX_BYTES;         // one tap: [96 n = 3 splits x 32 ch][32 k] bf16, 64B-swizzled: 6144 B
 constexpr int W_CONV_BYTES = 9 * W_BLOCK_BYTES;       // 55296 B per convolution
@@ -43,16 +42,21 @@ constexpr int TMEM_COLS = 256;                        // 2 accumulator buffers x
 
 struct TcSmemLayout {
   int w_off, stage_off, stage_bytes, x_off, z_off, outz_off, bar_off, total, nstage;
+  int row_bytes, copy_bytes, a_tile_bytes;
 };
 
-__host__ __device__ inline TcSmemLayout tc_smem_layout(bool rec) {
+__host__ __device__ inline TcSmemLayout tc_smem_layout(bool rec, int th, int tw) {
   TcSmemLayout l;
-  l.nstage = rec ? 2 : 4;
+  l.row_bytes = tw * PIX_BYTES;               // one row of an operand copy
+  l.copy_bytes = (th + 2) * l.row_bytes;      // one x-shifted operand copy (halo row above and below)
+  l.a_tile_bytes = 3 * l.copy_bytes;          // dx = -1, 0, +1
   l.w_off = 0;
   const int wbytes = rec ? 2 * W_CONV_BYTES : W_CONV_BYTES;
   l.x_off = 0;
-  l.z_off = A_TILE_BYTES;                                   // rec: halo tile of z; ff: centre tile of z
-  l.stage_bytes = l.z_off + (rec ? A_TILE_BYTES : Z_TILE_BYTES);
+  l.z_off = l.a_tile_bytes;                                 // rec: operand copies of z; ff: centre tile of z
+  l.stage_bytes = l.z_off + (rec ? l.a_tile_bytes : Z_TILE_BYTES);
+  l.nstage = (227 * 1024 - 1280 - Z_TILE_BYTES - wbytes) / l.stage_bytes;
+  if (l.nstage > 4) l.nstage = 4;
   l.stage_off = wbytes;
   l.outz_off = l.stage_off + l.nstage * l.stage_bytes;      // z_out staging
   l.bar_off = l.outz_off + Z_TILE_BYTES;
@@ -61,7 +65,7 @@ __host__ __device__ inline TcSmemLayout tc_smem_layout(bool rec) {
 }
 
 struct TcParams {
-  int B, H, W, tiles_x, tiles_y, n_tiles;
+  int B, H, W, tiles_x, tiles_y, n_tiles, th, tw;
   int has_rec, has_v, has_z, hard_reset;
   const uint16_t* w_split;
   const float* leak;
@@ -186,8 +190,9 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // swizzle atoms need an aligned carve-up
   const bool rec = p.has_rec != 0;
-  const TcSmemLayout L = tc_smem_layout(rec);
+  const TcSmemLayout L = tc_smem_layout(rec, p.th, p.tw);
   const int NST = L.nstage;
+  const int TH = p.th, TW = p.tw;
   const uint32_t s_base = smem_u32(smem);
   // barriers: [0] weights, [1..NST] full, [1+NST..2NST] empty, then acc_full[2], acc_empty[2]; then the TMEM address word
   const uint32_t bar_w = s_base + L.bar_off;
@@ -221,7 +226,7 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
   const uint32_t tmem_base = *tmem_slot;
 
   const int n_my = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  const uint32_t stage_tx = A_TILE_BYTES + (p.has_z ? (rec ? A_TILE_BYTES : Z_TILE_BYTES) : 0);
+  const uint32_t stage_tx = L.a_tile_bytes + (p.has_z ? (rec ? L.a_tile_bytes : Z_TILE_BYTES) : 0);
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
@@ -233,18 +238,18 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
       for (int it = 0; it < n_my; ++it) {
         const int tile = blockIdx.x + it * gridDim.x;
         const int b = tile / (p.tiles_x * p.tiles_y), r = tile % (p.tiles_x * p.tiles_y);
-        const int y0 = (r / p.tiles_x) * TC_TH, x0 = (r % p.tiles_x) * TC_TW;
+        const int y0 = (r / p.tiles_x) * TH, x0 = (r % p.tiles_x) * TW;
         const int s = it % NST;
         const uint32_t ph = (it / NST) & 1;
         mbar_wait(bar_empty(s), ph ^ 1);
         const uint32_t st = s_base + L.stage_off + s * L.stage_bytes;
         mbar_expect_tx(bar_full(s), stage_tx);
 #pragma unroll
-        for (int dx = 0; dx < 3; ++dx) tma_load_4d(st + L.x_off + dx * COPY_BYTES, &map_x, bar_full(s), 0, x0 + dx - 1, y0 - 1, b);
+        for (int dx = 0; dx < 3; ++dx) tma_load_4d(st + L.x_off + dx * L.copy_bytes, &map_x, bar_full(s), 0, x0 + dx - 1, y0 - 1, b);
         if (p.has_z) {
           if (rec) {
 #pragma unroll
-            for (int dx = 0; dx < 3; ++dx) tma_load_4d(st + L.z_off + dx * COPY_BYTES, &map_zh, bar_full(s), 0, x0 + dx - 1, y0 - 1, b);
+            for (int dx = 0; dx < 3; ++dx) tma_load_4d(st + L.z_off + dx * L.copy_bytes, &map_zh, bar_full(s), 0, x0 + dx - 1, y0 - 1, b);
           } else {
             tma_load_4d(st + L.z_off, &map_zc, bar_full(s), 0, x0, y0, b);
           }
@@ -275,7 +280,7 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
             const int dy = tap / 3, dx = tap % 3;
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) {
-              const uint64_t adesc = umma_desc_sw64(a_tile + dx * COPY_BYTES + dy * ATOM_BYTES + ks * 32);
+              const uint64_t adesc = umma_desc_sw64(a_tile + dx * L.copy_bytes + dy * L.row_bytes + ks * 32);
               const uint64_t bdesc = umma_desc_sw64(w_conv + tap * W_BLOCK_BYTES + ks * 32);
               umma_bf16(d_tmem, adesc, bdesc, acc);
               acc = 1;
@@ -292,7 +297,7 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
     const int q = warp & 3;                 // TMEM lane quadrant this warp may access (warp id % 4)
     const int hsel = (warp - 2) >> 2;       // channel half: channels [16*hsel, 16*hsel + 16)
     const int m = q * 32 + lane;            // GEMM row = pixel within the tile
-    const int ph_ = m >> 3, pw_ = m & 7;    // (row, col) inside the 16 x 8 tile
+    const int ph_ = m / TW, pw_ = m % TW;   // (row, col) inside the tile
     const bool store_thread = (threadIdx.x == 64);
     const int c0 = 16 * hsel;
     float lam[16], thr[16];
@@ -309,7 +314,7 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
       const int tile_ = blockIdx.x + it_ * gridDim.x;
       b_ = tile_ / (p.tiles_x * p.tiles_y);
       const int r_ = tile_ % (p.tiles_x * p.tiles_y);
-      y0_ = (r_ / p.tiles_x) * TC_TH, x0_ = (r_ % p.tiles_x) * TC_TW;
+      y0_ = (r_ / p.tiles_x) * TH, x0_ = (r_ % p.tiles_x) * TW;
     };
     auto load_v = [&](int it_, float (&dst)[16]) {
       int b_, y0_, x0_;
@@ -341,7 +346,7 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
         const int gg = 2 * hsel + g;
         if (!p.has_z) zq[g] = make_uint4(0, 0, 0, 0);
         else if (rec)  // centre of the dx = 0 copy (swizzled: 16-byte chunk index XOR ((pixel-in-row >> 1) & 3))
-          zq[g] = *reinterpret_cast<const uint4*>(st + L.z_off + COPY_BYTES + (ph_ + 1) * ATOM_BYTES + pw_ * PIX_BYTES + ((gg ^ ((pw_ >> 1) & 3)) << 4));
+          zq[g] = *reinterpret_cast<const uint4*>(st + L.z_off + L.copy_bytes + (ph_ + 1) * L.row_bytes + pw_ * PIX_BYTES + ((gg ^ ((pw_ >> 1) & 3)) << 4));
         else zq[g] = *reinterpret_cast<const uint4*>(st + L.z_off + m * PIX_BYTES + gg * 16);
       }
       __syncwarp();
@@ -448,7 +453,7 @@ static EncodeTiledFn encode_fn() {
 
 struct MapKey {
   const void* ptr;
-  int B, H, W, kind;
+  int B, H, W, kind;  // kind = box rows * 256 + box cols * 2 + swizzled
   bool operator==(const MapKey& o) const { return ptr == o.ptr && B == o.B && H == o.H && W == o.W && kind == o.kind; }
 };
 struct MapKeyHash {
@@ -457,9 +462,10 @@ struct MapKeyHash {
   }
 };
 
-// kind 0: operand copy box (32 ch x 8 px x 18 rows, 64B swizzle); kind 1: centre box (32 ch x 8 px x 16 rows, no swizzle)
-static int get_map(const void* ptr, int B, int H, int W, int kind, CUtensorMap* out) {
+// operand copy box: 32 ch x tw px x (th + 2) rows, 64B swizzle; centre box: 32 ch x tw px x th rows, no swizzle
+static int get_map(const void* ptr, int B, int H, int W, int rows, int cols, bool swizzled, CUtensorMap* out) {
   static thread_local std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  const int kind = rows * 256 + cols * 2 + (swizzled ? 1 : 0);
   const MapKey key{ptr, B, H, W, kind};
   auto it = cache.find(key);
   if (it != cache.end()) {
@@ -472,10 +478,10 @@ static int get_map(const void* ptr, int B, int H, int W, int kind, CUtensorMap* 
   {
     const cuuint64_t dims[4] = {32, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     const cuuint64_t strides[3] = {PIX_BYTES, (cuuint64_t)W * PIX_BYTES, (cuuint64_t)H * W * PIX_BYTES};
-    const cuuint32_t box[4] = {32, TC_TW, (cuuint32_t)(kind == 0 ? TC_HH : TC_TH), 1};
+    const cuuint32_t box[4] = {32, (cuuint32_t)cols, (cuuint32_t)rows, 1};
     const cuuint32_t es[4] = {1, 1, 1, 1};
     r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            kind == 0 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            swizzled ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   }
   if (r != CUDA_SUCCESS) return fail(EF_EINVAL, "cuTensorMapEncodeTiled failed (CUresult %d) for kind %d, B=%d H=%d W=%d ptr=%p", (int)r, kind, B, H, W, ptr);
@@ -502,19 +508,23 @@ int lif_conv_fwd_tc(const ef_lif_conv_params& p, cudaStream_t st) {
   const bool rec = p.w_rec != nullptr;
   TcParams q;
   q.B = p.B, q.H = p.H, q.W = p.W;
-  q.tiles_x = cdiv(p.W, TC_TW), q.tiles_y = cdiv(p.H, TC_TH), q.n_tiles = p.B * q.tiles_x * q.tiles_y;
+  q.th = 16, q.tw = 8;
+  if (!rec && p.W >= 32) q.th = 4, q.tw = 32;  // feed-forward cells: 128-byte membrane rows (see the tile-shape note above)
+  q.tiles_x = cdiv(p.W, q.tw), q.tiles_y = cdiv(p.H, q.th), q.n_tiles = p.B * q.tiles_x * q.tiles_y;
   q.has_rec = rec, q.has_v = p.v_in != nullptr, q.has_z = p.z_in_cl != nullptr, q.hard_reset = p.hard_reset;
   q.w_split = p.w_split, q.leak = p.leak, q.thresh = p.thresh, q.v_in = p.v_in, q.v_out = p.v_out;
   q.trace = g_tc_trace;
   CUtensorMap mx, mzh, mzc, mzo;
   int rc;
-  if ((rc = get_map(p.x_cl, p.B, p.H, p.W, 0, &mx))) return rc;
-  if ((rc = get_map(p.z_out_cl, p.B, p.H, p.W, 1, &mzo))) return rc;
+  if ((rc = get_map(p.x_cl, p.B, p.H, p.W, q.th + 2, q.tw, true, &mx))) return rc;
+  if ((rc = get_map(p.z_out_cl, p.B, p.H, p.W, q.th, q.tw, false, &mzo))) return rc;
   mzh = mx, mzc = mzo;  // placeholders when there is no previous state
   if (q.has_z) {
-    if ((rc = get_map(p.z_in_cl, p.B, p.H, p.W, rec ? 0 : 1, rec ? &mzh : &mzc))) return rc;
+    if (rec) rc = get_map(p.z_in_cl, p.B, p.H, p.W, q.th + 2, q.tw, true, &mzh);
+    else rc = get_map(p.z_in_cl, p.B, p.H, p.W, q.th, q.tw, false, &mzc);
+    if (rc) return rc;
   }
-  const TcSmemLayout L = tc_smem_layout(rec);
+  const TcSmemLayout L = tc_smem_layout(rec, q.th, q.tw);
   const int grid = q.n_tiles < n_sms ? q.n_tiles : n_sms;
   auto kern = p.hard_reset ? lif_conv_fwd_tc_kernel<true> : lif_conv_fwd_tc_kernel<false>;
   static bool attr_set[2] = {false, false};
