@@ -1,16 +1,19 @@
 // Fused conv3x3 + LIF step on the 5th-generation tensor cores (tcgen05 / TMEM / TMA), sm_100a only.
 //
 // Implicit GEMM per 16x8-pixel tile:  D[128 px, 96] = sum over 9 taps, 32 (or 64 with the recurrent conv) input channels
-//   A = bf16 spikes, channels-last.  Three TMA boxes per tile (x offsets -1, 0, +1; 18 rows x 8 px x 32 ch each, hardware
-//       zero-fill = the conv padding) land in shared memory in the canonical 64-byte-swizzled K-major UMMA layout: one
-//       pixel = one 64-byte row, one tile row (8 px) = one 512-byte swizzle atom.  A tap (dy, dx) is then just a
-//       descriptor start address: copy dx, plus dy atoms -- no im2col copy, every start stays atom-aligned;
+//   A = bf16 spikes, channels-last.  ONE TMA box per tile (18 rows x 16 px x 32 ch: the 16x8 tile, its 1-pixel halo, and
+//       padding up to whole 8-pixel atoms; hardware zero-fill = the conv padding) lands in shared memory in the canonical
+//       64-byte-swizzled K-major UMMA layout: one pixel = one 64-byte row, 8 pixels = one 512-byte swizzle atom, one tile
+//       row = 1024 bytes.  A tap (dy, dx) is then only a descriptor start address, tile + dy*1024 + dx*64, with
+//       SBO = 1024: no im2col copy.  The start is NOT atom-aligned for dx != 0; this works because the swizzle XOR is a
+//       function of the absolute shared-memory address bits [7:8] on both the TMA write and the UMMA read (verified
+//       bit-exactly against the CUDA-core kernel, tests/test_gpu_tc.py);
 //   B = weights, split into three bf16 terms hi+mid+lo == w (exact), resident in shared memory for the whole kernel and
 //       stacked along N: one MMA per (tap, k-step) with N = 96 = {hi, mid, lo} x 32 channels, so the A tile is read from
 //       shared memory once instead of three times; same swizzled K-major layout (written by ef_split_weights);
 //   D = fp32 accumulator in tensor memory, 96 columns (three partial sums, added in the epilogue), double buffered.
-// (A first version read tap-shifted windows of ONE un-swizzled halo tile; measured ~200 cycles per MMA, 3.6x the
-//  swizzled rate -- profiles/r01_tc_timeline.txt.)
+// History (profiles/r01_tc_kernel_notes.md): an un-swizzled halo tile made every MMA ~3.6x slower; three x-shifted
+// swizzled copies tripled the L2->SM traffic; the single padded swizzled tile is both the least traffic and full MMA rate.
 // Spikes are {0,1,2}: exactly representable in bf16, so every product is exact and only the fp32 summation order differs
 // from the CPU path (no TF32/BF16 rounding may enter a spiking conv).
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2-9 = epilogue: each warp owns a
@@ -27,9 +30,8 @@
 
 namespace ef {
 
-// Output tile = 128 pixels = TH rows x TW cols, TW a multiple of 8 (one 8-pixel run = one swizzle atom).  Two shapes:
-//   4 x 32  feed-forward cells: every fp32 membrane access of a warp is one full 128-byte line;
-//   16 x 8  recurrent cells (two operand tensors + two weight sets in shared memory: the smaller copies leave room for 2 stages).
+// Output tile = 128 pixels = 16 rows x 8 cols: one 8-pixel atom per tile row is the only shape whose tap-shifted windows
+// are expressible as ONE descriptor (constant stride between consecutive 8-row groups).
 constexpr int PIX_BYTES = 64;                         // 32 channels bf16 = one K-major row
 constexpr int ATOM_BYTES = 8 * PIX_BYTES;             // 8 pixels = one 64B-swizzle atom (8 rows x 64 B)
 constexpr int Z_TILE_BYTES = 128 * PIX_BYTES;         // centre spikes (not swizzled): 8192 B
@@ -47,9 +49,9 @@ struct TcSmemLayout {
 
 __host__ __device__ inline TcSmemLayout tc_smem_layout(bool rec, int th, int tw) {
   TcSmemLayout l;
-  l.row_bytes = tw * PIX_BYTES;               // one row of an operand copy
-  l.copy_bytes = (th + 2) * l.row_bytes;      // one x-shifted operand copy (halo row above and below)
-  l.a_tile_bytes = 3 * l.copy_bytes;          // dx = -1, 0, +1
+  l.row_bytes = (tw + 8) * PIX_BYTES;         // one row of the operand tile: tw + 2 pixels needed, padded to whole 8-pixel atoms
+  l.copy_bytes = (th + 2) * l.row_bytes;      // the operand tile (halo row above and below, halo pixel left and right)
+  l.a_tile_bytes = l.copy_bytes;
   l.w_off = 0;
   const int wbytes = rec ? 2 * W_CONV_BYTES : W_CONV_BYTES;
   l.x_off = 0;
@@ -73,6 +75,7 @@ struct TcParams {
   const float* v_in;
   float* v_out;
   long long* trace;  // debug: per-CTA timeline (clock64), NULL in production
+  int skip;          // debug: ablation mask (1 = no v_out stores, 2 = no v_in loads, 4 = no MMAs, 8 = no spike store, 16 = no tmem loads)
 };
 
 constexpr int TRACE_SLOTS = 8, TRACE_MAX_TILES = 32;  // [cta][tile][slot]
@@ -152,8 +155,8 @@ __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_
 // K-major, 64-byte-swizzled shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp): rows of 64 B, 8-row atoms of
 // 512 B (SBO between atoms), 16-byte chunks XOR-swizzled by address bits [7:8]; version 1 at bit 46, layout type 4
 // (SWIZZLE_64B) at bits 61-63; LBO is not used by swizzled K-major layouts (canonical value 1).
-__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t saddr) {
-  return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(ATOM_BYTES >> 4) << 32) | (1ull << 46) | (4ull << 61);
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t saddr, uint32_t sbo) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (4ull << 61);
 }
 // kind::f16 instruction descriptor: D = F32, A = B = BF16, both K-major, N = 96, M = 128.
 constexpr uint32_t UMMA_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((96u >> 3) << 17) | ((128u >> 4) << 24);
@@ -225,16 +228,22 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int n_my = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  int n_my = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  if (p.skip & 32) n_my = 0;               // debug: prologue + teardown only
+  else if ((p.skip & 128) && n_my > 1) n_my = 1;  // debug: one tile per CTA
   const uint32_t stage_tx = L.a_tile_bytes + (p.has_z ? (rec ? L.a_tile_bytes : Z_TILE_BYTES) : 0);
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
     if (lane == 0) {
       const uint32_t wbytes = rec ? 2 * W_CONV_BYTES : W_CONV_BYTES;
-      mbar_expect_tx(bar_w, wbytes);
-      for (uint32_t off = 0; off < wbytes; off += 13824)  // 55296 = 4 x 13824
-        bulk_load_1d(s_base + L.w_off + off, reinterpret_cast<const uint8_t*>(p.w_split) + off, 13824, bar_w);
+      if (p.skip & 64) {  // debug: no weight load
+        mbar_arrive(bar_w);
+      } else {
+        mbar_expect_tx(bar_w, wbytes);
+        for (uint32_t off = 0; off < wbytes; off += 13824)  // 55296 = 4 x 13824
+          bulk_load_1d(s_base + L.w_off + off, reinterpret_cast<const uint8_t*>(p.w_split) + off, 13824, bar_w);
+      }
       for (int it = 0; it < n_my; ++it) {
         const int tile = blockIdx.x + it * gridDim.x;
         const int b = tile / (p.tiles_x * p.tiles_y), r = tile % (p.tiles_x * p.tiles_y);
@@ -244,15 +253,10 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
         mbar_wait(bar_empty(s), ph ^ 1);
         const uint32_t st = s_base + L.stage_off + s * L.stage_bytes;
         mbar_expect_tx(bar_full(s), stage_tx);
-#pragma unroll
-        for (int dx = 0; dx < 3; ++dx) tma_load_4d(st + L.x_off + dx * L.copy_bytes, &map_x, bar_full(s), 0, x0 + dx - 1, y0 - 1, b);
+        tma_load_4d(st + L.x_off, &map_x, bar_full(s), 0, x0 - 1, y0 - 1, b);
         if (p.has_z) {
-          if (rec) {
-#pragma unroll
-            for (int dx = 0; dx < 3; ++dx) tma_load_4d(st + L.z_off + dx * L.copy_bytes, &map_zh, bar_full(s), 0, x0 + dx - 1, y0 - 1, b);
-          } else {
-            tma_load_4d(st + L.z_off, &map_zc, bar_full(s), 0, x0, y0, b);
-          }
+          if (rec) tma_load_4d(st + L.z_off, &map_zh, bar_full(s), 0, x0 - 1, y0 - 1, b);
+          else tma_load_4d(st + L.z_off, &map_zc, bar_full(s), 0, x0, y0, b);
         }
         EF_TRACE(it, 0);
       }
@@ -280,9 +284,9 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
             const int dy = tap / 3, dx = tap % 3;
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) {
-              const uint64_t adesc = umma_desc_sw64(a_tile + dx * L.copy_bytes + dy * L.row_bytes + ks * 32);
-              const uint64_t bdesc = umma_desc_sw64(w_conv + tap * W_BLOCK_BYTES + ks * 32);
-              umma_bf16(d_tmem, adesc, bdesc, acc);
+              const uint64_t adesc = umma_desc_sw64(a_tile + dy * L.row_bytes + dx * PIX_BYTES + ks * 32, L.row_bytes);
+              const uint64_t bdesc = umma_desc_sw64(w_conv + tap * W_BLOCK_BYTES + ks * 32, ATOM_BYTES);
+              if (!(p.skip & 4)) umma_bf16(d_tmem, adesc, bdesc, acc);
               acc = 1;
             }
           }
@@ -323,7 +327,7 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
       const bool ok = p.has_v && it_ < n_my && gy_ < p.H && gx_ < p.W;
       const size_t o_ = ((size_t)b_ * 32 + c0) * plane + (size_t)gy_ * p.W + gx_;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) dst[j] = ok ? __ldg(p.v_in + o_ + j * plane) : 0.f;
+      for (int j = 0; j < 16; ++j) dst[j] = (ok && !(p.skip & 2)) ? __ldg(p.v_in + o_ + j * plane) : 0.f;
     };
     float vin[16];
     load_v(0, vin);
@@ -345,8 +349,8 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
       for (int g = 0; g < 2; ++g) {
         const int gg = 2 * hsel + g;
         if (!p.has_z) zq[g] = make_uint4(0, 0, 0, 0);
-        else if (rec)  // centre of the dx = 0 copy (swizzled: 16-byte chunk index XOR ((pixel-in-row >> 1) & 3))
-          zq[g] = *reinterpret_cast<const uint4*>(st + L.z_off + L.copy_bytes + (ph_ + 1) * L.row_bytes + pw_ * PIX_BYTES + ((gg ^ ((pw_ >> 1) & 3)) << 4));
+        else if (rec)  // centre of the operand tile (swizzled: 16-byte chunk index XOR ((pixel-in-row >> 1) & 3))
+          zq[g] = *reinterpret_cast<const uint4*>(st + L.z_off + (ph_ + 1) * L.row_bytes + (pw_ + 1) * PIX_BYTES + ((gg ^ (((pw_ + 1) >> 1) & 3)) << 4));
         else zq[g] = *reinterpret_cast<const uint4*>(st + L.z_off + m * PIX_BYTES + gg * 16);
       }
       __syncwarp();
@@ -357,10 +361,15 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
       if (store_thread) EF_TRACE(it, 3);
       uint32_t a_hi[16], a_mid[16], a_lo[16];
       const uint32_t tacc = tmem_base + a * ACC_COLS + c0 + ((uint32_t)(q * 32) << 16);
-      tmem_ld16(tacc, a_hi);
-      tmem_ld16(tacc + 32, a_mid);
-      tmem_ld16(tacc + 64, a_lo);
-      tmem_ld_wait();
+      if (!(p.skip & 16)) {
+        tmem_ld16(tacc, a_hi);
+        tmem_ld16(tacc + 32, a_mid);
+        tmem_ld16(tacc + 64, a_lo);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) a_hi[j] = a_mid[j] = a_lo[j] = 0;
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_acce(a));  // accumulator buffer may be overwritten by the MMA of tile it+2
@@ -377,12 +386,13 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
         float vn;
         if (HARD) vn = __fadd_rn(__fmul_rn(__fmul_rn(v, lam[j]), __fsub_rn(1.0f, z)), __fmul_rn(oml, I));
         else vn = __fsub_rn(__fadd_rn(__fmul_rn(v, lam[j]), __fmul_rn(oml, I)), __fmul_rn(z, thr[j]));
-        if (inb) p.v_out[vo + j * plane] = vn;
+        if (inb && !(p.skip & 1)) p.v_out[vo + j * plane] = vn;
         const uint32_t zb = (__fsub_rn(vn, thr[j]) > 0.f) ? 0x3F80u : 0u;  // bf16(1.0) = 0x3F80
         if (j & 1) zpk[j >> 1] |= zb << 16;
         else zpk[j >> 1] = zb;
       }
       if (store_thread) EF_TRACE(it, 5);
+      if (p.skip & 8) continue;
       if (it > 0) {  // the staging buffer is free once the previous tile's TMA store has read it
         if (store_thread) bulk_wait_read0();
         named_bar_sync(1, 32 * TC_EPI_WARPS);
@@ -491,6 +501,7 @@ static int get_map(const void* ptr, int B, int H, int W, int rows, int cols, boo
 }
 
 static long long* g_tc_trace = nullptr;  // set through ef_debug_tc_trace (tools/tc_timeline.py)
+static int g_tc_skip = 0;                // set through ef_debug_tc_skip (tools/tc_ablation.py)
 
 bool lif_conv_tc_eligible(const ef_lif_conv_params& p) {
   return p.w_split && p.x_cl && p.z_out_cl && p.Cin == 32 && p.C == 32 && p.ksize == 3 && p.stride == 1 && p.neuron == EF_LIF &&
@@ -508,19 +519,19 @@ int lif_conv_fwd_tc(const ef_lif_conv_params& p, cudaStream_t st) {
   const bool rec = p.w_rec != nullptr;
   TcParams q;
   q.B = p.B, q.H = p.H, q.W = p.W;
-  q.th = 16, q.tw = 8;
-  if (!rec && p.W >= 32) q.th = 4, q.tw = 32;  // feed-forward cells: 128-byte membrane rows (see the tile-shape note above)
+  q.th = 16, q.tw = 8;  // one 8-pixel atom per tile row: the only shape whose tap-shifted windows are a single descriptor
   q.tiles_x = cdiv(p.W, q.tw), q.tiles_y = cdiv(p.H, q.th), q.n_tiles = p.B * q.tiles_x * q.tiles_y;
   q.has_rec = rec, q.has_v = p.v_in != nullptr, q.has_z = p.z_in_cl != nullptr, q.hard_reset = p.hard_reset;
   q.w_split = p.w_split, q.leak = p.leak, q.thresh = p.thresh, q.v_in = p.v_in, q.v_out = p.v_out;
   q.trace = g_tc_trace;
+  q.skip = g_tc_skip;
   CUtensorMap mx, mzh, mzc, mzo;
   int rc;
-  if ((rc = get_map(p.x_cl, p.B, p.H, p.W, q.th + 2, q.tw, true, &mx))) return rc;
+  if ((rc = get_map(p.x_cl, p.B, p.H, p.W, q.th + 2, q.tw + 8, true, &mx))) return rc;
   if ((rc = get_map(p.z_out_cl, p.B, p.H, p.W, q.th, q.tw, false, &mzo))) return rc;
   mzh = mx, mzc = mzo;  // placeholders when there is no previous state
   if (q.has_z) {
-    if (rec) rc = get_map(p.z_in_cl, p.B, p.H, p.W, q.th + 2, q.tw, true, &mzh);
+    if (rec) rc = get_map(p.z_in_cl, p.B, p.H, p.W, q.th + 2, q.tw + 8, true, &mzh);
     else rc = get_map(p.z_in_cl, p.B, p.H, p.W, q.th, q.tw, false, &mzc);
     if (rc) return rc;
   }
@@ -538,6 +549,11 @@ int lif_conv_fwd_tc(const ef_lif_conv_params& p, cudaStream_t st) {
 }
 
 }  // namespace ef
+
+extern "C" int ef_debug_tc_skip(int mask) {  // ablation switches for tools/tc_ablation.py; 0 = production behaviour
+  ef::g_tc_skip = mask;
+  return EF_OK;
+}
 
 extern "C" int ef_debug_tc_trace(long long* buf) {  // buf: device int64 [n_ctas][32 tiles][8 slots] or NULL to switch tracing off
   ef::g_tc_trace = buf;
