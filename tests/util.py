@@ -12,6 +12,7 @@ def spike_band_compare(v_mine, z_mine, v_ref, z_ref, thresh, band=1e-5, v_atol=N
     """
     if v_atol is None:
         v_atol = max(2e-5, 3e-6 * v_ref.abs().max().item())
+    band = max(band, v_atol)  # a neuron closer to threshold than the membrane tolerance may legitimately flip
     dv = (v_mine - v_ref).abs().max().item()
     near = (v_ref - thresh).abs() < band
     diff = z_mine != z_ref
