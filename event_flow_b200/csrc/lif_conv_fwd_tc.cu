@@ -265,6 +265,8 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
     // =============================== MMA issuer ===============================
     if (lane == 0) {
       mbar_wait(bar_w, 0);
+      const uint64_t b_ff = umma_desc_sw64(s_base + L.w_off, ATOM_BYTES);
+      const uint64_t b_rec = umma_desc_sw64(s_base + L.w_off + W_CONV_BYTES, ATOM_BYTES);
       for (int it = 0; it < n_my; ++it) {
         const int s = it % NST, a = it & 1;
         const uint32_t ph = (it / NST) & 1, aph = (it >> 1) & 1;
@@ -274,20 +276,25 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
         EF_TRACE(it, 1);
         const uint32_t st = s_base + L.stage_off + s * L.stage_bytes;
         const uint32_t d_tmem = tmem_base + a * ACC_COLS;
-        uint32_t acc = 0;
-        const int nconv = (rec && p.has_z) ? 2 : 1;
-        for (int cv = 0; cv < nconv; ++cv) {
-          const uint32_t a_tile = st + (cv == 0 ? L.x_off : L.z_off);
-          const uint32_t w_conv = s_base + L.w_off + cv * W_CONV_BYTES;
-#pragma unroll 1
-          for (int tap = 0; tap < 9; ++tap) {
-            const int dy = tap / 3, dx = tap % 3;
+        // One elected thread issues all MMAs of the tile: this instruction stream is serial, so everything per MMA is
+        // reduced to two 64-bit adds on precomputed descriptors (offsets in 16-byte units are compile-time constants).
+        if (!(p.skip & 4)) {
+          const uint64_t ax = umma_desc_sw64(st + L.x_off, L.row_bytes);
 #pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
-              const uint64_t adesc = umma_desc_sw64(a_tile + dy * L.row_bytes + dx * PIX_BYTES + ks * 32, L.row_bytes);
-              const uint64_t bdesc = umma_desc_sw64(w_conv + tap * W_BLOCK_BYTES + ks * 32, ATOM_BYTES);
-              if (!(p.skip & 4)) umma_bf16(d_tmem, adesc, bdesc, acc);
-              acc = 1;
+          for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks)
+              umma_bf16(d_tmem, ax + (uint64_t)((tap / 3) * (1024 / 16) + (tap % 3) * (PIX_BYTES / 16) + ks * 2),
+                        b_ff + (uint64_t)(tap * (W_BLOCK_BYTES / 16) + ks * 2), (tap | ks) != 0);
+          }
+          if (rec && p.has_z) {
+            const uint64_t az = umma_desc_sw64(st + L.z_off, L.row_bytes);
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+              for (int ks = 0; ks < 2; ++ks)
+                umma_bf16(d_tmem, az + (uint64_t)((tap / 3) * (1024 / 16) + (tap % 3) * (PIX_BYTES / 16) + ks * 2),
+                          b_rec + (uint64_t)(tap * (W_BLOCK_BYTES / 16) + ks * 2), 1u);
             }
           }
         }
@@ -325,9 +332,10 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
       tile_origin(it_, b_, y0_, x0_);
       const int gy_ = y0_ + ph_, gx_ = x0_ + pw_;
       const bool ok = p.has_v && it_ < n_my && gy_ < p.H && gx_ < p.W;
-      const size_t o_ = ((size_t)b_ * 32 + c0) * plane + (size_t)gy_ * p.W + gx_;
+      size_t o_ = ((size_t)b_ * 32 + c0) * plane + (size_t)gy_ * p.W + gx_, st_ = plane;
+      if (p.skip & 256) o_ = ((size_t)(blockIdx.x + it_ * gridDim.x) * 32 + c0) * 128 + m, st_ = 128;  // debug: tile-blocked membrane
 #pragma unroll
-      for (int j = 0; j < 16; ++j) dst[j] = (ok && !(p.skip & 2)) ? __ldg(p.v_in + o_ + j * plane) : 0.f;
+      for (int j = 0; j < 16; ++j) dst[j] = (ok && !(p.skip & 2)) ? __ldg(p.v_in + o_ + j * st_) : 0.f;
     };
     float vin[16];
     load_v(0, vin);
@@ -339,7 +347,8 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
       const uint8_t* st = smem + L.stage_off + s * L.stage_bytes;
       const int gy = y0 + ph_, gx = x0 + pw_;
       const bool inb = gy < p.H && gx < p.W;
-      const size_t vo = ((size_t)b * 32 + c0) * plane + (size_t)gy * p.W + gx;
+      size_t vo = ((size_t)b * 32 + c0) * plane + (size_t)gy * p.W + gx, vstride = plane;
+      if (p.skip & 256) vo = ((size_t)(blockIdx.x + it * gridDim.x) * 32 + c0) * 128 + m, vstride = 128;  // debug: tile-blocked membrane
       float vnext[16];
       load_v(it + 1, vnext);
 
@@ -386,7 +395,7 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
         float vn;
         if (HARD) vn = __fadd_rn(__fmul_rn(__fmul_rn(v, lam[j]), __fsub_rn(1.0f, z)), __fmul_rn(oml, I));
         else vn = __fsub_rn(__fadd_rn(__fmul_rn(v, lam[j]), __fmul_rn(oml, I)), __fmul_rn(z, thr[j]));
-        if (inb && !(p.skip & 1)) p.v_out[vo + j * plane] = vn;
+        if (inb && !(p.skip & 1)) p.v_out[vo + j * vstride] = vn;
         const uint32_t zb = (__fsub_rn(vn, thr[j]) > 0.f) ? 0x3F80u : 0u;  // bf16(1.0) = 0x3F80
         if (j & 1) zpk[j >> 1] |= zb << 16;
         else zpk[j >> 1] = zb;
@@ -520,6 +529,7 @@ int lif_conv_fwd_tc(const ef_lif_conv_params& p, cudaStream_t st) {
   TcParams q;
   q.B = p.B, q.H = p.H, q.W = p.W;
   q.th = 16, q.tw = 8;  // one 8-pixel atom per tile row: the only shape whose tap-shifted windows are a single descriptor
+  static_assert((8 + 8) * PIX_BYTES == 1024, "the MMA issue loop hard-codes a 1024-byte operand row");
   q.tiles_x = cdiv(p.W, q.tw), q.tiles_y = cdiv(p.H, q.th), q.n_tiles = p.B * q.tiles_x * q.tiles_y;
   q.has_rec = rec, q.has_v = p.v_in != nullptr, q.has_z = p.z_in_cl != nullptr, q.hard_reset = p.hard_reset;
   q.w_split = p.w_split, q.leak = p.leak, q.thresh = p.thresh, q.v_in = p.v_in, q.v_out = p.v_out;
