@@ -227,7 +227,8 @@ def run_ours(args):
                 "share_of_step": (sum(hidden) / allk) if allk else None}
 
     if rank == 0:
-        cpu = cpu_baseline(sample_steps=1)
+        # the CPU baseline is taken at N=1 only: under torchrun the other ranks spin in the barrier and steal the host cores
+        cpu = cpu_baseline(sample_steps=1) if world == 1 else None
         line = {
             "metric": "events/s (LIFFireNet fwd + EventWarping loss)", "value": events_per_step / (ms_value * 1e-3), "unit": "events/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_value, "higher_is_better": True, "scaling": "weak",

@@ -69,6 +69,21 @@ class IweImageParams(C.Structure):
     ]  # fmt: skip
 
 
+class IweMetricsParams(C.Structure):
+    _fields_ = [
+        ("B", _i32), ("T", _i32), ("T_maps", _i32), ("H", _i32), ("W", _i32), ("n_total", _i32), ("n_per_pass", _i32),
+        ("flow_scaling", C.c_float),
+        ("events", _f32p), ("pol_mask", _f32p), ("flow_maps", _f32p), ("pass_offsets", _f32p), ("workspace", _f32p), ("out", _f32p),
+    ]  # fmt: skip
+
+
+class AeeParams(C.Structure):
+    _fields_ = [
+        ("B", _i32), ("H", _i32), ("W", _i32), ("flow_scaling", C.c_float),
+        ("flow", _f32p), ("gtflow", _f32p), ("event_mask", _f32p), ("dt_ratio", _f32p), ("workspace", _f32p), ("out", _f32p),
+    ]  # fmt: skip
+
+
 class EncodeParams(C.Structure):
     _fields_ = [
         ("B", _i32), ("N", _i32), ("H", _i32), ("W", _i32), ("num_bins", _i32), ("round_ts", _i32),
@@ -96,6 +111,9 @@ EXPORTS = {
     "ef_iwe_loss_fwd": (C.c_int, [C.POINTER(IweLossParams), C.c_void_p]),
     "ef_iwe_loss_bwd": (C.c_int, [C.POINTER(IweLossParams), C.c_void_p]),
     "ef_iwe_image": (C.c_int, [C.POINTER(IweImageParams), C.c_void_p]),
+    "ef_iwe_metrics_workspace_elems": (C.c_int64, [_i32, _i32, _i32]),
+    "ef_iwe_metrics": (C.c_int, [C.POINTER(IweMetricsParams), C.c_void_p]),
+    "ef_aee": (C.c_int, [C.POINTER(AeeParams), C.c_void_p]),
     "ef_encode_events": (C.c_int, [C.POINTER(EncodeParams), C.c_void_p]),
     "ef_grad_sqnorm": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "ef_clip_adam": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_float, C.c_float,

@@ -357,6 +357,110 @@ __global__ void __launch_bounds__(256) iwe_image_kernel(const ef_iwe_image_param
   }
 }
 
+// ---- validation metrics: FWL / RSAT (loss/flow.py:468-579) and AEE (:582-628) -----------------------------------------
+// workspace: img [B][2 = warped, unwarped][4 = I+,I-,Th+,Th-][HW], then sums [B][2][4 = sum A^2, n, sum I, sum I^2]
+__global__ void __launch_bounds__(256) iwe_metric_scatter_kernel(const ef_iwe_metrics_params p, float* __restrict__ img) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+  if (i >= p.n_total) return;
+  const size_t hw = (size_t)p.H * p.W;
+  const float4 e = reinterpret_cast<const float4*>(p.events)[(size_t)b * p.n_total + i];
+  const float2 pm = reinterpret_cast<const float2*>(p.pol_mask)[(size_t)b * p.n_total + i];
+  int t_e = 0;
+  if (p.T_maps > 1) {
+    if (p.pass_offsets) {
+      while (t_e + 1 < p.T && i >= __ldg(p.pass_offsets + t_e + 1)) ++t_e;
+    } else {
+      t_e = min(i / p.n_per_pass, p.T_maps - 1);
+    }
+  }
+  const int pix = (int)(e.y * (float)p.W + e.z);
+  const float* fm = p.flow_maps + ((size_t)b * p.T_maps + t_e) * 2 * hw;
+  const float fx = __ldg(fm + pix), fy = __ldg(fm + hw + pix);
+  float* base = img + (size_t)b * 8 * hw;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {  // k = 0: warped to tref = T with the flow; k = 1: flow * 0 (image of events)
+    const float dt = __fsub_rn((float)p.T, e.x);
+    const float yw = rintf(__fadd_rn(e.y, __fmul_rn(__fmul_rn(dt, k == 0 ? fy : __fmul_rn(fy, 0.f)), p.flow_scaling)));
+    const float xw = rintf(__fadd_rn(e.z, __fmul_rn(__fmul_rn(dt, k == 0 ? fx : __fmul_rn(fx, 0.f)), p.flow_scaling)));
+    if (yw < 0.f || yw >= (float)p.H || xw < 0.f || xw >= (float)p.W) continue;
+    const int idx = (int)(yw * (float)p.W + xw);
+    float* d = base + (size_t)k * 4 * hw;
+    // FWL scatters weight 1 per event regardless of polarity (no mask); RSAT scatters per polarity.  Channels 0/1 serve
+    // both when every event has exactly one polarity bit; events with neither are still counted for FWL in channel 0.
+    if (pm.x != 0.f) { atomicAdd(d + idx, pm.x); atomicAdd(d + 2 * hw + idx, __fmul_rn(e.x, pm.x)); }
+    if (pm.y != 0.f) { atomicAdd(d + hw + idx, pm.y); atomicAdd(d + 3 * hw + idx, __fmul_rn(e.x, pm.y)); }
+  }
+}
+
+__global__ void __launch_bounds__(256) iwe_metric_reduce_kernel(const float* __restrict__ img, float* __restrict__ sums, int HW, float T) {
+  __shared__ float s_red[8];
+  const int bk = blockIdx.y;  // b*2 + k
+  const float* d = img + (size_t)bk * 4 * HW;
+  float ssq = 0.f, n = 0.f, s1 = 0.f, s2 = 0.f;
+  const int p0 = blockIdx.x * RED_PIX;
+  for (int i = p0 + threadIdx.x; i < min(p0 + RED_PIX, HW); i += 256) {
+    const float ip = d[i], in = d[HW + i], tp = d[2 * HW + i], tn = d[3 * HW + i];
+    const float ap = tp / (ip + 1e-9f) / T, an = tn / (in + 1e-9f) / T;
+    ssq += ap * ap + an * an;
+    n += (ip + in > 0.f) ? 1.f : 0.f;
+    s1 += ip + in;
+    s2 += (ip + in) * (ip + in);
+  }
+  const float r0 = block_sum256(ssq, s_red), r1 = block_sum256(n, s_red), r2 = block_sum256(s1, s_red), r3 = block_sum256(s2, s_red);
+  if (threadIdx.x == 0) {
+    atomicAdd(sums + bk * 4 + 0, r0);
+    atomicAdd(sums + bk * 4 + 1, r1);
+    atomicAdd(sums + bk * 4 + 2, r2);
+    atomicAdd(sums + bk * 4 + 3, r3);
+  }
+}
+
+__global__ void iwe_metric_finalize_kernel(const float* __restrict__ sums, int B, int HW, float* __restrict__ out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float* w = sums + (size_t)(b * 2 + 0) * 4;
+  const float* z = sums + (size_t)(b * 2 + 1) * 4;
+  const float n = (float)HW;
+  const float var_w = (w[3] - w[2] * w[2] / n) / (n - 1.f), var_z = (z[3] - z[2] * z[2] / n) / (n - 1.f);  // torch.var: unbiased
+  const float rs_w = w[0] / w[1], rs_z = z[0] / z[1];
+  out[b * 4 + 0] = var_w / var_z;
+  out[b * 4 + 1] = rs_w / rs_z;
+  out[b * 4 + 2] = rs_w;
+  out[b * 4 + 3] = rs_z;
+}
+
+__global__ void __launch_bounds__(256) aee_kernel(const ef_aee_params p, float* __restrict__ ws) {
+  __shared__ float s_red[8];
+  const int b = blockIdx.y;
+  const size_t hw = (size_t)p.H * p.W;
+  const float k = p.flow_scaling * p.dt_ratio[b];
+  float se = 0.f, sn = 0.f, so = 0.f;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < hw; i += (size_t)gridDim.x * 256) {
+    const float fx = p.flow[((size_t)b * 2) * hw + i] * k, fy = p.flow[((size_t)b * 2 + 1) * hw + i] * k;
+    const float gx = p.gtflow[((size_t)b * 2) * hw + i], gy = p.gtflow[((size_t)b * 2 + 1) * hw + i];
+    const bool valid = (p.event_mask[(size_t)b * hw + i] != 0.f) && !(gx == 0.f && gy == 0.f);
+    const float m = valid ? 1.f : 0.f;
+    const float err = sqrtf((fx - gx) * (fx - gx) + (fy - gy) * (fy - gy)) * m;
+    const float mag = sqrtf(fx * fx + fy * fy) * m;
+    se += err;
+    sn += m;
+    so += (err > 3.0f && err > 0.05f * mag) ? 1.f : 0.f;
+  }
+  const float r0 = block_sum256(se, s_red), r1 = block_sum256(sn, s_red), r2 = block_sum256(so, s_red);
+  if (threadIdx.x == 0) {
+    atomicAdd(ws + b, r0);
+    atomicAdd(ws + p.B + b, r1);
+    atomicAdd(ws + 2 * p.B, r2);  // outliers are summed over the whole batch (loss/flow.py:625)
+  }
+}
+
+__global__ void aee_finalize_kernel(const float* __restrict__ ws, int B, float* __restrict__ out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  out[b] = ws[b] / (ws[B + b] + 1e-9f);
+  out[B + b] = ws[2 * B] / (ws[B + b] + 1e-9f);
+}
+
 static int validate_loss(const ef_iwe_loss_params& p, const char* who) {
   EF_REQUIRE(p.S > 0 && p.B > 0 && p.T > 0 && p.H > 0 && p.W > 0 && p.n_total >= 0, EF_EINVAL, "%s: bad dimensions", who);
   EF_REQUIRE(p.T_maps == (p.overwrite_intermediate ? 1 : p.T), EF_EINVAL, "%s: T_maps must be 1 with overwrite_intermediate, else T", who);
@@ -447,4 +551,46 @@ extern "C" int ef_iwe_image(const ef_iwe_image_params* pp, void* stream) {
   if (p.N == 0) return EF_OK;
   iwe_image_kernel<<<dim3(cdiv(p.N, 256), p.B), 256, 0, st>>>(p);
   return check_launch("iwe_image_kernel");
+}
+
+extern "C" int64_t ef_iwe_metrics_workspace_elems(int32_t B, int32_t H, int32_t W) { return (int64_t)B * 8 * H * W + (int64_t)B * 8; }
+
+extern "C" int ef_iwe_metrics(const ef_iwe_metrics_params* pp, void* stream) {
+  using namespace ef;
+  EF_REQUIRE(pp, EF_ENULL, "ef_iwe_metrics: params is NULL");
+  const ef_iwe_metrics_params& p = *pp;
+  EF_REQUIRE(p.B > 0 && p.T > 0 && p.H > 0 && p.W > 0 && p.n_total >= 0, EF_EINVAL, "ef_iwe_metrics: bad dimensions");
+  EF_REQUIRE(p.T_maps == p.T || p.T_maps == 1, EF_EINVAL, "ef_iwe_metrics: T_maps must be T or 1");
+  EF_REQUIRE(p.T_maps == 1 || p.pass_offsets || p.n_per_pass > 0, EF_EINVAL, "ef_iwe_metrics: n_per_pass or pass_offsets needed");
+  EF_REQUIRE(p.workspace && p.out && (p.n_total == 0 || (p.events && p.pol_mask && p.flow_maps)), EF_ENULL, "ef_iwe_metrics: NULL tensor");
+  cudaStream_t st = as_stream(stream);
+  const int HW = p.H * p.W;
+  float* img = p.workspace;
+  float* sums = p.workspace + (size_t)p.B * 8 * HW;
+  cudaMemsetAsync(p.workspace, 0, ((size_t)p.B * 8 * HW + (size_t)p.B * 8) * sizeof(float), st);
+  int rc;
+  if (p.n_total > 0) {
+    iwe_metric_scatter_kernel<<<dim3(cdiv(p.n_total, 256), p.B), 256, 0, st>>>(p, img);
+    if ((rc = check_launch("iwe_metric_scatter_kernel"))) return rc;
+  }
+  iwe_metric_reduce_kernel<<<dim3(cdiv(HW, RED_PIX), p.B * 2), 256, 0, st>>>(img, sums, HW, (float)p.T);
+  if ((rc = check_launch("iwe_metric_reduce_kernel"))) return rc;
+  iwe_metric_finalize_kernel<<<cdiv(p.B, 64), 64, 0, st>>>(sums, p.B, HW, p.out);
+  return check_launch("iwe_metric_finalize_kernel");
+}
+
+extern "C" int ef_aee(const ef_aee_params* pp, void* stream) {
+  using namespace ef;
+  EF_REQUIRE(pp, EF_ENULL, "ef_aee: params is NULL");
+  const ef_aee_params& p = *pp;
+  EF_REQUIRE(p.B > 0 && p.H > 0 && p.W > 0, EF_EINVAL, "ef_aee: bad dimensions");
+  EF_REQUIRE(p.flow && p.gtflow && p.event_mask && p.dt_ratio && p.workspace && p.out, EF_ENULL, "ef_aee: NULL tensor");
+  cudaStream_t st = as_stream(stream);
+  cudaMemsetAsync(p.workspace, 0, (2 * (size_t)p.B + 1) * sizeof(float), st);
+  const int blocks = cdiv(p.H * p.W, 256 * 8);
+  aee_kernel<<<dim3(blocks, p.B), 256, 0, st>>>(p, p.workspace);
+  int rc;
+  if ((rc = check_launch("aee_kernel"))) return rc;
+  aee_finalize_kernel<<<cdiv(p.B, 64), 64, 0, st>>>(p.workspace, p.B, p.out);
+  return check_launch("aee_finalize_kernel");
 }

@@ -94,3 +94,136 @@ class EventWarping(torch.nn.Module):
             overwrite_intermediate=overwrite,
             pass_offsets=offsets,
         )
+
+
+class BaseValidationLoss(torch.nn.Module):
+    """
+    Bookkeeping of the validation metrics (loss/flow.py:304-465): accumulates the window in map form like EventWarping;
+    the metric itself is one call into libeventflow.so.
+    """
+
+    def __init__(self, config, device, flow_scaling=128):
+        super().__init__()
+        self.res = config["loader"]["resolution"]
+        self.flow_scaling = flow_scaling  # should be specified by the user
+        self.overwrite_intermediate = (
+            False if "overwrite_intermediate" not in config["loss"].keys() else config["loss"]["overwrite_intermediate"]
+        )
+        self.device = device
+        self.reset()
+
+    def reset(self):
+        self._passes = 0
+        self._events, self._pol_masks, self._masks, self._flow_map = [], [], [], []
+        self._num_events = 0
+        self._overwritten = False
+        self._gtflow = None
+
+    @property
+    def num_events(self):
+        return self._num_events
+
+    def event_flow_association(self, flow_list, inputs):
+        """
+        :param flow_list: [[batch_size x 2 x H x W]] list of optical flow (x, y) maps
+        :param inputs: dataloader dictionary
+        """
+        event_list = inputs["event_list"].to(self.device)
+        pol_mask = inputs["event_list_pol_mask"].to(self.device)
+        event_mask = inputs["event_mask"].to(self.device)
+        self._gtflow = inputs["gtflow"].to(self.device) if "gtflow" in inputs.keys() else None
+        flow = flow_list[-1]  # only highest resolution flow
+        if self._passes > 0:
+            event_list = event_list.clone()  # to prevent issues with other metrics (loss/flow.py:367)
+            event_list[:, :, 0:1] += self._passes
+        self._events.append(event_list)
+        self._pol_masks.append(pol_mask)
+        self._masks.append(event_mask)
+        self._flow_map.append(flow.view(flow.shape[0], 2, self.res[0], self.res[1]))
+        self._num_events += event_list.shape[1]
+        self._dt_input = inputs["dt_input"]
+        self._dt_gt = inputs["dt_gt"]
+        self._passes += 1
+
+    def overwrite_intermediate_flow(self, flow_list):
+        flow = flow_list[-1]
+        self._flow_map = [flow.view(flow.shape[0], 2, self.res[0], self.res[1])]
+        mask = torch.sum(torch.cat(self._masks, dim=1), dim=1, keepdim=True)
+        mask[mask > 1] = 1
+        self._masks = [mask]
+        self._overwritten = True
+
+    def _window(self):
+        events = self._events[0] if len(self._events) == 1 else torch.cat(self._events, dim=1)
+        pol = self._pol_masks[0] if len(self._pol_masks) == 1 else torch.cat(self._pol_masks, dim=1)
+        maps = torch.stack(self._flow_map, dim=1)  # [B,Tm,2,H,W]
+        counts = [e.shape[1] for e in self._events]
+        offsets = None
+        if not self._overwritten and len(set(counts)) > 1:
+            offsets = torch.tensor([0] + list(torch.tensor(counts).cumsum(0)), dtype=torch.int32, device=events.device)
+        return events, pol, maps, counts[0], offsets
+
+    def compute_window_events(self):
+        """Per-polarity image of the (non-warped) events of the window (loss/flow.py:425-435)."""
+        events, pol, _, _, _ = self._window()
+        zero = torch.zeros(events.shape[0], 2, self.res[0], self.res[1], device=events.device)
+        return ops.iwe_image(events, pol, self.res, flow=zero, tref=float(self._passes), flow_scaling=self.flow_scaling, round_idx=True)
+
+    def compute_masked_window_flow(self):
+        """loss/flow.py:437-447 (visualisation helper: elementwise tensor arithmetic on the flow maps)."""
+        masks = torch.cat(self._masks, dim=1)
+        if self.overwrite_intermediate:
+            return self._flow_map[-1] * masks
+        avg_flow = self._flow_map[0] * masks[:, 0:1]
+        for i in range(1, masks.shape[1]):
+            avg_flow = avg_flow + self._flow_map[i] * masks[:, i:i + 1]
+        return avg_flow / (torch.sum(masks, dim=1, keepdim=True) + 1e-9)
+
+    def compute_window_iwe(self, round_idx=True):
+        """Per-polarity image of warped events of the window (loss/flow.py:449-465)."""
+        events, pol, maps, n0, offsets = self._window()
+        B, N = events.shape[:2]
+        # per-event flow gathered from the map of the event's own pass (as event_flow_association does in the reference)
+        if maps.shape[1] == 1:
+            t_idx = torch.zeros(N, dtype=torch.long, device=events.device)
+        elif offsets is not None:
+            t_idx = torch.bucketize(torch.arange(N, device=events.device), offsets[1:].long(), right=True).clamp(max=maps.shape[1] - 1)
+        else:
+            t_idx = (torch.arange(N, device=events.device) // n0).clamp(max=maps.shape[1] - 1)
+        flat = (events[:, :, 1] * self.res[1] + events[:, :, 2]).long()
+        f = maps.reshape(B, maps.shape[1], 2, -1)
+        bi = torch.arange(B, device=events.device).view(B, 1).expand(B, N)
+        ev_flow = torch.stack([f[bi, t_idx.view(1, N).expand(B, N), 1, flat], f[bi, t_idx.view(1, N).expand(B, N), 0, flat]], dim=2)
+        return ops.iwe_image(events, pol, self.res, event_flow=ev_flow, tref=float(self._passes), flow_scaling=self.flow_scaling,
+                             round_idx=round_idx)
+
+
+class FWL(BaseValidationLoss):
+    """Flow Warp Loss (loss/flow.py:468-500): spatial variance of the IWE over that of the image of events, per sample."""
+
+    def forward(self):
+        events, pol, maps, n0, offsets = self._window()
+        fwl, _ = ops.iwe_metrics(maps, events, pol, passes=self._passes, n_per_pass=n0, flow_scaling=self.flow_scaling, pass_offsets=offsets)
+        return fwl
+
+
+class RSAT(BaseValidationLoss):
+    """Ratio of the squared averaged timestamps (loss/flow.py:503-579), per sample."""
+
+    def forward(self):
+        events, pol, maps, n0, offsets = self._window()
+        _, rsat = ops.iwe_metrics(maps, events, pol, passes=self._passes, n_per_pass=n0, flow_scaling=self.flow_scaling, pass_offsets=offsets)
+        return rsat
+
+
+class AEE(BaseValidationLoss):
+    """Average endpoint error and outlier percentage (loss/flow.py:582-628)."""
+
+    @property
+    def num_events(self):
+        return float("inf")
+
+    def forward(self):
+        masks = torch.cat(self._masks, dim=1)
+        dt_ratio = torch.as_tensor(self._dt_gt, dtype=torch.float32) / torch.as_tensor(self._dt_input, dtype=torch.float32)
+        return ops.aee(self._flow_map[-1], self._gtflow, masks[:, -1], dt_ratio, self.flow_scaling)

@@ -337,3 +337,40 @@ def lif_step_cl(x_cl, v_in, z_in_cl, w_ff, w_rec, leak, thresh, *, hard_reset=Tr
     p.v_out, p.z_out_cl = L.ptr(v_out), L.ptr(z_out)
     L.call("ef_lif_conv_fwd", p, tag=(Cin, C, w_rec is not None))
     return v_out, z_out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# validation metrics
+# ---------------------------------------------------------------------------------------------------------------------
+def iwe_metrics(flow_maps, events, pol_mask, *, passes, n_per_pass, flow_scaling, pass_offsets=None):
+    """FWL and RSAT of a validation window (loss/flow.py:468-579).  flow_maps [B,Tm,2,H,W].  Returns (FWL [B], RSAT [B])."""
+    flow_maps, events, pol_mask = _c(flow_maps.detach().float()), _c(events.float()), _c(pol_mask.float())
+    _need_cuda(flow_maps, events, pol_mask)
+    B, Tm, _, H, W = flow_maps.shape
+    p = L.IweMetricsParams()
+    p.B, p.T, p.T_maps, p.H, p.W = B, int(passes), Tm, H, W
+    p.n_total, p.n_per_pass, p.flow_scaling = events.shape[1], int(n_per_pass), float(flow_scaling)
+    ws = torch.empty(L.lib().ef_iwe_metrics_workspace_elems(B, H, W), device=events.device, dtype=torch.float32)
+    out = torch.empty((B, 4), device=events.device, dtype=torch.float32)
+    p.events, p.pol_mask, p.flow_maps, p.pass_offsets = L.ptr(events), L.ptr(pol_mask), L.ptr(flow_maps), L.ptr(pass_offsets)
+    p.workspace, p.out = L.ptr(ws), L.ptr(out)
+    L.call("ef_iwe_metrics", p)
+    return out[:, 0], out[:, 1]
+
+
+def aee(flow, gtflow, event_mask, dt_ratio, flow_scaling):
+    """AEE and outlier percentage (loss/flow.py:597-628).  flow/gtflow [B,2,H,W], event_mask [B,H,W], dt_ratio [B]."""
+    flow, gtflow, event_mask = _c(flow.detach().float()), _c(gtflow.float()), _c(event_mask.float())
+    dt_ratio = _c(dt_ratio.to(flow.device).float().reshape(-1))
+    _need_cuda(flow, gtflow, event_mask, dt_ratio)
+    B, _, H, W = flow.shape
+    if dt_ratio.numel() == 1 and B > 1:
+        dt_ratio = dt_ratio.expand(B).contiguous()
+    p = L.AeeParams()
+    p.B, p.H, p.W, p.flow_scaling = B, H, W, float(flow_scaling)
+    ws = torch.empty(2 * B + 1, device=flow.device, dtype=torch.float32)
+    out = torch.empty((2, B), device=flow.device, dtype=torch.float32)
+    p.flow, p.gtflow, p.event_mask, p.dt_ratio, p.workspace, p.out = (L.ptr(flow), L.ptr(gtflow), L.ptr(event_mask), L.ptr(dt_ratio),
+                                                                     L.ptr(ws), L.ptr(out))
+    L.call("ef_aee", p)
+    return out[0], out[1]

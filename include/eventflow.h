@@ -219,6 +219,45 @@ typedef struct ef_iwe_image_params {
 int ef_iwe_image(const ef_iwe_image_params* p, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * Validation metrics on rounded-index IWEs.  Replaces FWL.forward and RSAT.forward (loss/flow.py:468-579) with
+ * get_interpolation(round_idx=True) / interpolate (utils/iwe.py:20-92) and spatial_variance (loss/flow.py:13-23).
+ * Per-event flow comes from flow maps as in ef_iwe_loss_fwd (pass layout identical); with T_maps == 1 every event reads map 0.
+ * out: [B][4] = FWL, RSAT, and the two RSAT terms (warped, unwarped) for inspection.  workspace: B*8*H*W + B*8 floats.
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct ef_iwe_metrics_params {
+  int32_t B, T, T_maps, H, W, n_total, n_per_pass;
+  float flow_scaling;
+  const float* events;           /* [B,Ntot,4] (ts offset by pass index)                                               */
+  const float* pol_mask;         /* [B,Ntot,2]                                                                         */
+  const float* flow_maps;        /* [B,T_maps,2,H,W]                                                                   */
+  const int32_t* pass_offsets;   /* int32[T+1] or NULL                                                                 */
+  float* workspace;
+  float* out;                    /* [B,4]                                                                              */
+} ef_iwe_metrics_params;
+
+int64_t ef_iwe_metrics_workspace_elems(int32_t B, int32_t H, int32_t W);
+int ef_iwe_metrics(const ef_iwe_metrics_params* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Average endpoint error.  Replaces AEE.forward (loss/flow.py:597-628): flow * flow_scaling * dt_gt/dt_input against the
+ * ground truth, on pixels with events and valid ground truth; outliers: error > 3 px and > 5 % of the flow magnitude.
+ * out: [2][B] = AEE per sample, then percent_AEE per sample (batch-wide outlier count / per-sample valid pixels, as the
+ * reference computes it, loss/flow.py:625-626).  workspace: 2*B + 1 floats.
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct ef_aee_params {
+  int32_t B, H, W;
+  float flow_scaling;
+  const float* flow;             /* [B,2,H,W] network output (last flow map)                                           */
+  const float* gtflow;           /* [B,2,H,W]                                                                          */
+  const float* event_mask;       /* [B,H,W] mask of the last pass                                                      */
+  const float* dt_ratio;         /* [B] dt_gt / dt_input (device)                                                      */
+  float* workspace;
+  float* out;                    /* [2,B]                                                                              */
+} ef_aee_params;
+
+int ef_aee(const ef_aee_params* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * Event encodings for one batch.  Replaces dataloader/encodings.py:30-85 (events_to_image/voxel/channels) and
  * dataloader/base.py:148-222 (cnt, mask, voxel, polarity mask).  events: [B,N,4] (ts,y,x,p).  Outputs overwritten;
  * any may be NULL.  Counts are integer-valued fp32 and bit-exact.

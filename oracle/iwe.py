@@ -174,3 +174,45 @@ def event_warping_loss(
         sm = smoothness_loss(fm[:, :, 0], fm[:, :, 1], event_mask, smoothing_mask, overwrite_intermediate)
         loss = loss + fw + bw + weight * sm
     return loss / len(flow_maps)
+
+
+def spatial_variance(x):
+    """loss/flow.py:13-23: unbiased variance over the pixels of each [B,C,H,W] channel."""
+    return torch.var(x.view(x.shape[0], x.shape[1], 1, -1), dim=3, keepdim=True)
+
+
+def fwl_rsat(events, pol_mask, ev_flow, passes, res, flow_scaling):
+    """
+    FWL.forward and RSAT.forward (loss/flow.py:481-500, 514-579) on an accumulated validation window.
+    events [B,N,4] (ts offset by pass), ev_flow [B,N,2] per-event flow (fy,fx).  Returns (FWL [B], RSAT [B]).
+    """
+    max_ts = passes
+    ts = events[:, :, 0:1]
+    out = []
+    for flow in (ev_flow, ev_flow * 0):
+        idx, w = warp_and_split(events, flow, max_ts, res, flow_scaling, round_idx=True)
+        iwe = scatter_image(idx, w, res)
+        pos = scatter_image(idx, w, res, pol_mask[:, :, 0:1])
+        neg = scatter_image(idx, w, res, pol_mask[:, :, 1:2])
+        pos_ts = scatter_image(idx, w * ts, res, pol_mask[:, :, 0:1]) / (pos + 1e-9) / max_ts
+        neg_ts = scatter_image(idx, w * ts, res, pol_mask[:, :, 1:2]) / (neg + 1e-9) / max_ts
+        ssum = torch.sum(pos_ts.view(pos.shape[0], -1) ** 2, dim=1) + torch.sum(neg_ts.view(neg.shape[0], -1) ** 2, dim=1)
+        nz = pos + neg
+        nz[nz > 0] = 1
+        out.append((spatial_variance(iwe).view(-1), ssum / torch.sum(nz.view(nz.shape[0], -1), dim=1)))
+    return out[0][0] / out[1][0], out[0][1] / out[1][1]
+
+
+def aee(flow, gtflow, event_mask, dt_gt, dt_input, flow_scaling):
+    """AEE.forward (loss/flow.py:597-628).  flow, gtflow [B,2,H,W]; event_mask [B,H,W] (last pass).  Returns (AEE [B], pct [B])."""
+    flow = flow * flow_scaling
+    flow = flow * (dt_gt / dt_input)
+    flow_mag = flow.pow(2).sum(1).sqrt()
+    error = (flow - gtflow).pow(2).sum(1).sqrt()
+    gt_mask = ~((gtflow[:, 0] == 0.0) * (gtflow[:, 1] == 0.0))
+    mask = (event_mask.bool() * gt_mask).view(flow.shape[0], -1)
+    error = error.view(flow.shape[0], -1) * mask
+    flow_mag = flow_mag.view(flow.shape[0], -1) * mask
+    n_valid = torch.sum(mask, dim=1)
+    outliers = (error > 3.0) * (error > 0.05 * flow_mag)
+    return torch.sum(error, dim=1) / (n_valid + 1e-9), outliers.sum() / (n_valid + 1e-9)

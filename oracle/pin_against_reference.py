@@ -330,6 +330,57 @@ def pin_iwe_and_encodings(riwe, renc, golden):
     print("iwe image + encodings pinned")
 
 
+def pin_metrics(rflow, golden):
+    """FWL / RSAT / AEE (loss/flow.py:468-628) on a 3-pass validation window, with and without overwrite_intermediate."""
+    B, H, W, T, N = 2, 16, 20, 3, 200
+    g = torch.Generator().manual_seed(21)
+    cfg = {"loader": {"resolution": [H, W]}, "loss": {"overwrite_intermediate": False}}
+    d_all = {}
+    for overwrite in (False, True):
+        cfg["loss"]["overwrite_intermediate"] = overwrite
+        metrics = {n: getattr(rflow, n)(cfg, torch.device("cpu"), flow_scaling=max(H, W)) for n in ("FWL", "RSAT", "AEE")}
+        flows, inputs = [], []
+        for t in range(T):
+            ts, ys, xs, ps = oenc.synthetic_events(B, N, H, W, 700 + t)
+            d = oenc.encode_window(ts, ys, xs, ps, H, W, 2)
+            gt = (torch.rand((B, 2, H, W), generator=g) - 0.5) * 12
+            gt[:, :, :3, :] = 0  # some pixels without valid ground truth
+            inp = {"event_list": d["event_list"], "event_list_pol_mask": d["event_list_pol_mask"], "event_mask": d["event_mask"],
+                   "gtflow": gt, "dt_input": torch.tensor(0.01), "dt_gt": torch.tensor(0.03)}  # eval runs with batch size 1: scalar dt
+            f = (torch.rand((B, 2, H, W), generator=g) - 0.5) * 0.3
+            flows.append(f), inputs.append(inp)
+            for m in metrics.values():
+                m.event_flow_association([f], inp)
+        if overwrite:
+            for m in metrics.values():
+                m.overwrite_intermediate_flow([flows[-1]])
+        fwl_r, rsat_r = metrics["FWL"](), metrics["RSAT"]()
+        aee_r, pct_r = metrics["AEE"]()
+        # oracle
+        events = torch.cat([inp["event_list"].clone() for inp in inputs], dim=1)
+        for t in range(T):
+            events[:, t * N:(t + 1) * N, 0] += t
+        pol = torch.cat([inp["event_list_pol_mask"] for inp in inputs], dim=1)
+        ev_flow = torch.cat([oiwe.gather_event_flow(flows[-1] if overwrite else flows[t], inputs[t]["event_list"], (H, W)) for t in range(T)], dim=1)
+        fwl_o, rsat_o = oiwe.fwl_rsat(events, pol, ev_flow, T, (H, W), max(H, W))
+        last_mask = inputs[-1]["event_mask"][:, 0]
+        if overwrite:  # overwrite_intermediate_flow collapses the masks of the window into their union (loss/flow.py:412-414)
+            last_mask = torch.cat([inp["event_mask"] for inp in inputs], 1).sum(1).clamp(max=1)
+        aee_o, pct_o = oiwe.aee(flows[-1], inputs[-1]["gtflow"], last_mask, inputs[-1]["dt_gt"], inputs[-1]["dt_input"], max(H, W))
+        close(pct_o.reshape(-1), pct_r.reshape(-1), 1e-6, f"metrics overwrite={overwrite} percent_AEE")
+        tag = f"metrics overwrite={overwrite}"
+        close(fwl_o, fwl_r, 1e-6, tag + " FWL"), close(rsat_o, rsat_r, 1e-6, tag + " RSAT")
+        close(aee_o, aee_r.view(-1) if aee_r.dim() else aee_r, 1e-6, tag + " AEE")
+        k = "ow" if overwrite else "seq"
+        d_all.update({f"{k}_fwl": fwl_r, f"{k}_rsat": rsat_r, f"{k}_aee": aee_r.reshape(-1), f"{k}_pct": pct_r.reshape(-1)})
+        if not overwrite:
+            d_all.update({"events": events, "pol_mask": pol, "flows": torch.stack(flows, 1), "gtflow": inputs[-1]["gtflow"],
+                          "event_masks": torch.cat([inp["event_mask"] for inp in inputs], 1), "dt_input": inputs[-1]["dt_input"],
+                          "dt_gt": inputs[-1]["dt_gt"]})
+        print(tag, "FWL", fwl_r.tolist(), "RSAT", rsat_r.tolist(), "AEE", aee_r.reshape(-1).tolist())
+    golden["metrics"] = d_all
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--check", action="store_true")
@@ -343,6 +394,7 @@ def main():
     pin_firenet(rmodel, golden, (1, 16, 16, 3))
     pin_loss(rflow, golden)
     pin_iwe_and_encodings(riwe, renc, golden)
+    pin_metrics(rflow, golden)
     if args.check:
         print("oracle == reference on all cases (check only)")
         return

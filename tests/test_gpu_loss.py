@@ -176,3 +176,39 @@ def test_empty_and_ragged_windows():
     # empty event list: IWE image is all zeros, no launch failure
     out = ops.iwe_image(torch.zeros(1, 0, 4, device=DEV), torch.zeros(1, 0, 2, device=DEV), (H, W), flow=torch.zeros(1, 2, H, W, device=DEV))
     assert out.abs().sum().item() == 0
+
+
+@pytest.mark.parametrize("overwrite", [False, True])
+def test_validation_metrics_match_reference(overwrite):
+    """FWL / RSAT / AEE classes (loss/flow.py:468-628) through the drop-in API against the reference's golden numbers."""
+    from event_flow_b200.loss.flow import AEE, FWL, RSAT
+
+    g = load_golden("metrics")
+    B, T = g["flows"].shape[:2]
+    H, W = g["flows"].shape[-2:]
+    N = g["events"].shape[1] // T
+    cfg = {"loader": {"resolution": [H, W]}, "loss": {"overwrite_intermediate": overwrite}}
+    metrics = [cls(cfg, DEV, flow_scaling=max(H, W)) for cls in (FWL, RSAT, AEE)]
+    for t in range(T):
+        e = g["events"][:, t * N:(t + 1) * N].clone()
+        e[:, :, 0] -= t
+        inputs = {"event_list": e, "event_list_pol_mask": g["pol_mask"][:, t * N:(t + 1) * N], "event_mask": g["event_masks"][:, t:t + 1],
+                  "gtflow": g["gtflow"], "dt_input": g["dt_input"], "dt_gt": g["dt_gt"]}
+        for m in metrics:
+            m.event_flow_association([g["flows"][:, t].to(DEV)], inputs)
+    assert metrics[0].num_events == T * N and metrics[2].num_events == float("inf")
+    if overwrite:
+        for m in metrics:
+            m.overwrite_intermediate_flow([g["flows"][:, -1].to(DEV)])
+    key = "ow" if overwrite else "seq"
+    assert_rel(metrics[0](), g[f"{key}_fwl"], 1e-5, "FWL")
+    assert_rel(metrics[1](), g[f"{key}_rsat"], 1e-5, "RSAT")
+    aee, pct = metrics[2]()
+    assert_rel(aee, g[f"{key}_aee"], 1e-5, "AEE")
+    assert_rel(pct, g[f"{key}_pct"], 1e-5, "percent_AEE")
+    # window images used by eval_flow.py for visualisation
+    iwe = metrics[0].compute_window_iwe()
+    ev_img = metrics[0].compute_window_events()
+    assert iwe.shape == (B, 2, H, W) and ev_img.shape == (B, 2, H, W)
+    assert ev_img.sum().item() == B * T * N  # every event lands in bounds when it is not warped
+    assert metrics[0].compute_masked_window_flow().shape == (B, 2, H, W)

@@ -138,3 +138,20 @@ def test_surrogate_curves_closed_form():
     assert torch.allclose(osp.surrogate_grad(x, 10.0, "arctanspike"), 1 / (1 + 10 * x * x))
     assert torch.allclose(osp.surrogate_grad(x, 10.0, "superspike"), 1 / (1 + 10 * x.abs()) ** 2)
     assert torch.allclose(osp.surrogate_grad(x, 1.0, "trianglespike"), torch.relu(1 - x.abs()))
+
+
+def test_validation_metrics_match_reference():
+    g = load_golden("metrics")
+    B, T = g["flows"].shape[:2]
+    H, W = g["flows"].shape[-2:]
+    N = g["events"].shape[1] // T
+    for key, overwrite in (("seq", False), ("ow", True)):
+        ev_flow = torch.cat([oiwe.gather_event_flow(g["flows"][:, -1 if overwrite else t], g["events"][:, t * N:(t + 1) * N], (H, W))
+                             for t in range(T)], dim=1)
+        fwl, rsat = oiwe.fwl_rsat(g["events"], g["pol_mask"], ev_flow, T, (H, W), max(H, W))
+        torch.testing.assert_close(fwl, g[f"{key}_fwl"], rtol=1e-6, atol=0)
+        torch.testing.assert_close(rsat, g[f"{key}_rsat"], rtol=1e-6, atol=0)
+        mask = g["event_masks"].sum(1).clamp(max=1) if overwrite else g["event_masks"][:, -1]
+        aee, pct = oiwe.aee(g["flows"][:, -1], g["gtflow"], mask, g["dt_gt"], g["dt_input"], max(H, W))
+        torch.testing.assert_close(aee, g[f"{key}_aee"], rtol=1e-6, atol=0)
+        torch.testing.assert_close(pct.reshape(-1), g[f"{key}_pct"], rtol=1e-6, atol=0)
