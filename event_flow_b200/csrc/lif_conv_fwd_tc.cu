@@ -55,8 +55,8 @@ __host__ __device__ inline TcSmemLayout tc_smem_layout(bool rec, int th, int tw)
   l.w_off = 0;
   const int wbytes = rec ? 2 * W_CONV_BYTES : W_CONV_BYTES;
   l.x_off = 0;
-  l.z_off = l.a_tile_bytes;                                 // rec: operand copies of z; ff: centre tile of z
-  l.stage_bytes = l.z_off + (rec ? l.a_tile_bytes : Z_TILE_BYTES);
+  l.z_off = l.a_tile_bytes;                                 // rec: operand tile of the previous spikes
+  l.stage_bytes = l.z_off + (rec ? l.a_tile_bytes : 0);
   l.nstage = (227 * 1024 - 1280 - Z_TILE_BYTES - wbytes) / l.stage_bytes;
   if (l.nstage > 4) l.nstage = 4;
   l.stage_off = wbytes;
@@ -73,6 +73,7 @@ struct TcParams {
   const float* leak;
   const float* thresh;
   const float* v_in;
+  const uint16_t* z_in;  // previous spikes, channels-last (read directly by the epilogue)
   float* v_out;
   long long* trace;  // debug: per-CTA timeline (clock64), NULL in production
   int skip;          // debug: ablation mask (1 = no v_out stores, 2 = no v_in loads, 4 = no MMAs, 8 = no spike store, 16 = no tmem loads)
@@ -81,7 +82,7 @@ struct TcParams {
 constexpr int TRACE_SLOTS = 8, TRACE_MAX_TILES = 32;  // [cta][tile][slot]
 #define EF_TRACE(it_, slot_)                                                                              \
   do {                                                                                                    \
-    if (p.trace && (it_) < TRACE_MAX_TILES)                                                               \
+    if (DEBUG && p.trace && (it_) < TRACE_MAX_TILES)                                                      \
       p.trace[((size_t)blockIdx.x * TRACE_MAX_TILES + (it_)) * TRACE_SLOTS + (slot_)] = clock64() - t_cta; \
   } while (0)
 
@@ -102,7 +103,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
+#ifdef EF_MBAR_POLL
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+#else
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+#endif
       "selp.u32 %0, 1, 0, p;\n\t"
       "}"
       : "=r"(ok)
@@ -186,7 +191,9 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {  
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---- the kernel ----------------------------------------------------------------------------------------------------
-template <bool HARD>
+// DEBUG = true compiles in the timeline trace and the ablation switches (ef_debug_tc_trace / ef_debug_tc_skip); the production
+// instantiation carries none of that code in its loops.
+template <bool HARD, bool DEBUG>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_zh,
                        const __grid_constant__ CUtensorMap map_zc, const __grid_constant__ CUtensorMap map_zout) {
@@ -196,6 +203,7 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
   const TcSmemLayout L = tc_smem_layout(rec, p.th, p.tw);
   const int NST = L.nstage;
   const int TH = p.th, TW = p.tw;
+  const int skip = DEBUG ? p.skip : 0;
   const uint32_t s_base = smem_u32(smem);
   // barriers: [0] weights, [1..NST] full, [1+NST..2NST] empty, then acc_full[2], acc_empty[2]; then the TMEM address word
   const uint32_t bar_w = s_base + L.bar_off;
@@ -206,7 +214,7 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.bar_off + 8 * (5 + 2 * NST));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long t_cta = clock64();
+  const long long t_cta = DEBUG ? clock64() : 0;
   if (threadIdx.x == 0) {
     mbar_init(bar_w, 1);
     for (int s = 0; s < NST; ++s) {
@@ -229,15 +237,18 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
   const uint32_t tmem_base = *tmem_slot;
 
   int n_my = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  if (p.skip & 32) n_my = 0;               // debug: prologue + teardown only
-  else if ((p.skip & 128) && n_my > 1) n_my = 1;  // debug: one tile per CTA
-  const uint32_t stage_tx = L.a_tile_bytes + (p.has_z ? (rec ? L.a_tile_bytes : Z_TILE_BYTES) : 0);
+  if (DEBUG) {
+    if (skip & 32) n_my = 0;                        // prologue + teardown only
+    else if ((skip & 128) && n_my > 1) n_my = 1;    // one tile per CTA
+  }
+  const uint32_t stage_tx = L.a_tile_bytes + ((p.has_z && rec) ? L.a_tile_bytes : 0);
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
     if (lane == 0) {
       const uint32_t wbytes = rec ? 2 * W_CONV_BYTES : W_CONV_BYTES;
-      if (p.skip & 64) {  // debug: no weight load
+      if (DEBUG && (skip & 64)) {
         mbar_arrive(bar_w);
       } else {
         mbar_expect_tx(bar_w, wbytes);
@@ -246,18 +257,20 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
       }
       for (int it = 0; it < n_my; ++it) {
         const int tile = blockIdx.x + it * gridDim.x;
-        const int b = tile / (p.tiles_x * p.tiles_y), r = tile % (p.tiles_x * p.tiles_y);
-        const int y0 = (r / p.tiles_x) * TH, x0 = (r % p.tiles_x) * TW;
+        const int b = tile / tiles_per_img, r = tile - b * tiles_per_img;
+        const int ty = r / p.tiles_x;
+        const int y0 = ty * TH, x0 = (r - ty * p.tiles_x) * TW;
         const int s = it % NST;
         const uint32_t ph = (it / NST) & 1;
         mbar_wait(bar_empty(s), ph ^ 1);
         const uint32_t st = s_base + L.stage_off + s * L.stage_bytes;
+        if (DEBUG && (skip & 512)) {  // no tile loads at all (pure barrier ring)
+          mbar_arrive(bar_full(s));
+          continue;
+        }
         mbar_expect_tx(bar_full(s), stage_tx);
         tma_load_4d(st + L.x_off, &map_x, bar_full(s), 0, x0 - 1, y0 - 1, b);
-        if (p.has_z) {
-          if (rec) tma_load_4d(st + L.z_off, &map_zh, bar_full(s), 0, x0 - 1, y0 - 1, b);
-          else tma_load_4d(st + L.z_off, &map_zc, bar_full(s), 0, x0, y0, b);
-        }
+        if (p.has_z && rec) tma_load_4d(st + L.z_off, &map_zh, bar_full(s), 0, x0 - 1, y0 - 1, b);
         EF_TRACE(it, 0);
       }
     }
@@ -267,6 +280,7 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
       mbar_wait(bar_w, 0);
       const uint64_t b_ff = umma_desc_sw64(s_base + L.w_off, ATOM_BYTES);
       const uint64_t b_rec = umma_desc_sw64(s_base + L.w_off + W_CONV_BYTES, ATOM_BYTES);
+      const bool do_rec = rec && p.has_z;
       for (int it = 0; it < n_my; ++it) {
         const int s = it % NST, a = it & 1;
         const uint32_t ph = (it / NST) & 1, aph = (it >> 1) & 1;
@@ -278,7 +292,7 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
         const uint32_t d_tmem = tmem_base + a * ACC_COLS;
         // One elected thread issues all MMAs of the tile: this instruction stream is serial, so everything per MMA is
         // reduced to two 64-bit adds on precomputed descriptors (offsets in 16-byte units are compile-time constants).
-        if (!(p.skip & 4)) {
+        if (!(DEBUG && (skip & 4))) {
           const uint64_t ax = umma_desc_sw64(st + L.x_off, L.row_bytes);
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
@@ -287,7 +301,7 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
               umma_bf16(d_tmem, ax + (uint64_t)((tap / 3) * (1024 / 16) + (tap % 3) * (PIX_BYTES / 16) + ks * 2),
                         b_ff + (uint64_t)(tap * (W_BLOCK_BYTES / 16) + ks * 2), (tap | ks) != 0);
           }
-          if (rec && p.has_z) {
+          if (do_rec) {
             const uint64_t az = umma_desc_sw64(st + L.z_off, L.row_bytes);
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
@@ -311,66 +325,91 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
     const int ph_ = m / TW, pw_ = m % TW;   // (row, col) inside the tile
     const bool store_thread = (threadIdx.x == 64);
     const int c0 = 16 * hsel;
-    float lam[16], thr[16];
+    float lam[16], thr[16], oml[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       lam[j] = sigmoidf_acc(__ldg(p.leak + c0 + j));
       thr[j] = fmaxf(__ldg(p.thresh + c0 + j), 0.01f);
+      oml[j] = __fsub_rn(1.0f, lam[j]);
     }
     uint4* zout_s = reinterpret_cast<uint4*>(smem + L.outz_off);
     const size_t plane = (size_t)p.H * p.W;
-    // membrane potential of the NEXT tile is prefetched into registers while the current tile is processed, so that the
-    // DRAM latency of these loads (the only operand not staged by TMA) is off the per-tile critical path
-    auto tile_origin = [&](int it_, int& b_, int& y0_, int& x0_) {
-      const int tile_ = blockIdx.x + it_ * gridDim.x;
-      b_ = tile_ / (p.tiles_x * p.tiles_y);
-      const int r_ = tile_ % (p.tiles_x * p.tiles_y);
-      y0_ = (r_ / p.tiles_x) * TH, x0_ = (r_ % p.tiles_x) * TW;
-    };
-    auto load_v = [&](int it_, float (&dst)[16]) {
-      int b_, y0_, x0_;
-      tile_origin(it_, b_, y0_, x0_);
-      const int gy_ = y0_ + ph_, gx_ = x0_ + pw_;
-      const bool ok = p.has_v && it_ < n_my && gy_ < p.H && gx_ < p.W;
-      size_t o_ = ((size_t)b_ * 32 + c0) * plane + (size_t)gy_ * p.W + gx_, st_ = plane;
-      if (p.skip & 256) o_ = ((size_t)(blockIdx.x + it_ * gridDim.x) * 32 + c0) * 128 + m, st_ = 128;  // debug: tile-blocked membrane
-#pragma unroll
-      for (int j = 0; j < 16; ++j) dst[j] = (ok && !(p.skip & 2)) ? __ldg(p.v_in + o_ + j * st_) : 0.f;
-    };
-    float vin[16];
-    load_v(0, vin);
-    for (int it = 0; it < n_my; ++it) {
+    // The membrane potential of the NEXT tile is prefetched into registers while the current tile is processed, so the DRAM
+    // latency of these loads (the only operand not staged by TMA) stays off the per-tile critical path.
+    struct TileAt {
+      const float* vin;   // &v_in[b][c0][gy][gx] or nullptr when there is nothing to load
+      const uint4* zin;   // &z_in[b][gy][gx][c0] (32 bytes = this thread's 16 channels) or nullptr
+      float* vout;        // &v_out[b][c0][gy][gx] or nullptr when the pixel is outside the image
       int b, y0, x0;
-      tile_origin(it, b, y0, x0);
+    };
+    // tile coordinates advance incrementally by gridDim.x tiles per iteration (no integer division inside the loop)
+    const int G = gridDim.x;
+    const int g_b = G / tiles_per_img, g_r = G - g_b * tiles_per_img, g_ty = g_r / p.tiles_x, g_tx = g_r - g_ty * p.tiles_x;
+    int nb = blockIdx.x / tiles_per_img, nty, ntx;
+    {
+      const int r0 = blockIdx.x - nb * tiles_per_img;
+      nty = r0 / p.tiles_x, ntx = r0 - nty * p.tiles_x;
+    }
+    int n_it = 0;  // iteration index the (nb, nty, ntx) cursor points at
+    auto locate_next = [&]() {
+      TileAt t;
+      t.b = nb, t.y0 = nty * TH, t.x0 = ntx * TW;
+      const int gy_ = t.y0 + ph_, gx_ = t.x0 + pw_;
+      const bool in_ = n_it < n_my && gy_ < p.H && gx_ < p.W;
+      const size_t o_ = ((size_t)t.b * 32 + c0) * plane + (size_t)gy_ * p.W + gx_;
+      t.vout = in_ ? p.v_out + o_ : nullptr;
+      t.vin = (in_ && p.has_v && !(DEBUG && (skip & 2))) ? p.v_in + o_ : nullptr;
+      t.zin = (in_ && p.has_z) ? reinterpret_cast<const uint4*>(p.z_in + (((size_t)t.b * p.H + gy_) * p.W + gx_) * 32 + c0) : nullptr;
+      // advance the cursor by G tiles
+      ntx += g_tx;
+      if (ntx >= p.tiles_x) ntx -= p.tiles_x, ++nty;
+      nty += g_ty;
+      if (nty >= p.tiles_y) nty -= p.tiles_y, ++nb;
+      nb += g_b;
+      ++n_it;
+      return t;
+    };
+    auto load_v = [&](const float* src, float (&dst)[16]) {
+      if (src) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) dst[j] = __ldg(src + j * plane);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) dst[j] = 0.f;
+      }
+    };
+    // The previous spikes of the pixel are read from global memory as well (32 bytes per thread), NOT from the TMA-written
+    // operand tile: an ordinary shared-memory load of TMA-written data right after the mbarrier wait occasionally returned
+    // a few stale 16-byte pieces (tools/tc_determinism.py), so no generic-proxy read of async-proxy data is left in this kernel.
+    auto load_z = [&](const uint4* src, uint4 (&dst)[2]) {
+      dst[0] = src ? __ldg(src) : make_uint4(0, 0, 0, 0);
+      dst[1] = src ? __ldg(src + 1) : make_uint4(0, 0, 0, 0);
+    };
+    TileAt cur = locate_next();
+    float vin[16];
+    uint4 zq[2];
+    load_v(cur.vin, vin);
+    load_z(cur.zin, zq);
+    for (int it = 0; it < n_my; ++it) {
       const int s = it % NST, a = it & 1;
       const uint32_t ph = (it / NST) & 1, aph = (it >> 1) & 1;
       const uint8_t* st = smem + L.stage_off + s * L.stage_bytes;
-      const int gy = y0 + ph_, gx = x0 + pw_;
-      const bool inb = gy < p.H && gx < p.W;
-      size_t vo = ((size_t)b * 32 + c0) * plane + (size_t)gy * p.W + gx, vstride = plane;
-      if (p.skip & 256) vo = ((size_t)(blockIdx.x + it * gridDim.x) * 32 + c0) * 128 + m, vstride = 128;  // debug: tile-blocked membrane
+      const TileAt nxt = locate_next();
       float vnext[16];
-      load_v(it + 1, vnext);
+      uint4 znext[2];
+      load_v(nxt.vin, vnext);
+      load_z(nxt.zin, znext);
 
-      mbar_wait(bar_full(s), ph);  // z_in of this tile has landed (acquire)
-      uint4 zq[2];
-#pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        const int gg = 2 * hsel + g;
-        if (!p.has_z) zq[g] = make_uint4(0, 0, 0, 0);
-        else if (rec)  // centre of the operand tile (swizzled: 16-byte chunk index XOR ((pixel-in-row >> 1) & 3))
-          zq[g] = *reinterpret_cast<const uint4*>(st + L.z_off + (ph_ + 1) * L.row_bytes + (pw_ + 1) * PIX_BYTES + ((gg ^ (((pw_ + 1) >> 1) & 3)) << 4));
-        else zq[g] = *reinterpret_cast<const uint4*>(st + L.z_off + m * PIX_BYTES + gg * 16);
-      }
+      mbar_wait(bar_full(s), ph);  // keeps the epilogue in step with the producer ring (it reads nothing from the stage)
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_empty(s));  // done reading this stage
+      if (lane == 0) mbar_arrive(bar_empty(s));
 
       mbar_wait(bar_accf(a), aph);
       tc_fence_after();
       if (store_thread) EF_TRACE(it, 3);
       uint32_t a_hi[16], a_mid[16], a_lo[16];
       const uint32_t tacc = tmem_base + a * ACC_COLS + c0 + ((uint32_t)(q * 32) << 16);
-      if (!(p.skip & 16)) {
+      if (!(DEBUG && (skip & 16))) {
         tmem_ld16(tacc, a_hi);
         tmem_ld16(tacc + 32, a_mid);
         tmem_ld16(tacc + 64, a_lo);
@@ -384,39 +423,43 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
       if (lane == 0) mbar_arrive(bar_acce(a));  // accumulator buffer may be overwritten by the MMA of tile it+2
       if (store_thread) EF_TRACE(it, 4);
 
+      const uint32_t zw[8] = {zq[0].x, zq[0].y, zq[0].z, zq[0].w, zq[1].x, zq[1].y, zq[1].z, zq[1].w};
+      float vn[16];
       uint32_t zpk[8];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         const float I = __fadd_rn(__fadd_rn(__uint_as_float(a_lo[j]), __uint_as_float(a_mid[j])), __uint_as_float(a_hi[j]));
-        const float v = vin[j];
-        const uint32_t zw = (&zq[j >> 3].x)[(j & 7) >> 1];
-        const float z = (j & 1) ? bf16_hi(zw) : bf16_lo(zw);
-        const float oml = __fsub_rn(1.0f, lam[j]);
-        float vn;
-        if (HARD) vn = __fadd_rn(__fmul_rn(__fmul_rn(v, lam[j]), __fsub_rn(1.0f, z)), __fmul_rn(oml, I));
-        else vn = __fsub_rn(__fadd_rn(__fmul_rn(v, lam[j]), __fmul_rn(oml, I)), __fmul_rn(z, thr[j]));
-        if (inb && !(p.skip & 1)) p.v_out[vo + j * vstride] = vn;
-        const uint32_t zb = (__fsub_rn(vn, thr[j]) > 0.f) ? 0x3F80u : 0u;  // bf16(1.0) = 0x3F80
+        const float z = (j & 1) ? bf16_hi(zw[j >> 1]) : bf16_lo(zw[j >> 1]);
+        if (HARD) vn[j] = __fadd_rn(__fmul_rn(__fmul_rn(vin[j], lam[j]), __fsub_rn(1.0f, z)), __fmul_rn(oml[j], I));
+        else vn[j] = __fsub_rn(__fadd_rn(__fmul_rn(vin[j], lam[j]), __fmul_rn(oml[j], I)), __fmul_rn(z, thr[j]));
+        const uint32_t zb = (__fsub_rn(vn[j], thr[j]) > 0.f) ? 0x3F80u : 0u;  // bf16(1.0) = 0x3F80
         if (j & 1) zpk[j >> 1] |= zb << 16;
         else zpk[j >> 1] = zb;
       }
-      if (store_thread) EF_TRACE(it, 5);
-      if (p.skip & 8) continue;
-      if (it > 0) {  // the staging buffer is free once the previous tile's TMA store has read it
-        if (store_thread) bulk_wait_read0();
-        named_bar_sync(1, 32 * TC_EPI_WARPS);
-      }
+      if (cur.vout && !(DEBUG && (skip & 1))) {
 #pragma unroll
-      for (int g = 0; g < 2; ++g) zout_s[m * 4 + 2 * hsel + g] = make_uint4(zpk[4 * g], zpk[4 * g + 1], zpk[4 * g + 2], zpk[4 * g + 3]);
+        for (int j = 0; j < 16; ++j) cur.vout[j * plane] = vn[j];
+      }
+      if (store_thread) EF_TRACE(it, 5);
+      if (!(DEBUG && (skip & 8))) {
+        if (it > 0) {  // the staging buffer is free once the previous tile's TMA store has read it
+          if (store_thread) bulk_wait_read0();
+          named_bar_sync(1, 32 * TC_EPI_WARPS);
+        }
+#pragma unroll
+        for (int g = 0; g < 2; ++g) zout_s[m * 4 + 2 * hsel + g] = make_uint4(zpk[4 * g], zpk[4 * g + 1], zpk[4 * g + 2], zpk[4 * g + 3]);
+        fence_proxy_async();  // make the staged spikes visible to the TMA engine
+        named_bar_sync(1, 32 * TC_EPI_WARPS);
+        if (store_thread) {
+          tma_store_4d(&map_zout, smem_u32(zout_s), 0, cur.x0, cur.y0, cur.b);
+          bulk_commit();
+          EF_TRACE(it, 6);
+        }
+      }
 #pragma unroll
       for (int j = 0; j < 16; ++j) vin[j] = vnext[j];
-      fence_proxy_async();  // make the staged spikes visible to the TMA engine
-      named_bar_sync(1, 32 * TC_EPI_WARPS);
-      if (store_thread) {
-        tma_store_4d(&map_zout, smem_u32(zout_s), 0, x0, y0, b);
-        bulk_commit();
-        EF_TRACE(it, 6);
-      }
+      zq[0] = znext[0], zq[1] = znext[1];
+      cur = nxt;
     }
     if (store_thread) {
       bulk_wait0();
@@ -532,7 +575,7 @@ int lif_conv_fwd_tc(const ef_lif_conv_params& p, cudaStream_t st) {
   static_assert((8 + 8) * PIX_BYTES == 1024, "the MMA issue loop hard-codes a 1024-byte operand row");
   q.tiles_x = cdiv(p.W, q.tw), q.tiles_y = cdiv(p.H, q.th), q.n_tiles = p.B * q.tiles_x * q.tiles_y;
   q.has_rec = rec, q.has_v = p.v_in != nullptr, q.has_z = p.z_in_cl != nullptr, q.hard_reset = p.hard_reset;
-  q.w_split = p.w_split, q.leak = p.leak, q.thresh = p.thresh, q.v_in = p.v_in, q.v_out = p.v_out;
+  q.w_split = p.w_split, q.leak = p.leak, q.thresh = p.thresh, q.v_in = p.v_in, q.z_in = p.z_in_cl, q.v_out = p.v_out;
   q.trace = g_tc_trace;
   q.skip = g_tc_skip;
   CUtensorMap mx, mzh, mzc, mzo;
@@ -541,18 +584,19 @@ int lif_conv_fwd_tc(const ef_lif_conv_params& p, cudaStream_t st) {
   if ((rc = get_map(p.z_out_cl, p.B, p.H, p.W, q.th, q.tw, false, &mzo))) return rc;
   mzh = mx, mzc = mzo;  // placeholders when there is no previous state
   if (q.has_z) {
-    if (rec) rc = get_map(p.z_in_cl, p.B, p.H, p.W, q.th + 2, q.tw + 8, true, &mzh);
-    else rc = get_map(p.z_in_cl, p.B, p.H, p.W, q.th, q.tw, false, &mzc);
-    if (rc) return rc;
+    if (rec && (rc = get_map(p.z_in_cl, p.B, p.H, p.W, q.th + 2, q.tw + 8, true, &mzh))) return rc;
   }
   const TcSmemLayout L = tc_smem_layout(rec, q.th, q.tw);
   const int grid = q.n_tiles < n_sms ? q.n_tiles : n_sms;
-  auto kern = p.hard_reset ? lif_conv_fwd_tc_kernel<true> : lif_conv_fwd_tc_kernel<false>;
-  static bool attr_set[2] = {false, false};
-  if (!attr_set[p.hard_reset ? 1 : 0]) {
+  const bool dbg = q.trace != nullptr || q.skip != 0;
+  auto kern = p.hard_reset ? (dbg ? lif_conv_fwd_tc_kernel<true, true> : lif_conv_fwd_tc_kernel<true, false>)
+                           : (dbg ? lif_conv_fwd_tc_kernel<false, true> : lif_conv_fwd_tc_kernel<false, false>);
+  static bool attr_set[4] = {false, false, false, false};
+  const int ki = (p.hard_reset ? 2 : 0) + (dbg ? 1 : 0);
+  if (!attr_set[ki]) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
       return check_launch("cudaFuncSetAttribute(lif_conv_fwd_tc_kernel)");
-    attr_set[p.hard_reset ? 1 : 0] = true;
+    attr_set[ki] = true;
   }
   kern<<<grid, TC_THREADS, L.total, st>>>(q, mx, mzh, mzc, mzo);
   return check_launch("lif_conv_fwd_tc_kernel");

@@ -93,3 +93,26 @@ def test_head_kernel_matches_generic_and_oracle(cin, hard, with_state):
     out_o, ns_o = osp.cell_step("lif", x, st, params, hard_reset=hard)
     spike_band_compare(v_h.cpu(), ops.unpack_cl(z_h).cpu(), ns_o[0], ns_o[1], params["thresh"].clamp_min(0.01))
     assert ops.unpack_cl(z_h).mean() > 0.02
+
+
+@pytest.mark.parametrize("rec", [False, True])
+def test_tc_kernel_repeated_launches_are_bit_identical(rec):
+    """
+    Race detector.  The kernel is a 10-warp producer / MMA / epilogue pipeline over mbarriers; a missing dependency shows up
+    as a few wrong values in a few launches (it did during development: tools/tc_determinism.py).  Launch a multi-tile-per-CTA
+    problem repeatedly: every launch must be bit-identical to the first and match the CUDA-core kernel.
+    """
+    from event_flow_b200 import ops
+
+    B, H, W = 16, 128, 128  # 2048 tiles on 148 persistent CTAs: ~14 pipelined tiles per CTA
+    params, x, st = make_case(B, H, W, rec, seed=5)
+    pd = {k: v.to(DEV).contiguous() for k, v in params.items()}
+    x_cl, v_in, z_in = ops.pack_cl(x.to(DEV)), st[0].to(DEV).contiguous(), ops.pack_cl(st[1].to(DEV))
+    ws = ops.split_weights(pd["ff"], pd.get("rec"))
+    args = (x_cl, v_in, z_in, pd["ff"], pd.get("rec"), pd["leak"].reshape(-1), pd["thresh"].reshape(-1))
+    v_cc, z_cc = ops.lif_step_cl(*args, hard_reset=True, w_split=None)
+    v0, z0 = ops.lif_step_cl(*args, hard_reset=True, w_split=ws)
+    assert (v0 - v_cc).abs().max() < 1e-4 and (z0 != z_cc).float().mean() < 1e-5
+    for _ in range(30):
+        v, z = ops.lif_step_cl(*args, hard_reset=True, w_split=ws)
+        assert torch.equal(v, v0) and torch.equal(z, z0)

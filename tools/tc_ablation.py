@@ -43,7 +43,7 @@ for rec in (False, True):
     for mask, name in ((0, "full"), (256, "tile-blocked membrane addressing"), (1, "no v_out stores"), (2, "no v_in loads"), (3, "no v traffic"), (4, "no MMAs"), (8, "no spike store/barriers"),
                        (16, "no tmem loads"), (4 + 16, "no MMA, no tmem ld"), (1 + 2 + 8, "no v traffic, no spike store"), (31, "everything off"),
                        (32, "prologue+teardown only"), (32 + 64, "prologue w/o weights"), (128, "1 tile per CTA"), (128 + 31, "1 tile/CTA, everything off"),
-                       (64 + 31, "everything off, no weights")):
+                       (64 + 31, "everything off, no weights"), (512 + 31, "everything off, no tile loads (barrier ring only)")):
         L.lib().ef_debug_tc_skip(mask)
         ts = []
         for _ in range(12):
