@@ -69,6 +69,16 @@ class IweImageParams(C.Structure):
     ]  # fmt: skip
 
 
+class ConvAnnParams(C.Structure):
+    _fields_ = [
+        ("B", _i32), ("C1", _i32), ("C2", _i32), ("Cout", _i32), ("H", _i32), ("W", _i32), ("act", _i32),
+        ("x1", _f32p), ("x2", _f32p), ("x2_scale", _f32p),
+        ("x1_bstride", C.c_int64), ("x2_bstride", C.c_int64), ("x2_scale_bstride", C.c_int64),
+        ("w", _f32p), ("bias", _f32p), ("residual", _f32p), ("blend_h", _f32p), ("blend_u", _f32p),
+        ("blend_h_bstride", C.c_int64), ("blend_u_bstride", C.c_int64), ("out", _f32p),
+    ]  # fmt: skip
+
+
 class IweMetricsParams(C.Structure):
     _fields_ = [
         ("B", _i32), ("T", _i32), ("T_maps", _i32), ("H", _i32), ("W", _i32), ("n_total", _i32), ("n_per_pass", _i32),
@@ -111,6 +121,7 @@ EXPORTS = {
     "ef_iwe_loss_fwd": (C.c_int, [C.POINTER(IweLossParams), C.c_void_p]),
     "ef_iwe_loss_bwd": (C.c_int, [C.POINTER(IweLossParams), C.c_void_p]),
     "ef_iwe_image": (C.c_int, [C.POINTER(IweImageParams), C.c_void_p]),
+    "ef_conv_ann_fwd": (C.c_int, [C.POINTER(ConvAnnParams), C.c_void_p]),
     "ef_iwe_metrics_workspace_elems": (C.c_int64, [_i32, _i32, _i32]),
     "ef_iwe_metrics": (C.c_int, [C.POINTER(IweMetricsParams), C.c_void_p]),
     "ef_aee": (C.c_int, [C.POINTER(AeeParams), C.c_void_p]),

@@ -18,26 +18,24 @@ from .spiking_submodules import (
     ConvXLIF,
     ConvXLIFRecurrent,
 )
-from .submodules import ConvLayer
+from .submodules import ConvGRU, ConvLayer, ConvLayer_
 
 
 class FireNet(BaseModel):
     """
     7-cell chain head-G1-R1a-R1b-G2-R2a-R2b + 1x1 tanh prediction (models/model.py:148-286).
-    The base class itself (ANN cells: ConvLayer_ / ConvGRU) is not on the CUDA path yet; use the spiking subclasses.
+    The base class is the ANN FireNet (ConvLayer_ + ConvGRU cells, forward only in this version).
     """
 
-    head_neuron = None
-    ff_neuron = None
-    rec_neuron = None
+    head_neuron = ConvLayer_
+    ff_neuron = ConvLayer_
+    rec_neuron = ConvGRU
     residual = False
     num_recurrent_units = 7
     w_scale_pred = None
 
     def __init__(self, unet_kwargs):
         super().__init__()
-        if self.head_neuron is None:
-            raise NotImplementedError("ANN FireNet (ConvLayer_/ConvGRU cells) is not implemented in this version; use LIFFireNet etc.")
         self.num_bins = unet_kwargs["num_bins"]
         base_num_channels = unet_kwargs["base_num_channels"]
         kernel_size = unet_kwargs["kernel_size"]
@@ -129,6 +127,16 @@ class FireNet(BaseModel):
             activity = None
 
         return {"flow": [flow], "activity": activity}
+
+
+class FireFlowNet(FireNet):
+    """EV-FireFlowNet: all-feed-forward ANN FireNet (models/model.py:398-409)."""
+
+    head_neuron = ConvLayer_
+    ff_neuron = ConvLayer_
+    rec_neuron = ConvLayer_
+    residual = False
+    w_scale_pred = 0.01
 
 
 class LIFFireNet(FireNet):

@@ -374,3 +374,59 @@ def aee(flow, gtflow, event_mask, dt_ratio, flow_scaling):
                                                                      L.ptr(ws), L.ptr(out))
     L.call("ef_aee", p)
     return out[0], out[1]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# ANN cells (forward only in this version)
+# ---------------------------------------------------------------------------------------------------------------------
+_ACT_CODES = {None: 0, "relu": 1, "sigmoid": 2, "tanh": 3}
+
+
+class _NoBackward(torch.autograd.Function):
+    """Marks tensors produced by forward-only kernels: asking for their gradient fails loudly instead of silently giving zeros."""
+
+    @staticmethod
+    def forward(ctx, out, *deps):
+        return out.view_as(out)
+
+    @staticmethod
+    def backward(ctx, g):
+        raise NotImplementedError("event_flow_b200: the backward of the ANN cells (ConvLayer_/ConvGRU) is not built yet")
+
+
+def conv_ann(x1, weight, bias, act, *, x2=None, x2_scale=None, residual=None, blend_h=None, blend_u=None):
+    """
+    act(conv3x3(cat([x1, x2 * x2_scale]), weight) + bias + residual), optionally blended h*(1-u) + (.)*u.
+    x2 / x2_scale / blend_* may be channel slices of larger NCHW tensors (only the batch stride may be non-dense).
+    """
+    def plane_ok(t):
+        return t is None or (t.stride(-1) == 1 and t.stride(-2) == t.shape[-1] and t.stride(1) == t.shape[-1] * t.shape[-2])
+
+    x1 = x1 if plane_ok(x1) else x1.contiguous()
+    tensors = [x2, x2_scale, residual, blend_h, blend_u]
+    tensors = [t if plane_ok(t) else t.contiguous() for t in tensors]
+    x2, x2_scale, residual, blend_h, blend_u = tensors
+    weight, bias = _c(weight.detach()), (None if bias is None else _c(bias.detach()))
+    residual = None if residual is None else residual.contiguous()
+    _need_cuda(x1, x2, x2_scale, residual, blend_h, blend_u, weight, bias)
+    B, C1, H, W = x1.shape
+    C2 = 0 if x2 is None else x2.shape[1]
+    Cout = weight.shape[0]
+    assert weight.shape[1] == C1 + C2 and weight.shape[2:] == (3, 3), "conv_ann: weight shape does not match the inputs"
+    out = torch.empty((B, Cout, H, W), device=x1.device, dtype=torch.float32)
+    p = L.ConvAnnParams()
+    p.B, p.C1, p.C2, p.Cout, p.H, p.W, p.act = B, C1, C2, Cout, H, W, _ACT_CODES[act]
+    raw = lambda t: None if t is None else t.data_ptr()  # noqa: E731  (slices are not "contiguous"; strides are passed explicitly)
+    p.x1, p.x2, p.x2_scale = raw(x1), raw(x2), raw(x2_scale)
+    p.x1_bstride = x1.stride(0)
+    p.x2_bstride = 0 if x2 is None else x2.stride(0)
+    p.x2_scale_bstride = 0 if x2_scale is None else x2_scale.stride(0)
+    p.w, p.bias, p.residual = L.ptr(weight), L.ptr(bias), L.ptr(residual)
+    p.blend_h, p.blend_u = raw(blend_h), raw(blend_u)
+    p.blend_h_bstride = 0 if blend_h is None else blend_h.stride(0)
+    p.blend_u_bstride = 0 if blend_u is None else blend_u.stride(0)
+    p.out = L.ptr(out)
+    L.call("ef_conv_ann_fwd", p)
+    if torch.is_grad_enabled() and (x1.requires_grad or weight.requires_grad):
+        out = _NoBackward.apply(out)
+    return out

@@ -161,6 +161,32 @@ int ef_pred_fwd(const ef_pred_params* p, void* stream);
 int ef_pred_bwd(const ef_pred_params* p, void* stream); /* needs y (forward output), x, g_y */
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * ANN cells: 3x3 convolution (pad 1, stride 1) + bias + residual + activation, optionally over cat([x1, x2 * x2_scale])
+ * and with a gated blend out = h*(1-u) + act(...)*u.  Replaces ConvLayer.forward / ConvLayer_.forward
+ * (models/submodules.py:52-83) and, in two calls, ConvGRU.forward (models/submodules.py:400-418):
+ *   call 1: x1 = input, x2 = h, w = [update_gate.weight; reset_gate.weight], act = sigmoid      -> ur [B, 2C, H, W]
+ *   call 2: x1 = input, x2 = h, x2_scale = reset, w = out_gate.weight, act = tanh, blend_h = h, blend_u = update -> new h
+ * Tensors are fp32 NCHW planes; the *_bstride fields are the element distance between samples (lets a channel slice of a
+ * larger tensor be passed).  act: 0 none, 1 relu, 2 sigmoid, 3 tanh.  Forward only in this version.
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct ef_conv_ann_params {
+  int32_t B, C1, C2, Cout, H, W, act;
+  const float* x1;               /* [B,C1,H,W]                                                                         */
+  const float* x2;               /* [B,C2,H,W] or NULL (C2 = 0)                                                        */
+  const float* x2_scale;         /* [B,C2,H,W] elementwise multiplier of x2 or NULL                                    */
+  int64_t x1_bstride, x2_bstride, x2_scale_bstride;
+  const float* w;                /* [Cout, C1 + C2, 3, 3]                                                              */
+  const float* bias;             /* [Cout] or NULL                                                                     */
+  const float* residual;         /* [B,Cout,H,W] added before the activation, or NULL                                  */
+  const float* blend_h;          /* [B,Cout,H,W] or NULL                                                               */
+  const float* blend_u;          /* [B,Cout,H,W] or NULL                                                               */
+  int64_t blend_h_bstride, blend_u_bstride;
+  float* out;                    /* [B,Cout,H,W]                                                                       */
+} ef_conv_ann_params;
+
+int ef_conv_ann_fwd(const ef_conv_ann_params* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * Contrast-maximisation event-warping loss over one training window.
  * Replaces EventWarping.forward (loss/flow.py:176-301) with utils/iwe.py:4-92 (purge_unfeasible, get_interpolation,
  * interpolate) and the per-event flow gather of event_flow_association (loss/flow.py:65-79), and -- ef_iwe_loss_bwd --

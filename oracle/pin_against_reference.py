@@ -330,6 +330,51 @@ def pin_iwe_and_encodings(riwe, renc, golden):
     print("iwe image + encodings pinned")
 
 
+def ann_params_of(m, recurrent):
+    params = {}
+    for name in osp.FIRENET_LAYERS:
+        cell = getattr(m, name)
+        if recurrent and name in osp.FIRENET_RECURRENT:
+            params[name] = {"update_w": cell.update_gate.weight, "update_b": cell.update_gate.bias, "reset_w": cell.reset_gate.weight,
+                            "reset_b": cell.reset_gate.bias, "out_w": cell.out_gate.weight, "out_b": cell.out_gate.bias}
+        else:
+            params[name] = {"w": cell.conv2d.weight, "b": cell.conv2d.bias}
+    params["pred"] = {"weight": m.pred.conv2d.weight, "bias": m.pred.conv2d.bias}
+    return params
+
+
+def pin_ann_firenet(rmodel, golden):
+    """ANN FireNet (ConvGRU) and FireFlowNet, BASELINE cfg 1 plumbing: 1 voxel bin, batch 1; plus a 2-bin cnt variant."""
+    for cls, recurrent, bins, enc in ((rmodel.FireNet, True, 1, "voxel"), (rmodel.FireFlowNet, False, 2, "cnt")):
+        cls.kwargs = [{}] * 7
+        torch.manual_seed(7)
+        cfg = dict(name="x", encoding=enc, round_encoding=False, norm_input=False, num_bins=bins, base_num_channels=32, kernel_size=3,
+                   activations=["relu", None], mask_output=True, spiking_neuron=None)
+        m = cls(cfg).eval()
+        params = ann_params_of(m, recurrent)
+        B, H, W, T = 1, 32, 40, 3
+        m.reset_states()
+        states = [None] * 7
+        d_all = {}
+        with torch.no_grad():
+            for t in range(T):
+                ts, ys, xs, ps = oenc.synthetic_events(B, 1000, H, W, 4000 + t)
+                d = oenc.encode_window(ts, ys, xs, ps, H, W, bins)
+                x = d["event_voxel"] if enc == "voxel" else d["event_cnt"]
+                out = m(d["event_voxel"].clone(), d["event_cnt"].clone())
+                flow_o, states, _ = osp.firenet_ann_step(params, states, x, recurrent=recurrent)
+                close(flow_o, out["flow"][0], 0, f"ann {cls.__name__} flow[{t}]")
+                d_all[f"x_{t}"], d_all[f"flow_{t}"] = x, out["flow"][0]
+            for i, s_ in enumerate(m.states):
+                if recurrent and i in (1, 4):
+                    close(states[i], s_, 0, f"ann {cls.__name__} state[{i}]")
+                    d_all[f"state_{i}"] = s_
+        for nm, q in m.state_dict().items():
+            d_all["sd_" + nm] = q
+        golden[f"ann_{cls.__name__.lower()}"] = d_all
+        print(f"ann {cls.__name__} pinned; |flow| max {out['flow'][0].abs().max().item():.4f}")
+
+
 def pin_metrics(rflow, golden):
     """FWL / RSAT / AEE (loss/flow.py:468-628) on a 3-pass validation window, with and without overwrite_intermediate."""
     B, H, W, T, N = 2, 16, 20, 3, 200
@@ -395,6 +440,7 @@ def main():
     pin_loss(rflow, golden)
     pin_iwe_and_encodings(riwe, renc, golden)
     pin_metrics(rflow, golden)
+    pin_ann_firenet(rmodel, golden)
     if args.check:
         print("oracle == reference on all cases (check only)")
         return

@@ -239,3 +239,46 @@ def init_firenet_params(neuron, num_bins, channels=32, ksize=3, seed=0, weight_g
         params[name] = p
     params["pred"] = {"weight": U((2, channels, 1, 1), 0.01), "bias": torch.zeros(2)}
     return params
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# ANN cells of the FireNet family (models/submodules.py:64-83, 377-418) and the ANN chain (models/model.py:254-265)
+# ---------------------------------------------------------------------------------------------------------------------
+def conv_layer_step(x, weight, bias, activation="relu", residual=0):
+    """ConvLayer_.forward (submodules.py:69-83): conv + bias, += residual, activation."""
+    out = F.conv2d(x, weight, bias, 1, weight.shape[-1] // 2)
+    out = out + residual
+    if activation is not None:
+        out = getattr(torch, activation)(out)
+    return out
+
+
+def conv_gru_step(x, h, p):
+    """ConvGRU.forward (submodules.py:400-418).  p: update_w/b, reset_w/b, out_w/b; h may be None (zeros)."""
+    if h is None:
+        h = torch.zeros(x.shape[0], p["out_w"].shape[0], *x.shape[2:], dtype=x.dtype)
+    stacked = torch.cat([x, h], dim=1)
+    update = torch.sigmoid(F.conv2d(stacked, p["update_w"], p["update_b"], 1, 1))
+    reset = torch.sigmoid(F.conv2d(stacked, p["reset_w"], p["reset_b"], 1, 1))
+    out = torch.tanh(F.conv2d(torch.cat([x, h * reset], dim=1), p["out_w"], p["out_b"], 1, 1))
+    return h * (1 - update) + out * update
+
+
+def firenet_ann_step(params, states, x, ff_act="relu", recurrent=True):
+    """
+    ANN FireNet (recurrent=True: ConvGRU at G1/G2) or FireFlowNet (all ConvLayer_) forward pass.
+    params[layer] = {"w","b"} for conv cells, the 6 gate tensors for GRU cells; params["pred"] = {"weight","bias"}.
+    states: list of 7 (GRU hidden state or None).  Returns flow, new states, per-layer outputs.
+    """
+    new_states, acts = [], []
+    h = x
+    for i, name in enumerate(FIRENET_LAYERS):
+        if recurrent and name in FIRENET_RECURRENT:
+            h = conv_gru_step(h, states[i], params[name])
+            new_states.append(h)
+        else:
+            h = conv_layer_step(h, params[name]["w"], params[name]["b"], ff_act)
+            new_states.append(None)
+        acts.append(h)
+    flow = pred_head(h, params["pred"]["weight"], params["pred"]["bias"])
+    return flow, new_states, acts

@@ -212,3 +212,33 @@ def test_dropin_training_loop_like_train_flow():
     assert any((a - b.detach()).abs().max() > 0 for a, b in zip(before, model.parameters()))
     for s in [k for k in sys.modules if k.split(".")[0] in ("models", "loss", "utils", "dataloader")]:
         sys.modules.pop(s, None)
+
+
+@pytest.mark.parametrize("name,recurrent", [("ann_firenet", True), ("ann_fireflownet", False)])
+def test_ann_firenet_forward_matches_reference_golden(name, recurrent):
+    """BASELINE cfg 1: ANN FireNet (ConvLayer_ + ConvGRU) forward, 1 voxel bin, batch 1; and FireFlowNet.  fp32 CUDA cores: 1e-4."""
+    import event_flow_b200.models.model as M
+
+    g = load_golden(name)
+    bins = g["x_0"].shape[1]
+    cls = M.FireNet if recurrent else M.FireFlowNet
+    cfg = dict(name="x", encoding="voxel" if bins == 1 else "cnt", round_encoding=False, norm_input=False, num_bins=bins, base_num_channels=32,
+               kernel_size=3, activations=["relu", None], mask_output=True, spiking_neuron=None)
+    m = cls(cfg)
+    m.load_state_dict({k[3:]: v for k, v in g.items() if k.startswith("sd_")})
+    m = m.to(DEV).eval()
+    T = sum(1 for k in g if k.startswith("x_"))
+    with torch.no_grad():
+        for t in range(T):
+            x = g[f"x_{t}"].to(DEV)
+            out = m(x, x)
+            torch.testing.assert_close(out["flow"][0].cpu(), g[f"flow_{t}"], rtol=1e-4, atol=1e-6)
+    if recurrent:
+        for i in (1, 4):
+            torch.testing.assert_close(m.states[i].cpu(), g[f"state_{i}"], rtol=1e-4, atol=1e-6)
+    # the backward of the ANN cells is not built: asking for it must fail loudly, not return zeros
+    x = g["x_0"].to(DEV)
+    m.reset_states()
+    out = m(x, x)
+    with pytest.raises(NotImplementedError):
+        out["flow"][0].sum().backward()

@@ -155,3 +155,25 @@ def test_validation_metrics_match_reference():
         aee, pct = oiwe.aee(g["flows"][:, -1], g["gtflow"], mask, g["dt_gt"], g["dt_input"], max(H, W))
         torch.testing.assert_close(aee, g[f"{key}_aee"], rtol=1e-6, atol=0)
         torch.testing.assert_close(pct.reshape(-1), g[f"{key}_pct"], rtol=1e-6, atol=0)
+
+
+def ann_params_from_golden(g, recurrent):
+    params = {}
+    for name in osp.FIRENET_LAYERS:
+        if recurrent and name in osp.FIRENET_RECURRENT:
+            params[name] = {f"{k}_{s}": g[f"sd_{name}.{k}_gate.{'weight' if s == 'w' else 'bias'}"] for k in ("update", "reset", "out") for s in ("w", "b")}
+        else:
+            params[name] = {"w": g[f"sd_{name}.conv2d.weight"], "b": g[f"sd_{name}.conv2d.bias"]}
+    params["pred"] = {"weight": g["sd_pred.conv2d.weight"], "bias": g["sd_pred.conv2d.bias"]}
+    return params
+
+
+@pytest.mark.parametrize("name,recurrent", [("ann_firenet", True), ("ann_fireflownet", False)])
+def test_ann_firenet_matches_reference(name, recurrent):
+    g = load_golden(name)
+    params = ann_params_from_golden(g, recurrent)
+    states = [None] * 7
+    T = sum(1 for k in g if k.startswith("x_"))
+    for t in range(T):
+        flow, states, _ = osp.firenet_ann_step(params, states, g[f"x_{t}"], recurrent=recurrent)
+        assert torch.equal(flow, g[f"flow_{t}"])
