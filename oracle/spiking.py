@@ -264,7 +264,7 @@ def conv_gru_step(x, h, p):
     return h * (1 - update) + out * update
 
 
-def firenet_ann_step(params, states, x, ff_act="relu", recurrent=True):
+def firenet_ann_step(params, states, x, ff_act="relu", rec_act=None, recurrent=True):
     """
     ANN FireNet (recurrent=True: ConvGRU at G1/G2) or FireFlowNet (all ConvLayer_) forward pass.
     params[layer] = {"w","b"} for conv cells, the 6 gate tensors for GRU cells; params["pred"] = {"weight","bias"}.
@@ -276,8 +276,8 @@ def firenet_ann_step(params, states, x, ff_act="relu", recurrent=True):
         if recurrent and name in FIRENET_RECURRENT:
             h = conv_gru_step(h, states[i], params[name])
             new_states.append(h)
-        else:
-            h = conv_layer_step(h, params[name]["w"], params[name]["b"], ff_act)
+        else:  # FireFlowNet builds G1/G2 as ConvLayer_ with the *recurrent* activation of the config (model.py:175-187)
+            h = conv_layer_step(h, params[name]["w"], params[name]["b"], rec_act if name in FIRENET_RECURRENT else ff_act)
             new_states.append(None)
         acts.append(h)
     flow = pred_head(h, params["pred"]["weight"], params["pred"]["bias"])
