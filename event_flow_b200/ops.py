@@ -390,7 +390,7 @@ class _NoBackward(torch.autograd.Function):
         return out.view_as(out)
 
     @staticmethod
-    def backward(ctx, g):
+    def backward(ctx, *g):
         raise NotImplementedError("event_flow_b200: the backward of the ANN cells (ConvLayer_/ConvGRU) is not built yet")
 
 
@@ -406,6 +406,7 @@ def conv_ann(x1, weight, bias, act, *, x2=None, x2_scale=None, residual=None, bl
     tensors = [x2, x2_scale, residual, blend_h, blend_u]
     tensors = [t if plane_ok(t) else t.contiguous() for t in tensors]
     x2, x2_scale, residual, blend_h, blend_u = tensors
+    grad_deps = [t for t in (x1, x2, weight, bias) if t is not None and t.requires_grad] if torch.is_grad_enabled() else []
     weight, bias = _c(weight.detach()), (None if bias is None else _c(bias.detach()))
     residual = None if residual is None else residual.contiguous()
     _need_cuda(x1, x2, x2_scale, residual, blend_h, blend_u, weight, bias)
@@ -427,6 +428,6 @@ def conv_ann(x1, weight, bias, act, *, x2=None, x2_scale=None, residual=None, bl
     p.blend_u_bstride = 0 if blend_u is None else blend_u.stride(0)
     p.out = L.ptr(out)
     L.call("ef_conv_ann_fwd", p)
-    if torch.is_grad_enabled() and (x1.requires_grad or weight.requires_grad):
-        out = _NoBackward.apply(out)
+    if grad_deps:
+        out = _NoBackward.apply(out, *grad_deps)
     return out
