@@ -8,7 +8,7 @@ LIB       := event_flow_b200/lib/libeventflow.so
 
 all: $(LIB)
 
-build/%.o: event_flow_b200/csrc/%.cu event_flow_b200/csrc/common.cuh include/eventflow.h
+build/%.o: event_flow_b200/csrc/%.cu event_flow_b200/csrc/common.cuh event_flow_b200/csrc/tc_common.cuh include/eventflow.h
 	@mkdir -p build
 	$(NVCC) $(NVCCFLAGS) -c $< -o $@ 2> build/$*.ptxas.log || (cat build/$*.ptxas.log; false)
 

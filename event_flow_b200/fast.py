@@ -74,8 +74,9 @@ class _Arena:
         if self.bwd is None:
             B, H, W, dev = self.key
             mk = lambda: torch.empty((B, 32, H, W), device=dev, dtype=torch.float32)  # noqa: E731
+            mkcl = lambda: torch.empty((B, H, W, 32), device=dev, dtype=torch.bfloat16)  # noqa: E731
             self.bwd = {"g_h": [mk(), mk()], "scratch": mk(), "g_v": [[mk() for _ in range(N_L)] for _ in range(2)],
-                        "g_z": [[mk() for _ in range(N_L)] for _ in range(2)]}
+                        "g_z": [[mk() for _ in range(N_L)] for _ in range(2)], "gI_hi": mkcl(), "gI_mid": mkcl()}
         return self.bwd
 
 
@@ -123,10 +124,12 @@ def _split_cache(model):
         key = (cell.ff.weight._version, cell.ff.weight.data_ptr(), None if rec is None else rec._version, model.__dict__.get("_w_epoch", 0))
         hit = cache.get(name)
         if hit is None or hit[0] != key:
-            buf = None if hit is None or hit[1].device != cell.ff.weight.device else hit[1]
-            hit = (key, ops.split_weights(cell.ff.weight, rec, out=buf))
+            same_dev = hit is not None and hit[1].device == cell.ff.weight.device
+            hit = (key, ops.split_weights(cell.ff.weight, rec, out=hit[1] if same_dev else None),
+                   ops.split_weights_bwd(cell.ff.weight, rec, out=hit[2] if same_dev else None))
             cache[name] = hit
         out[name] = hit[1]
+        out[name + ".bwd"] = hit[2]
     return out
 
 
@@ -209,6 +212,7 @@ class _FireNetStep(torch.autograd.Function):
             slot.x_in.copy_(x)
             key = (tuple(p.data_ptr() for p in params), tuple(0 if v is None else v.data_ptr() for v in v_in),
                    tuple(splits[n].data_ptr() for n in LAYERS[1:]))
+            ctx.splits = splits
             g = slot.graphs.get(key)
             if g is None:
                 _launch_step(model, slot.x_in, v_in, z_in, slot, splits, B, Cin0, H, W)  # eager: results + lazy init
@@ -223,6 +227,7 @@ class _FireNetStep(torch.autograd.Function):
         else:
             _launch_step(model, x, v_in, z_in, slot, splits, B, Cin0, H, W)
             x_used = x
+            ctx.splits = splits
         saved = []
         for i, name in enumerate(LAYERS):
             saved.append((x_used if i == 0 else None, slot.z[i - 1] if i > 0 else None, v_in[i], z_in[i], slot.v[i]))
@@ -278,27 +283,40 @@ class _FireNetStep(torch.autograd.Function):
             x_f32, x_cl, v_in, z_in, v_out = ctx.saved[i]
             gi -= 4 if cell.recurrent else 3
             leak, thresh = cell.leak.detach().reshape(-1), cell.thresh.detach().reshape(-1)
-            q = L.LifConvBwdParams()
-            _fill_fwd(q.f, B, Cin0 if i == 0 else 32, H, W, cell, x_f32, x_cl, v_in, z_in, v_out, leak, thresh)
-            q.g_out, q.g_v_out, q.g_z_out = L.ptr(g_h), L.ptr(carry.g_v[i]), L.ptr(carry.g_z[i])
-            q.scratch_gI = L.ptr(buf["scratch"])
             g_x = (buf["g_h"][1] if g_h is buf["g_h"][0] else buf["g_h"][0]) if i > 0 else None
-            q.g_x = L.ptr(g_x)
             g_v_in = g_z_in = None
             if not ctx.first and v_in is not None:
                 g_v_in = buf["g_v"][par][i]
-                q.g_v_in = L.ptr(g_v_in)
                 if cell.recurrent:
                     g_z_in = buf["g_z"][par][i]
-                    q.g_z_in = L.ptr(g_z_in)
             k = gi
-            q.g_w_ff = L.ptr(grads[k])
+            g_w_ff = grads[k]
             k += 1
+            g_w_rec = None
             if cell.recurrent:
-                q.g_w_rec = L.ptr(grads[k])
+                g_w_rec = grads[k]
                 k += 1
-            q.g_leak, q.g_thresh = L.ptr(grads[k]), L.ptr(grads[k + 1])
-            L.call("ef_lif_conv_bwd", q)
+            g_leak, g_thresh = grads[k], grads[k + 1]
+            if i > 0 and model.__dict__.get("_tc_backward", True):
+                # 32 -> 32 cells: pointwise + tensor-core data gradient + channels-last weight gradient
+                t = L.LifBwdTcParams()
+                t.B, t.H, t.W, t.has_rec, t.hard_reset = B, H, W, int(cell.recurrent), int(cell.hard_reset)
+                t.surrogate, t.act_width = L.SURROGATE_CODES[cell.activation], float(cell._act_width_f)
+                t.x_cl, t.z_in_cl, t.v_in, t.v_out = L.ptr(x_cl), L.ptr(z_in), L.ptr(v_in), L.ptr(v_out)
+                t.g_out, t.g_v_out, t.g_z_out = L.ptr(g_h), L.ptr(carry.g_v[i]), L.ptr(carry.g_z[i])
+                t.leak, t.thresh, t.w_bwd = L.ptr(leak), L.ptr(thresh), L.ptr(ctx.splits[LAYERS[i] + ".bwd"])
+                t.gI_hi, t.gI_mid = L.ptr(buf["gI_hi"]), L.ptr(buf["gI_mid"])
+                t.g_x, t.g_v_in, t.g_z_in = L.ptr(g_x), L.ptr(g_v_in), L.ptr(g_z_in)
+                t.g_w_ff, t.g_w_rec, t.g_leak, t.g_thresh = L.ptr(g_w_ff), L.ptr(g_w_rec), L.ptr(g_leak), L.ptr(g_thresh)
+                L.call("ef_lif_bwd_tc", t)
+            else:
+                q = L.LifConvBwdParams()
+                _fill_fwd(q.f, B, Cin0 if i == 0 else 32, H, W, cell, x_f32, x_cl, v_in, z_in, v_out, leak, thresh)
+                q.g_out, q.g_v_out, q.g_z_out = L.ptr(g_h), L.ptr(carry.g_v[i]), L.ptr(carry.g_z[i])
+                q.scratch_gI = L.ptr(buf["scratch"])
+                q.g_x, q.g_v_in, q.g_z_in = L.ptr(g_x), L.ptr(g_v_in), L.ptr(g_z_in)
+                q.g_w_ff, q.g_w_rec, q.g_leak, q.g_thresh = L.ptr(g_w_ff), L.ptr(g_w_rec), L.ptr(g_leak), L.ptr(g_thresh)
+                L.call("ef_lif_conv_bwd", q)
             carry.g_v[i], carry.g_z[i] = g_v_in, g_z_in
             g_h = g_x
         if not ctx.first:  # parameter gradients keep accumulating in carry.flat; the window's first step hands them over

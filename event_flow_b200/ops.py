@@ -312,6 +312,18 @@ def split_weights(w_ff, w_rec=None, out=None):
     return out
 
 
+def split_weights_bwd(w_ff, w_rec=None, out=None):
+    """Flipped / transposed bf16 hi+mid weight image for the tensor-core data gradient (ef_split_weights_bwd)."""
+    w_ff, w_rec = _c(w_ff.detach()), (None if w_rec is None else _c(w_rec.detach()))
+    _need_cuda(w_ff, w_rec)
+    n = L.lib().ef_split_weights_bwd_elems(int(w_rec is not None))
+    if out is None or out.numel() != n:
+        out = torch.empty(n, device=w_ff.device, dtype=torch.int16)
+    L.LAUNCHES += 1
+    L.check(L.lib().ef_split_weights_bwd(L.ptr(w_ff), L.ptr(w_rec), L.ptr(out), L.stream()), "ef_split_weights_bwd")
+    return out
+
+
 def lif_step_cl(x_cl, v_in, z_in_cl, w_ff, w_rec, leak, thresh, *, hard_reset=True, w_split=None, x_f32=None):
     """
     One fused conv + LIF step on the internal formats: spikes bf16 channels-last [B,H,W,C], membrane fp32 NCHW.

@@ -124,6 +124,42 @@ typedef struct ef_lif_conv_bwd_params {
 
 int ef_lif_conv_bwd(const ef_lif_conv_bwd_params* p, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Backward of a 32 -> 32 LIF cell-step on the fast-path formats (same maths as ef_lif_conv_bwd; tensor-core data gradient).
+ * x_cl / z_in_cl: channels-last bf16 spikes the forward consumed; v_in / v_out: fp32 NCHW membrane before / after the step.
+ * g_out: dL/d(output spikes) from the layer above; g_v_out / g_z_out: dL/d(new state) from step t+1 (NULL = 0).
+ * gI_hi / gI_mid: caller-provided bf16 [B,H,W,32] workspaces (receive g_I = (1-leak) g_v as two bf16 terms).
+ * w_bwd: flipped / transposed weight image from ef_split_weights_bwd.  g_x (and g_z_in for a recurrent cell) are overwritten,
+ * g_v_in is overwritten, weight / per-channel gradients are accumulated (+=).
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct ef_lif_bwd_tc_params {
+  int32_t B, H, W, has_rec, hard_reset, surrogate;
+  float act_width;
+  const uint16_t* x_cl;          /* [B,H,W,32]                                                                         */
+  const uint16_t* z_in_cl;       /* [B,H,W,32] or NULL (no previous state)                                             */
+  const float* v_in;             /* [B,32,H,W] or NULL                                                                 */
+  const float* v_out;            /* [B,32,H,W]                                                                         */
+  const float* g_out;            /* [B,32,H,W] or NULL                                                                 */
+  const float* g_v_out;          /* or NULL                                                                            */
+  const float* g_z_out;          /* or NULL                                                                            */
+  const float* leak;             /* [32] raw parameters                                                                */
+  const float* thresh;           /* [32]                                                                               */
+  const uint16_t* w_bwd;         /* ef_split_weights_bwd image                                                         */
+  uint16_t* gI_hi;               /* [B,H,W,32] workspace                                                               */
+  uint16_t* gI_mid;              /* [B,H,W,32] workspace                                                               */
+  float* g_x;                    /* [B,32,H,W]                                                                         */
+  float* g_v_in;                 /* [B,32,H,W] or NULL                                                                 */
+  float* g_z_in;                 /* [B,32,H,W] or NULL (recurrent cells)                                               */
+  float* g_w_ff;                 /* [32,32,3,3] += or NULL                                                             */
+  float* g_w_rec;                /* [32,32,3,3] += or NULL                                                             */
+  float* g_leak;                 /* [32] += or NULL                                                                    */
+  float* g_thresh;               /* [32] += or NULL                                                                    */
+} ef_lif_bwd_tc_params;
+
+int ef_lif_bwd_tc(const ef_lif_bwd_tc_params* p, void* stream);
+int64_t ef_split_weights_bwd_elems(int32_t has_rec);
+int ef_split_weights_bwd(const float* w_ff, const float* w_rec, uint16_t* out, void* stream);
+
 /* Split fp32 conv weights [C,Cin,3,3] (+ optional recurrent [C,C,3,3]) into three bf16 terms hi+mid+lo == w exactly,
  * laid out as the tcgen05 B operand.  out: uint16 [ef_split_weights_elems(Cin, C, has_rec)].  (no reference analogue) */
 int64_t ef_split_weights_elems(int32_t Cin, int32_t C, int32_t has_rec);
