@@ -48,7 +48,11 @@ class LifBwdTcParams(C.Structure):
         ("x_cl", _f32p), ("z_in_cl", _f32p), ("v_in", _f32p), ("v_out", _f32p), ("g_out", _f32p), ("g_v_out", _f32p), ("g_z_out", _f32p),
         ("leak", _f32p), ("thresh", _f32p), ("w_bwd", _f32p), ("gI_hi", _f32p), ("gI_mid", _f32p),
         ("g_x", _f32p), ("g_v_in", _f32p), ("g_z_in", _f32p), ("g_w_ff", _f32p), ("g_w_rec", _f32p), ("g_leak", _f32p), ("g_thresh", _f32p),
+        ("wg_partial", _f32p), ("wg_flags", _i32),
     ]  # fmt: skip
+
+
+EF_WG_ACCUMULATE, EF_WG_FINALIZE = 1, 2
 
 
 class PredParams(C.Structure):
@@ -120,6 +124,7 @@ EXPORTS = {
     "ef_lif_conv_bwd": (C.c_int, [C.POINTER(LifConvBwdParams), C.c_void_p]),
     "ef_lif_bwd_tc": (C.c_int, [C.POINTER(LifBwdTcParams), C.c_void_p]),
     "ef_split_weights_bwd_elems": (C.c_int64, [_i32]),
+    "ef_lif_wgrad_partial_elems": (C.c_int64, [_i32, _i32, _i32, _i32]),
     "ef_split_weights_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ef_split_weights_elems": (C.c_int64, [_i32, _i32, _i32]),
     "ef_split_weights": (C.c_int, [C.c_void_p, C.c_void_p, _i32, _i32, C.c_void_p, C.c_void_p]),

@@ -14,9 +14,12 @@ namespace ef {
 // ---------------------------------------------------------------------------------------------------------------------
 // (1) pointwise
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int PWC_THREADS = 256, PWC_PPT = 2;
+constexpr int PWC_THREADS = 256, PWC_PPT = 1, PWC_CB = 8;
 
-__global__ void __launch_bounds__(PWC_THREADS) lif_bwd_pointwise_cl_kernel(const ef_lif_bwd_tc_params p) {
+// One pixel per thread, channels in batches of PWC_CB: all loads of a batch are issued before any store (the output pointers
+// may alias the inputs as far as the compiler knows, so interleaved stores would serialise the loads).
+template <int SURR, bool HARD>
+__global__ void __launch_bounds__(PWC_THREADS, 2) lif_bwd_pointwise_cl_kernel(const ef_lif_bwd_tc_params p) {
   __shared__ float s_sum[64], lam[32], thr[32];
   const int tid = threadIdx.x, lane = tid & 31;
   const size_t hw = (size_t)p.H * p.W;
@@ -27,43 +30,64 @@ __global__ void __launch_bounds__(PWC_THREADS) lif_bwd_pointwise_cl_kernel(const
     thr[tid] = fmaxf(__ldg(p.thresh + tid), 0.01f);
   }
   __syncthreads();
-  float s_lam[32], s_thr[32];
+  const bool has_gout = p.g_out != nullptr, has_gv = p.g_v_out != nullptr, has_gz = p.g_z_out != nullptr, has_v = p.v_in != nullptr;
+  const size_t pix = (size_t)blockIdx.x * PWC_THREADS + tid;
+  const bool live = pix < hw;
+  const size_t pc = live ? pix : hw - 1;  // out-of-range threads compute on a valid pixel and contribute nothing
+  uint4 zq[4];
 #pragma unroll
-  for (int c = 0; c < 32; ++c) s_lam[c] = s_thr[c] = 0.f;
-  const bool hard = p.hard_reset != 0;
-#pragma unroll 1
-  for (int k = 0; k < PWC_PPT; ++k) {
-    const size_t pix = ((size_t)blockIdx.x * PWC_PPT + k) * PWC_THREADS + tid;
-    if (pix >= hw) break;
-    uint4 zq[4];
+  for (int g = 0; g < 4; ++g)
+    zq[g] = p.z_in_cl ? __ldg(reinterpret_cast<const uint4*>(p.z_in_cl + ((size_t)b * hw + pc) * 32 + g * 8)) : make_uint4(0, 0, 0, 0);
+  const uint32_t zw[16] = {zq[0].x, zq[0].y, zq[0].z, zq[0].w, zq[1].x, zq[1].y, zq[1].z, zq[1].w,
+                           zq[2].x, zq[2].y, zq[2].z, zq[2].w, zq[3].x, zq[3].y, zq[3].z, zq[3].w};
+  uint32_t hi[16], mid[16];
 #pragma unroll
-    for (int g = 0; g < 4; ++g)
-      zq[g] = p.z_in_cl ? __ldg(reinterpret_cast<const uint4*>(p.z_in_cl + ((size_t)b * hw + pix) * 32 + g * 8)) : make_uint4(0, 0, 0, 0);
-    const uint32_t zw[16] = {zq[0].x, zq[0].y, zq[0].z, zq[0].w, zq[1].x, zq[1].y, zq[1].z, zq[1].w,
-                             zq[2].x, zq[2].y, zq[2].z, zq[2].w, zq[3].x, zq[3].y, zq[3].z, zq[3].w};
-    uint32_t hi[16], mid[16];
+  for (int c0 = 0; c0 < 32; c0 += PWC_CB) {
+    float v_p[PWC_CB], v_n[PWC_CB], g_o[PWC_CB], g_s[PWC_CB], g_vo[PWC_CB];
 #pragma unroll
-    for (int c = 0; c < 32; ++c) {
-      const size_t o = ((size_t)b * 32 + c) * hw + pix;
-      const float v_p = p.v_in ? __ldg(p.v_in + o) : 0.f;
+    for (int k = 0; k < PWC_CB; ++k) {
+      const size_t o = ((size_t)b * 32 + c0 + k) * hw + pc;
+      v_p[k] = has_v ? __ldg(p.v_in + o) : 0.f;
+      v_n[k] = __ldg(p.v_out + o);
+      g_o[k] = has_gout ? __ldg(p.g_out + o) : 0.f;
+      g_s[k] = has_gz ? __ldg(p.g_z_out + o) : 0.f;
+      g_vo[k] = has_gv ? __ldg(p.g_v_out + o) : 0.f;
+    }
+    float g_vin[PWC_CB], r_lam[PWC_CB], r_thr[PWC_CB];
+#pragma unroll
+    for (int k = 0; k < PWC_CB; ++k) {
+      const int c = c0 + k;
       const float z_p = (c & 1) ? bf16_hi(zw[c >> 1]) : bf16_lo(zw[c >> 1]);
-      const float v_n = __ldg(p.v_out + o);
-      const float g_z = (p.g_out ? __ldg(p.g_out + o) : 0.f) + (p.g_z_out ? __ldg(p.g_z_out + o) : 0.f);
-      const float sg = surrogate_grad(p.surrogate, v_n - thr[c], p.act_width);
-      const float g_v = (p.g_v_out ? __ldg(p.g_v_out + o) : 0.f) + g_z * sg;
+      const float g_z = g_o[k] + g_s[k];
+      const float sg = surrogate_grad(SURR, v_n[k] - thr[c], p.act_width);
+      const float g_v = g_vo[k] + g_z * sg;
       const float oml = 1.0f - lam[c];
       const float g_I = oml * g_v;
-      const float keep = hard ? v_p * (1.0f - z_p) : v_p;
-      const float drive = hard ? (v_n - lam[c] * keep) / oml : (v_n - lam[c] * v_p + z_p * thr[c]) / oml;
-      s_lam[c] += g_v * (keep - drive);
-      s_thr[c] += -g_z * sg - (hard ? 0.f : z_p * g_v);
-      if (p.g_v_in) p.g_v_in[o] = hard ? g_v * lam[c] * (1.0f - z_p) : g_v * lam[c];
+      const float keep = HARD ? v_p[k] * (1.0f - z_p) : v_p[k];
+      const float drive = HARD ? (v_n[k] - lam[c] * keep) / oml : (v_n[k] - lam[c] * v_p[k] + z_p * thr[c]) / oml;
+      r_lam[k] = live ? g_v * (keep - drive) : 0.f;
+      r_thr[k] = live ? -g_z * sg - (HARD ? 0.f : z_p * g_v) : 0.f;
+      g_vin[k] = HARD ? g_v * lam[c] * (1.0f - z_p) : g_v * lam[c];
       const __nv_bfloat16 h = __float2bfloat16_rn(g_I);
       const __nv_bfloat16 m = __float2bfloat16_rn(g_I - __bfloat162float(h));
       const uint32_t hb = *reinterpret_cast<const uint16_t*>(&h), mb = *reinterpret_cast<const uint16_t*>(&m);
       if (c & 1) hi[c >> 1] |= hb << 16, mid[c >> 1] |= mb << 16;
       else hi[c >> 1] = hb, mid[c >> 1] = mb;
     }
+    if (p.g_v_in && live) {
+#pragma unroll
+      for (int k = 0; k < PWC_CB; ++k) p.g_v_in[((size_t)b * 32 + c0 + k) * hw + pix] = g_vin[k];
+    }
+#pragma unroll
+    for (int k = 0; k < PWC_CB; ++k) {
+      const float a = warp_sum(r_lam[k]), t = warp_sum(r_thr[k]);
+      if (lane == 0) {
+        atomicAdd(&s_sum[c0 + k], a);
+        atomicAdd(&s_sum[32 + c0 + k], t);
+      }
+    }
+  }
+  if (live) {
     uint4* dh = reinterpret_cast<uint4*>(p.gI_hi + ((size_t)b * hw + pix) * 32);
     uint4* dm = reinterpret_cast<uint4*>(p.gI_mid + ((size_t)b * hw + pix) * 32);
 #pragma unroll
@@ -72,19 +96,11 @@ __global__ void __launch_bounds__(PWC_THREADS) lif_bwd_pointwise_cl_kernel(const
       dm[g] = make_uint4(mid[4 * g], mid[4 * g + 1], mid[4 * g + 2], mid[4 * g + 3]);
     }
   }
-#pragma unroll
-  for (int c = 0; c < 32; ++c) {
-    const float a = warp_sum(s_lam[c]), t = warp_sum(s_thr[c]);
-    if (lane == 0) {
-      atomicAdd(&s_sum[c], a);
-      atomicAdd(&s_sum[32 + c], t);
-    }
-  }
   __syncthreads();
   if (tid < 32) {
-    const float l = sigmoidf_acc(p.leak[tid]);
+    const float l = lam[tid];
     if (p.g_leak) atomicAdd(p.g_leak + tid, s_sum[tid] * l * (1.0f - l));
-    if (p.g_thresh && p.thresh[tid] >= 0.01f) atomicAdd(p.g_thresh + tid, s_sum[32 + tid]);
+    if (p.g_thresh && __ldg(p.thresh + tid) >= 0.01f) atomicAdd(p.g_thresh + tid, s_sum[32 + tid]);
   }
 }
 
@@ -355,7 +371,192 @@ __global__ void __launch_bounds__(WGC_THREADS) conv_wgrad_cl_kernel(const uint16
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// (4) weight gradient on the tensor cores:  g_w[co,ci,dy,dx] = sum_{b,y,x} in[b,y+dy-1,x+dx-1,ci] * (gI_hi + gI_mid)[b,y,x,co]
+//     The reduction runs over pixels, so both operands are MN-major (channels are the contiguous dimension of the
+//     channels-last tensors).  Per 16x8-pixel tile the CTA holds the padded, 64B-swizzled halo tile of the input
+//     [18 rows][16 px][64 B] and the plain tiles of g_I (hi, mid) [16 rows][8 px][64 B].  One MMA has
+//       A: M = 128 = 4 pixel shifts x 32 ci  (LBO = 64 B = one pixel to the right; shift 3 is unused),
+//          K = 16 = 2 tile rows x 8 pixels  (SBO = 1024 B = one halo-tile row), start address = row 2*ks + dy
+//       B: N = 64 = [gI_hi | gI_mid] x 32 co (LBO = distance between the two tiles), K as for A (SBO = 512 B)
+//     and accumulates into D[conv][dy] (64 columns each), which stays in tensor memory for all tiles of the CTA.  The epilogue
+//     folds hi + mid and writes / adds the CTA's slice of wg_partial [conv][cta][dy][dx][ci][co].
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int WG_TH = 16, WG_TW = 8;
+constexpr int WG_XROW = (WG_TW + 8) * PIX_BYTES;        // 1024
+constexpr int WG_XTILE = (WG_TH + 2) * WG_XROW;         // 18432
+constexpr int WG_GTILE = WG_TH * WG_TW * PIX_BYTES;     // 8192
+constexpr int WG_THREADS = 32 * 6;                      // TMA, MMA, 4 epilogue warps (one per TMEM lane quadrant)
+constexpr int WG_NST = 4;
+constexpr int WG_SLICE = 9 * 32 * 32;                   // floats per (conv, cta)
+
+struct WgParams {
+  int B, H, W, tiles_x, tiles_y, n_tiles, accumulate;
+  float* partial;
+};
+
+template <bool REC>
+__global__ void __launch_bounds__(WG_THREADS, 1)
+lif_wgrad_tc_kernel(const WgParams p, const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_z,
+                    const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_mid) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  constexpr int NCONV = REC ? 2 : 1;
+  constexpr int G_OFF = NCONV * WG_XTILE;
+  constexpr int STAGE = G_OFF + 2 * WG_GTILE;
+  constexpr int BAR_OFF = WG_NST * STAGE;
+  constexpr uint32_t TMEM_COLS = REC ? 512 : 256;
+  const uint32_t s_base = smem_u32(smem);
+  const uint32_t bar_w = s_base + BAR_OFF;
+  auto bar_full = [&](int s) { return bar_w + 8u * s; };
+  auto bar_empty = [&](int s) { return bar_w + 8u * (WG_NST + s); };
+  const uint32_t bar_done = bar_w + 8u * (2 * WG_NST);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + BAR_OFF + 8 * (2 * WG_NST + 1));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < WG_NST; ++s) {
+      mbar_init(bar_full(s), 1);
+      mbar_init(bar_empty(s), 1);
+    }
+    mbar_init(bar_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int n_my = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ---- TMA producer
+      for (int it = 0; it < n_my; ++it) {
+        const int tile = blockIdx.x + it * gridDim.x;
+        const int b = tile / tiles_per_img, r = tile - b * tiles_per_img, ty = r / p.tiles_x;
+        const int y0 = ty * WG_TH, x0 = (r - ty * p.tiles_x) * WG_TW;
+        const int s = it % WG_NST;
+        mbar_wait(bar_empty(s), ((it / WG_NST) & 1) ^ 1);
+        const uint32_t st = s_base + s * STAGE;
+        mbar_expect_tx(bar_full(s), STAGE);
+        tma_load_4d(st, &map_x, bar_full(s), 0, x0 - 1, y0 - 1, b);
+        if (REC) tma_load_4d(st + WG_XTILE, &map_z, bar_full(s), 0, x0 - 1, y0 - 1, b);
+        tma_load_4d(st + G_OFF, &map_hi, bar_full(s), 0, x0, y0, b);
+        tma_load_4d(st + G_OFF + WG_GTILE, &map_mid, bar_full(s), 0, x0, y0, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ---- MMA issuer
+      constexpr uint32_t IDESC = umma_idesc(64, true, true);
+      for (int it = 0; it < n_my; ++it) {
+        const int s = it % WG_NST;
+        mbar_wait(bar_full(s), (it / WG_NST) & 1);
+        tc_fence_after();
+        const uint32_t st = s_base + s * STAGE;
+        const uint64_t bdesc = umma_desc_sw64_mn(st + G_OFF, WG_GTILE, ATOM_BYTES);
+#pragma unroll
+        for (int cv = 0; cv < NCONV; ++cv) {
+          const uint64_t adesc = umma_desc_sw64_mn(st + cv * WG_XTILE, PIX_BYTES, WG_XROW);
+#pragma unroll
+          for (int dy = 0; dy < 3; ++dy) {
+#pragma unroll
+            for (int ks = 0; ks < WG_TH / 2; ++ks)
+              umma_bf16<IDESC>(tmem_base + (cv * 3 + dy) * 64, adesc + (uint64_t)((2 * ks + dy) * (WG_XROW / 16)),
+                               bdesc + (uint64_t)(ks * (2 * ATOM_BYTES / 16)), (it | ks) != 0);
+          }
+        }
+        umma_commit(bar_empty(s));
+      }
+      umma_commit(bar_done);
+    }
+  } else {
+    // ---- epilogue (once): thread = accumulator row m = (dx shift, ci); 64 columns = [hi | mid] x co
+    const int q = warp & 3;
+    mbar_wait(bar_done, 0);
+    tc_fence_after();
+    if (q < 3) {
+#pragma unroll 1
+      for (int a = 0; a < NCONV * 3; ++a) {
+        const int cv = a / 3, dy = a - cv * 3;
+        const uint32_t tacc = tmem_base + a * 64 + ((uint32_t)(q * 32) << 16);
+        uint32_t h0[16], h1[16], m0[16], m1[16];
+        tmem_ld16(tacc, h0);
+        tmem_ld16(tacc + 16, h1);
+        tmem_ld16(tacc + 32, m0);
+        tmem_ld16(tacc + 48, m1);
+        tmem_ld_wait();
+        float4* dst = reinterpret_cast<float4*>(p.partial + ((size_t)cv * gridDim.x + blockIdx.x) * WG_SLICE + ((dy * 3 + q) * 32 + lane) * 32);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float4 lo = make_float4(__uint_as_float(h0[4 * j]) + __uint_as_float(m0[4 * j]), __uint_as_float(h0[4 * j + 1]) + __uint_as_float(m0[4 * j + 1]),
+                                  __uint_as_float(h0[4 * j + 2]) + __uint_as_float(m0[4 * j + 2]), __uint_as_float(h0[4 * j + 3]) + __uint_as_float(m0[4 * j + 3]));
+          float4 hi = make_float4(__uint_as_float(h1[4 * j]) + __uint_as_float(m1[4 * j]), __uint_as_float(h1[4 * j + 1]) + __uint_as_float(m1[4 * j + 1]),
+                                  __uint_as_float(h1[4 * j + 2]) + __uint_as_float(m1[4 * j + 2]), __uint_as_float(h1[4 * j + 3]) + __uint_as_float(m1[4 * j + 3]));
+          if (p.accumulate) {
+            const float4 a0 = dst[j], a1 = dst[4 + j];
+            lo.x += a0.x, lo.y += a0.y, lo.z += a0.z, lo.w += a0.w;
+            hi.x += a1.x, hi.y += a1.y, hi.z += a1.z, hi.w += a1.w;
+          }
+          dst[j] = lo;
+          dst[4 + j] = hi;
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// g_w[co,ci,dy,dx] += sum over CTAs of partial[conv][cta][dy][dx][ci][co], CTAs in a fixed order (bit-reproducible).
+// Block = 32 co x 8 CTA groups for one (conv, dy, dx, ci).
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, int n_cta, float* __restrict__ g_w_ff,
+                                                           float* __restrict__ g_w_rec) {
+  __shared__ float s[8][32];
+  const int co = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const int row = blockIdx.x % 288, cv = blockIdx.x / 288;  // row = (dy*3 + dx)*32 + ci
+  const float* src = partial + (size_t)cv * n_cta * WG_SLICE + row * 32 + co;
+  float acc = 0.f;
+  for (int c = grp; c < n_cta; c += 8) acc += __ldg(src + (size_t)c * WG_SLICE);
+  s[grp][co] = acc;
+  __syncthreads();
+  if (grp == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) t += s[g][co];
+    float* g_w = cv == 0 ? g_w_ff : g_w_rec;
+    if (g_w) g_w[(co * 32 + (row & 31)) * 9 + (row >> 5)] += t;
+  }
+}
+
+inline int wg_n_sms() {
+  static int n_sms = 0;
+  if (n_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n_sms;
+}
+inline int wg_grid(int B, int H, int W) {
+  const int n_tiles = B * cdiv(W, WG_TW) * cdiv(H, WG_TH), n = wg_n_sms();
+  return n_tiles < n ? n_tiles : n;
+}
+
 }  // namespace ef
+
+extern "C" int64_t ef_lif_wgrad_partial_elems(int32_t B, int32_t H, int32_t W, int32_t has_rec) {
+  if (B <= 0 || H <= 0 || W <= 0) return 0;
+  return (int64_t)(has_rec ? 2 : 1) * ef::wg_grid(B, H, W) * ef::WG_SLICE;
+}
 
 extern "C" int64_t ef_split_weights_bwd_elems(int32_t has_rec) { return (int64_t)ef::dg_layout(has_rec != 0).w_bytes / 2; }
 
@@ -375,15 +576,25 @@ extern "C" int ef_lif_bwd_tc(const ef_lif_bwd_tc_params* pp, void* stream) {
   EF_REQUIRE(p.x_cl && p.v_out && p.leak && p.thresh && p.w_bwd && p.gI_hi && p.gI_mid && p.g_x, EF_ENULL, "ef_lif_bwd_tc: NULL tensor");
   EF_REQUIRE(!p.has_rec || !p.z_in_cl || p.g_z_in || true, EF_ENULL, "ef_lif_bwd_tc");
   cudaStream_t st = as_stream(stream);
-  static int n_sms = 0;
-  if (n_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev);
-  }
+  const int n_sms = wg_n_sms();
   int rc;
   const int hw = p.H * p.W;
-  lif_bwd_pointwise_cl_kernel<<<dim3(cdiv(hw, PWC_THREADS * PWC_PPT), p.B), PWC_THREADS, 0, st>>>(p);
+  {
+    const dim3 pgrid(cdiv(hw, PWC_THREADS * PWC_PPT), p.B);
+#define EF_PW(S_, H_) lif_bwd_pointwise_cl_kernel<S_, H_><<<pgrid, PWC_THREADS, 0, st>>>(p)
+    switch (p.surrogate * 2 + (p.hard_reset ? 1 : 0)) {
+      case 0: EF_PW(EF_ARCTAN, false); break;
+      case 1: EF_PW(EF_ARCTAN, true); break;
+      case 2: EF_PW(EF_SUPERSPIKE, false); break;
+      case 3: EF_PW(EF_SUPERSPIKE, true); break;
+      case 4: EF_PW(EF_TRIANGLE, false); break;
+      case 5: EF_PW(EF_TRIANGLE, true); break;
+      case 6: EF_PW(EF_MULTIGAUSS, false); break;
+      case 7: EF_PW(EF_MULTIGAUSS, true); break;
+      default: return fail(EF_EINVAL, "ef_lif_bwd_tc: bad surrogate %d", p.surrogate);
+    }
+#undef EF_PW
+  }
   if ((rc = check_launch("lif_bwd_pointwise_cl_kernel"))) return rc;
 
   const bool rec = p.has_rec != 0;
@@ -407,6 +618,40 @@ extern "C" int ef_lif_bwd_tc(const ef_lif_bwd_tc_params* pp, void* stream) {
   else lif_dgrad_tc_kernel<false><<<grid, DG_THREADS, L.total, st>>>(q, mh, mm);
   if ((rc = check_launch("lif_dgrad_tc_kernel"))) return rc;
 
+  if (p.wg_partial) {  // tensor-core weight gradient into per-CTA partial sums
+    const bool wrec = rec && p.z_in_cl;
+    const int wgrid_n = wg_grid(p.B, p.H, p.W);
+    WgParams w;
+    w.B = p.B, w.H = p.H, w.W = p.W, w.tiles_x = q.tiles_x, w.tiles_y = q.tiles_y, w.n_tiles = q.n_tiles;
+    w.accumulate = (p.wg_flags & EF_WG_ACCUMULATE) ? 1 : 0;
+    w.partial = p.wg_partial;
+    if (rec && !wrec && !w.accumulate) {  // recurrent cell without a previous state: its recurrent slices start at zero
+      if (cudaMemsetAsync(p.wg_partial + (size_t)wgrid_n * WG_SLICE, 0, (size_t)wgrid_n * WG_SLICE * sizeof(float), st) != cudaSuccess)
+        return check_launch("cudaMemsetAsync(wg_partial)");
+    }
+    CUtensorMap mx, mz, gh, gm;
+    if ((rc = get_map(p.x_cl, p.B, p.H, p.W, WG_TH + 2, WG_TW + 8, true, &mx))) return rc;
+    mz = mx;
+    if (wrec && (rc = get_map(p.z_in_cl, p.B, p.H, p.W, WG_TH + 2, WG_TW + 8, true, &mz))) return rc;
+    if ((rc = get_map(p.gI_hi, p.B, p.H, p.W, WG_TH, WG_TW, true, &gh))) return rc;
+    if ((rc = get_map(p.gI_mid, p.B, p.H, p.W, WG_TH, WG_TW, true, &gm))) return rc;
+    static bool wattr[2] = {false, false};
+    if (!wattr[wrec ? 1 : 0]) {
+      const cudaError_t e = wrec ? cudaFuncSetAttribute(lif_wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
+                                 : cudaFuncSetAttribute(lif_wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (e != cudaSuccess) return check_launch("cudaFuncSetAttribute(lif_wgrad_tc_kernel)");
+      wattr[wrec ? 1 : 0] = true;
+    }
+    const int wsmem = WG_NST * ((wrec ? 2 : 1) * WG_XTILE + 2 * WG_GTILE) + 256 + 1024;
+    if (wrec) lif_wgrad_tc_kernel<true><<<wgrid_n, WG_THREADS, wsmem, st>>>(w, mx, mz, gh, gm);
+    else lif_wgrad_tc_kernel<false><<<wgrid_n, WG_THREADS, wsmem, st>>>(w, mx, mz, gh, gm);
+    if ((rc = check_launch("lif_wgrad_tc_kernel"))) return rc;
+    if (p.wg_flags & EF_WG_FINALIZE) {
+      wgrad_reduce_kernel<<<(rec ? 2 : 1) * 288, 256, 0, st>>>(p.wg_partial, wgrid_n, p.g_w_ff, rec ? p.g_w_rec : nullptr);
+      if ((rc = check_launch("wgrad_reduce_kernel"))) return rc;
+    }
+    return EF_OK;
+  }
   const dim3 wgrid(cdiv(p.W, 16), cdiv(p.H, 16), p.B);
   if (p.g_w_ff) {
     conv_wgrad_cl_kernel<<<wgrid, WGC_THREADS, 0, st>>>(p.x_cl, p.gI_hi, p.gI_mid, p.g_w_ff, p.B, p.H, p.W);

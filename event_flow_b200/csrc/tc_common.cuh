@@ -90,6 +90,13 @@ __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_
 __device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t saddr, uint32_t sbo) {
   return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (4ull << 61);
 }
+// MN-major, 64-byte-swizzled descriptor (cute/atom/mma_traits_sm100.hpp, "((T,4,m),(8,k)):((1,T,LBO),(4T,SBO))"): 32
+// contiguous MN elements per 64-byte row, 8 K-rows per 512-byte atom; LBO = byte stride between 32-element groups along
+// MN, SBO = byte stride between 8-row groups along K.
+__device__ __forceinline__ uint64_t umma_desc_sw64_mn(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) |
+         (1ull << 46) | (4ull << 61);
+}
 // kind::f16 instruction descriptor (cute/arch/mma_sm100_desc.hpp): D = F32, A = B = BF16, M = 128; a_mn / b_mn select
 // MN-major (transposed) operands instead of K-major.
 __host__ __device__ constexpr uint32_t umma_idesc(uint32_t n, bool a_mn = false, bool b_mn = false) {

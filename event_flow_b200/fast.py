@@ -76,7 +76,10 @@ class _Arena:
             mk = lambda: torch.empty((B, 32, H, W), device=dev, dtype=torch.float32)  # noqa: E731
             mkcl = lambda: torch.empty((B, H, W, 32), device=dev, dtype=torch.bfloat16)  # noqa: E731
             self.bwd = {"g_h": [mk(), mk()], "scratch": mk(), "g_v": [[mk() for _ in range(N_L)] for _ in range(2)],
-                        "g_z": [[mk() for _ in range(N_L)] for _ in range(2)], "gI_hi": mkcl(), "gI_mid": mkcl()}
+                        "g_z": [[mk() for _ in range(N_L)] for _ in range(2)], "gI_hi": mkcl(), "gI_mid": mkcl(),
+                        # per-CTA partial sums of the tensor-core weight gradient, one buffer per hidden cell (kept over a sweep)
+                        "wg": [None] + [torch.empty(L.lib().ef_lif_wgrad_partial_elems(B, H, W, 1), device=dev, dtype=torch.float32)
+                                        for _ in range(N_L - 1)]}
         return self.bwd
 
 
@@ -260,6 +263,7 @@ class _FireNetStep(torch.autograd.Function):
                 carry.flat.zero_()
             carry.g_v, carry.g_z = [None] * N_L, [None] * N_L
         par = carry.sweep & 1  # ping-pong of the state-gradient buffers between consecutive steps
+        wg_flags = (L.EF_WG_ACCUMULATE if carry.sweep > 0 else 0) | (L.EF_WG_FINALIZE if ctx.first else 0)
         carry.sweep += 1
         grads, o = [], 0
         for p in params:
@@ -308,6 +312,8 @@ class _FireNetStep(torch.autograd.Function):
                 t.gI_hi, t.gI_mid = L.ptr(buf["gI_hi"]), L.ptr(buf["gI_mid"])
                 t.g_x, t.g_v_in, t.g_z_in = L.ptr(g_x), L.ptr(g_v_in), L.ptr(g_z_in)
                 t.g_w_ff, t.g_w_rec, t.g_leak, t.g_thresh = L.ptr(g_w_ff), L.ptr(g_w_rec), L.ptr(g_leak), L.ptr(g_thresh)
+                if model.__dict__.get("_tc_wgrad", True):
+                    t.wg_partial, t.wg_flags = L.ptr(buf["wg"][i]), wg_flags
                 L.call("ef_lif_bwd_tc", t)
             else:
                 q = L.LifConvBwdParams()

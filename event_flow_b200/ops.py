@@ -351,6 +351,43 @@ def lif_step_cl(x_cl, v_in, z_in_cl, w_ff, w_rec, leak, thresh, *, hard_reset=Tr
     return v_out, z_out
 
 
+def lif_bwd_cl(x_cl, v_in, z_in_cl, v_out, g_out, g_v_out, g_z_out, w_ff, w_rec, leak, thresh, *, hard_reset=True,
+               surrogate="arctanspike", act_width=10.0, tc_wgrad=True, steps=1):
+    """
+    Backward of one 32->32 LIF cell-step on the internal formats (ef_lif_bwd_tc): tensor-core data gradient and, with
+    `tc_wgrad`, the tensor-core weight gradient (`steps` > 1 repeats the call to exercise the accumulate / finalize
+    protocol: the weight gradients are then `steps` times those of one call).  Returns a dict of gradients.  No autograd.
+    """
+    B, H, W, _ = x_cl.shape
+    dev = x_cl.device
+    rec = w_rec is not None
+    f32 = lambda *shape: torch.zeros(shape, device=dev, dtype=torch.float32)  # noqa: E731
+    out = {"g_x": f32(B, 32, H, W), "g_v_in": f32(B, 32, H, W), "g_w_ff": f32(32, 32, 3, 3), "g_leak": f32(32), "g_thresh": f32(32)}
+    if rec:
+        out["g_z_in"], out["g_w_rec"] = f32(B, 32, H, W), f32(32, 32, 3, 3)
+    gI_hi = torch.empty((B, H, W, 32), device=dev, dtype=torch.bfloat16)
+    gI_mid = torch.empty_like(gI_hi)
+    w_bwd = split_weights_bwd(w_ff, w_rec)
+    partial = torch.empty(L.lib().ef_lif_wgrad_partial_elems(B, H, W, int(rec)), device=dev, dtype=torch.float32) if tc_wgrad else None
+    for k in range(steps):
+        t = L.LifBwdTcParams()
+        t.B, t.H, t.W, t.has_rec, t.hard_reset = B, H, W, int(rec), int(hard_reset)
+        t.surrogate, t.act_width = L.SURROGATE_CODES[surrogate], float(act_width)
+        t.x_cl, t.z_in_cl, t.v_in, t.v_out = L.ptr(x_cl), L.ptr(z_in_cl), L.ptr(v_in), L.ptr(v_out)
+        t.g_out, t.g_v_out, t.g_z_out = L.ptr(g_out), L.ptr(g_v_out), L.ptr(g_z_out)
+        t.leak, t.thresh, t.w_bwd = L.ptr(leak), L.ptr(thresh), L.ptr(w_bwd)
+        t.gI_hi, t.gI_mid = L.ptr(gI_hi), L.ptr(gI_mid)
+        t.g_x, t.g_v_in, t.g_z_in = L.ptr(out["g_x"]), L.ptr(out["g_v_in"]), L.ptr(out.get("g_z_in"))
+        t.g_w_ff, t.g_w_rec = L.ptr(out["g_w_ff"]), L.ptr(out.get("g_w_rec"))
+        t.g_leak, t.g_thresh = L.ptr(out["g_leak"]), L.ptr(out["g_thresh"])
+        if tc_wgrad:
+            t.wg_partial = L.ptr(partial)
+            t.wg_flags = (L.EF_WG_ACCUMULATE if k > 0 else 0) | (L.EF_WG_FINALIZE if k == steps - 1 else 0)
+        L.call("ef_lif_bwd_tc", t)
+    out["gI"] = gI_hi.float() + gI_mid.float()
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # validation metrics
 # ---------------------------------------------------------------------------------------------------------------------

@@ -154,7 +154,19 @@ typedef struct ef_lif_bwd_tc_params {
   float* g_w_rec;                /* [32,32,3,3] += or NULL                                                             */
   float* g_leak;                 /* [32] += or NULL                                                                    */
   float* g_thresh;               /* [32] += or NULL                                                                    */
+  float* wg_partial;             /* ef_lif_wgrad_partial_elems() floats or NULL: selects the tensor-core weight gradient */
+  int32_t wg_flags;              /* EF_WG_* below                                                                      */
 } ef_lif_bwd_tc_params;
+
+/* Tensor-core weight gradient (wg_partial != NULL): every CTA keeps its share of
+ * sum_{b,y,x} x[b,y+dy-1,x+dx-1,ci] g_I[b,y,x,co] in tensor memory and writes it to its own slice of wg_partial; nothing is
+ * added to g_w_ff / g_w_rec until a call carries EF_WG_FINALIZE, which reduces the slices in a fixed order (bit-reproducible)
+ * and adds the result to g_w_*.  A BPTT sweep passes the same wg_partial for every step of one cell: first call without
+ * flags, later calls with EF_WG_ACCUMULATE, the last one with EF_WG_FINALIZE as well.
+ * wg_partial == NULL: CUDA-core kernel, g_w_* += at once. */
+#define EF_WG_ACCUMULATE 1       /* wg_partial already holds the sums of earlier calls: add to them                      */
+#define EF_WG_FINALIZE 2         /* after this call: g_w_ff / g_w_rec += reduced wg_partial                              */
+int64_t ef_lif_wgrad_partial_elems(int32_t B, int32_t H, int32_t W, int32_t has_rec);
 
 int ef_lif_bwd_tc(const ef_lif_bwd_tc_params* p, void* stream);
 int64_t ef_split_weights_bwd_elems(int32_t has_rec);

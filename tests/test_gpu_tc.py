@@ -116,3 +116,69 @@ def test_tc_kernel_repeated_launches_are_bit_identical(rec):
     for _ in range(30):
         v, z = ops.lif_step_cl(*args, hard_reset=True, w_split=ws)
         assert torch.equal(v, v0) and torch.equal(z, z0)
+
+
+@pytest.mark.parametrize("rec", [False, True])
+@pytest.mark.parametrize("shape", [(1, 16, 8), (2, 37, 52), (8, 128, 128), (1, 5, 3)])
+@pytest.mark.parametrize("with_state", [True, False])
+def test_tc_weight_gradient_matches_cuda_core_and_fp64(rec, shape, with_state):
+    """
+    Weight gradient on tcgen05 (MN-major operands, per-CTA partial sums, fixed-order reduction) against the CUDA-core
+    kernel on the same g_I terms and against an fp64 correlation of the same operands.  Tolerance 1e-4 relative to the
+    largest entry (fp32 accumulation order differs; the operands are identical bf16 values).  Three calls under the
+    accumulate / finalize protocol must give three times the gradient of one call.
+    """
+    import torch.nn.functional as F
+
+    from event_flow_b200 import ops
+
+    B, H, W = shape
+    params, x, st = make_case(B, H, W, rec, seed=B * 11 + W, with_state=with_state)
+    pd = {k: v.to(DEV).contiguous() for k, v in params.items()}
+    g = torch.Generator().manual_seed(3)
+    x_cl = ops.pack_cl(x.to(DEV))
+    v_in = z_in = None
+    if st is not None:
+        v_in, z_in = st[0].to(DEV).contiguous(), ops.pack_cl(st[1].to(DEV))
+    leak, thresh = pd["leak"].reshape(-1), pd["thresh"].reshape(-1)
+    v_out, _ = ops.lif_step_cl(x_cl, v_in, z_in, pd["ff"], pd.get("rec"), leak, thresh)
+    g_out = torch.randn((B, 32, H, W), generator=g).to(DEV)
+    g_v = torch.randn((B, 32, H, W), generator=g).to(DEV) * 0.1
+    args = (x_cl, v_in, z_in, v_out, g_out, g_v, None, pd["ff"], pd.get("rec"), leak, thresh)
+    tc = ops.lif_bwd_cl(*args, tc_wgrad=True)
+    cc = ops.lif_bwd_cl(*args, tc_wgrad=False)
+    tc3 = ops.lif_bwd_cl(*args, tc_wgrad=True, steps=3)
+    torch.cuda.synchronize()
+    names = ["g_w_ff"] + (["g_w_rec"] if rec else [])
+    gI = tc["gI"].double().permute(0, 3, 1, 2)  # [B,co,H,W]
+    for n in names:
+        src = x if n == "g_w_ff" else (st[1] if st is not None else torch.zeros_like(x))
+        xp = F.pad(src.double().to(DEV), (1, 1, 1, 1))
+        ref = torch.stack([torch.stack([torch.einsum("bchw,bkhw->kc", xp[:, :, dy:dy + H, dx:dx + W], gI) for dx in range(3)], -1)
+                           for dy in range(3)], -2)  # [co,ci,dy,dx]
+        scale = ref.abs().max().item() + 1e-12
+        assert (tc[n].double() - ref).abs().max().item() <= 1e-4 * scale, n
+        assert (cc[n].double() - ref).abs().max().item() <= 1e-4 * scale, n
+        assert (tc3[n].double() - 3 * ref).abs().max().item() <= 3e-4 * scale, n
+        assert scale > 1e-3 or st is None
+    for n in ("g_x", "g_v_in"):
+        assert torch.equal(tc[n], cc[n]), n
+    for n in ("g_leak", "g_thresh"):  # block sums land through atomics: order-dependent rounding
+        assert torch.allclose(tc[n], cc[n], rtol=1e-4, atol=1e-6), n
+
+
+def test_tc_weight_gradient_is_bit_reproducible():
+    from event_flow_b200 import ops
+
+    B, H, W = 8, 128, 128
+    params, x, st = make_case(B, H, W, True, seed=9)
+    pd = {k: v.to(DEV).contiguous() for k, v in params.items()}
+    x_cl, v_in, z_in = ops.pack_cl(x.to(DEV)), st[0].to(DEV).contiguous(), ops.pack_cl(st[1].to(DEV))
+    leak, thresh = pd["leak"].reshape(-1), pd["thresh"].reshape(-1)
+    v_out, _ = ops.lif_step_cl(x_cl, v_in, z_in, pd["ff"], pd["rec"], leak, thresh)
+    g_out = torch.randn((B, 32, H, W), generator=torch.Generator().manual_seed(1)).to(DEV)
+    args = (x_cl, v_in, z_in, v_out, g_out, None, None, pd["ff"], pd["rec"], leak, thresh)
+    first = ops.lif_bwd_cl(*args, tc_wgrad=True)
+    for _ in range(10):
+        again = ops.lif_bwd_cl(*args, tc_wgrad=True)
+        assert torch.equal(again["g_w_ff"], first["g_w_ff"]) and torch.equal(again["g_w_rec"], first["g_w_rec"])
