@@ -17,9 +17,10 @@
 // Spikes are {0,1,2}: exactly representable in bf16, so every product is exact and only the fp32 summation order differs
 // from the CPU path (no TF32/BF16 rounding may enter a spiking conv).
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2-9 = epilogue: each warp owns a
-// TMEM lane quadrant (32 pixels) and one half of the channels; membrane potentials go straight global <-> registers
-// (32-byte row segments are a poor fit for TMA), spikes leave through a staged TMA store.  Persistent over tiles; mbarrier
-// pipelines between the roles.
+// TMEM lane quadrant (32 pixels) and one half of the channels; membrane potentials, previous spikes and new spikes go
+// straight global <-> registers (the next tile's loads are in flight while the current tile is computed; nothing in the
+// epilogue touches shared memory, so no proxy fence or CTA barrier sits on the per-tile path).  Persistent over tiles;
+// mbarrier pipelines between the roles.
 // Reference semantics: models/spiking_submodules.py:96-126 (ConvLIF), :516-551 (ConvLIFRecurrent).
 #include "tc_common.cuh"
 
@@ -27,7 +28,6 @@ namespace ef {
 
 // Output tile = 128 pixels = 16 rows x 8 cols: one 8-pixel atom per tile row is the only shape whose tap-shifted windows
 // are expressible as ONE descriptor (constant stride between consecutive 8-row groups).
-constexpr int Z_TILE_BYTES = 128 * PIX_BYTES;         // centre spikes (not swizzled): 8192 B
 constexpr int W_BLOCK_BYTES = 96 * PIX_BYTES;         // one tap: [96 n = 3 splits x 32 ch][32 k] bf16, 64B-swizzled: 6144 B
 constexpr int W_CONV_BYTES = 9 * W_BLOCK_BYTES;       // 55296 B per convolution
 constexpr int TC_EPI_WARPS = 8;
@@ -36,7 +36,7 @@ constexpr int ACC_COLS = 96;                          // fp32 accumulator column
 constexpr int TMEM_COLS = 256;                        // 2 accumulator buffers x 96 columns, rounded up to a power of two
 
 struct TcSmemLayout {
-  int w_off, stage_off, stage_bytes, x_off, z_off, outz_off, bar_off, total, nstage;
+  int w_off, stage_off, stage_bytes, x_off, z_off, bar_off, total, nstage;
   int row_bytes, copy_bytes, a_tile_bytes;
 };
 
@@ -50,11 +50,10 @@ __host__ __device__ inline TcSmemLayout tc_smem_layout(bool rec, int th, int tw)
   l.x_off = 0;
   l.z_off = l.a_tile_bytes;                                 // rec: operand tile of the previous spikes
   l.stage_bytes = l.z_off + (rec ? l.a_tile_bytes : 0);
-  l.nstage = (227 * 1024 - 1280 - Z_TILE_BYTES - wbytes) / l.stage_bytes;
+  l.nstage = (227 * 1024 - 1280 - wbytes) / l.stage_bytes;
   if (l.nstage > 4) l.nstage = 4;
   l.stage_off = wbytes;
-  l.outz_off = l.stage_off + l.nstage * l.stage_bytes;      // z_out staging
-  l.bar_off = l.outz_off + Z_TILE_BYTES;
+  l.bar_off = l.stage_off + l.nstage * l.stage_bytes;
   l.total = l.bar_off + 256 + 1024;  // + slack to align the carve-up to 1024 B at run time
   return l;
 }
@@ -68,6 +67,7 @@ struct TcParams {
   const float* v_in;
   const uint16_t* z_in;  // previous spikes, channels-last (read directly by the epilogue)
   float* v_out;
+  uint16_t* z_out;       // new spikes, channels-last (written directly by the epilogue)
   long long* trace;  // debug: per-CTA timeline (clock64), NULL in production
   int skip;          // debug: ablation mask (1 = no v_out stores, 2 = no v_in loads, 4 = no MMAs, 8 = no spike store, 16 = no tmem loads)
 };
@@ -85,8 +85,7 @@ constexpr int TRACE_SLOTS = 8, TRACE_MAX_TILES = 32;  // [cta][tile][slot]
 // instantiation carries none of that code in its loops.
 template <bool HARD, bool DEBUG>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_zh,
-                       const __grid_constant__ CUtensorMap map_zc, const __grid_constant__ CUtensorMap map_zout) {
+lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_zh) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // swizzle atoms need an aligned carve-up
   const bool rec = p.has_rec != 0;
@@ -109,7 +108,7 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
     mbar_init(bar_w, 1);
     for (int s = 0; s < NST; ++s) {
       mbar_init(bar_full(s), 1);
-      mbar_init(bar_empty(s), 1 + TC_EPI_WARPS);  // MMA commit + one arrive per epilogue warp
+      mbar_init(bar_empty(s), 1);  // MMA commit (the epilogue reads nothing from the operand stages)
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_accf(a), 1);
@@ -222,7 +221,6 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
       thr[j] = fmaxf(__ldg(p.thresh + c0 + j), 0.01f);
       oml[j] = __fsub_rn(1.0f, lam[j]);
     }
-    uint4* zout_s = reinterpret_cast<uint4*>(smem + L.outz_off);
     const size_t plane = (size_t)p.H * p.W;
     // The membrane potential of the NEXT tile is prefetched into registers while the current tile is processed, so the DRAM
     // latency of these loads (the only operand not staged by TMA) stays off the per-tile critical path.
@@ -230,6 +228,7 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
       const float* vin;   // &v_in[b][c0][gy][gx] or nullptr when there is nothing to load
       const uint4* zin;   // &z_in[b][gy][gx][c0] (32 bytes = this thread's 16 channels) or nullptr
       float* vout;        // &v_out[b][c0][gy][gx] or nullptr when the pixel is outside the image
+      uint4* zout;        // &z_out[b][gy][gx][c0]
       int b, y0, x0;
     };
     // tile coordinates advance incrementally by gridDim.x tiles per iteration (no integer division inside the loop)
@@ -249,7 +248,9 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
       const size_t o_ = ((size_t)t.b * 32 + c0) * plane + (size_t)gy_ * p.W + gx_;
       t.vout = in_ ? p.v_out + o_ : nullptr;
       t.vin = (in_ && p.has_v && !(DEBUG && (skip & 2))) ? p.v_in + o_ : nullptr;
-      t.zin = (in_ && p.has_z) ? reinterpret_cast<const uint4*>(p.z_in + (((size_t)t.b * p.H + gy_) * p.W + gx_) * 32 + c0) : nullptr;
+      const size_t oz_ = (((size_t)t.b * p.H + gy_) * p.W + gx_) * 32 + c0;
+      t.zin = (in_ && p.has_z) ? reinterpret_cast<const uint4*>(p.z_in + oz_) : nullptr;
+      t.zout = reinterpret_cast<uint4*>(p.z_out + oz_);
       // advance the cursor by G tiles
       ntx += g_tx;
       if (ntx >= p.tiles_x) ntx -= p.tiles_x, ++nty;
@@ -275,24 +276,16 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
       dst[0] = src ? __ldg(src) : make_uint4(0, 0, 0, 0);
       dst[1] = src ? __ldg(src + 1) : make_uint4(0, 0, 0, 0);
     };
-    TileAt cur = locate_next();
-    float vin[16];
-    uint4 zq[2];
-    load_v(cur.vin, vin);
-    load_z(cur.zin, zq);
-    for (int it = 0; it < n_my; ++it) {
-      const int s = it % NST, a = it & 1;
-      const uint32_t ph = (it / NST) & 1, aph = (it >> 1) & 1;
-      const uint8_t* st = smem + L.stage_off + s * L.stage_bytes;
-      const TileAt nxt = locate_next();
-      float vnext[16];
-      uint4 znext[2];
-      load_v(nxt.vin, vnext);
-      load_z(nxt.zin, znext);
-
-      mbar_wait(bar_full(s), ph);  // keeps the epilogue in step with the producer ring (it reads nothing from the stage)
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_empty(s));
+    // One tile of the epilogue.  (cur, vc, zc) describe the tile processed now (its membrane potential and previous spikes
+    // are already in registers or in flight), (nxt, vnx, znx) receive the prefetch of the following tile.  The loop below
+    // calls this twice per trip with the two register sets swapped, so no register of a pending load is ever copied
+    // (a MOV from an in-flight load would stall for the DRAM latency and serialise the tiles).
+    auto tile_body = [&](const int it, const int a, const TileAt& cur, const float (&vc)[16], const uint4 (&zc)[2], TileAt& nxt, float (&vnx)[16],
+                         uint4 (&znx)[2]) {
+      const uint32_t aph = (it >> 1) & 1;
+      nxt = locate_next();
+      load_v(nxt.vin, vnx);
+      load_z(nxt.zin, znx);
 
       mbar_wait(bar_accf(a), aph);
       tc_fence_after();
@@ -313,48 +306,45 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
       if (lane == 0) mbar_arrive(bar_acce(a));  // accumulator buffer may be overwritten by the MMA of tile it+2
       if (store_thread) EF_TRACE(it, 4);
 
-      const uint32_t zw[8] = {zq[0].x, zq[0].y, zq[0].z, zq[0].w, zq[1].x, zq[1].y, zq[1].z, zq[1].w};
+      const uint32_t zw[8] = {zc[0].x, zc[0].y, zc[0].z, zc[0].w, zc[1].x, zc[1].y, zc[1].z, zc[1].w};
       float vn[16];
       uint32_t zpk[8];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         const float I = __fadd_rn(__fadd_rn(__uint_as_float(a_lo[j]), __uint_as_float(a_mid[j])), __uint_as_float(a_hi[j]));
         const float z = (j & 1) ? bf16_hi(zw[j >> 1]) : bf16_lo(zw[j >> 1]);
-        if (HARD) vn[j] = __fadd_rn(__fmul_rn(__fmul_rn(vin[j], lam[j]), __fsub_rn(1.0f, z)), __fmul_rn(oml[j], I));
-        else vn[j] = __fsub_rn(__fadd_rn(__fmul_rn(vin[j], lam[j]), __fmul_rn(oml[j], I)), __fmul_rn(z, thr[j]));
+        if (HARD) vn[j] = __fadd_rn(__fmul_rn(__fmul_rn(vc[j], lam[j]), __fsub_rn(1.0f, z)), __fmul_rn(oml[j], I));
+        else vn[j] = __fsub_rn(__fadd_rn(__fmul_rn(vc[j], lam[j]), __fmul_rn(oml[j], I)), __fmul_rn(z, thr[j]));
         const uint32_t zb = (__fsub_rn(vn[j], thr[j]) > 0.f) ? 0x3F80u : 0u;  // bf16(1.0) = 0x3F80
         if (j & 1) zpk[j >> 1] |= zb << 16;
         else zpk[j >> 1] = zb;
       }
-      if (cur.vout && !(DEBUG && (skip & 1))) {
+      if (cur.vout) {
+        if (!(DEBUG && (skip & 1))) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) cur.vout[j * plane] = vn[j];
+          for (int j = 0; j < 16; ++j) cur.vout[j * plane] = vn[j];
+        }
+        // spikes: this thread's 16 channels are 32 contiguous bytes of the channels-last pixel row -- stored straight from
+        // registers (fire and forget).  A staged TMA store needs fence.proxy.async, which waits for every outstanding
+        // global load of the thread, i.e. it would turn the prefetch above into a synchronous load (ncu: long-scoreboard
+        // stalls on the fence were the top stall of the previous version).
+        if (!(DEBUG && (skip & 8))) {
+          cur.zout[0] = make_uint4(zpk[0], zpk[1], zpk[2], zpk[3]);
+          cur.zout[1] = make_uint4(zpk[4], zpk[5], zpk[6], zpk[7]);
+        }
       }
       if (store_thread) EF_TRACE(it, 5);
-      if (!(DEBUG && (skip & 8))) {
-        if (it > 0) {  // the staging buffer is free once the previous tile's TMA store has read it
-          if (store_thread) bulk_wait_read0();
-          named_bar_sync(1, 32 * TC_EPI_WARPS);
-        }
-#pragma unroll
-        for (int g = 0; g < 2; ++g) zout_s[m * 4 + 2 * hsel + g] = make_uint4(zpk[4 * g], zpk[4 * g + 1], zpk[4 * g + 2], zpk[4 * g + 3]);
-        fence_proxy_async();  // make the staged spikes visible to the TMA engine
-        named_bar_sync(1, 32 * TC_EPI_WARPS);
-        if (store_thread) {
-          tma_store_4d(&map_zout, smem_u32(zout_s), 0, cur.x0, cur.y0, cur.b);
-          bulk_commit();
-          EF_TRACE(it, 6);
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 16; ++j) vin[j] = vnext[j];
-      zq[0] = znext[0], zq[1] = znext[1];
-      cur = nxt;
+    };
+    TileAt tA = locate_next(), tB;
+    float vA[16], vB[16];
+    uint4 zA[2], zB[2];
+    load_v(tA.vin, vA);
+    load_z(tA.zin, zA);
+    for (int it = 0; it < n_my; it += 2) {
+      tile_body(it, 0, tA, vA, zA, tB, vB, zB);
+      if (it + 1 < n_my) tile_body(it + 1, 1, tB, vB, zB, tA, vA, zA);
     }
-    if (store_thread) {
-      bulk_wait0();
-      EF_TRACE(n_my > 0 ? n_my - 1 : 0, 7);
-    }
+    if (store_thread) EF_TRACE(n_my > 0 ? n_my - 1 : 0, 7);
   }
 
   tc_fence_before();
@@ -410,14 +400,13 @@ int lif_conv_fwd_tc(const ef_lif_conv_params& p, cudaStream_t st) {
   static_assert((8 + 8) * PIX_BYTES == 1024, "the MMA issue loop hard-codes a 1024-byte operand row");
   q.tiles_x = cdiv(p.W, q.tw), q.tiles_y = cdiv(p.H, q.th), q.n_tiles = p.B * q.tiles_x * q.tiles_y;
   q.has_rec = rec, q.has_v = p.v_in != nullptr, q.has_z = p.z_in_cl != nullptr, q.hard_reset = p.hard_reset;
-  q.w_split = p.w_split, q.leak = p.leak, q.thresh = p.thresh, q.v_in = p.v_in, q.z_in = p.z_in_cl, q.v_out = p.v_out;
+  q.w_split = p.w_split, q.leak = p.leak, q.thresh = p.thresh, q.v_in = p.v_in, q.z_in = p.z_in_cl, q.v_out = p.v_out, q.z_out = p.z_out_cl;
   q.trace = g_tc_trace;
   q.skip = g_tc_skip;
-  CUtensorMap mx, mzh, mzc, mzo;
+  CUtensorMap mx, mzh;
   int rc;
   if ((rc = get_map(p.x_cl, p.B, p.H, p.W, q.th + 2, q.tw + 8, true, &mx))) return rc;
-  if ((rc = get_map(p.z_out_cl, p.B, p.H, p.W, q.th, q.tw, false, &mzo))) return rc;
-  mzh = mx, mzc = mzo;  // placeholders when there is no previous state
+  mzh = mx;  // placeholder when there is no previous state
   if (q.has_z) {
     if (rec && (rc = get_map(p.z_in_cl, p.B, p.H, p.W, q.th + 2, q.tw + 8, true, &mzh))) return rc;
   }
@@ -433,7 +422,7 @@ int lif_conv_fwd_tc(const ef_lif_conv_params& p, cudaStream_t st) {
       return check_launch("cudaFuncSetAttribute(lif_conv_fwd_tc_kernel)");
     attr_set[ki] = true;
   }
-  kern<<<grid, TC_THREADS, L.total, st>>>(q, mx, mzh, mzc, mzo);
+  kern<<<grid, TC_THREADS, L.total, st>>>(q, mx, mzh);
   return check_launch("lif_conv_fwd_tc_kernel");
 }
 
