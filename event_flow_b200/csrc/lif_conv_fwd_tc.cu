@@ -16,7 +16,8 @@
 // swizzled copies tripled the L2->SM traffic; the single padded swizzled tile is both the least traffic and full MMA rate.
 // Spikes are {0,1,2}: exactly representable in bf16, so every product is exact and only the fp32 summation order differs
 // from the CPU path (no TF32/BF16 rounding may enter a spiking conv).
-// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2-9 = epilogue: each warp owns a
+// Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner (warps 2-3 idle: setmaxnreg moves the
+// registers of this warpgroup to the others), warps 4-11 = epilogue: each warp owns a
 // TMEM lane quadrant (32 pixels) and one half of the channels; membrane potentials, previous spikes and new spikes go
 // straight global <-> registers (the next tile's loads are in flight while the current tile is computed; nothing in the
 // epilogue touches shared memory, so no proxy fence or CTA barrier sits on the per-tile path).  Persistent over tiles;
@@ -31,7 +32,7 @@ namespace ef {
 constexpr int W_BLOCK_BYTES = 96 * PIX_BYTES;         // one tap: [96 n = 3 splits x 32 ch][32 k] bf16, 64B-swizzled: 6144 B
 constexpr int W_CONV_BYTES = 9 * W_BLOCK_BYTES;       // 55296 B per convolution
 constexpr int TC_EPI_WARPS = 8;
-constexpr int TC_THREADS = 32 * (2 + TC_EPI_WARPS);
+constexpr int TC_THREADS = 32 * (4 + TC_EPI_WARPS);   // warpgroup 0: TMA warp, MMA warp, two idle warps; warpgroups 1-2: epilogue
 constexpr int ACC_COLS = 96;                          // fp32 accumulator columns per tile
 constexpr int TMEM_COLS = 256;                        // 2 accumulator buffers x 96 columns, rounded up to a power of two
 
@@ -133,6 +134,10 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
   const uint32_t stage_tx = L.a_tile_bytes + ((p.has_z && rec) ? L.a_tile_bytes : 0);
   const int tiles_per_img = p.tiles_x * p.tiles_y;
 
+  if (warp < 4) {
+  // Register re-allocation between the warpgroups: the launch allocates 384 x 168 = 64512 registers; afterwards
+  // 128 x 96 + 256 x 200 = 63488 <= 64512 are in use, so the setmaxnreg.inc below can always be satisfied.
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");    // the producer warpgroup hands its registers ...
   if (warp == 0) {
     // =============================== TMA producer ===============================
     if (lane == 0) {
@@ -181,7 +186,16 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
         const uint32_t d_tmem = tmem_base + a * ACC_COLS;
         // One elected thread issues all MMAs of the tile: this instruction stream is serial, so everything per MMA is
         // reduced to two 64-bit adds on precomputed descriptors (offsets in 16-byte units are compile-time constants).
-        if (!(DEBUG && (skip & 4))) {
+        if (DEBUG && (skip & (2048 | 4096 | 8192))) {  // timing experiments only (results are wrong): what paces the MMAs?
+          const uint64_t ax = umma_desc_sw64(st + L.x_off, L.row_bytes);
+          for (int tap = 0; tap < 9; ++tap)
+            for (int ks = 0; ks < 2; ++ks) {
+              const uint64_t ad = ax + (uint64_t)((tap / 3) * (1024 / 16) + ((skip & 4096) ? 0 : (tap % 3) * (PIX_BYTES / 16)) + ((skip & 8192) ? 0 : ks * 2));
+              const uint64_t bd = b_ff + (uint64_t)(tap * (W_BLOCK_BYTES / 16) + ks * 2);
+              if (skip & 2048) umma_bf16<umma_idesc(32)>(d_tmem, ad, bd, (tap | ks) != 0);
+              else umma_bf16<umma_idesc(96)>(d_tmem, ad, bd, (tap | ks) != 0);
+            }
+        } else if (!(DEBUG && (skip & 4))) {
           const uint64_t ax = umma_desc_sw64(st + L.x_off, L.row_bytes);
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
@@ -206,30 +220,28 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
         EF_TRACE(it, 2);
       }
     }
+  }
   } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");  // ... to the epilogue warps (three prefetch register sets)
     // =============================== epilogue (8 warps: 4 lane quadrants x 2 channel halves) ===============================
     const int q = warp & 3;                 // TMEM lane quadrant this warp may access (warp id % 4)
-    const int hsel = (warp - 2) >> 2;       // channel half: channels [16*hsel, 16*hsel + 16)
+    const int hsel = (warp - 4) >> 2;       // channel half: channels [16*hsel, 16*hsel + 16)
     const int m = q * 32 + lane;            // GEMM row = pixel within the tile
     const int ph_ = m / TW, pw_ = m % TW;   // (row, col) inside the tile
-    const bool store_thread = (threadIdx.x == 64);
+    const bool store_thread = (threadIdx.x == 128);
     const int c0 = 16 * hsel;
-    float lam[16], thr[16], oml[16];
+    float lam[16], thr[16];  // 1 - lambda is recomputed per use (one FADD) instead of held in 16 more registers
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       lam[j] = sigmoidf_acc(__ldg(p.leak + c0 + j));
       thr[j] = fmaxf(__ldg(p.thresh + c0 + j), 0.01f);
-      oml[j] = __fsub_rn(1.0f, lam[j]);
     }
     const size_t plane = (size_t)p.H * p.W;
     // The membrane potential of the NEXT tile is prefetched into registers while the current tile is processed, so the DRAM
     // latency of these loads (the only operand not staged by TMA) stays off the per-tile critical path.
     struct TileAt {
-      const float* vin;   // &v_in[b][c0][gy][gx] or nullptr when there is nothing to load
-      const uint4* zin;   // &z_in[b][gy][gx][c0] (32 bytes = this thread's 16 channels) or nullptr
-      float* vout;        // &v_out[b][c0][gy][gx] or nullptr when the pixel is outside the image
-      uint4* zout;        // &z_out[b][gy][gx][c0]
-      int b, y0, x0;
+      int ov;  // element offset of [b][c0][gy][gx] in the membrane tensors, or -1 when the pixel is outside the image / past the last tile
+      int oz;  // element offset of [b][gy][gx][c0] in the channels-last spike tensors
     };
     // tile coordinates advance incrementally by gridDim.x tiles per iteration (no integer division inside the loop)
     const int G = gridDim.x;
@@ -240,17 +252,14 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
       nty = r0 / p.tiles_x, ntx = r0 - nty * p.tiles_x;
     }
     int n_it = 0;  // iteration index the (nb, nty, ntx) cursor points at
+    const int iplane = p.H * p.W;
     auto locate_next = [&]() {
       TileAt t;
-      t.b = nb, t.y0 = nty * TH, t.x0 = ntx * TW;
-      const int gy_ = t.y0 + ph_, gx_ = t.x0 + pw_;
+      const int gy_ = nty * TH + ph_, gx_ = ntx * TW + pw_;
       const bool in_ = n_it < n_my && gy_ < p.H && gx_ < p.W;
-      const size_t o_ = ((size_t)t.b * 32 + c0) * plane + (size_t)gy_ * p.W + gx_;
-      t.vout = in_ ? p.v_out + o_ : nullptr;
-      t.vin = (in_ && p.has_v && !(DEBUG && (skip & 2))) ? p.v_in + o_ : nullptr;
-      const size_t oz_ = (((size_t)t.b * p.H + gy_) * p.W + gx_) * 32 + c0;
-      t.zin = (in_ && p.has_z) ? reinterpret_cast<const uint4*>(p.z_in + oz_) : nullptr;
-      t.zout = reinterpret_cast<uint4*>(p.z_out + oz_);
+      const int pix_ = (nb * p.H + gy_) * p.W + gx_;
+      t.ov = in_ ? (nb * 32 + c0) * iplane + gy_ * p.W + gx_ : -1;
+      t.oz = pix_ * 32 + c0;
       // advance the cursor by G tiles
       ntx += g_tx;
       if (ntx >= p.tiles_x) ntx -= p.tiles_x, ++nty;
@@ -260,8 +269,10 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
       ++n_it;
       return t;
     };
-    auto load_v = [&](const float* src, float (&dst)[16]) {
-      if (src) {
+    const bool ld_v = p.has_v && !(DEBUG && (skip & 2));
+    auto load_v = [&](const TileAt& t, float (&dst)[16]) {
+      if (t.ov >= 0 && ld_v) {
+        const float* src = p.v_in + t.ov;
 #pragma unroll
         for (int j = 0; j < 16; ++j) dst[j] = __ldg(src + j * plane);
       } else {
@@ -272,77 +283,94 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
     // The previous spikes of the pixel are read from global memory as well (32 bytes per thread), NOT from the TMA-written
     // operand tile: an ordinary shared-memory load of TMA-written data right after the mbarrier wait occasionally returned
     // a few stale 16-byte pieces (tools/tc_determinism.py), so no generic-proxy read of async-proxy data is left in this kernel.
-    auto load_z = [&](const uint4* src, uint4 (&dst)[2]) {
-      dst[0] = src ? __ldg(src) : make_uint4(0, 0, 0, 0);
-      dst[1] = src ? __ldg(src + 1) : make_uint4(0, 0, 0, 0);
+    auto load_z = [&](const TileAt& t, uint4 (&dst)[2]) {
+      const bool ld = t.ov >= 0 && p.has_z && !(DEBUG && (skip & 1024));
+      const uint4* src = reinterpret_cast<const uint4*>(p.z_in + t.oz);
+      dst[0] = ld ? __ldg(src) : make_uint4(0, 0, 0, 0);
+      dst[1] = ld ? __ldg(src + 1) : make_uint4(0, 0, 0, 0);
     };
     // One tile of the epilogue.  (cur, vc, zc) describe the tile processed now (its membrane potential and previous spikes
-    // are already in registers or in flight), (nxt, vnx, znx) receive the prefetch of the following tile.  The loop below
-    // calls this twice per trip with the two register sets swapped, so no register of a pending load is ever copied
-    // (a MOV from an in-flight load would stall for the DRAM latency and serialise the tiles).
-    auto tile_body = [&](const int it, const int a, const TileAt& cur, const float (&vc)[16], const uint4 (&zc)[2], TileAt& nxt, float (&vnx)[16],
+    // are already in registers or in flight), (nxt, vnx, znx) receive the prefetch of the tile TWO iterations ahead: one
+    // tile time (~0.5 us) is shorter than the DRAM latency under load, two are not.  The loop below calls this three times
+    // per trip with the three register sets rotated, so no register of a pending load is ever copied (a MOV from an
+    // in-flight load would stall for the DRAM latency and serialise the tiles).
+    auto tile_body = [&](const int it, const TileAt& cur, const float (&vc)[16], const uint4 (&zc)[2], TileAt& nxt, float (&vnx)[16],
                          uint4 (&znx)[2]) {
+      const int a = it & 1;
       const uint32_t aph = (it >> 1) & 1;
       nxt = locate_next();
-      load_v(nxt.vin, vnx);
-      load_z(nxt.zin, znx);
+      load_v(nxt, vnx);
+      load_z(nxt, znx);
 
       mbar_wait(bar_accf(a), aph);
       tc_fence_after();
       if (store_thread) EF_TRACE(it, 3);
-      uint32_t a_hi[16], a_mid[16], a_lo[16];
       const uint32_t tacc = tmem_base + a * ACC_COLS + c0 + ((uint32_t)(q * 32) << 16);
-      if (!(DEBUG && (skip & 16))) {
-        tmem_ld16(tacc, a_hi);
-        tmem_ld16(tacc + 32, a_mid);
-        tmem_ld16(tacc + 64, a_lo);
-        tmem_ld_wait();
-      } else {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) a_hi[j] = a_mid[j] = a_lo[j] = 0;
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_acce(a));  // accumulator buffer may be overwritten by the MMA of tile it+2
-      if (store_thread) EF_TRACE(it, 4);
-
       const uint32_t zw[8] = {zc[0].x, zc[0].y, zc[0].z, zc[0].w, zc[1].x, zc[1].y, zc[1].z, zc[1].w};
       float vn[16];
       uint32_t zpk[8];
+      // the accumulator is read in two halves of 8 channels (3 x 8 live registers instead of 3 x 16: the three prefetch
+      // register sets need the room)
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float I = __fadd_rn(__fadd_rn(__uint_as_float(a_lo[j]), __uint_as_float(a_mid[j])), __uint_as_float(a_hi[j]));
-        const float z = (j & 1) ? bf16_hi(zw[j >> 1]) : bf16_lo(zw[j >> 1]);
-        if (HARD) vn[j] = __fadd_rn(__fmul_rn(__fmul_rn(vc[j], lam[j]), __fsub_rn(1.0f, z)), __fmul_rn(oml[j], I));
-        else vn[j] = __fsub_rn(__fadd_rn(__fmul_rn(vc[j], lam[j]), __fmul_rn(oml[j], I)), __fmul_rn(z, thr[j]));
-        const uint32_t zb = (__fsub_rn(vn[j], thr[j]) > 0.f) ? 0x3F80u : 0u;  // bf16(1.0) = 0x3F80
-        if (j & 1) zpk[j >> 1] |= zb << 16;
-        else zpk[j >> 1] = zb;
+      for (int h = 0; h < 2; ++h) {
+        uint32_t a_hi[8], a_mid[8], a_lo[8];
+        if (!(DEBUG && (skip & 16))) {
+          tmem_ld8(tacc + 8 * h, a_hi);
+          tmem_ld8(tacc + 32 + 8 * h, a_mid);
+          tmem_ld8(tacc + 64 + 8 * h, a_lo);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) a_hi[j] = a_mid[j] = a_lo[j] = 0;
+        }
+        if (h == 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_acce(a));  // accumulator buffer may be overwritten by the MMA of tile it+2
+          if (store_thread) EF_TRACE(it, 4);
+        }
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          const int j = 8 * h + jj;
+          const float I = __fadd_rn(__fadd_rn(__uint_as_float(a_lo[jj]), __uint_as_float(a_mid[jj])), __uint_as_float(a_hi[jj]));
+          const float z = (j & 1) ? bf16_hi(zw[j >> 1]) : bf16_lo(zw[j >> 1]);
+          if (HARD) vn[j] = __fadd_rn(__fmul_rn(__fmul_rn(vc[j], lam[j]), __fsub_rn(1.0f, z)), __fmul_rn(__fsub_rn(1.0f, lam[j]), I));
+          else vn[j] = __fsub_rn(__fadd_rn(__fmul_rn(vc[j], lam[j]), __fmul_rn(__fsub_rn(1.0f, lam[j]), I)), __fmul_rn(z, thr[j]));
+          const uint32_t zb = (__fsub_rn(vn[j], thr[j]) > 0.f) ? 0x3F80u : 0u;  // bf16(1.0) = 0x3F80
+          if (j & 1) zpk[j >> 1] |= zb << 16;
+          else zpk[j >> 1] = zb;
+        }
       }
-      if (cur.vout) {
+      if (cur.ov >= 0) {
         if (!(DEBUG && (skip & 1))) {
+          float* vout = p.v_out + cur.ov;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) cur.vout[j * plane] = vn[j];
+          for (int j = 0; j < 16; ++j) vout[j * plane] = vn[j];
         }
         // spikes: this thread's 16 channels are 32 contiguous bytes of the channels-last pixel row -- stored straight from
         // registers (fire and forget).  A staged TMA store needs fence.proxy.async, which waits for every outstanding
         // global load of the thread, i.e. it would turn the prefetch above into a synchronous load (ncu: long-scoreboard
         // stalls on the fence were the top stall of the previous version).
         if (!(DEBUG && (skip & 8))) {
-          cur.zout[0] = make_uint4(zpk[0], zpk[1], zpk[2], zpk[3]);
-          cur.zout[1] = make_uint4(zpk[4], zpk[5], zpk[6], zpk[7]);
+          uint4* zout = reinterpret_cast<uint4*>(p.z_out + cur.oz);
+          zout[0] = make_uint4(zpk[0], zpk[1], zpk[2], zpk[3]);
+          zout[1] = make_uint4(zpk[4], zpk[5], zpk[6], zpk[7]);
         }
       }
       if (store_thread) EF_TRACE(it, 5);
     };
-    TileAt tA = locate_next(), tB;
-    float vA[16], vB[16];
-    uint4 zA[2], zB[2];
-    load_v(tA.vin, vA);
-    load_z(tA.zin, zA);
-    for (int it = 0; it < n_my; it += 2) {
-      tile_body(it, 0, tA, vA, zA, tB, vB, zB);
-      if (it + 1 < n_my) tile_body(it + 1, 1, tB, vB, zB, tA, vA, zA);
+    TileAt tA = locate_next(), tB, tC;
+    float vA[16], vB[16], vC[16];
+    uint4 zA[2], zB[2], zC[2];
+    load_v(tA, vA);
+    load_z(tA, zA);
+    tB = locate_next();
+    load_v(tB, vB);
+    load_z(tB, zB);
+    for (int it = 0; it < n_my; it += 3) {
+      tile_body(it, tA, vA, zA, tC, vC, zC);
+      if (it + 1 < n_my) tile_body(it + 1, tB, vB, zB, tA, vA, zA);
+      if (it + 2 < n_my) tile_body(it + 2, tC, vC, zC, tB, vB, zB);
     }
     if (store_thread) EF_TRACE(n_my > 0 ? n_my - 1 : 0, 7);
   }
@@ -382,7 +410,7 @@ static int g_tc_skip = 0;                // set through ef_debug_tc_skip (tools/
 
 bool lif_conv_tc_eligible(const ef_lif_conv_params& p) {
   return p.w_split && p.x_cl && p.z_out_cl && p.Cin == 32 && p.C == 32 && p.ksize == 3 && p.stride == 1 && p.neuron == EF_LIF &&
-         !p.residual && !p.out && !p.z_out && !p.out_cl && (!p.v_in == !p.z_in_cl) && !p.z_in && !p.x && ((uintptr_t)p.x_cl % 16 == 0) &&
+         !p.residual && !p.out && !p.z_out && !p.out_cl && (!p.v_in == !p.z_in_cl) && !p.z_in && !p.x && ((uintptr_t)p.x_cl % 16 == 0) && ((long long)p.B * p.H * p.W * 32 < (1ll << 31)) &&
          ((uintptr_t)p.z_out_cl % 16 == 0) && p.v_in != p.v_out;
 }
 

@@ -25,11 +25,35 @@ __global__ void __launch_bounds__(256) pred_fwd_kernel(const ef_pred_params p) {
   float acc[PRED_MAX_COUT];
 #pragma unroll
   for (int o = 0; o < PRED_MAX_COUT; ++o) acc[o] = 0.f;
-  for (int c = 0; c < p.Cin; ++c) {
-    const float xv = ld_x(p, b, c, pix, hw);
+  if (p.x_cl && (p.Cin & 7) == 0) {
+    // channels-last spikes: the pixel's channels are contiguous -- 16-byte loads, all issued before the first use; the
+    // accumulation order over channels is the same as in the scalar loop below
+    const uint4* row = reinterpret_cast<const uint4*>(p.x_cl + ((size_t)b * hw + pix) * p.Cin);
+    const int nq = p.Cin >> 3;
+    uint4 q[PRED_MAX_CIN / 8];
 #pragma unroll
-    for (int o = 0; o < PRED_MAX_COUT; ++o)
-      if (o < p.Cout) acc[o] = fmaf(xv, s_w[o * p.Cin + c], acc[o]);
+    for (int k = 0; k < PRED_MAX_CIN / 8; ++k)
+      if (k < nq) q[k] = __ldg(row + k);
+#pragma unroll
+    for (int k = 0; k < PRED_MAX_CIN / 8; ++k) {
+      if (k < nq) {
+        const uint32_t u[4] = {q[k].x, q[k].y, q[k].z, q[k].w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float xv = (e & 1) ? bf16_hi(u[e >> 1]) : bf16_lo(u[e >> 1]);
+#pragma unroll
+          for (int o = 0; o < PRED_MAX_COUT; ++o)
+            if (o < p.Cout) acc[o] = fmaf(xv, s_w[o * p.Cin + k * 8 + e], acc[o]);
+        }
+      }
+    }
+  } else {
+    for (int c = 0; c < p.Cin; ++c) {
+      const float xv = ld_x(p, b, c, pix, hw);
+#pragma unroll
+      for (int o = 0; o < PRED_MAX_COUT; ++o)
+        if (o < p.Cout) acc[o] = fmaf(xv, s_w[o * p.Cin + c], acc[o]);
+    }
   }
 #pragma unroll
   for (int o = 0; o < PRED_MAX_COUT; ++o)

@@ -163,8 +163,8 @@ def test_tc_weight_gradient_matches_cuda_core_and_fp64(rec, shape, with_state):
         assert scale > 1e-3 or st is None
     for n in ("g_x", "g_v_in"):
         assert torch.equal(tc[n], cc[n]), n
-    for n in ("g_leak", "g_thresh"):  # block sums land through atomics: order-dependent rounding
-        assert torch.allclose(tc[n], cc[n], rtol=1e-4, atol=1e-6), n
+    for n in ("g_leak", "g_thresh"):  # block sums land through atomics: order-dependent rounding (relative to the largest entry)
+        assert (tc[n] - cc[n]).abs().max().item() <= 1e-4 * cc[n].abs().max().item() + 1e-6, n
 
 
 def test_tc_weight_gradient_is_bit_reproducible():

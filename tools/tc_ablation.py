@@ -40,7 +40,7 @@ for rec in (False, True):
     pd = {k: t.to(DEV).contiguous() for k, t in params.items()}
     ws = ops.split_weights(pd["ff"], pd.get("rec"))
     args = (x_cl, v, z_cl, pd["ff"], pd.get("rec"), pd["leak"].reshape(-1), pd["thresh"].reshape(-1))
-    for mask, name in ((0, "full"), (256, "tile-blocked membrane addressing"), (1, "no v_out stores"), (2, "no v_in loads"), (3, "no v traffic"), (4, "no MMAs"), (8, "no spike store/barriers"),
+    for mask, name in ((0, "full"), (256, "tile-blocked membrane addressing"), (1, "no v_out stores"), (2, "no v_in loads"), (1024, "no z_in loads"), (2 + 1024, "no v_in, no z_in loads"), (1 + 8, "no v_out, no z_out stores"), (3, "no v traffic"), (4, "no MMAs"), (8, "no spike store/barriers"),
                        (16, "no tmem loads"), (4 + 16, "no MMA, no tmem ld"), (1 + 2 + 8, "no v traffic, no spike store"), (31, "everything off"),
                        (32, "prologue+teardown only"), (32 + 64, "prologue w/o weights"), (128, "1 tile per CTA"), (128 + 31, "1 tile/CTA, everything off"),
                        (64 + 31, "everything off, no weights"), (512 + 31, "everything off, no tile loads (barrier ring only)")):
