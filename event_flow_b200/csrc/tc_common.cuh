@@ -189,5 +189,28 @@ inline int get_map(const void* ptr, int B, int H, int W, int rows, int cols, boo
   return EF_OK;
 }
 
+// membrane tensor fp32 NCHW [B][32][H][W]: box = cols px x rows x 32 ch (one tile of all channels), not swizzled; loads
+// zero-fill outside the image, stores clip
+inline int get_map_v(const void* ptr, int B, int H, int W, int rows, int cols, CUtensorMap* out) {
+  static thread_local std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  const MapKey key{ptr, B, H, W, rows * 256 + cols};
+  auto it = cache.find(key);
+  if (it != cache.end()) {
+    *out = it->second;
+    return EF_OK;
+  }
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return fail(EF_EUNSUPPORTED, "cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, 32, (cuuint64_t)B};
+  const cuuint64_t strides[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)32 * H * W * 4};
+  const cuuint32_t box[4] = {(cuuint32_t)cols, (cuuint32_t)rows, 32, 1};
+  const cuuint32_t es[4] = {1, 1, 1, 1};
+  const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(EF_EINVAL, "cuTensorMapEncodeTiled (membrane) failed (CUresult %d), B=%d H=%d W=%d ptr=%p", (int)r, B, H, W, ptr);
+  if (cache.size() > 4096) cache.clear();
+  cache.emplace(key, *out);
+  return EF_OK;
+}
 
 }  // namespace ef

@@ -182,6 +182,8 @@ int ef_split_weights(const float* w_ff, const float* w_rec, int32_t Cin, int32_t
 int ef_debug_tc_trace(long long* buf);
 /* Debug aid: ablation mask for the tensor-core kernel (results become wrong; timing experiments only).  0 = off. */
 int ef_debug_tc_skip(int mask);
+/* Epilogue shape of the tensor-core forward kernel: 16 channels per thread (8 epilogue warps, default) or 8 (16 warps). */
+int ef_debug_tc_cpt(int cpt);
 
 /* fp32 NCHW <-> cl bf16 layout conversion at the API boundary (model.states getter/setter, first input). */
 int ef_pack_cl(const float* src, uint16_t* dst, int32_t B, int32_t C, int32_t H, int32_t W, void* stream);

@@ -74,6 +74,9 @@ def fill(p, cell, cin, x_f32, x_cl, d, ws):
 
 
 def main():
+    if len(sys.argv) > 1:
+        L.lib().ef_debug_tc_cpt(int(sys.argv[1]))
+        print("tensor-core kernel: channels per epilogue thread =", sys.argv[1])
     sets = rnd_sets(cin_f32=5)
     res = {}
     alg = 4 * H * W * (32 + 2 * 2 * 32) * B
