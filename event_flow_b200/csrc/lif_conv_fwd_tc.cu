@@ -118,31 +118,6 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long t_cta = DEBUG ? clock64() : 0;
   const bool z_from_halo = REC && p.has_z;  // the epilogue reads the previous spikes from the operand stage
-  if (threadIdx.x == 0) {
-    mbar_init(bar_w, 1);
-    for (int s = 0; s < NOP; ++s) {
-      mbar_init(bar_opf(s), 1);
-      mbar_init(bar_ope(s), 1 + (z_from_halo ? EPI_WARPS : 0));  // MMA commit (+ the epilogue warps that read z from the stage)
-    }
-    for (int s = 0; s < NV; ++s) {
-      mbar_init(bar_vf(s), 1);
-      mbar_init(bar_ve(s), 1);  // the store thread, once the TMA store has read the stage
-    }
-    for (int a = 0; a < 2; ++a) {
-      mbar_init(bar_accf(a), 1);
-      mbar_init(bar_acce(a), EPI_WARPS);
-    }
-    fence_barrier_init();
-  }
-  if (warp == 1) {  // TMEM allocation (whole warp), address lands in shared memory
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
   int n_my = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   if (DEBUG) {
     if (skip & 32) n_my = 0;                        // prologue + teardown only
@@ -156,44 +131,92 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
     const int r = tile - b * tiles_per_img, ty = r / p.tiles_x;
     y0 = ty * TC_TH, x0 = (r - ty * p.tiles_x) * TC_TW;
   };
+  const uint32_t op_tx = HALO_BYTES * (z_from_halo ? 2 : 1);
+  auto op_issue = [&](int it) {  // operand tiles of tile `it` into stage it % NOP (the caller has waited for the stage)
+    int b, y0, x0;
+    tile_origin(it, b, y0, x0);
+    const int s = it % NOP;
+    const uint32_t st = s_base + C::OP_OFF + s * C::OP_STAGE;
+    mbar_expect_tx(bar_opf(s), op_tx);
+    tma_load_4d(st, &map_x, bar_opf(s), 0, x0 - 1, y0 - 1, b);
+    if (z_from_halo) tma_load_4d(st + HALO_STAGE, &map_zh, bar_opf(s), 0, x0 - 1, y0 - 1, b);
+  };
+  const bool ld_zc = !REC && p.has_z && !(DEBUG && (skip & 1024));
+  const bool ld_v = p.has_v && !(DEBUG && (skip & 2));
+  const uint32_t v_tx = (ld_v ? V_TILE_BYTES : 0) + (ld_zc ? ZC_TILE_BYTES : 0);
+  auto v_issue = [&](int it) {  // membrane tile (+ centre spikes) of tile `it` into stage it % NV
+    int b, y0, x0;
+    tile_origin(it, b, y0, x0);
+    const int s = it % NV;
+    const uint32_t st = s_base + C::V_OFF + s * C::V_STAGE;
+    if (v_tx == 0) {
+      mbar_arrive(bar_vf(s));
+      return;
+    }
+    mbar_expect_tx(bar_vf(s), v_tx);
+    if (ld_v) tma_load_4d(st, &map_vin, bar_vf(s), x0, y0, 0, b);
+    if (ld_zc) tma_load_4d(st + V_TILE_BYTES, &map_zc, bar_vf(s), 0, x0, y0, b);
+  };
+  // The two producer threads initialise their own barriers and start the first loads right away, BEFORE the CTA-wide sync:
+  // barrier setup by the other thread, the TMEM allocation and the descriptor fetches overlap the first DRAM round trip.
+  const int n_op0 = n_my < NOP ? n_my : NOP, n_v0 = n_my < NV ? n_my : NV;
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&map_x);
+    if (z_from_halo) prefetch_tensormap(&map_zh);
+    mbar_init(bar_w, 1);
+    for (int s = 0; s < NOP; ++s) {
+      mbar_init(bar_opf(s), 1);
+      mbar_init(bar_ope(s), 1 + (z_from_halo ? EPI_WARPS : 0));  // MMA commit (+ the epilogue warps that read z from the stage)
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_accf(a), 1);
+      mbar_init(bar_acce(a), EPI_WARPS);
+    }
+    fence_barrier_init();
+    for (int it = 0; it < n_op0; ++it) {
+      op_issue(it);
+      EF_TRACE(it, 0);
+    }
+    mbar_expect_tx(bar_w, C::W_BYTES);
+    for (uint32_t off = 0; off < (uint32_t)C::W_BYTES; off += 13824)  // 55296 = 4 x 13824
+      bulk_load_1d(s_base + off, reinterpret_cast<const uint8_t*>(p.w_split) + off, 13824, bar_w);
+  } else if (threadIdx.x == 64) {
+    if (p.has_v) prefetch_tensormap(&map_vin);
+    if (ld_zc) prefetch_tensormap(&map_zc);
+    for (int s = 0; s < NV; ++s) {
+      mbar_init(bar_vf(s), 1);
+      mbar_init(bar_ve(s), 1);  // the store thread, once the TMA store has read the stage
+    }
+    fence_barrier_init();
+    for (int it = 0; it < n_v0; ++it) v_issue(it);
+  } else if (threadIdx.x == 128) {
+    prefetch_tensormap(&map_vout);
+    prefetch_tensormap(&map_zout);
+  }
+  if (warp == 1) {  // TMEM allocation (whole warp), address lands in shared memory
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     // =============================== operand TMA producer ===============================
     if (lane == 0) {
-      mbar_expect_tx(bar_w, C::W_BYTES);
-      for (uint32_t off = 0; off < (uint32_t)C::W_BYTES; off += 13824)  // 55296 = 4 x 13824
-        bulk_load_1d(s_base + off, reinterpret_cast<const uint8_t*>(p.w_split) + off, 13824, bar_w);
-      const uint32_t tx = HALO_BYTES * (z_from_halo ? 2 : 1);
-      for (int it = 0; it < n_my; ++it) {
-        int b, y0, x0;
-        tile_origin(it, b, y0, x0);
-        const int s = it % NOP;
-        mbar_wait(bar_ope(s), ((it / NOP) & 1) ^ 1);
-        const uint32_t st = s_base + C::OP_OFF + s * C::OP_STAGE;
-        mbar_expect_tx(bar_opf(s), tx);
-        tma_load_4d(st, &map_x, bar_opf(s), 0, x0 - 1, y0 - 1, b);
-        if (z_from_halo) tma_load_4d(st + HALO_STAGE, &map_zh, bar_opf(s), 0, x0 - 1, y0 - 1, b);
+      for (int it = n_op0; it < n_my; ++it) {
+        mbar_wait(bar_ope(it % NOP), ((it / NOP) & 1) ^ 1);
+        op_issue(it);
         EF_TRACE(it, 0);
       }
     }
   } else if (warp == 2) {
     // =============================== membrane / centre-spike TMA producer ===============================
     if (lane == 0) {
-      const bool ld_zc = !REC && p.has_z;
-      const uint32_t tx = (p.has_v ? V_TILE_BYTES : 0) + (ld_zc ? ZC_TILE_BYTES : 0);
-      for (int it = 0; it < n_my; ++it) {
-        int b, y0, x0;
-        tile_origin(it, b, y0, x0);
-        const int s = it % NV;
-        mbar_wait(bar_ve(s), ((it / NV) & 1) ^ 1);
-        const uint32_t st = s_base + C::V_OFF + s * C::V_STAGE;
-        if (tx == 0) {
-          mbar_arrive(bar_vf(s));
-          continue;
-        }
-        mbar_expect_tx(bar_vf(s), tx);
-        if (p.has_v) tma_load_4d(st, &map_vin, bar_vf(s), x0, y0, 0, b);
-        if (ld_zc) tma_load_4d(st + V_TILE_BYTES, &map_zc, bar_vf(s), 0, x0, y0, b);
+      for (int it = n_v0; it < n_my; ++it) {
+        mbar_wait(bar_ve(it % NV), ((it / NV) & 1) ^ 1);
+        v_issue(it);
       }
     }
   } else if (warp == 1) {
@@ -332,8 +355,8 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
       if (store_thread) {
         int b, y0, x0;
         tile_origin(it, b, y0, x0);
-        tma_store_4d(&map_vout, vst, x0, y0, 0, b);
-        tma_store_4d(&map_zout, REC ? (s_base + C::ZOUT_OFF) : (vst + V_TILE_BYTES), 0, x0, y0, b);
+        if (!(DEBUG && (skip & 1))) tma_store_4d(&map_vout, vst, x0, y0, 0, b);
+        if (!(DEBUG && (skip & 8))) tma_store_4d(&map_zout, REC ? (s_base + C::ZOUT_OFF) : (vst + V_TILE_BYTES), 0, x0, y0, b);
         bulk_commit();
         EF_TRACE(it, 6);
       }
@@ -376,7 +399,7 @@ __global__ void split_weights_kernel(const float* __restrict__ w_ff, const float
 
 static long long* g_tc_trace = nullptr;  // set through ef_debug_tc_trace (tools/tc_timeline.py)
 static int g_tc_skip = 0;                // set through ef_debug_tc_skip (tools/tc_ablation.py)
-static int g_tc_cpt = 16;                // channels per epilogue thread: 16 (8 epilogue warps) or 8 (16 warps); ef_debug_tc_cpt
+static int g_tc_cpt = 0;                 // channels per epilogue thread: 16 (8 epilogue warps), 8 (16 warps), 0 = per kernel kind; ef_debug_tc_cpt
 
 bool lif_conv_tc_eligible(const ef_lif_conv_params& p) {
   return p.w_split && p.x_cl && p.z_out_cl && p.Cin == 32 && p.C == 32 && p.ksize == 3 && p.stride == 1 && p.neuron == EF_LIF &&
@@ -431,8 +454,10 @@ int lif_conv_fwd_tc(const ef_lif_conv_params& p, cudaStream_t st) {
   }
   const int grid = q.n_tiles < n_sms ? q.n_tiles : n_sms;
   const bool dbg = q.trace != nullptr || q.skip != 0;
-  if (p.hard_reset) return rec ? launch_tc2<true, true>(q, grid, m, st, dbg, g_tc_cpt) : launch_tc2<true, false>(q, grid, m, st, dbg, g_tc_cpt);
-  return rec ? launch_tc2<false, true>(q, grid, m, st, dbg, g_tc_cpt) : launch_tc2<false, false>(q, grid, m, st, dbg, g_tc_cpt);
+  // measured (tools/kbench.py): the feed-forward kernel is faster with 16 epilogue warps, the recurrent one (MMA-paced) with 8
+  const int cpt = g_tc_cpt ? g_tc_cpt : (rec ? 16 : 8);
+  if (p.hard_reset) return rec ? launch_tc2<true, true>(q, grid, m, st, dbg, cpt) : launch_tc2<true, false>(q, grid, m, st, dbg, cpt);
+  return rec ? launch_tc2<false, true>(q, grid, m, st, dbg, cpt) : launch_tc2<false, false>(q, grid, m, st, dbg, cpt);
 }
 
 }  // namespace ef
@@ -443,7 +468,7 @@ extern "C" int ef_debug_tc_skip(int mask) {  // ablation switches for tools/tc_a
 }
 
 extern "C" int ef_debug_tc_cpt(int cpt) {  // 16 = 8 epilogue warps (default), 8 = 16 epilogue warps
-  if (cpt != 8 && cpt != 16) return EF_EINVAL;
+  if (cpt != 0 && cpt != 8 && cpt != 16) return EF_EINVAL;
   ef::g_tc_cpt = cpt;
   return EF_OK;
 }

@@ -43,21 +43,27 @@ def rnd_sets(cin_f32=None):
 
 
 def timed(fn, label, alg_bytes):
+    """REPS x NSET launches captured in ONE CUDA graph (no host launch cost in the figure, like a model step), best of 3 replays."""
     for i in range(NSET):
         fn(i)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        for r in range(REPS):
+            for i in range(NSET):
+                fn(i)
+    graph.replay()
     torch.cuda.synchronize()
     best = 1e9
     for _ in range(3):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for r in range(REPS):
-            for i in range(NSET):
-                fn(i)
+        graph.replay()
         e1.record()
         torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1) * 1e3 / (REPS * NSET))
     gbs = alg_bytes / best / 1e3
-    print(f"{label:34s} {best:8.2f} us/launch   {gbs:8.0f} GB/s algorithmic = {100 * gbs / PEAK:5.1f}% of measured {PEAK:.0f} GB/s")
+    print(f"{label:34s} {best:8.2f} us/launch   {gbs:8.0f} GB/s algorithmic = {100 * gbs / PEAK:5.1f}% of measured {PEAK:.0f} GB/s", flush=True)
     return best
 
 
@@ -73,12 +79,34 @@ def fill(p, cell, cin, x_f32, x_cl, d, ws):
     p.w_split = L.ptr(ws)
 
 
+def ablate(sets):
+    """Per-stream cost inside the tensor-core kernel (debug build; results are wrong under these switches)."""
+    alg = 4 * H * W * (32 + 2 * 2 * 32) * B
+    for rec in (False, True):
+        cell = {k: t.to(DEV).contiguous().reshape(-1) if k in ("leak", "thresh") else t.to(DEV).contiguous()
+                for k, t in osp.init_firenet_params("lif", 32, 32, seed=1, weight_gain=2.0)["G1" if rec else "R1a"].items()}
+        ws = ops.split_weights(cell["ff"], cell.get("rec"))
+        ps = []
+        for d in sets:
+            p = L.LifConvParams()
+            fill(p, cell, 32, None, d["x_cl"], d, ws)
+            ps.append(p)
+        for mask, name in ((0, "production build"), (16384, "debug build, nothing off"), (1, "no v_out TMA store"), (2, "no v_in TMA load"), (3, "no v traffic"),
+                           (8, "no z_out TMA store"), (1024, "no centre-z TMA load (ff)"), (1 + 2 + 8 + 1024, "only operand loads"), (4, "no MMAs"),
+                           (4 + 1 + 2 + 8 + 1024, "no MMAs, only operand loads"), (32, "prologue + teardown only"), (128, "one tile per CTA")):
+            L.lib().ef_debug_tc_skip(mask)
+            timed(lambda i: L.call("ef_lif_conv_fwd", ps[i]), f"rec={int(rec)} {name}", alg)
+        L.lib().ef_debug_tc_skip(0)
+
+
 def main():
     if len(sys.argv) > 1:
         L.lib().ef_debug_tc_cpt(int(sys.argv[1]))
         print("tensor-core kernel: channels per epilogue thread =", sys.argv[1])
     sets = rnd_sets(cin_f32=5)
     res = {}
+    if len(sys.argv) > 2 and sys.argv[2] == "ablate":
+        return ablate(sets)
     alg = 4 * H * W * (32 + 2 * 2 * 32) * B
     for rec in (False, True):
         cell = {k: t.to(DEV).contiguous().reshape(-1) if k in ("leak", "thresh") else t.to(DEV).contiguous()

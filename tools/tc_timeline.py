@@ -12,6 +12,8 @@ from oracle import spiking as osp  # noqa: E402
 DEV = "cuda"
 B, H, W = int(sys.argv[1]) if len(sys.argv) > 1 else 8, 128, 128
 rec = len(sys.argv) > 2 and sys.argv[2] == "rec"
+if len(sys.argv) > 3:
+    L.lib().ef_debug_tc_cpt(int(sys.argv[3]))
 g = torch.Generator().manual_seed(1)
 x_cl = ops.pack_cl((torch.rand((B, 32, H, W), generator=g) < 0.3).float().to(DEV))
 z_cl = ops.pack_cl((torch.rand((B, 32, H, W), generator=g) < 0.3).float().to(DEV))
@@ -24,7 +26,7 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
 for _ in range(3):
     ops.lif_step_cl(*args, hard_reset=True, w_split=ws)
 trace = torch.zeros((148, 32, 8), dtype=torch.int64, device=DEV)
-for cold in (True, False):
+for cold in (False,):
     trace.zero_()
     if cold:
         flush.fill_(1)
@@ -35,7 +37,7 @@ for cold in (True, False):
     torch.cuda.synchronize()
     L.lib().ef_debug_tc_trace(None)
     t = trace.cpu().double()
-    names = ["loads issued", "TMA landed (MMA start)", "MMAs issued", "acc complete (epi)", "tmem read", "computed", "store issued", "stores done"]
+    names = ["loads issued", "TMA landed (MMA start)", "MMAs issued", "acc complete (epi)", "tmem read", "STS done", "store issued", "end"]
     print(f"--- {'cold L2' if cold else 'warm L2'}: B={B} rec={rec}; median over CTAs of cycles since CTA start (1965 MHz: 1000 cyc = 0.51 us)")
     n_t = min(32, (B * 128 + 147) // 148)
     for it in range(min(n_t, 8)):
