@@ -180,81 +180,119 @@ __global__ void __launch_bounds__(NTHREADS) lif_conv_fwd_kernel(const ef_lif_con
 // 32 output channels, LIF.  One thread = one pixel x 32 channels; 32 x 8 pixel tile so that every fp32 NCHW access of a
 // warp is one 128-byte line.  Writes the membrane fp32 NCHW and the spikes in cl for the tensor-core layers.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int HD_TW = 32, HD_TH = 2, HD_THREADS = 64, HD_MAXC = 8;
+constexpr int HD_THREADS = 128, HD_MAXC = 8, HD_CTAS_PER_SM = 3;
 
+// packed fp32 pairs (sm_100: two IEEE fmas per instruction; each lane is an ordinary fma.rn, so the result is bit-identical
+// to the scalar loop)
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+
+// One warp = one strip of 32 x 2 pixels; one thread = two vertically adjacent pixels x 32 channels, so every weight read
+// from shared memory (one 16-byte broadcast load = 4 channels) feeds 8 fmas, issued as 4 packed-pair instructions.  Inputs
+// are read straight from global memory (L1-resident 3x4 neighbourhood per input channel, prefetched one channel ahead);
+// every fp32 NCHW access of a warp is one 128-byte line.  Warps loop over strips independently (no CTA barrier after the
+// weight staging).
 template <bool HARD>
-__global__ void __launch_bounds__(HD_THREADS) lif_head_fwd_kernel(const ef_lif_conv_params p, int tiles_x, int tiles_y, int n_tiles) {
-  __shared__ float s_x[HD_MAXC * (HD_TH + 2) * (HD_TW + 2)];
+__global__ void __launch_bounds__(HD_THREADS, HD_CTAS_PER_SM) lif_head_fwd_kernel(const ef_lif_conv_params p, int strips_x, int strips_y, int n_strips) {
   __shared__ __align__(16) float s_w[HD_MAXC * 9 * 32];
   __shared__ ChanConst s_k[32];
-  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int Cin = p.Cin, H = p.H, W = p.W;
   if (tid < 32) s_k[tid] = load_chan_const(p, tid);
   for (int i = tid; i < Cin * 9 * 32; i += HD_THREADS) {  // s_w[(ci*9 + tap)*32 + co] = w[co][ci][tap]
     const int co = i & 31, r = i >> 5;
     s_w[i] = p.w_ff[(size_t)co * Cin * 9 + r];
   }
-  constexpr int HW_ = HD_TW + 2, HH_ = HD_TH + 2;
+  __syncthreads();
   const size_t plane = (size_t)H * W;
-  // persistent over tiles: the grid is sized to the machine (no tail wave), weights are staged once per CTA
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int b = tile / (tiles_x * tiles_y), r = tile % (tiles_x * tiles_y);
-    const int x0 = (r % tiles_x) * HD_TW, y0 = (r / tiles_x) * HD_TH;
-    __syncthreads();
-    for (int i = tid; i < Cin * HH_ * HW_; i += HD_THREADS) {
-      const int ci = i / (HH_ * HW_), q = i % (HH_ * HW_), y = y0 - 1 + q / HW_, x = x0 - 1 + q % HW_;
-      s_x[i] = (y >= 0 && y < H && x >= 0 && x < W) ? __ldg(p.x + (((size_t)b * Cin + ci) * H + y) * W + x) : 0.f;
-    }
-    const int y = y0 + ty, x = x0 + tx;
-    const bool inb = y < H && x < W;
-    const size_t pix = (size_t)y * W + x;
-    // previous state: issued before the convolution so that the DRAM latency overlaps the FMAs
-    float vin[32];
-    uint4 zq[4];
+  const int per_img = strips_x * strips_y;
+  for (int strip = blockIdx.x * (HD_THREADS / 32) + warp; strip < n_strips; strip += gridDim.x * (HD_THREADS / 32)) {
+    const int b = strip / per_img, r = strip - b * per_img;
+    const int sy = r / strips_x;
+    const int y0 = sy * 2, x = (r - sy * strips_x) * 32 + lane;
+    const bool in_x = x < W;
+    const float* xb = p.x + (size_t)b * Cin * plane;
+    // 4 rows x 3 columns around the pixel pair, zero outside the image
+    auto load_nb = [&](int ci, float (&nb)[12]) {
+      const float* xc = xb + (size_t)ci * plane;
 #pragma unroll
-    for (int c = 0; c < 32; ++c) vin[c] = (inb && p.v_in) ? __ldg(p.v_in + ((size_t)b * 32 + c) * plane + pix) : 0.f;
+      for (int ry = 0; ry < 4; ++ry) {
+        const int y = y0 - 1 + ry;
+        const bool in_y = y >= 0 && y < H;
 #pragma unroll
-    for (int g = 0; g < 4; ++g)
-      zq[g] = (inb && p.z_in_cl) ? __ldg(reinterpret_cast<const uint4*>(p.z_in_cl + ((size_t)b * plane + pix) * 32 + g * 8)) : make_uint4(0, 0, 0, 0);
-    __syncthreads();
-    float acc[32];
-#pragma unroll
-    for (int c = 0; c < 32; ++c) acc[c] = 0.f;
-    for (int ci = 0; ci < Cin; ++ci) {
-      float xv[9];
-#pragma unroll
-      for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-        for (int dx = 0; dx < 3; ++dx) xv[dy * 3 + dx] = s_x[(ci * HH_ + ty + dy) * HW_ + tx + dx];
-#pragma unroll
-      for (int tap = 0; tap < 9; ++tap) {
-        const float4* wr = reinterpret_cast<const float4*>(s_w + (ci * 9 + tap) * 32);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 w4 = wr[q];
-          acc[4 * q + 0] = fmaf(xv[tap], w4.x, acc[4 * q + 0]);
-          acc[4 * q + 1] = fmaf(xv[tap], w4.y, acc[4 * q + 1]);
-          acc[4 * q + 2] = fmaf(xv[tap], w4.z, acc[4 * q + 2]);
-          acc[4 * q + 3] = fmaf(xv[tap], w4.w, acc[4 * q + 3]);
+        for (int rx = 0; rx < 3; ++rx) {
+          const int xx = x - 1 + rx;
+          nb[ry * 3 + rx] = (in_y && xx >= 0 && xx < W) ? __ldg(xc + (size_t)y * W + xx) : 0.f;
         }
       }
-    }
-    if (!inb) continue;
-    uint32_t zpk[16];
+    };
+    unsigned long long accA[16], accB[16];
 #pragma unroll
-    for (int c = 0; c < 32; ++c) {
-      const uint32_t zw = (&zq[c >> 3].x)[(c & 7) >> 1];
-      const float z = (c & 1) ? bf16_hi(zw) : bf16_lo(zw);
-      float vo, zo, ao, thr;
-      neuron_update<EF_LIF, HARD>(acc[c], vin[c], z, 0.f, 0.f, s_k[c], vo, zo, ao, thr);
-      p.v_out[((size_t)b * 32 + c) * plane + pix] = vo;
-      const uint32_t zb = zo > 0.f ? 0x3F80u : 0u;
-      if (c & 1) zpk[c >> 1] |= zb << 16;
-      else zpk[c >> 1] = zb;
-    }
+    for (int j = 0; j < 16; ++j) accA[j] = accB[j] = 0ull;
+    float nb[12], nb_next[12];
+    load_nb(0, nb);
+#pragma unroll 1
+    for (int ci = 0; ci < Cin; ++ci) {
+      if (ci + 1 < Cin) load_nb(ci + 1, nb_next);
 #pragma unroll
-    for (int g = 0; g < 4; ++g)
-      *reinterpret_cast<uint4*>(p.z_out_cl + ((size_t)b * plane + pix) * 32 + g * 8) = make_uint4(zpk[4 * g], zpk[4 * g + 1], zpk[4 * g + 2], zpk[4 * g + 3]);
+      for (int tap = 0; tap < 9; ++tap) {
+        const int dy = tap / 3, dx = tap % 3;
+        const unsigned long long xa = pack2(nb[dy * 3 + dx], nb[dy * 3 + dx]);
+        const unsigned long long xbp = pack2(nb[(dy + 1) * 3 + dx], nb[(dy + 1) * 3 + dx]);
+        const ulonglong2* wr = reinterpret_cast<const ulonglong2*>(s_w + (ci * 9 + tap) * 32);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const ulonglong2 w4 = wr[q];  // channels 4q .. 4q+3
+          accA[2 * q] = fma2(xa, w4.x, accA[2 * q]);
+          accA[2 * q + 1] = fma2(xa, w4.y, accA[2 * q + 1]);
+          accB[2 * q] = fma2(xbp, w4.x, accB[2 * q]);
+          accB[2 * q + 1] = fma2(xbp, w4.y, accB[2 * q + 1]);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 12; ++k) nb[k] = nb_next[k];
+    }
+    // neuron update of the two pixels
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int y = y0 + half;
+      if (!(in_x && y < H)) continue;
+      const size_t pix = (size_t)y * W + x;
+      float vin[32];
+      uint4 zq[4];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) vin[c] = p.v_in ? __ldg(p.v_in + ((size_t)b * 32 + c) * plane + pix) : 0.f;
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        zq[g] = p.z_in_cl ? __ldg(reinterpret_cast<const uint4*>(p.z_in_cl + ((size_t)b * plane + pix) * 32 + g * 8)) : make_uint4(0, 0, 0, 0);
+      uint32_t zpk[16];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        float a0, a1;
+        unpack2(half == 0 ? accA[c >> 1] : accB[c >> 1], a0, a1);
+        const float I = (c & 1) ? a1 : a0;
+        const uint32_t zw = (&zq[c >> 3].x)[(c & 7) >> 1];
+        const float z = (c & 1) ? bf16_hi(zw) : bf16_lo(zw);
+        float vo, zo, ao, thr;
+        neuron_update<EF_LIF, HARD>(I, vin[c], z, 0.f, 0.f, s_k[c], vo, zo, ao, thr);
+        p.v_out[((size_t)b * 32 + c) * plane + pix] = vo;
+        const uint32_t zb = zo > 0.f ? 0x3F80u : 0u;
+        if (c & 1) zpk[c >> 1] |= zb << 16;
+        else zpk[c >> 1] = zb;
+      }
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        *reinterpret_cast<uint4*>(p.z_out_cl + ((size_t)b * plane + pix) * 32 + g * 8) = make_uint4(zpk[4 * g], zpk[4 * g + 1], zpk[4 * g + 2], zpk[4 * g + 3]);
+    }
   }
 }
 
@@ -270,20 +308,14 @@ static int launch_head(const ef_lif_conv_params& p, cudaStream_t st) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev);
   }
-  static int per_sm[2] = {0, 0};
-  const int hi = p.hard_reset ? 1 : 0;
-  if (per_sm[hi] == 0) {
-    if (hi) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[hi], lif_head_fwd_kernel<true>, HD_THREADS, 0);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[hi], lif_head_fwd_kernel<false>, HD_THREADS, 0);
-    if (per_sm[hi] < 1) per_sm[hi] = 1;
-  }
-  const int tiles_x = cdiv(p.W, HD_TW), tiles_y = cdiv(p.H, HD_TH), n_tiles = tiles_x * tiles_y * p.B;
-  const int slots = n_sms * per_sm[hi];  // persistent grid = exactly one resident wave
-  const int grid = n_tiles < slots ? n_tiles : slots;
+  const int strips_x = cdiv(p.W, 32), strips_y = cdiv(p.H, 2), n_strips = strips_x * strips_y * p.B;
+  const int slots = n_sms * HD_CTAS_PER_SM;  // persistent grid = one resident wave of CTAs, warps loop over strips
+  const int want = cdiv(n_strips, HD_THREADS / 32);
+  const int grid = want < slots ? want : slots;
   if (p.hard_reset)
-    lif_head_fwd_kernel<true><<<grid, HD_THREADS, 0, st>>>(p, tiles_x, tiles_y, n_tiles);
+    lif_head_fwd_kernel<true><<<grid, HD_THREADS, 0, st>>>(p, strips_x, strips_y, n_strips);
   else
-    lif_head_fwd_kernel<false><<<grid, HD_THREADS, 0, st>>>(p, tiles_x, tiles_y, n_tiles);
+    lif_head_fwd_kernel<false><<<grid, HD_THREADS, 0, st>>>(p, strips_x, strips_y, n_strips);
   return check_launch("lif_head_fwd_kernel");
 }
 

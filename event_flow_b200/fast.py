@@ -167,10 +167,13 @@ def _fill_fwd(p, B, Cin, H, W, cell, x_f32, x_cl, v_in, z_in, v_out, leak, thres
     p.v_out = L.ptr(v_out)
 
 
-def _launch_step(model, x, v_in, z_in, slot, splits, B, Cin0, H, W):
+def _launch_step(model, x, v_in, z_in, slot, splits, B, Cin0, H, W, only_hidden=False):
     """The 8 kernels of one model step: head, 6 tensor-core cells, prediction head.  All tensors are caller-provided."""
     h = None
     for i, name in enumerate(LAYERS):
+        if only_hidden and i == 0:  # measurement replays (bench.py): the head's spikes are already in the slot
+            h = slot.z[0]
+            continue
         cell = getattr(model, name)
         leak, thresh = cell.leak.detach().reshape(-1), cell.thresh.detach().reshape(-1)
         p = L.LifConvParams()
@@ -180,11 +183,44 @@ def _launch_step(model, x, v_in, z_in, slot, splits, B, Cin0, H, W):
             p.w_split = L.ptr(splits[name])
         L.call("ef_lif_conv_fwd", p, tag=(p.Cin, 32, cell.recurrent))
         h = slot.z[i]
+    if only_hidden:
+        return
     w, b = model.pred.conv2d.weight.detach(), model.pred.conv2d.bias.detach()
     pp = L.PredParams()
     pp.B, pp.Cin, pp.Cout, pp.H, pp.W = B, 32, 2, H, W
     pp.x_cl, pp.w, pp.b, pp.y = L.ptr(h), L.ptr(w), L.ptr(b), L.ptr(slot.flow)
     L.call("ef_pred_fwd", pp)
+
+
+def capture_window(model, xs, only_hidden=False):
+    """
+    Measurement aid (bench.py roofline): the kernels of len(xs) - 1 consecutive model steps on private activation slots,
+    captured as ONE CUDA graph (step 0 runs eagerly from the zero state and provides the previous state of step 1).
+    With only_hidden the graph holds just the six 32 -> 32 tensor-core cell launches of every step.  Replaying it repeats
+    the same computation on the same operands (every launch streams its own ~59 MB, the whole replay far more than L2).
+    Returns (graph, kernel launches per replay).
+    """
+    x0 = xs[0]
+    B, Cin0, H, W = x0.shape
+    for name in LAYERS:
+        cell = getattr(model, name)
+        if not hasattr(cell, "_act_width_f"):
+            cell._act_width_f = float(cell.act_width)
+    splits = _split_cache(model)
+    slots = [_Slot(B, H, W, x0.device) for _ in xs]
+    none = [None] * N_L
+    xs = [x.contiguous() for x in xs]
+    with torch.no_grad():
+        _launch_step(model, xs[0], none, none, slots[0], splits, B, Cin0, H, W)
+        for t in range(1, len(xs)):  # eager pass: fills every slot (the hidden-only replay needs the head spikes in place)
+            _launch_step(model, xs[t], slots[t - 1].v, slots[t - 1].z, slots[t], splits, B, Cin0, H, W)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for t in range(1, len(xs)):
+                _launch_step(model, xs[t], slots[t - 1].v, slots[t - 1].z, slots[t], splits, B, Cin0, H, W, only_hidden=only_hidden)
+    g._keepalive = (slots, xs, splits)
+    return g, (len(xs) - 1) * (N_L - 1 if only_hidden else N_L + 1)
 
 
 class _FireNetStep(torch.autograd.Function):
