@@ -133,6 +133,8 @@ EXPORTS = {
     "ef_debug_tc_cpt": (C.c_int, [C.c_int]),
     "ef_pack_cl": (C.c_int, [C.c_void_p, C.c_void_p, _i32, _i32, _i32, _i32, C.c_void_p]),
     "ef_unpack_cl": (C.c_int, [C.c_void_p, C.c_void_p, _i32, _i32, _i32, _i32, C.c_void_p]),
+    "ef_upsample_bilinear2x": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, _i32, _i32, C.c_void_p]),
+    "ef_upsample_nearest": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, _i32, _i32, _i32, _i32, C.c_void_p]),
     "ef_pred_fwd": (C.c_int, [C.POINTER(PredParams), C.c_void_p]),
     "ef_pred_bwd": (C.c_int, [C.POINTER(PredParams), C.c_void_p]),
     "ef_iwe_loss_workspace_elems": (C.c_int64, [_i32, _i32, _i32, _i32]),

@@ -4,7 +4,8 @@
 
 namespace ef {
 
-constexpr int PRED_MAX_CIN = 64, PRED_MAX_COUT = 4;
+constexpr int PRED_MAX_CIN = 512, PRED_MAX_COUT = 4;  // U-Net prediction layers read up to 8 x base channels
+constexpr int PRED_VEC_CIN = 64;                        // widest channels-last row held in registers by the vector path
 
 __device__ __forceinline__ float ld_x(const ef_pred_params& p, int b, int c, size_t pix, size_t hw) {
   if (p.x) return p.x[((size_t)b * p.Cin + c) * hw + pix];
@@ -25,17 +26,17 @@ __global__ void __launch_bounds__(256) pred_fwd_kernel(const ef_pred_params p) {
   float acc[PRED_MAX_COUT];
 #pragma unroll
   for (int o = 0; o < PRED_MAX_COUT; ++o) acc[o] = 0.f;
-  if (p.x_cl && (p.Cin & 7) == 0) {
+  if (p.x_cl && (p.Cin & 7) == 0 && p.Cin <= PRED_VEC_CIN) {
     // channels-last spikes: the pixel's channels are contiguous -- 16-byte loads, all issued before the first use; the
     // accumulation order over channels is the same as in the scalar loop below
     const uint4* row = reinterpret_cast<const uint4*>(p.x_cl + ((size_t)b * hw + pix) * p.Cin);
     const int nq = p.Cin >> 3;
-    uint4 q[PRED_MAX_CIN / 8];
+    uint4 q[PRED_VEC_CIN / 8];
 #pragma unroll
-    for (int k = 0; k < PRED_MAX_CIN / 8; ++k)
+    for (int k = 0; k < PRED_VEC_CIN / 8; ++k)
       if (k < nq) q[k] = __ldg(row + k);
 #pragma unroll
-    for (int k = 0; k < PRED_MAX_CIN / 8; ++k) {
+    for (int k = 0; k < PRED_VEC_CIN / 8; ++k) {
       if (k < nq) {
         const uint32_t u[4] = {q[k].x, q[k].y, q[k].z, q[k].w};
 #pragma unroll

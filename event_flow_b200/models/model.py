@@ -5,9 +5,9 @@ XLIFFireNet :672, LIFFireFlowNet :684).  Each forward pass is 7 fused conv+neuro
 """
 import torch
 
-from .. import fast
+from .. import fast, ops
 from .base import BaseModel
-from .model_util import copy_states
+from .model_util import CropParameters, copy_states
 from .spiking_submodules import (
     ConvALIF,
     ConvALIFRecurrent,
@@ -19,6 +19,7 @@ from .spiking_submodules import (
     ConvXLIFRecurrent,
 )
 from .submodules import ConvGRU, ConvLayer, ConvLayer_
+from .unet import SpikingMultiResUNetRecurrent
 
 
 class FireNet(BaseModel):
@@ -187,3 +188,153 @@ class LIFFireFlowNet(FireNet):
     rec_neuron = ConvLIF
     residual = False
     w_scale_pred = 0.01
+
+
+class RecEVFlowNet(BaseModel):
+    """
+    Recurrent EV-FlowNet (models/model.py:410-547): input encoding select, optional input normalisation and padding, the
+    multi-resolution recurrent U-Net, nearest-neighbour upsampling of every flow estimate to the input resolution, crop.
+    The spiking subclasses (SpikingRecEVFlowNet :550, PLIF :561, ALIF :572, XLIF :583) run on the CUDA cells; the ANN
+    base (ConvGRU / ConvLSTM encoders of unet.py:314-416) is not built.
+    """
+
+    unet_type = None
+    recurrent_block_type = "convgru"
+    spiking_feedforward_block_type = None
+
+    def __init__(self, unet_kwargs):
+        super().__init__()
+        if self.unet_type is None:
+            raise NotImplementedError("event_flow_b200: the ANN RecEVFlowNet (ConvGRU / ConvLSTM U-Net) is not on the CUDA path yet; "
+                                      "the spiking variants (SpikingRecEVFlowNet, PLIF/ALIF/XLIFRecEVFlowNet) are")
+        norm = None
+        use_upsample_conv = True
+        if "norm" in unet_kwargs.keys():
+            norm = unet_kwargs["norm"]
+        if "use_upsample_conv" in unet_kwargs.keys():
+            use_upsample_conv = unet_kwargs["use_upsample_conv"]
+
+        RecEVFlowNet_kwargs = {
+            "base_num_channels": unet_kwargs["base_num_channels"],
+            "num_encoders": 4,
+            "num_residual_blocks": 2,
+            "num_output_channels": 2,
+            "skip_type": "concat",
+            "norm": norm,
+            "use_upsample_conv": use_upsample_conv,
+            "kernel_size": unet_kwargs["kernel_size"],
+            "channel_multiplier": 2,
+            "recurrent_block_type": self.recurrent_block_type,
+            "final_activation": "tanh",
+            "spiking_feedforward_block_type": self.spiking_feedforward_block_type,
+            "spiking_neuron": unet_kwargs["spiking_neuron"],
+        }
+
+        self.crop = None
+        self.mask = unet_kwargs["mask_output"]
+        self.norm_input = False if "norm_input" not in unet_kwargs.keys() else unet_kwargs["norm_input"]
+        self.encoding = unet_kwargs["encoding"]
+        self.num_bins = unet_kwargs["num_bins"]
+        self.num_encoders = RecEVFlowNet_kwargs["num_encoders"]
+
+        unet_kwargs.update(RecEVFlowNet_kwargs)  # in place on the caller's dict, like the reference (model.py:456-461)
+        unet_kwargs.pop("name", None)
+        unet_kwargs.pop("encoding", None)
+        unet_kwargs.pop("round_encoding", None)
+        unet_kwargs.pop("norm_input", None)
+        unet_kwargs.pop("mask_output", None)
+
+        self.multires_unetrec = self.unet_type(unet_kwargs)
+
+    @property
+    def states(self):
+        return copy_states(self.multires_unetrec.states)
+
+    @states.setter
+    def states(self, states):
+        self.multires_unetrec.states = states
+
+    def detach_states(self):
+        detached_states = []
+        for state in self.multires_unetrec.states:
+            if type(state) is tuple:
+                detached_states.append(tuple(hidden.detach() for hidden in state))
+            else:
+                detached_states.append(state.detach())
+        self.multires_unetrec.states = detached_states
+
+    def reset_states(self):
+        self.multires_unetrec.states = [None] * self.multires_unetrec.num_states
+
+    def init_cropping(self, width, height, safety_margin=0):
+        self.crop = CropParameters(width, height, self.num_encoders, safety_margin)
+
+    def forward(self, event_voxel, event_cnt, log=False):
+        """
+        :param event_voxel: N x num_bins x H x W
+        :param event_cnt: N x 2 x H x W per-polarity event counts
+        :return {"flow": [N x 2 x H x W] * num_encoders (coarse to fine, all at input resolution), "activity": None}
+        """
+        if self.encoding == "voxel":
+            x = event_voxel
+        elif self.encoding == "cnt" and self.num_bins == 2:
+            x = event_cnt
+        else:
+            print("Model error: Incorrect input encoding.")
+            raise AttributeError
+
+        if self.norm_input:
+            mean, stddev = x[x != 0].mean(), x[x != 0].std()
+            x[x != 0] = (x[x != 0] - mean) / stddev
+
+        if self.crop is not None:
+            x = self.crop.pad(x)
+
+        multires_flow = self.multires_unetrec.forward(x)
+
+        if log:
+            raise NotImplementedError("Activity logging not implemented")
+        activity = None
+
+        flow_list = []
+        full_h, full_w = multires_flow[-1].shape[2], multires_flow[-1].shape[3]
+        for flow in multires_flow:
+            flow_list.append(ops.upsample_nearest(flow, full_h // flow.shape[2], full_w // flow.shape[3]))
+
+        if self.crop is not None:
+            for i, flow in enumerate(flow_list):
+                flow_list[i] = flow[:, :, self.crop.iy0:self.crop.iy1, self.crop.ix0:self.crop.ix1].contiguous()
+
+        return {"flow": flow_list, "activity": activity}
+
+
+class SpikingRecEVFlowNet(RecEVFlowNet):
+    """models/model.py:550-558."""
+
+    unet_type = SpikingMultiResUNetRecurrent
+    recurrent_block_type = "lif"
+    spiking_feedforward_block_type = "lif"
+
+
+class PLIFRecEVFlowNet(RecEVFlowNet):
+    """models/model.py:561-569."""
+
+    unet_type = SpikingMultiResUNetRecurrent
+    recurrent_block_type = "plif"
+    spiking_feedforward_block_type = "plif"
+
+
+class ALIFRecEVFlowNet(RecEVFlowNet):
+    """models/model.py:572-580."""
+
+    unet_type = SpikingMultiResUNetRecurrent
+    recurrent_block_type = "alif"
+    spiking_feedforward_block_type = "alif"
+
+
+class XLIFRecEVFlowNet(RecEVFlowNet):
+    """models/model.py:583-591."""
+
+    unet_type = SpikingMultiResUNetRecurrent
+    recurrent_block_type = "xlif"
+    spiking_feedforward_block_type = "xlif"

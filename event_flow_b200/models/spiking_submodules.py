@@ -175,3 +175,73 @@ class ConvXLIFRecurrent(_SpikingConvCell):
 
     def forward(self, input_, prev_state):
         return super().forward(input_, prev_state)
+
+
+_FF_BLOCKS = {"lif": ConvLIF, "alif": ConvALIF, "plif": ConvPLIF, "xlif": ConvXLIF}
+_REC_BLOCKS = {"lif": ConvLIFRecurrent, "alif": ConvALIFRecurrent, "plif": ConvPLIFRecurrent, "xlif": ConvXLIFRecurrent}
+
+
+class SpikingRecurrentConvLayer(nn.Module):
+    """
+    Convolution followed by a recurrent convolutional block, both spiking (models/spiking_submodules.py:878-930): the
+    encoder stage of the spiking U-Net.  Two fused conv+neuron kernels; state = stack([ff_state, rec_state]).
+    """
+
+    def __init__(self, in_channels, out_channels, kernel_size=3, stride=1, recurrent_block_type="lif", activation_ff="arctanspike",
+                 activation_rec="arctanspike", **kwargs):
+        super().__init__()
+        assert recurrent_block_type in ["lif", "alif", "plif", "xlif"]
+        kwargs.pop("spiking_feedforward_block_type", None)
+        self.conv = _FF_BLOCKS[recurrent_block_type](in_channels, out_channels, kernel_size, stride, activation_ff, **kwargs)
+        self.recurrent_block = _REC_BLOCKS[recurrent_block_type](out_channels, out_channels, kernel_size, activation=activation_rec, **kwargs)
+
+    def forward(self, x, prev_state):
+        if prev_state is None:
+            prev_state = [None, None]
+        ff, rec = prev_state  # unbind op, removes dimension
+        x1, ff = self.conv(x, ff)
+        x2, rec = self.recurrent_block(x1, rec)
+        return x2, torch.stack([ff, rec])
+
+
+class SpikingResidualBlock(nn.Module):
+    """Spiking residual block (models/spiking_submodules.py:933-975); the residual is added inside the second cell's kernel."""
+
+    def __init__(self, in_channels, out_channels, stride=1, spiking_feedforward_block_type="lif", activation="arctanspike", **kwargs):
+        super().__init__()
+        assert spiking_feedforward_block_type in ["lif", "alif", "plif", "xlif"]
+        block = _FF_BLOCKS[spiking_feedforward_block_type]
+        self.conv1 = block(in_channels, out_channels, kernel_size=3, stride=stride, activation=activation, **kwargs)
+        self.conv2 = block(out_channels, out_channels, kernel_size=3, stride=1, activation=activation, **kwargs)
+
+    def forward(self, x, prev_state):
+        if prev_state is None:
+            prev_state = [None, None]
+        conv1, conv2 = prev_state  # unbind op, removes dimension
+        residual = x
+        x1, conv1 = self.conv1(x, conv1)
+        x2, conv2 = self.conv2(x1, conv2, residual=residual)  # add res inside
+        return x2, torch.stack([conv1, conv2])
+
+
+class SpikingUpsampleConvLayer(nn.Module):
+    """Bilinear x2 upsampling + spiking conv cell (models/spiking_submodules.py:978-1013): the decoder stage of the spiking U-Net."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, spiking_feedforward_block_type="lif", activation="arctanspike",
+                 **kwargs):
+        super().__init__()
+        assert spiking_feedforward_block_type in ["lif", "alif", "plif", "xlif"]
+        self.conv2d = _FF_BLOCKS[spiking_feedforward_block_type](in_channels, out_channels, kernel_size, stride=stride, activation=activation,
+                                                                 **kwargs)
+
+    def forward(self, x, prev_state):
+        x_up = ops.upsample_bilinear2x(x)
+        x1, state = self.conv2d(x_up, prev_state)
+        return x1, state
+
+
+class SpikingTransposedConvLayer(nn.Module):
+    """models/spiking_submodules.py:1016-1062 (use_upsample_conv=False); no shipped config selects it."""
+
+    def __init__(self, *args, **kwargs):
+        raise NotImplementedError("event_flow_b200: SpikingTransposedConvLayer (use_upsample_conv=False) is not on the CUDA path")

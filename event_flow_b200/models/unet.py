@@ -1,0 +1,122 @@
+"""
+Spiking multi-resolution recurrent U-Net with the constructor contract, module names (state_dict keys) and state layout of
+models/unet.py: BaseUNet (:28-120), MultiResUNetRecurrent (:314-416), SpikingMultiResUNetRecurrent (:418-465).
+Every encoder / residual / decoder stage is built from the fused conv+neuron cells (ef_lif_conv_fwd); the 2x bilinear
+upsampling is ef_upsample_bilinear2x and the per-scale prediction ef_pred_fwd.  Forward only in this version (the
+stride-2 and upsampling backward kernels are not built: calling it under autograd raises).
+"""
+import torch
+import torch.nn as nn
+
+from .model_util import skip_concat, skip_sum  # noqa: F401  (resolved by name like the reference: "skip_" + skip_type)
+from .spiking_submodules import SpikingRecurrentConvLayer, SpikingResidualBlock, SpikingTransposedConvLayer, SpikingUpsampleConvLayer
+from .submodules import ConvLayer
+
+
+class SpikingMultiResUNetRecurrent(nn.Module):
+    ff_type = ConvLayer
+    res_type = SpikingResidualBlock
+    upsample_type = SpikingUpsampleConvLayer
+    transpose_type = SpikingTransposedConvLayer
+    rec_type = SpikingRecurrentConvLayer
+    w_scale_pred = 0.01
+
+    def __init__(self, unet_kwargs):
+        super().__init__()
+        kw = dict(unet_kwargs)
+        self.final_activation = kw.pop("final_activation", None)
+        self.base_num_channels = kw["base_num_channels"]
+        self.num_encoders = kw["num_encoders"]
+        self.num_residual_blocks = kw["num_residual_blocks"]
+        self.num_output_channels = kw["num_output_channels"]
+        self.kernel_size = kw.get("kernel_size", 5)
+        self.skip_type = kw["skip_type"]
+        self.norm = kw["norm"]
+        self.num_bins = kw["num_bins"]
+        self.recurrent_block_type = kw.get("recurrent_block_type")
+        self.channel_multiplier = kw.get("channel_multiplier", 2)
+        self.ff_act, self.rec_act = kw.get("activations", ["relu", None])
+        if self.norm is not None:
+            raise NotImplementedError("event_flow_b200: norm=%r is not on the CUDA path (no shipped config sets it)" % (self.norm,))
+        if self.kernel_size != 3:
+            raise NotImplementedError("event_flow_b200: the spiking U-Net is built for kernel_size 3 (got %r)" % (self.kernel_size,))
+
+        self.spiking_kwargs = {}
+        if kw.get("spiking_feedforward_block_type") is not None:
+            self.spiking_kwargs["spiking_feedforward_block_type"] = kw["spiking_feedforward_block_type"]
+        if type(kw.get("spiking_neuron")) is dict:
+            self.spiking_kwargs.update(kw["spiking_neuron"])
+
+        self.skip_ftn = {"concat": skip_concat, "sum": skip_sum}[self.skip_type]
+        self.UpsampleLayer = self.upsample_type if kw["use_upsample_conv"] else self.transpose_type
+        assert self.num_output_channels > 0
+
+        self.encoder_input_sizes = [int(self.base_num_channels * pow(self.channel_multiplier, i)) for i in range(self.num_encoders)]
+        self.encoder_output_sizes = [int(self.base_num_channels * pow(self.channel_multiplier, i + 1)) for i in range(self.num_encoders)]
+        self.max_num_channels = self.encoder_output_sizes[-1]
+
+        # construction order = the reference's (unet.py:329-332): same torch seed, same initial values
+        self.encoders = self.build_recurrent_encoders()
+        self.resblocks = self.build_resblocks()
+        self.decoders = self.build_multires_prediction_decoders()
+        self.preds = self.build_multires_prediction_layer()
+        self.num_states = self.num_encoders * 2 + self.num_residual_blocks
+        self.states = [None] * self.num_states
+
+    def build_recurrent_encoders(self):
+        encoders = nn.ModuleList()
+        for i, (input_size, output_size) in enumerate(zip(self.encoder_input_sizes, self.encoder_output_sizes)):
+            if i == 0:
+                input_size = self.num_bins
+            kw = {k: v for k, v in self.spiking_kwargs.items()}
+            encoders.append(self.rec_type(input_size, output_size, kernel_size=self.kernel_size, stride=2,
+                                          recurrent_block_type=self.recurrent_block_type, activation_ff=self.ff_act, activation_rec=self.rec_act,
+                                          norm=self.norm, **kw))
+        return encoders
+
+    def build_resblocks(self):
+        resblocks = nn.ModuleList()
+        for _ in range(self.num_residual_blocks):
+            resblocks.append(self.res_type(self.max_num_channels, self.max_num_channels, activation=self.ff_act, norm=self.norm,
+                                           **self.spiking_kwargs))
+        return resblocks
+
+    def build_multires_prediction_layer(self):
+        preds = nn.ModuleList()
+        for output_size in reversed(self.encoder_input_sizes):
+            preds.append(self.ff_type(output_size, self.num_output_channels, 1, activation=self.final_activation, norm=self.norm,
+                                      w_scale=self.w_scale_pred))
+        return preds
+
+    def build_multires_prediction_decoders(self):
+        decoders = nn.ModuleList()
+        for i, (input_size, output_size) in enumerate(zip(reversed(self.encoder_output_sizes), reversed(self.encoder_input_sizes))):
+            prediction_channels = 0 if i == 0 else self.num_output_channels
+            decoders.append(self.UpsampleLayer(2 * input_size + prediction_channels, output_size, kernel_size=self.kernel_size,
+                                               activation=self.ff_act, norm=self.norm, **self.spiking_kwargs))
+        return decoders
+
+    def forward(self, x):
+        """
+        :param x: N x num_input_channels x H x W
+        :return: [N x num_output_channels x H x W for i in range(self.num_encoders)]
+        """
+        blocks = []
+        offset = 0
+        for i, encoder in enumerate(self.encoders):
+            x, self.states[i] = encoder(x, self.states[i])
+            blocks.append(x)
+
+        offset += self.num_encoders
+        for i, resblock in enumerate(self.resblocks):
+            x, self.states[offset + i] = resblock(x, self.states[offset + i])
+
+        predictions = []
+        offset += self.num_residual_blocks
+        for i, (decoder, pred) in enumerate(zip(self.decoders, self.preds)):
+            x = self.skip_ftn(x, blocks[self.num_encoders - i - 1])
+            if i > 0:
+                x = self.skip_ftn(predictions[-1], x)
+            x, self.states[offset + i] = decoder(x, self.states[offset + i])
+            predictions.append(pred(x))
+        return predictions

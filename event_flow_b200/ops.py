@@ -272,6 +272,34 @@ def encode_events(events, res, num_bins, *, round_ts=False, want=("cnt", "voxel"
     return out
 
 
+def upsample_bilinear2x(x):
+    """F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False) on fp32 NCHW (forward only in this version)."""
+    if torch.is_grad_enabled() and x.requires_grad:
+        raise NotImplementedError("event_flow_b200: the backward of the U-Net decoders (bilinear upsampling) is not built yet")
+    x = _c(x)
+    _need_cuda(x)
+    B, Cc, H, W = x.shape
+    out = torch.empty((B, Cc, 2 * H, 2 * W), device=x.device, dtype=torch.float32)
+    L.LAUNCHES += 1
+    L.check(L.lib().ef_upsample_bilinear2x(L.ptr(x), L.ptr(out), B * Cc, H, W, L.stream()), "ef_upsample_bilinear2x")
+    return out
+
+
+def upsample_nearest(x, fy, fx):
+    """F.interpolate(x, scale_factor=(fy, fx)) (nearest) for integer factors (models/model.py:528-539); no gradient (forward only)."""
+    if torch.is_grad_enabled() and x.requires_grad:
+        raise NotImplementedError("event_flow_b200: the backward of the multi-resolution flow upsampling is not built yet")
+    if fy == 1 and fx == 1:
+        return x
+    x = _c(x)
+    _need_cuda(x)
+    B, Cc, H, W = x.shape
+    out = torch.empty((B, Cc, H * fy, W * fx), device=x.device, dtype=torch.float32)
+    L.LAUNCHES += 1
+    L.check(L.lib().ef_upsample_nearest(L.ptr(x), L.ptr(out), B * Cc, H, W, int(fy), int(fx), L.stream()), "ef_upsample_nearest")
+    return out
+
+
 def pack_cl(x):
     """fp32 NCHW -> bf16 channels-last [B,H,W,C] (internal spike format)."""
     x = _c(x)

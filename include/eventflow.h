@@ -185,6 +185,13 @@ int ef_debug_tc_skip(int mask);
 /* Epilogue shape of the tensor-core forward kernel: 16 channels per thread (8 epilogue warps, default) or 8 (16 warps). */
 int ef_debug_tc_cpt(int cpt);
 
+/* Resampling glue of the U-Net family.  src [n_planes,H,W] fp32 (n_planes = B*C), dst [n_planes,2H,2W]:
+ * F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False) of models/spiking_submodules.py:1010 /
+ * submodules.py UpsampleConvLayer; and the nearest-neighbour upsampling by integer factors of the multi-resolution flow
+ * maps (models/model.py:528-539), dst [n_planes,H*fy,W*fx]. */
+int ef_upsample_bilinear2x(const float* src, float* dst, int64_t n_planes, int32_t H, int32_t W, void* stream);
+int ef_upsample_nearest(const float* src, float* dst, int64_t n_planes, int32_t H, int32_t W, int32_t fy, int32_t fx, void* stream);
+
 /* fp32 NCHW <-> cl bf16 layout conversion at the API boundary (model.states getter/setter, first input). */
 int ef_pack_cl(const float* src, uint16_t* dst, int32_t B, int32_t C, int32_t H, int32_t W, void* stream);
 int ef_unpack_cl(const uint16_t* src, float* dst, int32_t B, int32_t C, int32_t H, int32_t W, void* stream);

@@ -29,6 +29,7 @@ sys.path.insert(0, ROOT)
 from oracle import encodings as oenc  # noqa: E402
 from oracle import iwe as oiwe  # noqa: E402
 from oracle import spiking as osp  # noqa: E402
+from oracle import unet as ounet  # noqa: E402
 
 
 def import_reference():
@@ -426,6 +427,51 @@ def pin_metrics(rflow, golden):
     golden["metrics"] = d_all
 
 
+def pin_unet(rmodel, golden, shape=(1, 32, 48, 3)):
+    """Spiking recurrent EV-FlowNet, LIF / PLIF / ALIF / XLIF cells, base_num_channels 4: T-step rollout."""
+    classes = {"lif": rmodel.SpikingRecEVFlowNet, "plif": rmodel.PLIFRecEVFlowNet, "alif": rmodel.ALIFRecEVFlowNet, "xlif": rmodel.XLIFRecEVFlowNet}
+    B, H, W, T = shape
+    for neuron, cls in classes.items():
+        torch.manual_seed(11)
+        cfg = dict(name="x", encoding="cnt", round_encoding=False, norm_input=False, num_bins=2, base_num_channels=4, kernel_size=3,
+                   activations=["arctanspike", "arctanspike"], mask_output=True, spiking_neuron=None if neuron == "lif" else {})
+        m = cls(cfg)
+        with torch.no_grad():
+            for nm, q in m.named_parameters():
+                if nm.endswith("ff.weight") or nm.endswith("rec.weight"):
+                    q.mul_(3.0)
+                if "preds" in nm and nm.endswith("weight"):
+                    q.mul_(20.0)
+        sd = {k: v.detach() for k, v in m.state_dict().items()}
+        P = ounet.unet_params(sd, neuron)
+        xs = []
+        for t in range(T):
+            ts, ys, xx, ps = oenc.synthetic_events(B, 1500, H, W, 2000 + t)
+            xs.append(oenc.encode_window(ts, ys, xx, ps, H, W, 2)["event_cnt"])
+        m.reset_states()
+        states = [None] * 10
+        acts = []
+        with torch.no_grad():
+            for t in range(T):
+                o = m(None, xs[t].clone())
+                trace = []
+                preds, flows, states = ounet.unet_step(neuron, P, states, xs[t], trace=trace)
+                for i in range(4):
+                    close(flows[i], o["flow"][i], 0, f"unet {neuron} flow[{t}][{i}]")
+                acts = [tr[3].ne(0).float().mean().item() for tr in trace]
+        states_r = m.states
+        for i in range(10):
+            close(states[i], states_r[i], 0, f"unet {neuron} state[{i}]")
+        print(f"unet {neuron}: activity per cell, last step:", ["%.3f" % a for a in acts])
+        if golden is not None:
+            d = {"x_%d" % t: xs[t] for t in range(T)}
+            d.update({"flow_%d_%d" % (T - 1, i): o["flow"][i] for i in range(4)})
+            d.update({"state_%d" % i: states_r[i] for i in (0, 3, 5, 9)})
+            for nm, q in sd.items():
+                d["sd_" + nm] = q
+            golden[f"unet_{neuron}"] = d
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--check", action="store_true")
@@ -441,6 +487,7 @@ def main():
     pin_iwe_and_encodings(riwe, renc, golden)
     pin_metrics(rflow, golden)
     pin_ann_firenet(rmodel, golden)
+    pin_unet(rmodel, golden)
     if args.check:
         print("oracle == reference on all cases (check only)")
         return

@@ -1,0 +1,151 @@
+"""
+GPU parity of the spiking recurrent EV-FlowNet family (BASELINE config 4 is this model at 256x256):
+per-cell teacher-forced comparison with the CPU oracle on the reference's golden weights, the resampling kernels against
+torch, the state API, and a larger-shape run (256x256, base 32 channels) checked the same way.
+"""
+import glob
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import encodings as oenc
+from oracle import spiking as osp
+from oracle import unet as ounet
+from tests.conftest import GOLDEN, load_golden
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+UNETS = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "unet_*.npz")))
+CLASSES = {"lif": "SpikingRecEVFlowNet", "plif": "PLIFRecEVFlowNet", "alif": "ALIFRecEVFlowNet", "xlif": "XLIFRecEVFlowNet"}
+
+
+def unet_cfg(neuron, base=4):
+    return dict(name="x", encoding="cnt", round_encoding=False, norm_input=False, num_bins=2, base_num_channels=base, kernel_size=3,
+                activations=["arctanspike", "arctanspike"], mask_output=True, spiking_neuron=None if neuron == "lif" else {})
+
+
+def hook_cells(model):
+    """(name, x_in, state_in, out, state_out) of every spiking cell, in execution order, as CPU tensors."""
+    from event_flow_b200.models.spiking_submodules import _SpikingConvCell
+
+    trace, handles = [], []
+    for name, mod in model.named_modules():
+        if isinstance(mod, _SpikingConvCell):
+            def hook(m, inputs, kwargs, output, name=name):
+                st = inputs[1] if len(inputs) > 1 else None
+                res = kwargs.get("residual", inputs[2] if len(inputs) > 2 else 0)
+                trace.append((name, inputs[0].detach().cpu(), None if st is None else st.detach().cpu(),
+                              res.detach().cpu() if torch.is_tensor(res) else 0, output[0].detach().cpu(), output[1].detach().cpu(), m.stride))
+            handles.append(mod.register_forward_hook(hook, with_kwargs=True))
+    return trace, handles
+
+
+def check_trace(neuron, sd, trace):
+    worst, flips_in, n_tot = 0.0, 0, 0
+    for name, x_in, st_in, res, out, st_out, stride in trace:
+        p = ounet.cell_params(sd, name + ".", neuron)
+        out_o, st_o = osp.cell_step(neuron, x_in, st_in, p, stride=stride, residual=res)
+        if neuron in ("lif", "plif"):
+            thr = p["thresh"].clamp_min(0.01)
+        else:
+            thr = p["t0"].clamp_min(0.01) + p["t1"].clamp_min(0) * st_o[2]
+        tol = max(2e-5, 3e-6 * st_o[0].abs().max().item())  # fp32 summation-order noise, magnitude scaled (tests/util.py)
+        dv = (st_out[0] - st_o[0]).abs().max().item()
+        assert dv <= tol, f"{name}: max|dv| {dv:.2e} > {tol:.2e}"
+        near = (st_o[0] - thr).abs() < tol
+        diff = st_out[1] != st_o[1]
+        assert int((diff & ~near).sum()) == 0, f"{name}: spike flips outside the tolerance band"
+        assert torch.equal(out[~diff], out_o[~diff]), f"{name}: output (spikes + residual)"
+        if st_o.shape[0] == 3:
+            assert (st_out[2] - st_o[2]).abs().max().item() <= 1e-5, f"{name}: trace state"
+        worst, flips_in, n_tot = max(worst, dv / tol), flips_in + int((diff & near).sum()), n_tot + diff.numel()
+    return worst, flips_in, n_tot
+
+
+@pytest.mark.parametrize("name", UNETS)
+def test_unet_cells_match_oracle_on_reference_weights(name):
+    import event_flow_b200.models.model as M
+
+    g = load_golden(name)
+    neuron = name.split("_")[1]
+    m = getattr(M, CLASSES[neuron])(unet_cfg(neuron))
+    sd = {k[3:]: v for k, v in g.items() if k.startswith("sd_")}
+    m.load_state_dict(sd)  # checkpoint compatibility: the reference's state_dict loads unchanged
+    m = m.to(DEV)
+    trace, handles = hook_cells(m)
+    T = len([k for k in g if k.startswith("x_")])
+    with torch.no_grad():
+        for t in range(T):
+            out = m(None, g["x_%d" % t].to(DEV))
+    assert len(trace) == 16 * T and len(out["flow"]) == 4
+    worst, flips_in, n_tot = check_trace(neuron, sd, trace)
+    # the last step's flows: every scale upsampled to the input resolution, same shapes as the reference's
+    for i in range(4):
+        assert out["flow"][i].shape == g["flow_%d_%d" % (T - 1, i)].shape
+    states = m.states
+    assert len(states) == 10 and states[0].shape == g["state_0"].shape and states[9].shape == g["state_9"].shape
+    print(f"{name}: worst |dv|/tol {worst:.2f}, {flips_in}/{n_tot} borderline flips inside the band")
+
+
+def test_resampling_kernels_match_torch():
+    from event_flow_b200 import ops
+
+    g = torch.Generator().manual_seed(3)
+    for shape in ((2, 5, 7, 9), (1, 3, 1, 1), (2, 8, 16, 24)):
+        x = torch.randn(shape, generator=g)
+        up = ops.upsample_bilinear2x(x.to(DEV)).cpu()
+        ref = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False)
+        assert (up - ref).abs().max().item() <= 2e-7 * ref.abs().max().item()
+        z = (torch.rand(shape, generator=g) < 0.4).float()  # spikes: products with 0.25 / 0.75 are exact
+        assert torch.equal(ops.upsample_bilinear2x(z.to(DEV)).cpu(), F.interpolate(z, scale_factor=2, mode="bilinear", align_corners=False))
+        for f in (1, 2, 4, 8):
+            assert torch.equal(ops.upsample_nearest(x.to(DEV), f, f).cpu(), F.interpolate(x, scale_factor=(float(f), float(f))))
+
+
+def test_unet_state_api_and_cropping():
+    import event_flow_b200.models.model as M
+
+    torch.manual_seed(0)
+    m = M.SpikingRecEVFlowNet(unet_cfg("lif")).to(DEV)
+    m.init_cropping(40, 24)  # 24 x 40 is padded to 32 x 48 and cropped back
+    ts, ys, xs, ps = oenc.synthetic_events(1, 600, 24, 40, 5)
+    cnt = oenc.encode_window(ts, ys, xs, ps, 24, 40, 2)["event_cnt"].to(DEV)
+    with torch.no_grad():
+        out = m(None, cnt)
+    assert [tuple(f.shape) for f in out["flow"]] == [(1, 2, 24, 40)] * 4
+    st = m.states
+    assert len(st) == 10 and tuple(st[0].shape) == (2, 2, 1, 8, 16, 24) and tuple(st[9].shape) == (2, 1, 4, 32, 48)
+    m.detach_states()
+    m.states = st
+    m.reset_states()
+    assert all(s is None for s in m.states)
+    with pytest.raises(AttributeError):  # bad encoding: same exception as models/model.py:497-499
+        M.SpikingRecEVFlowNet(dict(unet_cfg("lif"), encoding="nope")).to(DEV)(cnt, cnt)
+    # training through the U-Net is not built yet (stride-2 / upsampling backward): it must fail loudly, never fall back
+    m2 = M.SpikingRecEVFlowNet(unet_cfg("lif")).to(DEV)
+    with pytest.raises(NotImplementedError):
+        m2(None, cnt[:, :, :16, :32].contiguous())
+
+
+def test_unet_full_size_cells_match_oracle():
+    """BASELINE config 4 shape per GPU reduced to B=1: 256x256, base 32 channels (2->64->128->256->512), two steps."""
+    import event_flow_b200.models.model as M
+
+    torch.manual_seed(3)
+    m = M.SpikingRecEVFlowNet(unet_cfg("lif", base=32))
+    with torch.no_grad():
+        for nm, q in m.named_parameters():
+            if nm.endswith("ff.weight") or nm.endswith("rec.weight"):
+                q.mul_(3.0)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    m = m.to(DEV)
+    trace, handles = hook_cells(m)
+    with torch.no_grad():
+        for t in range(2):
+            ts, ys, xs, ps = oenc.synthetic_events(1, 50000, 256, 256, 40 + t)
+            out = m(None, oenc.encode_window(ts, ys, xs, ps, 256, 256, 2)["event_cnt"].to(DEV))
+    assert [tuple(f.shape) for f in out["flow"]] == [(1, 2, 256, 256)] * 4
+    worst, flips_in, n_tot = check_trace("lif", sd, trace)
+    print(f"full size: worst |dv|/tol {worst:.2f}, {flips_in}/{n_tot} borderline flips")

@@ -177,3 +177,26 @@ def test_ann_firenet_matches_reference(name, recurrent):
     for t in range(T):
         flow, states, _ = osp.firenet_ann_step(params, states, g[f"x_{t}"], recurrent=recurrent)
         assert torch.equal(flow, g[f"flow_{t}"])
+
+
+UNETS = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "unet_*.npz")))
+
+
+@pytest.mark.parametrize("name", UNETS)
+def test_spiking_unet_rollout_matches_reference(name):
+    """the oracle's U-Net restatement reproduces the reference's SpikingRecEVFlowNet family bit for bit."""
+    from oracle import unet as ounet
+
+    g = load_golden(name)
+    neuron = name.split("_")[1]
+    sd = {k[3:]: v for k, v in g.items() if k.startswith("sd_")}
+    P = ounet.unet_params(sd, neuron)
+    T = len([k for k in g if k.startswith("x_")])
+    states = [None] * 10
+    with torch.no_grad():
+        for t in range(T):
+            preds, flows, states = ounet.unet_step(neuron, P, states, g["x_%d" % t])
+    for i in range(4):
+        assert torch.equal(flows[i], g["flow_%d_%d" % (T - 1, i)]), f"flow scale {i}"
+    for i in (0, 3, 5, 9):
+        assert torch.equal(states[i], g["state_%d" % i]), f"state {i}"
