@@ -89,6 +89,15 @@ class FireNet(BaseModel):
     def init_cropping(self, width, height):
         pass
 
+    def _apply(self, fn, *args, **kwargs):
+        # .to() / .cuda() / .float(): parameter storage moves, so the pointer-keyed caches of the fast path are dropped
+        out = super()._apply(fn, *args, **kwargs)
+        for k in ("_fast_params", "_fast_cells", "_fast_eligible", "_w_split_cache", "_arena"):
+            self.__dict__.pop(k, None)
+        if getattr(self, "_fast", None) is not None:
+            self._fast.param_sig = None
+        return out
+
     def forward(self, event_voxel, event_cnt, log=False):
         """
         :param event_voxel: N x num_bins x H x W

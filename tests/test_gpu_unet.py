@@ -51,7 +51,10 @@ def check_trace(neuron, sd, trace):
             thr = p["thresh"].clamp_min(0.01)
         else:
             thr = p["t0"].clamp_min(0.01) + p["t1"].clamp_min(0) * st_o[2]
-        tol = max(2e-5, 3e-6 * st_o[0].abs().max().item())  # fp32 summation-order noise, magnitude scaled (tests/util.py)
+        # fp32 summation-order noise, magnitude scaled (tests/util.py: 3e-6 * max|v| was measured for sums of <= 576 terms);
+        # it grows with the square root of the number of accumulated terms (the 1024 -> 256 decoder adds 9216 per output)
+        k_terms = 9 * (p["ff"].shape[1] + (p["rec"].shape[1] if "rec" in p else 0))
+        tol = max(2e-5, 3e-6 * st_o[0].abs().max().item() * max(1.0, (k_terms / 576.0) ** 0.5))
         dv = (st_out[0] - st_o[0]).abs().max().item()
         assert dv <= tol, f"{name}: max|dv| {dv:.2e} > {tol:.2e}"
         near = (st_o[0] - thr).abs() < tol
