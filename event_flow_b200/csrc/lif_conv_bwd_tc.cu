@@ -14,93 +14,93 @@ namespace ef {
 // ---------------------------------------------------------------------------------------------------------------------
 // (1) pointwise
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int PWC_THREADS = 256, PWC_PPT = 1, PWC_CB = 8;
+constexpr int PWC_THREADS = 128, PWC_CB = 8, PWC_GROUPS = 32 / PWC_CB;
 
-// One pixel per thread, channels in batches of PWC_CB: all loads of a batch are issued before any store (the output pointers
-// may alias the inputs as far as the compiler knows, so interleaved stores would serialise the loads).
+// Sums of v[0..15] over the 32 lanes of a warp, all 16 entries at once: 16 shuffles instead of 16 x 5.  Step by step the
+// lanes trade halves of their arrays (lane bit set: keep the upper half, send the lower one); after the four halving steps
+// lanes l and l ^ 16 hold partial sums of the same entry, which the last shuffle combines.  Returns the total of entry
+// `entry` (valid on every lane; lanes l and l ^ 16 return the same entry).
+__device__ __forceinline__ float warp_transpose_sum16(float (&v)[16], int lane, int& entry) {
+  entry = 0;
+#pragma unroll
+  for (int half = 8; half >= 1; half >>= 1) {
+    const bool up = (lane & half) != 0;
+#pragma unroll
+    for (int k = 0; k < half; ++k) {
+      const float keep = up ? v[k + half] : v[k];
+      const float send = up ? v[k] : v[k + half];
+      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+    }
+    entry += up ? half : 0;
+  }
+  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 16);
+}
+
+// One thread = one pixel x PWC_CB channels (its 16-byte piece of the channels-last rows): 40 independent loads in flight per
+// thread at ~60 registers, so that enough warps are resident to cover the DRAM latency (the one-pixel-x-32-channels version
+// ran at 12 warps per SM and 50 % of the HBM roofline).  Per-channel parameter-gradient terms are reduced over the warp with
+// the transposing butterfly above, then over the block in shared memory.
 template <int SURR, bool HARD>
-__global__ void __launch_bounds__(PWC_THREADS, 2) lif_bwd_pointwise_cl_kernel(const ef_lif_bwd_tc_params p) {
-  __shared__ float s_sum[64], lam[32], thr[32];
+__global__ void __launch_bounds__(PWC_THREADS) lif_bwd_pointwise_cl_kernel(const ef_lif_bwd_tc_params p) {
+  __shared__ float s_sum[2 * PWC_CB];
   const int tid = threadIdx.x, lane = tid & 31;
   const size_t hw = (size_t)p.H * p.W;
   const int b = blockIdx.y;
-  if (tid < 64) s_sum[tid] = 0.f;
-  if (tid < 32) {
-    lam[tid] = sigmoidf_acc(__ldg(p.leak + tid));
-    thr[tid] = fmaxf(__ldg(p.thresh + tid), 0.01f);
-  }
+  const int c0 = (blockIdx.x % PWC_GROUPS) * PWC_CB;
+  if (tid < 2 * PWC_CB) s_sum[tid] = 0.f;
   __syncthreads();
   const bool has_gout = p.g_out != nullptr, has_gv = p.g_v_out != nullptr, has_gz = p.g_z_out != nullptr, has_v = p.v_in != nullptr;
-  const size_t pix = (size_t)blockIdx.x * PWC_THREADS + tid;
+  const size_t pix = (size_t)(blockIdx.x / PWC_GROUPS) * PWC_THREADS + tid;
   const bool live = pix < hw;
   const size_t pc = live ? pix : hw - 1;  // out-of-range threads compute on a valid pixel and contribute nothing
-  uint4 zq[4];
+  const uint4 zq = p.z_in_cl ? __ldg(reinterpret_cast<const uint4*>(p.z_in_cl + ((size_t)b * hw + pc) * 32 + c0)) : make_uint4(0, 0, 0, 0);
+  const uint32_t zw[4] = {zq.x, zq.y, zq.z, zq.w};
+  float v_p[PWC_CB], v_n[PWC_CB], g_o[PWC_CB], g_s[PWC_CB], g_vo[PWC_CB], lam[PWC_CB], thr[PWC_CB];
 #pragma unroll
-  for (int g = 0; g < 4; ++g)
-    zq[g] = p.z_in_cl ? __ldg(reinterpret_cast<const uint4*>(p.z_in_cl + ((size_t)b * hw + pc) * 32 + g * 8)) : make_uint4(0, 0, 0, 0);
-  const uint32_t zw[16] = {zq[0].x, zq[0].y, zq[0].z, zq[0].w, zq[1].x, zq[1].y, zq[1].z, zq[1].w,
-                           zq[2].x, zq[2].y, zq[2].z, zq[2].w, zq[3].x, zq[3].y, zq[3].z, zq[3].w};
-  uint32_t hi[16], mid[16];
+  for (int k = 0; k < PWC_CB; ++k) {
+    const size_t o = ((size_t)b * 32 + c0 + k) * hw + pc;
+    v_p[k] = has_v ? __ldg(p.v_in + o) : 0.f;
+    v_n[k] = __ldg(p.v_out + o);
+    g_o[k] = has_gout ? __ldg(p.g_out + o) : 0.f;
+    g_s[k] = has_gz ? __ldg(p.g_z_out + o) : 0.f;
+    g_vo[k] = has_gv ? __ldg(p.g_v_out + o) : 0.f;
+    lam[k] = sigmoidf_acc(__ldg(p.leak + c0 + k));
+    thr[k] = fmaxf(__ldg(p.thresh + c0 + k), 0.01f);
+  }
+  float red[2 * PWC_CB];
+  uint32_t hi[PWC_CB / 2], mid[PWC_CB / 2];
 #pragma unroll
-  for (int c0 = 0; c0 < 32; c0 += PWC_CB) {
-    float v_p[PWC_CB], v_n[PWC_CB], g_o[PWC_CB], g_s[PWC_CB], g_vo[PWC_CB];
-#pragma unroll
-    for (int k = 0; k < PWC_CB; ++k) {
-      const size_t o = ((size_t)b * 32 + c0 + k) * hw + pc;
-      v_p[k] = has_v ? __ldg(p.v_in + o) : 0.f;
-      v_n[k] = __ldg(p.v_out + o);
-      g_o[k] = has_gout ? __ldg(p.g_out + o) : 0.f;
-      g_s[k] = has_gz ? __ldg(p.g_z_out + o) : 0.f;
-      g_vo[k] = has_gv ? __ldg(p.g_v_out + o) : 0.f;
-    }
-    float g_vin[PWC_CB], r_lam[PWC_CB], r_thr[PWC_CB];
-#pragma unroll
-    for (int k = 0; k < PWC_CB; ++k) {
-      const int c = c0 + k;
-      const float z_p = (c & 1) ? bf16_hi(zw[c >> 1]) : bf16_lo(zw[c >> 1]);
-      const float g_z = g_o[k] + g_s[k];
-      const float sg = surrogate_grad(SURR, v_n[k] - thr[c], p.act_width);
-      const float g_v = g_vo[k] + g_z * sg;
-      const float oml = 1.0f - lam[c];
-      const float g_I = oml * g_v;
-      const float keep = HARD ? v_p[k] * (1.0f - z_p) : v_p[k];
-      const float drive = HARD ? (v_n[k] - lam[c] * keep) / oml : (v_n[k] - lam[c] * v_p[k] + z_p * thr[c]) / oml;
-      r_lam[k] = live ? g_v * (keep - drive) : 0.f;
-      r_thr[k] = live ? -g_z * sg - (HARD ? 0.f : z_p * g_v) : 0.f;
-      g_vin[k] = HARD ? g_v * lam[c] * (1.0f - z_p) : g_v * lam[c];
-      const __nv_bfloat16 h = __float2bfloat16_rn(g_I);
-      const __nv_bfloat16 m = __float2bfloat16_rn(g_I - __bfloat162float(h));
-      const uint32_t hb = *reinterpret_cast<const uint16_t*>(&h), mb = *reinterpret_cast<const uint16_t*>(&m);
-      if (c & 1) hi[c >> 1] |= hb << 16, mid[c >> 1] |= mb << 16;
-      else hi[c >> 1] = hb, mid[c >> 1] = mb;
-    }
-    if (p.g_v_in && live) {
-#pragma unroll
-      for (int k = 0; k < PWC_CB; ++k) p.g_v_in[((size_t)b * 32 + c0 + k) * hw + pix] = g_vin[k];
-    }
-#pragma unroll
-    for (int k = 0; k < PWC_CB; ++k) {
-      const float a = warp_sum(r_lam[k]), t = warp_sum(r_thr[k]);
-      if (lane == 0) {
-        atomicAdd(&s_sum[c0 + k], a);
-        atomicAdd(&s_sum[32 + c0 + k], t);
-      }
-    }
+  for (int k = 0; k < PWC_CB; ++k) {
+    const float z_p = (k & 1) ? bf16_hi(zw[k >> 1]) : bf16_lo(zw[k >> 1]);
+    const float g_z = g_o[k] + g_s[k];
+    const float sg = surrogate_grad(SURR, v_n[k] - thr[k], p.act_width);
+    const float g_v = g_vo[k] + g_z * sg;
+    const float oml = 1.0f - lam[k];
+    const float g_I = oml * g_v;
+    const float keep = HARD ? v_p[k] * (1.0f - z_p) : v_p[k];
+    const float drive = HARD ? (v_n[k] - lam[k] * keep) / oml : (v_n[k] - lam[k] * v_p[k] + z_p * thr[k]) / oml;
+    red[k] = live ? g_v * (keep - drive) : 0.f;
+    red[PWC_CB + k] = live ? -g_z * sg - (HARD ? 0.f : z_p * g_v) : 0.f;
+    const float g_vin = HARD ? g_v * lam[k] * (1.0f - z_p) : g_v * lam[k];
+    if (p.g_v_in && live) p.g_v_in[((size_t)b * 32 + c0 + k) * hw + pix] = g_vin;
+    const __nv_bfloat16 h = __float2bfloat16_rn(g_I);
+    const __nv_bfloat16 m = __float2bfloat16_rn(g_I - __bfloat162float(h));
+    const uint32_t hb = *reinterpret_cast<const uint16_t*>(&h), mb = *reinterpret_cast<const uint16_t*>(&m);
+    if (k & 1) hi[k >> 1] |= hb << 16, mid[k >> 1] |= mb << 16;
+    else hi[k >> 1] = hb, mid[k >> 1] = mb;
   }
   if (live) {
-    uint4* dh = reinterpret_cast<uint4*>(p.gI_hi + ((size_t)b * hw + pix) * 32);
-    uint4* dm = reinterpret_cast<uint4*>(p.gI_mid + ((size_t)b * hw + pix) * 32);
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      dh[g] = make_uint4(hi[4 * g], hi[4 * g + 1], hi[4 * g + 2], hi[4 * g + 3]);
-      dm[g] = make_uint4(mid[4 * g], mid[4 * g + 1], mid[4 * g + 2], mid[4 * g + 3]);
-    }
+    *reinterpret_cast<uint4*>(p.gI_hi + ((size_t)b * hw + pix) * 32 + c0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(p.gI_mid + ((size_t)b * hw + pix) * 32 + c0) = make_uint4(mid[0], mid[1], mid[2], mid[3]);
   }
+  int entry;
+  const float tot = warp_transpose_sum16(red, lane, entry);
+  if (lane < 16) atomicAdd(&s_sum[entry], tot);
   __syncthreads();
-  if (tid < 32) {
-    const float l = lam[tid];
-    if (p.g_leak) atomicAdd(p.g_leak + tid, s_sum[tid] * l * (1.0f - l));
-    if (p.g_thresh && __ldg(p.thresh + tid) >= 0.01f) atomicAdd(p.g_thresh + tid, s_sum[32 + tid]);
+  if (tid < PWC_CB) {
+    const float l = sigmoidf_acc(__ldg(p.leak + c0 + tid));
+    if (p.g_leak) atomicAdd(p.g_leak + c0 + tid, s_sum[tid] * l * (1.0f - l));
+    if (p.g_thresh && __ldg(p.thresh + c0 + tid) >= 0.01f) atomicAdd(p.g_thresh + c0 + tid, s_sum[PWC_CB + tid]);
   }
 }
 
@@ -580,7 +580,7 @@ extern "C" int ef_lif_bwd_tc(const ef_lif_bwd_tc_params* pp, void* stream) {
   int rc;
   const int hw = p.H * p.W;
   {
-    const dim3 pgrid(cdiv(hw, PWC_THREADS * PWC_PPT), p.B);
+    const dim3 pgrid(cdiv(hw, PWC_THREADS) * PWC_GROUPS, p.B);
 #define EF_PW(S_, H_) lif_bwd_pointwise_cl_kernel<S_, H_><<<pgrid, PWC_THREADS, 0, st>>>(p)
     switch (p.surrogate * 2 + (p.hard_reset ? 1 : 0)) {
       case 0: EF_PW(EF_ARCTAN, false); break;
