@@ -107,6 +107,73 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+# event-warping loss in isolation (BASELINE metric: "IWE warp Mevents/s"; SURVEY 8d: also on a large stream)
+# ---------------------------------------------------------------------------------------------------------------------
+def iwe_bench(dev, peak_gbs, reps=10):
+    """
+    Kernel time of ef_iwe_loss_fwd (+ ef_iwe_loss_bwd) through ops.event_warping_loss on device-resident windows: the cfg-2
+    window (B=8, 128x128, T=10, 1000 events per pass) and the large stream of SURVEY 8d (B=32, 256x256, T=10, 50 000 events
+    per pass = 16 M events).  The calls are captured in a CUDA graph (kernels + memsets only) and replayed between CUDA events.
+    Algorithmic bytes per sample: fwd 32*Ntot + 4*HW*(2T*S + T + 16*S), bwd 32*Ntot + 4*HW*(8*S + 2T*S).
+    """
+    from event_flow_b200 import _lib as L
+
+    out = {}
+    for name, (B, Hh, Ww, Tt, N) in (("cfg2_B8_128x128_T10_N1000", (8, 128, 128, 10, 1000)), ("large_B32_256x256_T10_N50000", (32, 256, 256, 10, 50000))):
+        g = torch.Generator(device="cpu").manual_seed(99)
+        ntot = Tt * N
+        ts = torch.rand((B, Tt, N), generator=g).sort(dim=2).values + torch.arange(Tt).view(1, Tt, 1)  # pass offset already added (loss/flow.py:90)
+        ys = torch.randint(0, Hh, (B, Tt, N), generator=g).float()
+        xs = torch.randint(0, Ww, (B, Tt, N), generator=g).float()
+        ps = (torch.rand((B, Tt, N), generator=g) < 0.5).float() * 2 - 1
+        events = torch.stack([ts, ys, xs, ps], dim=3).reshape(B, ntot, 4).to(dev)
+        pol = torch.stack([(ps > 0).float(), (ps < 0).float()], dim=3).reshape(B, ntot, 2).to(dev)
+        flow = ((torch.rand((1, B, Tt, 2, Hh, Ww), generator=g) - 0.5) * 0.008).to(dev)
+        mask = (torch.rand((B, Tt, Hh, Ww), generator=g) < 0.3).float().to(dev)
+        del ts, ys, xs, ps
+        p = L.IweLossParams()
+        p.S, p.B, p.T, p.T_maps, p.H, p.W = 1, B, Tt, Tt, Hh, Ww
+        p.n_total, p.n_per_pass = ntot, N
+        p.flow_scaling, p.weight = float(max(Hh, Ww)), 0.001
+        p.loss_scaling, p.smoothing_mask, p.overwrite_intermediate = 1, 1, 0
+        ws = torch.empty(L.lib().ef_iwe_loss_workspace_elems(1, B, Hh, Ww), device=dev, dtype=torch.float32)
+        loss = torch.empty((), device=dev)
+        g_loss = torch.ones((), device=dev)
+        g_maps = torch.empty_like(flow)
+        p.events, p.pol_mask, p.flow_maps, p.event_mask = L.ptr(events), L.ptr(pol), L.ptr(flow), L.ptr(mask)
+        p.workspace, p.loss, p.g_loss, p.g_flow_maps = L.ptr(ws), L.ptr(loss), L.ptr(g_loss), L.ptr(g_maps)
+
+        def timed_graph(fn):
+            fn()
+            torch.cuda.synchronize()
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                fn()
+            gr.replay()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                gr.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / reps
+
+        ms_f = timed_graph(lambda: L.call("ef_iwe_loss_fwd", p))
+        ms_fb = timed_graph(lambda: (L.call("ef_iwe_loss_fwd", p), L.call("ef_iwe_loss_bwd", p)))
+        hw = Hh * Ww
+        bytes_f = B * (32 * ntot + 4 * hw * (2 * Tt + Tt + 16))
+        bytes_b = B * (32 * ntot + 4 * hw * (8 + 2 * Tt))
+        out[name] = {"events": B * ntot, "fwd_ms": ms_f, "fwd_bwd_ms": ms_fb, "fwd_Mev_s": B * ntot / ms_f / 1e3, "fwd_bwd_Mev_s": B * ntot / ms_fb / 1e3,
+                     "fwd_GBs_algorithmic": bytes_f / ms_f / 1e6, "fwd_frac_of_hbm_peak": bytes_f / ms_f / 1e6 / peak_gbs,
+                     "fwd_bwd_GBs_algorithmic": (bytes_f + bytes_b) / ms_fb / 1e6, "fwd_bwd_frac_of_hbm_peak": (bytes_f + bytes_b) / ms_fb / 1e6 / peak_gbs,
+                     "loss": float(loss.item())}
+        del events, pol, flow, mask, ws, g_maps
+    torch.cuda.empty_cache()
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------------------------
 def run_ours(args):
@@ -241,12 +308,14 @@ def run_ours(args):
     avg_ms = ms_hidden / n_hidden
     achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "fused conv3x3+LIF step, 32->32 ch (lif_conv_fwd_tc_kernel via ef_lif_conv_fwd)", "achieved": achieved,
-                "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": 58720256, "peak_source": pk_kind + " (burst copy)",
+                "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": 34393088, "peak_source": pk_kind + " (burst copy)",
                 "bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_ms, "launches_per_step": n_hidden,
-                "traffic_source": "ncu dram__bytes_read.sum 33.65 MB + writes 25.07 MB (writes mostly still in L2 at kernel end: computed from the tensor sizes)",
+                "traffic_source": "ncu --set full, profiles/r01b_ncu_tc_fwd_v5.txt: dram__bytes_read.sum 33 643 520 (= x 8.4 + z 8.4 + v 16.8 MB, exactly compulsory) + "
+                                  "dram__bytes_write.sum 749 568 (the 25.2 MB of outputs are still in the 126 MB L2 when the kernel ends); fast-path formats move 58.7 MB per launch",
                 "how": f"{n_hidden} launches (4 feed-forward + 2 recurrent cells x {T} steps) replayed as one CUDA graph, CUDA events around the replays",
                 "share_of_step": ms_hidden / ms_all, "model_kernels_ms_per_window": ms_all, "clocks": clocks_k.summary()}
 
+    iwe = iwe_bench(dev, pk["hbm_gbs"]) if rank == 0 else None
     if rank == 0:
         # the CPU baseline is taken at N=1 only: under torchrun the other ranks spin in the barrier and steal the host cores
         cpu = cpu_baseline(sample_steps=1) if world == 1 else None
@@ -262,7 +331,7 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "train": {"ms_per_step": ms_train, "events_per_s": events_per_step / (ms_train * 1e-3), "gpu_launches": int(launches_train),
                       "what": "fwd x10 + loss + BPTT + grad all-reduce(SUM) + clip(100) + Adam, batch 8 per GPU"},
-            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks.summary(),
+            "roofline": roofline, "iwe": iwe, "cpu_baseline": cpu, "clocks": clocks.summary(),
         }
         print(json.dumps(line))
     if world > 1:
