@@ -38,7 +38,7 @@ class LifConvBwdParams(C.Structure):
         ("scratch_gI", _f32p), ("scratch_gP", _f32p),
         ("g_x", _f32p), ("g_v_in", _f32p), ("g_z_in", _f32p), ("g_aux_in", _f32p),
         ("g_w_ff", _f32p), ("g_w_rec", _f32p), ("g_leak", _f32p), ("g_thresh", _f32p), ("g_leak_aux", _f32p),
-        ("g_add_pt", _f32p), ("g_t0", _f32p), ("g_t1", _f32p),
+        ("g_add_pt", _f32p), ("g_t0", _f32p), ("g_t1", _f32p), ("scratch_gI_up", _f32p), ("scratch_gP_up", _f32p),
     ]  # fmt: skip
 
 
@@ -135,6 +135,8 @@ EXPORTS = {
     "ef_unpack_cl": (C.c_int, [C.c_void_p, C.c_void_p, _i32, _i32, _i32, _i32, C.c_void_p]),
     "ef_upsample_bilinear2x": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, _i32, _i32, C.c_void_p]),
     "ef_upsample_nearest": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, _i32, _i32, _i32, _i32, C.c_void_p]),
+    "ef_upsample_bilinear2x_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, _i32, _i32, C.c_void_p]),
+    "ef_upsample_nearest_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, _i32, _i32, _i32, _i32, C.c_void_p]),
     "ef_pred_fwd": (C.c_int, [C.POINTER(PredParams), C.c_void_p]),
     "ef_pred_bwd": (C.c_int, [C.POINTER(PredParams), C.c_void_p]),
     "ef_iwe_loss_workspace_elems": (C.c_int64, [_i32, _i32, _i32, _i32]),

@@ -309,6 +309,18 @@ __global__ void __launch_bounds__(WG_THREADS) conv_wgrad_kernel(const float* __r
   }
 }
 
+// Stride 2: the transposed convolution / the weight correlation of a stride-2 conv equal the stride-1 ones applied to the
+// output gradient with zeros inserted between its pixels (up[2oy][2ox] = g[oy][ox]), so the stride-1 kernels above are reused
+// on an input-resolution copy (4x their minimal FLOPs; the four encoder convs of the U-Net are the only stride-2 layers).
+__global__ void __launch_bounds__(256) zero_insert2_kernel(const float* __restrict__ g, float* __restrict__ up, size_t n_planes, int H, int W, int Ho,
+                                                        int Wo) {
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n_planes * H * W) return;
+  const int x = i % W, y = (i / W) % H;
+  const size_t pl = i / ((size_t)W * H);
+  up[i] = ((x | y) & 1) ? 0.f : g[pl * Ho * Wo + (size_t)(y >> 1) * Wo + (x >> 1)];
+}
+
 template <int NEURON, bool HARD>
 static int launch_pointwise(const ef_lif_conv_bwd_params& q, int Ho, int Wo, float* gP_sum, cudaStream_t st) {
   dim3 grid(cdiv(Ho * Wo, PW_THREADS * PW_PER_THREAD), q.f.C, q.f.B);
@@ -323,7 +335,8 @@ extern "C" int ef_lif_conv_bwd(const ef_lif_conv_bwd_params* q, void* stream) {
   EF_REQUIRE(q, EF_ENULL, "ef_lif_conv_bwd: params is NULL");
   const ef_lif_conv_params& p = q->f;
   EF_REQUIRE(p.B > 0 && p.Cin > 0 && p.C > 0 && p.H > 0 && p.W > 0, EF_EINVAL, "ef_lif_conv_bwd: non-positive dimension");
-  EF_REQUIRE(p.ksize == 3 && p.stride == 1, EF_EUNSUPPORTED, "ef_lif_conv_bwd: kernel_size 3, stride 1 only in this version");
+  EF_REQUIRE(p.ksize == 3 && (p.stride == 1 || p.stride == 2), EF_EUNSUPPORTED, "ef_lif_conv_bwd: kernel_size 3, stride 1 or 2");
+  EF_REQUIRE(p.stride == 1 || q->scratch_gI_up, EF_ENULL, "ef_lif_conv_bwd: stride 2 needs scratch_gI_up");
   EF_REQUIRE((p.x || p.x_cl) && p.w_ff && p.leak && p.v_out && q->scratch_gI, EF_ENULL, "ef_lif_conv_bwd: x / w_ff / leak / v_out / scratch is NULL");
   EF_REQUIRE(p.x || !(p.neuron == EF_PLIF || p.neuron == EF_XLIF) || !q->g_x, EF_EUNSUPPORTED, "ef_lif_conv_bwd: PLIF / XLIF data gradient needs the fp32 input");
   EF_REQUIRE(p.neuron == EF_LIF || p.aux_out, EF_ENULL, "ef_lif_conv_bwd: aux_out is NULL");
@@ -351,9 +364,25 @@ extern "C" int ef_lif_conv_bwd(const ef_lif_conv_bwd_params* q, void* stream) {
   }
   if (rc) return rc;
 
+  // gradient of the feed-forward conv output at the resolution the stride-1 kernels expect
+  const float* gI_ff = q->scratch_gI;
+  const float* gP_ff = gP_sum;
+  if (p.stride == 2) {
+    const size_t n = (size_t)p.B * p.C * p.H * p.W;
+    zero_insert2_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(q->scratch_gI, q->scratch_gI_up, (size_t)p.B * p.C, p.H, p.W, Ho, Wo);
+    if ((rc = check_launch("zero_insert2_kernel"))) return rc;
+    gI_ff = q->scratch_gI_up;
+    if (gP_sum) {
+      EF_REQUIRE(q->scratch_gP_up, EF_ENULL, "ef_lif_conv_bwd: stride-2 PLIF / XLIF data gradient needs scratch_gP_up");
+      const size_t m = (size_t)p.B * p.H * p.W;
+      zero_insert2_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(gP_sum, q->scratch_gP_up, (size_t)p.B, p.H, p.W, Ho, Wo);
+      if ((rc = check_launch("zero_insert2_kernel(gP)"))) return rc;
+      gP_ff = q->scratch_gP_up;
+    }
+  }
   if (q->g_x) {
     dim3 grid(cdiv(p.W, 16), cdiv(p.H, 16), p.B * cdiv(p.Cin, DG_CIB));
-    conv_dgrad_kernel<<<grid, DG_THREADS, 0, st>>>(q->scratch_gI, p.w_ff, q->g_x, 0, p.B, p.Cin, p.C, p.H, p.W, gP_sum, p.x);
+    conv_dgrad_kernel<<<grid, DG_THREADS, 0, st>>>(gI_ff, p.w_ff, q->g_x, 0, p.B, p.Cin, p.C, p.H, p.W, gP_ff, p.x);
     if ((rc = check_launch("conv_dgrad_kernel(ff)"))) return rc;
   }
   if (p.w_rec && q->g_z_in && (p.z_in || p.z_in_cl)) {
@@ -362,8 +391,9 @@ extern "C" int ef_lif_conv_bwd(const ef_lif_conv_bwd_params* q, void* stream) {
     if ((rc = check_launch("conv_dgrad_kernel(rec)"))) return rc;
   }
   if (q->g_w_ff) {
-    dim3 grid(cdiv(Wo, 16), cdiv(Ho, 16), p.B * cdiv(p.C, 32));
-    conv_wgrad_kernel<<<grid, WG_THREADS, 0, st>>>(p.x, p.x_cl, q->scratch_gI, q->g_w_ff, p.B, p.Cin, p.C, p.H, p.W, Ho, Wo);
+    const int Hg = p.stride == 2 ? p.H : Ho, Wg = p.stride == 2 ? p.W : Wo;
+    dim3 grid(cdiv(Wg, 16), cdiv(Hg, 16), p.B * cdiv(p.C, 32));
+    conv_wgrad_kernel<<<grid, WG_THREADS, 0, st>>>(p.x, p.x_cl, gI_ff, q->g_w_ff, p.B, p.Cin, p.C, p.H, p.W, Hg, Wg);
     if ((rc = check_launch("conv_wgrad_kernel(ff)"))) return rc;
   }
   if (p.w_rec && q->g_w_rec && (p.z_in || p.z_in_cl)) {

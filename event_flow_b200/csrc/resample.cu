@@ -42,7 +42,68 @@ __global__ void __launch_bounds__(256) upsample_nearest_kernel(const float* __re
   dst[i] = src[pl * H * W + (size_t)(y / fy) * W + x / fx];
 }
 
+// adjoint of upsample_bilinear2x_kernel in gather form: every source pixel collects from the (at most) 4 x 4 destination pixels
+// whose interpolation stencil contains it, with exactly the forward weights (recomputed from the forward index map)
+__device__ __forceinline__ float bilinear2x_weight(int d, int n_in, int i) {
+  int i0, i1;
+  float l0, l1;
+  bilinear2x_src(d, n_in, i0, i1, l0, l1);
+  return (i0 == i ? l0 : 0.f) + (i1 == i ? l1 : 0.f);
+}
+
+__global__ void __launch_bounds__(256) upsample_bilinear2x_bwd_kernel(const float* __restrict__ g_dst, float* __restrict__ g_src, size_t n_planes, int H,
+                                                                   int W) {
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n_planes * H * W) return;
+  const int x = i % W, y = (i / W) % H;
+  const size_t pl = i / ((size_t)W * H);
+  const float* g = g_dst + pl * 4 * H * W;
+  float acc = 0.f;
+  for (int dy = 2 * y - 1; dy <= 2 * y + 2; ++dy) {
+    if (dy < 0 || dy >= 2 * H) continue;
+    const float wy = bilinear2x_weight(dy, H, y);
+    if (wy == 0.f) continue;
+    for (int dx = 2 * x - 1; dx <= 2 * x + 2; ++dx) {
+      if (dx < 0 || dx >= 2 * W) continue;
+      const float wx = bilinear2x_weight(dx, W, x);
+      acc += wy * wx * g[(size_t)dy * 2 * W + dx];
+    }
+  }
+  g_src[i] = acc;
+}
+
+__global__ void __launch_bounds__(256) upsample_nearest_bwd_kernel(const float* __restrict__ g_dst, float* __restrict__ g_src, size_t n_planes, int H, int W,
+                                                                int fy, int fx) {
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n_planes * H * W) return;
+  const int x = i % W, y = (i / W) % H;
+  const size_t pl = i / ((size_t)W * H);
+  const float* g = g_dst + pl * H * W * fy * fx;
+  float acc = 0.f;
+  for (int a = 0; a < fy; ++a)
+    for (int b = 0; b < fx; ++b) acc += g[(size_t)(y * fy + a) * W * fx + x * fx + b];
+  g_src[i] = acc;
+}
+
 }  // namespace ef
+
+extern "C" int ef_upsample_bilinear2x_bwd(const float* g_dst, float* g_src, int64_t n_planes, int32_t H, int32_t W, void* stream) {
+  using namespace ef;
+  EF_REQUIRE(g_dst && g_src, EF_ENULL, "ef_upsample_bilinear2x_bwd: NULL tensor");
+  EF_REQUIRE(n_planes > 0 && H > 0 && W > 0, EF_EINVAL, "ef_upsample_bilinear2x_bwd: non-positive dimension");
+  const size_t n = (size_t)n_planes * H * W;
+  upsample_bilinear2x_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(g_dst, g_src, (size_t)n_planes, H, W);
+  return check_launch("upsample_bilinear2x_bwd_kernel");
+}
+
+extern "C" int ef_upsample_nearest_bwd(const float* g_dst, float* g_src, int64_t n_planes, int32_t H, int32_t W, int32_t fy, int32_t fx, void* stream) {
+  using namespace ef;
+  EF_REQUIRE(g_dst && g_src, EF_ENULL, "ef_upsample_nearest_bwd: NULL tensor");
+  EF_REQUIRE(n_planes > 0 && H > 0 && W > 0 && fy > 0 && fx > 0, EF_EINVAL, "ef_upsample_nearest_bwd: non-positive dimension or factor");
+  const size_t n = (size_t)n_planes * H * W;
+  upsample_nearest_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(g_dst, g_src, (size_t)n_planes, H, W, fy, fx);
+  return check_launch("upsample_nearest_bwd_kernel");
+}
 
 extern "C" int ef_upsample_bilinear2x(const float* src, float* dst, int64_t n_planes, int32_t H, int32_t W, void* stream) {
   using namespace ef;

@@ -105,10 +105,16 @@ class _CellStep(torch.autograd.Function):
         need = ctx.needs_input_grad  # (meta, x, state_in, w_ff, w_rec, residual, *chan)
         g_x = torch.empty_like(x) if need[1] else None
         q.g_x = L.ptr(g_x)
-        scratch_p = None
+        scratch_p = scratch_up = scratch_p_up = None
         if g_x is not None and neuron in ("plif", "xlif"):
             scratch_p = torch.empty((B, Ho, Wo), device=dev, dtype=torch.float32)
             q.scratch_gP = L.ptr(scratch_p)
+        if stride == 2:  # the stride-1 gradient kernels run on the zero-inserted output gradient (csrc/lif_conv_bwd.cu)
+            scratch_up = torch.empty((B, Cout, H, W), device=dev, dtype=torch.float32)
+            q.scratch_gI_up = L.ptr(scratch_up)
+            if scratch_p is not None:
+                scratch_p_up = torch.empty((B, H, W), device=dev, dtype=torch.float32)
+                q.scratch_gP_up = L.ptr(scratch_p_up)
         g_state_in = None
         if state_in is not None and need[2]:
             g_state_in = torch.empty_like(state_in)
@@ -272,32 +278,60 @@ def encode_events(events, res, num_bins, *, round_ts=False, want=("cnt", "voxel"
     return out
 
 
+class _UpsampleBilinear2x(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = _c(x)
+        _need_cuda(x)
+        B, Cc, H, W = x.shape
+        out = torch.empty((B, Cc, 2 * H, 2 * W), device=x.device, dtype=torch.float32)
+        L.LAUNCHES += 1
+        L.check(L.lib().ef_upsample_bilinear2x(L.ptr(x), L.ptr(out), B * Cc, H, W, L.stream()), "ef_upsample_bilinear2x")
+        ctx.shape = (B, Cc, H, W)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        B, Cc, H, W = ctx.shape
+        g = _c(g)
+        g_x = torch.empty((B, Cc, H, W), device=g.device, dtype=torch.float32)
+        L.LAUNCHES += 1
+        L.check(L.lib().ef_upsample_bilinear2x_bwd(L.ptr(g), L.ptr(g_x), B * Cc, H, W, L.stream()), "ef_upsample_bilinear2x_bwd")
+        return g_x
+
+
 def upsample_bilinear2x(x):
-    """F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False) on fp32 NCHW (forward only in this version)."""
-    if torch.is_grad_enabled() and x.requires_grad:
-        raise NotImplementedError("event_flow_b200: the backward of the U-Net decoders (bilinear upsampling) is not built yet")
-    x = _c(x)
-    _need_cuda(x)
-    B, Cc, H, W = x.shape
-    out = torch.empty((B, Cc, 2 * H, 2 * W), device=x.device, dtype=torch.float32)
-    L.LAUNCHES += 1
-    L.check(L.lib().ef_upsample_bilinear2x(L.ptr(x), L.ptr(out), B * Cc, H, W, L.stream()), "ef_upsample_bilinear2x")
-    return out
+    """F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False) on fp32 NCHW, differentiable."""
+    return _UpsampleBilinear2x.apply(x)
+
+
+class _UpsampleNearest(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, fy, fx):
+        x = _c(x)
+        _need_cuda(x)
+        B, Cc, H, W = x.shape
+        out = torch.empty((B, Cc, H * fy, W * fx), device=x.device, dtype=torch.float32)
+        L.LAUNCHES += 1
+        L.check(L.lib().ef_upsample_nearest(L.ptr(x), L.ptr(out), B * Cc, H, W, fy, fx, L.stream()), "ef_upsample_nearest")
+        ctx.meta = (B, Cc, H, W, fy, fx)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        B, Cc, H, W, fy, fx = ctx.meta
+        g = _c(g)
+        g_x = torch.empty((B, Cc, H, W), device=g.device, dtype=torch.float32)
+        L.LAUNCHES += 1
+        L.check(L.lib().ef_upsample_nearest_bwd(L.ptr(g), L.ptr(g_x), B * Cc, H, W, fy, fx, L.stream()), "ef_upsample_nearest_bwd")
+        return g_x, None, None
 
 
 def upsample_nearest(x, fy, fx):
-    """F.interpolate(x, scale_factor=(fy, fx)) (nearest) for integer factors (models/model.py:528-539); no gradient (forward only)."""
-    if torch.is_grad_enabled() and x.requires_grad:
-        raise NotImplementedError("event_flow_b200: the backward of the multi-resolution flow upsampling is not built yet")
+    """F.interpolate(x, scale_factor=(fy, fx)) (nearest) for integer factors (models/model.py:528-539), differentiable."""
     if fy == 1 and fx == 1:
         return x
-    x = _c(x)
-    _need_cuda(x)
-    B, Cc, H, W = x.shape
-    out = torch.empty((B, Cc, H * fy, W * fx), device=x.device, dtype=torch.float32)
-    L.LAUNCHES += 1
-    L.check(L.lib().ef_upsample_nearest(L.ptr(x), L.ptr(out), B * Cc, H, W, int(fy), int(fx), L.stream()), "ef_upsample_nearest")
-    return out
+    return _UpsampleNearest.apply(x, int(fy), int(fx))
 
 
 def pack_cl(x):

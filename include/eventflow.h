@@ -120,6 +120,8 @@ typedef struct ef_lif_conv_bwd_params {
   float* g_add_pt;
   float* g_t0;
   float* g_t1;
+  float* scratch_gI_up;         /* stride 2 only: [B,C,H,W] workspace (g_I zero-inserted to the input resolution)         */
+  float* scratch_gP_up;         /* stride 2, PLIF / XLIF with g_x: [B,H,W] workspace                                      */
 } ef_lif_conv_bwd_params;
 
 int ef_lif_conv_bwd(const ef_lif_conv_bwd_params* p, void* stream);
@@ -191,6 +193,9 @@ int ef_debug_tc_cpt(int cpt);
  * maps (models/model.py:528-539), dst [n_planes,H*fy,W*fx]. */
 int ef_upsample_bilinear2x(const float* src, float* dst, int64_t n_planes, int32_t H, int32_t W, void* stream);
 int ef_upsample_nearest(const float* src, float* dst, int64_t n_planes, int32_t H, int32_t W, int32_t fy, int32_t fx, void* stream);
+/* Their adjoints (what autograd derives for the two F.interpolate calls): g_dst has the upsampled shape, g_src [n_planes,H,W]. */
+int ef_upsample_bilinear2x_bwd(const float* g_dst, float* g_src, int64_t n_planes, int32_t H, int32_t W, void* stream);
+int ef_upsample_nearest_bwd(const float* g_dst, float* g_src, int64_t n_planes, int32_t H, int32_t W, int32_t fy, int32_t fx, void* stream);
 
 /* fp32 NCHW <-> cl bf16 layout conversion at the API boundary (model.states getter/setter, first input). */
 int ef_pack_cl(const float* src, uint16_t* dst, int32_t B, int32_t C, int32_t H, int32_t W, void* stream);

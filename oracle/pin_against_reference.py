@@ -463,12 +463,40 @@ def pin_unet(rmodel, golden, shape=(1, 32, 48, 3)):
         for i in range(10):
             close(states[i], states_r[i], 0, f"unet {neuron} state[{i}]")
         print(f"unet {neuron}: activity per cell, last step:", ["%.3f" % a for a in acts])
+        # BPTT gradient of a random linear functional of all flow scales of all steps: reference autograd vs oracle autograd
+        g = torch.Generator().manual_seed(123)
+        gw = [[torch.rand((B, 2, H, W), generator=g) - 0.5 for _ in range(4)] for _ in range(T)]
+        named = [(n_, q) for n_, q in m.named_parameters() if q.requires_grad]
+        plist = [q for _, q in named]
+        m.reset_states()
+        loss_r = 0.0
+        for t in range(T):
+            o_g = m(None, xs[t].clone())
+            loss_r = loss_r + sum((f * w).sum() for f, w in zip(o_g["flow"], gw[t]))
+        grads_r = torch.autograd.grad(loss_r, plist, allow_unused=True)
+        Pg = ounet.unet_params(dict(m.named_parameters()) | {k: v for k, v in m.named_buffers()}, neuron)
+        st = [None] * 10
+        loss_o = 0.0
+        for t in range(T):
+            _, fl, st = ounet.unet_step(neuron, Pg, st, xs[t])
+            loss_o = loss_o + sum((f * w).sum() for f, w in zip(fl, gw[t]))
+        grads_o = torch.autograd.grad(loss_o, plist, allow_unused=True)
+        for (nm, _), go, gr in zip(named, grads_o, grads_r):
+            if gr is not None:
+                close(go, gr, 1e-5, f"unet {neuron} grad {nm}")
         if golden is not None:
             d = {"x_%d" % t: xs[t] for t in range(T)}
             d.update({"flow_%d_%d" % (T - 1, i): o["flow"][i] for i in range(4)})
             d.update({"state_%d" % i: states_r[i] for i in (0, 3, 5, 9)})
             for nm, q in sd.items():
                 d["sd_" + nm] = q
+            for t in range(T):
+                for i in range(4):
+                    d["gw_%d_%d" % (t, i)] = gw[t][i]
+            for (nm, _), gr in zip(named, grads_r):
+                if gr is not None and (neuron == "lif" or gr.numel() <= 5000):
+                    d["grad_" + nm] = gr
+            d["loss"] = loss_r.detach()
             golden[f"unet_{neuron}"] = d
 
 

@@ -126,10 +126,118 @@ def test_unet_state_api_and_cropping():
     assert all(s is None for s in m.states)
     with pytest.raises(AttributeError):  # bad encoding: same exception as models/model.py:497-499
         M.SpikingRecEVFlowNet(dict(unet_cfg("lif"), encoding="nope")).to(DEV)(cnt, cnt)
-    # training through the U-Net is not built yet (stride-2 / upsampling backward): it must fail loudly, never fall back
-    m2 = M.SpikingRecEVFlowNet(unet_cfg("lif")).to(DEV)
-    with pytest.raises(NotImplementedError):
-        m2(None, cnt[:, :, :16, :32].contiguous())
+
+
+@pytest.mark.parametrize("neuron", ["lif", "plif", "alif", "xlif"])
+@pytest.mark.parametrize("rec", [False, True])
+def test_stride2_and_wide_cell_backward_matches_oracle_autograd(neuron, rec):
+    """Cell-level gradients for the U-Net shapes: stride 2 (encoders), many channels, residual input (resblocks)."""
+    import event_flow_b200.models.spiking_submodules as S
+
+    torch.manual_seed(7)
+    stride = 1 if rec else 2
+    cin, c, H, W = (12, 12, 10, 14) if rec else (6, 20, 13, 18)
+    cls = {("lif", False): S.ConvLIF, ("plif", False): S.ConvPLIF, ("alif", False): S.ConvALIF, ("xlif", False): S.ConvXLIF,
+           ("lif", True): S.ConvLIFRecurrent, ("plif", True): S.ConvPLIFRecurrent, ("alif", True): S.ConvALIFRecurrent,
+           ("xlif", True): S.ConvXLIFRecurrent}[(neuron, rec)]
+    cell = cls(cin, c, 3) if rec else cls(cin, c, 3, stride)
+    with torch.no_grad():
+        cell.ff.weight.mul_(2.0)
+    g = torch.Generator().manual_seed(5)
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    x = ((torch.rand((2, cin, H, W), generator=g) < 0.4).float() * (torch.rand((2, cin, H, W), generator=g) + 0.5)).requires_grad_(True)
+    n_state = 2 if neuron == "lif" else 3
+    st = torch.rand((n_state, 2, c, Ho, Wo), generator=g)
+    st[1] = (st[1] < 0.3).float()
+    st.requires_grad_(True)
+    res = torch.rand((2, c, Ho, Wo), generator=g).requires_grad_(True)
+    gw_out, gw_st = torch.randn((2, c, Ho, Wo), generator=g), torch.randn((n_state, 2, c, Ho, Wo), generator=g) * 0.3
+    # oracle (CPU autograd)
+    p = {"ff": cell.ff.weight.detach().clone().requires_grad_(True)}
+    if rec:
+        p["rec"] = cell.rec.weight.detach().clone().requires_grad_(True)
+    for n in ounet.CELL_PARAM_NAMES[neuron]:
+        p[n] = getattr(cell, n).detach().clone().requires_grad_(True)
+    out_o, st_o = osp.cell_step(neuron, x, st, p, stride=stride, residual=0 if rec else res)  # recurrent cells take no residual
+    ((out_o * gw_out).sum() + (st_o * gw_st).sum()).backward()
+    # CUDA path
+    cell = cell.to(DEV)
+    xg, stg, resg = (t.detach().to(DEV).requires_grad_(True) for t in (x, st, res))
+    out, st_n = cell(xg, stg) if rec else cell(xg, stg, residual=resg)
+    ((out * gw_out.to(DEV)).sum() + (st_n * gw_st.to(DEV)).sum()).backward()
+    assert not (st_n[1].cpu() != st_o[1]).any(), "spike flip in the gradient test case (pick another seed)"
+
+    def chk(mine, ref, what):
+        scale = ref.abs().max().item() + 1e-12
+        err = (mine.cpu() - ref).abs().max().item()
+        assert err <= 1e-3 * scale, f"{what}: {err:.3e} vs scale {scale:.3e}"
+
+    chk(xg.grad, x.grad, "g_x")
+    chk(stg.grad, st.grad, "g_state")
+    if not rec:
+        chk(resg.grad, res.grad, "g_residual")
+    chk(cell.ff.weight.grad, p["ff"].grad, "g_w_ff")
+    if rec:
+        chk(cell.rec.weight.grad, p["rec"].grad, "g_w_rec")
+    for n in ounet.CELL_PARAM_NAMES[neuron]:
+        if getattr(cell, n).requires_grad:
+            chk(getattr(cell, n).grad, p[n].grad, "g_" + n)
+
+
+def test_resampling_backward_matches_torch_autograd():
+    from event_flow_b200 import ops
+
+    g = torch.Generator().manual_seed(4)
+    for shape in ((2, 3, 5, 7), (1, 2, 1, 1), (1, 4, 8, 2)):
+        x = torch.randn(shape, generator=g, requires_grad=True)
+        w = torch.randn((shape[0], shape[1], 2 * shape[2], 2 * shape[3]), generator=g)
+        (F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False) * w).sum().backward()
+        xg = x.detach().to(DEV).requires_grad_(True)
+        (ops.upsample_bilinear2x(xg) * w.to(DEV)).sum().backward()
+        assert (xg.grad.cpu() - x.grad).abs().max().item() <= 1e-6 * x.grad.abs().max().item()
+        for f in (2, 4):
+            x2 = torch.randn(shape, generator=g, requires_grad=True)
+            w2 = torch.randn((shape[0], shape[1], f * shape[2], f * shape[3]), generator=g)
+            (F.interpolate(x2, scale_factor=(float(f), float(f))) * w2).sum().backward()
+            xg2 = x2.detach().to(DEV).requires_grad_(True)
+            (ops.upsample_nearest(xg2, f, f) * w2.to(DEV)).sum().backward()
+            assert (xg2.grad.cpu() - x2.grad).abs().max().item() <= 1e-5 * x2.grad.abs().max().item()
+
+
+@pytest.mark.parametrize("name", UNETS)
+def test_unet_bptt_gradients_match_reference_golden(name):
+    """Training through the U-Net: BPTT gradients of a linear functional of all flow scales of 3 steps vs the reference's autograd."""
+    import event_flow_b200.models.model as M
+
+    g = load_golden(name)
+    neuron = name.split("_")[1]
+    m = getattr(M, CLASSES[neuron])(unet_cfg(neuron))
+    m.load_state_dict({k[3:]: v for k, v in g.items() if k.startswith("sd_")})
+    m = m.to(DEV)
+    T = len([k for k in g if k.startswith("x_")])
+    loss = 0.0
+    for t in range(T):
+        out = m(None, g["x_%d" % t].to(DEV))
+        loss = loss + sum((f * g["gw_%d_%d" % (t, i)].to(DEV)).sum() for i, f in enumerate(out["flow"]))
+    loss.backward()
+    m.detach_states()
+    # threshold chaos (SURVEY 7.3): a single borderline spike flip changes the trajectory, and with it the gradients; the
+    # comparison is only meaningful on an identical spike trajectory, which the final states witness
+    states = m.states
+    spikes = lambda t: t[:, 1] if t.dim() == 6 else t[1]  # noqa: E731  (encoders / resblocks stack two cell states)
+    same = all(torch.equal(spikes(states[i]).cpu(), spikes(g["state_%d" % i])) for i in (0, 3, 5, 9))
+    if not same:
+        pytest.skip("a borderline spike flipped on this box: trajectories differ, gradients are not comparable")
+    assert abs(loss.item() - g["loss"].item()) <= 1e-4 * abs(g["loss"].item()) + 1e-5
+    checked = 0
+    for nm, q in m.named_parameters():
+        if "grad_" + nm in g:
+            ref = g["grad_" + nm]
+            scale = ref.abs().max().item() + 1e-12
+            err = (q.grad.cpu() - ref).abs().max().item()
+            assert err <= 1e-3 * scale, f"{nm}: {err:.3e} vs scale {scale:.3e}"
+            checked += 1
+    assert checked >= 20
 
 
 def test_unet_full_size_cells_match_oracle():
