@@ -35,14 +35,23 @@ constexpr int HALO_BYTES = HALO_H * HALO_PITCH;        // 11520 B landed by TMA
 constexpr int HALO_STAGE = 12288;                      // padded to a multiple of 1024 B
 constexpr int V_TILE_BYTES = 32 * 128 * 4;             // [32 ch][16][8] fp32
 constexpr int ZC_TILE_BYTES = 128 * PIX_BYTES;         // [16][8][32 ch] bf16, 64B-swizzled
-constexpr int W_BLOCK_BYTES = 96 * PIX_BYTES;          // one tap: [96 n = 3 splits x 32 ch][32 k] bf16, 64B-swizzled: 6144 B
-constexpr int W_CONV_BYTES = 9 * W_BLOCK_BYTES;        // 55296 B per convolution
-constexpr int ACC_COLS = 96;                           // fp32 accumulator columns per tile
-constexpr int TMEM_COLS = 256;                         // 2 accumulator buffers x 96 columns, rounded up to a power of two
+// Weight terms stacked along N.  W_NSPLIT = 3: three bf16 terms, hi + mid + lo == w bit for bit (N = 96).  W_NSPLIT = 2: two
+// fp16 terms of the weight scaled by a per-layer power of two s, w*s = hi + mid * 2^-11 + e with |e| <= half an ulp of the
+// fp32 weight (N = 64: one third fewer tensor-core cycles, weight image and accumulator columns); the spikes stay bf16
+// (kind::f16 encodes the A and B formats independently) -- but the hardware rejects the mixed descriptor (measured: "illegal
+// instruction" on B200 for A = BF16, B = F16), and fp16 spikes would need fp16 gradients in the backward MMAs, so the
+// two-term variant is kept as a compile-time option only.  The epilogue undoes the scalings exactly (powers of two).
+constexpr int W_NSPLIT = 3;
+constexpr int W_BLOCK_BYTES = W_NSPLIT * 32 * PIX_BYTES;  // one tap: [W_NSPLIT x 32 ch][32 k] 16-bit, 64B-swizzled
+constexpr int W_CONV_BYTES = 9 * W_BLOCK_BYTES;           // 36864 B (55296 B with three terms) per convolution
+constexpr int W_CHUNK = W_CONV_BYTES / 4;                 // bulk-copy granule of the weight image
+constexpr int ACC_COLS = 32 * W_NSPLIT;                   // fp32 accumulator columns per tile
+constexpr int TMEM_COLS = W_NSPLIT == 2 ? 128 : 256;      // 2 accumulator buffers, rounded up to a power of two
+constexpr uint32_t W_IDESC = umma_idesc(ACC_COLS, false, false, W_NSPLIT == 2);
 
 template <bool REC>
 struct TcCfg {
-  static constexpr int NOP = REC ? 2 : 4;                                            // operand stages
+  static constexpr int NOP = REC ? (W_NSPLIT == 2 ? 3 : 2) : 4;                      // operand stages
   static constexpr int NV = REC ? 3 : 4;                                             // membrane stages
   static constexpr int W_BYTES = (REC ? 2 : 1) * W_CONV_BYTES;
   static constexpr int OP_STAGE = (REC ? 2 : 1) * HALO_STAGE;                        // x halo tile (+ previous-spike halo tile)
@@ -178,8 +187,8 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
       EF_TRACE(it, 0);
     }
     mbar_expect_tx(bar_w, C::W_BYTES);
-    for (uint32_t off = 0; off < (uint32_t)C::W_BYTES; off += 13824)  // 55296 = 4 x 13824
-      bulk_load_1d(s_base + off, reinterpret_cast<const uint8_t*>(p.w_split) + off, 13824, bar_w);
+    for (uint32_t off = 0; off < (uint32_t)C::W_BYTES; off += W_CHUNK)
+      bulk_load_1d(s_base + off, reinterpret_cast<const uint8_t*>(p.w_split) + off, W_CHUNK, bar_w);
   } else if (threadIdx.x == 64) {
     if (p.has_v) prefetch_tensormap(&map_vin);
     if (ld_zc) prefetch_tensormap(&map_zc);
@@ -241,7 +250,7 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
           for (int tap = 0; tap < 9; ++tap) {
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks)
-              umma_bf16<umma_idesc(96)>(d_tmem, ax + (uint64_t)((tap / 3) * (HALO_PITCH / 16) + (tap % 3) * (PIX_BYTES / 16) + ks * 2),
+              umma_bf16<W_IDESC>(d_tmem, ax + (uint64_t)((tap / 3) * (HALO_PITCH / 16) + (tap % 3) * (PIX_BYTES / 16) + ks * 2),
                                         b_ff + (uint64_t)(tap * (W_BLOCK_BYTES / 16) + ks * 2), (tap | ks) != 0);
           }
           if (z_from_halo) {
@@ -250,7 +259,7 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
             for (int tap = 0; tap < 9; ++tap) {
 #pragma unroll
               for (int ks = 0; ks < 2; ++ks)
-                umma_bf16<umma_idesc(96)>(d_tmem, az + (uint64_t)((tap / 3) * (HALO_PITCH / 16) + (tap % 3) * (PIX_BYTES / 16) + ks * 2),
+                umma_bf16<W_IDESC>(d_tmem, az + (uint64_t)((tap / 3) * (HALO_PITCH / 16) + (tap % 3) * (PIX_BYTES / 16) + ks * 2),
                                           b_rec + (uint64_t)(tap * (W_BLOCK_BYTES / 16) + ks * 2), 1u);
             }
           }
@@ -274,6 +283,9 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
       lam[j] = sigmoidf_acc(__ldg(p.leak + c0 + j));
       thr[j] = fmaxf(__ldg(p.thresh + c0 + j), 0.01f);
     }
+    // power-of-two scales the weight image was built with (appended to it by ef_split_weights); 1 and unused with three terms
+    const float inv_s = W_NSPLIT == 2 ? __ldg(reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(p.w_split) + C::W_BYTES)) : 1.0f;
+    const float mid_s = W_NSPLIT == 2 ? __ldg(reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(p.w_split) + C::W_BYTES) + 1) : 1.0f;
     constexpr int NCH = CPT / 8;  // 16-byte spike chunks per thread
     for (int it = 0; it < n_my; ++it) {
       const int sv = it % NV, so = it % NOP, a = it & 1;
@@ -311,7 +323,7 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
         uint32_t a_hi[8], a_mid[8], a_lo[8];
         tmem_ld8(tacc + 8 * h, a_hi);
         tmem_ld8(tacc + 32 + 8 * h, a_mid);
-        tmem_ld8(tacc + 64 + 8 * h, a_lo);
+        if (W_NSPLIT == 3) tmem_ld8(tacc + 64 + 8 * h, a_lo);
         tmem_ld_wait();
         if (h == NCH - 1) {
           tc_fence_before();
@@ -323,7 +335,10 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
 #pragma unroll
         for (int jj = 0; jj < 8; ++jj) {
           const int j = 8 * h + jj;
-          const float I = __fadd_rn(__fadd_rn(__uint_as_float(a_lo[jj]), __uint_as_float(a_mid[jj])), __uint_as_float(a_hi[jj]));
+          // three terms: lo + mid + hi; two terms: (hi + mid * 2^-11) / s -- the products with powers of two are exact
+          const float I = W_NSPLIT == 3
+                              ? __fadd_rn(__fadd_rn(__uint_as_float(a_lo[jj]), __uint_as_float(a_mid[jj])), __uint_as_float(a_hi[jj]))
+                              : __fmul_rn(__fmaf_rn(__uint_as_float(a_mid[jj]), mid_s, __uint_as_float(a_hi[jj])), inv_s);
           const float z = (jj & 1) ? bf16_hi(zw[jj >> 1]) : bf16_lo(zw[jj >> 1]);
           if (HARD) vn[j] = __fadd_rn(__fmul_rn(__fmul_rn(vc[j], lam[j]), __fsub_rn(1.0f, z)), __fmul_rn(__fsub_rn(1.0f, lam[j]), I));
           else vn[j] = __fsub_rn(__fadd_rn(__fmul_rn(vc[j], lam[j]), __fmul_rn(__fsub_rn(1.0f, lam[j]), I)), __fmul_rn(z, thr[j]));
@@ -377,23 +392,60 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
 
 // ---- weight split kernel --------------------------------------------------------------------------------------------
 // out block index conv*9 + tap; inside a block row n' = split*32 + n holds K = 32 input channels (64 B); 8-row atoms of
-// 512 B; the 16-byte chunk k/8 of row r = n'%8 is stored at chunk (k/8) ^ ((r >> 1) & 3)  (64-byte swizzle)
-__global__ void split_weights_kernel(const float* __restrict__ w_ff, const float* __restrict__ w_rec, uint16_t* __restrict__ out, int nconv) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // over nconv * 32 (n) * 32 (ci) * 9 (tap)
-  if (i >= nconv * 32 * 32 * 9) return;
-  const int tap = i % 9, ci = (i / 9) % 32, n = (i / (9 * 32)) % 32, cv = i / (9 * 32 * 32);
-  const float w = (cv == 0 ? w_ff : w_rec)[(n * 32 + ci) * 9 + tap];
-  const __nv_bfloat16 hi = __float2bfloat16_rn(w);
-  const float r1 = w - __bfloat162float(hi);
-  const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
-  const float r2 = r1 - __bfloat162float(mid);
-  const __nv_bfloat16 lo = __float2bfloat16_rn(r2);
-  const __nv_bfloat16 parts[3] = {hi, mid, lo};
-  const size_t blk = (size_t)cv * 9 + tap;
-  for (int sp = 0; sp < 3; ++sp) {
-    const int nn = sp * 32 + n, r = nn & 7;
-    const int chunk = (ci >> 3) ^ ((r >> 1) & 3);
-    out[blk * (W_BLOCK_BYTES / 2) + (nn >> 3) * 256 + r * 32 + chunk * 8 + (ci & 7)] = *reinterpret_cast<const uint16_t*>(&parts[sp]);
+// 512 B; the 16-byte chunk k/8 of row r = n'%8 is stored at chunk (k/8) ^ ((r >> 1) & 3)  (64-byte swizzle).
+// One block: the two-term image needs the largest |w| of the layer (both convolutions share the accumulator, hence the scale).
+__global__ void __launch_bounds__(1024) split_weights_kernel(const float* __restrict__ w_ff, const float* __restrict__ w_rec, uint16_t* __restrict__ out,
+                                                             int nconv) {
+  __shared__ float s_max[32];
+  __shared__ float s_scale;
+  const int n_el = nconv * 32 * 32 * 9;
+  float scale = 1.0f;
+  if (W_NSPLIT == 2) {
+    float m = 0.f;
+    for (int i = threadIdx.x; i < n_el; i += blockDim.x) m = fmaxf(m, fabsf(i < 9216 ? w_ff[i] : w_rec[i - 9216]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int k = 1; k < (int)blockDim.x / 32; ++k) m = fmaxf(m, s_max[k]);
+      int e = 0;
+      if (m > 0.f && m < 3.0e38f) frexpf(m, &e);  // m = f * 2^e, f in [0.5, 1)
+      int k = 14 - e;                               // max|w| * 2^k in [2^13, 2^14): inside the fp16 range with headroom
+      k = k > 100 ? 100 : (k < -100 ? -100 : k);
+      s_scale = ldexpf(1.0f, k);
+      float* tail = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(out) + (size_t)nconv * W_CONV_BYTES);
+      tail[0] = ldexpf(1.0f, -k);  // 1 / s
+      tail[1] = ldexpf(1.0f, -11); // scale of the second term
+      tail[2] = tail[3] = 0.f;
+    }
+    __syncthreads();
+    scale = s_scale;
+  }
+  for (int i = threadIdx.x; i < n_el; i += blockDim.x) {  // over nconv * 32 (n) * 32 (ci) * 9 (tap)
+    const int tap = i % 9, ci = (i / 9) % 32, n = (i / (9 * 32)) % 32, cv = i / (9 * 32 * 32);
+    const float w = (cv == 0 ? w_ff : w_rec)[(n * 32 + ci) * 9 + tap];
+    uint16_t parts[3];
+    if (W_NSPLIT == 2) {
+      const float ws = w * scale;                                   // exact (power of two)
+      const __half hi = __float2half_rn(ws);
+      const float r1 = ws - __half2float(hi);                       // exact
+      const __half mid = __float2half_rn(r1 * 2048.0f);             // |r1| <= 2^-11 |ws|: the scaled residual is in range again
+      parts[0] = __half_as_ushort(hi), parts[1] = __half_as_ushort(mid), parts[2] = 0;
+    } else {
+      const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+      const float r1 = w - __bfloat162float(hi);
+      const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+      const float r2 = r1 - __bfloat162float(mid);
+      const __nv_bfloat16 lo = __float2bfloat16_rn(r2);
+      parts[0] = __bfloat16_as_ushort(hi), parts[1] = __bfloat16_as_ushort(mid), parts[2] = __bfloat16_as_ushort(lo);
+    }
+    const size_t blk = (size_t)cv * 9 + tap;
+    for (int sp = 0; sp < W_NSPLIT; ++sp) {
+      const int nn = sp * 32 + n, r = nn & 7;
+      const int chunk = (ci >> 3) ^ ((r >> 1) & 3);
+      out[blk * (W_BLOCK_BYTES / 2) + (nn >> 3) * 256 + r * 32 + chunk * 8 + (ci & 7)] = parts[sp];
+    }
   }
 }
 
@@ -480,7 +532,7 @@ extern "C" int ef_debug_tc_trace(long long* buf) {  // buf: device int64 [n_ctas
 
 extern "C" int64_t ef_split_weights_elems(int32_t Cin, int32_t C, int32_t has_rec) {
   if (Cin != 32 || C != 32) return 0;
-  return (int64_t)(has_rec ? 2 : 1) * ef::W_CONV_BYTES / 2;
+  return (int64_t)(has_rec ? 2 : 1) * ef::W_CONV_BYTES / 2 + 8;  // + 16 bytes: the power-of-two scales of the two-term image
 }
 
 extern "C" int ef_split_weights(const float* w_ff, const float* w_rec, int32_t Cin, int32_t C, uint16_t* out, void* stream) {
@@ -488,6 +540,6 @@ extern "C" int ef_split_weights(const float* w_ff, const float* w_rec, int32_t C
   EF_REQUIRE(w_ff && out, EF_ENULL, "ef_split_weights: NULL tensor");
   EF_REQUIRE(Cin == 32 && C == 32, EF_EUNSUPPORTED, "ef_split_weights: the tensor-core path covers 32 -> 32 channels (got %d -> %d)", Cin, C);
   const int nconv = w_rec ? 2 : 1;
-  split_weights_kernel<<<cdiv(nconv * 32 * 32 * 9, 256), 256, 0, as_stream(stream)>>>(w_ff, w_rec, out, nconv);
+  split_weights_kernel<<<1, 1024, 0, as_stream(stream)>>>(w_ff, w_rec, out, nconv);
   return check_launch("split_weights_kernel");
 }

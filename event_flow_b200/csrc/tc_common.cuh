@@ -100,8 +100,9 @@ __device__ __forceinline__ uint64_t umma_desc_sw64_mn(uint32_t saddr, uint32_t l
 }
 // kind::f16 instruction descriptor (cute/arch/mma_sm100_desc.hpp): D = F32, A = B = BF16, M = 128; a_mn / b_mn select
 // MN-major (transposed) operands instead of K-major.
-__host__ __device__ constexpr uint32_t umma_idesc(uint32_t n, bool a_mn = false, bool b_mn = false) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+__host__ __device__ constexpr uint32_t umma_idesc(uint32_t n, bool a_mn = false, bool b_mn = false, bool b_f16 = false) {
+  // bits 4-5 D format (1 = F32), 7-9 A format, 10-12 B format (0 = F16, 1 = BF16; A and B are independent 16-bit types)
+  return (1u << 4) | (1u << 7) | ((b_f16 ? 0u : 1u) << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) | ((n >> 3) << 17) | ((128u >> 4) << 24);
 }
 
 template <uint32_t IDESC>
