@@ -19,7 +19,7 @@ from .spiking_submodules import (
     ConvXLIFRecurrent,
 )
 from .submodules import ConvGRU, ConvLayer, ConvLayer_
-from .unet import SpikingMultiResUNetRecurrent
+from .unet import MultiResUNet, SpikingMultiResUNetRecurrent
 
 
 class FireNet(BaseModel):
@@ -197,6 +197,70 @@ class LIFFireFlowNet(FireNet):
     rec_neuron = ConvLIF
     residual = False
     w_scale_pred = 0.01
+
+
+class EVFlowNet(BaseModel):
+    """EV-FlowNet (models/model.py:289-395): the stateless ANN U-Net; forward only in this version."""
+
+    def __init__(self, unet_kwargs):
+        super().__init__()
+        EVFlowNet_kwargs = {
+            "base_num_channels": unet_kwargs["base_num_channels"],
+            "num_encoders": 4,
+            "num_residual_blocks": 2,
+            "num_output_channels": 2,
+            "skip_type": "concat",
+            "norm": None,
+            "use_upsample_conv": True,
+            "kernel_size": unet_kwargs["kernel_size"],
+            "channel_multiplier": 2,
+            "final_activation": "tanh",
+        }
+        self.crop = None
+        self.mask = unet_kwargs["mask_output"]
+        self.norm_input = False if "norm_input" not in unet_kwargs.keys() else unet_kwargs["norm_input"]
+        self.encoding = unet_kwargs["encoding"]
+        self.num_bins = unet_kwargs["num_bins"]
+        self.num_encoders = EVFlowNet_kwargs["num_encoders"]
+
+        unet_kwargs.update(EVFlowNet_kwargs)  # in place on the caller's dict, like the reference (model.py:318-325)
+        for k in ("name", "eval", "encoding", "round_encoding", "mask_output", "norm_input", "spiking_neuron"):
+            unet_kwargs.pop(k, None)
+        self.multires_unet = MultiResUNet(unet_kwargs)
+
+    def detach_states(self):
+        pass
+
+    def reset_states(self):
+        pass
+
+    def init_cropping(self, width, height, safety_margin=0):
+        self.crop = CropParameters(width, height, self.num_encoders, safety_margin)
+
+    def forward(self, event_voxel, event_cnt, log=False):
+        if self.encoding == "voxel":
+            x = event_voxel
+        elif self.encoding == "cnt" and self.num_bins == 2:
+            x = event_cnt
+        else:
+            print("Model error: Incorrect input encoding.")
+            raise AttributeError
+        if self.norm_input:
+            mean, stddev = x[x != 0].mean(), x[x != 0].std()
+            x[x != 0] = (x[x != 0] - mean) / stddev
+        if self.crop is not None:
+            x = self.crop.pad(x)
+        multires_flow = self.multires_unet.forward(x)
+        if log:
+            raise NotImplementedError("Activity logging not implemented")
+        flow_list = []
+        full_h, full_w = multires_flow[-1].shape[2], multires_flow[-1].shape[3]
+        for flow in multires_flow:
+            flow_list.append(ops.upsample_nearest(flow, full_h // flow.shape[2], full_w // flow.shape[3]))
+        if self.crop is not None:
+            for i, flow in enumerate(flow_list):
+                flow_list[i] = flow[:, :, self.crop.iy0:self.crop.iy1, self.crop.ix0:self.crop.ix1].contiguous()
+        return {"flow": flow_list, "activity": None}
 
 
 class RecEVFlowNet(BaseModel):

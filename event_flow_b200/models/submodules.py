@@ -16,7 +16,7 @@ class ConvLayer(nn.Module):
         super().__init__()
         if norm is not None:
             raise NotImplementedError("event_flow_b200 ConvLayer: norm=%r is not on the CUDA path (no shipped FireNet config uses it)" % (norm,))
-        if stride != 1 or kernel_size not in (1, 3):
+        if kernel_size not in (1, 3) or stride not in (1, 2) or (kernel_size == 1 and stride != 1):
             raise NotImplementedError(f"event_flow_b200 ConvLayer: kernel_size={kernel_size}, stride={stride} not on the CUDA path yet")
         if kernel_size == 1 and activation != "tanh":
             raise NotImplementedError("event_flow_b200 ConvLayer: the 1x1 layer is built for the tanh prediction head only")
@@ -28,13 +28,19 @@ class ConvLayer(nn.Module):
             nn.init.uniform_(self.conv2d.weight, -w_scale, w_scale)
             nn.init.zeros_(self.conv2d.bias)
         self.kernel_size = kernel_size
+        self.stride = stride
         self.activation = activation
         self.norm = norm
 
     def forward(self, x):
         if self.kernel_size == 1:
             return ops.pred_head(x, self.conv2d.weight, self.conv2d.bias)
-        return ops.conv_ann(x, self.conv2d.weight, self.conv2d.bias, self.activation)
+        out = ops.conv_ann(x, self.conv2d.weight, self.conv2d.bias, self.activation)
+        if self.stride == 2:
+            # a stride-2 3x3 conv with padding 1 is the stride-1 result at the even pixels (same window, same summation order);
+            # first version of the U-Net encoders: 4x the minimal FLOPs on these four layers
+            out = out[:, :, ::2, ::2].contiguous()
+        return out
 
 
 class ConvLayer_(ConvLayer):
@@ -46,6 +52,44 @@ class ConvLayer_(ConvLayer):
         res = residual if torch.is_tensor(residual) else None
         out = ops.conv_ann(x, self.conv2d.weight, self.conv2d.bias, self.activation, residual=res)
         return out, prev_state
+
+
+class ResidualBlock(nn.Module):
+    """He et al. residual block (models/submodules.py:238-312): conv+act, conv + residual + act.  Two launches."""
+
+    def __init__(self, in_channels, out_channels, stride=1, activation="relu", downsample=None, norm=None, BN_momentum=0.1):
+        super().__init__()
+        if norm is not None or downsample is not None or stride != 1 or in_channels != out_channels:
+            raise NotImplementedError("event_flow_b200 ResidualBlock: norm / downsample / stride are not on the CUDA path (no shipped config uses them)")
+        if activation not in (None, "relu", "sigmoid", "tanh"):
+            raise NotImplementedError(f"event_flow_b200 ResidualBlock: activation={activation!r} not on the CUDA path")
+        self.conv1 = nn.Conv2d(in_channels, out_channels, kernel_size=3, stride=stride, padding=1, bias=True)
+        self.activation = activation
+        self.norm = norm
+        self.conv2 = nn.Conv2d(out_channels, out_channels, kernel_size=3, stride=1, padding=1, bias=True)
+        self.downsample = downsample
+
+    def forward(self, x):
+        out1 = ops.conv_ann(x, self.conv1.weight, self.conv1.bias, self.activation)
+        out2 = ops.conv_ann(out1, self.conv2.weight, self.conv2.bias, self.activation, residual=x)
+        return out2, out1
+
+
+class UpsampleConvLayer(nn.Module):
+    """Bilinear x2 upsampling + conv + activation (models/submodules.py:140-185): the decoder stage of the ANN U-Net."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, activation="relu", norm=None):
+        super().__init__()
+        if norm is not None or stride != 1 or kernel_size != 3:
+            raise NotImplementedError("event_flow_b200 UpsampleConvLayer: kernel_size 3, stride 1, no norm")
+        if activation not in (None, "relu", "sigmoid", "tanh"):
+            raise NotImplementedError(f"event_flow_b200 UpsampleConvLayer: activation={activation!r} not on the CUDA path")
+        self.conv2d = nn.Conv2d(in_channels, out_channels, kernel_size, stride, kernel_size // 2, bias=True)
+        self.activation = activation
+        self.norm = norm
+
+    def forward(self, x):
+        return ops.conv_ann(ops.upsample_bilinear2x(x), self.conv2d.weight, self.conv2d.bias, self.activation)
 
 
 class ConvGRU(nn.Module):

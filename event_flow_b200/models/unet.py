@@ -10,7 +10,7 @@ import torch.nn as nn
 
 from .model_util import skip_concat, skip_sum  # noqa: F401  (resolved by name like the reference: "skip_" + skip_type)
 from .spiking_submodules import SpikingRecurrentConvLayer, SpikingResidualBlock, SpikingTransposedConvLayer, SpikingUpsampleConvLayer
-from .submodules import ConvLayer
+from .submodules import ConvLayer, ResidualBlock, UpsampleConvLayer
 
 
 class SpikingMultiResUNetRecurrent(nn.Module):
@@ -118,5 +118,63 @@ class SpikingMultiResUNetRecurrent(nn.Module):
             if i > 0:
                 x = self.skip_ftn(predictions[-1], x)
             x, self.states[offset + i] = decoder(x, self.states[offset + i])
+            predictions.append(pred(x))
+        return predictions
+
+
+class MultiResUNet(nn.Module):
+    """
+    ANN multi-resolution U-Net of EV-FlowNet (models/unet.py:224-311): four stride-2 conv encoders, two residual blocks, four
+    bilinear-upsampling decoders with concat skips, a 1x1 tanh prediction per scale.  Forward only (the ANN cells have no
+    backward kernels yet).
+    """
+
+    def __init__(self, unet_kwargs):
+        super().__init__()
+        kw = dict(unet_kwargs)
+        self.final_activation = kw.pop("final_activation", None)
+        self.base_num_channels = kw["base_num_channels"]
+        self.num_encoders = kw["num_encoders"]
+        self.num_residual_blocks = kw["num_residual_blocks"]
+        self.num_output_channels = kw["num_output_channels"]
+        self.kernel_size = kw.get("kernel_size", 5)
+        self.skip_type = kw["skip_type"]
+        self.norm = kw["norm"]
+        self.num_bins = kw["num_bins"]
+        self.channel_multiplier = kw.get("channel_multiplier", 2)
+        self.ff_act, self.rec_act = kw.get("activations", ["relu", None])
+        if self.norm is not None or self.kernel_size != 3 or not kw["use_upsample_conv"]:
+            raise NotImplementedError("event_flow_b200 MultiResUNet: kernel_size 3, no norm, upsample-conv decoders only")
+        self.skip_ftn = {"concat": skip_concat, "sum": skip_sum}[self.skip_type]
+        self.encoder_input_sizes = [int(self.base_num_channels * pow(self.channel_multiplier, i)) for i in range(self.num_encoders)]
+        self.encoder_output_sizes = [int(self.base_num_channels * pow(self.channel_multiplier, i + 1)) for i in range(self.num_encoders)]
+        self.max_num_channels = self.encoder_output_sizes[-1]
+        # construction order = the reference's (unet.py:236-239)
+        self.encoders = nn.ModuleList()
+        for i, (cin, cout) in enumerate(zip(self.encoder_input_sizes, self.encoder_output_sizes)):
+            self.encoders.append(ConvLayer(self.num_bins if i == 0 else cin, cout, kernel_size=self.kernel_size, stride=2, activation=self.ff_act,
+                                           norm=self.norm))
+        self.resblocks = nn.ModuleList([ResidualBlock(self.max_num_channels, self.max_num_channels, activation=self.ff_act, norm=self.norm)
+                                        for _ in range(self.num_residual_blocks)])
+        self.decoders = nn.ModuleList()
+        for i, (cin, cout) in enumerate(zip(reversed(self.encoder_output_sizes), reversed(self.encoder_input_sizes))):
+            self.decoders.append(UpsampleConvLayer(2 * cin + (0 if i == 0 else self.num_output_channels), cout, kernel_size=self.kernel_size,
+                                                   activation=self.ff_act, norm=self.norm))
+        self.preds = nn.ModuleList([ConvLayer(cout, self.num_output_channels, 1, activation=self.final_activation, norm=self.norm)
+                                    for cout in reversed(self.encoder_input_sizes)])
+
+    def forward(self, x):
+        blocks = []
+        for encoder in self.encoders:
+            x = encoder(x)
+            blocks.append(x)
+        for resblock in self.resblocks:
+            x, _ = resblock(x)
+        predictions = []
+        for i, (decoder, pred) in enumerate(zip(self.decoders, self.preds)):
+            x = self.skip_ftn(x, blocks[self.num_encoders - i - 1])
+            if i > 0:
+                x = self.skip_ftn(predictions[-1], x)
+            x = decoder(x)
             predictions.append(pred(x))
         return predictions

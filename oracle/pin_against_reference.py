@@ -500,6 +500,30 @@ def pin_unet(rmodel, golden, shape=(1, 32, 48, 3)):
             golden[f"unet_{neuron}"] = d
 
 
+def pin_ann_unet(rmodel, golden, shape=(1, 32, 48)):
+    """EV-FlowNet (ANN twin of the spiking U-Net), base_num_channels 4: one forward pass, all four flow scales."""
+    B, H, W = shape
+    torch.manual_seed(21)
+    cfg = dict(name="x", encoding="cnt", round_encoding=False, norm_input=False, num_bins=2, base_num_channels=4, kernel_size=3,
+               activations=["relu", None], mask_output=True, spiking_neuron=None)
+    m = rmodel.EVFlowNet(cfg)
+    sd = {k: v.detach() for k, v in m.state_dict().items()}
+    ts, ys, xx, ps = oenc.synthetic_events(B, 1500, H, W, 3000)
+    x = oenc.encode_window(ts, ys, xx, ps, H, W, 2)["event_cnt"]
+    with torch.no_grad():
+        o = m(None, x.clone())
+        preds, flows = ounet.ann_unet_forward(sd, x)
+    for i in range(4):
+        close(flows[i], o["flow"][i], 0, f"ann unet flow[{i}]")
+    print("ann EVFlowNet pinned; |flow| max %.4f" % max(f.abs().max().item() for f in flows))
+    if golden is not None:
+        d = {"x": x}
+        d.update({"flow_%d" % i: o["flow"][i] for i in range(4)})
+        for nm, q in sd.items():
+            d["sd_" + nm] = q
+        golden["annunet_evflownet"] = d
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--check", action="store_true")
@@ -516,6 +540,7 @@ def main():
     pin_metrics(rflow, golden)
     pin_ann_firenet(rmodel, golden)
     pin_unet(rmodel, golden)
+    pin_ann_unet(rmodel, golden)
     if args.check:
         print("oracle == reference on all cases (check only)")
         return

@@ -87,3 +87,39 @@ def unet_step(neuron, P, states, x, trace=None, **cell_kwargs):
         preds.append(osp.pred_head(x, w, b))
     flows = [F.interpolate(f, scale_factor=(preds[-1].shape[2] / f.shape[2], preds[-1].shape[3] / f.shape[3])) for f in preds]
     return preds, flows, new_states
+
+
+def ann_unet_forward(sd, x, act="relu", num_encoders=4, num_residual_blocks=2, prefix="multires_unet.", trace=None):
+    """
+    EV-FlowNet's ANN U-Net (models/unet.py:224-311 with the blocks of models/submodules.py:12-61, 140-185, 238-312):
+    stride-2 conv+bias+ReLU encoders, residual blocks, bilinear-upsampling decoders with concat skips, 1x1 tanh predictions.
+    Returns (multires predictions, flows upsampled to the input resolution as in models/model.py:370-383).
+    trace: optional list receiving (name, input, output) of every 3x3 conv layer.
+    """
+    f_act = {"relu": torch.relu, "tanh": torch.tanh, "sigmoid": torch.sigmoid, None: (lambda t: t)}[act]
+
+    def conv(name, t, stride=1, residual=None):
+        out = F.conv2d(t, sd[prefix + name + ".weight"], sd[prefix + name + ".bias"], stride, 1)
+        if residual is not None:
+            out = out + residual
+        out = f_act(out)
+        if trace is not None:
+            trace.append((name, t, out))
+        return out
+
+    blocks = []
+    for i in range(num_encoders):
+        x = conv(f"encoders.{i}.conv2d", x, stride=2)
+        blocks.append(x)
+    for i in range(num_residual_blocks):
+        out1 = conv(f"resblocks.{i}.conv1", x)
+        x = conv(f"resblocks.{i}.conv2", out1, residual=x)
+    preds = []
+    for i in range(num_encoders):
+        x = skip_concat(x, blocks[num_encoders - i - 1])
+        if i > 0:
+            x = skip_concat(preds[-1], x)
+        x = conv(f"decoders.{i}.conv2d", F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False))
+        preds.append(torch.tanh(F.conv2d(x, sd[prefix + f"preds.{i}.conv2d.weight"], sd[prefix + f"preds.{i}.conv2d.bias"])))
+    flows = [F.interpolate(f, scale_factor=(preds[-1].shape[2] / f.shape[2], preds[-1].shape[3] / f.shape[3])) for f in preds]
+    return preds, flows

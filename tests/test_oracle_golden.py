@@ -200,3 +200,14 @@ def test_spiking_unet_rollout_matches_reference(name):
         assert torch.equal(flows[i], g["flow_%d_%d" % (T - 1, i)]), f"flow scale {i}"
     for i in (0, 3, 5, 9):
         assert torch.equal(states[i], g["state_%d" % i]), f"state {i}"
+
+
+def test_ann_evflownet_matches_reference():
+    from oracle import unet as ounet
+
+    g = load_golden("annunet_evflownet")
+    sd = {k[3:]: v for k, v in g.items() if k.startswith("sd_")}
+    with torch.no_grad():
+        _, flows = ounet.ann_unet_forward(sd, g["x"])
+    for i in range(4):
+        assert torch.equal(flows[i], g["flow_%d" % i])
