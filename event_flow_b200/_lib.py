@@ -48,7 +48,7 @@ class LifBwdTcParams(C.Structure):
         ("x_cl", _f32p), ("z_in_cl", _f32p), ("v_in", _f32p), ("v_out", _f32p), ("g_out", _f32p), ("g_v_out", _f32p), ("g_z_out", _f32p),
         ("leak", _f32p), ("thresh", _f32p), ("w_bwd", _f32p), ("gI_hi", _f32p), ("gI_mid", _f32p),
         ("g_x", _f32p), ("g_v_in", _f32p), ("g_z_in", _f32p), ("g_w_ff", _f32p), ("g_w_rec", _f32p), ("g_leak", _f32p), ("g_thresh", _f32p),
-        ("wg_partial", _f32p), ("wg_flags", _i32),
+        ("wg_partial", _f32p), ("wg_flags", _i32), ("Cin", _i32), ("x_f32", _f32p), ("gI_f32", _f32p),
     ]  # fmt: skip
 
 

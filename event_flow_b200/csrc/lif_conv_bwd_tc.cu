@@ -83,13 +83,14 @@ __global__ void __launch_bounds__(PWC_THREADS) lif_bwd_pointwise_cl_kernel(const
     red[PWC_CB + k] = live ? -g_z * sg - (HARD ? 0.f : z_p * g_v) : 0.f;
     const float g_vin = HARD ? g_v * lam[k] * (1.0f - z_p) : g_v * lam[k];
     if (p.g_v_in && live) p.g_v_in[((size_t)b * 32 + c0 + k) * hw + pix] = g_vin;
+    if (p.gI_f32 && live) p.gI_f32[((size_t)b * 32 + c0 + k) * hw + pix] = g_I;  // head mode: fp32 NCHW for the CUDA-core weight gradient
     const __nv_bfloat16 h = __float2bfloat16_rn(g_I);
     const __nv_bfloat16 m = __float2bfloat16_rn(g_I - __bfloat162float(h));
     const uint32_t hb = *reinterpret_cast<const uint16_t*>(&h), mb = *reinterpret_cast<const uint16_t*>(&m);
     if (k & 1) hi[k >> 1] |= hb << 16, mid[k >> 1] |= mb << 16;
     else hi[k >> 1] = hb, mid[k >> 1] = mb;
   }
-  if (live) {
+  if (live && !p.gI_f32) {
     *reinterpret_cast<uint4*>(p.gI_hi + ((size_t)b * hw + pix) * 32 + c0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     *reinterpret_cast<uint4*>(p.gI_mid + ((size_t)b * hw + pix) * 32 + c0) = make_uint4(mid[0], mid[1], mid[2], mid[3]);
   }
@@ -101,6 +102,76 @@ __global__ void __launch_bounds__(PWC_THREADS) lif_bwd_pointwise_cl_kernel(const
     const float l = sigmoidf_acc(__ldg(p.leak + c0 + tid));
     if (p.g_leak) atomicAdd(p.g_leak + c0 + tid, s_sum[tid] * l * (1.0f - l));
     if (p.g_thresh && __ldg(p.thresh + c0 + tid) >= 0.01f) atomicAdd(p.g_thresh + c0 + tid, s_sum[PWC_CB + tid]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// (1b) weight gradient of the head layer: g_w[co][ci][tap] += sum_{b,y,x} x[b,ci,y+dy-1,x+dx-1] * g_I[b,co,y,x], Cin <= 8 fractional
+//      fp32 inputs (not a tensor-core shape).  A block owns 32 x 8-pixel tiles; slice s (64 threads) owns tile row s; thread j of
+//      a slice owns one (ci, tap) pair and all 32 output channels in registers: per pixel ONE shifted input value and eight
+//      16-byte broadcast loads of g_I feed 32 FMAs.  Accumulators live across the block's tiles; one reduction at the end.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int HW_THREADS = 512, HW_TW = 32, HW_TH = 8, HW_MAXC = 8;
+
+__global__ void __launch_bounds__(HW_THREADS, 2) lif_head_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ g_I, float* __restrict__ g_w,
+                                                                     int B, int Cin, int H, int W, int tiles_x, int tiles_y, int n_tiles) {
+  __shared__ __align__(16) float s_g[HW_TW * HW_TH * 32];                  // [pixel][32 co], 16-byte groups XOR-swizzled by (pixel & 7)
+  __shared__ float s_x[HW_MAXC * (HW_TH + 2) * (HW_TW + 2)];
+  const int tid = threadIdx.x, slice = tid >> 6, j = tid & 63;
+  const int n_pairs = Cin * 9;
+  const bool active = j < n_pairs;
+  const int ci = active ? j / 9 : 0, tap = active ? j % 9 : 0, dy = tap / 3, dx = tap % 3;
+  const size_t plane = (size_t)H * W;
+  float acc[32];
+#pragma unroll
+  for (int c = 0; c < 32; ++c) acc[c] = 0.f;
+  constexpr int XW = HW_TW + 2, XH = HW_TH + 2;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int b = tile / (tiles_x * tiles_y), r = tile % (tiles_x * tiles_y);
+    const int x0 = (r % tiles_x) * HW_TW, y0 = (r / tiles_x) * HW_TH;
+    __syncthreads();
+    for (int i = tid; i < 32 * HW_TH * HW_TW; i += HW_THREADS) {  // coalesced along x; zero outside the image
+      const int px = i % HW_TW, py = (i / HW_TW) % HW_TH, co = i / (HW_TW * HW_TH);
+      const int y = y0 + py, xx = x0 + px, pix = py * HW_TW + px;
+      const float v = (y < H && xx < W) ? __ldg(g_I + ((size_t)b * 32 + co) * plane + (size_t)y * W + xx) : 0.f;
+      s_g[pix * 32 + (((co >> 2) ^ (pix & 7)) << 2) + (co & 3)] = v;
+    }
+    for (int i = tid; i < Cin * XH * XW; i += HW_THREADS) {
+      const int c = i / (XH * XW), q = i % (XH * XW), y = y0 - 1 + q / XW, xx = x0 - 1 + q % XW;
+      s_x[i] = (y >= 0 && y < H && xx >= 0 && xx < W) ? __ldg(x + ((size_t)b * Cin + c) * plane + (size_t)y * W + xx) : 0.f;
+    }
+    __syncthreads();
+    if (active) {
+      const float* xr = s_x + (ci * XH + slice + dy) * XW + dx;
+#pragma unroll 4
+      for (int px = 0; px < HW_TW; ++px) {
+        const float xv = xr[px];
+        const int pix = slice * HW_TW + px;
+        const float4* gr = reinterpret_cast<const float4*>(s_g + pix * 32);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 g4 = gr[q ^ (pix & 7)];
+          acc[4 * q + 0] = fmaf(xv, g4.x, acc[4 * q + 0]);
+          acc[4 * q + 1] = fmaf(xv, g4.y, acc[4 * q + 1]);
+          acc[4 * q + 2] = fmaf(xv, g4.z, acc[4 * q + 2]);
+          acc[4 * q + 3] = fmaf(xv, g4.w, acc[4 * q + 3]);
+        }
+      }
+    }
+  }
+  // reduce the 8 slices in shared memory (reusing s_g as [32 co][64 pairs]: conflict-free, one slice at a time, no shared
+  // atomics -- float atomicAdd on shared memory is a CAS loop and serialises badly), then one global atomic per weight
+  for (int sl = 0; sl < HW_THREADS / 64; ++sl) {
+    __syncthreads();
+    if (slice == sl && active) {
+#pragma unroll
+      for (int c = 0; c < 32; ++c) s_g[c * 64 + j] = (sl == 0 ? 0.f : s_g[c * 64 + j]) + acc[c];
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < 32 * 64; i += HW_THREADS) {
+    const int pair = i & 63, co = i >> 6;
+    if (pair < n_pairs) atomicAdd(g_w + ((size_t)co * Cin + pair / 9) * 9 + pair % 9, s_g[i]);
   }
 }
 
@@ -573,7 +644,13 @@ extern "C" int ef_lif_bwd_tc(const ef_lif_bwd_tc_params* pp, void* stream) {
   EF_REQUIRE(pp, EF_ENULL, "ef_lif_bwd_tc: params is NULL");
   const ef_lif_bwd_tc_params& p = *pp;
   EF_REQUIRE(p.B > 0 && p.H > 0 && p.W > 0, EF_EINVAL, "ef_lif_bwd_tc: bad dimensions");
-  EF_REQUIRE(p.x_cl && p.v_out && p.leak && p.thresh && p.w_bwd && p.gI_hi && p.gI_mid && p.g_x, EF_ENULL, "ef_lif_bwd_tc: NULL tensor");
+  const bool head = p.x_f32 != nullptr;
+  if (head) {
+    EF_REQUIRE(p.v_out && p.leak && p.thresh && p.gI_f32, EF_ENULL, "ef_lif_bwd_tc (head mode): NULL tensor");
+    EF_REQUIRE(p.Cin > 0 && p.Cin <= HW_MAXC, EF_EUNSUPPORTED, "ef_lif_bwd_tc (head mode): Cin <= %d (got %d)", HW_MAXC, p.Cin);
+  } else {
+    EF_REQUIRE(p.x_cl && p.v_out && p.leak && p.thresh && p.w_bwd && p.gI_hi && p.gI_mid && p.g_x, EF_ENULL, "ef_lif_bwd_tc: NULL tensor");
+  }
   EF_REQUIRE(!p.has_rec || !p.z_in_cl || p.g_z_in || true, EF_ENULL, "ef_lif_bwd_tc");
   cudaStream_t st = as_stream(stream);
   const int n_sms = wg_n_sms();
@@ -596,6 +673,15 @@ extern "C" int ef_lif_bwd_tc(const ef_lif_bwd_tc_params* pp, void* stream) {
 #undef EF_PW
   }
   if ((rc = check_launch("lif_bwd_pointwise_cl_kernel"))) return rc;
+  if (head) {
+    if (p.g_w_ff) {
+      const int tiles_x = cdiv(p.W, HW_TW), tiles_y = cdiv(p.H, HW_TH), n_tiles = tiles_x * tiles_y * p.B;
+      const int grid = n_tiles < 2 * n_sms ? n_tiles : 2 * n_sms;
+      lif_head_wgrad_kernel<<<grid, HW_THREADS, 0, st>>>(p.x_f32, p.gI_f32, p.g_w_ff, p.B, p.Cin, p.H, p.W, tiles_x, tiles_y, n_tiles);
+      if ((rc = check_launch("lif_head_wgrad_kernel"))) return rc;
+    }
+    return EF_OK;
+  }
 
   const bool rec = p.has_rec != 0;
   DgParams q;

@@ -48,6 +48,7 @@ class _Slot:
         self.flow = torch.empty((B, 2, H, W), device=dev, dtype=torch.float32)
         self.x_in = None   # static copy of the model input (graph replay reads a fixed address)
         self.graphs = {}   # (pointer signature) -> torch.cuda.CUDAGraph of this step's 8 kernels
+        self.bwd_calls = {}  # (pointer signature, sweep position) -> prepared argument structs of this step's backward kernels
 
 
 class _Arena:
@@ -63,6 +64,7 @@ class _Arena:
         self.banks = ([], [])
         self.parity = 0
         self.bwd = None
+        self.flat = None   # fp32 [n_params]: parameter gradients of the window being back-propagated (static address)
 
     def slot(self, parity, idx):
         bank = self.banks[parity]
@@ -277,6 +279,7 @@ class _FireNetStep(torch.autograd.Function):
                 fs.param_sig = (tuple(p.data_ptr() for p in params), tuple(splits[n].data_ptr() for n in LAYERS[1:]))
             key = (fs.param_sig, tuple(0 if v is None else v.data_ptr() for v in v_in))
             ctx.splits = splits
+            ctx.fkey = key
             g = slot.graphs.get(key)
             if g is None:
                 _launch_step(model, slot.x_in, v_in, z_in, slot, splits, B, Cin0, H, W)  # eager: results + lazy init
@@ -292,6 +295,7 @@ class _FireNetStep(torch.autograd.Function):
             _launch_step(model, x, v_in, z_in, slot, splits, B, Cin0, H, W)
             x_used = x
             ctx.splits = splits
+            ctx.fkey = None
         saved = []
         for i, name in enumerate(LAYERS):
             saved.append((x_used if i == 0 else None, slot.z[i - 1] if i > 0 else None, v_in[i], z_in[i], slot.v[i]))
@@ -303,7 +307,7 @@ class _FireNetStep(torch.autograd.Function):
             fs.v[i], fs.z[i] = slot.v[i], slot.z[i]
         flow = slot.flow.clone()  # the caller may keep the flow for as long as it likes; the slot is recycled
         ctx.model, ctx.saved, ctx.flow, ctx.first, ctx.z_last = model, saved, slot.flow, token is None, slot.z[N_L - 1]
-        ctx.carry, ctx.arena = fs.carry, arena
+        ctx.carry, ctx.arena, ctx.slot = fs.carry, arena, slot
         ctx.shapes = (B, Cin0, H, W)
         model._last_spikes = slot.z
         if isinstance(ctx, _NoCtx):
@@ -318,16 +322,48 @@ class _FireNetStep(torch.autograd.Function):
         params = _params_of(model)
         dev = ctx.flow.device
         buf = ctx.arena.bwd_buffers()
-        if carry.sweep == 0:  # first backward call of this sweep = last step of the window
+        arena = ctx.arena
+        sweep_first = carry.sweep == 0
+        if sweep_first:  # first backward call of this sweep = last step of the window
             n = sum(p.numel() for p in params)
-            if carry.flat is None:
-                carry.flat = torch.zeros(n, device=dev, dtype=torch.float32)
+            if arena.flat is None or arena.flat.numel() != n:
+                arena.flat = torch.zeros(n, device=dev, dtype=torch.float32)
             else:
-                carry.flat.zero_()
+                arena.flat.zero_()
+            carry.flat = arena.flat
             carry.g_v, carry.g_z = [None] * N_L, [None] * N_L
         par = carry.sweep & 1  # ping-pong of the state-gradient buffers between consecutive steps
         wg_flags = (L.EF_WG_ACCUMULATE if carry.sweep > 0 else 0) | (L.EF_WG_FINALIZE if ctx.first else 0)
         carry.sweep += 1
+        if g_flow is None:
+            g_flow = torch.zeros_like(ctx.flow)
+        g_flow = g_flow.contiguous()
+        # Steady state: the argument structs of this step's ~8 library calls depend only on static addresses (arena slots,
+        # ping-pong buffers, the flat gradient buffer) -- they are built once per (slot, sweep position) and replayed; only the
+        # incoming flow gradient lives at a fresh address.
+        ckey = None if ctx.fkey is None else (ctx.fkey, par, sweep_first, ctx.first, model.__dict__.get("_tc_backward", True),
+                                              model.__dict__.get("_tc_wgrad", True))
+        hit = ctx.slot.bwd_calls.get(ckey) if ckey is not None else None
+        if hit is not None:
+            calls, g_v_next, g_z_next = hit
+            calls[0][1].g_y = L.ptr(g_flow)
+            for name, st in calls:
+                L.call(name, st)
+            carry.g_v, carry.g_z = list(g_v_next), list(g_z_next)
+            if not ctx.first:
+                return (None, None, torch.zeros((), device=dev, dtype=torch.float32), *([None] * len(params)))
+            carry.sweep = 0
+            grads, o = [], 0
+            for p in params:
+                grads.append(carry.flat[o:o + p.numel()].view(p.shape))
+                o += p.numel()
+            return (None, None, None, *[g.clone() if p.requires_grad else None for p, g in zip(params, grads)])
+        calls = []
+
+        def emit(name, st):
+            calls.append((name, st))
+            L.call(name, st)
+
         grads, o = [], 0
         for p in params:
             grads.append(carry.flat[o:o + p.numel()].view(p.shape))
@@ -339,11 +375,9 @@ class _FireNetStep(torch.autograd.Function):
         pp.B, pp.Cin, pp.Cout, pp.H, pp.W = B, 32, 2, H, W
         z7 = ctx.z_last
         w, b = model.pred.conv2d.weight.detach(), model.pred.conv2d.bias.detach()
-        if g_flow is None:
-            g_flow = torch.zeros_like(ctx.flow)
-        pp.x_cl, pp.w, pp.b, pp.y, pp.g_y = L.ptr(z7), L.ptr(w), L.ptr(b), L.ptr(ctx.flow), L.ptr(g_flow.contiguous())
+        pp.x_cl, pp.w, pp.b, pp.y, pp.g_y = L.ptr(z7), L.ptr(w), L.ptr(b), L.ptr(ctx.flow), L.ptr(g_flow)
         pp.g_x, pp.g_w, pp.g_b = L.ptr(g_h), L.ptr(grads[gi]), L.ptr(grads[gi + 1])
-        L.call("ef_pred_bwd", pp)
+        emit("ef_pred_bwd", pp)
         # cells, last to first
         for i in reversed(range(len(LAYERS))):
             cell = getattr(model, LAYERS[i])
@@ -364,7 +398,18 @@ class _FireNetStep(torch.autograd.Function):
                 g_w_rec = grads[k]
                 k += 1
             g_leak, g_thresh = grads[k], grads[k + 1]
-            if i > 0 and model.__dict__.get("_tc_backward", True):
+            if i == 0 and Cin0 <= 8 and model.__dict__.get("_tc_backward", True):
+                # head layer on the fast formats: pointwise (fp32 g_I) + register-tiled CUDA-core weight gradient, no data gradient
+                t = L.LifBwdTcParams()
+                t.B, t.H, t.W, t.has_rec, t.hard_reset = B, H, W, 0, int(cell.hard_reset)
+                t.surrogate, t.act_width = L.SURROGATE_CODES[cell.activation], float(cell._act_width_f)
+                t.z_in_cl, t.v_in, t.v_out = L.ptr(z_in), L.ptr(v_in), L.ptr(v_out)
+                t.g_out, t.g_v_out, t.g_z_out = L.ptr(g_h), L.ptr(carry.g_v[i]), L.ptr(carry.g_z[i])
+                t.leak, t.thresh = L.ptr(leak), L.ptr(thresh)
+                t.g_v_in, t.g_w_ff, t.g_leak, t.g_thresh = L.ptr(g_v_in), L.ptr(g_w_ff), L.ptr(g_leak), L.ptr(g_thresh)
+                t.Cin, t.x_f32, t.gI_f32 = Cin0, L.ptr(x_f32), L.ptr(buf["scratch"])
+                emit("ef_lif_bwd_tc", t)
+            elif i > 0 and model.__dict__.get("_tc_backward", True):
                 # 32 -> 32 cells: pointwise + tensor-core data gradient + channels-last weight gradient
                 t = L.LifBwdTcParams()
                 t.B, t.H, t.W, t.has_rec, t.hard_reset = B, H, W, int(cell.recurrent), int(cell.hard_reset)
@@ -377,7 +422,7 @@ class _FireNetStep(torch.autograd.Function):
                 t.g_w_ff, t.g_w_rec, t.g_leak, t.g_thresh = L.ptr(g_w_ff), L.ptr(g_w_rec), L.ptr(g_leak), L.ptr(g_thresh)
                 if model.__dict__.get("_tc_wgrad", True):
                     t.wg_partial, t.wg_flags = L.ptr(buf["wg"][i]), wg_flags
-                L.call("ef_lif_bwd_tc", t)
+                emit("ef_lif_bwd_tc", t)
             else:
                 q = L.LifConvBwdParams()
                 _fill_fwd(q.f, B, Cin0 if i == 0 else 32, H, W, cell, x_f32, x_cl, v_in, z_in, v_out, leak, thresh)
@@ -385,9 +430,11 @@ class _FireNetStep(torch.autograd.Function):
                 q.scratch_gI = L.ptr(buf["scratch"])
                 q.g_x, q.g_v_in, q.g_z_in = L.ptr(g_x), L.ptr(g_v_in), L.ptr(g_z_in)
                 q.g_w_ff, q.g_w_rec, q.g_leak, q.g_thresh = L.ptr(g_w_ff), L.ptr(g_w_rec), L.ptr(g_leak), L.ptr(g_thresh)
-                L.call("ef_lif_conv_bwd", q)
+                emit("ef_lif_conv_bwd", q)
             carry.g_v[i], carry.g_z[i] = g_v_in, g_z_in
             g_h = g_x
+        if ckey is not None:
+            ctx.slot.bwd_calls[ckey] = (calls, list(carry.g_v), list(carry.g_z))
         if not ctx.first:  # parameter gradients keep accumulating in carry.flat; the window's first step hands them over
             return (None, None, torch.zeros((), device=dev, dtype=torch.float32), *([None] * len(params)))
         carry.sweep = 0

@@ -158,6 +158,11 @@ typedef struct ef_lif_bwd_tc_params {
   float* g_thresh;               /* [32] += or NULL                                                                    */
   float* wg_partial;             /* ef_lif_wgrad_partial_elems() floats or NULL: selects the tensor-core weight gradient */
   int32_t wg_flags;              /* EF_WG_* below                                                                      */
+  /* Head-layer mode (x_f32 != NULL): the cell's input is the fp32 NCHW network input with Cin <= 8 channels (event counts /  */
+  /* voxel bins); no data gradient is produced, x_cl / w_bwd / gI_hi / gI_mid / g_x / wg_partial are ignored.                */
+  int32_t Cin;                   /* input channels of the head layer                                                   */
+  const float* x_f32;            /* [B,Cin,H,W] or NULL (= 32 -> 32 cell)                                              */
+  float* gI_f32;                 /* [B,32,H,W] workspace (head mode)                                                   */
 } ef_lif_bwd_tc_params;
 
 /* Tensor-core weight gradient (wg_partial != NULL): every CTA keeps its share of

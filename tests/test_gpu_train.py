@@ -60,3 +60,47 @@ def test_trainer_step_on_firenet_changes_parameters_and_keeps_grad_views():
     tr.step()
     assert (tr.flat_param - before).abs().max() > 0 and tr.flat_grad.abs().max() == 0
     assert torch.isfinite(tr.flat_param).all()
+
+
+def test_cached_backward_arguments_reproduce_the_first_window():
+    """
+    The fast path builds the argument structs of a step's backward calls once per (arena slot, sweep position) and replays
+    them afterwards.  Windows 3 and 4 (same arena banks as windows 1 and 2) must give the gradients of the uncached windows.
+    """
+    from event_flow_b200.loss.flow import EventWarping
+    from event_flow_b200.models.model import LIFFireNet
+    from oracle import encodings as oenc
+    from tests.util import firenet_cfg
+
+    torch.manual_seed(0)
+    H, W, B, T = 32, 48, 2, 3
+    model = LIFFireNet(firenet_cfg(5, "voxel"))
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if n.endswith("ff.weight") or n.endswith("rec.weight"):
+                p.mul_(2.5)
+        model.pred.conv2d.weight.mul_(20.0)
+    model = model.to(DEV)
+    cfg = {"loader": {"resolution": [H, W]}, "loss": {"flow_regul_weight": 0.001, "overwrite_intermediate": False}, "model": {"mask_output": True}}
+    lossf = EventWarping(cfg, DEV)
+    wins = [oenc.encode_window(*oenc.synthetic_events(B, 300, H, W, 50 + t), H, W, 5) for t in range(T)]
+
+    def window():
+        model.zero_grad(set_to_none=True)
+        model.reset_states()
+        lossf.reset()
+        for d in wins:
+            out = model(d["event_voxel"].to(DEV), d["event_cnt"].to(DEV))
+            lossf.event_flow_association(out["flow"], d["event_list"].clone().to(DEV), d["event_list_pol_mask"].to(DEV), d["event_mask"].to(DEV))
+        loss = lossf()
+        loss.backward()
+        model.detach_states()
+        return loss.item(), {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
+
+    ref_loss, ref = window()
+    for k in range(4):
+        loss, grads = window()
+        assert loss == ref_loss
+        for n, g in grads.items():
+            scale = ref[n].abs().max().item() + 1e-20
+            assert (g - ref[n]).abs().max().item() <= 1e-5 * scale, f"window {k + 2}: {n}"
