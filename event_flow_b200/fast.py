@@ -48,7 +48,8 @@ class _Slot:
         self.flow = torch.empty((B, 2, H, W), device=dev, dtype=torch.float32)
         self.x_in = None   # static copy of the model input (graph replay reads a fixed address)
         self.graphs = {}   # (pointer signature) -> torch.cuda.CUDAGraph of this step's 8 kernels
-        self.bwd_calls = {}  # (pointer signature, sweep position) -> prepared argument structs of this step's backward kernels
+        self.bwd_calls = {}  # (pointer signature, sweep position) -> prepared argument structs (+ CUDA graph) of this step's backward
+        self.g_flow_in = None  # static copy of the incoming flow gradient (graph replay reads a fixed address)
 
 
 class _Arena:
@@ -345,10 +346,26 @@ class _FireNetStep(torch.autograd.Function):
                                               model.__dict__.get("_tc_wgrad", True))
         hit = ctx.slot.bwd_calls.get(ckey) if ckey is not None else None
         if hit is not None:
-            calls, g_v_next, g_z_next = hit
-            calls[0][1].g_y = L.ptr(g_flow)
-            for name, st in calls:
-                L.call(name, st)
+            calls, g_v_next, g_z_next, graph, n_kernels = hit
+            slot = ctx.slot
+            if slot.g_flow_in is None:
+                slot.g_flow_in = torch.empty_like(ctx.flow)
+            slot.g_flow_in.copy_(g_flow)  # fixed address for the replay, like the model input of the forward graph
+            calls[0][1].g_y = L.ptr(slot.g_flow_in)
+            if graph is None and model.__dict__.get("_use_graphs", True) and L.PROFILE is None and not torch.cuda.is_current_stream_capturing():
+                graph = torch.cuda.CUDAGraph()  # second visit of this (slot, sweep position): capture the ~25 kernels once
+                n0 = L.lib().ef_launch_count()
+                with torch.cuda.graph(graph):
+                    for name, st in calls:
+                        L.call(name, st)
+                n_kernels = L.lib().ef_launch_count() - n0  # kernels recorded into the graph (counted by the library itself)
+                slot.bwd_calls[ckey] = (calls, g_v_next, g_z_next, graph, n_kernels)
+            if graph is not None:
+                graph.replay()
+                L.GRAPH_KERNELS += n_kernels
+            else:
+                for name, st in calls:
+                    L.call(name, st)
             carry.g_v, carry.g_z = list(g_v_next), list(g_z_next)
             if not ctx.first:
                 return (None, None, torch.zeros((), device=dev, dtype=torch.float32), *([None] * len(params)))
@@ -434,7 +451,7 @@ class _FireNetStep(torch.autograd.Function):
             carry.g_v[i], carry.g_z[i] = g_v_in, g_z_in
             g_h = g_x
         if ckey is not None:
-            ctx.slot.bwd_calls[ckey] = (calls, list(carry.g_v), list(carry.g_z))
+            ctx.slot.bwd_calls[ckey] = (calls, list(carry.g_v), list(carry.g_z), None, 0)
         if not ctx.first:  # parameter gradients keep accumulating in carry.flat; the window's first step hands them over
             return (None, None, torch.zeros((), device=dev, dtype=torch.float32), *([None] * len(params)))
         carry.sweep = 0
