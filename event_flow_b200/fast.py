@@ -277,7 +277,7 @@ class _FireNetStep(torch.autograd.Function):
                 slot.x_in, slot.graphs = torch.empty_like(x), {}
             slot.x_in.copy_(x)
             if fs.param_sig is None:  # refreshed per sequence (reset_states) and whenever the module is moved (FireNet._apply)
-                fs.param_sig = (tuple(p.data_ptr() for p in params), tuple(splits[n].data_ptr() for n in LAYERS[1:]))
+                fs.param_sig = (tuple(p.data_ptr() for p in _params_of(model)), tuple(splits[n].data_ptr() for n in LAYERS[1:]))
             key = (fs.param_sig, tuple(0 if v is None else v.data_ptr() for v in v_in))
             ctx.splits = splits
             ctx.fkey = key
@@ -368,7 +368,7 @@ class _FireNetStep(torch.autograd.Function):
                     L.call(name, st)
             carry.g_v, carry.g_z = list(g_v_next), list(g_z_next)
             if not ctx.first:
-                return (None, None, torch.zeros((), device=dev, dtype=torch.float32), *([None] * len(params)))
+                return (None, None, torch.zeros((), device=dev, dtype=torch.float32))
             carry.sweep = 0
             grads, o = [], 0
             for p in params:
@@ -453,7 +453,7 @@ class _FireNetStep(torch.autograd.Function):
         if ckey is not None:
             ctx.slot.bwd_calls[ckey] = (calls, list(carry.g_v), list(carry.g_z), None, 0)
         if not ctx.first:  # parameter gradients keep accumulating in carry.flat; the window's first step hands them over
-            return (None, None, torch.zeros((), device=dev, dtype=torch.float32), *([None] * len(params)))
+            return (None, None, torch.zeros((), device=dev, dtype=torch.float32))
         carry.sweep = 0
         out = [g.clone() if p.requires_grad else None for p, g in zip(params, grads)]
         return (None, None, None, *out)
@@ -473,7 +473,12 @@ def forward(model, x, log=False):
     need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
     if need_grad:
         token = fs.token
-        flow, fs.token = _FireNetStep.apply(model, x, token, *params)
+        # the parameters are autograd inputs of the window's FIRST step only (its backward hands over the gradients accumulated
+        # over the whole window); later steps are chained through the token, which keeps their apply() cheap
+        if token is None:
+            flow, fs.token = _FireNetStep.apply(model, x, None, *params)
+        else:
+            flow, fs.token = _FireNetStep.apply(model, x, token)
     else:
         with torch.no_grad():
             flow, _ = _FireNetStep.forward(_NoCtx(), model, x, None, *params)
