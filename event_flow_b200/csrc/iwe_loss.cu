@@ -8,8 +8,10 @@
 namespace ef {
 
 // workspace layout (floats):
-//   img  [S][B][2 dir][4 = I+,I-,Th+,Th-][HW]      forward accumulators
-//   adj  [S][B][2 dir][4][HW]                      adjoint images (backward)
+//   img  [S][B][2 dir][HW][4 = I+,Th+,I-,Th-]      forward accumulators, pixel-interleaved: an event adds (w, w*tau) of its
+//                                                  polarity with ONE 8-byte vector atomic per corner (red.global.add.v2.f32),
+//                                                  the reductions read one 16-byte vector per pixel
+//   adj  [S][B][2 dir][HW][4]                      adjoint images (backward), same layout
 //   sums [S][B][2 dir][2 = sum A^2, n]             per-sample reductions
 //   smooth [S]
 struct WsLayout {
@@ -91,14 +93,9 @@ __global__ void __launch_bounds__(256) iwe_scatter_kernel(const ef_iwe_loss_para
       const float w = __fmul_rn(c[k].wy, c[k].wx);
       if (w == 0.f) continue;
       const float wt = __fmul_rn(w, tau);
-      if (pm.x != 0.f) {
-        atomicAdd(d + 0 * hw + c[k].idx, __fmul_rn(w, pm.x));
-        atomicAdd(d + 2 * hw + c[k].idx, __fmul_rn(wt, pm.x));
-      }
-      if (pm.y != 0.f) {
-        atomicAdd(d + 1 * hw + c[k].idx, __fmul_rn(w, pm.y));
-        atomicAdd(d + 3 * hw + c[k].idx, __fmul_rn(wt, pm.y));
-      }
+      float2* q = reinterpret_cast<float2*>(d + (size_t)c[k].idx * 4);  // [I+, Th+], [I-, Th-]
+      if (pm.x != 0.f) atomicAdd(q, make_float2(__fmul_rn(w, pm.x), __fmul_rn(wt, pm.x)));
+      if (pm.y != 0.f) atomicAdd(q + 1, make_float2(__fmul_rn(w, pm.y), __fmul_rn(wt, pm.y)));
     }
   }
 }
@@ -126,7 +123,8 @@ __global__ void __launch_bounds__(256) iwe_reduce_kernel(const float* __restrict
   float ssq = 0.f, n = 0.f;
   const int p0 = blockIdx.x * RED_PIX;
   for (int i = p0 + threadIdx.x; i < min(p0 + RED_PIX, HW); i += 256) {
-    const float ip = d[i], in = d[HW + i], tp = d[2 * HW + i], tn = d[3 * HW + i];
+    const float4 q = reinterpret_cast<const float4*>(d)[i];
+    const float ip = q.x, tp = q.y, in = q.z, tn = q.w;
     const float ap = tp / (ip + 1e-9f) / T, an = tn / (in + 1e-9f) / T;
     ssq += ap * ap + an * an;
     n += (ip + in > 0.f) ? 1.f : 0.f;
@@ -254,7 +252,8 @@ __global__ void __launch_bounds__(256) iwe_adjoint_kernel(const float* __restric
   float* a = adj + (size_t)sbd * 4 * HW;
   const float ssq = sums[sbd * 2], n = sums[sbd * 2 + 1];
   const float g = g_loss[0] * inv_S / (loss_scaling ? n : 1.f);
-  const float ip = d[i], in = d[HW + i], tp = d[2 * HW + i], tn = d[3 * HW + i];
+  const float4 q = reinterpret_cast<const float4*>(d)[i];
+  const float ip = q.x, tp = q.y, in = q.z, tn = q.w;
   const float ap = tp / (ip + 1e-9f) / T, an = tn / (in + 1e-9f) / T;
   const float gtp = g * 2.f * ap / ((ip + 1e-9f) * T), gtn = g * 2.f * an / ((in + 1e-9f) * T);
   float gip = -gtp * tp / (ip + 1e-9f), gin = -gtn * tn / (in + 1e-9f);
@@ -263,10 +262,7 @@ __global__ void __launch_bounds__(256) iwe_adjoint_kernel(const float* __restric
     gip += gn;
     gin += gn;
   }
-  a[i] = gip;
-  a[HW + i] = gin;
-  a[2 * HW + i] = gtp;
-  a[3 * HW + i] = gtn;
+  reinterpret_cast<float4*>(a)[i] = make_float4(gip, gtp, gin, gtn);
 }
 
 // d max(0, 1-|d|) / d d with torch's tie conventions: abs'(0) = 0; maximum splits the gradient at equality.
@@ -304,8 +300,15 @@ __global__ void __launch_bounds__(256) iwe_event_grad_kernel(const ef_iwe_loss_p
     for (int k = 0; k < 4; ++k) {
       if (c[k].idx < 0) continue;
       float delta = 0.f;
-      if (pm.x != 0.f) delta += pm.x * (a[c[k].idx] + tau * a[2 * hw + c[k].idx]);
-      if (pm.y != 0.f) delta += pm.y * (a[hw + c[k].idx] + tau * a[3 * hw + c[k].idx]);
+      const float2* q = reinterpret_cast<const float2*>(a + (size_t)c[k].idx * 4);  // adjoints of [I+, Th+], [I-, Th-]
+      if (pm.x != 0.f) {
+        const float2 g2 = __ldg(q);
+        delta += pm.x * (g2.x + tau * g2.y);
+      }
+      if (pm.y != 0.f) {
+        const float2 g2 = __ldg(q + 1);
+        delta += pm.y * (g2.x + tau * g2.y);
+      }
       gfy += delta * dweight(c[k].dy) * c[k].wx * kk;
       gfx += delta * c[k].wy * dweight(c[k].dx) * kk;
     }
@@ -358,7 +361,8 @@ __global__ void __launch_bounds__(256) iwe_image_kernel(const ef_iwe_image_param
 }
 
 // ---- validation metrics: FWL / RSAT (loss/flow.py:468-579) and AEE (:582-628) -----------------------------------------
-// workspace: img [B][2 = warped, unwarped][4 = I+,I-,Th+,Th-][HW], then sums [B][2][4 = sum A^2, n, sum I, sum I^2]
+// workspace: img [B][2 = warped, unwarped][HW][4 = I+,Th+,I-,Th-] (pixel-interleaved like the loss workspace), then sums
+// [B][2][4 = sum A^2, n, sum I, sum I^2]
 __global__ void __launch_bounds__(256) iwe_metric_scatter_kernel(const ef_iwe_metrics_params p, float* __restrict__ img) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
   if (i >= p.n_total) return;
@@ -387,8 +391,9 @@ __global__ void __launch_bounds__(256) iwe_metric_scatter_kernel(const ef_iwe_me
     float* d = base + (size_t)k * 4 * hw;
     // FWL scatters weight 1 per event regardless of polarity (no mask); RSAT scatters per polarity.  Channels 0/1 serve
     // both when every event has exactly one polarity bit; events with neither are still counted for FWL in channel 0.
-    if (pm.x != 0.f) { atomicAdd(d + idx, pm.x); atomicAdd(d + 2 * hw + idx, __fmul_rn(e.x, pm.x)); }
-    if (pm.y != 0.f) { atomicAdd(d + hw + idx, pm.y); atomicAdd(d + 3 * hw + idx, __fmul_rn(e.x, pm.y)); }
+    float2* q = reinterpret_cast<float2*>(d + (size_t)idx * 4);
+    if (pm.x != 0.f) atomicAdd(q, make_float2(pm.x, __fmul_rn(e.x, pm.x)));
+    if (pm.y != 0.f) atomicAdd(q + 1, make_float2(pm.y, __fmul_rn(e.x, pm.y)));
   }
 }
 
@@ -399,7 +404,8 @@ __global__ void __launch_bounds__(256) iwe_metric_reduce_kernel(const float* __r
   float ssq = 0.f, n = 0.f, s1 = 0.f, s2 = 0.f;
   const int p0 = blockIdx.x * RED_PIX;
   for (int i = p0 + threadIdx.x; i < min(p0 + RED_PIX, HW); i += 256) {
-    const float ip = d[i], in = d[HW + i], tp = d[2 * HW + i], tn = d[3 * HW + i];
+    const float4 q = reinterpret_cast<const float4*>(d)[i];
+    const float ip = q.x, tp = q.y, in = q.z, tn = q.w;
     const float ap = tp / (ip + 1e-9f) / T, an = tn / (in + 1e-9f) / T;
     ssq += ap * ap + an * an;
     n += (ip + in > 0.f) ? 1.f : 0.f;

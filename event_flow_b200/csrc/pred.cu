@@ -129,6 +129,79 @@ __global__ void __launch_bounds__(256) pred_bwd_kernel(const ef_pred_params p) {
   if (threadIdx.x < p.Cout && p.g_b) atomicAdd(p.g_b + threadIdx.x, s_acc[PRED_MAX_COUT * PRED_MAX_CIN + threadIdx.x]);
 }
 
+// Sums of v[0..31] over the 32 lanes of a warp, all 32 entries at once (31 shuffles instead of 32 x 5): step by step the lanes
+// trade halves of their arrays (lane bit set: keep the upper half, send the lower one); lane l ends up with the total of entry
+// `entry` (a bijection lane -> entry).
+__device__ __forceinline__ float warp_transpose_sum32(float (&v)[32], int lane, int& entry) {
+  entry = 0;
+#pragma unroll
+  for (int half = 16; half >= 1; half >>= 1) {
+    const bool up = (lane & half) != 0;
+#pragma unroll
+    for (int k = 0; k < half; ++k) {
+      const float keep = up ? v[k + half] : v[k];
+      const float send = up ? v[k] : v[k + half];
+      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+    }
+    entry += up ? half : 0;
+  }
+  return v[0];
+}
+
+// Backward of the FireNet prediction head on the fast formats: 32 channels-last bf16 input channels, 2 outputs.  One pixel per
+// thread and iteration (4 x 16-byte loads of the spike row), g_x written fp32 NCHW (one 128-byte line per channel and warp),
+// weight-gradient terms kept in registers over the thread's pixels and reduced once with the transposing butterfly.
+constexpr int PBC_THREADS = 128, PBC_PIX = 4;
+__global__ void __launch_bounds__(PBC_THREADS) pred_bwd_cl32_kernel(const ef_pred_params p) {
+  __shared__ float s_w[64], s_acc[66];
+  const int tid = threadIdx.x, lane = tid & 31;
+  if (tid < 64) s_w[tid] = p.w[tid];
+  if (tid < 66) s_acc[tid] = 0.f;
+  __syncthreads();
+  const size_t hw = (size_t)p.H * p.W, n = (size_t)p.B * hw;
+  float gw0[32], gw1[32], gb0 = 0.f, gb1 = 0.f;
+#pragma unroll
+  for (int c = 0; c < 32; ++c) gw0[c] = gw1[c] = 0.f;
+#pragma unroll 1
+  for (int k = 0; k < PBC_PIX; ++k) {
+    const size_t i = ((size_t)blockIdx.x * PBC_PIX + k) * PBC_THREADS + tid;
+    if (i >= n) break;
+    const int b = i / hw;
+    const size_t pix = i % hw;
+    const uint4* row = reinterpret_cast<const uint4*>(p.x_cl + i * 32);
+    uint4 q[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) q[g] = __ldg(row + g);
+    const size_t o0 = ((size_t)b * 2) * hw + pix;
+    const float y0 = p.y[o0], y1 = p.y[o0 + hw];
+    const float gp0 = p.g_y[o0] * (1.0f - y0 * y0), gp1 = p.g_y[o0 + hw] * (1.0f - y1 * y1);
+    gb0 += gp0, gb1 += gp1;
+    float* gx = p.g_x ? p.g_x + (size_t)b * 32 * hw + pix : nullptr;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const uint32_t u[4] = {q[g].x, q[g].y, q[g].z, q[g].w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int c = g * 8 + e;
+        const float xv = (e & 1) ? bf16_hi(u[e >> 1]) : bf16_lo(u[e >> 1]);
+        gw0[c] = fmaf(gp0, xv, gw0[c]);
+        gw1[c] = fmaf(gp1, xv, gw1[c]);
+        if (gx) gx[(size_t)c * hw] = fmaf(gp1, s_w[32 + c], gp0 * s_w[c]);
+      }
+    }
+  }
+  int e0, e1;
+  const float t0 = warp_transpose_sum32(gw0, lane, e0);
+  const float t1 = warp_transpose_sum32(gw1, lane, e1);
+  atomicAdd(&s_acc[e0], t0);
+  atomicAdd(&s_acc[32 + e1], t1);
+  const float b0 = warp_sum(gb0), b1 = warp_sum(gb1);
+  if (lane == 0) atomicAdd(&s_acc[64], b0), atomicAdd(&s_acc[65], b1);
+  __syncthreads();
+  if (tid < 64 && p.g_w) atomicAdd(p.g_w + tid, s_acc[tid]);
+  if (tid < 2 && p.g_b) atomicAdd(p.g_b + tid, s_acc[64 + tid]);
+}
+
 static int validate_pred(const ef_pred_params& p, const char* who) {
   EF_REQUIRE(p.B > 0 && p.Cin > 0 && p.Cout > 0 && p.H > 0 && p.W > 0, EF_EINVAL, "%s: bad dimensions", who);
   EF_REQUIRE(p.Cin <= PRED_MAX_CIN && p.Cout <= PRED_MAX_COUT, EF_EUNSUPPORTED, "%s: Cin <= %d, Cout <= %d", who, PRED_MAX_CIN, PRED_MAX_COUT);
@@ -154,6 +227,10 @@ extern "C" int ef_pred_bwd(const ef_pred_params* p, void* stream) {
   if (int rc = validate_pred(*p, "ef_pred_bwd")) return rc;
   EF_REQUIRE(p->g_y, EF_ENULL, "ef_pred_bwd: g_y is NULL");
   const size_t n = (size_t)p->B * p->H * p->W;
+  if (p->x_cl && p->Cin == 32 && p->Cout == 2) {
+    pred_bwd_cl32_kernel<<<(unsigned)((n + PBC_THREADS * PBC_PIX - 1) / (PBC_THREADS * PBC_PIX)), PBC_THREADS, 0, as_stream(stream)>>>(*p);
+    return check_launch("pred_bwd_cl32_kernel");
+  }
   pred_bwd_kernel<<<(unsigned)((n + 256 * PB_PIX - 1) / (256 * PB_PIX)), 256, 0, as_stream(stream)>>>(*p);
   return check_launch("pred_bwd_kernel");
 }
