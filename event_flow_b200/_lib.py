@@ -144,6 +144,7 @@ EXPORTS = {
     "ef_iwe_loss_bwd": (C.c_int, [C.POINTER(IweLossParams), C.c_void_p]),
     "ef_iwe_image": (C.c_int, [C.POINTER(IweImageParams), C.c_void_p]),
     "ef_conv_ann_fwd": (C.c_int, [C.POINTER(ConvAnnParams), C.c_void_p]),
+    "ef_conv3x3_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, _i32, _i32, _i32, _i32, _i32, C.c_void_p]),
     "ef_iwe_metrics_workspace_elems": (C.c_int64, [_i32, _i32, _i32]),
     "ef_iwe_metrics": (C.c_int, [C.POINTER(IweMetricsParams), C.c_void_p]),
     "ef_aee": (C.c_int, [C.POINTER(AeeParams), C.c_void_p]),

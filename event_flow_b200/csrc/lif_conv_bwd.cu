@@ -403,3 +403,26 @@ extern "C" int ef_lif_conv_bwd(const ef_lif_conv_bwd_params* q, void* stream) {
   }
   return EF_OK;
 }
+
+/* Gradients of a plain 3x3, stride-1, padding-1 convolution on fp32 NCHW tensors (the ANN cells, models/submodules.py): the
+ * data gradient g_x = conv^T(g_pre, w) (overwritten, may be NULL) and the weight gradient g_w += x * g_pre (may be NULL). */
+extern "C" int ef_conv3x3_bwd(const float* g_pre, const float* x, const float* w, float* g_x, float* g_w, int32_t B, int32_t Cin, int32_t C,
+                              int32_t H, int32_t W, void* stream) {
+  using namespace ef;
+  EF_REQUIRE(g_pre && w, EF_ENULL, "ef_conv3x3_bwd: g_pre / w is NULL");
+  EF_REQUIRE(B > 0 && Cin > 0 && C > 0 && H > 0 && W > 0, EF_EINVAL, "ef_conv3x3_bwd: non-positive dimension");
+  EF_REQUIRE(!g_w || x, EF_ENULL, "ef_conv3x3_bwd: the weight gradient needs x");
+  cudaStream_t st = as_stream(stream);
+  int rc;
+  if (g_x) {
+    dim3 grid(cdiv(W, 16), cdiv(H, 16), B * cdiv(Cin, DG_CIB));
+    conv_dgrad_kernel<<<grid, DG_THREADS, 0, st>>>(g_pre, w, g_x, 0, B, Cin, C, H, W, nullptr, nullptr);
+    if ((rc = check_launch("conv_dgrad_kernel(ann)"))) return rc;
+  }
+  if (g_w) {
+    dim3 grid(cdiv(W, 16), cdiv(H, 16), B * cdiv(C, 32));
+    conv_wgrad_kernel<<<grid, WG_THREADS, 0, st>>>(x, nullptr, g_pre, g_w, B, Cin, C, H, W, H, W);
+    if ((rc = check_launch("conv_wgrad_kernel(ann)"))) return rc;
+  }
+  return EF_OK;
+}

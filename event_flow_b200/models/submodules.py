@@ -1,7 +1,7 @@
 """
 ANN layers of models/submodules.py used by the FireNet family: ConvLayer (:12-61), ConvLayer_ (:64-83), ConvGRU (:377-418),
 with the reference's constructor signatures, parameter names and initialisers.  Forward passes are CUDA kernels
-(ef_conv_ann_fwd / ef_pred_fwd); the backward of the 3x3 ANN cells is not built in this version (it raises).
+(ef_conv_ann_fwd / ef_pred_fwd); under autograd the convolution gradients come from ef_conv3x3_bwd (ops._ConvAnn).
 """
 import torch
 import torch.nn as nn

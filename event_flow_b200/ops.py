@@ -493,23 +493,70 @@ def aee(flow, gtflow, event_mask, dt_ratio, flow_scaling):
 _ACT_CODES = {None: 0, "relu": 1, "sigmoid": 2, "tanh": 3}
 
 
-class _NoBackward(torch.autograd.Function):
-    """Marks tensors produced by forward-only kernels: asking for their gradient fails loudly instead of silently giving zeros."""
+class _ConvAnn(torch.autograd.Function):
+    """
+    act(conv3x3(cat([x1, x2]), w) + b + residual) with gradients: forward = ef_conv_ann_fwd, backward = the activation
+    derivative (elementwise), ef_conv3x3_bwd for the data and weight gradients of the convolution, a sum for the bias.
+    """
 
     @staticmethod
-    def forward(ctx, out, *deps):
-        return out.view_as(out)
+    def forward(ctx, x1, x2, weight, bias, residual, act):
+        out = _conv_ann_launch(x1, weight, bias, act, x2=x2, residual=residual)
+        ctx.act = act
+        ctx.has = (x2 is not None, bias is not None, residual is not None)
+        ctx.save_for_backward(x1, x2, weight, out)
+        return out
 
     @staticmethod
-    def backward(ctx, *g):
-        raise NotImplementedError("event_flow_b200: the backward of the ANN cells (ConvLayer_/ConvGRU) is not built yet")
+    def backward(ctx, g):
+        x1, x2, weight, out = ctx.saved_tensors
+        has_x2, has_bias, has_res = ctx.has
+        g = g.contiguous()
+        if ctx.act == "relu":
+            g_pre = g * (out > 0)
+        elif ctx.act == "tanh":
+            g_pre = g * (1.0 - out * out)
+        elif ctx.act == "sigmoid":
+            g_pre = g * (out * (1.0 - out))
+        else:
+            g_pre = g
+        g_pre = g_pre.contiguous()
+        x = x1.contiguous() if x2 is None else torch.cat([x1, x2], dim=1)
+        B, Cin, H, W = x.shape
+        Cout = weight.shape[0]
+        need = ctx.needs_input_grad  # (x1, x2, weight, bias, residual, act)
+        g_x = torch.empty_like(x) if (need[0] or (has_x2 and need[1])) else None
+        g_w = torch.zeros_like(weight) if need[2] else None
+        L.LAUNCHES += 1
+        L.check(L.lib().ef_conv3x3_bwd(L.ptr(g_pre), L.ptr(x), L.ptr(_c(weight)), L.ptr(g_x), L.ptr(g_w), B, Cin, Cout, H, W, L.stream()),
+                "ef_conv3x3_bwd")
+        C1 = x1.shape[1]
+        g_x1 = g_x[:, :C1] if (g_x is not None and need[0]) else None
+        g_x2 = g_x[:, C1:] if (g_x is not None and has_x2 and need[1]) else None
+        g_b = g_pre.sum(dim=(0, 2, 3)) if (has_bias and need[3]) else None
+        g_r = g_pre if (has_res and need[4]) else None
+        return g_x1, g_x2, g_w, g_b, g_r, None
 
 
 def conv_ann(x1, weight, bias, act, *, x2=None, x2_scale=None, residual=None, blend_h=None, blend_u=None):
     """
     act(conv3x3(cat([x1, x2 * x2_scale]), weight) + bias + residual), optionally blended h*(1-u) + (.)*u.
     x2 / x2_scale / blend_* may be channel slices of larger NCHW tensors (only the batch stride may be non-dense).
+    Without gradient tracking this is ONE fused launch; under autograd the gate product and the blend are separate
+    (elementwise) steps around a differentiable conv + activation (_ConvAnn).
     """
+    tracked = torch.is_grad_enabled() and any(t is not None and t.requires_grad
+                                              for t in (x1, x2, x2_scale, weight, bias, residual, blend_h, blend_u))
+    if tracked:
+        x2_eff = x2 if x2_scale is None or x2 is None else x2 * x2_scale
+        out = _ConvAnn.apply(x1, x2_eff, weight, bias, residual, act)
+        if blend_h is not None:
+            out = blend_h * (1.0 - blend_u) + out * blend_u
+        return out
+    return _conv_ann_launch(x1, weight, bias, act, x2=x2, x2_scale=x2_scale, residual=residual, blend_h=blend_h, blend_u=blend_u)
+
+
+def _conv_ann_launch(x1, weight, bias, act, *, x2=None, x2_scale=None, residual=None, blend_h=None, blend_u=None):
     def plane_ok(t):
         return t is None or (t.stride(-1) == 1 and t.stride(-2) == t.shape[-1] and t.stride(1) == t.shape[-1] * t.shape[-2])
 
@@ -517,7 +564,6 @@ def conv_ann(x1, weight, bias, act, *, x2=None, x2_scale=None, residual=None, bl
     tensors = [x2, x2_scale, residual, blend_h, blend_u]
     tensors = [t if plane_ok(t) else t.contiguous() for t in tensors]
     x2, x2_scale, residual, blend_h, blend_u = tensors
-    grad_deps = [t for t in (x1, x2, weight, bias) if t is not None and t.requires_grad] if torch.is_grad_enabled() else []
     weight, bias = _c(weight.detach()), (None if bias is None else _c(bias.detach()))
     residual = None if residual is None else residual.contiguous()
     _need_cuda(x1, x2, x2_scale, residual, blend_h, blend_u, weight, bias)
@@ -539,6 +585,4 @@ def conv_ann(x1, weight, bias, act, *, x2=None, x2_scale=None, residual=None, bl
     p.blend_u_bstride = 0 if blend_u is None else blend_u.stride(0)
     p.out = L.ptr(out)
     L.call("ef_conv_ann_fwd", p)
-    if grad_deps:
-        out = _NoBackward.apply(out, *grad_deps)
     return out

@@ -253,6 +253,12 @@ typedef struct ef_conv_ann_params {
 
 int ef_conv_ann_fwd(const ef_conv_ann_params* p, void* stream);
 
+/* Gradients of the 3x3 stride-1 convolution inside the ANN cells (what autograd derives for the nn.Conv2d of
+ * models/submodules.py:22,159,256,281,386-388): g_pre = dL/d(conv output) [B,C,H,W]; g_x [B,Cin,H,W] is overwritten (NULL = skip),
+ * g_w [C,Cin,3,3] is accumulated (NULL = skip; needs x [B,Cin,H,W]). */
+int ef_conv3x3_bwd(const float* g_pre, const float* x, const float* w, float* g_x, float* g_w, int32_t B, int32_t Cin, int32_t C,
+                   int32_t H, int32_t W, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * Contrast-maximisation event-warping loss over one training window.
  * Replaces EventWarping.forward (loss/flow.py:176-301) with utils/iwe.py:4-92 (purge_unfeasible, get_interpolation,

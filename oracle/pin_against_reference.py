@@ -370,6 +370,22 @@ def pin_ann_firenet(rmodel, golden):
                 if recurrent and i in (1, 4):
                     close(states[i], s_, 0, f"ann {cls.__name__} state[{i}]")
                     d_all[f"state_{i}"] = s_
+        # BPTT gradients of a random linear functional of the flows (reference autograd; the ANN cells are smooth, so the
+        # GPU path is compared at 1e-3 relative without any trajectory caveat)
+        g = torch.Generator().manual_seed(31)
+        gw = [torch.rand((B, 2, H, W), generator=g) - 0.5 for _ in range(T)]
+        named = [(n_, q) for n_, q in m.named_parameters() if q.requires_grad]
+        m.reset_states()
+        loss = 0.0
+        for t in range(T):
+            xt = d_all[f"x_{t}"]
+            loss = loss + (m(xt.clone(), xt.clone())["flow"][0] * gw[t]).sum()
+        grads = torch.autograd.grad(loss, [q for _, q in named], allow_unused=True)
+        for t in range(T):
+            d_all[f"gw_{t}"] = gw[t]
+        for (nm, _), gr in zip(named, grads):
+            if gr is not None:
+                d_all["grad_" + nm] = gr
         for nm, q in m.state_dict().items():
             d_all["sd_" + nm] = q
         golden[f"ann_{cls.__name__.lower()}"] = d_all

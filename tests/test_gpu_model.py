@@ -236,9 +236,20 @@ def test_ann_firenet_forward_matches_reference_golden(name, recurrent):
     if recurrent:
         for i in (1, 4):
             torch.testing.assert_close(m.states[i].cpu(), g[f"state_{i}"], rtol=1e-4, atol=1e-6)
-    # the backward of the ANN cells is not built: asking for it must fail loudly, not return zeros
-    x = g["x_0"].to(DEV)
+    # BPTT through the ANN cells (ConvLayer_ / ConvGRU): gradients vs the reference's autograd, 1e-3 relative to each tensor's scale
+    m.train()
     m.reset_states()
-    out = m(x, x)
-    with pytest.raises(NotImplementedError):
-        out["flow"][0].sum().backward()
+    loss = 0.0
+    for t in range(T):
+        x = g[f"x_{t}"].to(DEV)
+        loss = loss + (m(x, x)["flow"][0] * g[f"gw_{t}"].to(DEV)).sum()
+    loss.backward()
+    checked = 0
+    for nm, q in m.named_parameters():
+        if "grad_" + nm in g:
+            ref = g["grad_" + nm]
+            scale = ref.abs().max().item() + 1e-12
+            err = (q.grad.cpu() - ref).abs().max().item()
+            assert err <= 1e-3 * scale, f"{nm}: {err:.3e} vs scale {scale:.3e}"
+            checked += 1
+    assert checked >= 10
