@@ -532,9 +532,18 @@ def pin_ann_unet(rmodel, golden, shape=(1, 32, 48)):
     for i in range(4):
         close(flows[i], o["flow"][i], 0, f"ann unet flow[{i}]")
     print("ann EVFlowNet pinned; |flow| max %.4f" % max(f.abs().max().item() for f in flows))
+    g = torch.Generator().manual_seed(41)
+    gw = [torch.rand((B, 2, H, W), generator=g) - 0.5 for _ in range(4)]
+    named = [(n_, q) for n_, q in m.named_parameters() if q.requires_grad]
+    loss = sum((f * w).sum() for f, w in zip(m(None, x.clone())["flow"], gw))
+    grads = torch.autograd.grad(loss, [q for _, q in named], allow_unused=True)
     if golden is not None:
         d = {"x": x}
         d.update({"flow_%d" % i: o["flow"][i] for i in range(4)})
+        d.update({"gw_%d" % i: gw[i] for i in range(4)})
+        for (nm, _), gr in zip(named, grads):
+            if gr is not None:
+                d["grad_" + nm] = gr
         for nm, q in sd.items():
             d["sd_" + nm] = q
         golden["annunet_evflownet"] = d

@@ -281,6 +281,17 @@ def test_ann_evflownet_forward_matches_reference_golden_and_oracle():
         assert out["flow"][i].shape == ref.shape
         err = (out["flow"][i].cpu() - ref).abs().max().item()
         assert err <= 1e-3 * ref.abs().max().item() + 1e-6, f"flow scale {i}: {err:.3e}"  # north-star tolerance 1e-3 rel; measured ~1e-6
+    # training: gradients of a linear functional of all four flow scales vs the reference's autograd
+    loss = sum((f * g["gw_%d" % i].to(DEV)).sum() for i, f in enumerate(m(None, g["x"].to(DEV))["flow"]))
+    loss.backward()
+    checked = 0
+    for nm, q in m.named_parameters():
+        if "grad_" + nm in g:
+            ref = g["grad_" + nm]
+            scale = ref.abs().max().item() + 1e-12
+            assert (q.grad.cpu() - ref).abs().max().item() <= 1e-3 * scale, nm
+            checked += 1
+    assert checked >= 20
     m.reset_states(), m.detach_states()
     m.init_cropping(40, 24)
     with torch.no_grad():
