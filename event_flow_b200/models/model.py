@@ -19,7 +19,7 @@ from .spiking_submodules import (
     ConvXLIFRecurrent,
 )
 from .submodules import ConvGRU, ConvLayer, ConvLayer_
-from .unet import MultiResUNet, SpikingMultiResUNetRecurrent
+from .unet import MultiResUNet, MultiResUNetRecurrent, SpikingMultiResUNetRecurrent
 
 
 class FireNet(BaseModel):
@@ -267,19 +267,16 @@ class RecEVFlowNet(BaseModel):
     """
     Recurrent EV-FlowNet (models/model.py:410-547): input encoding select, optional input normalisation and padding, the
     multi-resolution recurrent U-Net, nearest-neighbour upsampling of every flow estimate to the input resolution, crop.
-    The spiking subclasses (SpikingRecEVFlowNet :550, PLIF :561, ALIF :572, XLIF :583) run on the CUDA cells; the ANN
-    base (ConvGRU / ConvLSTM encoders of unet.py:314-416) is not built.
+    The spiking subclasses (SpikingRecEVFlowNet :550, PLIF :561, ALIF :572, XLIF :583) run on the fused spiking cells, the
+    ANN base class on the ConvLayer / ConvGRU kernels (ConvLSTM / ConvRecurrent encoders raise).
     """
 
-    unet_type = None
+    unet_type = MultiResUNetRecurrent
     recurrent_block_type = "convgru"
     spiking_feedforward_block_type = None
 
     def __init__(self, unet_kwargs):
         super().__init__()
-        if self.unet_type is None:
-            raise NotImplementedError("event_flow_b200: the ANN RecEVFlowNet (ConvGRU / ConvLSTM U-Net) is not on the CUDA path yet; "
-                                      "the spiking variants (SpikingRecEVFlowNet, PLIF/ALIF/XLIFRecEVFlowNet) are")
         norm = None
         use_upsample_conv = True
         if "norm" in unet_kwargs.keys():

@@ -54,6 +54,26 @@ class ConvLayer_(ConvLayer):
         return out, prev_state
 
 
+class RecurrentConvLayer(nn.Module):
+    """Convolution followed by a recurrent block (models/submodules.py:188-235); ConvGRU blocks only on the CUDA path."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=3, stride=1, recurrent_block_type="convlstm", activation_ff="relu",
+                 activation_rec=None, norm=None, BN_momentum=0.1):
+        super().__init__()
+        assert recurrent_block_type in ["convlstm", "convgru", "convrnn"]
+        if recurrent_block_type != "convgru":
+            raise NotImplementedError(f"event_flow_b200 RecurrentConvLayer: recurrent_block_type={recurrent_block_type!r} is not on the CUDA path "
+                                      "(ConvGRU is)")
+        self.recurrent_block_type = recurrent_block_type
+        self.conv = ConvLayer(in_channels, out_channels, kernel_size, stride, activation_ff, norm, BN_momentum=BN_momentum)
+        self.recurrent_block = ConvGRU(input_size=out_channels, hidden_size=out_channels, kernel_size=3, activation=activation_rec)
+
+    def forward(self, x, prev_state):
+        x = self.conv(x)
+        x, state = self.recurrent_block(x, prev_state)
+        return x, state
+
+
 class ResidualBlock(nn.Module):
     """He et al. residual block (models/submodules.py:238-312): conv+act, conv + residual + act.  Two launches."""
 

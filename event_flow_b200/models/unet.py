@@ -10,7 +10,7 @@ import torch.nn as nn
 
 from .model_util import skip_concat, skip_sum  # noqa: F401  (resolved by name like the reference: "skip_" + skip_type)
 from .spiking_submodules import SpikingRecurrentConvLayer, SpikingResidualBlock, SpikingTransposedConvLayer, SpikingUpsampleConvLayer
-from .submodules import ConvLayer, ResidualBlock, UpsampleConvLayer
+from .submodules import ConvLayer, RecurrentConvLayer, ResidualBlock, UpsampleConvLayer
 
 
 class SpikingMultiResUNetRecurrent(nn.Module):
@@ -149,11 +149,9 @@ class MultiResUNet(nn.Module):
         self.encoder_input_sizes = [int(self.base_num_channels * pow(self.channel_multiplier, i)) for i in range(self.num_encoders)]
         self.encoder_output_sizes = [int(self.base_num_channels * pow(self.channel_multiplier, i + 1)) for i in range(self.num_encoders)]
         self.max_num_channels = self.encoder_output_sizes[-1]
-        # construction order = the reference's (unet.py:236-239)
-        self.encoders = nn.ModuleList()
-        for i, (cin, cout) in enumerate(zip(self.encoder_input_sizes, self.encoder_output_sizes)):
-            self.encoders.append(ConvLayer(self.num_bins if i == 0 else cin, cout, kernel_size=self.kernel_size, stride=2, activation=self.ff_act,
-                                           norm=self.norm))
+        self.recurrent_block_type = kw.get("recurrent_block_type")
+        # construction order = the reference's (unet.py:236-239, 329-332)
+        self.encoders = self.build_encoders()
         self.resblocks = nn.ModuleList([ResidualBlock(self.max_num_channels, self.max_num_channels, activation=self.ff_act, norm=self.norm)
                                         for _ in range(self.num_residual_blocks)])
         self.decoders = nn.ModuleList()
@@ -163,11 +161,22 @@ class MultiResUNet(nn.Module):
         self.preds = nn.ModuleList([ConvLayer(cout, self.num_output_channels, 1, activation=self.final_activation, norm=self.norm)
                                     for cout in reversed(self.encoder_input_sizes)])
 
-    def forward(self, x):
+    def build_encoders(self):
+        encoders = nn.ModuleList()
+        for i, (cin, cout) in enumerate(zip(self.encoder_input_sizes, self.encoder_output_sizes)):
+            encoders.append(ConvLayer(self.num_bins if i == 0 else cin, cout, kernel_size=self.kernel_size, stride=2, activation=self.ff_act,
+                                      norm=self.norm))
+        return encoders
+
+    def encode(self, x):
         blocks = []
         for encoder in self.encoders:
             x = encoder(x)
             blocks.append(x)
+        return x, blocks
+
+    def forward(self, x):
+        x, blocks = self.encode(x)
         for resblock in self.resblocks:
             x, _ = resblock(x)
         predictions = []
@@ -178,3 +187,27 @@ class MultiResUNet(nn.Module):
             x = decoder(x)
             predictions.append(pred(x))
         return predictions
+
+
+class MultiResUNetRecurrent(MultiResUNet):
+    """Recurrent ANN U-Net (models/unet.py:314-416): every stride-2 encoder conv is followed by a ConvGRU; one state per encoder."""
+
+    def __init__(self, unet_kwargs):
+        super().__init__(unet_kwargs)
+        self.num_states = self.num_encoders
+        self.states = [None] * self.num_states
+
+    def build_encoders(self):
+        encoders = nn.ModuleList()
+        for i, (cin, cout) in enumerate(zip(self.encoder_input_sizes, self.encoder_output_sizes)):
+            encoders.append(RecurrentConvLayer(self.num_bins if i == 0 else cin, cout, kernel_size=self.kernel_size, stride=2,
+                                               recurrent_block_type=self.recurrent_block_type, activation_ff=self.ff_act,
+                                               activation_rec=self.rec_act, norm=self.norm))
+        return encoders
+
+    def encode(self, x):
+        blocks = []
+        for i, encoder in enumerate(self.encoders):
+            x, self.states[i] = encoder(x, self.states[i])
+            blocks.append(x)
+        return x, blocks

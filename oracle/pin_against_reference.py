@@ -549,6 +549,53 @@ def pin_ann_unet(rmodel, golden, shape=(1, 32, 48)):
         golden["annunet_evflownet"] = d
 
 
+def pin_ann_rec_unet(rmodel, golden, shape=(1, 32, 48, 3)):
+    """RecEVFlowNet (ConvGRU encoders), base_num_channels 4: T-step rollout, final flows, states and BPTT gradients."""
+    B, H, W, T = shape
+    torch.manual_seed(23)
+    cfg = dict(name="x", encoding="cnt", round_encoding=False, norm_input=False, num_bins=2, base_num_channels=4, kernel_size=3,
+               activations=["relu", None], mask_output=True, spiking_neuron=None)
+    m = rmodel.RecEVFlowNet(cfg)
+    sd = {k: v.detach() for k, v in m.state_dict().items()}
+    xs = []
+    for t in range(T):
+        ts, ys, xx, ps = oenc.synthetic_events(B, 1500, H, W, 3100 + t)
+        xs.append(oenc.encode_window(ts, ys, xx, ps, H, W, 2)["event_cnt"])
+    m.reset_states()
+    states = [None] * 4
+    with torch.no_grad():
+        for t in range(T):
+            o = m(None, xs[t].clone())
+            preds, flows = ounet.ann_unet_forward(sd, xs[t], prefix="multires_unetrec.", states=states)
+            for i in range(4):
+                close(flows[i], o["flow"][i], 0, f"ann rec unet flow[{t}][{i}]")
+    states_r = m.states
+    for i in range(4):
+        close(states[i], states_r[i], 0, f"ann rec unet state[{i}]")
+    g = torch.Generator().manual_seed(43)
+    gw = [[torch.rand((B, 2, H, W), generator=g) - 0.5 for _ in range(4)] for _ in range(T)]
+    named = [(n_, q) for n_, q in m.named_parameters() if q.requires_grad]
+    m.reset_states()
+    loss = 0.0
+    for t in range(T):
+        loss = loss + sum((f * w).sum() for f, w in zip(m(None, xs[t].clone())["flow"], gw[t]))
+    grads = torch.autograd.grad(loss, [q for _, q in named], allow_unused=True)
+    print("ann RecEVFlowNet pinned; |flow| max %.4f" % max(f.abs().max().item() for f in flows))
+    if golden is not None:
+        d = {"x_%d" % t: xs[t] for t in range(T)}
+        d.update({"flow_%d" % i: o["flow"][i] for i in range(4)})
+        d.update({"state_%d" % i: states_r[i] for i in range(4)})
+        for t in range(T):
+            for i in range(4):
+                d["gw_%d_%d" % (t, i)] = gw[t][i]
+        for (nm, _), gr in zip(named, grads):
+            if gr is not None:
+                d["grad_" + nm] = gr
+        for nm, q in sd.items():
+            d["sd_" + nm] = q
+        golden["annunet_recevflownet"] = d
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--check", action="store_true")
@@ -566,6 +613,7 @@ def main():
     pin_ann_firenet(rmodel, golden)
     pin_unet(rmodel, golden)
     pin_ann_unet(rmodel, golden)
+    pin_ann_rec_unet(rmodel, golden)
     if args.check:
         print("oracle == reference on all cases (check only)")
         return

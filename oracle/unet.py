@@ -89,12 +89,15 @@ def unet_step(neuron, P, states, x, trace=None, **cell_kwargs):
     return preds, flows, new_states
 
 
-def ann_unet_forward(sd, x, act="relu", num_encoders=4, num_residual_blocks=2, prefix="multires_unet.", trace=None):
+def ann_unet_forward(sd, x, act="relu", num_encoders=4, num_residual_blocks=2, prefix="multires_unet.", trace=None, states=None):
     """
     EV-FlowNet's ANN U-Net (models/unet.py:224-311 with the blocks of models/submodules.py:12-61, 140-185, 238-312):
     stride-2 conv+bias+ReLU encoders, residual blocks, bilinear-upsampling decoders with concat skips, 1x1 tanh predictions.
     Returns (multires predictions, flows upsampled to the input resolution as in models/model.py:370-383).
     trace: optional list receiving (name, input, output) of every 3x3 conv layer.
+    states: None for EV-FlowNet; for the recurrent variant (RecEVFlowNet, models/unet.py:314-416 with RecurrentConvLayer,
+    submodules.py:188-235) a list of num_encoders ConvGRU hidden states (None = zeros), updated IN PLACE; the state_dict prefix
+    is then "multires_unetrec." and every encoder is conv (stride 2) + ConvGRU.
     """
     f_act = {"relu": torch.relu, "tanh": torch.tanh, "sigmoid": torch.sigmoid, None: (lambda t: t)}[act]
 
@@ -109,7 +112,15 @@ def ann_unet_forward(sd, x, act="relu", num_encoders=4, num_residual_blocks=2, p
 
     blocks = []
     for i in range(num_encoders):
-        x = conv(f"encoders.{i}.conv2d", x, stride=2)
+        if states is None:
+            x = conv(f"encoders.{i}.conv2d", x, stride=2)
+        else:
+            x = conv(f"encoders.{i}.conv.conv2d", x, stride=2)
+            g = prefix + f"encoders.{i}.recurrent_block."
+            gp = {"update_w": sd[g + "update_gate.weight"], "update_b": sd[g + "update_gate.bias"], "reset_w": sd[g + "reset_gate.weight"],
+                  "reset_b": sd[g + "reset_gate.bias"], "out_w": sd[g + "out_gate.weight"], "out_b": sd[g + "out_gate.bias"]}
+            x = osp.conv_gru_step(x, states[i], gp)
+            states[i] = x
         blocks.append(x)
     for i in range(num_residual_blocks):
         out1 = conv(f"resblocks.{i}.conv1", x)

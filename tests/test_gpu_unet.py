@@ -297,3 +297,37 @@ def test_ann_evflownet_forward_matches_reference_golden_and_oracle():
     with torch.no_grad():
         o2 = m(None, g["x"][:, :, :24, :40].contiguous().to(DEV))
     assert [tuple(f.shape) for f in o2["flow"]] == [(1, 2, 24, 40)] * 4
+
+
+def test_ann_recevflownet_rollout_and_gradients_match_reference_golden():
+    """RecEVFlowNet (stride-2 conv + ConvGRU encoders): 3-step rollout, final flows / states and BPTT gradients vs the reference."""
+    import event_flow_b200.models.model as M
+
+    g = load_golden("annunet_recevflownet")
+    cfg = dict(name="x", encoding="cnt", round_encoding=False, norm_input=False, num_bins=2, base_num_channels=4, kernel_size=3,
+               activations=["relu", None], mask_output=True, spiking_neuron=None)
+    m = M.RecEVFlowNet(cfg)
+    m.load_state_dict({k[3:]: v for k, v in g.items() if k.startswith("sd_")})
+    m = m.to(DEV)
+    T = len([k for k in g if k.startswith("x_")])
+    with torch.no_grad():
+        for t in range(T):
+            out = m(None, g["x_%d" % t].to(DEV))
+    for i in range(4):
+        ref = g["flow_%d" % i]
+        assert (out["flow"][i].cpu() - ref).abs().max().item() <= 1e-3 * ref.abs().max().item() + 1e-6
+        ref = g["state_%d" % i]
+        assert (m.states[i].cpu() - ref).abs().max().item() <= 1e-3 * ref.abs().max().item() + 1e-6
+    m.reset_states()
+    loss = 0.0
+    for t in range(T):
+        loss = loss + sum((f * g["gw_%d_%d" % (t, i)].to(DEV)).sum() for i, f in enumerate(m(None, g["x_%d" % t].to(DEV))["flow"]))
+    loss.backward()
+    m.detach_states()
+    checked = 0
+    for nm, q in m.named_parameters():
+        if "grad_" + nm in g:
+            ref = g["grad_" + nm]
+            assert (q.grad.cpu() - ref).abs().max().item() <= 1e-3 * (ref.abs().max().item() + 1e-12), nm
+            checked += 1
+    assert checked >= 40

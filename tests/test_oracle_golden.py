@@ -211,3 +211,17 @@ def test_ann_evflownet_matches_reference():
         _, flows = ounet.ann_unet_forward(sd, g["x"])
     for i in range(4):
         assert torch.equal(flows[i], g["flow_%d" % i])
+
+
+def test_ann_recevflownet_matches_reference():
+    from oracle import unet as ounet
+
+    g = load_golden("annunet_recevflownet")
+    sd = {k[3:]: v for k, v in g.items() if k.startswith("sd_")}
+    T = len([k for k in g if k.startswith("x_")])
+    states = [None] * 4
+    with torch.no_grad():
+        for t in range(T):
+            _, flows = ounet.ann_unet_forward(sd, g["x_%d" % t], prefix="multires_unetrec.", states=states)
+    for i in range(4):
+        assert torch.equal(flows[i], g["flow_%d" % i]) and torch.equal(states[i], g["state_%d" % i])
