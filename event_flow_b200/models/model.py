@@ -408,3 +408,22 @@ class XLIFRecEVFlowNet(RecEVFlowNet):
     unet_type = SpikingMultiResUNetRecurrent
     recurrent_block_type = "xlif"
     spiking_feedforward_block_type = "xlif"
+
+
+def _not_built(name, what):
+    """The rest of the reference's import list (train_flow.py:10-32): importable, so the drivers load; constructing raises."""
+
+    class _NotBuilt(BaseModel):
+        def __init__(self, *args, **kwargs):
+            raise NotImplementedError(f"event_flow_b200: {name} ({what}) is not on the CUDA path; see DESIGN.md section 7")
+
+    _NotBuilt.__name__ = _NotBuilt.__qualname__ = name
+    return _NotBuilt
+
+
+RNNFireNet = _not_built("RNNFireNet", "ConvRecurrent cells, models/model.py:594-603")
+LeakyFireNet = _not_built("LeakyFireNet", "ConvLeaky cells, models/model.py:606-618")
+LeakyFireFlowNet = _not_built("LeakyFireFlowNet", "ConvLeaky cells, models/model.py:621-633")
+E2VID = _not_built("E2VID", "ConvLSTM U-Net, models/model.py:29-145")
+LeakyRecEVFlowNet = _not_built("LeakyRecEVFlowNet", "leaky U-Net, models/model.py:696-704")
+RNNRecEVFlowNet = _not_built("RNNRecEVFlowNet", "ConvRecurrent U-Net encoders, models/model.py:594-603")

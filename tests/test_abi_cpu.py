@@ -121,3 +121,38 @@ def test_dropin_names_and_state_dict_keys(lib):
         sys.modules.pop(s, None)
     for s in [k for k in sys.modules if k.split(".")[0] in ("models", "loss", "utils", "dataloader")]:
         sys.modules.pop(s, None)
+
+
+def test_dropin_resolves_the_reference_import_list_and_falls_back_to_reference_files(tmp_path):
+    """
+    train_flow.py:8-34 imports 19 model names and modules this package does not replace (utils.utils, dataloader.h5, ...):
+    after install_dropin(reference_root=...) the former resolve here, the latter to the reference's own files.
+    """
+    import subprocess
+    import sys
+
+    ref = tmp_path / "ref"
+    (ref / "utils").mkdir(parents=True)
+    (ref / "dataloader").mkdir()
+    (ref / "utils" / "utils.py").write_text("def load_model(*a):\n    return 'reference utils.utils'\n")
+    (ref / "dataloader" / "h5.py").write_text("class H5Loader:\n    pass\n")
+    (ref / "train_flow.py").write_text("")
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "import event_flow_b200\n"
+        "event_flow_b200.install_dropin(reference_root=%r)\n"
+        "from dataloader.h5 import H5Loader\n"
+        "from loss.flow import EventWarping\n"
+        "from models.model import (FireNet, RNNFireNet, LeakyFireNet, FireFlowNet, LeakyFireFlowNet, E2VID, EVFlowNet, RecEVFlowNet,\n"
+        "    LeakyRecEVFlowNet, RNNRecEVFlowNet, LIFFireNet, PLIFFireNet, ALIFFireNet, XLIFFireNet, LIFFireFlowNet, SpikingRecEVFlowNet,\n"
+        "    PLIFRecEVFlowNet, ALIFRecEVFlowNet, XLIFRecEVFlowNet)\n"
+        "from utils.utils import load_model\n"
+        "from utils.iwe import compute_pol_iwe\n"
+        "import models.unet, models.spiking_submodules\n"
+        "assert load_model() == 'reference utils.utils' and EventWarping.__module__.startswith('event_flow_b200')\n"
+        "assert models.unet.SpikingMultiResUNetRecurrent.__module__ == 'event_flow_b200.models.unet'\n"
+        "try:\n    E2VID({})\n    raise SystemExit('E2VID must raise')\nexcept NotImplementedError:\n    pass\n"
+        "print('ok')\n"
+    ) % (ROOT, str(ref))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]
