@@ -394,7 +394,7 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
 // out block index conv*9 + tap; inside a block row n' = split*32 + n holds K = 32 input channels (64 B); 8-row atoms of
 // 512 B; the 16-byte chunk k/8 of row r = n'%8 is stored at chunk (k/8) ^ ((r >> 1) & 3)  (64-byte swizzle).
 // One block: the two-term image needs the largest |w| of the layer (both convolutions share the accumulator, hence the scale).
-__global__ void __launch_bounds__(1024) split_weights_kernel(const float* __restrict__ w_ff, const float* __restrict__ w_rec, uint16_t* __restrict__ out,
+__global__ void split_weights_kernel(const float* __restrict__ w_ff, const float* __restrict__ w_rec, uint16_t* __restrict__ out,
                                                              int nconv) {
   __shared__ float s_max[32];
   __shared__ float s_scale;
@@ -422,7 +422,8 @@ __global__ void __launch_bounds__(1024) split_weights_kernel(const float* __rest
     __syncthreads();
     scale = s_scale;
   }
-  for (int i = threadIdx.x; i < n_el; i += blockDim.x) {  // over nconv * 32 (n) * 32 (ci) * 9 (tap)
+  // over nconv * 32 (n) * 32 (ci) * 9 (tap); the three-term image needs no layer-wide scale and is built by many blocks
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_el; i += gridDim.x * blockDim.x) {
     const int tap = i % 9, ci = (i / 9) % 32, n = (i / (9 * 32)) % 32, cv = i / (9 * 32 * 32);
     const float w = (cv == 0 ? w_ff : w_rec)[(n * 32 + ci) * 9 + tap];
     uint16_t parts[3];
@@ -540,6 +541,7 @@ extern "C" int ef_split_weights(const float* w_ff, const float* w_rec, int32_t C
   EF_REQUIRE(w_ff && out, EF_ENULL, "ef_split_weights: NULL tensor");
   EF_REQUIRE(Cin == 32 && C == 32, EF_EUNSUPPORTED, "ef_split_weights: the tensor-core path covers 32 -> 32 channels (got %d -> %d)", Cin, C);
   const int nconv = w_rec ? 2 : 1;
-  split_weights_kernel<<<1, 1024, 0, as_stream(stream)>>>(w_ff, w_rec, out, nconv);
+  if (W_NSPLIT == 2) split_weights_kernel<<<1, 1024, 0, as_stream(stream)>>>(w_ff, w_rec, out, nconv);  // one block: layer-wide maximum
+  else split_weights_kernel<<<cdiv(nconv * 32 * 32 * 9, 256), 256, 0, as_stream(stream)>>>(w_ff, w_rec, out, nconv);
   return check_launch("split_weights_kernel");
 }
