@@ -18,8 +18,8 @@ from .spiking_submodules import (
     ConvXLIF,
     ConvXLIFRecurrent,
 )
-from .submodules import ConvGRU, ConvLayer, ConvLayer_
-from .unet import MultiResUNet, MultiResUNetRecurrent, SpikingMultiResUNetRecurrent
+from .submodules import ConvGRU, ConvLayer, ConvLayer_, ConvLeaky, ConvLeakyRecurrent, ConvRecurrent
+from .unet import LeakyMultiResUNetRecurrent, MultiResUNet, MultiResUNetRecurrent, SpikingMultiResUNetRecurrent, UNetRecurrent
 
 
 class FireNet(BaseModel):
@@ -410,20 +410,121 @@ class XLIFRecEVFlowNet(RecEVFlowNet):
     spiking_feedforward_block_type = "xlif"
 
 
-def _not_built(name, what):
-    """The rest of the reference's import list (train_flow.py:10-32): importable, so the drivers load; constructing raises."""
+class RNNRecEVFlowNet(RecEVFlowNet):
+    """models/model.py:594-601: ConvRecurrent instead of ConvGRU after every encoder conv."""
 
-    class _NotBuilt(BaseModel):
-        def __init__(self, *args, **kwargs):
-            raise NotImplementedError(f"event_flow_b200: {name} ({what}) is not on the CUDA path; see DESIGN.md section 7")
-
-    _NotBuilt.__name__ = _NotBuilt.__qualname__ = name
-    return _NotBuilt
+    unet_type = MultiResUNetRecurrent
+    recurrent_block_type = "convrnn"
 
 
-RNNFireNet = _not_built("RNNFireNet", "ConvRecurrent cells, models/model.py:594-603")
-LeakyFireNet = _not_built("LeakyFireNet", "ConvLeaky cells, models/model.py:606-618")
-LeakyFireFlowNet = _not_built("LeakyFireFlowNet", "ConvLeaky cells, models/model.py:621-633")
-E2VID = _not_built("E2VID", "ConvLSTM U-Net, models/model.py:29-145")
-LeakyRecEVFlowNet = _not_built("LeakyRecEVFlowNet", "leaky U-Net, models/model.py:696-704")
-RNNRecEVFlowNet = _not_built("RNNRecEVFlowNet", "ConvRecurrent U-Net encoders, models/model.py:594-603")
+class LeakyRecEVFlowNet(RecEVFlowNet):
+    """models/model.py:604-611: leaky (stateful ANN) cells throughout."""
+
+    unet_type = LeakyMultiResUNetRecurrent
+    recurrent_block_type = "convleaky"
+
+
+class RNNFireNet(FireNet):
+    """models/model.py:614-622."""
+
+    head_neuron = ConvLayer_
+    ff_neuron = ConvLayer_
+    rec_neuron = ConvRecurrent
+    residual = False
+
+
+class LeakyFireNet(FireNet):
+    """models/model.py:625-633."""
+
+    head_neuron = ConvLeaky
+    ff_neuron = ConvLeaky
+    rec_neuron = ConvLeakyRecurrent
+    residual = False
+
+
+class LeakyFireFlowNet(FireNet):
+    """models/model.py:696-704."""
+
+    head_neuron = ConvLeaky
+    ff_neuron = ConvLeaky
+    rec_neuron = ConvLeaky
+    residual = False
+
+
+class E2VID(BaseModel):
+    """E2VID adapted for flow (models/model.py:29-145): recurrent U-Net with ConvLSTM encoders and sum skips, one flow map."""
+
+    def __init__(self, unet_kwargs):
+        super().__init__()
+        norm = None
+        use_upsample_conv = True
+        if "norm" in unet_kwargs.keys():
+            norm = unet_kwargs["norm"]
+        if "use_upsample_conv" in unet_kwargs.keys():
+            use_upsample_conv = unet_kwargs["use_upsample_conv"]
+        E2VID_kwargs = {
+            "base_num_channels": unet_kwargs["base_num_channels"],
+            "num_encoders": 3,
+            "num_residual_blocks": 2,
+            "num_output_channels": 2,
+            "skip_type": "sum",
+            "norm": norm,
+            "use_upsample_conv": use_upsample_conv,
+            "kernel_size": unet_kwargs["kernel_size"],
+            "channel_multiplier": 2,
+            "recurrent_block_type": "convlstm",
+            "final_activation": "tanh",
+        }
+        self.crop = None
+        self.mask = unet_kwargs["mask_output"]
+        self.norm_input = False if "norm_input" not in unet_kwargs.keys() else unet_kwargs["norm_input"]
+        self.encoding = unet_kwargs["encoding"]
+        self.num_bins = unet_kwargs["num_bins"]
+        self.num_encoders = E2VID_kwargs["num_encoders"]
+        unet_kwargs.update(E2VID_kwargs)
+        for k in ("name", "encoding", "round_encoding", "norm_input", "mask_output", "spiking_neuron"):
+            unet_kwargs.pop(k, None)
+        self.unetrecurrent = UNetRecurrent(unet_kwargs)
+
+    @property
+    def states(self):
+        return copy_states(self.unetrecurrent.states)
+
+    @states.setter
+    def states(self, states):
+        self.unetrecurrent.states = states
+
+    def detach_states(self):
+        detached_states = []
+        for state in self.unetrecurrent.states:
+            if type(state) is tuple:
+                detached_states.append(tuple(hidden.detach() for hidden in state))
+            else:
+                detached_states.append(state.detach())
+        self.unetrecurrent.states = detached_states
+
+    def reset_states(self):
+        self.unetrecurrent.states = [None] * self.unetrecurrent.num_states
+
+    def init_cropping(self, width, height, safety_margin=0):
+        self.crop = CropParameters(width, height, self.num_encoders, safety_margin)
+
+    def forward(self, event_voxel, event_cnt, log=False):
+        if self.encoding == "voxel":
+            x = event_voxel
+        elif self.encoding == "cnt" and self.num_bins == 2:
+            x = event_cnt
+        else:
+            print("Model error: Incorrect input encoding.")
+            raise AttributeError
+        if self.norm_input:
+            mean, stddev = x[x != 0].mean(), x[x != 0].std()
+            x[x != 0] = (x[x != 0] - mean) / stddev
+        if self.crop is not None:
+            x = self.crop.pad(x)
+        flow = self.unetrecurrent.forward(x)
+        if log:
+            raise NotImplementedError("Activity logging not implemented")
+        if self.crop is not None:
+            flow = flow[:, :, self.crop.iy0:self.crop.iy1, self.crop.ix0:self.crop.ix1].contiguous()
+        return {"flow": [flow], "activity": None}

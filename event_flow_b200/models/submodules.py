@@ -55,22 +55,22 @@ class ConvLayer_(ConvLayer):
 
 
 class RecurrentConvLayer(nn.Module):
-    """Convolution followed by a recurrent block (models/submodules.py:188-235); ConvGRU blocks only on the CUDA path."""
+    """Convolution followed by a recurrent block (models/submodules.py:188-235): ConvLSTM, ConvGRU or ConvRecurrent."""
 
     def __init__(self, in_channels, out_channels, kernel_size=3, stride=1, recurrent_block_type="convlstm", activation_ff="relu",
                  activation_rec=None, norm=None, BN_momentum=0.1):
         super().__init__()
         assert recurrent_block_type in ["convlstm", "convgru", "convrnn"]
-        if recurrent_block_type != "convgru":
-            raise NotImplementedError(f"event_flow_b200 RecurrentConvLayer: recurrent_block_type={recurrent_block_type!r} is not on the CUDA path "
-                                      "(ConvGRU is)")
         self.recurrent_block_type = recurrent_block_type
+        block = {"convlstm": ConvLSTM, "convgru": ConvGRU, "convrnn": ConvRecurrent}[recurrent_block_type]
         self.conv = ConvLayer(in_channels, out_channels, kernel_size, stride, activation_ff, norm, BN_momentum=BN_momentum)
-        self.recurrent_block = ConvGRU(input_size=out_channels, hidden_size=out_channels, kernel_size=3, activation=activation_rec)
+        self.recurrent_block = block(input_size=out_channels, hidden_size=out_channels, kernel_size=3, activation=activation_rec)
 
     def forward(self, x, prev_state):
         x = self.conv(x)
         x, state = self.recurrent_block(x, prev_state)
+        if isinstance(self.recurrent_block, ConvLSTM):
+            state = (x, state)
         return x, state
 
 
@@ -143,3 +143,181 @@ class ConvGRU(nn.Module):
         new_state = ops.conv_ann(input_, self.out_gate.weight, self.out_gate.bias, "tanh", x2=prev_state, x2_scale=ur[:, C:],
                                  blend_h=prev_state, blend_u=ur[:, :C])
         return new_state, new_state
+
+
+# ---- the rest of the cell zoo: convolutions on ef_conv_ann_fwd / ef_conv3x3_bwd, the leak / gate arithmetic as
+# ---- elementwise tensor ops around them (first version: these models carry little benchmark weight) --------------------------
+_ACTS = {None: None, "relu": torch.relu, "tanh": torch.tanh, "sigmoid": torch.sigmoid}
+
+
+def _zeros_like_out(x, channels, stride=1):
+    h, w = (x.shape[2] - 1) // stride + 1, (x.shape[3] - 1) // stride + 1
+    return torch.zeros((x.shape[0], channels, h, w), dtype=x.dtype, device=x.device)
+
+
+class ConvLSTM(nn.Module):
+    """Convolutional LSTM cell (models/submodules.py:314-374): one conv launch for the four gates of cat([x, h])."""
+
+    def __init__(self, input_size, hidden_size, kernel_size, activation=None):
+        super().__init__()
+        if kernel_size != 3:
+            raise NotImplementedError("event_flow_b200 ConvLSTM: kernel_size 3 only")
+        self.input_size = input_size
+        self.hidden_size = hidden_size
+        assert activation is None, "ConvLSTM activation cannot be set (just for compatibility)"
+        self.zero_tensors = {}
+        self.Gates = nn.Conv2d(input_size + hidden_size, 4 * hidden_size, kernel_size, padding=kernel_size // 2)
+
+    def forward(self, input_, prev_state=None):
+        if prev_state is None:
+            z = _zeros_like_out(input_, self.hidden_size)
+            prev_state = (z, z.clone())
+        prev_hidden, prev_cell = prev_state
+        gates = ops.conv_ann(input_, self.Gates.weight, self.Gates.bias, None, x2=prev_hidden)
+        in_gate, remember_gate, out_gate, cell_gate = gates.chunk(4, 1)
+        in_gate, remember_gate, out_gate = torch.sigmoid(in_gate), torch.sigmoid(remember_gate), torch.sigmoid(out_gate)
+        cell_gate = torch.tanh(cell_gate)
+        cell = (remember_gate * prev_cell) + (in_gate * cell_gate)
+        hidden = out_gate * torch.tanh(cell)
+        return hidden, cell
+
+
+class ConvRecurrent(nn.Module):
+    """Convolutional recurrent cell (models/submodules.py:421-451): tanh(ff(x) + rec(h)) as ONE conv over cat([x, h]), then out conv + ReLU."""
+
+    def __init__(self, input_size, hidden_size, kernel_size, activation=None):
+        super().__init__()
+        if kernel_size != 3:
+            raise NotImplementedError("event_flow_b200 ConvRecurrent: kernel_size 3 only")
+        padding = kernel_size // 2
+        self.input_size = input_size
+        self.hidden_size = hidden_size
+        self.ff = nn.Conv2d(input_size, hidden_size, kernel_size, padding=padding)
+        self.rec = nn.Conv2d(input_size, hidden_size, kernel_size, padding=padding)
+        self.out = nn.Conv2d(input_size, hidden_size, kernel_size, padding=padding)
+        assert activation is None, "ConvRecurrent activation cannot be set (just for compatibility)"
+
+    def forward(self, input_, prev_state):
+        if prev_state is None:
+            prev_state = _zeros_like_out(input_, self.hidden_size)
+        w = torch.cat([self.ff.weight, self.rec.weight], dim=1)
+        state = ops.conv_ann(input_, w, self.ff.bias + self.rec.bias, "tanh", x2=prev_state)
+        out = ops.conv_ann(state, self.out.weight, self.out.bias, "relu")
+        return out, state
+
+
+class ConvLeakyRecurrent(nn.Module):
+    """Leaky convolutional recurrent cell (models/submodules.py:454-499)."""
+
+    def __init__(self, input_size, hidden_size, kernel_size, activation=None, leak=(-4.0, 0.1), learn_leak=True, norm=None):
+        super().__init__()
+        if kernel_size != 3 or norm is not None:
+            raise NotImplementedError("event_flow_b200 ConvLeakyRecurrent: kernel_size 3, no norm")
+        padding = kernel_size // 2
+        self.input_size = input_size
+        self.hidden_size = hidden_size
+        self.ff = nn.Conv2d(input_size, hidden_size, kernel_size, padding=padding)
+        self.rec = nn.Conv2d(input_size, hidden_size, kernel_size, padding=padding)
+        self.out = nn.Conv2d(input_size, hidden_size, kernel_size, padding=padding)
+        if learn_leak:
+            self.leak = nn.Parameter(torch.randn(hidden_size, 1, 1) * leak[1] + leak[0])
+        else:
+            self.register_buffer("leak", torch.randn(hidden_size, 1, 1) * leak[1] + leak[0])
+        assert activation is None, "ConvLeakyRecurrent activation cannot be set (just for compatibility)"
+
+    def forward(self, input_, prev_state):
+        if prev_state is None:
+            prev_state = _zeros_like_out(input_, self.hidden_size)
+        w = torch.cat([self.ff.weight, self.rec.weight], dim=1)
+        pre = ops.conv_ann(input_, w, self.ff.bias + self.rec.bias, None, x2=prev_state)  # ff(x) + rec(h)
+        leak = torch.sigmoid(self.leak)
+        state = torch.tanh(prev_state * leak + (1 - leak) * pre)
+        out = ops.conv_ann(state, self.out.weight, self.out.bias, "relu")
+        return out, state
+
+
+class ConvLeaky(nn.Module):
+    """Leaky stateful convolutional cell (models/submodules.py:502-554)."""
+
+    def __init__(self, input_size, hidden_size, kernel_size, stride=1, activation="relu", leak=(-4.0, 0.1), learn_leak=True, norm=None):
+        super().__init__()
+        if kernel_size != 3 or stride not in (1, 2) or norm is not None or activation not in _ACTS:
+            raise NotImplementedError(f"event_flow_b200 ConvLeaky: kernel_size 3, stride 1|2, relu/tanh/sigmoid/None (got {kernel_size}, {stride}, {activation!r})")
+        padding = kernel_size // 2
+        self.input_size = input_size
+        self.hidden_size = hidden_size
+        self.stride = stride
+        self.ff = nn.Conv2d(input_size, hidden_size, kernel_size, stride=stride, padding=padding)
+        if learn_leak:
+            self.leak = nn.Parameter(torch.randn(hidden_size, 1, 1) * leak[1] + leak[0])
+        else:
+            self.register_buffer("leak", torch.randn(hidden_size, 1, 1) * leak[1] + leak[0])
+        self.activation = _ACTS[activation]
+
+    def forward(self, input_, prev_state, residual=0):
+        ff = ops.conv_ann(input_, self.ff.weight, self.ff.bias, None)
+        if self.stride == 2:
+            ff = ff[:, :, ::2, ::2].contiguous()  # stride-2 conv = the stride-1 result at the even pixels
+        if prev_state is None:
+            prev_state = torch.zeros_like(ff)
+        leak = torch.sigmoid(self.leak)
+        state = prev_state * leak + (1 - leak) * (ff + residual)
+        out = self.activation(state) if self.activation is not None else state
+        return out, state
+
+
+class LeakyResidualBlock(nn.Module):
+    """models/submodules.py:557-592."""
+
+    def __init__(self, in_channels, out_channels, stride=1, feedforward_block_type="convleaky", activation="relu", **kwargs):
+        super().__init__()
+        assert feedforward_block_type in ["convleaky"]
+        self.conv1 = ConvLeaky(in_channels, out_channels, kernel_size=3, stride=stride, activation=activation, **kwargs)
+        self.conv2 = ConvLeaky(out_channels, out_channels, kernel_size=3, stride=1, activation=activation, **kwargs)
+
+    def forward(self, x, prev_state):
+        if prev_state is None:
+            prev_state = [None, None]
+        conv1, conv2 = prev_state
+        residual = x
+        x1, conv1 = self.conv1(x, conv1)
+        x2, conv2 = self.conv2(x1, conv2, residual=residual)
+        return x2, torch.stack([conv1, conv2])
+
+
+class LeakyUpsampleConvLayer(nn.Module):
+    """models/submodules.py:595-623."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, feedforward_block_type="convleaky", activation="relu", **kwargs):
+        super().__init__()
+        assert feedforward_block_type in ["convleaky"]
+        self.conv2d = ConvLeaky(in_channels, out_channels, kernel_size, stride=stride, activation=activation, **kwargs)
+
+    def forward(self, x, prev_state):
+        return self.conv2d(ops.upsample_bilinear2x(x), prev_state)
+
+
+class LeakyTransposedConvLayer(nn.Module):
+    """models/submodules.py:626-641 (raises in the reference as well)."""
+
+    def __init__(self, *args, **kwargs):
+        raise NotImplementedError
+
+
+class LeakyRecurrentConvLayer(nn.Module):
+    """models/submodules.py:644-686."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=3, stride=2, recurrent_block_type="convleaky", activation_ff="relu",
+                 activation_rec=None, **kwargs):
+        super().__init__()
+        assert recurrent_block_type in ["convleaky"]
+        self.conv = ConvLeaky(in_channels, out_channels, kernel_size, stride, activation_ff, **kwargs)
+        self.recurrent_block = ConvLeakyRecurrent(out_channels, out_channels, kernel_size, activation=activation_rec, **kwargs)
+
+    def forward(self, x, prev_state):
+        if prev_state is None:
+            prev_state = [None, None]
+        ff, rec = prev_state
+        x1, ff = self.conv(x, ff)
+        x2, rec = self.recurrent_block(x1, rec)
+        return x2, torch.stack([ff, rec])

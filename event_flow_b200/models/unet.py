@@ -10,7 +10,8 @@ import torch.nn as nn
 
 from .model_util import skip_concat, skip_sum  # noqa: F401  (resolved by name like the reference: "skip_" + skip_type)
 from .spiking_submodules import SpikingRecurrentConvLayer, SpikingResidualBlock, SpikingTransposedConvLayer, SpikingUpsampleConvLayer
-from .submodules import ConvLayer, RecurrentConvLayer, ResidualBlock, UpsampleConvLayer
+from .submodules import (ConvLayer, LeakyRecurrentConvLayer, LeakyResidualBlock, LeakyTransposedConvLayer, LeakyUpsampleConvLayer,
+                         RecurrentConvLayer, ResidualBlock, UpsampleConvLayer)
 
 
 class SpikingMultiResUNetRecurrent(nn.Module):
@@ -211,3 +212,72 @@ class MultiResUNetRecurrent(MultiResUNet):
             x, self.states[i] = encoder(x, self.states[i])
             blocks.append(x)
         return x, blocks
+
+
+class LeakyMultiResUNetRecurrent(SpikingMultiResUNetRecurrent):
+    """Leaky (stateful ANN) twin of the spiking U-Net (models/unet.py:468-480): same wiring, ConvLeaky / ConvLeakyRecurrent cells."""
+
+    res_type = LeakyResidualBlock
+    upsample_type = LeakyUpsampleConvLayer
+    transpose_type = LeakyTransposedConvLayer
+    rec_type = LeakyRecurrentConvLayer
+
+
+class UNetRecurrent(nn.Module):
+    """
+    E2VID's recurrent U-Net (models/unet.py:148-222): stride-1 head conv, stride-2 conv + ConvLSTM encoders, residual blocks,
+    upsampling decoders with SUM skips, one full-resolution 1x1 prediction + final activation.
+    """
+
+    def __init__(self, unet_kwargs):
+        super().__init__()
+        kw = dict(unet_kwargs)
+        self.final_activation = kw.pop("final_activation", "none")
+        if self.final_activation != "tanh":
+            raise NotImplementedError("event_flow_b200 UNetRecurrent: final_activation tanh (E2VID) only")
+        self.base_num_channels = kw["base_num_channels"]
+        self.num_encoders = kw["num_encoders"]
+        self.num_residual_blocks = kw["num_residual_blocks"]
+        self.num_output_channels = kw["num_output_channels"]
+        self.kernel_size = kw.get("kernel_size", 5)
+        self.skip_type = kw["skip_type"]
+        self.norm = kw["norm"]
+        self.num_bins = kw["num_bins"]
+        self.recurrent_block_type = kw.get("recurrent_block_type")
+        self.channel_multiplier = kw.get("channel_multiplier", 2)
+        self.ff_act, self.rec_act = kw.get("activations", ["relu", None])
+        if self.norm is not None or self.kernel_size != 3 or not kw["use_upsample_conv"]:
+            raise NotImplementedError("event_flow_b200 UNetRecurrent: kernel_size 3, no norm, upsample-conv decoders only")
+        self.skip_ftn = {"concat": skip_concat, "sum": skip_sum}[self.skip_type]
+        self.encoder_input_sizes = [int(self.base_num_channels * pow(self.channel_multiplier, i)) for i in range(self.num_encoders)]
+        self.encoder_output_sizes = [int(self.base_num_channels * pow(self.channel_multiplier, i + 1)) for i in range(self.num_encoders)]
+        self.max_num_channels = self.encoder_output_sizes[-1]
+        mult = 1 if self.skip_type == "sum" else 2
+        # construction order = the reference's (unet.py:161-172)
+        self.head = ConvLayer(self.num_bins, self.base_num_channels, kernel_size=self.kernel_size, stride=1)
+        self.encoders = nn.ModuleList([RecurrentConvLayer(cin, cout, kernel_size=self.kernel_size, stride=2,
+                                                          recurrent_block_type=self.recurrent_block_type, activation_ff=self.ff_act,
+                                                          activation_rec=self.rec_act, norm=self.norm)
+                                       for cin, cout in zip(self.encoder_input_sizes, self.encoder_output_sizes)])
+        self.resblocks = nn.ModuleList([ResidualBlock(self.max_num_channels, self.max_num_channels, activation=self.ff_act, norm=self.norm)
+                                        for _ in range(self.num_residual_blocks)])
+        self.decoders = nn.ModuleList([UpsampleConvLayer(mult * cin, cout, kernel_size=self.kernel_size, activation=self.ff_act, norm=self.norm)
+                                       for cin, cout in zip(reversed(self.encoder_output_sizes), reversed(self.encoder_input_sizes))])
+        # reference: ConvLayer(k=1, activation=None) followed by the final tanh -- one fused 1x1 + tanh launch here
+        self.pred = ConvLayer(mult * self.base_num_channels, self.num_output_channels, 1, activation="tanh", norm=self.norm)
+        self.num_states = self.num_encoders
+        self.states = [None] * self.num_states
+
+    def forward(self, x):
+        x = self.head(x)
+        head = x
+        blocks = []
+        for i, encoder in enumerate(self.encoders):
+            x, state = encoder(x, self.states[i])
+            blocks.append(x)
+            self.states[i] = state
+        for resblock in self.resblocks:
+            x, _ = resblock(x)
+        for i, decoder in enumerate(self.decoders):
+            x = decoder(self.skip_ftn(x, blocks[self.num_encoders - i - 1]))
+        return self.pred(self.skip_ftn(x, head))

@@ -30,6 +30,7 @@ from oracle import encodings as oenc  # noqa: E402
 from oracle import iwe as oiwe  # noqa: E402
 from oracle import spiking as osp  # noqa: E402
 from oracle import unet as ounet  # noqa: E402
+from oracle import annzoo as ozoo  # noqa: E402
 
 
 def import_reference():
@@ -596,6 +597,79 @@ def pin_ann_rec_unet(rmodel, golden, shape=(1, 32, 48, 3)):
         golden["annunet_recevflownet"] = d
 
 
+def pin_ann_zoo(rmodel, golden, shape=(1, 32, 48, 3)):
+    """The rest of the import list: RNN / Leaky FireNets and EV-FlowNets, E2VID: T-step rollouts + BPTT gradients."""
+    B, H, W, T = shape
+    cases = (("RNNFireNet", "rnn"), ("LeakyFireNet", "leaky"), ("LeakyFireFlowNet", "leakyflow"), ("RNNRecEVFlowNet", "rnnunet"),
+             ("LeakyRecEVFlowNet", "leakyunet"), ("E2VID", "e2vid"))
+    xs = []
+    for t in range(T):
+        ts, ys, xx, ps = oenc.synthetic_events(B, 1500, H, W, 3300 + t)
+        xs.append(oenc.encode_window(ts, ys, xx, ps, H, W, 2)["event_cnt"])
+    for name, kind in cases:
+        cls = getattr(rmodel, name)
+        if hasattr(cls, "kwargs"):
+            cls.kwargs = [{}] * 7
+        torch.manual_seed(29)
+        fire = "Fire" in name
+        cfg = dict(name="x", encoding="cnt", round_encoding=False, norm_input=False, num_bins=2, base_num_channels=8 if fire else 4, kernel_size=3,
+                   activations=["relu", None], mask_output=True, spiking_neuron={} if "Leaky" in name else None)
+        m = cls(cfg)
+        sd = {k: v.detach() for k, v in m.state_dict().items()}
+        n_states = {"rnn": 7, "leaky": 7, "leakyflow": 7, "rnnunet": 4, "leakyunet": 10, "e2vid": 3}[kind]
+
+        def oracle_rollout(sdict):
+            st = [None] * n_states
+            outs = []
+            for t in range(T):
+                if kind in ("rnn", "leaky", "leakyflow"):
+                    f, st = ozoo.firenet_zoo_step(kind, sdict, st, xs[t])
+                    outs.append([f])
+                elif kind == "rnnunet":
+                    outs.append(ozoo.rnn_unet_forward(sdict, xs[t], st))
+                elif kind == "leakyunet":
+                    outs.append(ozoo.leaky_unet_step(sdict, st, xs[t]))
+                else:
+                    outs.append([ozoo.e2vid_step(sdict, st, xs[t])])
+            return outs
+
+        m.reset_states()
+        with torch.no_grad():
+            ref_out = [m(None, xs[t].clone())["flow"] for t in range(T)]
+            ora_out = oracle_rollout(sd)
+        for t in range(T):
+            for i, (a, b) in enumerate(zip(ora_out[t], ref_out[t])):
+                close(a, b, 0, f"{name} flow[{t}][{i}]")
+        g = torch.Generator().manual_seed(47)
+        gw = [[torch.rand(f.shape, generator=g) - 0.5 for f in ref_out[t]] for t in range(T)]
+        named = [(n_, q) for n_, q in m.named_parameters() if q.requires_grad]
+        m.reset_states()
+        loss = 0.0
+        for t in range(T):
+            loss = loss + sum((f * w).sum() for f, w in zip(m(None, xs[t].clone())["flow"], gw[t]))
+        grads = torch.autograd.grad(loss, [q for _, q in named], allow_unused=True)
+        live = dict(m.named_parameters()) | dict(m.named_buffers())
+        loss_o = sum((f * w).sum() for t, fl in enumerate(oracle_rollout(live)) for f, w in zip(fl, gw[t]))
+        grads_o = torch.autograd.grad(loss_o, [q for _, q in named], allow_unused=True)
+        for (nm, _), go, gr in zip(named, grads_o, grads):
+            if gr is not None:
+                close(go, gr, 1e-5, f"{name} grad {nm}")
+        print(f"{name} pinned; |flow| max {max(f.abs().max().item() for f in ref_out[-1]):.4f}")
+        if golden is not None:
+            d = {"x_%d" % t: xs[t] for t in range(T)}
+            for i, f in enumerate(ref_out[-1]):
+                d["flow_%d" % i] = f
+            for t in range(T):
+                for i, w in enumerate(gw[t]):
+                    d["gw_%d_%d" % (t, i)] = w
+            for (nm, _), gr in zip(named, grads):
+                if gr is not None and gr.numel() <= 20000:
+                    d["grad_" + nm] = gr
+            for nm, q in sd.items():
+                d["sd_" + nm] = q
+            golden["annzoo_" + name.lower()] = d
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--check", action="store_true")
@@ -614,6 +688,7 @@ def main():
     pin_unet(rmodel, golden)
     pin_ann_unet(rmodel, golden)
     pin_ann_rec_unet(rmodel, golden)
+    pin_ann_zoo(rmodel, golden)
     if args.check:
         print("oracle == reference on all cases (check only)")
         return

@@ -331,3 +331,42 @@ def test_ann_recevflownet_rollout_and_gradients_match_reference_golden():
             assert (q.grad.cpu() - ref).abs().max().item() <= 1e-3 * (ref.abs().max().item() + 1e-12), nm
             checked += 1
     assert checked >= 40
+
+
+ZOO_CLASSES = {"rnnfirenet": "RNNFireNet", "leakyfirenet": "LeakyFireNet", "leakyfireflownet": "LeakyFireFlowNet",
+               "rnnrecevflownet": "RNNRecEVFlowNet", "leakyrecevflownet": "LeakyRecEVFlowNet", "e2vid": "E2VID"}
+
+
+@pytest.mark.parametrize("name", sorted(ZOO_CLASSES))
+def test_ann_zoo_rollout_and_gradients_match_reference_golden(name):
+    """SURVEY 8 f4 (ConvRecurrent / ConvLeaky* / ConvLSTM models): 3-step rollout and BPTT gradients vs the reference's numbers."""
+    import event_flow_b200.models.model as M
+
+    g = load_golden("annzoo_" + name)
+    cls = ZOO_CLASSES[name]
+    fire = "Fire" in cls
+    cfg = dict(name="x", encoding="cnt", round_encoding=False, norm_input=False, num_bins=2, base_num_channels=8 if fire else 4, kernel_size=3,
+               activations=["relu", None], mask_output=True, spiking_neuron={} if "Leaky" in cls else None)
+    m = getattr(M, cls)(cfg)
+    m.load_state_dict({k[3:]: v for k, v in g.items() if k.startswith("sd_")})
+    m = m.to(DEV)
+    T = len([k for k in g if k.startswith("x_")])
+    with torch.no_grad():
+        for t in range(T):
+            out = m(None, g["x_%d" % t].to(DEV))
+    for i, f in enumerate(out["flow"]):
+        ref = g["flow_%d" % i]
+        assert (f.cpu() - ref).abs().max().item() <= 1e-3 * ref.abs().max().item() + 1e-7, f"flow {i}"
+    m.reset_states()
+    loss = 0.0
+    for t in range(T):
+        loss = loss + sum((f * g["gw_%d_%d" % (t, i)].to(DEV)).sum() for i, f in enumerate(m(None, g["x_%d" % t].to(DEV))["flow"]))
+    loss.backward()
+    m.detach_states()
+    checked = 0
+    for nm, q in m.named_parameters():
+        if "grad_" + nm in g:
+            ref = g["grad_" + nm]
+            assert (q.grad.cpu() - ref).abs().max().item() <= 1e-3 * (ref.abs().max().item() + 1e-12), nm
+            checked += 1
+    assert checked >= 8

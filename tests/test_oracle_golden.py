@@ -225,3 +225,33 @@ def test_ann_recevflownet_matches_reference():
             _, flows = ounet.ann_unet_forward(sd, g["x_%d" % t], prefix="multires_unetrec.", states=states)
     for i in range(4):
         assert torch.equal(flows[i], g["flow_%d" % i]) and torch.equal(states[i], g["state_%d" % i])
+
+
+ZOO = {"rnnfirenet": "rnn", "leakyfirenet": "leaky", "leakyfireflownet": "leakyflow", "rnnrecevflownet": "rnnunet",
+       "leakyrecevflownet": "leakyunet", "e2vid": "e2vid"}
+
+
+@pytest.mark.parametrize("name", sorted(ZOO))
+def test_ann_zoo_rollout_matches_reference(name):
+    """the oracle restatement of the remaining ANN cell zoo reproduces the reference's rollouts bit for bit."""
+    from oracle import annzoo as ozoo
+
+    g = load_golden("annzoo_" + name)
+    kind = ZOO[name]
+    sd = {k[3:]: v for k, v in g.items() if k.startswith("sd_")}
+    T = len([k for k in g if k.startswith("x_")])
+    st = [None] * {"rnn": 7, "leaky": 7, "leakyflow": 7, "rnnunet": 4, "leakyunet": 10, "e2vid": 3}[kind]
+    with torch.no_grad():
+        for t in range(T):
+            x = g["x_%d" % t]
+            if kind in ("rnn", "leaky", "leakyflow"):
+                f, st = ozoo.firenet_zoo_step(kind, sd, st, x)
+                flows = [f]
+            elif kind == "rnnunet":
+                flows = ozoo.rnn_unet_forward(sd, x, st)
+            elif kind == "leakyunet":
+                flows = ozoo.leaky_unet_step(sd, st, x)
+            else:
+                flows = [ozoo.e2vid_step(sd, st, x)]
+    for i, f in enumerate(flows):
+        assert torch.equal(f, g["flow_%d" % i])
