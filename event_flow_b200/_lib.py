@@ -131,6 +131,7 @@ EXPORTS = {
     "ef_debug_tc_trace": (C.c_int, [C.c_void_p]),
     "ef_debug_tc_skip": (C.c_int, [C.c_int]),
     "ef_debug_tc_cpt": (C.c_int, [C.c_int]),
+    "ef_debug_pdl": (C.c_int, [C.c_int]),
     "ef_pack_cl": (C.c_int, [C.c_void_p, C.c_void_p, _i32, _i32, _i32, _i32, C.c_void_p]),
     "ef_unpack_cl": (C.c_int, [C.c_void_p, C.c_void_p, _i32, _i32, _i32, _i32, C.c_void_p]),
     "ef_upsample_bilinear2x": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, _i32, _i32, C.c_void_p]),

@@ -1,4 +1,6 @@
 // Library-level entry points: version, error string, device check.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace ef {
@@ -25,7 +27,21 @@ int check_launch(const char* what) {
   return fail((int)e, "%s: %s", what, cudaGetErrorString(e));
 }
 
+static int g_pdl = -1;  // -1 = not decided yet (EF_PDL environment variable, default on)
+bool pdl_enabled() {
+  if (g_pdl < 0) {
+    const char* e = getenv("EF_PDL");
+    g_pdl = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_pdl != 0;
+}
+
 }  // namespace ef
+
+extern "C" int ef_debug_pdl(int on) {  // programmatic dependent launch of the forward kernels of a model step (default on)
+  ef::g_pdl = on ? 1 : 0;
+  return EF_OK;
+}
 
 extern "C" int ef_version(void) { return EF_VERSION; }
 extern "C" uint64_t ef_launch_count(void) { return __atomic_load_n(&ef::g_launches, __ATOMIC_RELAXED); }

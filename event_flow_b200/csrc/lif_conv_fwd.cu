@@ -207,6 +207,8 @@ __global__ void __launch_bounds__(HD_THREADS, HD_CTAS_PER_SM) lif_head_fwd_kerne
   __shared__ ChanConst s_k[32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int Cin = p.Cin, H = p.H, W = p.W;
+  pdl_launch_dependents();  // first kernel of a model step: the next one (a fused cell) may start its prologue early
+  pdl_wait();               // everything this kernel reads may come from the previous kernel in the stream
   if (tid < 32) s_k[tid] = load_chan_const(p, tid);
   for (int i = tid; i < Cin * 9 * 32; i += HD_THREADS) {  // s_w[(ci*9 + tap)*32 + co] = w[co][ci][tap]
     const int co = i & 31, r = i >> 5;
@@ -313,9 +315,9 @@ static int launch_head(const ef_lif_conv_params& p, cudaStream_t st) {
   const int want = cdiv(n_strips, HD_THREADS / 32);
   const int grid = want < slots ? want : slots;
   if (p.hard_reset)
-    lif_head_fwd_kernel<true><<<grid, HD_THREADS, 0, st>>>(p, strips_x, strips_y, n_strips);
+    launch_pdl(lif_head_fwd_kernel<true>, dim3(grid), dim3(HD_THREADS), 0, st, p, strips_x, strips_y, n_strips);
   else
-    lif_head_fwd_kernel<false><<<grid, HD_THREADS, 0, st>>>(p, strips_x, strips_y, n_strips);
+    launch_pdl(lif_head_fwd_kernel<false>, dim3(grid), dim3(HD_THREADS), 0, st, p, strips_x, strips_y, n_strips);
   return check_launch("lif_head_fwd_kernel");
 }
 

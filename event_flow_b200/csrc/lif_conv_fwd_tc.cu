@@ -169,6 +169,10 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
   // The two producer threads initialise their own barriers and start the first loads right away, BEFORE the CTA-wide sync:
   // barrier setup by the other thread, the TMEM allocation and the descriptor fetches overlap the first DRAM round trip.
   const int n_op0 = n_my < NOP ? n_my : NOP, n_v0 = n_my < NV ? n_my : NV;
+  // Programmatic dependent launch: the next kernel of the step may be scheduled as soon as every CTA has passed this point (its
+  // CTAs take over SMs as ours exit and run their own prologue); everything of OURS that does not depend on the previous kernel
+  // (barrier setup, TMEM allocation, descriptor prefetch, the weight image) happens before pdl_wait().
+  pdl_launch_dependents();
   if (threadIdx.x == 0) {
     prefetch_tensormap(&map_x);
     if (z_from_halo) prefetch_tensormap(&map_zh);
@@ -182,13 +186,14 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
       mbar_init(bar_acce(a), EPI_WARPS);
     }
     fence_barrier_init();
+    mbar_expect_tx(bar_w, C::W_BYTES);  // the weight image is not written by the previous kernel of the step: load it right away
+    for (uint32_t off = 0; off < (uint32_t)C::W_BYTES; off += W_CHUNK)
+      bulk_load_1d(s_base + off, reinterpret_cast<const uint8_t*>(p.w_split) + off, W_CHUNK, bar_w);
+    pdl_wait();  // the spikes of the previous layer
     for (int it = 0; it < n_op0; ++it) {
       op_issue(it);
       EF_TRACE(it, 0);
     }
-    mbar_expect_tx(bar_w, C::W_BYTES);
-    for (uint32_t off = 0; off < (uint32_t)C::W_BYTES; off += W_CHUNK)
-      bulk_load_1d(s_base + off, reinterpret_cast<const uint8_t*>(p.w_split) + off, W_CHUNK, bar_w);
   } else if (threadIdx.x == 64) {
     if (p.has_v) prefetch_tensormap(&map_vin);
     if (ld_zc) prefetch_tensormap(&map_zc);
@@ -197,6 +202,7 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
       mbar_init(bar_ve(s), 1);  // the store thread, once the TMA store has read the stage
     }
     fence_barrier_init();
+    pdl_wait();
     for (int it = 0; it < n_v0; ++it) v_issue(it);
   } else if (threadIdx.x == 128) {
     prefetch_tensormap(&map_vout);
@@ -277,6 +283,7 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
     const int m = q * 32 + lane;            // GEMM row = pixel within the tile
     const int ty = m >> 3, tx = m & 7;      // (row, col) inside the tile
     const bool store_thread = (threadIdx.x == 128);
+    if (store_thread) pdl_wait();  // the thread that issues the global stores
     float lam[CPT], thr[CPT];
 #pragma unroll
     for (int j = 0; j < CPT; ++j) {
@@ -469,7 +476,8 @@ static int launch_tc(const TcParams& q, int grid, const CUtensorMap* m, cudaStre
       return check_launch("cudaFuncSetAttribute(lif_conv_fwd_tc_kernel)");
     attr_set = true;
   }
-  kern<<<grid, 128 + 32 * 4 * (32 / CPT), TcCfg<REC>::TOTAL, st>>>(q, m[0], m[1], m[2], m[3], m[4], m[5]);
+  const cudaError_t le = launch_pdl(kern, dim3(grid), dim3(128 + 32 * 4 * (32 / CPT)), TcCfg<REC>::TOTAL, st, q, m[0], m[1], m[2], m[3], m[4], m[5]);
+  (void)le;
   return check_launch("lif_conv_fwd_tc_kernel");
 }
 

@@ -15,6 +15,8 @@ __device__ __forceinline__ float ld_x(const ef_pred_params& p, int b, int c, siz
 
 __global__ void __launch_bounds__(256) pred_fwd_kernel(const ef_pred_params p) {
   __shared__ float s_w[PRED_MAX_COUT * PRED_MAX_CIN], s_b[PRED_MAX_COUT];
+  pdl_launch_dependents();
+  pdl_wait();  // the spikes of the last cell
   for (int i = threadIdx.x; i < p.Cout * p.Cin; i += 256) s_w[i] = p.w[i];
   if (threadIdx.x < p.Cout) s_b[threadIdx.x] = p.b[threadIdx.x];
   __syncthreads();
@@ -217,7 +219,7 @@ extern "C" int ef_pred_fwd(const ef_pred_params* p, void* stream) {
   EF_REQUIRE(p, EF_ENULL, "ef_pred_fwd: params is NULL");
   if (int rc = validate_pred(*p, "ef_pred_fwd")) return rc;
   const size_t n = (size_t)p->B * p->H * p->W;
-  pred_fwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(*p);
+  launch_pdl(pred_fwd_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, as_stream(stream), *p);
   return check_launch("pred_fwd_kernel");
 }
 

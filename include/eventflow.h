@@ -191,6 +191,9 @@ int ef_debug_tc_trace(long long* buf);
 int ef_debug_tc_skip(int mask);
 /* Epilogue shape of the tensor-core forward kernel: 16 channels per thread (8 epilogue warps, default) or 8 (16 warps). */
 int ef_debug_tc_cpt(int cpt);
+/* Programmatic dependent launch of the forward kernels of a model step (head, fused cells, prediction): on by default, EF_PDL=0
+ * in the environment or ef_debug_pdl(0) falls back to plain stream-ordered launches. */
+int ef_debug_pdl(int on);
 
 /* Resampling glue of the U-Net family.  src [n_planes,H,W] fp32 (n_planes = B*C), dst [n_planes,2H,2W]:
  * F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False) of models/spiking_submodules.py:1010 /
