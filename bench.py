@@ -308,10 +308,10 @@ def run_ours(args):
     avg_ms = ms_hidden / n_hidden
     achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "fused conv3x3+LIF step, 32->32 ch (lif_conv_fwd_tc_kernel via ef_lif_conv_fwd)", "achieved": achieved,
-                "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": 34393088, "peak_source": pk_kind + " (burst copy)",
+                "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": 34274304, "peak_source": pk_kind + " (burst copy)",
                 "bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_ms, "launches_per_step": n_hidden,
-                "traffic_source": "ncu --set full, profiles/r01b_ncu_tc_fwd_v5.txt: dram__bytes_read.sum 33 643 520 (= x 8.4 + z 8.4 + v 16.8 MB, exactly compulsory) + "
-                                  "dram__bytes_write.sum 749 568 (the 25.2 MB of outputs are still in the 126 MB L2 when the kernel ends); fast-path formats move 58.7 MB per launch",
+                "traffic_source": "ncu --set full, profiles/r01d_ncu_tc_fwd_v5.txt: dram__bytes_read.sum 33 643 008 (= x 8.4 + z 8.4 + v 16.8 MB, exactly compulsory) + "
+                                  "dram__bytes_write.sum 631 296 (the 25.2 MB of outputs are still in the 126 MB L2 when the kernel ends); fast-path formats move 58.7 MB per launch",
                 "how": f"{n_hidden} launches (4 feed-forward + 2 recurrent cells x {T} steps) replayed as one CUDA graph, CUDA events around the replays",
                 "share_of_step": ms_hidden / ms_all, "model_kernels_ms_per_window": ms_all, "clocks": clocks_k.summary()}
 
