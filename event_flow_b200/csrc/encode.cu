@@ -43,9 +43,14 @@ extern "C" int ef_encode_events(const ef_encode_params* pp, void* stream) {
   EF_REQUIRE(!p.voxel || p.num_bins >= 1, EF_EINVAL, "ef_encode_events: num_bins must be >= 1");
   cudaStream_t st = as_stream(stream);
   const size_t hw = (size_t)p.H * p.W;
-  if (p.cnt) cudaMemsetAsync(p.cnt, 0, (size_t)p.B * 2 * hw * sizeof(float), st);
-  if (p.voxel) cudaMemsetAsync(p.voxel, 0, (size_t)p.B * p.num_bins * hw * sizeof(float), st);
-  if (p.mask) cudaMemsetAsync(p.mask, 0, (size_t)p.B * hw * sizeof(float), st);
+  const size_t n_cnt = (size_t)p.B * 2 * hw, n_vox = (size_t)p.B * p.num_bins * hw, n_mask = (size_t)p.B * hw;
+  if (p.cnt && p.voxel && p.mask && p.voxel == p.cnt + n_cnt && p.mask == p.voxel + n_vox) {
+    cudaMemsetAsync(p.cnt, 0, (n_cnt + n_vox + n_mask) * sizeof(float), st);  // the three images share one allocation: one fill
+  } else {
+    if (p.cnt) cudaMemsetAsync(p.cnt, 0, n_cnt * sizeof(float), st);
+    if (p.voxel) cudaMemsetAsync(p.voxel, 0, n_vox * sizeof(float), st);
+    if (p.mask) cudaMemsetAsync(p.mask, 0, n_mask * sizeof(float), st);
+  }
   if (p.N == 0) return EF_OK;
   encode_kernel<<<dim3(cdiv(p.N, 256), p.B), 256, 0, st>>>(p);
   return check_launch("encode_kernel");

@@ -262,15 +262,24 @@ def encode_events(events, res, num_bins, *, round_ts=False, want=("cnt", "voxel"
     p = L.EncodeParams()
     p.B, p.N, p.H, p.W, p.num_bins, p.round_ts = B, N, H, W, int(num_bins), int(round_ts)
     p.events = L.ptr(events)
-    if "cnt" in want:
-        out["event_cnt"] = torch.empty((B, 2, H, W), device=dev, dtype=torch.float32)
-        p.cnt = L.ptr(out["event_cnt"])
-    if "voxel" in want:
-        out["event_voxel"] = torch.empty((B, num_bins, H, W), device=dev, dtype=torch.float32)
-        p.voxel = L.ptr(out["event_voxel"])
-    if "mask" in want:
-        out["event_mask"] = torch.empty((B, 1, H, W), device=dev, dtype=torch.float32)
-        p.mask = L.ptr(out["event_mask"])
+    if "cnt" in want and "voxel" in want and "mask" in want:
+        # one allocation for the three images (cnt | voxel | mask): the library zero-fills them with a single memset
+        flat = torch.empty(B * (2 + num_bins + 1) * H * W, device=dev, dtype=torch.float32)
+        n1, n2 = B * 2 * H * W, B * num_bins * H * W
+        out["event_cnt"] = flat[:n1].view(B, 2, H, W)
+        out["event_voxel"] = flat[n1:n1 + n2].view(B, num_bins, H, W)
+        out["event_mask"] = flat[n1 + n2:].view(B, 1, H, W)
+        p.cnt, p.voxel, p.mask = L.ptr(out["event_cnt"]), L.ptr(out["event_voxel"]), L.ptr(out["event_mask"])
+    else:
+        if "cnt" in want:
+            out["event_cnt"] = torch.empty((B, 2, H, W), device=dev, dtype=torch.float32)
+            p.cnt = L.ptr(out["event_cnt"])
+        if "voxel" in want:
+            out["event_voxel"] = torch.empty((B, num_bins, H, W), device=dev, dtype=torch.float32)
+            p.voxel = L.ptr(out["event_voxel"])
+        if "mask" in want:
+            out["event_mask"] = torch.empty((B, 1, H, W), device=dev, dtype=torch.float32)
+            p.mask = L.ptr(out["event_mask"])
     if "pol_mask" in want:
         out["event_list_pol_mask"] = torch.empty((B, N, 2), device=dev, dtype=torch.float32)
         p.pol_mask = L.ptr(out["event_list_pol_mask"])
