@@ -147,7 +147,7 @@ def iwe_bench(dev, peak_gbs, reps=10):
             fn()
             torch.cuda.synchronize()
             gr = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(gr):
+            with torch.cuda.graph(gr, capture_error_mode="thread_local"):
                 fn()
             gr.replay()
             torch.cuda.synchronize()

@@ -244,7 +244,7 @@ def capture_window(model, xs, only_hidden=False):
             _launch_step(model, xs[t], slots[t - 1].v, slots[t - 1].z, slots[t], splits, B, Cin0, H, W)
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        with torch.cuda.graph(g, capture_error_mode="thread_local"):
             for t in range(1, len(xs)):
                 _launch_step(model, xs[t], slots[t - 1].v, slots[t - 1].z, slots[t], splits, B, Cin0, H, W, only_hidden=only_hidden)
     g._keepalive = (slots, xs, splits)
@@ -285,7 +285,8 @@ class _FireNetStep(torch.autograd.Function):
             if g is None:
                 _launch_step(model, slot.x_in, v_in, z_in, slot, splits, B, Cin0, H, W)  # eager: results + lazy init
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
+                # thread_local: other threads (the NCCL watchdog under data parallelism) keep issuing CUDA calls during a capture
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
                     _launch_step(model, slot.x_in, v_in, z_in, slot, splits, B, Cin0, H, W)
                 slot.graphs[key] = g
             else:
@@ -355,7 +356,7 @@ class _FireNetStep(torch.autograd.Function):
             if graph is None and model.__dict__.get("_use_graphs", True) and L.PROFILE is None and not torch.cuda.is_current_stream_capturing():
                 graph = torch.cuda.CUDAGraph()  # second visit of this (slot, sweep position): capture the ~25 kernels once
                 n0 = L.lib().ef_launch_count()
-                with torch.cuda.graph(graph):
+                with torch.cuda.graph(graph, capture_error_mode="thread_local"):
                     for name, st in calls:
                         L.call(name, st)
                 n_kernels = L.lib().ef_launch_count() - n0  # kernels recorded into the graph (counted by the library itself)
