@@ -3,8 +3,6 @@ Model zoo with the class names, constructor contract, state API and output dict 
 Round 1: the spiking FireNet family (FireNet base :148-286; LIFFireNet :636, PLIFFireNet :648, ALIFFireNet :660,
 XLIFFireNet :672, LIFFireFlowNet :684).  Each forward pass is 7 fused conv+neuron kernels and one prediction-head kernel.
 """
-import torch
-
 from .. import fast, ops
 from .base import BaseModel
 from .model_util import CropParameters, copy_states

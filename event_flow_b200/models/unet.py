@@ -5,7 +5,6 @@ Every encoder / residual / decoder stage is built from the fused conv+neuron cel
 upsampling is ef_upsample_bilinear2x and the per-scale prediction ef_pred_fwd.  Forward only in this version (the
 stride-2 and upsampling backward kernels are not built: calling it under autograd raises).
 """
-import torch
 import torch.nn as nn
 
 from .model_util import skip_concat, skip_sum  # noqa: F401  (resolved by name like the reference: "skip_" + skip_type)
