@@ -1,16 +1,13 @@
-"""Mirror of models/base.py:1-31 (BaseModel: abstract forward, __str__ with the trainable-parameter count)."""
-from abc import abstractmethod
-
-import numpy as np
+"""Common base of the model classes (role of models/base.py:1-31): abstract forward, trainable-parameter count in str()."""
 import torch.nn as nn
 
 
 class BaseModel(nn.Module):
-    @abstractmethod
     def forward(self, *inputs):
-        raise NotImplementedError
+        raise NotImplementedError(f"{type(self).__name__} does not define forward()")
+
+    def trainable_parameters(self):
+        return sum(p.numel() for p in self.parameters() if p.requires_grad)
 
     def __str__(self):
-        model_parameters = filter(lambda p: p.requires_grad, self.parameters())
-        params = sum([np.prod(p.size()) for p in model_parameters])
-        return super().__str__() + "\nTrainable parameters: {}".format(params)
+        return f"{super().__str__()}\nTrainable parameters: {self.trainable_parameters()}"

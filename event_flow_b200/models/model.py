@@ -1,63 +1,91 @@
 """
-Model zoo with the class names, constructor contract, state API and output dict of models/model.py.
-Round 1: the spiking FireNet family (FireNet base :148-286; LIFFireNet :636, PLIFFireNet :648, ALIFFireNet :660,
-XLIFFireNet :672, LIFFireFlowNet :684).  Each forward pass is 7 fused conv+neuron kernels and one prediction-head kernel.
+Model zoo behind the class names, constructor contract (`config["model"]` dict), state API and output dict of the reference's
+models/model.py, so that `eval(config["model"]["name"])(config["model"])` in train_flow.py:78-81 / eval_flow.py:93-101 keeps
+working.  Two families:
+
+* FireNet chain (models/model.py:148-286 and its subclasses :398-409, :614-704): seven conv cells + a 1x1 tanh prediction.  The
+  LIF variants run on the fused tcgen05 path (event_flow_b200/fast.py), everything else cell by cell through ops.*.
+* U-Net models (models/model.py:29-145, :289-395, :410-611): input selection / normalisation / padding, one of the U-Nets of
+  models/unet.py, flow post-processing (nearest upsampling of the coarse scales, crop).
+
+The nineteen public classes are declared at the bottom from two small tables (which cell types a FireNet variant uses; which
+U-Net and recurrent block a U-Net model uses) instead of one hand-written subclass each.
 """
 from .. import fast, ops
+from . import spiking_submodules as snn
+from . import submodules as ann
+from . import unet as nets
 from .base import BaseModel
 from .model_util import CropParameters, copy_states
-from .spiking_submodules import (
-    ConvALIF,
-    ConvALIFRecurrent,
-    ConvLIF,
-    ConvLIFRecurrent,
-    ConvPLIF,
-    ConvPLIFRecurrent,
-    ConvXLIF,
-    ConvXLIFRecurrent,
-)
-from .submodules import ConvGRU, ConvLayer, ConvLayer_, ConvLeaky, ConvLeakyRecurrent, ConvRecurrent
-from .unet import LeakyMultiResUNetRecurrent, MultiResUNet, MultiResUNetRecurrent, SpikingMultiResUNetRecurrent, UNetRecurrent
+
+_CHAIN = ("head", "G1", "R1a", "R1b", "G2", "R2a", "R2b")   # execution (and construction) order of the FireNet cells
+_GATED = ("G1", "G2")                                         # built from `rec_neuron`; their output feeds the optional residuals
+_RESIDUAL_INTO = ("R1b", "R2b")                               # receive the last gated output as residual when `residual` is set
+_ACTIVITY_KEYS = ["0:input", "1:head", "2:G1", "3:R1a", "4:R1b", "5:G2", "6:R2a", "7:R2b", "8:pred"]
 
 
+def _network_input(model, event_voxel, event_cnt):
+    """Encoding select + optional in-place normalisation of the non-zero entries (models/model.py:236-252, identical in every model)."""
+    if model.encoding == "voxel":
+        x = event_voxel
+    elif model.encoding == "cnt" and model.num_bins == 2:
+        x = event_cnt
+    else:
+        print("Model error: Incorrect input encoding.")
+        raise AttributeError
+    if model.norm_input:  # on the caller's tensor, like the reference
+        nz = x != 0
+        mean, stddev = x[nz].mean(), x[nz].std()
+        x[nz] = (x[nz] - mean) / stddev
+    return x
+
+
+def _detach_all(states):
+    """detach() of every state entry; LSTM states are (hidden, cell) tuples (models/model.py:211-221)."""
+    return [tuple(h.detach() for h in s) if type(s) is tuple else s.detach() for s in states]
+
+
+def _common_options(model, cfg):
+    model.num_bins = cfg["num_bins"]
+    model.encoding = cfg["encoding"]
+    model.norm_input = cfg["norm_input"] if "norm_input" in cfg.keys() else False
+    model.mask = cfg["mask_output"]
+
+
+# =====================================================================================================================
+# FireNet family
+# =====================================================================================================================
 class FireNet(BaseModel):
     """
-    7-cell chain head-G1-R1a-R1b-G2-R2a-R2b + 1x1 tanh prediction (models/model.py:148-286).
-    The base class is the ANN FireNet (ConvLayer_ + ConvGRU cells, forward only in this version).
+    head - G1 - R1a - R1b - G2 - R2a - R2b + 1x1 tanh prediction (models/model.py:148-286).  This base class is the ANN FireNet
+    (ConvLayer_ cells, ConvGRU at G1 / G2); the variants below only swap the three cell types.
     """
 
-    head_neuron = ConvLayer_
-    ff_neuron = ConvLayer_
-    rec_neuron = ConvGRU
+    head_neuron = ann.ConvLayer_
+    ff_neuron = ann.ConvLayer_
+    rec_neuron = ann.ConvGRU
     residual = False
-    num_recurrent_units = 7
+    num_recurrent_units = len(_CHAIN)
     w_scale_pred = None
 
     def __init__(self, unet_kwargs):
         super().__init__()
-        self.num_bins = unet_kwargs["num_bins"]
-        base_num_channels = unet_kwargs["base_num_channels"]
-        kernel_size = unet_kwargs["kernel_size"]
-        self.encoding = unet_kwargs["encoding"]
-        self.norm_input = False if "norm_input" not in unet_kwargs.keys() else unet_kwargs["norm_input"]
-        self.mask = unet_kwargs["mask_output"]
+        _common_options(self, unet_kwargs)
+        width, ksize = unet_kwargs["base_num_channels"], unet_kwargs["kernel_size"]
         ff_act, rec_act = unet_kwargs["activations"]
-        # the reference shares one class-level list of dicts between all models (model.py:159,171-173); per-instance here
-        kwargs = dict(unet_kwargs["spiking_neuron"]) if type(unet_kwargs.get("spiking_neuron")) is dict else {}
-
-        self.head = self.head_neuron(self.num_bins, base_num_channels, kernel_size, activation=ff_act, **kwargs)
-        self.G1 = self.rec_neuron(base_num_channels, base_num_channels, kernel_size, activation=rec_act, **kwargs)
-        self.R1a = self.ff_neuron(base_num_channels, base_num_channels, kernel_size, activation=ff_act, **kwargs)
-        self.R1b = self.ff_neuron(base_num_channels, base_num_channels, kernel_size, activation=ff_act, **kwargs)
-        self.G2 = self.rec_neuron(base_num_channels, base_num_channels, kernel_size, activation=rec_act, **kwargs)
-        self.R2a = self.ff_neuron(base_num_channels, base_num_channels, kernel_size, activation=ff_act, **kwargs)
-        self.R2b = self.ff_neuron(base_num_channels, base_num_channels, kernel_size, activation=ff_act, **kwargs)
-        self.pred = ConvLayer(base_num_channels, out_channels=2, kernel_size=1, activation="tanh", w_scale=self.w_scale_pred)
+        # the reference keeps ONE class-level list of kwargs dicts shared by all instances (model.py:159,171-173); per instance here
+        extra = dict(unet_kwargs["spiking_neuron"]) if type(unet_kwargs.get("spiking_neuron")) is dict else {}
+        for name in _CHAIN:  # creation order = the reference's, so the same torch seed gives the same initial values
+            make = self.head_neuron if name == "head" else (self.rec_neuron if name in _GATED else self.ff_neuron)
+            cell = make(self.num_bins if name == "head" else width, width, ksize, activation=rec_act if name in _GATED else ff_act, **extra)
+            setattr(self, name, cell)
+        self.pred = ann.ConvLayer(width, out_channels=2, kernel_size=1, activation="tanh", w_scale=self.w_scale_pred)
         self.reset_states()
 
+    # ---- state API (models/model.py:203-227) ----
     @property
     def states(self):
-        if self._fast is not None:  # internal (cl spike) state -> the reference's stacked fp32 format; fresh tensors = clones
+        if self._fast is not None:  # internal (channels-last spike) state -> the reference's stacked fp32 format; fresh tensors = clones
             return fast.states_of(self)
         return copy_states(self._states)
 
@@ -70,13 +98,7 @@ class FireNet(BaseModel):
         if self._fast is not None:  # cut the BPTT chain without copying any state
             fast.detach(self)
             return
-        detached_states = []
-        for state in self.states:
-            if type(state) is tuple:
-                detached_states.append(tuple(hidden.detach() for hidden in state))
-            else:
-                detached_states.append(state.detach())
-        self.states = detached_states
+        self.states = _detach_all(self.states)
 
     def reset_states(self):
         self._states = [None] * self.num_recurrent_units
@@ -102,427 +124,198 @@ class FireNet(BaseModel):
         :param event_cnt: N x 2 x H x W per-polarity event counts
         :return {"flow": [N x 2 x H x W], "activity": dict | None}
         """
-        if self.encoding == "voxel":
-            x = event_voxel
-        elif self.encoding == "cnt" and self.num_bins == 2:
-            x = event_cnt
-        else:
-            print("Model error: Incorrect input encoding.")
-            raise AttributeError
-
-        if self.norm_input:  # model.py:247-252 (in place on the caller's tensor, like the reference)
-            mean, stddev = x[x != 0].mean(), x[x != 0].std()
-            x[x != 0] = (x[x != 0] - mean) / stddev
-
+        x = _network_input(self, event_voxel, event_cnt)
         if fast.eligible(self, x):  # LIF, 32 channels: tcgen05 kernels on the internal spike format, one autograd node per step
             return fast.forward(self, x, log)
 
-        x1, self._states[0] = self.head(x, self._states[0])
-        x2, self._states[1] = self.G1(x1, self._states[1])
-        x3, self._states[2] = self.R1a(x2, self._states[2])
-        x4, self._states[3] = self.R1b(x3, self._states[3], residual=x2 if self.residual else 0)
-        x5, self._states[4] = self.G2(x4, self._states[4])
-        x6, self._states[5] = self.R2a(x5, self._states[5])
-        x7, self._states[6] = self.R2b(x6, self._states[6], residual=x5 if self.residual else 0)
-        flow = self.pred(x7)
+        seen, h, gated = [x], x, None
+        for i, name in enumerate(_CHAIN):
+            cell = getattr(self, name)
+            if name in _RESIDUAL_INTO:
+                h, self._states[i] = cell(h, self._states[i], residual=gated if self.residual else 0)
+            else:
+                h, self._states[i] = cell(h, self._states[i])
+            if name in _GATED:
+                gated = h
+            seen.append(h)
+        flow = self.pred(h)
+        seen.append(flow)
 
+        activity = None
         if log:
-            activity = {}
-            name = ["0:input", "1:head", "2:G1", "3:R1a", "4:R1b", "5:G2", "6:R2a", "7:R2b", "8:pred"]
-            for n, l in zip(name, [x, x1, x2, x3, x4, x5, x6, x7, flow]):
-                activity[n] = l.detach().ne(0).float().mean().item()
-        else:
-            activity = None
-
+            activity = {key: t.detach().ne(0).float().mean().item() for key, t in zip(_ACTIVITY_KEYS, seen)}
         return {"flow": [flow], "activity": activity}
 
 
-class FireFlowNet(FireNet):
-    """EV-FireFlowNet: all-feed-forward ANN FireNet (models/model.py:398-409)."""
-
-    head_neuron = ConvLayer_
-    ff_neuron = ConvLayer_
-    rec_neuron = ConvLayer_
-    residual = False
-    w_scale_pred = 0.01
+def _firenet_variant(name, head, ff, rec, w_scale_pred, where):
+    """A FireNet subclass that only swaps the cell types (what every subclass in the reference does)."""
+    cls = type(name, (FireNet,), {"head_neuron": head, "ff_neuron": ff, "rec_neuron": rec, "residual": False,
+                                  "w_scale_pred": w_scale_pred, "__doc__": f"{where}.", "__module__": __name__})
+    cls.__qualname__ = name  # picklable under models.model.<name> (utils/utils.py:19-20 pickles whole modules)
+    return cls
 
 
-class LIFFireNet(FireNet):
-    """models/model.py:636-645."""
-
-    head_neuron = ConvLIF
-    ff_neuron = ConvLIF
-    rec_neuron = ConvLIFRecurrent
-    residual = False
-    w_scale_pred = 0.01
-
-
-class PLIFFireNet(FireNet):
-    """models/model.py:648-657."""
-
-    head_neuron = ConvPLIF
-    ff_neuron = ConvPLIF
-    rec_neuron = ConvPLIFRecurrent
-    residual = False
-    w_scale_pred = 0.01
+# name                      head cell          feed-forward cell   G1 / G2 cell             w_scale_pred  reference
+FireFlowNet = _firenet_variant("FireFlowNet", ann.ConvLayer_, ann.ConvLayer_, ann.ConvLayer_, 0.01, "EV-FireFlowNet: all-feed-forward ANN FireNet (models/model.py:398-409)")
+RNNFireNet = _firenet_variant("RNNFireNet", ann.ConvLayer_, ann.ConvLayer_, ann.ConvRecurrent, None, "models/model.py:614-622")
+LeakyFireNet = _firenet_variant("LeakyFireNet", ann.ConvLeaky, ann.ConvLeaky, ann.ConvLeakyRecurrent, None, "models/model.py:625-633")
+LeakyFireFlowNet = _firenet_variant("LeakyFireFlowNet", ann.ConvLeaky, ann.ConvLeaky, ann.ConvLeaky, None, "models/model.py:696-704")
+LIFFireNet = _firenet_variant("LIFFireNet", snn.ConvLIF, snn.ConvLIF, snn.ConvLIFRecurrent, 0.01, "models/model.py:636-645")
+PLIFFireNet = _firenet_variant("PLIFFireNet", snn.ConvPLIF, snn.ConvPLIF, snn.ConvPLIFRecurrent, 0.01, "models/model.py:648-657")
+ALIFFireNet = _firenet_variant("ALIFFireNet", snn.ConvALIF, snn.ConvALIF, snn.ConvALIFRecurrent, 0.01, "models/model.py:660-669")
+XLIFFireNet = _firenet_variant("XLIFFireNet", snn.ConvXLIF, snn.ConvXLIF, snn.ConvXLIFRecurrent, 0.01, "models/model.py:672-681")
+LIFFireFlowNet = _firenet_variant("LIFFireFlowNet", snn.ConvLIF, snn.ConvLIF, snn.ConvLIF, 0.01, "models/model.py:684-693")
 
 
-class ALIFFireNet(FireNet):
-    """models/model.py:660-669."""
+# =====================================================================================================================
+# U-Net models
+# =====================================================================================================================
+class _UNetFlowModel(BaseModel):
+    """
+    What EVFlowNet (models/model.py:289-395), RecEVFlowNet (:410-547) and E2VID (:29-145) share: the option handling of the
+    constructor (the architecture constants are written into the caller's dict and the driver-only keys popped, as the reference
+    does), zero-padding of the input to a size the encoder pyramid divides, and the flow post-processing.
+    """
 
-    head_neuron = ConvALIF
-    ff_neuron = ConvALIF
-    rec_neuron = ConvALIFRecurrent
-    residual = False
-    w_scale_pred = 0.01
+    net_attr = None        # attribute name of the wrapped U-Net (part of the state_dict keys)
+    net_type = None
+    num_pyramid_levels = 4
+    drop_keys = ("name", "encoding", "round_encoding", "norm_input", "mask_output")
 
-
-class XLIFFireNet(FireNet):
-    """models/model.py:672-681."""
-
-    head_neuron = ConvXLIF
-    ff_neuron = ConvXLIF
-    rec_neuron = ConvXLIFRecurrent
-    residual = False
-    w_scale_pred = 0.01
-
-
-class LIFFireFlowNet(FireNet):
-    """models/model.py:684-693."""
-
-    head_neuron = ConvLIF
-    ff_neuron = ConvLIF
-    rec_neuron = ConvLIF
-    residual = False
-    w_scale_pred = 0.01
-
-
-class EVFlowNet(BaseModel):
-    """EV-FlowNet (models/model.py:289-395): the stateless ANN U-Net; forward only in this version."""
+    def architecture(self, cfg):
+        """Architecture constants of this model (merged into the constructor dict)."""
+        raise NotImplementedError
 
     def __init__(self, unet_kwargs):
         super().__init__()
-        EVFlowNet_kwargs = {
-            "base_num_channels": unet_kwargs["base_num_channels"],
-            "num_encoders": 4,
-            "num_residual_blocks": 2,
-            "num_output_channels": 2,
-            "skip_type": "concat",
-            "norm": None,
-            "use_upsample_conv": True,
-            "kernel_size": unet_kwargs["kernel_size"],
-            "channel_multiplier": 2,
-            "final_activation": "tanh",
-        }
+        fixed = self.architecture(unet_kwargs)
         self.crop = None
-        self.mask = unet_kwargs["mask_output"]
-        self.norm_input = False if "norm_input" not in unet_kwargs.keys() else unet_kwargs["norm_input"]
-        self.encoding = unet_kwargs["encoding"]
-        self.num_bins = unet_kwargs["num_bins"]
-        self.num_encoders = EVFlowNet_kwargs["num_encoders"]
+        _common_options(self, unet_kwargs)
+        self.num_encoders = fixed["num_encoders"]
+        unet_kwargs.update(fixed)  # in place on the caller's dict, like the reference
+        for key in self.drop_keys:
+            unet_kwargs.pop(key, None)
+        setattr(self, self.net_attr, self.network_class()(unet_kwargs))
+        unet_kwargs.pop("final_activation", None)  # the reference's U-Nets pop it from the caller's dict (unet.py:233,152,326)
 
-        unet_kwargs.update(EVFlowNet_kwargs)  # in place on the caller's dict, like the reference (model.py:318-325)
-        for k in ("name", "eval", "encoding", "round_encoding", "mask_output", "norm_input", "spiking_neuron"):
-            unet_kwargs.pop(k, None)
-        self.multires_unet = MultiResUNet(unet_kwargs)
-
-    def detach_states(self):
-        pass
-
-    def reset_states(self):
-        pass
-
-    def init_cropping(self, width, height, safety_margin=0):
-        self.crop = CropParameters(width, height, self.num_encoders, safety_margin)
-
-    def forward(self, event_voxel, event_cnt, log=False):
-        if self.encoding == "voxel":
-            x = event_voxel
-        elif self.encoding == "cnt" and self.num_bins == 2:
-            x = event_cnt
-        else:
-            print("Model error: Incorrect input encoding.")
-            raise AttributeError
-        if self.norm_input:
-            mean, stddev = x[x != 0].mean(), x[x != 0].std()
-            x[x != 0] = (x[x != 0] - mean) / stddev
-        if self.crop is not None:
-            x = self.crop.pad(x)
-        multires_flow = self.multires_unet.forward(x)
-        if log:
-            raise NotImplementedError("Activity logging not implemented")
-        flow_list = []
-        full_h, full_w = multires_flow[-1].shape[2], multires_flow[-1].shape[3]
-        for flow in multires_flow:
-            flow_list.append(ops.upsample_nearest(flow, full_h // flow.shape[2], full_w // flow.shape[3]))
-        if self.crop is not None:
-            for i, flow in enumerate(flow_list):
-                flow_list[i] = flow[:, :, self.crop.iy0:self.crop.iy1, self.crop.ix0:self.crop.ix1].contiguous()
-        return {"flow": flow_list, "activity": None}
-
-
-class RecEVFlowNet(BaseModel):
-    """
-    Recurrent EV-FlowNet (models/model.py:410-547): input encoding select, optional input normalisation and padding, the
-    multi-resolution recurrent U-Net, nearest-neighbour upsampling of every flow estimate to the input resolution, crop.
-    The spiking subclasses (SpikingRecEVFlowNet :550, PLIF :561, ALIF :572, XLIF :583) run on the fused spiking cells, the
-    ANN base class on the ConvLayer / ConvGRU kernels (ConvLSTM / ConvRecurrent encoders raise).
-    """
-
-    unet_type = MultiResUNetRecurrent
-    recurrent_block_type = "convgru"
-    spiking_feedforward_block_type = None
-
-    def __init__(self, unet_kwargs):
-        super().__init__()
-        norm = None
-        use_upsample_conv = True
-        if "norm" in unet_kwargs.keys():
-            norm = unet_kwargs["norm"]
-        if "use_upsample_conv" in unet_kwargs.keys():
-            use_upsample_conv = unet_kwargs["use_upsample_conv"]
-
-        RecEVFlowNet_kwargs = {
-            "base_num_channels": unet_kwargs["base_num_channels"],
-            "num_encoders": 4,
-            "num_residual_blocks": 2,
-            "num_output_channels": 2,
-            "skip_type": "concat",
-            "norm": norm,
-            "use_upsample_conv": use_upsample_conv,
-            "kernel_size": unet_kwargs["kernel_size"],
-            "channel_multiplier": 2,
-            "recurrent_block_type": self.recurrent_block_type,
-            "final_activation": "tanh",
-            "spiking_feedforward_block_type": self.spiking_feedforward_block_type,
-            "spiking_neuron": unet_kwargs["spiking_neuron"],
-        }
-
-        self.crop = None
-        self.mask = unet_kwargs["mask_output"]
-        self.norm_input = False if "norm_input" not in unet_kwargs.keys() else unet_kwargs["norm_input"]
-        self.encoding = unet_kwargs["encoding"]
-        self.num_bins = unet_kwargs["num_bins"]
-        self.num_encoders = RecEVFlowNet_kwargs["num_encoders"]
-
-        unet_kwargs.update(RecEVFlowNet_kwargs)  # in place on the caller's dict, like the reference (model.py:456-461)
-        unet_kwargs.pop("name", None)
-        unet_kwargs.pop("encoding", None)
-        unet_kwargs.pop("round_encoding", None)
-        unet_kwargs.pop("norm_input", None)
-        unet_kwargs.pop("mask_output", None)
-
-        self.multires_unetrec = self.unet_type(unet_kwargs)
+    def network_class(self):
+        return self.net_type
 
     @property
-    def states(self):
-        return copy_states(self.multires_unetrec.states)
-
-    @states.setter
-    def states(self, states):
-        self.multires_unetrec.states = states
-
-    def detach_states(self):
-        detached_states = []
-        for state in self.multires_unetrec.states:
-            if type(state) is tuple:
-                detached_states.append(tuple(hidden.detach() for hidden in state))
-            else:
-                detached_states.append(state.detach())
-        self.multires_unetrec.states = detached_states
-
-    def reset_states(self):
-        self.multires_unetrec.states = [None] * self.multires_unetrec.num_states
+    def net(self):
+        return getattr(self, self.net_attr)
 
     def init_cropping(self, width, height, safety_margin=0):
         self.crop = CropParameters(width, height, self.num_encoders, safety_margin)
+
+    def detach_states(self):
+        pass
+
+    def reset_states(self):
+        pass
 
     def forward(self, event_voxel, event_cnt, log=False):
         """
         :param event_voxel: N x num_bins x H x W
         :param event_cnt: N x 2 x H x W per-polarity event counts
-        :return {"flow": [N x 2 x H x W] * num_encoders (coarse to fine, all at input resolution), "activity": None}
+        :return {"flow": list of N x 2 x H x W maps at the input resolution (coarse to fine), "activity": None}
         """
-        if self.encoding == "voxel":
-            x = event_voxel
-        elif self.encoding == "cnt" and self.num_bins == 2:
-            x = event_cnt
-        else:
-            print("Model error: Incorrect input encoding.")
-            raise AttributeError
-
-        if self.norm_input:
-            mean, stddev = x[x != 0].mean(), x[x != 0].std()
-            x[x != 0] = (x[x != 0] - mean) / stddev
-
+        x = _network_input(self, event_voxel, event_cnt)
         if self.crop is not None:
             x = self.crop.pad(x)
-
-        multires_flow = self.multires_unetrec.forward(x)
-
+        out = self.net.forward(x)
         if log:
             raise NotImplementedError("Activity logging not implemented")
-        activity = None
-
-        flow_list = []
-        full_h, full_w = multires_flow[-1].shape[2], multires_flow[-1].shape[3]
-        for flow in multires_flow:
-            flow_list.append(ops.upsample_nearest(flow, full_h // flow.shape[2], full_w // flow.shape[3]))
-
+        if isinstance(out, (list, tuple)):  # multi-resolution estimates: nearest-neighbour upsampling to the finest one
+            full_h, full_w = out[-1].shape[2], out[-1].shape[3]
+            flows = [ops.upsample_nearest(f, full_h // f.shape[2], full_w // f.shape[3]) for f in out]
+        else:
+            flows = [out]
         if self.crop is not None:
-            for i, flow in enumerate(flow_list):
-                flow_list[i] = flow[:, :, self.crop.iy0:self.crop.iy1, self.crop.ix0:self.crop.ix1].contiguous()
-
-        return {"flow": flow_list, "activity": activity}
-
-
-class SpikingRecEVFlowNet(RecEVFlowNet):
-    """models/model.py:550-558."""
-
-    unet_type = SpikingMultiResUNetRecurrent
-    recurrent_block_type = "lif"
-    spiking_feedforward_block_type = "lif"
+            c = self.crop
+            flows = [f[:, :, c.iy0:c.iy1, c.ix0:c.ix1].contiguous() for f in flows]
+        return {"flow": flows, "activity": None}
 
 
-class PLIFRecEVFlowNet(RecEVFlowNet):
-    """models/model.py:561-569."""
-
-    unet_type = SpikingMultiResUNetRecurrent
-    recurrent_block_type = "plif"
-    spiking_feedforward_block_type = "plif"
-
-
-class ALIFRecEVFlowNet(RecEVFlowNet):
-    """models/model.py:572-580."""
-
-    unet_type = SpikingMultiResUNetRecurrent
-    recurrent_block_type = "alif"
-    spiking_feedforward_block_type = "alif"
-
-
-class XLIFRecEVFlowNet(RecEVFlowNet):
-    """models/model.py:583-591."""
-
-    unet_type = SpikingMultiResUNetRecurrent
-    recurrent_block_type = "xlif"
-    spiking_feedforward_block_type = "xlif"
-
-
-class RNNRecEVFlowNet(RecEVFlowNet):
-    """models/model.py:594-601: ConvRecurrent instead of ConvGRU after every encoder conv."""
-
-    unet_type = MultiResUNetRecurrent
-    recurrent_block_type = "convrnn"
-
-
-class LeakyRecEVFlowNet(RecEVFlowNet):
-    """models/model.py:604-611: leaky (stateful ANN) cells throughout."""
-
-    unet_type = LeakyMultiResUNetRecurrent
-    recurrent_block_type = "convleaky"
-
-
-class RNNFireNet(FireNet):
-    """models/model.py:614-622."""
-
-    head_neuron = ConvLayer_
-    ff_neuron = ConvLayer_
-    rec_neuron = ConvRecurrent
-    residual = False
-
-
-class LeakyFireNet(FireNet):
-    """models/model.py:625-633."""
-
-    head_neuron = ConvLeaky
-    ff_neuron = ConvLeaky
-    rec_neuron = ConvLeakyRecurrent
-    residual = False
-
-
-class LeakyFireFlowNet(FireNet):
-    """models/model.py:696-704."""
-
-    head_neuron = ConvLeaky
-    ff_neuron = ConvLeaky
-    rec_neuron = ConvLeaky
-    residual = False
-
-
-class E2VID(BaseModel):
-    """E2VID adapted for flow (models/model.py:29-145): recurrent U-Net with ConvLSTM encoders and sum skips, one flow map."""
-
-    def __init__(self, unet_kwargs):
-        super().__init__()
-        norm = None
-        use_upsample_conv = True
-        if "norm" in unet_kwargs.keys():
-            norm = unet_kwargs["norm"]
-        if "use_upsample_conv" in unet_kwargs.keys():
-            use_upsample_conv = unet_kwargs["use_upsample_conv"]
-        E2VID_kwargs = {
-            "base_num_channels": unet_kwargs["base_num_channels"],
-            "num_encoders": 3,
-            "num_residual_blocks": 2,
-            "num_output_channels": 2,
-            "skip_type": "sum",
-            "norm": norm,
-            "use_upsample_conv": use_upsample_conv,
-            "kernel_size": unet_kwargs["kernel_size"],
-            "channel_multiplier": 2,
-            "recurrent_block_type": "convlstm",
-            "final_activation": "tanh",
-        }
-        self.crop = None
-        self.mask = unet_kwargs["mask_output"]
-        self.norm_input = False if "norm_input" not in unet_kwargs.keys() else unet_kwargs["norm_input"]
-        self.encoding = unet_kwargs["encoding"]
-        self.num_bins = unet_kwargs["num_bins"]
-        self.num_encoders = E2VID_kwargs["num_encoders"]
-        unet_kwargs.update(E2VID_kwargs)
-        for k in ("name", "encoding", "round_encoding", "norm_input", "mask_output", "spiking_neuron"):
-            unet_kwargs.pop(k, None)
-        self.unetrecurrent = UNetRecurrent(unet_kwargs)
+class _RecurrentUNetFlowModel(_UNetFlowModel):
+    """State API of the recurrent U-Net models (models/model.py:466-487): the states live in the wrapped network."""
 
     @property
     def states(self):
-        return copy_states(self.unetrecurrent.states)
+        return copy_states(self.net.states)
 
     @states.setter
     def states(self, states):
-        self.unetrecurrent.states = states
+        self.net.states = states
 
     def detach_states(self):
-        detached_states = []
-        for state in self.unetrecurrent.states:
-            if type(state) is tuple:
-                detached_states.append(tuple(hidden.detach() for hidden in state))
-            else:
-                detached_states.append(state.detach())
-        self.unetrecurrent.states = detached_states
+        self.net.states = _detach_all(self.net.states)
 
     def reset_states(self):
-        self.unetrecurrent.states = [None] * self.unetrecurrent.num_states
+        self.net.states = [None] * self.net.num_states
 
-    def init_cropping(self, width, height, safety_margin=0):
-        self.crop = CropParameters(width, height, self.num_encoders, safety_margin)
 
-    def forward(self, event_voxel, event_cnt, log=False):
-        if self.encoding == "voxel":
-            x = event_voxel
-        elif self.encoding == "cnt" and self.num_bins == 2:
-            x = event_cnt
-        else:
-            print("Model error: Incorrect input encoding.")
-            raise AttributeError
-        if self.norm_input:
-            mean, stddev = x[x != 0].mean(), x[x != 0].std()
-            x[x != 0] = (x[x != 0] - mean) / stddev
-        if self.crop is not None:
-            x = self.crop.pad(x)
-        flow = self.unetrecurrent.forward(x)
-        if log:
-            raise NotImplementedError("Activity logging not implemented")
-        if self.crop is not None:
-            flow = flow[:, :, self.crop.iy0:self.crop.iy1, self.crop.ix0:self.crop.ix1].contiguous()
-        return {"flow": [flow], "activity": None}
+def _optional(cfg, key, default):
+    return cfg[key] if key in cfg.keys() else default
+
+
+class EVFlowNet(_UNetFlowModel):
+    """EV-FlowNet (models/model.py:289-395): the stateless ANN multi-resolution U-Net."""
+
+    net_attr, net_type = "multires_unet", nets.MultiResUNet
+    drop_keys = _UNetFlowModel.drop_keys + ("eval", "spiking_neuron")
+
+    def architecture(self, cfg):
+        return {"base_num_channels": cfg["base_num_channels"], "num_encoders": 4, "num_residual_blocks": 2, "num_output_channels": 2,
+                "skip_type": "concat", "norm": None, "use_upsample_conv": True, "kernel_size": cfg["kernel_size"],
+                "channel_multiplier": 2, "final_activation": "tanh"}
+
+
+class RecEVFlowNet(_RecurrentUNetFlowModel):
+    """
+    Recurrent EV-FlowNet (models/model.py:410-547): a recurrent block after every encoder conv.  The base class uses ConvGRU;
+    the subclasses below select other recurrent blocks or the spiking / leaky U-Nets.
+    """
+
+    net_attr, net_type = "multires_unetrec", nets.MultiResUNetRecurrent
+    unet_type = nets.MultiResUNetRecurrent
+    recurrent_block_type = "convgru"
+    spiking_feedforward_block_type = None
+
+    def network_class(self):
+        return self.unet_type  # the attribute name the reference's subclasses override (models/model.py:418,556)
+
+    def architecture(self, cfg):
+        return {"base_num_channels": cfg["base_num_channels"], "num_encoders": 4, "num_residual_blocks": 2, "num_output_channels": 2,
+                "skip_type": "concat", "norm": _optional(cfg, "norm", None), "use_upsample_conv": _optional(cfg, "use_upsample_conv", True),
+                "kernel_size": cfg["kernel_size"], "channel_multiplier": 2, "recurrent_block_type": self.recurrent_block_type,
+                "final_activation": "tanh", "spiking_feedforward_block_type": self.spiking_feedforward_block_type,
+                "spiking_neuron": cfg["spiking_neuron"]}
+
+
+def _rec_evflownet_variant(name, unet_type, block, spiking_block, where):
+    cls = type(name, (RecEVFlowNet,), {"unet_type": unet_type, "recurrent_block_type": block, "spiking_feedforward_block_type": spiking_block,
+                                       "__doc__": f"{where}.", "__module__": __name__})
+    cls.__qualname__ = name
+    return cls
+
+
+SpikingRecEVFlowNet = _rec_evflownet_variant("SpikingRecEVFlowNet", nets.SpikingMultiResUNetRecurrent, "lif", "lif", "models/model.py:550-558")
+PLIFRecEVFlowNet = _rec_evflownet_variant("PLIFRecEVFlowNet", nets.SpikingMultiResUNetRecurrent, "plif", "plif", "models/model.py:561-569")
+ALIFRecEVFlowNet = _rec_evflownet_variant("ALIFRecEVFlowNet", nets.SpikingMultiResUNetRecurrent, "alif", "alif", "models/model.py:572-580")
+XLIFRecEVFlowNet = _rec_evflownet_variant("XLIFRecEVFlowNet", nets.SpikingMultiResUNetRecurrent, "xlif", "xlif", "models/model.py:583-591")
+RNNRecEVFlowNet = _rec_evflownet_variant("RNNRecEVFlowNet", nets.MultiResUNetRecurrent, "convrnn", None, "models/model.py:594-601")
+LeakyRecEVFlowNet = _rec_evflownet_variant("LeakyRecEVFlowNet", nets.LeakyMultiResUNetRecurrent, "convleaky", None, "models/model.py:604-611")
+
+
+class E2VID(_RecurrentUNetFlowModel):
+    """E2VID adapted for flow (models/model.py:29-145): recurrent U-Net with ConvLSTM encoders and sum skips, one flow map."""
+
+    net_attr, net_type = "unetrecurrent", nets.UNetRecurrent
+    num_pyramid_levels = 3
+    drop_keys = _UNetFlowModel.drop_keys + ("spiking_neuron",)
+
+    def architecture(self, cfg):
+        return {"base_num_channels": cfg["base_num_channels"], "num_encoders": 3, "num_residual_blocks": 2, "num_output_channels": 2,
+                "skip_type": "sum", "norm": _optional(cfg, "norm", None), "use_upsample_conv": _optional(cfg, "use_upsample_conv", True),
+                "kernel_size": cfg["kernel_size"], "channel_multiplier": 2, "recurrent_block_type": "convlstm", "final_activation": "tanh"}

@@ -1,8 +1,17 @@
-"""State-copy helpers with the semantics of models/model_util.py:82-102 (model.states returns clones)."""
+"""
+Helpers shared by the model classes (role of models/model_util.py): state copies for `model.states` (:82-102), the skip
+connections of the U-Nets (:14-27) and the pad / crop bookkeeping for inputs whose size the encoder pyramid does not divide
+(:30-80).
+"""
 import copy
+import math
+
+import torch
+import torch.nn.functional as F
 
 
 def recursive_clone(tensor):
+    """clone() of a tensor, or of every tensor inside nested tuples / lists (LSTM states are (hidden, cell) tuples)."""
     if hasattr(tensor, "clone"):
         return tensor.clone()
     try:
@@ -12,61 +21,52 @@ def recursive_clone(tensor):
 
 
 def copy_states(states):
-    if states[0] is None:
-        return copy.deepcopy(states)
-    return recursive_clone(states)
+    """`model.states` hands out copies: a deepcopy of the all-None list, clones otherwise."""
+    return copy.deepcopy(states) if states[0] is None else recursive_clone(states)
 
 
-# ---- helpers of the U-Net family (models/model_util.py:14-80) ------------------------------------------------------------
-from math import ceil, floor  # noqa: E402
-
-import torch  # noqa: E402
-from torch.nn import ZeroPad2d  # noqa: E402
+def _centre_pad_to(x, like):
+    """Zero-pad x symmetrically (extra pixel on the bottom / right) to the spatial size of `like`."""
+    dy, dx = like.shape[2] - x.shape[2], like.shape[3] - x.shape[3]
+    if dy == 0 and dx == 0:
+        return x
+    return F.pad(x, (dx // 2, dx - dx // 2, dy // 2, dy - dy // 2))
 
 
 def skip_concat(x1, x2):
-    diffY = x2.size()[2] - x1.size()[2]
-    diffX = x2.size()[3] - x1.size()[3]
-    if diffX or diffY:
-        x1 = ZeroPad2d((diffX // 2, diffX - diffX // 2, diffY // 2, diffY - diffY // 2))(x1)
-    return torch.cat([x1, x2], dim=1)
+    return torch.cat([_centre_pad_to(x1, x2), x2], dim=1)
 
 
 def skip_sum(x1, x2):
-    diffY = x2.size()[2] - x1.size()[2]
-    diffX = x2.size()[3] - x1.size()[3]
-    if diffX or diffY:
-        x1 = ZeroPad2d((diffX // 2, diffX - diffX // 2, diffY // 2, diffY - diffY // 2))(x1)
-    return x1 + x2
+    return _centre_pad_to(x1, x2) + x2
 
 
 def optimal_crop_size(max_size, max_subsample_factor, safety_margin=0):
-    """Smallest size >= max_size divisible by 2^max_subsample_factor (+ margin)."""
-    crop_size = int(pow(2, max_subsample_factor) * ceil(max_size / pow(2, max_subsample_factor)))
-    crop_size += safety_margin * pow(2, max_subsample_factor)
-    return crop_size
+    """Smallest size >= max_size that 2^max_subsample_factor divides, plus `safety_margin` such blocks."""
+    block = 2 ** max_subsample_factor
+    return int(block * math.ceil(max_size / block)) + safety_margin * block
 
 
 class CropParameters:
-    """Zero-padding of the input to a size the encoder pyramid divides, and the crop back (models/model_util.py:40-80)."""
+    """
+    Input padding to a size the encoder pyramid divides and the window that crops the output back.  Attribute names follow the
+    reference (the models read ix0, ix1, iy0, iy1 and call .pad / .crop).
+    """
 
     def __init__(self, width, height, num_encoders, safety_margin=0):
-        self.height = height
-        self.width = width
-        self.num_encoders = num_encoders
-        self.width_crop_size = optimal_crop_size(self.width, num_encoders, safety_margin)
-        self.height_crop_size = optimal_crop_size(self.height, num_encoders, safety_margin)
-        self.padding_top = ceil(0.5 * (self.height_crop_size - self.height))
-        self.padding_bottom = floor(0.5 * (self.height_crop_size - self.height))
-        self.padding_left = ceil(0.5 * (self.width_crop_size - self.width))
-        self.padding_right = floor(0.5 * (self.width_crop_size - self.width))
-        self.pad = ZeroPad2d((self.padding_left, self.padding_right, self.padding_top, self.padding_bottom))
-        self.cx = floor(self.width_crop_size / 2)
-        self.cy = floor(self.height_crop_size / 2)
-        self.ix0 = self.cx - floor(self.width / 2)
-        self.ix1 = self.cx + ceil(self.width / 2)
-        self.iy0 = self.cy - floor(self.height / 2)
-        self.iy1 = self.cy + ceil(self.height / 2)
+        self.width, self.height, self.num_encoders = width, height, num_encoders
+        self.width_crop_size = optimal_crop_size(width, num_encoders, safety_margin)
+        self.height_crop_size = optimal_crop_size(height, num_encoders, safety_margin)
+        extra_h, extra_w = self.height_crop_size - height, self.width_crop_size - width
+        # the larger half of an odd surplus goes to the top / left
+        self.padding_top, self.padding_bottom = math.ceil(0.5 * extra_h), math.floor(0.5 * extra_h)
+        self.padding_left, self.padding_right = math.ceil(0.5 * extra_w), math.floor(0.5 * extra_w)
+        self.cx, self.cy = self.width_crop_size // 2, self.height_crop_size // 2
+        self.ix0, self.ix1 = self.cx - width // 2, self.cx + math.ceil(width / 2)
+        self.iy0, self.iy1 = self.cy - height // 2, self.cy + math.ceil(height / 2)
+
+    def pad(self, x):
+        return F.pad(x, (self.padding_left, self.padding_right, self.padding_top, self.padding_bottom))
 
     def crop(self, img):
         return img[..., self.iy0:self.iy1, self.ix0:self.ix1]
