@@ -82,6 +82,11 @@ class FireNet(BaseModel):
         self.pred = ann.ConvLayer(width, out_channels=2, kernel_size=1, activation="tanh", w_scale=self.w_scale_pred)
         self.reset_states()
 
+    def __getattr__(self, name):
+        if name == "_fast":  # a FireNet unpickled from a checkpoint the reference wrote has no fast-path state yet
+            return None
+        return super().__getattr__(name)
+
     # ---- state API (models/model.py:203-227) ----
     @property
     def states(self):

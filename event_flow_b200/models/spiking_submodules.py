@@ -47,6 +47,16 @@ class _SpikingConvCell(nn.Module):
         self.detach = detach
         self.norm = None
 
+    def __getattr__(self, name):
+        # Cells unpickled from a checkpoint the REFERENCE wrote (utils/utils.py:19-20 pickles whole modules; the aliased module
+        # paths make them resolve to these classes) carry the reference's attributes only: derive the two this package adds.
+        if name == "stride":
+            return self.ff.stride[0]
+        if name == "activation":
+            fn = self.spike_fn
+            return getattr(fn, "name", getattr(fn, "__name__", "arctanspike"))
+        return super().__getattr__(name)
+
     def forward(self, input_, prev_state, residual=0):
         chan = {n: getattr(self, n) for n in ops.param_names(self.neuron)}
         return ops.cell_step(

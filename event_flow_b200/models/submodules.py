@@ -32,10 +32,20 @@ class ConvLayer(nn.Module):
         self.activation = activation
         self.norm = norm
 
+    def __getattr__(self, name):
+        # layers unpickled from a checkpoint the REFERENCE wrote keep only its attributes: derive the ones this package adds
+        if name in ("kernel_size", "stride"):
+            return getattr(self.conv2d, name)[0]
+        return super().__getattr__(name)
+
+    def _act_name(self):
+        act = self.activation  # a name here; a torch function (torch.relu, torch.tanh, ...) in objects the reference pickled
+        return getattr(act, "__name__", act) if callable(act) else act
+
     def forward(self, x):
         if self.kernel_size == 1:
             return ops.pred_head(x, self.conv2d.weight, self.conv2d.bias)
-        out = ops.conv_ann(x, self.conv2d.weight, self.conv2d.bias, self.activation)
+        out = ops.conv_ann(x, self.conv2d.weight, self.conv2d.bias, self._act_name())
         if self.stride == 2:
             # a stride-2 3x3 conv with padding 1 is the stride-1 result at the even pixels (same window, same summation order);
             # first version of the U-Net encoders: 4x the minimal FLOPs on these four layers
@@ -50,7 +60,7 @@ class ConvLayer_(ConvLayer):
         if prev_state is None:
             prev_state = torch.tensor(0)  # not used
         res = residual if torch.is_tensor(residual) else None
-        out = ops.conv_ann(x, self.conv2d.weight, self.conv2d.bias, self.activation, residual=res)
+        out = ops.conv_ann(x, self.conv2d.weight, self.conv2d.bias, self._act_name(), residual=res)
         return out, prev_state
 
 

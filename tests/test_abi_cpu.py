@@ -156,3 +156,35 @@ def test_dropin_resolves_the_reference_import_list_and_falls_back_to_reference_f
     ) % (ROOT, str(ref))
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/models"), reason="needs the reference tree (build container only)")
+def test_whole_module_checkpoint_written_by_the_reference_unpickles_into_this_package(tmp_path):
+    """
+    utils/utils.py:19-20,36-37 saves and loads WHOLE modules.  A LIFFireNet pickled by the unmodified reference must unpickle,
+    under the drop-in aliases, into this package's classes with identical parameters and a usable cell / state API.
+    """
+    ckpt = str(tmp_path / "ref_model.pt")
+    cfg = ("dict(name='LIFFireNet', encoding='voxel', round_encoding=False, norm_input=False, num_bins=5, base_num_channels=32, kernel_size=3, "
+           "activations=['arctanspike', 'arctanspike'], mask_output=True, spiking_neuron=dict(leak=[-4.0, 0.1], thresh=[0.8, 0.1], "
+           "learn_leak=True, learn_thresh=True, hard_reset=True))")
+    save = ("import sys, torch; sys.path.insert(0, '/root/reference')\n"
+            "import models.model as M\n"
+            "M.LIFFireNet.kwargs = [{}] * 7\n"
+            "torch.manual_seed(3); m = M.LIFFireNet(%s)\n"
+            "torch.save(m, %r); torch.save(m.state_dict(), %r)\n") % (cfg, ckpt, ckpt + ".sd")
+    load = ("import sys, torch; sys.path.insert(0, %r)\n"
+            "import event_flow_b200; event_flow_b200.install_dropin()\n"
+            "m = torch.load(%r, weights_only=False)\n"
+            "sd = torch.load(%r)\n"
+            "assert type(m).__module__ == 'event_flow_b200.models.model' and type(m).__name__ == 'LIFFireNet', type(m)\n"
+            "assert type(m.G1).__module__ == 'event_flow_b200.models.spiking_submodules'\n"
+            "mine = m.state_dict()\n"
+            "assert list(mine) == list(sd) and all(torch.equal(mine[k], sd[k]) for k in sd)\n"
+            "assert m.G1.stride == 1 and m.head.activation == 'arctanspike' and m.G1.recurrent and m.head.neuron == 'lif'\n"
+            "assert m._fast is None and m.states == [None] * 7\n"
+            "m.reset_states(); print('ok')\n") % (ROOT, ckpt, ckpt + ".sd")
+    for code in (save, load):
+        out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stderr[-2000:]
+    assert out.stdout.strip().endswith("ok")
