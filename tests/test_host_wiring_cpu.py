@@ -109,3 +109,75 @@ def _close(a, b, exact, what):
         assert torch.equal(a, b), what
     else:      # ANN cells: gate convolutions are batched differently from the reference (one conv for update+reset): fp32 noise
         assert (a - b).abs().max().item() <= 1e-5 * max(1.0, b.abs().max().item()), what
+
+
+LOSSES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "loss_*.npz")))
+
+
+@pytest.mark.parametrize("name", LOSSES)
+def test_event_warping_bookkeeping_reproduces_reference_loss_on_cpu(name, monkeypatch):
+    """
+    EventWarping's host side (window accumulation, in-place timestamp offset, pass bookkeeping, overwrite_intermediate_flow,
+    num_events / event_mask) with the kernel call replaced by the oracle's loss: value and flow gradients must be the reference's.
+    """
+    from event_flow_b200 import ops
+    from event_flow_b200.loss.flow import EventWarping
+    from oracle import iwe as oiwe
+
+    def loss_stub(flow_maps, events, pol_mask, event_mask, *, passes, n_per_pass, flow_scaling, weight, loss_scaling=True, smoothing_mask=True,
+                  overwrite_intermediate=False, pass_offsets=None):
+        n_tot = events.shape[1]
+        if pass_offsets is not None:
+            bounds = pass_offsets.tolist()
+            pass_of = torch.cat([torch.full((bounds[t + 1] - bounds[t],), t) for t in range(passes)])
+        else:
+            pass_of = torch.arange(n_tot) // n_per_pass
+        return oiwe.event_warping_loss(events, pol_mask, pass_of.long(), [flow_maps[s] for s in range(flow_maps.shape[0])], event_mask,
+                                       tuple(flow_maps.shape[-2:]), flow_scaling=flow_scaling, weight=weight, loss_scaling=loss_scaling,
+                                       smoothing_mask=smoothing_mask, overwrite_intermediate=overwrite_intermediate, passes=passes)
+
+    monkeypatch.setattr(ops, "event_warping_loss", loss_stub)
+    g = load_golden(name)
+    scaling, smask, overwrite, weight, T, N = g["cfg"].tolist()
+    T, N = int(T), int(N)
+    flow = g["flow"]
+    H, W = flow.shape[-2:]
+    cfg = {"loader": {"resolution": [H, W]}, "loss": {"flow_regul_weight": weight, "overwrite_intermediate": bool(overwrite)},
+           "model": {"mask_output": bool(smask)}}
+    L = EventWarping(cfg, "cpu", loss_scaling=bool(scaling))
+    flows = [flow[:, t].clone().requires_grad_(True) for t in range(T)]
+    for t in range(T):
+        e = g["events"][:, t * N:(t + 1) * N].clone()
+        e[:, :, 0] -= t  # the fixture stores offset timestamps; the API offsets them itself, in place (loss/flow.py:90)
+        L.event_flow_association([flows[t]], e, g["pol_mask"][:, t * N:(t + 1) * N], g["event_mask"][:, t:t + 1])
+        assert torch.equal(e, g["events"][:, t * N:(t + 1) * N]), "the caller's event tensor must carry the pass offset afterwards"
+    assert L.num_events == T * N
+    if overwrite:
+        L.overwrite_intermediate_flow([flows[-1]])
+        assert L.event_mask.shape[1] == 1
+    loss = L()
+    loss.backward()
+    assert abs(loss.item() - g["loss"].item()) <= 1e-6 * abs(g["loss"].item())
+    for t, f in enumerate(flows):
+        if f"grad_{t}" in g:
+            ref = g[f"grad_{t}"]
+            assert (f.grad - ref).abs().max().item() <= 1e-5 * ref.abs().max().item() + 1e-12
+    L.reset()
+    assert L.num_events == 0
+
+
+def test_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours): one JSON line with the contract's keys."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(GOLDEN.rstrip("/")).rsplit("/tests", 1)[0]
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "events/s" and line["higher_is_better"] is True and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and "sample" in line["cpu_baseline"]
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
+    assert "workload" in line["config"] and line["metric"].startswith("events/s")
