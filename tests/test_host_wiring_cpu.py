@@ -181,3 +181,46 @@ def test_reference_arm_prints_the_contract_line():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and "sample" in line["cpu_baseline"]
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
     assert "workload" in line["config"] and line["metric"].startswith("events/s")
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/models"), reason="needs the reference tree (build container only)")
+@pytest.mark.parametrize("cls", ["EVFlowNet", "RecEVFlowNet", "SpikingRecEVFlowNet", "E2VID"])
+def test_cropping_and_input_normalisation_match_the_live_reference(cls, cpu_ops):
+    """init_cropping (pad to a size the pyramid divides, crop back) and norm_input against the unmodified reference, run live on CPU."""
+    import importlib
+    import sys
+
+    import event_flow_b200.models.model as M
+
+    spiking = "Spiking" in cls
+    cfg = dict(name=cls, encoding="cnt", round_encoding=False, norm_input=True, num_bins=2, base_num_channels=4, kernel_size=3,
+               activations=["arctanspike", "arctanspike"] if spiking else ["relu", None], mask_output=True, spiking_neuron=None)
+    saved = {k: sys.modules.pop(k) for k in list(sys.modules) if k == "models" or k.startswith("models.")}
+    sys.path.insert(0, "/root/reference")
+    try:
+        ref_model = importlib.import_module("models.model")
+        torch.manual_seed(5)
+        ref = getattr(ref_model, cls)(dict(cfg))
+    finally:
+        sys.path.remove("/root/reference")
+        for k in [k for k in sys.modules if k == "models" or k.startswith("models.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+    torch.manual_seed(5)
+    mine = getattr(M, cls)(dict(cfg))
+    mine.load_state_dict(ref.state_dict())
+    H, W = 27, 43  # neither is divisible by 2^3 / 2^4
+    ref.init_cropping(W, H), mine.init_cropping(W, H)
+    g = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        for _ in range(2):
+            cnt = torch.randint(0, 3, (1, 2, H, W), generator=g).float()
+            a = mine(None, cnt.clone())["flow"]
+            b = ref(None, cnt.clone())["flow"]
+            assert len(a) == len(b)
+            for fa, fb in zip(a, b):
+                assert fa.shape == fb.shape == (1, 2, H, W)
+                if spiking:
+                    assert torch.equal(fa, fb)
+                else:
+                    assert (fa - fb).abs().max().item() <= 1e-5 * max(1.0, fb.abs().max().item())
