@@ -85,7 +85,10 @@ def test_model_wiring_reproduces_reference_flows_on_cpu(name, cpu_ops):
     out = None
     with torch.no_grad():
         for t, x in enumerate(xs):
-            out = m(x.clone(), x.clone())
+            out = m(x.clone(), x.clone(), log=name.startswith("firenet_"))
+            if name.startswith("firenet_") and "activity" in g:  # log=True: fraction of non-zero entries per layer (model.py:267-284)
+                assert list(out["activity"].keys()) == ["0:input", "1:head", "2:G1", "3:R1a", "4:R1b", "5:G2", "6:R2a", "7:R2b", "8:pred"]
+                assert torch.allclose(torch.tensor(list(out["activity"].values())), g["activity"][t].float(), atol=1e-7)
             per_step = "flow_%d" % t in g and len(xs) > 1 and "flow_%d_0" % (len(xs) - 1) not in g and not name.startswith("annzoo") \
                 and not name.startswith("annunet")
             if per_step:  # fixtures that store the flow of every step (FireNet families)
