@@ -74,11 +74,35 @@ class IweLossParams(C.Structure):
     ]  # fmt: skip
 
 
+EF_IWE_MAX_PASSES, EF_IWE_MAX_SCALES = 32, 4
+
+
+class IweLossPassParams(C.Structure):
+    _fields_ = [
+        ("S", _i32), ("B", _i32), ("T", _i32), ("T_maps", _i32), ("H", _i32), ("W", _i32),
+        ("flow_scaling", C.c_float), ("weight", C.c_float),
+        ("loss_scaling", _i32), ("smoothing_mask", _i32), ("overwrite_intermediate", _i32),
+        ("n_pass", _i32 * EF_IWE_MAX_PASSES),
+        ("events", _f32p * EF_IWE_MAX_PASSES), ("pol_mask", _f32p * EF_IWE_MAX_PASSES),
+        ("flow", _f32p * (EF_IWE_MAX_SCALES * EF_IWE_MAX_PASSES)), ("event_mask", _f32p * EF_IWE_MAX_PASSES),
+        ("workspace", _f32p), ("loss", _f32p), ("g_loss", _f32p),
+        ("g_flow", _f32p * (EF_IWE_MAX_SCALES * EF_IWE_MAX_PASSES)),
+    ]  # fmt: skip
+
+
 class IweImageParams(C.Structure):
     _fields_ = [
         ("B", _i32), ("N", _i32), ("H", _i32), ("W", _i32), ("round_idx", _i32),
         ("tref", C.c_float), ("flow_scaling", C.c_float),
         ("events", _f32p), ("pol_mask", _f32p), ("flow", _f32p), ("event_flow", _f32p), ("iwe", _f32p),
+    ]  # fmt: skip
+
+
+class IweInterpParams(C.Structure):
+    _fields_ = [
+        ("B", _i32), ("N", _i32), ("H", _i32), ("W", _i32), ("round_idx", _i32),
+        ("tref", C.c_float), ("flow_scaling", C.c_float),
+        ("events", _f32p), ("flow", _f32p), ("idx", _f32p), ("weights", _f32p),
     ]  # fmt: skip
 
 
@@ -143,7 +167,14 @@ EXPORTS = {
     "ef_iwe_loss_workspace_elems": (C.c_int64, [_i32, _i32, _i32, _i32]),
     "ef_iwe_loss_fwd": (C.c_int, [C.POINTER(IweLossParams), C.c_void_p]),
     "ef_iwe_loss_bwd": (C.c_int, [C.POINTER(IweLossParams), C.c_void_p]),
+    "ef_iwe_loss_fwd_passes": (C.c_int, [C.POINTER(IweLossPassParams), C.c_void_p]),
+    "ef_iwe_loss_bwd_passes": (C.c_int, [C.POINTER(IweLossPassParams), C.c_void_p]),
     "ef_iwe_image": (C.c_int, [C.POINTER(IweImageParams), C.c_void_p]),
+    "ef_iwe_purge_unfeasible": (C.c_int, [C.c_void_p, C.c_int64, _i32, _i32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ef_iwe_get_interpolation": (C.c_int, [C.POINTER(IweInterpParams), C.c_void_p]),
+    "ef_iwe_interpolate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, _i32, _i32, _i32, _i32, C.c_void_p, C.c_void_p]),
+    "ef_spike_fwd": (C.c_int, [C.c_void_p, C.c_void_p, _i32, _i32, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
+    "ef_spike_bwd": (C.c_int, [C.c_void_p, C.c_void_p, _i32, _i32, C.c_int64, C.c_int64, C.c_void_p, _i32, C.c_float, C.c_void_p, C.c_void_p]),
     "ef_conv_ann_fwd": (C.c_int, [C.POINTER(ConvAnnParams), C.c_void_p]),
     "ef_conv3x3_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, _i32, _i32, _i32, _i32, _i32, C.c_void_p]),
     "ef_iwe_metrics_workspace_elems": (C.c_int64, [_i32, _i32, _i32]),

@@ -21,7 +21,9 @@ __global__ void __launch_bounds__(256) encode_kernel(const ef_encode_params p) {
     if (pol > 0.f) atomicAdd(p.cnt + ((size_t)b * 2 + 0) * hw + pix, pol * pol);
     if (pol < 0.f) atomicAdd(p.cnt + ((size_t)b * 2 + 1) * hw + pix, pol * pol);
   }
-  if (p.mask) p.mask[(size_t)b * hw + pix] = fabsf(pol);  // index_put_ without accumulate: any writer wins, all write |p|
+  // index_put_ without accumulate: any writer wins; real events all write |p| = 1.  A padded (p = 0) event must not race a
+  // real one at the same pixel and clear the mask, so it does not write at all (the image is zero-filled anyway).
+  if (p.mask && pol != 0.f) p.mask[(size_t)b * hw + pix] = fabsf(pol);
   if (p.voxel) {  // encodings.py:48-67
     float ts = __fmul_rn(e.x, (float)(p.num_bins - 1));
     if (p.round_ts) ts = rintf(ts);

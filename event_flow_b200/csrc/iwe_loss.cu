@@ -3,28 +3,56 @@
 // interpolate), loss/flow.py:65-79 (per-event flow gather), utils/iwe.py:95-153 (deblur_events, compute_pol_iwe).
 // Sub-gradient conventions at ties (integer warped coordinates, empty pixels) follow SURVEY.md 7.4, i.e. what
 // torch.autograd produces for the reference expressions.
+#include <string.h>
+
 #include "common.cuh"
 
 namespace ef {
 
-// workspace layout (floats):
-//   img  [S][B][2 dir][HW][4 = I+,Th+,I-,Th-]      forward accumulators, pixel-interleaved: an event adds (w, w*tau) of its
-//                                                  polarity with ONE 8-byte vector atomic per corner (red.global.add.v2.f32),
-//                                                  the reductions read one 16-byte vector per pixel
-//   adj  [S][B][2 dir][HW][4]                      adjoint images (backward), same layout
-//   sums [S][B][2 dir][2 = sum A^2, n]             per-sample reductions
-//   smooth [S]
-struct WsLayout {
-  size_t img, adj, sums, smooth, total;
+// ---- window descriptor (device side) ------------------------------------------------------------------------------
+// Both public forms of a window -- concatenated ("map form", ef_iwe_loss_params) and per-pass pointer tables
+// (ef_iwe_loss_pass_params: nothing is concatenated or copied) -- are lowered to this by-value table: pass t has its own
+// base pointers and its own sample stride.
+constexpr int MAXP = EF_IWE_MAX_PASSES, MAXS = EF_IWE_MAX_SCALES;
+struct IweWin {
+  int S, B, T, Tm, H, W;
+  int loss_scaling, use_mask, use_dt;
+  float flow_scaling, smooth_coef;  // smooth_coef = weight / components / T_maps
+  int n_items;                      // chunks of IWE_CHUNK events of one (scale, sample): sum_t ceil(n_t / IWE_CHUNK)
+  int chunk_off[MAXP + 1];          // first chunk of pass t
+  int n_pass[MAXP];                 // events of pass t (per sample)
+  const float* ev[MAXP];            // pass t: [B][n_t][4], sample stride ev_bs[t] floats
+  const float* pm[MAXP];            // pass t: [B][n_t][2], sample stride pm_bs[t] floats
+  long long ev_bs[MAXP], pm_bs[MAXP];
+  const float* flow[MAXS * MAXP];   // (s, map m): [B][2][H][W], sample stride flow_bs floats
+  long long flow_bs;
+  const float* mask[MAXP];          // map m: [B][H][W], sample stride mask_bs floats (NULL without smoothing mask)
+  long long mask_bs;
+  float* g_flow[MAXS * MAXP];       // backward: (s, map m): [B][2][H][W], sample stride g_bs
+  long long g_bs;
 };
+constexpr int IWE_CHUNK = 256, IWE_THREADS = 256;
+constexpr int RED_PIX = 2048;  // pixels per block of the reductions
+
+// workspace layout (floats):
+//   ctr  [16]  (as uint32) grid-barrier counters.  Must be ZERO when a buffer is first used; every call leaves them zero.
+//   img  [S][B][2 dir][2 pol][HW][2 = I, Th]   forward accumulators.  Polarity-planar, (I, Th) interleaved per pixel: an event
+//        adds (w, w*tau) of a corner with ONE 8-byte vector atomic, and the two corners of a row with ONE 16-byte vector
+//        atomic when the left pixel index is even (red.global.add.v4.f32): 6 instead of 16 atomics per event on average
+//   sums [S][B][2 dir][2 = sum A^2, n]
+//   smooth_part [S][MAX_GRID]                  per-CTA partial sums of the smoothness term (fixed-order final reduction)
+struct WsLayout {
+  size_t ctr, img, sums, smooth, total;
+};
+constexpr int IWE_MAX_GRID = 148 * 8;
 __host__ __device__ inline WsLayout ws_layout(int S, int B, int H, int W) {
   WsLayout l;
   const size_t hw = (size_t)H * W;
-  l.img = 0;
-  l.adj = l.img + (size_t)S * B * 8 * hw;
-  l.sums = l.adj + (size_t)S * B * 8 * hw;
+  l.ctr = 0;
+  l.img = 16;
+  l.sums = l.img + (size_t)S * B * 8 * hw;
   l.smooth = l.sums + (size_t)S * B * 4;
-  l.total = l.smooth + S;
+  l.total = l.smooth + (size_t)S * IWE_MAX_GRID;
   return l;
 }
 
@@ -55,51 +83,6 @@ __device__ __forceinline__ void warp_event(float ts, float y, float x, float fy,
   }
 }
 
-__device__ __forceinline__ int pass_of_event(const ef_iwe_loss_params& p, int i) {
-  if (p.T_maps <= 1) return 0;
-  if (p.pass_offsets) {
-    int t = 0;
-    while (t + 1 < p.T && i >= __ldg(p.pass_offsets + t + 1)) ++t;
-    return t;
-  }
-  return min(i / p.n_per_pass, p.T_maps - 1);
-}
-
-// ---- forward: scatter ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) iwe_scatter_kernel(const ef_iwe_loss_params p, float* __restrict__ img) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int b = blockIdx.y, s = blockIdx.z;
-  if (i >= p.n_total) return;
-  const size_t hw = (size_t)p.H * p.W;
-  const float4 e = reinterpret_cast<const float4*>(p.events)[(size_t)b * p.n_total + i];  // ts, y, x, p
-  const float2 pm = reinterpret_cast<const float2*>(p.pol_mask)[(size_t)b * p.n_total + i];
-  if (pm.x == 0.f && pm.y == 0.f) return;
-  const int t_e = pass_of_event(p, i);
-  const int pix = (int)(e.y * (float)p.W + e.z);
-  const float* fm = p.flow_maps + (((size_t)s * p.B + b) * p.T_maps + t_e) * 2 * hw;
-  const float fx = __ldg(fm + pix), fy = __ldg(fm + hw + pix);
-  float* base = img + ((size_t)s * p.B + b) * 8 * hw;
-#pragma unroll
-  for (int dir = 0; dir < 2; ++dir) {
-    const float tref = dir == 0 ? (float)p.T : 0.f;
-    const float tau = dir == 0 ? e.x : __fsub_rn((float)p.T, e.x);
-    float yw, xw;
-    Corner c[4];
-    warp_event(e.x, e.y, e.z, fy, fx, tref, p.flow_scaling, p.H, p.W, yw, xw, c);
-    float* d = base + (size_t)dir * 4 * hw;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (c[k].idx < 0) continue;
-      const float w = __fmul_rn(c[k].wy, c[k].wx);
-      if (w == 0.f) continue;
-      const float wt = __fmul_rn(w, tau);
-      float2* q = reinterpret_cast<float2*>(d + (size_t)c[k].idx * 4);  // [I+, Th+], [I-, Th-]
-      if (pm.x != 0.f) atomicAdd(q, make_float2(__fmul_rn(w, pm.x), __fmul_rn(wt, pm.x)));
-      if (pm.y != 0.f) atomicAdd(q + 1, make_float2(__fmul_rn(w, pm.y), __fmul_rn(wt, pm.y)));
-    }
-  }
-}
-
 __device__ __forceinline__ float block_sum256(float v, float* s_red) {
   v = warp_sum(v);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -114,34 +97,24 @@ __device__ __forceinline__ float block_sum256(float v, float* s_red) {
   return r;
 }
 
-// ---- forward: per-(scale,sample,direction) contrast sums --------------------------------------------------------
-constexpr int RED_PIX = 2048;  // pixels per block
-__global__ void __launch_bounds__(256) iwe_reduce_kernel(const float* __restrict__ img, float* __restrict__ sums, int HW, float T) {
-  __shared__ float s_red[8];
-  const int sbd = blockIdx.y;  // (s*B + b)*2 + dir
-  const float* d = img + (size_t)sbd * 4 * HW;
-  float ssq = 0.f, n = 0.f;
-  const int p0 = blockIdx.x * RED_PIX;
-  for (int i = p0 + threadIdx.x; i < min(p0 + RED_PIX, HW); i += 256) {
-    const float4 q = reinterpret_cast<const float4*>(d)[i];
-    const float ip = q.x, tp = q.y, in = q.z, tn = q.w;
-    const float ap = tp / (ip + 1e-9f) / T, an = tn / (in + 1e-9f) / T;
-    ssq += ap * ap + an * an;
-    n += (ip + in > 0.f) ? 1.f : 0.f;
-  }
-  const float r0 = block_sum256(ssq, s_red);
-  const float r1 = block_sum256(n, s_red);
+// ---- grid-wide barrier of a co-resident (cooperative) grid ------------------------------------------------------------
+// ctr is zero on entry; the caller resets it once every CTA is known to have left the spin (i.e. after a LATER barrier).
+// Bounded spin: a protocol bug traps (an error the host sees) instead of hanging the GPU.
+__device__ __forceinline__ void grid_barrier(unsigned int* ctr, unsigned int n) {
+  __syncthreads();
   if (threadIdx.x == 0) {
-    atomicAdd(sums + sbd * 2 + 0, r0);
-    atomicAdd(sums + sbd * 2 + 1, r1);
+    __threadfence();
+    atomicAdd(ctr, 1u);
+    const long long t0 = clock64();
+    unsigned int seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ctr) : "memory");
+      if (seen < n && clock64() - t0 > 4000000000ll) __trap();
+    } while (seen < n);
+    __threadfence();
   }
+  __syncthreads();
 }
-
-// ---- smoothness (loss/flow.py:262-294), forward value and gradient ----------------------------------------------
-struct SmoothGeom {
-  int B, T, H, W;
-  bool use_mask, use_dt;
-};
 
 __device__ __forceinline__ float charb_pair(const float* fxm, const float* fym, const float* mk, size_t a, size_t b, bool use_mask,
                                             float& dcoef) {
@@ -152,117 +125,175 @@ __device__ __forceinline__ float charb_pair(const float* fxm, const float* fym, 
   return m * c;
 }
 
-// flow maps of one scale: [B][T][2][H][W]; mask [B][T][H][W]
-__global__ void __launch_bounds__(256) smooth_fwd_kernel(const float* __restrict__ fm, const float* __restrict__ mask, SmoothGeom g,
-                                                         float* __restrict__ out) {
+// item -> (scale*B + sample, pass, first event of the chunk)
+__device__ __forceinline__ void decode_item(const IweWin& w, int item, int& sb, int& t, int& i0) {
+  sb = item / w.n_items;
+  const int c = item - sb * w.n_items;
+  t = 0;
+  while (t + 1 < w.T && c >= w.chunk_off[t + 1]) ++t;
+  i0 = (c - w.chunk_off[t]) * IWE_CHUNK;
+}
+
+// vector reductions without a return value (RED, not ATOM: nothing waits for the round trip)
+__device__ __forceinline__ void red2(float* q, float a, float b) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(q), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void red4(float* q, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(q), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// ---- forward: ONE launch ----------------------------------------------------------------------------------------------
+//   phase 0  zero the accumulators; Charbonnier smoothness of the flow maps (loss/flow.py:262-294) into per-CTA partials
+//   phase 1  per event: gather flow, warp forward (tref = T) and backward (tref = 0), bilinear scatter (loss/flow.py:193-259,
+//            utils/iwe.py:20-92)
+//   phase 2  per (scale, sample, direction): sum of squared average timestamps and number of pixels with events (:212-226)
+//   phase 3  last CTA: the scalar
+__global__ void __launch_bounds__(IWE_THREADS) iwe_loss_fwd_kernel(const __grid_constant__ IweWin w, float* __restrict__ ws, float* __restrict__ loss) {
   __shared__ float s_red[8];
-  const size_t hw = (size_t)g.H * g.W, n = (size_t)g.B * g.T * hw;
-  float acc = 0.f;
-  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
-    const int x = i % g.W, y = (i / g.W) % g.H;
-    const size_t bt = i / hw;
-    const int t = bt % g.T;
-    const float* fxm = fm + bt * 2 * hw;
-    const float* fym = fxm + hw;
-    const float* mk = mask ? mask + bt * hw : nullptr;
-    const size_t o = (size_t)y * g.W + x;
-    float dc;
-    if (x + 1 < g.W) acc += charb_pair(fxm, fym, mk, o, o + 1, g.use_mask, dc);
-    if (y + 1 < g.H) acc += charb_pair(fxm, fym, mk, o, o + g.W, g.use_mask, dc);
-    if (x + 1 < g.W && y + 1 < g.H) {
-      acc += charb_pair(fxm, fym, mk, o, o + g.W + 1, g.use_mask, dc);      // down-right
-      acc += charb_pair(fxm, fym, mk, o + g.W, o + 1, g.use_mask, dc);      // up-right: (y+1,x) - (y,x+1)
-    }
-    if (g.use_dt && t + 1 < g.T) {  // temporal: same pixel, next pass.  Masks of both passes.
-      const float d = (fxm[o] - fxm[o + 2 * hw]) + (fym[o] - fym[o + 2 * hw]);
-      const float m = g.use_mask ? mk[o] * mk[o + hw] : 1.f;
-      acc += m * sqrtf(d * d + 1e-6f);
+  __shared__ bool s_last;
+  const WsLayout l = ws_layout(w.S, w.B, w.H, w.W);
+  unsigned int* ctr = reinterpret_cast<unsigned int*>(ws + l.ctr);
+  float* img = ws + l.img;
+  float* sums = ws + l.sums;
+  const size_t hw = (size_t)w.H * w.W;
+  const int tid = threadIdx.x;
+  const size_t gtid = (size_t)blockIdx.x * IWE_THREADS + tid, gsz = (size_t)gridDim.x * IWE_THREADS;
+
+  // ---- phase 0
+  {
+    float4* z = reinterpret_cast<float4*>(img);
+    const size_t n4 = ((size_t)w.S * w.B * 8 * hw + (size_t)w.S * w.B * 4) / 4;  // images + sums (contiguous, multiple of 4 floats)
+    for (size_t i = gtid; i < n4; i += gsz) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const size_t n = (size_t)w.B * w.Tm * hw;
+    for (int s = 0; s < w.S; ++s) {
+      float acc = 0.f;
+      if (w.smooth_coef != 0.f) {
+        for (size_t i = gtid; i < n; i += gsz) {
+          const int x = i % w.W, y = (i / w.W) % w.H;
+          const size_t bt = i / hw;
+          const int t = bt % w.Tm, b = bt / w.Tm;
+          const float* fxm = w.flow[s * w.Tm + t] + (size_t)b * w.flow_bs;
+          const float* fym = fxm + hw;
+          const float* mk = w.use_mask ? w.mask[t] + (size_t)b * w.mask_bs : nullptr;
+          const size_t o = (size_t)y * w.W + x;
+          float dc;
+          if (x + 1 < w.W) acc += charb_pair(fxm, fym, mk, o, o + 1, w.use_mask, dc);
+          if (y + 1 < w.H) acc += charb_pair(fxm, fym, mk, o, o + w.W, w.use_mask, dc);
+          if (x + 1 < w.W && y + 1 < w.H) {
+            acc += charb_pair(fxm, fym, mk, o, o + w.W + 1, w.use_mask, dc);  // down-right
+            acc += charb_pair(fxm, fym, mk, o + w.W, o + 1, w.use_mask, dc);  // up-right: (y+1,x) - (y,x+1)
+          }
+          if (w.use_dt && t + 1 < w.Tm) {  // temporal: same pixel, next pass.  Masks of both passes.
+            const float* fxn = w.flow[s * w.Tm + t + 1] + (size_t)b * w.flow_bs;
+            const float d = (fxm[o] - fxn[o]) + (fym[o] - fxn[hw + o]);
+            const float m = w.use_mask ? mk[o] * (w.mask[t + 1] + (size_t)b * w.mask_bs)[o] : 1.f;
+            acc += m * sqrtf(d * d + 1e-6f);
+          }
+        }
+      }
+      const float r = block_sum256(acc, s_red);
+      if (tid == 0) ws[l.smooth + (size_t)s * IWE_MAX_GRID + blockIdx.x] = r;
     }
   }
-  const float r = block_sum256(acc, s_red);
-  if (threadIdx.x == 0) atomicAdd(out, r);
-}
+  grid_barrier(ctr + 0, gridDim.x);
 
-// gradient of the smoothness term wrt both flow channels of every pixel (gather form, no atomics); writes g_fm.
-__global__ void __launch_bounds__(256) smooth_bwd_kernel(const float* __restrict__ fm, const float* __restrict__ mask, SmoothGeom g,
-                                                         const float* __restrict__ g_loss, float coef, float* __restrict__ g_fm) {
-  const size_t hw = (size_t)g.H * g.W, n = (size_t)g.B * g.T * hw;
-  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
-  if (i >= n) return;
-  const int x = i % g.W, y = (i / g.W) % g.H;
-  const size_t bt = i / hw;
-  const int t = bt % g.T;
-  const float* fxm = fm + bt * 2 * hw;
-  const float* fym = fxm + hw;
-  const float* mk = mask ? mask + bt * hw : nullptr;
-  const size_t o = (size_t)y * g.W + x;
-  const int W = g.W, H = g.H;
-  float acc = 0.f, dc;
-  // as first element of a pair: +, as second: -
-  if (x + 1 < W) { charb_pair(fxm, fym, mk, o, o + 1, g.use_mask, dc); acc += dc; }
-  if (x >= 1) { charb_pair(fxm, fym, mk, o - 1, o, g.use_mask, dc); acc -= dc; }
-  if (y + 1 < H) { charb_pair(fxm, fym, mk, o, o + W, g.use_mask, dc); acc += dc; }
-  if (y >= 1) { charb_pair(fxm, fym, mk, o - W, o, g.use_mask, dc); acc -= dc; }
-  if (x + 1 < W && y + 1 < H) { charb_pair(fxm, fym, mk, o, o + W + 1, g.use_mask, dc); acc += dc; }
-  if (x >= 1 && y >= 1) { charb_pair(fxm, fym, mk, o - W - 1, o, g.use_mask, dc); acc -= dc; }
-  if (y >= 1 && x + 1 < W) { charb_pair(fxm, fym, mk, o, o - W + 1, g.use_mask, dc); acc += dc; }   // first of up-right pair (y-1,x)
-  if (y + 1 < H && x >= 1) { charb_pair(fxm, fym, mk, o + W - 1, o, g.use_mask, dc); acc -= dc; }   // second of pair (y,x-1)
-  if (g.use_dt) {
-    if (t + 1 < g.T) {
-      const float d = (fxm[o] - fxm[o + 2 * hw]) + (fym[o] - fym[o + 2 * hw]);
-      const float m = g.use_mask ? mk[o] * mk[o + hw] : 1.f;
-      acc += m * d / sqrtf(d * d + 1e-6f);
-    }
-    if (t >= 1) {
-      const float d = (fxm[o - 2 * hw] - fxm[o]) + (fym[o - 2 * hw] - fym[o]);
-      const float m = g.use_mask ? mk[o - hw] * mk[o] : 1.f;
-      acc -= m * d / sqrtf(d * d + 1e-6f);
+  // ---- phase 1
+  const float Tf = (float)w.T;
+  const int total_items = w.S * w.B * w.n_items;
+  for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+    int sb, t, i0;
+    decode_item(w, item, sb, t, i0);
+    const int i = i0 + tid;
+    if (i >= w.n_pass[t]) continue;
+    const int s = sb / w.B, b = sb - s * w.B;
+    const float4 e = __ldg(reinterpret_cast<const float4*>(w.ev[t] + (size_t)b * w.ev_bs[t]) + i);  // ts, y, x, p
+    const float2 pm = __ldg(reinterpret_cast<const float2*>(w.pm[t] + (size_t)b * w.pm_bs[t]) + i);
+    if (pm.x == 0.f && pm.y == 0.f) continue;
+    const int pix = (int)(e.y * (float)w.W + e.z);
+    const float* fm = w.flow[s * w.Tm + (w.Tm > 1 ? t : 0)] + (size_t)b * w.flow_bs;
+    const float fx = __ldg(fm + pix), fy = __ldg(fm + hw + pix);
+    float* base = img + (size_t)sb * 8 * hw;
+#pragma unroll
+    for (int dir = 0; dir < 2; ++dir) {
+      const float tref = dir == 0 ? Tf : 0.f;
+      const float tau = dir == 0 ? e.x : __fsub_rn(Tf, e.x);
+      float yw, xw;
+      Corner c[4];
+      warp_event(e.x, e.y, e.z, fy, fx, tref, w.flow_scaling, w.H, w.W, yw, xw, c);
+      float* d = base + (size_t)dir * 4 * hw;
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {  // top row (corners 0,1), bottom row (2,3): left and right pixels are neighbours in memory
+        const Corner &cl = c[2 * r], &cr = c[2 * r + 1];
+        const float wl = cl.idx >= 0 ? __fmul_rn(cl.wy, cl.wx) : 0.f, wr = cr.idx >= 0 ? __fmul_rn(cr.wy, cr.wx) : 0.f;
+        const float tl = __fmul_rn(wl, tau), tr = __fmul_rn(wr, tau);
+#pragma unroll
+        for (int pol = 0; pol < 2; ++pol) {
+          const float m = pol == 0 ? pm.x : pm.y;
+          if (m == 0.f) continue;
+          float* plane = d + (size_t)pol * 2 * hw;
+          if (wl != 0.f && wr != 0.f && !(cl.idx & 1) && cr.idx == cl.idx + 1) {
+            red4(plane + (size_t)cl.idx * 2, __fmul_rn(wl, m), __fmul_rn(tl, m), __fmul_rn(wr, m), __fmul_rn(tr, m));
+          } else {
+            if (wl != 0.f) red2(plane + (size_t)cl.idx * 2, __fmul_rn(wl, m), __fmul_rn(tl, m));
+            if (wr != 0.f) red2(plane + (size_t)cr.idx * 2, __fmul_rn(wr, m), __fmul_rn(tr, m));
+          }
+        }
+      }
     }
   }
-  const float v = acc * coef * g_loss[0];
-  g_fm[bt * 2 * hw + o] = v;
-  g_fm[bt * 2 * hw + hw + o] = v;
-}
+  grid_barrier(ctr + 1, gridDim.x);
 
-// ---- forward: final scalar --------------------------------------------------------------------------------------
-__global__ void iwe_finalize_kernel(const float* __restrict__ sums, const float* __restrict__ smooth, int S, int B, int loss_scaling,
-                                    float smooth_coef, float* __restrict__ loss) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  // ---- phase 2: chunks of RED_PIX pixels of one (scale, sample, direction)
+  {
+    const int chunks = (int)((hw + RED_PIX - 1) / RED_PIX), n_sbd = w.S * w.B * 2;
+    for (int item = blockIdx.x; item < n_sbd * chunks; item += gridDim.x) {
+      const int sbd = item / chunks, p0 = (item - sbd * chunks) * RED_PIX;
+      const float2* pos = reinterpret_cast<const float2*>(img + (size_t)sbd * 4 * hw);
+      const float2* neg = pos + hw;
+      float ssq = 0.f, n = 0.f;
+      const int p1 = min(p0 + RED_PIX, (int)hw);
+      for (int i = p0 + tid; i < p1; i += IWE_THREADS) {
+        const float2 qp = __ldcg(pos + i), qn = __ldcg(neg + i);
+        const float ap = qp.y / (qp.x + 1e-9f) / Tf, an = qn.y / (qn.x + 1e-9f) / Tf;
+        ssq += ap * ap + an * an;
+        n += (qp.x + qn.x > 0.f) ? 1.f : 0.f;
+      }
+      const float r0 = block_sum256(ssq, s_red);
+      const float r1 = block_sum256(n, s_red);
+      if (tid == 0) {
+        atomicAdd(sums + sbd * 2 + 0, r0);
+        atomicAdd(sums + sbd * 2 + 1, r1);
+      }
+    }
+  }
+
+  // ---- phase 3: the last CTA to get here computes the scalar and restores the counters
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    s_last = atomicInc(ctr + 2, gridDim.x - 1) == gridDim.x - 1;  // wraps to 0 with the last arrival
+    __threadfence();
+  }
+  __syncthreads();
+  if (!s_last) return;
   float total = 0.f;
-  for (int s = 0; s < S; ++s) {
-    float fw = 0.f, bw = 0.f;
-    for (int b = 0; b < B; ++b) {
-      const float* q = sums + ((size_t)(s * B + b) * 2) * 2;
-      fw += loss_scaling ? q[0] / q[1] : q[0];
-      bw += loss_scaling ? q[2] / q[3] : q[2];
+  for (int s = 0; s < w.S; ++s) {
+    float sm = 0.f;
+    for (int c = tid; c < (int)gridDim.x; c += IWE_THREADS) sm += __ldcg(ws + l.smooth + (size_t)s * IWE_MAX_GRID + c);
+    sm = block_sum256(sm, s_red);
+    float fb = 0.f;
+    for (int k = tid; k < w.B * 2; k += IWE_THREADS) {
+      const float ssq = __ldcg(sums + ((size_t)s * w.B * 2 + k) * 2), n = __ldcg(sums + ((size_t)s * w.B * 2 + k) * 2 + 1);
+      fb += w.loss_scaling ? ssq / n : ssq;
     }
-    total += fw + bw + smooth_coef * smooth[s];
+    fb = block_sum256(fb, s_red);
+    total += fb + w.smooth_coef * sm;
   }
-  loss[0] = total / (float)S;
-}
-
-// ---- backward: adjoint images -----------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) iwe_adjoint_kernel(const float* __restrict__ img, const float* __restrict__ sums,
-                                                          float* __restrict__ adj, int HW, float T, int loss_scaling, float inv_S,
-                                                          const float* __restrict__ g_loss) {
-  const int sbd = blockIdx.y;
-  const int i = blockIdx.x * 256 + threadIdx.x;
-  if (i >= HW) return;
-  const float* d = img + (size_t)sbd * 4 * HW;
-  float* a = adj + (size_t)sbd * 4 * HW;
-  const float ssq = sums[sbd * 2], n = sums[sbd * 2 + 1];
-  const float g = g_loss[0] * inv_S / (loss_scaling ? n : 1.f);
-  const float4 q = reinterpret_cast<const float4*>(d)[i];
-  const float ip = q.x, tp = q.y, in = q.z, tn = q.w;
-  const float ap = tp / (ip + 1e-9f) / T, an = tn / (in + 1e-9f) / T;
-  const float gtp = g * 2.f * ap / ((ip + 1e-9f) * T), gtn = g * 2.f * an / ((in + 1e-9f) * T);
-  float gip = -gtp * tp / (ip + 1e-9f), gin = -gtn * tn / (in + 1e-9f);
-  if (loss_scaling && !(ip + in > 0.f)) {  // empty pixel keeps gradient 1 into the divisor (in-place masked assignment)
-    const float gn = -g_loss[0] * inv_S * ssq / (n * n);
-    gip += gn;
-    gin += gn;
+  if (tid == 0) {
+    loss[0] = total / (float)w.S;
+    ctr[0] = 0u;
+    ctr[1] = 0u;
   }
-  reinterpret_cast<float4*>(a)[i] = make_float4(gip, gtp, gin, gtn);
 }
 
 // d max(0, 1-|d|) / d d with torch's tie conventions: abs'(0) = 0; maximum splits the gradient at equality.
@@ -272,49 +303,148 @@ __device__ __forceinline__ float dweight(float d) {
   return u > 0.f ? s : (u == 0.f ? 0.5f * s : 0.f);
 }
 
-// ---- backward: per-event gradient, scattered to the flow maps ----------------------------------------------------
-__global__ void __launch_bounds__(256) iwe_event_grad_kernel(const ef_iwe_loss_params p, const float* __restrict__ adj) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int b = blockIdx.y, s = blockIdx.z;
-  if (i >= p.n_total) return;
-  const size_t hw = (size_t)p.H * p.W;
-  const float4 e = reinterpret_cast<const float4*>(p.events)[(size_t)b * p.n_total + i];
-  const float2 pm = reinterpret_cast<const float2*>(p.pol_mask)[(size_t)b * p.n_total + i];
-  if (pm.x == 0.f && pm.y == 0.f) return;
-  const int t_e = pass_of_event(p, i);
-  const int pix = (int)(e.y * (float)p.W + e.z);
-  const size_t mo = (((size_t)s * p.B + b) * p.T_maps + t_e) * 2 * hw;
-  const float fx = __ldg(p.flow_maps + mo + pix), fy = __ldg(p.flow_maps + mo + hw + pix);
-  const float* abase = adj + ((size_t)s * p.B + b) * 8 * hw;
-  float gfy = 0.f, gfx = 0.f;
-#pragma unroll
-  for (int dir = 0; dir < 2; ++dir) {
-    const float tref = dir == 0 ? (float)p.T : 0.f;
-    const float tau = dir == 0 ? e.x : ((float)p.T - e.x);
-    const float kk = (tref - e.x) * p.flow_scaling;
-    float yw, xw;
-    Corner c[4];
-    warp_event(e.x, e.y, e.z, fy, fx, tref, p.flow_scaling, p.H, p.W, yw, xw, c);
-    const float* a = abase + (size_t)dir * 4 * hw;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (c[k].idx < 0) continue;
-      float delta = 0.f;
-      const float2* q = reinterpret_cast<const float2*>(a + (size_t)c[k].idx * 4);  // adjoints of [I+, Th+], [I-, Th-]
-      if (pm.x != 0.f) {
-        const float2 g2 = __ldg(q);
-        delta += pm.x * (g2.x + tau * g2.y);
+// ---- backward: ONE launch ---------------------------------------------------------------------------------------------
+//   phase 0  gradient of the smoothness term wrt both flow channels of every pixel (gather form) -> g_flow (overwrites)
+//   phase 1  per event and corner: the adjoint of the contrast term is computed on the fly from the accumulator images and
+//            the per-(scale, sample, direction) sums, scattered onto the event's own pixel of g_flow
+__global__ void __launch_bounds__(IWE_THREADS) iwe_loss_bwd_kernel(const __grid_constant__ IweWin w, float* __restrict__ ws,
+                                                                   const float* __restrict__ g_loss) {
+  __shared__ bool s_last;
+  const WsLayout l = ws_layout(w.S, w.B, w.H, w.W);
+  unsigned int* ctr = reinterpret_cast<unsigned int*>(ws + l.ctr);
+  const float* img = ws + l.img;
+  const float* sums = ws + l.sums;
+  const size_t hw = (size_t)w.H * w.W;
+  const int tid = threadIdx.x;
+  const size_t gtid = (size_t)blockIdx.x * IWE_THREADS + tid, gsz = (size_t)gridDim.x * IWE_THREADS;
+  const float gl = __ldg(g_loss);
+  const int W = w.W, H = w.H;
+
+  // ---- phase 0
+  {
+    const size_t n = (size_t)w.B * w.Tm * hw;
+    const float coef = w.smooth_coef / (float)w.S * gl;
+    for (int s = 0; s < w.S; ++s) {
+      for (size_t i = gtid; i < n; i += gsz) {
+        const int x = i % W, y = (i / W) % H;
+        const size_t bt = i / hw;
+        const int t = bt % w.Tm, b = bt / w.Tm;
+        float acc = 0.f;
+        if (w.smooth_coef != 0.f) {
+          const float* fxm = w.flow[s * w.Tm + t] + (size_t)b * w.flow_bs;
+          const float* fym = fxm + hw;
+          const float* mk = w.use_mask ? w.mask[t] + (size_t)b * w.mask_bs : nullptr;
+          const size_t o = (size_t)y * W + x;
+          float dc;
+          // as first element of a pair: +, as second: -
+          if (x + 1 < W) { charb_pair(fxm, fym, mk, o, o + 1, w.use_mask, dc); acc += dc; }
+          if (x >= 1) { charb_pair(fxm, fym, mk, o - 1, o, w.use_mask, dc); acc -= dc; }
+          if (y + 1 < H) { charb_pair(fxm, fym, mk, o, o + W, w.use_mask, dc); acc += dc; }
+          if (y >= 1) { charb_pair(fxm, fym, mk, o - W, o, w.use_mask, dc); acc -= dc; }
+          if (x + 1 < W && y + 1 < H) { charb_pair(fxm, fym, mk, o, o + W + 1, w.use_mask, dc); acc += dc; }
+          if (x >= 1 && y >= 1) { charb_pair(fxm, fym, mk, o - W - 1, o, w.use_mask, dc); acc -= dc; }
+          if (y >= 1 && x + 1 < W) { charb_pair(fxm, fym, mk, o, o - W + 1, w.use_mask, dc); acc += dc; }  // first of up-right pair (y-1,x)
+          if (y + 1 < H && x >= 1) { charb_pair(fxm, fym, mk, o + W - 1, o, w.use_mask, dc); acc -= dc; }  // second of pair (y,x-1)
+          if (w.use_dt) {
+            if (t + 1 < w.Tm) {
+              const float* fxn = w.flow[s * w.Tm + t + 1] + (size_t)b * w.flow_bs;
+              const float d = (fxm[o] - fxn[o]) + (fym[o] - fxn[hw + o]);
+              const float m = w.use_mask ? mk[o] * (w.mask[t + 1] + (size_t)b * w.mask_bs)[o] : 1.f;
+              acc += m * d / sqrtf(d * d + 1e-6f);
+            }
+            if (t >= 1) {
+              const float* fxq = w.flow[s * w.Tm + t - 1] + (size_t)b * w.flow_bs;
+              const float d = (fxq[o] - fxm[o]) + (fxq[hw + o] - fym[o]);
+              const float m = w.use_mask ? (w.mask[t - 1] + (size_t)b * w.mask_bs)[o] * mk[o] : 1.f;
+              acc -= m * d / sqrtf(d * d + 1e-6f);
+            }
+          }
+        }
+        const float v = acc * coef;
+        float* g = w.g_flow[s * w.Tm + t] + (size_t)b * w.g_bs + (size_t)y * W + x;
+        g[0] = v;
+        g[hw] = v;
       }
-      if (pm.y != 0.f) {
-        const float2 g2 = __ldg(q + 1);
-        delta += pm.y * (g2.x + tau * g2.y);
-      }
-      gfy += delta * dweight(c[k].dy) * c[k].wx * kk;
-      gfx += delta * c[k].wy * dweight(c[k].dx) * kk;
     }
   }
-  if (gfx != 0.f) atomicAdd(p.g_flow_maps + mo + pix, gfx);
-  if (gfy != 0.f) atomicAdd(p.g_flow_maps + mo + hw + pix, gfy);
+  grid_barrier(ctr + 3, gridDim.x);
+
+  // ---- phase 1
+  const float Tf = (float)w.T, inv_S = 1.0f / (float)w.S;
+  const int total_items = w.S * w.B * w.n_items;
+  for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+    int sb, t, i0;
+    decode_item(w, item, sb, t, i0);
+    const int i = i0 + tid;
+    if (i >= w.n_pass[t]) continue;
+    const int s = sb / w.B, b = sb - s * w.B;
+    const float4 e = __ldg(reinterpret_cast<const float4*>(w.ev[t] + (size_t)b * w.ev_bs[t]) + i);
+    const float2 pm = __ldg(reinterpret_cast<const float2*>(w.pm[t] + (size_t)b * w.pm_bs[t]) + i);
+    if (pm.x == 0.f && pm.y == 0.f) continue;
+    const int pix = (int)(e.y * (float)W + e.z);
+    const int m_idx = s * w.Tm + (w.Tm > 1 ? t : 0);
+    const float* fm = w.flow[m_idx] + (size_t)b * w.flow_bs;
+    const float fx = __ldg(fm + pix), fy = __ldg(fm + hw + pix);
+    const float* ibase = img + (size_t)sb * 8 * hw;
+    float gfy = 0.f, gfx = 0.f;
+#pragma unroll
+    for (int dir = 0; dir < 2; ++dir) {
+      const float tref = dir == 0 ? Tf : 0.f;
+      const float tau = dir == 0 ? e.x : (Tf - e.x);
+      const float kk = (tref - e.x) * w.flow_scaling;
+      const float ssq = __ldcg(sums + (sb * 2 + dir) * 2), n = __ldcg(sums + (sb * 2 + dir) * 2 + 1);
+      const float g = gl * inv_S / (w.loss_scaling ? n : 1.f);
+      const float gn = -gl * inv_S * ssq / (n * n);  // through the divisor: empty pixels keep gradient 1 into it (in-place masked assignment)
+      float yw, xw;
+      Corner c[4];
+      warp_event(e.x, e.y, e.z, fy, fx, tref, w.flow_scaling, H, W, yw, xw, c);
+      const float2* pos = reinterpret_cast<const float2*>(ibase + (size_t)dir * 4 * hw);
+      const float2* neg = pos + hw;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (c[k].idx < 0) continue;
+        const float dwy = dweight(c[k].dy) * c[k].wx, dwx = c[k].wy * dweight(c[k].dx);
+        if (dwy == 0.f && dwx == 0.f) continue;
+        float delta = 0.f;
+        float2 qp = make_float2(0.f, 0.f), qn = make_float2(0.f, 0.f);
+        bool have_p = false, have_n = false;
+#pragma unroll
+        for (int pol = 0; pol < 2; ++pol) {
+          const float m = pol == 0 ? pm.x : pm.y;
+          if (m == 0.f) continue;
+          float2& q = pol == 0 ? qp : qn;
+          q = __ldcg((pol == 0 ? pos : neg) + c[k].idx);
+          (pol == 0 ? have_p : have_n) = true;
+          const float a = q.y / (q.x + 1e-9f) / Tf;
+          const float gth = g * 2.f * a / ((q.x + 1e-9f) * Tf);
+          float gi = -gth * q.y / (q.x + 1e-9f);
+          if (w.loss_scaling && !(q.x > 0.f)) {  // own-polarity image empty here: the pixel counts as empty iff the other one is too
+            float2& o = pol == 0 ? qn : qp;
+            bool& have_o = pol == 0 ? have_n : have_p;
+            if (!have_o) {
+              o = __ldcg((pol == 0 ? neg : pos) + c[k].idx);
+              have_o = true;
+            }
+            if (!(q.x + o.x > 0.f)) gi += gn;
+          }
+          delta += m * (gi + tau * gth);
+        }
+        gfy += delta * dwy * kk;
+        gfx += delta * dwx * kk;
+      }
+    }
+    float* g_out = w.g_flow[m_idx] + (size_t)b * w.g_bs;
+    if (gfx != 0.f) atomicAdd(g_out + pix, gfx);
+    if (gfy != 0.f) atomicAdd(g_out + hw + pix, gfy);
+  }
+
+  // ---- restore the counters: the last CTA to finish knows everyone has left the barrier
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    s_last = atomicInc(ctr + 4, gridDim.x - 1) == gridDim.x - 1;
+    if (s_last) ctr[3] = 0u;
+  }
 }
 
 // ---- per-polarity IWE image (utils/iwe.py:95-153) ------------------------------------------------------------------
@@ -361,9 +491,9 @@ __global__ void __launch_bounds__(256) iwe_image_kernel(const ef_iwe_image_param
 }
 
 // ---- validation metrics: FWL / RSAT (loss/flow.py:468-579) and AEE (:582-628) -----------------------------------------
-// workspace: img [B][2 = warped, unwarped][HW][4 = I+,Th+,I-,Th-] (pixel-interleaved like the loss workspace), then sums
-// [B][2][4 = sum A^2, n, sum I, sum I^2]
-__global__ void __launch_bounds__(256) iwe_metric_scatter_kernel(const ef_iwe_metrics_params p, float* __restrict__ img) {
+// workspace: img [B][2 = warped, unwarped][HW][4 = I+,Th+,I-,Th-] (pixel-interleaved), then extra [B][2][HW] (what FWL counts
+// beyond I+ + I-), then sums [B][2][4 = sum A^2, n, sum I, sum I^2]
+__global__ void __launch_bounds__(256) iwe_metric_scatter_kernel(const ef_iwe_metrics_params p, float* __restrict__ img, float* __restrict__ extra) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
   if (i >= p.n_total) return;
   const size_t hw = (size_t)p.H * p.W;
@@ -389,18 +519,23 @@ __global__ void __launch_bounds__(256) iwe_metric_scatter_kernel(const ef_iwe_me
     if (yw < 0.f || yw >= (float)p.H || xw < 0.f || xw >= (float)p.W) continue;
     const int idx = (int)(yw * (float)p.W + xw);
     float* d = base + (size_t)k * 4 * hw;
-    // FWL scatters weight 1 per event regardless of polarity (no mask); RSAT scatters per polarity.  Channels 0/1 serve
-    // both when every event has exactly one polarity bit; events with neither are still counted for FWL in channel 0.
+    // RSAT scatters per polarity (weights = the polarity mask); FWL scatters weight 1 per event regardless of polarity
+    // (loss/flow.py:488,494: interpolate without a mask).  The FWL image is I+ + I- + extra with extra = 1 - pm.x - pm.y: zero for
+    // the loaders' one-hot masks, 1 for padded / p = 0 events, so that every event counts exactly once.
     float2* q = reinterpret_cast<float2*>(d + (size_t)idx * 4);
     if (pm.x != 0.f) atomicAdd(q, make_float2(pm.x, __fmul_rn(e.x, pm.x)));
     if (pm.y != 0.f) atomicAdd(q + 1, make_float2(pm.y, __fmul_rn(e.x, pm.y)));
+    const float ex = 1.0f - pm.x - pm.y;
+    if (ex != 0.f) atomicAdd(extra + ((size_t)b * 2 + k) * hw + idx, ex);
   }
 }
 
-__global__ void __launch_bounds__(256) iwe_metric_reduce_kernel(const float* __restrict__ img, float* __restrict__ sums, int HW, float T) {
+__global__ void __launch_bounds__(256) iwe_metric_reduce_kernel(const float* __restrict__ img, const float* __restrict__ extra,
+                                                                float* __restrict__ sums, int HW, float T) {
   __shared__ float s_red[8];
   const int bk = blockIdx.y;  // b*2 + k
   const float* d = img + (size_t)bk * 4 * HW;
+  const float* ex = extra + (size_t)bk * HW;
   float ssq = 0.f, n = 0.f, s1 = 0.f, s2 = 0.f;
   const int p0 = blockIdx.x * RED_PIX;
   for (int i = p0 + threadIdx.x; i < min(p0 + RED_PIX, HW); i += 256) {
@@ -409,8 +544,9 @@ __global__ void __launch_bounds__(256) iwe_metric_reduce_kernel(const float* __r
     const float ap = tp / (ip + 1e-9f) / T, an = tn / (in + 1e-9f) / T;
     ssq += ap * ap + an * an;
     n += (ip + in > 0.f) ? 1.f : 0.f;
-    s1 += ip + in;
-    s2 += (ip + in) * (ip + in);
+    const float cnt = ip + in + ex[i];
+    s1 += cnt;
+    s2 += cnt * cnt;
   }
   const float r0 = block_sum256(ssq, s_red), r1 = block_sum256(n, s_red), r2 = block_sum256(s1, s_red), r3 = block_sum256(s2, s_red);
   if (threadIdx.x == 0) {
@@ -467,14 +603,130 @@ __global__ void aee_finalize_kernel(const float* __restrict__ ws, int B, float* 
   out[B + b] = ws[2 * B] / (ws[B + b] + 1e-9f);
 }
 
-static int validate_loss(const ef_iwe_loss_params& p, const char* who) {
-  EF_REQUIRE(p.S > 0 && p.B > 0 && p.T > 0 && p.H > 0 && p.W > 0 && p.n_total >= 0, EF_EINVAL, "%s: bad dimensions", who);
-  EF_REQUIRE(p.T_maps == (p.overwrite_intermediate ? 1 : p.T), EF_EINVAL, "%s: T_maps must be 1 with overwrite_intermediate, else T", who);
-  EF_REQUIRE(p.T_maps == 1 || p.pass_offsets || (p.n_per_pass > 0 && (int64_t)p.n_per_pass * p.T >= p.n_total), EF_EINVAL,
-             "%s: n_per_pass * T must cover n_total", who);
-  EF_REQUIRE(p.events && p.pol_mask && p.flow_maps && p.workspace, EF_ENULL, "%s: NULL tensor", who);
-  EF_REQUIRE(!p.smoothing_mask || p.event_mask, EF_ENULL, "%s: smoothing_mask without event_mask", who);
+// ---- host side: lowering of the two public window forms, launch ------------------------------------------------------
+static int finish_window(IweWin& w, const char* who) {
+  EF_REQUIRE(w.S > 0 && w.S <= MAXS && w.B > 0 && w.T > 0 && w.T <= MAXP && w.H > 0 && w.W > 0, EF_EINVAL,
+             "%s: bad dimensions (S <= %d, T <= %d)", who, MAXS, MAXP);
+  EF_REQUIRE(w.Tm == 1 || w.Tm == w.T, EF_EINVAL, "%s: T_maps must be 1 (overwrite_intermediate) or T", who);
+  EF_REQUIRE(((size_t)w.H * w.W) % 2 == 0, EF_EUNSUPPORTED, "%s: H*W must be even (16-byte vector accumulators)", who);
+  w.chunk_off[0] = 0;
+  for (int t = 0; t < w.T; ++t) {
+    EF_REQUIRE(w.n_pass[t] >= 0, EF_EINVAL, "%s: negative event count in pass %d", who, t);
+    EF_REQUIRE(w.n_pass[t] == 0 || (w.ev[t] && w.pm[t]), EF_ENULL, "%s: NULL events / pol_mask of pass %d", who, t);
+    w.chunk_off[t + 1] = w.chunk_off[t] + cdiv(w.n_pass[t], IWE_CHUNK);
+  }
+  w.n_items = w.chunk_off[w.T];
+  for (int i = 0; i < w.S * w.Tm; ++i) EF_REQUIRE(w.flow[i], EF_ENULL, "%s: NULL flow map", who);
+  if (w.use_mask)
+    for (int t = 0; t < w.Tm; ++t) EF_REQUIRE(w.mask[t], EF_ENULL, "%s: smoothing_mask without event_mask", who);
   return EF_OK;
+}
+
+static int lower(const ef_iwe_loss_params& p, IweWin& w, const char* who) {
+  memset(&w, 0, sizeof(w));
+  EF_REQUIRE(p.T > 0 && p.T <= MAXP, EF_EINVAL, "%s: T must be in [1, %d]", who, MAXP);
+  EF_REQUIRE(p.T_maps == (p.overwrite_intermediate ? 1 : p.T), EF_EINVAL, "%s: T_maps must be 1 with overwrite_intermediate, else T", who);
+  EF_REQUIRE(p.n_total >= 0 && (p.T_maps == 1 || p.pass_offsets || (p.n_per_pass > 0 && (int64_t)p.n_per_pass * p.T >= p.n_total)), EF_EINVAL,
+             "%s: n_per_pass * T must cover n_total", who);
+  EF_REQUIRE((p.n_total == 0 || (p.events && p.pol_mask)) && p.flow_maps && p.workspace, EF_ENULL, "%s: NULL tensor", who);
+  w.S = p.S, w.B = p.B, w.T = p.T, w.Tm = p.T_maps, w.H = p.H, w.W = p.W;
+  w.loss_scaling = p.loss_scaling, w.use_mask = p.smoothing_mask != 0, w.use_dt = !p.overwrite_intermediate;
+  w.flow_scaling = p.flow_scaling;
+  w.smooth_coef = p.weight / (p.overwrite_intermediate ? 4.f : 5.f) / (float)p.T_maps;
+  const size_t hw = (size_t)p.H * p.W;
+  for (int t = 0; t < p.T; ++t) {
+    int o0, o1;
+    if (p.pass_offsets) o0 = p.pass_offsets[t], o1 = p.pass_offsets[t + 1];
+    else if (p.T_maps == 1 && p.n_per_pass <= 0) o0 = t == 0 ? 0 : p.n_total, o1 = p.n_total;  // one map: the pass structure is irrelevant
+    else o0 = min(t * p.n_per_pass, p.n_total), o1 = t + 1 == p.T ? p.n_total : min((t + 1) * p.n_per_pass, p.n_total);
+    EF_REQUIRE(o0 >= 0 && o1 >= o0 && o1 <= p.n_total, EF_EINVAL, "%s: bad pass_offsets", who);
+    w.n_pass[t] = o1 - o0;
+    w.ev[t] = p.events ? p.events + (size_t)o0 * 4 : nullptr, w.pm[t] = p.pol_mask ? p.pol_mask + (size_t)o0 * 2 : nullptr;
+    w.ev_bs[t] = (long long)p.n_total * 4, w.pm_bs[t] = (long long)p.n_total * 2;
+  }
+  for (int s = 0; s < p.S && s < MAXS; ++s)
+    for (int m = 0; m < p.T_maps; ++m) {
+      w.flow[s * p.T_maps + m] = p.flow_maps + ((size_t)s * p.B * p.T_maps + m) * 2 * hw;
+      if (p.g_flow_maps) w.g_flow[s * p.T_maps + m] = p.g_flow_maps + ((size_t)s * p.B * p.T_maps + m) * 2 * hw;
+    }
+  w.flow_bs = w.g_bs = (long long)p.T_maps * 2 * hw;
+  for (int m = 0; m < p.T_maps; ++m) w.mask[m] = p.event_mask ? p.event_mask + (size_t)m * hw : nullptr;
+  w.mask_bs = (long long)p.T_maps * hw;
+  return finish_window(w, who);
+}
+
+static int lower(const ef_iwe_loss_pass_params& p, IweWin& w, const char* who) {
+  memset(&w, 0, sizeof(w));
+  EF_REQUIRE(p.T > 0 && p.T <= MAXP && p.S > 0 && p.S <= MAXS, EF_EINVAL, "%s: T must be in [1, %d], S in [1, %d]", who, MAXP, MAXS);
+  EF_REQUIRE(p.T_maps == (p.overwrite_intermediate ? 1 : p.T), EF_EINVAL, "%s: T_maps must be 1 with overwrite_intermediate, else T", who);
+  EF_REQUIRE(p.workspace, EF_ENULL, "%s: NULL workspace", who);
+  w.S = p.S, w.B = p.B, w.T = p.T, w.Tm = p.T_maps, w.H = p.H, w.W = p.W;
+  w.loss_scaling = p.loss_scaling, w.use_mask = p.smoothing_mask != 0, w.use_dt = !p.overwrite_intermediate;
+  w.flow_scaling = p.flow_scaling;
+  w.smooth_coef = p.weight / (p.overwrite_intermediate ? 4.f : 5.f) / (float)p.T_maps;
+  const size_t hw = (size_t)p.H * p.W;
+  for (int t = 0; t < p.T; ++t) {
+    w.n_pass[t] = p.n_pass[t];
+    w.ev[t] = p.events[t], w.pm[t] = p.pol_mask[t];
+    w.ev_bs[t] = (long long)p.n_pass[t] * 4, w.pm_bs[t] = (long long)p.n_pass[t] * 2;
+  }
+  for (int i = 0; i < p.S * p.T_maps; ++i) w.flow[i] = p.flow[i], w.g_flow[i] = p.g_flow[i];
+  w.flow_bs = w.g_bs = (long long)2 * hw;
+  for (int m = 0; m < p.T_maps; ++m) w.mask[m] = p.event_mask[m];
+  w.mask_bs = (long long)hw;
+  return finish_window(w, who);
+}
+
+// Co-resident grid: the kernels synchronise all their CTAs, so the launch carries the cooperative attribute (it fails instead
+// of dead-locking should the grid not fit) and the grid is capped by the occupancy of the device.
+template <typename K>
+static int coop_grid(K kernel, long long work_ctas, int* grid) {
+  static int cap = 0;
+  if (cap == 0) {
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, IWE_THREADS, 0) != cudaSuccess || per_sm < 1) return check_launch("occupancy query");
+    cap = sms * (per_sm < 6 ? per_sm : 6);
+    if (cap > IWE_MAX_GRID) cap = IWE_MAX_GRID;
+  }
+  long long g = work_ctas < cap ? work_ctas : cap;
+  *grid = (int)(g < 1 ? 1 : g);
+  return EF_OK;
+}
+
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_coop(void (*kernel)(KArgs...), int grid, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid), cfg.blockDim = dim3(IWE_THREADS), cfg.dynamicSmemBytes = 0, cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr, cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+static long long loss_work_ctas(const IweWin& w) {
+  // enough CTAs for the event chunks and for one pass over the pixels, whichever is larger; small windows get small grids
+  // (the cost of a grid barrier grows with the number of CTAs)
+  const long long ev = (long long)w.S * w.B * w.n_items;
+  const long long px = ((long long)w.S * w.B * 2 * w.H * w.W + 8191) / 8192;
+  return ev > px ? ev : px;
+}
+
+static int run_fwd(const IweWin& w, float* ws, float* loss, cudaStream_t st) {
+  int grid, rc;
+  if ((rc = coop_grid(iwe_loss_fwd_kernel, loss_work_ctas(w), &grid))) return rc;
+  launch_coop(iwe_loss_fwd_kernel, grid, st, w, ws, loss);
+  return check_launch("iwe_loss_fwd_kernel");
+}
+
+static int run_bwd(const IweWin& w, float* ws, const float* g_loss, cudaStream_t st) {
+  for (int i = 0; i < w.S * w.Tm; ++i) EF_REQUIRE(w.g_flow[i], EF_ENULL, "ef_iwe_loss_bwd: NULL g_flow");
+  int grid, rc;
+  if ((rc = coop_grid(iwe_loss_bwd_kernel, loss_work_ctas(w), &grid))) return rc;
+  launch_coop(iwe_loss_bwd_kernel, grid, st, w, ws, g_loss);
+  return check_launch("iwe_loss_bwd_kernel");
 }
 
 }  // namespace ef
@@ -486,64 +738,37 @@ extern "C" int64_t ef_iwe_loss_workspace_elems(int32_t S, int32_t B, int32_t H, 
 extern "C" int ef_iwe_loss_fwd(const ef_iwe_loss_params* pp, void* stream) {
   using namespace ef;
   EF_REQUIRE(pp, EF_ENULL, "ef_iwe_loss_fwd: params is NULL");
-  const ef_iwe_loss_params& p = *pp;
-  if (int rc = validate_loss(p, "ef_iwe_loss_fwd")) return rc;
-  EF_REQUIRE(p.loss, EF_ENULL, "ef_iwe_loss_fwd: loss is NULL");
-  cudaStream_t st = as_stream(stream);
-  const WsLayout l = ws_layout(p.S, p.B, p.H, p.W);
-  const int HW = p.H * p.W;
-  float* ws = p.workspace;
-  cudaMemsetAsync(ws + l.img, 0, (l.adj - l.img) * sizeof(float), st);
-  cudaMemsetAsync(ws + l.sums, 0, (l.total - l.sums) * sizeof(float), st);
-  int rc;
-  if (p.n_total > 0) {
-    iwe_scatter_kernel<<<dim3(cdiv(p.n_total, 256), p.B, p.S), 256, 0, st>>>(p, ws + l.img);
-    if ((rc = check_launch("iwe_scatter_kernel"))) return rc;
-  }
-  iwe_reduce_kernel<<<dim3(cdiv(HW, RED_PIX), p.S * p.B * 2), 256, 0, st>>>(ws + l.img, ws + l.sums, HW, (float)p.T);
-  if ((rc = check_launch("iwe_reduce_kernel"))) return rc;
-  const SmoothGeom g{p.B, p.T_maps, p.H, p.W, p.smoothing_mask != 0, !p.overwrite_intermediate};
-  const size_t n = (size_t)p.B * p.T_maps * HW;
-  const int blocks = (int)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184);
-  for (int s = 0; s < p.S; ++s) {
-    smooth_fwd_kernel<<<blocks, 256, 0, st>>>(p.flow_maps + (size_t)s * p.B * p.T_maps * 2 * HW, p.smoothing_mask ? p.event_mask : nullptr, g,
-                                              ws + l.smooth + s);
-    if ((rc = check_launch("smooth_fwd_kernel"))) return rc;
-  }
-  const float components = p.overwrite_intermediate ? 4.f : 5.f;
-  iwe_finalize_kernel<<<1, 32, 0, st>>>(ws + l.sums, ws + l.smooth, p.S, p.B, p.loss_scaling, p.weight / components / (float)p.T_maps, p.loss);
-  return check_launch("iwe_finalize_kernel");
+  EF_REQUIRE(pp->loss, EF_ENULL, "ef_iwe_loss_fwd: loss is NULL");
+  IweWin w;
+  if (int rc = lower(*pp, w, "ef_iwe_loss_fwd")) return rc;
+  return run_fwd(w, pp->workspace, pp->loss, as_stream(stream));
 }
 
 extern "C" int ef_iwe_loss_bwd(const ef_iwe_loss_params* pp, void* stream) {
   using namespace ef;
   EF_REQUIRE(pp, EF_ENULL, "ef_iwe_loss_bwd: params is NULL");
-  const ef_iwe_loss_params& p = *pp;
-  if (int rc = validate_loss(p, "ef_iwe_loss_bwd")) return rc;
-  EF_REQUIRE(p.g_loss && p.g_flow_maps, EF_ENULL, "ef_iwe_loss_bwd: g_loss / g_flow_maps is NULL");
-  cudaStream_t st = as_stream(stream);
-  const WsLayout l = ws_layout(p.S, p.B, p.H, p.W);
-  const int HW = p.H * p.W;
-  float* ws = p.workspace;
-  int rc;
-  const SmoothGeom g{p.B, p.T_maps, p.H, p.W, p.smoothing_mask != 0, !p.overwrite_intermediate};
-  const size_t n = (size_t)p.B * p.T_maps * HW;
-  const float components = p.overwrite_intermediate ? 4.f : 5.f;
-  const float coef = p.weight / components / (float)p.T_maps / (float)p.S;
-  for (int s = 0; s < p.S; ++s) {
-    const size_t off = (size_t)s * p.B * p.T_maps * 2 * HW;
-    smooth_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p.flow_maps + off, p.smoothing_mask ? p.event_mask : nullptr, g, p.g_loss, coef,
-                                                                   p.g_flow_maps + off);
-    if ((rc = check_launch("smooth_bwd_kernel"))) return rc;
-  }
-  iwe_adjoint_kernel<<<dim3(cdiv(HW, 256), p.S * p.B * 2), 256, 0, st>>>(ws + l.img, ws + l.sums, ws + l.adj, HW, (float)p.T, p.loss_scaling,
-                                                                         1.0f / (float)p.S, p.g_loss);
-  if ((rc = check_launch("iwe_adjoint_kernel"))) return rc;
-  if (p.n_total > 0) {
-    iwe_event_grad_kernel<<<dim3(cdiv(p.n_total, 256), p.B, p.S), 256, 0, st>>>(p, ws + l.adj);
-    if ((rc = check_launch("iwe_event_grad_kernel"))) return rc;
-  }
-  return EF_OK;
+  EF_REQUIRE(pp->g_loss && pp->g_flow_maps, EF_ENULL, "ef_iwe_loss_bwd: g_loss / g_flow_maps is NULL");
+  IweWin w;
+  if (int rc = lower(*pp, w, "ef_iwe_loss_bwd")) return rc;
+  return run_bwd(w, pp->workspace, pp->g_loss, as_stream(stream));
+}
+
+extern "C" int ef_iwe_loss_fwd_passes(const ef_iwe_loss_pass_params* pp, void* stream) {
+  using namespace ef;
+  EF_REQUIRE(pp, EF_ENULL, "ef_iwe_loss_fwd_passes: params is NULL");
+  EF_REQUIRE(pp->loss, EF_ENULL, "ef_iwe_loss_fwd_passes: loss is NULL");
+  IweWin w;
+  if (int rc = lower(*pp, w, "ef_iwe_loss_fwd_passes")) return rc;
+  return run_fwd(w, pp->workspace, pp->loss, as_stream(stream));
+}
+
+extern "C" int ef_iwe_loss_bwd_passes(const ef_iwe_loss_pass_params* pp, void* stream) {
+  using namespace ef;
+  EF_REQUIRE(pp, EF_ENULL, "ef_iwe_loss_bwd_passes: params is NULL");
+  EF_REQUIRE(pp->g_loss, EF_ENULL, "ef_iwe_loss_bwd_passes: g_loss is NULL");
+  IweWin w;
+  if (int rc = lower(*pp, w, "ef_iwe_loss_bwd_passes")) return rc;
+  return run_bwd(w, pp->workspace, pp->g_loss, as_stream(stream));
 }
 
 extern "C" int ef_iwe_image(const ef_iwe_image_params* pp, void* stream) {
@@ -559,7 +784,7 @@ extern "C" int ef_iwe_image(const ef_iwe_image_params* pp, void* stream) {
   return check_launch("iwe_image_kernel");
 }
 
-extern "C" int64_t ef_iwe_metrics_workspace_elems(int32_t B, int32_t H, int32_t W) { return (int64_t)B * 8 * H * W + (int64_t)B * 8; }
+extern "C" int64_t ef_iwe_metrics_workspace_elems(int32_t B, int32_t H, int32_t W) { return (int64_t)B * 10 * H * W + (int64_t)B * 8; }
 
 extern "C" int ef_iwe_metrics(const ef_iwe_metrics_params* pp, void* stream) {
   using namespace ef;
@@ -572,14 +797,15 @@ extern "C" int ef_iwe_metrics(const ef_iwe_metrics_params* pp, void* stream) {
   cudaStream_t st = as_stream(stream);
   const int HW = p.H * p.W;
   float* img = p.workspace;
-  float* sums = p.workspace + (size_t)p.B * 8 * HW;
-  cudaMemsetAsync(p.workspace, 0, ((size_t)p.B * 8 * HW + (size_t)p.B * 8) * sizeof(float), st);
+  float* extra = p.workspace + (size_t)p.B * 8 * HW;
+  float* sums = extra + (size_t)p.B * 2 * HW;
+  cudaMemsetAsync(p.workspace, 0, ((size_t)p.B * 10 * HW + (size_t)p.B * 8) * sizeof(float), st);
   int rc;
   if (p.n_total > 0) {
-    iwe_metric_scatter_kernel<<<dim3(cdiv(p.n_total, 256), p.B), 256, 0, st>>>(p, img);
+    iwe_metric_scatter_kernel<<<dim3(cdiv(p.n_total, 256), p.B), 256, 0, st>>>(p, img, extra);
     if ((rc = check_launch("iwe_metric_scatter_kernel"))) return rc;
   }
-  iwe_metric_reduce_kernel<<<dim3(cdiv(HW, RED_PIX), p.B * 2), 256, 0, st>>>(img, sums, HW, (float)p.T);
+  iwe_metric_reduce_kernel<<<dim3(cdiv(HW, RED_PIX), p.B * 2), 256, 0, st>>>(img, extra, sums, HW, (float)p.T);
   if ((rc = check_launch("iwe_metric_reduce_kernel"))) return rc;
   iwe_metric_finalize_kernel<<<cdiv(p.B, 64), 64, 0, st>>>(sums, p.B, HW, p.out);
   return check_launch("iwe_metric_finalize_kernel");

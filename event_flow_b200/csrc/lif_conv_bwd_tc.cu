@@ -651,7 +651,6 @@ extern "C" int ef_lif_bwd_tc(const ef_lif_bwd_tc_params* pp, void* stream) {
   } else {
     EF_REQUIRE(p.x_cl && p.v_out && p.leak && p.thresh && p.w_bwd && p.gI_hi && p.gI_mid && p.g_x, EF_ENULL, "ef_lif_bwd_tc: NULL tensor");
   }
-  EF_REQUIRE(!p.has_rec || !p.z_in_cl || p.g_z_in || true, EF_ENULL, "ef_lif_bwd_tc");
   cudaStream_t st = as_stream(stream);
   const int n_sms = wg_n_sms();
   int rc;

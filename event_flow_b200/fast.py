@@ -46,6 +46,7 @@ class _Slot:
             self.z.append(self.slab[o:o + nz].view(torch.bfloat16).view(B, H, W, 32))
             o += nz
         self.flow = torch.empty((B, 2, H, W), device=dev, dtype=torch.float32)
+        self.gen = 0       # bumped every time a forward step (re)writes this slot: saved activations of older steps are then gone
         self.x_in = None   # static copy of the model input (graph replay reads a fixed address)
         self.graphs = {}   # (pointer signature) -> torch.cuda.CUDAGraph of this step's 8 kernels
         self.bwd_calls = {}  # (pointer signature, sweep position) -> prepared argument structs (+ CUDA graph) of this step's backward
@@ -56,8 +57,10 @@ class _Arena:
     """
     Activation storage owned by the model and reused window after window (no allocator traffic in steady state, static
     addresses for CUDA-graph replay).  Two banks alternate per BPTT window: window w writes bank w%2, its initial state
-    lives in bank (w-1)%2.  CONTRACT: the saved activations of a window are recycled two detach_states()/reset_states()
-    calls later, i.e. loss.backward() of a window must run before the window after next starts (train_flow.py:154-171 does).
+    lives in the last slot of bank (w-1)%2.  CONTRACT: loss.backward() of window w must run before window w+1 COMPLETES
+    (window w+1 overwrites, at its own last step, the slot that holds window w's initial state; window w+2 overwrites
+    window w's activations) -- train_flow.py:154-171 runs backward right at the window end.  The contract is enforced:
+    every slot carries a generation counter, a step's backward raises if a slot it saved from has been rewritten since.
     """
 
     def __init__(self, B, H, W, dev):
@@ -96,6 +99,7 @@ class FastState:
         self.carry = _Carry()
         self.step = 0              # index of the next step inside the current window
         self.param_sig = None      # data pointers of the parameters / weight images, part of the graph-cache key
+        self.src = None            # (slot, generation) that holds the current state tensors (None: set through the state API)
 
     def detach(self, arena=None):
         self.token = None
@@ -163,6 +167,15 @@ def _split_cache(model):
 def invalidate_weights(model):
     """Call after updating parameters outside torch's version tracking (e.g. the fused Adam kernel)."""
     model.__dict__["_w_epoch"] = model.__dict__.get("_w_epoch", 0) + 1
+
+
+def invalidate_pointers(model):
+    """Call after re-binding parameter storage (p.data = ...): cached graphs / argument structs hold the old addresses."""
+    for k in ("_fast_params", "_w_split_cache", "_arena"):
+        model.__dict__.pop(k, None)
+    if model.__dict__.get("_fast") is not None:
+        model._fast.param_sig = None
+        model._fast.src = None
 
 
 def _params_of(model):
@@ -267,7 +280,10 @@ class _FireNetStep(torch.autograd.Function):
             arena = model.__dict__["_arena"] = _Arena(B, H, W, dev)
         slot = arena.slot(arena.parity, fs.step)
         fs.step += 1
+        slot.gen += 1
         v_in, z_in = list(fs.v), list(fs.z)
+        ctx.guards = [(slot, slot.gen)] + ([fs.src] if fs.src is not None and fs.src[0] is not slot else [])
+        fs.src = (slot, slot.gen)
         cap = model.__dict__.get("_capture")
         use_graph = (model.__dict__.get("_use_graphs", True) and cap is None and L.PROFILE is None
                      and not torch.cuda.is_current_stream_capturing())
@@ -320,6 +336,12 @@ class _FireNetStep(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_flow, g_token):
         model, carry = ctx.model, ctx.carry
+        for slot_, gen_ in ctx.guards:
+            if slot_.gen != gen_:
+                raise RuntimeError(
+                    "event_flow_b200 fast path: the activations this backward step needs were overwritten by a later forward pass. "
+                    "loss.backward() of a BPTT window must run before the next window completes (see fast._Arena); "
+                    "use model._use_graphs / per-cell API for other schedules.")
         B, Cin0, H, W = ctx.shapes
         params = _params_of(model)
         dev = ctx.flow.device

@@ -70,29 +70,22 @@ class EventWarping(torch.nn.Module):
         return self._masks[-1]
 
     def forward(self):
-        T = self._passes
-        events = self._events[0] if T == 1 else torch.cat(self._events, dim=1)
-        pol = self._pol_masks[0] if T == 1 else torch.cat(self._pol_masks, dim=1)
-        masks = self._masks[0] if len(self._masks) == 1 else torch.cat(self._masks, dim=1)
-        flow_maps = torch.stack([torch.stack(per_pass, dim=1) for per_pass in self._flow_maps], dim=0)  # [S,B,Tm,2,H,W]
-        overwrite = self._overwritten
-        counts = [e.shape[1] for e in self._events]
-        offsets = None
-        if not overwrite and len(set(counts)) > 1:
-            offsets = torch.tensor([0] + list(torch.tensor(counts).cumsum(0)), dtype=torch.int32, device=events.device)
-        return ops.event_warping_loss(
-            flow_maps.float(),
-            events.float(),
-            pol.float(),
-            masks.float(),
-            passes=T,
-            n_per_pass=counts[0],
+        """
+        loss/flow.py:176-301 in ONE kernel launch (ef_iwe_loss_fwd_passes), differentiable wrt the flow maps (one more launch,
+        ef_iwe_loss_bwd_passes).  The window is handed over in pass form: the tensors event_flow_association received stay where
+        they are -- no torch.cat / torch.stack (the reference re-concatenates its lists every pass).
+        """
+        f32 = lambda ts: [t if t.dtype == torch.float32 else t.float() for t in ts]  # noqa: E731
+        return ops.event_warping_loss_passes(
+            [f32(per_scale) for per_scale in self._flow_maps],
+            f32(self._events),
+            f32(self._pol_masks),
+            f32(self._masks),
             flow_scaling=self.flow_scaling,
             weight=self.weight,
             loss_scaling=self.loss_scaling,
             smoothing_mask=self.smoothing_mask,
-            overwrite_intermediate=overwrite,
-            pass_offsets=offsets,
+            overwrite_intermediate=self._overwritten,
         )
 
 
@@ -161,7 +154,7 @@ class BaseValidationLoss(torch.nn.Module):
         offsets = None
         if not self._overwritten and len(set(counts)) > 1:
             offsets = torch.tensor([0] + list(torch.tensor(counts).cumsum(0)), dtype=torch.int32, device=events.device)
-        return events, pol, maps, counts[0], offsets
+        return events.float(), pol.float(), maps.float(), counts[0], offsets
 
     def compute_window_events(self):
         """Per-polarity image of the (non-warped) events of the window (loss/flow.py:425-435)."""

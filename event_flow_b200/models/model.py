@@ -87,6 +87,20 @@ class FireNet(BaseModel):
             return None
         return super().__getattr__(name)
 
+    # Run-time caches of the fast path (CUDA graphs, ctypes argument structs, activation slabs, weight images): none of them
+    # can or should travel with a checkpoint.  The reference checkpoints by pickling the whole module (utils/utils.py:36,
+    # mlflow.pytorch.log_model) and callers deepcopy models; both go through __getstate__.
+    _RUNTIME_KEYS = ("_fast_params", "_fast_cells", "_fast_eligible", "_w_split_cache", "_arena", "_capture", "_last_spikes", "_w_epoch")
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        if state.get("_fast") is not None:  # internal state -> the reference's stacked fp32 tensors (detached copies)
+            state["_states"] = [None if s is None else s.detach() for s in fast.states_of(self)]
+        state["_fast"] = None
+        for k in self._RUNTIME_KEYS:
+            state.pop(k, None)
+        return state
+
     # ---- state API (models/model.py:203-227) ----
     @property
     def states(self):

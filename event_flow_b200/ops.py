@@ -3,6 +3,8 @@ Host-side operators over libeventflow.so: tensor allocation, argument marshallin
 Every function here launches CUDA kernels through the C ABI (event_flow_b200/_lib.py); none has a CPU path.
 """
 
+import ctypes as C
+
 import torch
 
 from . import _lib as L
@@ -32,6 +34,12 @@ def _need_cuda(*ts):
 
 def _c(t):
     return None if t is None else t.contiguous()
+
+
+def _need_f32(*ts):
+    for t in ts:
+        if t is not None and t.dtype != torch.float32:
+            raise L.EventFlowError("event_flow_b200 kernels read fp32 tensors; got %s (cast with .float() first)" % t.dtype)
 
 
 def _fill_cell_params(p, neuron, x, state_in, w_ff, w_rec, chan, residual, state_out, out, hard_reset, surrogate, width, stride):
@@ -193,38 +201,70 @@ def pred_head(x, weight, bias):
 # ---------------------------------------------------------------------------------------------------------------------
 # event-warping loss
 # ---------------------------------------------------------------------------------------------------------------------
+# Workspaces of the loss kernels are recycled: the kernels need the first 16 words zero when a buffer is first used and leave
+# them zero (include/eventflow.h), so a buffer is cleared exactly once.  A buffer travels with the autograd node of its
+# forward call (the backward reads the accumulator images) and goes back to the pool when the backward has been enqueued --
+# reuse is ordered by the stream, hence the stream in the key.
+_WS_POOL = {}
+
+
+def _ws_take(n, dev):
+    key = (n, dev, torch.cuda.current_stream(dev).cuda_stream)
+    pool = _WS_POOL.setdefault(key, [])
+    if pool:
+        return pool.pop(), key
+    ws = torch.empty(n, device=dev, dtype=torch.float32)
+    ws[:16].zero_()
+    return ws, key
+
+
+def _ws_give(ws, key):
+    pool = _WS_POOL.setdefault(key, [])
+    if len(pool) < 4:
+        pool.append(ws)
+
+
 class _EventWarpingLoss(torch.autograd.Function):
+    """Window in map form: everything concatenated (ef_iwe_loss_fwd / ef_iwe_loss_bwd)."""
+
     @staticmethod
     def forward(ctx, flow_maps, events, pol_mask, event_mask, pass_offsets, meta):
-        # flow_maps [S,B,Tm,2,H,W]; events [B,N,4]; pol_mask [B,N,2]; event_mask [B,Tm,H,W]; pass_offsets int32 [T+1] | None
+        # flow_maps [S,B,Tm,2,H,W]; events [B,N,4]; pol_mask [B,N,2]; event_mask [B,Tm,H,W]; pass_offsets: list of T+1 ints | None
         T, n_per_pass, flow_scaling, weight, loss_scaling, smoothing_mask, overwrite = meta
         flow_maps, events, pol_mask, event_mask = _c(flow_maps), _c(events), _c(pol_mask), _c(event_mask)
         _need_cuda(flow_maps, events, pol_mask, event_mask)
+        _need_f32(flow_maps, events, pol_mask, event_mask)
         S, B, Tm, _, H, W = flow_maps.shape
         p = L.IweLossParams()
         p.S, p.B, p.T, p.T_maps, p.H, p.W = S, B, T, Tm, H, W
         p.n_total, p.n_per_pass = events.shape[1], n_per_pass
         p.flow_scaling, p.weight = float(flow_scaling), float(weight)
         p.loss_scaling, p.smoothing_mask, p.overwrite_intermediate = int(loss_scaling), int(smoothing_mask), int(overwrite)
-        ws = torch.empty(L.lib().ef_iwe_loss_workspace_elems(S, B, H, W), device=flow_maps.device, dtype=torch.float32)
+        ws, key = _ws_take(L.lib().ef_iwe_loss_workspace_elems(S, B, H, W), flow_maps.device)
         loss = torch.empty((), device=flow_maps.device, dtype=torch.float32)
         p.events, p.pol_mask, p.flow_maps, p.event_mask = L.ptr(events), L.ptr(pol_mask), L.ptr(flow_maps), L.ptr(event_mask)
         p.workspace, p.loss = L.ptr(ws), L.ptr(loss)
-        p.pass_offsets = L.ptr(pass_offsets)
+        ctx.offsets = None
+        if pass_offsets is not None:  # host array, read during the call only
+            ctx.offsets = (C.c_int32 * (T + 1))(*[int(v) for v in pass_offsets])
+            p.pass_offsets = C.cast(ctx.offsets, C.c_void_p)
         L.call("ef_iwe_loss_fwd", p)
-        ctx.p = p
-        ctx.save_for_backward(flow_maps, events, pol_mask, event_mask, ws, pass_offsets)
+        ctx.p, ctx.ws, ctx.key = p, ws, key
+        ctx.save_for_backward(flow_maps, events, pol_mask, event_mask)
+        if not (torch.is_grad_enabled() and flow_maps.requires_grad):
+            _ws_give(ws, key)
         return loss
 
     @staticmethod
     def backward(ctx, g_loss):
-        flow_maps, events, pol_mask, event_mask, ws, _ = ctx.saved_tensors
+        flow_maps = ctx.saved_tensors[0]
         p = ctx.p
         g_loss = g_loss.contiguous().to(torch.float32)
         g_maps = torch.empty_like(flow_maps)
         p.g_loss, p.g_flow_maps = L.ptr(g_loss), L.ptr(g_maps)
         L.call("ef_iwe_loss_bwd", p)
         p.g_loss = p.g_flow_maps = None
+        _ws_give(ctx.ws, ctx.key)
         return g_maps, None, None, None, None, None
 
 
@@ -233,12 +273,90 @@ def event_warping_loss(flow_maps, events, pol_mask, event_mask, *, passes, n_per
     """EventWarping.forward (loss/flow.py:176-301) on a window in map form; differentiable wrt flow_maps."""
     meta = (int(passes), int(n_per_pass), float(flow_scaling), float(weight), bool(loss_scaling), bool(smoothing_mask),
             bool(overwrite_intermediate))
+    if pass_offsets is not None and torch.is_tensor(pass_offsets):
+        pass_offsets = pass_offsets.tolist()
     return _EventWarpingLoss.apply(flow_maps, events, pol_mask, event_mask, pass_offsets, meta)
+
+
+class _EventWarpingLossPasses(torch.autograd.Function):
+    """
+    Window in pass form: the tensors of every pass stay where event_flow_association received them (ef_iwe_loss_fwd_passes /
+    ef_iwe_loss_bwd_passes); no torch.cat / torch.stack, no copies.  Differentiable wrt the flow maps.
+    """
+
+    @staticmethod
+    def forward(ctx, meta, events, pol_masks, masks, *flows):
+        S, Tm, T, flow_scaling, weight, loss_scaling, smoothing_mask, overwrite = meta
+        B, _, H, W = flows[0].shape
+        dev = flows[0].device
+        p = L.IweLossPassParams()
+        p.S, p.B, p.T, p.T_maps, p.H, p.W = S, B, T, Tm, H, W
+        p.flow_scaling, p.weight = float(flow_scaling), float(weight)
+        p.loss_scaling, p.smoothing_mask, p.overwrite_intermediate = int(loss_scaling), int(smoothing_mask), int(overwrite)
+        keep = []
+        for t in range(T):
+            e, m = _c(events[t]), _c(pol_masks[t])
+            _need_cuda(e, m)
+            _need_f32(e, m)
+            keep += [e, m]
+            p.n_pass[t] = e.shape[1]
+            p.events[t], p.pol_mask[t] = L.ptr(e), L.ptr(m)
+        for i, f in enumerate(flows):
+            f = _c(f)
+            _need_cuda(f)
+            _need_f32(f)
+            keep.append(f)
+            p.flow[i] = L.ptr(f)
+        if smoothing_mask:
+            for m in range(Tm):
+                k = _c(masks[m])
+                _need_cuda(k)
+                _need_f32(k)
+                keep.append(k)
+                p.event_mask[m] = L.ptr(k)
+        ws, key = _ws_take(L.lib().ef_iwe_loss_workspace_elems(S, B, H, W), dev)
+        loss = torch.empty((), device=dev, dtype=torch.float32)
+        p.workspace, p.loss = L.ptr(ws), L.ptr(loss)
+        L.call("ef_iwe_loss_fwd_passes", p)
+        ctx.p, ctx.ws, ctx.key, ctx.keep, ctx.shape = p, ws, key, keep, (S * Tm, B, 2, H, W)
+        if not (torch.is_grad_enabled() and any(f.requires_grad for f in flows)):
+            _ws_give(ws, key)
+            ctx.keep = None
+        return loss
+
+    @staticmethod
+    def backward(ctx, g_loss):
+        p = ctx.p
+        g_loss = g_loss.contiguous().to(torch.float32)
+        g = torch.empty(ctx.shape, device=g_loss.device, dtype=torch.float32)  # one slab, a dense [B,2,H,W] gradient per flow map
+        p.g_loss = L.ptr(g_loss)
+        for i in range(ctx.shape[0]):
+            p.g_flow[i] = L.ptr(g[i])
+        L.call("ef_iwe_loss_bwd_passes", p)
+        _ws_give(ctx.ws, ctx.key)
+        return (None, None, None, None, *g.unbind(0))
+
+
+def event_warping_loss_passes(flows, events, pol_masks, masks, *, flow_scaling, weight, loss_scaling=True, smoothing_mask=True,
+                              overwrite_intermediate=False):
+    """
+    EventWarping.forward (loss/flow.py:176-301) on a window in pass form.
+    :param flows: per scale a list of the window's flow maps [B,2,H,W] (one per pass, or the single final map with overwrite)
+    :param events / pol_masks: per pass [B,N_t,4] (ts offset by the pass index) / [B,N_t,2]
+    :param masks: per flow map [B,1,H,W]
+    """
+    S, Tm, T = len(flows), len(flows[0]), len(events)
+    if T > L.EF_IWE_MAX_PASSES or S > L.EF_IWE_MAX_SCALES:
+        raise L.EventFlowError(f"event-warping loss: at most {L.EF_IWE_MAX_PASSES} passes and {L.EF_IWE_MAX_SCALES} flow scales per window")
+    meta = (S, Tm, T, float(flow_scaling), float(weight), bool(loss_scaling), bool(smoothing_mask), bool(overwrite_intermediate))
+    flat = [f for per_scale in flows for f in per_scale]
+    return _EventWarpingLossPasses.apply(meta, list(events), list(pol_masks), list(masks), *flat)
 
 
 def iwe_image(events, pol_mask, res, *, flow=None, event_flow=None, tref=1.0, flow_scaling=128.0, round_idx=True):
     """Per-polarity image of warped events [B,2,H,W] (utils/iwe.py:95-153)."""
-    events, pol_mask, flow, event_flow = _c(events), _c(pol_mask), _c(flow), _c(event_flow)
+    f32 = lambda t: None if t is None else _c(t.float())  # noqa: E731  (callers pass float64 event lists straight from the loaders)
+    events, pol_mask, flow, event_flow = f32(events), f32(pol_mask), f32(flow), f32(event_flow)
     _need_cuda(events, pol_mask, flow, event_flow)
     B, N = events.shape[:2]
     H, W = res

@@ -36,6 +36,11 @@ class DataParallelTrainer:
         self.group = process_group
         self.step_count = 0
         self.model = model
+        # the parameters moved into flat_param: drop everything of the model's fast path that is keyed on the old pointers
+        # (cached step graphs, prepared backward calls, weight images)
+        from . import fast
+
+        fast.invalidate_pointers(model)
 
     @property
     def world_size(self):

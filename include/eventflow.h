@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define EF_VERSION 100 /* 0.1.0 */
+#define EF_VERSION 200 /* 0.2.0 */
 
 /* neuron models: models/spiking_submodules.py ConvLIF :24, ConvPLIF :129, ConvALIF :230, ConvXLIF :337 (+Recurrent) */
 enum { EF_LIF = 0, EF_PLIF = 1, EF_ALIF = 2, EF_XLIF = 3 };
@@ -274,9 +274,20 @@ int ef_conv3x3_bwd(const float* g_pre, const float* x, const float* w, float* g_
  * have different lengths).  With overwrite_intermediate, T_maps == 1 and every
  * event reads map 0 (loss/flow.py:118-146).
  *
- * workspace: float[ef_iwe_loss_workspace_elems(S,B,H,W)], zeroed by the call itself; holds the 8 IWE images per
- * (scale, sample), the per-(scale,sample,direction) sums and pixel counts, kept for the backward.
+ * workspace: float[ef_iwe_loss_workspace_elems(S,B,H,W)]: grid-barrier counters, the 8 IWE images per (scale, sample), the
+ * per-(scale,sample,direction) sums and pixel counts (kept for the backward), per-CTA partial sums of the smoothness term.
+ * CONTRACT: the first 16 words of a workspace buffer must be ZERO when the buffer is first used (cudaMemset the whole buffer
+ * once, or torch.zeros); every forward / backward call leaves them zero again, so a buffer can be reused call after call
+ * without being cleared.  Everything else in the buffer is initialised by the forward call itself.
+ *
+ * ONE kernel launch per direction.  Forward: zero accumulators + smoothness -> (grid barrier) -> per-event warp and bilinear
+ * scatter with 8/16-byte vector atomics -> (grid barrier) -> contrast reduction -> last CTA writes the scalar.  Backward:
+ * smoothness gradient -> (grid barrier) -> per-event analytic gradient, adjoint images evaluated on the fly per corner.
+ * The launches are cooperative (all CTAs co-resident); limits: T <= EF_IWE_MAX_PASSES, S <= EF_IWE_MAX_SCALES, H*W even.
  * ------------------------------------------------------------------------------------------------------------------ */
+#define EF_IWE_MAX_PASSES 32
+#define EF_IWE_MAX_SCALES 4
+
 typedef struct ef_iwe_loss_params {
   int32_t S, B, T, T_maps, H, W; /* T = number of passes (max_ts); T_maps = T, or 1 with overwrite_intermediate       */
   int32_t n_total, n_per_pass;   /* Ntot events per sample; events per pass                                           */
@@ -289,8 +300,8 @@ typedef struct ef_iwe_loss_params {
   const float* pol_mask;         /* [B,Ntot,2]                                                                        */
   const float* flow_maps;        /* [S,B,T_maps,2,H,W]                                                                */
   const float* event_mask;       /* [B,T_maps,H,W] (only read when smoothing_mask)                                    */
-  const int32_t* pass_offsets;   /* device int32[T+1], first event column of each pass (ragged passes), or NULL =      */
-                                 /* uniform passes of n_per_pass events                                               */
+  const int32_t* pass_offsets;   /* HOST int32[T+1], first event column of each pass (ragged passes), or NULL =        */
+                                 /* uniform passes of n_per_pass events.  Read during the call only.                  */
   float* workspace;
   float* loss;                   /* [1]                                                                               */
   /* backward only */
@@ -301,6 +312,29 @@ typedef struct ef_iwe_loss_params {
 int64_t ef_iwe_loss_workspace_elems(int32_t S, int32_t B, int32_t H, int32_t W);
 int ef_iwe_loss_fwd(const ef_iwe_loss_params* p, void* stream);
 int ef_iwe_loss_bwd(const ef_iwe_loss_params* p, void* stream);
+
+/* The same loss on a window in "pass form": what EventWarping.event_flow_association (loss/flow.py:56-116) receives pass
+ * by pass is handed over as pointer tables -- nothing is concatenated or copied (the reference grows its lists with
+ * torch.cat every pass: O(T^2) copying).  Pass t: events[t] [B,n_pass[t],4] (ts already offset by t),
+ * pol_mask[t] [B,n_pass[t],2]; flow[s*T_maps + m] [B,2,H,W] = scale s, map m; event_mask[m] [B,1,H,W]; g_flow likewise.  All
+ * dense.  With overwrite_intermediate T_maps == 1: flow[s] is the final map, event_mask[0] the union mask (:118-146). */
+typedef struct ef_iwe_loss_pass_params {
+  int32_t S, B, T, T_maps, H, W;
+  float flow_scaling, weight;
+  int32_t loss_scaling, smoothing_mask, overwrite_intermediate;
+  int32_t n_pass[EF_IWE_MAX_PASSES];
+  const float* events[EF_IWE_MAX_PASSES];
+  const float* pol_mask[EF_IWE_MAX_PASSES];
+  const float* flow[EF_IWE_MAX_SCALES * EF_IWE_MAX_PASSES];
+  const float* event_mask[EF_IWE_MAX_PASSES];
+  float* workspace;              /* as above                                                                          */
+  float* loss;                   /* [1]                                                                               */
+  const float* g_loss;           /* backward only: [1]                                                                */
+  float* g_flow[EF_IWE_MAX_SCALES * EF_IWE_MAX_PASSES]; /* backward only: [B,2,H,W] each, overwritten                 */
+} ef_iwe_loss_pass_params;
+
+int ef_iwe_loss_fwd_passes(const ef_iwe_loss_pass_params* p, void* stream);
+int ef_iwe_loss_bwd_passes(const ef_iwe_loss_pass_params* p, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Per-polarity image of warped events.  Replaces compute_pol_iwe / deblur_events (utils/iwe.py:95-153) and the
@@ -321,10 +355,42 @@ typedef struct ef_iwe_image_params {
 int ef_iwe_image(const ef_iwe_image_params* p, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * Stand-alone IWE primitives, for callers that use the reference's helpers directly (utils/iwe.py:4-92).  Inside the loss /
+ * metric / image entry points above they are fused; these reproduce the reference's intermediate tensors one launch each.
+ * Forward only (the differentiable path is ef_iwe_loss_fwd / ef_iwe_loss_bwd).
+ *   ef_iwe_purge_unfeasible  purge_unfeasible (:4-17):  x [n,2] (y,x) -> x_out = x * mask, mask [n,1]
+ *   ef_iwe_get_interpolation get_interpolation (:20-74): events [B,N,4], flow [B,N,2] (fy,fx) -> idx, weights [B,4N,1]
+ *                            (corner order TL,TR,BL,BR along N; [B,N,1] with round_idx); out-of-bounds: weight 0, index 0
+ *   ef_iwe_interpolate       interpolate (:77-92): scatter-add of weights (* polarity_mask [B,M,1] or NULL) at idx -> iwe
+ *                            [B,1,H,W], overwritten
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct ef_iwe_interp_params {
+  int32_t B, N, H, W, round_idx;
+  float tref, flow_scaling;
+  const float* events;           /* [B,N,4]                                                                           */
+  const float* flow;             /* [B,N,2] (fy,fx) per event                                                         */
+  float* idx;                    /* [B,4N,1] ([B,N,1] with round_idx) flat pixel index, as fp32 like the reference    */
+  float* weights;                /* same shape                                                                        */
+} ef_iwe_interp_params;
+
+int ef_iwe_purge_unfeasible(const float* x, int64_t n, int32_t H, int32_t W, float* x_out, float* mask, void* stream);
+int ef_iwe_get_interpolation(const ef_iwe_interp_params* p, void* stream);
+int ef_iwe_interpolate(const float* idx, const float* weights, const float* polarity_mask, int32_t B, int32_t M, int32_t H, int32_t W,
+                       float* iwe, void* stream);
+
+/* Stand-alone spike functions (models/spiking_util.py:13-109): z = (x - thresh > 0) as fp32; backward g_x = g * sg(x - thresh)
+ * with sg the surrogate EF_ARCTAN.. of the given width.  thresh_mode 0: one scalar; 1: per channel (thresh [C], x [B,C,hw]);
+ * 2: thresh has x's shape.  n = number of elements of x.  Inside ef_lif_conv_fwd / _bwd these are fused. */
+int ef_spike_fwd(const float* x, const float* thresh, int32_t thresh_mode, int32_t C, int64_t hw, int64_t n, float* z, void* stream);
+int ef_spike_bwd(const float* x, const float* thresh, int32_t thresh_mode, int32_t C, int64_t hw, int64_t n, const float* g,
+                 int32_t surrogate, float width, float* g_x, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * Validation metrics on rounded-index IWEs.  Replaces FWL.forward and RSAT.forward (loss/flow.py:468-579) with
  * get_interpolation(round_idx=True) / interpolate (utils/iwe.py:20-92) and spatial_variance (loss/flow.py:13-23).
  * Per-event flow comes from flow maps as in ef_iwe_loss_fwd (pass layout identical); with T_maps == 1 every event reads map 0.
- * out: [B][4] = FWL, RSAT, and the two RSAT terms (warped, unwarped) for inspection.  workspace: B*8*H*W + B*8 floats.
+ * out: [B][4] = FWL, RSAT, and the two RSAT terms (warped, unwarped) for inspection.  workspace:
+ * ef_iwe_metrics_workspace_elems(B,H,W) floats.
  * ------------------------------------------------------------------------------------------------------------------ */
 typedef struct ef_iwe_metrics_params {
   int32_t B, T, T_maps, H, W, n_total, n_per_pass;

@@ -212,3 +212,135 @@ def test_validation_metrics_match_reference(overwrite):
     assert iwe.shape == (B, 2, H, W) and ev_img.shape == (B, 2, H, W)
     assert ev_img.sum().item() == B * T * N  # every event lands in bounds when it is not warped
     assert metrics[0].compute_masked_window_flow().shape == (B, 2, H, W)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# stand-alone primitives of utils/iwe.py (idx + weights exact) and models/spiking_util.py
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("round_idx", [False, True])
+def test_get_interpolation_interpolate_purge_exact(round_idx):
+    """utils.iwe.get_interpolation / interpolate / purge_unfeasible against the oracle restatement: bit-exact idx and weights."""
+    from event_flow_b200.utils import iwe as U
+
+    B, N, H, W = 3, 700, 24, 40
+    g = torch.Generator().manual_seed(11)
+    ts = torch.rand((B, N, 1), generator=g) * 3
+    ys = torch.randint(0, H, (B, N, 1), generator=g).float()
+    xs = torch.randint(0, W, (B, N, 1), generator=g).float()
+    ps = (torch.rand((B, N, 1), generator=g) < 0.5).float() * 2 - 1
+    events = torch.cat([ts, ys, xs, ps], 2)
+    flow = (torch.rand((B, N, 2), generator=g) - 0.5) * 0.2  # +-10 px over the window at scaling 40: plenty of out-of-bounds corners
+    flow[:, :50] = 0.0                                       # exactly-integer warps (ties)
+    flow[:, 50:100] = 0.5 / (3.0 * 40)                       # half-pixel cases for torch.round (half to even)
+    idx_o, w_o = oiwe.warp_and_split(events, flow, 3.0, (H, W), 40.0, round_idx=round_idx)
+    idx, w = U.get_interpolation(events.to(DEV), flow.to(DEV), 3.0, (H, W), 40.0, round_idx=round_idx)
+    assert idx.shape == idx_o.shape and w.shape == w_o.shape
+    assert torch.equal(idx.cpu(), idx_o) and torch.equal(w.cpu(), w_o)
+    assert (w_o == 0).any() and (w_o > 0).any()
+    pm = (ps > 0).float() if round_idx else torch.cat([(ps > 0).float()] * 4, 1)
+    for mask in (None, pm):
+        img = U.interpolate(idx.long(), w, (H, W), polarity_mask=None if mask is None else mask.to(DEV))
+        img_o = oiwe.scatter_image(idx_o, w_o, (H, W), mask)
+        assert img.shape == (B, 1, H, W)
+        torch.testing.assert_close(img.cpu(), img_o, rtol=1e-5, atol=1e-6)
+    x = torch.stack([ys[..., 0] + (torch.rand((B, N), generator=g) - 0.5) * 60, xs[..., 0] + (torch.rand((B, N), generator=g) - 0.5) * 90], 2)
+    out, m = U.purge_unfeasible(x.to(DEV), (H, W))
+    m_o = torch.ones(B, N, 1)
+    m_o[((x[:, :, 0:1] < 0) + (x[:, :, 0:1] >= H) + (x[:, :, 1:2] < 0) + (x[:, :, 1:2] >= W))] = 0
+    assert torch.equal(m.cpu(), m_o) and torch.equal(out.cpu(), x * m_o)
+
+
+@pytest.mark.parametrize("name,width", [("arctanspike", 10.0), ("superspike", 10.0), ("trianglespike", 1.0), ("mgspike", 0.5)])
+def test_standalone_spike_functions(name, width):
+    """models.spiking_util.<fn>(x, thresh, width) called like the reference's cells do: Heaviside forward, surrogate backward."""
+    from event_flow_b200.models import spiking_util as S
+    from oracle import spiking as osp
+
+    g = torch.Generator().manual_seed(2)
+    x = (torch.randn((2, 6, 9, 11), generator=g)).requires_grad_(True)
+    th = (torch.rand((6, 1, 1), generator=g) + 0.3).requires_grad_(True)
+    xd, thd = x.detach().to(DEV).requires_grad_(True), th.detach().to(DEV).requires_grad_(True)
+    z = getattr(S, name)(xd, thd, torch.tensor(width))
+    up = torch.randn((2, 6, 9, 11), generator=g)
+    z.backward(up.to(DEV))
+    u = x.detach() - th.detach()
+    assert torch.equal(z.cpu(), (u > 0).float())
+    sg = osp.surrogate_grad(u, width, name)
+    torch.testing.assert_close(xd.grad.cpu(), up * sg, rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(thd.grad.cpu(), -(up * sg).sum(dim=(0, 2, 3)).view(6, 1, 1), rtol=1e-4, atol=1e-6)
+    # scalar threshold, default width
+    z2 = getattr(S, name)(xd.detach())
+    assert torch.equal(z2.cpu(), (x.detach() - 1.0 > 0).float())
+
+
+def test_pass_form_equals_map_form_and_workspace_is_reusable():
+    """
+    The two public window forms (concatenated map form / per-pass pointer tables) run the same kernels: equal results.  The
+    workspace's barrier counters are restored by every call, so repeated calls on a recycled workspace agree to the bit-level
+    noise of the atomics (rel 1e-6); ragged passes and overwrite_intermediate go through both forms.
+    """
+    from event_flow_b200 import ops
+
+    B, H, W, T = 3, 32, 48, 4
+    Ns = [300, 120, 0, 511]
+    g = torch.Generator().manual_seed(3)
+    evs, pms, masks, flows = [], [], [], []
+    for t, n in enumerate(Ns):
+        d = oenc.encode_window(*oenc.synthetic_events(B, max(n, 1), H, W, 90 + t), H, W, 2)
+        e = d["event_list"][:, :n].clone()
+        e[:, :, 0] += t
+        evs.append(e.to(DEV)), pms.append(d["event_list_pol_mask"][:, :n].contiguous().to(DEV)), masks.append(d["event_mask"].to(DEV))
+        flows.append(((torch.rand((B, 2, H, W), generator=g) - 0.5) * 0.2).to(DEV))
+    offs = [0]
+    for n in Ns:
+        offs.append(offs[-1] + n)
+    for overwrite in (False, True):
+        fl = [flows[-1]] if overwrite else flows
+        mk = [torch.cat(masks, 1).sum(1, keepdim=True).clamp(max=1)] if overwrite else masks
+        leafs = [f.clone().requires_grad_(True) for f in fl]
+        kw = dict(flow_scaling=48.0, weight=0.01, overwrite_intermediate=overwrite)
+        lp = ops.event_warping_loss_passes([leafs], evs, pms, mk, **kw)
+        lp.backward()
+        maps = torch.stack(fl, 1).unsqueeze(0).clone().requires_grad_(True)
+        lm = ops.event_warping_loss(maps, torch.cat(evs, 1), torch.cat(pms, 1), torch.cat(mk, 1), passes=T, n_per_pass=Ns[0],
+                                    pass_offsets=offs, **kw)
+        lm.backward()
+        assert_rel(lp, lm, 1e-6, "pass form vs map form")
+        for t, f in enumerate(leafs):
+            assert_rel(f.grad, maps.grad[0, :, t], 1e-5, f"grad of map {t}")
+        # the same oracle number
+        pass_of = torch.cat([torch.full((n,), t) for t, n in enumerate(Ns)])
+        lo = oiwe.event_warping_loss(torch.cat(evs, 1).cpu(), torch.cat(pms, 1).cpu(), pass_of, [torch.stack(fl, 1).cpu()], torch.cat(mk, 1).cpu(),
+                                     (H, W), flow_scaling=48.0, weight=0.01, passes=T, overwrite_intermediate=overwrite)
+        assert_rel(lp, lo, 1e-5, "vs oracle")
+        for _ in range(3):  # recycled workspace (ops._WS_POOL): counters must have been restored
+            again = ops.event_warping_loss_passes([[f.detach() for f in fl]], evs, pms, mk, **kw)
+            assert_rel(again, lp, 1e-6, "repeated call")
+    torch.cuda.synchronize()
+
+
+def test_fwl_counts_events_without_polarity():
+    """FWL scatters weight 1 per event regardless of the polarity mask (loss/flow.py:488-494); RSAT uses the mask.  Padded events
+    (p = 0 -> mask (0,0)) must count for FWL only; the encoder must not let them clear the event mask."""
+    from event_flow_b200 import ops
+    from event_flow_b200.dataloader import encodings as E
+
+    B, H, W, N = 2, 20, 28, 400
+    ts, ys, xs, ps = oenc.synthetic_events(B, N, H, W, 5)
+    ps[:, ::5] = 0.0  # every fifth event carries no polarity
+    events = torch.stack([ts, ys, xs, ps], 2)
+    pol = torch.stack([(ps > 0).float(), (ps < 0).float()], 2)
+    g = torch.Generator().manual_seed(6)
+    flow = (torch.rand((B, 1, 2, H, W), generator=g) - 0.5) * 0.3
+    ev_flow = oiwe.gather_event_flow(flow[:, 0], events, (H, W))
+    fwl_o, rsat_o = oiwe.fwl_rsat(events, pol, ev_flow, 1, (H, W), float(max(H, W)))
+    fwl, rsat = ops.iwe_metrics(flow.to(DEV), events.to(DEV), pol.to(DEV), passes=1, n_per_pass=N, flow_scaling=float(max(H, W)))
+    assert_rel(fwl, fwl_o, 1e-5, "FWL with unpolarised events")
+    assert_rel(rsat, rsat_o, 1e-5, "RSAT with unpolarised events")
+    # encoder: a p = 0 event at the pixel of a real event leaves the mask set
+    ev = events.clone()
+    ev[:, 1, 1:3] = ev[:, 0, 1:3]
+    ev[:, 0, 3], ev[:, 1, 3] = 1.0, 0.0
+    d = E.encode_batch(ev.to(DEV), (H, W), 2)
+    for b in range(B):
+        assert d["event_mask"][b, 0, int(ev[b, 0, 1]), int(ev[b, 0, 2])].item() == 1.0

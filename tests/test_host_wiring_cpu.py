@@ -127,19 +127,17 @@ def test_event_warping_bookkeeping_reproduces_reference_loss_on_cpu(name, monkey
     from event_flow_b200.loss.flow import EventWarping
     from oracle import iwe as oiwe
 
-    def loss_stub(flow_maps, events, pol_mask, event_mask, *, passes, n_per_pass, flow_scaling, weight, loss_scaling=True, smoothing_mask=True,
-                  overwrite_intermediate=False, pass_offsets=None):
-        n_tot = events.shape[1]
-        if pass_offsets is not None:
-            bounds = pass_offsets.tolist()
-            pass_of = torch.cat([torch.full((bounds[t + 1] - bounds[t],), t) for t in range(passes)])
-        else:
-            pass_of = torch.arange(n_tot) // n_per_pass
-        return oiwe.event_warping_loss(events, pol_mask, pass_of.long(), [flow_maps[s] for s in range(flow_maps.shape[0])], event_mask,
-                                       tuple(flow_maps.shape[-2:]), flow_scaling=flow_scaling, weight=weight, loss_scaling=loss_scaling,
+    def loss_stub(flows, events, pol_masks, masks, *, flow_scaling, weight, loss_scaling=True, smoothing_mask=True,
+                  overwrite_intermediate=False):
+        # the window arrives in pass form (per-pass tensors, nothing concatenated): restate it for the oracle
+        passes = len(events)
+        pass_of = torch.cat([torch.full((e.shape[1],), t) for t, e in enumerate(events)])
+        maps = [torch.stack(per_scale, dim=1) for per_scale in flows]
+        return oiwe.event_warping_loss(torch.cat(events, 1), torch.cat(pol_masks, 1), pass_of.long(), maps, torch.cat(masks, 1),
+                                       tuple(maps[0].shape[-2:]), flow_scaling=flow_scaling, weight=weight, loss_scaling=loss_scaling,
                                        smoothing_mask=smoothing_mask, overwrite_intermediate=overwrite_intermediate, passes=passes)
 
-    monkeypatch.setattr(ops, "event_warping_loss", loss_stub)
+    monkeypatch.setattr(ops, "event_warping_loss_passes", loss_stub)
     g = load_golden(name)
     scaling, smask, overwrite, weight, T, N = g["cfg"].tolist()
     T, N = int(T), int(N)
