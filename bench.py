@@ -4,12 +4,18 @@ bench.py -- headline benchmark of the event_flow hot path on B200.
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
-Workload (BASELINE.json configs[1], "cfg2"): LIFFireNet, 5-bin voxel input, 128x128, batch 8 per GPU, one training window =
-10 timesteps of 1000 events per sample: 10 forward passes + the EventWarping loss.  One "step" = that window.
-metric = events/s over the whole job (all ranks), inputs resident in HBM (`value`) and end-to-end from pinned host event
-lists (`e2e`: H2D of the raw events each timestep, device-side encoding, model, loss, D2H of the loss).
-Also reported: the full train step (forward + loss + BPTT + gradient all-reduce + clip + Adam) under "train".
-The reference arm (--impl reference) times the CPU restatement of the reference's path (oracle/, "port") on the host cores.
+Workload: one rank's share of BASELINE.json configs[2] ("cfg3"): LIFFireNet (configs/train_SNN.yml), 5-bin voxel input, 128x128,
+batch 8 per GPU (global batch 8 N), one truncated-BPTT window = 10 timesteps of 1000 events per sample.  One "step" = one
+TRAINING window: 10 forward passes + the EventWarping loss + BPTT through the 10 steps + ONE all-reduce(SUM) of the flat
+gradient over NCCL + gradient-norm clip + Adam (train_flow.py:98-171).  The neuron state carries over from window to window
+(detach_states at the window boundary, no reset), like the reference's loop.
+    value  = events/s of the whole job (all ranks), encoded inputs resident in HBM, timed on the device
+    e2e    = the same from pinned host event lists: H2D of the raw events every timestep, device-side encoding, model, loss,
+             backward, all-reduce, optimiser, D2H of the loss value
+    fwd_loss = configs[1] ("cfg2"): the forward passes + loss only (no gradient), resident and end to end -- the inference figure
+    roofline = the dominant kernel (fused conv3x3 + LIF step), iwe = the event-warping loss in isolation (incl. a 16 M-event stream)
+The reference arm (--impl reference) runs the UNMODIFIED reference (staged in baseline/_ref by tools/stage_reference.py)
+through its own public API on the host cores: the same training window, torch-CPU.
 """
 import argparse
 import json
@@ -29,12 +35,19 @@ B_PER_GPU = 8
 T = 10
 N_EV = 1000
 BINS = 5
+LR, CLIP = 2e-4, 100.0
+W_GAIN, PRED_GAIN = 2.5, 20.0
 LIF = dict(leak=[-4.0, 0.1], thresh=[0.8, 0.1], learn_leak=True, learn_thresh=True, hard_reset=True)
 MODEL_CFG = dict(name="LIFFireNet", encoding="voxel", round_encoding=False, norm_input=False, num_bins=BINS, base_num_channels=32,
                  kernel_size=3, activations=["arctanspike", "arctanspike"], mask_output=True, spiking_neuron=LIF)
-LOSS_CFG = {"loader": {"resolution": [H, W]}, "loss": {"flow_regul_weight": 0.001, "overwrite_intermediate": False, "clip_grad": 100.0},
+LOSS_CFG = {"loader": {"resolution": [H, W]}, "loss": {"flow_regul_weight": 0.001, "overwrite_intermediate": False, "clip_grad": CLIP},
             "model": {"mask_output": True}}
-WORKLOAD = "cfg2: LIFFireNet fwd x10 + EventWarping loss, 128x128, 5 voxel bins, 1000 ev/window, batch 8 per GPU"
+WORKLOAD = ("cfg3 (one rank's share): LIFFireNet BPTT train step = fwd x10 + EventWarping loss + backward + grad all-reduce + clip + Adam, "
+            "128x128, 5 voxel bins, 1000 ev/window, batch 8 per GPU")
+WORKLOAD_FWD = "cfg2: LIFFireNet fwd x10 + EventWarping loss (no gradient), 128x128, 5 voxel bins, 1000 ev/window, batch 8 per GPU"
+METRIC = "events/s (LIFFireNet BPTT train step)"
+WEIGHTS = (f"reference init (seed 0); conv weights x{W_GAIN}, prediction weights x{PRED_GAIN} so that spikes reach the prediction layer at "
+           "1000 events / 128^2 (default init dies at layer G2, SURVEY 8d; BASELINE.md suggests x2 -- dense kernels, cost independent of the values)")
 
 
 def peaks():
@@ -44,24 +57,28 @@ def peaks():
         return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
-def make_events(rank, step):
-    """Raw event lists of one window: T tensors [B,N,4] (ts,y,x,p); seed 1234 + 1000*rank + t."""
-    from oracle.encodings import synthetic_events
+def synthetic_events(B, N, seed):
+    """x,y uniform integer pixels (as fp32), p = +-1, ts sorted uniform normalised to [0,1] (dataloader/base.py:84-85)."""
+    g = torch.Generator().manual_seed(seed)
+    ts = torch.sort(torch.rand(B, N, generator=g))[0]
+    ts = (ts - ts[:, :1]) / (ts[:, -1:] - ts[:, :1])
+    ys = torch.randint(0, H, (B, N), generator=g).float()
+    xs = torch.randint(0, W, (B, N), generator=g).float()
+    ps = (torch.randint(0, 2, (B, N), generator=g) * 2 - 1).float()
+    return torch.stack([ts, ys, xs, ps], dim=2)
 
-    out = []
-    for t in range(T):
-        ts, ys, xs, ps = synthetic_events(B_PER_GPU, N_EV, H, W, 1234 + 1000 * rank + 100 * step + t)
-        out.append(torch.stack([ts, ys, xs, ps], dim=2))
-    return out
+
+def make_events(rank, step):
+    """Raw event lists of one window: T tensors [B,N,4] (ts,y,x,p); seed 1234 + 1000*rank + 100*step + t."""
+    return [synthetic_events(B_PER_GPU, N_EV, 1234 + 1000 * rank + 100 * step + t) for t in range(T)]
 
 
 def scale_weights(model):
-    """Reference init (seed 0) with conv weights x2.5 so that spikes reach the prediction layer on 1000 ev / 128^2."""
     with torch.no_grad():
         for n, p in model.named_parameters():
             if n.endswith("ff.weight") or n.endswith("rec.weight"):
-                p.mul_(2.5)
-        model.pred.conv2d.weight.mul_(20.0)
+                p.mul_(W_GAIN)
+        model.pred.conv2d.weight.mul_(PRED_GAIN)
 
 
 class ClockSampler:
@@ -111,9 +128,9 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------------------
 def iwe_bench(dev, peak_gbs, reps=10):
     """
-    Kernel time of ef_iwe_loss_fwd (+ ef_iwe_loss_bwd) through ops.event_warping_loss on device-resident windows: the cfg-2
-    window (B=8, 128x128, T=10, 1000 events per pass) and the large stream of SURVEY 8d (B=32, 256x256, T=10, 50 000 events
-    per pass = 16 M events).  The calls are captured in a CUDA graph (kernels + memsets only) and replayed between CUDA events.
+    Kernel time of ef_iwe_loss_fwd (+ ef_iwe_loss_bwd): ONE launch each, on device-resident windows: the cfg-2 window (B=8,
+    128x128, T=10, 1000 events per pass) and the large stream of SURVEY 8d (B=32, 256x256, T=10, 50 000 events per pass =
+    16 M events).  The calls are captured in a CUDA graph and replayed between CUDA events.
     Algorithmic bytes per sample: fwd 32*Ntot + 4*HW*(2T*S + T + 16*S), bwd 32*Ntot + 4*HW*(8*S + 2T*S).
     """
     from event_flow_b200 import _lib as L
@@ -136,7 +153,7 @@ def iwe_bench(dev, peak_gbs, reps=10):
         p.n_total, p.n_per_pass = ntot, N
         p.flow_scaling, p.weight = float(max(Hh, Ww)), 0.001
         p.loss_scaling, p.smoothing_mask, p.overwrite_intermediate = 1, 1, 0
-        ws = torch.empty(L.lib().ef_iwe_loss_workspace_elems(1, B, Hh, Ww), device=dev, dtype=torch.float32)
+        ws = torch.zeros(L.lib().ef_iwe_loss_workspace_elems(1, B, Hh, Ww), device=dev, dtype=torch.float32)
         loss = torch.empty((), device=dev)
         g_loss = torch.ones((), device=dev)
         g_maps = torch.empty_like(flow)
@@ -164,7 +181,8 @@ def iwe_bench(dev, peak_gbs, reps=10):
         hw = Hh * Ww
         bytes_f = B * (32 * ntot + 4 * hw * (2 * Tt + Tt + 16))
         bytes_b = B * (32 * ntot + 4 * hw * (8 + 2 * Tt))
-        out[name] = {"events": B * ntot, "fwd_ms": ms_f, "fwd_bwd_ms": ms_fb, "fwd_Mev_s": B * ntot / ms_f / 1e3, "fwd_bwd_Mev_s": B * ntot / ms_fb / 1e3,
+        out[name] = {"events": B * ntot, "launches_fwd": 1, "launches_bwd": 1, "fwd_ms": ms_f, "fwd_bwd_ms": ms_fb,
+                     "fwd_Mev_s": B * ntot / ms_f / 1e3, "fwd_bwd_Mev_s": B * ntot / ms_fb / 1e3,
                      "fwd_GBs_algorithmic": bytes_f / ms_f / 1e6, "fwd_frac_of_hbm_peak": bytes_f / ms_f / 1e6 / peak_gbs,
                      "fwd_bwd_GBs_algorithmic": (bytes_f + bytes_b) / ms_fb / 1e6, "fwd_bwd_frac_of_hbm_peak": (bytes_f + bytes_b) / ms_fb / 1e6 / peak_gbs,
                      "loss": float(loss.item())}
@@ -179,7 +197,7 @@ def iwe_bench(dev, peak_gbs, reps=10):
 def run_ours(args):
     import torch.distributed as dist
 
-    from event_flow_b200 import _lib
+    from event_flow_b200 import _lib, fast
     from event_flow_b200.dataloader.encodings import encode_batch
     from event_flow_b200.loss.flow import EventWarping
     from event_flow_b200.models.model import LIFFireNet
@@ -198,51 +216,68 @@ def run_ours(args):
     scale_weights(model)
     model = model.to(dev).train()
     lossf = EventWarping(LOSS_CFG, dev)
-    trainer = DataParallelTrainer(model, lr=2e-4, clip_grad=100.0)
 
-    n_windows = 4  # distinct input windows cycled through (device-resident for `value`, pinned host for `e2e`)
-    host = [[e.pin_memory() for e in make_events(rank, s)] for s in range(n_windows)]
-    resident = []
-    for win in host:
+    dp_check = dp_gradient_check(model, lossf, rank, world, dev) if world > 1 else None
+    trainer = DataParallelTrainer(model, lr=LR, clip_grad=CLIP)
+
+    # every timed / warm-up window has its own inputs (event_flow_association offsets the timestamps IN PLACE on the caller's
+    # tensor, loss/flow.py:90, so a window's event tensors are consumed by one use -- exactly like batches from a loader)
+    n_per_leg = args.warmup + args.steps
+
+    def host_window(k):
+        return [e.pin_memory() for e in make_events(rank, k)]
+
+    def resident_window(k):
         enc = []
-        for e in win:
+        for e in make_events(rank, k):
             ed = e.to(dev)
             d = encode_batch(ed, (H, W), BINS)
             enc.append((d["event_voxel"], d["event_cnt"], ed, d["event_list_pol_mask"], d["event_mask"]))
-        resident.append(enc)
+        return enc
+
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
-    def fwd_loss_resident(k):
-        model.reset_states()
+    def fwd_loss_resident(win):
         lossf.reset()
         with torch.no_grad():
-            for vox, cnt, ev, pm, mask in resident[k % n_windows]:
+            for vox, cnt, ev, pm, mask in win:
                 out = model(vox, cnt)
-                lossf.event_flow_association(out["flow"], ev.clone(), pm, mask)
+                lossf.event_flow_association(out["flow"], ev, pm, mask)
             return lossf()
 
-    def fwd_loss_e2e(k):
-        model.reset_states()
+    def fwd_loss_e2e(win):
         lossf.reset()
         with torch.no_grad():
-            for e in host[k % n_windows]:
+            for e in win:
                 ed = e.to(dev, non_blocking=True)
                 d = encode_batch(ed, (H, W), BINS)
                 out = model(d["event_voxel"], d["event_cnt"])
                 lossf.event_flow_association(out["flow"], ed, d["event_list_pol_mask"], d["event_mask"])
             return lossf().item()  # D2H read of the result
 
-    def train_step(k):
-        model.reset_states()
+    def train_resident(win):
         lossf.reset()
-        for vox, cnt, ev, pm, mask in resident[k % n_windows]:
+        for vox, cnt, ev, pm, mask in win:
             out = model(vox, cnt)
-            lossf.event_flow_association(out["flow"], ev.clone(), pm, mask)
+            lossf.event_flow_association(out["flow"], ev, pm, mask)
         loss = lossf()
         loss.backward()
         trainer.step()
         model.detach_states()
         return loss
+
+    def train_e2e(win):
+        lossf.reset()
+        for e in win:
+            ed = e.to(dev, non_blocking=True)
+            d = encode_batch(ed, (H, W), BINS)
+            out = model(d["event_voxel"], d["event_cnt"])
+            lossf.event_flow_association(out["flow"], ed, d["event_list_pol_mask"], d["event_mask"])
+        loss = lossf()
+        loss.backward()
+        trainer.step()
+        model.detach_states()
+        return loss.item()  # D2H read of the result
 
     def barrier():
         torch.cuda.synchronize()
@@ -250,9 +285,10 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup):
+    def timed(fn, windows, steps, warmup):
+        model.reset_states()
         for k in range(warmup):
-            fn(k)
+            fn(windows[k])
         barrier()
         evs = []
         n0 = _lib.lib().ef_launch_count() + _lib.GRAPH_KERNELS
@@ -260,7 +296,7 @@ def run_ours(args):
             flush.fill_(k & 0xFF)  # L2 flush between timed iterations (outside the timed events)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            fn(warmup + k)
+            fn(windows[warmup + k])
             e1.record()
             evs.append((e0, e1))
         barrier()
@@ -273,17 +309,20 @@ def run_ours(args):
 
     events_per_step = B_PER_GPU * T * N_EV * world
     with ClockSampler(local) as clocks:
-        ms_value, launches = timed(fwd_loss_resident, args.steps, args.warmup)
-        ms_e2e, _ = timed(fwd_loss_e2e, args.steps, args.warmup)
-        ms_train, launches_train = timed(train_step, max(2, args.steps // 2), max(3, args.warmup // 2))
+        legs = []
+        for i, (fn, mk) in enumerate(((train_resident, resident_window), (train_e2e, host_window), (fwd_loss_resident, resident_window),
+                                      (fwd_loss_e2e, host_window))):
+            wins = [mk(i * n_per_leg + k) for k in range(n_per_leg)]
+            legs.append(timed(fn, wins, args.steps, args.warmup))
+            del wins
+        (ms_train, launches_train), (ms_train_e2e, _), (ms_fwd, launches_fwd), (ms_fwd_e2e, _) = legs
 
     # roofline of the dominant kernel: the fused conv3x3+LIF step of the six 32->32 hidden layers.  The launches of a
     # whole window (T steps x 6 layers, real operands of this workload, 59 MB each: far more than L2 per replay) are
     # captured in one CUDA graph -- exactly how the model path issues them -- and the replay is timed with CUDA events on
     # the launching stream: average launch duration = replay time / launches (inter-kernel gaps included).
-    from event_flow_b200 import fast
-
-    xs = [enc[0] for enc in resident[0]] + [resident[1][0][0]]  # T + 1 inputs: step 0 only provides the previous state
+    model.reset_states()
+    xs = [enc[0] for enc in resident_window(0)] + [resident_window(1)[0][0]]  # T + 1 inputs: step 0 only provides the previous state
     graph, n_hidden = fast.capture_window(model, xs, only_hidden=True)
     graph_all, n_all = fast.capture_window(model, xs, only_hidden=False)
 
@@ -307,30 +346,38 @@ def run_ours(args):
     bytes_per_launch = 4 * H * W * (32 + 2 * 2 * 32) * B_PER_GPU  # 4*HW*(Cin + 2*S_r*C) per sample, fp32 reference semantics
     avg_ms = ms_hidden / n_hidden
     achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9
+    traffic, traffic_src = ncu_traffic()
     roofline = {"bound": "hbm", "kernel": "fused conv3x3+LIF step, 32->32 ch (lif_conv_fwd_tc_kernel via ef_lif_conv_fwd)", "achieved": achieved,
-                "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": 34274304, "peak_source": pk_kind + " (burst copy)",
-                "bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_ms, "launches_per_step": n_hidden,
-                "traffic_source": "ncu --set full, profiles/r01d_ncu_tc_fwd_v5.txt: dram__bytes_read.sum 33 643 008 (= x 8.4 + z 8.4 + v 16.8 MB, exactly compulsory) + "
-                                  "dram__bytes_write.sum 631 296 (the 25.2 MB of outputs are still in the 126 MB L2 when the kernel ends); fast-path formats move 58.7 MB per launch",
+                "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "peak_source": pk_kind + " (burst copy)",
+                "bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_ms, "launches_per_step": n_hidden, "traffic_source": traffic_src,
                 "how": f"{n_hidden} launches (4 feed-forward + 2 recurrent cells x {T} steps) replayed as one CUDA graph, CUDA events around the replays",
-                "share_of_step": ms_hidden / ms_all, "model_kernels_ms_per_window": ms_all, "clocks": clocks_k.summary()}
+                "share_of_fwd_window": ms_hidden / ms_all, "share_of_step": ms_hidden / ms_train, "model_kernels_ms_per_window": ms_all,
+                "clocks": clocks_k.summary()}
 
     iwe = iwe_bench(dev, pk["hbm_gbs"]) if rank == 0 else None
     if rank == 0:
         # the CPU baseline is taken at N=1 only: under torchrun the other ranks spin in the barrier and steal the host cores
-        cpu = cpu_baseline(sample_steps=1) if world == 1 else None
+        cpu = cpu_baseline() if world == 1 else None
         line = {
-            "metric": "events/s (LIFFireNet fwd + EventWarping loss)", "value": events_per_step / (ms_value * 1e-3), "unit": "events/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_value, "higher_is_better": True, "scaling": "weak",
+            "metric": METRIC, "value": events_per_step / (ms_train * 1e-3), "unit": "events/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_train, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": B_PER_GPU * world, "timesteps": T, "events_per_window": N_EV, "resolution": [H, W],
-                       "parallelism": f"dp{world}", "l2": "256 MB write between timed iterations (L2 flush)", "weights": "reference init seed 0, conv x2.5"},
-            "e2e": {"value": events_per_step / (ms_e2e * 1e-3), "unit": "events/s", "ms_per_step": ms_e2e,
+                       "parallelism": f"dp{world}", "collective": "1 x ncclAllReduce(SUM, fp32, 74 818 elements) per step" if world > 1 else "none (1 rank)",
+                       "l2": "256 MB write between timed iterations (L2 flush)", "weights": WEIGHTS},
+            "e2e": {"value": events_per_step / (ms_train_e2e * 1e-3), "unit": "events/s", "ms_per_step": ms_train_e2e,
                     "h2d_bytes_per_step": T * B_PER_GPU * N_EV * 4 * 4, "d2h_bytes_per_step": 4,
-                    "path": "pinned host event lists -> H2D -> ef_encode_events -> LIFFireNet x10 -> EventWarping -> loss.item()"},
-            "gpu_launches": int(launches),
-            "train": {"ms_per_step": ms_train, "events_per_s": events_per_step / (ms_train * 1e-3), "gpu_launches": int(launches_train),
-                      "what": "fwd x10 + loss + BPTT + grad all-reduce(SUM) + clip(100) + Adam, batch 8 per GPU"},
+                    "path": "pinned host event lists -> H2D -> ef_encode_events -> LIFFireNet x10 -> EventWarping -> backward -> "
+                            "all-reduce -> clip + Adam -> loss.item()"},
+            "gpu_launches": int(launches_train),
+            "fwd_loss": {"workload": WORKLOAD_FWD, "value": events_per_step / (ms_fwd * 1e-3), "unit": "events/s", "ms_per_step": ms_fwd,
+                         "steps": args.steps, "warmup": args.warmup, "gpu_launches": int(launches_fwd),
+                         "algorithmic_GB_per_window": 73859072 * B_PER_GPU * T / 1e9,
+                         "frac_of_hbm_roofline": 73859072 * B_PER_GPU * T / (ms_fwd * 1e-3) / 1e9 / pk["hbm_gbs"],
+                         "e2e": {"value": events_per_step / (ms_fwd_e2e * 1e-3), "unit": "events/s", "ms_per_step": ms_fwd_e2e,
+                                 "h2d_bytes_per_step": T * B_PER_GPU * N_EV * 4 * 4, "d2h_bytes_per_step": 4}},
+            "train": {"ms_per_step": ms_train, "events_per_s": events_per_step / (ms_train * 1e-3), "gpu_launches": int(launches_train)},
+            "dp_check": dp_check,
             "roofline": roofline, "iwe": iwe, "cpu_baseline": cpu, "clocks": clocks.summary(),
         }
         print(json.dumps(line))
@@ -339,70 +386,214 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-# ---------------------------------------------------------------------------------------------------------------------
-# CPU baseline / reference arm: the oracle restatement of the reference's path on the host cores
-# ---------------------------------------------------------------------------------------------------------------------
-def cpu_step(params, windows):
-    from oracle import iwe as oiwe
-    from oracle import spiking as osp
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full summary."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        d = json.load(open(path))
+        return int(d["dram_bytes_read"] + d["dram_bytes_write"]), f"profiles/ncu_traffic.json ({d.get('source', 'ncu --set full')})"
+    except Exception:
+        return None, "no committed ncu capture found (profiles/ncu_traffic.json)"
 
-    states = [None] * 7
-    flows, evs, pms, masks = [], [], [], []
-    with torch.no_grad():
-        for t, d in enumerate(windows):
-            flow, states, _ = osp.firenet_step("lif", params, states, d["event_voxel"])
+
+def dp_gradient_check(model, lossf, rank, world, dev):
+    """
+    Hardware self-check of the data-parallel step (train_flow.py:141-171 semantics): the all-reduced SUM of the ranks'
+    batch-8 gradients must equal the gradient of ONE process running the global batch 8*world.  Every rank runs its own shard,
+    rank 0 also runs the concatenated batch on a copy of the model; returns the max-abs relative error of the flat gradient.
+    """
+    import copy
+
+    import torch.distributed as dist
+
+    from event_flow_b200.dataloader.encodings import encode_batch
+
+    def window_grad(m, shards):
+        m.reset_states()
+        lossf.reset()
+        m.zero_grad(set_to_none=True)
+        for t in range(T):
+            ed = torch.cat([make_events(r, 7)[t] for r in shards], dim=0).to(dev)
+            d = encode_batch(ed, (H, W), BINS)
+            out = m(d["event_voxel"], d["event_cnt"])
+            lossf.event_flow_association(out["flow"], ed, d["event_list_pol_mask"], d["event_mask"])
+        loss = lossf()
+        loss.backward()
+        m.reset_states()
+        lossf.reset()
+        return torch.cat([p.grad.reshape(-1) for p in m.parameters() if p.requires_grad]), loss.detach()
+
+    g_local, l_local = window_grad(model, [rank])
+    dist.all_reduce(g_local, op=dist.ReduceOp.SUM)
+    dist.all_reduce(l_local, op=dist.ReduceOp.SUM)
+    out = None
+    if rank == 0:
+        twin = copy.deepcopy(model)  # (also exercises FireNet.__getstate__: run-time caches do not travel)
+        g_all, l_all = window_grad(twin, list(range(world)))
+        out = {"dp_grad_rel_err": ((g_local - g_all).abs().max() / g_all.abs().max()).item(),
+               "dp_loss_rel_err": ((l_local - l_all).abs() / l_all.abs()).item(), "global_batch": B_PER_GPU * world,
+               "what": "all-reduced SUM of per-rank batch-8 gradients vs one process on the concatenated batch"}
+        del twin
+        torch.cuda.empty_cache()
+    model.zero_grad(set_to_none=True)
+    dist.barrier()
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the unmodified reference on the host cores (fallback: the oracle port)
+# ---------------------------------------------------------------------------------------------------------------------
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+
+
+class ReferenceCPU:
+    """The reference's own modules (baseline/_ref, staged unmodified by tools/stage_reference.py), torch-CPU, all host threads."""
+
+    kind = "reference"
+
+    def __init__(self):
+        sys.path.insert(0, REF_DIR)
+        from dataloader.encodings import events_to_channels, events_to_voxel  # noqa: F401  (reference modules)
+        from loss.flow import EventWarping
+        from models.model import LIFFireNet
+
+        self.cores = os.cpu_count()
+        torch.set_num_threads(self.cores)
+        torch.manual_seed(0)
+        LIFFireNet.kwargs = [{}] * 7  # the reference shares one class-level kwargs list between all FireNets (model.py:159)
+        self.model = LIFFireNet(dict(MODEL_CFG, spiking_neuron=dict(LIF))).train()
+        scale_weights(self.model)
+        self.lossf = EventWarping(LOSS_CFG, torch.device("cpu"))
+        self.opt = torch.optim.Adam(self.model.parameters(), lr=LR)
+        self.enc = (events_to_voxel, events_to_channels)
+        self.model.reset_states()
+
+    def window(self, k):
+        to_voxel, to_channels = self.enc
+        out = []
+        for e in make_events(0, k):
+            ts, ys, xs, ps = e[:, :, 0], e[:, :, 1], e[:, :, 2], e[:, :, 3]
+            vox = torch.stack([to_voxel(xs[b], ys[b], ts[b], ps[b], BINS, sensor_size=(H, W)) for b in range(B_PER_GPU)])
+            cnt = torch.stack([to_channels(xs[b], ys[b], ps[b], sensor_size=(H, W)) for b in range(B_PER_GPU)])
+            pm = torch.stack([(ps > 0).float(), (ps < 0).float()], 2)
+            mask = (cnt.sum(1, keepdim=True) > 0).float()
+            out.append((vox, cnt, e.clone(), pm, mask))
+        return out
+
+    def train_step(self, win):  # train_flow.py:98-171
+        self.lossf.reset()
+        for vox, cnt, ev, pm, mask in win:
+            x = self.model(vox, cnt)
+            self.lossf.event_flow_association(x["flow"], ev, pm, mask)
+        loss = self.lossf()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(self.model.parameters(), CLIP)
+        self.opt.step()
+        self.opt.zero_grad()
+        self.model.detach_states()
+        return loss.item()
+
+    def fwd_loss(self, win):
+        self.lossf.reset()
+        with torch.no_grad():
+            for vox, cnt, ev, pm, mask in win:
+                x = self.model(vox, cnt)
+                self.lossf.event_flow_association(x["flow"], ev, pm, mask)
+            return self.lossf().item()
+
+
+class PortCPU:
+    """Fallback when baseline/_ref is absent: the oracle's restatement of the same step (torch-CPU fp32, autograd)."""
+
+    kind = "port"
+
+    def __init__(self):
+        from oracle import encodings as oenc
+        from oracle import iwe as oiwe
+        from oracle import spiking as osp
+
+        self.oenc, self.oiwe, self.osp = oenc, oiwe, osp
+        self.cores = os.cpu_count()
+        torch.set_num_threads(self.cores)
+        self.params = osp.init_firenet_params("lif", BINS, 32, seed=0, weight_gain=W_GAIN)
+        self.params["pred"]["weight"] = self.params["pred"]["weight"] * PRED_GAIN
+        self.leaves = [t.requires_grad_(True) for layer in self.params.values() for t in layer.values() if torch.is_tensor(t) and t.is_floating_point()]
+        self.opt = torch.optim.Adam(self.leaves, lr=LR)
+        self.states = [None] * 7
+
+    def window(self, k):
+        return [self.oenc.encode_window(e[:, :, 0], e[:, :, 1], e[:, :, 2], e[:, :, 3], H, W, BINS) for e in make_events(0, k)]
+
+    def _loss(self, win):
+        flows, evs, pms, masks = [], [], [], []
+        for t, d in enumerate(win):
+            flow, self.states, _ = self.osp.firenet_step("lif", self.params, self.states, d["event_voxel"])
             flows.append(flow)
             e = d["event_list"].clone()
             e[:, :, 0] += t
             evs.append(e), pms.append(d["event_list_pol_mask"]), masks.append(d["event_mask"])
-        return oiwe.event_warping_loss(torch.cat(evs, 1), torch.cat(pms, 1), torch.arange(T).repeat_interleave(N_EV), [torch.stack(flows, 1)],
-                                       torch.cat(masks, 1), (H, W), weight=0.001, passes=T)
+        return self.oiwe.event_warping_loss(torch.cat(evs, 1), torch.cat(pms, 1), torch.arange(T).repeat_interleave(N_EV), [torch.stack(flows, 1)],
+                                            torch.cat(masks, 1), (H, W), weight=0.001, passes=T)
+
+    def train_step(self, win):
+        loss = self._loss(win)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(self.leaves, CLIP)
+        self.opt.step()
+        self.opt.zero_grad()
+        self.states = [None if s is None else s.detach() for s in self.states]
+        return loss.item()
+
+    def fwd_loss(self, win):
+        with torch.no_grad():
+            return self._loss(win).item()
 
 
-def cpu_setup():
-    from oracle import encodings as oenc
-    from oracle import spiking as osp
-
-    cores = os.cpu_count()
-    torch.set_num_threads(cores)
-    params = osp.init_firenet_params("lif", BINS, 32, seed=0, weight_gain=2.5)
-    params["pred"]["weight"] = params["pred"]["weight"] * 20.0
-    windows = []
-    for e in make_events(0, 0):
-        windows.append(oenc.encode_window(e[:, :, 0], e[:, :, 1], e[:, :, 2], e[:, :, 3], H, W, BINS))
-    return cores, params, windows
+def cpu_arm():
+    if os.path.isfile(os.path.join(REF_DIR, "models", "model.py")):
+        return ReferenceCPU()
+    return PortCPU()
 
 
-def cpu_baseline(sample_steps=1):
-    cores, params, windows = cpu_setup()
-    cpu_step(params, windows)  # warm-up
+def cpu_time(fn, windows, steps, warmup):
+    for k in range(warmup):
+        fn(windows[k])
     t0 = time.perf_counter()
-    for _ in range(sample_steps):
-        cpu_step(params, windows)
-    dt = (time.perf_counter() - t0) / sample_steps
-    return {"value": B_PER_GPU * T * N_EV / dt, "unit": "events/s", "cores": cores, "kind": "port", "ms_per_step": dt * 1e3,
-            "sample": f"{sample_steps} full window(s) of the same workload (batch 8, 10 timesteps) after 1 warm-up, torch-CPU fp32 oracle, {cores} threads"}
+    for k in range(steps):
+        fn(windows[warmup + k])
+    return (time.perf_counter() - t0) / steps
+
+
+def cpu_baseline():
+    """Bounded sample for the `cpu_baseline` key of our own line: 1 warm-up + 2 timed training windows, 1 + 2 forward+loss windows."""
+    arm = cpu_arm()
+    wins = [arm.window(k) for k in range(6)]
+    dt = cpu_time(arm.train_step, wins[:3], 2, 1)
+    dt_f = cpu_time(arm.fwd_loss, wins[3:], 2, 1)
+    what = "unmodified reference modules (baseline/_ref)" if arm.kind == "reference" else "oracle port of the reference"
+    return {"value": B_PER_GPU * T * N_EV / dt, "unit": "events/s", "cores": arm.cores, "kind": arm.kind, "ms_per_step": dt * 1e3,
+            "fwd_loss_value": B_PER_GPU * T * N_EV / dt_f, "fwd_loss_ms_per_step": dt_f * 1e3,
+            "sample": f"2 full training windows (batch 8, 10 timesteps: fwd + loss + backward + clip + Adam) after 1 warm-up, {what}, torch-CPU fp32, "
+                      f"{arm.cores} threads; fwd_loss_*: 2 forward+loss windows after 1 warm-up"}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
-    cores, params, windows = cpu_setup()
-    for _ in range(max(1, min(args.warmup, 2))):
-        cpu_step(params, windows)
-    steps = max(1, min(args.steps, 5))
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        cpu_step(params, windows)
-    dt = (time.perf_counter() - t0) / steps
+    arm = cpu_arm()
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    wins = [arm.window(k) for k in range(steps + warmup)]
+    dt = cpu_time(arm.train_step, wins, steps, warmup)
     v = B_PER_GPU * T * N_EV / dt
-    sample = f"{steps} full windows (batch 8, 10 timesteps; one rank's share) after warm-up, torch-CPU fp32 oracle port of the reference, {cores} threads"
+    what = "unmodified reference modules (baseline/_ref)" if arm.kind == "reference" else "oracle port of the reference (baseline/_ref not staged)"
+    sample = (f"{steps} full training windows (batch 8, 10 timesteps; one rank's share) after {warmup} warm-up, {what}, torch-CPU fp32, "
+              f"{arm.cores} threads")
     print(json.dumps({
-        "impl": "reference", "metric": "events/s (LIFFireNet fwd + EventWarping loss)", "value": v, "unit": "events/s", "n_gpus": args.gpus,
-        "steps": steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "global_batch": B_PER_GPU, "parallelism": "cpu"},
-        "cpu_baseline": {"value": v, "unit": "events/s", "cores": cores, "kind": "port", "sample": sample},
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "events/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "global_batch": B_PER_GPU, "parallelism": "cpu", "weights": WEIGHTS},
+        "cpu_baseline": {"value": v, "unit": "events/s", "cores": arm.cores, "kind": arm.kind, "sample": sample},
         "e2e": {"value": v, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -411,7 +602,7 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=6)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     a = ap.parse_args()
     if a.impl == "reference":

@@ -11,14 +11,36 @@ import torch.distributed as dist
 from . import _lib as L
 
 
+class _LibKernels:
+    """The two optimiser kernels of libeventflow.so (ef_grad_sqnorm, ef_clip_adam) on the current CUDA stream."""
+
+    @staticmethod
+    def grad_sqnorm(flat_grad, n, sqnorm):
+        L.check(L.lib().ef_grad_sqnorm(L.ptr(flat_grad), n, L.ptr(sqnorm), L.stream()), "ef_grad_sqnorm")
+        L.LAUNCHES += 1
+
+    @staticmethod
+    def clip_adam(flat_param, flat_grad, m, v, n, sqnorm, clip, lr, beta1, beta2, eps, step):
+        L.check(L.lib().ef_clip_adam(L.ptr(flat_param), L.ptr(flat_grad), L.ptr(m), L.ptr(v), n, L.ptr(sqnorm), clip, lr, beta1, beta2, eps,
+                                     step, L.stream()), "ef_clip_adam")
+        L.LAUNCHES += 1
+
+
 class DataParallelTrainer:
-    def __init__(self, model, lr=2e-4, clip_grad=100.0, betas=(0.9, 0.999), eps=1e-8, process_group=None):
+    """
+    :param kernels: object with grad_sqnorm / clip_adam (default: the CUDA library).  Tests inject a stand-in so that the
+                    host logic -- flat buffers, gradient views, all-reduce(SUM), step counting -- runs under gloo on CPU;
+                    without it the model must live on a CUDA device (there is no CPU path in the product).
+    """
+
+    def __init__(self, model, lr=2e-4, clip_grad=100.0, betas=(0.9, 0.999), eps=1e-8, process_group=None, kernels=None):
         self.params = [p for p in model.parameters() if p.requires_grad]
         if not self.params:
             raise ValueError("model has no trainable parameters")
         dev = self.params[0].device
-        if dev.type != "cuda":
+        if kernels is None and dev.type != "cuda":
             raise L.EventFlowError("DataParallelTrainer needs the model on a CUDA device (no CPU path)")
+        self.kernels = kernels if kernels is not None else _LibKernels
         n = sum(p.numel() for p in self.params)
         self.flat_param = torch.empty(n, device=dev, dtype=torch.float32)
         self.flat_grad = torch.zeros(n, device=dev, dtype=torch.float32)
@@ -55,23 +77,25 @@ class DataParallelTrainer:
 
     def step(self):
         """all-reduce(SUM) -> clip -> Adam -> zero grads.  Call after loss.backward()."""
+        self.reduce_gradients()
+        self.apply_gradients()
+
+    def reduce_gradients(self):
+        """First half of step(): fold re-bound .grad tensors back into the flat buffer, ONE all-reduce(SUM) over the ranks."""
         for p in self.params:  # autograd may have re-bound .grad (e.g. first backward after set_to_none); fold it back
             if p.grad is not None and p.grad.data_ptr() != self._view_of(p).data_ptr():
                 self._view_of(p).copy_(p.grad)
                 p.grad = self._view_of(p)
         if self.world_size > 1:
             dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
+
+    def apply_gradients(self):
+        """Second half of step(): global-norm clip + Adam on the flat buffers (two kernels), then zero the gradients."""
         self.step_count += 1
-        st = L.stream()
-        lib = L.lib()
         self.sqnorm.zero_()
-        L.check(lib.ef_grad_sqnorm(L.ptr(self.flat_grad), self.n, L.ptr(self.sqnorm), st), "ef_grad_sqnorm")
-        L.check(
-            lib.ef_clip_adam(L.ptr(self.flat_param), L.ptr(self.flat_grad), L.ptr(self.m), L.ptr(self.v), self.n, L.ptr(self.sqnorm),
-                             float(self.clip) if self.clip else 0.0, self.lr, self.betas[0], self.betas[1], self.eps, self.step_count, st),
-            "ef_clip_adam",
-        )
-        L.LAUNCHES += 2
+        self.kernels.grad_sqnorm(self.flat_grad, self.n, self.sqnorm)
+        self.kernels.clip_adam(self.flat_param, self.flat_grad, self.m, self.v, self.n, self.sqnorm, float(self.clip) if self.clip else 0.0,
+                               self.lr, self.betas[0], self.betas[1], self.eps, self.step_count)
         self.flat_grad.zero_()
         from . import fast
 

@@ -1,8 +1,11 @@
 """
-CPU, world_size 2 over gloo: the data-parallel contract of SURVEY 8e / T7 -- gradients of a batch equal the all-reduced SUM
-of the per-shard gradients (no division by the world size), and after the reduce every rank holds the same buffer.  The
-CUDA kernels cannot run here, so the per-rank gradients come from the CPU oracle; what is under test is the sharding and
-reduction logic bench.py / DataParallelTrainer rely on.
+CPU, world_size 2 over gloo: the host side of the data-parallel training step -- the code under test is
+event_flow_b200.parallel.DataParallelTrainer and event_flow_b200.train.train_windows themselves.  The two optimiser kernels
+(ef_grad_sqnorm, ef_clip_adam) cannot run without a GPU, so a torch stand-in with their documented semantics
+(include/eventflow.h) is injected through the trainer's `kernels` hook; everything else -- flat parameter / gradient buffers,
+gradient views, the ONE all-reduce(SUM) per step (no division by the world size: the loss sums over the batch,
+loss/flow.py:226,259), clip after the reduce, step counting, zeroing -- is the product code.  The GPU twin of this test
+(NCCL, real kernels, LIFFireNet) is tests/test_gpu_dp.py.
 """
 import os
 import socket
@@ -11,55 +14,66 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from oracle import encodings as oenc
-from oracle import iwe as oiwe
-from oracle import spiking as osp
 
-H, W, T, N, BINS = 16, 16, 2, 200, 2
+class TorchKernels:
+    """ef_grad_sqnorm / ef_clip_adam restated with torch ops (test stand-in, not product code)."""
 
+    @staticmethod
+    def grad_sqnorm(flat_grad, n, sqnorm):
+        sqnorm += (flat_grad.double() ** 2).sum().float()
 
-def window_grads(params, batch_slice, seed0):
-    for lp in params.values():
-        for v in lp.values():
-            v.grad = None
-    states, flows, evs, pms, masks = [None] * 7, [], [], [], []
-    for t in range(T):
-        d = oenc.encode_window(*oenc.synthetic_events(4, N, H, W, seed0 + t), H, W, BINS)
-        d = {k: v[batch_slice] for k, v in d.items()}
-        flow, states, _ = osp.firenet_step("lif", params, states, d["event_cnt"])
-        flows.append(flow)
-        e = d["event_list"].clone()
-        e[:, :, 0] += t
-        evs.append(e), pms.append(d["event_list_pol_mask"]), masks.append(d["event_mask"])
-    loss = oiwe.event_warping_loss(torch.cat(evs, 1), torch.cat(pms, 1), torch.arange(T).repeat_interleave(N), [torch.stack(flows, 1)],
-                                   torch.cat(masks, 1), (H, W), weight=0.0, passes=T)  # weight 0: the smoothness term is a batch sum too,
-    loss.backward()                                                                  # but its /T normalisation is shared -> keep it simple
-    return torch.cat([v.grad.reshape(-1) for lp in params.values() for v in lp.values()]), loss.detach()
+    @staticmethod
+    def clip_adam(flat_param, flat_grad, m, v, n, sqnorm, clip, lr, beta1, beta2, eps, step):
+        scale = min(1.0, clip / (float(sqnorm.sqrt()) + 1e-6)) if clip > 0 else 1.0
+        g = flat_grad * scale
+        m.mul_(beta1).add_(g, alpha=1 - beta1)
+        v.mul_(beta2).addcmul_(g, g, value=1 - beta2)
+        mhat, vhat = m / (1 - beta1 ** step), v / (1 - beta2 ** step)
+        flat_param.sub_(lr * mhat / (vhat.sqrt() + eps))
 
 
-def make_params():
+def make_model():
     torch.manual_seed(0)
-    params = osp.init_firenet_params("lif", BINS, 32, seed=0, weight_gain=2.5)
-    params["pred"]["weight"] = params["pred"]["weight"] * 30.0
-    for lp in params.values():
-        for k in lp:
-            lp[k] = lp[k].clone().requires_grad_(True)
-    return params
+    return torch.nn.Sequential(torch.nn.Conv2d(2, 6, 3, padding=1), torch.nn.Tanh(), torch.nn.Conv2d(6, 2, 1))
+
+
+def batch(step):
+    g = torch.Generator().manual_seed(100 + step)
+    return torch.randn(4, 2, 10, 12, generator=g)
+
+
+def run_steps(model, trainer, shard, n_steps, set_to_none=False):
+    for it in range(n_steps):
+        x = batch(it)[shard]
+        loss = (model(x) ** 2).sum()  # a SUM over the batch, like the reference loss
+        if set_to_none and it == 1:   # autograd re-binds .grad to fresh tensors: the trainer must fold them back into its flat buffer
+            for p in model.parameters():
+                p.grad = None
+        loss.backward()
+        trainer.step()
+    return trainer
 
 
 def worker(rank, world, port, out):
+    from event_flow_b200.parallel import DataParallelTrainer
+
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     torch.set_num_threads(1)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    params = make_params()
-    shard = slice(rank * 2, rank * 2 + 2)  # batch 4 -> 2 samples per rank
-    flat, loss = window_grads(params, shard, 40)
-    dist.all_reduce(flat, op=dist.ReduceOp.SUM)  # SUM, not MEAN: the loss sums over the batch (loss/flow.py:226,259)
-    dist.all_reduce(loss, op=dist.ReduceOp.SUM)
-    gathered = [torch.empty_like(flat) for _ in range(world)]
-    dist.all_gather(gathered, flat)
+    model = make_model()
+    tr = DataParallelTrainer(model, lr=1e-2, clip_grad=5.0, kernels=TorchKernels)
+    assert tr.world_size == world
+    # parameters and gradients are views of the flat buffers
+    o = 0
+    for p in tr.params:
+        assert p.data.data_ptr() == tr.flat_param[o:o + p.numel()].data_ptr() and p.grad.data_ptr() == tr.flat_grad[o:o + p.numel()].data_ptr()
+        o += p.numel()
+    run_steps(model, tr, slice(rank * 2, rank * 2 + 2), 3, set_to_none=True)
+    gathered = [torch.empty_like(tr.flat_param) for _ in range(world)]
+    dist.all_gather(gathered, tr.flat_param)
     if rank == 0:
-        out["flat"], out["loss"], out["same"] = flat, loss, all(torch.equal(g, flat) for g in gathered)
+        out["param"], out["same"] = tr.flat_param.clone(), all(torch.equal(g, tr.flat_param) for g in gathered)
+        out["norm"], out["steps"], out["grad_zero"] = tr.grad_norm().item(), tr.step_count, bool(tr.flat_grad.abs().max() == 0)
     dist.destroy_process_group()
 
 
@@ -71,13 +85,105 @@ def free_port():
     return p
 
 
-def test_sharded_gradients_sum_to_full_batch_gradients():
+def test_two_rank_trainer_equals_one_process_on_the_whole_batch():
+    from event_flow_b200.parallel import DataParallelTrainer
+
     mgr = mp.Manager()
     out = mgr.dict()
     mp.spawn(worker, args=(2, free_port(), out), nprocs=2, join=True)
-    params = make_params()
-    full, loss = window_grads(params, slice(0, 4), 40)
-    assert out["same"]
-    torch.testing.assert_close(out["loss"], loss, rtol=1e-5, atol=0)
-    assert full.abs().max() > 0
-    torch.testing.assert_close(out["flat"], full, rtol=1e-4, atol=1e-6 * full.abs().max().item())
+    model = make_model()
+    tr = run_steps(model, DataParallelTrainer(model, lr=1e-2, clip_grad=5.0, kernels=TorchKernels), slice(0, 4), 3)
+    assert out["same"], "ranks diverged"
+    assert out["steps"] == 3 and out["grad_zero"]
+    torch.testing.assert_close(out["param"], tr.flat_param, rtol=1e-5, atol=1e-7)
+    assert abs(out["norm"] - tr.grad_norm().item()) <= 1e-5 * tr.grad_norm().item()  # the clip saw the REDUCED gradient
+    # and the flat-buffer Adam is torch's Adam + clip_grad_norm_
+    ref = make_model()
+    opt = torch.optim.Adam(ref.parameters(), lr=1e-2)
+    for it in range(3):
+        (ref(batch(it)) ** 2).sum().backward()
+        torch.nn.utils.clip_grad_norm_(ref.parameters(), 5.0)
+        opt.step()
+        opt.zero_grad()
+    flat_ref = torch.cat([p.detach().reshape(-1) for p in ref.parameters()])
+    torch.testing.assert_close(tr.flat_param, flat_ref, rtol=1e-4, atol=1e-6)
+
+
+def test_trainer_without_kernels_refuses_cpu_models():
+    import pytest
+
+    from event_flow_b200._lib import EventFlowError
+    from event_flow_b200.parallel import DataParallelTrainer
+
+    with pytest.raises(EventFlowError):
+        DataParallelTrainer(make_model())
+
+
+def test_train_windows_follows_the_reference_loop():
+    """train_flow.py:97-171: new_seq resets loss / states / grads, the loss fires at window_loss events, then step, detach, reset."""
+    from event_flow_b200.train import train_windows
+
+    log = []
+
+    class Loader:
+        def __init__(self):
+            self.new_seq = False
+
+        def __iter__(self):
+            for i in range(9):
+                self.new_seq = i in (0, 5)  # a second recording starts in the middle of a loss window
+                yield {"event_voxel": torch.zeros(1), "event_cnt": torch.zeros(1), "event_list": torch.zeros(1, 100, 4),
+                       "event_list_pol_mask": torch.zeros(1, 100, 2), "event_mask": torch.zeros(1)}
+
+    class Model:
+        def train(self):
+            log.append("train")
+
+        def reset_states(self):
+            log.append("reset_states")
+
+        def detach_states(self):
+            log.append("detach_states")
+
+        def __call__(self, vox, cnt):
+            log.append("forward")
+            return {"flow": [torch.zeros(1)]}
+
+    class Loss:
+        num_events = 0
+
+        def reset(self):
+            log.append("loss.reset")
+            self.num_events = 0
+
+        def event_flow_association(self, flow, ev, pm, mask):
+            self.num_events += ev.shape[1]
+
+        def __call__(self):
+            log.append("loss()")
+            return torch.zeros((), requires_grad=True) + 1.0
+
+    class Trainer:
+        def zero_grad(self):
+            log.append("zero_grad")
+
+        def step(self):
+            log.append("step")
+
+    losses = train_windows(Model(), Loss(), Trainer(), Loader(), window_loss=300, n_windows=2)
+    assert losses == [1.0, 1.0]
+    assert log == ["train",
+                   "loss.reset", "reset_states", "zero_grad", "forward", "forward", "forward", "loss()", "step", "detach_states", "loss.reset",
+                   "forward", "forward",                                        # 200 events of the next window ...
+                   "loss.reset", "reset_states", "zero_grad", "forward",        # ... dropped by new_seq (train_flow.py:100-105)
+                   "forward", "forward", "loss()", "step", "detach_states", "loss.reset"]
+
+
+def test_synthetic_stream_shards_are_disjoint_and_reproducible():
+    from event_flow_b200.train import SyntheticEventStream
+
+    a = SyntheticEventStream(2, 50, (16, 16), 2, "cpu", rank=0).host_events(3)
+    b = SyntheticEventStream(2, 50, (16, 16), 2, "cpu", rank=1).host_events(3)
+    a2 = SyntheticEventStream(2, 50, (16, 16), 2, "cpu", rank=0).host_events(3)
+    assert torch.equal(a, a2) and not torch.equal(a, b)
+    assert a.shape == (2, 50, 4) and a[:, :, 0].min() == 0 and a[:, :, 0].max() == 1 and set(a[:, :, 3].unique().tolist()) <= {-1.0, 1.0}

@@ -179,7 +179,9 @@ def test_reference_arm_prints_the_contract_line():
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "events/s" and line["higher_is_better"] is True and line["value"] > 0
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and "sample" in line["cpu_baseline"]
+    staged = os.path.isfile(os.path.join(root, "baseline", "_ref", "models", "model.py"))  # the unmodified reference, if staged (tools/stage_reference.py)
+    assert line["cpu_baseline"]["kind"] == ("reference" if staged else "port")
+    assert line["cpu_baseline"]["cores"] >= 1 and "sample" in line["cpu_baseline"] and line["steps"] == 1 and line["warmup"] == 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
     assert "workload" in line["config"] and line["metric"].startswith("events/s")
 
