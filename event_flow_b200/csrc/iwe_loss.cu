@@ -738,9 +738,9 @@ extern "C" int64_t ef_iwe_loss_workspace_elems(int32_t S, int32_t B, int32_t H, 
 extern "C" int ef_iwe_loss_fwd(const ef_iwe_loss_params* pp, void* stream) {
   using namespace ef;
   EF_REQUIRE(pp, EF_ENULL, "ef_iwe_loss_fwd: params is NULL");
-  EF_REQUIRE(pp->loss, EF_ENULL, "ef_iwe_loss_fwd: loss is NULL");
   IweWin w;
   if (int rc = lower(*pp, w, "ef_iwe_loss_fwd")) return rc;
+  EF_REQUIRE(pp->loss, EF_ENULL, "ef_iwe_loss_fwd: loss is NULL");
   return run_fwd(w, pp->workspace, pp->loss, as_stream(stream));
 }
 
@@ -756,9 +756,9 @@ extern "C" int ef_iwe_loss_bwd(const ef_iwe_loss_params* pp, void* stream) {
 extern "C" int ef_iwe_loss_fwd_passes(const ef_iwe_loss_pass_params* pp, void* stream) {
   using namespace ef;
   EF_REQUIRE(pp, EF_ENULL, "ef_iwe_loss_fwd_passes: params is NULL");
-  EF_REQUIRE(pp->loss, EF_ENULL, "ef_iwe_loss_fwd_passes: loss is NULL");
   IweWin w;
   if (int rc = lower(*pp, w, "ef_iwe_loss_fwd_passes")) return rc;
+  EF_REQUIRE(pp->loss, EF_ENULL, "ef_iwe_loss_fwd_passes: loss is NULL");
   return run_fwd(w, pp->workspace, pp->loss, as_stream(stream));
 }
 

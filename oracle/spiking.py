@@ -77,9 +77,13 @@ def cell_step(
     width=10.0,
     stride=1,
     residual=0,
+    forced_z=None,
 ):
     """
     One step of a conv spiking cell.
+    :param forced_z: teacher forcing for BPTT comparisons: the returned spikes take these VALUES (the spikes another
+                     implementation emitted) while the gradient still flows through this step's own surrogate, so a borderline
+                     spike that flipped elsewhere cannot cascade into the comparison (threshold chaos).
     :param neuron: "lif" | "plif" | "alif" | "xlif"
     :param x: [B,Cin,H,W]
     :param state: None or stacked [2|3,B,C,H',W'] (v, z[, trace])
@@ -155,6 +159,9 @@ def cell_step(
         new_state = torch.stack([v_out, z_out, pt_out])
     else:
         raise ValueError(neuron)
+    if forced_z is not None:
+        z_out = forced_z.to(z_out.dtype) + (z_out - z_out.detach())
+        new_state = torch.stack([new_state[0], z_out] + ([new_state[2]] if new_state.shape[0] == 3 else []))
     return z_out + residual, new_state
 
 
@@ -167,17 +174,18 @@ FIRENET_LAYERS = ("head", "G1", "R1a", "R1b", "G2", "R2a", "R2b")
 FIRENET_RECURRENT = ("G1", "G2")
 
 
-def firenet_step(neuron, params, states, x, **cell_kwargs):
+def firenet_step(neuron, params, states, x, forced=None, **cell_kwargs):
     """
     One forward pass of a spiking FireNet (model.py:254-265).
     :param params: {"head": {...}, "G1": {... incl. "rec"}, ..., "pred": {"weight","bias"}}
     :param states: list of 7 (None or stacked state)
+    :param forced: optional list of 7 spike tensors (teacher forcing, see cell_step)
     :return flow [B,2,H,W], new states list, list of layer outputs (for activity / per-layer parity)
     """
     new_states, acts = [], []
     h = x
     for i, name in enumerate(FIRENET_LAYERS):
-        h, s = cell_step(neuron, h, states[i], params[name], **cell_kwargs)
+        h, s = cell_step(neuron, h, states[i], params[name], forced_z=None if forced is None else forced[i], **cell_kwargs)
         new_states.append(s)
         acts.append(h)
     flow = pred_head(h, params["pred"]["weight"], params["pred"]["bias"])

@@ -38,7 +38,7 @@ def test_library_exports_every_declared_symbol(lib):
 
 
 def test_version_and_error_string(lib):
-    assert lib.lib().ef_version() == 100
+    assert lib.lib().ef_version() == 200
     assert isinstance(lib.lib().ef_last_error(), bytes)
 
 
@@ -63,6 +63,12 @@ def test_ctypes_structs_match_c_layout(lib, tmp_path):
         "ef_lif_conv_bwd_params": lib.LifConvBwdParams,
         "ef_pred_params": lib.PredParams,
         "ef_iwe_loss_params": lib.IweLossParams,
+        "ef_iwe_loss_pass_params": lib.IweLossPassParams,
+        "ef_iwe_interp_params": lib.IweInterpParams,
+        "ef_lif_bwd_tc_params": lib.LifBwdTcParams,
+        "ef_iwe_metrics_params": lib.IweMetricsParams,
+        "ef_aee_params": lib.AeeParams,
+        "ef_conv_ann_params": lib.ConvAnnParams,
         "ef_iwe_image_params": lib.IweImageParams,
         "ef_encode_params": lib.EncodeParams,
     }

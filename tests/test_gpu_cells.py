@@ -54,12 +54,14 @@ def test_cell_step_matches_reference_golden(name):
     if ns.shape[0] == 3:
         torch.testing.assert_close(ns[2], g["new_state"][2], rtol=1e-5, atol=1e-6)
     assert torch.equal(out, ns[1])
-    if torch.equal(ns[1], g["new_state"][1]):  # gradients are only comparable when no borderline spike flipped
-        assert_rel(grads["x"], g["grad_x"], 1e-3, "g_x")
-        assert_rel(grads["state"], g["grad_state"], 1e-3, "g_state")
-        for k in p:
-            if "grad_" + k in g:
-                assert_rel(grads[k], g["grad_" + k], 1e-3, "g_" + k)
+    # The backward of ONE cell step reads its inputs, the new membrane potential and the parameters -- never the emitted spikes
+    # (the surrogate is evaluated at v - thresh, a continuous function) -- so the gradients are comparable UNCONDITIONALLY: a
+    # borderline output spike that flipped (|v - thresh| < 1e-5) changes them by O(1e-5), far inside the tolerance.
+    assert_rel(grads["x"], g["grad_x"], 1e-3, "g_x")
+    assert_rel(grads["state"], g["grad_state"], 1e-3, "g_state")
+    for k in p:
+        if "grad_" + k in g:
+            assert_rel(grads[k], g["grad_" + k], 1e-3, "g_" + k)
 
 
 CASES = [(n, rec, hard) for n in osp.NEURONS for rec in (False, True) for hard in (True, False)]
@@ -88,14 +90,13 @@ def test_cell_step_matches_oracle_ragged_shape(neuron, rec, hard, state_given):
     po = {k: v.clone().requires_grad_(True) for k, v in params.items()}
     out_o, ns_o = osp.cell_step(neuron, xo, so, po, hard_reset=hard)
     spike_band_compare(ns[0], ns[1], ns_o[0].detach(), ns_o[1].detach(), _thresh_map(neuron, params, ns_o.detach()))
-    if torch.equal(ns[1], ns_o[1].detach()):
-        ((out_o * g_out).sum() + (ns_o * g_state).sum()).backward()
-        assert_rel(grads["x"], xo.grad, 1e-3, "g_x")
-        if so is not None:
-            assert_rel(grads["state"], so.grad, 1e-3, "g_state")
-        for k, v in po.items():
-            if v.grad is not None and v.grad.abs().max() > 0:
-                assert_rel(grads[k], v.grad, 1e-3, "g_" + k)
+    ((out_o * g_out).sum() + (ns_o * g_state).sum()).backward()  # unconditional: see test_cell_step_matches_reference_golden
+    assert_rel(grads["x"], xo.grad, 1e-3, "g_x")
+    if so is not None:
+        assert_rel(grads["state"], so.grad, 1e-3, "g_state")
+    for k, v in po.items():
+        if v.grad is not None and v.grad.abs().max() > 0:
+            assert_rel(grads[k], v.grad, 1e-3, "g_" + k)
 
 
 @pytest.mark.parametrize("surrogate,width", [("superspike", 10.0), ("trianglespike", 1.0), ("mgspike", 0.5)])

@@ -72,3 +72,54 @@ def oracle_params_of(model):
                 params[l][k] = getattr(cell, k).detach().cpu().clone()
     params["pred"] = {"weight": model.pred.conv2d.weight.detach().cpu().clone(), "bias": model.pred.conv2d.bias.detach().cpu().clone()}
     return params
+
+
+def oracle_bptt_teacher_forced(neuron, params, xs, spikes, loss_of_flows, states0=None, **cell_kwargs):
+    """
+    BPTT of the oracle FireNet over the inputs `xs` with every layer's spikes FORCED to `spikes[t][layer]` (the spikes the path under
+    test emitted, e.g. `model.states[i][1]` after step t): both implementations then differentiate the same trajectory, and a
+    borderline spike that flipped in a free-running rollout cannot invalidate the gradient comparison.
+    :param loss_of_flows: callable(list of flows) -> scalar
+    :return (loss, {layer: {param: grad}}, flows)
+    """
+    from oracle import spiking as osp
+
+    leaves = {l: {k: v.detach().clone().requires_grad_(True) for k, v in lp.items()} for l, lp in params.items()}
+    states = [None] * 7 if states0 is None else [None if s is None else s.detach().clone() for s in states0]
+    flows = []
+    for t, x in enumerate(xs):
+        flow, states, _ = osp.firenet_step(neuron, leaves, states, x, forced=spikes[t], **cell_kwargs)
+        flows.append(flow)
+    loss = loss_of_flows(flows)
+    loss.backward()
+    return loss.detach(), {l: {k: v.grad for k, v in lp.items()} for l, lp in leaves.items()}, [f.detach() for f in flows]
+
+
+def model_grads_by_layer(model):
+    """Parameter gradients of a FireNet model keyed like the oracle's parameter dict."""
+    from oracle.spiking import FIRENET_LAYERS
+
+    out = {}
+    for l in FIRENET_LAYERS:
+        cell = getattr(model, l)
+        out[l] = {"ff": cell.ff.weight.grad}
+        if hasattr(cell, "rec"):
+            out[l]["rec"] = cell.rec.weight.grad
+        for k in ("leak", "thresh", "leak_v", "leak_pt", "leak_t", "add_pt", "t0", "t1"):
+            if hasattr(cell, k) and isinstance(getattr(cell, k), torch.nn.Parameter):
+                out[l][k] = getattr(cell, k).grad
+    out["pred"] = {"weight": model.pred.conv2d.weight.grad, "bias": model.pred.conv2d.bias.grad}
+    return out
+
+
+def compare_grads_by_layer(mine, ref, tol, min_ref=0.0):
+    """Every parameter gradient: max-abs error relative to the largest entry of the reference gradient."""
+    worst = 0.0
+    for l, lp in ref.items():
+        for k, g in lp.items():
+            if g is None or g.abs().max().item() <= min_ref:
+                continue
+            assert mine[l].get(k) is not None, f"no gradient for {l}.{k}"
+            r = assert_rel(mine[l][k].reshape(g.shape), g, tol, f"{l}.{k}")
+            worst = max(worst, r)
+    return worst
