@@ -3,6 +3,7 @@
 // interpolate), loss/flow.py:65-79 (per-event flow gather), utils/iwe.py:95-153 (deblur_events, compute_pol_iwe).
 // Sub-gradient conventions at ties (integer warped coordinates, empty pixels) follow SURVEY.md 7.4, i.e. what
 // torch.autograd produces for the reference expressions.
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -18,6 +19,7 @@ struct IweWin {
   int S, B, T, Tm, H, W;
   int loss_scaling, use_mask, use_dt;
   float flow_scaling, smooth_coef;  // smooth_coef = weight / components / T_maps
+  int debug_skip;                   // timing experiments only (EF_IWE_SKIP): 1 = no smoothness, 2 = no event pass, 4 = no reduction / adjoint pass
   int n_items;                      // chunks of IWE_CHUNK events of one (scale, sample): sum_t ceil(n_t / IWE_CHUNK)
   int chunk_off[MAXP + 1];          // first chunk of pass t
   int n_pass[MAXP];                 // events of pass t (per sample)
@@ -33,6 +35,7 @@ struct IweWin {
 };
 constexpr int IWE_CHUNK = 256, IWE_THREADS = 256;
 constexpr int RED_PIX = 2048;  // pixels per block of the reductions
+constexpr int SM_ROWS = 8;      // image rows per work item of the smoothness passes
 
 // workspace layout (floats):
 //   ctr  [16]  (as uint32) grid-barrier counters.  Must be ZERO when a buffer is first used; every call leaves them zero.
@@ -41,8 +44,9 @@ constexpr int RED_PIX = 2048;  // pixels per block of the reductions
 //        atomic when the left pixel index is even (red.global.add.v4.f32): 6 instead of 16 atomics per event on average
 //   sums [S][B][2 dir][2 = sum A^2, n]
 //   smooth_part [S][MAX_GRID]                  per-CTA partial sums of the smoothness term (fixed-order final reduction)
+//   adj  [S][B][2 dir][2 pol][HW][2 = dL/dI, dL/dTh]   adjoint images, written and read by the backward only
 struct WsLayout {
-  size_t ctr, img, sums, smooth, total;
+  size_t ctr, img, sums, smooth, adj, total;
 };
 constexpr int IWE_MAX_GRID = 148 * 8;
 __host__ __device__ inline WsLayout ws_layout(int S, int B, int H, int W) {
@@ -52,7 +56,8 @@ __host__ __device__ inline WsLayout ws_layout(int S, int B, int H, int W) {
   l.img = 16;
   l.sums = l.img + (size_t)S * B * 8 * hw;
   l.smooth = l.sums + (size_t)S * B * 4;
-  l.total = l.smooth + (size_t)S * IWE_MAX_GRID;
+  l.adj = l.smooth + (size_t)S * IWE_MAX_GRID;  // backward only: adjoint images, same layout as img
+  l.total = l.adj + (size_t)S * B * 8 * hw;
   return l;
 }
 
@@ -164,30 +169,37 @@ __global__ void __launch_bounds__(IWE_THREADS) iwe_loss_fwd_kernel(const __grid_
     float4* z = reinterpret_cast<float4*>(img);
     const size_t n4 = ((size_t)w.S * w.B * 8 * hw + (size_t)w.S * w.B * 4) / 4;  // images + sums (contiguous, multiple of 4 floats)
     for (size_t i = gtid; i < n4; i += gsz) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    const size_t n = (size_t)w.B * w.Tm * hw;
+    // smoothness: work item = ROWS_PER_ITEM rows of one (scale, sample, map) plane; a thread walks columns x = tid, tid + 256, ...
+    // (32-bit index arithmetic only; neighbouring rows / the next map hit L1)
+    const int rb = (w.H + SM_ROWS - 1) / SM_ROWS, planes = w.B * w.Tm;
     for (int s = 0; s < w.S; ++s) {
       float acc = 0.f;
-      if (w.smooth_coef != 0.f) {
-        for (size_t i = gtid; i < n; i += gsz) {
-          const int x = i % w.W, y = (i / w.W) % w.H;
-          const size_t bt = i / hw;
-          const int t = bt % w.Tm, b = bt / w.Tm;
+      if (w.smooth_coef != 0.f && !(w.debug_skip & 1)) {
+        for (int item = blockIdx.x; item < planes * rb; item += gridDim.x) {
+          const int bt = item / rb, y0 = (item - bt * rb) * SM_ROWS;
+          const int b = bt / w.Tm, t = bt - b * w.Tm;
           const float* fxm = w.flow[s * w.Tm + t] + (size_t)b * w.flow_bs;
           const float* fym = fxm + hw;
           const float* mk = w.use_mask ? w.mask[t] + (size_t)b * w.mask_bs : nullptr;
-          const size_t o = (size_t)y * w.W + x;
-          float dc;
-          if (x + 1 < w.W) acc += charb_pair(fxm, fym, mk, o, o + 1, w.use_mask, dc);
-          if (y + 1 < w.H) acc += charb_pair(fxm, fym, mk, o, o + w.W, w.use_mask, dc);
-          if (x + 1 < w.W && y + 1 < w.H) {
-            acc += charb_pair(fxm, fym, mk, o, o + w.W + 1, w.use_mask, dc);  // down-right
-            acc += charb_pair(fxm, fym, mk, o + w.W, o + 1, w.use_mask, dc);  // up-right: (y+1,x) - (y,x+1)
-          }
-          if (w.use_dt && t + 1 < w.Tm) {  // temporal: same pixel, next pass.  Masks of both passes.
-            const float* fxn = w.flow[s * w.Tm + t + 1] + (size_t)b * w.flow_bs;
-            const float d = (fxm[o] - fxn[o]) + (fym[o] - fxn[hw + o]);
-            const float m = w.use_mask ? mk[o] * (w.mask[t + 1] + (size_t)b * w.mask_bs)[o] : 1.f;
-            acc += m * sqrtf(d * d + 1e-6f);
+          const bool dt = w.use_dt && t + 1 < w.Tm;
+          const float* fxn = dt ? w.flow[s * w.Tm + t + 1] + (size_t)b * w.flow_bs : nullptr;
+          const float* mkn = (dt && w.use_mask) ? w.mask[t + 1] + (size_t)b * w.mask_bs : nullptr;
+          const int y1 = min(y0 + SM_ROWS, w.H), n_px = (y1 - y0) * w.W;
+          for (int q = tid; q < n_px; q += IWE_THREADS) {
+            const int yy = q / w.W, x = q - yy * w.W, y = y0 + yy;
+            const int o = y * w.W + x;
+            float dc;
+            if (x + 1 < w.W) acc += charb_pair(fxm, fym, mk, o, o + 1, w.use_mask, dc);
+            if (y + 1 < w.H) acc += charb_pair(fxm, fym, mk, o, o + w.W, w.use_mask, dc);
+            if (x + 1 < w.W && y + 1 < w.H) {
+              acc += charb_pair(fxm, fym, mk, o, o + w.W + 1, w.use_mask, dc);  // down-right
+              acc += charb_pair(fxm, fym, mk, o + w.W, o + 1, w.use_mask, dc);  // up-right: (y+1,x) - (y,x+1)
+            }
+            if (dt) {  // temporal: same pixel, next pass.  Masks of both passes.
+              const float d = (fxm[o] - fxn[o]) + (fym[o] - fxn[hw + o]);
+              const float m = w.use_mask ? mk[o] * mkn[o] : 1.f;
+              acc += m * sqrtf(d * d + 1e-6f);
+            }
           }
         }
       }
@@ -199,7 +211,7 @@ __global__ void __launch_bounds__(IWE_THREADS) iwe_loss_fwd_kernel(const __grid_
 
   // ---- phase 1
   const float Tf = (float)w.T;
-  const int total_items = w.S * w.B * w.n_items;
+  const int total_items = (w.debug_skip & 2) ? 0 : w.S * w.B * w.n_items;
   for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
     int sb, t, i0;
     decode_item(w, item, sb, t, i0);
@@ -245,7 +257,7 @@ __global__ void __launch_bounds__(IWE_THREADS) iwe_loss_fwd_kernel(const __grid_
 
   // ---- phase 2: chunks of RED_PIX pixels of one (scale, sample, direction)
   {
-    const int chunks = (int)((hw + RED_PIX - 1) / RED_PIX), n_sbd = w.S * w.B * 2;
+    const int chunks = (int)((hw + RED_PIX - 1) / RED_PIX), n_sbd = (w.debug_skip & 4) ? 0 : w.S * w.B * 2;
     for (int item = blockIdx.x; item < n_sbd * chunks; item += gridDim.x) {
       const int sbd = item / chunks, p0 = (item - sbd * chunks) * RED_PIX;
       const float2* pos = reinterpret_cast<const float2*>(img + (size_t)sbd * 4 * hw);
@@ -313,28 +325,36 @@ __global__ void __launch_bounds__(IWE_THREADS) iwe_loss_bwd_kernel(const __grid_
   const WsLayout l = ws_layout(w.S, w.B, w.H, w.W);
   unsigned int* ctr = reinterpret_cast<unsigned int*>(ws + l.ctr);
   const float* img = ws + l.img;
+  float* adj = ws + l.adj;
   const float* sums = ws + l.sums;
   const size_t hw = (size_t)w.H * w.W;
   const int tid = threadIdx.x;
-  const size_t gtid = (size_t)blockIdx.x * IWE_THREADS + tid, gsz = (size_t)gridDim.x * IWE_THREADS;
   const float gl = __ldg(g_loss);
   const int W = w.W, H = w.H;
 
-  // ---- phase 0
+  // ---- phase 0a: smoothness gradient of every pixel (gather form) -> g_flow
   {
-    const size_t n = (size_t)w.B * w.Tm * hw;
     const float coef = w.smooth_coef / (float)w.S * gl;
-    for (int s = 0; s < w.S; ++s) {
-      for (size_t i = gtid; i < n; i += gsz) {
-        const int x = i % W, y = (i / W) % H;
-        const size_t bt = i / hw;
-        const int t = bt % w.Tm, b = bt / w.Tm;
+    const int rb = (H + SM_ROWS - 1) / SM_ROWS, planes = w.B * w.Tm;
+    for (int item = blockIdx.x; item < w.S * planes * rb; item += gridDim.x) {
+      const int s = item / (planes * rb), r0 = item - s * planes * rb;
+      const int bt = r0 / rb, y0 = (r0 - bt * rb) * SM_ROWS;
+      const int b = bt / w.Tm, t = bt - b * w.Tm;
+      const float* fxm = w.flow[s * w.Tm + t] + (size_t)b * w.flow_bs;
+      const float* fym = fxm + hw;
+      const float* mk = w.use_mask ? w.mask[t] + (size_t)b * w.mask_bs : nullptr;
+      const bool dtn = w.use_dt && t + 1 < w.Tm, dtp = w.use_dt && t >= 1;
+      const float* fxn = dtn ? w.flow[s * w.Tm + t + 1] + (size_t)b * w.flow_bs : nullptr;
+      const float* fxq = dtp ? w.flow[s * w.Tm + t - 1] + (size_t)b * w.flow_bs : nullptr;
+      const float* mkn = (dtn && w.use_mask) ? w.mask[t + 1] + (size_t)b * w.mask_bs : nullptr;
+      const float* mkq = (dtp && w.use_mask) ? w.mask[t - 1] + (size_t)b * w.mask_bs : nullptr;
+      float* g = w.g_flow[s * w.Tm + t] + (size_t)b * w.g_bs;
+      const int y1 = min(y0 + SM_ROWS, H), n_px = (y1 - y0) * W;
+      for (int q = tid; q < n_px; q += IWE_THREADS) {
+        const int yy = q / W, x = q - yy * W, y = y0 + yy;
+        const int o = y * W + x;
         float acc = 0.f;
         if (w.smooth_coef != 0.f) {
-          const float* fxm = w.flow[s * w.Tm + t] + (size_t)b * w.flow_bs;
-          const float* fym = fxm + hw;
-          const float* mk = w.use_mask ? w.mask[t] + (size_t)b * w.mask_bs : nullptr;
-          const size_t o = (size_t)y * W + x;
           float dc;
           // as first element of a pair: +, as second: -
           if (x + 1 < W) { charb_pair(fxm, fym, mk, o, o + 1, w.use_mask, dc); acc += dc; }
@@ -345,32 +365,54 @@ __global__ void __launch_bounds__(IWE_THREADS) iwe_loss_bwd_kernel(const __grid_
           if (x >= 1 && y >= 1) { charb_pair(fxm, fym, mk, o - W - 1, o, w.use_mask, dc); acc -= dc; }
           if (y >= 1 && x + 1 < W) { charb_pair(fxm, fym, mk, o, o - W + 1, w.use_mask, dc); acc += dc; }  // first of up-right pair (y-1,x)
           if (y + 1 < H && x >= 1) { charb_pair(fxm, fym, mk, o + W - 1, o, w.use_mask, dc); acc -= dc; }  // second of pair (y,x-1)
-          if (w.use_dt) {
-            if (t + 1 < w.Tm) {
-              const float* fxn = w.flow[s * w.Tm + t + 1] + (size_t)b * w.flow_bs;
-              const float d = (fxm[o] - fxn[o]) + (fym[o] - fxn[hw + o]);
-              const float m = w.use_mask ? mk[o] * (w.mask[t + 1] + (size_t)b * w.mask_bs)[o] : 1.f;
-              acc += m * d / sqrtf(d * d + 1e-6f);
-            }
-            if (t >= 1) {
-              const float* fxq = w.flow[s * w.Tm + t - 1] + (size_t)b * w.flow_bs;
-              const float d = (fxq[o] - fxm[o]) + (fxq[hw + o] - fym[o]);
-              const float m = w.use_mask ? (w.mask[t - 1] + (size_t)b * w.mask_bs)[o] * mk[o] : 1.f;
-              acc -= m * d / sqrtf(d * d + 1e-6f);
-            }
+          if (dtn) {
+            const float d = (fxm[o] - fxn[o]) + (fym[o] - fxn[hw + o]);
+            const float m = w.use_mask ? mk[o] * mkn[o] : 1.f;
+            acc += m * d / sqrtf(d * d + 1e-6f);
+          }
+          if (dtp) {
+            const float d = (fxq[o] - fxm[o]) + (fxq[hw + o] - fym[o]);
+            const float m = w.use_mask ? mkq[o] * mk[o] : 1.f;
+            acc -= m * d / sqrtf(d * d + 1e-6f);
           }
         }
         const float v = acc * coef;
-        float* g = w.g_flow[s * w.Tm + t] + (size_t)b * w.g_bs + (size_t)y * W + x;
-        g[0] = v;
-        g[hw] = v;
+        g[o] = v;
+        g[hw + o] = v;
+      }
+    }
+  }
+  // ---- phase 0b: adjoint images (one pixel pass): adj [sbd][pol][px][2 = dL/dI, dL/dTh]
+  const float Tf = (float)w.T, inv_S = 1.0f / (float)w.S;
+  {
+    const int chunks = (int)((hw + RED_PIX - 1) / RED_PIX), n_sbd = w.S * w.B * 2;
+    for (int item = blockIdx.x; item < n_sbd * chunks; item += gridDim.x) {
+      const int sbd = item / chunks, p0 = (item - sbd * chunks) * RED_PIX;
+      const float2* pos = reinterpret_cast<const float2*>(img + (size_t)sbd * 4 * hw);
+      const float2* neg = pos + hw;
+      float2* apos = reinterpret_cast<float2*>(adj + (size_t)sbd * 4 * hw);
+      float2* aneg = apos + hw;
+      const float ssq = __ldcg(sums + sbd * 2), n = __ldcg(sums + sbd * 2 + 1);
+      const float g = gl * inv_S / (w.loss_scaling ? n : 1.f);
+      const float gn = -gl * inv_S * ssq / (n * n);  // through the divisor: empty pixels keep gradient 1 into it (in-place masked assignment)
+      const int p1 = min(p0 + RED_PIX, (int)hw);
+      for (int i = p0 + tid; i < p1; i += IWE_THREADS) {
+        const float2 qp = __ldcg(pos + i), qn = __ldcg(neg + i);
+        const float ap = qp.y / (qp.x + 1e-9f) / Tf, an = qn.y / (qn.x + 1e-9f) / Tf;
+        const float gtp = g * 2.f * ap / ((qp.x + 1e-9f) * Tf), gtn = g * 2.f * an / ((qn.x + 1e-9f) * Tf);
+        float gip = -gtp * qp.y / (qp.x + 1e-9f), gin = -gtn * qn.y / (qn.x + 1e-9f);
+        if (w.loss_scaling && !(qp.x + qn.x > 0.f)) {
+          gip += gn;
+          gin += gn;
+        }
+        apos[i] = make_float2(gip, gtp);
+        aneg[i] = make_float2(gin, gtn);
       }
     }
   }
   grid_barrier(ctr + 3, gridDim.x);
 
-  // ---- phase 1
-  const float Tf = (float)w.T, inv_S = 1.0f / (float)w.S;
+  // ---- phase 1: per event and corner delta = dL/dI + tau dL/dTh of the event's polarity, chained through the bilinear weights
   const int total_items = w.S * w.B * w.n_items;
   for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
     int sb, t, i0;
@@ -385,49 +427,31 @@ __global__ void __launch_bounds__(IWE_THREADS) iwe_loss_bwd_kernel(const __grid_
     const int m_idx = s * w.Tm + (w.Tm > 1 ? t : 0);
     const float* fm = w.flow[m_idx] + (size_t)b * w.flow_bs;
     const float fx = __ldg(fm + pix), fy = __ldg(fm + hw + pix);
-    const float* ibase = img + (size_t)sb * 8 * hw;
+    const float* abase = adj + (size_t)sb * 8 * hw;
     float gfy = 0.f, gfx = 0.f;
 #pragma unroll
     for (int dir = 0; dir < 2; ++dir) {
       const float tref = dir == 0 ? Tf : 0.f;
       const float tau = dir == 0 ? e.x : (Tf - e.x);
       const float kk = (tref - e.x) * w.flow_scaling;
-      const float ssq = __ldcg(sums + (sb * 2 + dir) * 2), n = __ldcg(sums + (sb * 2 + dir) * 2 + 1);
-      const float g = gl * inv_S / (w.loss_scaling ? n : 1.f);
-      const float gn = -gl * inv_S * ssq / (n * n);  // through the divisor: empty pixels keep gradient 1 into it (in-place masked assignment)
       float yw, xw;
       Corner c[4];
       warp_event(e.x, e.y, e.z, fy, fx, tref, w.flow_scaling, H, W, yw, xw, c);
-      const float2* pos = reinterpret_cast<const float2*>(ibase + (size_t)dir * 4 * hw);
-      const float2* neg = pos + hw;
+      const float2* apos = reinterpret_cast<const float2*>(abase + (size_t)dir * 4 * hw);
+      const float2* aneg = apos + hw;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         if (c[k].idx < 0) continue;
         const float dwy = dweight(c[k].dy) * c[k].wx, dwx = c[k].wy * dweight(c[k].dx);
         if (dwy == 0.f && dwx == 0.f) continue;
         float delta = 0.f;
-        float2 qp = make_float2(0.f, 0.f), qn = make_float2(0.f, 0.f);
-        bool have_p = false, have_n = false;
-#pragma unroll
-        for (int pol = 0; pol < 2; ++pol) {
-          const float m = pol == 0 ? pm.x : pm.y;
-          if (m == 0.f) continue;
-          float2& q = pol == 0 ? qp : qn;
-          q = __ldcg((pol == 0 ? pos : neg) + c[k].idx);
-          (pol == 0 ? have_p : have_n) = true;
-          const float a = q.y / (q.x + 1e-9f) / Tf;
-          const float gth = g * 2.f * a / ((q.x + 1e-9f) * Tf);
-          float gi = -gth * q.y / (q.x + 1e-9f);
-          if (w.loss_scaling && !(q.x > 0.f)) {  // own-polarity image empty here: the pixel counts as empty iff the other one is too
-            float2& o = pol == 0 ? qn : qp;
-            bool& have_o = pol == 0 ? have_n : have_p;
-            if (!have_o) {
-              o = __ldcg((pol == 0 ? neg : pos) + c[k].idx);
-              have_o = true;
-            }
-            if (!(q.x + o.x > 0.f)) gi += gn;
-          }
-          delta += m * (gi + tau * gth);
+        if (pm.x != 0.f) {
+          const float2 a2 = __ldcg(apos + c[k].idx);
+          delta += pm.x * (a2.x + tau * a2.y);
+        }
+        if (pm.y != 0.f) {
+          const float2 a2 = __ldcg(aneg + c[k].idx);
+          delta += pm.y * (a2.x + tau * a2.y);
         }
         gfy += delta * dwy * kk;
         gfx += delta * dwx * kk;
@@ -604,6 +628,11 @@ __global__ void aee_finalize_kernel(const float* __restrict__ ws, int B, float* 
 }
 
 // ---- host side: lowering of the two public window forms, launch ------------------------------------------------------
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
 static int finish_window(IweWin& w, const char* who) {
   EF_REQUIRE(w.S > 0 && w.S <= MAXS && w.B > 0 && w.T > 0 && w.T <= MAXP && w.H > 0 && w.W > 0, EF_EINVAL,
              "%s: bad dimensions (S <= %d, T <= %d)", who, MAXS, MAXP);
@@ -616,6 +645,8 @@ static int finish_window(IweWin& w, const char* who) {
     w.chunk_off[t + 1] = w.chunk_off[t] + cdiv(w.n_pass[t], IWE_CHUNK);
   }
   w.n_items = w.chunk_off[w.T];
+  static const int dbg = env_int("EF_IWE_SKIP", 0);
+  w.debug_skip = dbg;
   for (int i = 0; i < w.S * w.Tm; ++i) EF_REQUIRE(w.flow[i], EF_ENULL, "%s: NULL flow map", who);
   if (w.use_mask)
     for (int t = 0; t < w.Tm; ++t) EF_REQUIRE(w.mask[t], EF_ENULL, "%s: smoothing_mask without event_mask", who);
@@ -697,16 +728,19 @@ static int coop_grid(K kernel, long long work_ctas, int* grid) {
 
 template <typename... KArgs, typename... Args>
 static cudaError_t launch_coop(void (*kernel)(KArgs...), int grid, cudaStream_t st, Args... args) {
+  static const int coop = env_int("EF_IWE_COOP", 1);  // 0: plain launch (the grid is capped to the resident capacity either way)
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid), cfg.blockDim = dim3(IWE_THREADS), cfg.dynamicSmemBytes = 0, cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeCooperative;
   attr[0].val.cooperative = 1;
-  cfg.attrs = attr, cfg.numAttrs = 1;
+  cfg.attrs = attr, cfg.numAttrs = coop ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
 static long long loss_work_ctas(const IweWin& w) {
+  static const int force = env_int("EF_IWE_GRID", 0);
+  if (force > 0) return force;
   // enough CTAs for the event chunks and for one pass over the pixels, whichever is larger; small windows get small grids
   // (the cost of a grid barrier grows with the number of CTAs)
   const long long ev = (long long)w.S * w.B * w.n_items;

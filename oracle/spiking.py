@@ -160,7 +160,7 @@ def cell_step(
     else:
         raise ValueError(neuron)
     if forced_z is not None:
-        z_out = forced_z.to(z_out.dtype) + (z_out - z_out.detach())
+        z_out = forced_z.detach().to(z_out.dtype) + (z_out - z_out.detach())
         new_state = torch.stack([new_state[0], z_out] + ([new_state[2]] if new_state.shape[0] == 3 else []))
     return z_out + residual, new_state
 

@@ -262,8 +262,9 @@ def test_config_size_bptt_matches_oracle_autograd():
     The path bench.py times: LIFFireNet fast path (CUDA-graph forward steps, cached + graph-replayed backward calls), the
     EventWarping loss kernels, BPTT over a full cfg-3 window (B=8, 128x128, T=10, 1000 events per step).  Three windows are run so
     that the third one executes entirely from cached / replayed launches; its parameter gradients are compared with the CPU
-    oracle's autograd of the SAME window (initial states = the states the CUDA path carried over, spikes teacher-forced,
-    loss = the oracle's event-warping loss): rel 1e-3 per parameter tensor.
+    oracle's autograd of the SAME window (initial states = the states the CUDA path carried over, spikes and flow values
+    teacher-forced -- see tests/util.py:oracle_bptt_teacher_forced for why --, loss = the oracle's event-warping loss):
+    rel 1e-3 per parameter tensor.
     """
     import event_flow_b200.models.model as M
     from event_flow_b200.loss.flow import EventWarping
@@ -286,7 +287,7 @@ def test_config_size_bptt_matches_oracle_autograd():
         states0 = None if win == 0 else [s.cpu() for s in m.states]
         lossf.reset()
         m.zero_grad(set_to_none=True)
-        data, spikes = [], []
+        data, spikes, flows = [], [], []
         for t in range(T):
             d = oenc.encode_window(*oenc.synthetic_events(B, N, H, W, 7000 + 100 * win + t), H, W, bins)
             data.append(d)
@@ -294,6 +295,7 @@ def test_config_size_bptt_matches_oracle_autograd():
             lossf.event_flow_association(out["flow"], d["event_list"].clone().to(DEV), d["event_list_pol_mask"].to(DEV), d["event_mask"].to(DEV))
             if win == 2:
                 spikes.append([s[1].cpu() for s in m.states])
+                flows.append(out["flow"][0].detach().cpu())
         loss = lossf()
         loss.backward()
         if win < 2:
@@ -309,7 +311,10 @@ def test_config_size_bptt_matches_oracle_autograd():
         return oiwe.event_warping_loss(torch.cat(evs, 1), torch.cat([d["event_list_pol_mask"] for d in data], 1), torch.arange(T).repeat_interleave(N),
                                        [torch.stack(flows, 1)], torch.cat([d["event_mask"] for d in data], 1), (H, W), weight=0.001, passes=T)
 
-    loss_o, ref, _ = oracle_bptt_teacher_forced("lif", params, [d["event_voxel"] for d in data], spikes, oracle_loss, states0=states0)
+    loss_o, ref, flows_o = oracle_bptt_teacher_forced("lif", params, [d["event_voxel"] for d in data], spikes, oracle_loss, states0=states0,
+                                                      forced_flows=flows)
+    for f, fo in zip(flows, flows_o):
+        torch.testing.assert_close(f, fo, rtol=1e-5, atol=1e-7)
     assert_rel(loss, loss_o, 1e-5, "loss of the config-size window")
     worst = compare_grads_by_layer(model_grads_by_layer(m), ref, 1e-3)
     print(f"config-size BPTT: worst relative gradient error {worst:.2e}")
@@ -430,7 +435,8 @@ def test_model_pickles_and_deepcopies_after_fast_path_training(tmp_path):
         m.detach_states()
     path = tmp_path / "model.pth"
     torch.save(m, path)
-    assert path.stat().st_size < 2_000_000, "activation slabs leaked into the checkpoint"
+    state_bytes = sum(t.numel() * 4 for t in m.states) + sum(p.numel() * 4 for p in m.parameters())
+    assert path.stat().st_size < state_bytes + 500_000, "run-time caches (activation slabs, graphs) leaked into the checkpoint"
     loaded = torch.load(path, weights_only=False)
     twin = copy.deepcopy(m)
     for other in (loaded, twin):  # the neuron states travel in the reference's stacked format
