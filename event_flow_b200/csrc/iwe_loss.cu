@@ -34,7 +34,7 @@ struct IweWin {
   long long g_bs;
 };
 constexpr int IWE_CHUNK = 256, IWE_THREADS = 256;
-constexpr int RED_PIX = 2048;  // pixels per block of the reductions
+constexpr int RED_PIX = 1024;  // pixels per work item of the per-pixel passes
 constexpr int SM_ROWS = 8;      // image rows per work item of the smoothness passes
 
 // workspace layout (floats):
@@ -130,6 +130,39 @@ __device__ __forceinline__ float charb_pair(const float* fxm, const float* fym, 
   return m * c;
 }
 
+
+// ---- smoothness on register strips -----------------------------------------------------------------------------------
+// A thread owns SM_R consecutive rows of one column: the values of a row are loaded once and reused by the pairs that involve the
+// row above / below; all loads of a strip are independent, so one memory round trip covers SM_R pixels.
+constexpr int SM_R = 2;
+struct PixF {
+  float fx, fy, m;
+};
+__device__ __forceinline__ float load_mask(const float* mk, int idx, bool ok, bool use_mask) { return ok ? (use_mask ? __ldg(mk + idx) : 1.f) : 0.f; }
+__device__ __forceinline__ void load_flow(PixF& p, const float* fxm, const float* fym, int idx, bool ok) {
+  p.fx = ok ? __ldg(fxm + idx) : 0.f;
+  p.fy = ok ? __ldg(fym + idx) : 0.f;
+}
+__device__ __forceinline__ float sqrt_fast(float x) {  // sqrt.approx (1 ulp class): far inside the 1e-5 tolerance of the loss value
+  float r;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// one Charbonnier pair term m_a m_b sqrt((dfx + dfy)^2 + 1e-6) (loss/flow.py:273-286).  Event masks are sparse: pairs whose mask
+// product is zero contribute exactly 0 and are skipped (out-of-image pixels carry mask 0, which also encodes the pair's existence).
+__device__ __forceinline__ float charb(const PixF& a, const PixF& b) {
+  const float m = a.m * b.m;
+  if (m == 0.f) return 0.f;
+  const float d = (a.fx - b.fx) + (a.fy - b.fy);
+  return m * sqrt_fast(d * d + 1e-6f);
+}
+__device__ __forceinline__ float dcharb(const PixF& a, const PixF& b) {  // d(term)/d f[a] (both channels); minus for f[b]
+  const float m = a.m * b.m;
+  if (m == 0.f) return 0.f;
+  const float d = (a.fx - b.fx) + (a.fy - b.fy);
+  return m * d * rsqrtf(d * d + 1e-6f);
+}
+
 // item -> (scale*B + sample, pass, first event of the chunk)
 __device__ __forceinline__ void decode_item(const IweWin& w, int item, int& sb, int& t, int& i0) {
   sb = item / w.n_items;
@@ -153,7 +186,7 @@ __device__ __forceinline__ void red4(float* q, float a, float b, float c, float 
 //            utils/iwe.py:20-92)
 //   phase 2  per (scale, sample, direction): sum of squared average timestamps and number of pixels with events (:212-226)
 //   phase 3  last CTA: the scalar
-__global__ void __launch_bounds__(IWE_THREADS) iwe_loss_fwd_kernel(const __grid_constant__ IweWin w, float* __restrict__ ws, float* __restrict__ loss) {
+__global__ void __launch_bounds__(IWE_THREADS, 4) iwe_loss_fwd_kernel(const __grid_constant__ IweWin w, float* __restrict__ ws, float* __restrict__ loss) {
   __shared__ float s_red[8];
   __shared__ bool s_last;
   const WsLayout l = ws_layout(w.S, w.B, w.H, w.W);
@@ -184,21 +217,37 @@ __global__ void __launch_bounds__(IWE_THREADS) iwe_loss_fwd_kernel(const __grid_
           const bool dt = w.use_dt && t + 1 < w.Tm;
           const float* fxn = dt ? w.flow[s * w.Tm + t + 1] + (size_t)b * w.flow_bs : nullptr;
           const float* mkn = (dt && w.use_mask) ? w.mask[t + 1] + (size_t)b * w.mask_bs : nullptr;
-          const int y1 = min(y0 + SM_ROWS, w.H), n_px = (y1 - y0) * w.W;
-          for (int q = tid; q < n_px; q += IWE_THREADS) {
-            const int yy = q / w.W, x = q - yy * w.W, y = y0 + yy;
-            const int o = y * w.W + x;
-            float dc;
-            if (x + 1 < w.W) acc += charb_pair(fxm, fym, mk, o, o + 1, w.use_mask, dc);
-            if (y + 1 < w.H) acc += charb_pair(fxm, fym, mk, o, o + w.W, w.use_mask, dc);
-            if (x + 1 < w.W && y + 1 < w.H) {
-              acc += charb_pair(fxm, fym, mk, o, o + w.W + 1, w.use_mask, dc);  // down-right
-              acc += charb_pair(fxm, fym, mk, o + w.W, o + 1, w.use_mask, dc);  // up-right: (y+1,x) - (y,x+1)
+          // thread -> (column, strip of SM_R rows); SM_ROWS / SM_R strips per item
+          constexpr int STRIPS = SM_ROWS / SM_R;
+          for (int q = tid; q < w.W * STRIPS; q += IWE_THREADS) {
+            const int st = q / w.W, x = q - st * w.W, ys = y0 + st * SM_R;
+            if (ys >= w.H) continue;
+            PixF c[SM_R + 1][2], nx[SM_R];
+            float any = 0.f;
+#pragma unroll
+            for (int r = 0; r <= SM_R; ++r) {
+#pragma unroll
+              for (int k = 0; k < 2; ++k) {
+                c[r][k].m = load_mask(mk, (ys + r) * w.W + x + k, ys + r < w.H && x + k < w.W, w.use_mask);
+                any += (r < SM_R && k == 0) ? c[r][k].m : 0.f;  // every pair of the strip has one of these pixels as first or only partner ...
+              }
             }
-            if (dt) {  // temporal: same pixel, next pass.  Masks of both passes.
-              const float d = (fxm[o] - fxn[o]) + (fym[o] - fxn[hw + o]);
-              const float m = w.use_mask ? mk[o] * mkn[o] : 1.f;
-              acc += m * sqrtf(d * d + 1e-6f);
+            any += c[SM_R][0].m;  // ... except the up-right pair of the last row: ((y+1,x),(y,x+1))
+#pragma unroll
+            for (int r = 0; r < SM_R; ++r) nx[r].m = dt ? load_mask(mkn, (ys + r) * w.W + x, ys + r < w.H, w.use_mask) : 0.f;
+            if (any == 0.f) continue;  // nothing of this strip survives the masks: no flow loads at all
+#pragma unroll
+            for (int r = 0; r <= SM_R; ++r) {
+#pragma unroll
+              for (int k = 0; k < 2; ++k) load_flow(c[r][k], fxm, fym, (ys + r) * w.W + x + k, c[r][k].m != 0.f);
+            }
+#pragma unroll
+            for (int r = 0; r < SM_R; ++r) load_flow(nx[r], fxn, fxn + hw, (ys + r) * w.W + x, nx[r].m != 0.f);
+#pragma unroll
+            for (int r = 0; r < SM_R; ++r) {
+              // pairs: right, down, down-right, up-right ((y+1,x) - (y,x+1)), temporal (same pixel, next pass; masks of both passes)
+              acc += charb(c[r][0], c[r][1]) + charb(c[r][0], c[r + 1][0]) + charb(c[r][0], c[r + 1][1]) + charb(c[r + 1][0], c[r][1]) +
+                     charb(c[r][0], nx[r]);
             }
           }
         }
@@ -319,7 +368,7 @@ __device__ __forceinline__ float dweight(float d) {
 //   phase 0  gradient of the smoothness term wrt both flow channels of every pixel (gather form) -> g_flow (overwrites)
 //   phase 1  per event and corner: the adjoint of the contrast term is computed on the fly from the accumulator images and
 //            the per-(scale, sample, direction) sums, scattered onto the event's own pixel of g_flow
-__global__ void __launch_bounds__(IWE_THREADS) iwe_loss_bwd_kernel(const __grid_constant__ IweWin w, float* __restrict__ ws,
+__global__ void __launch_bounds__(IWE_THREADS, 4) iwe_loss_bwd_kernel(const __grid_constant__ IweWin w, float* __restrict__ ws,
                                                                    const float* __restrict__ g_loss) {
   __shared__ bool s_last;
   const WsLayout l = ws_layout(w.S, w.B, w.H, w.W);
@@ -349,43 +398,67 @@ __global__ void __launch_bounds__(IWE_THREADS) iwe_loss_bwd_kernel(const __grid_
       const float* mkn = (dtn && w.use_mask) ? w.mask[t + 1] + (size_t)b * w.mask_bs : nullptr;
       const float* mkq = (dtp && w.use_mask) ? w.mask[t - 1] + (size_t)b * w.mask_bs : nullptr;
       float* g = w.g_flow[s * w.Tm + t] + (size_t)b * w.g_bs;
-      const int y1 = min(y0 + SM_ROWS, H), n_px = (y1 - y0) * W;
-      for (int q = tid; q < n_px; q += IWE_THREADS) {
-        const int yy = q / W, x = q - yy * W, y = y0 + yy;
-        const int o = y * W + x;
-        float acc = 0.f;
-        if (w.smooth_coef != 0.f) {
-          float dc;
-          // as first element of a pair: +, as second: -
-          if (x + 1 < W) { charb_pair(fxm, fym, mk, o, o + 1, w.use_mask, dc); acc += dc; }
-          if (x >= 1) { charb_pair(fxm, fym, mk, o - 1, o, w.use_mask, dc); acc -= dc; }
-          if (y + 1 < H) { charb_pair(fxm, fym, mk, o, o + W, w.use_mask, dc); acc += dc; }
-          if (y >= 1) { charb_pair(fxm, fym, mk, o - W, o, w.use_mask, dc); acc -= dc; }
-          if (x + 1 < W && y + 1 < H) { charb_pair(fxm, fym, mk, o, o + W + 1, w.use_mask, dc); acc += dc; }
-          if (x >= 1 && y >= 1) { charb_pair(fxm, fym, mk, o - W - 1, o, w.use_mask, dc); acc -= dc; }
-          if (y >= 1 && x + 1 < W) { charb_pair(fxm, fym, mk, o, o - W + 1, w.use_mask, dc); acc += dc; }  // first of up-right pair (y-1,x)
-          if (y + 1 < H && x >= 1) { charb_pair(fxm, fym, mk, o + W - 1, o, w.use_mask, dc); acc -= dc; }  // second of pair (y,x-1)
-          if (dtn) {
-            const float d = (fxm[o] - fxn[o]) + (fym[o] - fxn[hw + o]);
-            const float m = w.use_mask ? mk[o] * mkn[o] : 1.f;
-            acc += m * d / sqrtf(d * d + 1e-6f);
+      constexpr int STRIPS = SM_ROWS / SM_R;
+      for (int q = tid; q < W * STRIPS; q += IWE_THREADS) {
+        const int st = q / W, x = q - st * W, ys = y0 + st * SM_R;
+        if (ys >= H) continue;
+        float acc[SM_R];
+#pragma unroll
+        for (int r = 0; r < SM_R; ++r) acc[r] = 0.f;
+        if (w.smooth_coef != 0.f && !(w.debug_skip & 1)) {
+          PixF c[SM_R + 2][3], nx[SM_R], pv[SM_R];  // rows ys-1 .. ys+SM_R, columns x-1 .. x+1
+          float any = 0.f;
+#pragma unroll
+          for (int r = 0; r < SM_R + 2; ++r) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+              const int yy = ys - 1 + r, xx = x - 1 + k;
+              c[r][k].m = load_mask(mk, yy * W + xx, yy >= 0 && yy < H && xx >= 0 && xx < W, w.use_mask);
+            }
           }
-          if (dtp) {
-            const float d = (fxq[o] - fxm[o]) + (fxq[hw + o] - fym[o]);
-            const float m = w.use_mask ? mkq[o] * mk[o] : 1.f;
-            acc -= m * d / sqrtf(d * d + 1e-6f);
+#pragma unroll
+          for (int r = 0; r < SM_R; ++r) any += c[r + 1][1].m;  // every term of a pixel's gradient carries the pixel's own mask
+          if (any != 0.f) {
+#pragma unroll
+            for (int r = 0; r < SM_R; ++r) {
+              nx[r].m = dtn ? load_mask(mkn, (ys + r) * W + x, ys + r < H, w.use_mask) : 0.f;
+              pv[r].m = dtp ? load_mask(mkq, (ys + r) * W + x, ys + r < H, w.use_mask) : 0.f;
+            }
+#pragma unroll
+            for (int r = 0; r < SM_R + 2; ++r) {
+#pragma unroll
+              for (int k = 0; k < 3; ++k) load_flow(c[r][k], fxm, fym, (ys - 1 + r) * W + x - 1 + k, c[r][k].m != 0.f);
+            }
+#pragma unroll
+            for (int r = 0; r < SM_R; ++r) {
+              load_flow(nx[r], fxn, fxn + hw, (ys + r) * W + x, nx[r].m != 0.f);
+              load_flow(pv[r], fxq, fxq + hw, (ys + r) * W + x, pv[r].m != 0.f);
+            }
+#pragma unroll
+            for (int r = 0; r < SM_R; ++r) {
+              const PixF& o = c[r + 1][1];
+              // as first element of a pair: +, as second: -.  Pairs: right / left, down / up, down-right / up-left, the up-right pair
+              // ((y,x),(y-1,x+1)) as first and ((y+1,x-1),(y,x)) as second, temporal next / previous.  Missing neighbours carry mask 0.
+              acc[r] = dcharb(o, c[r + 1][2]) - dcharb(c[r + 1][0], o) + dcharb(o, c[r + 2][1]) - dcharb(c[r][1], o) + dcharb(o, c[r + 2][2]) -
+                       dcharb(c[r][0], o) + dcharb(o, c[r][2]) - dcharb(c[r + 2][0], o) + dcharb(o, nx[r]) - dcharb(pv[r], o);
+            }
           }
         }
-        const float v = acc * coef;
-        g[o] = v;
-        g[hw + o] = v;
+#pragma unroll
+        for (int r = 0; r < SM_R; ++r) {
+          if (ys + r >= H) break;
+          const float v = acc[r] * coef;
+          const int o = (ys + r) * W + x;
+          g[o] = v;
+          g[hw + o] = v;
+        }
       }
     }
   }
   // ---- phase 0b: adjoint images (one pixel pass): adj [sbd][pol][px][2 = dL/dI, dL/dTh]
-  const float Tf = (float)w.T, inv_S = 1.0f / (float)w.S;
+  const float Tf = (float)w.T, inv_S = 1.0f / (float)w.S, inv_T = 1.0f / Tf;
   {
-    const int chunks = (int)((hw + RED_PIX - 1) / RED_PIX), n_sbd = w.S * w.B * 2;
+    const int chunks = (int)((hw + RED_PIX - 1) / RED_PIX), n_sbd = (w.debug_skip & 4) ? 0 : w.S * w.B * 2;
     for (int item = blockIdx.x; item < n_sbd * chunks; item += gridDim.x) {
       const int sbd = item / chunks, p0 = (item - sbd * chunks) * RED_PIX;
       const float2* pos = reinterpret_cast<const float2*>(img + (size_t)sbd * 4 * hw);
@@ -398,9 +471,10 @@ __global__ void __launch_bounds__(IWE_THREADS) iwe_loss_bwd_kernel(const __grid_
       const int p1 = min(p0 + RED_PIX, (int)hw);
       for (int i = p0 + tid; i < p1; i += IWE_THREADS) {
         const float2 qp = __ldcg(pos + i), qn = __ldcg(neg + i);
-        const float ap = qp.y / (qp.x + 1e-9f) / Tf, an = qn.y / (qn.x + 1e-9f) / Tf;
-        const float gtp = g * 2.f * ap / ((qp.x + 1e-9f) * Tf), gtn = g * 2.f * an / ((qn.x + 1e-9f) * Tf);
-        float gip = -gtp * qp.y / (qp.x + 1e-9f), gin = -gtn * qn.y / (qn.x + 1e-9f);
+        const float rp = __frcp_rn(qp.x + 1e-9f), rn = __frcp_rn(qn.x + 1e-9f);  // gradients are checked to 1e-3: one reciprocal per image
+        const float ap = qp.y * rp * inv_T, an = qn.y * rn * inv_T;
+        const float gtp = g * 2.f * ap * rp * inv_T, gtn = g * 2.f * an * rn * inv_T;
+        float gip = -gtp * qp.y * rp, gin = -gtn * qn.y * rn;
         if (w.loss_scaling && !(qp.x + qn.x > 0.f)) {
           gip += gn;
           gin += gn;
@@ -413,7 +487,7 @@ __global__ void __launch_bounds__(IWE_THREADS) iwe_loss_bwd_kernel(const __grid_
   grid_barrier(ctr + 3, gridDim.x);
 
   // ---- phase 1: per event and corner delta = dL/dI + tau dL/dTh of the event's polarity, chained through the bilinear weights
-  const int total_items = w.S * w.B * w.n_items;
+  const int total_items = (w.debug_skip & 2) ? 0 : w.S * w.B * w.n_items;
   for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
     int sb, t, i0;
     decode_item(w, item, sb, t, i0);

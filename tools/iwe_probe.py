@@ -9,8 +9,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     r = bench.iwe_bench(torch.device("cuda"), pk["hbm_gbs"], reps=20)
     print("RESULT " + json.dumps({k: (round(v["fwd_ms"] * 1e3, 1), round((v["fwd_bwd_ms"] - v["fwd_ms"]) * 1e3, 1)) for k, v in r.items()}))
 else:
-    for env in ({}, {"EF_IWE_COOP": "0"}, {"EF_IWE_SKIP": "1"}, {"EF_IWE_SKIP": "2"}, {"EF_IWE_SKIP": "4"}, {"EF_IWE_SKIP": "7"}, {"EF_IWE_GRID": "148"},
-                {"EF_IWE_GRID": "296"}, {"EF_IWE_GRID": "592"}, {"EF_IWE_GRID": "888"}, {"EF_IWE_COOP": "0", "EF_IWE_GRID": "148"}):
+    for env in ({}, {"EF_IWE_SKIP": "1"}, {"EF_IWE_SKIP": "2"}, {"EF_IWE_SKIP": "4"}, {"EF_IWE_SKIP": "7"}):
         out = subprocess.run([sys.executable, __file__, "child"], env=dict(os.environ, **env), capture_output=True, text=True)
         res = [l for l in out.stdout.splitlines() if l.startswith("RESULT")]
         print(env, res[0][7:] if res else out.stderr[-400:], "(fwd us, bwd us)", flush=True)
