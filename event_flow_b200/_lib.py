@@ -55,6 +55,16 @@ class LifBwdTcParams(C.Structure):
 EF_WG_ACCUMULATE, EF_WG_FINALIZE = 1, 2
 
 
+class LifBwdWindowParams(C.Structure):
+    _fields_ = [
+        ("B", _i32), ("T", _i32), ("H", _i32), ("W", _i32), ("hard_reset", _i32), ("surrogate", _i32), ("act_width", C.c_float),
+        ("x_cl", _f32p), ("z_cl", _f32p), ("z_prev_cl", _f32p), ("v", _f32p), ("v_prev", _f32p), ("g_out", _f32p),
+        ("leak", _f32p), ("thresh", _f32p), ("w_bwd", _f32p), ("gI_hi", _f32p), ("gI_mid", _f32p),
+        ("g_x", _f32p), ("g_v_prev", _f32p), ("g_w_ff", _f32p), ("g_leak", _f32p), ("g_thresh", _f32p), ("wg_partial", _f32p),
+        ("Cin", _i32), ("x_f32", _f32p), ("gI_f32", _f32p),
+    ]  # fmt: skip
+
+
 class PredParams(C.Structure):
     _fields_ = [
         ("B", _i32), ("Cin", _i32), ("Cout", _i32), ("H", _i32), ("W", _i32),
@@ -147,6 +157,9 @@ EXPORTS = {
     "ef_lif_conv_fwd": (C.c_int, [C.POINTER(LifConvParams), C.c_void_p]),
     "ef_lif_conv_bwd": (C.c_int, [C.POINTER(LifConvBwdParams), C.c_void_p]),
     "ef_lif_bwd_tc": (C.c_int, [C.POINTER(LifBwdTcParams), C.c_void_p]),
+    "ef_lif_bwd_window": (C.c_int, [C.POINTER(LifBwdWindowParams), C.c_void_p]),
+    "ef_lif_wgrad_tc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, _i32, _i32, _i32, _i32, C.c_void_p, _i32, C.c_void_p, C.c_void_p,
+                                  C.c_void_p]),
     "ef_split_weights_bwd_elems": (C.c_int64, [_i32]),
     "ef_lif_wgrad_partial_elems": (C.c_int64, [_i32, _i32, _i32, _i32]),
     "ef_split_weights_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -105,6 +105,92 @@ __global__ void __launch_bounds__(PWC_THREADS) lif_bwd_pointwise_cl_kernel(const
   }
 }
 
+// (1w) the same neuron backward for a WHOLE BPTT window of a feed-forward cell, time loop inside the kernel: a thread owns one pixel x
+//      PWC_CB channels and walks t = T-1 ... 0 with dL/dv carried in registers (it never touches memory), every membrane tensor is
+//      read once (v[t-1] is "previous potential" at step t and "new potential" at step t-1) and the per-channel parameter-gradient
+//      terms are reduced once per window instead of once per step.  Replaces T launches of the kernel above and the
+//      [B,32,H,W] dL/dv round trip between them (north-star: state kept in registers across the inner time loop).
+template <int SURR, bool HARD>
+__global__ void __launch_bounds__(PWC_THREADS) lif_bwd_pointwise_window_kernel(const ef_lif_bwd_window_params p) {
+  __shared__ float s_sum[2 * PWC_CB];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const size_t hw = (size_t)p.H * p.W;
+  const int b = blockIdx.y;
+  const int c0 = (blockIdx.x % PWC_GROUPS) * PWC_CB;
+  if (tid < 2 * PWC_CB) s_sum[tid] = 0.f;
+  __syncthreads();
+  const size_t pix = (size_t)(blockIdx.x / PWC_GROUPS) * PWC_THREADS + tid;
+  const bool live = pix < hw;
+  const size_t pc = live ? pix : hw - 1;  // out-of-range threads compute on a valid pixel and contribute nothing
+  const size_t sv = (size_t)p.B * 32 * hw, sz = (size_t)p.B * hw * 32;  // step strides of the fp32 NCHW / bf16 channels-last tensors
+  const size_t ov = ((size_t)b * 32 + c0) * hw + pc, oz = ((size_t)b * hw + pc) * 32 + c0;
+  float lam[PWC_CB], thr[PWC_CB], g_v[PWC_CB], v_n[PWC_CB], red[2 * PWC_CB];
+#pragma unroll
+  for (int k = 0; k < PWC_CB; ++k) {
+    lam[k] = sigmoidf_acc(__ldg(p.leak + c0 + k));
+    thr[k] = fmaxf(__ldg(p.thresh + c0 + k), 0.01f);
+    g_v[k] = 0.f;
+    red[k] = red[PWC_CB + k] = 0.f;
+    v_n[k] = __ldg(p.v + (size_t)(p.T - 1) * sv + ov + k * hw);
+  }
+  for (int t = p.T - 1; t >= 0; --t) {
+    float v_p[PWC_CB], g_o[PWC_CB];
+    uint4 zq = make_uint4(0, 0, 0, 0);
+    if (t > 0) zq = __ldg(reinterpret_cast<const uint4*>(p.z_cl + (size_t)(t - 1) * sz + oz));
+    else if (p.z_prev_cl) zq = __ldg(reinterpret_cast<const uint4*>(p.z_prev_cl + oz));
+    const float* vp = t > 0 ? p.v + (size_t)(t - 1) * sv : p.v_prev;
+#pragma unroll
+    for (int k = 0; k < PWC_CB; ++k) {
+      v_p[k] = vp ? __ldg(vp + ov + k * hw) : 0.f;
+      g_o[k] = __ldg(p.g_out + (size_t)t * sv + ov + k * hw);
+    }
+    const uint32_t zw[4] = {zq.x, zq.y, zq.z, zq.w};
+    uint32_t hi[PWC_CB / 2], mid[PWC_CB / 2];
+#pragma unroll
+    for (int k = 0; k < PWC_CB; ++k) {
+      const float z_p = (k & 1) ? bf16_hi(zw[k >> 1]) : bf16_lo(zw[k >> 1]);
+      const float g_z = g_o[k];
+      const float sg = surrogate_grad(SURR, v_n[k] - thr[k], p.act_width);
+      const float gv = g_v[k] + g_z * sg;
+      const float oml = 1.0f - lam[k];
+      const float g_I = oml * gv;
+      const float keep = HARD ? v_p[k] * (1.0f - z_p) : v_p[k];
+      const float drive = HARD ? (v_n[k] - lam[k] * keep) / oml : (v_n[k] - lam[k] * v_p[k] + z_p * thr[k]) / oml;
+      red[k] += gv * (keep - drive);
+      red[PWC_CB + k] += -g_z * sg - (HARD ? 0.f : z_p * gv);
+      g_v[k] = HARD ? gv * lam[k] * (1.0f - z_p) : gv * lam[k];  // dL/dv of step t-1, stays in the register
+      if (p.gI_f32 && live) p.gI_f32[(size_t)t * sv + ov + k * hw] = g_I;  // head mode: fp32 NCHW for the CUDA-core weight gradient
+      const __nv_bfloat16 h = __float2bfloat16_rn(g_I);
+      const __nv_bfloat16 m = __float2bfloat16_rn(g_I - __bfloat162float(h));
+      const uint32_t hb = *reinterpret_cast<const uint16_t*>(&h), mb = *reinterpret_cast<const uint16_t*>(&m);
+      if (k & 1) hi[k >> 1] |= hb << 16, mid[k >> 1] |= mb << 16;
+      else hi[k >> 1] = hb, mid[k >> 1] = mb;
+      v_n[k] = v_p[k];
+    }
+    if (live && !p.gI_f32) {
+      *reinterpret_cast<uint4*>(p.gI_hi + (size_t)t * sz + oz) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(p.gI_mid + (size_t)t * sz + oz) = make_uint4(mid[0], mid[1], mid[2], mid[3]);
+    }
+  }
+  if (p.g_v_prev && live) {
+#pragma unroll
+    for (int k = 0; k < PWC_CB; ++k) p.g_v_prev[ov + k * hw] = g_v[k];
+  }
+  if (!live) {
+#pragma unroll
+    for (int k = 0; k < 2 * PWC_CB; ++k) red[k] = 0.f;
+  }
+  int entry;
+  const float tot = warp_transpose_sum16(red, lane, entry);
+  if (lane < 16) atomicAdd(&s_sum[entry], tot);
+  __syncthreads();
+  if (tid < PWC_CB) {
+    const float l = sigmoidf_acc(__ldg(p.leak + c0 + tid));
+    if (p.g_leak) atomicAdd(p.g_leak + c0 + tid, s_sum[tid] * l * (1.0f - l));
+    if (p.g_thresh && __ldg(p.thresh + c0 + tid) >= 0.01f) atomicAdd(p.g_thresh + c0 + tid, s_sum[PWC_CB + tid]);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // (1b) weight gradient of the head layer: g_w[co][ci][tap] += sum_{b,y,x} x[b,ci,y+dy-1,x+dx-1] * g_I[b,co,y,x], Cin <= 8 fractional
 //      fp32 inputs (not a tensor-core shape).  A block owns 32 x 8-pixel tiles; slice s (64 threads) owns tile row s; thread j of
@@ -639,6 +725,123 @@ extern "C" int ef_split_weights_bwd(const float* w_ff, const float* w_rec, uint1
   return check_launch("split_weights_bwd_kernel");
 }
 
+namespace ef {
+
+// ---- launch helpers shared by the per-step and the per-window entry points --------------------------------------------------------
+template <int DUMMY = 0>
+static int run_pointwise_step(const ef_lif_bwd_tc_params& p, cudaStream_t st) {
+  const int hw = p.H * p.W;
+  const dim3 pgrid(cdiv(hw, PWC_THREADS) * PWC_GROUPS, p.B);
+#define EF_PW(S_, H_) lif_bwd_pointwise_cl_kernel<S_, H_><<<pgrid, PWC_THREADS, 0, st>>>(p)
+  switch (p.surrogate * 2 + (p.hard_reset ? 1 : 0)) {
+    case 0: EF_PW(EF_ARCTAN, false); break;
+    case 1: EF_PW(EF_ARCTAN, true); break;
+    case 2: EF_PW(EF_SUPERSPIKE, false); break;
+    case 3: EF_PW(EF_SUPERSPIKE, true); break;
+    case 4: EF_PW(EF_TRIANGLE, false); break;
+    case 5: EF_PW(EF_TRIANGLE, true); break;
+    case 6: EF_PW(EF_MULTIGAUSS, false); break;
+    case 7: EF_PW(EF_MULTIGAUSS, true); break;
+    default: return fail(EF_EINVAL, "ef_lif_bwd_tc: bad surrogate %d", p.surrogate);
+  }
+#undef EF_PW
+  return check_launch("lif_bwd_pointwise_cl_kernel");
+}
+
+static int run_pointwise_window(const ef_lif_bwd_window_params& p, cudaStream_t st) {
+  const int hw = p.H * p.W;
+  const dim3 pgrid(cdiv(hw, PWC_THREADS) * PWC_GROUPS, p.B);
+#define EF_PW(S_, H_) lif_bwd_pointwise_window_kernel<S_, H_><<<pgrid, PWC_THREADS, 0, st>>>(p)
+  switch (p.surrogate * 2 + (p.hard_reset ? 1 : 0)) {
+    case 0: EF_PW(EF_ARCTAN, false); break;
+    case 1: EF_PW(EF_ARCTAN, true); break;
+    case 2: EF_PW(EF_SUPERSPIKE, false); break;
+    case 3: EF_PW(EF_SUPERSPIKE, true); break;
+    case 4: EF_PW(EF_TRIANGLE, false); break;
+    case 5: EF_PW(EF_TRIANGLE, true); break;
+    case 6: EF_PW(EF_MULTIGAUSS, false); break;
+    case 7: EF_PW(EF_MULTIGAUSS, true); break;
+    default: return fail(EF_EINVAL, "ef_lif_bwd_window: bad surrogate %d", p.surrogate);
+  }
+#undef EF_PW
+  return check_launch("lif_bwd_pointwise_window_kernel");
+}
+
+static int run_head_wgrad(const float* x_f32, const float* gI_f32, float* g_w_ff, int B, int Cin, int H, int W, cudaStream_t st) {
+  const int n_sms = wg_n_sms();
+  const int tiles_x = cdiv(W, HW_TW), tiles_y = cdiv(H, HW_TH), n_tiles = tiles_x * tiles_y * B;
+  const int grid = n_tiles < 2 * n_sms ? n_tiles : 2 * n_sms;
+  lif_head_wgrad_kernel<<<grid, HW_THREADS, 0, st>>>(x_f32, gI_f32, g_w_ff, B, Cin, H, W, tiles_x, tiles_y, n_tiles);
+  return check_launch("lif_head_wgrad_kernel");
+}
+
+// data gradient of B images: g_x (and g_z_in of a recurrent cell) = transposed conv of g_I = gI_hi + gI_mid with the weights
+static int run_dgrad(const uint16_t* gI_hi, const uint16_t* gI_mid, const uint16_t* w_bwd, bool rec, float* g_x, float* g_z_in, int B, int H, int W,
+                     cudaStream_t st) {
+  const int n_sms = wg_n_sms();
+  DgParams q;
+  q.B = B, q.H = H, q.W = W, q.has_rec = rec;
+  q.tiles_x = cdiv(W, DG_TW), q.tiles_y = cdiv(H, DG_TH), q.n_tiles = B * q.tiles_x * q.tiles_y;
+  q.w_bwd = w_bwd, q.g_x = g_x, q.g_z_in = rec ? g_z_in : nullptr;
+  CUtensorMap mh, mm;
+  int rc;
+  if ((rc = get_map(gI_hi, B, H, W, DG_TH + 2, DG_TW + 8, true, &mh))) return rc;
+  if ((rc = get_map(gI_mid, B, H, W, DG_TH + 2, DG_TW + 8, true, &mm))) return rc;
+  const DgLayout L = dg_layout(rec);
+  const int grid = q.n_tiles < n_sms ? q.n_tiles : n_sms;
+  static bool attr_set[2] = {false, false};
+  if (!attr_set[rec ? 1 : 0]) {
+    const cudaError_t e = rec ? cudaFuncSetAttribute(lif_dgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
+                              : cudaFuncSetAttribute(lif_dgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return check_launch("cudaFuncSetAttribute(lif_dgrad_tc_kernel)");
+    attr_set[rec ? 1 : 0] = true;
+  }
+  if (rec) lif_dgrad_tc_kernel<true><<<grid, DG_THREADS, L.total, st>>>(q, mh, mm);
+  else lif_dgrad_tc_kernel<false><<<grid, DG_THREADS, L.total, st>>>(q, mh, mm);
+  return check_launch("lif_dgrad_tc_kernel");
+}
+
+// tensor-core weight gradient of B images into per-CTA partial sums (+ the fixed-order reduction with EF_WG_FINALIZE).  `rec`: the
+// cell has a recurrent convolution (two slices per CTA in wg_partial); z_in_cl may still be NULL (no previous state at this step).
+static int run_wgrad(const uint16_t* x_cl, const uint16_t* z_in_cl, const uint16_t* gI_hi, const uint16_t* gI_mid, bool rec, int B, int H, int W,
+                     float* wg_partial, int flags, float* g_w_ff, float* g_w_rec, cudaStream_t st) {
+  const bool wrec = rec && z_in_cl;
+  const int wgrid_n = wg_grid(B, H, W);
+  WgParams w;
+  w.B = B, w.H = H, w.W = W, w.tiles_x = cdiv(W, WG_TW), w.tiles_y = cdiv(H, WG_TH), w.n_tiles = B * w.tiles_x * w.tiles_y;
+  w.accumulate = (flags & EF_WG_ACCUMULATE) ? 1 : 0;
+  w.partial = wg_partial;
+  int rc;
+  if (rec && !wrec && !w.accumulate) {  // recurrent cell without a previous state: its recurrent slices start at zero
+    if (cudaMemsetAsync(wg_partial + (size_t)wgrid_n * WG_SLICE, 0, (size_t)wgrid_n * WG_SLICE * sizeof(float), st) != cudaSuccess)
+      return check_launch("cudaMemsetAsync(wg_partial)");
+  }
+  CUtensorMap mx, mz, gh, gm;
+  if ((rc = get_map(x_cl, B, H, W, WG_TH + 2, WG_TW + 8, true, &mx))) return rc;
+  mz = mx;
+  if (wrec && (rc = get_map(z_in_cl, B, H, W, WG_TH + 2, WG_TW + 8, true, &mz))) return rc;
+  if ((rc = get_map(gI_hi, B, H, W, WG_TH, WG_TW, true, &gh))) return rc;
+  if ((rc = get_map(gI_mid, B, H, W, WG_TH, WG_TW, true, &gm))) return rc;
+  static bool wattr[2] = {false, false};
+  if (!wattr[wrec ? 1 : 0]) {
+    const cudaError_t e = wrec ? cudaFuncSetAttribute(lif_wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
+                               : cudaFuncSetAttribute(lif_wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return check_launch("cudaFuncSetAttribute(lif_wgrad_tc_kernel)");
+    wattr[wrec ? 1 : 0] = true;
+  }
+  const int wsmem = WG_NST * ((wrec ? 2 : 1) * WG_XTILE + 2 * WG_GTILE) + 256 + 1024;
+  if (wrec) lif_wgrad_tc_kernel<true><<<wgrid_n, WG_THREADS, wsmem, st>>>(w, mx, mz, gh, gm);
+  else lif_wgrad_tc_kernel<false><<<wgrid_n, WG_THREADS, wsmem, st>>>(w, mx, mz, gh, gm);
+  if ((rc = check_launch("lif_wgrad_tc_kernel"))) return rc;
+  if (flags & EF_WG_FINALIZE) {
+    wgrad_reduce_kernel<<<(rec ? 2 : 1) * 288, 256, 0, st>>>(wg_partial, wgrid_n, g_w_ff, rec ? g_w_rec : nullptr);
+    if ((rc = check_launch("wgrad_reduce_kernel"))) return rc;
+  }
+  return EF_OK;
+}
+
+}  // namespace ef
+
 extern "C" int ef_lif_bwd_tc(const ef_lif_bwd_tc_params* pp, void* stream) {
   using namespace ef;
   EF_REQUIRE(pp, EF_ENULL, "ef_lif_bwd_tc: params is NULL");
@@ -652,91 +855,12 @@ extern "C" int ef_lif_bwd_tc(const ef_lif_bwd_tc_params* pp, void* stream) {
     EF_REQUIRE(p.x_cl && p.v_out && p.leak && p.thresh && p.w_bwd && p.gI_hi && p.gI_mid && p.g_x, EF_ENULL, "ef_lif_bwd_tc: NULL tensor");
   }
   cudaStream_t st = as_stream(stream);
-  const int n_sms = wg_n_sms();
   int rc;
-  const int hw = p.H * p.W;
-  {
-    const dim3 pgrid(cdiv(hw, PWC_THREADS) * PWC_GROUPS, p.B);
-#define EF_PW(S_, H_) lif_bwd_pointwise_cl_kernel<S_, H_><<<pgrid, PWC_THREADS, 0, st>>>(p)
-    switch (p.surrogate * 2 + (p.hard_reset ? 1 : 0)) {
-      case 0: EF_PW(EF_ARCTAN, false); break;
-      case 1: EF_PW(EF_ARCTAN, true); break;
-      case 2: EF_PW(EF_SUPERSPIKE, false); break;
-      case 3: EF_PW(EF_SUPERSPIKE, true); break;
-      case 4: EF_PW(EF_TRIANGLE, false); break;
-      case 5: EF_PW(EF_TRIANGLE, true); break;
-      case 6: EF_PW(EF_MULTIGAUSS, false); break;
-      case 7: EF_PW(EF_MULTIGAUSS, true); break;
-      default: return fail(EF_EINVAL, "ef_lif_bwd_tc: bad surrogate %d", p.surrogate);
-    }
-#undef EF_PW
-  }
-  if ((rc = check_launch("lif_bwd_pointwise_cl_kernel"))) return rc;
-  if (head) {
-    if (p.g_w_ff) {
-      const int tiles_x = cdiv(p.W, HW_TW), tiles_y = cdiv(p.H, HW_TH), n_tiles = tiles_x * tiles_y * p.B;
-      const int grid = n_tiles < 2 * n_sms ? n_tiles : 2 * n_sms;
-      lif_head_wgrad_kernel<<<grid, HW_THREADS, 0, st>>>(p.x_f32, p.gI_f32, p.g_w_ff, p.B, p.Cin, p.H, p.W, tiles_x, tiles_y, n_tiles);
-      if ((rc = check_launch("lif_head_wgrad_kernel"))) return rc;
-    }
-    return EF_OK;
-  }
-
+  if ((rc = run_pointwise_step(p, st))) return rc;
+  if (head) return p.g_w_ff ? run_head_wgrad(p.x_f32, p.gI_f32, p.g_w_ff, p.B, p.Cin, p.H, p.W, st) : EF_OK;
   const bool rec = p.has_rec != 0;
-  DgParams q;
-  q.B = p.B, q.H = p.H, q.W = p.W, q.has_rec = rec;
-  q.tiles_x = cdiv(p.W, DG_TW), q.tiles_y = cdiv(p.H, DG_TH), q.n_tiles = p.B * q.tiles_x * q.tiles_y;
-  q.w_bwd = p.w_bwd, q.g_x = p.g_x, q.g_z_in = (rec && p.z_in_cl) ? p.g_z_in : nullptr;
-  CUtensorMap mh, mm;
-  if ((rc = get_map(p.gI_hi, p.B, p.H, p.W, DG_TH + 2, DG_TW + 8, true, &mh))) return rc;
-  if ((rc = get_map(p.gI_mid, p.B, p.H, p.W, DG_TH + 2, DG_TW + 8, true, &mm))) return rc;
-  const DgLayout L = dg_layout(rec);
-  const int grid = q.n_tiles < n_sms ? q.n_tiles : n_sms;
-  static bool attr_set[2] = {false, false};
-  if (!attr_set[rec ? 1 : 0]) {
-    const cudaError_t e = rec ? cudaFuncSetAttribute(lif_dgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
-                              : cudaFuncSetAttribute(lif_dgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return check_launch("cudaFuncSetAttribute(lif_dgrad_tc_kernel)");
-    attr_set[rec ? 1 : 0] = true;
-  }
-  if (rec) lif_dgrad_tc_kernel<true><<<grid, DG_THREADS, L.total, st>>>(q, mh, mm);
-  else lif_dgrad_tc_kernel<false><<<grid, DG_THREADS, L.total, st>>>(q, mh, mm);
-  if ((rc = check_launch("lif_dgrad_tc_kernel"))) return rc;
-
-  if (p.wg_partial) {  // tensor-core weight gradient into per-CTA partial sums
-    const bool wrec = rec && p.z_in_cl;
-    const int wgrid_n = wg_grid(p.B, p.H, p.W);
-    WgParams w;
-    w.B = p.B, w.H = p.H, w.W = p.W, w.tiles_x = q.tiles_x, w.tiles_y = q.tiles_y, w.n_tiles = q.n_tiles;
-    w.accumulate = (p.wg_flags & EF_WG_ACCUMULATE) ? 1 : 0;
-    w.partial = p.wg_partial;
-    if (rec && !wrec && !w.accumulate) {  // recurrent cell without a previous state: its recurrent slices start at zero
-      if (cudaMemsetAsync(p.wg_partial + (size_t)wgrid_n * WG_SLICE, 0, (size_t)wgrid_n * WG_SLICE * sizeof(float), st) != cudaSuccess)
-        return check_launch("cudaMemsetAsync(wg_partial)");
-    }
-    CUtensorMap mx, mz, gh, gm;
-    if ((rc = get_map(p.x_cl, p.B, p.H, p.W, WG_TH + 2, WG_TW + 8, true, &mx))) return rc;
-    mz = mx;
-    if (wrec && (rc = get_map(p.z_in_cl, p.B, p.H, p.W, WG_TH + 2, WG_TW + 8, true, &mz))) return rc;
-    if ((rc = get_map(p.gI_hi, p.B, p.H, p.W, WG_TH, WG_TW, true, &gh))) return rc;
-    if ((rc = get_map(p.gI_mid, p.B, p.H, p.W, WG_TH, WG_TW, true, &gm))) return rc;
-    static bool wattr[2] = {false, false};
-    if (!wattr[wrec ? 1 : 0]) {
-      const cudaError_t e = wrec ? cudaFuncSetAttribute(lif_wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
-                                 : cudaFuncSetAttribute(lif_wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-      if (e != cudaSuccess) return check_launch("cudaFuncSetAttribute(lif_wgrad_tc_kernel)");
-      wattr[wrec ? 1 : 0] = true;
-    }
-    const int wsmem = WG_NST * ((wrec ? 2 : 1) * WG_XTILE + 2 * WG_GTILE) + 256 + 1024;
-    if (wrec) lif_wgrad_tc_kernel<true><<<wgrid_n, WG_THREADS, wsmem, st>>>(w, mx, mz, gh, gm);
-    else lif_wgrad_tc_kernel<false><<<wgrid_n, WG_THREADS, wsmem, st>>>(w, mx, mz, gh, gm);
-    if ((rc = check_launch("lif_wgrad_tc_kernel"))) return rc;
-    if (p.wg_flags & EF_WG_FINALIZE) {
-      wgrad_reduce_kernel<<<(rec ? 2 : 1) * 288, 256, 0, st>>>(p.wg_partial, wgrid_n, p.g_w_ff, rec ? p.g_w_rec : nullptr);
-      if ((rc = check_launch("wgrad_reduce_kernel"))) return rc;
-    }
-    return EF_OK;
-  }
+  if ((rc = run_dgrad(p.gI_hi, p.gI_mid, p.w_bwd, rec, p.g_x, (rec && p.z_in_cl) ? p.g_z_in : nullptr, p.B, p.H, p.W, st))) return rc;
+  if (p.wg_partial) return run_wgrad(p.x_cl, p.z_in_cl, p.gI_hi, p.gI_mid, rec, p.B, p.H, p.W, p.wg_partial, p.wg_flags, p.g_w_ff, p.g_w_rec, st);
   const dim3 wgrid(cdiv(p.W, 16), cdiv(p.H, 16), p.B);
   if (p.g_w_ff) {
     conv_wgrad_cl_kernel<<<wgrid, WGC_THREADS, 0, st>>>(p.x_cl, p.gI_hi, p.gI_mid, p.g_w_ff, p.B, p.H, p.W);
@@ -747,4 +871,42 @@ extern "C" int ef_lif_bwd_tc(const ef_lif_bwd_tc_params* pp, void* stream) {
     if ((rc = check_launch("conv_wgrad_cl_kernel(rec)"))) return rc;
   }
   return EF_OK;
+}
+
+// Backward of a feed-forward 32 -> 32 LIF cell (or, head mode, of the Cin <= 8 input cell) over a whole BPTT window: ONE time-fused
+// pointwise launch, ONE data-gradient launch and ONE weight-gradient launch (+ its reduction) for all T steps -- the step index is
+// folded into the batch dimension of the tensor-core kernels.
+extern "C" int ef_lif_bwd_window(const ef_lif_bwd_window_params* pp, void* stream) {
+  using namespace ef;
+  EF_REQUIRE(pp, EF_ENULL, "ef_lif_bwd_window: params is NULL");
+  const ef_lif_bwd_window_params& p = *pp;
+  EF_REQUIRE(p.B > 0 && p.T > 0 && p.H > 0 && p.W > 0 && (int64_t)p.B * p.T < (1 << 20), EF_EINVAL, "ef_lif_bwd_window: bad dimensions");
+  const bool head = p.x_f32 != nullptr;
+  EF_REQUIRE(p.v && p.g_out && p.leak && p.thresh && (p.T == 1 || p.z_cl), EF_ENULL, "ef_lif_bwd_window: NULL tensor");
+  if (head) {
+    EF_REQUIRE(p.gI_f32, EF_ENULL, "ef_lif_bwd_window (head mode): gI_f32 is NULL");
+    EF_REQUIRE(p.Cin > 0 && p.Cin <= HW_MAXC, EF_EUNSUPPORTED, "ef_lif_bwd_window (head mode): Cin <= %d (got %d)", HW_MAXC, p.Cin);
+  } else {
+    EF_REQUIRE(p.x_cl && p.w_bwd && p.gI_hi && p.gI_mid, EF_ENULL, "ef_lif_bwd_window: NULL tensor");
+    EF_REQUIRE(!p.g_w_ff || p.wg_partial, EF_ENULL, "ef_lif_bwd_window: g_w_ff wanted but wg_partial is NULL");
+  }
+  cudaStream_t st = as_stream(stream);
+  int rc;
+  if ((rc = run_pointwise_window(p, st))) return rc;
+  const int BT = p.B * p.T;
+  if (head) return p.g_w_ff ? run_head_wgrad(p.x_f32, p.gI_f32, p.g_w_ff, BT, p.Cin, p.H, p.W, st) : EF_OK;
+  if (p.g_x && (rc = run_dgrad(p.gI_hi, p.gI_mid, p.w_bwd, false, p.g_x, nullptr, BT, p.H, p.W, st))) return rc;
+  if (p.g_w_ff) return run_wgrad(p.x_cl, nullptr, p.gI_hi, p.gI_mid, false, BT, p.H, p.W, p.wg_partial, EF_WG_FINALIZE, p.g_w_ff, nullptr, st);
+  return EF_OK;
+}
+
+// Tensor-core weight gradient alone (the last stage of ef_lif_bwd_tc) for B images whose g_I = gI_hi + gI_mid already exists: lets a
+// recurrent cell run pointwise + data gradient step by step (the recurrent path needs them in order) and the weight gradient of the
+// whole window in one or two batched calls.  Protocol of wg_partial / flags as for ef_lif_bwd_tc.
+extern "C" int ef_lif_wgrad_tc(const uint16_t* x_cl, const uint16_t* z_in_cl, const uint16_t* gI_hi, const uint16_t* gI_mid, int32_t has_rec, int32_t B,
+                               int32_t H, int32_t W, float* wg_partial, int32_t wg_flags, float* g_w_ff, float* g_w_rec, void* stream) {
+  using namespace ef;
+  EF_REQUIRE(B > 0 && H > 0 && W > 0, EF_EINVAL, "ef_lif_wgrad_tc: bad dimensions");
+  EF_REQUIRE(x_cl && gI_hi && gI_mid && wg_partial, EF_ENULL, "ef_lif_wgrad_tc: NULL tensor");
+  return run_wgrad(x_cl, z_in_cl, gI_hi, gI_mid, has_rec != 0, B, H, W, wg_partial, wg_flags, g_w_ff, g_w_rec, as_stream(stream));
 }

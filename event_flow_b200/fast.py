@@ -2,10 +2,19 @@
 Fast path of the spiking FireNet chain (models/model.py:254-265) on the internal formats.
 
 Between the cells, spikes never exist as fp32 NCHW tensors: every cell writes bf16 channels-last spikes ("cl") that the
-next cell's tcgen05 kernel consumes through TMA; membrane potentials stay fp32 NCHW (the reference's state format).  One
-torch.autograd node per MODEL step (instead of ~100 per step in the reference) carries the BPTT: the per-layer state
-gradients travel from step t+1 to step t in a side structure (`_Carry`), the autograd graph only orders the steps through
-a scalar token and routes the flow / parameter gradients.
+next cell's tcgen05 kernel consumes through TMA; membrane potentials stay fp32 NCHW (the reference's state format).
+
+Activations of a BPTT window live in a per-model arena, LAYER-MAJOR and STEP-CONTIGUOUS: for every layer one tensor
+[steps, B, ...] of membrane potentials and one of spikes.  That is what makes the backward cheap: the reference (and round 1 of
+this package) back-propagates step by step; here the backward of a window is DEFERRED to the window's first step (the last
+autograd node to run) and executed layer by layer over the whole window:
+  * feed-forward cells: ONE time-fused neuron-backward launch (dL/dv stays in registers over the T steps, every membrane tensor
+    is read once), ONE tensor-core data-gradient launch and ONE tensor-core weight-gradient launch over T*B images
+    (ef_lif_bwd_window);
+  * recurrent cells (G1, G2): pointwise + data gradient step by step (the recurrent path needs dL/dz of step t+1 first), the
+    weight gradient of the whole window in one batched launch (ef_lif_bwd_tc + ef_lif_wgrad_tc);
+  * prediction head: one launch over T*B images.
+One torch.autograd node per MODEL step only orders the steps (scalar token) and collects dL/dflow.
 """
 import torch
 
@@ -13,79 +22,116 @@ from . import _lib as L
 from . import ops
 
 LAYERS = ("head", "G1", "R1a", "R1b", "G2", "R2a", "R2b")
-
-
 N_L = len(LAYERS)
+DEFAULT_WINDOW_CAP = 12  # steps a bank holds before it has to grow (train_SNN.yml: window_loss / window = 10)
 
 
 class _Carry:
-    """
-    BPTT side channel of one window: dL/d(v, z) of every layer's state, handed from the backward of step t+1 to the
-    backward of step t, and the flat parameter-gradient buffer the kernels accumulate into over the whole window.
-    """
+    """What the steps of one BPTT window hand to the deferred window backward."""
 
     def __init__(self):
-        self.g_v = [None] * N_L
-        self.g_z = [None] * N_L
-        self.flat = None      # fp32 [n_params]: += by every step's backward kernels, handed to autograd by the window's first step
-        self.sweep = 0        # number of backward steps executed in the current sweep (0 = next call starts a new sweep)
+        self.g_flows = {}     # step index -> dL/dflow of that step
+        self.n = 0            # steps of the window so far
+        self.prev = None      # (v, z) lists: the state the window started from (detached), entries may be None
+        self.parity = None    # arena bank of the window
 
 
 class _Slot:
-    """Activations of one model step: membrane fp32 [B,32,H,W] and spikes bf16 [B,H,W,32] of the 7 layers, one allocation."""
+    """One model step inside a bank: views of the step's activations, its CUDA graphs and its generation counter."""
 
-    def __init__(self, B, H, W, dev):
-        nv, nz = B * 32 * H * W * 4, B * 32 * H * W * 2
-        self.slab = torch.empty(N_L * (nv + nz), device=dev, dtype=torch.uint8)
-        self.v, self.z = [], []
-        o = 0
-        for _ in range(N_L):
-            self.v.append(self.slab[o:o + nv].view(torch.float32).view(B, 32, H, W))
-            o += nv
-        for _ in range(N_L):
-            self.z.append(self.slab[o:o + nz].view(torch.bfloat16).view(B, H, W, 32))
-            o += nz
-        self.flow = torch.empty((B, 2, H, W), device=dev, dtype=torch.float32)
+    def __init__(self, bank, idx):
         self.gen = 0       # bumped every time a forward step (re)writes this slot: saved activations of older steps are then gone
-        self.x_in = None   # static copy of the model input (graph replay reads a fixed address)
         self.graphs = {}   # (pointer signature) -> torch.cuda.CUDAGraph of this step's 8 kernels
-        self.bwd_calls = {}  # (pointer signature, sweep position) -> prepared argument structs (+ CUDA graph) of this step's backward
-        self.g_flow_in = None  # static copy of the incoming flow gradient (graph replay reads a fixed address)
+        self.bind(bank, idx)
+
+    def bind(self, bank, idx):
+        self.v = [bank.v[i][idx] for i in range(N_L)]
+        self.z = [bank.zs[i][idx + 1] for i in range(N_L)]
+        self.flow = bank.flow[idx]
+        self.x_in = None if bank.x_in is None else bank.x_in[idx]  # static copy of the model input (graph replay / head weight gradient)
+        self.graphs = {}
+
+
+class _Bank:
+    """
+    Activations of one BPTT window: per layer membrane fp32 [cap,B,32,H,W] and spikes bf16 [cap+1,B,H,W,32] (index 0 is reserved for
+    the spikes BEFORE the window's first step, so that "previous spikes of steps 0..T-1" is one dense tensor for the batched
+    weight gradient of the recurrent cells), the flow maps [cap,B,2,H,W] and the model inputs [cap,B,Cin,H,W].
+    """
+
+    def __init__(self, key, cap):
+        B, H, W, dev = key
+        self.key, self.cap = key, cap
+        self.v = [torch.empty((cap, B, 32, H, W), device=dev, dtype=torch.float32) for _ in range(N_L)]
+        self.zs = [torch.empty((cap + 1, B, H, W, 32), device=dev, dtype=torch.bfloat16) for _ in range(N_L)]
+        self.flow = torch.empty((cap, B, 2, H, W), device=dev, dtype=torch.float32)
+        self.x_in = None
+        self.slots = []
+
+    def slot(self, idx):
+        while len(self.slots) <= idx:
+            self.slots.append(_Slot(self, len(self.slots)))
+        return self.slots[idx]
+
+    def need_input(self, cin):
+        if self.x_in is None or self.x_in.shape[2] != cin:
+            B, H, W, dev = self.key
+            self.x_in = torch.empty((self.cap, B, cin, H, W), device=dev, dtype=torch.float32)
+            for i, s in enumerate(self.slots):
+                s.bind(self, i)
+
+    def grow(self, n_used):
+        """A window longer than the bank: double the capacity, keep the steps recorded so far (graphs are re-captured)."""
+        new = _Bank(self.key, 2 * self.cap)
+        for i in range(N_L):
+            new.v[i][:n_used].copy_(self.v[i][:n_used])
+            new.zs[i][:n_used + 1].copy_(self.zs[i][:n_used + 1])
+        new.flow[:n_used].copy_(self.flow[:n_used])
+        if self.x_in is not None:
+            new.need_input(self.x_in.shape[2])
+            new.x_in[:n_used].copy_(self.x_in[:n_used])
+        self.cap, self.v, self.zs, self.flow, self.x_in = new.cap, new.v, new.zs, new.flow, new.x_in
+        for i, s in enumerate(self.slots):
+            s.bind(self, i)
 
 
 class _Arena:
     """
     Activation storage owned by the model and reused window after window (no allocator traffic in steady state, static
     addresses for CUDA-graph replay).  Two banks alternate per BPTT window: window w writes bank w%2, its initial state
-    lives in the last slot of bank (w-1)%2.  CONTRACT: loss.backward() of window w must run before window w+1 COMPLETES
+    lives in the last used slot of bank (w-1)%2.  CONTRACT: loss.backward() of window w must run before window w+1 COMPLETES
     (window w+1 overwrites, at its own last step, the slot that holds window w's initial state; window w+2 overwrites
     window w's activations) -- train_flow.py:154-171 runs backward right at the window end.  The contract is enforced:
     every slot carries a generation counter, a step's backward raises if a slot it saved from has been rewritten since.
     """
 
-    def __init__(self, B, H, W, dev):
+    def __init__(self, B, H, W, dev, cap):
         self.key = (B, H, W, dev)
-        self.banks = ([], [])
+        self.cap = cap
+        self.banks = [None, None]
         self.parity = 0
-        self.bwd = None
-        self.flat = None   # fp32 [n_params]: parameter gradients of the window being back-propagated (static address)
+        self.flat = None   # fp32 [n_params]: parameter gradients of the window being back-propagated
+        self.bwd = None    # buffers of the window backward
 
-    def slot(self, parity, idx):
-        bank = self.banks[parity]
-        while len(bank) <= idx:
-            bank.append(_Slot(*self.key))
-        return bank[idx]
+    def bank(self, parity):
+        if self.banks[parity] is None:
+            self.banks[parity] = _Bank(self.key, self.cap)
+        return self.banks[parity]
 
-    def bwd_buffers(self):
-        if self.bwd is None:
+    def window_buffers(self, cap):
+        """Gradient buffers of the window backward, sized for `cap` steps."""
+        if self.bwd is None or self.bwd["cap"] < cap:
             B, H, W, dev = self.key
-            mk = lambda: torch.empty((B, 32, H, W), device=dev, dtype=torch.float32)  # noqa: E731
-            mkcl = lambda: torch.empty((B, H, W, 32), device=dev, dtype=torch.bfloat16)  # noqa: E731
-            self.bwd = {"g_h": [mk(), mk()], "scratch": mk(), "g_v": [[mk() for _ in range(N_L)] for _ in range(2)],
-                        "g_z": [[mk() for _ in range(N_L)] for _ in range(2)], "gI_hi": mkcl(), "gI_mid": mkcl(),
-                        # per-CTA partial sums of the tensor-core weight gradient, one buffer per hidden cell (kept over a sweep)
-                        "wg": [None] + [torch.empty(L.lib().ef_lif_wgrad_partial_elems(B, H, W, 1), device=dev, dtype=torch.float32)
-                                        for _ in range(N_L - 1)]}
+            f32 = lambda *s: torch.empty(s, device=dev, dtype=torch.float32)  # noqa: E731
+            bf = lambda *s: torch.empty(s, device=dev, dtype=torch.bfloat16)  # noqa: E731
+            self.bwd = {
+                "cap": cap,
+                "g_h": [f32(cap, B, 32, H, W), f32(cap, B, 32, H, W)],    # dL/d(spikes) of all steps, ping-pong between neighbouring layers
+                "gI_hi": bf(cap, B, H, W, 32), "gI_mid": bf(cap, B, H, W, 32),
+                "g_flow": f32(cap, B, 2, H, W),
+                "g_v": [f32(B, 32, H, W), f32(B, 32, H, W)], "g_z": [f32(B, 32, H, W), f32(B, 32, H, W)],  # recurrent cells, step to step
+                "wg": f32(L.lib().ef_lif_wgrad_partial_elems(cap * B, H, W, 1)),
+            }
         return self.bwd
 
 
@@ -114,6 +160,8 @@ def _cells(model):
     c = model.__dict__.get("_fast_cells")
     if c is None:
         c = model.__dict__["_fast_cells"] = [getattr(model, n) for n in LAYERS]
+        for cell in c:
+            cell.__dict__["_act_width_f"] = float(cell.act_width)
     return c
 
 
@@ -235,7 +283,7 @@ def _launch_step(model, x, v_in, z_in, slot, splits, B, Cin0, H, W, only_hidden=
 
 def capture_window(model, xs, only_hidden=False):
     """
-    Measurement aid (bench.py roofline): the kernels of len(xs) - 1 consecutive model steps on private activation slots,
+    Measurement aid (bench.py roofline): the kernels of len(xs) - 1 consecutive model steps on a private activation bank,
     captured as ONE CUDA graph (step 0 runs eagerly from the zero state and provides the previous state of step 1).
     With only_hidden the graph holds just the six 32 -> 32 tensor-core cell launches of every step.  Replaying it repeats
     the same computation on the same operands (every launch streams its own ~59 MB, the whole replay far more than L2).
@@ -243,12 +291,10 @@ def capture_window(model, xs, only_hidden=False):
     """
     x0 = xs[0]
     B, Cin0, H, W = x0.shape
-    for name in LAYERS:
-        cell = getattr(model, name)
-        if not hasattr(cell, "_act_width_f"):
-            cell._act_width_f = float(cell.act_width)
+    _cells(model)
     splits = _split_cache(model)
-    slots = [_Slot(B, H, W, x0.device) for _ in xs]
+    bank = _Bank((B, H, W, x0.device), len(xs))
+    slots = [bank.slot(t) for t in range(len(xs))]
     none = [None] * N_L
     xs = [x.contiguous() for x in xs]
     with torch.no_grad():
@@ -260,7 +306,7 @@ def capture_window(model, xs, only_hidden=False):
         with torch.cuda.graph(g, capture_error_mode="thread_local"):
             for t in range(1, len(xs)):
                 _launch_step(model, xs[t], slots[t - 1].v, slots[t - 1].z, slots[t], splits, B, Cin0, H, W, only_hidden=only_hidden)
-    g._keepalive = (slots, xs, splits)
+    g._keepalive = (bank, xs, splits)
     return g, (len(xs) - 1) * (N_L - 1 if only_hidden else N_L + 1)
 
 
@@ -271,32 +317,35 @@ class _FireNetStep(torch.autograd.Function):
         x = x.contiguous()
         B, Cin0, H, W = x.shape
         dev = x.device
-        for cell in _cells(model):
-            if "_act_width_f" not in cell.__dict__:
-                cell._act_width_f = float(cell.act_width)
+        _cells(model)
         splits = _split_cache(model)
         arena = model.__dict__.get("_arena")
         if arena is None or arena.key != (B, H, W, dev):
-            arena = model.__dict__["_arena"] = _Arena(B, H, W, dev)
-        slot = arena.slot(arena.parity, fs.step)
+            arena = model.__dict__["_arena"] = _Arena(B, H, W, dev, int(model.__dict__.get("_window_cap", DEFAULT_WINDOW_CAP)))
+        parity = arena.parity
+        bank = arena.bank(parity)
+        if fs.step >= bank.cap:
+            bank.grow(fs.step)
+        bank.need_input(Cin0)
+        idx = fs.step
+        slot = bank.slot(idx)
         fs.step += 1
         slot.gen += 1
         v_in, z_in = list(fs.v), list(fs.z)
         ctx.guards = [(slot, slot.gen)] + ([fs.src] if fs.src is not None and fs.src[0] is not slot else [])
         fs.src = (slot, slot.gen)
+        carry = fs.carry
+        if idx == 0:
+            carry.prev, carry.parity = (v_in, z_in), parity
+        carry.n = idx + 1
         cap = model.__dict__.get("_capture")
+        slot.x_in.copy_(x)  # fixed address: CUDA-graph replay of the step, and the window-wide weight gradient of the head layer
         use_graph = (model.__dict__.get("_use_graphs", True) and cap is None and L.PROFILE is None
                      and not torch.cuda.is_current_stream_capturing())
         if use_graph:
-            # CUDA-graph replay of the step: the input is copied to a fixed address, everything else already is static
-            if slot.x_in is None or slot.x_in.shape != x.shape:
-                slot.x_in, slot.graphs = torch.empty_like(x), {}
-            slot.x_in.copy_(x)
             if fs.param_sig is None:  # refreshed per sequence (reset_states) and whenever the module is moved (FireNet._apply)
                 fs.param_sig = (tuple(p.data_ptr() for p in _params_of(model)), tuple(splits[n].data_ptr() for n in LAYERS[1:]))
-            key = (fs.param_sig, tuple(0 if v is None else v.data_ptr() for v in v_in))
-            ctx.splits = splits
-            ctx.fkey = key
+            key = (fs.param_sig, tuple(0 if v is None else v.data_ptr() for v in v_in), slot.x_in.data_ptr())
             g = slot.graphs.get(key)
             if g is None:
                 _launch_step(model, slot.x_in, v_in, z_in, slot, splits, B, Cin0, H, W)  # eager: results + lazy init
@@ -308,15 +357,9 @@ class _FireNetStep(torch.autograd.Function):
             else:
                 g.replay()
                 L.GRAPH_KERNELS += N_L + 1
-            x_used = slot.x_in
         else:
-            _launch_step(model, x, v_in, z_in, slot, splits, B, Cin0, H, W)
-            x_used = x
-            ctx.splits = splits
-            ctx.fkey = None
-        saved = []
+            _launch_step(model, slot.x_in, v_in, z_in, slot, splits, B, Cin0, H, W)
         for i, name in enumerate(LAYERS):
-            saved.append((x_used if i == 0 else None, slot.z[i - 1] if i > 0 else None, v_in[i], z_in[i], slot.v[i]))
             if cap is not None:  # test hook: what this layer consumed and produced, in the reference's tensor format
                 xin = x if i == 0 else ops.unpack_cl(slot.z[i - 1])
                 sin = None if v_in[i] is None else torch.stack([v_in[i], ops.unpack_cl(z_in[i])]).cpu()
@@ -324,8 +367,7 @@ class _FireNetStep(torch.autograd.Function):
                 cap[name] = (xin.detach().cpu(), sin, zo.cpu(), torch.stack([slot.v[i], zo]).cpu())
             fs.v[i], fs.z[i] = slot.v[i], slot.z[i]
         flow = slot.flow.clone()  # the caller may keep the flow for as long as it likes; the slot is recycled
-        ctx.model, ctx.saved, ctx.flow, ctx.first, ctx.z_last = model, saved, slot.flow, token is None, slot.z[N_L - 1]
-        ctx.carry, ctx.arena, ctx.slot = fs.carry, arena, slot
+        ctx.model, ctx.arena, ctx.carry, ctx.idx, ctx.first = model, arena, carry, idx, token is None
         ctx.shapes = (B, Cin0, H, W)
         model._last_spikes = slot.z
         if isinstance(ctx, _NoCtx):
@@ -340,146 +382,218 @@ class _FireNetStep(torch.autograd.Function):
             if slot_.gen != gen_:
                 raise RuntimeError(
                     "event_flow_b200 fast path: the activations this backward step needs were overwritten by a later forward pass. "
-                    "loss.backward() of a BPTT window must run before the next window completes (see fast._Arena); "
-                    "use model._use_graphs / per-cell API for other schedules.")
-        B, Cin0, H, W = ctx.shapes
+                    "loss.backward() of a BPTT window must run before the next window completes (see fast._Arena).")
+        if g_flow is not None:
+            carry.g_flows[ctx.idx] = g_flow
+        dev = ctx.arena.key[3]
+        if not ctx.first:  # nothing is computed yet: the window's first step (the last node to run) back-propagates the whole window
+            return (None, None, torch.zeros((), device=dev, dtype=torch.float32))
         params = _params_of(model)
-        dev = ctx.flow.device
-        buf = ctx.arena.bwd_buffers()
-        arena = ctx.arena
-        sweep_first = carry.sweep == 0
-        if sweep_first:  # first backward call of this sweep = last step of the window
-            n = sum(p.numel() for p in params)
-            if arena.flat is None or arena.flat.numel() != n:
-                arena.flat = torch.zeros(n, device=dev, dtype=torch.float32)
-            else:
-                arena.flat.zero_()
-            carry.flat = arena.flat
-            carry.g_v, carry.g_z = [None] * N_L, [None] * N_L
-        par = carry.sweep & 1  # ping-pong of the state-gradient buffers between consecutive steps
-        wg_flags = (L.EF_WG_ACCUMULATE if carry.sweep > 0 else 0) | (L.EF_WG_FINALIZE if ctx.first else 0)
-        carry.sweep += 1
-        if g_flow is None:
-            g_flow = torch.zeros_like(ctx.flow)
-        g_flow = g_flow.contiguous()
-        # Steady state: the argument structs of this step's ~8 library calls depend only on static addresses (arena slots,
-        # ping-pong buffers, the flat gradient buffer) -- they are built once per (slot, sweep position) and replayed; only the
-        # incoming flow gradient lives at a fresh address.
-        ckey = None if ctx.fkey is None else (ctx.fkey, par, sweep_first, ctx.first, model.__dict__.get("_tc_backward", True),
-                                              model.__dict__.get("_tc_wgrad", True))
-        hit = ctx.slot.bwd_calls.get(ckey) if ckey is not None else None
-        if hit is not None:
-            calls, g_v_next, g_z_next, graph, n_kernels = hit
-            slot = ctx.slot
-            if slot.g_flow_in is None:
-                slot.g_flow_in = torch.empty_like(ctx.flow)
-            slot.g_flow_in.copy_(g_flow)  # fixed address for the replay, like the model input of the forward graph
-            calls[0][1].g_y = L.ptr(slot.g_flow_in)
-            if graph is None and model.__dict__.get("_use_graphs", True) and L.PROFILE is None and not torch.cuda.is_current_stream_capturing():
-                graph = torch.cuda.CUDAGraph()  # second visit of this (slot, sweep position): capture the ~25 kernels once
-                n0 = L.lib().ef_launch_count()
-                with torch.cuda.graph(graph, capture_error_mode="thread_local"):
-                    for name, st in calls:
-                        L.call(name, st)
-                n_kernels = L.lib().ef_launch_count() - n0  # kernels recorded into the graph (counted by the library itself)
-                slot.bwd_calls[ckey] = (calls, g_v_next, g_z_next, graph, n_kernels)
-            if graph is not None:
-                graph.replay()
-                L.GRAPH_KERNELS += n_kernels
-            else:
-                for name, st in calls:
-                    L.call(name, st)
-            carry.g_v, carry.g_z = list(g_v_next), list(g_z_next)
-            if not ctx.first:
-                return (None, None, torch.zeros((), device=dev, dtype=torch.float32))
-            carry.sweep = 0
-            grads, o = [], 0
-            for p in params:
-                grads.append(carry.flat[o:o + p.numel()].view(p.shape))
-                o += p.numel()
-            return (None, None, None, *[g.clone() if p.requires_grad else None for p, g in zip(params, grads)])
-        calls = []
+        if model.__dict__.get("_window_backward", True) and model.__dict__.get("_tc_backward", True):
+            grads = _window_backward(model, ctx.arena, carry, ctx.shapes)
+        else:
+            grads = _stepwise_backward(model, ctx.arena, carry, ctx.shapes)
+        carry.g_flows = {}
+        return (None, None, None, *[g.clone() if p.requires_grad else None for p, g in zip(params, grads)])
 
-        def emit(name, st):
-            calls.append((name, st))
-            L.call(name, st)
 
-        grads, o = [], 0
-        for p in params:
-            grads.append(carry.flat[o:o + p.numel()].view(p.shape))
-            o += p.numel()
-        gi = len(grads) - 2
-        # prediction head
-        g_h = buf["g_h"][0]
+def _flat_grads(arena, params, dev):
+    n = sum(p.numel() for p in params)
+    if arena.flat is None or arena.flat.numel() != n:
+        arena.flat = torch.zeros(n, device=dev, dtype=torch.float32)
+    else:
+        arena.flat.zero_()
+    grads, o = [], 0
+    for p in params:
+        grads.append(arena.flat[o:o + p.numel()].view(p.shape))
+        o += p.numel()
+    return grads
+
+
+def _grad_slots(cells, grads):
+    """Per layer the views of the flat gradient buffer: (g_w_ff, g_w_rec | None, g_leak, g_thresh); then pred (g_w, g_b)."""
+    out, k = [], 0
+    for cell in cells:
+        g_ff = grads[k]
+        k += 1
+        g_rec = None
+        if cell.recurrent:
+            g_rec = grads[k]
+            k += 1
+        out.append((g_ff, g_rec, grads[k], grads[k + 1]))
+        k += 2
+    out.append((grads[k], grads[k + 1]))
+    return out
+
+
+def _window_g_flow(carry, Tn, B, H, W, buf):
+    """dL/dflow of all steps as one dense [Tn,B,2,H,W] tensor: the loss kernel's gradient slab itself when the steps' gradients are its
+    consecutive slices (the usual case), a gathered copy otherwise (flows used elsewhere, missing steps)."""
+    gs = [carry.g_flows.get(t) for t in range(Tn)]
+    n = B * 2 * H * W
+    g0 = gs[0]
+    if g0 is not None and all(g is not None and g.dtype == torch.float32 and g.is_contiguous() and g.shape == (B, 2, H, W)
+                              and g.data_ptr() == g0.data_ptr() + 4 * n * t for t, g in enumerate(gs)):
+        try:
+            return g0.as_strided((Tn, B, 2, H, W), (n, 2 * H * W, H * W, W, 1))
+        except RuntimeError:
+            pass
+    out = buf["g_flow"][:Tn]
+    for t, g in enumerate(gs):
+        if g is None:
+            out[t].zero_()
+        else:
+            out[t].copy_(g)
+    return out
+
+
+def _window_backward(model, arena, carry, shapes):
+    """BPTT of one whole window, layer by layer (see the module docstring).  Returns the parameter gradients (views of arena.flat)."""
+    B, Cin0, H, W = shapes
+    dev = arena.key[3]
+    bank = arena.banks[carry.parity]
+    Tn = carry.n
+    cells, params, splits = _cells(model), _params_of(model), _split_cache(model)
+    grads = _flat_grads(arena, params, dev)
+    gs = _grad_slots(cells, grads)
+    buf = arena.window_buffers(bank.cap)
+    v0, z0 = carry.prev
+    # prediction head, all steps at once
+    g_flow = _window_g_flow(carry, Tn, B, H, W, buf)
+    cur = 0
+    pp = L.PredParams()
+    pp.B, pp.Cin, pp.Cout, pp.H, pp.W = Tn * B, 32, 2, H, W
+    w, b = model.pred.conv2d.weight.detach(), model.pred.conv2d.bias.detach()
+    pp.x_cl, pp.w, pp.b, pp.y, pp.g_y = L.ptr(bank.zs[N_L - 1][1:Tn + 1]), L.ptr(w), L.ptr(b), L.ptr(bank.flow[:Tn]), L.ptr(g_flow)
+    pp.g_x, pp.g_w, pp.g_b = L.ptr(buf["g_h"][cur][:Tn]), L.ptr(gs[N_L][0]), L.ptr(gs[N_L][1])
+    L.call("ef_pred_bwd", pp)
+    for i in reversed(range(N_L)):
+        cell = cells[i]
+        g_ff, g_rec, g_leak, g_thresh = gs[i]
+        leak, thresh = cell.leak.detach().reshape(-1), cell.thresh.detach().reshape(-1)
+        surr, width, hard = L.SURROGATE_CODES[cell.activation], float(cell._act_width_f), int(cell.hard_reset)
+        g_out, g_x = buf["g_h"][cur], buf["g_h"][cur ^ 1]
+        if not cell.recurrent:  # head and feed-forward cells: three launches for the whole window
+            q = L.LifBwdWindowParams()
+            q.B, q.T, q.H, q.W, q.hard_reset, q.surrogate, q.act_width = B, Tn, H, W, hard, surr, width
+            q.z_cl, q.z_prev_cl = L.ptr(bank.zs[i][1:Tn + 1]), L.ptr(z0[i])
+            q.v, q.v_prev, q.g_out = L.ptr(bank.v[i][:Tn]), L.ptr(v0[i]), L.ptr(g_out[:Tn])
+            q.leak, q.thresh = L.ptr(leak), L.ptr(thresh)
+            q.g_w_ff, q.g_leak, q.g_thresh = L.ptr(g_ff), L.ptr(g_leak), L.ptr(g_thresh)
+            if i == 0:
+                q.Cin, q.x_f32, q.gI_f32 = Cin0, L.ptr(bank.x_in[:Tn]), L.ptr(g_x[:Tn])  # (the other ping-pong buffer is free: nothing below the head)
+            else:
+                q.x_cl, q.w_bwd = L.ptr(bank.zs[i - 1][1:Tn + 1]), L.ptr(splits[LAYERS[i] + ".bwd"])
+                q.gI_hi, q.gI_mid = L.ptr(buf["gI_hi"][:Tn]), L.ptr(buf["gI_mid"][:Tn])
+                q.g_x, q.wg_partial = L.ptr(g_x[:Tn]), L.ptr(buf["wg"])
+            L.call("ef_lif_bwd_window", q)
+        else:  # recurrent cells: dL/dz of step t+1 reaches step t through the recurrent convolution, so pointwise + data gradient go step by step
+            if z0[i] is not None:
+                bank.zs[i][0].copy_(z0[i])  # previous spikes of steps 0..Tn-1 become ONE dense tensor for the batched weight gradient
+            else:
+                bank.zs[i][0].zero_()
+            g_v_next = g_z_next = None
+            for t in reversed(range(Tn)):
+                par = t & 1
+                has_prev = t > 0 or v0[i] is not None
+                q = L.LifBwdTcParams()
+                q.B, q.H, q.W, q.has_rec, q.hard_reset, q.surrogate, q.act_width = B, H, W, 1, hard, surr, width
+                q.x_cl = L.ptr(bank.zs[i - 1][t + 1])
+                q.z_in_cl = L.ptr(bank.zs[i][t]) if has_prev else None
+                q.v_in = L.ptr(bank.v[i][t - 1] if t > 0 else v0[i])
+                q.v_out = L.ptr(bank.v[i][t])
+                q.g_out, q.g_v_out, q.g_z_out = L.ptr(g_out[t]), L.ptr(g_v_next), L.ptr(g_z_next)
+                q.leak, q.thresh, q.w_bwd = L.ptr(leak), L.ptr(thresh), L.ptr(splits[LAYERS[i] + ".bwd"])
+                q.gI_hi, q.gI_mid = L.ptr(buf["gI_hi"][t]), L.ptr(buf["gI_mid"][t])
+                q.g_x = L.ptr(g_x[t])
+                g_v_next = g_z_next = None
+                if t > 0:  # (the state before step 0 is detached: nobody consumes its gradient)
+                    g_v_next, g_z_next = buf["g_v"][par], buf["g_z"][par]
+                    q.g_v_in, q.g_z_in = L.ptr(g_v_next), L.ptr(g_z_next)
+                q.g_leak, q.g_thresh = L.ptr(g_leak), L.ptr(g_thresh)
+                L.call("ef_lif_bwd_tc", q)  # no weight-gradient pointers: pointwise + data gradient only
+            L.LAUNCHES += 1
+            L.check(L.lib().ef_lif_wgrad_tc(L.ptr(bank.zs[i - 1][1:Tn + 1]), L.ptr(bank.zs[i][:Tn]), L.ptr(buf["gI_hi"][:Tn]), L.ptr(buf["gI_mid"][:Tn]),
+                                            1, Tn * B, H, W, L.ptr(buf["wg"]), L.EF_WG_FINALIZE, L.ptr(g_ff), L.ptr(g_rec), L.stream()),
+                    "ef_lif_wgrad_tc")
+        cur ^= 1
+    return grads
+
+
+def _stepwise_backward(model, arena, carry, shapes):
+    """
+    Fallback / A-B reference (model._window_backward = False or model._tc_backward = False): the same BPTT step by step, one cell-step
+    per library call, state gradients handed from step t+1 to step t in fp32 buffers.  With _tc_backward = False every cell runs on the
+    generic CUDA-core backward (ef_lif_conv_bwd).
+    """
+    B, Cin0, H, W = shapes
+    dev = arena.key[3]
+    bank = arena.banks[carry.parity]
+    Tn = carry.n
+    cells, params, splits = _cells(model), _params_of(model), _split_cache(model)
+    grads = _flat_grads(arena, params, dev)
+    gs = _grad_slots(cells, grads)
+    tc = model.__dict__.get("_tc_backward", True)
+    mk = lambda: torch.empty((B, 32, H, W), device=dev, dtype=torch.float32)  # noqa: E731
+    g_hh = [mk(), mk()]
+    g_vb = [[mk() for _ in range(N_L)] for _ in range(2)]
+    g_zb = [[mk() for _ in range(N_L)] for _ in range(2)]
+    scratch = mk()
+    gI_hi = torch.empty((B, H, W, 32), device=dev, dtype=torch.bfloat16)
+    gI_mid = torch.empty_like(gI_hi)
+    v0, z0 = carry.prev
+    g_v, g_z = [None] * N_L, [None] * N_L
+    w, b = model.pred.conv2d.weight.detach(), model.pred.conv2d.bias.detach()
+    for t in reversed(range(Tn)):
+        par = t & 1
+        g_flow = carry.g_flows.get(t)
+        g_flow = torch.zeros((B, 2, H, W), device=dev) if g_flow is None else g_flow.contiguous()
+        g_h = g_hh[0]
         pp = L.PredParams()
         pp.B, pp.Cin, pp.Cout, pp.H, pp.W = B, 32, 2, H, W
-        z7 = ctx.z_last
-        w, b = model.pred.conv2d.weight.detach(), model.pred.conv2d.bias.detach()
-        pp.x_cl, pp.w, pp.b, pp.y, pp.g_y = L.ptr(z7), L.ptr(w), L.ptr(b), L.ptr(ctx.flow), L.ptr(g_flow)
-        pp.g_x, pp.g_w, pp.g_b = L.ptr(g_h), L.ptr(grads[gi]), L.ptr(grads[gi + 1])
-        emit("ef_pred_bwd", pp)
-        # cells, last to first
-        for i in reversed(range(len(LAYERS))):
-            cell = getattr(model, LAYERS[i])
-            x_f32, x_cl, v_in, z_in, v_out = ctx.saved[i]
-            gi -= 4 if cell.recurrent else 3
+        pp.x_cl, pp.w, pp.b, pp.y, pp.g_y = L.ptr(bank.zs[N_L - 1][t + 1]), L.ptr(w), L.ptr(b), L.ptr(bank.flow[t]), L.ptr(g_flow)
+        pp.g_x, pp.g_w, pp.g_b = L.ptr(g_h), L.ptr(gs[N_L][0]), L.ptr(gs[N_L][1])
+        L.call("ef_pred_bwd", pp)
+        for i in reversed(range(N_L)):
+            cell = cells[i]
+            g_ff, g_rec, g_leak, g_thresh = gs[i]
             leak, thresh = cell.leak.detach().reshape(-1), cell.thresh.detach().reshape(-1)
-            g_x = (buf["g_h"][1] if g_h is buf["g_h"][0] else buf["g_h"][0]) if i > 0 else None
+            v_in = bank.v[i][t - 1] if t > 0 else v0[i]
+            z_in = bank.zs[i][t] if t > 0 else z0[i]
+            v_out = bank.v[i][t]
+            x_cl = bank.zs[i - 1][t + 1] if i > 0 else None
+            g_x = (g_hh[1] if g_h is g_hh[0] else g_hh[0]) if i > 0 else None
             g_v_in = g_z_in = None
-            if not ctx.first and v_in is not None:
-                g_v_in = buf["g_v"][par][i]
+            if t > 0:
+                g_v_in = g_vb[par][i]
                 if cell.recurrent:
-                    g_z_in = buf["g_z"][par][i]
-            k = gi
-            g_w_ff = grads[k]
-            k += 1
-            g_w_rec = None
-            if cell.recurrent:
-                g_w_rec = grads[k]
-                k += 1
-            g_leak, g_thresh = grads[k], grads[k + 1]
-            if i == 0 and Cin0 <= 8 and model.__dict__.get("_tc_backward", True):
-                # head layer on the fast formats: pointwise (fp32 g_I) + register-tiled CUDA-core weight gradient, no data gradient
-                t = L.LifBwdTcParams()
-                t.B, t.H, t.W, t.has_rec, t.hard_reset = B, H, W, 0, int(cell.hard_reset)
-                t.surrogate, t.act_width = L.SURROGATE_CODES[cell.activation], float(cell._act_width_f)
-                t.z_in_cl, t.v_in, t.v_out = L.ptr(z_in), L.ptr(v_in), L.ptr(v_out)
-                t.g_out, t.g_v_out, t.g_z_out = L.ptr(g_h), L.ptr(carry.g_v[i]), L.ptr(carry.g_z[i])
-                t.leak, t.thresh = L.ptr(leak), L.ptr(thresh)
-                t.g_v_in, t.g_w_ff, t.g_leak, t.g_thresh = L.ptr(g_v_in), L.ptr(g_w_ff), L.ptr(g_leak), L.ptr(g_thresh)
-                t.Cin, t.x_f32, t.gI_f32 = Cin0, L.ptr(x_f32), L.ptr(buf["scratch"])
-                emit("ef_lif_bwd_tc", t)
-            elif i > 0 and model.__dict__.get("_tc_backward", True):
-                # 32 -> 32 cells: pointwise + tensor-core data gradient + channels-last weight gradient
-                t = L.LifBwdTcParams()
-                t.B, t.H, t.W, t.has_rec, t.hard_reset = B, H, W, int(cell.recurrent), int(cell.hard_reset)
-                t.surrogate, t.act_width = L.SURROGATE_CODES[cell.activation], float(cell._act_width_f)
-                t.x_cl, t.z_in_cl, t.v_in, t.v_out = L.ptr(x_cl), L.ptr(z_in), L.ptr(v_in), L.ptr(v_out)
-                t.g_out, t.g_v_out, t.g_z_out = L.ptr(g_h), L.ptr(carry.g_v[i]), L.ptr(carry.g_z[i])
-                t.leak, t.thresh, t.w_bwd = L.ptr(leak), L.ptr(thresh), L.ptr(ctx.splits[LAYERS[i] + ".bwd"])
-                t.gI_hi, t.gI_mid = L.ptr(buf["gI_hi"]), L.ptr(buf["gI_mid"])
-                t.g_x, t.g_v_in, t.g_z_in = L.ptr(g_x), L.ptr(g_v_in), L.ptr(g_z_in)
-                t.g_w_ff, t.g_w_rec, t.g_leak, t.g_thresh = L.ptr(g_w_ff), L.ptr(g_w_rec), L.ptr(g_leak), L.ptr(g_thresh)
-                if model.__dict__.get("_tc_wgrad", True):
-                    t.wg_partial, t.wg_flags = L.ptr(buf["wg"][i]), wg_flags
-                emit("ef_lif_bwd_tc", t)
+                    g_z_in = g_zb[par][i]
+            if tc:
+                q = L.LifBwdTcParams()
+                q.B, q.H, q.W, q.has_rec, q.hard_reset = B, H, W, int(cell.recurrent), int(cell.hard_reset)
+                q.surrogate, q.act_width = L.SURROGATE_CODES[cell.activation], float(cell._act_width_f)
+                q.z_in_cl, q.v_in, q.v_out = L.ptr(z_in), L.ptr(v_in), L.ptr(v_out)
+                q.g_out, q.g_v_out, q.g_z_out = L.ptr(g_h), L.ptr(g_v[i]), L.ptr(g_z[i])
+                q.leak, q.thresh = L.ptr(leak), L.ptr(thresh)
+                q.g_v_in, q.g_w_ff, q.g_leak, q.g_thresh = L.ptr(g_v_in), L.ptr(g_ff), L.ptr(g_leak), L.ptr(g_thresh)
+                if i == 0:
+                    q.Cin, q.x_f32, q.gI_f32 = Cin0, L.ptr(bank.x_in[t]), L.ptr(scratch)
+                else:
+                    q.x_cl, q.w_bwd = L.ptr(x_cl), L.ptr(splits[LAYERS[i] + ".bwd"])
+                    q.gI_hi, q.gI_mid = L.ptr(gI_hi), L.ptr(gI_mid)
+                    q.g_x, q.g_z_in, q.g_w_rec = L.ptr(g_x), L.ptr(g_z_in), L.ptr(g_rec)
+                L.call("ef_lif_bwd_tc", q)  # wg_partial NULL: CUDA-core weight gradient, added to g_w_* at once
             else:
                 q = L.LifConvBwdParams()
-                _fill_fwd(q.f, B, Cin0 if i == 0 else 32, H, W, cell, x_f32, x_cl, v_in, z_in, v_out, leak, thresh)
-                q.g_out, q.g_v_out, q.g_z_out = L.ptr(g_h), L.ptr(carry.g_v[i]), L.ptr(carry.g_z[i])
-                q.scratch_gI = L.ptr(buf["scratch"])
+                _fill_fwd(q.f, B, Cin0 if i == 0 else 32, H, W, cell, bank.x_in[t] if i == 0 else None, x_cl, v_in, z_in, v_out, leak, thresh)
+                q.g_out, q.g_v_out, q.g_z_out = L.ptr(g_h), L.ptr(g_v[i]), L.ptr(g_z[i])
+                q.scratch_gI = L.ptr(scratch)
                 q.g_x, q.g_v_in, q.g_z_in = L.ptr(g_x), L.ptr(g_v_in), L.ptr(g_z_in)
-                q.g_w_ff, q.g_w_rec, q.g_leak, q.g_thresh = L.ptr(g_w_ff), L.ptr(g_w_rec), L.ptr(g_leak), L.ptr(g_thresh)
-                emit("ef_lif_conv_bwd", q)
-            carry.g_v[i], carry.g_z[i] = g_v_in, g_z_in
+                q.g_w_ff, q.g_w_rec, q.g_leak, q.g_thresh = L.ptr(g_ff), L.ptr(g_rec), L.ptr(g_leak), L.ptr(g_thresh)
+                L.call("ef_lif_conv_bwd", q)
+            g_v[i], g_z[i] = g_v_in, g_z_in
             g_h = g_x
-        if ckey is not None:
-            ctx.slot.bwd_calls[ckey] = (calls, list(carry.g_v), list(carry.g_z), None, 0)
-        if not ctx.first:  # parameter gradients keep accumulating in carry.flat; the window's first step hands them over
-            return (None, None, torch.zeros((), device=dev, dtype=torch.float32))
-        carry.sweep = 0
-        out = [g.clone() if p.requires_grad else None for p, g in zip(params, grads)]
-        return (None, None, None, *out)
+    return grads
 
 
 def forward(model, x, log=False):
@@ -496,8 +610,8 @@ def forward(model, x, log=False):
     need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
     if need_grad:
         token = fs.token
-        # the parameters are autograd inputs of the window's FIRST step only (its backward hands over the gradients accumulated
-        # over the whole window); later steps are chained through the token, which keeps their apply() cheap
+        # the parameters are autograd inputs of the window's FIRST step only (its backward runs the window's whole BPTT and hands
+        # over the gradients); later steps are chained through the token, which keeps their apply() cheap
         if token is None:
             flow, fs.token = _FireNetStep.apply(model, x, None, *params)
         else:

@@ -177,6 +177,43 @@ int64_t ef_lif_wgrad_partial_elems(int32_t B, int32_t H, int32_t W, int32_t has_
 
 int ef_lif_bwd_tc(const ef_lif_bwd_tc_params* p, void* stream);
 int64_t ef_split_weights_bwd_elems(int32_t has_rec);
+/* Backward of a FEED-FORWARD 32 -> 32 LIF cell over a whole BPTT window of T steps (same maths as T calls of ef_lif_bwd_tc walking
+ * t = T-1 ... 0 from a zero incoming state gradient).  Three launches for the whole window: (1) the neuron backward with the time
+ * loop INSIDE the kernel -- dL/dv stays in registers from step to step, every membrane tensor is read once; (2) the tensor-core data
+ * gradient and (3) the tensor-core weight gradient over T*B images at once.  Tensors hold the window step-major and dense:
+ * x_cl / z_cl / gI_* [T,B,H,W,32], v / g_out / g_x [T,B,32,H,W]; the state before step 0 comes separately (NULL = zero state).
+ * Head mode (x_f32 != NULL): the Cin <= 8 input cell, x_f32 [T,B,Cin,H,W], gI_f32 [T,B,32,H,W] workspace, no data gradient. */
+typedef struct ef_lif_bwd_window_params {
+  int32_t B, T, H, W, hard_reset, surrogate;
+  float act_width;
+  const uint16_t* x_cl;          /* input spikes of the cell at steps 0..T-1                                            */
+  const uint16_t* z_cl;          /* spikes the cell emitted at steps 0..T-1 (step t reads z_cl[t-1] as previous spikes) */
+  const uint16_t* z_prev_cl;     /* [B,H,W,32] spikes before step 0, or NULL                                            */
+  const float* v;                /* membrane potential after steps 0..T-1                                               */
+  const float* v_prev;           /* [B,32,H,W] before step 0, or NULL                                                   */
+  const float* g_out;            /* dL/d(output spikes) of steps 0..T-1                                                 */
+  const float* leak;             /* [32] raw parameters                                                                 */
+  const float* thresh;           /* [32]                                                                                */
+  const uint16_t* w_bwd;         /* ef_split_weights_bwd image                                                          */
+  uint16_t* gI_hi;               /* [T,B,H,W,32] workspace                                                              */
+  uint16_t* gI_mid;              /* [T,B,H,W,32] workspace                                                              */
+  float* g_x;                    /* [T,B,32,H,W] overwritten, or NULL                                                   */
+  float* g_v_prev;               /* [B,32,H,W] dL/d(membrane before step 0), overwritten, or NULL                       */
+  float* g_w_ff;                 /* [32,32,3,3] ([32,Cin,3,3] in head mode) += or NULL                                  */
+  float* g_leak;                 /* [32] += or NULL                                                                     */
+  float* g_thresh;               /* [32] += or NULL                                                                     */
+  float* wg_partial;             /* ef_lif_wgrad_partial_elems(T*B, H, W, 0) floats (needed with g_w_ff, not in head mode) */
+  int32_t Cin;                   /* head mode: input channels                                                           */
+  const float* x_f32;            /* head mode: [T,B,Cin,H,W]                                                            */
+  float* gI_f32;                 /* head mode: [T,B,32,H,W] workspace                                                   */
+} ef_lif_bwd_window_params;
+
+int ef_lif_bwd_window(const ef_lif_bwd_window_params* p, void* stream);
+/* The weight-gradient stage of ef_lif_bwd_tc alone, for B images whose g_I = gI_hi + gI_mid exists already (a recurrent cell runs
+ * pointwise + data gradient step by step, then this once over the window).  wg_partial / wg_flags as for ef_lif_bwd_tc. */
+int ef_lif_wgrad_tc(const uint16_t* x_cl, const uint16_t* z_in_cl, const uint16_t* gI_hi, const uint16_t* gI_mid, int32_t has_rec, int32_t B,
+                    int32_t H, int32_t W, float* wg_partial, int32_t wg_flags, float* g_w_ff, float* g_w_rec, void* stream);
+
 int ef_split_weights_bwd(const float* w_ff, const float* w_rec, uint16_t* out, void* stream);
 
 /* Split fp32 conv weights [C,Cin,3,3] (+ optional recurrent [C,C,3,3]) into three bf16 terms hi+mid+lo == w exactly,

@@ -70,10 +70,8 @@ def run(tag, windows, use_loss=True, **flags):
     print(f"[{tag}] loss {loss.item():.6f} vs {loss_o.item():.6f}\n   " + " ".join(row), flush=True)
 
 
-run("tc, graphs, window 1", 1)
-run("tc, graphs, window 3", 3)
-run("tc, no graphs, window 1", 1, _use_graphs=False)
-run("cuda-core bwd, window 1", 1, _tc_backward=False)
-run("tc dgrad + cuda-core wgrad, window 1", 1, _tc_wgrad=False)
-run("tc, random-weight loss, window 1", 1, use_loss=False)
-run("cuda-core bwd, random-weight loss, window 1", 1, use_loss=False, _tc_backward=False)
+run("window backward, random-weight loss, window 1", 1, use_loss=False)
+run("window backward, random-weight loss, window 3", 3, use_loss=False)
+run("step-by-step tc backward, random-weight loss, window 3", 3, use_loss=False, _window_backward=False)
+run("step-by-step cuda-core backward, random-weight loss, window 1", 1, use_loss=False, _tc_backward=False)
+run("window backward, event-warping loss, window 3 (flows not forced: see profiles/r02_loss_gradient_noise_floor.txt)", 3)
