@@ -146,7 +146,9 @@ def iwe_bench(dev, peak_gbs, reps=10):
         events = torch.stack([ts, ys, xs, ps], dim=3).reshape(B, ntot, 4).to(dev)
         pol = torch.stack([(ps > 0).float(), (ps < 0).float()], dim=3).reshape(B, ntot, 2).to(dev)
         flow = ((torch.rand((1, B, Tt, 2, Hh, Ww), generator=g) - 0.5) * 0.008).to(dev)
-        mask = (torch.rand((B, Tt, Hh, Ww), generator=g) < 0.3).float().to(dev)
+        mask = torch.zeros((B, Tt, Hh * Ww))  # event mask of every pass: pixels that received an event (dataloader/base.py:159-172)
+        mask.scatter_(2, (ys * Ww + xs).long(), 1.0)
+        mask = mask.view(B, Tt, Hh, Ww).to(dev)
         del ts, ys, xs, ps
         p = L.IweLossParams()
         p.S, p.B, p.T, p.T_maps, p.H, p.W = 1, B, Tt, Tt, Hh, Ww

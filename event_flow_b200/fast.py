@@ -161,7 +161,8 @@ def _cells(model):
     if c is None:
         c = model.__dict__["_fast_cells"] = [getattr(model, n) for n in LAYERS]
         for cell in c:
-            cell.__dict__["_act_width_f"] = float(cell.act_width)
+            if "act_width" in cell._buffers:  # spiking cells only (eligible() also inspects the ANN FireNets)
+                cell.__dict__["_act_width_f"] = float(cell.act_width)
     return c
 
 
