@@ -85,6 +85,7 @@ class IweLossParams(C.Structure):
 
 
 EF_IWE_MAX_PASSES, EF_IWE_MAX_SCALES = 32, 4
+EF_HEAD_MAX_CIN = 10
 
 
 class IweLossPassParams(C.Structure):
@@ -169,6 +170,8 @@ EXPORTS = {
     "ef_debug_tc_skip": (C.c_int, [C.c_int]),
     "ef_debug_tc_cpt": (C.c_int, [C.c_int]),
     "ef_debug_pdl": (C.c_int, [C.c_int]),
+    "ef_pack_split_cl": (C.c_int, [C.c_void_p, C.c_void_p, _i32, _i32, _i32, _i32, C.c_void_p]),
+    "ef_split_weights_head": (C.c_int, [C.c_void_p, _i32, C.c_void_p, C.c_void_p]),
     "ef_pack_cl": (C.c_int, [C.c_void_p, C.c_void_p, _i32, _i32, _i32, _i32, C.c_void_p]),
     "ef_unpack_cl": (C.c_int, [C.c_void_p, C.c_void_p, _i32, _i32, _i32, _i32, C.c_void_p]),
     "ef_upsample_bilinear2x": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, _i32, _i32, C.c_void_p]),

@@ -31,7 +31,42 @@ __global__ void __launch_bounds__(256) unpack_cl_kernel(const uint16_t* __restri
   }
 }
 
+// fp32 NCHW [B,Cin,H,W] with Cin <= 10 -> bf16 channels-last [B,H,W,32] holding the EXACT three-way split of every value:
+// slot s (0 = hi, 1 = mid, 2 = lo) of channel c sits at channel s*SL + c (SL = 8 for Cin <= 8, else 10), the rest is zero;
+// hi + mid + lo == x bit for bit.  This lets the fractional network input (voxel grids) run through the tensor-core cell kernel
+// with fp32-exact products: the head layer's weight image repeats w[.,c] in the three slots of c (ef_split_weights_head).
+__global__ void __launch_bounds__(256) pack_split_cl_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, int B, int Cin, int SL, size_t hw) {
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;  // over B * hw
+  if (i >= (size_t)B * hw) return;
+  const size_t pix = i % hw, b = i / hw;
+  uint16_t o[32];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) o[k] = 0;
+  for (int c = 0; c < Cin; ++c) {
+    const float x = __ldg(src + ((size_t)b * Cin + c) * hw + pix);
+    const __nv_bfloat16 hi = __float2bfloat16_rn(x);
+    const float r1 = x - __bfloat162float(hi);
+    const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+    o[c] = __bfloat16_as_ushort(hi), o[SL + c] = __bfloat16_as_ushort(mid), o[2 * SL + c] = __bfloat16_as_ushort(lo);
+  }
+  uint4* d = reinterpret_cast<uint4*>(dst + i * 32);
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    d[k] = make_uint4(o[8 * k] | ((uint32_t)o[8 * k + 1] << 16), o[8 * k + 2] | ((uint32_t)o[8 * k + 3] << 16), o[8 * k + 4] | ((uint32_t)o[8 * k + 5] << 16),
+                      o[8 * k + 6] | ((uint32_t)o[8 * k + 7] << 16));
+}
+
 }  // namespace ef
+
+extern "C" int ef_pack_split_cl(const float* src, uint16_t* dst, int32_t B, int32_t Cin, int32_t H, int32_t W, void* stream) {
+  using namespace ef;
+  EF_REQUIRE(src && dst, EF_ENULL, "ef_pack_split_cl: NULL tensor");
+  EF_REQUIRE(B > 0 && Cin > 0 && Cin <= EF_HEAD_MAX_CIN && H > 0 && W > 0, EF_EINVAL, "ef_pack_split_cl: 1 <= Cin <= %d", EF_HEAD_MAX_CIN);
+  const size_t n = (size_t)B * H * W;
+  pack_split_cl_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(src, dst, B, Cin, EF_HEAD_SLOT(Cin), (size_t)H * W);
+  return check_launch("pack_split_cl_kernel");
+}
 
 extern "C" int ef_pack_cl(const float* src, uint16_t* dst, int32_t B, int32_t C, int32_t H, int32_t W, void* stream) {
   using namespace ef;

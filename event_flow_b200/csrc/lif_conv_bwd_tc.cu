@@ -694,6 +694,27 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
   }
 }
 
+// Head layer on split inputs (ef_pack_split_cl): the three slots of input channel c all multiply w[.,c], so the weight gradient of
+// w[co][c][tap] is the sum of the rows s*SL + c, s = 0..2, of the tensor-core result.  One block per (tap, slot row).
+__global__ void __launch_bounds__(256) wgrad_reduce_head_kernel(const float* __restrict__ partial, int n_cta, float* __restrict__ g_w, int Cin, int SL) {
+  __shared__ float s[8][32];
+  const int co = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const int row = blockIdx.x;  // (dy*3 + dx)*32 + k
+  const int k = row & 31, c = k % SL, slot = k / SL;
+  if (slot >= 3 || c >= Cin) return;
+  const float* src = partial + row * 32 + co;
+  float acc = 0.f;
+  for (int i = grp; i < n_cta; i += 8) acc += __ldg(src + (size_t)i * WG_SLICE);
+  s[grp][co] = acc;
+  __syncthreads();
+  if (grp == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) t += s[g][co];
+    atomicAdd(g_w + ((size_t)co * Cin + c) * 9 + (row >> 5), t);
+  }
+}
+
 inline int wg_n_sms() {
   static int n_sms = 0;
   if (n_sms == 0) {
@@ -882,11 +903,15 @@ extern "C" int ef_lif_bwd_window(const ef_lif_bwd_window_params* pp, void* strea
   const ef_lif_bwd_window_params& p = *pp;
   EF_REQUIRE(p.B > 0 && p.T > 0 && p.H > 0 && p.W > 0 && (int64_t)p.B * p.T < (1 << 20), EF_EINVAL, "ef_lif_bwd_window: bad dimensions");
   const bool head = p.x_f32 != nullptr;
+  const bool head_tc = !head && p.Cin > 0 && p.Cin < 32;  // head layer on split inputs: x_cl from ef_pack_split_cl, no data gradient
   EF_REQUIRE(p.v && p.g_out && p.leak && p.thresh && (p.T == 1 || p.z_cl), EF_ENULL, "ef_lif_bwd_window: NULL tensor");
-  if (head) {
+  if (head_tc) {
+    EF_REQUIRE(p.Cin <= EF_HEAD_MAX_CIN && p.x_cl && p.gI_hi && p.gI_mid && !p.g_x, EF_EINVAL, "ef_lif_bwd_window (split-input head): bad arguments");
+    EF_REQUIRE(!p.g_w_ff || p.wg_partial, EF_ENULL, "ef_lif_bwd_window: g_w_ff wanted but wg_partial is NULL");
+  } else if (head) {
     EF_REQUIRE(p.gI_f32, EF_ENULL, "ef_lif_bwd_window (head mode): gI_f32 is NULL");
     EF_REQUIRE(p.Cin > 0 && p.Cin <= HW_MAXC, EF_EUNSUPPORTED, "ef_lif_bwd_window (head mode): Cin <= %d (got %d)", HW_MAXC, p.Cin);
-  } else {
+  } else if (!head_tc) {
     EF_REQUIRE(p.x_cl && p.w_bwd && p.gI_hi && p.gI_mid, EF_ENULL, "ef_lif_bwd_window: NULL tensor");
     EF_REQUIRE(!p.g_w_ff || p.wg_partial, EF_ENULL, "ef_lif_bwd_window: g_w_ff wanted but wg_partial is NULL");
   }
@@ -895,6 +920,12 @@ extern "C" int ef_lif_bwd_window(const ef_lif_bwd_window_params* pp, void* strea
   if ((rc = run_pointwise_window(p, st))) return rc;
   const int BT = p.B * p.T;
   if (head) return p.g_w_ff ? run_head_wgrad(p.x_f32, p.gI_f32, p.g_w_ff, BT, p.Cin, p.H, p.W, st) : EF_OK;
+  if (head_tc) {
+    if (!p.g_w_ff) return EF_OK;
+    if ((rc = run_wgrad(p.x_cl, nullptr, p.gI_hi, p.gI_mid, false, BT, p.H, p.W, p.wg_partial, 0, nullptr, nullptr, st))) return rc;
+    wgrad_reduce_head_kernel<<<288, 256, 0, st>>>(p.wg_partial, wg_grid(BT, p.H, p.W), p.g_w_ff, p.Cin, EF_HEAD_SLOT(p.Cin));
+    return check_launch("wgrad_reduce_head_kernel");
+  }
   if (p.g_x && (rc = run_dgrad(p.gI_hi, p.gI_mid, p.w_bwd, false, p.g_x, nullptr, BT, p.H, p.W, st))) return rc;
   if (p.g_w_ff) return run_wgrad(p.x_cl, nullptr, p.gI_hi, p.gI_mid, false, BT, p.H, p.W, p.wg_partial, EF_WG_FINALIZE, p.g_w_ff, nullptr, st);
   return EF_OK;

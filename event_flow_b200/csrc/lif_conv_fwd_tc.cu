@@ -457,6 +457,26 @@ __global__ void split_weights_kernel(const float* __restrict__ w_ff, const float
   }
 }
 
+// Weight image of the HEAD layer for inputs packed by ef_pack_split_cl: input slot k = s*SL + c (s = 0..2) carries w[n][c][tap], every
+// other k is zero -- the tensor core then forms (x_hi + x_mid + x_lo) * (w_hi + w_mid + w_lo) from nine exact partial products.
+__global__ void split_weights_head_kernel(const float* __restrict__ w_ff, uint16_t* __restrict__ out, int Cin, int SL) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // over 32 (n) * 32 (k slot) * 9 (tap)
+  if (i >= 32 * 32 * 9) return;
+  const int tap = i % 9, k = (i / 9) % 32, n = i / (9 * 32);
+  const int c = k % SL, s = k / SL;
+  const float w = (s < 3 && c < Cin) ? w_ff[(n * Cin + c) * 9 + tap] : 0.f;
+  const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+  const float r1 = w - __bfloat162float(hi);
+  const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+  const __nv_bfloat16 lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+  const uint16_t parts[3] = {__bfloat16_as_ushort(hi), __bfloat16_as_ushort(mid), __bfloat16_as_ushort(lo)};
+  for (int sp = 0; sp < 3; ++sp) {
+    const int nn = sp * 32 + n, r = nn & 7;
+    const int chunk = (k >> 3) ^ ((r >> 1) & 3);
+    out[(size_t)tap * (W_BLOCK_BYTES / 2) + (nn >> 3) * 256 + r * 32 + chunk * 8 + (k & 7)] = parts[sp];
+  }
+}
+
 static long long* g_tc_trace = nullptr;  // set through ef_debug_tc_trace (tools/tc_timeline.py)
 static int g_tc_skip = 0;                // set through ef_debug_tc_skip (tools/tc_ablation.py)
 static int g_tc_cpt = 0;                 // channels per epilogue thread: 16 (8 epilogue warps), 8 (16 warps), 0 = per kernel kind; ef_debug_tc_cpt
@@ -544,6 +564,15 @@ extern "C" int ef_debug_tc_trace(long long* buf) {  // buf: device int64 [n_ctas
 extern "C" int64_t ef_split_weights_elems(int32_t Cin, int32_t C, int32_t has_rec) {
   if (Cin != 32 || C != 32) return 0;
   return (int64_t)(has_rec ? 2 : 1) * ef::W_CONV_BYTES / 2 + 8;  // + 16 bytes: the power-of-two scales of the two-term image
+}
+
+extern "C" int ef_split_weights_head(const float* w_ff, int32_t Cin, uint16_t* out, void* stream) {
+  using namespace ef;
+  static_assert(W_NSPLIT == 3, "the head image assumes the three-term weight split");
+  EF_REQUIRE(w_ff && out, EF_ENULL, "ef_split_weights_head: NULL tensor");
+  EF_REQUIRE(Cin > 0 && Cin <= EF_HEAD_MAX_CIN, EF_EUNSUPPORTED, "ef_split_weights_head: 1 <= Cin <= %d (got %d)", EF_HEAD_MAX_CIN, Cin);
+  split_weights_head_kernel<<<cdiv(32 * 32 * 9, 256), 256, 0, as_stream(stream)>>>(w_ff, out, Cin, EF_HEAD_SLOT(Cin));
+  return check_launch("split_weights_head_kernel");
 }
 
 extern "C" int ef_split_weights(const float* w_ff, const float* w_rec, int32_t Cin, int32_t C, uint16_t* out, void* stream) {

@@ -34,6 +34,7 @@ class _Carry:
         self.n = 0            # steps of the window so far
         self.prev = None      # (v, z) lists: the state the window started from (detached), entries may be None
         self.parity = None    # arena bank of the window
+        self.head_tc = False  # the head layer ran on the tensor cores (split input in bank.x_cl)
 
 
 class _Slot:
@@ -48,7 +49,8 @@ class _Slot:
         self.v = [bank.v[i][idx] for i in range(N_L)]
         self.z = [bank.zs[i][idx + 1] for i in range(N_L)]
         self.flow = bank.flow[idx]
-        self.x_in = None if bank.x_in is None else bank.x_in[idx]  # static copy of the model input (graph replay / head weight gradient)
+        self.x_in = None if bank.x_in is None else bank.x_in[idx]  # fp32 copy of the model input (legacy head kernels only)
+        self.x_cl = None if bank.x_cl is None else bank.x_cl[idx]  # the model input as exact bf16 hi/mid/lo split, channels-last
         self.graphs = {}
 
 
@@ -65,7 +67,8 @@ class _Bank:
         self.v = [torch.empty((cap, B, 32, H, W), device=dev, dtype=torch.float32) for _ in range(N_L)]
         self.zs = [torch.empty((cap + 1, B, H, W, 32), device=dev, dtype=torch.bfloat16) for _ in range(N_L)]
         self.flow = torch.empty((cap, B, 2, H, W), device=dev, dtype=torch.float32)
-        self.x_in = None
+        self.x_in = None   # [cap,B,Cin,H,W] fp32, allocated on demand
+        self.x_cl = None   # [cap,B,H,W,32] bf16 split input of the head layer (Cin <= 10), allocated on demand
         self.slots = []
 
     def slot(self, idx):
@@ -73,10 +76,14 @@ class _Bank:
             self.slots.append(_Slot(self, len(self.slots)))
         return self.slots[idx]
 
-    def need_input(self, cin):
-        if self.x_in is None or self.x_in.shape[2] != cin:
-            B, H, W, dev = self.key
-            self.x_in = torch.empty((self.cap, B, cin, H, W), device=dev, dtype=torch.float32)
+    def need_input(self, cin, f32, split):
+        B, H, W, dev = self.key
+        changed = False
+        if f32 and (self.x_in is None or self.x_in.shape[2] != cin):
+            self.x_in, changed = torch.empty((self.cap, B, cin, H, W), device=dev, dtype=torch.float32), True
+        if split and self.x_cl is None:
+            self.x_cl, changed = torch.empty((self.cap, B, H, W, 32), device=dev, dtype=torch.bfloat16), True
+        if changed:
             for i, s in enumerate(self.slots):
                 s.bind(self, i)
 
@@ -87,10 +94,12 @@ class _Bank:
             new.v[i][:n_used].copy_(self.v[i][:n_used])
             new.zs[i][:n_used + 1].copy_(self.zs[i][:n_used + 1])
         new.flow[:n_used].copy_(self.flow[:n_used])
+        new.need_input(0 if self.x_in is None else self.x_in.shape[2], self.x_in is not None, self.x_cl is not None)
         if self.x_in is not None:
-            new.need_input(self.x_in.shape[2])
             new.x_in[:n_used].copy_(self.x_in[:n_used])
-        self.cap, self.v, self.zs, self.flow, self.x_in = new.cap, new.v, new.zs, new.flow, new.x_in
+        if self.x_cl is not None:
+            new.x_cl[:n_used].copy_(self.x_cl[:n_used])
+        self.cap, self.v, self.zs, self.flow, self.x_in, self.x_cl = new.cap, new.v, new.zs, new.flow, new.x_in, new.x_cl
         for i, s in enumerate(self.slots):
             s.bind(self, i)
 
@@ -192,12 +201,21 @@ def _split_cache(model):
     cache = model.__dict__.setdefault("_w_split_cache", {})
     cells = _cells(model)
     # steady state (weights unchanged since the last call): one tuple comparison
-    sig = tuple(c.ff.weight._version for c in cells[1:]) + tuple(c.rec.weight._version for c in cells[1:] if c.recurrent) + (
+    sig = tuple(c.ff.weight._version for c in cells) + tuple(c.rec.weight._version for c in cells[1:] if c.recurrent) + (
         model.__dict__.get("_w_epoch", 0), cells[1].ff.weight.data_ptr())
     last = cache.get("__last__")
     if last is not None and last[0] == sig:
         return last[1]
     out = {}
+    head = cells[0]
+    if head.input_size <= L.EF_HEAD_MAX_CIN:  # head layer on the tensor cores: weight image for split inputs
+        key = (head.ff.weight._version, head.ff.weight.data_ptr(), model.__dict__.get("_w_epoch", 0))
+        hit = cache.get("head")
+        if hit is None or hit[0] != key:
+            same_dev = hit is not None and hit[1].device == head.ff.weight.device
+            hit = (key, ops.split_weights_head(head.ff.weight, out=hit[1] if same_dev else None))
+            cache["head"] = hit
+        out["head"] = hit[1]
     for name, cell in zip(LAYERS[1:], cells[1:]):
         rec = cell.rec.weight if cell.recurrent else None
         key = (cell.ff.weight._version, cell.ff.weight.data_ptr(), None if rec is None else rec._version, model.__dict__.get("_w_epoch", 0))
@@ -257,7 +275,10 @@ def _fill_fwd(p, B, Cin, H, W, cell, x_f32, x_cl, v_in, z_in, v_out, leak, thres
 
 
 def _launch_step(model, x, v_in, z_in, slot, splits, B, Cin0, H, W, only_hidden=False):
-    """The 8 kernels of one model step: head, 6 tensor-core cells, prediction head.  All tensors are caller-provided."""
+    """
+    The 8 kernels of one model step: head, 6 tensor-core cells, prediction head.  All tensors are caller-provided.
+    x: the fp32 network input (legacy CUDA-core head kernel) or None = the head runs on the tensor cores from slot.x_cl.
+    """
     h = None
     cells = _cells(model)
     for i, name in enumerate(LAYERS):
@@ -267,9 +288,12 @@ def _launch_step(model, x, v_in, z_in, slot, splits, B, Cin0, H, W, only_hidden=
         cell = cells[i]
         leak, thresh = cell.leak.detach().reshape(-1), cell.thresh.detach().reshape(-1)
         p = L.LifConvParams()
-        _fill_fwd(p, B, Cin0 if i == 0 else 32, H, W, cell, x if i == 0 else None, h, v_in[i], z_in[i], slot.v[i], leak, thresh)
+        if i == 0 and x is None:  # split input [B,H,W,32]: the 32 -> 32 tensor-core kernel with the head's weight image
+            _fill_fwd(p, B, 32, H, W, cell, None, slot.x_cl, v_in[i], z_in[i], slot.v[i], leak, thresh)
+        else:
+            _fill_fwd(p, B, Cin0 if i == 0 else 32, H, W, cell, x if i == 0 else None, h, v_in[i], z_in[i], slot.v[i], leak, thresh)
         p.z_out_cl = L.ptr(slot.z[i])
-        if i > 0:
+        if i > 0 or x is None:
             p.w_split = L.ptr(splits[name])
         L.call("ef_lif_conv_fwd", p, tag=(p.Cin, 32, cell.recurrent))
         h = slot.z[i]
@@ -295,9 +319,15 @@ def capture_window(model, xs, only_hidden=False):
     _cells(model)
     splits = _split_cache(model)
     bank = _Bank((B, H, W, x0.device), len(xs))
+    head_tc = "head" in splits
+    bank.need_input(Cin0, False, head_tc)
     slots = [bank.slot(t) for t in range(len(xs))]
     none = [None] * N_L
     xs = [x.contiguous() for x in xs]
+    if head_tc:
+        for t, x in enumerate(xs):
+            ops.pack_split_cl(x, out=slots[t].x_cl)
+        xs = [None] * len(xs)
     with torch.no_grad():
         _launch_step(model, xs[0], none, none, slots[0], splits, B, Cin0, H, W)
         for t in range(1, len(xs)):  # eager pass: fills every slot (the hidden-only replay needs the head spikes in place)
@@ -327,7 +357,11 @@ class _FireNetStep(torch.autograd.Function):
         bank = arena.bank(parity)
         if fs.step >= bank.cap:
             bank.grow(fs.step)
-        bank.need_input(Cin0)
+        # head layer: tensor cores on the exact bf16 split of the input (Cin <= 10); the fp32 copy is only kept for the legacy /
+        # step-by-step backward paths
+        head_tc = "head" in splits and model.__dict__.get("_tc_head", True)
+        keep_f32 = not head_tc or not (model.__dict__.get("_window_backward", True) and model.__dict__.get("_tc_backward", True))
+        bank.need_input(Cin0, keep_f32, head_tc)
         idx = fs.step
         slot = bank.slot(idx)
         fs.step += 1
@@ -340,26 +374,32 @@ class _FireNetStep(torch.autograd.Function):
             carry.prev, carry.parity = (v_in, z_in), parity
         carry.n = idx + 1
         cap = model.__dict__.get("_capture")
-        slot.x_in.copy_(x)  # fixed address: CUDA-graph replay of the step, and the window-wide weight gradient of the head layer
+        # the input moves to a fixed address (CUDA-graph replay of the step; the window-wide weight gradient of the head layer)
+        if keep_f32:
+            slot.x_in.copy_(x)
+        if head_tc:
+            ops.pack_split_cl(x, out=slot.x_cl)
+        x_step = None if head_tc else slot.x_in
+        carry.head_tc = head_tc
         use_graph = (model.__dict__.get("_use_graphs", True) and cap is None and L.PROFILE is None
                      and not torch.cuda.is_current_stream_capturing())
         if use_graph:
             if fs.param_sig is None:  # refreshed per sequence (reset_states) and whenever the module is moved (FireNet._apply)
-                fs.param_sig = (tuple(p.data_ptr() for p in _params_of(model)), tuple(splits[n].data_ptr() for n in LAYERS[1:]))
-            key = (fs.param_sig, tuple(0 if v is None else v.data_ptr() for v in v_in), slot.x_in.data_ptr())
+                fs.param_sig = (tuple(p.data_ptr() for p in _params_of(model)), tuple(splits[n].data_ptr() for n in LAYERS if n in splits))
+            key = (fs.param_sig, tuple(0 if v is None else v.data_ptr() for v in v_in), (slot.x_cl if head_tc else slot.x_in).data_ptr())
             g = slot.graphs.get(key)
             if g is None:
-                _launch_step(model, slot.x_in, v_in, z_in, slot, splits, B, Cin0, H, W)  # eager: results + lazy init
+                _launch_step(model, x_step, v_in, z_in, slot, splits, B, Cin0, H, W)  # eager: results + lazy init
                 g = torch.cuda.CUDAGraph()
                 # thread_local: other threads (the NCCL watchdog under data parallelism) keep issuing CUDA calls during a capture
                 with torch.cuda.graph(g, capture_error_mode="thread_local"):
-                    _launch_step(model, slot.x_in, v_in, z_in, slot, splits, B, Cin0, H, W)
+                    _launch_step(model, x_step, v_in, z_in, slot, splits, B, Cin0, H, W)
                 slot.graphs[key] = g
             else:
                 g.replay()
                 L.GRAPH_KERNELS += N_L + 1
         else:
-            _launch_step(model, slot.x_in, v_in, z_in, slot, splits, B, Cin0, H, W)
+            _launch_step(model, x_step, v_in, z_in, slot, splits, B, Cin0, H, W)
         for i, name in enumerate(LAYERS):
             if cap is not None:  # test hook: what this layer consumed and produced, in the reference's tensor format
                 xin = x if i == 0 else ops.unpack_cl(slot.z[i - 1])
@@ -481,7 +521,10 @@ def _window_backward(model, arena, carry, shapes):
             q.v, q.v_prev, q.g_out = L.ptr(bank.v[i][:Tn]), L.ptr(v0[i]), L.ptr(g_out[:Tn])
             q.leak, q.thresh = L.ptr(leak), L.ptr(thresh)
             q.g_w_ff, q.g_leak, q.g_thresh = L.ptr(g_ff), L.ptr(g_leak), L.ptr(g_thresh)
-            if i == 0:
+            if i == 0 and carry.head_tc:  # split-input head: tensor-core weight gradient, no data gradient
+                q.Cin, q.x_cl = Cin0, L.ptr(bank.x_cl[:Tn])
+                q.gI_hi, q.gI_mid, q.wg_partial = L.ptr(buf["gI_hi"][:Tn]), L.ptr(buf["gI_mid"][:Tn]), L.ptr(buf["wg"])
+            elif i == 0:
                 q.Cin, q.x_f32, q.gI_f32 = Cin0, L.ptr(bank.x_in[:Tn]), L.ptr(g_x[:Tn])  # (the other ping-pong buffer is free: nothing below the head)
             else:
                 q.x_cl, q.w_bwd = L.ptr(bank.zs[i - 1][1:Tn + 1]), L.ptr(splits[LAYERS[i] + ".bwd"])

@@ -472,6 +472,31 @@ def pack_cl(x):
     return out
 
 
+def pack_split_cl(x, out=None):
+    """fp32 NCHW [B,Cin<=10,H,W] -> bf16 cl [B,H,W,32] holding the exact hi/mid/lo split of every value (ef_pack_split_cl)."""
+    x = _c(x)
+    _need_cuda(x)
+    _need_f32(x)
+    B, Cin, H, W = x.shape
+    if out is None:
+        out = torch.empty((B, H, W, 32), device=x.device, dtype=torch.bfloat16)
+    L.LAUNCHES += 1
+    L.check(L.lib().ef_pack_split_cl(L.ptr(x), L.ptr(out), B, Cin, H, W, L.stream()), "ef_pack_split_cl")
+    return out
+
+
+def split_weights_head(w_ff, out=None):
+    """Weight image of the head layer for inputs packed by pack_split_cl (ef_split_weights_head)."""
+    w_ff = _c(w_ff.detach())
+    _need_cuda(w_ff)
+    n = L.lib().ef_split_weights_elems(32, 32, 0)
+    if out is None or out.numel() != n:
+        out = torch.empty(n, device=w_ff.device, dtype=torch.int16)
+    L.LAUNCHES += 1
+    L.check(L.lib().ef_split_weights_head(L.ptr(w_ff), w_ff.shape[1], L.ptr(out), L.stream()), "ef_split_weights_head")
+    return out
+
+
 def unpack_cl(x):
     """bf16 channels-last [B,H,W,C] -> fp32 NCHW."""
     x = _c(x)

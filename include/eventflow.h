@@ -182,7 +182,8 @@ int64_t ef_split_weights_bwd_elems(int32_t has_rec);
  * loop INSIDE the kernel -- dL/dv stays in registers from step to step, every membrane tensor is read once; (2) the tensor-core data
  * gradient and (3) the tensor-core weight gradient over T*B images at once.  Tensors hold the window step-major and dense:
  * x_cl / z_cl / gI_* [T,B,H,W,32], v / g_out / g_x [T,B,32,H,W]; the state before step 0 comes separately (NULL = zero state).
- * Head mode (x_f32 != NULL): the Cin <= 8 input cell, x_f32 [T,B,Cin,H,W], gI_f32 [T,B,32,H,W] workspace, no data gradient. */
+ * Head mode (x_f32 != NULL): the Cin <= 8 input cell, x_f32 [T,B,Cin,H,W], gI_f32 [T,B,32,H,W] workspace, no data gradient.
+ * Split-input head (x_f32 == NULL, 0 < Cin < 32): x_cl [T,B,H,W,32] from ef_pack_split_cl, weight gradient on the tensor cores. */
 typedef struct ef_lif_bwd_window_params {
   int32_t B, T, H, W, hard_reset, surrogate;
   float act_width;
@@ -203,7 +204,7 @@ typedef struct ef_lif_bwd_window_params {
   float* g_leak;                 /* [32] += or NULL                                                                     */
   float* g_thresh;               /* [32] += or NULL                                                                     */
   float* wg_partial;             /* ef_lif_wgrad_partial_elems(T*B, H, W, 0) floats (needed with g_w_ff, not in head mode) */
-  int32_t Cin;                   /* head mode: input channels                                                           */
+  int32_t Cin;                   /* head modes: input channels of the head layer (0 = a 32 -> 32 cell)                  */
   const float* x_f32;            /* head mode: [T,B,Cin,H,W]                                                            */
   float* gI_f32;                 /* head mode: [T,B,32,H,W] workspace                                                   */
 } ef_lif_bwd_window_params;
@@ -241,6 +242,17 @@ int ef_upsample_nearest(const float* src, float* dst, int64_t n_planes, int32_t 
 /* Their adjoints (what autograd derives for the two F.interpolate calls): g_dst has the upsampled shape, g_src [n_planes,H,W]. */
 int ef_upsample_bilinear2x_bwd(const float* g_dst, float* g_src, int64_t n_planes, int32_t H, int32_t W, void* stream);
 int ef_upsample_nearest_bwd(const float* g_dst, float* g_src, int64_t n_planes, int32_t H, int32_t W, int32_t fy, int32_t fx, void* stream);
+
+/* Head layer (Cin <= EF_HEAD_MAX_CIN fractional fp32 inputs: voxel grids) on the tensor-core cell kernel with fp32-exact products:
+ * ef_pack_split_cl turns x [B,Cin,H,W] into a cl tensor [B,H,W,32] whose channel s*EF_HEAD_SLOT(Cin) + c holds term s (hi, mid, lo) of
+ * the exact three-way bf16 split of x[.,c] (hi + mid + lo == x), ef_split_weights_head builds the matching weight image (w[.,c] repeated
+ * in the three slots of c; out: uint16[ef_split_weights_elems(32, 32, 0)]).  ef_lif_conv_fwd is then called with Cin = 32, x_cl = the packed
+ * tensor, w_split = that image; ef_lif_bwd_window with 0 < Cin < 32 and the packed x_cl computes the head's weight gradient on the
+ * tensor cores (no data gradient). */
+#define EF_HEAD_MAX_CIN 10
+#define EF_HEAD_SLOT(cin) ((cin) <= 8 ? 8 : 10)
+int ef_pack_split_cl(const float* src, uint16_t* dst, int32_t B, int32_t Cin, int32_t H, int32_t W, void* stream);
+int ef_split_weights_head(const float* w_ff, int32_t Cin, uint16_t* out, void* stream);
 
 /* fp32 NCHW <-> cl bf16 layout conversion at the API boundary (model.states getter/setter, first input). */
 int ef_pack_cl(const float* src, uint16_t* dst, int32_t B, int32_t C, int32_t H, int32_t W, void* stream);

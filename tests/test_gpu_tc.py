@@ -183,3 +183,65 @@ def test_tc_weight_gradient_is_bit_reproducible():
     for _ in range(10):
         again = ops.lif_bwd_cl(*args, tc_wgrad=True)
         assert torch.equal(again["g_w_ff"], first["g_w_ff"]) and torch.equal(again["g_w_rec"], first["g_w_rec"])
+
+
+@pytest.mark.parametrize("cin", [1, 2, 5, 10])
+def test_head_layer_on_tensor_cores_split_input(cin):
+    """
+    Head layer (fractional fp32 voxel inputs, Cin <= 10) through the tensor-core cell kernel: ef_pack_split_cl writes the exact
+    hi/mid/lo bf16 split of the input, ef_split_weights_head the weight image with w[.,c] in the three slots of c -> nine exact
+    partial products per (input, weight) pair, fp32 accumulate.  Split exactness bit for bit; membrane / spikes vs the CPU oracle
+    and vs the fp32 CUDA-core head kernel within the T1 band; weight gradient through ef_lif_bwd_window vs oracle autograd.
+    """
+    from event_flow_b200 import _lib as L
+    from event_flow_b200 import ops
+
+    B, H, W = 2, 37, 52
+    g = torch.Generator().manual_seed(cin)
+    params = osp.init_firenet_params("lif", cin, 32, seed=cin, weight_gain=3.0)["head"]
+    x = torch.randn((B, cin, H, W), generator=g) * (torch.rand((B, cin, H, W), generator=g) < 0.4)
+    x[0, 0, 0, :4] = torch.tensor([1.0, 3.0e-5, -0.333333343267, 1.0e-30])[: min(4, W)]
+    st = torch.rand((2, B, 32, H, W), generator=g) * 1.2 - 0.1
+    st[1] = (st[1] < 0.3).float()
+    pd = {k: v.to(DEV).contiguous() for k, v in params.items()}
+    x_cl = ops.pack_split_cl(x.to(DEV))
+    assert x_cl.shape == (B, H, W, 32) and x_cl.dtype == torch.bfloat16
+    SL = 8 if cin <= 8 else 10
+    parts = x_cl.float().cpu()
+    rebuilt = parts[..., 0:cin] + parts[..., SL:SL + cin] + parts[..., 2 * SL:2 * SL + cin]  # (hi + mid) + lo is exact in fp32
+    assert torch.equal(rebuilt.permute(0, 3, 1, 2), x) or torch.equal((parts[..., 0:cin].double() + parts[..., SL:SL + cin].double()
+                                                                      + parts[..., 2 * SL:2 * SL + cin].double()).float().permute(0, 3, 1, 2), x)
+    assert parts[..., 3 * SL:].abs().max() == 0
+    w_head = ops.split_weights_head(pd["ff"])
+    leak, thresh = pd["leak"].reshape(-1), pd["thresh"].reshape(-1)
+    v_in, z_in = st[0].to(DEV).contiguous(), ops.pack_cl(st[1].to(DEV))
+    v_tc, z_tc = ops.lif_step_cl(x_cl, v_in, z_in, pd["ff"], None, leak, thresh, hard_reset=True, w_split=w_head)
+    v_cc, z_cc = ops.lif_step_cl(None, v_in, z_in, pd["ff"], None, leak, thresh, hard_reset=True, x_f32=x.to(DEV))
+    thr = params["thresh"].clamp_min(0.01)
+    z_tc_f = ops.unpack_cl(z_tc).cpu()
+    spike_band_compare(v_tc.cpu(), z_tc_f, v_cc.cpu(), ops.unpack_cl(z_cc).cpu(), thr)
+    xo = x.clone()
+    po = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    out_o, ns_o = osp.cell_step("lif", xo, st, po, hard_reset=True)
+    spike_band_compare(v_tc.cpu(), z_tc_f, ns_o[0].detach(), ns_o[1].detach(), thr)
+    assert z_tc_f.mean() > 0.02
+    # weight gradient of the head on the tensor cores (one-step window)
+    g_out = torch.rand((B, 32, H, W), generator=g)
+    (out_o * g_out).sum().backward()
+    q = L.LifBwdWindowParams()
+    q.B, q.T, q.H, q.W, q.hard_reset, q.surrogate, q.act_width = B, 1, H, W, 1, 0, 10.0
+    g_w = torch.zeros_like(pd["ff"])
+    g_leak, g_thresh = torch.zeros(32, device=DEV), torch.zeros(32, device=DEV)
+    gI_hi = torch.empty((B, H, W, 32), device=DEV, dtype=torch.bfloat16)
+    gI_mid = torch.empty_like(gI_hi)
+    wg = torch.empty(L.lib().ef_lif_wgrad_partial_elems(B, H, W, 0), device=DEV)
+    god = g_out.to(DEV)
+    q.Cin, q.x_cl, q.z_prev_cl, q.v, q.v_prev, q.g_out = cin, L.ptr(x_cl), L.ptr(z_in), L.ptr(v_tc), L.ptr(v_in), L.ptr(god)
+    q.leak, q.thresh, q.gI_hi, q.gI_mid, q.wg_partial = L.ptr(leak), L.ptr(thresh), L.ptr(gI_hi), L.ptr(gI_mid), L.ptr(wg)
+    q.g_w_ff, q.g_leak, q.g_thresh = L.ptr(g_w), L.ptr(g_leak), L.ptr(g_thresh)
+    L.call("ef_lif_bwd_window", q)
+    from tests.util import assert_rel
+
+    assert_rel(g_w, po["ff"].grad, 1e-3, "head g_w_ff (tensor cores)")
+    assert_rel(g_leak, po["leak"].grad.reshape(-1), 1e-3, "head g_leak")
+    assert_rel(g_thresh, po["thresh"].grad.reshape(-1), 1e-3, "head g_thresh")
