@@ -133,17 +133,23 @@ __global__ void __launch_bounds__(PWC_THREADS) lif_bwd_pointwise_window_kernel(c
     red[k] = red[PWC_CB + k] = 0.f;
     v_n[k] = __ldg(p.v + (size_t)(p.T - 1) * sv + ov + k * hw);
   }
-  for (int t = p.T - 1; t >= 0; --t) {
-    float v_p[PWC_CB], g_o[PWC_CB];
-    uint4 zq = make_uint4(0, 0, 0, 0);
-    if (t > 0) zq = __ldg(reinterpret_cast<const uint4*>(p.z_cl + (size_t)(t - 1) * sz + oz));
-    else if (p.z_prev_cl) zq = __ldg(reinterpret_cast<const uint4*>(p.z_prev_cl + oz));
+  // software pipeline: the loads of step t-1 are issued before step t is computed (one more memory round trip in flight per thread)
+  float v_p[PWC_CB], g_o[PWC_CB], v_q[PWC_CB], g_q[PWC_CB];
+  uint4 zq = make_uint4(0, 0, 0, 0), zq_q = make_uint4(0, 0, 0, 0);
+  auto load_step = [&](int t, float (&vp_)[PWC_CB], float (&go_)[PWC_CB], uint4& z_) {
+    z_ = make_uint4(0, 0, 0, 0);
+    if (t > 0) z_ = __ldg(reinterpret_cast<const uint4*>(p.z_cl + (size_t)(t - 1) * sz + oz));
+    else if (p.z_prev_cl) z_ = __ldg(reinterpret_cast<const uint4*>(p.z_prev_cl + oz));
     const float* vp = t > 0 ? p.v + (size_t)(t - 1) * sv : p.v_prev;
 #pragma unroll
     for (int k = 0; k < PWC_CB; ++k) {
-      v_p[k] = vp ? __ldg(vp + ov + k * hw) : 0.f;
-      g_o[k] = __ldg(p.g_out + (size_t)t * sv + ov + k * hw);
+      vp_[k] = vp ? __ldg(vp + ov + k * hw) : 0.f;
+      go_[k] = __ldg(p.g_out + (size_t)t * sv + ov + k * hw);
     }
+  };
+  load_step(p.T - 1, v_p, g_o, zq);
+  for (int t = p.T - 1; t >= 0; --t) {
+    if (t > 0) load_step(t - 1, v_q, g_q, zq_q);
     const uint32_t zw[4] = {zq.x, zq.y, zq.z, zq.w};
     uint32_t hi[PWC_CB / 2], mid[PWC_CB / 2];
 #pragma unroll
@@ -171,6 +177,9 @@ __global__ void __launch_bounds__(PWC_THREADS) lif_bwd_pointwise_window_kernel(c
       *reinterpret_cast<uint4*>(p.gI_hi + (size_t)t * sz + oz) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
       *reinterpret_cast<uint4*>(p.gI_mid + (size_t)t * sz + oz) = make_uint4(mid[0], mid[1], mid[2], mid[3]);
     }
+#pragma unroll
+    for (int k = 0; k < PWC_CB; ++k) v_p[k] = v_q[k], g_o[k] = g_q[k];
+    zq = zq_q;
   }
   if (p.g_v_prev && live) {
 #pragma unroll
