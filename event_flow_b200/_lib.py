@@ -53,6 +53,20 @@ class LifBwdTcParams(C.Structure):
 
 
 EF_WG_ACCUMULATE, EF_WG_FINALIZE = 1, 2
+EF_TCG_MAX_SRC = 4
+
+
+class WSrc(C.Structure):
+    _fields_ = [("w", _f32p), ("c_total", _i32), ("ch0", _i32), ("n", _i32), ("split", _i32)]
+
+
+class LifConvGParams(C.Structure):
+    _fields_ = [
+        ("B", _i32), ("H", _i32), ("W", _i32), ("C", _i32), ("n_src", _i32), ("hard_reset", _i32),
+        ("src", _f32p * EF_TCG_MAX_SRC), ("src_c", _i32 * EF_TCG_MAX_SRC),
+        ("v_in", _f32p), ("z_in_cl", _f32p), ("residual_cl", _f32p), ("leak", _f32p), ("thresh", _f32p), ("w_image", _f32p),
+        ("v_out", _f32p), ("z_out_cl", _f32p), ("out_cl", _f32p),
+    ]  # fmt: skip
 
 
 class LifBwdWindowParams(C.Structure):
@@ -161,6 +175,9 @@ EXPORTS = {
     "ef_lif_bwd_window": (C.c_int, [C.POINTER(LifBwdWindowParams), C.c_void_p]),
     "ef_lif_wgrad_tc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, _i32, _i32, _i32, _i32, C.c_void_p, _i32, C.c_void_p, C.c_void_p,
                                   C.c_void_p]),
+    "ef_split_weights_g_elems": (C.c_int64, [_i32, _i32, C.POINTER(WSrc)]),
+    "ef_split_weights_g": (C.c_int, [C.POINTER(WSrc), _i32, _i32, C.c_void_p, C.c_void_p]),
+    "ef_lif_conv_fwd_g": (C.c_int, [C.POINTER(LifConvGParams), C.c_void_p]),
     "ef_split_weights_bwd_elems": (C.c_int64, [_i32]),
     "ef_lif_wgrad_partial_elems": (C.c_int64, [_i32, _i32, _i32, _i32]),
     "ef_split_weights_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -215,4 +215,62 @@ inline int get_map_v(const void* ptr, int B, int H, int W, int rows, int cols, C
   return EF_OK;
 }
 
+// General channel counts (multiples of 32): channels-last bf16 [B,H,W,C], box = 32 channels x cols px x rows; and the membrane
+// tensor fp32 NCHW [B,C,H,W], box = cols px x rows x 32 channels.  The channel offset of a box is a TMA coordinate.
+struct MapKeyC {
+  const void* ptr;
+  int B, H, W, C, kind;
+  bool operator==(const MapKeyC& o) const { return ptr == o.ptr && B == o.B && H == o.H && W == o.W && C == o.C && kind == o.kind; }
+};
+struct MapKeyCHash {
+  size_t operator()(const MapKeyC& k) const {
+    return std::hash<const void*>()(k.ptr) ^ (size_t)(k.B * 1000003u) ^ ((size_t)k.H << 20) ^ ((size_t)k.W << 8) ^ ((size_t)k.C << 32) ^ (size_t)k.kind;
+  }
+};
+
+inline int get_map_c(const void* ptr, int B, int H, int W, int C, int rows, int cols, bool swizzled, CUtensorMap* out) {
+  static thread_local std::unordered_map<MapKeyC, CUtensorMap, MapKeyCHash> cache;
+  const MapKeyC key{ptr, B, H, W, C, rows * 256 + cols * 2 + (swizzled ? 1 : 0)};
+  auto it = cache.find(key);
+  if (it != cache.end()) {
+    *out = it->second;
+    return EF_OK;
+  }
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return fail(EF_EUNSUPPORTED, "cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  const cuuint32_t box[4] = {32, (cuuint32_t)cols, (cuuint32_t)rows, 1};
+  const cuuint32_t es[4] = {1, 1, 1, 1};
+  const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         swizzled ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(EF_EINVAL, "cuTensorMapEncodeTiled failed (CUresult %d), B=%d H=%d W=%d C=%d ptr=%p", (int)r, B, H, W, C, ptr);
+  if (cache.size() > 4096) cache.clear();
+  cache.emplace(key, *out);
+  return EF_OK;
+}
+
+inline int get_map_vc(const void* ptr, int B, int H, int W, int C, int rows, int cols, CUtensorMap* out) {
+  static thread_local std::unordered_map<MapKeyC, CUtensorMap, MapKeyCHash> cache;
+  const MapKeyC key{ptr, B, H, W, C, rows * 256 + cols};
+  auto it = cache.find(key);
+  if (it != cache.end()) {
+    *out = it->second;
+    return EF_OK;
+  }
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return fail(EF_EUNSUPPORTED, "cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)C, (cuuint64_t)B};
+  const cuuint64_t strides[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)C * H * W * 4};
+  const cuuint32_t box[4] = {(cuuint32_t)cols, (cuuint32_t)rows, 32, 1};
+  const cuuint32_t es[4] = {1, 1, 1, 1};
+  const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(EF_EINVAL, "cuTensorMapEncodeTiled (membrane) failed (CUresult %d), B=%d H=%d W=%d C=%d ptr=%p", (int)r, B, H, W, C, ptr);
+  if (cache.size() > 4096) cache.clear();
+  cache.emplace(key, *out);
+  return EF_OK;
+}
+
 }  // namespace ef

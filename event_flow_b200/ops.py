@@ -538,6 +538,50 @@ def split_weights_bwd(w_ff, w_rec=None, out=None):
     return out
 
 
+def split_weights_g(sources, C):
+    """
+    Weight image of a general tensor-core cell (ef_split_weights_g).  sources: list of (weight [C,c_total,3,3], ch0, n, split) -- the
+    channel slices of the conv weights that multiply each input source, in input order.  Returns (image, list of source channel counts).
+    """
+    n = len(sources)
+    arr = (L.WSrc * n)()
+    keep = []
+    for i, (w, ch0, cnt, split) in enumerate(sources):
+        w = _c(w.detach())
+        _need_cuda(w)
+        _need_f32(w)
+        keep.append(w)
+        arr[i].w, arr[i].c_total, arr[i].ch0, arr[i].n, arr[i].split = L.ptr(w), w.shape[1], int(ch0), int(cnt), int(bool(split))
+    elems = L.lib().ef_split_weights_g_elems(C, n, arr)
+    if elems <= 0:
+        raise L.EventFlowError("split_weights_g: unsupported shape (C must be a multiple of 32)")
+    out = torch.empty(elems, device=keep[0].device, dtype=torch.int16)
+    L.LAUNCHES += 1
+    L.check(L.lib().ef_split_weights_g(arr, n, C, L.ptr(out), L.stream()), "ef_split_weights_g")
+    return out
+
+
+def lif_step_g(srcs, v_in, z_in_cl, w_image, leak, thresh, C, *, hard_reset=True, residual_cl=None):
+    """
+    One fused conv + LIF step of a general-channel cell on the tensor cores (ef_lif_conv_fwd_g).  srcs: cl bf16 tensors [B,H,W,c_s]
+    (c_s multiples of 32) in the order of the weight image's sources.  Returns (v_out fp32 NCHW, z_out cl, out cl | None).  No autograd.
+    """
+    B, H, W, _ = srcs[0].shape
+    dev = srcs[0].device
+    v_out = torch.empty((B, C, H, W), device=dev, dtype=torch.float32)
+    z_out = torch.empty((B, H, W, C), device=dev, dtype=torch.bfloat16)
+    out = torch.empty_like(z_out) if residual_cl is not None else None
+    p = L.LifConvGParams()
+    p.B, p.H, p.W, p.C, p.n_src, p.hard_reset = B, H, W, C, len(srcs), int(hard_reset)
+    for i, s in enumerate(srcs):
+        p.src[i], p.src_c[i] = L.ptr(s), s.shape[3]
+    p.v_in, p.z_in_cl, p.residual_cl = L.ptr(v_in), L.ptr(z_in_cl), L.ptr(residual_cl)
+    p.leak, p.thresh, p.w_image = L.ptr(leak), L.ptr(thresh), L.ptr(w_image)
+    p.v_out, p.z_out_cl, p.out_cl = L.ptr(v_out), L.ptr(z_out), L.ptr(out)
+    L.call("ef_lif_conv_fwd_g", p)
+    return v_out, z_out, out
+
+
 def lif_step_cl(x_cl, v_in, z_in_cl, w_ff, w_rec, leak, thresh, *, hard_reset=True, w_split=None, x_f32=None):
     """
     One fused conv + LIF step on the internal formats: spikes bf16 channels-last [B,H,W,C], membrane fp32 NCHW.

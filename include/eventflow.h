@@ -222,6 +222,48 @@ int ef_split_weights_bwd(const float* w_ff, const float* w_rec, uint16_t* out, v
 int64_t ef_split_weights_elems(int32_t Cin, int32_t C, int32_t has_rec);
 int ef_split_weights(const float* w_ff, const float* w_rec, int32_t Cin, int32_t C, uint16_t* out, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Fused conv3x3 + LIF step on the tensor cores for GENERAL channel counts and several concatenated input sources: the cells of the
+ * EV-FlowNet family (models/unet.py:418-465 with spiking_submodules.py:878-1013; ConvLIF / ConvLIFRecurrent at 64..512 channels,
+ * residual blocks, decoders on cat[prediction, x, skip]).  Stride 1, kernel 3, LIF, C a multiple of 32, W a multiple of 4.
+ *   I      = sum over sources s of conv(src[s], W_s)          (the recurrent convolution of a ConvLIFRecurrent is one more source:
+ *            src = z_in_cl, W = rec.weight; the channel concat of a decoder is never materialised)
+ *   v_out  = LIF update of (v_in, z_in_cl) with I; z_out = (v_out - thresh > 0); out = z_out + residual (optional)
+ * Sources are cl bf16 tensors [B,H,W,src_c[s]] with src_c a multiple of 32 (unused channels zero) whose values are EXACT in bf16
+ * (spikes, residual sums, their bilinear x2 upsampling, event counts); a fractional fp32 source is passed as its exact hi/mid/lo
+ * split (ef_pack_split_cl, src_c = 32).  The weights come as one image built by ef_split_weights_g from the same source list
+ * (three exact bf16 terms per weight, tcgen05 B-operand layout, blocked [C/32][K/32]); products are fp32-exact.
+ * ------------------------------------------------------------------------------------------------------------------ */
+#define EF_TCG_MAX_SRC 4
+typedef struct ef_wsrc {
+  const float* w;                /* fp32 conv weight [C, c_total, 3, 3] this source's channels are a slice of            */
+  int32_t c_total;               /* input channels of that weight tensor                                              */
+  int32_t ch0, n;                /* first channel and channel count of the slice                                      */
+  int32_t split;                 /* 1: the source tensor is an ef_pack_split_cl split (n <= EF_HEAD_MAX_CIN)            */
+} ef_wsrc;
+/* out: uint16[ef_split_weights_g_elems(C, n_src, srcs)] */
+int64_t ef_split_weights_g_elems(int32_t C, int32_t n_src, const ef_wsrc* srcs);
+int ef_split_weights_g(const ef_wsrc* srcs, int32_t n_src, int32_t C, uint16_t* out, void* stream);
+
+typedef struct ef_lif_conv_g_params {
+  int32_t B, H, W, C;            /* outputs: membrane [B,C,H,W] fp32, spikes [B,H,W,C] cl                              */
+  int32_t n_src;                 /* 1..EF_TCG_MAX_SRC input sources, in the order given to ef_split_weights_g          */
+  int32_t hard_reset;
+  const uint16_t* src[EF_TCG_MAX_SRC];  /* [B,H,W,src_c[s]] cl                                                         */
+  int32_t src_c[EF_TCG_MAX_SRC]; /* channels of each source tensor, multiples of 32                                   */
+  const float* v_in;             /* [B,C,H,W] or NULL (zero state; then z_in_cl is NULL too)                           */
+  const uint16_t* z_in_cl;       /* [B,H,W,C] previous spikes (reset term) or NULL                                     */
+  const uint16_t* residual_cl;   /* [B,H,W,C] or NULL                                                                  */
+  const float* leak;             /* [C] raw parameters                                                                 */
+  const float* thresh;           /* [C]                                                                                */
+  const uint16_t* w_image;       /* ef_split_weights_g image                                                           */
+  float* v_out;                  /* [B,C,H,W]                                                                          */
+  uint16_t* z_out_cl;            /* [B,H,W,C]                                                                          */
+  uint16_t* out_cl;              /* [B,H,W,C] = z_out + residual (given iff residual_cl is)                            */
+} ef_lif_conv_g_params;
+
+int ef_lif_conv_fwd_g(const ef_lif_conv_g_params* p, void* stream);
+
 /* Debug aid: subsequent tensor-core launches write a per-CTA clock64 timeline into buf (device int64 [n_ctas][32][8]);
  * NULL switches it off (default).  Not part of the reference's interface. */
 int ef_debug_tc_trace(long long* buf);

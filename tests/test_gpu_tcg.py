@@ -1,0 +1,119 @@
+"""
+GPU parity of the general-channel tensor-core cell (ef_lif_conv_fwd_g: K / N blocked, several concatenated sources, streamed
+weights) against the CPU oracle: the cell shapes of the EV-FlowNet family.  Tolerances as T1: |dv| <= max(2e-5, 3e-6 max|v|)
+(x sqrt(K/576) for longer sums), spikes exact outside that band.
+"""
+import math
+
+import pytest
+import torch
+
+from oracle import spiking as osp
+from tests.util import spike_band_compare
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def lif_params(cin, c, rec, seed, gain=2.0):
+    g = torch.Generator().manual_seed(seed)
+    p = {"ff": (torch.rand((c, cin, 3, 3), generator=g) * 2 - 1) * math.sqrt(1 / cin) * gain,
+         "leak": torch.randn((c, 1, 1), generator=g) * 0.1 - 4.0, "thresh": torch.randn((c, 1, 1), generator=g) * 0.1 + 0.8}
+    if rec:
+        p["rec"] = (torch.rand((c, c, 3, 3), generator=g) * 2 - 1) * math.sqrt(1 / c) * gain
+    return p
+
+
+def pad_cl(x, ops):
+    """fp32 NCHW with any channel count -> cl bf16 with the channels zero-padded to a multiple of 32."""
+    B, C, H, W = x.shape
+    Cp = (C + 31) // 32 * 32
+    if Cp != C:
+        x = torch.cat([x, torch.zeros(B, Cp - C, H, W)], 1)
+    return ops.pack_cl(x.to(DEV))
+
+
+def check(v, z, ns_o, thr, K):
+    scale = max(1.0, math.sqrt(K / 576))
+    v_atol = scale * max(2e-5, 3e-6 * ns_o[0].abs().max().item())
+    spike_band_compare(v.cpu(), z, ns_o[0], ns_o[1], thr, v_atol=v_atol)
+
+
+@pytest.mark.parametrize("C,shape", [(64, (2, 37, 52)), (128, (1, 32, 32)), (512, (1, 16, 16))])
+@pytest.mark.parametrize("hard", [True, False])
+@pytest.mark.parametrize("with_state", [True, False])
+def test_recurrent_cell_general_channels(C, shape, hard, with_state):
+    """ConvLIFRecurrent C -> C (encoder stages of the spiking U-Net): the recurrent convolution is a second input source."""
+    from event_flow_b200 import ops
+
+    B, H, W = shape
+    g = torch.Generator().manual_seed(C + H)
+    p = lif_params(C, C, True, C)
+    x = (torch.rand((B, C, H, W), generator=g) < 0.25).float()
+    st = None
+    if with_state:
+        st = torch.rand((2, B, C, H, W), generator=g) * 1.2 - 0.1
+        st[1] = (st[1] < 0.3).float()
+    pd = {k: v.to(DEV).contiguous() for k, v in p.items()}
+    x_cl = ops.pack_cl(x.to(DEV))
+    v_in = z_in = None
+    srcs, wsrcs = [x_cl], [(pd["ff"], 0, C, False)]
+    if st is not None:
+        v_in, z_in = st[0].to(DEV).contiguous(), ops.pack_cl(st[1].to(DEV))
+        srcs.append(z_in)
+        wsrcs.append((pd["rec"], 0, C, False))
+    img = ops.split_weights_g(wsrcs, C)
+    v, z, _ = ops.lif_step_g(srcs, v_in, z_in, img, pd["leak"].reshape(-1), pd["thresh"].reshape(-1), C, hard_reset=hard)
+    out_o, ns_o = osp.cell_step("lif", x, st, p, hard_reset=hard)
+    zf = ops.unpack_cl(z).cpu()
+    check(v, zf, ns_o, p["thresh"].clamp_min(0.01), 9 * C * (2 if st is not None else 1))
+    assert zf.mean() > 0.01
+
+
+@pytest.mark.parametrize("hard", [True, False])
+def test_decoder_cell_three_sources_with_fractional_flow(hard):
+    """
+    Decoder stage (unet.py:451-462): input = cat[upsampled prediction (2 fractional fp32 channels), upsampled x, upsampled skip];
+    the concat is never built: three sources, the prediction as an exact hi/mid/lo split with the weight rows repeated per slot.
+    """
+    from event_flow_b200 import ops
+
+    B, H, W, Cx, C = 2, 40, 48, 64, 32
+    g = torch.Generator().manual_seed(3)
+    p = lif_params(2 + 2 * Cx, C, False, 5, gain=1.5)
+    pred = torch.tanh(torch.randn((B, 2, H, W), generator=g))                           # fractional
+    xu = torch.randint(0, 33, (B, Cx, H, W), generator=g).float() / 16.0 * (torch.rand((B, Cx, H, W), generator=g) < 0.3)   # k/16
+    sk = torch.randint(0, 17, (B, Cx, H, W), generator=g).float() / 16.0 * (torch.rand((B, Cx, H, W), generator=g) < 0.3)
+    st = torch.rand((2, B, C, H, W), generator=g) * 1.2 - 0.1
+    st[1] = (st[1] < 0.3).float()
+    pd = {k: v.to(DEV).contiguous() for k, v in p.items()}
+    srcs = [ops.pack_split_cl(pred.to(DEV)), ops.pack_cl(xu.to(DEV)), ops.pack_cl(sk.to(DEV))]
+    img = ops.split_weights_g([(pd["ff"], 0, 2, True), (pd["ff"], 2, Cx, False), (pd["ff"], 2 + Cx, Cx, False)], C)
+    v_in, z_in = st[0].to(DEV).contiguous(), ops.pack_cl(st[1].to(DEV))
+    v, z, _ = ops.lif_step_g(srcs, v_in, z_in, img, pd["leak"].reshape(-1), pd["thresh"].reshape(-1), C, hard_reset=hard)
+    out_o, ns_o = osp.cell_step("lif", torch.cat([pred, xu, sk], 1), st, p, hard_reset=hard)
+    zf = ops.unpack_cl(z).cpu()
+    check(v, zf, ns_o, p["thresh"].clamp_min(0.01), 9 * (2 + 2 * Cx))
+    assert zf.mean() > 0.01
+
+
+def test_residual_cell_and_channel_padding():
+    """Second cell of a spiking residual block (spiking_submodules.py:933-975): out = spikes + block input; C = 96 (three output
+    blocks), a source whose channel count is not a multiple of 32 (zero-padded tensor, `n` real channels in the weight slice)."""
+    from event_flow_b200 import ops
+
+    B, H, W, C, Cin = 2, 24, 36, 96, 80
+    g = torch.Generator().manual_seed(8)
+    p = lif_params(Cin, C, False, 9)
+    x = (torch.rand((B, Cin, H, W), generator=g) < 0.3).float()
+    res = (torch.rand((B, C, H, W), generator=g) < 0.4).float()
+    st = torch.rand((2, B, C, H, W), generator=g) * 1.2 - 0.1
+    st[1] = (st[1] < 0.3).float()
+    pd = {k: v.to(DEV).contiguous() for k, v in p.items()}
+    img = ops.split_weights_g([(pd["ff"], 0, Cin, False)], C)
+    v, z, out = ops.lif_step_g([pad_cl(x, ops)], st[0].to(DEV).contiguous(), ops.pack_cl(st[1].to(DEV)), img, pd["leak"].reshape(-1),
+                               pd["thresh"].reshape(-1), C, hard_reset=True, residual_cl=ops.pack_cl(res.to(DEV)))
+    out_o, ns_o = osp.cell_step("lif", x, st, p, hard_reset=True, residual=res)
+    zf = ops.unpack_cl(z).cpu()
+    check(v, zf, ns_o, p["thresh"].clamp_min(0.01), 9 * Cin)
+    assert torch.equal(ops.unpack_cl(out).cpu(), zf + res)
