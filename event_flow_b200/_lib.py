@@ -192,6 +192,7 @@ EXPORTS = {
     "ef_pack_cl": (C.c_int, [C.c_void_p, C.c_void_p, _i32, _i32, _i32, _i32, C.c_void_p]),
     "ef_unpack_cl": (C.c_int, [C.c_void_p, C.c_void_p, _i32, _i32, _i32, _i32, C.c_void_p]),
     "ef_upsample_bilinear2x": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, _i32, _i32, C.c_void_p]),
+    "ef_upsample_bilinear2x_cl": (C.c_int, [C.c_void_p, C.c_void_p, _i32, _i32, _i32, _i32, C.c_void_p]),
     "ef_upsample_nearest": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, _i32, _i32, _i32, _i32, C.c_void_p]),
     "ef_upsample_bilinear2x_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, _i32, _i32, C.c_void_p]),
     "ef_upsample_nearest_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, _i32, _i32, _i32, _i32, C.c_void_p]),

@@ -32,6 +32,42 @@ __global__ void __launch_bounds__(256) upsample_bilinear2x_kernel(const float* _
   dst[i] = __fadd_rn(__fmul_rn(hy0, top), __fmul_rn(hy1, bot));
 }
 
+// The same upsampling on the internal spike format: bf16 channels-last [B,H,W,C] -> [B,2H,2W,C], one thread = one output pixel x 8
+// channels (16-byte loads / stores).  Inputs are spikes / residual sums (small integers): the bilinear weights are multiples of 1/16,
+// every result is a multiple of 1/16 below 2^8 and therefore EXACT in bf16 -- the fp32 expression tree above, then a lossless rounding.
+__global__ void __launch_bounds__(256) upsample_bilinear2x_cl_kernel(const uint16_t* __restrict__ src, uint16_t* __restrict__ dst, int B, int H, int W,
+                                                                     int C) {
+  const int Wo = 2 * W, Ho = 2 * H, G = C >> 3;
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= (size_t)B * Ho * Wo * G) return;
+  const int g = i % G;
+  const size_t pix = i / G;
+  const int x = pix % Wo, y = (pix / Wo) % Ho, b = pix / ((size_t)Wo * Ho);
+  int y0, y1, x0, x1;
+  float hy0, hy1, hx0, hx1;
+  bilinear2x_src(y, H, y0, y1, hy0, hy1);
+  bilinear2x_src(x, W, x0, x1, hx0, hx1);
+  const uint16_t* s = src + (size_t)b * H * W * C + g * 8;
+  const uint4 a = __ldg(reinterpret_cast<const uint4*>(s + ((size_t)y0 * W + x0) * C)), bq = __ldg(reinterpret_cast<const uint4*>(s + ((size_t)y0 * W + x1) * C));
+  const uint4 c = __ldg(reinterpret_cast<const uint4*>(s + ((size_t)y1 * W + x0) * C)), d = __ldg(reinterpret_cast<const uint4*>(s + ((size_t)y1 * W + x1) * C));
+  const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {bq.x, bq.y, bq.z, bq.w}, cw[4] = {c.x, c.y, c.z, c.w}, dw[4] = {d.x, d.y, d.z, d.w};
+  uint32_t o[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float r[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float va = h ? bf16_hi(aw[k]) : bf16_lo(aw[k]), vb = h ? bf16_hi(bw[k]) : bf16_lo(bw[k]);
+      const float vc = h ? bf16_hi(cw[k]) : bf16_lo(cw[k]), vd = h ? bf16_hi(dw[k]) : bf16_lo(dw[k]);
+      const float top = __fadd_rn(__fmul_rn(hx0, va), __fmul_rn(hx1, vb));
+      const float bot = __fadd_rn(__fmul_rn(hx0, vc), __fmul_rn(hx1, vd));
+      r[h] = __fadd_rn(__fmul_rn(hy0, top), __fmul_rn(hy1, bot));
+    }
+    o[k] = pack_bf16x2(r[0], r[1]);
+  }
+  *reinterpret_cast<uint4*>(dst + (((size_t)b * Ho + y) * Wo + x) * C + g * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
 __global__ void __launch_bounds__(256) upsample_nearest_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t n_planes, int H, int W,
                                                                int fy, int fx) {
   const int Wo = W * fx, Ho = H * fy;
@@ -121,4 +157,13 @@ extern "C" int ef_upsample_nearest(const float* src, float* dst, int64_t n_plane
   const size_t n = (size_t)n_planes * H * W * fy * fx;
   upsample_nearest_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(src, dst, (size_t)n_planes, H, W, fy, fx);
   return check_launch("upsample_nearest_kernel");
+}
+
+extern "C" int ef_upsample_bilinear2x_cl(const uint16_t* src, uint16_t* dst, int32_t B, int32_t H, int32_t W, int32_t C, void* stream) {
+  using namespace ef;
+  EF_REQUIRE(src && dst, EF_ENULL, "ef_upsample_bilinear2x_cl: NULL tensor");
+  EF_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, EF_EINVAL, "ef_upsample_bilinear2x_cl: C must be a positive multiple of 8");
+  const size_t n = (size_t)B * 4 * H * W * (C / 8);
+  upsample_bilinear2x_cl_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(src, dst, B, H, W, C);
+  return check_launch("upsample_bilinear2x_cl_kernel");
 }

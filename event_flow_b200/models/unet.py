@@ -7,6 +7,7 @@ stride-2 and upsampling backward kernels are not built: calling it under autogra
 """
 import torch.nn as nn
 
+from .. import fast_unet
 from .model_util import skip_concat, skip_sum  # noqa: F401  (resolved by name like the reference: "skip_" + skip_type)
 from .spiking_submodules import SpikingRecurrentConvLayer, SpikingResidualBlock, SpikingTransposedConvLayer, SpikingUpsampleConvLayer
 from .submodules import (ConvLayer, LeakyRecurrentConvLayer, LeakyResidualBlock, LeakyTransposedConvLayer, LeakyUpsampleConvLayer,
@@ -63,6 +64,29 @@ class SpikingMultiResUNetRecurrent(nn.Module):
         self.num_states = self.num_encoders * 2 + self.num_residual_blocks
         self.states = [None] * self.num_states
 
+    # The states live either in the reference's format (list of stacked fp32 tensors, what the cell-by-cell path reads and writes) or,
+    # after a step of the tensor-core inference path (event_flow_b200/fast_unet.py), in the internal format (membrane fp32 + spikes
+    # bf16 channels-last); the property converts lazily at this API boundary.
+    @property
+    def states(self):
+        if self.__dict__.get("_tc_state") is not None:
+            self._states = fast_unet.export_states(self)
+            self.__dict__["_tc_state"] = None
+        return self._states
+
+    @states.setter
+    def states(self, value):
+        self._states = value
+        self.__dict__["_tc_state"] = None
+
+    def __getstate__(self):  # checkpoints / deepcopy: states in the reference format, no run-time caches
+        state = self.__dict__.copy()
+        if state.get("_tc_state") is not None:
+            state["_states"] = [None if t is None else t.detach() for t in fast_unet.export_states(self)]
+        for k in ("_tc_state", "_tc_images", "_tc_eligible"):
+            state.pop(k, None)
+        return state
+
     def build_recurrent_encoders(self):
         encoders = nn.ModuleList()
         for i, (input_size, output_size) in enumerate(zip(self.encoder_input_sizes, self.encoder_output_sizes)):
@@ -101,6 +125,10 @@ class SpikingMultiResUNetRecurrent(nn.Module):
         :param x: N x num_input_channels x H x W
         :return: [N x num_output_channels x H x W for i in range(self.num_encoders)]
         """
+        if fast_unet.eligible(self, x):  # LIF cells, no gradient tracked: tcgen05 cells on the internal spike format
+            if self.__dict__.get("_tc_state") is None:
+                self._states = self.states  # (materialised reference-format list the importer reads)
+            return fast_unet.forward(self, x)
         blocks = []
         offset = 0
         for i, encoder in enumerate(self.encoders):

@@ -472,6 +472,17 @@ def pack_cl(x):
     return out
 
 
+def upsample_bilinear2x_cl(x_cl):
+    """Bilinear x2 upsampling of a cl bf16 tensor [B,H,W,C] (exact for spikes / residual sums).  No autograd."""
+    x_cl = _c(x_cl)
+    _need_cuda(x_cl)
+    B, H, W, Cc = x_cl.shape
+    out = torch.empty((B, 2 * H, 2 * W, Cc), device=x_cl.device, dtype=torch.bfloat16)
+    L.LAUNCHES += 1
+    L.check(L.lib().ef_upsample_bilinear2x_cl(L.ptr(x_cl), L.ptr(out), B, H, W, Cc, L.stream()), "ef_upsample_bilinear2x_cl")
+    return out
+
+
 def pack_split_cl(x, out=None):
     """fp32 NCHW [B,Cin<=10,H,W] -> bf16 cl [B,H,W,32] holding the exact hi/mid/lo split of every value (ef_pack_split_cl)."""
     x = _c(x)
@@ -582,7 +593,7 @@ def lif_step_g(srcs, v_in, z_in_cl, w_image, leak, thresh, C, *, hard_reset=True
     return v_out, z_out, out
 
 
-def lif_step_cl(x_cl, v_in, z_in_cl, w_ff, w_rec, leak, thresh, *, hard_reset=True, w_split=None, x_f32=None):
+def lif_step_cl(x_cl, v_in, z_in_cl, w_ff, w_rec, leak, thresh, *, hard_reset=True, w_split=None, x_f32=None, stride=1):
     """
     One fused conv + LIF step on the internal formats: spikes bf16 channels-last [B,H,W,C], membrane fp32 NCHW.
     With `w_split` (ops.split_weights) and 32->32 channels the tcgen05 kernel runs, otherwise the CUDA-core kernel.
@@ -594,11 +605,12 @@ def lif_step_cl(x_cl, v_in, z_in_cl, w_ff, w_rec, leak, thresh, *, hard_reset=Tr
         B, Cin, H, W = x_f32.shape
     C = w_ff.shape[0]
     dev = w_ff.device
-    v_out = torch.empty((B, C, H, W), device=dev, dtype=torch.float32)
-    z_out = torch.empty((B, H, W, C), device=dev, dtype=torch.bfloat16)
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    v_out = torch.empty((B, C, Ho, Wo), device=dev, dtype=torch.float32)
+    z_out = torch.empty((B, Ho, Wo, C), device=dev, dtype=torch.bfloat16)
     p = L.LifConvParams()
     p.B, p.Cin, p.C, p.H, p.W = B, Cin, C, H, W
-    p.ksize, p.stride, p.neuron, p.hard_reset = 3, 1, L.EF_LIF, int(hard_reset)
+    p.ksize, p.stride, p.neuron, p.hard_reset = 3, int(stride), L.EF_LIF, int(hard_reset)
     p.surrogate, p.act_width = 0, 10.0
     p.x, p.x_cl = L.ptr(x_f32), L.ptr(x_cl)
     p.v_in, p.z_in_cl = L.ptr(v_in), L.ptr(z_in_cl)

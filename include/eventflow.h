@@ -281,6 +281,9 @@ int ef_debug_pdl(int on);
  * maps (models/model.py:528-539), dst [n_planes,H*fy,W*fx]. */
 int ef_upsample_bilinear2x(const float* src, float* dst, int64_t n_planes, int32_t H, int32_t W, void* stream);
 int ef_upsample_nearest(const float* src, float* dst, int64_t n_planes, int32_t H, int32_t W, int32_t fy, int32_t fx, void* stream);
+/* The bilinear x2 upsampling on the internal spike format: src [B,H,W,C] cl bf16 -> dst [B,2H,2W,C]; exact for spikes and residual sums
+ * (results are multiples of 1/16).  C a multiple of 8. */
+int ef_upsample_bilinear2x_cl(const uint16_t* src, uint16_t* dst, int32_t B, int32_t H, int32_t W, int32_t C, void* stream);
 /* Their adjoints (what autograd derives for the two F.interpolate calls): g_dst has the upsampled shape, g_src [n_planes,H,W]. */
 int ef_upsample_bilinear2x_bwd(const float* g_dst, float* g_src, int64_t n_planes, int32_t H, int32_t W, void* stream);
 int ef_upsample_nearest_bwd(const float* g_dst, float* g_src, int64_t n_planes, int32_t H, int32_t W, int32_t fy, int32_t fx, void* stream);

@@ -26,11 +26,20 @@ def unet_cfg(neuron, base=4):
                 activations=["arctanspike", "arctanspike"], mask_output=True, spiking_neuron=None if neuron == "lif" else {})
 
 
-def hook_cells(model):
-    """(name, x_in, state_in, out, state_out) of every spiking cell, in execution order, as CPU tensors."""
+def hook_cells(model, tc=False):
+    """
+    (name, x_in, state_in, out, state_out) of every spiking cell, in execution order, as CPU tensors.  tc=False pins the cell-by-cell
+    path (forward hooks on the cells); tc=True records the same tuples from the tensor-core inference path (fast_unet._capture).
+    """
     from event_flow_b200.models.spiking_submodules import _SpikingConvCell
 
     trace, handles = [], []
+    net = getattr(model, "net", None)
+    if net is not None and hasattr(net, "num_encoders"):
+        net.__dict__["_use_tc"] = tc
+        if tc:
+            net.__dict__["_capture"], net.__dict__["_capture_prefix"] = trace, model.net_attr + "."
+            return trace, handles
     for name, mod in model.named_modules():
         if isinstance(mod, _SpikingConvCell):
             def hook(m, inputs, kwargs, output, name=name):
@@ -240,8 +249,13 @@ def test_unet_bptt_gradients_match_reference_golden(name):
     assert checked >= 20
 
 
-def test_unet_full_size_cells_match_oracle():
-    """BASELINE config 4 shape per GPU reduced to B=1: 256x256, base 32 channels (2->64->128->256->512), two steps."""
+@pytest.mark.parametrize("tc", [True, False])
+def test_unet_full_size_cells_match_oracle(tc):
+    """
+    BASELINE config 4 shape per GPU reduced to B=1: 256x256, base 32 channels (2->64->128->256->512), two steps; every cell of every
+    step teacher-forced against the oracle.  tc=True: the tensor-core inference path (general tcgen05 cell kernel, multi-source
+    decoders, cl upsampling); tc=False: the fp32 cell-by-cell path (what training uses).
+    """
     import event_flow_b200.models.model as M
 
     torch.manual_seed(3)
@@ -252,14 +266,49 @@ def test_unet_full_size_cells_match_oracle():
                 q.mul_(3.0)
     sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
     m = m.to(DEV)
-    trace, handles = hook_cells(m)
+    trace, handles = hook_cells(m, tc=tc)
     with torch.no_grad():
         for t in range(2):
             ts, ys, xs, ps = oenc.synthetic_events(1, 50000, 256, 256, 40 + t)
             out = m(None, oenc.encode_window(ts, ys, xs, ps, 256, 256, 2)["event_cnt"].to(DEV))
     assert [tuple(f.shape) for f in out["flow"]] == [(1, 2, 256, 256)] * 4
+    assert len(trace) == 16 * 2, "every cell of both steps must have been recorded"
     worst, flips_in, n_tot = check_trace("lif", sd, trace)
-    print(f"full size: worst |dv|/tol {worst:.2f}, {flips_in}/{n_tot} borderline flips")
+    # the last decoder's spikes through the prediction layer = the finest flow map
+    last = trace[-1]
+    flow_o = osp.pred_head(last[4], sd[m.net_attr + ".preds.3.conv2d.weight"], sd[m.net_attr + ".preds.3.conv2d.bias"])
+    torch.testing.assert_close(out["flow"][3].cpu(), flow_o, rtol=1e-5, atol=1e-7)
+    # state API: the reference's layout whichever path ran
+    st = m.states
+    assert len(st) == 10 and st[0].shape == (2, 2, 1, 64, 128, 128) and st[9].shape == (2, 1, 32, 256, 256)
+    assert torch.equal(st[9][1].cpu(), last[4]) and torch.equal(st[9].cpu(), last[5])
+    print(f"full size (tc={tc}): worst |dv|/tol {worst:.2f}, {flips_in}/{n_tot} borderline flips")
+
+
+def test_unet_tc_path_continues_the_cell_path_rollout():
+    """Switching paths mid-sequence (states converted at the API boundary): step 2 on the tensor-core path from the states the cell path
+    left equals, cell by cell within the T1 band, step 2 on the cell path."""
+    import event_flow_b200.models.model as M
+
+    torch.manual_seed(4)
+    m = M.SpikingRecEVFlowNet(unet_cfg("lif", base=32))
+    with torch.no_grad():
+        for nm, q in m.named_parameters():
+            if nm.endswith("ff.weight") or nm.endswith("rec.weight"):
+                q.mul_(3.0)
+    m = m.to(DEV)
+    xs = [oenc.encode_window(*oenc.synthetic_events(1, 20000, 128, 128, 60 + t), 128, 128, 2)["event_cnt"].to(DEV) for t in range(2)]
+    net = m.net
+    with torch.no_grad():
+        net.__dict__["_use_tc"] = False
+        m(None, xs[0])
+        saved = m.states
+        a = m(None, xs[1])["flow"]
+        m.states = saved
+        net.__dict__["_use_tc"] = True
+        b = m(None, xs[1])["flow"]
+    for fa, fb in zip(a, b):
+        assert (fa - fb).abs().max().item() <= 1e-3 * max(1e-6, fa.abs().max().item())
 
 
 def test_ann_evflownet_forward_matches_reference_golden_and_oracle():
