@@ -57,12 +57,12 @@ EF_TCG_MAX_SRC = 4
 
 
 class WSrc(C.Structure):
-    _fields_ = [("w", _f32p), ("c_total", _i32), ("ch0", _i32), ("n", _i32), ("split", _i32)]
+    _fields_ = [("w", _f32p), ("c_total", _i32), ("ch0", _i32), ("n", _i32), ("split", _i32), ("s2d", _i32)]
 
 
 class LifConvGParams(C.Structure):
     _fields_ = [
-        ("B", _i32), ("H", _i32), ("W", _i32), ("C", _i32), ("n_src", _i32), ("hard_reset", _i32),
+        ("B", _i32), ("H", _i32), ("W", _i32), ("C", _i32), ("n_src", _i32), ("hard_reset", _i32), ("s2d", _i32),
         ("src", _f32p * EF_TCG_MAX_SRC), ("src_c", _i32 * EF_TCG_MAX_SRC),
         ("v_in", _f32p), ("z_in_cl", _f32p), ("residual_cl", _f32p), ("leak", _f32p), ("thresh", _f32p), ("w_image", _f32p),
         ("v_out", _f32p), ("z_out_cl", _f32p), ("out_cl", _f32p),
@@ -189,6 +189,8 @@ EXPORTS = {
     "ef_debug_pdl": (C.c_int, [C.c_int]),
     "ef_pack_split_cl": (C.c_int, [C.c_void_p, C.c_void_p, _i32, _i32, _i32, _i32, C.c_void_p]),
     "ef_split_weights_head": (C.c_int, [C.c_void_p, _i32, C.c_void_p, C.c_void_p]),
+    "ef_pack_split_s2d_cl": (C.c_int, [C.c_void_p, C.c_void_p, _i32, _i32, _i32, _i32, C.c_void_p]),
+    "ef_space_to_depth_cl": (C.c_int, [C.c_void_p, C.c_void_p, _i32, _i32, _i32, _i32, C.c_void_p]),
     "ef_pack_cl": (C.c_int, [C.c_void_p, C.c_void_p, _i32, _i32, _i32, _i32, C.c_void_p]),
     "ef_unpack_cl": (C.c_int, [C.c_void_p, C.c_void_p, _i32, _i32, _i32, _i32, C.c_void_p]),
     "ef_upsample_bilinear2x": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, _i32, _i32, C.c_void_p]),

@@ -57,7 +57,64 @@ __global__ void __launch_bounds__(256) pack_split_cl_kernel(const float* __restr
                       o[8 * k + 6] | ((uint32_t)o[8 * k + 7] << 16));
 }
 
+// space-to-depth variants for the stride-2 cells: virtual channel vc = (py*2 + px)*Cin + c of output pixel (Y, X) = input (2Y+py, 2X+px, c)
+__global__ void __launch_bounds__(256) pack_split_s2d_cl_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, int B, int Cin, int SL, int H, int W) {
+  const int Ho = H >> 1, Wo = W >> 1;
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;  // over B * Ho * Wo
+  if (i >= (size_t)B * Ho * Wo) return;
+  const int X = i % Wo, Y = (i / Wo) % Ho, b = i / ((size_t)Wo * Ho);
+  uint16_t o[32];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) o[k] = 0;
+  for (int par = 0; par < 4; ++par) {
+    for (int c = 0; c < Cin; ++c) {
+      const float x = __ldg(src + (((size_t)b * Cin + c) * H + 2 * Y + (par >> 1)) * W + 2 * X + (par & 1));
+      const __nv_bfloat16 hi = __float2bfloat16_rn(x);
+      const float r1 = x - __bfloat162float(hi);
+      const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+      const __nv_bfloat16 lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+      const int vc = par * Cin + c;
+      o[vc] = __bfloat16_as_ushort(hi), o[SL + vc] = __bfloat16_as_ushort(mid), o[2 * SL + vc] = __bfloat16_as_ushort(lo);
+    }
+  }
+  uint4* d = reinterpret_cast<uint4*>(dst + i * 32);
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    d[k] = make_uint4(o[8 * k] | ((uint32_t)o[8 * k + 1] << 16), o[8 * k + 2] | ((uint32_t)o[8 * k + 3] << 16), o[8 * k + 4] | ((uint32_t)o[8 * k + 5] << 16),
+                      o[8 * k + 6] | ((uint32_t)o[8 * k + 7] << 16));
+}
+
+__global__ void __launch_bounds__(256) space_to_depth_cl_kernel(const uint16_t* __restrict__ src, uint16_t* __restrict__ dst, int B, int H, int W, int C) {
+  const int Ho = H >> 1, Wo = W >> 1, G = C >> 3;
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;  // over B * Ho * Wo * 4 * G (16-byte pieces of the output)
+  if (i >= (size_t)B * Ho * Wo * 4 * G) return;
+  const int g = i % G, par = (i / G) % 4;
+  const size_t pix = i / (4 * G);
+  const int X = pix % Wo, Y = (pix / Wo) % Ho, b = pix / ((size_t)Wo * Ho);
+  const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + (((size_t)b * H + 2 * Y + (par >> 1)) * W + 2 * X + (par & 1)) * C + g * 8));
+  *reinterpret_cast<uint4*>(dst + pix * 4 * C + (size_t)par * C + g * 8) = v;
+}
+
 }  // namespace ef
+
+extern "C" int ef_pack_split_s2d_cl(const float* src, uint16_t* dst, int32_t B, int32_t Cin, int32_t H, int32_t W, void* stream) {
+  using namespace ef;
+  EF_REQUIRE(src && dst, EF_ENULL, "ef_pack_split_s2d_cl: NULL tensor");
+  EF_REQUIRE(B > 0 && Cin > 0 && 4 * Cin <= EF_HEAD_MAX_CIN && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, EF_EINVAL,
+             "ef_pack_split_s2d_cl: 4*Cin <= %d, even H and W", EF_HEAD_MAX_CIN);
+  const size_t n = (size_t)B * (H / 2) * (W / 2);
+  pack_split_s2d_cl_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(src, dst, B, Cin, EF_HEAD_SLOT(4 * Cin), H, W);
+  return check_launch("pack_split_s2d_cl_kernel");
+}
+
+extern "C" int ef_space_to_depth_cl(const uint16_t* src, uint16_t* dst, int32_t B, int32_t H, int32_t W, int32_t C, void* stream) {
+  using namespace ef;
+  EF_REQUIRE(src && dst, EF_ENULL, "ef_space_to_depth_cl: NULL tensor");
+  EF_REQUIRE(B > 0 && C > 0 && C % 8 == 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, EF_EINVAL, "ef_space_to_depth_cl: C %% 8 == 0, even H and W");
+  const size_t n = (size_t)B * (H / 2) * (W / 2) * 4 * (C / 8);
+  space_to_depth_cl_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(src, dst, B, H, W, C);
+  return check_launch("space_to_depth_cl_kernel");
+}
 
 extern "C" int ef_pack_split_cl(const float* src, uint16_t* dst, int32_t B, int32_t Cin, int32_t H, int32_t W, void* stream) {
   using namespace ef;

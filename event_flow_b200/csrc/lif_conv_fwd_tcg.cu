@@ -44,6 +44,7 @@ struct TcgParams {
   int B, H, W, C, tiles_x, tiles_y, n_tiles, nnb, nkb, n_items;
   int has_v, has_z, has_res;
   int n_src, src_blocks[EF_TCG_MAX_SRC];
+  int tap_mask;  // bit t set: tap t (= ky*3 + kx) has non-zero weights.  Stride-2 cells on space-to-depth inputs use 4 of the 9 taps
   const uint16_t* w_image;
   const float* leak;
   const float* thresh;
@@ -192,6 +193,7 @@ lif_conv_fwd_tcg_kernel(const TcgParams p, const __grid_constant__ CUtensorMap m
         const int a = it & 1;
         mbar_wait(bar_acce(a), ((it >> 1) & 1) ^ 1);
         const uint32_t d_tmem = tmem_base + a * G_ACC_COLS;
+        uint32_t acc_started = 0u;
         for (int kb = 0; kb < p.nkb; ++kb, ++ksg) {
           const int so = ksg % G_NOP, sw = ksg % G_NW;
           mbar_wait(bar_opf(so), (ksg / G_NOP) & 1);
@@ -201,10 +203,13 @@ lif_conv_fwd_tcg_kernel(const TcgParams p, const __grid_constant__ CUtensorMap m
           const uint64_t bw = umma_desc_sw64(s_base + G_W_OFF + sw * G_WBLOCK, ATOM_BYTES);
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
+            if (!((p.tap_mask >> tap) & 1)) continue;
 #pragma unroll
-            for (int ks = 0; ks < 2; ++ks)
+            for (int ks = 0; ks < 2; ++ks) {
               umma_bf16<G_IDESC>(d_tmem, ax + (uint64_t)((tap / 3) * (G_HALO_PITCH / 16) + (tap % 3) * (PIX_BYTES / 16) + ks * 2),
-                                 bw + (uint64_t)(tap * (G_WTAP / 16) + ks * 2), (kb | tap | ks) != 0);
+                                 bw + (uint64_t)(tap * (G_WTAP / 16) + ks * 2), acc_started);
+              acc_started = 1u;
+            }
           }
           umma_commit(bar_ope(so));  // operand tile and weight block may be overwritten once these MMAs have read them
           umma_commit(bar_we(sw));
@@ -301,7 +306,7 @@ lif_conv_fwd_tcg_kernel(const TcgParams p, const __grid_constant__ CUtensorMap m
 // ---- weight image: [C/32 output blocks][K blocks][9 taps][96 = {hi, mid, lo} x 32 n][32 k] bf16, 64B-swizzled per tap (as ef_split_weights) -----
 struct WSrc {
   const float* w;   // [C][c_total][3][3]
-  int c_total, ch0, n, split, blocks;
+  int c_total, ch0, n, split, s2d, blocks;
 };
 struct WSrcs {
   WSrc s[EF_TCG_MAX_SRC];
@@ -317,12 +322,28 @@ __global__ void __launch_bounds__(256) split_weights_g_kernel(const WSrcs ws, ui
   while (s + 1 < ws.n_src && j >= ws.s[s].blocks) j -= ws.s[s].blocks, ++s;
   const WSrc& src = ws.s[s];
   float w = 0.f;
+  // virtual channel of the source tensor this K row holds (-1: padding)
+  const int nv = src.s2d ? 4 * src.n : src.n;  // space-to-depth sources carry the four pixel parities of every channel
+  int vc = -1;
   if (src.split) {  // exact hi/mid/lo slots of a fractional source: every slot multiplies the same weight
-    const int SL = EF_HEAD_SLOT(src.n), c = k % SL, slot = k / SL;
-    if (slot < 3 && c < src.n) w = src.w[((size_t)co * src.c_total + src.ch0 + c) * 9 + tap];
+    const int SL = EF_HEAD_SLOT(nv), c = k % SL, slot = k / SL;
+    if (slot < 3 && c < nv) vc = c;
   } else {
     const int c = j * 32 + k;
-    if (c < src.n) w = src.w[((size_t)co * src.c_total + src.ch0 + c) * 9 + tap];
+    if (c < nv) vc = c;
+  }
+  if (vc >= 0) {
+    if (!src.s2d) {
+      w = src.w[((size_t)co * src.c_total + src.ch0 + vc) * 9 + tap];
+    } else {
+      // stride-2 convolution as a stride-1 convolution over the space-to-depth input: s2d[Y, X, (py*2 + px)*n + c] = in[2Y + py, 2X + px, c].
+      // Output (y, x) reads input row 2y + dy - 1: dy = 0 -> (Y = y-1, py = 1), dy = 1 -> (Y = y, py = 0), dy = 2 -> (Y = y, py = 1); same in x.
+      // In the 3x3 stride-1 kernel over s2d, tap ky = 0 is Y = y-1 and ky = 1 is Y = y; ky = 2 is never used (tap mask 0b000011011).
+      const int par = vc / src.n, c = vc - par * src.n, py = par >> 1, px = par & 1, ky = tap / 3, kx = tap % 3;
+      const int dy = ky == 0 ? (py == 1 ? 0 : -1) : (ky == 1 ? (py == 0 ? 1 : 2) : -1);
+      const int dx = kx == 0 ? (px == 1 ? 0 : -1) : (kx == 1 ? (px == 0 ? 1 : 2) : -1);
+      if (dy >= 0 && dx >= 0) w = src.w[((size_t)co * src.c_total + src.ch0 + c) * 9 + dy * 3 + dx];
+    }
   }
   const __nv_bfloat16 hi = __float2bfloat16_rn(w);
   const float r1 = w - __bfloat162float(hi);
@@ -339,14 +360,14 @@ __global__ void __launch_bounds__(256) split_weights_g_kernel(const WSrcs ws, ui
   }
 }
 
-static int src_blocks_of(int32_t n, int32_t split) { return split ? 1 : (n + 31) / 32; }
+static int src_blocks_of(int32_t n, int32_t split, int32_t s2d) { return split ? 1 : ((s2d ? 4 * n : n) + 31) / 32; }
 
 }  // namespace ef
 
 extern "C" int64_t ef_split_weights_g_elems(int32_t C, int32_t n_src, const ef_wsrc* srcs) {
   if (C <= 0 || C % 32 || n_src < 1 || n_src > EF_TCG_MAX_SRC || !srcs) return 0;
   int nkb = 0;
-  for (int i = 0; i < n_src; ++i) nkb += ef::src_blocks_of(srcs[i].n, srcs[i].split);
+  for (int i = 0; i < n_src; ++i) nkb += ef::src_blocks_of(srcs[i].n, srcs[i].split, srcs[i].s2d);
   return (int64_t)(C / 32) * nkb * (ef::G_WBLOCK / 2);
 }
 
@@ -359,9 +380,11 @@ extern "C" int ef_split_weights_g(const ef_wsrc* srcs, int32_t n_src, int32_t C,
   ws.n_src = n_src, ws.C = C, ws.nkb = 0;
   for (int i = 0; i < n_src; ++i) {
     EF_REQUIRE(srcs[i].w && srcs[i].n > 0 && srcs[i].ch0 >= 0 && srcs[i].ch0 + srcs[i].n <= srcs[i].c_total, EF_EINVAL, "ef_split_weights_g: bad source %d", i);
-    EF_REQUIRE(!srcs[i].split || srcs[i].n <= EF_HEAD_MAX_CIN, EF_EUNSUPPORTED, "ef_split_weights_g: a split source has at most %d channels", EF_HEAD_MAX_CIN);
+    EF_REQUIRE(!srcs[i].split || (srcs[i].s2d ? 4 : 1) * srcs[i].n <= EF_HEAD_MAX_CIN, EF_EUNSUPPORTED,
+               "ef_split_weights_g: a split source has at most %d (virtual) channels", EF_HEAD_MAX_CIN);
     ws.s[i].w = srcs[i].w, ws.s[i].c_total = srcs[i].c_total, ws.s[i].ch0 = srcs[i].ch0, ws.s[i].n = srcs[i].n, ws.s[i].split = srcs[i].split;
-    ws.s[i].blocks = src_blocks_of(srcs[i].n, srcs[i].split);
+    ws.s[i].s2d = srcs[i].s2d;
+    ws.s[i].blocks = src_blocks_of(srcs[i].n, srcs[i].split, srcs[i].s2d);
     ws.nkb += ws.s[i].blocks;
   }
   const long long total = (long long)C * ws.nkb * 32 * 9;
@@ -416,6 +439,7 @@ extern "C" int ef_lif_conv_fwd_g(const ef_lif_conv_g_params* pp, void* stream) {
     if ((rc = get_map_c(p.out_cl, p.B, p.H, p.W, p.C, G_TH, G_TW, true, &mout))) return rc;
   }
   q.w_image = p.w_image, q.leak = p.leak, q.thresh = p.thresh;
+  q.tap_mask = p.s2d ? 0x1B : 0x1FF;  // stride-2 cells on space-to-depth inputs: taps (ky, kx) in {0,1}^2 only
   cudaStream_t st = as_stream(stream);
   const int grid = q.n_items < n_sms ? q.n_items : n_sms;
   static bool attr_set[2] = {false, false};

@@ -131,13 +131,21 @@ def forward(net, x):
         ff, rec = S[2 * i], S[2 * i + 1]
         c = enc.conv
         leak, thresh = _chan(c)
-        before = _ref_state(ff) if net.__dict__.get("_capture") is not None else None
+        capturing = net.__dict__.get("_capture") is not None
+        before = _ref_state(ff) if capturing else None
         x_in = x if i == 0 else h
-        if i == 0:
+        cin = c.input_size
+        if c.stride == 2 and (i > 0 or 4 * cin <= L.EF_HEAD_MAX_CIN):
+            # stride-2 cell on the tensor cores: a stride-1 cell at the output resolution over the space-to-depth form of the input
+            # (the fp32 network input additionally as its exact hi/mid/lo split)
+            src = ops.pack_split_s2d_cl(x) if i == 0 else ops.space_to_depth_cl(h)
+            img = _weights(net, ("enc_ff", i), c, [(c.ff.weight, 0, cin, i == 0, True)])
+            ff.v, ff.z, _ = ops.lif_step_g([src], ff.v, ff.z, img, leak, thresh, c.hidden_size, hard_reset=c.hard_reset, s2d=True)
+        elif i == 0:
             ff.v, ff.z = ops.lif_step_cl(None, ff.v, ff.z, c.ff.weight, None, leak, thresh, hard_reset=c.hard_reset, x_f32=x.contiguous(), stride=c.stride)
         else:
             ff.v, ff.z = ops.lif_step_cl(h, ff.v, ff.z, c.ff.weight, None, leak, thresh, hard_reset=c.hard_reset, stride=c.stride)
-        if net.__dict__.get("_capture") is not None:
+        if capturing:
             _capture(net, f"encoders.{i}.conv", x_in if i == 0 else ops.unpack_cl(x_in), before, None, ff.z, ff, c.stride)
         rb = enc.recurrent_block
         h = _step_g(net, ("enc", i), rb, rec, [ff.z], [(rb.ff.weight, 0, rb.input_size, False)], name=f"encoders.{i}.recurrent_block")

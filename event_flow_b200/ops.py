@@ -483,6 +483,29 @@ def upsample_bilinear2x_cl(x_cl):
     return out
 
 
+def space_to_depth_cl(x_cl):
+    """cl [B,H,W,C] -> [B,H/2,W/2,4C]: the four pixel parities of every channel side by side (input form of the stride-2 tensor-core cell)."""
+    x_cl = _c(x_cl)
+    _need_cuda(x_cl)
+    B, H, W, Cc = x_cl.shape
+    out = torch.empty((B, H // 2, W // 2, 4 * Cc), device=x_cl.device, dtype=torch.bfloat16)
+    L.LAUNCHES += 1
+    L.check(L.lib().ef_space_to_depth_cl(L.ptr(x_cl), L.ptr(out), B, H, W, Cc, L.stream()), "ef_space_to_depth_cl")
+    return out
+
+
+def pack_split_s2d_cl(x):
+    """fp32 NCHW [B,Cin,H,W], 4*Cin <= 10 -> cl [B,H/2,W/2,32]: exact hi/mid/lo split of the space-to-depth form (first stride-2 encoder)."""
+    x = _c(x)
+    _need_cuda(x)
+    _need_f32(x)
+    B, Cin, H, W = x.shape
+    out = torch.empty((B, H // 2, W // 2, 32), device=x.device, dtype=torch.bfloat16)
+    L.LAUNCHES += 1
+    L.check(L.lib().ef_pack_split_s2d_cl(L.ptr(x), L.ptr(out), B, Cin, H, W, L.stream()), "ef_pack_split_s2d_cl")
+    return out
+
+
 def pack_split_cl(x, out=None):
     """fp32 NCHW [B,Cin<=10,H,W] -> bf16 cl [B,H,W,32] holding the exact hi/mid/lo split of every value (ef_pack_split_cl)."""
     x = _c(x)
@@ -557,12 +580,15 @@ def split_weights_g(sources, C):
     n = len(sources)
     arr = (L.WSrc * n)()
     keep = []
-    for i, (w, ch0, cnt, split) in enumerate(sources):
+    for i, src in enumerate(sources):
+        w, ch0, cnt, split = src[:4]
+        s2d = src[4] if len(src) > 4 else False
         w = _c(w.detach())
         _need_cuda(w)
         _need_f32(w)
         keep.append(w)
         arr[i].w, arr[i].c_total, arr[i].ch0, arr[i].n, arr[i].split = L.ptr(w), w.shape[1], int(ch0), int(cnt), int(bool(split))
+        arr[i].s2d = int(bool(s2d))
     elems = L.lib().ef_split_weights_g_elems(C, n, arr)
     if elems <= 0:
         raise L.EventFlowError("split_weights_g: unsupported shape (C must be a multiple of 32)")
@@ -572,7 +598,7 @@ def split_weights_g(sources, C):
     return out
 
 
-def lif_step_g(srcs, v_in, z_in_cl, w_image, leak, thresh, C, *, hard_reset=True, residual_cl=None):
+def lif_step_g(srcs, v_in, z_in_cl, w_image, leak, thresh, C, *, hard_reset=True, residual_cl=None, s2d=False):
     """
     One fused conv + LIF step of a general-channel cell on the tensor cores (ef_lif_conv_fwd_g).  srcs: cl bf16 tensors [B,H,W,c_s]
     (c_s multiples of 32) in the order of the weight image's sources.  Returns (v_out fp32 NCHW, z_out cl, out cl | None).  No autograd.
@@ -583,7 +609,7 @@ def lif_step_g(srcs, v_in, z_in_cl, w_image, leak, thresh, C, *, hard_reset=True
     z_out = torch.empty((B, H, W, C), device=dev, dtype=torch.bfloat16)
     out = torch.empty_like(z_out) if residual_cl is not None else None
     p = L.LifConvGParams()
-    p.B, p.H, p.W, p.C, p.n_src, p.hard_reset = B, H, W, C, len(srcs), int(hard_reset)
+    p.B, p.H, p.W, p.C, p.n_src, p.hard_reset, p.s2d = B, H, W, C, len(srcs), int(hard_reset), int(bool(s2d))
     for i, s in enumerate(srcs):
         p.src[i], p.src_c[i] = L.ptr(s), s.shape[3]
     p.v_in, p.z_in_cl, p.residual_cl = L.ptr(v_in), L.ptr(z_in_cl), L.ptr(residual_cl)

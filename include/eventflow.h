@@ -233,6 +233,10 @@ int ef_split_weights(const float* w_ff, const float* w_rec, int32_t Cin, int32_t
  * (spikes, residual sums, their bilinear x2 upsampling, event counts); a fractional fp32 source is passed as its exact hi/mid/lo
  * split (ef_pack_split_cl, src_c = 32).  The weights come as one image built by ef_split_weights_g from the same source list
  * (three exact bf16 terms per weight, tcgen05 B-operand layout, blocked [C/32][K/32]); products are fp32-exact.
+ * STRIDE 2 (the encoder cells, unet.py:83-89 / spiking_submodules.py:878-930) runs as a stride-1 cell at the OUTPUT resolution over the
+ * space-to-depth form of the input, s2d[b, Y, X, (py*2 + px)*n + c] = in[b, 2Y + py, 2X + px, c] (ef_space_to_depth_cl, or
+ * ef_pack_split_cl with s2d = 1 for fp32 inputs): ef_wsrc.s2d = 1 remaps the 3x3 stride-2 weights onto the four taps (ky, kx) in {0,1}^2
+ * of that input, ef_lif_conv_g_params.s2d = 1 makes the kernel skip the five all-zero taps.  B, H, W are then the output's.
  * ------------------------------------------------------------------------------------------------------------------ */
 #define EF_TCG_MAX_SRC 4
 typedef struct ef_wsrc {
@@ -240,6 +244,7 @@ typedef struct ef_wsrc {
   int32_t c_total;               /* input channels of that weight tensor                                              */
   int32_t ch0, n;                /* first channel and channel count of the slice                                      */
   int32_t split;                 /* 1: the source tensor is an ef_pack_split_cl split (n <= EF_HEAD_MAX_CIN)            */
+  int32_t s2d;                   /* 1: the source tensor is the SPACE-TO-DEPTH form of the stride-2 cell's input (below)  */
 } ef_wsrc;
 /* out: uint16[ef_split_weights_g_elems(C, n_src, srcs)] */
 int64_t ef_split_weights_g_elems(int32_t C, int32_t n_src, const ef_wsrc* srcs);
@@ -249,6 +254,7 @@ typedef struct ef_lif_conv_g_params {
   int32_t B, H, W, C;            /* outputs: membrane [B,C,H,W] fp32, spikes [B,H,W,C] cl                              */
   int32_t n_src;                 /* 1..EF_TCG_MAX_SRC input sources, in the order given to ef_split_weights_g          */
   int32_t hard_reset;
+  int32_t s2d;                   /* 1: stride-2 cell on a space-to-depth source (a single source)                      */
   const uint16_t* src[EF_TCG_MAX_SRC];  /* [B,H,W,src_c[s]] cl                                                         */
   int32_t src_c[EF_TCG_MAX_SRC]; /* channels of each source tensor, multiples of 32                                   */
   const float* v_in;             /* [B,C,H,W] or NULL (zero state; then z_in_cl is NULL too)                           */
@@ -297,6 +303,11 @@ int ef_upsample_nearest_bwd(const float* g_dst, float* g_src, int64_t n_planes, 
 #define EF_HEAD_MAX_CIN 10
 #define EF_HEAD_SLOT(cin) ((cin) <= 8 ? 8 : 10)
 int ef_pack_split_cl(const float* src, uint16_t* dst, int32_t B, int32_t Cin, int32_t H, int32_t W, void* stream);
+/* The same split of the space-to-depth form of x (stride-2 first encoder): dst [B,H/2,W/2,32], virtual channel (py*2 + px)*Cin + c,
+ * 4*Cin <= EF_HEAD_MAX_CIN, H and W even. */
+int ef_pack_split_s2d_cl(const float* src, uint16_t* dst, int32_t B, int32_t Cin, int32_t H, int32_t W, void* stream);
+/* Space-to-depth of a cl tensor: src [B,H,W,C] -> dst [B,H/2,W/2,4C], dst[b,Y,X,(py*2+px)*C + c] = src[b,2Y+py,2X+px,c]; C % 8 == 0. */
+int ef_space_to_depth_cl(const uint16_t* src, uint16_t* dst, int32_t B, int32_t H, int32_t W, int32_t C, void* stream);
 int ef_split_weights_head(const float* w_ff, int32_t Cin, uint16_t* out, void* stream);
 
 /* fp32 NCHW <-> cl bf16 layout conversion at the API boundary (model.states getter/setter, first input). */

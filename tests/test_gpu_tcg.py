@@ -117,3 +117,41 @@ def test_residual_cell_and_channel_padding():
     zf = ops.unpack_cl(z).cpu()
     check(v, zf, ns_o, p["thresh"].clamp_min(0.01), 9 * Cin)
     assert torch.equal(ops.unpack_cl(out).cpu(), zf + res)
+
+
+@pytest.mark.parametrize("cin,C,shape", [(2, 64, (2, 64, 96)), (64, 128, (2, 32, 48)), (96, 64, (1, 40, 56))])
+@pytest.mark.parametrize("with_state", [True, False])
+def test_stride2_cell_on_space_to_depth_input(cin, C, shape, with_state):
+    """Stride-2 ConvLIF (the U-Net encoders) as a stride-1 tensor-core cell over the space-to-depth input; the first encoder's fp32
+    counts additionally as an exact hi/mid/lo split.  Against the oracle's stride-2 cell."""
+    from event_flow_b200 import ops
+
+    B, H, W = shape
+    g = torch.Generator().manual_seed(cin + H)
+    p = lif_params(cin, C, False, cin + 1, gain=2.5)
+    if cin == 2:
+        x = torch.randint(0, 6, (B, cin, H, W), generator=g).float() * (torch.rand((B, cin, H, W), generator=g) < 0.5)
+        x[0, 0, 0, 0], x[0, 1, 3, 5] = 300.0, 1000.0  # counts beyond the bf16 integer range: the split keeps them exact
+        src = ops.pack_split_s2d_cl(x.to(DEV))
+    else:
+        x = (torch.rand((B, cin, H, W), generator=g) < 0.3).float()
+        src = ops.space_to_depth_cl(pad_cl(x, ops)) if cin % 32 else ops.space_to_depth_cl(ops.pack_cl(x.to(DEV)))
+    Ho, Wo = H // 2, W // 2
+    st = None
+    if with_state:
+        st = torch.rand((2, B, C, Ho, Wo), generator=g) * 1.2 - 0.1
+        st[1] = (st[1] < 0.3).float()
+    pd = {k: v.to(DEV).contiguous() for k, v in p.items()}
+    n_real = cin if cin % 32 == 0 or cin == 2 else (cin + 31) // 32 * 32  # a zero-padded tensor: the padded channels are part of the s2d layout
+    w = pd["ff"]
+    if n_real != cin:  # weights of the padded channels are zero
+        w = torch.cat([w, torch.zeros(C, n_real - cin, 3, 3, device=DEV)], 1).contiguous()
+    img = ops.split_weights_g([(w, 0, n_real, cin == 2, True)], C)
+    v_in = z_in = None
+    if st is not None:
+        v_in, z_in = st[0].to(DEV).contiguous(), ops.pack_cl(st[1].to(DEV))
+    v, z, _ = ops.lif_step_g([src], v_in, z_in, img, pd["leak"].reshape(-1), pd["thresh"].reshape(-1), C, hard_reset=True, s2d=True)
+    out_o, ns_o = osp.cell_step("lif", x, st, p, hard_reset=True, stride=2)
+    zf = ops.unpack_cl(z).cpu()
+    check(v, zf, ns_o, p["thresh"].clamp_min(0.01), 9 * cin)
+    assert zf.mean() > 0.01

@@ -14,7 +14,14 @@ sys.path.insert(0, ROOT)
 import event_flow_b200.models.model as M  # noqa: E402
 from event_flow_b200.dataloader.encodings import encode_batch  # noqa: E402
 from event_flow_b200.loss.flow import EventWarping  # noqa: E402
-from oracle.encodings import synthetic_events  # noqa: E402
+from bench import synthetic_events as _syn  # noqa: E402
+
+
+def synthetic_events(B, N, H, W, seed):
+    import bench
+    bench.H, bench.W = H, W
+    e = _syn(B, N, seed)
+    return e[:, :, 0], e[:, :, 1], e[:, :, 2], e[:, :, 3]
 
 dev = torch.device("cuda")
 
@@ -70,7 +77,10 @@ def run(name, cls, cfg, B, N, H, W, T, bins, gain):
         loss.backward()
         model.detach_states()
 
-    ms_f = timed(fwd)
+    ms_f = timed(fwd, reps=5)
+    if os.environ.get("EF_FWD_ONLY"):
+        print(json.dumps({"config": name, "model": cls, "batch": B, "resolution": [H, W], "timesteps": T, "fwd_ms_per_step": ms_f / T}), flush=True)
+        return
     ms_t = timed(train)
     print(json.dumps({"config": name, "model": cls, "batch": B, "resolution": [H, W], "timesteps": T, "events_per_window": N,
                       "fwd_ms_per_step": ms_f / T, "fwd_loss_bwd_ms_per_window": ms_t, "events_per_s_train": B * N * T / ms_t * 1e3}), flush=True)
