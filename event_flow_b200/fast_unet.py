@@ -61,7 +61,7 @@ class _Cell:
 def _weights(net, key, cell, sources):
     """Cached weight image of a cell for a given source list; rebuilt when a weight tensor changed."""
     cache = net.__dict__.setdefault("_tc_images", {})
-    ver = tuple((w._version, w.data_ptr()) for w, _, _, _ in sources)
+    ver = tuple((src[0]._version, src[0].data_ptr()) for src in sources)
     hit = cache.get(key)
     if hit is None or hit[0] != ver:
         hit = (ver, ops.split_weights_g(sources, cell.hidden_size))
