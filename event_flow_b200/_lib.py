@@ -31,6 +31,14 @@ class LifConvParams(C.Structure):
     ]  # fmt: skip
 
 
+class LifConvWindowParams(C.Structure):
+    _fields_ = [
+        ("B", _i32), ("T", _i32), ("H", _i32), ("W", _i32), ("hard_reset", _i32), ("save_all_v", _i32),
+        ("x_cl", _f32p), ("v_in", _f32p), ("z_in_cl", _f32p), ("leak", _f32p), ("thresh", _f32p), ("w_split", _f32p),
+        ("v_out", _f32p), ("z_out_cl", _f32p),
+    ]  # fmt: skip
+
+
 class LifConvBwdParams(C.Structure):
     _fields_ = [
         ("f", LifConvParams),
@@ -170,6 +178,7 @@ EXPORTS = {
     "ef_device_ok": (C.c_int, []),
     "ef_launch_count": (C.c_uint64, []),
     "ef_lif_conv_fwd": (C.c_int, [C.POINTER(LifConvParams), C.c_void_p]),
+    "ef_lif_conv_fwd_window": (C.c_int, [C.POINTER(LifConvWindowParams), C.c_void_p]),
     "ef_lif_conv_bwd": (C.c_int, [C.POINTER(LifConvBwdParams), C.c_void_p]),
     "ef_lif_bwd_tc": (C.c_int, [C.POINTER(LifBwdTcParams), C.c_void_p]),
     "ef_lif_bwd_window": (C.c_int, [C.POINTER(LifBwdWindowParams), C.c_void_p]),

@@ -66,6 +66,8 @@ struct TcCfg {
 
 struct TcParams {
   int B, H, W, tiles_x, tiles_y, n_tiles;
+  int T;           // feed-forward cells only: steps of a window fused into this launch (x / z_out hold T*B images, step-major); 1 = one step
+  int save_all_v;  // T > 1: store the membrane potential of every step (training) or only of the last one (inference)
   int has_v, has_z;
   const uint16_t* w_split;
   const float* leak;
@@ -127,18 +129,28 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long t_cta = DEBUG ? clock64() : 0;
   const bool z_from_halo = REC && p.has_z;  // the epilogue reads the previous spikes from the operand stage
-  int n_my = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  // items of this CTA: its tiles, each for T consecutive steps (time is the INNER loop: the state of a tile stays on chip over the window)
+  const int T = REC ? 1 : p.T;
+  int n_my = ((p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * T;
   if (DEBUG) {
     if (skip & 32) n_my = 0;                        // prologue + teardown only
     else if ((skip & 128) && n_my > 1) n_my = 1;    // one tile per CTA
   }
   const int tiles_per_img = p.tiles_x * p.tiles_y;
   // tile -> (b, y0, x0) for the single-thread roles (one division per tile is off their critical path)
-  auto tile_origin = [&](int it, int& b, int& y0, int& x0) {
-    const int tile = blockIdx.x + it * gridDim.x;
+  // item -> (image b of the state tensors, image bt = t*B + b of the per-step tensors, tile origin, step)
+  auto tile_origin4 = [&](int it, int& b, int& bt, int& y0, int& x0, int& t) {
+    const int k = it / T;
+    t = it - k * T;
+    const int tile = blockIdx.x + k * gridDim.x;
     b = tile / tiles_per_img;
+    bt = t * p.B + b;
     const int r = tile - b * tiles_per_img, ty = r / p.tiles_x;
     y0 = ty * TC_TH, x0 = (r - ty * p.tiles_x) * TC_TW;
+  };
+  auto tile_origin = [&](int it, int& b, int& y0, int& x0) {  // per-step tensors (operands, outputs)
+    int b0, t;
+    tile_origin4(it, b0, b, y0, x0, t);
   };
   const uint32_t op_tx = HALO_BYTES * (z_from_halo ? 2 : 1);
   auto op_issue = [&](int it) {  // operand tiles of tile `it` into stage it % NOP (the caller has waited for the stage)
@@ -154,11 +166,11 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
   const bool ld_v = p.has_v && !(DEBUG && (skip & 2));
   const uint32_t v_tx = (ld_v ? V_TILE_BYTES : 0) + (ld_zc ? ZC_TILE_BYTES : 0);
   auto v_issue = [&](int it) {  // membrane tile (+ centre spikes) of tile `it` into stage it % NV
-    int b, y0, x0;
-    tile_origin(it, b, y0, x0);
+    int b, bt, y0, x0, t;
+    tile_origin4(it, b, bt, y0, x0, t);
     const int s = it % NV;
     const uint32_t st = s_base + C::V_OFF + s * C::V_STAGE;
-    if (v_tx == 0) {
+    if (v_tx == 0 || t > 0) {  // steps t > 0 of a fused window carry their state in registers: the stage is only the store staging buffer
       mbar_arrive(bar_vf(s));
       return;
     }
@@ -294,20 +306,24 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
     const float inv_s = W_NSPLIT == 2 ? __ldg(reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(p.w_split) + C::W_BYTES)) : 1.0f;
     const float mid_s = W_NSPLIT == 2 ? __ldg(reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(p.w_split) + C::W_BYTES) + 1) : 1.0f;
     constexpr int NCH = CPT / 8;  // 16-byte spike chunks per thread
+    // state of this thread's pixel x CPT channels.  In a fused window (T > 1) it lives HERE, in registers, from step to step of a
+    // tile: only step 0 reads it from the membrane stage, no later step reads any state from memory
+    float vc[CPT];
+    uint4 zc[NCH];
     for (int it = 0; it < n_my; ++it) {
       const int sv = it % NV, so = it % NOP, a = it & 1;
+      const int t_step = REC ? 0 : it % T;
       const uint32_t vst = s_base + C::V_OFF + sv * C::V_STAGE;
       const uint32_t v_addr = vst + (uint32_t)(c0 * 512 + m * 4);  // [ch][16][8] fp32
-      // previous state of this pixel
-      float vc[CPT];
-      uint4 zc[NCH];
-      mbar_wait(bar_vf(sv), (it / NV) & 1);
-      if (p.has_v) {
+      mbar_wait(bar_vf(sv), (it / NV) & 1);  // stage landed (step 0) / free to be used as store staging buffer (later steps)
+      if (t_step == 0) {
+        if (p.has_v) {
 #pragma unroll
-        for (int j = 0; j < CPT; ++j) vc[j] = lds_f32(v_addr + j * 512);
-      } else {
+          for (int j = 0; j < CPT; ++j) vc[j] = lds_f32(v_addr + j * 512);
+        } else {
 #pragma unroll
-        for (int j = 0; j < CPT; ++j) vc[j] = 0.f;
+          for (int j = 0; j < CPT; ++j) vc[j] = 0.f;
+        }
       }
       uint32_t z_row;  // shared address of this pixel's 64-byte spike row (input in REC = halo tile, else the in-place centre tile)
       if (REC) {
@@ -316,8 +332,10 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
       } else {
         z_row = vst + V_TILE_BYTES + (uint32_t)(m * PIX_BYTES);
       }
+      if (t_step == 0) {
 #pragma unroll
-      for (int k = 0; k < NCH; ++k) zc[k] = p.has_z ? lds_u4(sw64(z_row, c0 / 8 + k)) : make_uint4(0, 0, 0, 0);
+        for (int k = 0; k < NCH; ++k) zc[k] = p.has_z ? lds_u4(sw64(z_row, c0 / 8 + k)) : make_uint4(0, 0, 0, 0);
+      }
 
       mbar_wait(bar_accf(a), (it >> 1) & 1);
       tc_fence_after();
@@ -365,20 +383,30 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
         mbar_arrive(bar_ve((it - 1) % NV));
       }
       if (REC) named_bar_sync(1, 32 * EPI_WARPS);
-      // new state, written in place (same addresses this thread read) / into the spike staging tile
+      // new state, written in place (same addresses this thread read) / into the spike staging tile.  In a fused window the membrane
+      // potential only goes to memory when it is wanted there: every step for training, the last step otherwise
+      const bool store_v = T == 1 || p.save_all_v || t_step == T - 1;
+      if (store_v) {
 #pragma unroll
-      for (int j = 0; j < CPT; ++j) sts_f32(v_addr + j * 512, vn[j]);
+        for (int j = 0; j < CPT; ++j) sts_f32(v_addr + j * 512, vn[j]);
+      }
       const uint32_t zo_row = REC ? (s_base + C::ZOUT_OFF + (uint32_t)(m * PIX_BYTES)) : z_row;
 #pragma unroll
-      for (int k = 0; k < NCH; ++k) sts_u4(sw64(zo_row, c0 / 8 + k), make_uint4(zpk[4 * k], zpk[4 * k + 1], zpk[4 * k + 2], zpk[4 * k + 3]));
+      for (int k = 0; k < NCH; ++k) {
+        const uint4 zn = make_uint4(zpk[4 * k], zpk[4 * k + 1], zpk[4 * k + 2], zpk[4 * k + 3]);
+        sts_u4(sw64(zo_row, c0 / 8 + k), zn);
+        zc[k] = zn;  // next step's previous spikes
+      }
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) vc[j] = vn[j];  // next step's previous potential
       fence_proxy_async();  // generic-proxy writes -> visible to the TMA store
       if (store_thread) EF_TRACE(it, 5);
       named_bar_sync(2, 32 * EPI_WARPS);
       if (store_thread) {
-        int b, y0, x0;
-        tile_origin(it, b, y0, x0);
-        if (!(DEBUG && (skip & 1))) tma_store_4d(&map_vout, vst, x0, y0, 0, b);
-        if (!(DEBUG && (skip & 8))) tma_store_4d(&map_zout, REC ? (s_base + C::ZOUT_OFF) : (vst + V_TILE_BYTES), 0, x0, y0, b);
+        int b, bt, y0, x0, t;
+        tile_origin4(it, b, bt, y0, x0, t);
+        if (store_v && !(DEBUG && (skip & 1))) tma_store_4d(&map_vout, vst, x0, y0, 0, (T == 1 || p.save_all_v) ? bt : b);
+        if (!(DEBUG && (skip & 8))) tma_store_4d(&map_zout, REC ? (s_base + C::ZOUT_OFF) : (vst + V_TILE_BYTES), 0, x0, y0, bt);
         bulk_commit();
         EF_TRACE(it, 6);
       }
@@ -507,7 +535,13 @@ static int launch_tc2(const TcParams& q, int grid, const CUtensorMap* m, cudaStr
   return cpt == 8 ? launch_tc<HARD, REC, 8, false>(q, grid, m, st) : launch_tc<HARD, REC, 16, false>(q, grid, m, st);
 }
 
-int lif_conv_fwd_tc(const ef_lif_conv_params& p, cudaStream_t st) {
+static int lif_conv_fwd_tc_window(const ef_lif_conv_params& p, int T, int save_all_v, cudaStream_t st);
+
+int lif_conv_fwd_tc(const ef_lif_conv_params& p, cudaStream_t st) { return lif_conv_fwd_tc_window(p, 1, 1, st); }
+
+// T > 1 (feed-forward cells only): x_cl / z_out_cl hold T*B images step-major, v_out T*B images (save_all_v) or the B images of the last
+// step; v_in / z_in_cl are the B images of the state before step 0.
+static int lif_conv_fwd_tc_window(const ef_lif_conv_params& p, int T, int save_all_v, cudaStream_t st) {
   static int n_sms = 0;
   if (n_sms == 0) {
     int dev = 0;
@@ -519,14 +553,16 @@ int lif_conv_fwd_tc(const ef_lif_conv_params& p, cudaStream_t st) {
   q.B = p.B, q.H = p.H, q.W = p.W;
   q.tiles_x = cdiv(p.W, TC_TW), q.tiles_y = cdiv(p.H, TC_TH), q.n_tiles = p.B * q.tiles_x * q.tiles_y;
   q.has_v = p.v_in != nullptr, q.has_z = p.z_in_cl != nullptr;
+  q.T = T, q.save_all_v = save_all_v;
   q.w_split = p.w_split, q.leak = p.leak, q.thresh = p.thresh;
   q.trace = g_tc_trace;
   q.skip = g_tc_skip;
   CUtensorMap m[6];  // x halo, z halo, v_in, v_out, z centre in, z out
   int rc;
-  if ((rc = get_map(p.x_cl, p.B, p.H, p.W, HALO_H, HALO_W, true, &m[0]))) return rc;
-  if ((rc = get_map_v(p.v_out, p.B, p.H, p.W, TC_TH, TC_TW, &m[3]))) return rc;
-  if ((rc = get_map(p.z_out_cl, p.B, p.H, p.W, TC_TH, TC_TW, true, &m[5]))) return rc;
+  const int BT = p.B * T;
+  if ((rc = get_map(p.x_cl, BT, p.H, p.W, HALO_H, HALO_W, true, &m[0]))) return rc;
+  if ((rc = get_map_v(p.v_out, (T == 1 || save_all_v) ? BT : p.B, p.H, p.W, TC_TH, TC_TW, &m[3]))) return rc;
+  if ((rc = get_map(p.z_out_cl, BT, p.H, p.W, TC_TH, TC_TW, true, &m[5]))) return rc;
   m[1] = m[0], m[2] = m[3], m[4] = m[5];  // placeholders when there is no previous state
   if (q.has_v && (rc = get_map_v(p.v_in, p.B, p.H, p.W, TC_TH, TC_TW, &m[2]))) return rc;
   if (q.has_z) {
@@ -544,6 +580,26 @@ int lif_conv_fwd_tc(const ef_lif_conv_params& p, cudaStream_t st) {
 }
 
 }  // namespace ef
+
+// Feed-forward 32 -> 32 LIF cell (or the head layer on split inputs) over a whole window of T steps in ONE launch: time is the inner
+// loop of every tile, the membrane potential and the previous spikes stay in registers from step to step.
+extern "C" int ef_lif_conv_fwd_window(const ef_lif_conv_window_params* pp, void* stream) {
+  using namespace ef;
+  EF_REQUIRE(pp, EF_ENULL, "ef_lif_conv_fwd_window: params is NULL");
+  const ef_lif_conv_window_params& w = *pp;
+  EF_REQUIRE(w.B > 0 && w.T > 0 && w.H > 0 && w.W > 0 && w.W % 4 == 0 && (int64_t)w.B * w.T < (1 << 20), EF_EINVAL,
+             "ef_lif_conv_fwd_window: bad dimensions (W must be a multiple of 4)");
+  EF_REQUIRE(w.x_cl && w.w_split && w.leak && w.thresh && w.v_out && w.z_out_cl, EF_ENULL, "ef_lif_conv_fwd_window: NULL tensor");
+  EF_REQUIRE(!w.v_in == !w.z_in_cl, EF_EINVAL, "ef_lif_conv_fwd_window: v_in and z_in_cl come together");
+  ef_lif_conv_params p = {};
+  p.B = w.B, p.Cin = 32, p.C = 32, p.H = w.H, p.W = w.W, p.ksize = 3, p.stride = 1, p.neuron = EF_LIF, p.hard_reset = w.hard_reset;
+  p.x_cl = w.x_cl, p.v_in = w.v_in, p.z_in_cl = w.z_in_cl, p.leak = w.leak, p.thresh = w.thresh, p.w_split = w.w_split;
+  p.v_out = w.v_out, p.z_out_cl = w.z_out_cl;
+  EF_REQUIRE(((uintptr_t)p.x_cl % 16 == 0) && ((uintptr_t)p.z_out_cl % 16 == 0) && ((uintptr_t)p.v_out % 16 == 0) && ((uintptr_t)p.v_in % 16 == 0) &&
+                 p.v_in != p.v_out,
+             EF_EINVAL, "ef_lif_conv_fwd_window: tensors must be 16-byte aligned and v_out must not alias v_in");
+  return lif_conv_fwd_tc_window(p, w.T, w.save_all_v ? 1 : 0, as_stream(stream));
+}
 
 extern "C" int ef_debug_tc_skip(int mask) {  // ablation switches for tools/tc_ablation.py; 0 = production behaviour
   ef::g_tc_skip = mask;

@@ -35,6 +35,7 @@ class _Carry:
         self.prev = None      # (v, z) lists: the state the window started from (detached), entries may be None
         self.parity = None    # arena bank of the window
         self.head_tc = False  # the head layer ran on the tensor cores (split input in bank.x_cl)
+        self.flow_y = None    # window entry point: the flows [T,B,2,H,W] as computed (tanh outputs the prediction backward needs)
 
 
 class _Slot:
@@ -638,6 +639,141 @@ def _stepwise_backward(model, arena, carry, shapes):
             g_v[i], g_z[i] = g_v_in, g_z_in
             g_h = g_x
     return grads
+
+
+def _launch_window(model, bank, T, v0, z0, splits, B, H, W, save_all_v):
+    """
+    The launches of a whole window of T steps, LAYER-MAJOR: every feed-forward cell runs its T steps in ONE time-fused launch
+    (ef_lif_conv_fwd_window: the state of a tile stays in registers over the window), the two recurrent cells run step by step (their
+    recurrent convolution needs the neighbours' spikes of the previous step), the prediction head runs once over T*B images.
+    Inputs: bank.x_cl[:T] (split network inputs); outputs: bank.v / bank.zs / bank.flow of steps 0..T-1.
+    """
+    cells = _cells(model)
+    for i, name in enumerate(LAYERS):
+        cell = cells[i]
+        leak, thresh = cell.leak.detach().reshape(-1), cell.thresh.detach().reshape(-1)
+        x_all = bank.x_cl[:T] if i == 0 else bank.zs[i - 1][1:T + 1]
+        if not cell.recurrent:
+            q = L.LifConvWindowParams()
+            q.B, q.T, q.H, q.W, q.hard_reset, q.save_all_v = B, T, H, W, int(cell.hard_reset), int(save_all_v)
+            q.x_cl, q.v_in, q.z_in_cl = L.ptr(x_all), L.ptr(v0[i]), L.ptr(z0[i])
+            q.leak, q.thresh, q.w_split = L.ptr(leak), L.ptr(thresh), L.ptr(splits[name])
+            q.v_out = L.ptr(bank.v[i][:T] if save_all_v else bank.v[i][T - 1])
+            q.z_out_cl = L.ptr(bank.zs[i][1:T + 1])
+            L.call("ef_lif_conv_fwd_window", q)
+        else:
+            for t in range(T):
+                p = L.LifConvParams()
+                _fill_fwd(p, B, 32, H, W, cell, None, x_all[t], v0[i] if t == 0 else bank.v[i][t - 1], z0[i] if t == 0 else bank.zs[i][t],
+                          bank.v[i][t], leak, thresh)
+                p.z_out_cl, p.w_split = L.ptr(bank.zs[i][t + 1]), L.ptr(splits[name])
+                L.call("ef_lif_conv_fwd", p, tag=(32, 32, True))
+    w, b = model.pred.conv2d.weight.detach(), model.pred.conv2d.bias.detach()
+    pp = L.PredParams()
+    pp.B, pp.Cin, pp.Cout, pp.H, pp.W = T * B, 32, 2, H, W
+    pp.x_cl, pp.w, pp.b, pp.y = L.ptr(bank.zs[N_L - 1][1:T + 1]), L.ptr(w), L.ptr(b), L.ptr(bank.flow[:T])
+    L.call("ef_pred_fwd", pp)
+
+
+WINDOW_LAUNCHES = lambda T: 5 + 2 * T + 1  # noqa: E731  kernels of one window forward: 5 fused cells + 2 recurrent cells x T + prediction
+
+
+class _FireNetWindow(torch.autograd.Function):
+    """T model steps at once (model.forward_window).  One autograd node per WINDOW; its backward is the deferred window backward."""
+
+    @staticmethod
+    def forward(ctx, model, xs, *params):
+        fs = model._fast
+        T, B, Cin0, H, W = xs.shape
+        dev = xs.device
+        _cells(model)
+        splits = _split_cache(model)
+        if "head" not in splits:
+            raise L.EventFlowError(f"forward_window: the head layer needs at most {L.EF_HEAD_MAX_CIN} input channels (got {Cin0})")
+        if fs.step != 0:
+            raise RuntimeError("forward_window must start at a window boundary (after reset_states() / detach_states())")
+        arena = model.__dict__.get("_arena")
+        if arena is None or arena.key != (B, H, W, dev):
+            arena = model.__dict__["_arena"] = _Arena(B, H, W, dev, max(T, int(model.__dict__.get("_window_cap", DEFAULT_WINDOW_CAP))))
+        parity = arena.parity
+        bank = arena.bank(parity)
+        while T > bank.cap:
+            bank.grow(0)
+        bank.need_input(Cin0, False, True)
+        need_grad = not isinstance(ctx, _NoCtx)
+        v0, z0 = list(fs.v), list(fs.z)
+        guards = [] if fs.src is None else [fs.src]
+        for t in range(T):
+            slot = bank.slot(t)
+            slot.gen += 1
+            guards.append((slot, slot.gen))
+        ops.pack_split_cl(xs.reshape(T * B, Cin0, H, W), out=bank.x_cl[:T].view(T * B, H, W, 32))
+        use_graph = model.__dict__.get("_use_graphs", True) and L.PROFILE is None and not torch.cuda.is_current_stream_capturing()
+        if use_graph:
+            if fs.param_sig is None:
+                fs.param_sig = (tuple(p.data_ptr() for p in _params_of(model)), tuple(splits[n].data_ptr() for n in LAYERS if n in splits))
+            key = ("window", fs.param_sig, tuple(0 if v is None else v.data_ptr() for v in v0), T, need_grad, bank.x_cl.data_ptr())
+            graphs = bank.__dict__.setdefault("window_graphs", {})
+            g = graphs.get(key)
+            if g is None:
+                _launch_window(model, bank, T, v0, z0, splits, B, H, W, need_grad)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                    _launch_window(model, bank, T, v0, z0, splits, B, H, W, need_grad)
+                graphs[key] = g
+            else:
+                g.replay()
+                L.GRAPH_KERNELS += WINDOW_LAUNCHES(T)
+        else:
+            _launch_window(model, bank, T, v0, z0, splits, B, H, W, need_grad)
+        last = bank.slot(T - 1)
+        for i in range(N_L):
+            fs.v[i], fs.z[i] = last.v[i], last.z[i]
+        fs.src = (last, last.gen)
+        fs.step = T
+        carry = fs.carry
+        carry.prev, carry.parity, carry.n, carry.head_tc = (v0, z0), parity, T, True
+        flows = bank.flow[:T].clone()  # the caller may keep the flows for as long as it likes; the bank is recycled
+        ctx.model, ctx.arena, ctx.carry, ctx.guards, ctx.shapes = model, arena, carry, guards, (B, Cin0, H, W)
+        model._last_spikes = last.z
+        return tuple(flows.unbind(0))
+
+    @staticmethod
+    def backward(ctx, *g_flows):
+        model, carry = ctx.model, ctx.carry
+        for slot_, gen_ in ctx.guards:
+            if slot_.gen != gen_:
+                raise RuntimeError(
+                    "event_flow_b200 fast path: the activations this backward needs were overwritten by a later forward pass. "
+                    "loss.backward() of a BPTT window must run before the next window completes (see fast._Arena).")
+        carry.g_flows = {t: g for t, g in enumerate(g_flows) if g is not None}
+        params = _params_of(model)
+        grads = _window_backward(model, ctx.arena, carry, ctx.shapes)
+        carry.g_flows = {}
+        return (None, None, *[g.clone() if p.requires_grad else None for p, g in zip(params, grads)])
+
+
+def forward_window(model, xs):
+    """
+    T forward passes of a LIF FireNet at once, layer-major and time-fused (model.forward_window).  xs [T,B,Cin,H,W].
+    Returns the list of the T flow maps [B,2,H,W]; numerically the same steps as T calls of forward().
+    """
+    fs = model._fast
+    if fs is None:
+        fs = FastState(len(LAYERS))
+        for i, s in enumerate(model._states):
+            if s is not None:
+                fs.v[i] = s[0].detach().contiguous()
+                fs.z[i] = ops.pack_cl(s[1].detach())
+        model._fast = fs
+    params = _params_of(model)
+    xs = xs.contiguous()
+    if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+        return list(_FireNetWindow.apply(model, xs, *params))
+    with torch.no_grad():
+        flows = list(_FireNetWindow.forward(_NoCtx(), model, xs, *params))
+    fs.detach(model.__dict__.get("_arena"))
+    return flows
 
 
 def forward(model, x, log=False):

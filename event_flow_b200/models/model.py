@@ -11,6 +11,8 @@ working.  Two families:
 The nineteen public classes are declared at the bottom from two small tables (which cell types a FireNet variant uses; which
 U-Net and recurrent block a U-Net model uses) instead of one hand-written subclass each.
 """
+import torch
+
 from .. import fast, ops
 from . import spiking_submodules as snn
 from . import submodules as ann
@@ -164,6 +166,26 @@ class FireNet(BaseModel):
         if log:
             activity = {key: t.detach().ne(0).float().mean().item() for key, t in zip(_ACTIVITY_KEYS, seen)}
         return {"flow": [flow], "activity": activity}
+
+
+def _forward_window(self, event_voxels, event_cnts, log=False):
+    """
+    The forward passes of a whole loss window at once: `event_voxels` [T x N x num_bins x H x W], `event_cnts` [T x N x 2 x H x W].
+    Returns the list of the T per-step output dicts -- numerically the steps `model(event_voxels[t], event_cnts[t])`, t = 0..T-1, would
+    produce.  On the LIF fast path the window runs layer-major with the time loop INSIDE the kernels of the feed-forward cells (their
+    state stays on chip over the T steps) and back-propagates as one window; other models simply loop over the steps.  Must start at
+    a window boundary (after reset_states() / detach_states()), like the loop of train_flow.py:97-171 does.
+    """
+    if not log and not self.norm_input:  # (input normalisation is per step: the statistics of one step's tensor, model.py:246-252)
+        x = _network_input(self, event_voxels, event_cnts)
+        if torch.is_tensor(x) and x.dim() == 5 and fast.eligible(self, x[0]) and x.shape[2] <= fast.L.EF_HEAD_MAX_CIN:
+            return [{"flow": [f], "activity": None} for f in fast.forward_window(self, x)]
+    vox = event_voxels if event_voxels is not None else [None] * len(event_cnts)
+    cnt = event_cnts if event_cnts is not None else [None] * len(event_voxels)
+    return [self(v, c, log=log) for v, c in zip(vox, cnt)]
+
+
+FireNet.forward_window = _forward_window
 
 
 def _firenet_variant(name, head, ff, rec, w_scale_pred, where):

@@ -92,6 +92,28 @@ typedef struct ef_lif_conv_params {
 int ef_lif_conv_fwd(const ef_lif_conv_params* p, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * A FEED-FORWARD 32 -> 32 LIF cell (or the head layer on split inputs, ef_pack_split_cl) over a whole window of T steps in ONE launch
+ * (the time loop of train_flow.py:98-141 / models/model.py:255-265 moved inside the kernel for the cells without a recurrent
+ * convolution: head, R1a, R1b, R2a, R2b).  Every tile runs its T steps back to back; the membrane potential and the previous spikes
+ * stay in REGISTERS from step to step -- only step 0 reads a state from memory.  x_cl [T,B,H,W,32] (the inputs of all steps must exist:
+ * layer-major execution of a window), v_in / z_in_cl [B,...] = the state before step 0 (NULL = zero), z_out_cl [T,B,H,W,32], v_out
+ * [T,B,32,H,W] with save_all_v (training: the backward needs every step) or [B,32,H,W] = the last step only (inference).
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct ef_lif_conv_window_params {
+  int32_t B, T, H, W, hard_reset, save_all_v;
+  const uint16_t* x_cl;
+  const float* v_in;
+  const uint16_t* z_in_cl;
+  const float* leak;             /* [32] raw parameters                                                                 */
+  const float* thresh;           /* [32]                                                                                */
+  const uint16_t* w_split;       /* ef_split_weights (no recurrent part) / ef_split_weights_head image                 */
+  float* v_out;
+  uint16_t* z_out_cl;
+} ef_lif_conv_window_params;
+
+int ef_lif_conv_fwd_window(const ef_lif_conv_window_params* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * Backward of one cell-step (what autograd derives from the spans above; recurrences in SURVEY.md 8a).
  * Given g_out (dL/d out), g_v_out, g_z_out, g_aux_out (dL/d new state from step t+1, NULL = 0) and the tensors the
  * forward read/wrote, produces g_x, g_v_in, g_z_in, g_aux_in and ACCUMULATES (+=) weight / per-channel gradients.
