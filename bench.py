@@ -227,54 +227,78 @@ def run_ours(args):
     n_per_leg = args.warmup + args.steps
 
     def host_window(k):
-        return [e.pin_memory() for e in make_events(rank, k)]
+        return torch.stack(make_events(rank, k)).pin_memory()  # [T,B,N,4]: the raw events of one window, staged by the loader
 
     def resident_window(k):
-        enc = []
-        for e in make_events(rank, k):
-            ed = e.to(dev)
-            d = encode_batch(ed, (H, W), BINS)
-            enc.append((d["event_voxel"], d["event_cnt"], ed, d["event_list_pol_mask"], d["event_mask"]))
-        return enc
+        ed = torch.stack(make_events(rank, k)).to(dev)
+        d = encode_batch(ed.view(T * B_PER_GPU, N_EV, 4), (H, W), BINS)  # one launch for the T*B images of the window
+        return (d["event_voxel"].view(T, B_PER_GPU, BINS, H, W), d["event_cnt"].view(T, B_PER_GPU, 2, H, W), ed,
+                d["event_list_pol_mask"].view(T, B_PER_GPU, N_EV, 2), d["event_mask"].view(T, B_PER_GPU, 1, H, W))
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
+    # The model runs through its WINDOWED entry point (model.forward_window: the T forward passes of a loss window, layer-major with the
+    # time loop inside the kernels of the feed-forward cells) -- what event_flow_b200.train.train_windows(staged=True) calls; the
+    # per-step API model(voxel, cnt) of the reference is timed beside it (`stepwise` keys).
+    def associate(outs, ed, pm, mask):
+        for t in range(T):
+            lossf.event_flow_association(outs[t]["flow"], ed[t], pm[t], mask[t])
+
+    def stage_e2e(e):
+        ed = e.to(dev, non_blocking=True)  # H2D of the window's raw events
+        d = encode_batch(ed.view(T * B_PER_GPU, N_EV, 4), (H, W), BINS)
+        return (d["event_voxel"].view(T, B_PER_GPU, BINS, H, W), d["event_cnt"].view(T, B_PER_GPU, 2, H, W), ed,
+                d["event_list_pol_mask"].view(T, B_PER_GPU, N_EV, 2), d["event_mask"].view(T, B_PER_GPU, 1, H, W))
+
     def fwd_loss_resident(win):
+        vox, cnt, ed, pm, mask = win
         lossf.reset()
         with torch.no_grad():
-            for vox, cnt, ev, pm, mask in win:
-                out = model(vox, cnt)
-                lossf.event_flow_association(out["flow"], ev, pm, mask)
+            associate(model.forward_window(vox, cnt), ed, pm, mask)
             return lossf()
 
-    def fwd_loss_e2e(win):
+    def fwd_loss_e2e(e):
         lossf.reset()
         with torch.no_grad():
-            for e in win:
-                ed = e.to(dev, non_blocking=True)
-                d = encode_batch(ed, (H, W), BINS)
-                out = model(d["event_voxel"], d["event_cnt"])
-                lossf.event_flow_association(out["flow"], ed, d["event_list_pol_mask"], d["event_mask"])
+            vox, cnt, ed, pm, mask = stage_e2e(e)
+            associate(model.forward_window(vox, cnt), ed, pm, mask)
             return lossf().item()  # D2H read of the result
 
-    def train_resident(win):
+    def fwd_loss_stepwise(win):
+        vox, cnt, ed, pm, mask = win
         lossf.reset()
-        for vox, cnt, ev, pm, mask in win:
-            out = model(vox, cnt)
-            lossf.event_flow_association(out["flow"], ev, pm, mask)
+        with torch.no_grad():
+            for t in range(T):
+                out = model(vox[t], cnt[t])
+                lossf.event_flow_association(out["flow"], ed[t], pm[t], mask[t])
+            return lossf()
+
+    def train_resident(win):
+        vox, cnt, ed, pm, mask = win
+        lossf.reset()
+        associate(model.forward_window(vox, cnt), ed, pm, mask)
         loss = lossf()
         loss.backward()
         trainer.step()
         model.detach_states()
         return loss
 
-    def train_e2e(win):
+    def train_stepwise(win):
+        vox, cnt, ed, pm, mask = win
         lossf.reset()
-        for e in win:
-            ed = e.to(dev, non_blocking=True)
-            d = encode_batch(ed, (H, W), BINS)
-            out = model(d["event_voxel"], d["event_cnt"])
-            lossf.event_flow_association(out["flow"], ed, d["event_list_pol_mask"], d["event_mask"])
+        for t in range(T):
+            out = model(vox[t], cnt[t])
+            lossf.event_flow_association(out["flow"], ed[t], pm[t], mask[t])
+        loss = lossf()
+        loss.backward()
+        trainer.step()
+        model.detach_states()
+        return loss
+
+    def train_e2e(e):
+        lossf.reset()
+        vox, cnt, ed, pm, mask = stage_e2e(e)
+        associate(model.forward_window(vox, cnt), ed, pm, mask)
         loss = lossf()
         loss.backward()
         trainer.step()
@@ -313,20 +337,27 @@ def run_ours(args):
     with ClockSampler(local) as clocks:
         legs = []
         for i, (fn, mk) in enumerate(((train_resident, resident_window), (train_e2e, host_window), (fwd_loss_resident, resident_window),
-                                      (fwd_loss_e2e, host_window))):
+                                      (fwd_loss_e2e, host_window), (train_stepwise, resident_window), (fwd_loss_stepwise, resident_window))):
             wins = [mk(i * n_per_leg + k) for k in range(n_per_leg)]
             legs.append(timed(fn, wins, args.steps, args.warmup))
             del wins
-        (ms_train, launches_train), (ms_train_e2e, _), (ms_fwd, launches_fwd), (ms_fwd_e2e, _) = legs
+        (ms_train, launches_train), (ms_train_e2e, _), (ms_fwd, launches_fwd), (ms_fwd_e2e, _), (ms_train_sw, launches_train_sw), (ms_fwd_sw, launches_fwd_sw) = legs
 
-    # roofline of the dominant kernel: the fused conv3x3+LIF step of the six 32->32 hidden layers.  The launches of a
-    # whole window (T steps x 6 layers, real operands of this workload, 59 MB each: far more than L2 per replay) are
-    # captured in one CUDA graph -- exactly how the model path issues them -- and the replay is timed with CUDA events on
-    # the launching stream: average launch duration = replay time / launches (inter-kernel gaps included).
+    # roofline of the dominant kernel: the fused conv3x3+LIF cell (lif_conv_fwd_tc_kernel).  In a window it is launched in two ways:
+    #   * recurrent cells G1, G2: one launch per step (the recurrent convolution needs the neighbours' spikes of the previous step),
+    #     T x 2 launches per window -- the largest share of the forward window, hence the `roofline` block;
+    #   * feed-forward cells R1a, R1b, R2a, R2b (and the head on split inputs): ONE launch per window, time loop inside, state in registers.
+    # Each population is captured as one CUDA graph on the workload's real operands (exactly how the model path issues them; every replay
+    # streams far more than L2) and timed with CUDA events on the launching stream: average launch duration = replay time / launches.
     model.reset_states()
-    xs = [enc[0] for enc in resident_window(0)] + [resident_window(1)[0][0]]  # T + 1 inputs: step 0 only provides the previous state
-    graph, n_hidden = fast.capture_window(model, xs, only_hidden=True)
-    graph_all, n_all = fast.capture_window(model, xs, only_hidden=False)
+    vox0, vox1 = resident_window(0)[0], resident_window(1)[0]
+    FF, REC = ("R1a", "R1b", "R2a", "R2b"), ("G1", "G2")
+    g_rec, n_rec, _ = fast.capture_window_fused(model, vox0, vox1, only=REC)
+    g_ff, n_ff, _ = fast.capture_window_fused(model, vox0, vox1, only=FF, save_all_v=False)
+    g_ff_train, _, _ = fast.capture_window_fused(model, vox0, vox1, only=FF, save_all_v=True)
+    g_head, _, _ = fast.capture_window_fused(model, vox0, vox1, only=("head",), save_all_v=False)
+    g_pred, _, _ = fast.capture_window_fused(model, vox0, vox1, only=("pred",))
+    g_all, n_all, _ = fast.capture_window_fused(model, vox0, vox1)
 
     def replay_ms(gr, reps):
         for _ in range(3):
@@ -340,21 +371,41 @@ def run_ours(args):
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / reps
 
+    reps = max(10, args.steps)
     with ClockSampler(local) as clocks_k:
-        ms_hidden = replay_ms(graph, max(10, args.steps))
-        ms_all = replay_ms(graph_all, max(10, args.steps))
-    del graph, graph_all
+        ms_rec, ms_ff, ms_ff_train = replay_ms(g_rec, reps), replay_ms(g_ff, reps), replay_ms(g_ff_train, reps)
+        ms_head, ms_pred, ms_all = replay_ms(g_head, reps), replay_ms(g_pred, reps), replay_ms(g_all, reps)
+    del g_rec, g_ff, g_ff_train, g_head, g_pred, g_all
     pk, pk_kind = peaks()
-    bytes_per_launch = 4 * H * W * (32 + 2 * 2 * 32) * B_PER_GPU  # 4*HW*(Cin + 2*S_r*C) per sample, fp32 reference semantics
-    avg_ms = ms_hidden / n_hidden
-    achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9
+    px = H * W * B_PER_GPU
+    cell_step_bytes = 4 * (32 + 2 * 2 * 32) * px  # 4*HW*(Cin + 2*S_r*C) per sample and cell-step, fp32 reference semantics
+    avg_ms = ms_rec / n_rec
+    achieved = cell_step_bytes / (avg_ms * 1e-3) / 1e9
     traffic, traffic_src = ncu_traffic()
-    roofline = {"bound": "hbm", "kernel": "fused conv3x3+LIF step, 32->32 ch (lif_conv_fwd_tc_kernel via ef_lif_conv_fwd)", "achieved": achieved,
-                "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "peak_source": pk_kind + " (burst copy)",
-                "bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_ms, "launches_per_step": n_hidden, "traffic_source": traffic_src,
-                "how": f"{n_hidden} launches (4 feed-forward + 2 recurrent cells x {T} steps) replayed as one CUDA graph, CUDA events around the replays",
-                "share_of_fwd_window": ms_hidden / ms_all, "share_of_step": ms_hidden / ms_train, "model_kernels_ms_per_window": ms_all,
-                "clocks": clocks_k.summary()}
+    gbs = lambda nbytes, ms: nbytes / (ms * 1e-3) / 1e9  # noqa: E731
+    # bytes a launch really moves (bf16 channels-last spikes, fp32 membrane): recurrent step = x 64 + z_in 64 + v_in 128 + v_out 128 + z_out 64
+    # per pixel; fused window launch = per step x 64 + z_out 64 (+ v_out 128 when the backward needs every step), state once per window
+    moved_rec = 448 * px
+    moved_ff, moved_ff_train = (128 * T + 448 - 128) * px, (256 * T + 448 - 128 - 128) * px
+    roofline = {"bound": "hbm", "kernel": "fused conv3x3+LIF step, 32->32 ch, recurrent cell (lif_conv_fwd_tc_kernel<REC> via ef_lif_conv_fwd)",
+                "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": traffic,
+                "peak_source": pk_kind + " (burst copy)", "bytes_per_launch": cell_step_bytes, "avg_launch_ms": avg_ms, "launches_per_step": n_rec,
+                "traffic_source": traffic_src, "moved_bytes_per_launch": moved_rec, "frac_on_moved_bytes": gbs(moved_rec, avg_ms) / pk["hbm_gbs"],
+                "how": f"{n_rec} launches (2 recurrent cells x {T} steps) replayed as one CUDA graph, CUDA events around the replays",
+                "share_of_fwd_window": ms_rec / ms_all, "share_of_step": ms_rec / ms_train, "model_kernels_ms_per_window": ms_all,
+                "clocks": clocks_k.summary(),
+                "fused_window_launch": {
+                    "kernel": "the same kernel, feed-forward cell over a whole window in one launch (ef_lif_conv_fwd_window): state in registers over T",
+                    "launches_per_step": n_ff, "cell_steps_per_launch": T, "algorithmic_bytes_per_launch": cell_step_bytes * T,
+                    "avg_launch_ms": ms_ff / n_ff, "achieved_algorithmic_GBs": gbs(cell_step_bytes * T, ms_ff / n_ff),
+                    "frac_algorithmic": gbs(cell_step_bytes * T, ms_ff / n_ff) / pk["hbm_gbs"],
+                    "note": "above 1 = faster than the HBM roofline of the step-by-step algorithm: the state bytes SURVEY 8d counts never move",
+                    "moved_bytes_per_launch": moved_ff, "frac_on_moved_bytes": gbs(moved_ff, ms_ff / n_ff) / pk["hbm_gbs"],
+                    "training": {"avg_launch_ms": ms_ff_train / n_ff, "moved_bytes_per_launch": moved_ff_train,
+                                 "frac_algorithmic": gbs(cell_step_bytes * T, ms_ff_train / n_ff) / pk["hbm_gbs"],
+                                 "frac_on_moved_bytes": gbs(moved_ff_train, ms_ff_train / n_ff) / pk["hbm_gbs"]},
+                    "share_of_fwd_window": ms_ff / ms_all},
+                "head_window_launch_ms": ms_head, "pred_window_launch_ms": ms_pred}
 
     iwe = iwe_bench(dev, pk["hbm_gbs"]) if rank == 0 else None
     if rank == 0:
@@ -369,8 +420,8 @@ def run_ours(args):
                        "l2": "256 MB write between timed iterations (L2 flush)", "weights": WEIGHTS},
             "e2e": {"value": events_per_step / (ms_train_e2e * 1e-3), "unit": "events/s", "ms_per_step": ms_train_e2e,
                     "h2d_bytes_per_step": T * B_PER_GPU * N_EV * 4 * 4, "d2h_bytes_per_step": 4,
-                    "path": "pinned host event lists -> H2D -> ef_encode_events -> LIFFireNet x10 -> EventWarping -> backward -> "
-                            "all-reduce -> clip + Adam -> loss.item()"},
+                    "path": "pinned host event lists of the window -> H2D -> ef_encode_events -> LIFFireNet.forward_window (10 steps) -> "
+                            "EventWarping -> backward -> all-reduce -> clip + Adam -> loss.item()"},
             "gpu_launches": int(launches_train),
             "fwd_loss": {"workload": WORKLOAD_FWD, "value": events_per_step / (ms_fwd * 1e-3), "unit": "events/s", "ms_per_step": ms_fwd,
                          "steps": args.steps, "warmup": args.warmup, "gpu_launches": int(launches_fwd),
@@ -379,6 +430,9 @@ def run_ours(args):
                          "e2e": {"value": events_per_step / (ms_fwd_e2e * 1e-3), "unit": "events/s", "ms_per_step": ms_fwd_e2e,
                                  "h2d_bytes_per_step": T * B_PER_GPU * N_EV * 4 * 4, "d2h_bytes_per_step": 4}},
             "train": {"ms_per_step": ms_train, "events_per_s": events_per_step / (ms_train * 1e-3), "gpu_launches": int(launches_train)},
+            "stepwise": {"what": "the same windows through the reference's per-step call model(voxel, cnt) (one CUDA graph of 8 kernels per step)",
+                         "train_ms_per_step": ms_train_sw, "train_gpu_launches": int(launches_train_sw),
+                         "fwd_loss_ms_per_step": ms_fwd_sw, "fwd_loss_gpu_launches": int(launches_fwd_sw)},
             "dp_check": dp_check,
             "roofline": roofline, "iwe": iwe, "cpu_baseline": cpu, "clocks": clocks.summary(),
         }

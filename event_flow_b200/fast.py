@@ -641,7 +641,7 @@ def _stepwise_backward(model, arena, carry, shapes):
     return grads
 
 
-def _launch_window(model, bank, T, v0, z0, splits, B, H, W, save_all_v):
+def _launch_window(model, bank, T, v0, z0, splits, B, H, W, save_all_v, only=None):
     """
     The launches of a whole window of T steps, LAYER-MAJOR: every feed-forward cell runs its T steps in ONE time-fused launch
     (ef_lif_conv_fwd_window: the state of a tile stays in registers over the window), the two recurrent cells run step by step (their
@@ -650,6 +650,8 @@ def _launch_window(model, bank, T, v0, z0, splits, B, H, W, save_all_v):
     """
     cells = _cells(model)
     for i, name in enumerate(LAYERS):
+        if only is not None and name not in only:  # measurement replays (capture_window_fused): a subset of the layers
+            continue
         cell = cells[i]
         leak, thresh = cell.leak.detach().reshape(-1), cell.thresh.detach().reshape(-1)
         x_all = bank.x_cl[:T] if i == 0 else bank.zs[i - 1][1:T + 1]
@@ -668,11 +670,44 @@ def _launch_window(model, bank, T, v0, z0, splits, B, H, W, save_all_v):
                           bank.v[i][t], leak, thresh)
                 p.z_out_cl, p.w_split = L.ptr(bank.zs[i][t + 1]), L.ptr(splits[name])
                 L.call("ef_lif_conv_fwd", p, tag=(32, 32, True))
+    if only is not None and "pred" not in only:
+        return
     w, b = model.pred.conv2d.weight.detach(), model.pred.conv2d.bias.detach()
     pp = L.PredParams()
     pp.B, pp.Cin, pp.Cout, pp.H, pp.W = T * B, 32, 2, H, W
     pp.x_cl, pp.w, pp.b, pp.y = L.ptr(bank.zs[N_L - 1][1:T + 1]), L.ptr(w), L.ptr(b), L.ptr(bank.flow[:T])
     L.call("ef_pred_fwd", pp)
+
+
+def capture_window_fused(model, xs0, xs, only=None, save_all_v=False):
+    """
+    Measurement aid (bench.py roofline): the launches of one time-fused window (xs [T,B,Cin,H,W]) on a private activation bank, captured
+    as ONE CUDA graph.  The window starts from the state a first eager window over xs0 leaves (a non-zero state, like every window but
+    the first of a sequence).  `only`: subset of LAYERS + ("pred",) to capture (the eager passes always run everything, so the inputs
+    of the selected layers are in place).  Returns (graph, kernel launches per replay, cell-steps per replay).
+    """
+    T, B, Cin0, H, W = xs.shape
+    _cells(model)
+    splits = _split_cache(model)
+    banks = [_Bank((B, H, W, xs.device), T), _Bank((B, H, W, xs.device), T)]
+    none = [None] * N_L
+    with torch.no_grad():
+        for bank, x in zip(banks, (xs0, xs)):
+            bank.need_input(Cin0, False, True)
+            ops.pack_split_cl(x.reshape(T * B, Cin0, H, W).contiguous(), out=bank.x_cl[:T].view(T * B, H, W, 32))
+        _launch_window(model, banks[0], T, none, none, splits, B, H, W, True)
+        v0 = [banks[0].v[i][T - 1] for i in range(N_L)]
+        z0 = [banks[0].zs[i][T] for i in range(N_L)]
+        _launch_window(model, banks[1], T, v0, z0, splits, B, H, W, save_all_v)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, capture_error_mode="thread_local"):
+            _launch_window(model, banks[1], T, v0, z0, splits, B, H, W, save_all_v, only=only)
+    g._keepalive = (banks, splits)
+    names = LAYERS + ("pred",) if only is None else only
+    cells = dict(zip(LAYERS, _cells(model)))
+    launches = sum(1 if n == "pred" or not cells[n].recurrent else T for n in names)
+    return g, launches, T * sum(1 for n in names if n != "pred")
 
 
 WINDOW_LAUNCHES = lambda T: 5 + 2 * T + 1  # noqa: E731  kernels of one window forward: 5 fused cells + 2 recurrent cells x T + prediction

@@ -58,36 +58,59 @@ class SyntheticEventStream:
             yield d
 
 
-def train_windows(model, loss_function, trainer, loader, window_loss, n_windows, overwrite_intermediate=False, log=None):
+def _finish_window(model, loss_function, trainer, last_flow, overwrite_intermediate, losses, log):
+    if overwrite_intermediate:
+        loss_function.overwrite_intermediate_flow(last_flow)
+    loss = loss_function()
+    loss.backward()
+    trainer.step()  # all-reduce(SUM) -> clip -> Adam -> zero grads
+    model.detach_states()
+    loss_function.reset()
+    value = loss.detach().clone()
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(value, op=dist.ReduceOp.SUM)  # for logging only: the global loss is the sum over the shards
+    losses.append(value)
+    if log is not None:
+        log(len(losses), value)
+
+
+def train_windows(model, loss_function, trainer, loader, window_loss, n_windows, overwrite_intermediate=False, log=None, staged=False):
     """
     train_flow.py:97-171 for `n_windows` loss windows.  `loader` yields batch dicts and exposes `.new_seq`; `trainer` is a
     DataParallelTrainer (or anything with step() / zero_grad()).  Returns the list of (summed over ranks) window losses.
+
+    staged=True: the loader items of a loss window are STAGED (the loss fires on the event count alone, :141, so the window's extent is
+    known without running the model) and the model runs the whole window through `model.forward_window` -- layer-major, the time loop
+    inside the kernels of the feed-forward cells.  Same arithmetic, same losses and gradients as the step-by-step loop; a `new_seq` in
+    the middle of a window drops the staged steps exactly like the reference drops its partial window (:100-105).
     """
     losses = []
     model.train()
+    staged = staged and hasattr(model, "forward_window")
+    pending, n_pending = [], 0
     for inputs in loader:
         if getattr(loader, "new_seq", False):
             loss_function.reset()
             model.reset_states()
             trainer.zero_grad()
-        x = model(inputs["event_voxel"], inputs["event_cnt"])
-        loss_function.event_flow_association(x["flow"], inputs["event_list"], inputs["event_list_pol_mask"], inputs["event_mask"])
-        if loss_function.num_events >= window_loss:
-            if overwrite_intermediate:
-                loss_function.overwrite_intermediate_flow(x["flow"])
-            loss = loss_function()
-            loss.backward()
-            trainer.step()  # all-reduce(SUM) -> clip -> Adam -> zero grads
-            model.detach_states()
-            loss_function.reset()
-            value = loss.detach().clone()
-            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-                dist.all_reduce(value, op=dist.ReduceOp.SUM)  # for logging only: the global loss is the sum over the shards
-            losses.append(value)
-            if log is not None:
-                log(len(losses), value)
-            if len(losses) >= n_windows:
-                break
+            pending, n_pending = [], 0
+        if staged:
+            pending.append(inputs)
+            n_pending += inputs["event_list"].shape[1]
+            if n_pending < window_loss:
+                continue
+            outs = model.forward_window(torch.stack([d["event_voxel"] for d in pending]), torch.stack([d["event_cnt"] for d in pending]))
+            for d, x in zip(pending, outs):
+                loss_function.event_flow_association(x["flow"], d["event_list"], d["event_list_pol_mask"], d["event_mask"])
+            pending, n_pending = [], 0
+            _finish_window(model, loss_function, trainer, outs[-1]["flow"], overwrite_intermediate, losses, log)
+        else:
+            x = model(inputs["event_voxel"], inputs["event_cnt"])
+            loss_function.event_flow_association(x["flow"], inputs["event_list"], inputs["event_list_pol_mask"], inputs["event_mask"])
+            if loss_function.num_events >= window_loss:
+                _finish_window(model, loss_function, trainer, x["flow"], overwrite_intermediate, losses, log)
+        if len(losses) >= n_windows:
+            break
     return [v.item() for v in losses]
 
 

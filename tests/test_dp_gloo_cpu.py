@@ -179,6 +179,63 @@ def test_train_windows_follows_the_reference_loop():
                    "forward", "forward", "loss()", "step", "detach_states", "loss.reset"]
 
 
+def test_train_windows_staged_runs_whole_windows_and_drops_partial_ones():
+    """staged=True: the items of a loss window are staged and handed to model.forward_window; new_seq drops the staged steps."""
+    from event_flow_b200.train import train_windows
+
+    log = []
+
+    class Loader:
+        def __init__(self):
+            self.new_seq = False
+
+        def __iter__(self):
+            for i in range(9):
+                self.new_seq = i in (0, 5)
+                yield {"event_voxel": torch.full((1,), float(i)), "event_cnt": torch.zeros(1), "event_list": torch.zeros(1, 100, 4),
+                       "event_list_pol_mask": torch.zeros(1, 100, 2), "event_mask": torch.zeros(1)}
+
+    class Model:
+        def train(self):
+            pass
+
+        def reset_states(self):
+            log.append("reset_states")
+
+        def detach_states(self):
+            log.append("detach_states")
+
+        def forward_window(self, vox, cnt):
+            log.append(("forward_window", vox.flatten().tolist()))
+            return [{"flow": [torch.zeros(1)]} for _ in range(vox.shape[0])]
+
+    class Loss:
+        num_events = 0
+
+        def reset(self):
+            self.num_events = 0
+
+        def event_flow_association(self, flow, ev, pm, mask):
+            self.num_events += ev.shape[1]
+
+        def __call__(self):
+            log.append(("loss()", self.num_events))
+            return torch.zeros((), requires_grad=True) + 1.0
+
+    class Trainer:
+        def zero_grad(self):
+            pass
+
+        def step(self):
+            log.append("step")
+
+    losses = train_windows(Model(), Loss(), Trainer(), Loader(), window_loss=300, n_windows=2, staged=True)
+    assert losses == [1.0, 1.0]
+    assert log == ["reset_states", ("forward_window", [0.0, 1.0, 2.0]), ("loss()", 300), "step", "detach_states",
+                   "reset_states",  # items 3, 4 were staged and are dropped by the new recording
+                   ("forward_window", [5.0, 6.0, 7.0]), ("loss()", 300), "step", "detach_states"]
+
+
 def test_synthetic_stream_shards_are_disjoint_and_reproducible():
     from event_flow_b200.train import SyntheticEventStream
 

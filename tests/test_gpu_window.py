@@ -70,7 +70,7 @@ def test_window_then_steps_continue_the_same_sequence():
 
 @pytest.mark.parametrize("shape", [(2, 32, 48, 4), (2, 64, 64, 10)])
 def test_window_bptt_gradients_are_the_stepwise_gradients(shape):
-    """Truncated BPTT over two windows through forward_window + EventWarping: loss bit-equal, parameter gradients to 1e-5 (same backward launches on the same activations)."""
+    """Truncated BPTT over two windows through forward_window + EventWarping: saved activations bit-equal, loss / gradients to the atomics' noise floor."""
     from event_flow_b200.loss.flow import EventWarping
 
     B, H, W, T = shape
@@ -92,19 +92,24 @@ def test_window_bptt_gradients_are_the_stepwise_gradients(shape):
             for d, out in zip(part, outs):
                 lossf.event_flow_association(out["flow"], d["event_list"].clone().to(DEV), d["event_list_pol_mask"].to(DEV), d["event_mask"].to(DEV))
             loss = lossf()
+            bank = model._arena.banks[model._arena.parity]  # what the backward will read: membrane potentials and spikes of every step
+            acts = [v[:T].clone() for v in bank.v] + [z[1:T + 1].clone() for z in bank.zs] + [bank.flow[:T].clone(), bank.x_cl[:T].clone()]
             loss.backward()
             lossf.reset()
             model.detach_states()
-            res.append((loss.item(), {n: p.grad.clone() for n, p in model.named_parameters()}))
+            res.append((loss.item(), {n: p.grad.clone() for n, p in model.named_parameters()}, acts))
         return res
 
     ra, rb = run(True), run(False)
-    for w, ((la, ga), (lb, gb)) in enumerate(zip(ra, rb)):
-        assert la == lb, f"window {w}: loss {la} vs {lb}"
+    for w, ((la, ga, aa), (lb, gb, ab)) in enumerate(zip(ra, rb)):
+        for k, (x, y) in enumerate(zip(aa, ab)):
+            assert torch.equal(x, y), f"window {w}: saved activation {k} differs"
+        # same launches on bit-identical activations (test above); what differs run to run is the summation order of the atomics in the
+        # loss kernels and the per-channel reductions (measured floor: profiles/r02_loss_gradient_noise_floor.txt, ~1e-6 .. 1e-5)
+        assert abs(la - lb) <= 1e-6 * abs(lb), f"window {w}: loss {la} vs {lb}"
         for n in gb:
-            # (the per-channel leak / threshold gradients are accumulated with atomics: same terms, free order)
             scale = gb[n].abs().max().item() + 1e-30
-            assert (ga[n] - gb[n]).abs().max().item() <= 1e-5 * scale, f"window {w}: gradient of {n} differs by {(ga[n] - gb[n]).abs().max().item():.3e}"
+            assert (ga[n] - gb[n]).abs().max().item() <= 5e-5 * scale, f"window {w}: gradient of {n} differs by {(ga[n] - gb[n]).abs().max().item():.3e}"
 
 
 def test_window_entry_refuses_to_start_inside_a_window():
@@ -124,3 +129,34 @@ def test_window_c_abi_rejects_bad_arguments():
     q.B, q.T, q.H, q.W = 1, 2, 16, 18  # W not a multiple of 4
     assert L.lib().ef_lif_conv_fwd_window(q, None) < 0
     assert L.lib().ef_lif_conv_fwd_window(None, None) < 0
+
+
+def test_staged_training_loop_is_the_stepwise_training_loop():
+    """event_flow_b200.train.train_windows(staged=True) vs the reference-shaped per-step loop: same window losses, same parameters."""
+    from event_flow_b200.loss.flow import EventWarping
+    from event_flow_b200.train import SyntheticEventStream, build_trainer, train_windows
+
+    H, W, B, T, N = 32, 48, 2, 4, 300
+    cfg = {"loader": {"resolution": [H, W]}, "loss": {"flow_regul_weight": 0.001, "overwrite_intermediate": False, "clip_grad": 100.0},
+           "model": {"mask_output": True}, "optimizer": {"lr": 2e-4}}
+
+    def run(staged, n_windows):
+        model = _model()
+        trainer = build_trainer(model, cfg)
+        loader = SyntheticEventStream(B, N, (H, W), 5, DEV, seq_len=3 * T + 2, n_items=8 * T)  # a new recording starts inside the 4th window
+        losses = train_windows(model, EventWarping(cfg, DEV), trainer, loader, T * N, n_windows, staged=staged)
+        return losses, trainer.flat_param.clone()
+
+    (la, pa), (lb, pb) = run(True, 1), run(False, 1)
+    # first optimiser step: same loss; Adam's first update is lr * sign(g) whatever |g| is, so the run-to-run noise of the atomics
+    # (1e-6 of the gradient scale) may flip the update of a parameter whose gradient is ~0: almost all parameters agree to rounding,
+    # none differs by more than 2 lr
+    assert abs(la[0] - lb[0]) <= 1e-6 * abs(lb[0])
+    d = (pa - pb).abs()
+    assert d.max().item() <= 2.1 * 2e-4 and (d > 1e-6).float().mean().item() < 0.01, (d.max().item(), (d > 1e-6).float().mean().item())
+    # five windows with a new recording inside the 4th: same number of optimiser steps, losses of the same trajectory family (spiking
+    # networks amplify the differences above, SURVEY 7.3)
+    (la, pa), (lb, pb) = run(True, 5), run(False, 5)
+    assert len(la) == len(lb) == 5
+    for a, b in zip(la, lb):
+        assert abs(a - b) <= 0.05 * abs(b), (la, lb)

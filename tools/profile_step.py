@@ -1,5 +1,6 @@
 """One warm forward window (+ loss) and one train step of the bench workload, for `ncu` launch lists.
-   ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv python tools/profile_step.py"""
+   ncu --metrics gpu__time_duration.sum --clock-control none --nvtx --nvtx-include "measured/" --csv --log-file gpurun_out/launches.csv \
+       python tools/profile_step.py [fwd|train|both] [stepwise]"""
 import os
 import sys
 
@@ -27,12 +28,19 @@ for e in bench.make_events(0, 0):
     win.append((d["event_voxel"], d["event_cnt"], ed, d["event_list_pol_mask"], d["event_mask"]))
 
 
+vox_all, cnt_all = torch.stack([w[0] for w in win]), torch.stack([w[1] for w in win])
+stepwise = len(sys.argv) > 2 and sys.argv[2] == "stepwise"
+
+
 def window(train):
     model.reset_states()
     lossf.reset()
     with torch.set_grad_enabled(train):
-        for vox, cnt, ev, pm, mask in win:
-            out = model(vox, cnt)
+        if stepwise:
+            outs = [model(vox, cnt) for vox, cnt, _, _, _ in win]
+        else:
+            outs = model.forward_window(vox_all, cnt_all)
+        for out, (_, _, ev, pm, mask) in zip(outs, win):
             lossf.event_flow_association(out["flow"], ev.clone(), pm, mask)
         loss = lossf()
     if train:

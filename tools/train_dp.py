@@ -33,6 +33,7 @@ def main():
     ap.add_argument("--num-bins", type=int, default=5)
     ap.add_argument("--seq-len", type=int, default=None, help="timesteps per synthetic recording (new_seq resets states); default: one long recording")
     ap.add_argument("--lr", type=float, default=2e-4)
+    ap.add_argument("--stepwise", action="store_true", help="call the model once per timestep (the reference's loop) instead of staging loss windows")
     ap.add_argument("--weight-gain", type=float, default=2.5, help="conv-weight gain so that spikes propagate on synthetic events")
     a = ap.parse_args()
 
@@ -77,12 +78,12 @@ def main():
 
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    losses = train_windows(model, loss_function, trainer, loader, a.window_loss, a.windows, log=log)
+    losses = train_windows(model, loss_function, trainer, loader, a.window_loss, a.windows, log=log, staged=not a.stepwise)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     if rank == 0:
         ev = global_batch * a.window_loss * len(losses)
-        print(json.dumps({"model": a.model, "world_size": world, "global_batch": global_batch, "windows": len(losses), "seconds": dt,
+        print(json.dumps({"model": a.model, "world_size": world, "global_batch": global_batch, "windows": len(losses), "staged": not a.stepwise, "seconds": dt,
                           "events_per_s_incl_host_generation": ev / dt, "first_loss": losses[0], "last_loss": losses[-1],
                           "param_checksum": float(trainer.flat_param.double().sum().item())}))
     if world > 1:
