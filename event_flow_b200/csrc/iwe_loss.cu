@@ -19,6 +19,7 @@ struct IweWin {
   int S, B, T, Tm, H, W;
   int loss_scaling, use_mask, use_dt;
   float flow_scaling, smooth_coef;  // smooth_coef = weight / components / T_maps
+  int vec;                          // W % 4 == 0 and every flow / mask / gradient plane 16-byte aligned: the pixel passes use 16-byte accesses
   int debug_skip;                   // timing experiments only (EF_IWE_SKIP): 1 = no smoothness, 2 = no event pass, 4 = no reduction / adjoint pass
   int n_items;                      // chunks of IWE_CHUNK events of one (scale, sample): sum_t ceil(n_t / IWE_CHUNK)
   int chunk_off[MAXP + 1];          // first chunk of pass t
@@ -33,15 +34,31 @@ struct IweWin {
   float* g_flow[MAXS * MAXP];       // backward: (s, map m): [B][2][H][W], sample stride g_bs
   long long g_bs;
 };
-constexpr int IWE_CHUNK = 256, IWE_THREADS = 256;
+#ifndef EF_IWE_EPT
+#define EF_IWE_EPT 1
+#endif
+#ifndef EF_IWE_OCC_F
+#define EF_IWE_OCC_F 4
+#endif
+#ifndef EF_IWE_OCC_B
+#define EF_IWE_OCC_B 4
+#endif
+#ifndef EF_IWE_NX
+#define EF_IWE_NX 4
+#endif
+constexpr int IWE_THREADS = 256, IWE_EPT = EF_IWE_EPT, IWE_CHUNK = IWE_THREADS * IWE_EPT;  // events per thread and per work item of the event passes
 constexpr int RED_PIX = 1024;  // pixels per work item of the per-pixel passes
 constexpr int SM_ROWS = 8;      // image rows per work item of the smoothness passes
+constexpr int SM_NX = EF_IWE_NX;        // pixels per thread of the smoothness passes (vector path)
 
 // workspace layout (floats):
 //   ctr  [16]  (as uint32) grid-barrier counters.  Must be ZERO when a buffer is first used; every call leaves them zero.
-//   img  [S][B][2 dir][2 pol][HW][2 = I, Th]   forward accumulators.  Polarity-planar, (I, Th) interleaved per pixel: an event
-//        adds (w, w*tau) of a corner with ONE 8-byte vector atomic, and the two corners of a row with ONE 16-byte vector
-//        atomic when the left pixel index is even (red.global.add.v4.f32): 6 instead of 16 atomics per event on average
+//   img  [S][B][2 dir][2 pol][plane]   forward accumulators.  Polarity-planar, (I, Th) interleaved per pixel.  An event adds
+//        (w, w*tau) of the two corners of an image row -- neighbouring pixels l, l+1 -- with ONE 16-byte vector reduction
+//        (red.global.add.v4.f32), whatever the parity of l: a plane holds the image TWICE, copy A for pairs that start at an even
+//        pixel (entry = pixel) and copy B, shifted by one pixel (entry = pixel + 1), for pairs that start at an odd pixel; the
+//        per-pixel passes read A[i] + B[i + 1].  4 vector reductions per event instead of 16 scalar atomics (6 with one copy).
+//        plane = [HW (A) + HW + 2 (B)][2] floats
 //   sums [S][B][2 dir][2 = sum A^2, n]
 //   smooth_part [S][MAX_GRID]                  per-CTA partial sums of the smoothness term (fixed-order final reduction)
 //   adj  [S][B][2 dir][2 pol][HW][2 = dL/dI, dL/dTh]   adjoint images, written and read by the backward only
@@ -49,14 +66,16 @@ struct WsLayout {
   size_t ctr, img, sums, smooth, adj, total;
 };
 constexpr int IWE_MAX_GRID = 148 * 8;
+__host__ __device__ inline size_t plane_px(size_t hw) { return 2 * hw + 2; }  // entries (pixels) of one accumulator plane: A then B
 __host__ __device__ inline WsLayout ws_layout(int S, int B, int H, int W) {
   WsLayout l;
   const size_t hw = (size_t)H * W;
   l.ctr = 0;
   l.img = 16;
-  l.sums = l.img + (size_t)S * B * 8 * hw;
+  l.sums = l.img + (size_t)S * B * 4 * plane_px(hw) * 2;
   l.smooth = l.sums + (size_t)S * B * 4;
-  l.adj = l.smooth + (size_t)S * IWE_MAX_GRID;  // backward only: adjoint images, same layout as img
+  l.adj = l.smooth + (size_t)S * IWE_MAX_GRID;  // backward only: adjoint images [sbd][pol][HW][2]
+  l.adj = (l.adj + 3) & ~(size_t)3;
   l.total = l.adj + (size_t)S * B * 8 * hw;
   return l;
 }
@@ -121,46 +140,126 @@ __device__ __forceinline__ void grid_barrier(unsigned int* ctr, unsigned int n) 
   __syncthreads();
 }
 
-__device__ __forceinline__ float charb_pair(const float* fxm, const float* fym, const float* mk, size_t a, size_t b, bool use_mask,
-                                            float& dcoef) {
-  const float d = (fxm[a] - fxm[b]) + (fym[a] - fym[b]);
-  const float c = sqrtf(d * d + 1e-6f);
-  const float m = use_mask ? mk[a] * mk[b] : 1.f;
-  dcoef = m * d / c;  // d(term)/d f[a] (both channels); minus for f[b]
-  return m * c;
-}
 
-
-// ---- smoothness on register strips -----------------------------------------------------------------------------------
-// A thread owns SM_R consecutive rows of one column: the values of a row are loaded once and reused by the pairs that involve the
-// row above / below; all loads of a strip are independent, so one memory round trip covers SM_R pixels.
-constexpr int SM_R = 2;
-struct PixF {
-  float fx, fy, m;
-};
-__device__ __forceinline__ float load_mask(const float* mk, int idx, bool ok, bool use_mask) { return ok ? (use_mask ? __ldg(mk + idx) : 1.f) : 0.f; }
-__device__ __forceinline__ void load_flow(PixF& p, const float* fxm, const float* fym, int idx, bool ok) {
-  p.fx = ok ? __ldg(fxm + idx) : 0.f;
-  p.fy = ok ? __ldg(fym + idx) : 0.f;
-}
+// ---- smoothness: Charbonnier terms of the flow maps (loss/flow.py:262-294) ---------------------------------------------
+// A thread owns NX consecutive pixels of one image row and loads their 3 x (NX + 2) neighbourhood of (mask, fx, fy) -- 16-byte loads
+// for the NX = 4 centre columns -- plus the same pixels of the next / previous map, ALL in one round of independent loads (no
+// mask-then-flow dependency: the pass is latency-bound at training sizes, bandwidth-bound on large windows).  Out-of-image
+// neighbours carry mask 0, which also encodes that the pair does not exist.
 __device__ __forceinline__ float sqrt_fast(float x) {  // sqrt.approx (1 ulp class): far inside the 1e-5 tolerance of the loss value
   float r;
   asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
-// one Charbonnier pair term m_a m_b sqrt((dfx + dfy)^2 + 1e-6) (loss/flow.py:273-286).  Event masks are sparse: pairs whose mask
-// product is zero contribute exactly 0 and are skipped (out-of-image pixels carry mask 0, which also encodes the pair's existence).
-__device__ __forceinline__ float charb(const PixF& a, const PixF& b) {
-  const float m = a.m * b.m;
-  if (m == 0.f) return 0.f;
-  const float d = (a.fx - b.fx) + (a.fy - b.fy);
-  return m * sqrt_fast(d * d + 1e-6f);
+struct SmoothMaps {  // one (scale, sample, map): this map and its temporal neighbours
+  const float *fx, *mk;          // flow x plane (y plane = fx + hw), event mask (NULL: no smoothing mask)
+  const float *fx_n, *mk_n;      // next map (NULL: none)
+  const float *fx_p, *mk_p;      // previous map (gradient only)
+};
+template <int NX>
+__device__ __forceinline__ void load_row(float (&dst)[NX + 2], const float* __restrict__ src, int y, int x, int H, int W, float oob, bool have) {
+  // columns x-1 .. x+NX of row y; `have` false (no such array): the constant `oob`... of an absent mask is 1 inside the image
+  const bool row_ok = y >= 0 && y < H;
+  if (!row_ok || src == nullptr) {
+#pragma unroll
+    for (int k = 0; k < NX + 2; ++k) dst[k] = (row_ok && !have && x - 1 + k >= 0 && x - 1 + k < W) ? 1.f : oob;
+    return;
+  }
+  const float* r = src + (size_t)y * W;
+  dst[0] = x >= 1 ? __ldg(r + x - 1) : oob;
+  if (NX == 4) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(r + x));
+    dst[1] = v.x, dst[2] = v.y, dst[3] = v.z, dst[4] = v.w;
+  } else {
+#pragma unroll
+    for (int k = 0; k < NX; ++k) dst[1 + k] = __ldg(r + x + k);
+  }
+  dst[NX + 1] = x + NX < W ? __ldg(r + x + NX) : oob;
 }
-__device__ __forceinline__ float dcharb(const PixF& a, const PixF& b) {  // d(term)/d f[a] (both channels); minus for f[b]
-  const float m = a.m * b.m;
-  if (m == 0.f) return 0.f;
-  const float d = (a.fx - b.fx) + (a.fy - b.fy);
-  return m * d * rsqrtf(d * d + 1e-6f);
+template <int NX>
+__device__ __forceinline__ void load_ctr(float (&dst)[NX], const float* __restrict__ src, int y, int x, int W, bool have) {
+  if (src == nullptr) {
+#pragma unroll
+    for (int k = 0; k < NX; ++k) dst[k] = have ? 0.f : 1.f;
+    return;
+  }
+  const float* r = src + (size_t)y * W + x;
+  if (NX == 4) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(r));
+    dst[0] = v.x, dst[1] = v.y, dst[2] = v.z, dst[3] = v.w;
+  } else {
+#pragma unroll
+    for (int k = 0; k < NX; ++k) dst[k] = __ldg(r + k);
+  }
+}
+// one pair (a first, b second): value m sqrt(d^2 + eps), derivative wrt f[a] (both channels) m d / sqrt(d^2 + eps); minus for f[b]
+__device__ __forceinline__ void pair_term(float ma, float fxa, float fya, float mb, float fxb, float fyb, float& val, float& der) {
+  const float m = ma * mb;
+  val = der = 0.f;
+  if (m == 0.f) return;  // event masks are sparse: most pairs vanish
+  const float d = (fxa - fxb) + (fya - fyb);
+  const float q = d * d + 1e-6f;
+  const float r = rsqrtf(q);
+  val = m * q * r;
+  der = m * d * r;
+}
+// NX pixels (y, x .. x+NX-1) of one map.  Returns the sum of the pairs these pixels are the FIRST element of (right, down, down-right,
+// the up-right pair ((y+1,x),(y,x+1)), temporal next); with GRAD also g[k] = d(sum of ALL pairs) / d f(y, x+k) (gather form, unscaled).
+template <bool GRAD, int NX>
+__device__ __forceinline__ float smooth_strip(const SmoothMaps& sm, int y, int x, int H, int W, size_t hw, float (&g)[NX]) {
+  constexpr int R0 = GRAD ? 0 : 1;  // rows y-1 .. y+1 (gradient) or y .. y+1 (value)
+  float m[3][NX + 2], fx[3][NX + 2], fy[3][NX + 2];
+  float mn[NX], fxn[NX], fyn[NX], mp[NX], fxp[NX], fyp[NX];
+#pragma unroll
+  for (int r = R0; r < 3; ++r) {
+    load_row<NX>(m[r], sm.mk, y - 1 + r, x, H, W, 0.f, sm.mk != nullptr);
+    load_row<NX>(fx[r], sm.fx, y - 1 + r, x, H, W, 0.f, true);
+    load_row<NX>(fy[r], sm.fx + hw, y - 1 + r, x, H, W, 0.f, true);
+  }
+  const bool nxt = sm.fx_n != nullptr, prv = GRAD && sm.fx_p != nullptr;
+  if (nxt) {
+    load_ctr<NX>(mn, sm.mk_n, y, x, W, false);
+    load_ctr<NX>(fxn, sm.fx_n, y, x, W, true);
+    load_ctr<NX>(fyn, sm.fx_n + hw, y, x, W, true);
+  }
+  if (prv) {
+    load_ctr<NX>(mp, sm.mk_p, y, x, W, false);
+    load_ctr<NX>(fxp, sm.fx_p, y, x, W, true);
+    load_ctr<NX>(fyp, sm.fx_p + hw, y, x, W, true);
+  }
+  float acc = 0.f;
+#pragma unroll
+  for (int k = 0; k < NX; ++k) {
+    const int c = k + 1;
+    float v, d, gk = 0.f;
+    const float mo = m[1][c], fo = fx[1][c], go = fy[1][c];
+    pair_term(mo, fo, go, m[1][c + 1], fx[1][c + 1], fy[1][c + 1], v, d), acc += v, gk += d;            // right
+    pair_term(mo, fo, go, m[2][c], fx[2][c], fy[2][c], v, d), acc += v, gk += d;                        // down
+    pair_term(mo, fo, go, m[2][c + 1], fx[2][c + 1], fy[2][c + 1], v, d), acc += v, gk += d;            // down-right
+    pair_term(m[2][c], fx[2][c], fy[2][c], m[1][c + 1], fx[1][c + 1], fy[1][c + 1], v, d), acc += v;    // ((y+1,x),(y,x+1)): value only
+    if (nxt) pair_term(mo, fo, go, mn[k], fxn[k], fyn[k], v, d), acc += v, gk += d;                     // temporal
+    if (GRAD) {
+      pair_term(m[1][c - 1], fx[1][c - 1], fy[1][c - 1], mo, fo, go, v, d), gk -= d;                    // left neighbour's right pair
+      pair_term(m[0][c], fx[0][c], fy[0][c], mo, fo, go, v, d), gk -= d;                                // upper neighbour's down pair
+      pair_term(m[0][c - 1], fx[0][c - 1], fy[0][c - 1], mo, fo, go, v, d), gk -= d;                    // upper-left neighbour's down-right pair
+      pair_term(mo, fo, go, m[0][c + 1], fx[0][c + 1], fy[0][c + 1], v, d), gk += d;                    // ((y,x),(y-1,x+1)): first element
+      pair_term(m[2][c - 1], fx[2][c - 1], fy[2][c - 1], mo, fo, go, v, d), gk -= d;                    // ((y+1,x-1),(y,x)): second element
+      if (prv) pair_term(mp[k], fxp[k], fyp[k], mo, fo, go, v, d), gk -= d;                             // previous map's temporal pair
+      g[k] = gk;
+    }
+  }
+  return acc;
+}
+__device__ __forceinline__ SmoothMaps smooth_maps(const IweWin& w, int s, int b, int t, size_t hw, bool grad) {
+  SmoothMaps sm;
+  sm.fx = w.flow[s * w.Tm + t] + (size_t)b * w.flow_bs;
+  sm.mk = w.use_mask ? w.mask[t] + (size_t)b * w.mask_bs : nullptr;
+  const bool dtn = w.use_dt && t + 1 < w.Tm, dtp = grad && w.use_dt && t >= 1;
+  sm.fx_n = dtn ? w.flow[s * w.Tm + t + 1] + (size_t)b * w.flow_bs : nullptr;
+  sm.mk_n = (dtn && w.use_mask) ? w.mask[t + 1] + (size_t)b * w.mask_bs : nullptr;
+  sm.fx_p = dtp ? w.flow[s * w.Tm + t - 1] + (size_t)b * w.flow_bs : nullptr;
+  sm.mk_p = (dtp && w.use_mask) ? w.mask[t - 1] + (size_t)b * w.mask_bs : nullptr;
+  return sm;
 }
 
 // item -> (scale*B + sample, pass, first event of the chunk)
@@ -173,11 +272,80 @@ __device__ __forceinline__ void decode_item(const IweWin& w, int item, int& sb, 
 }
 
 // vector reductions without a return value (RED, not ATOM: nothing waits for the round trip)
-__device__ __forceinline__ void red2(float* q, float a, float b) {
-  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(q), "f"(a), "f"(b) : "memory");
+#ifndef EF_IWE_HINT
+#define EF_IWE_HINT 0  // measured on B200 (tools/iwe_sweep.sh): the policies change nothing (689 vs 681 us on the 16 M-event window)
+#endif
+// L2 policies: the accumulator images are hit again and again by later events (keep: evict_last), the flow values gathered per event
+// and the events themselves are used once (evict_first)
+__device__ __forceinline__ uint64_t l2_policy_keep() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
 }
-__device__ __forceinline__ void red4(float* q, float a, float b, float c, float d) {
+__device__ __forceinline__ uint64_t l2_policy_stream() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void red2(float* q, float a, float b, uint64_t pol) {
+#if EF_IWE_HINT
+  asm volatile("red.global.add.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" ::"l"(q), "f"(a), "f"(b), "l"(pol) : "memory");
+#else
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(q), "f"(a), "f"(b) : "memory");
+#endif
+}
+__device__ __forceinline__ void red4(float* q, float a, float b, float c, float d, uint64_t pol) {
+#if EF_IWE_HINT
+  asm volatile("red.global.add.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(q), "f"(a), "f"(b), "f"(c), "f"(d), "l"(pol) : "memory");
+#else
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(q), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+#endif
+}
+__device__ __forceinline__ float ldg_stream(const float* q, uint64_t pol) {
+#if EF_IWE_HINT
+  float v;
+  asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(q), "l"(pol));
+  return v;
+#else
+  return __ldg(q);
+#endif
+}
+
+// events of one work item: thread tid owns events i0 + tid + k * IWE_THREADS, k < IWE_EPT (all loads of a thread are issued before any is used)
+struct Ev {
+  float4 e;   // ts, y, x, p
+  float2 pm;
+  float fx, fy;
+  int pix;
+  bool on;
+};
+__device__ __forceinline__ void load_events(const IweWin& w, int s, int b, int t, int i0, size_t hw, Ev (&ev)[IWE_EPT], uint64_t pol_stream) {
+  const float4* ep = reinterpret_cast<const float4*>(w.ev[t] + (size_t)b * w.ev_bs[t]);
+  const float2* pp = reinterpret_cast<const float2*>(w.pm[t] + (size_t)b * w.pm_bs[t]);
+  const float* fm = w.flow[s * w.Tm + (w.Tm > 1 ? t : 0)] + (size_t)b * w.flow_bs;
+#pragma unroll
+  for (int k = 0; k < IWE_EPT; ++k) {
+    const int i = i0 + threadIdx.x + k * IWE_THREADS;
+    ev[k].on = i < w.n_pass[t];
+    if (ev[k].on) {
+      ev[k].e = __ldcs(ep + i);  // streamed once: evict-first, the accumulator images stay in L2
+      ev[k].pm = __ldcs(pp + i);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < IWE_EPT; ++k) {
+    ev[k].on = ev[k].on && !(ev[k].pm.x == 0.f && ev[k].pm.y == 0.f);
+    if (ev[k].on) {
+      ev[k].pix = (int)(ev[k].e.y * (float)w.W + ev[k].e.z);
+      ev[k].fx = ldg_stream(fm + ev[k].pix, pol_stream), ev[k].fy = ldg_stream(fm + hw + ev[k].pix, pol_stream);
+    }
+  }
+}
+
+// accumulated (I, Th) of pixel i of one plane: copy A + copy B (shifted by one pixel)
+__device__ __forceinline__ float2 acc_px(const float2* pl, int i, size_t hw) {
+  const float2 a = __ldcg(pl + i), b = __ldcg(pl + hw + i + 1);
+  return make_float2(a.x + b.x, a.y + b.y);
 }
 
 // ---- forward: ONE launch ----------------------------------------------------------------------------------------------
@@ -186,7 +354,7 @@ __device__ __forceinline__ void red4(float* q, float a, float b, float c, float 
 //            utils/iwe.py:20-92)
 //   phase 2  per (scale, sample, direction): sum of squared average timestamps and number of pixels with events (:212-226)
 //   phase 3  last CTA: the scalar
-__global__ void __launch_bounds__(IWE_THREADS, 4) iwe_loss_fwd_kernel(const __grid_constant__ IweWin w, float* __restrict__ ws, float* __restrict__ loss) {
+__global__ void __launch_bounds__(IWE_THREADS, EF_IWE_OCC_F) iwe_loss_fwd_kernel(const __grid_constant__ IweWin w, float* __restrict__ ws, float* __restrict__ loss) {
   __shared__ float s_red[8];
   __shared__ bool s_last;
   const WsLayout l = ws_layout(w.S, w.B, w.H, w.W);
@@ -194,60 +362,34 @@ __global__ void __launch_bounds__(IWE_THREADS, 4) iwe_loss_fwd_kernel(const __gr
   float* img = ws + l.img;
   float* sums = ws + l.sums;
   const size_t hw = (size_t)w.H * w.W;
+  const size_t plane = plane_px(hw) * 2;  // floats per (scale, sample, direction, polarity)
   const int tid = threadIdx.x;
   const size_t gtid = (size_t)blockIdx.x * IWE_THREADS + tid, gsz = (size_t)gridDim.x * IWE_THREADS;
 
   // ---- phase 0
   {
     float4* z = reinterpret_cast<float4*>(img);
-    const size_t n4 = ((size_t)w.S * w.B * 8 * hw + (size_t)w.S * w.B * 4) / 4;  // images + sums (contiguous, multiple of 4 floats)
+    const size_t n4 = (l.smooth - l.img) / 4;  // images + sums (contiguous, multiple of 4 floats)
     for (size_t i = gtid; i < n4; i += gsz) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    // smoothness: work item = ROWS_PER_ITEM rows of one (scale, sample, map) plane; a thread walks columns x = tid, tid + 256, ...
-    // (32-bit index arithmetic only; neighbouring rows / the next map hit L1)
+    // smoothness: work item = SM_ROWS rows of one (scale, sample, map) plane
     const int rb = (w.H + SM_ROWS - 1) / SM_ROWS, planes = w.B * w.Tm;
+    const int nx = w.vec ? SM_NX : 1, groups = w.W / nx;
     for (int s = 0; s < w.S; ++s) {
       float acc = 0.f;
       if (w.smooth_coef != 0.f && !(w.debug_skip & 1)) {
         for (int item = blockIdx.x; item < planes * rb; item += gridDim.x) {
           const int bt = item / rb, y0 = (item - bt * rb) * SM_ROWS;
           const int b = bt / w.Tm, t = bt - b * w.Tm;
-          const float* fxm = w.flow[s * w.Tm + t] + (size_t)b * w.flow_bs;
-          const float* fym = fxm + hw;
-          const float* mk = w.use_mask ? w.mask[t] + (size_t)b * w.mask_bs : nullptr;
-          const bool dt = w.use_dt && t + 1 < w.Tm;
-          const float* fxn = dt ? w.flow[s * w.Tm + t + 1] + (size_t)b * w.flow_bs : nullptr;
-          const float* mkn = (dt && w.use_mask) ? w.mask[t + 1] + (size_t)b * w.mask_bs : nullptr;
-          // thread -> (column, strip of SM_R rows); SM_ROWS / SM_R strips per item
-          constexpr int STRIPS = SM_ROWS / SM_R;
-          for (int q = tid; q < w.W * STRIPS; q += IWE_THREADS) {
-            const int st = q / w.W, x = q - st * w.W, ys = y0 + st * SM_R;
-            if (ys >= w.H) continue;
-            PixF c[SM_R + 1][2], nx[SM_R];
-            float any = 0.f;
-#pragma unroll
-            for (int r = 0; r <= SM_R; ++r) {
-#pragma unroll
-              for (int k = 0; k < 2; ++k) {
-                c[r][k].m = load_mask(mk, (ys + r) * w.W + x + k, ys + r < w.H && x + k < w.W, w.use_mask);
-                any += (r < SM_R && k == 0) ? c[r][k].m : 0.f;  // every pair of the strip has one of these pixels as first or only partner ...
-              }
-            }
-            any += c[SM_R][0].m;  // ... except the up-right pair of the last row: ((y+1,x),(y,x+1))
-#pragma unroll
-            for (int r = 0; r < SM_R; ++r) nx[r].m = dt ? load_mask(mkn, (ys + r) * w.W + x, ys + r < w.H, w.use_mask) : 0.f;
-            if (any == 0.f) continue;  // nothing of this strip survives the masks: no flow loads at all
-#pragma unroll
-            for (int r = 0; r <= SM_R; ++r) {
-#pragma unroll
-              for (int k = 0; k < 2; ++k) load_flow(c[r][k], fxm, fym, (ys + r) * w.W + x + k, c[r][k].m != 0.f);
-            }
-#pragma unroll
-            for (int r = 0; r < SM_R; ++r) load_flow(nx[r], fxn, fxn + hw, (ys + r) * w.W + x, nx[r].m != 0.f);
-#pragma unroll
-            for (int r = 0; r < SM_R; ++r) {
-              // pairs: right, down, down-right, up-right ((y+1,x) - (y,x+1)), temporal (same pixel, next pass; masks of both passes)
-              acc += charb(c[r][0], c[r][1]) + charb(c[r][0], c[r + 1][0]) + charb(c[r][0], c[r + 1][1]) + charb(c[r + 1][0], c[r][1]) +
-                     charb(c[r][0], nx[r]);
+          const SmoothMaps sm = smooth_maps(w, s, b, t, hw, false);
+          for (int q = tid; q < groups * SM_ROWS; q += IWE_THREADS) {
+            const int r = q / groups, y = y0 + r, x = (q - r * groups) * nx;
+            if (y >= w.H) continue;
+            if (w.vec) {
+              float g[SM_NX];
+              acc += smooth_strip<false, SM_NX>(sm, y, x, w.H, w.W, hw, g);
+            } else {
+              float g[1];
+              acc += smooth_strip<false, 1>(sm, y, x, w.H, w.W, hw, g);
             }
           }
         }
@@ -260,43 +402,46 @@ __global__ void __launch_bounds__(IWE_THREADS, 4) iwe_loss_fwd_kernel(const __gr
 
   // ---- phase 1
   const float Tf = (float)w.T;
+  const uint64_t pol_keep = l2_policy_keep(), pol_stream = l2_policy_stream();
   const int total_items = (w.debug_skip & 2) ? 0 : w.S * w.B * w.n_items;
   for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
     int sb, t, i0;
     decode_item(w, item, sb, t, i0);
-    const int i = i0 + tid;
-    if (i >= w.n_pass[t]) continue;
     const int s = sb / w.B, b = sb - s * w.B;
-    const float4 e = __ldg(reinterpret_cast<const float4*>(w.ev[t] + (size_t)b * w.ev_bs[t]) + i);  // ts, y, x, p
-    const float2 pm = __ldg(reinterpret_cast<const float2*>(w.pm[t] + (size_t)b * w.pm_bs[t]) + i);
-    if (pm.x == 0.f && pm.y == 0.f) continue;
-    const int pix = (int)(e.y * (float)w.W + e.z);
-    const float* fm = w.flow[s * w.Tm + (w.Tm > 1 ? t : 0)] + (size_t)b * w.flow_bs;
-    const float fx = __ldg(fm + pix), fy = __ldg(fm + hw + pix);
-    float* base = img + (size_t)sb * 8 * hw;
+    Ev ev[IWE_EPT];
+    load_events(w, s, b, t, i0, hw, ev, pol_stream);
+    float* base = img + (size_t)sb * 4 * plane;
 #pragma unroll
-    for (int dir = 0; dir < 2; ++dir) {
-      const float tref = dir == 0 ? Tf : 0.f;
-      const float tau = dir == 0 ? e.x : __fsub_rn(Tf, e.x);
-      float yw, xw;
-      Corner c[4];
-      warp_event(e.x, e.y, e.z, fy, fx, tref, w.flow_scaling, w.H, w.W, yw, xw, c);
-      float* d = base + (size_t)dir * 4 * hw;
+    for (int k = 0; k < IWE_EPT; ++k) {
+      if (!ev[k].on) continue;
+      const float4 e = ev[k].e;
 #pragma unroll
-      for (int r = 0; r < 2; ++r) {  // top row (corners 0,1), bottom row (2,3): left and right pixels are neighbours in memory
-        const Corner &cl = c[2 * r], &cr = c[2 * r + 1];
-        const float wl = cl.idx >= 0 ? __fmul_rn(cl.wy, cl.wx) : 0.f, wr = cr.idx >= 0 ? __fmul_rn(cr.wy, cr.wx) : 0.f;
-        const float tl = __fmul_rn(wl, tau), tr = __fmul_rn(wr, tau);
+      for (int dir = 0; dir < 2; ++dir) {
+        const float tref = dir == 0 ? Tf : 0.f;
+        const float tau = dir == 0 ? e.x : __fsub_rn(Tf, e.x);
+        float yw, xw;
+        Corner c[4];
+        warp_event(e.x, e.y, e.z, ev[k].fy, ev[k].fx, tref, w.flow_scaling, w.H, w.W, yw, xw, c);
+        float* d = base + (size_t)dir * 2 * plane;
 #pragma unroll
-        for (int pol = 0; pol < 2; ++pol) {
-          const float m = pol == 0 ? pm.x : pm.y;
-          if (m == 0.f) continue;
-          float* plane = d + (size_t)pol * 2 * hw;
-          if (wl != 0.f && wr != 0.f && !(cl.idx & 1) && cr.idx == cl.idx + 1) {
-            red4(plane + (size_t)cl.idx * 2, __fmul_rn(wl, m), __fmul_rn(tl, m), __fmul_rn(wr, m), __fmul_rn(tr, m));
-          } else {
-            if (wl != 0.f) red2(plane + (size_t)cl.idx * 2, __fmul_rn(wl, m), __fmul_rn(tl, m));
-            if (wr != 0.f) red2(plane + (size_t)cr.idx * 2, __fmul_rn(wr, m), __fmul_rn(tr, m));
+        for (int r = 0; r < 2; ++r) {  // top row (corners 0,1), bottom row (2,3): left and right pixels are neighbours in memory
+          const Corner &cl = c[2 * r], &cr = c[2 * r + 1];
+          const float wl = cl.idx >= 0 ? __fmul_rn(cl.wy, cl.wx) : 0.f, wr = cr.idx >= 0 ? __fmul_rn(cr.wy, cr.wx) : 0.f;
+          if (wl == 0.f && wr == 0.f) continue;
+          const float tl = __fmul_rn(wl, tau), tr = __fmul_rn(wr, tau);
+#pragma unroll
+          for (int pol = 0; pol < 2; ++pol) {
+            const float m = pol == 0 ? ev[k].pm.x : ev[k].pm.y;
+            if (m == 0.f) continue;
+            float* pl = d + (size_t)pol * plane;
+            if (cl.idx >= 0 && cr.idx == cl.idx + 1) {
+              // both pixels inside the image and neighbours in memory: one 16-byte reduction, into the copy whose pairs start at this parity
+              float* q = (cl.idx & 1) ? pl + 2 * hw + (size_t)(cl.idx + 1) * 2 : pl + (size_t)cl.idx * 2;
+              red4(q, __fmul_rn(wl, m), __fmul_rn(tl, m), __fmul_rn(wr, m), __fmul_rn(tr, m), pol_keep);
+            } else {  // image border: one of the two pixels only
+              if (wl != 0.f) red2(pl + (size_t)cl.idx * 2, __fmul_rn(wl, m), __fmul_rn(tl, m), pol_keep);
+              if (wr != 0.f) red2(pl + (size_t)cr.idx * 2, __fmul_rn(wr, m), __fmul_rn(tr, m), pol_keep);
+            }
           }
         }
       }
@@ -309,12 +454,12 @@ __global__ void __launch_bounds__(IWE_THREADS, 4) iwe_loss_fwd_kernel(const __gr
     const int chunks = (int)((hw + RED_PIX - 1) / RED_PIX), n_sbd = (w.debug_skip & 4) ? 0 : w.S * w.B * 2;
     for (int item = blockIdx.x; item < n_sbd * chunks; item += gridDim.x) {
       const int sbd = item / chunks, p0 = (item - sbd * chunks) * RED_PIX;
-      const float2* pos = reinterpret_cast<const float2*>(img + (size_t)sbd * 4 * hw);
-      const float2* neg = pos + hw;
+      const float2* pos = reinterpret_cast<const float2*>(img + (size_t)sbd * 2 * plane);
+      const float2* neg = reinterpret_cast<const float2*>(img + (size_t)sbd * 2 * plane + plane);
       float ssq = 0.f, n = 0.f;
       const int p1 = min(p0 + RED_PIX, (int)hw);
       for (int i = p0 + tid; i < p1; i += IWE_THREADS) {
-        const float2 qp = __ldcg(pos + i), qn = __ldcg(neg + i);
+        const float2 qp = acc_px(pos, i, hw), qn = acc_px(neg, i, hw);
         const float ap = qp.y / (qp.x + 1e-9f) / Tf, an = qn.y / (qn.x + 1e-9f) / Tf;
         ssq += ap * ap + an * an;
         n += (qp.x + qn.x > 0.f) ? 1.f : 0.f;
@@ -368,7 +513,7 @@ __device__ __forceinline__ float dweight(float d) {
 //   phase 0  gradient of the smoothness term wrt both flow channels of every pixel (gather form) -> g_flow (overwrites)
 //   phase 1  per event and corner: the adjoint of the contrast term is computed on the fly from the accumulator images and
 //            the per-(scale, sample, direction) sums, scattered onto the event's own pixel of g_flow
-__global__ void __launch_bounds__(IWE_THREADS, 4) iwe_loss_bwd_kernel(const __grid_constant__ IweWin w, float* __restrict__ ws,
+__global__ void __launch_bounds__(IWE_THREADS, EF_IWE_OCC_B) iwe_loss_bwd_kernel(const __grid_constant__ IweWin w, float* __restrict__ ws,
                                                                    const float* __restrict__ g_loss) {
   __shared__ bool s_last;
   const WsLayout l = ws_layout(w.S, w.B, w.H, w.W);
@@ -377,80 +522,37 @@ __global__ void __launch_bounds__(IWE_THREADS, 4) iwe_loss_bwd_kernel(const __gr
   float* adj = ws + l.adj;
   const float* sums = ws + l.sums;
   const size_t hw = (size_t)w.H * w.W;
+  const size_t plane = plane_px(hw) * 2;
   const int tid = threadIdx.x;
   const float gl = __ldg(g_loss);
   const int W = w.W, H = w.H;
 
-  // ---- phase 0a: smoothness gradient of every pixel (gather form) -> g_flow
+  // ---- phase 0a: smoothness gradient of every pixel (gather form) -> g_flow (both channels carry the same value)
   {
     const float coef = w.smooth_coef / (float)w.S * gl;
+    const bool on = w.smooth_coef != 0.f && !(w.debug_skip & 1);
     const int rb = (H + SM_ROWS - 1) / SM_ROWS, planes = w.B * w.Tm;
+    const int nx = w.vec ? SM_NX : 1, groups = W / nx;
     for (int item = blockIdx.x; item < w.S * planes * rb; item += gridDim.x) {
       const int s = item / (planes * rb), r0 = item - s * planes * rb;
       const int bt = r0 / rb, y0 = (r0 - bt * rb) * SM_ROWS;
       const int b = bt / w.Tm, t = bt - b * w.Tm;
-      const float* fxm = w.flow[s * w.Tm + t] + (size_t)b * w.flow_bs;
-      const float* fym = fxm + hw;
-      const float* mk = w.use_mask ? w.mask[t] + (size_t)b * w.mask_bs : nullptr;
-      const bool dtn = w.use_dt && t + 1 < w.Tm, dtp = w.use_dt && t >= 1;
-      const float* fxn = dtn ? w.flow[s * w.Tm + t + 1] + (size_t)b * w.flow_bs : nullptr;
-      const float* fxq = dtp ? w.flow[s * w.Tm + t - 1] + (size_t)b * w.flow_bs : nullptr;
-      const float* mkn = (dtn && w.use_mask) ? w.mask[t + 1] + (size_t)b * w.mask_bs : nullptr;
-      const float* mkq = (dtp && w.use_mask) ? w.mask[t - 1] + (size_t)b * w.mask_bs : nullptr;
+      const SmoothMaps sm = smooth_maps(w, s, b, t, hw, true);
       float* g = w.g_flow[s * w.Tm + t] + (size_t)b * w.g_bs;
-      constexpr int STRIPS = SM_ROWS / SM_R;
-      for (int q = tid; q < W * STRIPS; q += IWE_THREADS) {
-        const int st = q / W, x = q - st * W, ys = y0 + st * SM_R;
-        if (ys >= H) continue;
-        float acc[SM_R];
-#pragma unroll
-        for (int r = 0; r < SM_R; ++r) acc[r] = 0.f;
-        if (w.smooth_coef != 0.f && !(w.debug_skip & 1)) {
-          PixF c[SM_R + 2][3], nx[SM_R], pv[SM_R];  // rows ys-1 .. ys+SM_R, columns x-1 .. x+1
-          float any = 0.f;
-#pragma unroll
-          for (int r = 0; r < SM_R + 2; ++r) {
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-              const int yy = ys - 1 + r, xx = x - 1 + k;
-              c[r][k].m = load_mask(mk, yy * W + xx, yy >= 0 && yy < H && xx >= 0 && xx < W, w.use_mask);
-            }
-          }
-#pragma unroll
-          for (int r = 0; r < SM_R; ++r) any += c[r + 1][1].m;  // every term of a pixel's gradient carries the pixel's own mask
-          if (any != 0.f) {
-#pragma unroll
-            for (int r = 0; r < SM_R; ++r) {
-              nx[r].m = dtn ? load_mask(mkn, (ys + r) * W + x, ys + r < H, w.use_mask) : 0.f;
-              pv[r].m = dtp ? load_mask(mkq, (ys + r) * W + x, ys + r < H, w.use_mask) : 0.f;
-            }
-#pragma unroll
-            for (int r = 0; r < SM_R + 2; ++r) {
-#pragma unroll
-              for (int k = 0; k < 3; ++k) load_flow(c[r][k], fxm, fym, (ys - 1 + r) * W + x - 1 + k, c[r][k].m != 0.f);
-            }
-#pragma unroll
-            for (int r = 0; r < SM_R; ++r) {
-              load_flow(nx[r], fxn, fxn + hw, (ys + r) * W + x, nx[r].m != 0.f);
-              load_flow(pv[r], fxq, fxq + hw, (ys + r) * W + x, pv[r].m != 0.f);
-            }
-#pragma unroll
-            for (int r = 0; r < SM_R; ++r) {
-              const PixF& o = c[r + 1][1];
-              // as first element of a pair: +, as second: -.  Pairs: right / left, down / up, down-right / up-left, the up-right pair
-              // ((y,x),(y-1,x+1)) as first and ((y+1,x-1),(y,x)) as second, temporal next / previous.  Missing neighbours carry mask 0.
-              acc[r] = dcharb(o, c[r + 1][2]) - dcharb(c[r + 1][0], o) + dcharb(o, c[r + 2][1]) - dcharb(c[r][1], o) + dcharb(o, c[r + 2][2]) -
-                       dcharb(c[r][0], o) + dcharb(o, c[r][2]) - dcharb(c[r + 2][0], o) + dcharb(o, nx[r]) - dcharb(pv[r], o);
-            }
-          }
-        }
-#pragma unroll
-        for (int r = 0; r < SM_R; ++r) {
-          if (ys + r >= H) break;
-          const float v = acc[r] * coef;
-          const int o = (ys + r) * W + x;
-          g[o] = v;
-          g[hw + o] = v;
+      for (int q = tid; q < groups * SM_ROWS; q += IWE_THREADS) {
+        const int r = q / groups, y = y0 + r, x = (q - r * groups) * nx;
+        if (y >= H) continue;
+        const size_t o = (size_t)y * W + x;
+        if (w.vec) {
+          float gk[SM_NX] = {0.f, 0.f, 0.f, 0.f};
+          if (on) smooth_strip<true, SM_NX>(sm, y, x, H, W, hw, gk);
+          const float4 v = make_float4(gk[0] * coef, gk[1] * coef, gk[2] * coef, gk[3] * coef);
+          *reinterpret_cast<float4*>(g + o) = v;
+          *reinterpret_cast<float4*>(g + hw + o) = v;
+        } else {
+          float gk[1] = {0.f};
+          if (on) smooth_strip<true, 1>(sm, y, x, H, W, hw, gk);
+          g[o] = g[hw + o] = gk[0] * coef;
         }
       }
     }
@@ -461,8 +563,8 @@ __global__ void __launch_bounds__(IWE_THREADS, 4) iwe_loss_bwd_kernel(const __gr
     const int chunks = (int)((hw + RED_PIX - 1) / RED_PIX), n_sbd = (w.debug_skip & 4) ? 0 : w.S * w.B * 2;
     for (int item = blockIdx.x; item < n_sbd * chunks; item += gridDim.x) {
       const int sbd = item / chunks, p0 = (item - sbd * chunks) * RED_PIX;
-      const float2* pos = reinterpret_cast<const float2*>(img + (size_t)sbd * 4 * hw);
-      const float2* neg = pos + hw;
+      const float2* pos = reinterpret_cast<const float2*>(img + (size_t)sbd * 2 * plane);
+      const float2* neg = reinterpret_cast<const float2*>(img + (size_t)sbd * 2 * plane + plane);
       float2* apos = reinterpret_cast<float2*>(adj + (size_t)sbd * 4 * hw);
       float2* aneg = apos + hw;
       const float ssq = __ldcg(sums + sbd * 2), n = __ldcg(sums + sbd * 2 + 1);
@@ -470,7 +572,7 @@ __global__ void __launch_bounds__(IWE_THREADS, 4) iwe_loss_bwd_kernel(const __gr
       const float gn = -gl * inv_S * ssq / (n * n);  // through the divisor: empty pixels keep gradient 1 into it (in-place masked assignment)
       const int p1 = min(p0 + RED_PIX, (int)hw);
       for (int i = p0 + tid; i < p1; i += IWE_THREADS) {
-        const float2 qp = __ldcg(pos + i), qn = __ldcg(neg + i);
+        const float2 qp = acc_px(pos, i, hw), qn = acc_px(neg, i, hw);
         const float rp = __frcp_rn(qp.x + 1e-9f), rn = __frcp_rn(qn.x + 1e-9f);  // gradients are checked to 1e-3: one reciprocal per image
         const float ap = qp.y * rp * inv_T, an = qn.y * rn * inv_T;
         const float gtp = g * 2.f * ap * rp * inv_T, gtn = g * 2.f * an * rn * inv_T;
@@ -487,53 +589,54 @@ __global__ void __launch_bounds__(IWE_THREADS, 4) iwe_loss_bwd_kernel(const __gr
   grid_barrier(ctr + 3, gridDim.x);
 
   // ---- phase 1: per event and corner delta = dL/dI + tau dL/dTh of the event's polarity, chained through the bilinear weights
+  const uint64_t pol_stream = l2_policy_stream();
   const int total_items = (w.debug_skip & 2) ? 0 : w.S * w.B * w.n_items;
   for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
     int sb, t, i0;
     decode_item(w, item, sb, t, i0);
-    const int i = i0 + tid;
-    if (i >= w.n_pass[t]) continue;
     const int s = sb / w.B, b = sb - s * w.B;
-    const float4 e = __ldg(reinterpret_cast<const float4*>(w.ev[t] + (size_t)b * w.ev_bs[t]) + i);
-    const float2 pm = __ldg(reinterpret_cast<const float2*>(w.pm[t] + (size_t)b * w.pm_bs[t]) + i);
-    if (pm.x == 0.f && pm.y == 0.f) continue;
-    const int pix = (int)(e.y * (float)W + e.z);
+    Ev ev[IWE_EPT];
+    load_events(w, s, b, t, i0, hw, ev, pol_stream);
     const int m_idx = s * w.Tm + (w.Tm > 1 ? t : 0);
-    const float* fm = w.flow[m_idx] + (size_t)b * w.flow_bs;
-    const float fx = __ldg(fm + pix), fy = __ldg(fm + hw + pix);
     const float* abase = adj + (size_t)sb * 8 * hw;
-    float gfy = 0.f, gfx = 0.f;
-#pragma unroll
-    for (int dir = 0; dir < 2; ++dir) {
-      const float tref = dir == 0 ? Tf : 0.f;
-      const float tau = dir == 0 ? e.x : (Tf - e.x);
-      const float kk = (tref - e.x) * w.flow_scaling;
-      float yw, xw;
-      Corner c[4];
-      warp_event(e.x, e.y, e.z, fy, fx, tref, w.flow_scaling, H, W, yw, xw, c);
-      const float2* apos = reinterpret_cast<const float2*>(abase + (size_t)dir * 4 * hw);
-      const float2* aneg = apos + hw;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (c[k].idx < 0) continue;
-        const float dwy = dweight(c[k].dy) * c[k].wx, dwx = c[k].wy * dweight(c[k].dx);
-        if (dwy == 0.f && dwx == 0.f) continue;
-        float delta = 0.f;
-        if (pm.x != 0.f) {
-          const float2 a2 = __ldcg(apos + c[k].idx);
-          delta += pm.x * (a2.x + tau * a2.y);
-        }
-        if (pm.y != 0.f) {
-          const float2 a2 = __ldcg(aneg + c[k].idx);
-          delta += pm.y * (a2.x + tau * a2.y);
-        }
-        gfy += delta * dwy * kk;
-        gfx += delta * dwx * kk;
-      }
-    }
     float* g_out = w.g_flow[m_idx] + (size_t)b * w.g_bs;
-    if (gfx != 0.f) atomicAdd(g_out + pix, gfx);
-    if (gfy != 0.f) atomicAdd(g_out + hw + pix, gfy);
+#pragma unroll
+    for (int k = 0; k < IWE_EPT; ++k) {
+      if (!ev[k].on) continue;
+      const float4 e = ev[k].e;
+      const float2 pm = ev[k].pm;
+      float gfy = 0.f, gfx = 0.f;
+#pragma unroll
+      for (int dir = 0; dir < 2; ++dir) {
+        const float tref = dir == 0 ? Tf : 0.f;
+        const float tau = dir == 0 ? e.x : (Tf - e.x);
+        const float kk = (tref - e.x) * w.flow_scaling;
+        float yw, xw;
+        Corner c[4];
+        warp_event(e.x, e.y, e.z, ev[k].fy, ev[k].fx, tref, w.flow_scaling, H, W, yw, xw, c);
+        const float2* apos = reinterpret_cast<const float2*>(abase + (size_t)dir * 4 * hw);
+        const float2* aneg = apos + hw;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (c[q].idx < 0) continue;
+          const float dwy = dweight(c[q].dy) * c[q].wx, dwx = c[q].wy * dweight(c[q].dx);
+          if (dwy == 0.f && dwx == 0.f) continue;
+          float delta = 0.f;
+          if (pm.x != 0.f) {
+            const float2 a2 = __ldcg(apos + c[q].idx);
+            delta += pm.x * (a2.x + tau * a2.y);
+          }
+          if (pm.y != 0.f) {
+            const float2 a2 = __ldcg(aneg + c[q].idx);
+            delta += pm.y * (a2.x + tau * a2.y);
+          }
+          gfy += delta * dwy * kk;
+          gfx += delta * dwx * kk;
+        }
+      }
+      if (gfx != 0.f) atomicAdd(g_out + ev[k].pix, gfx);
+      if (gfy != 0.f) atomicAdd(g_out + hw + ev[k].pix, gfy);
+    }
   }
 
   // ---- restore the counters: the last CTA to finish knows everyone has left the barrier
@@ -719,6 +822,11 @@ static int finish_window(IweWin& w, const char* who) {
     w.chunk_off[t + 1] = w.chunk_off[t] + cdiv(w.n_pass[t], IWE_CHUNK);
   }
   w.n_items = w.chunk_off[w.T];
+  // 16-byte accesses of the pixel passes: rows of 4-pixel groups, every plane 16-byte aligned
+  auto al = [](const void* q, long long stride_floats) { return ((uintptr_t)q % 16 == 0) && (stride_floats % 4 == 0); };
+  w.vec = w.W % 4 == 0;
+  for (int i = 0; i < w.S * w.Tm && w.vec; ++i) w.vec = al(w.flow[i], w.flow_bs) && (!w.g_flow[i] || al(w.g_flow[i], w.g_bs));
+  for (int t = 0; t < w.Tm && w.vec && w.use_mask; ++t) w.vec = al(w.mask[t], w.mask_bs);
   static const int dbg = env_int("EF_IWE_SKIP", 0);
   w.debug_skip = dbg;
   for (int i = 0; i < w.S * w.Tm; ++i) EF_REQUIRE(w.flow[i], EF_ENULL, "%s: NULL flow map", who);
