@@ -408,6 +408,16 @@ def run_ours(args):
                 "head_window_launch_ms": ms_head, "pred_window_launch_ms": ms_pred}
 
     iwe = iwe_bench(dev, pk["hbm_gbs"]) if rank == 0 else None
+    other = None
+    if rank == 0 and world == 1:  # BASELINE configs 4 and 5 (parity-test cases; timed for the record, N = 1 only)
+        from tools import bench_configs
+
+        del model, trainer
+        torch.cuda.empty_cache()
+        try:
+            other = bench_configs.run_all(dev, pk, reps=2)
+        except Exception as exc:  # the headline must not depend on the extra configurations
+            other = {"error": repr(exc)}
     if rank == 0:
         # the CPU baseline is taken at N=1 only: under torchrun the other ranks spin in the barrier and steal the host cores
         cpu = cpu_baseline() if world == 1 else None
@@ -434,7 +444,7 @@ def run_ours(args):
                          "train_ms_per_step": ms_train_sw, "train_gpu_launches": int(launches_train_sw),
                          "fwd_loss_ms_per_step": ms_fwd_sw, "fwd_loss_gpu_launches": int(launches_fwd_sw)},
             "dp_check": dp_check,
-            "roofline": roofline, "iwe": iwe, "cpu_baseline": cpu, "clocks": clocks.summary(),
+            "roofline": roofline, "iwe": iwe, "other_configs": other, "cpu_baseline": cpu, "clocks": clocks.summary(),
         }
         print(json.dumps(line))
     if world > 1:
