@@ -137,46 +137,49 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
     else if ((skip & 128) && n_my > 1) n_my = 1;    // one tile per CTA
   }
   const int tiles_per_img = p.tiles_x * p.tiles_y;
-  // tile -> (b, y0, x0) for the single-thread roles (one division per tile is off their critical path)
-  // item -> (image b of the state tensors, image bt = t*B + b of the per-step tensors, tile origin, step)
-  auto tile_origin4 = [&](int it, int& b, int& bt, int& y0, int& x0, int& t) {
-    const int k = it / T;
-    t = it - k * T;
-    const int tile = blockIdx.x + k * gridDim.x;
-    b = tile / tiles_per_img;
-    bt = t * p.B + b;
-    const int r = tile - b * tiles_per_img, ty = r / p.tiles_x;
-    y0 = ty * TC_TH, x0 = (r - ty * p.tiles_x) * TC_TW;
+  // Item cursor of the single-thread roles (the two producers, the store thread): items are visited in order, so the decode
+  // tile -> (image, tile origin) -- two integer divisions -- runs once per TILE, off the per-step path of a fused window
+  // (b = image of the state tensors, bt = t*B + b = image of the per-step tensors)
+  struct Cursor {
+    int tile, t, b, bt, y0, x0;
   };
-  auto tile_origin = [&](int it, int& b, int& y0, int& x0) {  // per-step tensors (operands, outputs)
-    int b0, t;
-    tile_origin4(it, b0, b, y0, x0, t);
+  auto cur_decode = [&](Cursor& c) {
+    c.b = c.tile / tiles_per_img;
+    const int r = c.tile - c.b * tiles_per_img, ty = r / p.tiles_x;
+    c.y0 = ty * TC_TH, c.x0 = (r - ty * p.tiles_x) * TC_TW;
+    c.bt = c.b;
+  };
+  auto cur_init = [&](Cursor& c) {
+    c.tile = blockIdx.x, c.t = 0;
+    cur_decode(c);
+  };
+  auto cur_next = [&](Cursor& c) {
+    if (++c.t == T) {
+      c.t = 0, c.tile += gridDim.x;
+      cur_decode(c);
+    } else {
+      c.bt += p.B;
+    }
   };
   const uint32_t op_tx = HALO_BYTES * (z_from_halo ? 2 : 1);
-  auto op_issue = [&](int it) {  // operand tiles of tile `it` into stage it % NOP (the caller has waited for the stage)
-    int b, y0, x0;
-    tile_origin(it, b, y0, x0);
-    const int s = it % NOP;
+  auto op_issue = [&](const Cursor& c, int s) {  // operand tiles of the cursor's item into stage s (the caller has waited for the stage)
     const uint32_t st = s_base + C::OP_OFF + s * C::OP_STAGE;
     mbar_expect_tx(bar_opf(s), op_tx);
-    tma_load_4d(st, &map_x, bar_opf(s), 0, x0 - 1, y0 - 1, b);
-    if (z_from_halo) tma_load_4d(st + HALO_STAGE, &map_zh, bar_opf(s), 0, x0 - 1, y0 - 1, b);
+    tma_load_4d(st, &map_x, bar_opf(s), 0, c.x0 - 1, c.y0 - 1, c.bt);
+    if (z_from_halo) tma_load_4d(st + HALO_STAGE, &map_zh, bar_opf(s), 0, c.x0 - 1, c.y0 - 1, c.bt);
   };
   const bool ld_zc = !REC && p.has_z && !(DEBUG && (skip & 1024));
   const bool ld_v = p.has_v && !(DEBUG && (skip & 2));
   const uint32_t v_tx = (ld_v ? V_TILE_BYTES : 0) + (ld_zc ? ZC_TILE_BYTES : 0);
-  auto v_issue = [&](int it) {  // membrane tile (+ centre spikes) of tile `it` into stage it % NV
-    int b, bt, y0, x0, t;
-    tile_origin4(it, b, bt, y0, x0, t);
-    const int s = it % NV;
+  auto v_issue = [&](const Cursor& c, int s) {  // membrane tile (+ centre spikes) of the cursor's item into stage s
     const uint32_t st = s_base + C::V_OFF + s * C::V_STAGE;
-    if (v_tx == 0 || t > 0) {  // steps t > 0 of a fused window carry their state in registers: the stage is only the store staging buffer
+    if (v_tx == 0 || c.t > 0) {  // steps t > 0 of a fused window carry their state in registers: the stage is only the store staging buffer
       mbar_arrive(bar_vf(s));
       return;
     }
     mbar_expect_tx(bar_vf(s), v_tx);
-    if (ld_v) tma_load_4d(st, &map_vin, bar_vf(s), x0, y0, 0, b);
-    if (ld_zc) tma_load_4d(st + V_TILE_BYTES, &map_zc, bar_vf(s), 0, x0, y0, b);
+    if (ld_v) tma_load_4d(st, &map_vin, bar_vf(s), c.x0, c.y0, 0, c.b);
+    if (ld_zc) tma_load_4d(st + V_TILE_BYTES, &map_zc, bar_vf(s), 0, c.x0, c.y0, c.b);
   };
   // The two producer threads initialise their own barriers and start the first loads right away, BEFORE the CTA-wide sync:
   // barrier setup by the other thread, the TMEM allocation and the descriptor fetches overlap the first DRAM round trip.
@@ -185,6 +188,7 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
   // CTAs take over SMs as ours exit and run their own prologue); everything of OURS that does not depend on the previous kernel
   // (barrier setup, TMEM allocation, descriptor prefetch, the weight image) happens before pdl_wait().
   pdl_launch_dependents();
+  Cursor cur;  // used by threads 0 (operands), 64 (membrane) and 128 (stores), each walking the items on its own
   if (threadIdx.x == 0) {
     prefetch_tensormap(&map_x);
     if (z_from_halo) prefetch_tensormap(&map_zh);
@@ -202,8 +206,10 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
     for (uint32_t off = 0; off < (uint32_t)C::W_BYTES; off += W_CHUNK)
       bulk_load_1d(s_base + off, reinterpret_cast<const uint8_t*>(p.w_split) + off, W_CHUNK, bar_w);
     pdl_wait();  // the spikes of the previous layer
+    cur_init(cur);
     for (int it = 0; it < n_op0; ++it) {
-      op_issue(it);
+      op_issue(cur, it);
+      cur_next(cur);
       EF_TRACE(it, 0);
     }
   } else if (threadIdx.x == 64) {
@@ -215,7 +221,11 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
     }
     fence_barrier_init();
     pdl_wait();
-    for (int it = 0; it < n_v0; ++it) v_issue(it);
+    cur_init(cur);
+    for (int it = 0; it < n_v0; ++it) {
+      v_issue(cur, it);
+      cur_next(cur);
+    }
   } else if (threadIdx.x == 128) {
     prefetch_tensormap(&map_vout);
     prefetch_tensormap(&map_zout);
@@ -234,7 +244,8 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
     if (lane == 0) {
       for (int it = n_op0; it < n_my; ++it) {
         mbar_wait(bar_ope(it % NOP), ((it / NOP) & 1) ^ 1);
-        op_issue(it);
+        op_issue(cur, it % NOP);
+        cur_next(cur);
         EF_TRACE(it, 0);
       }
     }
@@ -243,7 +254,8 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
     if (lane == 0) {
       for (int it = n_v0; it < n_my; ++it) {
         mbar_wait(bar_ve(it % NV), ((it / NV) & 1) ^ 1);
-        v_issue(it);
+        v_issue(cur, it % NV);
+        cur_next(cur);
       }
     }
   } else if (warp == 1) {
@@ -295,7 +307,10 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
     const int m = q * 32 + lane;            // GEMM row = pixel within the tile
     const int ty = m >> 3, tx = m & 7;      // (row, col) inside the tile
     const bool store_thread = (threadIdx.x == 128);
-    if (store_thread) pdl_wait();  // the thread that issues the global stores
+    if (store_thread) {
+      pdl_wait();  // the thread that issues the global stores
+      cur_init(cur);
+    }
     float lam[CPT], thr[CPT];
 #pragma unroll
     for (int j = 0; j < CPT; ++j) {
@@ -310,12 +325,13 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
     // tile: only step 0 reads it from the membrane stage, no later step reads any state from memory
     float vc[CPT];
     uint4 zc[NCH];
+    int sv = 0, so = 0, t_step = 0;  // stage indices / step inside the window as counters (no per-item modulo by run-time values)
+    uint32_t ph_v = 0, ph_o = 0;     // phase parities of the two rings
     for (int it = 0; it < n_my; ++it) {
-      const int sv = it % NV, so = it % NOP, a = it & 1;
-      const int t_step = REC ? 0 : it % T;
+      const int a = it & 1;
       const uint32_t vst = s_base + C::V_OFF + sv * C::V_STAGE;
       const uint32_t v_addr = vst + (uint32_t)(c0 * 512 + m * 4);  // [ch][16][8] fp32
-      mbar_wait(bar_vf(sv), (it / NV) & 1);  // stage landed (step 0) / free to be used as store staging buffer (later steps)
+      mbar_wait(bar_vf(sv), ph_v);  // stage landed (step 0) / free to be used as store staging buffer (later steps)
       if (t_step == 0) {
         if (p.has_v) {
 #pragma unroll
@@ -328,7 +344,7 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
       uint32_t z_row;  // shared address of this pixel's 64-byte spike row (input in REC = halo tile, else the in-place centre tile)
       if (REC) {
         z_row = s_base + C::OP_OFF + so * C::OP_STAGE + HALO_STAGE + (uint32_t)((ty + 1) * HALO_PITCH + (tx + 1) * PIX_BYTES);
-        if (p.has_z) mbar_wait(bar_opf(so), (it / NOP) & 1);  // TMA-written data: observe the barrier before the generic-proxy read
+        if (p.has_z) mbar_wait(bar_opf(so), ph_o);  // TMA-written data: observe the barrier before the generic-proxy read
       } else {
         z_row = vst + V_TILE_BYTES + (uint32_t)(m * PIX_BYTES);
       }
@@ -380,7 +396,7 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
       // stage goes back to its producer, and (REC) the spike staging buffer may be overwritten after the barrier
       if (store_thread && it > 0) {
         bulk_wait_read0();
-        mbar_arrive(bar_ve((it - 1) % NV));
+        mbar_arrive(bar_ve(sv == 0 ? NV - 1 : sv - 1));
       }
       if (REC) named_bar_sync(1, 32 * EPI_WARPS);
       // new state, written in place (same addresses this thread read) / into the spike staging tile.  In a fused window the membrane
@@ -403,13 +419,15 @@ lif_conv_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map
       if (store_thread) EF_TRACE(it, 5);
       named_bar_sync(2, 32 * EPI_WARPS);
       if (store_thread) {
-        int b, bt, y0, x0, t;
-        tile_origin4(it, b, bt, y0, x0, t);
-        if (store_v && !(DEBUG && (skip & 1))) tma_store_4d(&map_vout, vst, x0, y0, 0, (T == 1 || p.save_all_v) ? bt : b);
-        if (!(DEBUG && (skip & 8))) tma_store_4d(&map_zout, REC ? (s_base + C::ZOUT_OFF) : (vst + V_TILE_BYTES), 0, x0, y0, bt);
+        if (store_v && !(DEBUG && (skip & 1))) tma_store_4d(&map_vout, vst, cur.x0, cur.y0, 0, (T == 1 || p.save_all_v) ? cur.bt : cur.b);
+        if (!(DEBUG && (skip & 8))) tma_store_4d(&map_zout, REC ? (s_base + C::ZOUT_OFF) : (vst + V_TILE_BYTES), 0, cur.x0, cur.y0, cur.bt);
         bulk_commit();
+        cur_next(cur);
         EF_TRACE(it, 6);
       }
+      if (++sv == NV) sv = 0, ph_v ^= 1;
+      if (++so == NOP) so = 0, ph_o ^= 1;
+      if (!REC && ++t_step == T) t_step = 0;
     }
     if (store_thread) {
       bulk_wait0();

@@ -9,21 +9,40 @@ import torch.nn as nn
 from .. import ops
 
 
+_TORCH_ACT = {None: None, "relu": torch.relu, "sigmoid": torch.sigmoid, "tanh": torch.tanh}
+
+
+def _make_norm(norm, channels, momentum=0.1):
+    """The reference's normalisation options of the ANN layers (models/submodules.py:45-49): "BN" / "IN" torch modules, else none."""
+    if norm == "BN":
+        return nn.BatchNorm2d(channels, momentum=momentum)
+    if norm == "IN":
+        return nn.InstanceNorm2d(channels, track_running_stats=True)
+    return None
+
+
+def _conv_norm_act(x, conv, norm_layer, act, residual=None):
+    """act(norm(conv3x3(x) + b) + residual).  Without a norm layer everything is ONE fused launch (ef_conv_ann_fwd); with one the kernel
+    stops after the bias and the normalisation module / residual / activation follow on its output (models/submodules.py:52-61)."""
+    if norm_layer is None:
+        return ops.conv_ann(x, conv.weight, conv.bias, act, residual=residual)
+    out = norm_layer(ops.conv_ann(x, conv.weight, conv.bias, None))
+    if residual is not None:
+        out = out + residual
+    return out if act is None else _TORCH_ACT[act](out)
+
+
 class ConvLayer(nn.Module):
-    """Convolutional layer: conv + bias + activation (default ReLU), no downsampling, no batch norm."""
+    """Convolutional layer: conv + bias [+ BN / IN] + activation (default ReLU) (models/submodules.py:12-61)."""
 
     def __init__(self, in_channels, out_channels, kernel_size, stride=1, activation="relu", norm=None, BN_momentum=0.1, w_scale=None):
         super().__init__()
-        if norm is not None:
-            raise NotImplementedError("event_flow_b200 ConvLayer: norm=%r is not on the CUDA path (no shipped FireNet config uses it)" % (norm,))
         if kernel_size not in (1, 3) or stride not in (1, 2) or (kernel_size == 1 and stride != 1):
             raise NotImplementedError(f"event_flow_b200 ConvLayer: kernel_size={kernel_size}, stride={stride} not on the CUDA path yet")
-        if kernel_size == 1 and activation != "tanh":
-            raise NotImplementedError("event_flow_b200 ConvLayer: the 1x1 layer is built for the tanh prediction head only")
-        if kernel_size == 3 and activation not in (None, "relu", "sigmoid", "tanh"):
+        if activation not in (None, "relu", "sigmoid", "tanh"):
             raise NotImplementedError(f"event_flow_b200 ConvLayer: activation={activation!r} not on the CUDA path")
         padding = kernel_size // 2
-        self.conv2d = nn.Conv2d(in_channels, out_channels, kernel_size, stride, padding, bias=True)
+        self.conv2d = nn.Conv2d(in_channels, out_channels, kernel_size, stride, padding, bias=norm != "BN")
         if w_scale is not None:
             nn.init.uniform_(self.conv2d.weight, -w_scale, w_scale)
             nn.init.zeros_(self.conv2d.bias)
@@ -31,6 +50,9 @@ class ConvLayer(nn.Module):
         self.stride = stride
         self.activation = activation
         self.norm = norm
+        layer = _make_norm(norm, out_channels, BN_momentum)
+        if layer is not None:
+            self.norm_layer = layer
 
     def __getattr__(self, name):
         # layers unpickled from a checkpoint the REFERENCE wrote keep only its attributes: derive the ones this package adds
@@ -43,14 +65,62 @@ class ConvLayer(nn.Module):
         return getattr(act, "__name__", act) if callable(act) else act
 
     def forward(self, x):
+        norm_layer = self._modules.get("norm_layer")
+        act = self._act_name()
         if self.kernel_size == 1:
-            return ops.pred_head(x, self.conv2d.weight, self.conv2d.bias)
-        out = ops.conv_ann(x, self.conv2d.weight, self.conv2d.bias, self._act_name())
+            if norm_layer is None and act == "tanh":
+                return ops.pred_head(x, self.conv2d.weight, self.conv2d.bias)  # the prediction layers: 1x1 conv + bias + tanh in one kernel
+            # other 1x1 layers (normalised predictions, no shipped config): the 1x1 weight as the centre tap of a 3x3 kernel
+            w3 = torch.nn.functional.pad(self.conv2d.weight, (1, 1, 1, 1))
+            out = ops.conv_ann(x, w3, self.conv2d.bias, None if norm_layer is not None else act)
+            if norm_layer is None:
+                return out
+            out = norm_layer(out)
+            return out if act is None else _TORCH_ACT[act](out)
         if self.stride == 2:
             # a stride-2 3x3 conv with padding 1 is the stride-1 result at the even pixels (same window, same summation order);
             # first version of the U-Net encoders: 4x the minimal FLOPs on these four layers
-            out = out[:, :, ::2, ::2].contiguous()
-        return out
+            if norm_layer is None:
+                return ops.conv_ann(x, self.conv2d.weight, self.conv2d.bias, act)[:, :, ::2, ::2].contiguous()
+            out = norm_layer(ops.conv_ann(x, self.conv2d.weight, self.conv2d.bias, None)[:, :, ::2, ::2].contiguous())
+            return out if act is None else _TORCH_ACT[act](out)
+        return _conv_norm_act(x, self.conv2d, norm_layer, act)
+
+
+class TransposedConvLayer(nn.Module):
+    """
+    Transposed convolutional layer (x2 resolution) of the ANN decoders with `use_upsample_conv=False` (models/submodules.py:86-137):
+    ConvTranspose2d(kernel 3, stride 2, padding 1, output_padding 1) [+ BN / IN] + activation.  Computed as a stride-1 convolution
+    (ef_conv_ann_fwd / ef_conv3x3_bwd) over the zero-inserted input with the flipped, transposed kernel:
+    out[o] = sum_i x[i] w[o + 1 - 2 i]  =  sum_j z[j] w'[j - o + 1],  z[2 i] = x[i],  w'[co, ci, ky, kx] = w[ci, co, 2 - ky, 2 - kx].
+    """
+
+    def __init__(self, in_channels, out_channels, kernel_size, activation="relu", norm=None):
+        super().__init__()
+        if kernel_size != 3:
+            raise NotImplementedError("event_flow_b200 TransposedConvLayer: kernel_size 3 only")
+        if activation not in (None, "relu", "sigmoid", "tanh"):
+            raise NotImplementedError(f"event_flow_b200 TransposedConvLayer: activation={activation!r} not on the CUDA path")
+        self.transposed_conv2d = nn.ConvTranspose2d(in_channels, out_channels, kernel_size, stride=2, padding=kernel_size // 2,
+                                                    output_padding=1, bias=norm != "BN")
+        self.activation = activation
+        self.norm = norm
+        layer = _make_norm(norm, out_channels)
+        if layer is not None:
+            self.norm_layer = layer
+
+    def forward(self, x):
+        B, C, H, W = x.shape
+        z = x.new_zeros((B, C, 2 * H, 2 * W))
+        z[:, :, ::2, ::2] = x
+        conv = self.transposed_conv2d
+        w = conv.weight.flip(2, 3).transpose(0, 1).contiguous()  # [Cout, Cin, 3, 3] of the equivalent correlation
+        act = getattr(self.activation, "__name__", self.activation) if callable(self.activation) else self.activation
+        norm_layer = self._modules.get("norm_layer")
+        if norm_layer is None:
+            return ops.conv_ann(z, w, conv.bias, act)
+        out = norm_layer(ops.conv_ann(z, w, conv.bias, None))
+        return out if act is None else _TORCH_ACT[act](out)
 
 
 class ConvLayer_(ConvLayer):
@@ -85,41 +155,51 @@ class RecurrentConvLayer(nn.Module):
 
 
 class ResidualBlock(nn.Module):
-    """He et al. residual block (models/submodules.py:238-312): conv+act, conv + residual + act.  Two launches."""
+    """He et al. residual block (models/submodules.py:238-312): conv [+ norm] + act, conv [+ norm] + residual + act.  Two launches
+    without normalisation."""
 
     def __init__(self, in_channels, out_channels, stride=1, activation="relu", downsample=None, norm=None, BN_momentum=0.1):
         super().__init__()
-        if norm is not None or downsample is not None or stride != 1 or in_channels != out_channels:
-            raise NotImplementedError("event_flow_b200 ResidualBlock: norm / downsample / stride are not on the CUDA path (no shipped config uses them)")
+        if stride != 1:
+            raise NotImplementedError("event_flow_b200 ResidualBlock: stride 1 only (no model of the reference builds another)")
         if activation not in (None, "relu", "sigmoid", "tanh"):
             raise NotImplementedError(f"event_flow_b200 ResidualBlock: activation={activation!r} not on the CUDA path")
-        self.conv1 = nn.Conv2d(in_channels, out_channels, kernel_size=3, stride=stride, padding=1, bias=True)
+        self.conv1 = nn.Conv2d(in_channels, out_channels, kernel_size=3, stride=stride, padding=1, bias=norm != "BN")
         self.activation = activation
         self.norm = norm
-        self.conv2 = nn.Conv2d(out_channels, out_channels, kernel_size=3, stride=1, padding=1, bias=True)
+        if norm in ("BN", "IN"):
+            self.bn1 = _make_norm(norm, out_channels, BN_momentum)
+            self.bn2 = _make_norm(norm, out_channels, BN_momentum)
+        self.conv2 = nn.Conv2d(out_channels, out_channels, kernel_size=3, stride=1, padding=1, bias=norm != "BN")
         self.downsample = downsample
 
     def forward(self, x):
-        out1 = ops.conv_ann(x, self.conv1.weight, self.conv1.bias, self.activation)
-        out2 = ops.conv_ann(out1, self.conv2.weight, self.conv2.bias, self.activation, residual=x)
+        act = getattr(self.activation, "__name__", self.activation) if callable(self.activation) else self.activation
+        residual = self.downsample(x) if self.downsample else x
+        out1 = _conv_norm_act(x, self.conv1, self._modules.get("bn1"), act)
+        out2 = _conv_norm_act(out1, self.conv2, self._modules.get("bn2"), act, residual=residual)
         return out2, out1
 
 
 class UpsampleConvLayer(nn.Module):
-    """Bilinear x2 upsampling + conv + activation (models/submodules.py:140-185): the decoder stage of the ANN U-Net."""
+    """Bilinear x2 upsampling + conv [+ norm] + activation (models/submodules.py:140-185): the decoder stage of the ANN U-Net."""
 
     def __init__(self, in_channels, out_channels, kernel_size, stride=1, activation="relu", norm=None):
         super().__init__()
-        if norm is not None or stride != 1 or kernel_size != 3:
-            raise NotImplementedError("event_flow_b200 UpsampleConvLayer: kernel_size 3, stride 1, no norm")
+        if stride != 1 or kernel_size != 3:
+            raise NotImplementedError("event_flow_b200 UpsampleConvLayer: kernel_size 3, stride 1")
         if activation not in (None, "relu", "sigmoid", "tanh"):
             raise NotImplementedError(f"event_flow_b200 UpsampleConvLayer: activation={activation!r} not on the CUDA path")
-        self.conv2d = nn.Conv2d(in_channels, out_channels, kernel_size, stride, kernel_size // 2, bias=True)
+        self.conv2d = nn.Conv2d(in_channels, out_channels, kernel_size, stride, kernel_size // 2, bias=norm != "BN")
         self.activation = activation
         self.norm = norm
+        layer = _make_norm(norm, out_channels)
+        if layer is not None:
+            self.norm_layer = layer
 
     def forward(self, x):
-        return ops.conv_ann(ops.upsample_bilinear2x(x), self.conv2d.weight, self.conv2d.bias, self.activation)
+        act = getattr(self.activation, "__name__", self.activation) if callable(self.activation) else self.activation
+        return _conv_norm_act(ops.upsample_bilinear2x(x), self.conv2d, self._modules.get("norm_layer"), act)
 
 
 class ConvGRU(nn.Module):

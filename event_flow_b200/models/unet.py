@@ -11,7 +11,7 @@ from .. import fast_unet
 from .model_util import skip_concat, skip_sum  # noqa: F401  (resolved by name like the reference: "skip_" + skip_type)
 from .spiking_submodules import SpikingRecurrentConvLayer, SpikingResidualBlock, SpikingTransposedConvLayer, SpikingUpsampleConvLayer
 from .submodules import (ConvLayer, LeakyRecurrentConvLayer, LeakyResidualBlock, LeakyTransposedConvLayer, LeakyUpsampleConvLayer,
-                         RecurrentConvLayer, ResidualBlock, UpsampleConvLayer)
+                         RecurrentConvLayer, ResidualBlock, TransposedConvLayer, UpsampleConvLayer)
 
 
 class SpikingMultiResUNetRecurrent(nn.Module):
@@ -153,8 +153,8 @@ class SpikingMultiResUNetRecurrent(nn.Module):
 class MultiResUNet(nn.Module):
     """
     ANN multi-resolution U-Net of EV-FlowNet (models/unet.py:224-311): four stride-2 conv encoders, two residual blocks, four
-    bilinear-upsampling decoders with concat skips, a 1x1 tanh prediction per scale.  Forward only (the ANN cells have no
-    backward kernels yet).
+    bilinear-upsampling (or, with use_upsample_conv=False, transposed-convolution) decoders with concat skips, a 1x1 tanh prediction
+    per scale; optional BN / IN normalisation of every layer.
     """
 
     def __init__(self, unet_kwargs):
@@ -171,8 +171,9 @@ class MultiResUNet(nn.Module):
         self.num_bins = kw["num_bins"]
         self.channel_multiplier = kw.get("channel_multiplier", 2)
         self.ff_act, self.rec_act = kw.get("activations", ["relu", None])
-        if self.norm is not None or self.kernel_size != 3 or not kw["use_upsample_conv"]:
-            raise NotImplementedError("event_flow_b200 MultiResUNet: kernel_size 3, no norm, upsample-conv decoders only")
+        if self.norm not in (None, "BN", "IN") or self.kernel_size != 3:
+            raise NotImplementedError("event_flow_b200 MultiResUNet: kernel_size 3, norm None / 'BN' / 'IN'")
+        self.use_upsample_conv = kw["use_upsample_conv"]
         self.skip_ftn = {"concat": skip_concat, "sum": skip_sum}[self.skip_type]
         self.encoder_input_sizes = [int(self.base_num_channels * pow(self.channel_multiplier, i)) for i in range(self.num_encoders)]
         self.encoder_output_sizes = [int(self.base_num_channels * pow(self.channel_multiplier, i + 1)) for i in range(self.num_encoders)]
@@ -184,8 +185,9 @@ class MultiResUNet(nn.Module):
                                         for _ in range(self.num_residual_blocks)])
         self.decoders = nn.ModuleList()
         for i, (cin, cout) in enumerate(zip(reversed(self.encoder_output_sizes), reversed(self.encoder_input_sizes))):
-            self.decoders.append(UpsampleConvLayer(2 * cin + (0 if i == 0 else self.num_output_channels), cout, kernel_size=self.kernel_size,
-                                                   activation=self.ff_act, norm=self.norm))
+            up = UpsampleConvLayer if self.use_upsample_conv else TransposedConvLayer  # models/unet.py:77-81
+            self.decoders.append(up(2 * cin + (0 if i == 0 else self.num_output_channels), cout, kernel_size=self.kernel_size,
+                                    activation=self.ff_act, norm=self.norm))
         self.preds = nn.ModuleList([ConvLayer(cout, self.num_output_channels, 1, activation=self.final_activation, norm=self.norm)
                                     for cout in reversed(self.encoder_input_sizes)])
 

@@ -421,3 +421,81 @@ def test_ann_zoo_rollout_and_gradients_match_reference_golden(name):
             assert (q.grad.cpu() - ref).abs().max().item() <= 1e-3 * (ref.abs().max().item() + 1e-12), nm
             checked += 1
     assert checked >= 8
+
+
+# ---- optional layers of the ANN U-Nets: normalisation and transposed-convolution decoders (models/submodules.py:45-49, 86-137) ----------------
+# The reference's classes are thin wrappers of torch modules (nn.ConvTranspose2d, nn.BatchNorm2d, nn.InstanceNorm2d, torch activations), so
+# the same torch modules on the same weights ARE the reference here; wiring against the live reference: tests/test_host_wiring_cpu.py.
+@pytest.mark.parametrize("norm", [None, "BN", "IN"])
+@pytest.mark.parametrize("act", ["relu", "tanh", None])
+def test_transposed_conv_layer_matches_torch(norm, act):
+    from event_flow_b200.models.submodules import TransposedConvLayer
+
+    torch.manual_seed(3)
+    mine = TransposedConvLayer(6, 10, 3, activation=act, norm=norm).to(DEV).train()
+    conv = torch.nn.ConvTranspose2d(6, 10, 3, stride=2, padding=1, output_padding=1, bias=norm != "BN").to(DEV)
+    conv.load_state_dict(mine.transposed_conv2d.state_dict())
+    nl = {None: None, "BN": torch.nn.BatchNorm2d(10), "IN": torch.nn.InstanceNorm2d(10, track_running_stats=True)}[norm]
+    nl = None if nl is None else nl.to(DEV).train()
+    x = torch.randn(2, 6, 9, 13, device=DEV, requires_grad=True)
+    x2 = x.detach().clone().requires_grad_(True)
+    out = mine(x)
+    ref = conv(x2)
+    ref = ref if nl is None else nl(ref)
+    ref = ref if act is None else getattr(torch, act)(ref)
+    assert out.shape == ref.shape == (2, 10, 18, 26)
+    assert (out - ref).abs().max().item() <= 2e-5 * max(1.0, ref.abs().max().item())
+    g = torch.randn_like(ref)
+    out.backward(g), ref.backward(g)
+    scale = max(p.grad.abs().max().item() for p in conv.parameters())
+    assert (x.grad - x2.grad).abs().max().item() <= 1e-4 * x2.grad.abs().max().item()
+    for (n, a), b in zip(mine.transposed_conv2d.named_parameters(), conv.parameters()):
+        assert (a.grad - b.grad).abs().max().item() <= 1e-4 * max(b.grad.abs().max().item(), 1e-2 * scale), n
+    if nl is not None:  # running statistics follow torch's modules
+        assert torch.allclose(mine.norm_layer.running_mean, nl.running_mean, atol=1e-5) and torch.allclose(mine.norm_layer.running_var, nl.running_var, rtol=1e-4)
+
+
+@pytest.mark.parametrize("norm", ["BN", "IN"])
+def test_normalised_ann_layers_match_torch(norm):
+    import torch.nn.functional as F
+
+    from event_flow_b200.models.submodules import ConvLayer, ResidualBlock, UpsampleConvLayer
+
+    torch.manual_seed(4)
+    mk = (lambda c: torch.nn.BatchNorm2d(c)) if norm == "BN" else (lambda c: torch.nn.InstanceNorm2d(c, track_running_stats=True))
+    x = torch.randn(3, 8, 12, 16, device=DEV)
+    for stride, k, act in ((1, 3, "relu"), (2, 3, "relu"), (1, 1, "tanh")):
+        layer = ConvLayer(8, 12, k, stride=stride, activation=act, norm=norm).to(DEV).train()
+        nl = mk(12).to(DEV).train()
+        ref = getattr(torch, act)(nl(F.conv2d(x, layer.conv2d.weight, layer.conv2d.bias, stride, k // 2)))
+        out = layer(x)
+        assert out.shape == ref.shape and (out - ref).abs().max().item() <= 2e-5 * max(1.0, ref.abs().max().item()), (stride, k)
+    up = UpsampleConvLayer(8, 6, 3, activation="relu", norm=norm).to(DEV).train()
+    nl = mk(6).to(DEV).train()
+    ref = torch.relu(nl(F.conv2d(F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False), up.conv2d.weight, up.conv2d.bias, 1, 1)))
+    assert (up(x) - ref).abs().max().item() <= 2e-5 * max(1.0, ref.abs().max().item())
+    rb = ResidualBlock(8, 8, activation="relu", norm=norm).to(DEV).train()
+    n1, n2 = mk(8).to(DEV).train(), mk(8).to(DEV).train()
+    o1 = torch.relu(n1(F.conv2d(x, rb.conv1.weight, rb.conv1.bias, 1, 1)))
+    o2 = torch.relu(n2(F.conv2d(o1, rb.conv2.weight, rb.conv2.bias, 1, 1)) + x)
+    a2, a1 = rb(x)
+    assert (a1 - o1).abs().max().item() <= 2e-5 * max(1.0, o1.abs().max().item()) and (a2 - o2).abs().max().item() <= 2e-5 * max(1.0, o2.abs().max().item())
+
+
+def test_recevflownet_with_norm_and_transposed_decoders_trains():
+    """RecEVFlowNet(norm="BN", use_upsample_conv=False): forward, backward and an optimiser step run on the CUDA path (values: the tests above)."""
+    import event_flow_b200.models.model as M
+
+    torch.manual_seed(0)
+    cfg = dict(name="RecEVFlowNet", encoding="cnt", round_encoding=False, norm_input=False, num_bins=2, base_num_channels=8, kernel_size=3,
+               activations=["relu", None], mask_output=True, spiking_neuron=None, norm="BN", use_upsample_conv=False)
+    m = M.RecEVFlowNet(cfg).to(DEV).train()
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+    cnt = torch.randint(0, 3, (2, 2, 64, 64), device=DEV).float()
+    before = [p.detach().clone() for p in m.parameters()]
+    flows = m(None, cnt)["flow"]
+    assert len(flows) == 4 and all(f.shape == (2, 2, 64, 64) and torch.isfinite(f).all() for f in flows)
+    sum(f.square().mean() for f in flows).backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters())
+    opt.step()
+    assert any((a - b).abs().max() > 0 for a, b in zip(m.parameters(), before))

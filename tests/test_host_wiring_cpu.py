@@ -227,3 +227,50 @@ def test_cropping_and_input_normalisation_match_the_live_reference(cls, cpu_ops)
                     assert torch.equal(fa, fb)
                 else:
                     assert (fa - fb).abs().max().item() <= 1e-5 * max(1.0, fb.abs().max().item())
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/models"), reason="needs the reference tree (build container only)")
+@pytest.mark.parametrize("opts", [dict(norm="BN"), dict(norm="IN"), dict(use_upsample_conv=False), dict(norm="BN", use_upsample_conv=False)])
+def test_norm_and_transposed_conv_options_match_the_live_reference(opts, cpu_ops):
+    """
+    The optional layers of the ANN U-Nets (models/model.py:39-52: `norm`, `use_upsample_conv`; models/submodules.py:45-49,86-137):
+    same state_dict names, same flows and recurrent states as the unmodified reference (train mode: batch statistics), run live on CPU.
+    """
+    import importlib
+    import sys
+
+    import event_flow_b200.models.model as M
+
+    cfg = dict(name="RecEVFlowNet", encoding="cnt", round_encoding=False, norm_input=False, num_bins=2, base_num_channels=4, kernel_size=3,
+               activations=["relu", None], mask_output=True, spiking_neuron=None, **opts)
+    saved = {k: sys.modules.pop(k) for k in list(sys.modules) if k == "models" or k.startswith("models.")}
+    sys.path.insert(0, "/root/reference")
+    try:
+        ref_model = importlib.import_module("models.model")
+        torch.manual_seed(7)
+        ref = ref_model.RecEVFlowNet(dict(cfg)).train()
+    finally:
+        sys.path.remove("/root/reference")
+        for k in [k for k in sys.modules if k == "models" or k.startswith("models.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+    torch.manual_seed(7)
+    mine = M.RecEVFlowNet(dict(cfg)).train()
+    assert list(mine.state_dict().keys()) == list(ref.state_dict().keys())
+    for a, b in zip(mine.state_dict().values(), ref.state_dict().values()):
+        assert torch.equal(a, b), "same seed, same initial values"
+    g = torch.Generator().manual_seed(2)
+    H, W = 32, 48
+    for _ in range(2):
+        cnt = torch.randint(0, 3, (3, 2, H, W), generator=g).float()
+        a, b = mine(None, cnt.clone())["flow"], ref(None, cnt.clone())["flow"]
+        assert len(a) == len(b) == 4
+        for fa, fb in zip(a, b):
+            assert fa.shape == fb.shape and (fa - fb).abs().max().item() <= 2e-5 * max(1.0, fb.abs().max().item())
+    loss_a, loss_b = sum(f.square().sum() for f in a), sum(f.square().sum() for f in b)
+    loss_a.backward(), loss_b.backward()
+    # (a conv bias in front of an instance norm has an exactly-zero true gradient: what autograd reports there is rounding noise, so
+    # the scale of the comparison is the largest gradient of the model, not of the parameter)
+    scale = max(pb.grad.abs().max().item() for pb in ref.parameters())
+    for (n, pa), pb in zip(mine.named_parameters(), ref.parameters()):
+        assert (pa.grad - pb.grad).abs().max().item() <= 1e-3 * max(pb.grad.abs().max().item(), 1e-2 * scale), n
