@@ -428,9 +428,10 @@ def test_ann_zoo_rollout_and_gradients_match_reference_golden(name):
 # the same torch modules on the same weights ARE the reference here; wiring against the live reference: tests/test_host_wiring_cpu.py.
 @pytest.mark.parametrize("norm", [None, "BN", "IN"])
 @pytest.mark.parametrize("act", ["relu", "tanh", None])
-def test_transposed_conv_layer_matches_torch(norm, act):
+def test_transposed_conv_layer_matches_torch(norm, act, monkeypatch):
     from event_flow_b200.models.submodules import TransposedConvLayer
 
+    monkeypatch.setattr(torch.backends.cudnn, "allow_tf32", False)  # the comparison is against torch's fp32 convolution, not its TF32 default
     torch.manual_seed(3)
     mine = TransposedConvLayer(6, 10, 3, activation=act, norm=norm).to(DEV).train()
     conv = torch.nn.ConvTranspose2d(6, 10, 3, stride=2, padding=1, output_padding=1, bias=norm != "BN").to(DEV)
@@ -456,11 +457,12 @@ def test_transposed_conv_layer_matches_torch(norm, act):
 
 
 @pytest.mark.parametrize("norm", ["BN", "IN"])
-def test_normalised_ann_layers_match_torch(norm):
+def test_normalised_ann_layers_match_torch(norm, monkeypatch):
     import torch.nn.functional as F
 
     from event_flow_b200.models.submodules import ConvLayer, ResidualBlock, UpsampleConvLayer
 
+    monkeypatch.setattr(torch.backends.cudnn, "allow_tf32", False)
     torch.manual_seed(4)
     mk = (lambda c: torch.nn.BatchNorm2d(c)) if norm == "BN" else (lambda c: torch.nn.InstanceNorm2d(c, track_running_stats=True))
     x = torch.randn(3, 8, 12, 16, device=DEV)

@@ -1,5 +1,5 @@
 """Per-CTA timeline (clock64) of the TIME-FUSED tensor-core conv+LIF launch (ef_lif_conv_fwd_window, T steps per tile): per item (tile, step)
-the cycles of the pipeline events, medians over the CTAs.  usage: python tools/tc_window_timeline.py [T] [save_all_v]"""
+the cycles of the pipeline events, medians over the CTAs.  usage: python tools/tc_window_timeline.py [T] [save_all_v] [cpt]"""
 import os
 import sys
 
@@ -14,6 +14,8 @@ DEV = "cuda"
 B, H, W = 8, 128, 128
 T = int(sys.argv[1]) if len(sys.argv) > 1 else 10
 save_all = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+if len(sys.argv) > 3:
+    L.lib().ef_debug_tc_cpt(int(sys.argv[3]))  # channels per epilogue thread: 8 = 16 epilogue warps (default), 16 = 8 warps
 g = torch.Generator().manual_seed(1)
 x_cl = torch.stack([ops.pack_cl((torch.rand((B, 32, H, W), generator=g) < 0.3).float().to(DEV)) for _ in range(T)])
 z_cl = ops.pack_cl((torch.rand((B, 32, H, W), generator=g) < 0.3).float().to(DEV))
