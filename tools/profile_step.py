@@ -1,5 +1,5 @@
 """One warm forward window (+ loss) and one train step of the bench workload, for `ncu` launch lists.
-   ncu --metrics gpu__time_duration.sum --clock-control none --nvtx --nvtx-include "measured/" --csv --log-file gpurun_out/launches.csv \
+   ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/launches.csv \
        python tools/profile_step.py [fwd|train|both] [stepwise]"""
 import os
 import sys
@@ -55,11 +55,11 @@ for _ in range(2):
     if mode != "fwd":
         window(True)
 torch.cuda.synchronize()
-torch.cuda.nvtx.range_push("measured")
+torch.cuda.profiler.start()  # ncu --profile-from-start off: only the measured window(s), on every thread (the backward runs on autograd's)
 if mode in ("fwd", "both"):
     window(False)
 if mode in ("train", "both"):
     window(True)
 torch.cuda.synchronize()
-torch.cuda.nvtx.range_pop()
+torch.cuda.profiler.stop()
 print("done")
