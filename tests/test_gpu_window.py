@@ -160,3 +160,59 @@ def test_staged_training_loop_is_the_stepwise_training_loop():
     assert len(la) == len(lb) == 5
     for a, b in zip(la, lb):
         assert abs(a - b) <= 0.05 * abs(b), (la, lb)
+
+
+@pytest.mark.parametrize("T", [1, 13])
+def test_window_lengths_one_step_and_longer_than_the_bank(T):
+    """T = 1 (the fused launch degenerates to a step) and T = 13 (> the default bank capacity of 12: the arena grows)."""
+    B, H, W = 2, 32, 48
+    wins = _windows(B, 300, H, W, T, 5, 150)
+    a, b = _model(), _model()
+    vox = torch.stack([d["event_voxel"] for d in wins]).to(DEV)
+    outs = a.forward_window(vox, None)
+    for t, d in enumerate(wins):
+        assert torch.equal(outs[t]["flow"][0], b(d["event_voxel"].to(DEV), None)["flow"][0]), f"step {t}"
+    sum(o["flow"][0].square().sum() for o in outs).backward()
+    b_loss = None
+    b.zero_grad(set_to_none=True)
+    b.reset_states()
+    b_loss = sum(b(d["event_voxel"].to(DEV), None)["flow"][0].square().sum() for d in wins)
+    b_loss.backward()
+    for (n, pa), pb in zip(a.named_parameters(), b.parameters()):
+        assert (pa.grad - pb.grad).abs().max().item() <= 2e-5 * (pb.grad.abs().max().item() + 1e-30), n
+
+
+def test_window_starts_from_states_set_through_the_state_api_and_soft_reset():
+    """model.states = ... (reference format, [2,B,C,H,W] per layer) before a window; soft-reset cells (hard_reset=False)."""
+    from event_flow_b200.models.model import LIFFireNet
+
+    B, H, W, T = 2, 32, 48, 3
+    cfg = firenet_cfg(5, "voxel")
+    cfg["spiking_neuron"] = dict(cfg["spiking_neuron"], hard_reset=False)
+    wins = _windows(B, 400, H, W, 2 * T, 5, 170)
+
+    def mk():
+        torch.manual_seed(1)
+        m = LIFFireNet(dict(cfg, spiking_neuron=dict(cfg["spiking_neuron"])))
+        with torch.no_grad():
+            for n, p in m.named_parameters():
+                if n.endswith("ff.weight") or n.endswith("rec.weight"):
+                    p.mul_(2.5)
+            m.pred.conv2d.weight.mul_(20.0)
+        return m.to(DEV)
+
+    a, b, c = mk(), mk(), mk()
+    with torch.no_grad():
+        for d in wins[:T]:
+            c(d["event_voxel"].to(DEV), None)
+        states = c.states  # clones in the reference's format
+        a.states = [s.clone() for s in states]
+        b.states = [s.clone() for s in states]
+        part = wins[T:]
+        outs = a.forward_window(torch.stack([d["event_voxel"] for d in part]).to(DEV), None)
+        for t, d in enumerate(part):
+            ref = b(d["event_voxel"].to(DEV), None)["flow"][0]
+            assert torch.equal(outs[t]["flow"][0], ref), f"step {t}"
+            assert torch.equal(ref, c(d["event_voxel"].to(DEV), None)["flow"][0])
+        for sa, sb in zip(a.states, b.states):
+            assert torch.equal(sa, sb)
