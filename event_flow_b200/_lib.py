@@ -179,6 +179,7 @@ EXPORTS = {
     "ef_launch_count": (C.c_uint64, []),
     "ef_lif_conv_fwd": (C.c_int, [C.POINTER(LifConvParams), C.c_void_p]),
     "ef_lif_conv_fwd_window": (C.c_int, [C.POINTER(LifConvWindowParams), C.c_void_p]),
+    "ef_lif_neuron_fwd": (C.c_int, [C.POINTER(LifConvParams), C.c_void_p, C.c_void_p]),
     "ef_lif_conv_bwd": (C.c_int, [C.POINTER(LifConvBwdParams), C.c_void_p]),
     "ef_lif_bwd_tc": (C.c_int, [C.POINTER(LifBwdTcParams), C.c_void_p]),
     "ef_lif_bwd_window": (C.c_int, [C.POINTER(LifBwdWindowParams), C.c_void_p]),

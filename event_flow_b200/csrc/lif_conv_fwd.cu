@@ -363,6 +363,121 @@ int validate_lif_conv(const ef_lif_conv_params& p, const char* who) {
   return EF_OK;
 }
 
+// ---- neuron update on a GIVEN synaptic current ----------------------------------------------------------------------------------
+// The second half of a cell step whose convolution ran elsewhere (ef_lif_neuron_fwd): the tensor-core kernel computes
+// cur = conv(x, w_ff) (+ conv(z, w_rec)) for 32-channel cells of any neuron kind, this kernel applies the PLIF / ALIF / XLIF / LIF update
+// (models/spiking_submodules.py:164-227, 265-334, 372-435 and the recurrent twins) on the reference's fp32 NCHW state tensors.
+// Block = 32 x 8 pixels of one sample, thread = pixel: per channel all accesses of a warp are one 128-byte row segment.
+constexpr int NU_TW = 32, NU_TH = 8;
+template <int NEURON, bool HARD>
+__global__ void __launch_bounds__(NU_TW * NU_TH) neuron_fwd_kernel(const ef_lif_conv_params p, const float* __restrict__ cur) {
+  constexpr bool TRACE = (NEURON == EF_PLIF || NEURON == EF_XLIF);
+  __shared__ float s_abs[TRACE ? (NU_TH + 2) * (NU_TW + 2) : 1];
+  __shared__ ChanConst s_k[64];
+  const int tid = threadIdx.x, tx = tid % NU_TW, ty = tid / NU_TW;
+  const int b = blockIdx.z, x0 = blockIdx.x * NU_TW, y0 = blockIdx.y * NU_TH;
+  const int H = p.H, W = p.W, C = p.C;
+  const size_t plane = (size_t)H * W;
+  if (TRACE) {  // sum_c |x| on the tile and its 1-pixel halo (zero outside the image: count_include_pad)
+    for (int i = tid; i < (NU_TH + 2) * (NU_TW + 2); i += NU_TW * NU_TH) {
+      const int hy = i / (NU_TW + 2), hx = i - hy * (NU_TW + 2);
+      const int y = y0 + hy - 1, x = x0 + hx - 1;
+      float a = 0.f;
+      if (y >= 0 && y < H && x >= 0 && x < W) {
+        const float* xp = p.x + (size_t)b * p.Cin * plane + (size_t)y * W + x;
+        int c = 0;
+        for (; c + 8 <= p.Cin; c += 8) {  // 8 independent loads in flight
+          float t[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) t[j] = __ldg(xp + (size_t)(c + j) * plane);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) a += fabsf(t[j]);
+        }
+        for (; c < p.Cin; ++c) a += fabsf(__ldg(xp + (size_t)c * plane));
+      }
+      s_abs[i] = a;
+    }
+  }
+  const int y = y0 + ty, x = x0 + tx;
+  const bool inside = y < H && x < W;
+  float P = 0.f;
+  for (int c0 = 0; c0 < C; c0 += 64) {  // channel constants in blocks of 64
+    __syncthreads();
+    if (tid < 64 && c0 + tid < C) s_k[tid] = load_chan_const(p, c0 + tid);
+    __syncthreads();
+    if (TRACE && c0 == 0) {
+      float s = 0.f;
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) s += s_abs[(ty + dy) * (NU_TW + 2) + tx + dx] / (float)p.Cin;
+      P = s / 9.0f;
+    }
+    if (!inside) continue;
+    const int cn = min(64, C - c0);
+    for (int g0 = 0; g0 < cn; g0 += 8) {  // 8 channels = one 16-byte piece of the channels-last outputs
+      // all loads of the group first, then the updates and stores (the tensors come without restrict: a store between the loads of two
+      // channels would serialise them)
+      float in_c[8], in_v[8], in_z[8], in_a[8], in_r[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = c0 + g0 + j;
+        const size_t o = ((size_t)b * C + min(c, C - 1)) * plane + (size_t)y * W + x;
+        in_c[j] = __ldg(cur + o);
+        in_v[j] = p.v_in ? __ldg(p.v_in + o) : 0.f;
+        in_z[j] = p.z_in ? __ldg(p.z_in + o) : 0.f;
+        in_a[j] = p.aux_in ? __ldg(p.aux_in + o) : 0.f;
+        in_r[j] = p.residual ? __ldg(p.residual + o) : 0.f;
+      }
+      uint32_t zpk[4] = {0, 0, 0, 0}, opk[4] = {0, 0, 0, 0};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = c0 + g0 + j;
+        float zo = 0.f, oo = 0.f;
+        if (c < C) {
+          const size_t o = ((size_t)b * C + c) * plane + (size_t)y * W + x;
+          float vo, ao, thr;
+          neuron_update<NEURON, HARD>(in_c[j], in_v[j], in_z[j], in_a[j], P, s_k[g0 + j], vo, zo, ao, thr);
+          p.v_out[o] = vo;
+          if (p.z_out) p.z_out[o] = zo;
+          if (p.aux_out) p.aux_out[o] = ao;
+          oo = p.residual ? __fadd_rn(zo, in_r[j]) : zo;
+          if (p.out) p.out[o] = oo;
+        }
+        const uint32_t zb = pack_bf16x2(zo, 0.f) & 0xffffu, ob = pack_bf16x2(oo, 0.f) & 0xffffu;
+        zpk[j >> 1] |= (j & 1) ? (zb << 16) : zb;
+        opk[j >> 1] |= (j & 1) ? (ob << 16) : ob;
+      }
+      if (C % 8 == 0) {
+        const size_t o8 = (((size_t)b * H + y) * W + x) * C + c0 + g0;
+        if (p.z_out_cl) *reinterpret_cast<uint4*>(p.z_out_cl + o8) = make_uint4(zpk[0], zpk[1], zpk[2], zpk[3]);
+        if (p.out_cl) *reinterpret_cast<uint4*>(p.out_cl + o8) = make_uint4(opk[0], opk[1], opk[2], opk[3]);
+      }
+    }
+  }
+}
+
+template <int NEURON, bool HARD>
+static int launch_neuron(const ef_lif_conv_params& p, const float* cur, cudaStream_t st) {
+  const dim3 grid(cdiv(p.W, NU_TW), cdiv(p.H, NU_TH), p.B);
+  neuron_fwd_kernel<NEURON, HARD><<<grid, NU_TW * NU_TH, 0, st>>>(p, cur);
+  return check_launch("neuron_fwd_kernel");
+}
+
+int neuron_fwd(const ef_lif_conv_params& p, const float* cur, cudaStream_t st) {
+  switch (p.neuron * 2 + (p.hard_reset ? 1 : 0)) {
+    case EF_LIF * 2 + 0: return launch_neuron<EF_LIF, false>(p, cur, st);
+    case EF_LIF * 2 + 1: return launch_neuron<EF_LIF, true>(p, cur, st);
+    case EF_PLIF * 2 + 0: return launch_neuron<EF_PLIF, false>(p, cur, st);
+    case EF_PLIF * 2 + 1: return launch_neuron<EF_PLIF, true>(p, cur, st);
+    case EF_ALIF * 2 + 0: return launch_neuron<EF_ALIF, false>(p, cur, st);
+    case EF_ALIF * 2 + 1: return launch_neuron<EF_ALIF, true>(p, cur, st);
+    case EF_XLIF * 2 + 0: return launch_neuron<EF_XLIF, false>(p, cur, st);
+    case EF_XLIF * 2 + 1: return launch_neuron<EF_XLIF, true>(p, cur, st);
+  }
+  return fail(EF_EINVAL, "ef_lif_neuron_fwd: bad neuron kind %d", p.neuron);
+}
+
 int lif_conv_fwd_tc(const ef_lif_conv_params& p, cudaStream_t st);  // lif_conv_fwd_tc.cu
 bool lif_conv_tc_eligible(const ef_lif_conv_params& p);
 
@@ -374,4 +489,15 @@ extern "C" int ef_lif_conv_fwd(const ef_lif_conv_params* p, void* stream) {
   if (ef::lif_conv_tc_eligible(*p)) return ef::lif_conv_fwd_tc(*p, ef::as_stream(stream));
   if (ef::head_eligible(*p)) return ef::launch_head(*p, ef::as_stream(stream));
   return ef::lif_conv_fwd_generic(*p, ef::as_stream(stream));
+}
+
+// The neuron update of a cell step on a synaptic current computed elsewhere (the tensor-core convolution): same parameter block as
+// ef_lif_conv_fwd; stride 1, fp32 NCHW x (read for the pre-synaptic trace of PLIF / XLIF only) and states; w_ff / w_rec are not read.
+extern "C" int ef_lif_neuron_fwd(const ef_lif_conv_params* p, const float* cur, void* stream) {
+  EF_REQUIRE(p && cur, EF_ENULL, "ef_lif_neuron_fwd: params / current is NULL");
+  if (int rc = ef::validate_lif_conv(*p, "ef_lif_neuron_fwd")) return rc;
+  EF_REQUIRE(p->stride == 1, EF_EUNSUPPORTED, "ef_lif_neuron_fwd: stride 1 only");
+  EF_REQUIRE(!p->z_in_cl, EF_EUNSUPPORTED, "ef_lif_neuron_fwd: previous spikes as fp32 NCHW (z_in)");
+  EF_REQUIRE((p->neuron != EF_PLIF && p->neuron != EF_XLIF) || p->x, EF_ENULL, "ef_lif_neuron_fwd: PLIF / XLIF need the fp32 input x");
+  return ef::neuron_fwd(*p, cur, ef::as_stream(stream));
 }

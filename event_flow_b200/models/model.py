@@ -81,8 +81,23 @@ class FireNet(BaseModel):
             make = self.head_neuron if name == "head" else (self.rec_neuron if name in _GATED else self.ff_neuron)
             cell = make(self.num_bins if name == "head" else width, width, ksize, activation=rec_act if name in _GATED else ff_act, **extra)
             setattr(self, name, cell)
+        self._mark_inputs()
         self.pred = ann.ConvLayer(width, out_channels=2, kernel_size=1, activation="tanh", w_scale=self.w_scale_pred)
         self.reset_states()
+
+    def _mark_inputs(self):
+        """
+        Tell the spiking cells what their input is, so that their convolution may run on the tensor cores with exact products: the head
+        sees the (fractional) event encoding -> exact bf16 split; every later cell sees the spikes of a spiking cell (plus, in the
+        residual variants, another spike tensor: small integers) -> exact in bf16 as they are.
+        """
+        prev_spiking = False
+        for name in _CHAIN:
+            cell = getattr(self, name)
+            spiking = isinstance(cell, snn._SpikingConvCell)
+            if spiking:
+                cell.__dict__["_x_kind"] = "split" if name == "head" else ("spikes" if prev_spiking else None)
+            prev_spiking = spiking
 
     def __getattr__(self, name):
         if name == "_fast":  # a FireNet unpickled from a checkpoint the reference wrote has no fast-path state yet

@@ -57,6 +57,14 @@ class _SpikingConvCell(nn.Module):
             return getattr(fn, "name", getattr(fn, "__name__", "arctanspike"))
         return super().__getattr__(name)
 
+    def _width(self):
+        """float(act_width) without a device-to-host copy per call: the buffer's value is read once per version."""
+        w = self.act_width
+        hit = self.__dict__.get("_width_cache")
+        if hit is None or hit[0] != (w._version, w.data_ptr()):
+            hit = self.__dict__["_width_cache"] = ((w._version, w.data_ptr()), float(w))
+        return hit[1]
+
     def forward(self, input_, prev_state, residual=0):
         chan = {n: getattr(self, n) for n in ops.param_names(self.neuron)}
         return ops.cell_step(
@@ -68,9 +76,10 @@ class _SpikingConvCell(nn.Module):
             chan,
             hard_reset=self.hard_reset,
             surrogate=self.activation,
-            width=float(self.act_width),
+            width=self._width(),
             stride=self.stride,
             residual=residual,
+            x_kind=self.__dict__.get("_x_kind"),  # set by the model that owns the cell when it knows what the cell's input is
         )
 
 

@@ -4,6 +4,7 @@ Every function here launches CUDA kernels through the C ABI (event_flow_b200/_li
 """
 
 import ctypes as C
+import weakref
 
 import torch
 
@@ -70,7 +71,7 @@ class _CellStep(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, meta, x, state_in, w_ff, w_rec, residual, *chan_vals):
-        neuron, hard_reset, surrogate, width, stride = meta
+        neuron, hard_reset, surrogate, width, stride, x_kind = meta
         names = param_names(neuron)
         chan = {n: _c(v.reshape(-1)) for n, v in zip(names, chan_vals)}
         x, state_in, w_ff, w_rec, residual = _c(x), _c(state_in), _c(w_ff), _c(w_rec), _c(residual)
@@ -82,7 +83,21 @@ class _CellStep(torch.autograd.Function):
         out = torch.empty((B, Cout, Ho, Wo), device=x.device, dtype=torch.float32)  # z (+ residual); a tensor of its own
         p = L.LifConvParams()
         _fill_cell_params(p, neuron, x, state_in, w_ff, w_rec, chan, residual, state_out, out, hard_reset, surrogate, width, stride)
-        L.call("ef_lif_conv_fwd", p, tag=(x.shape[1], Cout, w_rec is not None))
+        if _tc_conv_ok(x, w_ff, w_rec, stride, x_kind):
+            # 32-channel cell of ANY neuron kind: the convolution on the tensor cores (exact products), the neuron update on its current
+            cur = _tc_conv_current(x, state_in, w_ff, w_rec, x_kind)
+            # the same spikes also in the internal format, for the next cell's / next step's tensor-core convolution (no re-packing)
+            out_cl = torch.empty((B, Ho, Wo, Cout), device=x.device, dtype=torch.bfloat16)
+            p.out_cl = L.ptr(out_cl)
+            z_cl = out_cl
+            if residual is not None:
+                z_cl = torch.empty_like(out_cl)
+                p.z_out_cl = L.ptr(z_cl)
+            L.LAUNCHES += 1
+            L.check(L.lib().ef_lif_neuron_fwd(C.byref(p), L.ptr(cur), L.stream()), "ef_lif_neuron_fwd")
+            out._ef_cl, state_out._ef_z_cl = out_cl, z_cl
+        else:
+            L.call("ef_lif_conv_fwd", p, tag=(x.shape[1], Cout, w_rec is not None))
         ctx.meta = meta
         ctx.chan_names = names
         ctx.save_for_backward(x, state_in, w_ff, w_rec, residual, state_out, *[chan[n] for n in names])
@@ -92,7 +107,7 @@ class _CellStep(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_out, g_state):
-        neuron, hard_reset, surrogate, width, stride = ctx.meta
+        neuron, hard_reset, surrogate, width, stride, _ = ctx.meta
         x, state_in, w_ff, w_rec, residual, state_out, *chan_vals = ctx.saved_tensors
         names = ctx.chan_names
         chan = dict(zip(names, chan_vals))
@@ -146,17 +161,77 @@ class _CellStep(torch.autograd.Function):
         return (None, g_x, g_state_in, g_w_ff, g_w_rec, g_res, *g_chan)
 
 
-def cell_step(neuron, x, state, w_ff, w_rec, chan, *, hard_reset, surrogate="arctanspike", width=10.0, stride=1, residual=None):
+_TC_CONSTS = {}
+
+
+def _tc_conv_ok(x, w_ff, w_rec, stride, x_kind):
+    """The convolution of this cell step can run on the tcgen05 kernel: 32 output channels, 3x3, stride 1, inputs the caller vouches to be
+    exactly representable in bf16 ("spikes": 32 channels of spikes / residual sums) or few fractional channels ("split": exact three-way
+    bf16 split, feed-forward cells only)."""
+    if x_kind is None or stride != 1 or w_ff.shape[0] != 32 or w_ff.shape[-1] != 3 or x.shape[-1] % 4 != 0 or not x.is_cuda:
+        return False
+    if x_kind == "spikes":
+        return x.shape[1] == 32
+    return x_kind == "split" and x.shape[1] <= L.EF_HEAD_MAX_CIN and w_rec is None
+
+
+def _tc_conv_current(x, state_in, w_ff, w_rec, x_kind):
+    """cur = conv(x, w_ff) (+ conv(z_in, w_rec)) [B,32,H,W] fp32 on the tensor cores: the fused LIF kernel run as a pure convolution --
+    leak = -inf makes sigmoid(leak) = 0, so its membrane output is (1 - 0) * current exactly, whatever state it is given."""
+    dev = x.device
+    consts = _TC_CONSTS.get(dev)
+    if consts is None:
+        consts = _TC_CONSTS[dev] = (torch.full((32,), float("-inf"), device=dev), torch.ones(32, device=dev))
+    neg_inf, ones = consts
+    # weight image: rebuilt when the weight tensors changed (torch's version counters; WEIGHT_EPOCH for in-place updates behind them)
+    # (keyed on the identity of the weight tensor OBJECTS, held weakly: a freed tensor's address may be reused by other values)
+    key = (w_ff.data_ptr(), w_ff._version, None if w_rec is None else (w_rec.data_ptr(), w_rec._version), WEIGHT_EPOCH, x_kind)
+    hit = _TC_IMAGES.get(id(w_ff))
+    if hit is None or hit[0] != key or hit[2]() is not w_ff or (w_rec is not None and hit[3]() is not w_rec):
+        image = split_weights_head(w_ff) if x_kind == "split" else split_weights(w_ff, w_rec)
+        if len(_TC_IMAGES) > 64:
+            _TC_IMAGES.clear()
+        hit = _TC_IMAGES[id(w_ff)] = (key, image, weakref.ref(w_ff), None if w_rec is None else weakref.ref(w_rec))
+    image = hit[1]
+    # input / previous spikes in the internal format: handed over by the cell that produced them (attributes of the tensors), else packed here
+    x_cl = getattr(x, "_ef_cl", None)
+    if x_kind == "split":
+        x_cl = pack_split_cl(x)
+    elif x_cl is None or x_cl.shape[:3] != (x.shape[0], x.shape[2], x.shape[3]):
+        x_cl = pack_cl(x)
+    v_in = z_cl = None
+    if w_rec is not None and state_in is not None:
+        v_in = state_in[0]  # (only has to be finite: it is multiplied by sigmoid(-inf) = 0)
+        z_cl = getattr(state_in, "_ef_z_cl", None)
+        if z_cl is None:
+            z_cl = pack_cl(state_in[1])
+    cur, _ = lif_step_cl(x_cl, v_in, z_cl, w_ff, w_rec, neg_inf, ones, hard_reset=True, w_split=image)
+    return cur
+
+
+WEIGHT_EPOCH = 0
+_TC_IMAGES = {}
+
+
+def invalidate_weight_images():
+    """Call after updating parameters outside torch's version tracking (the fused Adam kernel writes through raw pointers)."""
+    global WEIGHT_EPOCH
+    WEIGHT_EPOCH += 1
+
+
+def cell_step(neuron, x, state, w_ff, w_rec, chan, *, hard_reset, surrogate="arctanspike", width=10.0, stride=1, residual=None, x_kind=None):
     """
     Fused forward of a spiking conv cell.  Mirrors `cell.forward(input_, prev_state, residual)` of
     models/spiking_submodules.py: returns (out, new_state) with new_state = stack([v, z(, trace)]).
     :param chan: dict of per-channel parameters named as in the reference module (leak, thresh, leak_v, ...)
+    :param x_kind: None (anything: CUDA-core kernel), "spikes" (the caller vouches that x holds spikes / small integer sums, i.e. is exact
+                   in bf16) or "split" (<= 10 fractional channels): the convolution of a 32-channel cell then runs on the tensor cores
     """
     if neuron not in _N_STATE:
         raise ValueError(neuron)
     if torch.is_tensor(residual) is False:
         residual = None if (residual is None or residual == 0) else torch.as_tensor(residual)
-    meta = (neuron, bool(hard_reset), surrogate, float(width), int(stride))
+    meta = (neuron, bool(hard_reset), surrogate, float(width), int(stride), x_kind)
     vals = [chan[n] for n in param_names(neuron)]
     return _CellStep.apply(meta, x, state, w_ff, w_rec, residual, *vals)
 

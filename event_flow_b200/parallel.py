@@ -97,9 +97,10 @@ class DataParallelTrainer:
         self.kernels.clip_adam(self.flat_param, self.flat_grad, self.m, self.v, self.n, self.sqnorm, float(self.clip) if self.clip else 0.0,
                                self.lr, self.betas[0], self.betas[1], self.eps, self.step_count)
         self.flat_grad.zero_()
-        from . import fast
+        from . import fast, ops
 
         fast.invalidate_weights(self.model)  # the kernel wrote the parameters behind torch's version counters
+        ops.invalidate_weight_images()
 
     def _view_of(self, p):
         if not hasattr(self, "_offsets"):

@@ -91,6 +91,14 @@ typedef struct ef_lif_conv_params {
 
 int ef_lif_conv_fwd(const ef_lif_conv_params* p, void* stream);
 
+/* The neuron update of a cell step on a synaptic current computed elsewhere: cur [B,C,H,W] = conv(x, w_ff) (+ conv(z_in, w_rec)), e.g. the
+ * membrane output of the tensor-core kernel run as a pure convolution (zero state, leak = -inf: v_out = current).  Same parameter block as
+ * ef_lif_conv_fwd -- state in / out, per-channel parameters, residual, out / z_out (fp32 NCHW and / or channels-last bf16) -- for all four
+ * neuron kinds (models/spiking_submodules.py:108-126, 200-227, 310-334, 409-435 and the recurrent twins); stride 1; x (fp32 NCHW) is
+ * only read for the pre-synaptic trace of PLIF / XLIF; w_ff / w_rec are not read.  This is how 32-channel PLIF / ALIF / XLIF cells get
+ * their convolution onto the tensor cores (event_flow_b200/ops.py, _CellStep). */
+int ef_lif_neuron_fwd(const ef_lif_conv_params* p, const float* cur, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * A FEED-FORWARD 32 -> 32 LIF cell (or the head layer on split inputs, ef_pack_split_cl) over a whole window of T steps in ONE launch
  * (the time loop of train_flow.py:98-141 / models/model.py:255-265 moved inside the kernel for the cells without a recurrent

@@ -245,3 +245,76 @@ def test_head_layer_on_tensor_cores_split_input(cin):
     assert_rel(g_w, po["ff"].grad, 1e-3, "head g_w_ff (tensor cores)")
     assert_rel(g_leak, po["leak"].grad.reshape(-1), 1e-3, "head g_leak")
     assert_rel(g_thresh, po["thresh"].grad.reshape(-1), 1e-3, "head g_thresh")
+
+
+# ---- 32-channel cells of every neuron kind: convolution on the tensor cores + neuron update on its current (ops._CellStep, x_kind) -------------
+def _cell_case(neuron, layer, B, H, W, seed, with_state, bins=5):
+    g = torch.Generator().manual_seed(seed)
+    params = osp.init_firenet_params(neuron, bins, 32, seed=seed, weight_gain=2.0)[layer]
+    if layer == "head":
+        x = torch.randn((B, bins, H, W), generator=g) * (torch.rand((B, bins, H, W), generator=g) < 0.4).float()  # fractional voxel-like input
+    else:
+        x = (torch.rand((B, 32, H, W), generator=g) < 0.3).float()
+    st = None
+    if with_state:
+        n = 2 if neuron == "lif" else 3
+        st = torch.rand((n, B, 32, H, W), generator=g) * 1.2 - 0.1
+        st[1] = (st[1] < 0.3).float()
+        if n == 3:
+            st[2] = st[2].abs() * 0.3
+    return params, x, st
+
+
+@pytest.mark.parametrize("neuron", ["lif", "plif", "alif", "xlif"])
+@pytest.mark.parametrize("layer", ["head", "R1a", "G1"])
+@pytest.mark.parametrize("hard", [True, False])
+@pytest.mark.parametrize("with_state", [True, False])
+def test_tensor_core_conv_plus_neuron_update_matches_generic_kernel_and_oracle(neuron, layer, hard, with_state):
+    """
+    ops.cell_step(x_kind="spikes" | "split") = tcgen05 convolution (exact products) + ef_lif_neuron_fwd, against the fused CUDA-core kernel
+    on the same tensors and against the oracle: membrane / trace to summation-order noise, spikes exact outside the band; then the
+    backward (same kernel for both, fed by each path's saved state) to 1e-4.
+    """
+    from event_flow_b200 import ops
+
+    B, H, W = 2, 36, 44
+    params, x, st = _cell_case(neuron, layer, B, H, W, seed=11, with_state=with_state)
+    pd = {k: v.to(DEV).contiguous() for k, v in params.items()}
+    chan = {n: pd[n] for n in ops.param_names(neuron)}
+    kind = "split" if layer == "head" else "spikes"
+    res = {}
+    for tag, xk in (("tc", kind), ("cc", None)):
+        xd = x.to(DEV).requires_grad_(True)
+        sd = None if st is None else st.to(DEV).requires_grad_(True)
+        ws = {k: pd[k].clone().requires_grad_(True) for k in ("ff", "rec") if k in pd}
+        out, ns = ops.cell_step(neuron, xd, sd, ws["ff"], ws.get("rec"), chan, hard_reset=hard, x_kind=xk)
+        gen = torch.Generator().manual_seed(5)
+        g_out, g_ns = torch.randn(out.shape, generator=gen).to(DEV), torch.randn(ns.shape, generator=gen).to(DEV)
+        g_ns[1] = 0  # (the spikes inside the state are the same tensor values as `out`)
+        torch.autograd.backward([out, ns], [g_out, g_ns])
+        res[tag] = (out.detach().cpu(), ns.detach().cpu(), xd.grad.cpu(), None if sd is None else sd.grad.cpu(), {k: w.grad.cpu() for k, w in ws.items()})
+    out_o, ns_o = osp.cell_step(neuron, x, st, params, hard_reset=hard)
+    if neuron in ("lif", "plif"):
+        thr = params["thresh"].clamp_min(0.01)
+    else:
+        thr = params["t0"].clamp_min(0.01) + params["t1"].clamp_min(0) * ns_o[2]
+    for other_v, other_z, other_aux in ((res["cc"][1][0], res["cc"][1][1], res["cc"][1][2] if neuron != "lif" else None),
+                                        (ns_o[0], ns_o[1], ns_o[2] if neuron != "lif" else None)):
+        _, _, in_flips = spike_band_compare(res["tc"][1][0], res["tc"][1][1], other_v, other_z, thr)
+        if other_aux is not None:
+            assert (res["tc"][1][2] - other_aux).abs().max().item() <= 1e-6 * max(1.0, other_aux.abs().max().item())
+    assert torch.equal(res["tc"][0], res["tc"][1][1])  # out = spikes (no residual)
+    if torch.equal(res["tc"][1][1], res["cc"][1][1]):  # same spikes (no borderline neuron in this case): same backward inputs up to 1e-6
+        for a, b, what in ((res["tc"][2], res["cc"][2], "g_x"), (res["tc"][3], res["cc"][3], "g_state")) + tuple(
+                (res["tc"][4][k], res["cc"][4][k], "g_" + k) for k in res["cc"][4]):
+            if b is not None:
+                assert (a - b).abs().max().item() <= 1e-4 * (b.abs().max().item() + 1e-20), what
+    assert res["tc"][1][1].mean() > 0.01
+
+
+def test_neuron_step_c_abi_rejects_bad_arguments():
+    from event_flow_b200 import _lib as L
+
+    assert L.lib().ef_lif_neuron_fwd(None, None, None) < 0
+    p = L.LifConvParams()
+    assert L.lib().ef_lif_neuron_fwd(p, None, None) < 0

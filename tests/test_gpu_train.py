@@ -104,3 +104,41 @@ def test_cached_backward_arguments_reproduce_the_first_window():
         for n, g in grads.items():
             scale = ref[n].abs().max().item() + 1e-20
             assert (g - ref[n]).abs().max().item() <= 1e-5 * scale, f"window {k + 2}: {n}"
+
+
+def test_weight_images_of_the_cell_path_follow_the_fused_optimizer():
+    """
+    PLIF FireNet (cells on the tensor-core convolution + neuron kernel; weight images cached per weight tensor): after a fused
+    clip + Adam step -- which writes the parameters behind torch's version counters -- the next forward must use the NEW weights.
+    """
+    import copy
+
+    from event_flow_b200.models.model import PLIFFireNet
+    from event_flow_b200.parallel import DataParallelTrainer
+
+    H = W = 32
+    torch.manual_seed(0)
+    cfg = firenet_cfg(5, "voxel", neuron="plif")
+    m = PLIFFireNet(cfg)
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if n.endswith("ff.weight") or n.endswith("rec.weight"):
+                p.mul_(2.5)
+        m.pred.conv2d.weight.mul_(50.0)
+    m = m.to(DEV)
+    tr = DataParallelTrainer(m, lr=1e-2)  # a large step: stale weights would be obvious
+    d = oenc.encode_window(*oenc.synthetic_events(2, 400, H, W, 3), H, W, 5)
+    vox = d["event_voxel"].to(DEV)
+    m(vox, None)["flow"][0].square().sum().backward()
+    tr.step()
+    m.reset_states()
+    with torch.no_grad():
+        after = m(vox, None)["flow"][0].clone()
+    twin = copy.deepcopy(m)  # fresh run-time state, same (updated) parameters
+    twin.reset_states()
+    for cell in twin.modules():
+        cell.__dict__.pop("_x_kind", None)  # the twin runs the fused CUDA-core kernel: no weight images at all
+    with torch.no_grad():
+        ref = twin(vox, None)["flow"][0]
+    assert ref.abs().max() > 0
+    assert (after - ref).abs().max().item() <= 1e-4 * ref.abs().max().item()

@@ -20,7 +20,7 @@ from tests.conftest import GOLDEN, load_golden
 def cpu_ops(monkeypatch):
     from event_flow_b200 import ops
 
-    def cell_step(neuron, x, state, w_ff, w_rec, chan, *, hard_reset, surrogate="arctanspike", width=10.0, stride=1, residual=None):
+    def cell_step(neuron, x, state, w_ff, w_rec, chan, *, hard_reset, surrogate="arctanspike", width=10.0, stride=1, residual=None, x_kind=None):
         p = {"ff": w_ff, **chan}
         if w_rec is not None:
             p["rec"] = w_rec
