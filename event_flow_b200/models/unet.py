@@ -1,9 +1,10 @@
 """
 Spiking multi-resolution recurrent U-Net with the constructor contract, module names (state_dict keys) and state layout of
 models/unet.py: BaseUNet (:28-120), MultiResUNetRecurrent (:314-416), SpikingMultiResUNetRecurrent (:418-465).
-Every encoder / residual / decoder stage is built from the fused conv+neuron cells (ef_lif_conv_fwd); the 2x bilinear
-upsampling is ef_upsample_bilinear2x and the per-scale prediction ef_pred_fwd.  Forward only in this version (the
-stride-2 and upsampling backward kernels are not built: calling it under autograd raises).
+Every encoder / residual / decoder stage is built from the fused conv+neuron cells (ef_lif_conv_fwd, backward ef_lif_conv_bwd incl.
+stride 2); the 2x bilinear upsampling is ef_upsample_bilinear2x(_bwd) and the per-scale prediction ef_pred_fwd / ef_pred_bwd: forward
+and BPTT.  Without gradient tracking the LIF variant runs on the general tensor-core cell kernel (fast_unet.py: no concat, stride 2 through
+space-to-depth inputs).  Also here: the ANN twins (MultiResUNet, MultiResUNetRecurrent), the leaky U-Net and E2VID's UNetRecurrent.
 """
 import torch.nn as nn
 
