@@ -134,6 +134,7 @@ def iwe_bench(dev, peak_gbs, reps=10):
     Algorithmic bytes per sample: fwd 32*Ntot + 4*HW*(2T*S + T + 16*S), bwd 32*Ntot + 4*HW*(8*S + 2T*S).
     """
     from event_flow_b200 import _lib as L
+    from event_flow_b200 import fast
 
     out = {}
     for name, (B, Hh, Ww, Tt, N) in (("cfg2_B8_128x128_T10_N1000", (8, 128, 128, 10, 1000)), ("large_B32_256x256_T10_N50000", (32, 256, 256, 10, 50000))):
@@ -165,9 +166,7 @@ def iwe_bench(dev, peak_gbs, reps=10):
         def timed_graph(fn):
             fn()
             torch.cuda.synchronize()
-            gr = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(gr, capture_error_mode="thread_local"):
-                fn()
+            gr = fast._capture(fn)  # (garbage collector paused inside the capture)
             gr.replay()
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

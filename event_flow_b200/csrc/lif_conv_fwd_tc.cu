@@ -24,6 +24,8 @@
 // warp 3 idle, warps 4.. = epilogue (each owns a TMEM lane quadrant = 32 pixels and CPT channels).  Persistent over tiles;
 // mbarrier pipelines between the roles.
 // Reference semantics: models/spiking_submodules.py:96-126 (ConvLIF), :516-551 (ConvLIFRecurrent).
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace ef {
@@ -543,7 +545,12 @@ static int launch_tc(const TcParams& q, int grid, const CUtensorMap* m, cudaStre
     attr_set = true;
   }
   const cudaError_t le = launch_pdl(kern, dim3(grid), dim3(128 + 32 * 4 * (32 / CPT)), TcCfg<REC>::TOTAL, st, q, m[0], m[1], m[2], m[3], m[4], m[5]);
-  (void)le;
+  if (getenv("EF_DEBUG_CAPTURE")) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    const cudaError_t ce = cudaStreamIsCapturing(st, &cs);
+    fprintf(stderr, "[ef] tc launch REC=%d HARD=%d grid=%d T=%d has_v=%d has_z=%d -> launch rc=%d (%s), capture status=%d (query rc=%d)\n", (int)REC, (int)HARD, grid,
+            q.T, q.has_v, q.has_z, (int)le, cudaGetErrorName(le), (int)cs, (int)ce);
+  }
   return check_launch("lif_conv_fwd_tc_kernel");
 }
 

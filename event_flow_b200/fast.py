@@ -16,6 +16,8 @@ autograd node to run) and executed layer by layer over the whole window:
   * prediction head: one launch over T*B images.
 One torch.autograd node per MODEL step only orders the steps (scalar token) and collects dL/dflow.
 """
+import gc
+
 import torch
 
 from . import _lib as L
@@ -24,6 +26,25 @@ from . import ops
 LAYERS = ("head", "G1", "R1a", "R1b", "G2", "R2a", "R2b")
 N_L = len(LAYERS)
 DEFAULT_WINDOW_CAP = 12  # steps a bank holds before it has to grow (train_SNN.yml: window_loss / window = 10)
+
+
+def _capture(fn):
+    """
+    fn() captured into a CUDA graph.  thread_local error mode: other threads (the NCCL watchdog under data parallelism) keep issuing
+    CUDA calls during a capture.  The cyclic garbage collector is paused for the duration: a collection that happens to run inside the
+    capture may destroy CUDA objects of earlier models (graphs with their memory pools, tensors), i.e. issue calls that are illegal on a
+    capturing thread and invalidate the capture.
+    """
+    g = torch.cuda.CUDAGraph()
+    was_enabled = gc.isenabled()
+    with torch.cuda.graph(g, capture_error_mode="thread_local"):  # (its __enter__ runs a full collection first)
+        gc.disable()
+        try:
+            fn()
+        finally:
+            if was_enabled:
+                gc.enable()
+    return g
 
 
 class _Carry:
@@ -334,10 +355,11 @@ def capture_window(model, xs, only_hidden=False):
         for t in range(1, len(xs)):  # eager pass: fills every slot (the hidden-only replay needs the head spikes in place)
             _launch_step(model, xs[t], slots[t - 1].v, slots[t - 1].z, slots[t], splits, B, Cin0, H, W)
         torch.cuda.synchronize()
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g, capture_error_mode="thread_local"):
+        def replayed():
             for t in range(1, len(xs)):
                 _launch_step(model, xs[t], slots[t - 1].v, slots[t - 1].z, slots[t], splits, B, Cin0, H, W, only_hidden=only_hidden)
+
+        g = _capture(replayed)
     g._keepalive = (bank, xs, splits)
     return g, (len(xs) - 1) * (N_L - 1 if only_hidden else N_L + 1)
 
@@ -391,11 +413,7 @@ class _FireNetStep(torch.autograd.Function):
             g = slot.graphs.get(key)
             if g is None:
                 _launch_step(model, x_step, v_in, z_in, slot, splits, B, Cin0, H, W)  # eager: results + lazy init
-                g = torch.cuda.CUDAGraph()
-                # thread_local: other threads (the NCCL watchdog under data parallelism) keep issuing CUDA calls during a capture
-                with torch.cuda.graph(g, capture_error_mode="thread_local"):
-                    _launch_step(model, x_step, v_in, z_in, slot, splits, B, Cin0, H, W)
-                slot.graphs[key] = g
+                g = slot.graphs[key] = _capture(lambda: _launch_step(model, x_step, v_in, z_in, slot, splits, B, Cin0, H, W))
             else:
                 g.replay()
                 L.GRAPH_KERNELS += N_L + 1
@@ -700,9 +718,7 @@ def capture_window_fused(model, xs0, xs, only=None, save_all_v=False):
         z0 = [banks[0].zs[i][T] for i in range(N_L)]
         _launch_window(model, banks[1], T, v0, z0, splits, B, H, W, save_all_v)
         torch.cuda.synchronize()
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g, capture_error_mode="thread_local"):
-            _launch_window(model, banks[1], T, v0, z0, splits, B, H, W, save_all_v, only=only)
+        g = _capture(lambda: _launch_window(model, banks[1], T, v0, z0, splits, B, H, W, save_all_v, only=only))
     g._keepalive = (banks, splits)
     names = LAYERS + ("pred",) if only is None else only
     cells = dict(zip(LAYERS, _cells(model)))
@@ -752,10 +768,7 @@ class _FireNetWindow(torch.autograd.Function):
             g = graphs.get(key)
             if g is None:
                 _launch_window(model, bank, T, v0, z0, splits, B, H, W, need_grad)
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, capture_error_mode="thread_local"):
-                    _launch_window(model, bank, T, v0, z0, splits, B, H, W, need_grad)
-                graphs[key] = g
+                g = graphs[key] = _capture(lambda: _launch_window(model, bank, T, v0, z0, splits, B, H, W, need_grad))
             else:
                 g.replay()
                 L.GRAPH_KERNELS += WINDOW_LAUNCHES(T)
