@@ -47,6 +47,7 @@ class LifConvBwdParams(C.Structure):
         ("g_x", _f32p), ("g_v_in", _f32p), ("g_z_in", _f32p), ("g_aux_in", _f32p),
         ("g_w_ff", _f32p), ("g_w_rec", _f32p), ("g_leak", _f32p), ("g_thresh", _f32p), ("g_leak_aux", _f32p),
         ("g_add_pt", _f32p), ("g_t0", _f32p), ("g_t1", _f32p), ("scratch_gI_up", _f32p), ("scratch_gP_up", _f32p),
+        ("reset_grad", _i32),
     ]  # fmt: skip
 
 

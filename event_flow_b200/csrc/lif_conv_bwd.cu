@@ -100,6 +100,8 @@ __global__ void __launch_bounds__(PW_THREADS) lif_bwd_pointwise_kernel(const ef_
       g_aux_p = k.rho * g_pt - (HARD ? 0.f : z_p * k.t1 * g_v);
       if (gP_sum) atomicAdd(gP_sum + (size_t)b * plane + pix, (1.0f - k.rho) * g_pt);
     }
+    if (q.reset_grad)  // differentiable reset (detach=False): the previous spikes also act through the reset term of v_out
+      g_z_direct -= HARD ? g_v * k.lam * v_p : g_v * reset_thr;
     if (q.g_z_in) q.g_z_in[o] = g_z_direct;  // the recurrent dgrad (launch 2) accumulates on top
     if (NEURON != EF_LIF && q.g_aux_in) q.g_aux_in[o] = g_aux_p;
   }
@@ -340,6 +342,7 @@ extern "C" int ef_lif_conv_bwd(const ef_lif_conv_bwd_params* q, void* stream) {
   EF_REQUIRE((p.x || p.x_cl) && p.w_ff && p.leak && p.v_out && q->scratch_gI, EF_ENULL, "ef_lif_conv_bwd: x / w_ff / leak / v_out / scratch is NULL");
   EF_REQUIRE(p.x || !(p.neuron == EF_PLIF || p.neuron == EF_XLIF) || !q->g_x, EF_EUNSUPPORTED, "ef_lif_conv_bwd: PLIF / XLIF data gradient needs the fp32 input");
   EF_REQUIRE(p.neuron == EF_LIF || p.aux_out, EF_ENULL, "ef_lif_conv_bwd: aux_out is NULL");
+  EF_REQUIRE(!q->reset_grad || !(p.z_in || p.z_in_cl) || q->g_z_in, EF_ENULL, "ef_lif_conv_bwd: reset_grad needs g_z_in");
   cudaStream_t st = as_stream(stream);
   const int Ho = (p.H - 1) / p.stride + 1, Wo = (p.W - 1) / p.stride + 1;
 

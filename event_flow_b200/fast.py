@@ -209,6 +209,8 @@ def eligible(model, x):
                 break
             if getattr(cell, "neuron", None) != "lif" or cell.hidden_size != 32 or cell.ff.kernel_size != (3, 3) or cell.stride != 1:
                 ok = False
+            elif not cell.plain():  # normalisation options / differentiable reset: the cell path
+                ok = False
             elif name != "head" and cell.input_size != 32:
                 ok = False
         model.__dict__["_fast_eligible"] = ok

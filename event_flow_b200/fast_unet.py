@@ -27,7 +27,7 @@ def eligible(net, x):
     if ok is None:
         try:
             cells = _all_cells(net)
-            ok = all(getattr(c, "neuron", None) == "lif" and c.ff.kernel_size == (3, 3) for c in cells)
+            ok = all(getattr(c, "neuron", None) == "lif" and c.ff.kernel_size == (3, 3) and c.plain() for c in cells)
             ok = ok and all(c.hidden_size % 32 == 0 for c in cells) and net.skip_type == "concat" and net.num_output_channels <= L.EF_HEAD_MAX_CIN
             ok = ok and all(type(d).__name__ == "SpikingUpsampleConvLayer" for d in net.decoders)
         except AttributeError:  # other cell families (leaky ANN twins) share the wiring but not the kernels

@@ -19,10 +19,6 @@ class _SpikingConvCell(nn.Module):
 
     def _build(self, input_size, hidden_size, kernel_size, stride, activation, act_width, leak_group, thresh_group, learn_leak,
                learn_thresh, hard_reset, detach, norm):
-        if norm is not None:
-            raise NotImplementedError("norm=%r: no shipped config uses cell normalisation; not implemented on the CUDA path" % (norm,))
-        if not detach:
-            raise NotImplementedError("detach=False (differentiable reset) is not implemented on the CUDA path")
         padding = kernel_size // 2
         self.input_size, self.hidden_size, self.stride = input_size, hidden_size, stride
         # parameter creation order follows the reference so that the same torch seed gives the same initial values
@@ -45,7 +41,22 @@ class _SpikingConvCell(nn.Module):
         self.register_buffer("act_width", torch.tensor(act_width))
         self.hard_reset = hard_reset
         self.detach = detach
-        self.norm = None
+        # normalisation options of the reference (spiking_submodules.py:86-94): weight normalisation of the feed-forward convolution
+        # (parameters ff.weight_g / ff.weight_v) or a group norm of the INPUT; anything else means none
+        names = ("norm_ff", "norm_rec") if self.recurrent else ("norm",)  # attribute names of the reference (:86-94, :501-514)
+        if self.neuron == "lif":
+            for n in names:
+                setattr(self, n, None)
+        if self.neuron != "lif":
+            pass  # the reference's PLIF / ALIF / XLIF cells accept `norm` and ignore it (:153-227, 262-334, 361-435 have no norm code)
+        elif norm == "weight":
+            self.ff = nn.utils.weight_norm(self.ff)
+            if self.recurrent:
+                self.rec = nn.utils.weight_norm(self.rec)
+        elif norm == "group":
+            setattr(self, names[0], nn.GroupNorm(min(1, input_size // 4), input_size))
+            if self.recurrent:
+                self.norm_rec = nn.GroupNorm(min(1, hidden_size // 4), hidden_size)
 
     def __getattr__(self, name):
         # Cells unpickled from a checkpoint the REFERENCE wrote (utils/utils.py:19-20 pickles whole modules; the aliased module
@@ -65,21 +76,47 @@ class _SpikingConvCell(nn.Module):
             hit = self.__dict__["_width_cache"] = ((w._version, w.data_ptr()), float(w))
         return hit[1]
 
+    @staticmethod
+    def _kernel_of(conv):
+        """A convolution's kernel; with weight normalisation g * v / ||v|| (what nn.utils.weight_norm's hook computes when the conv is
+        called -- it never is here: the convolution runs inside the fused kernel)."""
+        if "weight_g" in conv._parameters:
+            return torch._weight_norm(conv.weight_v, conv.weight_g, 0)
+        return conv.weight
+
+    def plain(self):
+        """No normalisation, detached reset: what the fused fast paths (fast.py, fast_unet.py) implement."""
+        return (getattr(self, "detach", True) and "weight_g" not in self.ff._parameters
+                and all(self._modules.get(n) is None for n in ("norm", "norm_ff", "norm_rec")))
+
     def forward(self, input_, prev_state, residual=0):
         chan = {n: getattr(self, n) for n in ops.param_names(self.neuron)}
+        x_kind = self.__dict__.get("_x_kind")  # set by the model that owns the cell when it knows what the cell's input is
+        norm_in = self._modules.get("norm_ff" if self.recurrent else "norm")
+        if norm_in is not None:  # group norm of the input (:97-98, :518-519)
+            input_, x_kind = norm_in(input_), None
+        norm_rec = self._modules.get("norm_rec")
+        if norm_rec is not None:  # the recurrent cells normalise the previous spikes -- for the recurrent current AND the reset term (:528-529)
+            if prev_state is None:
+                h, w = (input_.shape[2] - 1) // self.stride + 1, (input_.shape[3] - 1) // self.stride + 1
+                prev_state = input_.new_zeros((2 if self.neuron == "lif" else 3, input_.shape[0], self.hidden_size, h, w))
+            parts = list(prev_state.unbind(0))
+            parts[1] = norm_rec(parts[1])
+            prev_state = torch.stack(parts)
         return ops.cell_step(
             self.neuron,
             input_,
             prev_state,
-            self.ff.weight,
-            self.rec.weight if self.recurrent else None,
+            self._kernel_of(self.ff),
+            self._kernel_of(self.rec) if self.recurrent else None,
             chan,
             hard_reset=self.hard_reset,
             surrogate=self.activation,
             width=self._width(),
             stride=self.stride,
             residual=residual,
-            x_kind=self.__dict__.get("_x_kind"),  # set by the model that owns the cell when it knows what the cell's input is
+            x_kind=x_kind,
+            detach=getattr(self, "detach", True),
         )
 
 

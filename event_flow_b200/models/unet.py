@@ -38,8 +38,6 @@ class SpikingMultiResUNetRecurrent(nn.Module):
         self.recurrent_block_type = kw.get("recurrent_block_type")
         self.channel_multiplier = kw.get("channel_multiplier", 2)
         self.ff_act, self.rec_act = kw.get("activations", ["relu", None])
-        if self.norm is not None:
-            raise NotImplementedError("event_flow_b200: norm=%r is not on the CUDA path (no shipped config sets it)" % (self.norm,))
         if self.kernel_size != 3:
             raise NotImplementedError("event_flow_b200: the spiking U-Net is built for kernel_size 3 (got %r)" % (self.kernel_size,))
 

@@ -71,7 +71,7 @@ class _CellStep(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, meta, x, state_in, w_ff, w_rec, residual, *chan_vals):
-        neuron, hard_reset, surrogate, width, stride, x_kind = meta
+        neuron, hard_reset, surrogate, width, stride, x_kind, _ = meta
         names = param_names(neuron)
         chan = {n: _c(v.reshape(-1)) for n, v in zip(names, chan_vals)}
         x, state_in, w_ff, w_rec, residual = _c(x), _c(state_in), _c(w_ff), _c(w_rec), _c(residual)
@@ -107,7 +107,7 @@ class _CellStep(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_out, g_state):
-        neuron, hard_reset, surrogate, width, stride, _ = ctx.meta
+        neuron, hard_reset, surrogate, width, stride, _, detach = ctx.meta
         x, state_in, w_ff, w_rec, residual, state_out, *chan_vals = ctx.saved_tensors
         names = ctx.chan_names
         chan = dict(zip(names, chan_vals))
@@ -156,6 +156,7 @@ class _CellStep(torch.autograd.Function):
                 g_chan.append(g.view(ctx.chan_shapes[i]))
             else:
                 g_chan.append(None)
+        q.reset_grad = int(not detach and g_state_in is not None)
         L.call("ef_lif_conv_bwd", q)
         g_res = g_out if (ctx.has_residual and need[5]) else None
         return (None, g_x, g_state_in, g_w_ff, g_w_rec, g_res, *g_chan)
@@ -219,11 +220,13 @@ def invalidate_weight_images():
     WEIGHT_EPOCH += 1
 
 
-def cell_step(neuron, x, state, w_ff, w_rec, chan, *, hard_reset, surrogate="arctanspike", width=10.0, stride=1, residual=None, x_kind=None):
+def cell_step(neuron, x, state, w_ff, w_rec, chan, *, hard_reset, surrogate="arctanspike", width=10.0, stride=1, residual=None, x_kind=None,
+              detach=True):
     """
     Fused forward of a spiking conv cell.  Mirrors `cell.forward(input_, prev_state, residual)` of
     models/spiking_submodules.py: returns (out, new_state) with new_state = stack([v, z(, trace)]).
     :param chan: dict of per-channel parameters named as in the reference module (leak, thresh, leak_v, ...)
+    :param detach: False = the reset term is differentiable (gradient reaches the previous spikes through it; backward only)
     :param x_kind: None (anything: CUDA-core kernel), "spikes" (the caller vouches that x holds spikes / small integer sums, i.e. is exact
                    in bf16) or "split" (<= 10 fractional channels): the convolution of a 32-channel cell then runs on the tensor cores
     """
@@ -231,7 +234,7 @@ def cell_step(neuron, x, state, w_ff, w_rec, chan, *, hard_reset, surrogate="arc
         raise ValueError(neuron)
     if torch.is_tensor(residual) is False:
         residual = None if (residual is None or residual == 0) else torch.as_tensor(residual)
-    meta = (neuron, bool(hard_reset), surrogate, float(width), int(stride), x_kind)
+    meta = (neuron, bool(hard_reset), surrogate, float(width), int(stride), x_kind, bool(detach))
     vals = [chan[n] for n in param_names(neuron)]
     return _CellStep.apply(meta, x, state, w_ff, w_rec, residual, *vals)
 

@@ -152,6 +152,8 @@ typedef struct ef_lif_conv_bwd_params {
   float* g_t1;
   float* scratch_gI_up;         /* stride 2 only: [B,C,H,W] workspace (g_I zero-inserted to the input resolution)         */
   float* scratch_gP_up;         /* stride 2, PLIF / XLIF with g_x: [B,H,W] workspace                                      */
+  int32_t reset_grad;           /* 1: the reset term is differentiable (cells built with detach=False, spiking_submodules.py:110-112): */
+                                /* dL/dz_in also receives -leak v_in g_v (hard reset) / -thresh g_v (soft reset); needs g_z_in          */
 } ef_lif_conv_bwd_params;
 
 int ef_lif_conv_bwd(const ef_lif_conv_bwd_params* p, void* stream);

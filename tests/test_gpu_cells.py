@@ -25,7 +25,7 @@ def _thresh_map(neuron, p, new_state):
     return p["t0"].clamp_min(0.01) + p["t1"].clamp_min(0) * new_state[2]
 
 
-def run_cuda_cell(neuron, x, state, p, hard, surrogate="arctanspike", width=10.0, g_out=None, g_state=None, residual=None):
+def run_cuda_cell(neuron, x, state, p, hard, surrogate="arctanspike", width=10.0, g_out=None, g_state=None, residual=None, detach=True):
     from event_flow_b200 import ops
 
     xd = x.detach().to(DEV).requires_grad_(True)
@@ -33,7 +33,8 @@ def run_cuda_cell(neuron, x, state, p, hard, surrogate="arctanspike", width=10.0
     pd = {k: v.detach().to(DEV).requires_grad_(True) for k, v in p.items()}
     rd = None if residual is None else residual.to(DEV)
     chan = {k: v for k, v in pd.items() if k not in ("ff", "rec")}
-    out, ns = ops.cell_step(neuron, xd, sd, pd["ff"], pd.get("rec"), chan, hard_reset=hard, surrogate=surrogate, width=width, residual=rd)
+    out, ns = ops.cell_step(neuron, xd, sd, pd["ff"], pd.get("rec"), chan, hard_reset=hard, surrogate=surrogate, width=width, residual=rd,
+                            detach=detach)
     grads = None
     if g_out is not None:
         ((out * g_out.to(DEV)).sum() + (ns * g_state.to(DEV)).sum()).backward()
@@ -149,3 +150,79 @@ def test_cl_layout_roundtrip_and_cl_inputs():
     assert packed.shape == (2, 19, 23, 32) and packed.dtype == torch.bfloat16
     assert torch.equal(packed.float().permute(0, 3, 1, 2), x)
     assert torch.equal(ops.unpack_cl(packed), x)
+
+
+@pytest.mark.parametrize("neuron,rec,hard", CASES)
+def test_differentiable_reset_matches_oracle_autograd(neuron, rec, hard):
+    """detach=False (spiking_submodules.py:110-112 and twins): the previous spikes also receive gradient through the reset term."""
+    B, Cin, C, H, W = 2, 32, 32, 21, 28
+    g = torch.Generator().manual_seed(17)
+    params = osp.init_firenet_params(neuron, Cin, C, seed=6, weight_gain=2.0)["G1" if rec else "R1a"]
+    if neuron in ("alif", "xlif"):
+        params["t0"] = params["t0"] + 0.05
+    x = (torch.rand((B, Cin, H, W), generator=g) < 0.3).float()
+    n_state = 2 if neuron == "lif" else 3
+    st = torch.rand((n_state, B, C, H, W), generator=g)
+    st[1] = (st[1] < 0.3).float()
+    g_out, g_state = torch.rand((B, C, H, W), generator=g), torch.rand((n_state, B, C, H, W), generator=g)
+    g_state[1] = 0
+    out, ns, grads = run_cuda_cell(neuron, x, st, params, hard, g_out=g_out, g_state=g_state, detach=False)
+    _, _, grads_det = run_cuda_cell(neuron, x, st, params, hard, g_out=g_out, g_state=g_state, detach=True)
+    xo, so = x.clone().requires_grad_(True), st.clone().requires_grad_(True)
+    po = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    out_o, ns_o = osp.cell_step(neuron, xo, so, po, hard_reset=hard, detach=False)
+    ((out_o * g_out).sum() + (ns_o * g_state).sum()).backward()
+    assert_rel(grads["state"], so.grad, 1e-3, "g_state")
+    assert_rel(grads["x"], xo.grad, 1e-3, "g_x")
+    assert (grads["state"][1] - grads_det["state"][1]).abs().max() > 1e-3 * so.grad[1].abs().max()  # the reset path carries gradient
+    for k, v in po.items():
+        if v.grad is not None and v.grad.abs().max() > 0:
+            assert_rel(grads[k], v.grad, 1e-3, "g_" + k)
+
+
+@pytest.mark.parametrize("rec", [False, True])
+@pytest.mark.parametrize("norm", ["weight", "group"])
+def test_lif_cell_normalisation_options_match_torch_composition(rec, norm):
+    """
+    ConvLIF / ConvLIFRecurrent with norm="weight" | "group" (spiking_submodules.py:86-99, 501-529): the CUDA cell behind torch's own
+    weight-norm parametrisation / GroupNorm modules against the oracle cell step behind the same modules, values and gradients.
+    """
+    import event_flow_b200.models.spiking_submodules as S
+
+    torch.manual_seed(2)
+    cls = S.ConvLIFRecurrent if rec else S.ConvLIF
+    cell = cls(8, 16, 3, norm=norm).to(DEV)
+    with torch.no_grad():
+        for n, p in cell.named_parameters():
+            if n.endswith("weight_g") or n.endswith("ff.weight") or n.endswith("rec.weight"):
+                p.mul_(3.0)
+    g = torch.Generator().manual_seed(4)
+    x = torch.rand((2, 8, 20, 24), generator=g)
+    st = torch.rand((2, 2, 16, 20, 24), generator=g)
+    st[1] = (st[1] < 0.3).float()
+    g_out = torch.rand((2, 16, 20, 24), generator=g)
+    xd, sd = x.to(DEV).requires_grad_(True), st.to(DEV).requires_grad_(True)
+    out, ns = cell(xd, sd)
+    (out * g_out.to(DEV)).sum().backward()
+    # the same composition on the CPU: torch modules around the oracle's cell step
+    ref = cls(8, 16, 3, norm=norm)  # (a weight-normalised module holds a computed `weight` tensor: no deepcopy)
+    ref.load_state_dict({k: v.cpu() for k, v in cell.state_dict().items()})
+    xo, so = x.clone().requires_grad_(True), st.clone().requires_grad_(True)
+    xin, sin = xo, so
+    n_in = ref._modules.get("norm_ff" if rec else "norm")
+    if n_in is not None:
+        xin = n_in(xo)
+    if ref._modules.get("norm_rec") is not None:
+        sin = torch.stack([so[0], ref.norm_rec(so[1])])
+    po = {"ff": ref._kernel_of(ref.ff), "leak": ref.leak, "thresh": ref.thresh}
+    if rec:
+        po["rec"] = ref._kernel_of(ref.rec)
+    out_o, ns_o = osp.cell_step("lif", xin, sin, po, hard_reset=True)
+    (out_o * g_out).sum().backward()
+    spike_band_compare(ns[0].detach().cpu(), ns[1].detach().cpu(), ns_o[0].detach(), ns_o[1].detach(), ref.thresh.detach().clamp_min(0.01))
+    assert ns[1].mean() > 0.01
+    assert_rel(xd.grad, xo.grad, 1e-3, "g_x")
+    assert_rel(sd.grad, so.grad, 1e-3, "g_state")
+    for (n, pa), pb in zip(cell.named_parameters(), ref.parameters()):
+        if pb.grad is not None and pb.grad.abs().max() > 0:
+            assert_rel(pa.grad, pb.grad, 1e-3, "g_" + n)

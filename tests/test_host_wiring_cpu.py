@@ -20,12 +20,13 @@ from tests.conftest import GOLDEN, load_golden
 def cpu_ops(monkeypatch):
     from event_flow_b200 import ops
 
-    def cell_step(neuron, x, state, w_ff, w_rec, chan, *, hard_reset, surrogate="arctanspike", width=10.0, stride=1, residual=None, x_kind=None):
+    def cell_step(neuron, x, state, w_ff, w_rec, chan, *, hard_reset, surrogate="arctanspike", width=10.0, stride=1, residual=None, x_kind=None,
+                  detach=True):
         p = {"ff": w_ff, **chan}
         if w_rec is not None:
             p["rec"] = w_rec
         return osp.cell_step(neuron, x, state, p, hard_reset=hard_reset, surrogate=surrogate, width=width, stride=stride,
-                             residual=0 if residual is None else residual)
+                             residual=0 if residual is None else residual, detach=detach)
 
     def conv_ann(x1, weight, bias, act, *, x2=None, x2_scale=None, residual=None, blend_h=None, blend_u=None):
         x = x1 if x2 is None else torch.cat([x1, x2 if x2_scale is None else x2 * x2_scale], dim=1)
@@ -274,3 +275,68 @@ def test_norm_and_transposed_conv_options_match_the_live_reference(opts, cpu_ops
     scale = max(pb.grad.abs().max().item() for pb in ref.parameters())
     for (n, pa), pb in zip(mine.named_parameters(), ref.parameters()):
         assert (pa.grad - pb.grad).abs().max().item() <= 1e-3 * max(pb.grad.abs().max().item(), 1e-2 * scale), n
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/models"), reason="needs the reference tree (build container only)")
+@pytest.mark.parametrize("cls,opts", [("LIFFireNet", dict(norm="weight")), ("LIFFireNet", dict(norm="group")), ("LIFFireNet", dict(detach=False)),
+                                      ("ALIFFireNet", dict(detach=False, norm="weight")), ("PLIFFireNet", dict(detach=False)), ("XLIFFireNet", dict(detach=False)),
+                                      ("SpikingRecEVFlowNet", dict(norm="weight", detach=False))])
+def test_spiking_cell_options_match_the_live_reference(cls, opts, cpu_ops):
+    """
+    The cell options no shipped yml sets (spiking_submodules.py:86-94,110-112,501-514): weight / group normalisation and a
+    differentiable reset (detach=False): same state_dict names, same flows over three steps, same BPTT gradients as the unmodified
+    reference, run live on CPU (the kernel call replaced by the oracle's cell step).
+    """
+    import importlib
+    import sys
+
+    import event_flow_b200.models.model as M
+
+    fire = "FireNet" in cls
+    sn = dict(opts) if fire else dict(opts)
+    # (group norm: the reference builds GroupNorm(min(1, input_size // 4), input_size), which needs at least 4 input channels)
+    cfg = dict(name=cls, encoding="voxel" if fire else "cnt", round_encoding=False, norm_input=False, num_bins=4 if fire else 2,
+               base_num_channels=8 if fire else 4, kernel_size=3, activations=["arctanspike", "arctanspike"], mask_output=True, spiking_neuron=sn)
+    if not fire and "norm" in opts:
+        cfg["norm"] = opts["norm"]  # the U-Net takes the normalisation from the model config (model.py:426-439)
+        cfg["spiking_neuron"] = {k: v for k, v in opts.items() if k != "norm"}
+    saved = {k: sys.modules.pop(k) for k in list(sys.modules) if k == "models" or k.startswith("models.")}
+    sys.path.insert(0, "/root/reference")
+    try:
+        ref_model = importlib.import_module("models.model")
+        torch.manual_seed(11)
+        if fire:
+            getattr(ref_model, cls).kwargs = [{}] * 7
+        ref = getattr(ref_model, cls)({**cfg, "spiking_neuron": dict(cfg["spiking_neuron"])}).train()
+    finally:
+        sys.path.remove("/root/reference")
+        for k in [k for k in sys.modules if k == "models" or k.startswith("models.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+    torch.manual_seed(11)
+    mine = getattr(M, cls)({**cfg, "spiking_neuron": dict(cfg["spiking_neuron"])}).train()
+    assert list(mine.state_dict().keys()) == list(ref.state_dict().keys())
+    mine.load_state_dict(ref.state_dict())
+    with torch.no_grad():  # spikes through every layer on a small input
+        for m in (mine, ref):
+            for n, p in m.named_parameters():
+                if "ff.weight" in n or "rec.weight" in n:
+                    p.mul_(3.0)
+    g = torch.Generator().manual_seed(3)
+    H, W = 32, 32
+    la = lb = 0.0
+    for _ in range(3):
+        x = torch.randint(0, 3, (2, cfg["num_bins"], H, W), generator=g).float()
+        a = mine(x.clone(), x.clone())["flow"]
+        b = ref(x.clone(), x.clone())["flow"]
+        for fa, fb in zip(a, b):
+            assert (fa - fb).abs().max().item() <= 1e-5 * max(1.0, fb.abs().max().item())
+        la, lb = la + sum(f.square().sum() for f in a), lb + sum(f.square().sum() for f in b)
+    la.backward(), lb.backward()
+    scale = max(pb.grad.abs().max().item() for pb in ref.parameters() if pb.grad is not None)
+    assert scale > 0
+    for (n, pa), pb in zip(mine.named_parameters(), ref.parameters()):
+        if pb.grad is None:
+            assert pa.grad is None or pa.grad.abs().max() == 0, n
+            continue
+        assert (pa.grad - pb.grad).abs().max().item() <= 1e-4 * max(pb.grad.abs().max().item(), 1e-2 * scale), n
