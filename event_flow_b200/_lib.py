@@ -147,6 +147,16 @@ class ConvAnnParams(C.Structure):
         ("x1_bstride", C.c_int64), ("x2_bstride", C.c_int64), ("x2_scale_bstride", C.c_int64),
         ("w", _f32p), ("bias", _f32p), ("residual", _f32p), ("blend_h", _f32p), ("blend_u", _f32p),
         ("blend_h_bstride", C.c_int64), ("blend_u_bstride", C.c_int64), ("out", _f32p),
+        ("stride", _i32), ("act_out", _f32p),
+    ]  # fmt: skip
+
+
+class AnnGateBwdParams(C.Structure):
+    _fields_ = [
+        ("B", _i32), ("C", _i32), ("H", _i32), ("W", _i32), ("act", _i32),
+        ("g_y", _f32p), ("act_out", _f32p), ("blend_h", _f32p), ("blend_u", _f32p),
+        ("blend_h_bstride", C.c_int64), ("blend_u_bstride", C.c_int64),
+        ("g_pre", _f32p), ("g_h", _f32p), ("g_u", _f32p), ("g_bias", _f32p),
     ]  # fmt: skip
 
 
@@ -224,6 +234,10 @@ EXPORTS = {
     "ef_spike_bwd": (C.c_int, [C.c_void_p, C.c_void_p, _i32, _i32, C.c_int64, C.c_int64, C.c_void_p, _i32, C.c_float, C.c_void_p, C.c_void_p]),
     "ef_conv_ann_fwd": (C.c_int, [C.POINTER(ConvAnnParams), C.c_void_p]),
     "ef_conv3x3_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, _i32, _i32, _i32, _i32, _i32, C.c_void_p]),
+    "ef_conv3x3_bwd_s": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, _i32, _i32, _i32, _i32, _i32, _i32, C.c_void_p]),
+    "ef_ann_gate_bwd": (C.c_int, [C.POINTER(AnnGateBwdParams), C.c_void_p]),
+    "ef_ann_cat_scale": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, _i32, _i32, _i32, _i32, _i32, C.c_int64, C.c_int64, C.c_int64, C.c_void_p]),
+    "ef_ann_scale_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, _i32, _i32, _i32, _i32, _i32, C.c_int64, C.c_int64, C.c_void_p]),
     "ef_iwe_metrics_workspace_elems": (C.c_int64, [_i32, _i32, _i32]),
     "ef_iwe_metrics": (C.c_int, [C.POINTER(IweMetricsParams), C.c_void_p]),
     "ef_aee": (C.c_int, [C.POINTER(AeeParams), C.c_void_p]),

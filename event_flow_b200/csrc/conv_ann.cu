@@ -16,17 +16,23 @@ __device__ __forceinline__ float act_apply(int act, float v) {
   }
 }
 
-// out[b,co,y,x] = blend( act( sum_{ci,tap} in[b,ci,y+dy-1,x+dx-1] * w[co,ci,tap] + bias[co] + residual ) )
-// in = cat(x1 [C1], x2 [C2] (* x2_scale)) along channels; blend(o) = h*(1-u) + o*u when blend_h is given.
+// out[b,co,y,x] = blend( act( sum_{ci,tap} in[b,ci,S*y+dy-1,S*x+dx-1] * w[co,ci,tap] + bias[co] + residual ) ), S = stride (1 or 2)
+// in = cat(x1 [C1], x2 [C2] (* x2_scale)) along channels; blend(o) = h*(1-u) + o*u when blend_h is given; act_out (optional) receives
+// the activation before the blend (what the backward of the blend and of the activation needs).
+// Stride 2 (the encoders of the ANN U-Nets, models/unet.py:241-255): the 16x16 OUTPUT tile reads a 34x34 input tile -- the minimal
+// multiply-accumulates, where the first version computed the stride-1 result and kept the even pixels.
+template <int S>
 __global__ void __launch_bounds__(CA_THREADS) conv_ann_fwd_kernel(const ef_conv_ann_params p) {
-  __shared__ __align__(16) float s_x[CA_CK * 18 * 18];
+  constexpr int TI = 16 * S + 2;  // input tile side
+  __shared__ __align__(16) float s_x[CA_CK * TI * TI];
   __shared__ __align__(16) float s_w[CA_CK * 9 * CA_WP];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int cblocks = (p.Cout + CA_COB - 1) / CA_COB;
   const int b = blockIdx.z / cblocks, co0 = (blockIdx.z % cblocks) * CA_COB;
-  const int x0 = blockIdx.x * 16, y0 = blockIdx.y * 16;
+  const int x0 = blockIdx.x * 16, y0 = blockIdx.y * 16;  // output tile origin
   const int Cin = p.C1 + p.C2, H = p.H, W = p.W;
-  const size_t hw = (size_t)H * W;
+  const int Ho = (H - 1) / S + 1, Wo = (W - 1) / S + 1;
+  const size_t hw = (size_t)H * W, hwo = (size_t)Ho * Wo;
   float acc[2][CA_COB];
 #pragma unroll
   for (int i = 0; i < 2; ++i)
@@ -35,8 +41,8 @@ __global__ void __launch_bounds__(CA_THREADS) conv_ann_fwd_kernel(const ef_conv_
 
   for (int ci0 = 0; ci0 < Cin; ci0 += CA_CK) {
     __syncthreads();
-    for (int i = tid; i < CA_CK * 324; i += CA_THREADS) {
-      const int ci = ci0 + i / 324, r = i % 324, y = y0 - 1 + r / 18, x = x0 - 1 + r % 18;
+    for (int i = tid; i < CA_CK * TI * TI; i += CA_THREADS) {
+      const int ci = ci0 + i / (TI * TI), r = i % (TI * TI), y = y0 * S - 1 + r / TI, x = x0 * S - 1 + r % TI;
       float v = 0.f;
       if (ci < Cin && y >= 0 && y < H && x >= 0 && x < W) {
         const size_t pix = (size_t)y * W + x;
@@ -59,14 +65,14 @@ __global__ void __launch_bounds__(CA_THREADS) conv_ann_fwd_kernel(const ef_conv_
     __syncthreads();
 #pragma unroll 1
     for (int ci = 0; ci < CA_CK; ++ci) {
-      const float* sx = s_x + ci * 324;
+      const float* sx = s_x + ci * TI * TI;
       float xa[9], xb[9];
 #pragma unroll
       for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
         for (int dx = 0; dx < 3; ++dx) {
-          xa[dy * 3 + dx] = sx[(ty + dy) * 18 + tx + dx];
-          xb[dy * 3 + dx] = sx[(ty + 8 + dy) * 18 + tx + dx];
+          xa[dy * 3 + dx] = sx[(ty * S + dy) * TI + tx * S + dx];
+          xb[dy * 3 + dx] = sx[((ty + 8) * S + dy) * TI + tx * S + dx];
         }
 #pragma unroll
       for (int tap = 0; tap < 9; ++tap) {
@@ -89,22 +95,89 @@ __global__ void __launch_bounds__(CA_THREADS) conv_ann_fwd_kernel(const ef_conv_
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
     const int y = y0 + ty + half * 8, x = x0 + tx;
-    if (y >= H || x >= W) continue;
-    const size_t pix = (size_t)y * W + x;
+    if (y >= Ho || x >= Wo) continue;
+    const size_t pix = (size_t)y * Wo + x;
 #pragma unroll
     for (int co = 0; co < CA_COB; ++co) {
       const int c = co0 + co;
       if (c >= p.Cout) break;
       float v = acc[half][co] + (p.bias ? p.bias[c] : 0.f);
-      if (p.residual) v += p.residual[(size_t)b * p.Cout * hw + (size_t)c * hw + pix];
+      if (p.residual) v += p.residual[(size_t)b * p.Cout * hwo + (size_t)c * hwo + pix];
       v = act_apply(p.act, v);
+      if (p.act_out) p.act_out[(size_t)b * p.Cout * hwo + (size_t)c * hwo + pix] = v;
       if (p.blend_h) {
-        const float h = p.blend_h[(size_t)b * p.blend_h_bstride + (size_t)c * hw + pix];
-        const float u = p.blend_u[(size_t)b * p.blend_u_bstride + (size_t)c * hw + pix];
+        const float h = p.blend_h[(size_t)b * p.blend_h_bstride + (size_t)c * hwo + pix];
+        const float u = p.blend_u[(size_t)b * p.blend_u_bstride + (size_t)c * hwo + pix];
         v = h * (1.0f - u) + v * u;
       }
-      p.out[(size_t)b * p.Cout * hw + (size_t)c * hw + pix] = v;
+      p.out[(size_t)b * p.Cout * hwo + (size_t)c * hwo + pix] = v;
     }
+  }
+}
+
+// ---- backward helpers of the ANN cells (what autograd derives around the convolution) ---------------------------------------------
+// (1) activation + gated blend: y = h (1 - u) + o u, o = act(pre):  g_h = g_y (1 - u), g_u = g_y (o - h), g_pre = g_y u act'(o)
+//     (without a blend: g_pre = g_y act'(o)); the bias gradient sum_{b,y,x} g_pre is accumulated per channel.
+__global__ void __launch_bounds__(256) ann_gate_bwd_kernel(const ef_ann_gate_bwd_params p) {
+  __shared__ float s_red[8];
+  const int c = blockIdx.y, b = blockIdx.z;
+  const size_t hw = (size_t)p.H * p.W;
+  const size_t base = ((size_t)b * p.C + c) * hw;
+  float acc = 0.f;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < hw; i += (size_t)gridDim.x * 256) {
+    const float gy = p.g_y[base + i], o = p.act_out[base + i];
+    float go = gy;
+    if (p.blend_h) {
+      const float h = p.blend_h[(size_t)b * p.blend_h_bstride + (size_t)c * hw + i], u = p.blend_u[(size_t)b * p.blend_u_bstride + (size_t)c * hw + i];
+      if (p.g_h) p.g_h[base + i] = gy * (1.0f - u);
+      if (p.g_u) p.g_u[base + i] = gy * (o - h);
+      go = gy * u;
+    }
+    float d = 1.0f;
+    if (p.act == 1) d = o > 0.f ? 1.0f : 0.f;
+    else if (p.act == 2) d = o * (1.0f - o);
+    else if (p.act == 3) d = 1.0f - o * o;
+    const float gp = go * d;
+    p.g_pre[base + i] = gp;
+    acc += gp;
+  }
+  if (p.g_bias) {
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      float r = threadIdx.x < 8 ? s_red[threadIdx.x] : 0.f;
+      r = warp_sum(r);
+      if (threadIdx.x == 0) atomicAdd(p.g_bias + c, r);
+    }
+  }
+}
+// (2) the convolution's input as ONE tensor for the weight gradient: out = cat([x1, x2 * scale]) (scale may be NULL)
+__global__ void __launch_bounds__(256) ann_cat_scale_kernel(const float* __restrict__ x1, const float* __restrict__ x2, const float* __restrict__ scale,
+                                                            float* __restrict__ out, int C1, int C2, size_t hw, long long x1_bs, long long x2_bs,
+                                                            long long scale_bs) {
+  const int c = blockIdx.y, b = blockIdx.z, C = C1 + C2;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < hw; i += (size_t)gridDim.x * 256) {
+    float v;
+    if (c < C1) {
+      v = x1[(size_t)b * x1_bs + (size_t)c * hw + i];
+    } else {
+      v = x2[(size_t)b * x2_bs + (size_t)(c - C1) * hw + i];
+      if (scale) v *= scale[(size_t)b * scale_bs + (size_t)(c - C1) * hw + i];
+    }
+    out[((size_t)b * C + c) * hw + i] = v;
+  }
+}
+// (3) back through the gate product of the second input: g_x2 = g_xcat[C1:] * scale, g_scale = g_xcat[C1:] * x2
+__global__ void __launch_bounds__(256) ann_scale_bwd_kernel(const float* __restrict__ g_xcat, const float* __restrict__ x2, const float* __restrict__ scale,
+                                                            float* __restrict__ g_x2, float* __restrict__ g_scale, int C1, int C2, size_t hw,
+                                                            long long x2_bs, long long scale_bs) {
+  const int c = blockIdx.y, b = blockIdx.z, C = C1 + C2;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < hw; i += (size_t)gridDim.x * 256) {
+    const float g = g_xcat[((size_t)b * C + C1 + c) * hw + i];
+    const size_t o = ((size_t)b * C2 + c) * hw + i;
+    if (g_x2) g_x2[o] = g * scale[(size_t)b * scale_bs + (size_t)c * hw + i];
+    if (g_scale) g_scale[o] = g * x2[(size_t)b * x2_bs + (size_t)c * hw + i];
   }
 }
 
@@ -118,7 +191,49 @@ extern "C" int ef_conv_ann_fwd(const ef_conv_ann_params* pp, void* stream) {
   EF_REQUIRE(p.act >= 0 && p.act <= 3, EF_EINVAL, "ef_conv_ann_fwd: bad activation code %d", p.act);
   EF_REQUIRE(p.x1 && p.w && p.out && (p.C2 == 0 || p.x2), EF_ENULL, "ef_conv_ann_fwd: NULL tensor");
   EF_REQUIRE(!p.blend_h == !p.blend_u, EF_ENULL, "ef_conv_ann_fwd: blend needs both h and u");
-  dim3 grid(cdiv(p.W, 16), cdiv(p.H, 16), p.B * cdiv(p.Cout, CA_COB));
-  conv_ann_fwd_kernel<<<grid, CA_THREADS, 0, as_stream(stream)>>>(p);
+  const int S = p.stride == 0 ? 1 : p.stride;
+  EF_REQUIRE(S == 1 || S == 2, EF_EUNSUPPORTED, "ef_conv_ann_fwd: stride %d not supported", p.stride);
+  const int Ho = (p.H - 1) / S + 1, Wo = (p.W - 1) / S + 1;
+  dim3 grid(cdiv(Wo, 16), cdiv(Ho, 16), p.B * cdiv(p.Cout, CA_COB));
+  if (S == 1) conv_ann_fwd_kernel<1><<<grid, CA_THREADS, 0, as_stream(stream)>>>(p);
+  else conv_ann_fwd_kernel<2><<<grid, CA_THREADS, 0, as_stream(stream)>>>(p);
   return check_launch("conv_ann_fwd_kernel");
+}
+
+extern "C" int ef_ann_gate_bwd(const ef_ann_gate_bwd_params* pp, void* stream) {
+  using namespace ef;
+  EF_REQUIRE(pp, EF_ENULL, "ef_ann_gate_bwd: params is NULL");
+  const ef_ann_gate_bwd_params& p = *pp;
+  EF_REQUIRE(p.B > 0 && p.C > 0 && p.H > 0 && p.W > 0 && p.act >= 0 && p.act <= 3, EF_EINVAL, "ef_ann_gate_bwd: bad dimensions / activation");
+  EF_REQUIRE(p.g_y && p.act_out && p.g_pre, EF_ENULL, "ef_ann_gate_bwd: NULL tensor");
+  EF_REQUIRE(!p.blend_h == !p.blend_u, EF_ENULL, "ef_ann_gate_bwd: blend needs both h and u");
+  const int hw = p.H * p.W;
+  int bx = cdiv(hw, 256 * 4);
+  if (bx > 64) bx = 64;
+  ann_gate_bwd_kernel<<<dim3(bx, p.C, p.B), 256, 0, as_stream(stream)>>>(p);
+  return check_launch("ann_gate_bwd_kernel");
+}
+
+extern "C" int ef_ann_cat_scale(const float* x1, const float* x2, const float* scale, float* out, int32_t B, int32_t C1, int32_t C2, int32_t H, int32_t W,
+                                int64_t x1_bstride, int64_t x2_bstride, int64_t scale_bstride, void* stream) {
+  using namespace ef;
+  EF_REQUIRE(x1 && out && (C2 == 0 || x2), EF_ENULL, "ef_ann_cat_scale: NULL tensor");
+  EF_REQUIRE(B > 0 && C1 > 0 && C2 >= 0 && H > 0 && W > 0, EF_EINVAL, "ef_ann_cat_scale: bad dimensions");
+  const size_t hw = (size_t)H * W;
+  int bx = cdiv((int)hw, 256 * 4);
+  if (bx > 64) bx = 64;
+  ann_cat_scale_kernel<<<dim3(bx, C1 + C2, B), 256, 0, as_stream(stream)>>>(x1, x2, scale, out, C1, C2, hw, x1_bstride, x2_bstride, scale_bstride);
+  return check_launch("ann_cat_scale_kernel");
+}
+
+extern "C" int ef_ann_scale_bwd(const float* g_xcat, const float* x2, const float* scale, float* g_x2, float* g_scale, int32_t B, int32_t C1, int32_t C2,
+                                int32_t H, int32_t W, int64_t x2_bstride, int64_t scale_bstride, void* stream) {
+  using namespace ef;
+  EF_REQUIRE(g_xcat && x2 && scale, EF_ENULL, "ef_ann_scale_bwd: NULL tensor");
+  EF_REQUIRE(B > 0 && C1 >= 0 && C2 > 0 && H > 0 && W > 0, EF_EINVAL, "ef_ann_scale_bwd: bad dimensions");
+  const size_t hw = (size_t)H * W;
+  int bx = cdiv((int)hw, 256 * 4);
+  if (bx > 64) bx = 64;
+  ann_scale_bwd_kernel<<<dim3(bx, C2, B), 256, 0, as_stream(stream)>>>(g_xcat, x2, scale, g_x2, g_scale, C1, C2, hw, x2_bstride, scale_bstride);
+  return check_launch("ann_scale_bwd_kernel");
 }

@@ -429,3 +429,17 @@ extern "C" int ef_conv3x3_bwd(const float* g_pre, const float* x, const float* w
   }
   return EF_OK;
 }
+
+extern "C" int ef_conv3x3_bwd_s(const float* g_pre, const float* x, const float* w, float* g_x, float* g_w, float* scratch_up, int32_t B, int32_t Cin,
+                                int32_t C, int32_t H, int32_t W, int32_t stride, void* stream) {
+  using namespace ef;
+  if (stride == 1 || stride == 0) return ef_conv3x3_bwd(g_pre, x, w, g_x, g_w, B, Cin, C, H, W, stream);
+  EF_REQUIRE(stride == 2, EF_EUNSUPPORTED, "ef_conv3x3_bwd_s: stride %d not supported", stride);
+  EF_REQUIRE(g_pre && scratch_up, EF_ENULL, "ef_conv3x3_bwd_s: g_pre / scratch_up is NULL");
+  EF_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, EF_EINVAL, "ef_conv3x3_bwd_s: non-positive dimension");
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  const size_t n = (size_t)B * C * H * W;
+  zero_insert2_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(g_pre, scratch_up, (size_t)B * C, H, W, Ho, Wo);
+  if (int rc = check_launch("zero_insert2_kernel(ann)")) return rc;
+  return ef_conv3x3_bwd(scratch_up, x, w, g_x, g_w, B, Cin, C, H, W, stream);
+}

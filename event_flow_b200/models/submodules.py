@@ -21,12 +21,12 @@ def _make_norm(norm, channels, momentum=0.1):
     return None
 
 
-def _conv_norm_act(x, conv, norm_layer, act, residual=None):
+def _conv_norm_act(x, conv, norm_layer, act, residual=None, stride=1):
     """act(norm(conv3x3(x) + b) + residual).  Without a norm layer everything is ONE fused launch (ef_conv_ann_fwd); with one the kernel
     stops after the bias and the normalisation module / residual / activation follow on its output (models/submodules.py:52-61)."""
     if norm_layer is None:
-        return ops.conv_ann(x, conv.weight, conv.bias, act, residual=residual)
-    out = norm_layer(ops.conv_ann(x, conv.weight, conv.bias, None))
+        return ops.conv_ann(x, conv.weight, conv.bias, act, residual=residual, stride=stride)
+    out = norm_layer(ops.conv_ann(x, conv.weight, conv.bias, None, stride=stride))
     if residual is not None:
         out = out + residual
     return out if act is None else _TORCH_ACT[act](out)
@@ -77,14 +77,7 @@ class ConvLayer(nn.Module):
                 return out
             out = norm_layer(out)
             return out if act is None else _TORCH_ACT[act](out)
-        if self.stride == 2:
-            # a stride-2 3x3 conv with padding 1 is the stride-1 result at the even pixels (same window, same summation order);
-            # first version of the U-Net encoders: 4x the minimal FLOPs on these four layers
-            if norm_layer is None:
-                return ops.conv_ann(x, self.conv2d.weight, self.conv2d.bias, act)[:, :, ::2, ::2].contiguous()
-            out = norm_layer(ops.conv_ann(x, self.conv2d.weight, self.conv2d.bias, None)[:, :, ::2, ::2].contiguous())
-            return out if act is None else _TORCH_ACT[act](out)
-        return _conv_norm_act(x, self.conv2d, norm_layer, act)
+        return _conv_norm_act(x, self.conv2d, norm_layer, act, stride=self.stride)  # (stride 2: the encoders of the ANN U-Nets)
 
 
 class TransposedConvLayer(nn.Module):
@@ -345,9 +338,7 @@ class ConvLeaky(nn.Module):
         self.activation = _ACTS[activation]
 
     def forward(self, input_, prev_state, residual=0):
-        ff = ops.conv_ann(input_, self.ff.weight, self.ff.bias, None)
-        if self.stride == 2:
-            ff = ff[:, :, ::2, ::2].contiguous()  # stride-2 conv = the stride-1 result at the even pixels
+        ff = ops.conv_ann(input_, self.ff.weight, self.ff.bias, None, stride=self.stride)
         if prev_state is None:
             prev_state = torch.zeros_like(ff)
         leak = torch.sigmoid(self.leak)

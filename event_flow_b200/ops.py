@@ -805,76 +805,103 @@ def aee(flow, gtflow, event_mask, dt_ratio, flow_scaling):
 _ACT_CODES = {None: 0, "relu": 1, "sigmoid": 2, "tanh": 3}
 
 
+def _plane_ok(t):
+    return t is None or (t.stride(-1) == 1 and t.stride(-2) == t.shape[-1] and t.stride(1) == t.shape[-1] * t.shape[-2])
+
+
 class _ConvAnn(torch.autograd.Function):
     """
-    act(conv3x3(cat([x1, x2]), w) + b + residual) with gradients: forward = ef_conv_ann_fwd, backward = the activation
-    derivative (elementwise), ef_conv3x3_bwd for the data and weight gradients of the convolution, a sum for the bias.
+    blend(act(conv3x3(cat([x1, x2 * x2_scale]), w) + b + residual)) with gradients for every tensor input, kernels only:
+    forward = ONE launch (ef_conv_ann_fwd, stride 1 or 2; with a blend it also stores the activation before the blend),
+    backward = ef_ann_gate_bwd (blend + activation derivative + bias gradient), ef_ann_cat_scale (the convolution's input as one
+    tensor, only when there is a second input), ef_conv3x3_bwd_s (data and weight gradients), ef_ann_scale_bwd (gate product).
     """
 
     @staticmethod
-    def forward(ctx, x1, x2, weight, bias, residual, act):
-        out = _conv_ann_launch(x1, weight, bias, act, x2=x2, residual=residual)
-        ctx.act = act
-        ctx.has = (x2 is not None, bias is not None, residual is not None)
-        ctx.save_for_backward(x1, x2, weight, out)
+    def forward(ctx, x1, x2, x2_scale, weight, bias, residual, blend_h, blend_u, act, stride):
+        need_o = blend_h is not None
+        out, act_out = _conv_ann_launch(x1, weight, bias, act, x2=x2, x2_scale=x2_scale, residual=residual, blend_h=blend_h, blend_u=blend_u,
+                                        stride=stride, want_act_out=need_o)
+        ctx.act, ctx.stride = act, stride
+        ctx.has = (x2 is not None, x2_scale is not None, bias is not None, residual is not None, blend_h is not None)
+        ctx.save_for_backward(x1, x2, x2_scale, weight, blend_h, blend_u, act_out if need_o else out)
         return out
 
     @staticmethod
     def backward(ctx, g):
-        x1, x2, weight, out = ctx.saved_tensors
-        has_x2, has_bias, has_res = ctx.has
+        x1, x2, x2_scale, weight, blend_h, blend_u, o = ctx.saved_tensors
+        has_x2, has_scale, has_bias, has_res, has_blend = ctx.has
+        need = ctx.needs_input_grad  # (x1, x2, x2_scale, weight, bias, residual, blend_h, blend_u, act, stride)
         g = g.contiguous()
-        if ctx.act == "relu":
-            g_pre = g * (out > 0)
-        elif ctx.act == "tanh":
-            g_pre = g * (1.0 - out * out)
-        elif ctx.act == "sigmoid":
-            g_pre = g * (out * (1.0 - out))
+        B, Cout, Ho, Wo = g.shape
+        dev = g.device
+        # (1) blend + activation + bias
+        q = L.AnnGateBwdParams()
+        q.B, q.C, q.H, q.W, q.act = B, Cout, Ho, Wo, _ACT_CODES[ctx.act]
+        g_pre = torch.empty_like(g)
+        g_h = torch.empty_like(g) if (has_blend and need[6]) else None
+        g_u = torch.empty_like(g) if (has_blend and need[7]) else None
+        g_b = torch.zeros(Cout, device=dev, dtype=torch.float32) if (has_bias and need[4]) else None
+        q.g_y, q.act_out, q.g_pre, q.g_h, q.g_u, q.g_bias = L.ptr(g), L.ptr(o), L.ptr(g_pre), L.ptr(g_h), L.ptr(g_u), L.ptr(g_b)
+        if has_blend:
+            bh = blend_h if _plane_ok(blend_h) else blend_h.contiguous()
+            bu = blend_u if _plane_ok(blend_u) else blend_u.contiguous()
+            q.blend_h, q.blend_u, q.blend_h_bstride, q.blend_u_bstride = bh.data_ptr(), bu.data_ptr(), bh.stride(0), bu.stride(0)
+        L.call("ef_ann_gate_bwd", q)
+        # (2) the convolution's input as one tensor
+        _, C1, H, W = x1.shape
+        C2 = x2.shape[1] if has_x2 else 0
+        if has_x2:
+            xa = x1 if _plane_ok(x1) else x1.contiguous()
+            xb = x2 if _plane_ok(x2) else x2.contiguous()
+            sc = None if not has_scale else (x2_scale if _plane_ok(x2_scale) else x2_scale.contiguous())
+            x = torch.empty((B, C1 + C2, H, W), device=dev, dtype=torch.float32)
+            L.LAUNCHES += 1
+            L.check(L.lib().ef_ann_cat_scale(xa.data_ptr(), xb.data_ptr(), None if sc is None else sc.data_ptr(), L.ptr(x), B, C1, C2, H, W,
+                                             xa.stride(0), xb.stride(0), 0 if sc is None else sc.stride(0), L.stream()), "ef_ann_cat_scale")
         else:
-            g_pre = g
-        g_pre = g_pre.contiguous()
-        x = x1.contiguous() if x2 is None else torch.cat([x1, x2], dim=1)
-        B, Cin, H, W = x.shape
-        Cout = weight.shape[0]
-        need = ctx.needs_input_grad  # (x1, x2, weight, bias, residual, act)
-        g_x = torch.empty_like(x) if (need[0] or (has_x2 and need[1])) else None
-        g_w = torch.zeros_like(weight) if need[2] else None
+            x = x1.contiguous()
+        # (3) convolution gradients
+        need_gx = need[0] or (has_x2 and (need[1] or (has_scale and need[2])))
+        g_x = torch.empty_like(x) if need_gx else None
+        g_w = torch.zeros_like(weight) if need[3] else None
+        up = torch.empty((B, Cout, H, W), device=dev, dtype=torch.float32) if ctx.stride == 2 else None
         L.LAUNCHES += 1
-        L.check(L.lib().ef_conv3x3_bwd(L.ptr(g_pre), L.ptr(x), L.ptr(_c(weight)), L.ptr(g_x), L.ptr(g_w), B, Cin, Cout, H, W, L.stream()),
-                "ef_conv3x3_bwd")
-        C1 = x1.shape[1]
+        L.check(L.lib().ef_conv3x3_bwd_s(L.ptr(g_pre), L.ptr(x), L.ptr(_c(weight)), L.ptr(g_x), L.ptr(g_w), L.ptr(up), B, C1 + C2, Cout, H, W,
+                                         int(ctx.stride), L.stream()), "ef_conv3x3_bwd_s")
         g_x1 = g_x[:, :C1] if (g_x is not None and need[0]) else None
-        g_x2 = g_x[:, C1:] if (g_x is not None and has_x2 and need[1]) else None
-        g_b = g_pre.sum(dim=(0, 2, 3)) if (has_bias and need[3]) else None
-        g_r = g_pre if (has_res and need[4]) else None
-        return g_x1, g_x2, g_w, g_b, g_r, None
+        g_x2 = g_sc = None
+        if has_x2 and g_x is not None:
+            if has_scale:
+                g_x2 = torch.empty((B, C2, H, W), device=dev, dtype=torch.float32) if need[1] else None
+                g_sc = torch.empty((B, C2, H, W), device=dev, dtype=torch.float32) if need[2] else None
+                if g_x2 is not None or g_sc is not None:
+                    L.LAUNCHES += 1
+                    L.check(L.lib().ef_ann_scale_bwd(L.ptr(g_x), xb.data_ptr(), sc.data_ptr(), L.ptr(g_x2), L.ptr(g_sc), B, C1, C2, H, W,
+                                                     xb.stride(0), sc.stride(0), L.stream()), "ef_ann_scale_bwd")
+            elif need[1]:
+                g_x2 = g_x[:, C1:]
+        g_r = g_pre if (has_res and need[5]) else None
+        return g_x1, g_x2, g_sc, g_w, g_b, g_r, g_h, g_u, None, None
 
 
-def conv_ann(x1, weight, bias, act, *, x2=None, x2_scale=None, residual=None, blend_h=None, blend_u=None):
+def conv_ann(x1, weight, bias, act, *, x2=None, x2_scale=None, residual=None, blend_h=None, blend_u=None, stride=1):
     """
-    act(conv3x3(cat([x1, x2 * x2_scale]), weight) + bias + residual), optionally blended h*(1-u) + (.)*u.
+    act(conv3x3(cat([x1, x2 * x2_scale]), weight) + bias + residual), optionally blended h*(1-u) + (.)*u; stride 1 or 2.
     x2 / x2_scale / blend_* may be channel slices of larger NCHW tensors (only the batch stride may be non-dense).
-    Without gradient tracking this is ONE fused launch; under autograd the gate product and the blend are separate
-    (elementwise) steps around a differentiable conv + activation (_ConvAnn).
+    ONE fused launch; differentiable wrt every tensor argument (_ConvAnn: the backward is kernels only).
     """
     tracked = torch.is_grad_enabled() and any(t is not None and t.requires_grad
                                               for t in (x1, x2, x2_scale, weight, bias, residual, blend_h, blend_u))
     if tracked:
-        x2_eff = x2 if x2_scale is None or x2 is None else x2 * x2_scale
-        out = _ConvAnn.apply(x1, x2_eff, weight, bias, residual, act)
-        if blend_h is not None:
-            out = blend_h * (1.0 - blend_u) + out * blend_u
-        return out
-    return _conv_ann_launch(x1, weight, bias, act, x2=x2, x2_scale=x2_scale, residual=residual, blend_h=blend_h, blend_u=blend_u)
+        return _ConvAnn.apply(x1, x2, x2_scale, weight, bias, residual, blend_h, blend_u, act, int(stride))
+    return _conv_ann_launch(x1, weight, bias, act, x2=x2, x2_scale=x2_scale, residual=residual, blend_h=blend_h, blend_u=blend_u, stride=stride)[0]
 
 
-def _conv_ann_launch(x1, weight, bias, act, *, x2=None, x2_scale=None, residual=None, blend_h=None, blend_u=None):
-    def plane_ok(t):
-        return t is None or (t.stride(-1) == 1 and t.stride(-2) == t.shape[-1] and t.stride(1) == t.shape[-1] * t.shape[-2])
-
-    x1 = x1 if plane_ok(x1) else x1.contiguous()
+def _conv_ann_launch(x1, weight, bias, act, *, x2=None, x2_scale=None, residual=None, blend_h=None, blend_u=None, stride=1, want_act_out=False):
+    x1 = x1 if _plane_ok(x1) else x1.contiguous()
     tensors = [x2, x2_scale, residual, blend_h, blend_u]
-    tensors = [t if plane_ok(t) else t.contiguous() for t in tensors]
+    tensors = [t if _plane_ok(t) else t.contiguous() for t in tensors]
     x2, x2_scale, residual, blend_h, blend_u = tensors
     weight, bias = _c(weight.detach()), (None if bias is None else _c(bias.detach()))
     residual = None if residual is None else residual.contiguous()
@@ -883,9 +910,12 @@ def _conv_ann_launch(x1, weight, bias, act, *, x2=None, x2_scale=None, residual=
     C2 = 0 if x2 is None else x2.shape[1]
     Cout = weight.shape[0]
     assert weight.shape[1] == C1 + C2 and weight.shape[2:] == (3, 3), "conv_ann: weight shape does not match the inputs"
-    out = torch.empty((B, Cout, H, W), device=x1.device, dtype=torch.float32)
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    out = torch.empty((B, Cout, Ho, Wo), device=x1.device, dtype=torch.float32)
+    act_out = torch.empty_like(out) if want_act_out else None
     p = L.ConvAnnParams()
     p.B, p.C1, p.C2, p.Cout, p.H, p.W, p.act = B, C1, C2, Cout, H, W, _ACT_CODES[act]
+    p.stride = int(stride)
     raw = lambda t: None if t is None else t.data_ptr()  # noqa: E731  (slices are not "contiguous"; strides are passed explicitly)
     p.x1, p.x2, p.x2_scale = raw(x1), raw(x2), raw(x2_scale)
     p.x1_bstride = x1.stride(0)
@@ -895,6 +925,6 @@ def _conv_ann_launch(x1, weight, bias, act, *, x2=None, x2_scale=None, residual=
     p.blend_h, p.blend_u = raw(blend_h), raw(blend_u)
     p.blend_h_bstride = 0 if blend_h is None else blend_h.stride(0)
     p.blend_u_bstride = 0 if blend_u is None else blend_u.stride(0)
-    p.out = L.ptr(out)
+    p.out, p.act_out = L.ptr(out), L.ptr(act_out)
     L.call("ef_conv_ann_fwd", p)
-    return out
+    return out, act_out

@@ -388,16 +388,48 @@ typedef struct ef_conv_ann_params {
   const float* blend_h;          /* [B,Cout,H,W] or NULL                                                               */
   const float* blend_u;          /* [B,Cout,H,W] or NULL                                                               */
   int64_t blend_h_bstride, blend_u_bstride;
-  float* out;                    /* [B,Cout,H,W]                                                                       */
+  float* out;                    /* [B,Cout,Ho,Wo]                                                                     */
+  int32_t stride;                /* 1 (0 = 1) or 2: output Ho = (H-1)/stride + 1; residual / blend / out at the output size */
+  float* act_out;                /* [B,Cout,Ho,Wo] or NULL: the activation BEFORE the blend (kept for the backward)      */
 } ef_conv_ann_params;
 
 int ef_conv_ann_fwd(const ef_conv_ann_params* p, void* stream);
+
+/* Backward helpers of the ANN cells: everything autograd derives AROUND the convolution, one launch each, so that the backward of a
+ * ConvLayer / ConvGRU step is kernels only (models/submodules.py:52-61, 400-418).
+ *  ef_ann_gate_bwd   y = h (1 - u) + o u with o = act(pre) (or y = o without a blend): g_pre = g_y [u] act'(o), g_h = g_y (1 - u),
+ *                    g_u = g_y (o - h); g_bias[c] += sum g_pre.  act_out = o as the forward stored it (ef_conv_ann_params.act_out, or
+ *                    its `out` when there is no blend).
+ *  ef_ann_cat_scale  out [B,C1+C2,H,W] = cat([x1, x2 * scale]): the convolution's input as one tensor (ef_conv3x3_bwd reads it for the
+ *                    weight gradient); scale may be NULL.
+ *  ef_ann_scale_bwd  through the gate product: g_x2 = g_xcat[:, C1:] * scale, g_scale = g_xcat[:, C1:] * x2 (either output may be NULL). */
+typedef struct ef_ann_gate_bwd_params {
+  int32_t B, C, H, W, act;
+  const float* g_y;              /* [B,C,H,W]                                                                          */
+  const float* act_out;          /* [B,C,H,W]                                                                          */
+  const float* blend_h;          /* [B,C,H,W] (batch stride blend_h_bstride) or NULL                                   */
+  const float* blend_u;
+  int64_t blend_h_bstride, blend_u_bstride;
+  float* g_pre;                  /* [B,C,H,W]                                                                          */
+  float* g_h;                    /* [B,C,H,W] or NULL                                                                  */
+  float* g_u;                    /* [B,C,H,W] or NULL                                                                  */
+  float* g_bias;                 /* [C] += or NULL                                                                     */
+} ef_ann_gate_bwd_params;
+int ef_ann_gate_bwd(const ef_ann_gate_bwd_params* p, void* stream);
+int ef_ann_cat_scale(const float* x1, const float* x2, const float* scale, float* out, int32_t B, int32_t C1, int32_t C2, int32_t H, int32_t W,
+                     int64_t x1_bstride, int64_t x2_bstride, int64_t scale_bstride, void* stream);
+int ef_ann_scale_bwd(const float* g_xcat, const float* x2, const float* scale, float* g_x2, float* g_scale, int32_t B, int32_t C1, int32_t C2,
+                     int32_t H, int32_t W, int64_t x2_bstride, int64_t scale_bstride, void* stream);
 
 /* Gradients of the 3x3 stride-1 convolution inside the ANN cells (what autograd derives for the nn.Conv2d of
  * models/submodules.py:22,159,256,281,386-388): g_pre = dL/d(conv output) [B,C,H,W]; g_x [B,Cin,H,W] is overwritten (NULL = skip),
  * g_w [C,Cin,3,3] is accumulated (NULL = skip; needs x [B,Cin,H,W]). */
 int ef_conv3x3_bwd(const float* g_pre, const float* x, const float* w, float* g_x, float* g_w, int32_t B, int32_t Cin, int32_t C,
                    int32_t H, int32_t W, void* stream);
+/* The same for a stride-2 convolution: g_pre [B,C,Ho,Wo] is zero-inserted into scratch_up [B,C,H,W] (caller-provided workspace) and the
+ * stride-1 gradient kernels run on it (what the transposed convolution is); stride 1 ignores scratch_up. */
+int ef_conv3x3_bwd_s(const float* g_pre, const float* x, const float* w, float* g_x, float* g_w, float* scratch_up, int32_t B, int32_t Cin,
+                     int32_t C, int32_t H, int32_t W, int32_t stride, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Contrast-maximisation event-warping loss over one training window.

@@ -501,3 +501,47 @@ def test_recevflownet_with_norm_and_transposed_decoders_trains():
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters())
     opt.step()
     assert any((a - b).abs().max() > 0 for a, b in zip(m.parameters(), before))
+
+
+# (the gated form -- ConvGRU -- is stride 1 by construction: its blend operands live at the input resolution)
+@pytest.mark.parametrize("stride,gated", [(1, True), (1, False), (2, False)])
+@pytest.mark.parametrize("act", ["tanh", "relu", "sigmoid", None])
+def test_conv_ann_every_input_gradient_matches_torch_autograd(stride, act, gated, monkeypatch):
+    """
+    ops.conv_ann with every option (second input with gate product, residual, gated blend, stride 2): the value and the gradient of EVERY
+    tensor argument against torch's own ops and autograd -- the backward here is kernels only (ef_ann_gate_bwd, ef_ann_cat_scale,
+    ef_conv3x3_bwd_s, ef_ann_scale_bwd).
+    """
+    import torch.nn.functional as F
+
+    from event_flow_b200 import ops
+
+    monkeypatch.setattr(torch.backends.cudnn, "allow_tf32", False)
+    g = torch.Generator().manual_seed(9)
+    B, C1, C2, Co, H, W = 2, 5, 7, 9, 19, 22
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    mk = lambda *s: torch.randn(*s, generator=g).to(DEV).requires_grad_(True)  # noqa: E731
+    big = torch.rand(B, 2 * C2, H, W, generator=g).to(DEV).requires_grad_(True)  # gate tensor: its channel halves are slices (non-dense batch stride)
+    t = {"x1": mk(B, C1, H, W), "x2": mk(B, C2, H, W), "w": mk(Co, C1 + C2, 3, 3), "b": mk(Co), "res": mk(B, Co, Ho, Wo)}
+    if gated:
+        t["h"], t["u"] = mk(B, Co, H, W), torch.rand(B, Co, H, W, generator=g).to(DEV).requires_grad_(True)
+    scale = big[:, C2:] if gated else None
+    out = ops.conv_ann(t["x1"], t["w"], t["b"], act, x2=t["x2"], x2_scale=scale, residual=t["res"], blend_h=t.get("h"), blend_u=t.get("u"), stride=stride)
+    g_out = torch.randn(out.shape, generator=g).to(DEV)
+    out.backward(g_out)
+    mine = {k: v.grad.clone() for k, v in t.items()}
+    mine["big"] = None if big.grad is None else big.grad.clone()
+    for v in list(t.values()) + [big]:
+        v.grad = None
+    x = torch.cat([t["x1"], t["x2"] * scale if gated else t["x2"]], 1)
+    ref = F.conv2d(x, t["w"], t["b"], stride, 1) + t["res"]
+    ref = ref if act is None else getattr(torch, act)(ref)
+    if gated:
+        ref = t["h"] * (1 - t["u"]) + ref * t["u"]
+    assert out.shape == ref.shape == (B, Co, Ho, Wo)
+    assert (out - ref).abs().max().item() <= 2e-5 * max(1.0, ref.abs().max().item())
+    ref.backward(g_out)
+    for k, v in t.items():
+        assert (mine[k] - v.grad).abs().max().item() <= 1e-4 * (v.grad.abs().max().item() + 1e-12), k
+    if gated:
+        assert (mine["big"] - big.grad).abs().max().item() <= 1e-4 * big.grad.abs().max().item()

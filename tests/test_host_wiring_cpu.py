@@ -28,9 +28,9 @@ def cpu_ops(monkeypatch):
         return osp.cell_step(neuron, x, state, p, hard_reset=hard_reset, surrogate=surrogate, width=width, stride=stride,
                              residual=0 if residual is None else residual, detach=detach)
 
-    def conv_ann(x1, weight, bias, act, *, x2=None, x2_scale=None, residual=None, blend_h=None, blend_u=None):
+    def conv_ann(x1, weight, bias, act, *, x2=None, x2_scale=None, residual=None, blend_h=None, blend_u=None, stride=1):
         x = x1 if x2 is None else torch.cat([x1, x2 if x2_scale is None else x2 * x2_scale], dim=1)
-        out = F.conv2d(x, weight, bias, 1, 1)
+        out = F.conv2d(x, weight, bias, stride, 1)
         if residual is not None:
             out = out + residual
         out = {None: lambda t: t, "relu": torch.relu, "tanh": torch.tanh, "sigmoid": torch.sigmoid}[act](out)
