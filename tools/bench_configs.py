@@ -1,6 +1,7 @@
 """
 Timings of the other BASELINE.json configurations (they are parity-test cases, not the bench line; bench.py reports them under
 `other_configs`, comparable with profiles/r01_reference_probe_b200.txt):
+  cfg 1  FireNet (ANN: ConvLayer_ cells + ConvGRU), 1 bin, batch 1, 128x128 (configs/eval_flow.yml plumbing): forward per step, training window;
   cfg 4  SpikingRecEVFlowNet 256x256, 50k events / window, batch 4 per GPU (32 over 8 GPUs): forward per step (general tcgen05 cell
          kernel, ef_lif_conv_fwd_g) with its tensor-pipe roofline, and the training window (fwd + EventWarping loss + BPTT);
   cfg 5  PLIF / ALIF FireNet, 20-step sequence, batch 8, 128x128: forward per step and the training window.
@@ -19,7 +20,10 @@ UNET = dict(name="x", encoding="cnt", round_encoding=False, norm_input=False, nu
             activations=["arctanspike", "arctanspike"], mask_output=True, spiking_neuron=None)
 FIRE = dict(name="x", encoding="voxel", round_encoding=False, norm_input=False, num_bins=5, base_num_channels=32, kernel_size=3,
             activations=["arctanspike", "arctanspike"], mask_output=True, spiking_neuron={})
+ANN = dict(name="x", encoding="voxel", round_encoding=False, norm_input=False, num_bins=1, base_num_channels=32, kernel_size=3,
+           activations=["relu", None], mask_output=True, spiking_neuron=None)
 CONFIGS = (
+    ("cfg1", "FireNet", ANN, dict(B=1, N=1000, H=128, W=128, T=10, bins=1, gain=1.0)),  # the reference's own CPU-runnable case, on the GPU
     ("cfg4", "SpikingRecEVFlowNet", UNET, dict(B=4, N=50000, H=256, W=256, T=4, bins=2, gain=3.0)),
     ("cfg5-plif", "PLIFFireNet", FIRE, dict(B=8, N=1000, H=128, W=128, T=20, bins=5, gain=2.5)),
     ("cfg5-alif", "ALIFFireNet", FIRE, dict(B=8, N=1000, H=128, W=128, T=20, bins=5, gain=2.5)),
