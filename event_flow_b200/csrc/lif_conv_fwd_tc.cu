@@ -545,7 +545,8 @@ static int launch_tc(const TcParams& q, int grid, const CUtensorMap* m, cudaStre
     attr_set = true;
   }
   const cudaError_t le = launch_pdl(kern, dim3(grid), dim3(128 + 32 * 4 * (32 / CPT)), TcCfg<REC>::TOTAL, st, q, m[0], m[1], m[2], m[3], m[4], m[5]);
-  if (getenv("EF_DEBUG_CAPTURE")) {
+  static const bool debug_capture = getenv("EF_DEBUG_CAPTURE") != nullptr;  // diagnostics: launch result and capture status of the stream
+  if (debug_capture) {
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     const cudaError_t ce = cudaStreamIsCapturing(st, &cs);
     fprintf(stderr, "[ef] tc launch REC=%d HARD=%d grid=%d T=%d has_v=%d has_z=%d -> launch rc=%d (%s), capture status=%d (query rc=%d)\n", (int)REC, (int)HARD, grid,
