@@ -57,6 +57,7 @@ class _Carry:
         self.parity = None    # arena bank of the window
         self.head_tc = False  # the head layer ran on the tensor cores (split input in bank.x_cl)
         self.flow_y = None    # window entry point: the flows [T,B,2,H,W] as computed (tanh outputs the prediction backward needs)
+        self.into_sink = False  # the window backward accumulated the parameter gradients straight into the trainer's flat buffer
 
 
 class _Slot:
@@ -451,12 +452,37 @@ class _FireNetStep(torch.autograd.Function):
         if not ctx.first:  # nothing is computed yet: the window's first step (the last node to run) back-propagates the whole window
             return (None, None, torch.zeros((), device=dev, dtype=torch.float32))
         params = _params_of(model)
+        carry.into_sink = False
         if model.__dict__.get("_window_backward", True) and model.__dict__.get("_tc_backward", True):
             grads = _window_backward(model, ctx.arena, carry, ctx.shapes)
         else:
             grads = _stepwise_backward(model, ctx.arena, carry, ctx.shapes)
         carry.g_flows = {}
+        if carry.into_sink:  # already accumulated into p.grad (views of the trainer's flat buffer)
+            return (None, None, None, *[None] * len(params))
         return (None, None, None, *[g.clone() if p.requires_grad else None for p, g in zip(params, grads)])
+
+
+def _grad_sink_views(model, params):
+    """
+    Gradient sink: when every parameter's .grad is a dense fp32 view into the flat gradient buffer of a DataParallelTrainer
+    (model._grad_sink), the window backward accumulates straight into those views -- every gradient kernel already accumulates (+=),
+    which is exactly autograd's `p.grad += g` -- and hands autograd no parameter gradients: this replaces a clone and an add kernel per
+    parameter (2 x 25 launches per window).  Returns the views in the parameter order of this path, or None when the layout does not hold
+    (gradients set to None, re-bound by autograd, a foreign buffer, ...).
+    """
+    sink = model.__dict__.get("_grad_sink")
+    if sink is None:
+        return None
+    lo, hi = sink.data_ptr(), sink.data_ptr() + 4 * sink.numel()
+    views = []
+    for q in params:
+        g = q.grad
+        if (not q.requires_grad or g is None or g.dtype != torch.float32 or not g.is_contiguous() or g.shape != q.shape
+                or g.data_ptr() < lo or g.data_ptr() + 4 * g.numel() > hi):
+            return None
+        views.append(g)
+    return views
 
 
 def _flat_grads(arena, params, dev):
@@ -516,7 +542,10 @@ def _window_backward(model, arena, carry, shapes):
     bank = arena.banks[carry.parity]
     Tn = carry.n
     cells, params, splits = _cells(model), _params_of(model), _split_cache(model)
-    grads = _flat_grads(arena, params, dev)
+    grads = _grad_sink_views(model, params)
+    carry.into_sink = grads is not None
+    if grads is None:
+        grads = _flat_grads(arena, params, dev)
     gs = _grad_slots(cells, grads)
     buf = arena.window_buffers(bank.cap)
     v0, z0 = carry.prev
@@ -800,6 +829,8 @@ class _FireNetWindow(torch.autograd.Function):
         params = _params_of(model)
         grads = _window_backward(model, ctx.arena, carry, ctx.shapes)
         carry.g_flows = {}
+        if carry.into_sink:  # already accumulated into p.grad (views of the trainer's flat buffer)
+            return (None, None, *[None] * len(params))
         return (None, None, *[g.clone() if p.requires_grad else None for p, g in zip(params, grads)])
 
 

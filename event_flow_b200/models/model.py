@@ -107,7 +107,7 @@ class FireNet(BaseModel):
     # Run-time caches of the fast path (CUDA graphs, ctypes argument structs, activation slabs, weight images): none of them
     # can or should travel with a checkpoint.  The reference checkpoints by pickling the whole module (utils/utils.py:36,
     # mlflow.pytorch.log_model) and callers deepcopy models; both go through __getstate__.
-    _RUNTIME_KEYS = ("_fast_params", "_fast_cells", "_fast_eligible", "_w_split_cache", "_arena", "_capture", "_last_spikes", "_w_epoch")
+    _RUNTIME_KEYS = ("_fast_params", "_fast_cells", "_fast_eligible", "_w_split_cache", "_arena", "_capture", "_last_spikes", "_w_epoch", "_grad_sink")
 
     def __getstate__(self):
         state = self.__dict__.copy()

@@ -63,6 +63,8 @@ class DataParallelTrainer:
         from . import fast
 
         fast.invalidate_pointers(model)
+        # the fast path may accumulate its parameter gradients straight into flat_grad (fast._grad_sink_views checks the layout every window)
+        model.__dict__["_grad_sink"] = self.flat_grad
 
     @property
     def world_size(self):

@@ -142,3 +142,54 @@ def test_weight_images_of_the_cell_path_follow_the_fused_optimizer():
         ref = twin(vox, None)["flow"][0]
     assert ref.abs().max() > 0
     assert (after - ref).abs().max().item() <= 1e-4 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("windowed", [True, False])
+def test_gradient_sink_equals_autograd_accumulation(windowed):
+    """
+    With a DataParallelTrainer the window backward accumulates the parameter gradients straight into the trainer's flat buffer (no clone
+    + add per parameter): the buffer must hold what autograd's own accumulation gives for the same window on a twin model, also when
+    TWO windows are accumulated before the optimiser step (p.grad += semantics).
+    """
+    import copy
+
+    from event_flow_b200.loss.flow import EventWarping
+    from event_flow_b200.models.model import LIFFireNet
+    from event_flow_b200.parallel import DataParallelTrainer
+
+    H, W, B, T = 32, 48, 2, 3
+    torch.manual_seed(0)
+    a = LIFFireNet(firenet_cfg(5, "voxel"))
+    with torch.no_grad():
+        for n, p in a.named_parameters():
+            if n.endswith("ff.weight") or n.endswith("rec.weight"):
+                p.mul_(2.5)
+        a.pred.conv2d.weight.mul_(20.0)
+    a = a.to(DEV)
+    b = copy.deepcopy(a)
+    tr = DataParallelTrainer(a)
+    cfg = {"loader": {"resolution": [H, W]}, "loss": {"flow_regul_weight": 0.001, "overwrite_intermediate": False}, "model": {"mask_output": True}}
+    wins = [oenc.encode_window(*oenc.synthetic_events(B, 300, H, W, 60 + t), H, W, 5) for t in range(2 * T)]
+
+    def run(m, sink_expected):
+        lossf = EventWarping(cfg, DEV)
+        for w in range(2):
+            part = wins[w * T:(w + 1) * T]
+            if windowed:
+                outs = m.forward_window(torch.stack([d["event_voxel"] for d in part]).to(DEV), torch.stack([d["event_cnt"] for d in part]).to(DEV))
+            else:
+                outs = [m(d["event_voxel"].to(DEV), d["event_cnt"].to(DEV)) for d in part]
+            for d, out in zip(part, outs):
+                lossf.event_flow_association(out["flow"], d["event_list"].clone().to(DEV), d["event_list_pol_mask"].to(DEV), d["event_mask"].to(DEV))
+            lossf().backward()
+            assert m._fast.carry.into_sink is sink_expected
+            lossf.reset()
+            m.detach_states()  # no optimiser step in between: the second window ACCUMULATES
+
+    run(a, True)
+    run(b, False)
+    ref = torch.cat([p.grad.reshape(-1) for p in b.parameters()])
+    assert ref.abs().max() > 0
+    assert (tr.flat_grad - ref).abs().max().item() <= 5e-5 * ref.abs().max().item()
+    for p in a.parameters():  # still views of the flat buffer
+        assert p.grad.data_ptr() >= tr.flat_grad.data_ptr() and p.grad.data_ptr() < tr.flat_grad.data_ptr() + 4 * tr.flat_grad.numel()
