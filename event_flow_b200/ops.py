@@ -95,7 +95,7 @@ class _CellStep(torch.autograd.Function):
                 p.z_out_cl = L.ptr(z_cl)
             L.LAUNCHES += 1
             L.check(L.lib().ef_lif_neuron_fwd(C.byref(p), L.ptr(cur), L.stream()), "ef_lif_neuron_fwd")
-            out._ef_cl, state_out._ef_z_cl = out_cl, z_cl
+            out._ef_cl, state_out._ef_z_cl = (out_cl, out._version), (z_cl, state_out._version)
         else:
             L.call("ef_lif_conv_fwd", p, tag=(x.shape[1], Cout, w_rec is not None))
         ctx.meta = meta
@@ -195,7 +195,12 @@ def _tc_conv_current(x, state_in, w_ff, w_rec, x_kind):
         hit = _TC_IMAGES[id(w_ff)] = (key, image, weakref.ref(w_ff), None if w_rec is None else weakref.ref(w_rec))
     image = hit[1]
     # input / previous spikes in the internal format: handed over by the cell that produced them (attributes of the tensors), else packed here
-    x_cl = getattr(x, "_ef_cl", None)
+    # (a hand-over is only trusted while the fp32 tensor it mirrors is unmodified: torch's version counter)
+    def handed(t, name):
+        hit = getattr(t, name, None)
+        return hit[0] if hit is not None and hit[1] == t._version else None
+
+    x_cl = handed(x, "_ef_cl")
     if x_kind == "split":
         x_cl = pack_split_cl(x)
     elif x_cl is None or x_cl.shape[:3] != (x.shape[0], x.shape[2], x.shape[3]):
@@ -203,7 +208,7 @@ def _tc_conv_current(x, state_in, w_ff, w_rec, x_kind):
     v_in = z_cl = None
     if w_rec is not None and state_in is not None:
         v_in = state_in[0]  # (only has to be finite: it is multiplied by sigmoid(-inf) = 0)
-        z_cl = getattr(state_in, "_ef_z_cl", None)
+        z_cl = handed(state_in, "_ef_z_cl")
         if z_cl is None:
             z_cl = pack_cl(state_in[1])
     cur, _ = lif_step_cl(x_cl, v_in, z_cl, w_ff, w_rec, neg_inf, ones, hard_reset=True, w_split=image)
