@@ -304,11 +304,12 @@ def test_tensor_core_conv_plus_neuron_update_matches_generic_kernel_and_oracle(n
         if other_aux is not None:
             assert (res["tc"][1][2] - other_aux).abs().max().item() <= 1e-6 * max(1.0, other_aux.abs().max().item())
     assert torch.equal(res["tc"][0], res["tc"][1][1])  # out = spikes (no residual)
-    if torch.equal(res["tc"][1][1], res["cc"][1][1]):  # same spikes (no borderline neuron in this case): same backward inputs up to 1e-6
-        for a, b, what in ((res["tc"][2], res["cc"][2], "g_x"), (res["tc"][3], res["cc"][3], "g_state")) + tuple(
-                (res["tc"][4][k], res["cc"][4][k], "g_" + k) for k in res["cc"][4]):
-            if b is not None:
-                assert (a - b).abs().max().item() <= 1e-4 * (b.abs().max().item() + 1e-20), what
+    # The backward of ONE cell step reads the inputs, the new membrane potential / trace and the parameters -- never the emitted spikes --
+    # so the gradients of the two paths are comparable UNCONDITIONALLY (a borderline spike that flipped changes nothing they read).
+    for a, b, what in ((res["tc"][2], res["cc"][2], "g_x"), (res["tc"][3], res["cc"][3], "g_state")) + tuple(
+            (res["tc"][4][k], res["cc"][4][k], "g_" + k) for k in res["cc"][4]):
+        if b is not None:
+            assert (a - b).abs().max().item() <= 1e-4 * (b.abs().max().item() + 1e-20), what
     assert res["tc"][1][1].mean() > 0.01
 
 
