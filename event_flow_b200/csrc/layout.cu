@@ -36,25 +36,34 @@ __global__ void __launch_bounds__(256) unpack_cl_kernel(const uint16_t* __restri
 // hi + mid + lo == x bit for bit.  This lets the fractional network input (voxel grids) run through the tensor-core cell kernel
 // with fp32-exact products: the head layer's weight image repeats w[.,c] in the three slots of c (ef_split_weights_head).
 __global__ void __launch_bounds__(256) pack_split_cl_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, int B, int Cin, int SL, size_t hw) {
-  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;  // over B * hw
-  if (i >= (size_t)B * hw) return;
-  const size_t pix = i % hw, b = i / hw;
-  uint16_t o[32];
+  // a block owns 256 consecutive pixels = 16 KB of contiguous output: the rows are assembled in shared memory (run-time channel
+  // positions are plain shared-memory addresses, not register indices) and leave as fully coalesced 16-byte stores
+  __shared__ __align__(16) uint16_t s_row[256 * 32];
+  const int tid = threadIdx.x;
+  const size_t n = (size_t)B * hw, i0 = (size_t)blockIdx.x * 256, i = i0 + tid;
+  uint4* mine = reinterpret_cast<uint4*>(s_row + tid * 32);
 #pragma unroll
-  for (int k = 0; k < 32; ++k) o[k] = 0;
-  for (int c = 0; c < Cin; ++c) {
-    const float x = __ldg(src + ((size_t)b * Cin + c) * hw + pix);
-    const __nv_bfloat16 hi = __float2bfloat16_rn(x);
-    const float r1 = x - __bfloat162float(hi);
-    const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
-    const __nv_bfloat16 lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
-    o[c] = __bfloat16_as_ushort(hi), o[SL + c] = __bfloat16_as_ushort(mid), o[2 * SL + c] = __bfloat16_as_ushort(lo);
+  for (int k = 0; k < 4; ++k) mine[k] = make_uint4(0, 0, 0, 0);
+  if (i < n) {
+    const size_t pix = i % hw, b = i / hw;
+    for (int c = 0; c < Cin; ++c) {
+      const float x = __ldg(src + ((size_t)b * Cin + c) * hw + pix);
+      const __nv_bfloat16 hi = __float2bfloat16_rn(x);
+      const float r1 = x - __bfloat162float(hi);
+      const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+      const __nv_bfloat16 lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+      uint16_t* o = s_row + tid * 32;
+      o[c] = __bfloat16_as_ushort(hi), o[SL + c] = __bfloat16_as_ushort(mid), o[2 * SL + c] = __bfloat16_as_ushort(lo);
+    }
   }
-  uint4* d = reinterpret_cast<uint4*>(dst + i * 32);
+  __syncthreads();
+  const uint4* s4 = reinterpret_cast<const uint4*>(s_row);
+  uint4* d4 = reinterpret_cast<uint4*>(dst) + i0 * 4;
 #pragma unroll
-  for (int k = 0; k < 4; ++k)
-    d[k] = make_uint4(o[8 * k] | ((uint32_t)o[8 * k + 1] << 16), o[8 * k + 2] | ((uint32_t)o[8 * k + 3] << 16), o[8 * k + 4] | ((uint32_t)o[8 * k + 5] << 16),
-                      o[8 * k + 6] | ((uint32_t)o[8 * k + 7] << 16));
+  for (int j = 0; j < 4; ++j) {
+    const int idx = j * 256 + tid;
+    if (i0 + (idx >> 2) < n) d4[idx] = s4[idx];
+  }
 }
 
 // space-to-depth variants for the stride-2 cells: virtual channel vc = (py*2 + px)*Cin + c of output pixel (Y, X) = input (2Y+py, 2X+px, c)
