@@ -220,6 +220,7 @@ def run_ours(args):
 
     dp_check = dp_gradient_check(model, lossf, rank, world, dev) if world > 1 else None
     trainer = DataParallelTrainer(model, lr=LR, clip_grad=CLIP)
+    trainer_fused = trainer.fused is not None
 
     # every timed / warm-up window has its own inputs (event_flow_association offsets the timestamps IN PLACE on the caller's
     # tensor, loss/flow.py:90, so a window's event tensors are consumed by one use -- exactly like batches from a loader)
@@ -425,7 +426,9 @@ def run_ours(args):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_train, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": B_PER_GPU * world, "timesteps": T, "events_per_window": N_EV, "resolution": [H, W],
-                       "parallelism": f"dp{world}", "collective": "1 x ncclAllReduce(SUM, fp32, 74 818 elements) per step" if world > 1 else "none (1 rank)",
+                       "parallelism": f"dp{world}", "collective": ("none (1 rank)" if world == 1 else
+                                      "1 x ef_dp_step per rank and step: one-shot all-reduce(SUM, fp32, 74 818 elements) over NVLink peer memory fused with "
+                                      "clip + Adam" if trainer_fused else "1 x ncclAllReduce(SUM, fp32, 74 818 elements) per step"),
                        "l2": "256 MB write between timed iterations (L2 flush)", "weights": WEIGHTS},
             "e2e": {"value": events_per_step / (ms_train_e2e * 1e-3), "unit": "events/s", "ms_per_step": ms_train_e2e,
                     "h2d_bytes_per_step": T * B_PER_GPU * N_EV * 4 * 4, "d2h_bytes_per_step": 4,

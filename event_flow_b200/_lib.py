@@ -151,6 +151,20 @@ class ConvAnnParams(C.Structure):
     ]  # fmt: skip
 
 
+EF_DP_MAX_RANKS = 8
+
+
+class DpStepParams(C.Structure):
+    _fields_ = [
+        ("world", _i32), ("rank", _i32), ("n", _i32), ("step", _i32),
+        ("clip", C.c_float), ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
+        ("bc1", C.c_float), ("bc2_sqrt", C.c_float),
+        ("epoch", C.c_uint32), ("epoch_launches", C.c_uint32), ("graceful", _i32), ("grid_expected", _i32),
+        ("grads", _f32p * EF_DP_MAX_RANKS), ("signals", _f32p * EF_DP_MAX_RANKS),
+        ("param", _f32p), ("m", _f32p), ("v", _f32p), ("sqnorm", _f32p), ("scratch", _f32p), ("status", _f32p),
+    ]  # fmt: skip
+
+
 class AnnGateBwdParams(C.Structure):
     _fields_ = [
         ("B", _i32), ("C", _i32), ("H", _i32), ("W", _i32), ("act", _i32),
@@ -236,6 +250,12 @@ EXPORTS = {
     "ef_conv3x3_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, _i32, _i32, _i32, _i32, _i32, C.c_void_p]),
     "ef_conv3x3_bwd_s": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, _i32, _i32, _i32, _i32, _i32, _i32, C.c_void_p]),
     "ef_ann_gate_bwd": (C.c_int, [C.POINTER(AnnGateBwdParams), C.c_void_p]),
+    "ef_dp_step": (C.c_int, [C.POINTER(DpStepParams), C.c_void_p]),
+    "ef_dp_step_grid": (_i32, [_i32]),
+    "ef_ipc_alloc": (C.c_int, [C.c_int64, C.POINTER(C.c_void_p), C.c_char_p]),
+    "ef_ipc_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "ef_ipc_close": (C.c_int, [C.c_void_p]),
+    "ef_ipc_free": (C.c_int, [C.c_void_p]),
     "ef_ann_cat_scale": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, _i32, _i32, _i32, _i32, _i32, C.c_int64, C.c_int64, C.c_int64, C.c_void_p]),
     "ef_ann_scale_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, _i32, _i32, _i32, _i32, _i32, C.c_int64, C.c_int64, C.c_void_p]),
     "ef_iwe_metrics_workspace_elems": (C.c_int64, [_i32, _i32, _i32]),

@@ -616,6 +616,38 @@ int ef_encode_events(const ef_encode_params* p, void* stream);
  * ef_clip_adam applies g *= min(1, max_norm/(sqrt(sqnorm)+1e-6)) and the Adam update (bias-corrected, eps outside sqrt).
  * ------------------------------------------------------------------------------------------------------------------ */
 int ef_grad_sqnorm(const float* g, int64_t n, float* sqnorm, void* stream);
+
+/* The data-parallel optimiser step as ONE launch per rank (csrc/dp_step.cu): one-shot all-reduce(SUM) of the flat gradient over NVLink
+ * peer memory -> global-norm clip -> Adam -> zero the own gradient; every rank reduces all buffers in rank order (identical replicas).
+ * grads[r] / signals[r]: the flat fp32 gradient [n] and the uint32 signal words [16] of rank r as mapped into THIS process (CUDA IPC;
+ * [rank] = the own buffers).  signal words must be zero before the first step; epoch = 1, 2, 3, ... the same on all ranks, one launch
+ * per epoch (epoch_launches = launches so far incl. this one: the grid barrier counts arrivals cumulatively).  scratch:
+ * float[ef_dp_step_grid(n)]; status: uint32, 0 = fine, 1 / 2 / 3 = a wait of phase A / B / C timed out (graceful = 1: the kernel then
+ * returns without updating; graceful = 0: it traps).  bc1 / bc2_sqrt are filled in by the call. */
+#define EF_DP_MAX_RANKS 8
+typedef struct ef_dp_step_params {
+  int32_t world, rank, n, step;
+  float clip, lr, beta1, beta2, eps;
+  float bc1, bc2_sqrt;           /* set by ef_dp_step                                                                   */
+  uint32_t epoch, epoch_launches;
+  int32_t graceful, grid_expected;
+  const float* grads[EF_DP_MAX_RANKS];
+  uint32_t* signals[EF_DP_MAX_RANKS];
+  float* param;
+  float* m;
+  float* v;
+  float* sqnorm;                 /* [1] receives sum g^2 of the reduced gradient                                        */
+  float* scratch;
+  uint32_t* status;
+} ef_dp_step_params;
+int ef_dp_step(const ef_dp_step_params* p, void* stream);
+int32_t ef_dp_step_grid(int32_t n);
+/* Buffers shared between the ranks through CUDA IPC: ef_ipc_alloc = cudaMalloc (zero-filled) + cudaIpcGetMemHandle (64-byte handle for the
+ * peers); ef_ipc_open = cudaIpcOpenMemHandle with lazy peer access on the CURRENT device; ef_ipc_close / ef_ipc_free undo them. */
+int ef_ipc_alloc(int64_t bytes, void** ptr, unsigned char* handle64);
+int ef_ipc_open(const unsigned char* handle64, void** ptr);
+int ef_ipc_close(void* ptr);
+int ef_ipc_free(void* ptr);
 int ef_clip_adam(float* param, const float* g, float* m, float* v, int64_t n, const float* sqnorm, float max_norm, float lr,
                  float beta1, float beta2, float eps, int32_t step, void* stream);
 

@@ -70,6 +70,7 @@ def test_ctypes_structs_match_c_layout(lib, tmp_path):
         "ef_aee_params": lib.AeeParams,
         "ef_conv_ann_params": lib.ConvAnnParams,
         "ef_ann_gate_bwd_params": lib.AnnGateBwdParams,
+        "ef_dp_step_params": lib.DpStepParams,
         "ef_iwe_image_params": lib.IweImageParams,
         "ef_encode_params": lib.EncodeParams,
     }
