@@ -147,7 +147,7 @@ class ConvAnnParams(C.Structure):
         ("x1_bstride", C.c_int64), ("x2_bstride", C.c_int64), ("x2_scale_bstride", C.c_int64),
         ("w", _f32p), ("bias", _f32p), ("residual", _f32p), ("blend_h", _f32p), ("blend_u", _f32p),
         ("blend_h_bstride", C.c_int64), ("blend_u_bstride", C.c_int64), ("out", _f32p),
-        ("stride", _i32), ("act_out", _f32p),
+        ("stride", _i32), ("act_out", _f32p), ("inference", _i32),
     ]  # fmt: skip
 
 

@@ -13,7 +13,7 @@ U-Net and recurrent block a U-Net model uses) instead of one hand-written subcla
 """
 import torch
 
-from .. import fast, ops
+from .. import fast, graphed, ops
 from . import spiking_submodules as snn
 from . import submodules as ann
 from . import unet as nets
@@ -107,7 +107,7 @@ class FireNet(BaseModel):
     # Run-time caches of the fast path (CUDA graphs, ctypes argument structs, activation slabs, weight images): none of them
     # can or should travel with a checkpoint.  The reference checkpoints by pickling the whole module (utils/utils.py:36,
     # mlflow.pytorch.log_model) and callers deepcopy models; both go through __getstate__.
-    _RUNTIME_KEYS = ("_fast_params", "_fast_cells", "_fast_eligible", "_w_split_cache", "_arena", "_capture", "_last_spikes", "_w_epoch", "_grad_sink")
+    _RUNTIME_KEYS = ("_fast_params", "_fast_cells", "_fast_eligible", "_w_split_cache", "_arena", "_capture", "_last_spikes", "_w_epoch", "_grad_sink") + BaseModel._GRAPH_KEYS
 
     def __getstate__(self):
         state = self.__dict__.copy()
@@ -148,7 +148,7 @@ class FireNet(BaseModel):
     def _apply(self, fn, *args, **kwargs):
         # .to() / .cuda() / .float(): parameter storage moves, so the pointer-keyed caches of the fast path are dropped
         out = super()._apply(fn, *args, **kwargs)
-        for k in ("_fast_params", "_fast_cells", "_fast_eligible", "_w_split_cache", "_arena"):
+        for k in ("_fast_params", "_fast_cells", "_fast_eligible", "_w_split_cache", "_arena") + BaseModel._GRAPH_KEYS:
             self.__dict__.pop(k, None)
         if getattr(self, "_fast", None) is not None:
             self._fast.param_sig = None
@@ -163,7 +163,13 @@ class FireNet(BaseModel):
         x = _network_input(self, event_voxel, event_cnt)
         if fast.eligible(self, x):  # LIF, 32 channels: tcgen05 kernels on the internal spike format, one autograd node per step
             return fast.forward(self, x, log)
+        if graphed.usable(self, x, log):  # evaluation loop (no_grad): the cell-by-cell step below, replayed as one CUDA graph
+            return graphed.step(self, x, self, "_states", self._cell_step)
+        graphed.leave(self, self, "_states")
+        return self._cell_step(x, log)
 
+    def _cell_step(self, x, log=False):
+        """The chain cell by cell (models/model.py:255-286); reads and replaces the entries of self._states."""
         seen, h, gated = [x], x, None
         for i, name in enumerate(_CHAIN):
             cell = getattr(self, name)
@@ -226,6 +232,13 @@ LIFFireFlowNet = _firenet_variant("LIFFireFlowNet", snn.ConvLIF, snn.ConvLIF, sn
 # =====================================================================================================================
 # U-Net models
 # =====================================================================================================================
+class _NoStates:
+    """State holder of the stateless U-Net (EVFlowNet) for graphed.step."""
+
+    def __init__(self):
+        self.states = []
+
+
 class _UNetFlowModel(BaseModel):
     """
     What EVFlowNet (models/model.py:289-395), RecEVFlowNet (:410-547) and E2VID (:29-145) share: the option handling of the
@@ -279,9 +292,18 @@ class _UNetFlowModel(BaseModel):
         x = _network_input(self, event_voxel, event_cnt)
         if self.crop is not None:
             x = self.crop.pad(x)
-        out = self.net.forward(x)
         if log:
             raise NotImplementedError("Activity logging not implemented")
+        where = nets.state_list_of(self.net, x)  # None: the spiking U-Net's tensor-core inference path (own state format, own launches)
+        if where is not None:
+            holder, attr = where if where[0] is not None else (self.__dict__.setdefault("_no_states", _NoStates()), "states")
+            if graphed.usable(self, x):  # evaluation loop (no_grad): the step below replayed as one CUDA graph
+                return graphed.step(self, x, holder, attr, self._net_step)
+            graphed.leave(self, holder, attr)
+        return self._net_step(x)
+
+    def _net_step(self, x):
+        out = self.net.forward(x)
         if isinstance(out, (list, tuple)):  # multi-resolution estimates: nearest-neighbour upsampling to the finest one
             full_h, full_w = out[-1].shape[2], out[-1].shape[3]
             flows = [ops.upsample_nearest(f, full_h // f.shape[2], full_w // f.shape[3]) for f in out]

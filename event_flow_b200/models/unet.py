@@ -149,6 +149,19 @@ class SpikingMultiResUNetRecurrent(nn.Module):
         return predictions
 
 
+def state_list_of(net, x):
+    """
+    Where a U-Net keeps the plain list of its recurrent states, as (object, attribute name) -- (None, None) for the stateless U-Net --,
+    or None if the step on `x` runs on the spiking U-Net's tensor-core inference path (states in its internal format).
+    """
+    if isinstance(net, SpikingMultiResUNetRecurrent):
+        if fast_unet.eligible(net, x):
+            return None
+        net.states  # (materialises the reference-format list if the last step left the internal format)
+        return net, "_states"
+    return (net, "states") if hasattr(net, "states") else (None, None)
+
+
 class MultiResUNet(nn.Module):
     """
     ANN multi-resolution U-Net of EV-FlowNet (models/unet.py:224-311): four stride-2 conv encoders, two residual blocks, four

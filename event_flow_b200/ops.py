@@ -900,10 +900,12 @@ def conv_ann(x1, weight, bias, act, *, x2=None, x2_scale=None, residual=None, bl
                                               for t in (x1, x2, x2_scale, weight, bias, residual, blend_h, blend_u))
     if tracked:
         return _ConvAnn.apply(x1, x2, x2_scale, weight, bias, residual, blend_h, blend_u, act, int(stride))
-    return _conv_ann_launch(x1, weight, bias, act, x2=x2, x2_scale=x2_scale, residual=residual, blend_h=blend_h, blend_u=blend_u, stride=stride)[0]
+    return _conv_ann_launch(x1, weight, bias, act, x2=x2, x2_scale=x2_scale, residual=residual, blend_h=blend_h, blend_u=blend_u, stride=stride,
+                            inference=True)[0]
 
 
-def _conv_ann_launch(x1, weight, bias, act, *, x2=None, x2_scale=None, residual=None, blend_h=None, blend_u=None, stride=1, want_act_out=False):
+def _conv_ann_launch(x1, weight, bias, act, *, x2=None, x2_scale=None, residual=None, blend_h=None, blend_u=None, stride=1, want_act_out=False,
+                     inference=False):
     x1 = x1 if _plane_ok(x1) else x1.contiguous()
     tensors = [x2, x2_scale, residual, blend_h, blend_u]
     tensors = [t if _plane_ok(t) else t.contiguous() for t in tensors]
@@ -920,7 +922,7 @@ def _conv_ann_launch(x1, weight, bias, act, *, x2=None, x2_scale=None, residual=
     act_out = torch.empty_like(out) if want_act_out else None
     p = L.ConvAnnParams()
     p.B, p.C1, p.C2, p.Cout, p.H, p.W, p.act = B, C1, C2, Cout, H, W, _ACT_CODES[act]
-    p.stride = int(stride)
+    p.stride, p.inference = int(stride), int(bool(inference))
     raw = lambda t: None if t is None else t.data_ptr()  # noqa: E731  (slices are not "contiguous"; strides are passed explicitly)
     p.x1, p.x2, p.x2_scale = raw(x1), raw(x2), raw(x2_scale)
     p.x1_bstride = x1.stride(0)

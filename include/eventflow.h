@@ -391,6 +391,8 @@ typedef struct ef_conv_ann_params {
   float* out;                    /* [B,Cout,Ho,Wo]                                                                     */
   int32_t stride;                /* 1 (0 = 1) or 2: output Ho = (H-1)/stride + 1; residual / blend / out at the output size */
   float* act_out;                /* [B,Cout,Ho,Wo] or NULL: the activation BEFORE the blend (kept for the backward)      */
+  int32_t inference;             /* != 0: no backward pass follows -- small launches may split the input-channel sum over thread
+                                  * groups (latency shape; sums differ in the last bit from the sequential channel order)     */
 } ef_conv_ann_params;
 
 int ef_conv_ann_fwd(const ef_conv_ann_params* p, void* stream);

@@ -90,6 +90,7 @@ def run(name, cls, cfg, B, N, H, W, T, bins, gain, dev, peaks=None, reps=3):
         loss.backward()
         model.detach_states()
 
+    fwd()  # (the no-grad step of the cell-by-cell models becomes a CUDA graph on its second visit: event_flow_b200/graphed.py)
     ms_f = _timed(fwd, reps)
     # tensor-core work of one forward window: multiply-accumulates of the general tcgen05 cell launches, counted from their arguments
     macs, orig = [0, 0], L.call
