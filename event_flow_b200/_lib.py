@@ -47,8 +47,17 @@ class LifConvBwdParams(C.Structure):
         ("g_x", _f32p), ("g_v_in", _f32p), ("g_z_in", _f32p), ("g_aux_in", _f32p),
         ("g_w_ff", _f32p), ("g_w_rec", _f32p), ("g_leak", _f32p), ("g_thresh", _f32p), ("g_leak_aux", _f32p),
         ("g_add_pt", _f32p), ("g_t0", _f32p), ("g_t1", _f32p), ("scratch_gI_up", _f32p), ("scratch_gP_up", _f32p),
-        ("reset_grad", _i32),
+        ("reset_grad", _i32), ("neuron_only", _i32),
     ]  # fmt: skip
+
+
+class Conv32BwdTcParams(C.Structure):
+    _fields_ = [
+        ("B", _i32), ("H", _i32), ("W", _i32), ("has_rec", _i32),
+        ("gI", _f32p), ("x_cl", C.c_void_p), ("z_in_cl", C.c_void_p), ("w_bwd", C.c_void_p), ("gI_hi", C.c_void_p), ("gI_mid", C.c_void_p),
+        ("g_x", _f32p), ("g_z_in", _f32p), ("g_z_tmp", _f32p), ("wg_partial", _f32p), ("wg_flags", _i32), ("g_w_ff", _f32p), ("g_w_rec", _f32p),
+        ("gP_sum", _f32p), ("x_f32", _f32p),
+    ]
 
 
 class LifBwdTcParams(C.Structure):
@@ -207,6 +216,7 @@ EXPORTS = {
     "ef_lif_neuron_fwd": (C.c_int, [C.POINTER(LifConvParams), C.c_void_p, C.c_void_p]),
     "ef_lif_conv_bwd": (C.c_int, [C.POINTER(LifConvBwdParams), C.c_void_p]),
     "ef_lif_bwd_tc": (C.c_int, [C.POINTER(LifBwdTcParams), C.c_void_p]),
+    "ef_conv32_bwd_tc": (C.c_int, [C.POINTER(Conv32BwdTcParams), C.c_void_p]),
     "ef_lif_bwd_window": (C.c_int, [C.POINTER(LifBwdWindowParams), C.c_void_p]),
     "ef_lif_wgrad_tc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, _i32, _i32, _i32, _i32, C.c_void_p, _i32, C.c_void_p, C.c_void_p,
                                   C.c_void_p]),

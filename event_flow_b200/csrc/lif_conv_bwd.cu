@@ -347,7 +347,7 @@ extern "C" int ef_lif_conv_bwd(const ef_lif_conv_bwd_params* q, void* stream) {
   const int Ho = (p.H - 1) / p.stride + 1, Wo = (p.W - 1) / p.stride + 1;
 
   float* gP_sum = nullptr;
-  if ((p.neuron == EF_PLIF || p.neuron == EF_XLIF) && q->g_x) {
+  if ((p.neuron == EF_PLIF || p.neuron == EF_XLIF) && (q->g_x || (q->neuron_only && q->scratch_gP))) {
     EF_REQUIRE(q->scratch_gP, EF_ENULL, "ef_lif_conv_bwd: PLIF / XLIF data gradient needs scratch_gP");
     gP_sum = q->scratch_gP;
     cudaMemsetAsync(gP_sum, 0, (size_t)p.B * Ho * Wo * sizeof(float), st);
@@ -366,6 +366,7 @@ extern "C" int ef_lif_conv_bwd(const ef_lif_conv_bwd_params* q, void* stream) {
     default: return fail(EF_EINVAL, "ef_lif_conv_bwd: bad neuron kind %d", p.neuron);
   }
   if (rc) return rc;
+  if (q->neuron_only) return EF_OK;
 
   // gradient of the feed-forward conv output at the resolution the stride-1 kernels expect
   const float* gI_ff = q->scratch_gI;

@@ -969,3 +969,80 @@ extern "C" int ef_lif_wgrad_tc(const uint16_t* x_cl, const uint16_t* z_in_cl, co
   EF_REQUIRE(x_cl && gI_hi && gI_mid && wg_partial, EF_ENULL, "ef_lif_wgrad_tc: NULL tensor");
   return run_wgrad(x_cl, z_in_cl, gI_hi, gI_mid, has_rec != 0, B, H, W, wg_partial, wg_flags, g_w_ff, g_w_rec, as_stream(stream));
 }
+
+namespace ef {
+
+// g_I fp32 NCHW [B,32,H,W] -> two bf16 channels-last terms [B,H,W,32] (hi + mid = g_I to 16 significant bits): the operand format of
+// the tensor-core gradient kernels, for a g_I that some other neuron backward (PLIF / ALIF / XLIF: lif_bwd_pointwise_kernel) produced.
+__global__ void __launch_bounds__(256) split2_pack_cl_kernel(const float* __restrict__ src, uint16_t* __restrict__ hi, uint16_t* __restrict__ mid, int B,
+                                                            size_t hw) {
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;  // over B * 4 channel groups * hw, pixel fastest
+  if (i >= (size_t)B * 4 * hw) return;
+  const size_t pix = i % hw, bg = i / hw;
+  const int g = (int)(bg % 4);
+  const size_t b = bg / 4;
+  const float* s = src + (b * 32 + g * 8) * hw + pix;
+  uint32_t h[4], m[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) split2_bf16(s[(2 * k) * hw], s[(2 * k + 1) * hw], h[k], m[k]);
+  const size_t o = (b * hw + pix) * 32 + g * 8;
+  *reinterpret_cast<uint4*>(hi + o) = make_uint4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<uint4*>(mid + o) = make_uint4(m[0], m[1], m[2], m[3]);
+}
+
+// after the tensor-core data gradient: g_z_in += conv^T part (kept apart because g_z_in already holds the neuron's direct terms) and the
+// PLIF / XLIF trace term of g_x, sign(x) / 32 * adjoint of the 3x3 average pool of gP_sum (as conv_dgrad_kernel adds it)
+__global__ void __launch_bounds__(256) conv32_bwd_fixup_kernel(float* __restrict__ g_x, const float* __restrict__ x, const float* __restrict__ gP_sum,
+                                                              float* __restrict__ g_z_in, const float* __restrict__ g_z_tmp, int B, int H, int W) {
+  const size_t hw = (size_t)H * W, n = (size_t)B * hw;
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  const size_t b = i / hw, pix = i % hw;
+  const int y = (int)(pix / W), xq = (int)(pix % W);
+  float tr = 0.f;
+  if (gP_sum) {
+    for (int dy = -1; dy <= 1; ++dy)
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int yy = y + dy, xx = xq + dx;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) tr += gP_sum[(b * H + yy) * W + xx];
+      }
+    tr = tr / 9.0f / 32.0f;
+  }
+#pragma unroll 4
+  for (int c = 0; c < 32; ++c) {
+    const size_t o = (b * 32 + c) * hw + pix;
+    if (gP_sum) {
+      const float xv = x[o];
+      g_x[o] += (xv > 0.f ? tr : (xv < 0.f ? -tr : 0.f));
+    }
+    if (g_z_in) g_z_in[o] += g_z_tmp[o];
+  }
+}
+
+}  // namespace ef
+
+extern "C" int ef_conv32_bwd_tc(const ef_conv32_bwd_tc_params* pp, void* stream) {
+  using namespace ef;
+  EF_REQUIRE(pp, EF_ENULL, "ef_conv32_bwd_tc: params is NULL");
+  const ef_conv32_bwd_tc_params& p = *pp;
+  EF_REQUIRE(p.B > 0 && p.H > 0 && p.W > 0 && p.W % 4 == 0, EF_EINVAL, "ef_conv32_bwd_tc: bad dimensions (W must be a multiple of 4)");
+  EF_REQUIRE(p.gI && p.x_cl && p.w_bwd && p.gI_hi && p.gI_mid && p.g_x, EF_ENULL, "ef_conv32_bwd_tc: NULL tensor");
+  EF_REQUIRE(!p.g_z_in || p.g_z_tmp, EF_ENULL, "ef_conv32_bwd_tc: g_z_in needs g_z_tmp");
+  EF_REQUIRE(!p.gP_sum || p.x_f32, EF_ENULL, "ef_conv32_bwd_tc: the trace term needs the fp32 input");
+  EF_REQUIRE(!(p.g_w_ff || p.g_w_rec) || p.wg_partial, EF_ENULL, "ef_conv32_bwd_tc: weight gradients need wg_partial");
+  cudaStream_t st = as_stream(stream);
+  const bool rec = p.has_rec != 0;
+  const size_t hw = (size_t)p.H * p.W, n = (size_t)p.B * 4 * hw;
+  split2_pack_cl_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p.gI, p.gI_hi, p.gI_mid, p.B, hw);
+  int rc;
+  if ((rc = check_launch("split2_pack_cl_kernel"))) return rc;
+  float* gz = (rec && p.z_in_cl && p.g_z_in) ? p.g_z_tmp : nullptr;
+  if ((rc = run_dgrad(p.gI_hi, p.gI_mid, p.w_bwd, rec, p.g_x, gz, p.B, p.H, p.W, st))) return rc;
+  if (gz || p.gP_sum) {
+    const size_t m = (size_t)p.B * hw;
+    conv32_bwd_fixup_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(p.g_x, p.x_f32, p.gP_sum, gz ? p.g_z_in : nullptr, gz, p.B, p.H, p.W);
+    if ((rc = check_launch("conv32_bwd_fixup_kernel"))) return rc;
+  }
+  if (p.g_w_ff || p.g_w_rec) return run_wgrad(p.x_cl, p.z_in_cl, p.gI_hi, p.gI_mid, rec, p.B, p.H, p.W, p.wg_partial, p.wg_flags, p.g_w_ff, p.g_w_rec, st);
+  return EF_OK;
+}

@@ -85,7 +85,9 @@ class _CellStep(torch.autograd.Function):
         _fill_cell_params(p, neuron, x, state_in, w_ff, w_rec, chan, residual, state_out, out, hard_reset, surrogate, width, stride)
         if _tc_conv_ok(x, w_ff, w_rec, stride, x_kind):
             # 32-channel cell of ANY neuron kind: the convolution on the tensor cores (exact products), the neuron update on its current
-            cur = _tc_conv_current(x, state_in, w_ff, w_rec, x_kind)
+            cur, x_cl, z_in_cl = _tc_conv_current(x, state_in, w_ff, w_rec, x_kind)
+            if x_kind == "spikes":  # the backward runs its convolution gradients on the tensor cores from the same operands
+                ctx.tc_operands = (x_cl, z_in_cl)
             # the same spikes also in the internal format, for the next cell's / next step's tensor-core convolution (no re-packing)
             out_cl = torch.empty((B, Ho, Wo, Cout), device=x.device, dtype=torch.bfloat16)
             p.out_cl = L.ptr(out_cl)
@@ -100,6 +102,8 @@ class _CellStep(torch.autograd.Function):
             L.call("ef_lif_conv_fwd", p, tag=(x.shape[1], Cout, w_rec is not None))
         ctx.meta = meta
         ctx.chan_names = names
+        if not hasattr(ctx, "tc_operands"):
+            ctx.tc_operands = None
         ctx.save_for_backward(x, state_in, w_ff, w_rec, residual, state_out, *[chan[n] for n in names])
         ctx.chan_shapes = [v.shape for v in chan_vals]
         ctx.has_residual = residual is not None
@@ -157,7 +161,37 @@ class _CellStep(torch.autograd.Function):
             else:
                 g_chan.append(None)
         q.reset_grad = int(not detach and g_state_in is not None)
-        L.call("ef_lif_conv_bwd", q)
+        if ctx.tc_operands is not None and (need[1] or need[3] or need[4] or g_state_in is not None):
+            # 32 -> 32 cell on spike inputs: neuron backward here, the convolution gradients on the tensor cores (any neuron kind)
+            x_cl, z_in_cl = ctx.tc_operands
+            if scratch_p is None and neuron in ("plif", "xlif"):
+                scratch_p = torch.empty((B, Ho, Wo), device=dev, dtype=torch.float32)
+                q.scratch_gP = L.ptr(scratch_p)
+            q.neuron_only = 1
+            L.call("ef_lif_conv_bwd", q)
+            rec = w_rec is not None
+            t = L.Conv32BwdTcParams()
+            t.B, t.H, t.W, t.has_rec = B, H, W, int(rec)
+            t.gI, t.x_cl, t.z_in_cl = L.ptr(scratch), L.ptr(x_cl), L.ptr(z_in_cl)
+            t.w_bwd = L.ptr(_weight_image(w_ff, w_rec, "bwd"))
+            gI_split = torch.empty((2, B, H, W, 32), device=dev, dtype=torch.bfloat16)
+            t.gI_hi, t.gI_mid = L.ptr(gI_split[0]), L.ptr(gI_split[1])
+            g_x_tc = g_x if g_x is not None else torch.empty_like(x)
+            t.g_x = L.ptr(g_x_tc)
+            g_z_tmp = None
+            if rec and z_in_cl is not None and g_state_in is not None:
+                g_z_tmp = torch.empty((B, 32, H, W), device=dev, dtype=torch.float32)
+                t.g_z_in, t.g_z_tmp = L.ptr(g_state_in[1]), L.ptr(g_z_tmp)
+            partial = None
+            if g_w_ff is not None or g_w_rec is not None:
+                partial = torch.empty(L.lib().ef_lif_wgrad_partial_elems(B, H, W, int(rec)), device=dev, dtype=torch.float32)
+                t.wg_partial, t.wg_flags = L.ptr(partial), L.EF_WG_FINALIZE
+                t.g_w_ff, t.g_w_rec = L.ptr(g_w_ff), L.ptr(g_w_rec)
+            if scratch_p is not None:
+                t.gP_sum, t.x_f32 = L.ptr(scratch_p), L.ptr(x)
+            L.call("ef_conv32_bwd_tc", t)
+        else:
+            L.call("ef_lif_conv_bwd", q)
         g_res = g_out if (ctx.has_residual and need[5]) else None
         return (None, g_x, g_state_in, g_w_ff, g_w_rec, g_res, *g_chan)
 
@@ -176,6 +210,27 @@ def _tc_conv_ok(x, w_ff, w_rec, stride, x_kind):
     return x_kind == "split" and x.shape[1] <= L.EF_HEAD_MAX_CIN and w_rec is None
 
 
+def _weight_image(w_ff, w_rec, kind):
+    """
+    bf16 operand image of a cell's weights for the tensor-core kernels -- kind "spikes" / "split": forward (ef_split_weights /
+    ef_split_weights_head), "bwd": data gradient (ef_split_weights_bwd).  Rebuilt when the weight tensors changed (torch's version
+    counters; WEIGHT_EPOCH for in-place updates behind them); keyed on the identity of the weight tensor OBJECTS, held weakly: a freed
+    tensor's address may be reused by other values.
+    """
+    key = (w_ff.data_ptr(), w_ff._version, None if w_rec is None else (w_rec.data_ptr(), w_rec._version), WEIGHT_EPOCH, kind)
+    slot = (id(w_ff), kind == "bwd")
+    hit = _TC_IMAGES.get(slot)
+    if hit is None or hit[0] != key or hit[2]() is not w_ff or (w_rec is not None and hit[3]() is not w_rec):
+        if kind == "bwd":
+            image = split_weights_bwd(w_ff, w_rec)
+        else:
+            image = split_weights_head(w_ff) if kind == "split" else split_weights(w_ff, w_rec)
+        if len(_TC_IMAGES) > 128:
+            _TC_IMAGES.clear()
+        hit = _TC_IMAGES[slot] = (key, image, weakref.ref(w_ff), None if w_rec is None else weakref.ref(w_rec))
+    return hit[1]
+
+
 def _tc_conv_current(x, state_in, w_ff, w_rec, x_kind):
     """cur = conv(x, w_ff) (+ conv(z_in, w_rec)) [B,32,H,W] fp32 on the tensor cores: the fused LIF kernel run as a pure convolution --
     leak = -inf makes sigmoid(leak) = 0, so its membrane output is (1 - 0) * current exactly, whatever state it is given."""
@@ -184,16 +239,7 @@ def _tc_conv_current(x, state_in, w_ff, w_rec, x_kind):
     if consts is None:
         consts = _TC_CONSTS[dev] = (torch.full((32,), float("-inf"), device=dev), torch.ones(32, device=dev))
     neg_inf, ones = consts
-    # weight image: rebuilt when the weight tensors changed (torch's version counters; WEIGHT_EPOCH for in-place updates behind them)
-    # (keyed on the identity of the weight tensor OBJECTS, held weakly: a freed tensor's address may be reused by other values)
-    key = (w_ff.data_ptr(), w_ff._version, None if w_rec is None else (w_rec.data_ptr(), w_rec._version), WEIGHT_EPOCH, x_kind)
-    hit = _TC_IMAGES.get(id(w_ff))
-    if hit is None or hit[0] != key or hit[2]() is not w_ff or (w_rec is not None and hit[3]() is not w_rec):
-        image = split_weights_head(w_ff) if x_kind == "split" else split_weights(w_ff, w_rec)
-        if len(_TC_IMAGES) > 64:
-            _TC_IMAGES.clear()
-        hit = _TC_IMAGES[id(w_ff)] = (key, image, weakref.ref(w_ff), None if w_rec is None else weakref.ref(w_rec))
-    image = hit[1]
+    image = _weight_image(w_ff, w_rec, x_kind)
     # input / previous spikes in the internal format: handed over by the cell that produced them (attributes of the tensors), else packed here
     # (a hand-over is only trusted while the fp32 tensor it mirrors is unmodified: torch's version counter)
     def handed(t, name):
@@ -212,7 +258,7 @@ def _tc_conv_current(x, state_in, w_ff, w_rec, x_kind):
         if z_cl is None:
             z_cl = pack_cl(state_in[1])
     cur, _ = lif_step_cl(x_cl, v_in, z_cl, w_ff, w_rec, neg_inf, ones, hard_reset=True, w_split=image)
-    return cur
+    return cur, x_cl, z_cl
 
 
 WEIGHT_EPOCH = 0

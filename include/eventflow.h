@@ -154,9 +154,39 @@ typedef struct ef_lif_conv_bwd_params {
   float* scratch_gP_up;         /* stride 2, PLIF / XLIF with g_x: [B,H,W] workspace                                      */
   int32_t reset_grad;           /* 1: the reset term is differentiable (cells built with detach=False, spiking_submodules.py:110-112): */
                                 /* dL/dz_in also receives -leak v_in g_v (hard reset) / -thresh g_v (soft reset); needs g_z_in          */
+  int32_t neuron_only;          /* 1: stop after the neuron backward -- scratch_gI (and scratch_gP, if given), g_v_in, the direct terms */
+                                /* of g_z_in and the per-channel gradients are produced, the convolution gradients are the caller's     */
+                                /* (ef_conv32_bwd_tc)                                                                                   */
 } ef_lif_conv_bwd_params;
 
 int ef_lif_conv_bwd(const ef_lif_conv_bwd_params* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Convolution gradients of a 32 -> 32, 3x3, stride-1 cell step on the tensor cores, for ANY neuron kind: what
+ * ef_lif_conv_bwd computes after its neuron backward, given that backward's g_I (scratch_gI of a neuron_only call).  The
+ * cell's inputs must be exact in bf16 (spikes, sums of spikes).  g_I is split into two bf16 terms (16 significant bits,
+ * as in ef_lif_bwd_tc).  g_x is overwritten; g_z_in is ADDED to (it holds the direct terms of the neuron backward);
+ * the weight gradients follow the wg_partial protocol of ef_lif_bwd_tc.
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct ef_conv32_bwd_tc_params {
+  int32_t B, H, W, has_rec;
+  const float* gI;               /* [B,32,H,W] dL/d(synaptic current)                                                   */
+  const uint16_t* x_cl;          /* [B,H,W,32] bf16 input of the step                                                   */
+  const uint16_t* z_in_cl;       /* [B,H,W,32] bf16 previous spikes, or NULL                                            */
+  const uint16_t* w_bwd;         /* ef_split_weights_bwd image                                                          */
+  uint16_t* gI_hi;               /* [B,H,W,32] workspace                                                                */
+  uint16_t* gI_mid;              /* [B,H,W,32] workspace                                                                */
+  float* g_x;                    /* [B,32,H,W]                                                                          */
+  float* g_z_in;                 /* [B,32,H,W] += or NULL                                                               */
+  float* g_z_tmp;                /* [B,32,H,W] workspace (with g_z_in)                                                  */
+  float* wg_partial;             /* ef_lif_wgrad_partial_elems() floats (with g_w_ff / g_w_rec)                         */
+  int32_t wg_flags;              /* EF_WG_*                                                                             */
+  float* g_w_ff;                 /* [32,32,3,3] += or NULL                                                              */
+  float* g_w_rec;                /* [32,32,3,3] += or NULL                                                              */
+  const float* gP_sum;           /* [B,H,W] or NULL: PLIF / XLIF trace gradient (scratch_gP of the neuron backward):    */
+  const float* x_f32;            /* [B,32,H,W] fp32 input (sign of x), needed with gP_sum; g_x += sign(x)/32 pool^T(gP) */
+} ef_conv32_bwd_tc_params;
+int ef_conv32_bwd_tc(const ef_conv32_bwd_tc_params* p, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Backward of a 32 -> 32 LIF cell-step on the fast-path formats (same maths as ef_lif_conv_bwd; tensor-core data gradient).

@@ -66,6 +66,7 @@ def test_ctypes_structs_match_c_layout(lib, tmp_path):
         "ef_iwe_loss_pass_params": lib.IweLossPassParams,
         "ef_iwe_interp_params": lib.IweInterpParams,
         "ef_lif_bwd_tc_params": lib.LifBwdTcParams,
+        "ef_conv32_bwd_tc_params": lib.Conv32BwdTcParams,
         "ef_iwe_metrics_params": lib.IweMetricsParams,
         "ef_aee_params": lib.AeeParams,
         "ef_conv_ann_params": lib.ConvAnnParams,
