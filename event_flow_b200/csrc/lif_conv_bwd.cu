@@ -45,33 +45,72 @@ __global__ void __launch_bounds__(PW_THREADS) lif_bwd_pointwise_kernel(const ef_
   const float oml = 1.0f - k.lam;
 
   float s_lam = 0.f, s_thr = 0.f, s_rho = 0.f, s_alpha = 0.f, s_t0 = 0.f, s_t1 = 0.f;
-  const size_t pix0 = ((size_t)blockIdx.x * PW_THREADS) * PW_PER_THREAD + threadIdx.x;
+  // a thread owns PW_PER_THREAD consecutive pixels: every tensor is read with ONE 16-byte load per thread (planes whose size is a
+  // multiple of 4 -- else element by element), all loads issued before the arithmetic, results leave as 16-byte stores
+  const size_t pix0 = ((size_t)blockIdx.x * PW_THREADS + threadIdx.x) * PW_PER_THREAD;
+  static_assert(PW_PER_THREAD == 4, "one float4 per tensor and thread");
+  const uintptr_t all_ptrs = (uintptr_t)p.v_in | (uintptr_t)p.z_in | (uintptr_t)p.aux_in | (uintptr_t)p.v_out | (uintptr_t)p.aux_out | (uintptr_t)q.g_out |
+                             (uintptr_t)q.g_z_out | (uintptr_t)q.g_v_out | (uintptr_t)q.g_aux_out | (uintptr_t)q.scratch_gI | (uintptr_t)q.g_v_in |
+                             (uintptr_t)q.g_z_in | (uintptr_t)q.g_aux_in;
+  const bool vec = (plane & 3) == 0 && (all_ptrs & 15) == 0;
+  const size_t o0 = base + pix0;
+  auto ld4 = [&](const float* __restrict__ ptr, float (&d)[4]) {
+    if (!ptr || pix0 >= plane) {
+      d[0] = d[1] = d[2] = d[3] = 0.f;
+    } else if (vec) {
+      const float4 t = *reinterpret_cast<const float4*>(ptr + o0);
+      d[0] = t.x, d[1] = t.y, d[2] = t.z, d[3] = t.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) d[j] = (pix0 + j < plane) ? ptr[o0 + j] : 0.f;
+    }
+  };
+  auto st4 = [&](float* __restrict__ ptr, const float (&d)[4]) {
+    if (!ptr || pix0 >= plane) return;
+    if (vec) {
+      *reinterpret_cast<float4*>(ptr + o0) = make_float4(d[0], d[1], d[2], d[3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (pix0 + j < plane) ptr[o0 + j] = d[j];
+    }
+  };
+  float v_p4[4], z_p4[4], a_p4[4], v_n4[4], a_n4[4], g_o4[4], g_zo4[4], g_vo4[4], g_ao4[4];
+  ld4(p.v_in, v_p4);
+  if (p.z_in) {
+    ld4(p.z_in, z_p4);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) z_p4[j] = (p.z_in_cl && pix0 + j < plane) ? ld_act2(p.z_in, p.z_in_cl, b, c, pix0 + j, p.C, plane) : 0.f;
+  }
+  ld4(NEURON != EF_LIF ? p.aux_in : nullptr, a_p4);
+  ld4(p.v_out, v_n4);
+  ld4(NEURON != EF_LIF ? p.aux_out : nullptr, a_n4);
+  ld4(q.g_out, g_o4);
+  ld4(q.g_z_out, g_zo4);
+  ld4(q.g_v_out, g_vo4);
+  ld4(NEURON != EF_LIF ? q.g_aux_out : nullptr, g_ao4);
+  float gI4[4], g_vi4[4], g_zi4[4], g_ai4[4];
+  const float inv_oml = 1.0f / oml, inv_omr = (NEURON == EF_PLIF || NEURON == EF_XLIF) ? 1.0f / (1.0f - k.rho) : 0.f;
 #pragma unroll
   for (int i = 0; i < PW_PER_THREAD; ++i) {
-    const size_t pix = pix0 + (size_t)i * PW_THREADS;
-    if (pix >= plane) break;
-    const size_t o = base + pix;
-    const float v_p = p.v_in ? p.v_in[o] : 0.f;
-    float z_p = 0.f;
-    if (p.z_in || p.z_in_cl) z_p = ld_act2(p.z_in, p.z_in_cl, b, c, pix, p.C, plane);
-    const float a_p = (NEURON != EF_LIF && p.aux_in) ? p.aux_in[o] : 0.f;
-    const float v_n = p.v_out[o];
-    const float a_n = (NEURON != EF_LIF) ? p.aux_out[o] : 0.f;
+    const size_t pix = pix0 + i;
+    const bool live = pix < plane;
+    const float v_p = v_p4[i], z_p = z_p4[i], a_p = a_p4[i], v_n = v_n4[i], a_n = a_n4[i];
     const float thr_t = (NEURON == EF_LIF || NEURON == EF_PLIF) ? k.thr : (k.t0 + k.t1 * a_n);
-    const float g_z = (q.g_out ? q.g_out[o] : 0.f) + (q.g_z_out ? q.g_z_out[o] : 0.f);
-    const float sg = surrogate_grad(p.surrogate, v_n - thr_t, p.act_width);
+    const float g_z = g_o4[i] + g_zo4[i];
+    const float sg = live ? surrogate_grad(p.surrogate, v_n - thr_t, p.act_width) : 0.f;
     const float g_thr = -g_z * sg;  // dL/d thresh_t
-    const float g_v = (q.g_v_out ? q.g_v_out[o] : 0.f) + g_z * sg;
-    const float g_I = oml * g_v;
-    q.scratch_gI[o] = g_I;
-    const float g_aux_n = (NEURON != EF_LIF && q.g_aux_out) ? q.g_aux_out[o] : 0.f;
+    const float g_v = g_vo4[i] + g_z * sg;
+    gI4[i] = oml * g_v;
+    const float g_aux_n = g_ao4[i];
 
     // what the (1-lam) factor multiplied in the forward ("drive"), recovered from v_out
     const float reset_thr = (NEURON == EF_LIF || NEURON == EF_PLIF) ? k.thr : (k.t0 + k.t1 * a_p);
     const float keep = HARD ? v_p * (1.0f - z_p) : v_p;
-    const float drive = HARD ? (v_n - k.lam * keep) / oml : (v_n - k.lam * v_p + z_p * reset_thr) / oml;
+    const float drive = HARD ? (v_n - k.lam * keep) * inv_oml : (v_n - k.lam * v_p + z_p * reset_thr) * inv_oml;
     s_lam += g_v * (keep - drive);
-    if (q.g_v_in) q.g_v_in[o] = HARD ? g_v * k.lam * (1.0f - z_p) : g_v * k.lam;
+    g_vi4[i] = HARD ? g_v * k.lam * (1.0f - z_p) : g_v * k.lam;
 
     float g_z_direct = 0.f, g_aux_p = 0.f;
     if (NEURON == EF_LIF) {
@@ -80,10 +119,10 @@ __global__ void __launch_bounds__(PW_THREADS) lif_bwd_pointwise_kernel(const ef_
       s_thr += g_thr - (HARD ? 0.f : z_p * g_v);
       const float g_pt = g_aux_n - oml * k.alpha * g_v;
       s_alpha += -oml * a_n * g_v;
-      const float P = (a_n - k.rho * a_p) / (1.0f - k.rho);
+      const float P = (a_n - k.rho * a_p) * inv_omr;
       s_rho += g_pt * (a_p - P);
       g_aux_p = k.rho * g_pt;
-      if (gP_sum) atomicAdd(gP_sum + (size_t)b * plane + pix, (1.0f - k.rho) * g_pt);
+      if (gP_sum && live) atomicAdd(gP_sum + (size_t)b * plane + pix, (1.0f - k.rho) * g_pt);
     } else if (NEURON == EF_ALIF) {
       const float g_a = g_aux_n + k.t1 * g_thr;
       s_t0 += g_thr - (HARD ? 0.f : z_p * g_v);
@@ -95,16 +134,20 @@ __global__ void __launch_bounds__(PW_THREADS) lif_bwd_pointwise_kernel(const ef_
       const float g_pt = g_aux_n + k.t1 * g_thr;
       s_t0 += g_thr - (HARD ? 0.f : z_p * g_v);
       s_t1 += g_thr * a_n - (HARD ? 0.f : z_p * a_p * g_v);
-      const float P = (a_n - k.rho * a_p) / (1.0f - k.rho);
+      const float P = (a_n - k.rho * a_p) * inv_omr;
       s_rho += g_pt * (a_p - P);
       g_aux_p = k.rho * g_pt - (HARD ? 0.f : z_p * k.t1 * g_v);
-      if (gP_sum) atomicAdd(gP_sum + (size_t)b * plane + pix, (1.0f - k.rho) * g_pt);
+      if (gP_sum && live) atomicAdd(gP_sum + (size_t)b * plane + pix, (1.0f - k.rho) * g_pt);
     }
     if (q.reset_grad)  // differentiable reset (detach=False): the previous spikes also act through the reset term of v_out
       g_z_direct -= HARD ? g_v * k.lam * v_p : g_v * reset_thr;
-    if (q.g_z_in) q.g_z_in[o] = g_z_direct;  // the recurrent dgrad (launch 2) accumulates on top
-    if (NEURON != EF_LIF && q.g_aux_in) q.g_aux_in[o] = g_aux_p;
+    g_zi4[i] = g_z_direct;  // the recurrent dgrad (launch 2) accumulates on top
+    g_ai4[i] = g_aux_p;
   }
+  st4(q.scratch_gI, gI4);
+  st4(q.g_v_in, g_vi4);
+  st4(q.g_z_in, g_zi4);
+  if (NEURON != EF_LIF) st4(q.g_aux_in, g_ai4);
 
   // per-channel raw-parameter gradients: chain through sigmoid / clamp_min
   float r;
