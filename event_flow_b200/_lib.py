@@ -308,6 +308,12 @@ def check(rc, what):
         raise EventFlowError(f"{what} failed (rc={rc}): {msg}")
 
 
+def planes(t):
+    """Device pointers of the slices t[0], t[1], ... of a contiguous CUDA tensor (no view tensors are created)."""
+    base, step = ptr(t), t.stride(0) * t.element_size()
+    return [base + i * step for i in range(t.shape[0])]
+
+
 def ptr(t):
     """Device pointer of a tensor (or None).  Tensors must be contiguous CUDA tensors."""
     if t is None:
@@ -320,7 +326,8 @@ def ptr(t):
 
 
 def stream():
-    return torch.cuda.current_stream().cuda_stream
+    """Raw handle of torch's current stream on the current device (the C-level getter: the Stream object costs several microseconds)."""
+    return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
 
 
 PROFILE = None  # set to a list to record (name, tag, start_event, end_event) around every struct-taking call (bench.py roofline)

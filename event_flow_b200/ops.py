@@ -52,17 +52,19 @@ def _fill_cell_params(p, neuron, x, state_in, w_ff, w_rec, chan, residual, state
     p.surrogate, p.act_width = L.SURROGATE_CODES[surrogate], float(width)
     p.x = L.ptr(x)
     if state_in is not None:
-        p.v_in, p.z_in = L.ptr(state_in[0]), L.ptr(state_in[1])
-        if state_in.shape[0] > 2:
-            p.aux_in = L.ptr(state_in[2])
+        planes = L.planes(state_in)
+        p.v_in, p.z_in = planes[0], planes[1]
+        if len(planes) > 2:
+            p.aux_in = planes[2]
     p.w_ff, p.w_rec = L.ptr(w_ff), L.ptr(w_rec)
     for field, name in zip(_STRUCT_FIELDS, _PARAM_FIELDS[neuron]):
         if name is not None:
             setattr(p, field, L.ptr(chan[name]))
     p.residual = L.ptr(residual)
-    p.v_out, p.z_out = L.ptr(state_out[0]), L.ptr(state_out[1])
-    if state_out.shape[0] > 2:
-        p.aux_out = L.ptr(state_out[2])
+    planes = L.planes(state_out)
+    p.v_out, p.z_out = planes[0], planes[1]
+    if len(planes) > 2:
+        p.aux_out = planes[2]
     p.out = L.ptr(out)
 
 
@@ -124,9 +126,10 @@ class _CellStep(torch.autograd.Function):
         g_state = _c(g_state)
         q.g_out = L.ptr(g_out)
         if g_state is not None:
-            q.g_v_out, q.g_z_out = L.ptr(g_state[0]), L.ptr(g_state[1])
+            planes = L.planes(g_state)
+            q.g_v_out, q.g_z_out = planes[0], planes[1]
             if S > 2:
-                q.g_aux_out = L.ptr(g_state[2])
+                q.g_aux_out = planes[2]
         scratch = torch.empty((B, Cout, Ho, Wo), device=dev, dtype=torch.float32)
         q.scratch_gI = L.ptr(scratch)
         need = ctx.needs_input_grad  # (meta, x, state_in, w_ff, w_rec, residual, *chan)
@@ -145,9 +148,10 @@ class _CellStep(torch.autograd.Function):
         g_state_in = None
         if state_in is not None and need[2]:
             g_state_in = torch.empty_like(state_in)
-            q.g_v_in, q.g_z_in = L.ptr(g_state_in[0]), L.ptr(g_state_in[1])
+            planes = L.planes(g_state_in)
+            q.g_v_in, q.g_z_in = planes[0], planes[1]
             if S > 2:
-                q.g_aux_in = L.ptr(g_state_in[2])
+                q.g_aux_in = planes[2]
         g_w_ff = torch.zeros_like(w_ff) if need[3] else None
         q.g_w_ff = L.ptr(g_w_ff)
         g_w_rec = torch.zeros_like(w_rec) if (w_rec is not None and need[4]) else None
@@ -175,13 +179,13 @@ class _CellStep(torch.autograd.Function):
             t.gI, t.x_cl, t.z_in_cl = L.ptr(scratch), L.ptr(x_cl), L.ptr(z_in_cl)
             t.w_bwd = L.ptr(_weight_image(w_ff, w_rec, "bwd"))
             gI_split = torch.empty((2, B, H, W, 32), device=dev, dtype=torch.bfloat16)
-            t.gI_hi, t.gI_mid = L.ptr(gI_split[0]), L.ptr(gI_split[1])
+            t.gI_hi, t.gI_mid = L.planes(gI_split)
             g_x_tc = g_x if g_x is not None else torch.empty_like(x)
             t.g_x = L.ptr(g_x_tc)
             g_z_tmp = None
             if rec and z_in_cl is not None and g_state_in is not None:
                 g_z_tmp = torch.empty((B, 32, H, W), device=dev, dtype=torch.float32)
-                t.g_z_in, t.g_z_tmp = L.ptr(g_state_in[1]), L.ptr(g_z_tmp)
+                t.g_z_in, t.g_z_tmp = q.g_z_in, L.ptr(g_z_tmp)
             partial = None
             if g_w_ff is not None or g_w_rec is not None:
                 partial = torch.empty(L.lib().ef_lif_wgrad_partial_elems(B, H, W, int(rec)), device=dev, dtype=torch.float32)

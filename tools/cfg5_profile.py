@@ -54,6 +54,17 @@ def main(cls="ALIFFireNet", B=8, N=1000, H=128, W=128, T=20, bins=5, gain=2.5):
     torch.cuda.synchronize()
     t3 = time.perf_counter()
     print(f"{cls}: host forward {1e3 * (t1 - t0):.1f} ms, host backward {1e3 * (t2 - t1):.1f} ms, wall {1e3 * (t3 - t0):.1f} ms")
+    if os.environ.get("EF_CPROFILE"):
+        import cProfile
+        import pstats
+
+        pr = cProfile.Profile()
+        pr.enable()
+        train()
+        pr.disable()
+        torch.cuda.synchronize()
+        pstats.Stats(pr).sort_stats("tottime").print_stats(38)
+        return
     with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
         train()
         torch.cuda.synchronize()
