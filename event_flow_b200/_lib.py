@@ -171,6 +171,7 @@ class DpStepParams(C.Structure):
         ("epoch", C.c_uint32), ("epoch_launches", C.c_uint32), ("graceful", _i32), ("grid_expected", _i32),
         ("grads", _f32p * EF_DP_MAX_RANKS), ("signals", _f32p * EF_DP_MAX_RANKS),
         ("param", _f32p), ("m", _f32p), ("v", _f32p), ("sqnorm", _f32p), ("scratch", _f32p), ("status", _f32p),
+        ("timeout_ms", _i32),
     ]  # fmt: skip
 
 

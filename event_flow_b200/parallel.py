@@ -112,6 +112,8 @@ class _PeerStep:
         p.world, p.rank, p.n, p.step = self.world, self.rank, tr.n, int(step)
         p.clip, p.lr, p.beta1, p.beta2, p.eps = float(tr.clip) if tr.clip else 0.0, tr.lr, tr.betas[0], tr.betas[1], tr.eps
         p.epoch, p.epoch_launches, p.graceful, p.grid_expected = self.epoch, self.epoch, int(graceful), self.grid
+        # how long a rank waits for late peers inside the kernel: the self test gives up quickly, training waits like NCCL's watchdog would
+        p.timeout_ms = 5000 if graceful else int(float(os.environ.get("EF_DP_TIMEOUT_S", "600")) * 1000)
         for r in range(self.world):
             p.grads[r], p.signals[r] = self.grad_ptrs[r], self.signal_ptrs[r]
         p.param, p.m, p.v = L.ptr(param), L.ptr(m), L.ptr(v)

@@ -671,6 +671,8 @@ typedef struct ef_dp_step_params {
   float* sqnorm;                 /* [1] receives sum g^2 of the reduced gradient                                        */
   float* scratch;
   uint32_t* status;
+  int32_t timeout_ms;            /* how long a rank waits for its peers before it gives up (status word, then trap unless graceful);   */
+                                 /* <= 0: 600 000 (ten minutes, NCCL's watchdog default) -- peers may legitimately be late (I/O, validation) */
 } ef_dp_step_params;
 int ef_dp_step(const ef_dp_step_params* p, void* stream);
 int32_t ef_dp_step_grid(int32_t n);
