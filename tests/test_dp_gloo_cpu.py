@@ -244,3 +244,54 @@ def test_synthetic_stream_shards_are_disjoint_and_reproducible():
     a2 = SyntheticEventStream(2, 50, (16, 16), 2, "cpu", rank=0).host_events(3)
     assert torch.equal(a, a2) and not torch.equal(a, b)
     assert a.shape == (2, 50, 4) and a[:, :, 0].min() == 0 and a[:, :, 0].max() == 1 and set(a[:, :, 3].unique().tolist()) <= {-1.0, 1.0}
+
+
+def test_rebinding_the_gradient_buffer_keeps_contents_views_and_sink():
+    """
+    The fused peer-memory step moves the flat gradient into a buffer the peers can map (parallel._PeerStep -> _bind_grad): the gradient
+    accumulated so far, the p.grad views, the offsets of _view_of and the model's gradient sink must all follow.
+    """
+    from event_flow_b200.parallel import DataParallelTrainer
+
+    torch.manual_seed(1)
+    model = make_model()
+    tr = DataParallelTrainer(model, lr=1e-2, clip_grad=5.0, kernels=TorchKernels)
+    x = batch(0)
+    (model(x) ** 2).sum().backward()
+    before = tr.flat_grad.clone()
+    assert before.abs().sum() > 0
+    shared = torch.full((tr.n,), 7.0)
+    tr._bind_grad(shared)
+    assert tr.flat_grad is shared and torch.equal(shared, before)
+    assert model.__dict__["_grad_sink"] is shared
+    o = 0
+    for p in tr.params:
+        assert p.grad.data_ptr() == shared[o:o + p.numel()].data_ptr() and p.grad.shape == p.shape
+        assert tr._view_of(p).data_ptr() == p.grad.data_ptr()
+        o += p.numel()
+    (model(x) ** 2).sum().backward()  # autograd accumulates into the new buffer
+    assert torch.allclose(shared, 2 * before)
+    tr.step()
+    assert shared.abs().max().item() == 0.0
+
+
+def test_graph_replay_bookkeeping_on_nested_states():
+    """Pure host logic of event_flow_b200/graphed.py: leaf order, structure signatures and rebuilding of nested recurrent states."""
+    from event_flow_b200 import graphed
+
+    a, b, c = torch.zeros(2, 3), torch.ones(4), torch.zeros(1)
+    states = [None, a, (b, c), [None, a]]
+    leaves = graphed._flat(states, [])
+    assert [t is u for t, u in zip(leaves, (a, b, c, a))] == [True] * 4
+    sig = graphed._shape_of(states)
+    assert sig == graphed._shape_of([None, a.clone(), (b.clone(), c.clone()), [None, a.clone()]])
+    assert sig != graphed._shape_of([None, a, (b, c), [a, None]]) and sig != graphed._shape_of([None, a.t(), (b, c), [None, a]])
+    fresh = [t + 1 for t in leaves]
+    rebuilt = graphed._rebuild(states, iter(fresh))
+    assert rebuilt[0] is None and rebuilt[1] is fresh[0] and type(rebuilt[2]) is tuple and rebuilt[2][1] is fresh[2] and rebuilt[3][1] is fresh[3]
+    m = torch.nn.Linear(2, 2)
+    assert not graphed.usable(m, torch.zeros(1, 2))  # CPU tensors never take the graph path
+    holder = type("H", (), {})()
+    holder.states = states
+    graphed.leave(m, holder, "states")  # no graphs: a no-op
+    assert holder.states is states
