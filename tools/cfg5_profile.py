@@ -1,4 +1,4 @@
-"""Kernel-time breakdown of one PLIF / ALIF FireNet training window (cfg 5) with torch.profiler: device time per kernel vs wall time."""
+"""Kernel-time breakdown of one PLIF / ALIF FireNet (cfg 5) or spiking EV-FlowNet (cfg 4) training window with torch.profiler: device time per kernel vs wall time."""
 import os
 import sys
 import time
@@ -12,13 +12,18 @@ from tools.bench_configs import FIRE, _events  # noqa: E402
 
 
 def main(cls="ALIFFireNet", B=8, N=1000, H=128, W=128, T=20, bins=5, gain=2.5):
+    cfg = FIRE
+    if cls.endswith("EVFlowNet"):  # cfg 4: the U-Net family at 256x256, 50k events per window, batch 4
+        from tools.bench_configs import UNET
+
+        cfg, B, N, H, W, T, bins, gain = UNET, 4, 50000, 256, 256, 4, 2, 3.0
     import event_flow_b200.models.model as M
     from event_flow_b200.dataloader.encodings import encode_batch
     from event_flow_b200.loss.flow import EventWarping
 
     dev = torch.device("cuda")
     torch.manual_seed(0)
-    model = getattr(M, cls)(dict(FIRE))
+    model = getattr(M, cls)(dict(cfg))
     with torch.no_grad():
         for n, p in model.named_parameters():
             if n.endswith("ff.weight") or n.endswith("rec.weight"):
