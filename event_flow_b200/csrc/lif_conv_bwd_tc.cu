@@ -972,20 +972,26 @@ extern "C" int ef_lif_wgrad_tc(const uint16_t* x_cl, const uint16_t* z_in_cl, co
 
 namespace ef {
 
-// g_I fp32 NCHW [B,32,H,W] -> two bf16 channels-last terms [B,H,W,32] (hi + mid = g_I to 16 significant bits): the operand format of
-// the tensor-core gradient kernels, for a g_I that some other neuron backward (PLIF / ALIF / XLIF: lif_bwd_pointwise_kernel) produced.
+// g_I fp32 NCHW [B,C,Hs,Ws] -> two bf16 channels-last terms [B,H,W,C] (hi + mid = g_I to 16 significant bits): the operand format of
+// the tensor-core gradient kernels, for a g_I that some other neuron backward (lif_bwd_pointwise_kernel) produced.  up = 2: the output is
+// the zero-inserted form at twice the resolution (H = 2 Hs or 2 Hs - 1), what the data gradient of a stride-2 convolution convolves.
 __global__ void __launch_bounds__(256) split2_pack_cl_kernel(const float* __restrict__ src, uint16_t* __restrict__ hi, uint16_t* __restrict__ mid, int B,
-                                                            size_t hw) {
-  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;  // over B * 4 channel groups * hw, pixel fastest
-  if (i >= (size_t)B * 4 * hw) return;
+                                                            int C, int H, int W, int Hs, int Ws, int up) {
+  const size_t hw = (size_t)H * W, hws = (size_t)Hs * Ws;
+  const int G = C >> 3;
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;  // over B * C/8 channel groups * hw, pixel fastest
+  if (i >= (size_t)B * G * hw) return;
   const size_t pix = i % hw, bg = i / hw;
-  const int g = (int)(bg % 4);
-  const size_t b = bg / 4;
-  const float* s = src + (b * 32 + g * 8) * hw + pix;
-  uint32_t h[4], m[4];
+  const int g = (int)(bg % G);
+  const size_t b = bg / G;
+  uint32_t h[4] = {0, 0, 0, 0}, m[4] = {0, 0, 0, 0};
+  const int y = (int)(pix / W), x = (int)(pix % W);
+  if (up == 1 || ((x | y) & 1) == 0) {
+    const float* s = src + (b * C + g * 8) * hws + (up == 1 ? pix : (size_t)(y >> 1) * Ws + (x >> 1));
 #pragma unroll
-  for (int k = 0; k < 4; ++k) split2_bf16(s[(2 * k) * hw], s[(2 * k + 1) * hw], h[k], m[k]);
-  const size_t o = (b * hw + pix) * 32 + g * 8;
+    for (int k = 0; k < 4; ++k) split2_bf16(s[(2 * k) * hws], s[(2 * k + 1) * hws], h[k], m[k]);
+  }
+  const size_t o = (b * hw + pix) * C + g * 8;
   *reinterpret_cast<uint4*>(hi + o) = make_uint4(h[0], h[1], h[2], h[3]);
   *reinterpret_cast<uint4*>(mid + o) = make_uint4(m[0], m[1], m[2], m[3]);
 }
@@ -1033,7 +1039,7 @@ extern "C" int ef_conv32_bwd_tc(const ef_conv32_bwd_tc_params* pp, void* stream)
   cudaStream_t st = as_stream(stream);
   const bool rec = p.has_rec != 0;
   const size_t hw = (size_t)p.H * p.W, n = (size_t)p.B * 4 * hw;
-  split2_pack_cl_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p.gI, p.gI_hi, p.gI_mid, p.B, hw);
+  split2_pack_cl_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p.gI, p.gI_hi, p.gI_mid, p.B, 32, p.H, p.W, p.H, p.W, 1);
   int rc;
   if ((rc = check_launch("split2_pack_cl_kernel"))) return rc;
   float* gz = (rec && p.z_in_cl && p.g_z_in) ? p.g_z_tmp : nullptr;
@@ -1045,4 +1051,19 @@ extern "C" int ef_conv32_bwd_tc(const ef_conv32_bwd_tc_params* pp, void* stream)
   }
   if (p.g_w_ff || p.g_w_rec) return run_wgrad(p.x_cl, p.z_in_cl, p.gI_hi, p.gI_mid, rec, p.B, p.H, p.W, p.wg_partial, p.wg_flags, p.g_w_ff, p.g_w_rec, st);
   return EF_OK;
+}
+
+// g fp32 NCHW [B,C,Hs,Ws] (C a multiple of 8) -> hi / mid bf16 channels-last [B,H,W,C]; (H, W) = (Hs, Ws), or the zero-inserted form at
+// the resolution (H, W) of a stride-2 convolution's input (Hs = (H-1)/2 + 1): the sources of a data gradient that runs as a plain
+// convolution on the general tensor-core kernel (ef_lif_conv_fwd_g with flipped / transposed weights).
+extern "C" int ef_split2_pack_cl(const float* src, uint16_t* hi, uint16_t* mid, int32_t B, int32_t C, int32_t H, int32_t W, int32_t Hs, int32_t Ws,
+                                 void* stream) {
+  using namespace ef;
+  EF_REQUIRE(src && hi && mid, EF_ENULL, "ef_split2_pack_cl: NULL tensor");
+  EF_REQUIRE(B > 0 && C > 0 && C % 8 == 0 && H > 0 && W > 0, EF_EINVAL, "ef_split2_pack_cl: C must be a positive multiple of 8");
+  const bool same = Hs == H && Ws == W, up2 = Hs == (H - 1) / 2 + 1 && Ws == (W - 1) / 2 + 1;
+  EF_REQUIRE(same || up2, EF_EINVAL, "ef_split2_pack_cl: source %dx%d is neither the output size %dx%d nor its stride-2 size", Hs, Ws, H, W);
+  const size_t n = (size_t)B * (C / 8) * H * W;
+  split2_pack_cl_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(src, hi, mid, B, C, H, W, Hs, Ws, same ? 1 : 2);
+  return check_launch("split2_pack_cl_kernel");
 }

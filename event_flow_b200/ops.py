@@ -68,6 +68,82 @@ def _fill_cell_params(p, neuron, x, state_in, w_ff, w_rec, chan, residual, state
     p.out = L.ptr(out)
 
 
+TCG_BACKWARD = True  # data gradients of cells with C % 32 == 0 outputs on the general tensor-core kernel (tests switch it off to compare)
+
+
+def _tcg_dgrad_ok(neuron, x, w_ff, stride, wanted):
+    """The convolution data gradients of this cell step can run as plain convolutions on the general tcgen05 kernel (_tcg_dgrad)."""
+    Cout, Cin = w_ff.shape[0], w_ff.shape[1]
+    H, W = x.shape[2], x.shape[3]
+    return (TCG_BACKWARD and wanted and x.is_cuda and neuron in ("lif", "alif") and w_ff.shape[-1] == 3 and Cout % 32 == 0 and Cout >= 32
+            and Cin >= 16 and stride in (1, 2) and W % 4 == 0 and ((W - 1) // stride + 1) % 4 == 0 and (stride == 1 or (H % 2 == 0 and W % 2 == 0)))
+
+
+def _tcg_consts(dev, C):
+    """Per-channel constants that turn the fused LIF kernel into a plain convolution: leak = -inf (sigmoid = 0), threshold 1."""
+    key = (dev, C)
+    hit = _TC_CONSTS.get(key)
+    if hit is None:
+        hit = _TC_CONSTS[key] = (torch.full((C,), float("-inf"), device=dev), torch.ones(C, device=dev))
+    return hit
+
+
+def _dgrad_image(w, rec_w=None):
+    """
+    Weight image of the DATA GRADIENT of a 3x3 convolution run as a convolution of g_I = hi + mid on the general tensor-core kernel:
+    the flipped, transposed kernel (rows padded to a multiple of 32 input channels; with `rec_w` the recurrent convolution's gradient
+    rides along as further output channels), once for each of the two g_I sources.  Cached per weight version like the forward images.
+    Returns (image, padded channel count of the feed-forward part, total output channels).
+    """
+    key = (w.data_ptr(), w._version, None if rec_w is None else (rec_w.data_ptr(), rec_w._version), WEIGHT_EPOCH, "dgrad")
+    slot = (id(w), "dgrad", rec_w is not None)
+    hit = _TC_IMAGES.get(slot)
+    if hit is None or hit[0] != key or hit[2]() is not w or (rec_w is not None and hit[3]() is not rec_w):
+        Cout, Cin = w.shape[0], w.shape[1]
+        cpad = (Cin + 31) // 32 * 32
+        wd = torch.zeros((cpad, Cout, 3, 3), device=w.device, dtype=torch.float32)
+        wd[:Cin] = w.detach().flip(2, 3).transpose(0, 1)
+        if rec_w is not None:
+            wd = torch.cat([wd, rec_w.detach().flip(2, 3).transpose(0, 1)], 0)
+        wd = wd.contiguous()
+        image = split_weights_g([(wd, 0, Cout, False), (wd, 0, Cout, False)], wd.shape[0])
+        if len(_TC_IMAGES) > 128:
+            _TC_IMAGES.clear()
+        hit = _TC_IMAGES[slot] = (key, (image, cpad, wd.shape[0]), weakref.ref(w), None if rec_w is None else weakref.ref(rec_w))
+    return hit[1]
+
+
+def _tcg_conv_of_grad(g, image, c_total, H, W):
+    """conv3x3(g, flipped kernel) on the general tensor-core kernel: g fp32 NCHW [B,C,Hs,Ws] enters as two bf16 terms, zero-inserted to
+    (H, W) when it is the output gradient of a stride-2 convolution.  Returns fp32 NCHW [B,c_total,H,W]."""
+    B, Cg, Hs, Ws = g.shape
+    terms = torch.empty((2, B, H, W, Cg), device=g.device, dtype=torch.bfloat16)
+    hi, mid = L.planes(terms)
+    L.LAUNCHES += 1
+    L.check(L.lib().ef_split2_pack_cl(L.ptr(g), hi, mid, B, Cg, H, W, Hs, Ws, L.stream()), "ef_split2_pack_cl")
+    neg_inf, ones = _tcg_consts(g.device, c_total)
+    v, _, _ = lif_step_g([terms[0], terms[1]], None, None, image, neg_inf, ones, c_total)
+    return v
+
+
+def _tcg_dgrad(gI, w_ff, w_rec, stride, H, W, want_x, want_z):
+    """Data gradients of a cell step's convolutions: (g_x [B,Cin,H,W] | None, recurrent part of g_z_in [B,C,Ho,Wo] | None)."""
+    Cin = w_ff.shape[1]
+    g_x = g_z = None
+    if stride == 1 and want_x and want_z:  # one launch: the recurrent gradient as extra output channels
+        image, cpad, ctot = _dgrad_image(w_ff, w_rec)
+        v = _tcg_conv_of_grad(gI, image, ctot, H, W)
+        return v[:, :Cin].contiguous(), v[:, cpad:].contiguous()
+    if want_x:
+        image, cpad, ctot = _dgrad_image(w_ff)
+        v = _tcg_conv_of_grad(gI, image, ctot, H, W)
+        g_x = v if cpad == Cin else v[:, :Cin].contiguous()
+    if want_z:
+        image, cpad, ctot = _dgrad_image(w_rec)
+        g_z = _tcg_conv_of_grad(gI, image, ctot, gI.shape[2], gI.shape[3])
+    return g_x, g_z
+
+
 class _CellStep(torch.autograd.Function):
     """One fused conv + neuron step on fp32 NCHW tensors (the reference cells' own tensor contract)."""
 
@@ -194,6 +270,25 @@ class _CellStep(torch.autograd.Function):
             if scratch_p is not None:
                 t.gP_sum, t.x_f32 = L.ptr(scratch_p), L.ptr(x)
             L.call("ef_conv32_bwd_tc", t)
+        elif _tcg_dgrad_ok(neuron, x, w_ff, stride, g_x is not None or (w_rec is not None and g_state_in is not None)):
+            # other channel counts (the U-Net family): neuron backward, data gradients as plain convolutions of g_I on the general
+            # tensor-core kernel, weight gradients on the CUDA cores
+            q.neuron_only = 1
+            L.call("ef_lif_conv_bwd", q)
+            want_z = w_rec is not None and g_state_in is not None
+            tc_x, tc_z = _tcg_dgrad(scratch, w_ff, w_rec if want_z else None, stride, H, W, g_x is not None, want_z)
+            if tc_x is not None:
+                g_x = tc_x
+            if tc_z is not None:
+                g_state_in[1] += tc_z
+            if g_w_ff is not None:
+                L.LAUNCHES += 1
+                L.check(L.lib().ef_conv3x3_bwd_s(L.ptr(scratch), L.ptr(x), L.ptr(w_ff), None, L.ptr(g_w_ff), L.ptr(scratch_up), B, Cin, Cout, H, W, int(stride),
+                                                 L.stream()), "ef_conv3x3_bwd_s")
+            if g_w_rec is not None and state_in is not None:
+                L.LAUNCHES += 1
+                L.check(L.lib().ef_conv3x3_bwd(L.ptr(scratch), L.planes(state_in)[1], L.ptr(w_rec), None, L.ptr(g_w_rec), B, Cout, Cout, Ho, Wo, L.stream()),
+                        "ef_conv3x3_bwd")
         else:
             L.call("ef_lif_conv_bwd", q)
         g_res = g_out if (ctx.has_residual and need[5]) else None

@@ -187,6 +187,10 @@ typedef struct ef_conv32_bwd_tc_params {
   const float* x_f32;            /* [B,32,H,W] fp32 input (sign of x), needed with gP_sum; g_x += sign(x)/32 pool^T(gP) */
 } ef_conv32_bwd_tc_params;
 int ef_conv32_bwd_tc(const ef_conv32_bwd_tc_params* p, void* stream);
+/* g fp32 NCHW [B,C,Hs,Ws] (C % 8 == 0) -> two bf16 channels-last terms hi / mid [B,H,W,C] (hi + mid = g to 16 significant bits), at the
+ * same resolution or zero-inserted to the input resolution (H, W) of a stride-2 convolution (Hs = (H-1)/2 + 1): the two sources of a
+ * data gradient computed as a plain convolution by ef_lif_conv_fwd_g (autograd of the cells with other channel counts than 32). */
+int ef_split2_pack_cl(const float* src, uint16_t* hi, uint16_t* mid, int32_t B, int32_t C, int32_t H, int32_t W, int32_t Hs, int32_t Ws, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Backward of a 32 -> 32 LIF cell-step on the fast-path formats (same maths as ef_lif_conv_bwd; tensor-core data gradient).

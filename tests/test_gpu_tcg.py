@@ -155,3 +155,47 @@ def test_stride2_cell_on_space_to_depth_input(cin, C, shape, with_state):
     zf = ops.unpack_cl(z).cpu()
     check(v, zf, ns_o, p["thresh"].clamp_min(0.01), 9 * cin)
     assert zf.mean() > 0.01
+
+
+@pytest.mark.parametrize("neuron", ["lif", "alif"])
+@pytest.mark.parametrize("cin,C,stride,rec,shape", [(64, 96, 1, True, (2, 24, 32)), (32, 64, 2, False, (2, 32, 48)), (66, 32, 1, False, (1, 20, 24)),
+                                                    (128, 128, 1, True, (1, 16, 16))])
+def test_data_gradient_as_convolution_on_the_general_kernel(neuron, cin, C, stride, rec, shape):
+    """
+    Backward of a cell step with other channel counts than 32 (the U-Net family): neuron backward + the data gradients as plain
+    convolutions of g_I (two bf16 terms, zero-inserted for stride 2, flipped / transposed weights) on ef_lif_conv_fwd_g, against the
+    CUDA-core data gradient of ef_lif_conv_bwd on the same tensors: 1e-4 of each gradient's scale (g_I carries 16 significant bits).
+    """
+    from event_flow_b200 import ops
+
+    B, H, W = shape
+    g = torch.Generator().manual_seed(cin + C + stride)
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    x = (torch.rand(B, cin, H, W, generator=g) < 0.2).float()
+    n_state = 2 if neuron == "lif" else 3
+    st = torch.randn(n_state, B, C, Ho, Wo, generator=g) * 0.5
+    st[1] = (st[1] > 0.3).float()
+    if n_state == 3:
+        st[2] = st[2].abs() * 0.3
+    w = {"ff": (torch.rand(C, cin, 3, 3, generator=g) * 2 - 1) * math.sqrt(1 / cin) * 2.0}
+    if rec:
+        w["rec"] = (torch.rand(C, C, 3, 3, generator=g) * 2 - 1) * math.sqrt(1 / C) * 2.0
+    chan = {n: (torch.randn(C, 1, 1, generator=g) * 0.1 + (0.8 if n in ("thresh", "t0") else (-4.0 if n == "leak" else 0.1))).to(DEV)
+            for n in ops.param_names(neuron)}
+    g_out, g_ns = torch.randn(B, C, Ho, Wo, generator=g).to(DEV), torch.randn(n_state, B, C, Ho, Wo, generator=g).to(DEV)
+    res = {}
+    for tc in (True, False):
+        ops.TCG_BACKWARD = tc
+        try:
+            xd, sd = x.to(DEV).requires_grad_(True), st.to(DEV).requires_grad_(True)
+            ws = {k: v.to(DEV).requires_grad_(True) for k, v in w.items()}
+            n0 = ops.L.lib().ef_launch_count() if hasattr(ops.L.lib(), "ef_launch_count") else 0
+            out, ns = ops.cell_step(neuron, xd, sd, ws["ff"], ws.get("rec"), chan, hard_reset=True, stride=stride)
+            torch.autograd.backward([out, ns], [g_out, g_ns])
+            res[tc] = (xd.grad.cpu(), sd.grad.cpu(), {k: v.grad.cpu() for k, v in ws.items()})
+        finally:
+            ops.TCG_BACKWARD = True
+    for a, b, what in ((res[True][0], res[False][0], "g_x"), (res[True][1], res[False][1], "g_state")) + tuple(
+            (res[True][2][k], res[False][2][k], "g_" + k) for k in w):
+        assert (a - b).abs().max().item() <= 1e-4 * (b.abs().max().item() + 1e-20), what
+    assert not torch.equal(res[True][0], res[False][0])  # (the two paths really are different kernels)
