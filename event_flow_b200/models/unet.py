@@ -10,7 +10,8 @@ import torch.nn as nn
 
 from .. import fast_unet
 from .model_util import skip_concat, skip_sum  # noqa: F401  (resolved by name like the reference: "skip_" + skip_type)
-from .spiking_submodules import SpikingRecurrentConvLayer, SpikingResidualBlock, SpikingTransposedConvLayer, SpikingUpsampleConvLayer
+from .spiking_submodules import (SpikingRecurrentConvLayer, SpikingResidualBlock, SpikingTransposedConvLayer, SpikingUpsampleConvLayer,
+                                 _SpikingConvCell)
 from .submodules import (ConvLayer, LeakyRecurrentConvLayer, LeakyResidualBlock, LeakyTransposedConvLayer, LeakyUpsampleConvLayer,
                          RecurrentConvLayer, ResidualBlock, TransposedConvLayer, UpsampleConvLayer)
 
@@ -62,6 +63,31 @@ class SpikingMultiResUNetRecurrent(nn.Module):
         self.preds = self.build_multires_prediction_layer()
         self.num_states = self.num_encoders * 2 + self.num_residual_blocks
         self.states = [None] * self.num_states
+        self._mark_inputs()
+
+    def _mark_inputs(self):
+        """
+        Tell the cells what their input is (as FireNet._mark_inputs does), so that LIF cells may run on the tensor cores with exact
+        products under autograd as well: every cell after the first sees spikes, sums of spikes or their bilinear x2 upsampling (multiples
+        of 1/16) -- exact in bf16; the decoders after the first additionally see the upsampled flow prediction in their first
+        `num_output_channels` input channels (cat order [prediction, x, skip], forward() below), which enters as its exact split.
+        """
+        if self.skip_type != "concat":
+            return
+
+        def mark(owner, name, kind):
+            cell = getattr(owner, name, None)
+            if isinstance(cell, _SpikingConvCell):  # (the leaky ANN twins share this wiring with other cell classes)
+                cell.__dict__["_x_kind"] = kind
+
+        for i, enc in enumerate(self.encoders):
+            if i > 0:
+                mark(enc, "conv", "spikes")
+            mark(enc, "recurrent_block", "spikes")
+        for r in self.resblocks:
+            mark(r, "conv1", "spikes"), mark(r, "conv2", "spikes")
+        for i, d in enumerate(self.decoders):
+            mark(d, "conv2d", "spikes" if i == 0 else ("mixed", self.num_output_channels))
 
     # The states live either in the reference's format (list of stacked fp32 tensors, what the cell-by-cell path reads and writes) or,
     # after a step of the tensor-core inference path (event_flow_b200/fast_unet.py), in the internal format (membrane fp32 + spikes

@@ -144,6 +144,100 @@ def _tcg_dgrad(gI, w_ff, w_rec, stride, H, W, want_x, want_z):
     return g_x, g_z
 
 
+TCG_FORWARD = True  # forward of LIF cells with C % 32 == 0 outputs under autograd on the general tensor-core kernel (tests switch it off)
+
+
+def _tcg_fwd_ok(neuron, x, state_in, w_ff, w_rec, stride, x_kind, residual):
+    """
+    This LIF cell step can run on the general tcgen05 kernel (ef_lif_conv_fwd_g) with fp32-exact products: the caller vouches for the
+    input -- "spikes": every channel exact in bf16 (spikes, sums of spikes, their bilinear x2 upsampling); ("mixed", n): the first
+    n <= 10 channels are arbitrary fp32 values (they enter as their exact three-way split), the rest exact in bf16.
+    """
+    if not (TCG_FORWARD and neuron == "lif" and x.is_cuda and w_ff.shape[-1] == 3 and w_ff.shape[0] % 32 == 0):
+        return False
+    Cin, H, W = x.shape[1], x.shape[2], x.shape[3]
+    if x_kind == "spikes":
+        if Cin % 32 != 0:
+            return False
+        if stride == 2:
+            return w_rec is None and H % 2 == 0 and W % 2 == 0 and (W // 2) % 4 == 0
+        return stride == 1 and W % 4 == 0
+    if type(x_kind) is tuple and x_kind[0] == "mixed":
+        n = x_kind[1]
+        return stride == 1 and W % 4 == 0 and 0 < n <= L.EF_HEAD_MAX_CIN and (Cin - n) % 32 == 0 and Cin > n and w_rec is None
+    return False
+
+
+def _handed(t, name):
+    """The channels-last companion a producing cell attached to `t`, if `t` was not modified since (torch's version counter)."""
+    hit = getattr(t, name, None)
+    return hit[0] if hit is not None and hit[1] == t._version else None
+
+
+def _fwdg_image(w_ff, w_rec, wsrcs, tag):
+    """Cached ef_split_weights_g image of a cell's weights for one source list (keyed like the other weight images)."""
+    key = (w_ff.data_ptr(), w_ff._version, None if w_rec is None else (w_rec.data_ptr(), w_rec._version), WEIGHT_EPOCH, tag)
+    slot = (id(w_ff), "fwdg", tag)
+    hit = _TC_IMAGES.get(slot)
+    if hit is None or hit[0] != key or hit[2]() is not w_ff or (w_rec is not None and hit[3]() is not w_rec):
+        image = split_weights_g(wsrcs, w_ff.shape[0])
+        if len(_TC_IMAGES) > 128:
+            _TC_IMAGES.clear()
+        hit = _TC_IMAGES[slot] = (key, image, weakref.ref(w_ff), None if w_rec is None else weakref.ref(w_rec))
+    return hit[1]
+
+
+def _tcg_forward(x, state_in, w_ff, w_rec, leak, thresh, residual, state_out, out, hard_reset, stride, x_kind):
+    """The LIF cell step on ef_lif_conv_fwd_g, results written into `state_out` [2,B,C,Ho,Wo] and `out`; returns (out_cl, z_cl)."""
+    B, Cin, H, W = x.shape
+    C = w_ff.shape[0]
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    s2d = stride == 2
+    if x_kind == "spikes":
+        x_cl = _handed(x, "_ef_cl")
+        if x_cl is None or x_cl.shape != (B, H, W, Cin):
+            x_cl = pack_cl(x)
+        srcs, wsrcs, tag = [space_to_depth_cl(x_cl) if s2d else x_cl], [(w_ff, 0, Cin, False, s2d)], ("spikes", s2d)
+    else:
+        n = x_kind[1]
+        srcs = [pack_split_cl(x[:, :n].contiguous()), pack_cl(x[:, n:].contiguous())]
+        wsrcs, tag = [(w_ff, 0, n, True), (w_ff, n, Cin - n, False)], ("mixed", n)
+    z_in_cl = v_in = None
+    if state_in is not None:
+        planes = L.planes(state_in)
+        v_in = planes[0]
+        z_in_cl = _handed(state_in, "_ef_z_cl")
+        if z_in_cl is None:
+            z_in_cl = pack_cl(state_in[1])
+        if w_rec is not None:
+            srcs, wsrcs, tag = srcs + [z_in_cl], wsrcs + [(w_rec, 0, C, False)], tag + ("rec",)
+    image = _fwdg_image(w_ff, w_rec if tag[-1] == "rec" else None, wsrcs, tag)
+    res_cl = None
+    if residual is not None:
+        res_cl = _handed(residual, "_ef_cl")
+        if res_cl is None:
+            res_cl = pack_cl(residual)
+    z_cl = torch.empty((B, Ho, Wo, C), device=x.device, dtype=torch.bfloat16)
+    out_cl = torch.empty_like(z_cl) if res_cl is not None else None
+    p = L.LifConvGParams()
+    p.B, p.H, p.W, p.C, p.n_src, p.hard_reset, p.s2d = B, Ho, Wo, C, len(srcs), int(bool(hard_reset)), int(s2d)
+    for i, t in enumerate(srcs):
+        p.src[i], p.src_c[i] = L.ptr(t), t.shape[3]
+    p.v_in, p.z_in_cl, p.residual_cl = v_in, L.ptr(z_in_cl), L.ptr(res_cl)
+    p.leak, p.thresh, p.w_image = L.ptr(leak), L.ptr(thresh), L.ptr(image)
+    so = L.planes(state_out)
+    p.v_out, p.z_out_cl, p.out_cl = so[0], L.ptr(z_cl), L.ptr(out_cl)
+    L.call("ef_lif_conv_fwd_g", p)
+    L.LAUNCHES += 1
+    L.check(L.lib().ef_unpack_cl(L.ptr(z_cl), so[1], B, C, Ho, Wo, L.stream()), "ef_unpack_cl")
+    if out_cl is not None:
+        L.LAUNCHES += 1
+        L.check(L.lib().ef_unpack_cl(L.ptr(out_cl), L.ptr(out), B, C, Ho, Wo, L.stream()), "ef_unpack_cl")
+    else:
+        out.copy_(state_out[1])
+    return (out_cl if out_cl is not None else z_cl), z_cl
+
+
 class _CellStep(torch.autograd.Function):
     """One fused conv + neuron step on fp32 NCHW tensors (the reference cells' own tensor contract)."""
 
@@ -175,6 +269,10 @@ class _CellStep(torch.autograd.Function):
                 p.z_out_cl = L.ptr(z_cl)
             L.LAUNCHES += 1
             L.check(L.lib().ef_lif_neuron_fwd(C.byref(p), L.ptr(cur), L.stream()), "ef_lif_neuron_fwd")
+            out._ef_cl, state_out._ef_z_cl = (out_cl, out._version), (z_cl, state_out._version)
+        elif _tcg_fwd_ok(neuron, x, state_in, w_ff, w_rec, stride, x_kind, residual):
+            # LIF cell of the U-Net family (other channel counts, stride 2, mixed inputs): the fused general tensor-core kernel
+            out_cl, z_cl = _tcg_forward(x, state_in, w_ff, w_rec, chan["leak"], chan["thresh"], residual, state_out, out, hard_reset, stride, x_kind)
             out._ef_cl, state_out._ef_z_cl = (out_cl, out._version), (z_cl, state_out._version)
         else:
             L.call("ef_lif_conv_fwd", p, tag=(x.shape[1], Cout, w_rec is not None))

@@ -199,3 +199,62 @@ def test_data_gradient_as_convolution_on_the_general_kernel(neuron, cin, C, stri
             (res[True][2][k], res[False][2][k], "g_" + k) for k in w):
         assert (a - b).abs().max().item() <= 1e-4 * (b.abs().max().item() + 1e-20), what
     assert not torch.equal(res[True][0], res[False][0])  # (the two paths really are different kernels)
+
+
+@pytest.mark.parametrize("cin,C,stride,rec,kind,residual,shape", [
+    (64, 96, 1, True, "spikes", False, (2, 24, 32)),       # recurrent block of an encoder
+    (32, 64, 2, False, "spikes", False, (2, 32, 48)),      # stride-2 encoder convolution (space-to-depth source)
+    (64, 64, 1, False, "spikes", True, (1, 20, 24)),       # second cell of a residual block
+    (66, 32, 1, False, ("mixed", 2), False, (2, 16, 32)),  # decoder: [flow prediction (fractional), x, skip]
+    (128, 128, 1, True, "spikes", False, (1, 16, 16))])
+@pytest.mark.parametrize("with_state", [True, False])
+def test_training_forward_of_general_lif_cells_on_the_tensor_cores(cin, C, stride, rec, kind, residual, shape, with_state):
+    """
+    ops.cell_step under autograd for LIF cells with other channel counts than 32 (x_kind vouching for the input): the fused general
+    tcgen05 kernel against the fused CUDA-core kernel and the oracle -- membrane to summation-order noise, spikes exact outside the band,
+    gradients (which read v_out, never the emitted spikes) to 1e-4 of their scale.
+    """
+    from event_flow_b200 import ops
+
+    B, H, W = shape
+    g = torch.Generator().manual_seed(cin + 3 * C + stride)
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    x = (torch.rand(B, cin, H, W, generator=g) < 0.2).float() * torch.randint(1, 3, (B, cin, H, W), generator=g).float() / 16 * 16
+    if type(kind) is tuple:
+        x[:, :kind[1]] = torch.randn(B, kind[1], H, W, generator=g)
+    st = None
+    if with_state:
+        st = torch.randn(2, B, C, Ho, Wo, generator=g) * 0.5
+        st[1] = (st[1] > 0.3).float()
+    params = lif_params(cin, C, rec, seed=5)
+    res_t = (torch.rand(B, C, Ho, Wo, generator=g) < 0.3).float() if residual else None
+    chan = {"leak": params["leak"].to(DEV), "thresh": params["thresh"].to(DEV)}
+    g_out, g_ns = torch.randn(B, C, Ho, Wo, generator=g).to(DEV), torch.randn(2, B, C, Ho, Wo, generator=g).to(DEV)
+    g_ns[1] = 0
+    res = {}
+    for tc in (True, False):
+        ops.TCG_FORWARD = tc
+        try:
+            xd = x.to(DEV).requires_grad_(True)
+            sd = None if st is None else st.to(DEV).requires_grad_(True)
+            ws = {k: params[k].to(DEV).requires_grad_(True) for k in ("ff", "rec") if k in params}
+            rd = None if res_t is None else res_t.to(DEV)
+            n0 = ops.L.LAUNCHES
+            out, ns = ops.cell_step("lif", xd, sd, ws["ff"], ws.get("rec"), chan, hard_reset=True, stride=stride, x_kind=kind, residual=rd)
+            torch.autograd.backward([out, ns], [g_out, g_ns])
+            res[tc] = (out.detach().cpu(), ns.detach().cpu(), xd.grad.cpu(), None if sd is None else sd.grad.cpu(), {k: v.grad.cpu() for k, v in ws.items()})
+        finally:
+            ops.TCG_FORWARD = True
+    out_o, ns_o = osp.cell_step("lif", x, st, params, hard_reset=True, stride=stride, residual=0 if res_t is None else res_t)
+    thr = params["thresh"].clamp_min(0.01)
+    K = 9 * (cin + (C if rec and with_state else 0))
+    scale = max(1.0, math.sqrt(K / 576))
+    for other in (res[False][1], ns_o):
+        spike_band_compare(res[True][1][0], res[True][1][1], other[0], other[1], thr, v_atol=scale * max(2e-5, 3e-6 * other[0].abs().max().item()))
+    extra = 0 if res_t is None else res_t
+    assert torch.equal(res[True][0], res[True][1][1] + extra)
+    assert not torch.equal(res[True][1][0], res[False][1][0])  # (different kernels: only the summation order may differ)
+    for a, b, what in ((res[True][2], res[False][2], "g_x"), (res[True][3], res[False][3], "g_state")) + tuple(
+            (res[True][4][k], res[False][4][k], "g_" + k) for k in res[False][4]):
+        if b is not None:
+            assert (a - b).abs().max().item() <= 1e-4 * (b.abs().max().item() + 1e-20), what
