@@ -219,6 +219,8 @@ EXPORTS = {
     "ef_lif_bwd_tc": (C.c_int, [C.POINTER(LifBwdTcParams), C.c_void_p]),
     "ef_conv32_bwd_tc": (C.c_int, [C.POINTER(Conv32BwdTcParams), C.c_void_p]),
     "ef_split2_pack_cl": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, _i32, _i32, _i32, _i32, _i32, _i32, C.c_void_p]),
+    "ef_wgrad_tcg_partial_elems": (C.c_int64, [_i32, _i32, _i32, _i32, _i32]),
+    "ef_wgrad_tcg": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, _i32, _i32, _i32, _i32, _i32, C.c_void_p, C.c_void_p, _i32, _i32, C.c_void_p]),
     "ef_lif_bwd_window": (C.c_int, [C.POINTER(LifBwdWindowParams), C.c_void_p]),
     "ef_lif_wgrad_tc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, _i32, _i32, _i32, _i32, C.c_void_p, _i32, C.c_void_p, C.c_void_p,
                                   C.c_void_p]),

@@ -743,6 +743,144 @@ __global__ void __launch_bounds__(256) wgrad_reduce_head_kernel(const float* __r
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// (4g) the same weight gradient for GENERAL channel counts (multiples of 32; the U-Net family): the channels-last tensors have
+//      Cin / Cout channels and a CTA works on one PAIR of 32-channel blocks (ci block, co block) -- the block offsets are the channel
+//      coordinates of its TMA boxes -- over its share ("chunk") of the pixel tiles: blockIdx.x = pair * chunks + chunk.  Layers with many
+//      block pairs and few pixels (512 x 512 channels at 16 x 16) spread over the SMs by pair, wide layers with few channels by chunk.
+//      partial[pair][chunk][dy][dx][ci][co]; wgrad_reduce_g_kernel sums the chunks in order (bit-reproducible) into g_w.
+// ---------------------------------------------------------------------------------------------------------------------
+struct WgGParams {
+  int B, H, W, tiles_x, tiles_y, n_tiles, chunks, n_co_blk;
+  float* partial;
+};
+
+__global__ void __launch_bounds__(WG_THREADS, 1)
+lif_wgrad_tcg_kernel(const WgGParams p, const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_hi,
+                     const __grid_constant__ CUtensorMap map_mid) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  constexpr int G_OFF = WG_XTILE;
+  constexpr int STAGE = G_OFF + 2 * WG_GTILE;
+  constexpr int BAR_OFF = WG_NST * STAGE;
+  constexpr uint32_t TMEM_COLS = 256;
+  const uint32_t s_base = smem_u32(smem);
+  const uint32_t bar_w = s_base + BAR_OFF;
+  auto bar_full = [&](int s) { return bar_w + 8u * s; };
+  auto bar_empty = [&](int s) { return bar_w + 8u * (WG_NST + s); };
+  const uint32_t bar_done = bar_w + 8u * (2 * WG_NST);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + BAR_OFF + 8 * (2 * WG_NST + 1));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < WG_NST; ++s) {
+      mbar_init(bar_full(s), 1);
+      mbar_init(bar_empty(s), 1);
+    }
+    mbar_init(bar_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int pair = (int)blockIdx.x / p.chunks, chunk = (int)blockIdx.x - pair * p.chunks;
+  const int ci0 = (pair / p.n_co_blk) * 32, co0 = (pair % p.n_co_blk) * 32;
+  const int n_my = (p.n_tiles - chunk + p.chunks - 1) / p.chunks;
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ---- TMA producer
+      for (int it = 0; it < n_my; ++it) {
+        const int tile = chunk + it * p.chunks;
+        const int b = tile / tiles_per_img, r = tile - b * tiles_per_img, ty = r / p.tiles_x;
+        const int y0 = ty * WG_TH, x0 = (r - ty * p.tiles_x) * WG_TW;
+        const int s = it % WG_NST;
+        mbar_wait(bar_empty(s), ((it / WG_NST) & 1) ^ 1);
+        const uint32_t st = s_base + s * STAGE;
+        mbar_expect_tx(bar_full(s), STAGE);
+        tma_load_4d(st, &map_x, bar_full(s), ci0, x0 - 1, y0 - 1, b);
+        tma_load_4d(st + G_OFF, &map_hi, bar_full(s), co0, x0, y0, b);
+        tma_load_4d(st + G_OFF + WG_GTILE, &map_mid, bar_full(s), co0, x0, y0, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ---- MMA issuer (operand layouts as in lif_wgrad_tc_kernel)
+      constexpr uint32_t IDESC = umma_idesc(64, true, true);
+      for (int it = 0; it < n_my; ++it) {
+        const int s = it % WG_NST;
+        mbar_wait(bar_full(s), (it / WG_NST) & 1);
+        tc_fence_after();
+        const uint32_t st = s_base + s * STAGE;
+        const uint64_t bdesc = umma_desc_sw64_mn(st + G_OFF, WG_GTILE, ATOM_BYTES);
+        const uint64_t adesc = umma_desc_sw64_mn(st, PIX_BYTES, WG_XROW);
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+#pragma unroll
+          for (int ks = 0; ks < WG_TH / 2; ++ks)
+            umma_bf16<IDESC>(tmem_base + dy * 64, adesc + (uint64_t)((2 * ks + dy) * (WG_XROW / 16)), bdesc + (uint64_t)(ks * (2 * ATOM_BYTES / 16)),
+                             (it | ks) != 0);
+        }
+        umma_commit(bar_empty(s));
+      }
+      umma_commit(bar_done);
+    }
+  } else {
+    // ---- epilogue (once): thread = accumulator row m = (dx shift, ci); 64 columns = [hi | mid] x co
+    const int q = warp & 3;
+    mbar_wait(bar_done, 0);
+    tc_fence_after();
+    if (q < 3) {
+#pragma unroll 1
+      for (int dy = 0; dy < 3; ++dy) {
+        const uint32_t tacc = tmem_base + dy * 64 + ((uint32_t)(q * 32) << 16);
+        uint32_t h0[16], h1[16], m0[16], m1[16];
+        tmem_ld16(tacc, h0);
+        tmem_ld16(tacc + 16, h1);
+        tmem_ld16(tacc + 32, m0);
+        tmem_ld16(tacc + 48, m1);
+        tmem_ld_wait();
+        float4* dst = reinterpret_cast<float4*>(p.partial + (size_t)blockIdx.x * WG_SLICE + ((dy * 3 + q) * 32 + lane) * 32);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          dst[j] = make_float4(__uint_as_float(h0[4 * j]) + __uint_as_float(m0[4 * j]), __uint_as_float(h0[4 * j + 1]) + __uint_as_float(m0[4 * j + 1]),
+                               __uint_as_float(h0[4 * j + 2]) + __uint_as_float(m0[4 * j + 2]), __uint_as_float(h0[4 * j + 3]) + __uint_as_float(m0[4 * j + 3]));
+          dst[4 + j] = make_float4(__uint_as_float(h1[4 * j]) + __uint_as_float(m1[4 * j]), __uint_as_float(h1[4 * j + 1]) + __uint_as_float(m1[4 * j + 1]),
+                                   __uint_as_float(h1[4 * j + 2]) + __uint_as_float(m1[4 * j + 2]), __uint_as_float(h1[4 * j + 3]) + __uint_as_float(m1[4 * j + 3]));
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// g_w[co0 + co][ci_off + ci0 + ci][dy][dx] += sum over the chunks (in order) of partial[pair][chunk][dy][dx][ci][co].
+// Block = 8 rows (row = (dy*3 + dx)*32 + ci) x 32 co of one pair.
+__global__ void __launch_bounds__(256) wgrad_reduce_g_kernel(const float* __restrict__ partial, int chunks, int n_co_blk, float* __restrict__ g_w,
+                                                             int cin_total, int ci_off) {
+  const int co = threadIdx.x & 31, row = (blockIdx.x % 36) * 8 + (threadIdx.x >> 5), pair = blockIdx.x / 36;
+  const int ci0 = (pair / n_co_blk) * 32, co0 = (pair % n_co_blk) * 32;
+  const float* src = partial + (size_t)pair * chunks * WG_SLICE + row * 32 + co;
+  float acc = 0.f;
+  for (int c = 0; c < chunks; ++c) acc += __ldg(src + (size_t)c * WG_SLICE);
+  g_w[((size_t)(co0 + co) * cin_total + ci_off + ci0 + (row & 31)) * 9 + (row >> 5)] += acc;
+}
+
+inline int wgg_chunks(int B, int H, int W, int pairs) {
+  const int n_tiles = B * cdiv(W, WG_TW) * cdiv(H, WG_TH);
+  int chunks = cdiv(2 * 148, pairs);
+  return chunks < n_tiles ? chunks : n_tiles;
+}
+
 inline int wg_n_sms() {
   static int n_sms = 0;
   if (n_sms == 0) {
@@ -1066,4 +1204,44 @@ extern "C" int ef_split2_pack_cl(const float* src, uint16_t* hi, uint16_t* mid, 
   const size_t n = (size_t)B * (C / 8) * H * W;
   split2_pack_cl_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(src, hi, mid, B, C, H, W, Hs, Ws, same ? 1 : 2);
   return check_launch("split2_pack_cl_kernel");
+}
+
+// Tensor-core weight gradient for general channel counts: g_w[co][ci_off + ci][dy][dx] += sum_{b,y,x} x_cl[b,y+dy-1,x+dx-1,ci] g[b,y,x,co] with
+// x_cl [B,H,W,cin] (values exact in bf16) and g = g_hi + g_mid [B,H,W,cout] (ef_split2_pack_cl; for a stride-2 convolution its zero-inserted
+// form at the input resolution); cin, cout multiples of 32.  g_w is [cout][cin_total][3][3]; ci_off places the cin channels inside it.
+extern "C" int64_t ef_wgrad_tcg_partial_elems(int32_t B, int32_t H, int32_t W, int32_t cin, int32_t cout) {
+  using namespace ef;
+  if (B <= 0 || H <= 0 || W <= 0 || cin <= 0 || cout <= 0 || cin % 32 || cout % 32) return 0;
+  const int pairs = (cin / 32) * (cout / 32);
+  return (int64_t)pairs * wgg_chunks(B, H, W, pairs) * WG_SLICE;
+}
+extern "C" int ef_wgrad_tcg(const uint16_t* x_cl, const uint16_t* g_hi, const uint16_t* g_mid, int32_t B, int32_t H, int32_t W, int32_t cin, int32_t cout,
+                            float* partial, float* g_w, int32_t cin_total, int32_t ci_off, void* stream) {
+  using namespace ef;
+  EF_REQUIRE(x_cl && g_hi && g_mid && partial && g_w, EF_ENULL, "ef_wgrad_tcg: NULL tensor");
+  EF_REQUIRE(B > 0 && H > 0 && W > 0 && cin > 0 && cout > 0 && cin % 32 == 0 && cout % 32 == 0, EF_EINVAL, "ef_wgrad_tcg: channel counts must be multiples of 32");
+  EF_REQUIRE(ci_off >= 0 && ci_off + cin <= cin_total, EF_EINVAL, "ef_wgrad_tcg: channel slice outside the weight tensor");
+  cudaStream_t st = as_stream(stream);
+  WgGParams w;
+  w.B = B, w.H = H, w.W = W, w.tiles_x = cdiv(W, WG_TW), w.tiles_y = cdiv(H, WG_TH), w.n_tiles = B * w.tiles_x * w.tiles_y;
+  w.n_co_blk = cout / 32;
+  const int pairs = (cin / 32) * w.n_co_blk;
+  w.chunks = wgg_chunks(B, H, W, pairs);
+  w.partial = partial;
+  CUtensorMap mx, gh, gm;
+  int rc;
+  if ((rc = get_map_c(x_cl, B, H, W, cin, WG_TH + 2, WG_TW + 8, true, &mx))) return rc;
+  if ((rc = get_map_c(g_hi, B, H, W, cout, WG_TH, WG_TW, true, &gh))) return rc;
+  if ((rc = get_map_c(g_mid, B, H, W, cout, WG_TH, WG_TW, true, &gm))) return rc;
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(lif_wgrad_tcg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+      return check_launch("cudaFuncSetAttribute(lif_wgrad_tcg_kernel)");
+    attr = true;
+  }
+  const int wsmem = WG_NST * (WG_XTILE + 2 * WG_GTILE) + 256 + 1024;
+  lif_wgrad_tcg_kernel<<<pairs * w.chunks, WG_THREADS, wsmem, st>>>(w, mx, gh, gm);
+  if ((rc = check_launch("lif_wgrad_tcg_kernel"))) return rc;
+  wgrad_reduce_g_kernel<<<pairs * 36, 256, 0, st>>>(partial, w.chunks, w.n_co_blk, g_w, cin_total, ci_off);
+  return check_launch("wgrad_reduce_g_kernel");
 }

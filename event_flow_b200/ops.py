@@ -113,35 +113,52 @@ def _dgrad_image(w, rec_w=None):
     return hit[1]
 
 
-def _tcg_conv_of_grad(g, image, c_total, H, W):
-    """conv3x3(g, flipped kernel) on the general tensor-core kernel: g fp32 NCHW [B,C,Hs,Ws] enters as two bf16 terms, zero-inserted to
-    (H, W) when it is the output gradient of a stride-2 convolution.  Returns fp32 NCHW [B,c_total,H,W]."""
+def _grad_terms(g, H, W):
+    """g fp32 NCHW [B,C,Hs,Ws] as two bf16 channels-last terms [2,B,H,W,C] (16 significant bits), zero-inserted to (H, W) when g is the
+    output gradient of a stride-2 convolution: the operand of the tensor-core data- and weight-gradient kernels."""
     B, Cg, Hs, Ws = g.shape
     terms = torch.empty((2, B, H, W, Cg), device=g.device, dtype=torch.bfloat16)
     hi, mid = L.planes(terms)
     L.LAUNCHES += 1
     L.check(L.lib().ef_split2_pack_cl(L.ptr(g), hi, mid, B, Cg, H, W, Hs, Ws, L.stream()), "ef_split2_pack_cl")
-    neg_inf, ones = _tcg_consts(g.device, c_total)
+    return terms
+
+
+def _tcg_conv_of_grad(terms, image, c_total):
+    """conv3x3(g, flipped kernel) on the general tensor-core kernel; returns fp32 NCHW [B,c_total,H,W]."""
+    neg_inf, ones = _tcg_consts(terms.device, c_total)
     v, _, _ = lif_step_g([terms[0], terms[1]], None, None, image, neg_inf, ones, c_total)
     return v
 
 
-def _tcg_dgrad(gI, w_ff, w_rec, stride, H, W, want_x, want_z):
-    """Data gradients of a cell step's convolutions: (g_x [B,Cin,H,W] | None, recurrent part of g_z_in [B,C,Ho,Wo] | None)."""
+def _tcg_dgrad(terms, w_ff, w_rec, want_x, want_z):
+    """Data gradients of a cell step's convolutions: (g_x [B,Cin,H,W] | None, recurrent part of g_z_in [B,C,Ho,Wo] | None).  A recurrent
+    cell has stride 1: `terms` serves both convolutions."""
     Cin = w_ff.shape[1]
     g_x = g_z = None
-    if stride == 1 and want_x and want_z:  # one launch: the recurrent gradient as extra output channels
+    if want_x and want_z:  # one launch: the recurrent gradient as extra output channels
         image, cpad, ctot = _dgrad_image(w_ff, w_rec)
-        v = _tcg_conv_of_grad(gI, image, ctot, H, W)
+        v = _tcg_conv_of_grad(terms, image, ctot)
         return v[:, :Cin].contiguous(), v[:, cpad:].contiguous()
     if want_x:
         image, cpad, ctot = _dgrad_image(w_ff)
-        v = _tcg_conv_of_grad(gI, image, ctot, H, W)
+        v = _tcg_conv_of_grad(terms, image, ctot)
         g_x = v if cpad == Cin else v[:, :Cin].contiguous()
     if want_z:
         image, cpad, ctot = _dgrad_image(w_rec)
-        g_z = _tcg_conv_of_grad(gI, image, ctot, gI.shape[2], gI.shape[3])
+        g_z = _tcg_conv_of_grad(terms, image, ctot)
     return g_x, g_z
+
+
+def _tcg_wgrad(x_cl, terms, g_w, ci_off):
+    """g_w[:, ci_off : ci_off + cin] += weight gradient of a 3x3 convolution on the tensor cores (ef_wgrad_tcg); x_cl [B,H,W,cin] exact in bf16."""
+    _, B, H, W, cout = terms.shape
+    cin = x_cl.shape[3]
+    partial = torch.empty(L.lib().ef_wgrad_tcg_partial_elems(B, H, W, cin, cout), device=x_cl.device, dtype=torch.float32)
+    hi, mid = L.planes(terms)
+    L.LAUNCHES += 2
+    L.check(L.lib().ef_wgrad_tcg(L.ptr(x_cl), hi, mid, B, H, W, cin, cout, L.ptr(partial), L.ptr(g_w), g_w.shape[1], int(ci_off), L.stream()),
+            "ef_wgrad_tcg")
 
 
 TCG_FORWARD = True  # forward of LIF cells with C % 32 == 0 outputs under autograd on the general tensor-core kernel (tests switch it off)
@@ -197,10 +214,11 @@ def _tcg_forward(x, state_in, w_ff, w_rec, leak, thresh, residual, state_out, ou
         x_cl = _handed(x, "_ef_cl")
         if x_cl is None or x_cl.shape != (B, H, W, Cin):
             x_cl = pack_cl(x)
-        srcs, wsrcs, tag = [space_to_depth_cl(x_cl) if s2d else x_cl], [(w_ff, 0, Cin, False, s2d)], ("spikes", s2d)
+        srcs, wsrcs, tag, n = [space_to_depth_cl(x_cl) if s2d else x_cl], [(w_ff, 0, Cin, False, s2d)], ("spikes", s2d), 0
     else:
         n = x_kind[1]
-        srcs = [pack_split_cl(x[:, :n].contiguous()), pack_cl(x[:, n:].contiguous())]
+        x_cl = pack_cl(x[:, n:].contiguous())
+        srcs = [pack_split_cl(x[:, :n].contiguous()), x_cl]
         wsrcs, tag = [(w_ff, 0, n, True), (w_ff, n, Cin - n, False)], ("mixed", n)
     z_in_cl = v_in = None
     if state_in is not None:
@@ -235,7 +253,9 @@ def _tcg_forward(x, state_in, w_ff, w_rec, leak, thresh, residual, state_out, ou
         L.check(L.lib().ef_unpack_cl(L.ptr(out_cl), L.ptr(out), B, C, Ho, Wo, L.stream()), "ef_unpack_cl")
     else:
         out.copy_(state_out[1])
-    return (out_cl if out_cl is not None else z_cl), z_cl
+    # (x_cl, n, z_in_cl): the bf16 operands the weight gradients can run on -- the exact channels of the input (from channel n on) and the
+    # previous spikes of a recurrent cell
+    return (out_cl if out_cl is not None else z_cl), z_cl, (x_cl, n, z_in_cl if tag[-1] == "rec" else None)
 
 
 class _CellStep(torch.autograd.Function):
@@ -272,7 +292,8 @@ class _CellStep(torch.autograd.Function):
             out._ef_cl, state_out._ef_z_cl = (out_cl, out._version), (z_cl, state_out._version)
         elif _tcg_fwd_ok(neuron, x, state_in, w_ff, w_rec, stride, x_kind, residual):
             # LIF cell of the U-Net family (other channel counts, stride 2, mixed inputs): the fused general tensor-core kernel
-            out_cl, z_cl = _tcg_forward(x, state_in, w_ff, w_rec, chan["leak"], chan["thresh"], residual, state_out, out, hard_reset, stride, x_kind)
+            out_cl, z_cl, ctx.tcg_operands = _tcg_forward(x, state_in, w_ff, w_rec, chan["leak"], chan["thresh"], residual, state_out, out, hard_reset,
+                                                          stride, x_kind)
             out._ef_cl, state_out._ef_z_cl = (out_cl, out._version), (z_cl, state_out._version)
         else:
             L.call("ef_lif_conv_fwd", p, tag=(x.shape[1], Cout, w_rec is not None))
@@ -280,6 +301,8 @@ class _CellStep(torch.autograd.Function):
         ctx.chan_names = names
         if not hasattr(ctx, "tc_operands"):
             ctx.tc_operands = None
+        if not hasattr(ctx, "tcg_operands"):
+            ctx.tcg_operands = None
         ctx.save_for_backward(x, state_in, w_ff, w_rec, residual, state_out, *[chan[n] for n in names])
         ctx.chan_shapes = [v.shape for v in chan_vals]
         ctx.has_residual = residual is not None
@@ -374,19 +397,34 @@ class _CellStep(torch.autograd.Function):
             q.neuron_only = 1
             L.call("ef_lif_conv_bwd", q)
             want_z = w_rec is not None and g_state_in is not None
-            tc_x, tc_z = _tcg_dgrad(scratch, w_ff, w_rec if want_z else None, stride, H, W, g_x is not None, want_z)
+            terms = _grad_terms(scratch, H, W)  # at the input resolution (zero-inserted for stride 2); a recurrent cell has stride 1
+            tc_x, tc_z = _tcg_dgrad(terms, w_ff, w_rec if want_z else None, g_x is not None, want_z)
             if tc_x is not None:
                 g_x = tc_x
             if tc_z is not None:
                 g_state_in[1] += tc_z
+            # weight gradients: on the tensor cores from the bf16 operands the forward ran on, else on the CUDA cores
+            x_exact_cl, n_real, z_in_cl = ctx.tcg_operands if ctx.tcg_operands is not None else (None, 0, None)
             if g_w_ff is not None:
-                L.LAUNCHES += 1
-                L.check(L.lib().ef_conv3x3_bwd_s(L.ptr(scratch), L.ptr(x), L.ptr(w_ff), None, L.ptr(g_w_ff), L.ptr(scratch_up), B, Cin, Cout, H, W, int(stride),
-                                                 L.stream()), "ef_conv3x3_bwd_s")
+                if x_exact_cl is not None:
+                    _tcg_wgrad(x_exact_cl, terms, g_w_ff, n_real)
+                    if n_real:  # the fractional channels of a mixed input: a narrow convolution of their own on the CUDA cores
+                        g_small = torch.zeros((Cout, n_real, 3, 3), device=dev, dtype=torch.float32)
+                        L.LAUNCHES += 1
+                        L.check(L.lib().ef_conv3x3_bwd(L.ptr(scratch), L.ptr(x[:, :n_real].contiguous()), L.ptr(w_ff), None, L.ptr(g_small), B, n_real, Cout,
+                                                       H, W, L.stream()), "ef_conv3x3_bwd")
+                        g_w_ff[:, :n_real] = g_small
+                else:
+                    L.LAUNCHES += 1
+                    L.check(L.lib().ef_conv3x3_bwd_s(L.ptr(scratch), L.ptr(x), L.ptr(w_ff), None, L.ptr(g_w_ff), L.ptr(scratch_up), B, Cin, Cout, H, W,
+                                                     int(stride), L.stream()), "ef_conv3x3_bwd_s")
             if g_w_rec is not None and state_in is not None:
-                L.LAUNCHES += 1
-                L.check(L.lib().ef_conv3x3_bwd(L.ptr(scratch), L.planes(state_in)[1], L.ptr(w_rec), None, L.ptr(g_w_rec), B, Cout, Cout, Ho, Wo, L.stream()),
-                        "ef_conv3x3_bwd")
+                if z_in_cl is not None:
+                    _tcg_wgrad(z_in_cl, terms, g_w_rec, 0)
+                else:
+                    L.LAUNCHES += 1
+                    L.check(L.lib().ef_conv3x3_bwd(L.ptr(scratch), L.planes(state_in)[1], L.ptr(w_rec), None, L.ptr(g_w_rec), B, Cout, Cout, Ho, Wo,
+                                                   L.stream()), "ef_conv3x3_bwd")
         else:
             L.call("ef_lif_conv_bwd", q)
         g_res = g_out if (ctx.has_residual and need[5]) else None

@@ -191,6 +191,13 @@ int ef_conv32_bwd_tc(const ef_conv32_bwd_tc_params* p, void* stream);
  * same resolution or zero-inserted to the input resolution (H, W) of a stride-2 convolution (Hs = (H-1)/2 + 1): the two sources of a
  * data gradient computed as a plain convolution by ef_lif_conv_fwd_g (autograd of the cells with other channel counts than 32). */
 int ef_split2_pack_cl(const float* src, uint16_t* hi, uint16_t* mid, int32_t B, int32_t C, int32_t H, int32_t W, int32_t Hs, int32_t Ws, void* stream);
+/* Tensor-core weight gradient of a 3x3 convolution for channel counts that are multiples of 32 (autograd of the U-Net cells):
+ * g_w[co][ci_off + ci][dy][dx] += sum_{b,y,x} x_cl[b,y+dy-1,x+dx-1,ci] (g_hi + g_mid)[b,y,x,co].  x_cl [B,H,W,cin] bf16 (exact values:
+ * spikes), g_hi / g_mid [B,H,W,cout] from ef_split2_pack_cl (a stride-2 convolution passes the zero-inserted form at its input resolution),
+ * g_w [cout][cin_total][3][3] fp32, partial = ef_wgrad_tcg_partial_elems() floats of workspace.  Fixed summation order. */
+int64_t ef_wgrad_tcg_partial_elems(int32_t B, int32_t H, int32_t W, int32_t cin, int32_t cout);
+int ef_wgrad_tcg(const uint16_t* x_cl, const uint16_t* g_hi, const uint16_t* g_mid, int32_t B, int32_t H, int32_t W, int32_t cin, int32_t cout,
+                 float* partial, float* g_w, int32_t cin_total, int32_t ci_off, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Backward of a 32 -> 32 LIF cell-step on the fast-path formats (same maths as ef_lif_conv_bwd; tensor-core data gradient).
