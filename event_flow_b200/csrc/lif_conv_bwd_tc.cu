@@ -864,15 +864,27 @@ lif_wgrad_tcg_kernel(const WgGParams p, const __grid_constant__ CUtensorMap map_
 }
 
 // g_w[co0 + co][ci_off + ci0 + ci][dy][dx] += sum over the chunks (in order) of partial[pair][chunk][dy][dx][ci][co].
-// Block = 8 rows (row = (dy*3 + dx)*32 + ci) x 32 co of one pair.
+// Block = one pair x 8 output channels: the sums are transposed through shared memory so that g_w is updated in runs of 288 contiguous
+// floats (the 32 ci x 9 taps of one output channel) instead of one 4-byte access per 32-byte sector.
 __global__ void __launch_bounds__(256) wgrad_reduce_g_kernel(const float* __restrict__ partial, int chunks, int n_co_blk, float* __restrict__ g_w,
                                                              int cin_total, int ci_off) {
-  const int co = threadIdx.x & 31, row = (blockIdx.x % 36) * 8 + (threadIdx.x >> 5), pair = blockIdx.x / 36;
+  __shared__ float s[8][289];
+  const int pair = blockIdx.x >> 2, cg = (blockIdx.x & 3) * 8;
   const int ci0 = (pair / n_co_blk) * 32, co0 = (pair % n_co_blk) * 32;
-  const float* src = partial + (size_t)pair * chunks * WG_SLICE + row * 32 + co;
-  float acc = 0.f;
-  for (int c = 0; c < chunks; ++c) acc += __ldg(src + (size_t)c * WG_SLICE);
-  g_w[((size_t)(co0 + co) * cin_total + ci_off + ci0 + (row & 31)) * 9 + (row >> 5)] += acc;
+  const int co_l = threadIdx.x & 7;
+  const float* src = partial + (size_t)pair * chunks * WG_SLICE + cg + co_l;
+#pragma unroll 3
+  for (int k = 0; k < 9; ++k) {
+    const int row = k * 32 + (threadIdx.x >> 3);  // (dy*3 + dx)*32 + ci
+    float acc = 0.f;
+    for (int c = 0; c < chunks; ++c) acc += __ldg(src + (size_t)c * WG_SLICE + row * 32);
+    s[co_l][(row & 31) * 9 + (row >> 5)] = acc;
+  }
+  __syncthreads();
+  const int co = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* dst = g_w + ((size_t)(co0 + cg + co) * cin_total + ci_off + ci0) * 9;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) dst[k * 32 + lane] += s[co][k * 32 + lane];
 }
 
 inline int wgg_chunks(int B, int H, int W, int pairs) {
@@ -1242,6 +1254,6 @@ extern "C" int ef_wgrad_tcg(const uint16_t* x_cl, const uint16_t* g_hi, const ui
   const int wsmem = WG_NST * (WG_XTILE + 2 * WG_GTILE) + 256 + 1024;
   lif_wgrad_tcg_kernel<<<pairs * w.chunks, WG_THREADS, wsmem, st>>>(w, mx, gh, gm);
   if ((rc = check_launch("lif_wgrad_tcg_kernel"))) return rc;
-  wgrad_reduce_g_kernel<<<pairs * 36, 256, 0, st>>>(partial, w.chunks, w.n_co_blk, g_w, cin_total, ci_off);
+  wgrad_reduce_g_kernel<<<pairs * 4, 256, 0, st>>>(partial, w.chunks, w.n_co_blk, g_w, cin_total, ci_off);
   return check_launch("wgrad_reduce_g_kernel");
 }

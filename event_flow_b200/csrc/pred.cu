@@ -64,71 +64,73 @@ __global__ void __launch_bounds__(256) pred_fwd_kernel(const ef_pred_params p) {
 }
 
 // g_pre = g_y (1 - y^2); g_x = W^T g_pre; g_w += sum g_pre x; g_b += sum g_pre
+// grid = (pixel blocks of 256 * PB_PIX, groups of 8 input channels): wide prediction layers (256 channels at 32 x 32 in the U-Net's coarse
+// scale) spread over the SMs by channel group, every block reduces its partial sums once.
 constexpr int PB_PIX = 4;
 __global__ void __launch_bounds__(256) pred_bwd_kernel(const ef_pred_params p) {
-  __shared__ float s_w[PRED_MAX_COUT * PRED_MAX_CIN];
-  __shared__ float s_acc[PRED_MAX_COUT * PRED_MAX_CIN + PRED_MAX_COUT];
-  for (int i = threadIdx.x; i < p.Cout * p.Cin; i += 256) s_w[i] = p.w[i];
-  for (int i = threadIdx.x; i < PRED_MAX_COUT * PRED_MAX_CIN + PRED_MAX_COUT; i += 256) s_acc[i] = 0.f;
+  __shared__ float s_w[PRED_MAX_COUT * 8];
+  __shared__ float s_acc[PRED_MAX_COUT * 8 + PRED_MAX_COUT];
+  const int c0 = blockIdx.y * 8;
+  for (int i = threadIdx.x; i < p.Cout * 8; i += 256) s_w[i] = (c0 + (i & 7) < p.Cin) ? p.w[(i >> 3) * p.Cin + c0 + (i & 7)] : 0.f;
+  for (int i = threadIdx.x; i < PRED_MAX_COUT * 8 + PRED_MAX_COUT; i += 256) s_acc[i] = 0.f;
   __syncthreads();
   const size_t hw = (size_t)p.H * p.W, n = (size_t)p.B * hw;
   const int lane = threadIdx.x & 31;
-  for (int c0 = 0; c0 < p.Cin; c0 += 8) {  // 8 input channels at a time keeps the register footprint small
-    float gw[PRED_MAX_COUT][8], gb[PRED_MAX_COUT];
+  float gw[PRED_MAX_COUT][8], gb[PRED_MAX_COUT];
+#pragma unroll
+  for (int o = 0; o < PRED_MAX_COUT; ++o) {
+    gb[o] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) gw[o][c] = 0.f;
+  }
+  for (int k = 0; k < PB_PIX; ++k) {
+    const size_t i = ((size_t)blockIdx.x * PB_PIX + k) * 256 + threadIdx.x;
+    if (i >= n) break;
+    const int b = i / hw;
+    const size_t pix = i % hw;
+    float gp[PRED_MAX_COUT];
 #pragma unroll
     for (int o = 0; o < PRED_MAX_COUT; ++o) {
-      gb[o] = 0.f;
-#pragma unroll
-      for (int c = 0; c < 8; ++c) gw[o][c] = 0.f;
+      gp[o] = 0.f;
+      if (o < p.Cout) {
+        const size_t oo = ((size_t)b * p.Cout + o) * hw + pix;
+        const float y = p.y[oo];
+        gp[o] = p.g_y[oo] * (1.0f - y * y);
+        gb[o] += gp[o];
+      }
     }
-    for (int k = 0; k < PB_PIX; ++k) {
-      const size_t i = ((size_t)blockIdx.x * PB_PIX + k) * 256 + threadIdx.x;
-      if (i >= n) break;
-      const int b = i / hw;
-      const size_t pix = i % hw;
-      float gp[PRED_MAX_COUT];
 #pragma unroll
-      for (int o = 0; o < PRED_MAX_COUT; ++o) {
-        gp[o] = 0.f;
+    for (int c = 0; c < 8; ++c) {
+      if (c0 + c >= p.Cin) break;
+      const float xv = ld_x(p, b, c0 + c, pix, hw);
+      float gx = 0.f;
+#pragma unroll
+      for (int o = 0; o < PRED_MAX_COUT; ++o)
         if (o < p.Cout) {
-          const size_t oo = ((size_t)b * p.Cout + o) * hw + pix;
-          const float y = p.y[oo];
-          gp[o] = p.g_y[oo] * (1.0f - y * y);
-          gb[o] += gp[o];
+          gw[o][c] = fmaf(gp[o], xv, gw[o][c]);
+          gx = fmaf(gp[o], s_w[o * 8 + c], gx);
         }
-      }
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        if (c0 + c >= p.Cin) break;
-        const float xv = ld_x(p, b, c0 + c, pix, hw);
-        float gx = 0.f;
-#pragma unroll
-        for (int o = 0; o < PRED_MAX_COUT; ++o)
-          if (o < p.Cout) {
-            gw[o][c] = fmaf(gp[o], xv, gw[o][c]);
-            gx = fmaf(gp[o], s_w[o * p.Cin + c0 + c], gx);
-          }
-        if (p.g_x) p.g_x[((size_t)b * p.Cin + c0 + c) * hw + pix] = gx;
-      }
+      if (p.g_x) p.g_x[((size_t)b * p.Cin + c0 + c) * hw + pix] = gx;
     }
+  }
 #pragma unroll
-    for (int o = 0; o < PRED_MAX_COUT; ++o) {
-      if (o >= p.Cout) break;
+  for (int o = 0; o < PRED_MAX_COUT; ++o) {
+    if (o >= p.Cout) break;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const float r = warp_sum(gw[o][c]);
-        if (lane == 0 && c0 + c < p.Cin) atomicAdd(&s_acc[o * p.Cin + c0 + c], r);
-      }
-      if (c0 == 0) {
-        const float r = warp_sum(gb[o]);
-        if (lane == 0) atomicAdd(&s_acc[PRED_MAX_COUT * PRED_MAX_CIN + o], r);
-      }
+    for (int c = 0; c < 8; ++c) {
+      const float r = warp_sum(gw[o][c]);
+      if (lane == 0) atomicAdd(&s_acc[o * 8 + c], r);
+    }
+    if (blockIdx.y == 0) {
+      const float r = warp_sum(gb[o]);
+      if (lane == 0) atomicAdd(&s_acc[PRED_MAX_COUT * 8 + o], r);
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < p.Cout * p.Cin; i += 256)
-    if (p.g_w) atomicAdd(p.g_w + i, s_acc[i]);
-  if (threadIdx.x < p.Cout && p.g_b) atomicAdd(p.g_b + threadIdx.x, s_acc[PRED_MAX_COUT * PRED_MAX_CIN + threadIdx.x]);
+  if (p.g_w)
+    for (int i = threadIdx.x; i < p.Cout * 8; i += 256)
+      if (c0 + (i & 7) < p.Cin) atomicAdd(p.g_w + (i >> 3) * p.Cin + c0 + (i & 7), s_acc[i]);
+  if (blockIdx.y == 0 && threadIdx.x < p.Cout && p.g_b) atomicAdd(p.g_b + threadIdx.x, s_acc[PRED_MAX_COUT * 8 + threadIdx.x]);
 }
 
 // Sums of v[0..31] over the 32 lanes of a warp, all 32 entries at once (31 shuffles instead of 32 x 5): step by step the lanes
@@ -233,6 +235,6 @@ extern "C" int ef_pred_bwd(const ef_pred_params* p, void* stream) {
     pred_bwd_cl32_kernel<<<(unsigned)((n + PBC_THREADS * PBC_PIX - 1) / (PBC_THREADS * PBC_PIX)), PBC_THREADS, 0, as_stream(stream)>>>(*p);
     return check_launch("pred_bwd_cl32_kernel");
   }
-  pred_bwd_kernel<<<(unsigned)((n + 256 * PB_PIX - 1) / (256 * PB_PIX)), 256, 0, as_stream(stream)>>>(*p);
+  pred_bwd_kernel<<<dim3((unsigned)((n + 256 * PB_PIX - 1) / (256 * PB_PIX)), (unsigned)((p->Cin + 7) / 8)), 256, 0, as_stream(stream)>>>(*p);
   return check_launch("pred_bwd_kernel");
 }
