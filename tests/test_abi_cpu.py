@@ -55,6 +55,16 @@ def test_argument_errors_are_reported_without_a_gpu(lib):
     assert h.ef_iwe_image(None, None) == -3
     assert h.ef_encode_events(None, None) == -3
     assert h.ef_pack_cl(None, None, 1, 8, 4, 4, None) == -3
+    # round-2 entry points: the general tensor-core gradients, the fused data-parallel step, the IPC helpers
+    assert h.ef_conv32_bwd_tc(None, None) == -3
+    assert h.ef_split2_pack_cl(None, None, None, 1, 32, 8, 8, 8, 8, None) == -3
+    assert h.ef_wgrad_tcg_partial_elems(1, 16, 16, 33, 32) == 0 and h.ef_wgrad_tcg_partial_elems(4, 16, 16, 512, 512) == 256 * 2 * 9 * 32 * 32
+    assert h.ef_wgrad_tcg(None, None, None, 1, 16, 16, 32, 32, None, None, 32, 0, None) == -3
+    assert h.ef_dp_step(None, None) == -3
+    d = lib.DpStepParams()
+    d.world, d.rank, d.n = 9, 0, 10
+    assert h.ef_dp_step(ctypes.byref(d), None) == -1 and b"world" in h.ef_last_error()
+    assert h.ef_ipc_alloc(0, None, None) == -3 and h.ef_ipc_open(None, None) == -3
 
 
 def test_ctypes_structs_match_c_layout(lib, tmp_path):
