@@ -265,7 +265,7 @@ class _CellStep(torch.autograd.Function):
     def forward(ctx, meta, x, state_in, w_ff, w_rec, residual, *chan_vals):
         neuron, hard_reset, surrogate, width, stride, x_kind, _ = meta
         names = param_names(neuron)
-        chan = {n: _c(v.reshape(-1)) for n, v in zip(names, chan_vals)}
+        chan = {n: _c(v) for n, v in zip(names, chan_vals)}  # [C,1,1] (or [C]) contiguous: the kernels read C values at the pointer
         x, state_in, w_ff, w_rec, residual = _c(x), _c(state_in), _c(w_ff), _c(w_rec), _c(residual)
         _need_cuda(x, state_in, w_ff, w_rec, residual, *chan.values())
         B, _, H, W = x.shape
@@ -298,6 +298,7 @@ class _CellStep(torch.autograd.Function):
         else:
             L.call("ef_lif_conv_fwd", p, tag=(x.shape[1], Cout, w_rec is not None))
         ctx.meta = meta
+        ctx.params = p  # the backward starts from a copy of this argument block (same tensors: all of them are saved below)
         ctx.chan_names = names
         if not hasattr(ctx, "tc_operands"):
             ctx.tc_operands = None
@@ -315,7 +316,11 @@ class _CellStep(torch.autograd.Function):
         names = ctx.chan_names
         chan = dict(zip(names, chan_vals))
         q = L.LifConvBwdParams()
-        _fill_cell_params(q.f, neuron, x, state_in, w_ff, w_rec, chan, None, state_out, None, hard_reset, surrogate, width, stride)
+        q.f = ctx.params  # (struct copy; the forward's output / residual pointers in it are never read by the backward kernels)
+        if q.f.x != x.data_ptr() or q.f.v_out != state_out.data_ptr() or q.f.w_ff != w_ff.data_ptr():
+            # the saved tensors came back in other storage (saved-tensor hooks: offloading, ...): rebuild the argument block
+            q.f = L.LifConvParams()
+            _fill_cell_params(q.f, neuron, x, state_in, w_ff, w_rec, chan, None, state_out, None, hard_reset, surrogate, width, stride)
         B, Cin, H, W = x.shape
         S, _, Cout, Ho, Wo = state_out.shape
         dev = x.device
