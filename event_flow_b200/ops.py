@@ -354,14 +354,21 @@ class _CellStep(torch.autograd.Function):
             q.g_v_in, q.g_z_in = planes[0], planes[1]
             if S > 2:
                 q.g_aux_in = planes[2]
-        g_w_ff = torch.zeros_like(w_ff) if need[3] else None
+        # every parameter gradient of this step out of ONE zero-filled buffer (one fill launch instead of one per tensor)
+        fields = [f for f, n in zip(_STRUCT_FIELDS, _PARAM_FIELDS[neuron]) if n is not None]
+        n_ff = w_ff.numel() if need[3] else 0
+        n_rec = w_rec.numel() if (w_rec is not None and need[4]) else 0
+        n_chan = sum(1 for i in range(len(fields)) if need[6 + i])
+        flat = torch.zeros(n_ff + n_rec + n_chan * Cout, device=dev, dtype=torch.float32)
+        g_w_ff = flat[:n_ff].view(w_ff.shape) if n_ff else None
         q.g_w_ff = L.ptr(g_w_ff)
-        g_w_rec = torch.zeros_like(w_rec) if (w_rec is not None and need[4]) else None
+        g_w_rec = flat[n_ff:n_ff + n_rec].view(w_rec.shape) if n_rec else None
         q.g_w_rec = L.ptr(g_w_rec)
-        g_chan = []
-        for i, (field, name) in enumerate([(f, n) for f, n in zip(_STRUCT_FIELDS, _PARAM_FIELDS[neuron]) if n is not None]):
+        g_chan, o = [], n_ff + n_rec
+        for i, field in enumerate(fields):
             if need[6 + i]:
-                g = torch.zeros(Cout, device=dev, dtype=torch.float32)
+                g = flat[o:o + Cout]
+                o += Cout
                 setattr(q, "g_" + field, L.ptr(g))
                 g_chan.append(g.view(ctx.chan_shapes[i]))
             else:
