@@ -18,7 +18,6 @@
 namespace ef {
 
 constexpr int DP_THREADS = 256, DP_MAX_PER_THREAD = 8;
-constexpr int EF_ERR_CLOSE = EF_EUNSUPPORTED;
 
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
   uint32_t v;
@@ -229,5 +228,19 @@ extern "C" int ef_ipc_open(const unsigned char* handle64, void** ptr) {
   *ptr = q;
   return EF_OK;
 }
-extern "C" int ef_ipc_close(void* ptr) { return (ptr && cudaIpcCloseMemHandle(ptr) != cudaSuccess) ? (cudaGetLastError(), ef::EF_ERR_CLOSE) : EF_OK; }
-extern "C" int ef_ipc_free(void* ptr) { return (ptr && cudaFree(ptr) != cudaSuccess) ? (cudaGetLastError(), ef::EF_ERR_CLOSE) : EF_OK; }
+extern "C" int ef_ipc_close(void* ptr) {
+  using namespace ef;
+  if (!ptr) return EF_OK;
+  const cudaError_t e = cudaIpcCloseMemHandle(ptr);
+  if (e == cudaSuccess) return EF_OK;
+  cudaGetLastError();
+  return fail(EF_EUNSUPPORTED, "ef_ipc_close: cudaIpcCloseMemHandle failed: %s", cudaGetErrorString(e));
+}
+extern "C" int ef_ipc_free(void* ptr) {
+  using namespace ef;
+  if (!ptr) return EF_OK;
+  const cudaError_t e = cudaFree(ptr);
+  if (e == cudaSuccess) return EF_OK;
+  cudaGetLastError();
+  return fail(EF_EUNSUPPORTED, "ef_ipc_free: cudaFree failed: %s", cudaGetErrorString(e));
+}

@@ -148,8 +148,3 @@ def step(model, x, holder, attr, eager):
             return eager(x)
     return g.replay(x)
 
-
-def drop(model):
-    """Forget the graphs (parameters moved, model copied)."""
-    model.__dict__.pop("_step_graphs", None)
-    model.__dict__.pop("_graph_params", None)

@@ -105,6 +105,26 @@ class _PeerStep:
         self._self_test()
         tr._bind_grad(self.own_grad)
 
+    def close(self):
+        """
+        Hand the gradient views back to an ordinary torch buffer and release the shared memory: the peers' mappings first, then -- once
+        every rank has closed its mappings of it -- this rank's own allocation.  Collective: every rank calls it.
+        """
+        tr, dev = self.tr, self.own_grad.device
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=tr.group)  # nobody is still inside a step that reads a peer's buffer
+        tr._bind_grad(torch.empty(tr.n, device=dev, dtype=torch.float32))  # (copies the current gradient over)
+        tr.fused = None
+        torch.cuda.synchronize(dev)
+        with torch.cuda.device(dev):
+            for r, ptr in enumerate(self.grad_ptrs):
+                if r != self.rank:
+                    L.check(L.lib().ef_ipc_close(ptr), "ef_ipc_close")
+            dist.barrier(group=tr.group)
+            self.own_grad = None
+            L.check(L.lib().ef_ipc_free(self.buffer.ptr), "ef_ipc_free")
+        self.buffer = None
+
     def _launch(self, param, m, v, step, graceful):
         tr = self.tr
         self.epoch += 1
@@ -194,6 +214,11 @@ class DataParallelTrainer:
                 self.fused = _PeerStep(self)
             except Exception as exc:  # IPC not available (allocator mode, container limits, ...): the NCCL path is always there
                 self.fused, self.fused_error = None, repr(exc)
+
+    def close(self):
+        """Release what the fused peer-memory step shares between the ranks (collective; the trainer keeps working over NCCL)."""
+        if self.fused is not None:
+            self.fused.close()
 
     def _bind_grad(self, flat_grad):
         """Make `flat_grad` (n fp32 values, current contents kept) the gradient buffer: every p.grad becomes a view of it."""

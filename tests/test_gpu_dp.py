@@ -148,6 +148,18 @@ def fused_worker(rank, world, port, nccl, res):
         torch.cuda.synchronize()
         assert tr.flat_grad.abs().max().item() == 0.0
         out[name] = (tr.fused is not None, tr.fused_error, norms, tr.flat_param.detach().cpu().clone())
+        if name == "auto" and tr.fused is not None:
+            # release the shared buffers: the gradient views move back to a torch buffer and the trainer carries on over NCCL
+            tr.close()
+            assert tr.fused is None and all(p.grad.data_ptr() == tr._view_of(p).data_ptr() for p in tr.params)
+            lossf.reset()
+            ev = stream.host_events(step).to(dev)
+            d = encode_batch(ev, (H, W), BINS)
+            lossf.event_flow_association(model(d["event_voxel"], d["event_cnt"])["flow"], ev, d["event_list_pol_mask"], d["event_mask"])
+            lossf().backward()
+            tr.step()
+            torch.cuda.synchronize()
+            assert tr.flat_grad.abs().max().item() == 0.0 and torch.isfinite(tr.flat_param).all()
     # every rank must hold the same parameters (replicas stay identical)
     mine = out["auto"][3].to(dev)
     other = mine.clone()
