@@ -340,3 +340,33 @@ def test_spiking_cell_options_match_the_live_reference(cls, opts, cpu_ops):
             assert pa.grad is None or pa.grad.abs().max() == 0, n
             continue
         assert (pa.grad - pb.grad).abs().max().item() <= 1e-4 * max(pb.grad.abs().max().item(), 1e-2 * scale), n
+
+
+def test_cells_are_told_what_their_input_is():
+    """
+    The input kinds the models vouch for (exact-in-bf16 "spikes", or ("mixed", n): n fractional channels first) decide whether a cell may
+    run on the tensor cores with exact products -- they must match the wiring of the forward passes: FireNet's head sees the encoding,
+    every later spiking cell spikes; in the spiking U-Net the decoders after the first receive cat[prediction, x, skip] (unet.py:418-465).
+    """
+    import event_flow_b200.models.model as M
+
+    fire = dict(name="x", encoding="voxel", round_encoding=False, norm_input=False, num_bins=5, base_num_channels=32, kernel_size=3,
+                activations=["arctanspike", "arctanspike"], mask_output=True, spiking_neuron={})
+    m = M.LIFFireNet(dict(fire))
+    kinds = {n: getattr(m, n).__dict__.get("_x_kind") for n in ("head", "G1", "R1a", "R1b", "G2", "R2a", "R2b")}
+    assert kinds == {"head": "split", "G1": "spikes", "R1a": "spikes", "R1b": "spikes", "G2": "spikes", "R2a": "spikes", "R2b": "spikes"}
+    unet = dict(name="x", encoding="cnt", round_encoding=False, norm_input=False, num_bins=2, base_num_channels=32, kernel_size=3,
+                activations=["arctanspike", "arctanspike"], mask_output=True, spiking_neuron=None)
+    net = M.SpikingRecEVFlowNet(dict(unet)).net
+    kind = lambda cell: cell.__dict__.get("_x_kind")  # noqa: E731
+    assert kind(net.encoders[0].conv) is None  # the network input: event counts or a voxel grid, whatever the caller feeds
+    assert all(kind(e.conv) == "spikes" for e in net.encoders[1:]) and all(kind(e.recurrent_block) == "spikes" for e in net.encoders)
+    assert all(kind(r.conv1) == "spikes" and kind(r.conv2) == "spikes" for r in net.resblocks)
+    assert kind(net.decoders[0].conv2d) == "spikes"
+    assert all(kind(d.conv2d) == ("mixed", net.num_output_channels) for d in net.decoders[1:])
+    # the channel bookkeeping behind ("mixed", n): prediction channels come first in the decoder's input
+    for i, d in enumerate(net.decoders[1:], start=1):
+        assert d.conv2d.input_size == 2 * net.encoder_output_sizes[::-1][i] + net.num_output_channels
+    # the ANN / leaky twins share the wiring but have no such cells: nothing to mark, nothing breaks
+    ann_cfg = dict(unet, activations=["relu", None])
+    M.LeakyRecEVFlowNet(dict(ann_cfg)), M.RecEVFlowNet(dict(ann_cfg))
