@@ -71,24 +71,28 @@ class _StepGraph:
         box = {}
 
         def body():
+            # (runs ONCE, under capture; written so that running it again -- the CPU stand-in of tests/test_graphed_cpu.py replays by
+            # re-running it -- reuses the same static tensors, as a replay of the real graph does)
             out = eager(self.x)
             after = getattr(holder, attr)
             new = _flat(after, [])
-            # a state that existed before the step is updated in place; one the step created (first step of a sequence) gets its own
-            # static tensor.  (Same leaf order before and after: cells that have a state keep it, the others turn None into a tensor.)
-            keep, it = [], iter(self.static_in)
-            box["alias"] = _shape_of(before) == _shape_of(after)
-            for t in new:
-                dst = next(it) if box["alias"] else torch.empty_like(t)
+            if "keep" not in box:
+                # a state that existed before the step is updated in place; one the step created (first step of a sequence) gets its
+                # own static tensor.  (Same leaf order before and after: cells that have a state keep it, the others turn None into one.)
+                alias = _shape_of(before) == _shape_of(after)
+                box["keep"] = list(self.static_in) if alias else [torch.empty_like(t) for t in new]
+                box["flows"], box["after"] = list(out["flow"]), after
+            else:
+                for dst, f in zip(box["flows"], out["flow"]):
+                    dst.copy_(f)
+            for dst, t in zip(box["keep"], new):
                 dst.copy_(t)
-                keep.append(dst)
-            box["out"], box["after"], box["keep"] = out, after, keep
 
         try:
             self.graph = fast._capture(body)
         finally:
             setattr(holder, attr, before)
-        self.flows = box["out"]["flow"]
+        self.flows = box["flows"]
         self.static_out = box["keep"]
         self.after = box["after"]
 
