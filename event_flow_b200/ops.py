@@ -166,11 +166,13 @@ TCG_FORWARD = True  # forward of LIF cells with C % 32 == 0 outputs under autogr
 
 def _tcg_fwd_ok(neuron, x, state_in, w_ff, w_rec, stride, x_kind, residual):
     """
-    This LIF cell step can run on the general tcgen05 kernel (ef_lif_conv_fwd_g) with fp32-exact products: the caller vouches for the
+    This cell step can run on the general tcgen05 kernel (ef_lif_conv_fwd_g; LIF: fused, other neurons: its convolution) with fp32-exact products: the caller vouches for the
     input -- "spikes": every channel exact in bf16 (spikes, sums of spikes, their bilinear x2 upsampling); ("mixed", n): the first
     n <= 10 channels are arbitrary fp32 values (they enter as their exact three-way split), the rest exact in bf16.
     """
-    if not (TCG_FORWARD and neuron == "lif" and x.is_cuda and w_ff.shape[-1] == 3 and w_ff.shape[0] % 32 == 0):
+    if not (TCG_FORWARD and x.is_cuda and w_ff.shape[-1] == 3 and w_ff.shape[0] % 32 == 0):
+        return False
+    if neuron != "lif" and stride != 1:  # (the other neuron kinds: convolution on this kernel + ef_lif_neuron_fwd, stride 1 only)
         return False
     Cin, H, W = x.shape[1], x.shape[2], x.shape[3]
     if x_kind == "spikes":
@@ -204,8 +206,12 @@ def _fwdg_image(w_ff, w_rec, wsrcs, tag):
     return hit[1]
 
 
-def _tcg_forward(x, state_in, w_ff, w_rec, leak, thresh, residual, state_out, out, hard_reset, stride, x_kind):
-    """The LIF cell step on ef_lif_conv_fwd_g, results written into `state_out` [2,B,C,Ho,Wo] and `out`; returns (out_cl, z_cl)."""
+def _tcg_forward(x, state_in, w_ff, w_rec, leak, thresh, residual, state_out, out, hard_reset, stride, x_kind, neuron_call=None):
+    """
+    The cell step on ef_lif_conv_fwd_g, results written into `state_out` and `out`; returns (out_cl, z_cl, operands for the backward).
+    LIF: the fused kernel.  Other neurons (`neuron_call` = their filled ef_lif_conv_params): the kernel as a pure convolution (leak =
+    -inf), then ef_lif_neuron_fwd on its current -- what the 32-channel cells do with the 32-channel kernel.
+    """
     B, Cin, H, W = x.shape
     C = w_ff.shape[0]
     Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
@@ -221,7 +227,7 @@ def _tcg_forward(x, state_in, w_ff, w_rec, leak, thresh, residual, state_out, ou
         srcs = [pack_split_cl(x[:, :n].contiguous()), x_cl]
         wsrcs, tag = [(w_ff, 0, n, True), (w_ff, n, Cin - n, False)], ("mixed", n)
     z_in_cl = v_in = None
-    if state_in is not None:
+    if state_in is not None and (neuron_call is None or w_rec is not None):
         planes = L.planes(state_in)
         v_in = planes[0]
         z_in_cl = _handed(state_in, "_ef_z_cl")
@@ -230,6 +236,20 @@ def _tcg_forward(x, state_in, w_ff, w_rec, leak, thresh, residual, state_out, ou
         if w_rec is not None:
             srcs, wsrcs, tag = srcs + [z_in_cl], wsrcs + [(w_rec, 0, C, False)], tag + ("rec",)
     image = _fwdg_image(w_ff, w_rec if tag[-1] == "rec" else None, wsrcs, tag)
+    operands = (x_cl, n, z_in_cl if tag[-1] == "rec" else None)
+    if neuron_call is not None:
+        neg_inf, ones = _tcg_consts(x.device, C)
+        cur, _, _ = lif_step_g(srcs, None, None, image, neg_inf, ones, C)
+        q = neuron_call
+        out_cl = torch.empty((B, Ho, Wo, C), device=x.device, dtype=torch.bfloat16)
+        q.out_cl = L.ptr(out_cl)
+        z_cl = out_cl
+        if residual is not None:
+            z_cl = torch.empty_like(out_cl)
+            q.z_out_cl = L.ptr(z_cl)
+        L.LAUNCHES += 1
+        L.check(L.lib().ef_lif_neuron_fwd(L.C.byref(q), L.ptr(cur), L.stream()), "ef_lif_neuron_fwd")
+        return out_cl, z_cl, operands
     res_cl = None
     if residual is not None:
         res_cl = _handed(residual, "_ef_cl")
@@ -253,9 +273,9 @@ def _tcg_forward(x, state_in, w_ff, w_rec, leak, thresh, residual, state_out, ou
         L.check(L.lib().ef_unpack_cl(L.ptr(out_cl), L.ptr(out), B, C, Ho, Wo, L.stream()), "ef_unpack_cl")
     else:
         out.copy_(state_out[1])
-    # (x_cl, n, z_in_cl): the bf16 operands the weight gradients can run on -- the exact channels of the input (from channel n on) and the
-    # previous spikes of a recurrent cell
-    return (out_cl if out_cl is not None else z_cl), z_cl, (x_cl, n, z_in_cl if tag[-1] == "rec" else None)
+    # operands = (x_cl, n, z_in_cl): the bf16 tensors the weight gradients can run on -- the exact channels of the input (from channel n
+    # on) and the previous spikes of a recurrent cell
+    return (out_cl if out_cl is not None else z_cl), z_cl, operands
 
 
 class _CellStep(torch.autograd.Function):
@@ -292,8 +312,8 @@ class _CellStep(torch.autograd.Function):
             out._ef_cl, state_out._ef_z_cl = (out_cl, out._version), (z_cl, state_out._version)
         elif _tcg_fwd_ok(neuron, x, state_in, w_ff, w_rec, stride, x_kind, residual):
             # LIF cell of the U-Net family (other channel counts, stride 2, mixed inputs): the fused general tensor-core kernel
-            out_cl, z_cl, ctx.tcg_operands = _tcg_forward(x, state_in, w_ff, w_rec, chan["leak"], chan["thresh"], residual, state_out, out, hard_reset,
-                                                          stride, x_kind)
+            out_cl, z_cl, ctx.tcg_operands = _tcg_forward(x, state_in, w_ff, w_rec, chan.get("leak"), chan.get("thresh"), residual, state_out, out,
+                                                          hard_reset, stride, x_kind, neuron_call=None if neuron == "lif" else p)
             out._ef_cl, state_out._ef_z_cl = (out_cl, out._version), (z_cl, state_out._version)
         else:
             L.call("ef_lif_conv_fwd", p, tag=(x.shape[1], Cout, w_rec is not None))

@@ -258,3 +258,49 @@ def test_training_forward_of_general_lif_cells_on_the_tensor_cores(cin, C, strid
             (res[True][4][k], res[False][4][k], "g_" + k) for k in res[False][4]):
         if b is not None:
             assert (a - b).abs().max().item() <= 1e-4 * (b.abs().max().item() + 1e-20), what
+
+
+@pytest.mark.parametrize("neuron", ["plif", "alif", "xlif"])
+@pytest.mark.parametrize("cin,C,rec,kind,residual", [(64, 96, True, "spikes", False), (64, 64, False, "spikes", True), (66, 32, False, ("mixed", 2), False)])
+def test_other_neuron_kinds_on_the_general_kernel(neuron, cin, C, rec, kind, residual):
+    """
+    PLIF / ALIF / XLIF cells with other channel counts than 32 under autograd: the general tensor-core kernel as a pure convolution +
+    ef_lif_neuron_fwd on its current (and the tensor-core gradients where they apply) against the fused CUDA-core kernels on the same
+    tensors: state to summation-order noise, gradients to 1e-4 of their scale.
+    """
+    from event_flow_b200 import ops
+
+    B, H, W = 2, 20, 24
+    g = torch.Generator().manual_seed(cin + C + len(neuron))
+    x = (torch.rand(B, cin, H, W, generator=g) < 0.2).float()
+    if type(kind) is tuple:
+        x[:, :kind[1]] = torch.randn(B, kind[1], H, W, generator=g)
+    st = torch.randn(3, B, C, H, W, generator=g) * 0.5
+    st[1] = (st[1] > 0.3).float()
+    st[2] = st[2].abs() * 0.3
+    w = {"ff": (torch.rand(C, cin, 3, 3, generator=g) * 2 - 1) * math.sqrt(1 / cin) * 2.0}
+    if rec:
+        w["rec"] = (torch.rand(C, C, 3, 3, generator=g) * 2 - 1) * math.sqrt(1 / C) * 2.0
+    base = {"thresh": 0.8, "t0": 0.8, "leak": -4.0, "leak_v": -4.0}
+    chan = {n: (torch.randn(C, 1, 1, generator=g) * 0.1 + base.get(n, 0.1)).to(DEV) for n in ops.param_names(neuron)}
+    res_t = (torch.rand(B, C, H, W, generator=g) < 0.3).float().to(DEV) if residual else None
+    g_out, g_ns = torch.randn(B, C, H, W, generator=g).to(DEV), torch.randn(3, B, C, H, W, generator=g).to(DEV)
+    g_ns[1] = 0
+    res = {}
+    for tc in (True, False):
+        ops.TCG_FORWARD = tc
+        try:
+            xd, sd = x.to(DEV).requires_grad_(True), st.to(DEV).requires_grad_(True)
+            ws = {k: v.to(DEV).requires_grad_(True) for k, v in w.items()}
+            out, ns = ops.cell_step(neuron, xd, sd, ws["ff"], ws.get("rec"), chan, hard_reset=True, x_kind=kind, residual=res_t)
+            torch.autograd.backward([out, ns], [g_out, g_ns])
+            res[tc] = (out.detach().cpu(), ns.detach().cpu(), xd.grad.cpu(), sd.grad.cpu(), {k: v.grad.cpu() for k, v in ws.items()})
+        finally:
+            ops.TCG_FORWARD = True
+    v_t, v_c = res[True][1][0], res[False][1][0]
+    assert not torch.equal(v_t, v_c)
+    assert (v_t - v_c).abs().max().item() <= max(2e-5, 3e-6 * v_c.abs().max().item())
+    assert (res[True][1][1] != res[False][1][1]).float().mean().item() < 1e-4  # (borderline spikes may flip with the summation order)
+    for a, b, what in ((res[True][2], res[False][2], "g_x"), (res[True][3], res[False][3], "g_state")) + tuple(
+            (res[True][4][k], res[False][4][k], "g_" + k) for k in w):
+        assert (a - b).abs().max().item() <= 1e-4 * (b.abs().max().item() + 1e-20), what
