@@ -295,3 +295,16 @@ def test_graph_replay_bookkeeping_on_nested_states():
     holder.states = states
     graphed.leave(m, holder, "states")  # no graphs: a no-op
     assert holder.states is states
+
+
+def test_launcher_builds_every_model_class():
+    """tools/train_dp.py --model <any class of the reference's import list>: the per-family neuron / activation settings construct the model."""
+    import event_flow_b200.models.model as M
+    from tools.train_dp import model_config
+
+    names = ["FireNet", "RNNFireNet", "LeakyFireNet", "FireFlowNet", "LeakyFireFlowNet", "E2VID", "EVFlowNet", "RecEVFlowNet", "LeakyRecEVFlowNet",
+             "RNNRecEVFlowNet", "LIFFireNet", "PLIFFireNet", "ALIFFireNet", "XLIFFireNet", "LIFFireFlowNet", "SpikingRecEVFlowNet", "PLIFRecEVFlowNet",
+             "ALIFRecEVFlowNet", "XLIFRecEVFlowNet"]
+    for name in names:
+        model = getattr(M, name)(dict(model_config(name, 5)))
+        assert sum(p.numel() for p in model.parameters()) > 0, name

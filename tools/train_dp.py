@@ -22,6 +22,19 @@ import torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
+def model_config(name, num_bins):
+    """
+    config["model"] for any class of event_flow_b200.models.model.  spiking_neuron: the LIF settings of configs/train_SNN.yml for the LIF
+    models (the other neuron kinds have their own keyword sets: the class defaults), None for the ANN models, whose activations are
+    those of the reference's ANN configs.
+    """
+    lif = name.startswith("LIF") or name == "SpikingRecEVFlowNet"
+    spiking = lif or any(name.startswith(k) for k in ("PLIF", "ALIF", "XLIF"))
+    neuron = dict(leak=[-4.0, 0.1], thresh=[0.8, 0.1], learn_leak=True, learn_thresh=True, hard_reset=True) if lif else ({} if spiking else None)
+    return dict(name=name, encoding="voxel", round_encoding=False, norm_input=False, num_bins=num_bins, base_num_channels=32, kernel_size=3,
+                activations=["arctanspike", "arctanspike"] if spiking else ["relu", None], mask_output=True, spiking_neuron=neuron)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--model", default="LIFFireNet")
@@ -50,15 +63,8 @@ def main():
     assert _lib.lib().ef_device_ok() == 1, "needs a compute-capability 10.x GPU (B200)"
     global_batch = a.batch_size or 8 * world
     assert global_batch % world == 0, "the global batch must divide over the ranks"
-    # spiking_neuron: the LIF settings of configs/train_SNN.yml for the LIF models (the other neuron kinds have their own keyword sets:
-    # the class defaults), None for the ANN models; their activations are those of the reference's ANN configs
-    lif = a.model.startswith("LIF") or a.model == "SpikingRecEVFlowNet"
-    spiking = lif or any(a.model.startswith(k) for k in ("PLIF", "ALIF", "XLIF"))
-    neuron = dict(leak=[-4.0, 0.1], thresh=[0.8, 0.1], learn_leak=True, learn_thresh=True, hard_reset=True) if lif else ({} if spiking else None)
     config = {
-        "model": dict(name=a.model, encoding="voxel", round_encoding=False, norm_input=False, num_bins=a.num_bins, base_num_channels=32,
-                      kernel_size=3, activations=["arctanspike", "arctanspike"] if spiking else ["relu", None], mask_output=True,
-                      spiking_neuron=neuron),
+        "model": model_config(a.model, a.num_bins),
         "loss": {"flow_regul_weight": 0.001, "clip_grad": 100.0, "overwrite_intermediate": False},
         "optimizer": {"name": "Adam", "lr": a.lr},
         "loader": {"resolution": a.resolution, "batch_size": global_batch},
